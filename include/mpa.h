@@ -1,0 +1,149 @@
+/*
+ * mpa.h — C ABI of libmpa.so, the B200 (sm_100a) replacement for the HCQT + patch-wise network hot path of
+ * christofw/multipitch_architectures.
+ *
+ * The reference has no FFI of its own: its boundary is the Python API surface.  The Python
+ * host layer in multipitch_architectures_b200/libdl mirrors that surface and reaches the GPU only through
+ * the entry points below (ctypes; see INTEGRATION.md for the binding a reference maintainer would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch tensors); the library never allocates
+ *     or frees caller-visible memory and never synchronises the device or the stream;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it;
+ *   - return value 0 = success, negative = error; mpa_last_error() returns a thread-local message;
+ *   - no CPU fallback exists: on a non-sm_100 device every call returns MPA_ERR_ARCH.
+ *   - layouts: "NCHW" = [B][C][T][F] fp32 contiguous (T = time frames, F = frequency bins), exactly the
+ *     tensors the reference modules exchange (libdl/nn_models/basic_cnns.py:410-423).
+ *     "CP8"  = bf16 channel-chunk planes [B][ceil(C/8)][TP][FP][8] with zero borders, TP = T + 2*PT,
+ *     FP = row pitch (multiple of 16, >= F + PF); real pixel (t,f) sits at row PT+t, column PF+f.
+ */
+#ifndef MPA_H_
+#define MPA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPA_OK 0
+#define MPA_ERR_ARG (-1)
+#define MPA_ERR_ARCH (-2)
+#define MPA_ERR_CUDA (-3)
+#define MPA_ERR_WORKSPACE (-4)
+
+/* activation codes for the fused epilogues */
+#define MPA_ACT_NONE 0
+#define MPA_ACT_LRELU 1   /* slope in `act_param` */
+#define MPA_ACT_RELU 2
+#define MPA_ACT_SIGMOID 3
+
+int mpa_version(void);
+const char* mpa_last_error(void);
+/* 0 when the current device is compute capability 10.x, MPA_ERR_ARCH otherwise. */
+int mpa_device_check(void);
+/* Number of kernels this library has launched since load (all streams); bench.py's `gpu_launches`. */
+long long mpa_launch_count(void);
+
+/* ---- N1: LayerNorm([C,F]) per (b,t) row with optional fused log compression ---------------------------
+ * replaces nn.LayerNorm on the transposed view (basic_cnns.py:371,411) and, when gamma_log > 0, the dataset's
+ * log(1 + gamma_log * x) (hcqt_datasets.py:105-106).  x,out NCHW [B,C,T,F]; ln_w, ln_b [C,F]. */
+int mpa_layernorm_cf_f32(const float* x, const float* ln_w, const float* ln_b, float* out,
+                         int B, int C, int T, int F, float eps, float gamma_log, void* stream);
+
+/* Frame-major variant used by the streaming inference engine: frames [C][N][F] (the HCQT layout) ->
+ * normalised frames; rows s with s < lead or s >= lead+N are the patch zero padding and come out as ln_b
+ * (LayerNorm of an all-zero row).  out_f32 [C][lead+N+trail][F] and/or out_cp8 CP8 plane (1 chunk). */
+int mpa_layernorm_frames(const float* frames, const float* ln_w, const float* ln_b, float* out_f32,
+                         void* out_cp8, int C, int N, int F, int lead, int trail, int cp8_pitch, int cp8_pf,
+                         float eps, float gamma_log, void* stream);
+
+/* ---- generic direct convolution, fp32 CUDA cores (all kernel sizes / strides of the model zoo) ---------
+ * replaces nn.Conv2d (+ eval BatchNorm2d folded as per-channel scale/shift) + activation.
+ * x NCHW [B,Cin,H,W]; if x2 != NULL the input is the channel concat [x (Cin1) | x2 (Cin-Cin1)] (U-Net skip).
+ * w_packed [Cin][KH*KW][CoutPad] fp32 with CoutPad = ceil(Cout/16)*16; bias/scale/shift [Cout] or NULL.
+ * out[b,co,ho,wo] = act( (conv + bias) * scale + shift ),  Ho = (H+2ph-KH)/sh+1, Wo likewise. */
+int mpa_conv2d_f32(const float* x, const float* x2, int Cin1, const float* w_packed, const float* bias,
+                   const float* scale, const float* shift, float* out, int B, int Cin, int H, int W,
+                   int Cout, int KH, int KW, int sh, int sw, int ph, int pw, int act, float act_param,
+                   void* stream);
+
+/* time max-pool (k,1) stride 1 pad k/2 (-inf padding) with optional residual: out = pool(x) + res. */
+int mpa_maxpool_time_f32(const float* x, const float* res, float* out, int B, int C, int T, int F, int k,
+                         void* stream);
+/* MaxPool2d((kh,kw), stride (sh,sw)), no padding, floor mode (unet_cnns.py:349-361, :2314). */
+int mpa_maxpool2d_f32(const float* x, float* out, int B, int C, int H, int W, int kh, int kw, int sh, int sw,
+                      void* stream);
+/* unet_up_concat_padding (unet_cnns.py:85-104): out[B,Cs+Cl,Hs,Ws] = cat(skip, pad(bilinear_x2_ac(low))). */
+int mpa_upsample2x_concat_f32(const float* low, const float* skip, float* out, int B, int Cl, int Hl, int Wl,
+                              int Cs, int Hs, int Ws, void* stream);
+/* train-mode BatchNorm2d statistics: mean/var (biased) per channel over (B,H,W) -> stats[2*C]. */
+int mpa_bn_stats_f32(const float* x, float* stats, int B, int C, int HW, void* stream);
+/* y = act((x - mean) * rsqrt(var+eps) * w + b) per channel, in place allowed. */
+int mpa_bn_apply_f32(const float* x, const float* stats, const float* w, const float* b, float* out, int B,
+                     int C, int HW, float eps, int act, float act_param, void* stream);
+
+/* ---- N8: transformer_enc_layer (unet_cnns.py:107-159), attention over the BATCH axis -------------------
+ * x, out NCHW [B,E,Th,Fw]; S = Th*Fw tokens per item.  Host-side folding (one-off, see nn_models/unet_cnns.py):
+ *   w_qkv [3E,E] = in_proj_weight blocks times {q,k,v}_linear.weight, b_qkv = in_proj_bias,
+ *   w_proj [E,E] = o_linear.weight @ out_proj.weight, b_proj = o_linear.weight @ out_proj.bias.
+ * pe [S,E] sinusoidal table or NULL.  workspace >= mpa_encoder_layer_workspace() bytes. */
+size_t mpa_encoder_layer_workspace(int B, int E, int S, int mlp_dim);
+int mpa_encoder_layer_f32(const float* x, float* out, int B, int E, int Th, int Fw, int num_heads, int mlp_dim,
+                          const float* pe, const float* w_qkv, const float* b_qkv, const float* w_proj,
+                          const float* b_proj, const float* ln1_w, const float* ln1_b, const float* mlp0_w,
+                          const float* mlp0_b, const float* mlp2_w, const float* mlp2_b, const float* ln2_w,
+                          const float* ln2_b, float eps, void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- tcgen05 implicit-GEMM convolution (the hot op: 96 % of DRCNN FLOPs) ------------------------------
+ * KHxKW "same" convolution, stride 1, on CP8 bf16 planes.  Weights pre-packed by mpa_conv_tc_pack_weights
+ * (host side, one-off).  out = act(conv + bias) in CP8 (pool / residual are applied by mpa_pool3_res_cp8).
+ * in_batch_stride_rows: rows between consecutive patches in the input plane; TP*1 for materialised patches,
+ * 1 for the streaming engine where patch i is rows [i, i+T) of one shared frame-major plane. */
+size_t mpa_conv_tc_packed_bytes(int Cin, int Cout, int KH, int KW);
+/* HOST function: w [Cout][Cin][KH][KW] fp32 (host) -> packed bf16 A-operand tiles (host buffer). */
+int mpa_conv_tc_pack_weights(const float* w_host, void* packed_host, int Cin, int Cout, int KH, int KW);
+int mpa_conv_tc_bf16(const void* in_cp8, const void* w_packed, const float* bias, void* out_cp8, int n_patches,
+                     int Cin, int Cout, int T, int F, int KH, int KW, int pitch, int pf, int pt,
+                     long long in_patch_stride_rows, int act, float act_param, void* stream);
+/* out = maxpool_time3(y) + res (res may be NULL), CP8 in/out, per patch. */
+int mpa_pool3_res_cp8(const void* y_cp8, const void* res_cp8, void* out_cp8, int n_patches, int C, int T, int F,
+                      int pitch, int pf, int pt, void* stream);
+/* layout converters (tests, and the seams between the fp32 and the bf16 paths). */
+int mpa_nchw_to_cp8(const float* x, void* out_cp8, int B, int C, int T, int F, int pitch, int pf, int pt,
+                    void* stream);
+int mpa_cp8_to_nchw(const void* in_cp8, float* out, int B, int C, int T, int F, int pitch, int pf, int pt,
+                    void* stream);
+
+/* ---- HCQT (H1-H3): batched multirate constant-Q filterbank ---------------------------------------------
+ * see multipitch_architectures_b200/libdl/data_preprocessing/hcqt.py for the host driver. */
+/* y_out[t] = sqrt(2) * sum_{|j|<=31} h[|j|] * y_in[2t+j]  (resampy kaiser_fast 2:1), n_out = ceil(n_in/2),
+ * last sample zero when n_in is odd.  half_taps: 32 floats on the device. */
+int mpa_decimate2_f32(const float* y_in, float* y_out, const float* half_taps, long long n_in, void* stream);
+/* STFT frames with a rectangular window ("ones"), centred, reflect padding: spec [n_frames][n_fft/2+1] complex64
+ * (interleaved re,im).  n_fft in {256,512,1024,2048}.  window == NULL -> ones, else n_fft floats. */
+int mpa_stft_f32(const float* y, long long n, const float* window, float* spec, int n_fft, int hop, int n_frames,
+                 void* stream);
+/* CQT octave response: out[h_ch][t][bin] = | sum_f basis[k][f] * spec[t][f] | * scale_k for the 36 (n_rows)
+ * filters of one octave bank; banded basis: row k covers bins [start_k, start_k+band) (zero padded).
+ * Scatters row k to up to 4 (channel, bin) destinations of the [H][n_frames][n_bins_out] fp32 output.
+ * bank selection by a device-resident tuning index: basis + tuning_idx[0]*bank_stride. */
+int mpa_cqt_octave_f32(const float* spec, int n_spec_bins, int n_frames, const float* basis_banded,
+                       const int* band_start, const float* row_scale, int n_rows, int band, long long bank_stride,
+                       long long start_stride, const int* tuning_idx, const int* dest, int n_dest, float* out,
+                       int out_frames, int out_bins, void* stream);
+/* estimate_tuning (H1): spec = hann STFT-2048 magnitudes path.  Writes tuning_idx[0] in [0,100): tuning =
+ * -0.5 + 0.01*idx.  workspace bytes from mpa_tuning_workspace(n_frames). */
+size_t mpa_tuning_workspace(int n_frames);
+int mpa_estimate_tuning_f32(const float* spec2048, int n_frames, float sr, int bins_per_octave, int* tuning_idx,
+                            void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- N11: BCELoss(mean) on sigmoid outputs with the -100 log clamp, forward + d(loss)/d(pred) ---------- */
+int mpa_bce_fwd_bwd_f32(const float* y_pred, const float* y_true, float* loss_sum, float* grad_pred, long long n,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPA_H_ */

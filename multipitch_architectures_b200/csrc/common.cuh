@@ -1,0 +1,60 @@
+// Shared helpers for libmpa (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/mpa.h"
+
+namespace mpa {
+
+void set_error(const char* fmt, ...);
+int check_arch();
+void count_launch(int n = 1);
+
+#define MPA_REQUIRE(cond, ...)                 \
+  do {                                         \
+    if (!(cond)) {                             \
+      mpa::set_error(__VA_ARGS__);             \
+      return MPA_ERR_ARG;                      \
+    }                                          \
+  } while (0)
+
+#define MPA_CHECK_ARCH()                       \
+  do {                                         \
+    int _a = mpa::check_arch();                \
+    if (_a != MPA_OK) return _a;               \
+  } while (0)
+
+#define MPA_CHECK_LAUNCH(name)                                                   \
+  do {                                                                           \
+    cudaError_t _e = cudaGetLastError();                                         \
+    if (_e != cudaSuccess) {                                                     \
+      mpa::set_error("%s: launch failed: %s", name, cudaGetErrorString(_e));     \
+      return MPA_ERR_CUDA;                                                       \
+    }                                                                            \
+    mpa::count_launch();                                                         \
+  } while (0)
+
+__device__ __forceinline__ float apply_act(float v, int act, float p) {
+  if (act == MPA_ACT_LRELU) return v >= 0.f ? v : p * v;
+  if (act == MPA_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == MPA_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
+  return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace mpa

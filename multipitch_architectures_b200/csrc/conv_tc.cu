@@ -1,0 +1,545 @@
+// tcgen05 / TMEM implicit-GEMM "same" convolution (stride 1) on bf16 channel-chunk planes (CP8).
+//
+// Formulation ("weights as A, one padded image row as N"):
+//   D[(j,co), n] += sum_k  A[(j,co), k] * B[k, n]
+//     M = 128 lanes  = J output rows x Cout channels  (J = floor(128/Cout); rows t0 .. t0+J-1 of one patch)
+//     N = row pitch  = every column of ONE padded image row (224 for F=216), so a tap shift is a pure
+//                      start-address shift of the shared-memory operand (no im2col is ever materialised)
+//     K = input rows (KH+J-1) x taps KW x input channels, walked 16 channels-or-taps at a time.
+//   A (weights) is pre-packed on the host in the exact order the MMA issuer walks K; the J row blocks hold the
+//   same filter shifted down by j rows, so one pass over KH+J-1 input rows yields J output rows.
+//   B (activations) lives in shared memory as [chunk][pixel][8 ch] (16 B per pixel per chunk), the K-major
+//   SWIZZLE_NONE canonical layout with SBO = 128 B: operand row r sits at start + 16*r, so the tap (df) of a
+//   15-wide filter is start + 16*df.  The second 16-byte K slice is reached through LBO: the next channel
+//   chunk (LBO = plane stride) or, for an odd chunk count, the next tap (LBO = 16 B).
+//   Zero padding in frequency is physical (zero gap columns between rows of the CP8 plane); zero padding in
+//   time is realised by skipping the K steps of out-of-range input rows.
+//
+// Pipeline (one CTA per SM, persistent over work units = (patch pair, row group)):
+//   warp 0  producer : cp.async.bulk (1-D TMA) of activation row slabs and packed weight stages -> mbarriers
+//   warp 1  MMA      : one thread issues tcgen05.mma (kind::f16, bf16 in, fp32 accumulate in TMEM);
+//                      each weight stage feeds TWO accumulators (two patches) to halve weight traffic
+//   warps 2-5 epilogue: tcgen05.ld -> +bias -> activation -> bf16 -> CP8 global store
+#include "common.cuh"
+#include <cuda.h>
+#include <vector>
+#include <string.h>
+
+namespace mpa {
+
+constexpr int kStageMMAs = 4;                 // MMAs (K=16 steps) per weight stage
+constexpr int kATileBytes = 2 * 128 * 16;     // one MMA's A tile: [2 k-slices][128 rows][16 B]
+constexpr int kAStageBytes = kStageMMAs * kATileBytes;
+constexpr int kNumAStages = 6;
+constexpr int kNumBStages = 2;
+constexpr int kThreads = 192;
+constexpr unsigned long long kWaitTimeoutNs = 4000000000ull;   // bounded waits: a protocol bug traps instead of hanging the GPU
+
+struct ConvTcParams {
+  const uint8_t* in;        // CP8 bf16 planes
+  const uint8_t* w;         // packed weights
+  const float* bias;        // [Cout]
+  __nv_bfloat16* out;       // CP8 bf16 planes [n_patches][NCo][TP][P][8]
+  long long in_patch_stride;   // bytes between patches in `in`
+  long long in_chunk_stride;   // bytes between channel chunks in `in`
+  long long in_row0;           // byte offset of (row 0, column 0) of patch 0 chunk 0
+  int n_patches, NC, Cout, J, T, F, KH, KW, P, pf, pt_out, TP_out, NCo;
+  int mmas_per_row, n_groups, n_units, slab_px;
+  int act;
+  float act_param;
+  uint32_t idesc;
+};
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const unsigned long long t0 = global_ns();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 255u) == 0 && global_ns() - t0 > kWaitTimeoutNs) __trap();
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+
+// ------------------------------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int slab_plane_bytes = p.slab_px * 16;
+  const int slab_bytes = p.NC * slab_plane_bytes;        // one patch, one input row
+  const int bstage_bytes = 2 * slab_bytes;               // two patches
+  uint8_t* a_smem = smem;                                // [kNumAStages][kAStageBytes]
+  uint8_t* b_smem = smem + kNumAStages * kAStageBytes;   // [kNumBStages][2][NC][slab_px][16B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + kNumBStages * bstage_bytes);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = bars + kNumAStages;
+  uint64_t* b_full = bars + 2 * kNumAStages;
+  uint64_t* b_empty = b_full + kNumBStages;
+  uint64_t* acc_full = b_empty + kNumBStages;
+  uint64_t* acc_empty = acc_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kNumAStages; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < kNumBStages; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int ph = p.KH / 2, pw = p.KW / 2;
+  const int rows_in = p.KH + p.J - 1;
+  const int n_pairs = (p.n_patches + 1) / 2;
+  (void)n_pairs;
+
+  if (warp == 0) {
+    // ===================================================== producer
+    if (lane == 0) {
+      int a_stage = 0, b_stage = 0;
+      uint32_t a_phase = 0, b_phase = 0;
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+        const int pair = u / p.n_groups, g = u % p.n_groups;
+        const int t0 = g * p.J;
+        const int b0 = pair * 2;
+        const int np = (b0 + 1 < p.n_patches) ? 2 : 1;
+        for (int r = 0; r < rows_in; ++r) {
+          const int row = t0 - ph + r;
+          if (row < 0 || row >= p.T) continue;
+          // activation slabs of this input row (both patches)
+          mbar_wait(&b_empty[b_stage], b_phase ^ 1);
+          mbar_expect_tx(&b_full[b_stage], (uint32_t)(np * slab_bytes));
+          for (int q = 0; q < np; ++q) {
+            const uint8_t* src = p.in + p.in_row0 + (long long)(b0 + q) * p.in_patch_stride + ((long long)row * p.P - pw) * 16;
+            uint8_t* dst = b_smem + b_stage * bstage_bytes + q * slab_bytes;
+            for (int c = 0; c < p.NC; ++c)
+              bulk_g2s(dst + c * slab_plane_bytes, src + (long long)c * p.in_chunk_stride, (uint32_t)slab_plane_bytes, &b_full[b_stage]);
+          }
+          if (++b_stage == kNumBStages) { b_stage = 0; b_phase ^= 1; }
+          // weight stages of this K row
+          const uint8_t* wrow = p.w + (size_t)r * p.mmas_per_row * kATileBytes;
+          for (int m0 = 0; m0 < p.mmas_per_row; m0 += kStageMMAs) {
+            const int nm = min(kStageMMAs, p.mmas_per_row - m0);
+            mbar_wait(&a_empty[a_stage], a_phase ^ 1);
+            mbar_expect_tx(&a_full[a_stage], (uint32_t)(nm * kATileBytes));
+            bulk_g2s(a_smem + a_stage * kAStageBytes, wrow + (size_t)m0 * kATileBytes, (uint32_t)(nm * kATileBytes), &a_full[a_stage]);
+            if (++a_stage == kNumAStages) { a_stage = 0; a_phase ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      int a_stage = 0, b_stage = 0;
+      uint32_t a_phase = 0, b_phase = 0, acc_phase = 0;
+      const int npairs_c = p.NC / 2;
+      const int n_paired = npairs_c * p.KW;
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+        const int pair = u / p.n_groups, g = u % p.n_groups;
+        const int t0 = g * p.J;
+        const int np = (pair * 2 + 1 < p.n_patches) ? 2 : 1;
+        mbar_wait(acc_empty, acc_phase ^ 1);     // epilogue has drained the accumulators of the previous unit
+        tc_fence_after();
+        uint32_t first = 1;
+        for (int r = 0; r < rows_in; ++r) {
+          const int row = t0 - ph + r;
+          if (row < 0 || row >= p.T) continue;
+          mbar_wait(&b_full[b_stage], b_phase);
+          const uint32_t bbase = smem_u32(b_smem + b_stage * bstage_bytes);
+          for (int m0 = 0; m0 < p.mmas_per_row; m0 += kStageMMAs) {
+            const int nm = min(kStageMMAs, p.mmas_per_row - m0);
+            mbar_wait(&a_full[a_stage], a_phase);
+            tc_fence_after();
+            const uint32_t abase = smem_u32(a_smem + a_stage * kAStageBytes);
+            for (int i = 0; i < nm; ++i) {
+              const int q = m0 + i;
+              uint32_t boff, lbo;
+              if (q < n_paired) {
+                const int cp = q / p.KW, df = q - cp * p.KW;
+                boff = (uint32_t)(2 * cp * slab_plane_bytes + df * 16);
+                lbo = (uint32_t)slab_plane_bytes;
+              } else {
+                const int dp = q - n_paired;
+                boff = (uint32_t)((p.NC - 1) * slab_plane_bytes + 2 * dp * 16);
+                lbo = 16u;
+              }
+              const uint64_t adesc = make_desc(abase + i * kATileBytes, 128 * 16, 128);
+              for (int pq = 0; pq < np; ++pq) {
+                const uint64_t bdesc = make_desc(bbase + pq * slab_bytes + boff, lbo, 128);
+                tc_mma_bf16(tmem_base + pq * 256, adesc, bdesc, p.idesc, first ? 0u : 1u);
+              }
+              first = 0;
+            }
+            tc_commit(&a_empty[a_stage]);       // frees the weight stage when its MMAs have retired
+            if (++a_stage == kNumAStages) { a_stage = 0; a_phase ^= 1; }
+          }
+          tc_commit(&b_empty[b_stage]);         // frees the activation slabs of this row
+          if (++b_stage == kNumBStages) { b_stage = 0; b_phase ^= 1; }
+        }
+        tc_commit(acc_full);                    // accumulators complete -> epilogue
+        acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================================== epilogue (warps 2..5 -> TMEM lane quadrants 2,3,0,1)
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;             // accumulator row = (j, co)
+    const int j = m / p.Cout, co = m - j * p.Cout;
+    const bool row_valid = (j < p.J);
+    const float bias = row_valid ? p.bias[co] : 0.f;
+    uint32_t acc_phase = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const int pair = u / p.n_groups, g = u % p.n_groups;
+      const int t = g * p.J + j;
+      const int np = (pair * 2 + 1 < p.n_patches) ? 2 : 1;
+      mbar_wait(acc_full, acc_phase);
+      tc_fence_after();
+      for (int pq = 0; pq < np; ++pq) {
+        const int b = pair * 2 + pq;
+        __nv_bfloat16* orow = p.out + ((((size_t)b * p.NCo + (co >> 3)) * p.TP_out + p.pt_out + t) * p.P) * 8 + (co & 7);
+        for (int c0 = 0; c0 < p.P; c0 += 32) {
+          uint32_t v[32];
+          tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(pq * 256 + c0), v);
+          tc_wait_ld();
+          if (row_valid && t < p.T) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int n = c0 + i;
+              if (n >= p.pf && n < p.pf + p.F) {
+                float x = __uint_as_float(v[i]) + bias;
+                x = apply_act(x, p.act, p.act_param);
+                orow[(size_t)n * 8] = __float2bfloat16(x);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(acc_empty);
+      acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
+// ------------------------------------------------------------------------------------------ helpers
+static inline int j_blocks(int Cout) { return Cout >= 128 ? 1 : 128 / Cout; }
+static inline int mmas_per_row(int NC, int KW) { return (NC / 2) * KW + ((NC & 1) ? (KW + 1) / 2 : 0); }
+
+static inline uint16_t f32_to_bf16_rne(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+// CP8 <-> NCHW converters ------------------------------------------------------------------------------
+__global__ void nchw_to_cp8_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long total, int C, int T,
+                                   int F, int NCk, int TP, int P, int pf, int pt) {
+  // one thread per (b, chunk, t, f): gathers 8 channels -> one 16-byte store
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int f = (int)(i % F);
+    long long r = i / F;
+    int t = (int)(r % T);
+    r /= T;
+    int ck = (int)(r % NCk);
+    int b = (int)(r / NCk);
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      int c = ck * 8 + e;
+      v[e] = __float2bfloat16(c < C ? x[(((size_t)b * C + c) * T + t) * F + f] : 0.f);
+    }
+    *reinterpret_cast<uint4*>(out + ((((size_t)b * NCk + ck) * TP + pt + t) * P + pf + f) * 8) = *reinterpret_cast<uint4*>(v);
+  }
+}
+
+__global__ void cp8_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, long long total, int C, int T,
+                                   int F, int NCk, int TP, int P, int pf, int pt) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int f = (int)(i % F);
+    long long r = i / F;
+    int t = (int)(r % T);
+    r /= T;
+    int c = (int)(r % C);
+    int b = (int)(r / C);
+    out[i] = __bfloat162float(in[((((size_t)b * NCk + (c >> 3)) * TP + pt + t) * P + pf + f) * 8 + (c & 7)]);
+  }
+}
+
+// out = maxpool_time3(y) + res on CP8 planes; one thread per 16-byte pixel-chunk
+__global__ void pool3_res_cp8_kernel(const uint4* __restrict__ y, const uint4* __restrict__ res, uint4* __restrict__ out,
+                                     long long total, int T, int F, int TP, int P, int pf, int pt) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int f = (int)(i % F);
+    long long r = i / F;
+    int t = (int)(r % T);
+    long long plane = r / T;
+    const size_t base = ((size_t)plane * TP + pt + t) * P + pf + f;
+    uint4 c = y[base];
+    __nv_bfloat162* cm = reinterpret_cast<__nv_bfloat162*>(&c);
+    if (t > 0) {
+      uint4 a = y[base - P];
+      __nv_bfloat162* am = reinterpret_cast<__nv_bfloat162*>(&a);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) cm[e] = __hmax2(cm[e], am[e]);
+    }
+    if (t < T - 1) {
+      uint4 a = y[base + P];
+      __nv_bfloat162* am = reinterpret_cast<__nv_bfloat162*>(&a);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) cm[e] = __hmax2(cm[e], am[e]);
+    }
+    if (res) {
+      uint4 rr = res[base];
+      __nv_bfloat162* rm = reinterpret_cast<__nv_bfloat162*>(&rr);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float2 a = __bfloat1622float2(cm[e]), b2 = __bfloat1622float2(rm[e]);
+        cm[e] = __floats2bfloat162_rn(a.x + b2.x, a.y + b2.y);
+      }
+    }
+    out[base] = c;
+  }
+}
+
+static inline int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  long long cap = 148LL * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace mpa
+
+using namespace mpa;
+
+extern "C" {
+
+size_t mpa_conv_tc_packed_bytes(int Cin, int Cout, int KH, int KW) {
+  if (Cin <= 0 || Cout <= 0 || Cout > 128 || KH <= 0 || KW <= 0) return 0;
+  const int NC = (Cin + 7) / 8, J = j_blocks(Cout);
+  return (size_t)(KH + J - 1) * mmas_per_row(NC, KW) * kATileBytes;
+}
+
+int mpa_conv_tc_pack_weights(const float* w, void* packed, int Cin, int Cout, int KH, int KW) {
+  MPA_REQUIRE(w && packed && Cin > 0 && Cout > 0 && Cout <= 128 && KH > 0 && KW > 0, "conv_tc_pack_weights: bad argument (Cout must be <= 128)");
+  const int NC = (Cin + 7) / 8, J = j_blocks(Cout), mpr = mmas_per_row(NC, KW);
+  const int n_paired = (NC / 2) * KW;
+  uint16_t* o = (uint16_t*)packed;
+  memset(o, 0, mpa_conv_tc_packed_bytes(Cin, Cout, KH, KW));
+  for (int r = 0; r < KH + J - 1; ++r) {
+    for (int q = 0; q < mpr; ++q) {
+      uint16_t* tile = o + ((size_t)r * mpr + q) * (kATileBytes / 2);
+      for (int kc = 0; kc < 2; ++kc) {
+        int df, c;
+        if (q < n_paired) {
+          int cp = q / KW;
+          df = q - cp * KW;
+          c = 2 * cp + kc;
+        } else {
+          df = 2 * (q - n_paired) + kc;
+          c = NC - 1;
+        }
+        if (df >= KW) continue;     // dummy half of the last odd-chunk MMA
+        for (int j = 0; j < J; ++j) {
+          const int kh = r - j;
+          if (kh < 0 || kh >= KH) continue;
+          for (int co = 0; co < Cout; ++co) {
+            const int mrow = j * Cout + co;
+            for (int e = 0; e < 8; ++e) {
+              const int ci = c * 8 + e;
+              if (ci >= Cin) continue;
+              tile[((size_t)kc * 128 + mrow) * 8 + e] = f32_to_bf16_rne(w[(((size_t)co * Cin + ci) * KH + kh) * KW + df]);
+            }
+          }
+        }
+      }
+    }
+  }
+  return MPA_OK;
+}
+
+int mpa_conv_tc_bf16(const void* in_cp8, const void* w_packed, const float* bias, void* out_cp8, int n_patches, int Cin, int Cout,
+                     int T, int F, int KH, int KW, int pitch, int pf, int pt, long long in_patch_stride_rows, int act,
+                     float act_param, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(in_cp8 && w_packed && bias && out_cp8 && n_patches > 0, "conv_tc: null argument");
+  MPA_REQUIRE(Cout > 0 && Cout <= 128 && Cin > 0, "conv_tc: Cout must be in 1..128 (got %d)", Cout);
+  MPA_REQUIRE((KH & 1) && (KW & 1), "conv_tc: odd kernel sizes only");
+  MPA_REQUIRE(pitch % 16 == 0 && pitch >= 16 && pitch <= 256, "conv_tc: row pitch must be a multiple of 16 in 16..256 (got %d)", pitch);
+  MPA_REQUIRE(pf >= KW / 2 && pitch - F >= KW / 2 && pitch >= pf + F, "conv_tc: pitch %d / left pad %d too small for F=%d KW=%d", pitch, pf, F, KW);
+  MPA_REQUIRE(pt >= 1, "conv_tc: at least one guard row above and below each plane is required");
+  MPA_REQUIRE(((uintptr_t)in_cp8 & 15) == 0 && ((uintptr_t)w_packed & 15) == 0 && ((uintptr_t)out_cp8 & 15) == 0, "conv_tc: 16-byte alignment required");
+  ConvTcParams p;
+  p.in = (const uint8_t*)in_cp8;
+  p.w = (const uint8_t*)w_packed;
+  p.bias = bias;
+  p.out = (__nv_bfloat16*)out_cp8;
+  p.n_patches = n_patches;
+  p.NC = (Cin + 7) / 8;
+  p.Cout = Cout;
+  p.J = j_blocks(Cout);
+  p.T = T; p.F = F; p.KH = KH; p.KW = KW; p.P = pitch; p.pf = pf;
+  p.pt_out = pt;
+  p.TP_out = T + 2 * pt;
+  p.NCo = (Cout + 7) / 8;
+  const long long TP = T + 2 * pt;
+  if (in_patch_stride_rows <= 0) {
+    // materialised patches: [n_patches][NC][TP][P][8]
+    p.in_chunk_stride = TP * pitch * 16;
+    p.in_patch_stride = p.in_chunk_stride * p.NC;
+    p.in_row0 = (long long)pt * pitch * 16;
+  } else {
+    // streaming: one shared plane per chunk [NC][rows][P][8]; patch b starts at row b*stride (+pt guard rows)
+    MPA_REQUIRE(p.NC == 1, "conv_tc: streaming input supports a single channel chunk");
+    p.in_chunk_stride = 0;
+    p.in_patch_stride = in_patch_stride_rows * pitch * 16;
+    p.in_row0 = (long long)pt * pitch * 16;
+  }
+  p.mmas_per_row = mmas_per_row(p.NC, KW);
+  p.n_groups = (T + p.J - 1) / p.J;
+  p.n_units = ((n_patches + 1) / 2) * p.n_groups;
+  p.slab_px = (pitch + 2 * (KW / 2) + 1 + 7) / 8 * 8;
+  p.act = act;
+  p.act_param = act_param;
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(pitch >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const size_t smem = (size_t)kNumAStages * kAStageBytes + (size_t)kNumBStages * 2 * p.NC * p.slab_px * 16 + 256;
+  MPA_REQUIRE(smem <= 227 * 1024, "conv_tc: needs %zu B of shared memory (Cin=%d pitch=%d)", smem, Cin, pitch);
+  static thread_local size_t attr_set = 0;
+  if (smem > attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("conv_tc: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+      return MPA_ERR_CUDA;
+    }
+    attr_set = smem;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = p.n_units < sms ? p.n_units : sms;
+  conv_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+  MPA_CHECK_LAUNCH("conv_tc");
+  return MPA_OK;
+}
+
+int mpa_pool3_res_cp8(const void* y_cp8, const void* res_cp8, void* out_cp8, int n_patches, int C, int T, int F, int pitch, int pf,
+                      int pt, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(y_cp8 && out_cp8 && n_patches > 0 && C > 0, "pool3_res_cp8: bad argument");
+  const int NCk = (C + 7) / 8;
+  long long total = (long long)n_patches * NCk * T * F;
+  pool3_res_cp8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)y_cp8, (const uint4*)res_cp8, (uint4*)out_cp8,
+                                                                                 total, T, F, T + 2 * pt, pitch, pf, pt);
+  MPA_CHECK_LAUNCH("pool3_res_cp8");
+  return MPA_OK;
+}
+
+int mpa_nchw_to_cp8(const float* x, void* out_cp8, int B, int C, int T, int F, int pitch, int pf, int pt, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(x && out_cp8 && B > 0 && C > 0 && pitch >= pf + F, "nchw_to_cp8: bad argument");
+  const int NCk = (C + 7) / 8;
+  long long total = (long long)B * NCk * T * F;
+  nchw_to_cp8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out_cp8, total, C, T, F, NCk, T + 2 * pt,
+                                                                               pitch, pf, pt);
+  MPA_CHECK_LAUNCH("nchw_to_cp8");
+  return MPA_OK;
+}
+
+int mpa_cp8_to_nchw(const void* in_cp8, float* out, int B, int C, int T, int F, int pitch, int pf, int pt, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(in_cp8 && out && B > 0 && C > 0 && pitch >= pf + F, "cp8_to_nchw: bad argument");
+  const int NCk = (C + 7) / 8;
+  long long total = (long long)B * C * T * F;
+  cp8_to_nchw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in_cp8, out, total, C, T, F, NCk,
+                                                                               T + 2 * pt, pitch, pf, pt);
+  MPA_CHECK_LAUNCH("cp8_to_nchw");
+  return MPA_OK;
+}
+
+}  // extern "C"

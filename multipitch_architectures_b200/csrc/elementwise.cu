@@ -1,0 +1,337 @@
+// HBM-bound stages of the patch-wise networks: LayerNorm(+log compression), pooling, bilinear upsample +
+// concat, BatchNorm statistics/apply, BCE loss.  fp32 NCHW.  All kernels are grid-stride / row-per-block with
+// coalesced accesses along F (the contiguous axis).
+#include "common.cuh"
+
+namespace mpa {
+
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float r = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.f;
+  if (w == 0) {
+    r = warp_sum(r);
+    if (l == 0) sh[0] = r;
+  }
+  __syncthreads();
+  return sh[0];
+}
+
+// one block per (b,t) row; the row is the C x F slab x[b, :, t, :]
+template <int MAXV>
+__global__ void __launch_bounds__(128) layernorm_cf_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                           const float* __restrict__ bsh, float* __restrict__ out,
+                                                           int C, int T, int F, float eps, float gamma_log) {
+  __shared__ float sh[8];
+  int b = blockIdx.x / T, t = blockIdx.x % T;
+  const int n = C * F;
+  const float* xr = x + ((size_t)b * C * T + t) * F;
+  float* orow = out + ((size_t)b * C * T + t) * F;
+  float v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int e = threadIdx.x + i * 128;
+    float val = 0.f;
+    if (e < n) {
+      int c = e / F, f = e - c * F;
+      val = xr[(size_t)c * T * F + f];
+      if (gamma_log > 0.f) val = logf(1.f + gamma_log * val);
+      s += val;
+    }
+    v[i] = val;
+  }
+  float mean = block_sum(s, sh) / n;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int e = threadIdx.x + i * 128;
+    if (e < n) {
+      float d = v[i] - mean;
+      q += d * d;
+    }
+  }
+  float rstd = rsqrtf(block_sum(q, sh) / n + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int e = threadIdx.x + i * 128;
+    if (e < n) {
+      int c = e / F, f = e - c * F;
+      orow[(size_t)c * T * F + f] = (v[i] - mean) * rstd * w[e] + bsh[e];
+    }
+  }
+}
+
+// frame-major: frames [C][N][F]; output rows s in [0, lead+N+trail); pad rows -> bias
+template <int MAXV>
+__global__ void __launch_bounds__(128) layernorm_frames_kernel(const float* __restrict__ frames, const float* __restrict__ w,
+                                                               const float* __restrict__ bsh, float* __restrict__ out_f32,
+                                                               __nv_bfloat16* __restrict__ out_cp8, int C, int N, int F, int lead,
+                                                               int trail, int pitch, int pf, float eps, float gamma_log) {
+  __shared__ float sh[8];
+  const int s = blockIdx.x;
+  const int NT = lead + N + trail;
+  const int n = C * F;
+  const int src = s - lead;
+  const bool real = (src >= 0 && src < N);
+  float v[MAXV];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int e = threadIdx.x + i * 128;
+    float val = 0.f;
+    if (real && e < n) {
+      int c = e / F, f = e - c * F;
+      val = frames[((size_t)c * N + src) * F + f];
+      if (gamma_log > 0.f) val = logf(1.f + gamma_log * val);
+      sum += val;
+    }
+    v[i] = val;
+  }
+  float mean = block_sum(sum, sh) / n;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int e = threadIdx.x + i * 128;
+    if (e < n) {
+      float d = v[i] - mean;
+      q += d * d;
+    }
+  }
+  float rstd = rsqrtf(block_sum(q, sh) / n + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int e = threadIdx.x + i * 128;
+    if (e < n) {
+      int c = e / F, f = e - c * F;
+      float r = (v[i] - mean) * rstd * w[e] + bsh[e];
+      if (out_f32) out_f32[((size_t)c * NT + s) * F + f] = r;
+      if (out_cp8) out_cp8[((size_t)s * pitch + pf + f) * 8 + c] = __float2bfloat16(r);
+    }
+  }
+}
+
+__global__ void maxpool_time_kernel(const float* __restrict__ x, const float* __restrict__ res, float* __restrict__ out,
+                                    long long total, int T, int F, int k) {
+  const int h = k / 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int f = (int)(i % F);
+    long long r = i / F;
+    int t = (int)(r % T);
+    long long plane = r / T;
+    const float* xp = x + plane * T * F + f;
+    int lo = max(0, t - h), hi = min(T - 1, t + h);
+    float m = -INFINITY;
+    for (int tt = lo; tt <= hi; ++tt) m = fmaxf(m, xp[(size_t)tt * F]);
+    if (res) m += res[i];
+    out[i] = m;
+  }
+}
+
+__global__ void maxpool2d_kernel(const float* __restrict__ x, float* __restrict__ out, long long total, int H, int W,
+                                 int Ho, int Wo, int kh, int kw, int sh, int sw) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int wo = (int)(i % Wo);
+    long long r = i / Wo;
+    int ho = (int)(r % Ho);
+    long long plane = r / Ho;
+    const float* xp = x + plane * H * W + (size_t)(ho * sh) * W + wo * sw;
+    float m = -INFINITY;
+    for (int a = 0; a < kh; ++a)
+      for (int b = 0; b < kw; ++b) m = fmaxf(m, xp[a * W + b]);
+    out[i] = m;
+  }
+}
+
+__global__ void upsample_concat_kernel(const float* __restrict__ low, const float* __restrict__ skip, float* __restrict__ out,
+                                       long long total, int Cl, int Hl, int Wl, int Cs, int Hs, int Ws) {
+  const int Ct = Cs + Cl;
+  const int Hu = 2 * Hl, Wu = 2 * Wl;
+  const int dY = Hs - Hu, dX = Ws - Wu;
+  const int top = dY / 2, left = dX / 2;
+  const float ry = (Hu > 1) ? (float)(Hl - 1) / (float)(Hu - 1) : 0.f;
+  const float rx = (Wu > 1) ? (float)(Wl - 1) / (float)(Wu - 1) : 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int w = (int)(i % Ws);
+    long long r = i / Ws;
+    int h = (int)(r % Hs);
+    r /= Hs;
+    int c = (int)(r % Ct);
+    int b = (int)(r / Ct);
+    float v;
+    if (c < Cs) {
+      v = skip[(((size_t)b * Cs + c) * Hs + h) * Ws + w];
+    } else {
+      int hu = h - top, wu = w - left;
+      if (hu < 0 || hu >= Hu || wu < 0 || wu >= Wu) {
+        v = 0.f;
+      } else {
+        // torch area_pixel_compute_source_index(align_corners=True): src = scale * dst
+        float sy = ry * hu, sx = rx * wu;
+        int y0 = (int)sy, x0 = (int)sx;
+        int y1 = min(y0 + 1, Hl - 1), x1 = min(x0 + 1, Wl - 1);
+        float ly = sy - y0, lx = sx - x0;
+        const float* lp = low + ((size_t)b * Cl + (c - Cs)) * Hl * Wl;
+        float v00 = lp[y0 * Wl + x0], v01 = lp[y0 * Wl + x1], v10 = lp[y1 * Wl + x0], v11 = lp[y1 * Wl + x1];
+        v = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+      }
+    }
+    out[i] = v;
+  }
+}
+
+// one block per channel; two-pass mean / biased variance over (B, HW)
+__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ x, float* __restrict__ stats, int B, int C, int HW) {
+  __shared__ float sh[8];
+  const int c = blockIdx.x;
+  const long long n = (long long)B * HW;
+  float s = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    int b = (int)(i / HW);
+    int p = (int)(i - (long long)b * HW);
+    s += x[((size_t)b * C + c) * HW + p];
+  }
+  float mean = block_sum(s, sh) / (float)n;
+  float q = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    int b = (int)(i / HW);
+    int p = (int)(i - (long long)b * HW);
+    float d = x[((size_t)b * C + c) * HW + p] - mean;
+    q += d * d;
+  }
+  float var = block_sum(q, sh) / (float)n;
+  if (threadIdx.x == 0) {
+    stats[c] = mean;
+    stats[C + c] = var;
+  }
+}
+
+__global__ void bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ w,
+                                const float* __restrict__ b, float* __restrict__ out, long long total, int C, int HW, float eps,
+                                int act, float act_param) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)((i / HW) % C);
+    float v = (x[i] - stats[c]) * rsqrtf(stats[C + c] + eps) * w[c] + b[c];
+    out[i] = apply_act(v, act, act_param);
+  }
+}
+
+__global__ void __launch_bounds__(256) bce_kernel(const float* __restrict__ yp, const float* __restrict__ yt, float* __restrict__ loss_sum,
+                                                  float* __restrict__ grad, long long n) {
+  __shared__ float sh[8];
+  float acc = 0.f;
+  const float inv_n = 1.f / (float)n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float p = yp[i], t = yt[i];
+    float lp = fmaxf(logf(p), -100.f), l1p = fmaxf(logf(1.f - p), -100.f);
+    acc -= t * lp + (1.f - t) * l1p;
+    if (grad) {
+      // d/dp of the clamped loss: the clamp kills the gradient where log < -100 (torch: p clamped via eps 1e-12)
+      float g = (p - t) / fmaxf(p * (1.f - p), 1e-12f);
+      grad[i] = g * inv_n;
+    }
+  }
+  float tot = block_sum(acc, sh);
+  if (threadIdx.x == 0) atomicAdd(loss_sum, tot * inv_n);
+}
+
+static inline int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  long long cap = 148LL * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace mpa
+
+using namespace mpa;
+
+extern "C" {
+
+int mpa_layernorm_cf_f32(const float* x, const float* ln_w, const float* ln_b, float* out, int B, int C, int T, int F,
+                         float eps, float gamma_log, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(x && ln_w && ln_b && out && B > 0 && C > 0 && T > 0 && F > 0, "layernorm_cf: bad argument");
+  MPA_REQUIRE(C * F <= 128 * 16, "layernorm_cf: C*F=%d exceeds the 2048-element row limit", C * F);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C * F <= 128 * 11)
+    layernorm_cf_kernel<11><<<B * T, 128, 0, st>>>(x, ln_w, ln_b, out, C, T, F, eps, gamma_log);
+  else
+    layernorm_cf_kernel<16><<<B * T, 128, 0, st>>>(x, ln_w, ln_b, out, C, T, F, eps, gamma_log);
+  MPA_CHECK_LAUNCH("layernorm_cf");
+  return MPA_OK;
+}
+
+int mpa_layernorm_frames(const float* frames, const float* ln_w, const float* ln_b, float* out_f32, void* out_cp8, int C,
+                         int N, int F, int lead, int trail, int cp8_pitch, int cp8_pf, float eps, float gamma_log,
+                         void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(frames && ln_w && ln_b && (out_f32 || out_cp8) && C > 0 && N > 0 && F > 0 && lead >= 0 && trail >= 0,
+              "layernorm_frames: bad argument");
+  MPA_REQUIRE(C * F <= 128 * 11, "layernorm_frames: C*F=%d exceeds 1408", C * F);
+  MPA_REQUIRE(!out_cp8 || (C <= 8 && cp8_pitch >= F + cp8_pf), "layernorm_frames: CP8 output needs C<=8 and pitch>=F+pf");
+  layernorm_frames_kernel<11><<<lead + N + trail, 128, 0, (cudaStream_t)stream>>>(
+      frames, ln_w, ln_b, out_f32, (__nv_bfloat16*)out_cp8, C, N, F, lead, trail, cp8_pitch, cp8_pf, eps, gamma_log);
+  MPA_CHECK_LAUNCH("layernorm_frames");
+  return MPA_OK;
+}
+
+int mpa_maxpool_time_f32(const float* x, const float* res, float* out, int B, int C, int T, int F, int k, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(x && out && B > 0 && C > 0 && T > 0 && F > 0 && k >= 1 && (k & 1), "maxpool_time: bad argument");
+  long long total = (long long)B * C * T * F;
+  maxpool_time_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, res, out, total, T, F, k);
+  MPA_CHECK_LAUNCH("maxpool_time");
+  return MPA_OK;
+}
+
+int mpa_maxpool2d_f32(const float* x, float* out, int B, int C, int H, int W, int kh, int kw, int sh, int sw, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(x && out && B > 0 && C > 0 && H >= kh && W >= kw && kh > 0 && kw > 0 && sh > 0 && sw > 0, "maxpool2d: bad argument");
+  int Ho = (H - kh) / sh + 1, Wo = (W - kw) / sw + 1;
+  long long total = (long long)B * C * Ho * Wo;
+  maxpool2d_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, out, total, H, W, Ho, Wo, kh, kw, sh, sw);
+  MPA_CHECK_LAUNCH("maxpool2d");
+  return MPA_OK;
+}
+
+int mpa_upsample2x_concat_f32(const float* low, const float* skip, float* out, int B, int Cl, int Hl, int Wl, int Cs,
+                              int Hs, int Ws, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(low && skip && out && B > 0 && Cl > 0 && Cs > 0 && Hs >= 2 * Hl && Ws >= 2 * Wl, "upsample2x_concat: bad argument");
+  long long total = (long long)B * (Cs + Cl) * Hs * Ws;
+  upsample_concat_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(low, skip, out, total, Cl, Hl, Wl, Cs, Hs, Ws);
+  MPA_CHECK_LAUNCH("upsample2x_concat");
+  return MPA_OK;
+}
+
+int mpa_bn_stats_f32(const float* x, float* stats, int B, int C, int HW, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(x && stats && B > 0 && C > 0 && HW > 0, "bn_stats: bad argument");
+  bn_stats_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(x, stats, B, C, HW);
+  MPA_CHECK_LAUNCH("bn_stats");
+  return MPA_OK;
+}
+
+int mpa_bn_apply_f32(const float* x, const float* stats, const float* w, const float* b, float* out, int B, int C, int HW,
+                     float eps, int act, float act_param, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(x && stats && w && b && out && B > 0 && C > 0 && HW > 0, "bn_apply: bad argument");
+  long long total = (long long)B * C * HW;
+  bn_apply_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, stats, w, b, out, total, C, HW, eps, act, act_param);
+  MPA_CHECK_LAUNCH("bn_apply");
+  return MPA_OK;
+}
+
+int mpa_bce_fwd_bwd_f32(const float* y_pred, const float* y_true, float* loss_sum, float* grad_pred, long long n, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(y_pred && y_true && loss_sum && n > 0, "bce: bad argument");
+  cudaMemsetAsync(loss_sum, 0, sizeof(float), (cudaStream_t)stream);
+  bce_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(y_pred, y_true, loss_sum, grad_pred, n);
+  MPA_CHECK_LAUNCH("bce");
+  return MPA_OK;
+}
+
+}  // extern "C"

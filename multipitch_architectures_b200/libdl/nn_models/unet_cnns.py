@@ -1,0 +1,189 @@
+"""Unet / SAUnet / SAUSnet / PUnet multi-pitch networks with the reference's constructor signatures and
+state_dict layout (/root/reference/libdl/nn_models/unet_cnns.py:30-159, 333-407, 496-575, 670-754,
+2251-2335), executed by libmpa CUDA kernels (see _exec.py).  torch.nn layers are parameter holders only."""
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from ... import _lib, ops
+from . import _exec
+from .basic_cnns import _MpaModel, _Stage, _head
+
+
+class double_conv(nn.Module):
+    """(Conv k x k -> BatchNorm2d -> ReLU -> Dropout(convdrop)) x 2; index layout 0,1,(2,3),4,5,(6,7) as in the
+    reference's default branch (convdrop=0, alt_order=False, unet_cnns.py:49-59)."""
+
+    def __init__(self, in_channels, out_channels, mid_channels=None, kernel_size=(3, 3), padding=(1, 1), convdrop=0,
+                 residual=False, alt_order=False):
+        super().__init__()
+        if alt_order:
+            raise NotImplementedError('alt_order=True (ELU/BN pre-activation variant) is not used by any experiment')
+        if residual:
+            raise NotImplementedError('residual double_conv is not used by the BASELINE configurations')
+        if not mid_channels:
+            mid_channels = out_channels
+        self.residual, self.out_channels = residual, out_channels
+        layers = [nn.Conv2d(in_channels, mid_channels, kernel_size=kernel_size, padding=padding), nn.BatchNorm2d(mid_channels),
+                  _Stage('ReLU')]
+        if convdrop is not None:
+            layers.append(_Stage(f'Dropout({convdrop})'))
+        layers += [nn.Conv2d(mid_channels, out_channels, kernel_size=kernel_size, padding=padding), nn.BatchNorm2d(out_channels),
+                   _Stage('ReLU')]
+        if convdrop is not None:
+            layers.append(_Stage(f'Dropout({convdrop})'))
+        self.double_conv = nn.Sequential(*layers)
+        if convdrop is None:
+            raise NotImplementedError('convdrop=None changes the Sequential indices; the experiments use convdrop=0')
+
+
+class transformer_enc_layer(nn.Module):
+    """Parameter holder of the bottleneck encoder layer (unet_cnns.py:107-159).  The sinusoidal table is a plain
+    attribute in the reference (not in the state_dict); here it is rebuilt on the input's device."""
+
+    def __init__(self, embed_dim=32, num_heads=8, mlp_dim=512, p_dropout=0.2, pos_encoding=None):
+        super().__init__()
+        if pos_encoding not in (None, 'sinusoidal'):
+            raise NotImplementedError("pos_encoding='learnable' is not used by any experiment")
+        self.embed_dim, self.num_heads, self.mlp_dim, self.pos_encoding = embed_dim, num_heads, mlp_dim, pos_encoding
+        self.p_dropout = p_dropout
+        self.q_linear = nn.Linear(embed_dim, embed_dim, bias=False)
+        self.v_linear = nn.Linear(embed_dim, embed_dim, bias=False)
+        self.k_linear = nn.Linear(embed_dim, embed_dim, bias=False)
+        self.attn = nn.MultiheadAttention(embed_dim=embed_dim, num_heads=num_heads)
+        self.o_linear = nn.Linear(embed_dim, embed_dim, bias=False)
+        self.mlp = nn.Sequential(nn.Linear(embed_dim, mlp_dim), _Stage('ReLU'), nn.Linear(mlp_dim, embed_dim))
+        self.layernorm1 = nn.LayerNorm(normalized_shape=[embed_dim])
+        self.layernorm2 = nn.LayerNorm(normalized_shape=[embed_dim])
+        self._cache = _exec.ParamCache()
+
+    def run(self, x):
+        B, E, Th, Fw = x.shape
+        S = Th * Fw
+        at = self.attn
+
+        def fold():
+            Wi, bi = at.in_proj_weight, at.in_proj_bias
+            wq = Wi[:E] @ self.q_linear.weight
+            wk = Wi[E:2 * E] @ self.k_linear.weight
+            wv = Wi[2 * E:] @ self.v_linear.weight
+            w_qkv = torch.cat([wq, wk, wv], 0).contiguous()
+            w_proj = (self.o_linear.weight @ at.out_proj.weight).contiguous()
+            b_proj = (self.o_linear.weight @ at.out_proj.bias).contiguous()
+            return w_qkv, bi.contiguous(), w_proj, b_proj
+        w_qkv, b_qkv, w_proj, b_proj = self._cache.get(
+            'fold', [at.in_proj_weight, at.in_proj_bias, self.q_linear.weight, self.k_linear.weight, self.v_linear.weight,
+                     self.o_linear.weight, at.out_proj.weight, at.out_proj.bias], fold)
+        pe = None
+        if self.pos_encoding == 'sinusoidal':
+            pe = self._cache.get(f'pe{S}', [self.layernorm1.weight], lambda: _exec.sinusoidal_pe(S, E, x.device).contiguous())
+        ws_bytes = _lib.lib().mpa_encoder_layer_workspace(B, E, S, self.mlp_dim)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        out = torch.empty_like(x)
+        _lib.call('encoder_layer_f32', x, out, B, E, Th, Fw, self.num_heads, self.mlp_dim, pe, w_qkv, b_qkv, w_proj, b_proj,
+                  self.layernorm1.weight, self.layernorm1.bias, self.mlp[0].weight, self.mlp[0].bias, self.mlp[2].weight,
+                  self.mlp[2].bias, self.layernorm2.weight, self.layernorm2.bias, float(self.layernorm1.eps), ws,
+                  _lib.usize(ws_bytes), _lib.stream_ptr())
+        return out
+
+
+def _down(cin, cout, k, **kw):
+    return nn.Sequential(_Stage('MaxPool(2,2)'), double_conv(cin, cout, mid_channels=cout, kernel_size=(k, k), padding=(k // 2, k // 2), **kw))
+
+
+class _UnetBase(_MpaModel):
+    def _build_trunk(self, n_in, n_ch, sc, **kw):
+        self.inc = double_conv(n_in, 64 // sc, mid_channels=64 // sc, kernel_size=(15, 15), padding=(7, 7),
+                               **{k: v for k, v in kw.items() if k != 'residual'})
+        self.down1 = _down(64 // sc, 128 // sc, 15, **kw)
+        self.down2 = _down(128 // sc, 256 // sc, 9, **kw)
+        self.down3 = _down(256 // sc, 512 // sc, 5, **kw)
+        self.down4 = _down(512 // sc, 1024 // (sc * 2), 3, **kw)
+
+    def _build_up(self, n_ch, sc, **kw):
+        self.upconcat = _Stage('bilinear x2 (align_corners) + pad + concat')
+        self.upconv1 = double_conv(1024 // sc, 512 // (sc * 2), mid_channels=1024 // (sc * 2), kernel_size=(3, 3), padding=(1, 1), **kw)
+        self.upconv2 = double_conv(512 // sc, 256 // (sc * 2), mid_channels=512 // (sc * 2), kernel_size=(5, 5), padding=(2, 2), **kw)
+        self.upconv3 = double_conv(256 // sc, 128 // (sc * 2), mid_channels=256 // (sc * 2), kernel_size=(9, 9), padding=(4, 4), **kw)
+        self.upconv4 = double_conv(128 // sc, n_ch[0], mid_channels=128 // (sc * 2), kernel_size=(15, 15), padding=(7, 7), **kw)
+
+    def _bn_train(self):
+        return self.training
+
+    def _run(self, x):
+        x = _exec._check_input(x, self.n_chan_input, self.n_bins_in)
+        if x.shape[2] < 75:
+            raise ValueError('U-Net models need at least 75 frames of context')
+        if torch.is_grad_enabled() and self.training:
+            raise NotImplementedError('U-Net training (backward) is not part of this round; wrap inference in torch.no_grad()')
+        self._guard_training()
+        train = self._bn_train()
+        x1, x2, x3, x4, x5 = _exec.unet_trunk_f32(self, x, train)
+        x5 = self._bottleneck(x5)
+        u = _exec.unet_up_f32(self, x5, (x1, x2, x3, x4), train)
+        return _exec.head_f32(self._cache, self, u, self.a_lrelu), x5
+
+    def _bottleneck(self, x5):
+        return x5
+
+
+class simple_u_net_largekernels(_UnetBase):
+    def __init__(self, n_chan_input=6, n_chan_layers=[64, 30, 20, 10], n_bins_in=216, n_bins_out=12, a_lrelu=0.3, p_dropout=0.2,
+                 scalefac=16, precision='fp32'):
+        super().__init__()
+        self._init_common(n_chan_input, n_bins_in, a_lrelu, p_dropout, precision)
+        self.layernorm = nn.LayerNorm(normalized_shape=[n_chan_input, n_bins_in])
+        self._build_trunk(n_chan_input, n_chan_layers, scalefac)
+        self._build_up(n_chan_layers, scalefac)
+        _head(self, n_chan_layers[0], n_chan_layers, n_bins_in, n_bins_out, a_lrelu, p_dropout)
+
+    def forward(self, x):
+        return self._run(x)[0]
+
+
+class simple_u_net_doubleselfattn(_UnetBase):
+    def __init__(self, n_chan_input=6, n_chan_layers=[64, 30, 20, 10], n_bins_in=216, n_bins_out=12, a_lrelu=0.3, p_dropout=0.2,
+                 convdrop=0, residual=False, alt_order=False, scalefac=16, embed_dim=4 * 8, num_heads=8, mlp_dim=512,
+                 pos_encoding=None, precision='fp32'):
+        super().__init__()
+        self._init_common(n_chan_input, n_bins_in, a_lrelu, p_dropout, precision)
+        kw = dict(convdrop=convdrop, residual=residual, alt_order=alt_order)
+        self.layernorm = nn.LayerNorm(normalized_shape=[n_chan_input, n_bins_in])
+        self._build_trunk(n_chan_input, n_chan_layers, scalefac, **kw)
+        self.attention1 = transformer_enc_layer(embed_dim=embed_dim, num_heads=num_heads, mlp_dim=mlp_dim, pos_encoding=pos_encoding)
+        self.attention2 = transformer_enc_layer(embed_dim=embed_dim, num_heads=num_heads, mlp_dim=mlp_dim)
+        self._build_up(n_chan_layers, scalefac, **kw)
+        _head(self, n_chan_layers[0], n_chan_layers, n_bins_in, n_bins_out, a_lrelu, p_dropout)
+
+    def _guard_training(self):
+        if self.training and (self.p_dropout > 0 or self.attention1.p_dropout > 0):
+            raise NotImplementedError('train-mode forward with dropout>0 is not available; call .eval() for inference')
+
+    def _bottleneck(self, x5):
+        return self.attention2.run(self.attention1.run(x5))
+
+    def forward(self, x):
+        return self._run(x)[0]
+
+
+class simple_u_net_polyphony_classif_softmax(_UnetBase):
+    def __init__(self, n_chan_input=6, n_chan_layers=[64, 30, 20, 10], n_bins_in=216, n_bins_out=12, a_lrelu=0.3, p_dropout=0.2,
+                 scalefac=16, num_polyphony_steps=24, precision='fp32'):
+        super().__init__()
+        self._init_common(n_chan_input, n_bins_in, a_lrelu, p_dropout, precision)
+        sc = scalefac
+        self.layernorm = nn.LayerNorm(normalized_shape=[n_chan_input, n_bins_in])
+        self._build_trunk(n_chan_input, n_chan_layers, sc)
+        self._build_up(n_chan_layers, sc)
+        _head(self, n_chan_layers[0], n_chan_layers, n_bins_in, n_bins_out, a_lrelu, p_dropout)
+        self.convP = nn.Sequential(nn.Conv2d(1024 // (sc * 2), 1024 // (sc * 4), (2, 5)), _Stage(f'LeakyReLU({a_lrelu})'),
+                                   _Stage('MaxPool(2,5)/s(1,2)'), _Stage(f'Dropout({p_dropout})'),
+                                   nn.Conv2d(1024 // (sc * 4), num_polyphony_steps, (2, 3)))
+
+    def forward(self, x):
+        y, x5 = self._run(x)
+        p = _exec.conv_f32(self._cache, 'convP.0', self.convP[0], x5, ops.ACT_LRELU, self.a_lrelu)
+        p = ops.maxpool2d(p, (2, 5), (1, 2))
+        n_pred = _exec.conv_f32(self._cache, 'convP.4', self.convP[4], p)
+        return y, n_pred

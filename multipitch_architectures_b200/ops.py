@@ -1,0 +1,154 @@
+"""Thin tensor-level wrappers over the C ABI (one call = one asynchronous launch sequence on the current stream)."""
+import torch
+
+from . import _lib
+from ._lib import call, stream_ptr
+
+ACT_NONE, ACT_LRELU, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3
+
+
+def _f32(t):
+    if t.dtype != torch.float32:
+        raise _lib.MpaError(f'expected float32 tensor, got {t.dtype}')
+    return t
+
+
+def pack_conv_weight(w):
+    """[Cout,Cin,KH,KW] -> [Cin][KH*KW][CoutPad16] fp32 (layout of mpa_conv2d_f32)."""
+    Cout, Cin, KH, KW = w.shape
+    CoutPad = (Cout + 15) // 16 * 16
+    p = torch.zeros(Cin, KH * KW, CoutPad, dtype=torch.float32, device=w.device)
+    p[:, :, :Cout] = w.detach().float().permute(1, 2, 3, 0).reshape(Cin, KH * KW, Cout)
+    return p.contiguous()
+
+
+def layernorm_cf(x, w, b, eps=1e-5, gamma_log=0.0):
+    B, C, T, F = x.shape
+    out = torch.empty_like(x)
+    call('layernorm_cf_f32', _f32(x), w, b, out, B, C, T, F, float(eps), float(gamma_log), stream_ptr())
+    return out
+
+
+def conv2d(x, wp, bias, Cout, ksize, stride=(1, 1), padding=(0, 0), act=ACT_NONE, act_param=0.0,
+           scale=None, shift=None, x2=None):
+    B, C1, H, W = x.shape
+    Cin = C1 + (x2.shape[1] if x2 is not None else 0)
+    KH, KW = ksize
+    Ho = (H + 2 * padding[0] - KH) // stride[0] + 1
+    Wo = (W + 2 * padding[1] - KW) // stride[1] + 1
+    out = torch.empty(B, Cout, Ho, Wo, dtype=torch.float32, device=x.device)
+    call('conv2d_f32', _f32(x), x2, C1, wp, bias, scale, shift, out, B, Cin, H, W, Cout, KH, KW,
+         stride[0], stride[1], padding[0], padding[1], act, float(act_param), stream_ptr())
+    return out
+
+
+def maxpool_time(x, k, res=None):
+    B, C, T, F = x.shape
+    out = torch.empty_like(x)
+    call('maxpool_time_f32', _f32(x), res, out, B, C, T, F, k, stream_ptr())
+    return out
+
+
+def maxpool2d(x, k, s):
+    B, C, H, W = x.shape
+    Ho, Wo = (H - k[0]) // s[0] + 1, (W - k[1]) // s[1] + 1
+    out = torch.empty(B, C, Ho, Wo, dtype=torch.float32, device=x.device)
+    call('maxpool2d_f32', _f32(x), out, B, C, H, W, k[0], k[1], s[0], s[1], stream_ptr())
+    return out
+
+
+def upsample2x_concat(low, skip):
+    B, Cl, Hl, Wl = low.shape
+    _, Cs, Hs, Ws = skip.shape
+    out = torch.empty(B, Cs + Cl, Hs, Ws, dtype=torch.float32, device=low.device)
+    call('upsample2x_concat_f32', _f32(low), _f32(skip), out, B, Cl, Hl, Wl, Cs, Hs, Ws, stream_ptr())
+    return out
+
+
+def bn_stats(x):
+    B, C, H, W = x.shape
+    stats = torch.empty(2 * C, dtype=torch.float32, device=x.device)
+    call('bn_stats_f32', _f32(x), stats, B, C, H * W, stream_ptr())
+    return stats
+
+
+def bn_apply(x, stats, w, b, eps=1e-5, act=ACT_NONE, act_param=0.0):
+    B, C, H, W = x.shape
+    out = torch.empty_like(x)
+    call('bn_apply_f32', _f32(x), stats, w, b, out, B, C, H * W, float(eps), act, float(act_param), stream_ptr())
+    return out
+
+
+def bce_fwd_bwd(y_pred, y_true, want_grad=True):
+    n = y_pred.numel()
+    loss = torch.empty(1, dtype=torch.float32, device=y_pred.device)
+    grad = torch.empty_like(y_pred) if want_grad else None
+    call('bce_fwd_bwd_f32', _f32(y_pred), _f32(y_true), loss, grad, _lib.i64(n), stream_ptr())
+    return loss, grad
+
+
+# ------------------------------------------------------------------------------------------------------
+# tcgen05 path: bf16 channel-chunk planes ("CP8", see include/mpa.h)
+class CP8:
+    """bf16 planes [B][ceil(C/8)][T+2*pt][pitch][8] with zero borders; real pixel (t,f) at [pt+t][pf+f]."""
+
+    def __init__(self, B, C, T, F, pitch=None, pf=8, pt=1, device='cuda', buf=None):
+        if pitch is None:
+            pitch = (F + pf + 15) // 16 * 16
+        self.B, self.C, self.T, self.F, self.pitch, self.pf, self.pt = B, C, T, F, pitch, pf, pt
+        self.NC = (C + 7) // 8
+        shape = (B, self.NC, T + 2 * pt, pitch, 8)
+        self.buf = buf if buf is not None else torch.zeros(shape, dtype=torch.bfloat16, device=device)
+        assert tuple(self.buf.shape) == shape
+
+    def like(self, C=None):
+        return CP8(self.B, self.C if C is None else C, self.T, self.F, self.pitch, self.pf, self.pt, self.buf.device)
+
+
+def nchw_to_cp8(x, pitch=None, pf=8, pt=1, out=None):
+    B, C, T, F = x.shape
+    out = out if out is not None else CP8(B, C, T, F, pitch, pf, pt, x.device)
+    call('nchw_to_cp8', _f32(x), out.buf, B, C, T, F, out.pitch, out.pf, out.pt, stream_ptr())
+    return out
+
+
+def cp8_to_nchw(a):
+    out = torch.empty(a.B, a.C, a.T, a.F, dtype=torch.float32, device=a.buf.device)
+    call('cp8_to_nchw', a.buf, out, a.B, a.C, a.T, a.F, a.pitch, a.pf, a.pt, stream_ptr())
+    return out
+
+
+def conv_tc_pack(w, device):
+    """[Cout,Cin,KH,KW] fp32 (any device) -> packed bf16 A-operand tiles on `device` (host-side one-off)."""
+    import ctypes
+    import numpy as np
+    wh = np.ascontiguousarray(w.detach().float().cpu().numpy())
+    Cout, Cin, KH, KW = wh.shape
+    nbytes = _lib.lib().mpa_conv_tc_packed_bytes(Cin, Cout, KH, KW)
+    if nbytes == 0:
+        raise _lib.MpaError(f'conv_tc cannot pack Cin={Cin} Cout={Cout} K={KH}x{KW}')
+    packed = np.zeros(nbytes, dtype=np.uint8)
+    rc = _lib.lib().mpa_conv_tc_pack_weights(wh.ctypes.data_as(ctypes.c_void_p), packed.ctypes.data_as(ctypes.c_void_p),
+                                             Cin, Cout, KH, KW)
+    if rc != 0:
+        raise _lib.MpaError('mpa_conv_tc_pack_weights: ' + _lib.last_error())
+    return torch.from_numpy(packed).to(device)
+
+
+def conv_tc(a, w_packed, bias, Cout, ksize, act=ACT_NONE, act_param=0.0, out=None, n_patches=None,
+            patch_stride_rows=0, T=None):
+    """a: CP8 input (materialised patches) or, with patch_stride_rows>0, one shared frame-major plane."""
+    T = a.T if T is None else T
+    n = a.B if n_patches is None else n_patches
+    if out is None:
+        out = CP8(n, Cout, T, a.F, a.pitch, a.pf, a.pt, a.buf.device)
+    call('conv_tc_bf16', a.buf, w_packed, bias, out.buf, n, a.C, Cout, T, a.F, ksize[0], ksize[1], a.pitch, a.pf, a.pt,
+         _lib.i64(patch_stride_rows), act, float(act_param), stream_ptr())
+    return out
+
+
+def pool3_res_cp8(y, res=None, out=None):
+    out = out if out is not None else y.like()
+    call('pool3_res_cp8', y.buf, None if res is None else res.buf, out.buf, y.B, y.C, y.T, y.F, y.pitch, y.pf, y.pt,
+         stream_ptr())
+    return out

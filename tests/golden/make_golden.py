@@ -1,0 +1,191 @@
+"""Generates the committed golden fixtures by running the UNMODIFIED reference (imported by path from
+/root/reference, never copied) in the build container.  Re-run:  python tests/golden/make_golden.py
+
+Outputs (tests/golden/*.npz) are what the `-m "not gpu"` suite pins the oracle against and what the
+`-m gpu` suite compares the CUDA path with.  /root/reference is NOT needed to run the tests."""
+import hashlib
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = '/root/reference'
+sys.dont_write_bytecode = True
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+
+from tests.weights import MODEL_SPECS, fill_state_dict, synth_patches, synth_targets  # noqa: E402
+from oracle import hcqt_oracle as HO  # noqa: E402
+
+
+def load_reference_hcqt():
+    """hcqt.py imports matplotlib / IPython / librosa at module scope; none is installed.  Stub them; the
+    librosa stub routes cqt / estimate_tuning to the oracle restatement so the reference's own bookkeeping
+    (hop size, harmonic plan, slicing, annotation rasteriser) runs unmodified."""
+    for name in ('matplotlib', 'matplotlib.pyplot', 'IPython', 'IPython.display'):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    lib = types.ModuleType('librosa')
+    lib.note_to_hz = lambda n: HO.C1_HZ
+    lib.cqt = lambda y, sr, hop_length, fmin, n_bins, bins_per_octave, tuning: HO.cqt(
+        y, sr=sr, hop_length=hop_length, fmin=fmin, n_bins=n_bins, bins_per_octave=bins_per_octave, tuning=tuning)
+    lib.estimate_tuning = lambda y, bins_per_octave: HO.estimate_tuning(y, bins_per_octave=bins_per_octave)
+    sys.modules['librosa'] = lib
+    spec = importlib.util.spec_from_file_location('ref_hcqt', os.path.join(REF, 'libdl/data_preprocessing/hcqt.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def build_reference_model(name):
+    import libdl.nn_models as M
+    spec = MODEL_SPECS[name]
+    kw = dict(spec['kw'])
+    if kw.get('pos_encoding') == 'sinusoidal':
+        # unet_cnns.py:121 hard-wires device="cuda:0"; drop the device kwarg while constructing on CPU
+        z = torch.zeros
+        torch.zeros = lambda *a, **k: z(*a, **{kk: vv for kk, vv in k.items() if kk != 'device'})
+        try:
+            m = getattr(M, spec['cls'])(**kw)
+        finally:
+            torch.zeros = z
+    else:
+        m = getattr(M, spec['cls'])(**kw)
+    return m
+
+
+def nn_goldens():
+    torch.set_num_threads(8)
+    cases = [  # (model, batch, seed, mode)
+        ('cnn_xs', 4, 11, 'eval'), ('drcnn_tiny', 3, 12, 'eval'), ('dcnn_tiny', 3, 13, 'eval'),
+        ('drcnn', 2, 14, 'eval'), ('unet_tiny', 3, 15, 'eval'), ('unet_tiny', 3, 15, 'train'),
+        ('unet_m', 2, 16, 'eval'), ('punet_tiny', 3, 17, 'eval'), ('punet', 2, 18, 'eval'),
+        ('saunet_tiny', 5, 19, 'eval'), ('saunet_l', 4, 20, 'eval'), ('saunet_tiny', 5, 19, 'train'),
+    ]
+    out = {}
+    for name, B, seed, mode in cases:
+        m = build_reference_model(name)
+        sd = fill_state_dict(m.state_dict(), seed)
+        m.load_state_dict(sd)
+        for mod in m.modules():                                # dropout off: RNG-free parity
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+        m.train(mode == 'train')
+        x = synth_patches(B, seed)
+        with torch.no_grad():
+            y = m(x)
+        tag = f'{name}__{mode}'
+        if isinstance(y, tuple):
+            out[tag + '__y'] = y[0].numpy()
+            out[tag + '__n'] = y[1].numpy()
+        else:
+            out[tag + '__y'] = y.numpy()
+        out[tag + '__meta'] = np.array([B, seed, float(sum(v.double().sum() for v in sd.values()))])
+        n_par = sum(p.numel() for p in m.parameters())
+        out[tag + '__nparams'] = np.array([n_par])
+        print(tag, 'params', n_par, 'y', out[tag + '__y'].reshape(-1)[:3])
+        if mode == 'eval' and name in ('cnn_xs', 'drcnn_tiny'):
+            # loss + gradients for the training path (BCELoss mean, exp126a:87,323)
+            m.train(True)
+            yt = synth_targets(B, seed)
+            m.zero_grad()
+            loss = torch.nn.BCELoss(reduction='mean')(m(x), yt)
+            loss.backward()
+            out[tag + '__loss'] = np.array([loss.item()])
+            for k, p in m.named_parameters():
+                out[tag + '__grad__' + k] = p.grad.numpy().copy()
+    np.savez_compressed(os.path.join(HERE, 'nn_golden.npz'), **out)
+
+
+def host_goldens():
+    ref = load_reference_hcqt()
+    out = {}
+    # H0 hop sizes
+    hs = []
+    for target, noct in ((50, 10), (91, 6), (43.0, 8), (100, 7), (25, 10)):
+        hop, fs = ref.compute_hopsize_cqt(target, 22050, noct)
+        hs.append((target, noct, hop, fs))
+    out['hopsize'] = np.array(hs)
+    # H6 annotation rasteriser on the shipped CSV (notebook 01 cell 7 usage)
+    csv = np.loadtxt(os.path.join(REF, 'data/MusicNet/csv/2382_Beethoven_OP130_StringQuartet.csv'),
+                     delimiter=',', skiprows=1, usecols=(0, 1, 3))
+    ev = csv.copy()
+    ev[:, :2] /= 44100.0
+    fs_hcqt = 22050 / 512
+    n_frames = int(np.floor(ev[:, 1].max() * fs_hcqt)) + 5
+    A = ref.compute_annotation_array_nooverlap(ev.copy(), np.zeros((216, n_frames, 6)), fs_hcqt, annot_type='pitch')
+    out['annot_shape'] = np.array(A.shape)
+    out['annot_sha1'] = np.frombuffer(hashlib.sha1(A.astype(np.uint8).tobytes()).digest(), dtype=np.uint8)
+    out['annot_nnz'] = np.argwhere(A > 0).astype(np.int32)
+    Apc = ref.compute_annotation_array_nooverlap(ev.copy(), np.zeros((216, n_frames, 6)), fs_hcqt,
+                                                 annot_type='pitch_class', shorten=0.5)
+    out['annot_pc_sha1'] = np.frombuffer(hashlib.sha1(Apc.astype(np.uint8).tobytes()).digest(), dtype=np.uint8)
+    # synthetic dense case with many vanishing / colliding events
+    rng = np.random.default_rng(5)
+    st = np.sort(rng.uniform(0, 4.0, size=300))
+    ev2 = np.stack([st, st + rng.choice([0.001, 0.01, 0.03, 0.2], size=300), rng.integers(30, 90, size=300)], 1)
+    A2 = ref.compute_annotation_array_nooverlap(ev2.copy(), np.zeros((216, 200, 6)), fs_hcqt, annot_type='pitch')
+    out['annot2_events'] = ev2
+    out['annot2'] = np.packbits(A2.astype(np.uint8))
+    # H4/H5 dataset_context
+    from libdl.data_loaders import dataset_context
+    inp = rng.uniform(0, 1, size=(6, 40, 216)) ** 4
+    tg = (rng.uniform(size=(40, 72)) < 0.05).astype(np.float64)
+    half = 75 // 2
+    inp_c = torch.from_numpy(np.pad(inp, ((0, 0), (half, half + 1), (0, 0))))
+    tg_c = torch.from_numpy(np.pad(tg, ((half, half + 1), (0, 0))))
+    ds = dataset_context(inp_c, tg_c, {'context': 75, 'stride': 1, 'compression': 10})
+    out['ds_in'] = inp.astype(np.float32)
+    out['ds_tg'] = tg.astype(np.float32)
+    out['ds_len'] = np.array([len(ds)])
+    idx = [0, 1, 17, 39]
+    out['ds_idx'] = np.array(idx)
+    out['ds_X'] = np.stack([ds[i][0].numpy() for i in idx])
+    out['ds_y'] = np.stack([ds[i][1].numpy() for i in idx])
+    ds3 = dataset_context(inp_c, tg_c, {'context': 75, 'stride': 3, 'compression': None})
+    out['ds3_len'] = np.array([len(ds3)])
+    out['ds3_X5_sum'] = np.array([ds3[5][0].double().sum().item()])
+    out['ds3_y5'] = ds3[5][1].numpy()
+    # N12 P/R/F through the reference eval function (libfmp import needs the same stubs)
+    spec = importlib.util.spec_from_file_location('ref_c5', os.path.join(REF, 'libfmp/c5/c5s2_chord_rec_template.py'))
+    sys.modules.setdefault('numba', __import__('numba'))
+    for name in ('libfmp', 'libfmp.b', 'libfmp.c3', 'libfmp.c4', 'matplotlib.colors'):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules['matplotlib'].colors = sys.modules['matplotlib.colors']
+    sys.modules['matplotlib'].pyplot = sys.modules['matplotlib.pyplot']
+    sys.modules['libfmp.b'].MultiplePlot = object
+    sys.modules['libfmp.b'].plot_matrix = None
+    sys.modules['libfmp.b'].plot_segments = None
+    sys.modules['libfmp.b'].read_csv = None
+    try:
+        c5 = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(c5)
+        pred = rng.uniform(size=(500, 72))
+        targ = (rng.uniform(size=(500, 72)) < 0.3)
+        out['prf_pred'] = pred.astype(np.float32)
+        out['prf_targ'] = targ
+        out['prf'] = np.array(c5.compute_eval_measures(targ, pred.astype(np.float32) >= 0.4), dtype=np.float64)
+    except Exception as e:                                     # pragma: no cover
+        print('libfmp.c5 not importable even with stubs:', e)
+    # H1-H3: the reference wrapper (with the oracle standing in for librosa) vs the oracle's own wrapper
+    y = HO.synth_clip(3, seconds=2.0)
+    f_ref, fs_h, hop = ref.compute_efficient_hcqt(y, fs=22050, fmin=HO.C1_HZ, fs_hcqt_target=50, bins_per_octave=36,
+                                                  num_octaves=6, num_harmonics=5, num_subharmonics=1)
+    f_or, fs_o, hop_o = HO.compute_efficient_hcqt(y, fs=22050, fmin=HO.C1_HZ, fs_hcqt_target=50, bins_per_octave=36,
+                                                  num_octaves=6, num_harmonics=5, num_subharmonics=1)
+    assert np.array_equal(f_ref, f_or) and hop == hop_o and fs_h == fs_o, 'oracle wrapper != reference wrapper'
+    out['hcqt_clip_seed'] = np.array([3])
+    out['hcqt_2s'] = f_ref.astype(np.float32)
+    out['hcqt_2s_tuning'] = np.array([HO.estimate_tuning(y, bins_per_octave=36)])
+    np.savez_compressed(os.path.join(HERE, 'host_golden.npz'), **out)
+    print('annot sha1', bytes(out['annot_sha1']).hex(), 'nnz', len(out['annot_nnz']), 'shape', A.shape)
+
+
+if __name__ == '__main__':
+    host_goldens()
+    nn_goldens()

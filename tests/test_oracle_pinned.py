@@ -1,0 +1,149 @@
+"""`-m "not gpu"`: pins the oracle restatements against fixtures produced by the reference itself
+(tests/golden/make_golden.py).  No CUDA, no /root/reference at run time."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import host_oracle as HO
+from oracle import hcqt_oracle as Q
+from oracle import nn_oracle as NO
+from tests.weights import MODEL_SPECS, fill_state_dict, synth_patches, synth_targets
+from tests.refshapes import reference_state_shapes
+
+NN_CASES = [('cnn_xs', 'eval'), ('drcnn_tiny', 'eval'), ('dcnn_tiny', 'eval'), ('drcnn', 'eval'),
+            ('unet_tiny', 'eval'), ('unet_tiny', 'train'), ('unet_m', 'eval'), ('punet_tiny', 'eval'),
+            ('punet', 'eval'), ('saunet_tiny', 'eval'), ('saunet_l', 'eval'), ('saunet_tiny', 'train')]
+
+
+def oracle_forward(name, sd, x, train=False):
+    spec = MODEL_SPECS[name]
+    kw = spec['kw']
+    if spec['cls'] in ('basic_cnn_segm_sigmoid', 'deep_cnn_segm_sigmoid'):
+        return NO.cnn_forward(sd, x, residual=kw.get('residual', False))
+    return NO.unet_forward(sd, x, train=train, num_heads=kw.get('num_heads', 8), pos_encoding=kw.get('pos_encoding'))
+
+
+@pytest.mark.parametrize('name,mode', NN_CASES)
+def test_nn_oracle_matches_reference_golden(nn_golden, name, mode):
+    tag = f'{name}__{mode}'
+    B, seed, wsum = nn_golden[tag + '__meta']
+    B, seed = int(B), int(seed)
+    shapes = reference_state_shapes(name)
+    sd = fill_state_dict(shapes, seed)
+    assert abs(float(sum(v.double().sum() for v in sd.values())) - wsum) < 1e-6 * max(1.0, abs(wsum))
+    n_par = sum(v.numel() for k, v in sd.items() if not k.endswith(('running_mean', 'running_var', 'num_batches_tracked')))
+    assert n_par == int(nn_golden[tag + '__nparams'][0])
+    x = synth_patches(B, seed)
+    with torch.no_grad():
+        y = oracle_forward(name, sd, x, train=(mode == 'train'))
+    if isinstance(y, tuple):
+        assert np.abs(y[1].numpy() - nn_golden[tag + "__n"]).max() < 2e-4
+        y = y[0]
+    assert y.shape == (B, 1, 1, 72)
+    assert np.abs(y.numpy() - nn_golden[tag + "__y"]).max() < 1e-4   # fp32 reassociation noise (thread count)
+
+
+@pytest.mark.parametrize('name', ['cnn_xs', 'drcnn_tiny'])
+def test_nn_oracle_loss_and_grads(nn_golden, name):
+    tag = f'{name}__eval'
+    B, seed, _ = nn_golden[tag + '__meta']
+    B, seed = int(B), int(seed)
+    sd = fill_state_dict(reference_state_shapes(name), seed)
+    sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    x = synth_patches(B, seed)
+    loss = NO.bce_mean(oracle_forward(name, sd, x), synth_targets(B, seed))
+    assert abs(loss.item() - float(nn_golden[tag + '__loss'][0])) < 1e-6
+    loss.backward()
+    for k, v in sd.items():
+        g = nn_golden[tag + '__grad__' + k]
+        # max-pool arg-max flips on fp32 near-ties move single contributions: bound relative to the tensor's scale
+        assert np.abs(v.grad.numpy() - g).max() <= 5e-3 * np.abs(g).max(), k
+        # weight gradients are 48600-term signed fp32 sums: summation order alone moves them by ~1e-4 relative
+        assert np.abs(v.grad.numpy() - g).mean() <= 1e-3 * np.abs(g).max(), k
+
+
+def test_bce_clamp():
+    y = torch.tensor([0.0, 1.0, 0.5])
+    t = torch.tensor([1.0, 0.0, 1.0])
+    assert abs(NO.bce_mean(y, t).item() - torch.nn.BCELoss()(y, t).item()) < 1e-6
+    assert abs(NO.bce_mean(y, t).item() - (100 + 100 + np.log(2)) / 3) < 1e-4
+
+
+def test_hopsize(host_golden):
+    for target, noct, hop, fs in host_golden['hopsize']:
+        h, f = Q.compute_hopsize_cqt(target, 22050, int(noct))
+        assert h == int(hop) and f == fs
+    assert Q.compute_hopsize_cqt(50, 22050, 10) == (512, 22050 / 512)
+
+
+def test_annotation_rasteriser(host_golden):
+    import os
+    ev = host_golden['annot2_events']
+    A2 = HO.annotation_array_nooverlap(ev, 200, 22050 / 512, 'pitch')
+    assert np.array_equal(np.packbits(A2.astype(np.uint8)), host_golden['annot2'])
+
+
+def test_annotation_shipped_csv_sha1(host_golden):
+    """Fixture: data/MusicNet/csv/2382_Beethoven_OP130_StringQuartet.csv of the reference; a copy of its three
+    used columns travels as tests/golden/annot_2382_events.npy (data, not code)."""
+    import os
+    p = os.path.join(os.path.dirname(__file__), 'golden', 'annot_2382_events.npy')
+    ev = np.load(p)
+    fs = 22050 / 512
+    n_frames = int(np.floor(ev[:, 1].max() * fs)) + 5
+    A = HO.annotation_array_nooverlap(ev, n_frames, fs, 'pitch')
+    assert A.shape == tuple(host_golden['annot_shape'])
+    assert hashlib.sha1(A.astype(np.uint8).tobytes()).hexdigest() == '61739265956b8f5fd717c438f2af4dce7c716576'
+    assert np.array_equal(np.argwhere(A > 0).astype(np.int32), host_golden['annot_nnz'])
+    Apc = HO.annotation_array_nooverlap(ev, n_frames, fs, 'pitch_class', shorten=0.5)
+    assert hashlib.sha1(Apc.astype(np.uint8).tobytes()).digest() == bytes(host_golden['annot_pc_sha1'])
+
+
+def test_dataset_context_index_math(host_golden):
+    inp, tg = host_golden['ds_in'], host_golden['ds_tg']
+    ip, tp = HO.pad_for_inference(inp, tg)
+    assert HO.context_len(ip.shape[1]) == int(host_golden['ds_len'][0]) == inp.shape[1]
+    for j, i in enumerate(host_golden['ds_idx']):
+        X, y = HO.context_item(ip.astype(np.float64), tp, int(i))
+        assert np.array_equal(y, host_golden['ds_y'][j])
+        assert np.abs(X - host_golden['ds_X'][j]).max() < 1e-6
+    assert HO.context_len(ip.shape[1], 75, 3) == int(host_golden['ds3_len'][0])
+    X, y = HO.context_item(ip.astype(np.float64), tp, 5, 75, 3, None)
+    assert abs(X.astype(np.float64).sum() - host_golden['ds3_X5_sum'][0]) < 1e-3
+    assert np.array_equal(y, host_golden['ds3_y5'])
+
+
+def test_prf(host_golden):
+    got = HO.eval_prf(host_golden['prf_targ'], host_golden['prf_pred'], 0.4)
+    assert np.allclose(np.array(got, dtype=np.float64), host_golden['prf'], rtol=0, atol=1e-12)
+
+
+def test_hcqt_oracle_golden_and_anchors(host_golden):
+    y = Q.synth_clip(int(host_golden['hcqt_clip_seed'][0]), seconds=2.0)
+    f, fs, hop = Q.compute_efficient_hcqt(y, fs=22050, fs_hcqt_target=50, bins_per_octave=36)
+    assert f.shape == (216, len(y) // 512 + 1, 6) and hop == 512 and fs == 22050 / 512
+    assert np.abs(f.astype(np.float32) - host_golden['hcqt_2s']).max() < 1e-5
+    assert abs(Q.estimate_tuning(y, bins_per_octave=36) - host_golden['hcqt_2s_tuning'][0]) < 1e-12
+    # h=4 is the same CQT as h=1 shifted by two octaves (hcqt.py:159-162)
+    assert np.array_equal(f[72:, :, 1], f[:144, :, 4])
+    # pure tone at MIDI p peaks at bin 3*(p-24)+1 of the fundamental channel
+    t = np.arange(3 * 22050) / 22050
+    for midi in (45, 60, 81):
+        tone = (0.5 * np.sin(2 * np.pi * 440 * 2 ** ((midi - 69) / 12) * t)).astype(np.float32)
+        g, _, _ = Q.compute_efficient_hcqt(tone, fs=22050, fs_hcqt_target=50, bins_per_octave=36, tuning_est=0.0)
+        mid = g.shape[1] // 2
+        assert int(np.argmax(g[:, mid, 1])) == 3 * (midi - 24) + 1
+        assert int(np.argmax(g[:, mid, 0])) == 3 * (midi - 24) + 1 + 36
+        if midi >= 48:
+            assert int(np.argmax(g[:, mid, 2])) == 3 * (midi - 24) + 1 - 36
+
+
+def test_resample_halfband_properties():
+    h = Q._kaiser_fast_halfband()
+    assert len(h) == 32 and abs(h[0] - 0.425) < 1e-12
+    y = np.ones(4001, dtype=np.float32)
+    z = Q.resample_2to1(y)
+    assert len(z) == 2001 and z[-1] == 0.0
+    assert abs(z[1000] - np.sqrt(2.0)) < 2e-3            # DC gain 1 then x sqrt(2)
