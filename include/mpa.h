@@ -116,29 +116,6 @@ int mpa_nchw_to_cp8(const float* x, void* out_cp8, int B, int C, int T, int F, i
 int mpa_cp8_to_nchw(const void* in_cp8, float* out, int B, int C, int T, int F, int pitch, int pf, int pt,
                     void* stream);
 
-/* ---- HCQT (H1-H3): batched multirate constant-Q filterbank ---------------------------------------------
- * see multipitch_architectures_b200/libdl/data_preprocessing/hcqt.py for the host driver. */
-/* y_out[t] = sqrt(2) * sum_{|j|<=31} h[|j|] * y_in[2t+j]  (resampy kaiser_fast 2:1), n_out = ceil(n_in/2),
- * last sample zero when n_in is odd.  half_taps: 32 floats on the device. */
-int mpa_decimate2_f32(const float* y_in, float* y_out, const float* half_taps, long long n_in, void* stream);
-/* STFT frames with a rectangular window ("ones"), centred, reflect padding: spec [n_frames][n_fft/2+1] complex64
- * (interleaved re,im).  n_fft in {256,512,1024,2048}.  window == NULL -> ones, else n_fft floats. */
-int mpa_stft_f32(const float* y, long long n, const float* window, float* spec, int n_fft, int hop, int n_frames,
-                 void* stream);
-/* CQT octave response: out[h_ch][t][bin] = | sum_f basis[k][f] * spec[t][f] | * scale_k for the 36 (n_rows)
- * filters of one octave bank; banded basis: row k covers bins [start_k, start_k+band) (zero padded).
- * Scatters row k to up to 4 (channel, bin) destinations of the [H][n_frames][n_bins_out] fp32 output.
- * bank selection by a device-resident tuning index: basis + tuning_idx[0]*bank_stride. */
-int mpa_cqt_octave_f32(const float* spec, int n_spec_bins, int n_frames, const float* basis_banded,
-                       const int* band_start, const float* row_scale, int n_rows, int band, long long bank_stride,
-                       long long start_stride, const int* tuning_idx, const int* dest, int n_dest, float* out,
-                       int out_frames, int out_bins, void* stream);
-/* estimate_tuning (H1): spec = hann STFT-2048 magnitudes path.  Writes tuning_idx[0] in [0,100): tuning =
- * -0.5 + 0.01*idx.  workspace bytes from mpa_tuning_workspace(n_frames). */
-size_t mpa_tuning_workspace(int n_frames);
-int mpa_estimate_tuning_f32(const float* spec2048, int n_frames, float sr, int bins_per_octave, int* tuning_idx,
-                            void* workspace, size_t ws_bytes, void* stream);
-
 /* ---- N11: BCELoss(mean) on sigmoid outputs with the -100 log clamp, forward + d(loss)/d(pred) ---------- */
 int mpa_bce_fwd_bwd_f32(const float* y_pred, const float* y_true, float* loss_sum, float* grad_pred, long long n,
                         void* stream);

@@ -8,6 +8,8 @@ ACT_NONE, ACT_LRELU, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3
 
 
 def _f32(t):
+    if not t.is_cuda:
+        raise _lib.MpaError('libmpa operators take CUDA tensors only (no CPU path exists)')
     if t.dtype != torch.float32:
         raise _lib.MpaError(f'expected float32 tensor, got {t.dtype}')
     return t

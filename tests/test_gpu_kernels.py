@@ -1,0 +1,152 @@
+"""`-m gpu`: kernel-level parity through the C ABI against torch fp32 references of the same op (the oracle's
+building blocks), on seeded inputs.  Tolerances are stated per test."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ops():
+    from multipitch_architectures_b200 import ops as o
+    from multipitch_architectures_b200 import _lib
+    assert _lib.lib().mpa_device_check() == 0, _lib.last_error()
+    return o
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+def test_layernorm_cf(ops):
+    from oracle import nn_oracle as NO
+    x = rnd(3, 6, 20, 216, seed=1).abs()
+    w, b = 1 + 0.1 * rnd(6, 216, seed=2), 0.1 * rnd(6, 216, seed=3)
+    got = ops.layernorm_cf(x.cuda(), w.cuda(), b.cuda()).cpu()
+    assert (got - NO.layernorm_cf(x, w, b)).abs().max() < 2e-5
+    got = ops.layernorm_cf(x.cuda(), w.cuda(), b.cuda(), gamma_log=10.0).cpu()
+    assert (got - NO.layernorm_cf(torch.log(1 + 10 * x), w, b)).abs().max() < 5e-5
+
+
+@pytest.mark.parametrize('cfg', [
+    # B, Cin, Cout, H, W, KH, KW, sh, sw, ph, pw
+    (2, 6, 20, 75, 216, 15, 15, 1, 1, 7, 7),
+    (2, 8, 8, 37, 108, 15, 15, 1, 1, 7, 7),
+    (3, 16, 32, 18, 54, 9, 9, 1, 1, 4, 4),
+    (2, 40, 40, 75, 216, 3, 3, 1, 3, 1, 0),
+    (2, 40, 30, 75, 72, 75, 1, 1, 1, 0, 0),
+    (2, 20, 10, 100, 72, 75, 1, 1, 1, 0, 0),
+    (4, 30, 10, 1, 72, 1, 1, 1, 1, 0, 0),
+    (4, 10, 1, 1, 72, 1, 1, 1, 1, 0, 0),
+    (2, 64, 32, 4, 13, 2, 5, 1, 1, 0, 0),
+    (2, 32, 24, 2, 3, 2, 3, 1, 1, 0, 0),
+    (1, 3, 17, 5, 7, 3, 3, 1, 1, 1, 1),
+])
+def test_conv2d_f32(ops, cfg):
+    B, Cin, Cout, H, W, KH, KW, sh, sw, ph, pw = cfg
+    x, w, b = rnd(B, Cin, H, W, seed=4), rnd(Cout, Cin, KH, KW, seed=5, scale=(Cin * KH * KW) ** -0.5), rnd(Cout, seed=6, scale=0.1)
+    ref = F.leaky_relu(F.conv2d(x, w, b, stride=(sh, sw), padding=(ph, pw)), 0.3)
+    got = ops.conv2d(x.cuda(), ops.pack_conv_weight(w.cuda()), b.cuda(), Cout, (KH, KW), (sh, sw), (ph, pw), ops.ACT_LRELU, 0.3).cpu()
+    assert got.shape == ref.shape
+    assert (got - ref).abs().max() < 2e-5 * max(1.0, ref.abs().max().item())      # fp32 FMA vs fp32 reference
+
+
+def test_conv2d_f32_concat_scale_shift_sigmoid(ops):
+    x1, x2 = rnd(2, 5, 9, 27, seed=1), rnd(2, 7, 9, 27, seed=2)
+    w, b = rnd(9, 12, 5, 5, seed=3, scale=0.06), rnd(9, seed=4, scale=0.1)
+    sc, sf = 1 + 0.2 * rnd(9, seed=5), 0.1 * rnd(9, seed=6)
+    ref = torch.relu(F.conv2d(torch.cat([x1, x2], 1), w, b, padding=2) * sc[None, :, None, None] + sf[None, :, None, None])
+    got = ops.conv2d(x1.cuda(), ops.pack_conv_weight(w.cuda()), b.cuda(), 9, (5, 5), (1, 1), (2, 2), ops.ACT_RELU, 0.0,
+                     scale=sc.cuda(), shift=sf.cuda(), x2=x2.cuda()).cpu()
+    assert (got - ref).abs().max() < 2e-5
+    ref = torch.sigmoid(F.conv2d(x1, w[:, :5], b, padding=2))
+    got = ops.conv2d(x1.cuda(), ops.pack_conv_weight(w[:, :5].contiguous().cuda()), b.cuda(), 9, (5, 5), (1, 1), (2, 2), ops.ACT_SIGMOID).cpu()
+    assert (got - ref).abs().max() < 1e-6
+
+
+def test_pools_upsample_bn_bce(ops):
+    from oracle import nn_oracle as NO
+    x = rnd(2, 5, 75, 72, seed=1)
+    r = rnd(2, 5, 75, 72, seed=2)
+    assert torch.equal(ops.maxpool_time(x.cuda(), 13).cpu(), NO.maxpool_t(x, 13))
+    assert torch.equal(ops.maxpool_time(x.cuda(), 3, res=r.cuda()).cpu(), NO.maxpool_t(x, 3) + r)
+    y = rnd(2, 3, 75, 216, seed=3)
+    assert torch.equal(ops.maxpool2d(y.cuda(), (2, 2), (2, 2)).cpu(), F.max_pool2d(y, (2, 2)))
+    z = rnd(2, 4, 3, 9, seed=4)
+    assert torch.equal(ops.maxpool2d(z.cuda(), (2, 5), (1, 2)).cpu(), F.max_pool2d(z, (2, 5), (1, 2)))
+    for (hl, wl, hs, ws) in ((4, 13, 9, 27), (9, 27, 18, 54), (18, 54, 37, 108), (37, 108, 75, 216)):
+        low, skip = rnd(2, 3, hl, wl, seed=5), rnd(2, 2, hs, ws, seed=6)
+        ref = NO.upconcat(low, skip)
+        ref2 = torch.cat([skip, F.pad(F.interpolate(low, scale_factor=2, mode='bilinear', align_corners=True),
+                                      [0, ws - 2 * wl, 0, hs - 2 * hl])], 1)
+        assert (ref - ref2).abs().max() < 1e-6
+        got = ops.upsample2x_concat(low.cuda(), skip.cuda()).cpu()
+        assert (got - ref2).abs().max() < 2e-6
+    a = rnd(3, 7, 9, 27, seed=7) * 2 + 0.5
+    st = ops.bn_stats(a.cuda())
+    assert (st[:7].cpu() - a.mean((0, 2, 3))).abs().max() < 1e-5
+    assert (st[7:].cpu() - a.var((0, 2, 3), unbiased=False)).abs().max() < 1e-4
+    w, b = 1 + 0.1 * rnd(7, seed=8), rnd(7, seed=9)
+    ref = torch.relu(F.batch_norm(a, None, None, w, b, training=True))
+    assert (ops.bn_apply(a.cuda(), st, w.cuda(), b.cuda(), act=ops.ACT_RELU).cpu() - ref).abs().max() < 2e-5
+    yp = torch.tensor([0.0, 1.0, 0.5, 0.2, 0.999999, 1e-30]).repeat(12)
+    yt = torch.tensor([1.0, 0.0, 1.0, 0.0, 1.0, 0.0]).repeat(12)
+    loss, grad = ops.bce_fwd_bwd(yp.cuda(), yt.cuda())
+    ypr = yp.clone().requires_grad_(True)
+    lref = torch.nn.BCELoss()(ypr, yt)
+    lref.backward()
+    assert abs(loss.item() - lref.item()) < 1e-4 * lref.item()
+    assert (grad.cpu() - ypr.grad).abs().max() <= 1e-5 * ypr.grad.abs().max()
+
+
+def test_cp8_roundtrip_and_pool(ops):
+    x = rnd(3, 40, 75, 216, seed=1)
+    xc = ops.nchw_to_cp8(x.cuda())
+    assert xc.buf.shape == (3, 5, 77, 224, 8)
+    back = ops.cp8_to_nchw(xc).cpu()
+    xb = x.to(torch.bfloat16).float()
+    assert torch.equal(back, xb)
+    # borders stay zero
+    assert float(xc.buf[:, :, 0].abs().max()) == 0 and float(xc.buf[:, :, :, :8].abs().max()) == 0
+    r = rnd(3, 40, 75, 216, seed=2)
+    rc = ops.nchw_to_cp8(r.cuda())
+    got = ops.cp8_to_nchw(ops.pool3_res_cp8(xc, rc)).cpu()
+    ref = (F.max_pool2d(xb, (3, 1), (1, 1), (1, 0)) + r.to(torch.bfloat16).float()).to(torch.bfloat16).float()
+    assert torch.equal(got, ref)
+
+
+@pytest.mark.parametrize('cfg', [
+    (2, 8, 40, 6, 24, 1, 1), (2, 16, 40, 7, 24, 3, 3), (3, 24, 40, 9, 40, 3, 3), (3, 6, 40, 20, 216, 15, 15),
+    (3, 40, 40, 75, 216, 15, 15), (2, 20, 20, 75, 216, 15, 15), (2, 64, 128, 9, 27, 5, 5), (1, 40, 40, 75, 216, 15, 15),
+])
+def test_conv_tc_bf16(ops, cfg):
+    """tcgen05 path vs an fp64 convolution of the SAME bf16-rounded operands: only fp32 accumulation order and the
+    final bf16 rounding of the output (2^-9 relative) may differ."""
+    B, Cin, Cout, T, Fq, KH, KW = cfg
+    x, w, b = rnd(B, Cin, T, Fq, seed=4), rnd(Cout, Cin, KH, KW, seed=5, scale=(Cin * KH * KW) ** -0.5), rnd(Cout, seed=6, scale=0.1)
+    xr, wr = x.to(torch.bfloat16).double(), w.to(torch.bfloat16).double()
+    ref = F.leaky_relu(F.conv2d(xr, wr, b.double(), padding=(KH // 2, KW // 2)), 0.3).float()
+    xc = ops.nchw_to_cp8(x.cuda())
+    yc = ops.conv_tc(xc, ops.conv_tc_pack(w, 'cuda'), b.cuda(), Cout, (KH, KW), ops.ACT_LRELU, 0.3)
+    got = ops.cp8_to_nchw(yc).cpu()
+    tol = 2 ** -8 * ref.abs().max().item() + 1e-4
+    assert (got - ref).abs().max() < tol
+    assert float(yc.buf[:, :, 0].abs().max()) == 0 and float(yc.buf[:, :, :, :8].abs().max()) == 0     # borders untouched
+
+
+def test_encoder_layer(ops):
+    from oracle import nn_oracle as NO
+    from tests.refshapes import build_model
+    from tests.weights import fill_state_dict
+    m = build_model('saunet_tiny')
+    sd = fill_state_dict(m.state_dict(), 3)
+    m.load_state_dict(sd)
+    m = m.cuda()
+    x5 = rnd(5, 32, 4, 13, seed=9)
+    with torch.no_grad():
+        got = m.attention1.run(x5.cuda()).cpu()
+        ref = NO.encoder_layer(x5, sd, 'attention1', 8, True)
+    assert (got - ref).abs().max() < 5e-5
