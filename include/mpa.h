@@ -116,6 +116,26 @@ int mpa_nchw_to_cp8(const float* x, void* out_cp8, int B, int C, int T, int F, i
 int mpa_cp8_to_nchw(const void* in_cp8, float* out, int B, int C, int T, int F, int pitch, int pf, int pt,
                     void* stream);
 
+/* ---- HCQT (H1-H3): batched multirate constant-Q filterbank ---------------------------------------------
+ * replaces librosa.cqt x3 + librosa.estimate_tuning as driven by libdl/data_preprocessing/hcqt.py:122,157-162;
+ * host driver: multipitch_architectures_b200/libdl/data_preprocessing/hcqt.py. */
+/* y_out[t] = sqrt(2) * sum_{|j|<=31} h[|j|] * y_in[2t+j] (resampy kaiser_fast at a 2:1 ratio, librosa scale=True);
+ * n_out = ceil(n_in/2), the last sample is zero when n_in is odd.  half_taps: 32 floats (device). */
+int mpa_decimate2_f32(const float* y_in, float* y_out, const float* half_taps, long long n_in, void* stream);
+/* One octave level: frame t is centred on sample t*hop of y_level (reflect padding), rectangular window, FFT of
+ * n_fft, then for each of the n_rows filter rows (every CQT that runs at this rate)
+ *   out[ch][t][bin] = | sum_f basis[row][f] * X[start_row + f] | * row_scale[row]   for each destination of the row.
+ * Tables are laid out [n_tunings][n_rows][...] and indexed by the device-resident tuning_idx[0] (NULL -> 0).
+ * basis: complex64 interleaved [.][n_rows][band]; dest: int [n_rows][n_dest] = (channel<<16 | bin) or -1. */
+int mpa_cqt_level_f32(const float* y_level, long long n_level, int n_fft, int hop, int n_frames, const float* basis,
+                      const int* band_start, const float* row_scale, int n_rows, int band, const int* tuning_idx,
+                      const int* dest, int n_dest, float* out, int out_frames, int out_bins, void* stream);
+/* librosa.estimate_tuning(y, sr, bins_per_octave) with n_fft=2048, hop=512, fmin=150, fmax=4000, threshold=0.1,
+ * resolution=0.01: writes tuning_idx[0] in [0,100), tuning = -0.5 + 0.01*idx.  hann2048: periodic hann window. */
+size_t mpa_tuning_workspace(int n_frames);
+int mpa_estimate_tuning_f32(const float* y, long long n, const float* hann2048, float sr, int bins_per_octave,
+                            int* tuning_idx, void* workspace, size_t ws_bytes, void* stream);
+
 /* ---- N11: BCELoss(mean) on sigmoid outputs with the -100 log clamp, forward + d(loss)/d(pred) ---------- */
 int mpa_bce_fwd_bwd_f32(const float* y_pred, const float* y_true, float* loss_sum, float* grad_pred, long long n,
                         void* stream);
