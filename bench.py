@@ -1,0 +1,256 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: HCQT feature extraction + patch-wise DRCNN inference (BASELINE.json north_star).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--seconds 30]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one 30 s synthetic 22.05 kHz clip per GPU (661,500 samples -> 1,292
+HCQT frames -> 1,292 stride-1 patches of 6x75x216 -> 1,292x72 pitch activations).  The metric is audio-seconds
+processed per wall second, whole job (all ranks).  Weak scaling: every rank owns its own clips; there is no
+data-path collective — only the timing barrier / max-over-ranks.
+
+Printed JSON line (rank 0): value = inputs resident in HBM; e2e = through the public API with pinned HOST audio
+in and HOST activations out (H2D + D2H inside the timed region); roofline = the dominant kernel (tcgen05 15x15
+40->40 convolution) from CUDA events recorded live in the timed region; cpu_baseline = the oracle (CPU
+restatement of the reference path) on a bounded sample on this box's host cores."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FPS = 22050 / 512
+DRCNN_KW = dict(n_chan_input=6, n_chan_layers=[40, 40, 30, 10], n_prefilt_layers=5, residual=True, n_bins_in=216, n_bins_out=72)
+HCQT_KW = dict(fs=22050, fs_hcqt_target=50, bins_per_octave=36, num_octaves=6, num_harmonics=5, num_subharmonics=1)
+GFLOP_PER_PATCH = 48.574          # SURVEY 8a row N3 (2*MAC of every Conv2d at T=75)
+GFLOP_PREFILT_LAYER = 11.664      # one 40->40 15x15 layer per patch
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get('bf16_tflops_sustained', 1386.1), d.get('hbm_gbs', 6541.5), 'measured (MEASURED_PEAKS.json, sustained)'
+    return 1400.0, 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+        while not self._stop_evt.is_set():
+            try:
+                r = subprocess.run(['nvidia-smi', '-i', str(self.index), f'--query-gpu={q}', '--format=csv,noheader,nounits'],
+                                   capture_output=True, text=True, timeout=5)
+                self.rows.append([c.strip() for c in r.stdout.strip().split(',')])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = sorted(int(r[0]) for r in self.rows if len(r) >= 6 and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) >= 6 and r[1].isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith('active') for r in self.rows)]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'samples': len(self.rows)}
+
+
+def make_weights(model, seed=0):
+    from tests.weights import fill_state_dict
+    model.load_state_dict(fill_state_dict(model.state_dict(), seed))
+
+
+def cpu_reference_arm(seconds, n_patches_sample, threads):
+    """The reference's CPU path restated by the oracle: NumPy HCQT of the whole clip + the fp32 DRCNN on a bounded
+    sample of patches (stride-1, compression 10), all host threads.  Returns (audio_s_per_s, description)."""
+    import numpy as np
+    import torch
+    from oracle import hcqt_oracle as HO
+    from oracle import host_oracle as PO
+    from oracle import nn_oracle as NO
+    from multipitch_architectures_b200.libdl.nn_models import deep_cnn_segm_sigmoid
+    torch.set_num_threads(threads)
+    m = deep_cnn_segm_sigmoid(**DRCNN_KW)
+    make_weights(m)
+    sd = m.state_dict()
+    y = HO.synth_clip(0, seconds=seconds)
+    t0 = time.perf_counter()
+    f, _, _ = HO.compute_efficient_hcqt(y, **HCQT_KW)
+    t_hcqt = time.perf_counter() - t0
+    n_frames = f.shape[1]
+    inp = np.transpose(f, (2, 1, 0))
+    ip, _ = PO.pad_for_inference(inp, np.zeros((n_frames, 72)))
+    n = min(n_patches_sample, n_frames)
+    t0 = time.perf_counter()
+    done = 0
+    with torch.no_grad():
+        for b0 in range(0, n, 50):
+            nb = min(50, n - b0)
+            X = torch.from_numpy(np.stack([PO.context_item(ip, np.zeros((ip.shape[1], 72)), b0 + i)[0] for i in range(nb)]))
+            NO.cnn_forward(sd, X, residual=True)
+            done += nb
+    t_nn = time.perf_counter() - t0
+    # whole-clip time = HCQT (measured on the whole clip) + network time extrapolated linearly from the sample
+    t_clip = t_hcqt + t_nn * (n_frames / done)
+    return seconds / t_clip, (f'oracle port: NumPy HCQT of the full {seconds:.0f} s clip ({t_hcqt:.2f} s) + fp32 DRCNN on the first {done} '
+                              f'of {n_frames} stride-1 patches ({t_nn:.2f} s), extrapolated linearly; torch threads={threads}')
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=6)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--seconds', type=float, default=30.0)
+    ap.add_argument('--chunk', type=int, default=646)
+    ap.add_argument('--cpu-sample', type=int, default=100)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    cores = os.cpu_count() or 1
+    workload = f'DRCNN[40,40,30,10]x5 residual: HCQT(6x216, hop 512) + stride-1 patch-wise inference of one {args.seconds:.0f} s 22.05 kHz clip per GPU per step'
+    config = {'workload': workload, 'patches_per_step_per_gpu': int(args.seconds * 22050) // 512 + 1, 'patch': '6x75x216',
+              'timing': 'CUDA events, inputs larger than L2 (>=1 GB of activations per step vs 126 MB L2)', 'weights': 'seeded random init (no checkpoint blobs exist)'}
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        vals = []
+        desc = ''
+        for i in range(args.warmup + args.steps):
+            v, desc = cpu_reference_arm(args.seconds, max(50, args.cpu_sample // 2), cores)
+            if i >= args.warmup:
+                vals.append(v)
+        v = len(vals) / sum(1.0 / x for x in vals)
+        line = {'impl': 'reference', 'metric': 'audio_seconds_per_second', 'value': v, 'unit': 'audio-s/s', 'n_gpus': args.gpus,
+                'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * args.seconds / v, 'higher_is_better': True,
+                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
+                'cpu_baseline': {'value': v, 'unit': 'audio-s/s', 'cores': cores, 'kind': 'port', 'sample': desc},
+                'e2e': {'value': v, 'unit': 'audio-s/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+        print(json.dumps(line))
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from multipitch_architectures_b200 import _lib
+    from multipitch_architectures_b200.engine import CnnStreamEngine
+    from multipitch_architectures_b200.libdl.data_preprocessing.hcqt import get_plan, C1_HZ
+    from multipitch_architectures_b200.libdl.nn_models import deep_cnn_segm_sigmoid
+    from oracle import hcqt_oracle as HO       # synthetic-clip generator only (test infrastructure, not the measured path)
+
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    assert _lib.lib().mpa_device_check() == 0, _lib.last_error()
+
+    model = deep_cnn_segm_sigmoid(**DRCNN_KW, precision='bf16')
+    make_weights(model)
+    model = model.to(dev).eval()
+    eng = CnnStreamEngine(model, chunk=args.chunk)
+    fmin = C1_HZ / 2 ** ((3 - 1) / (2 * 36))
+    plan = get_plan(22050, float(fmin), 512, 36, 6, 5, 1, str(dev))
+    n_clips = 2
+    clips_host = [torch.from_numpy(HO.synth_clip(1000 * rank + i, seconds=args.seconds)).pin_memory() for i in range(n_clips)]
+    clips_dev = [c.to(dev) for c in clips_host]
+    n_frames = clips_host[0].numel() // 512 + 1
+    out_host = torch.empty(n_frames, 72, dtype=torch.float32).pin_memory()
+
+    def step_resident(i):
+        with torch.no_grad():
+            return eng.predict_audio(clips_dev[i % n_clips], plan)[0]
+
+    def step_e2e(i):
+        with torch.no_grad():
+            y = clips_host[i % n_clips].to(dev, non_blocking=True)
+            act = eng.predict_audio(y, plan)[0]
+            out_host.copy_(act, non_blocking=True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for i in range(args.warmup):
+        step_resident(i)
+        step_e2e(i)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    eng.timers = []
+    n0 = _lib.launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = _lib.launch_count() - n0
+    timers, eng.timers = eng.timers, None
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if sampler else None
+
+    audio_s = args.seconds * args.steps * world
+    value = audio_s / (ms / 1e3)
+    e2e = audio_s / (ms_e2e / 1e3)
+    if rank == 0:
+        # roofline of the dominant kernel from the events recorded inside the timed region
+        by = {}
+        for tag, a, b in timers:
+            by.setdefault(tag, []).append(a.elapsed_time(b))
+        conv = by.get('conv_tc', [])
+        peak_tf, peak_bw, peak_src = measured_peaks()
+        per_launch_patches = n_frames / max(1, (n_frames + args.chunk - 1) // args.chunk)
+        flops_launch = GFLOP_PREFILT_LAYER * 1e9 * per_launch_patches
+        avg_ms = sum(conv) / max(1, len(conv))
+        achieved = flops_launch / (avg_ms * 1e-3) / 1e12 if conv else None
+        shares = {k: round(sum(v) / (ms) , 4) for k, v in by.items()}
+        line = {'metric': 'audio_seconds_per_second', 'value': value, 'unit': 'audio-s/s', 'n_gpus': world, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': 'bf16', 'data': 'synthetic', 'config': config, 'clocks': clocks, 'gpu_launches': int(launches),
+                'e2e': {'value': e2e, 'unit': 'audio-s/s', 'h2d_bytes_per_step': int(clips_host[0].numel() * 4),
+                        'd2h_bytes_per_step': int(n_frames * 72 * 4), 'ms_per_step': ms_e2e / args.steps},
+                'roofline': {'bound': 'tensor', 'kernel': 'conv_tc_kernel (tcgen05 15x15 40->40, bias+LeakyReLU epilogue)', 'achieved': achieved,
+                             'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': (achieved / peak_tf) if achieved else None, 'traffic': None,
+                             'peak_source': peak_src, 'launches_timed': len(conv), 'avg_launch_ms': avg_ms,
+                             'algorithmic_flops_per_launch': flops_launch, 'time_share_by_stage': shares},
+                'effective_tflops': value * FPS * GFLOP_PER_PATCH / 1e3}
+        if not args.no_cpu_baseline:
+            v, desc = cpu_reference_arm(args.seconds, args.cpu_sample, cores)
+            line['cpu_baseline'] = {'value': v, 'unit': 'audio-s/s', 'cores': cores, 'kind': 'port', 'sample': desc}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -59,6 +59,11 @@ int mpa_layernorm_frames(const float* frames, const float* ln_w, const float* ln
                          void* out_cp8, int C, int N, int F, int lead, int trail, int cp8_pitch, int cp8_pf,
                          float eps, float gamma_log, void* stream);
 
+/* H4/H5: dataset_context patch extraction (hcqt_datasets.py:63-75,105-106): out[b] = log(1+gamma*in[:, (i0+b)*stride : +T, :]),
+ * in [C][NT][F] (already zero-padded by the caller as exp126a:420 does), out [n][C][T][F]; gamma_log <= 0 -> no compression. */
+int mpa_gather_patches_f32(const float* in, float* out, int C, int NT, int F, int i0, int n, int T, int stride,
+                           float gamma_log, void* stream);
+
 /* ---- generic direct convolution, fp32 CUDA cores (all kernel sizes / strides of the model zoo) ---------
  * replaces nn.Conv2d (+ eval BatchNorm2d folded as per-channel scale/shift) + activation.
  * x NCHW [B,Cin,H,W]; if x2 != NULL the input is the channel concat [x (Cin1) | x2 (Cin-Cin1)] (U-Net skip).

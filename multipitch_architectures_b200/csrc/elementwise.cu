@@ -238,6 +238,21 @@ __global__ void __launch_bounds__(256) bce_kernel(const float* __restrict__ yp, 
   if (threadIdx.x == 0) atomicAdd(loss_sum, tot * inv_n);
 }
 
+// X[b][c][t][f] = log(1 + gamma * in[c][(i0+b)*stride + t][f])   (dataset_context.__getitem__, hcqt_datasets.py:67-75,105-106)
+__global__ void gather_patches_kernel(const float* __restrict__ in, float* __restrict__ out, long long total, int C, int NT, int F,
+                                      int i0, int T, int stride, float gamma) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int f = (int)(i % F);
+    long long r = i / F;
+    int t = (int)(r % T);
+    r /= T;
+    int c = (int)(r % C);
+    int b = (int)(r / C);
+    float v = in[((size_t)c * NT + (size_t)(i0 + b) * stride + t) * F + f];
+    out[i] = gamma > 0.f ? logf(1.f + gamma * v) : v;
+  }
+}
+
 static inline int grid_for(long long total, int block) {
   long long g = (total + block - 1) / block;
   long long cap = 148LL * 16;
@@ -275,6 +290,17 @@ int mpa_layernorm_frames(const float* frames, const float* ln_w, const float* ln
   layernorm_frames_kernel<11><<<lead + N + trail, 128, 0, (cudaStream_t)stream>>>(
       frames, ln_w, ln_b, out_f32, (__nv_bfloat16*)out_cp8, C, N, F, lead, trail, cp8_pitch, cp8_pf, eps, gamma_log);
   MPA_CHECK_LAUNCH("layernorm_frames");
+  return MPA_OK;
+}
+
+int mpa_gather_patches_f32(const float* in, float* out, int C, int NT, int F, int i0, int n, int T, int stride, float gamma_log,
+                           void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(in && out && C > 0 && F > 0 && n > 0 && T > 0 && stride > 0 && i0 >= 0, "gather_patches: bad argument");
+  MPA_REQUIRE((long long)(i0 + n - 1) * stride + T <= NT, "gather_patches: patch range exceeds the %d input frames", NT);
+  long long total = (long long)n * C * T * F;
+  gather_patches_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, total, C, NT, F, i0, T, stride, gamma_log);
+  MPA_CHECK_LAUNCH("gather_patches");
   return MPA_OK;
 }
 

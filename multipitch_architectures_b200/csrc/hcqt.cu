@@ -13,10 +13,13 @@
 
 namespace mpa {
 
+// numpy.pad(mode='reflect') for any pad width: reflection without edge repeat has period 2(n-1)
 __device__ __forceinline__ long long reflect_index(long long i, long long n) {
-  if (i < 0) i = -i;
-  if (i >= n) i = 2 * (n - 1) - i;
-  return i;
+  if (i >= 0 && i < n) return i;
+  const long long p = 2 * (n - 1);
+  i %= p;
+  if (i < 0) i += p;
+  return i < n ? i : p - i;
 }
 
 // in-place radix-2 DIT FFT on shared memory; `a` holds the bit-reversed input; tw[k] = exp(-2*pi*i*k/n), k < n/2
@@ -258,7 +261,7 @@ int mpa_cqt_level_f32(const float* y_level, long long n_level, int n_fft, int ho
   MPA_CHECK_ARCH();
   MPA_REQUIRE(y_level && basis && band_start && row_scale && dest && out, "cqt_level: null argument");
   MPA_REQUIRE(n_fft >= 64 && n_fft <= 4096 && (n_fft & (n_fft - 1)) == 0, "cqt_level: n_fft must be a power of two in 64..4096");
-  MPA_REQUIRE(n_level > n_fft / 2, "cqt_level: signal of %lld samples is too short for reflect padding of n_fft=%d", n_level, n_fft);
+  MPA_REQUIRE(n_level >= 2, "cqt_level: signal of %lld samples is too short", n_level);
   MPA_REQUIRE(hop >= 1 && n_frames >= 1 && n_frames <= out_frames && n_rows >= 1 && band >= 1 && n_dest >= 1 && out_bins < 65536,
               "cqt_level: bad shape");
   MPA_REQUIRE((long long)(n_frames - 1) * hop <= n_level, "cqt_level: %d frames at hop %d exceed the signal (%lld samples)", n_frames, hop, n_level);

@@ -1,0 +1,133 @@
+"""Streaming patch-wise inference: raw audio (or an HCQT) in, [n_frames, 72] pitch activations out.
+
+This is the B200 formulation of the reference's test loop
+(/root/reference/experiments/Exp1_SectionIV-B/exp126a_musicnet_cnn_basic.py:413-436): pad 37/38 zero frames,
+cut stride-1 patches of 75 frames, log-compress, run the network on every patch, keep the centre frame.  The
+patch-wise semantics are preserved exactly (zero padding at every patch edge reaches the centre frame), but
+patches are never materialised on the input side: LayerNorm(+log compression) is evaluated once per FRAME and the
+first convolution gathers its 75-row windows straight out of the frame-major plane (75x fewer input bytes)."""
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .libdl.nn_models import _exec
+from .libdl.nn_models.basic_cnns import basic_cnn_segm_sigmoid, deep_cnn_segm_sigmoid
+
+CONTEXT = 75
+HALF = CONTEXT // 2
+
+
+class CnnStreamEngine:
+    """DRCNN / DCNN / CNN inference over a whole recording with the tcgen05 (bf16) convolution stack."""
+
+    def __init__(self, model, chunk=592, compression=10.0):
+        if not isinstance(model, (basic_cnn_segm_sigmoid, deep_cnn_segm_sigmoid)):
+            raise TypeError('CnnStreamEngine serves the CNN / DCNN / DRCNN family')
+        self.model, self.chunk, self.compression = model, int(chunk), float(compression)
+        self.dev = next(model.parameters()).device
+        if self.dev.type != 'cuda':
+            raise _lib.MpaError('the engine needs the model on a CUDA (sm_100a) device')
+        self.blocks = [('conv1', model.conv1[0])] + [(f'prefilt_list.{i}', m[0]) for i, m in enumerate(getattr(model, 'prefilt_list', []))]
+        self.residual = getattr(model, 'residual', False)
+        self.F = model.n_bins_in
+        self.C0 = self.blocks[0][1].weight.shape[0]
+        self.pitch, self.pf, self.pt = (self.F + 8 + 15) // 16 * 16, 8, 1
+        self._bufs = None
+        self.timers = None          # optional: list collecting (tag, start_event, end_event)
+
+    # -- buffers are allocated once (zero borders are never written again)
+    def _buffers(self):
+        if self._bufs is None:
+            mk = lambda: ops.CP8(self.chunk, self.C0, CONTEXT, self.F, self.pitch, self.pf, self.pt, self.dev)
+            self._bufs = (mk(), mk(), mk())
+        return self._bufs
+
+    def _timed(self, tag, fn):
+        if self.timers is None:
+            return fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn()
+        e1.record()
+        self.timers.append((tag, e0, e1))
+        return r
+
+    def predict_hcqt(self, hcqt):
+        """hcqt: [C, N, F] fp32 CUDA, linear magnitudes (the reference's .npy transposed (2,1,0)) -> [N, n_out] fp32."""
+        m, cache, a = self.model, self.model._cache, self.model.a_lrelu
+        C, N, F = hcqt.shape
+        if C != m.n_chan_input or F != self.F:
+            raise ValueError(f'expected [{m.n_chan_input}, N, {self.F}], got {tuple(hcqt.shape)}')
+        hcqt = hcqt.contiguous().float()
+        lead, trail = self.pt + HALF, HALF + self.pt + 1
+        rows = lead + N + trail
+        plane = torch.zeros(rows, self.pitch, 8, dtype=torch.bfloat16, device=self.dev)
+        _lib.call('layernorm_frames', hcqt, m.layernorm.weight, m.layernorm.bias, None, plane, C, N, F, lead, trail, self.pitch,
+                  self.pf, float(m.layernorm.eps), self.compression, _lib.stream_ptr())
+        ya, za, zb = self._buffers()
+        n_out = m.conv4[3].weight.shape[0] * ((F // 3) - m.conv4[3].weight.shape[3] + 1)
+        out = torch.empty(N, n_out, dtype=torch.float32, device=self.dev)
+        for i0 in range(0, N, self.chunk):
+            n = min(self.chunk, N - i0)
+            z_prev = None
+            for li, (name, conv) in enumerate(self.blocks):
+                w = conv.weight
+                wp = cache.get(name + ':wtc', [w], lambda: ops.conv_tc_pack(w, self.dev))
+                if li == 0:
+                    src = ops.CP8.__new__(ops.CP8)
+                    src.B, src.C, src.T, src.F, src.pitch, src.pf, src.pt, src.NC = n, C, CONTEXT, F, self.pitch, self.pf, self.pt, 1
+                    src.buf = plane[i0:]
+                    self._timed('conv_tc_first', lambda: ops.conv_tc(src, wp, conv.bias, self.C0, (15, 15), ops.ACT_LRELU, a, out=ya,
+                                                                    n_patches=n, patch_stride_rows=1, T=CONTEXT))
+                    cur = za
+                    self._timed('pool3', lambda: ops.pool3_res_cp8(_view(ya, n), None, out=_view(cur, n)))
+                else:
+                    self._timed('conv_tc', lambda: ops.conv_tc(_view(z_prev, n), wp, conv.bias, self.C0, (15, 15), ops.ACT_LRELU, a,
+                                                              out=ya, n_patches=n))
+                    cur = zb if z_prev is za else za
+                    self._timed('pool3', lambda: ops.pool3_res_cp8(_view(ya, n), _view(z_prev, n) if self.residual else None,
+                                                                  out=_view(cur, n)))
+                z_prev = cur
+            def head():
+                z = ops.cp8_to_nchw(_view(z_prev, n))
+                return _exec.head_f32(cache, m, z, a)
+            y = self._timed('head', head)
+            out[i0:i0 + n] = y.reshape(n, n_out)
+        return out
+
+    def predict_audio(self, y, plan):
+        """y: 1-D float32 CUDA audio; plan: HCQTPlan.  -> ([N, 72] activations, tuning index tensor)."""
+        hcqt, tun = self._timed('hcqt', lambda: plan.run(y))
+        return self.predict_hcqt(hcqt), tun
+
+
+def _view(cp8, n):
+    """First n patches of a chunk-sized CP8 buffer (no copy)."""
+    if n == cp8.B:
+        return cp8
+    v = ops.CP8.__new__(ops.CP8)
+    v.B, v.C, v.T, v.F, v.pitch, v.pf, v.pt, v.NC = n, cp8.C, cp8.T, cp8.F, cp8.pitch, cp8.pf, cp8.pt, cp8.NC
+    v.buf = cp8.buf[:n]
+    return v
+
+
+def predict_patchwise(model, hcqt, batch=50):
+    """Reference-shaped loop for any model (U-Nets included): materialised stride-1 patches in batches of `batch`
+    consecutive frames (the batch composition matters for the SAUnet's batch-axis attention)."""
+    C, N, F = hcqt.shape
+    dev = hcqt.device
+    padded = torch.zeros(C, N + CONTEXT, F, dtype=torch.float32, device=dev)
+    padded[:, HALF:HALF + N] = hcqt
+    outs, npreds = [], []
+    for i0 in range(0, N, batch):
+        n = min(batch, N - i0)
+        x = torch.empty(n, C, CONTEXT, F, dtype=torch.float32, device=dev)
+        _lib.call('gather_patches_f32', padded, x, C, N + CONTEXT, F, i0, n, CONTEXT, 1, 10.0, _lib.stream_ptr())
+        with torch.no_grad():
+            y = model(x)
+        if isinstance(y, tuple):
+            npreds.append(y[1].reshape(n, -1))
+            y = y[0]
+        outs.append(y.reshape(n, -1))
+    out = torch.cat(outs, 0)
+    return (out, torch.cat(npreds, 0)) if npreds else out

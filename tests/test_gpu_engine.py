@@ -1,0 +1,94 @@
+"""`-m gpu`: the streaming inference engine (gather-from-frames, tcgen05 stack) and the reference-shaped patch loop
+against the oracle's patch-wise evaluation; thresholded activity and P/R/F to 3 decimals."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import host_oracle as HO
+from oracle import nn_oracle as NO
+from tests.refshapes import build_model
+from tests.weights import fill_state_dict
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_patchwise(sd, hcqt, residual):
+    C, N, F = hcqt.shape
+    ip, _ = HO.pad_for_inference(hcqt, np.zeros((N, 72)))
+    X = torch.from_numpy(np.stack([HO.context_item(ip, np.zeros((ip.shape[1], 72)), i)[0] for i in range(N)]))
+    with torch.no_grad():
+        return NO.cnn_forward(sd, X, residual=residual).reshape(N, 72).numpy()
+
+
+def fake_hcqt(N, seed):
+    rng = np.random.default_rng(seed)
+    h = np.abs(rng.normal(0, 0.05, size=(6, N, 216))) * (1 + np.sin(np.arange(216) / 7.0) ** 2)[None, None, :]
+    h *= rng.uniform(0.3, 2.0, size=(1, N, 1))
+    return h.astype(np.float32)
+
+
+@pytest.mark.parametrize('name,N,chunk', [('drcnn_tiny', 90, 64), ('cnn_xs', 40, 592)])
+def test_stream_engine_matches_oracle_patchwise(name, N, chunk):
+    from multipitch_architectures_b200.engine import CnnStreamEngine
+    m = build_model(name, precision='bf16')
+    sd = fill_state_dict(m.state_dict(), 21)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    h = fake_hcqt(N, 3)
+    got = CnnStreamEngine(m, chunk=chunk).predict_hcqt(torch.from_numpy(h).cuda()).cpu().numpy()
+    ref = oracle_patchwise(sd, h, getattr(m, 'residual', False))
+    err = np.abs(got - ref).max()
+    print(f'{name}: streaming bf16 engine vs oracle max|diff| = {err:.2e}')
+    assert got.shape == (N, 72) and err < 2.5e-2
+    targ = np.random.default_rng(1).uniform(size=(N, 72)) < 0.3
+    p_ref, p_got = HO.eval_prf(targ, ref, 0.4), HO.eval_prf(targ, got, 0.4)
+    near = np.abs(ref - 0.4) < 2.5e-2
+    assert not (((got >= 0.4) != (ref >= 0.4)) & ~near).any()
+    if not near.any():
+        assert all(round(a, 3) == round(b, 3) for a, b in zip(p_ref[:3], p_got[:3]))
+
+
+def test_patchwise_loop_fp32_matches_oracle_and_prf():
+    from multipitch_architectures_b200.engine import predict_patchwise
+    m = build_model('drcnn_tiny')
+    sd = fill_state_dict(m.state_dict(), 22)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    h = fake_hcqt(70, 4)
+    got = predict_patchwise(m, torch.from_numpy(h).cuda(), batch=50).cpu().numpy()
+    ref = oracle_patchwise(sd, h, True)
+    assert np.abs(got - ref).max() < 1e-3
+    targ = np.random.default_rng(2).uniform(size=ref.shape) < 0.3
+    flips = (got >= 0.4) != (ref >= 0.4)
+    assert not (flips & (np.abs(ref - 0.4) > 1e-3)).any()
+    if not flips.any():
+        assert HO.eval_prf(targ, got, 0.4) == HO.eval_prf(targ, ref, 0.4)
+
+
+def test_dataset_context_batch_kernel(host_golden):
+    from multipitch_architectures_b200.libdl.data_loaders import dataset_context
+    inp, tg = host_golden['ds_in'], host_golden['ds_tg']
+    ip, tp = HO.pad_for_inference(inp, tg)
+    ds = dataset_context(torch.from_numpy(ip).cuda(), torch.from_numpy(tp).cuda(), {'context': 75, 'stride': 1, 'compression': 10})
+    X, y = ds.batch(0, 40)
+    for j, i in enumerate(host_golden['ds_idx']):
+        assert np.abs(X[int(i)].cpu().numpy() - host_golden['ds_X'][j]).max() < 1e-6
+        assert np.array_equal(y[int(i)].cpu().numpy(), host_golden['ds_y'][j])
+
+
+def test_audio_to_activations_end_to_end():
+    """audio -> HCQT -> DRCNN(tiny) on the GPU vs the oracle chain on the same clip (bf16 bound)."""
+    from oracle import hcqt_oracle as Q
+    from multipitch_architectures_b200.engine import CnnStreamEngine
+    from multipitch_architectures_b200.libdl.data_preprocessing.hcqt import get_plan, C1_HZ
+    m = build_model('drcnn_tiny', precision='bf16')
+    sd = fill_state_dict(m.state_dict(), 23)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    y = Q.synth_clip(8, seconds=2.5)
+    plan = get_plan(22050, float(C1_HZ / 2 ** (2 / 72)), 512, 36, 6, 5, 1, 'cuda')
+    act, tun = CnnStreamEngine(m, chunk=64).predict_audio(torch.from_numpy(y).cuda(), plan)
+    f, _, _ = Q.compute_efficient_hcqt(y, fs=22050, fs_hcqt_target=50, bins_per_octave=36)
+    ref = oracle_patchwise(sd, np.transpose(f, (2, 1, 0)).astype(np.float32), True)
+    assert abs((-0.5 + 0.01 * int(tun.item())) - Q.estimate_tuning(y, bins_per_octave=36)) < 1e-9
+    assert np.abs(act.cpu().numpy() - ref).max() < 2.5e-2
