@@ -120,6 +120,7 @@ def main():
     ap.add_argument('--chunk', type=int, default=646)
     ap.add_argument('--cpu-sample', type=int, default=100)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--precision', default='fp16', choices=['fp16', 'bf16'])
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', 0))
@@ -163,7 +164,7 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
     assert _lib.lib().mpa_device_check() == 0, _lib.last_error()
 
-    model = deep_cnn_segm_sigmoid(**DRCNN_KW, precision='bf16')
+    model = deep_cnn_segm_sigmoid(**DRCNN_KW, precision=args.precision)
     make_weights(model)
     model = model.to(dev).eval()
     eng = CnnStreamEngine(model, chunk=args.chunk)
@@ -235,7 +236,7 @@ def main():
         shares = {k: round(sum(v) / (ms) , 4) for k, v in by.items()}
         line = {'metric': 'audio_seconds_per_second', 'value': value, 'unit': 'audio-s/s', 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-                'dtype': 'bf16', 'data': 'synthetic', 'config': config, 'clocks': clocks, 'gpu_launches': int(launches),
+                'dtype': args.precision, 'data': 'synthetic', 'config': config, 'clocks': clocks, 'gpu_launches': int(launches),
                 'e2e': {'value': e2e, 'unit': 'audio-s/s', 'h2d_bytes_per_step': int(clips_host[0].numel() * 4),
                         'd2h_bytes_per_step': int(n_frames * 72 * 4), 'ms_per_step': ms_e2e / args.steps},
                 'roofline': {'bound': 'tensor', 'kernel': 'conv_tc_kernel (tcgen05 15x15 40->40, bias+LeakyReLU epilogue)', 'achieved': achieved,

@@ -39,6 +39,10 @@ extern "C" {
 #define MPA_ACT_RELU 2
 #define MPA_ACT_SIGMOID 3
 
+/* 16-bit storage / tensor-core operand formats of the CP8 planes (fp32 accumulation in both cases) */
+#define MPA_FMT_F16 0     /* IEEE half: 11-bit significand, the default (same operand precision as TF32) */
+#define MPA_FMT_BF16 1    /* bfloat16: 8-bit significand */
+
 int mpa_version(void);
 const char* mpa_last_error(void);
 /* 0 when the current device is compute capability 10.x, MPA_ERR_ARCH otherwise. */
@@ -57,7 +61,7 @@ int mpa_layernorm_cf_f32(const float* x, const float* ln_w, const float* ln_b, f
  * (LayerNorm of an all-zero row).  out_f32 [C][lead+N+trail][F] and/or out_cp8 CP8 plane (1 chunk). */
 int mpa_layernorm_frames(const float* frames, const float* ln_w, const float* ln_b, float* out_f32,
                          void* out_cp8, int C, int N, int F, int lead, int trail, int cp8_pitch, int cp8_pf,
-                         float eps, float gamma_log, void* stream);
+                         float eps, float gamma_log, int fmt, void* stream);
 
 /* H4/H5: dataset_context patch extraction (hcqt_datasets.py:63-75,105-106): out[b] = log(1+gamma*in[:, (i0+b)*stride : +T, :]),
  * in [C][NT][F] (already zero-padded by the caller as exp126a:420 does), out [n][C][T][F]; gamma_log <= 0 -> no compression. */
@@ -104,22 +108,33 @@ int mpa_encoder_layer_f32(const float* x, float* out, int B, int E, int Th, int 
 /* ---- tcgen05 implicit-GEMM convolution (the hot op: 96 % of DRCNN FLOPs) ------------------------------
  * KHxKW "same" convolution, stride 1, on CP8 bf16 planes.  Weights pre-packed by mpa_conv_tc_pack_weights
  * (host side, one-off).  out = act(conv + bias) in CP8 (pool / residual are applied by mpa_pool3_res_cp8).
- * in_batch_stride_rows: rows between consecutive patches in the input plane; TP*1 for materialised patches,
+ * in_patch_stride_rows: 0 for materialised patches [n][NC][T+2pt][pitch][8];
  * 1 for the streaming engine where patch i is rows [i, i+T) of one shared frame-major plane. */
 size_t mpa_conv_tc_packed_bytes(int Cin, int Cout, int KH, int KW);
-/* HOST function: w [Cout][Cin][KH][KW] fp32 (host) -> packed bf16 A-operand tiles (host buffer). */
-int mpa_conv_tc_pack_weights(const float* w_host, void* packed_host, int Cin, int Cout, int KH, int KW);
-int mpa_conv_tc_bf16(const void* in_cp8, const void* w_packed, const float* bias, void* out_cp8, int n_patches,
-                     int Cin, int Cout, int T, int F, int KH, int KW, int pitch, int pf, int pt,
-                     long long in_patch_stride_rows, int act, float act_param, void* stream);
+/* HOST function: w [Cout][Cin][KH][KW] fp32 (host) -> packed 16-bit A-operand tiles (host buffer), fmt = MPA_FMT_*. */
+int mpa_conv_tc_pack_weights(const float* w_host, void* packed_host, int Cin, int Cout, int KH, int KW, int fmt);
+/* out_mode 0: `out` is a CP8 plane set [n_patches][ceil(Cout/8)][T+2pt][pitch][8] (16-bit, same fmt);
+ * out_mode 1: `out` is NCHW fp32 [n_patches][Cout][T][F_out] holding columns f = sub_offset + k*sub_stride only
+ *             (a stride-(1,s) convolution evaluated as the stride-1 one and sub-sampled in the epilogue). */
+int mpa_conv_tc_f16(const void* in_cp8, const void* w_packed, const float* bias, void* out, int out_mode,
+                    int sub_stride, int sub_offset, int n_patches, int Cin, int Cout, int T, int F, int KH, int KW,
+                    int pitch, int pf, int pt, long long in_patch_stride_rows, int act, float act_param, int fmt,
+                    void* stream);
 /* out = maxpool_time3(y) + res (res may be NULL), CP8 in/out, per patch. */
 int mpa_pool3_res_cp8(const void* y_cp8, const void* res_cp8, void* out_cp8, int n_patches, int C, int T, int F,
-                      int pitch, int pf, int pt, void* stream);
-/* layout converters (tests, and the seams between the fp32 and the bf16 paths). */
-int mpa_nchw_to_cp8(const float* x, void* out_cp8, int B, int C, int T, int F, int pitch, int pf, int pt,
+                      int pitch, int pf, int pt, int fmt, void* stream);
+/* layout converters (tests, and the seams between the fp32 and the 16-bit paths). */
+int mpa_nchw_to_cp8(const float* x, void* out_cp8, int B, int C, int T, int F, int pitch, int pf, int pt, int fmt,
                     void* stream);
-int mpa_cp8_to_nchw(const void* in_cp8, float* out, int B, int C, int T, int F, int pitch, int pf, int pt,
+int mpa_cp8_to_nchw(const void* in_cp8, float* out, int B, int C, int T, int F, int pitch, int pf, int pt, int fmt,
                     void* stream);
+
+/* Fused head tail for the patch-wise case (T == conv3 kernel height, conv4.3 kernel 1x1; basic_cnns.py:396-408):
+ * x NCHW fp32 [B,C1,T,Fo] (max-pooled conv2 output) -> out [B,Fo] = sigmoid(conv4.3(lrelu(conv4.0(lrelu(conv3(x)))))).
+ * w3 [C2][C1][T], w40 [C3][C2], w43 [C3] in state_dict layout.  C2 <= 32, C3 <= 16, Fo <= 256. */
+int mpa_head_tail_f32(const float* x, const float* w3, const float* b3, const float* w40, const float* b40,
+                      const float* w43, const float* b43, float* out, int B, int C1, int T, int Fo, int C2, int C3,
+                      float a_lrelu, void* stream);
 
 /* ---- HCQT (H1-H3): batched multirate constant-Q filterbank ---------------------------------------------
  * replaces librosa.cqt x3 + librosa.estimate_tuning as driven by libdl/data_preprocessing/hcqt.py:122,157-162;

@@ -1,4 +1,4 @@
-// tcgen05 / TMEM implicit-GEMM "same" convolution (stride 1) on bf16 channel-chunk planes (CP8).
+// tcgen05 / TMEM implicit-GEMM "same" convolution (stride 1) on 16-bit channel-chunk planes (CP8; fp16 or bf16).
 //
 // Formulation ("weights as A, one padded image row as N"):
 //   D[(j,co), n] += sum_k  A[(j,co), k] * B[k, n]
@@ -22,6 +22,7 @@
 //   warps 2-5 epilogue: tcgen05.ld -> +bias -> activation -> bf16 -> CP8 global store
 #include "common.cuh"
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <vector>
 #include <string.h>
 
@@ -33,18 +34,21 @@ constexpr int kAStageBytes = kStageMMAs * kATileBytes;
 constexpr int kNumAStages = 6;
 constexpr int kNumBStages = 2;
 constexpr int kThreads = 192;
+constexpr int kEpiPitch = 40;                 // 80-byte rows: conflict-free 16-byte reads in the transposing epilogue
 constexpr unsigned long long kWaitTimeoutNs = 4000000000ull;   // bounded waits: a protocol bug traps instead of hanging the GPU
 
 struct ConvTcParams {
   const uint8_t* in;        // CP8 bf16 planes
   const uint8_t* w;         // packed weights
   const float* bias;        // [Cout]
-  __nv_bfloat16* out;       // CP8 bf16 planes [n_patches][NCo][TP][P][8]
+  uint16_t* out;            // CP8 16-bit planes [n_patches][NCo][TP][P][8]   (out_mode 0)
+  float* out32;             // NCHW fp32 [n_patches][Cout][T][F_out], column-subsampled (out_mode 1)
+  int out_mode, sub_stride, sub_offset, F_out, fmt;
   long long in_patch_stride;   // bytes between patches in `in`
   long long in_chunk_stride;   // bytes between channel chunks in `in`
   long long in_row0;           // byte offset of (row 0, column 0) of patch 0 chunk 0
   int n_patches, NC, Cout, J, T, F, KH, KW, P, pf, pt_out, TP_out, NCo;
-  int mmas_per_row, n_groups, n_units, slab_px;
+  int mmas_per_row, n_groups, n_units, slab_px, epi_off;
   int act;
   float act_param;
   uint32_t idesc;
@@ -96,7 +100,7 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -116,6 +120,13 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
       : "r"(taddr));
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint16_t cvt16(float x, int fmt) {
+  return fmt == MPA_FMT_BF16 ? __bfloat16_as_ushort(__float2bfloat16(x)) : __half_as_ushort(__float2half_rn(x));
+}
+__device__ __forceinline__ float cvt32(uint16_t v, int fmt) {
+  return fmt == MPA_FMT_BF16 ? __bfloat162float(__ushort_as_bfloat16(v)) : __half2float(__ushort_as_half(v));
+}
 
 // K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -139,6 +150,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
   uint64_t* acc_full = b_empty + kNumBStages;
   uint64_t* acc_empty = acc_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+  uint32_t* btab = tmem_slot + 2;                                          // [mmas_per_row] B-descriptor low words
+  uint16_t* epi_smem = reinterpret_cast<uint16_t*>(smem + p.epi_off);      // 4 warps x [32][32] 16-bit staging
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -207,46 +220,56 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
     __syncwarp();
   } else if (warp == 1) {
     // ===================================================== MMA issuer
+    // B-descriptor table of one K row (identical for every row): low word = (offset>>4) | (LBO>>4)<<16
+    {
+      const int n_paired = (p.NC / 2) * p.KW;
+      for (int q = lane; q < p.mmas_per_row; q += 32) {
+        uint32_t boff, lbo;
+        if (q < n_paired) {
+          const int cp = q / p.KW, df = q - cp * p.KW;
+          boff = (uint32_t)(2 * cp * slab_plane_bytes + df * 16);
+          lbo = (uint32_t)slab_plane_bytes;
+        } else {
+          boff = (uint32_t)((p.NC - 1) * slab_plane_bytes + 2 * (q - n_paired) * 16);
+          lbo = 16u;
+        }
+        btab[q] = (boff >> 4) | ((lbo >> 4) << 16);
+      }
+      __syncwarp();
+    }
     if (lane == 0) {
       int a_stage = 0, b_stage = 0;
       uint32_t a_phase = 0, b_phase = 0, acc_phase = 0;
-      const int npairs_c = p.NC / 2;
-      const int n_paired = npairs_c * p.KW;
+      constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);                 // SBO = 128 B, descriptor version 1
+      constexpr uint32_t kALoFixed = ((128u * 16u) >> 4) << 16;              // A: LBO = 2048 B between the two k-slices
+      const uint32_t slab16 = (uint32_t)slab_bytes >> 4;
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
         const int pair = u / p.n_groups, g = u % p.n_groups;
         const int t0 = g * p.J;
-        const int np = (pair * 2 + 1 < p.n_patches) ? 2 : 1;
+        const bool two = (pair * 2 + 1 < p.n_patches);
         mbar_wait(acc_empty, acc_phase ^ 1);     // epilogue has drained the accumulators of the previous unit
         tc_fence_after();
-        uint32_t first = 1;
+        uint32_t accum = 0;
         for (int r = 0; r < rows_in; ++r) {
           const int row = t0 - ph + r;
           if (row < 0 || row >= p.T) continue;
           mbar_wait(&b_full[b_stage], b_phase);
-          const uint32_t bbase = smem_u32(b_smem + b_stage * bstage_bytes);
+          const uint32_t bbase16 = smem_u32(b_smem + b_stage * bstage_bytes) >> 4;
           for (int m0 = 0; m0 < p.mmas_per_row; m0 += kStageMMAs) {
             const int nm = min(kStageMMAs, p.mmas_per_row - m0);
             mbar_wait(&a_full[a_stage], a_phase);
             tc_fence_after();
-            const uint32_t abase = smem_u32(a_smem + a_stage * kAStageBytes);
-            for (int i = 0; i < nm; ++i) {
-              const int q = m0 + i;
-              uint32_t boff, lbo;
-              if (q < n_paired) {
-                const int cp = q / p.KW, df = q - cp * p.KW;
-                boff = (uint32_t)(2 * cp * slab_plane_bytes + df * 16);
-                lbo = (uint32_t)slab_plane_bytes;
-              } else {
-                const int dp = q - n_paired;
-                boff = (uint32_t)((p.NC - 1) * slab_plane_bytes + 2 * dp * 16);
-                lbo = 16u;
+            const uint32_t abase16 = smem_u32(a_smem + a_stage * kAStageBytes) >> 4;
+#pragma unroll
+            for (int i = 0; i < kStageMMAs; ++i) {
+              if (i < nm) {
+                const uint32_t e = btab[m0 + i];
+                const uint64_t adesc = ((uint64_t)kDescHi << 32) | (uint64_t)((abase16 + i * (kATileBytes >> 4)) | kALoFixed);
+                const uint64_t bdesc0 = ((uint64_t)kDescHi << 32) | (uint64_t)(bbase16 + e);
+                tc_mma_f16(tmem_base, adesc, bdesc0, p.idesc, accum);
+                if (two) tc_mma_f16(tmem_base + 256, adesc, bdesc0 + slab16, p.idesc, accum);
+                accum = 1;
               }
-              const uint64_t adesc = make_desc(abase + i * kATileBytes, 128 * 16, 128);
-              for (int pq = 0; pq < np; ++pq) {
-                const uint64_t bdesc = make_desc(bbase + pq * slab_bytes + boff, lbo, 128);
-                tc_mma_bf16(tmem_base + pq * 256, adesc, bdesc, p.idesc, first ? 0u : 1u);
-              }
-              first = 0;
             }
             tc_commit(&a_empty[a_stage]);       // frees the weight stage when its MMAs have retired
             if (++a_stage == kNumAStages) { a_stage = 0; a_phase ^= 1; }
@@ -266,6 +289,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
     const int j = m / p.Cout, co = m - j * p.Cout;
     const bool row_valid = (j < p.J);
     const float bias = row_valid ? p.bias[co] : 0.f;
+    // coalesced path: 8 consecutive lanes = the 8 channels of one chunk of one output row (needs Cout % 8 == 0)
+    const bool staged = (p.out_mode == 0) && ((p.Cout & 7) == 0);
+    uint16_t* stile = epi_smem + (warp - 2) * (32 * kEpiPitch);     // [32 columns][kEpiPitch >= 32 lanes] 16-bit
     uint32_t acc_phase = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const int pair = u / p.n_groups, g = u % p.n_groups;
@@ -275,19 +301,48 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
       tc_fence_after();
       for (int pq = 0; pq < np; ++pq) {
         const int b = pair * 2 + pq;
-        __nv_bfloat16* orow = p.out + ((((size_t)b * p.NCo + (co >> 3)) * p.TP_out + p.pt_out + t) * p.P) * 8 + (co & 7);
         for (int c0 = 0; c0 < p.P; c0 += 32) {
           uint32_t v[32];
           tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(pq * 256 + c0), v);
           tc_wait_ld();
-          if (row_valid && t < p.T) {
+          if (staged) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              const int n = c0 + i;
-              if (n >= p.pf && n < p.pf + p.F) {
-                float x = __uint_as_float(v[i]) + bias;
-                x = apply_act(x, p.act, p.act_param);
-                orow[(size_t)n * 8] = __float2bfloat16(x);
+              const float x = apply_act(__uint_as_float(v[i]) + bias, p.act, p.act_param);
+              stile[i * kEpiPitch + lane] = cvt16(x, p.fmt);
+            }
+            __syncwarp();
+            // lane -> column c0+lane; pass k -> the k-th 8-lane group of this warp
+            const int n = c0 + lane;
+            const bool col_ok = (n >= p.pf && n < p.pf + p.F);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int mg = quad * 32 + k * 8;                  // first accumulator row of the group
+              const int jg = mg / p.Cout, cog = mg - jg * p.Cout;
+              const int tg = g * p.J + jg;
+              if (col_ok && jg < p.J && tg < p.T) {
+                const uint4 val = *reinterpret_cast<const uint4*>(stile + lane * kEpiPitch + k * 8);
+                uint16_t* dst = p.out + ((((size_t)b * p.NCo + (cog >> 3)) * p.TP_out + p.pt_out + tg) * p.P + n) * 8;
+                *reinterpret_cast<uint4*>(dst) = val;
+              }
+            }
+            __syncwarp();
+          } else if (row_valid && t < p.T) {
+            if (p.out_mode == 0) {
+              uint16_t* orow = p.out + ((((size_t)b * p.NCo + (co >> 3)) * p.TP_out + p.pt_out + t) * p.P) * 8 + (co & 7);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const int n = c0 + i;
+                if (n >= p.pf && n < p.pf + p.F)
+                  orow[(size_t)n * 8] = cvt16(apply_act(__uint_as_float(v[i]) + bias, p.act, p.act_param), p.fmt);
+              }
+            } else {
+              float* orow = p.out32 + (((size_t)b * p.Cout + co) * p.T + t) * p.F_out;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const int f = c0 + i - p.pf - p.sub_offset;
+                if (f >= 0 && f < p.F_out * p.sub_stride && (f % p.sub_stride) == 0)
+                  orow[f / p.sub_stride] = apply_act(__uint_as_float(v[i]) + bias, p.act, p.act_param);
               }
             }
           }
@@ -310,6 +365,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
 static inline int j_blocks(int Cout) { return Cout >= 128 ? 1 : 128 / Cout; }
 static inline int mmas_per_row(int NC, int KW) { return (NC / 2) * KW + ((NC & 1) ? (KW + 1) / 2 : 0); }
 
+static inline uint16_t f32_to_f16_rne(float f) {
+  uint32_t x;
+  memcpy(&x, &f, 4);
+  const uint32_t sign = (x >> 16) & 0x8000u;
+  const int32_t exp = (int32_t)((x >> 23) & 0xff) - 127 + 15;
+  uint32_t man = x & 0x7fffffu;
+  if (((x >> 23) & 0xff) == 0xff) return (uint16_t)(sign | 0x7c00u | (man ? 0x200u : 0));
+  if (exp >= 31) return (uint16_t)(sign | 0x7c00u);
+  if (exp <= 0) {
+    if (exp < -10) return (uint16_t)sign;
+    man |= 0x800000u;
+    const int shift = 14 - exp;
+    uint32_t h = man >> shift;
+    const uint32_t rem = man & ((1u << shift) - 1), halfway = 1u << (shift - 1);
+    if (rem > halfway || (rem == halfway && (h & 1))) ++h;
+    return (uint16_t)(sign | h);
+  }
+  uint32_t h = ((uint32_t)exp << 10) | (man >> 13);
+  const uint32_t rem = man & 0x1fffu;
+  if (rem > 0x1000u || (rem == 0x1000u && (h & 1))) ++h;
+  return (uint16_t)(sign | h);
+}
+
 static inline uint16_t f32_to_bf16_rne(float f) {
   uint32_t u;
   memcpy(&u, &f, 4);
@@ -319,8 +397,8 @@ static inline uint16_t f32_to_bf16_rne(float f) {
 }
 
 // CP8 <-> NCHW converters ------------------------------------------------------------------------------
-__global__ void nchw_to_cp8_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long total, int C, int T,
-                                   int F, int NCk, int TP, int P, int pf, int pt) {
+__global__ void nchw_to_cp8_kernel(const float* __restrict__ x, uint16_t* __restrict__ out, long long total, int C, int T,
+                                   int F, int NCk, int TP, int P, int pf, int pt, int fmt) {
   // one thread per (b, chunk, t, f): gathers 8 channels -> one 16-byte store
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int f = (int)(i % F);
@@ -329,18 +407,18 @@ __global__ void nchw_to_cp8_kernel(const float* __restrict__ x, __nv_bfloat16* _
     r /= T;
     int ck = (int)(r % NCk);
     int b = (int)(r / NCk);
-    __align__(16) __nv_bfloat16 v[8];
+    __align__(16) uint16_t v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       int c = ck * 8 + e;
-      v[e] = __float2bfloat16(c < C ? x[(((size_t)b * C + c) * T + t) * F + f] : 0.f);
+      v[e] = cvt16(c < C ? x[(((size_t)b * C + c) * T + t) * F + f] : 0.f, fmt);
     }
     *reinterpret_cast<uint4*>(out + ((((size_t)b * NCk + ck) * TP + pt + t) * P + pf + f) * 8) = *reinterpret_cast<uint4*>(v);
   }
 }
 
-__global__ void cp8_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, long long total, int C, int T,
-                                   int F, int NCk, int TP, int P, int pf, int pt) {
+__global__ void cp8_to_nchw_kernel(const uint16_t* __restrict__ in, float* __restrict__ out, long long total, int C, int T,
+                                   int F, int NCk, int TP, int P, int pf, int pt, int fmt) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int f = (int)(i % F);
     long long r = i / F;
@@ -348,11 +426,46 @@ __global__ void cp8_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, float* 
     r /= T;
     int c = (int)(r % C);
     int b = (int)(r / C);
-    out[i] = __bfloat162float(in[((((size_t)b * NCk + (c >> 3)) * TP + pt + t) * P + pf + f) * 8 + (c & 7)]);
+    out[i] = cvt32(in[((((size_t)b * NCk + (c >> 3)) * TP + pt + t) * P + pf + f) * 8 + (c & 7)], fmt);
   }
 }
 
-// out = maxpool_time3(y) + res on CP8 planes; one thread per 16-byte pixel-chunk
+// out = maxpool_time3(y) + res on CP8 planes; one thread per 16-byte pixel-chunk (8 channels)
+template <int FMT>
+__device__ __forceinline__ void max8(uint4& c, const uint4& a) {
+  if (FMT == MPA_FMT_BF16) {
+    __nv_bfloat162* cm = reinterpret_cast<__nv_bfloat162*>(&c);
+    const __nv_bfloat162* am = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) cm[e] = __hmax2(cm[e], am[e]);
+  } else {
+    __half2* cm = reinterpret_cast<__half2*>(&c);
+    const __half2* am = reinterpret_cast<const __half2*>(&a);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) cm[e] = __hmax2(cm[e], am[e]);
+  }
+}
+template <int FMT>
+__device__ __forceinline__ void add8(uint4& c, const uint4& r) {
+  if (FMT == MPA_FMT_BF16) {
+    __nv_bfloat162* cm = reinterpret_cast<__nv_bfloat162*>(&c);
+    const __nv_bfloat162* rm = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float2 a = __bfloat1622float2(cm[e]), b2 = __bfloat1622float2(rm[e]);
+      cm[e] = __floats2bfloat162_rn(a.x + b2.x, a.y + b2.y);
+    }
+  } else {
+    __half2* cm = reinterpret_cast<__half2*>(&c);
+    const __half2* rm = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float2 a = __half22float2(cm[e]), b2 = __half22float2(rm[e]);
+      cm[e] = __floats2half2_rn(a.x + b2.x, a.y + b2.y);
+    }
+  }
+}
+template <int FMT>
 __global__ void pool3_res_cp8_kernel(const uint4* __restrict__ y, const uint4* __restrict__ res, uint4* __restrict__ out,
                                      long long total, int T, int F, int TP, int P, int pf, int pt) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -362,28 +475,9 @@ __global__ void pool3_res_cp8_kernel(const uint4* __restrict__ y, const uint4* _
     long long plane = r / T;
     const size_t base = ((size_t)plane * TP + pt + t) * P + pf + f;
     uint4 c = y[base];
-    __nv_bfloat162* cm = reinterpret_cast<__nv_bfloat162*>(&c);
-    if (t > 0) {
-      uint4 a = y[base - P];
-      __nv_bfloat162* am = reinterpret_cast<__nv_bfloat162*>(&a);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) cm[e] = __hmax2(cm[e], am[e]);
-    }
-    if (t < T - 1) {
-      uint4 a = y[base + P];
-      __nv_bfloat162* am = reinterpret_cast<__nv_bfloat162*>(&a);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) cm[e] = __hmax2(cm[e], am[e]);
-    }
-    if (res) {
-      uint4 rr = res[base];
-      __nv_bfloat162* rm = reinterpret_cast<__nv_bfloat162*>(&rr);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float2 a = __bfloat1622float2(cm[e]), b2 = __bfloat1622float2(rm[e]);
-        cm[e] = __floats2bfloat162_rn(a.x + b2.x, a.y + b2.y);
-      }
-    }
+    if (t > 0) max8<FMT>(c, y[base - P]);
+    if (t < T - 1) max8<FMT>(c, y[base + P]);
+    if (res) add8<FMT>(c, res[base]);
     out[base] = c;
   }
 }
@@ -406,7 +500,7 @@ size_t mpa_conv_tc_packed_bytes(int Cin, int Cout, int KH, int KW) {
   return (size_t)(KH + J - 1) * mmas_per_row(NC, KW) * kATileBytes;
 }
 
-int mpa_conv_tc_pack_weights(const float* w, void* packed, int Cin, int Cout, int KH, int KW) {
+int mpa_conv_tc_pack_weights(const float* w, void* packed, int Cin, int Cout, int KH, int KW, int fmt) {
   MPA_REQUIRE(w && packed && Cin > 0 && Cout > 0 && Cout <= 128 && KH > 0 && KW > 0, "conv_tc_pack_weights: bad argument (Cout must be <= 128)");
   const int NC = (Cin + 7) / 8, J = j_blocks(Cout), mpr = mmas_per_row(NC, KW);
   const int n_paired = (NC / 2) * KW;
@@ -434,7 +528,8 @@ int mpa_conv_tc_pack_weights(const float* w, void* packed, int Cin, int Cout, in
             for (int e = 0; e < 8; ++e) {
               const int ci = c * 8 + e;
               if (ci >= Cin) continue;
-              tile[((size_t)kc * 128 + mrow) * 8 + e] = f32_to_bf16_rne(w[(((size_t)co * Cin + ci) * KH + kh) * KW + df]);
+              const float wv = w[(((size_t)co * Cin + ci) * KH + kh) * KW + df];
+              tile[((size_t)kc * 128 + mrow) * 8 + e] = fmt == MPA_FMT_BF16 ? f32_to_bf16_rne(wv) : f32_to_f16_rne(wv);
             }
           }
         }
@@ -444,22 +539,30 @@ int mpa_conv_tc_pack_weights(const float* w, void* packed, int Cin, int Cout, in
   return MPA_OK;
 }
 
-int mpa_conv_tc_bf16(const void* in_cp8, const void* w_packed, const float* bias, void* out_cp8, int n_patches, int Cin, int Cout,
-                     int T, int F, int KH, int KW, int pitch, int pf, int pt, long long in_patch_stride_rows, int act,
-                     float act_param, void* stream) {
+int mpa_conv_tc_f16(const void* in_cp8, const void* w_packed, const float* bias, void* out, int out_mode, int sub_stride,
+                    int sub_offset, int n_patches, int Cin, int Cout, int T, int F, int KH, int KW, int pitch, int pf, int pt,
+                    long long in_patch_stride_rows, int act, float act_param, int fmt, void* stream) {
   MPA_CHECK_ARCH();
-  MPA_REQUIRE(in_cp8 && w_packed && bias && out_cp8 && n_patches > 0, "conv_tc: null argument");
+  MPA_REQUIRE(in_cp8 && w_packed && bias && out && n_patches > 0, "conv_tc: null argument");
   MPA_REQUIRE(Cout > 0 && Cout <= 128 && Cin > 0, "conv_tc: Cout must be in 1..128 (got %d)", Cout);
   MPA_REQUIRE((KH & 1) && (KW & 1), "conv_tc: odd kernel sizes only");
+  MPA_REQUIRE(fmt == MPA_FMT_F16 || fmt == MPA_FMT_BF16, "conv_tc: fmt must be MPA_FMT_F16 or MPA_FMT_BF16");
   MPA_REQUIRE(pitch % 16 == 0 && pitch >= 16 && pitch <= 256, "conv_tc: row pitch must be a multiple of 16 in 16..256 (got %d)", pitch);
   MPA_REQUIRE(pf >= KW / 2 && pitch - F >= KW / 2 && pitch >= pf + F, "conv_tc: pitch %d / left pad %d too small for F=%d KW=%d", pitch, pf, F, KW);
   MPA_REQUIRE(pt >= 1, "conv_tc: at least one guard row above and below each plane is required");
-  MPA_REQUIRE(((uintptr_t)in_cp8 & 15) == 0 && ((uintptr_t)w_packed & 15) == 0 && ((uintptr_t)out_cp8 & 15) == 0, "conv_tc: 16-byte alignment required");
+  MPA_REQUIRE(((uintptr_t)in_cp8 & 15) == 0 && ((uintptr_t)w_packed & 15) == 0 && ((uintptr_t)out & 15) == 0, "conv_tc: 16-byte alignment required");
+  MPA_REQUIRE(out_mode == 0 || (out_mode == 1 && sub_stride >= 1 && sub_offset >= 0 && sub_offset < sub_stride), "conv_tc: bad output mode");
   ConvTcParams p;
   p.in = (const uint8_t*)in_cp8;
   p.w = (const uint8_t*)w_packed;
   p.bias = bias;
-  p.out = (__nv_bfloat16*)out_cp8;
+  p.out = (uint16_t*)out;
+  p.out32 = (float*)out;
+  p.out_mode = out_mode;
+  p.sub_stride = out_mode ? sub_stride : 1;
+  p.sub_offset = out_mode ? sub_offset : 0;
+  p.F_out = out_mode ? (F - p.sub_offset + p.sub_stride - 1) / p.sub_stride : F;
+  p.fmt = fmt;
   p.n_patches = n_patches;
   p.NC = (Cin + 7) / 8;
   p.Cout = Cout;
@@ -475,7 +578,7 @@ int mpa_conv_tc_bf16(const void* in_cp8, const void* w_packed, const float* bias
     p.in_patch_stride = p.in_chunk_stride * p.NC;
     p.in_row0 = (long long)pt * pitch * 16;
   } else {
-    // streaming: one shared plane per chunk [NC][rows][P][8]; patch b starts at row b*stride (+pt guard rows)
+    // streaming: one shared frame-major plane [rows][P][8]; patch b starts at row b*stride (after pt guard rows)
     MPA_REQUIRE(p.NC == 1, "conv_tc: streaming input supports a single channel chunk");
     p.in_chunk_stride = 0;
     p.in_patch_stride = in_patch_stride_rows * pitch * 16;
@@ -487,9 +590,15 @@ int mpa_conv_tc_bf16(const void* in_cp8, const void* w_packed, const float* bias
   p.slab_px = (pitch + 2 * (KW / 2) + 1 + 7) / 8 * 8;
   p.act = act;
   p.act_param = act_param;
-  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(pitch >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  const size_t smem = (size_t)kNumAStages * kAStageBytes + (size_t)kNumBStages * 2 * p.NC * p.slab_px * 16 + 256;
+  const uint32_t f = (fmt == MPA_FMT_BF16) ? 1u : 0u;
+  p.idesc = (1u << 4) | (f << 7) | (f << 10) | ((uint32_t)(pitch >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  size_t off = (size_t)kNumAStages * kAStageBytes + (size_t)kNumBStages * 2 * p.NC * p.slab_px * 16;
+  off += 256 + (size_t)p.mmas_per_row * 4;      // barriers + tmem slot, descriptor table
+  off = (off + 127) / 128 * 128;
+  p.epi_off = (int)off;
+  const size_t smem = off + 4 * 32 * kEpiPitch * 2;
   MPA_REQUIRE(smem <= 227 * 1024, "conv_tc: needs %zu B of shared memory (Cin=%d pitch=%d)", smem, Cin, pitch);
+  MPA_REQUIRE(p.mmas_per_row * 4 <= 4096, "conv_tc: K row too long");
   static thread_local size_t attr_set = 0;
   if (smem > attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -509,35 +618,39 @@ int mpa_conv_tc_bf16(const void* in_cp8, const void* w_packed, const float* bias
 }
 
 int mpa_pool3_res_cp8(const void* y_cp8, const void* res_cp8, void* out_cp8, int n_patches, int C, int T, int F, int pitch, int pf,
-                      int pt, void* stream) {
+                      int pt, int fmt, void* stream) {
   MPA_CHECK_ARCH();
   MPA_REQUIRE(y_cp8 && out_cp8 && n_patches > 0 && C > 0, "pool3_res_cp8: bad argument");
   const int NCk = (C + 7) / 8;
   long long total = (long long)n_patches * NCk * T * F;
-  pool3_res_cp8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)y_cp8, (const uint4*)res_cp8, (uint4*)out_cp8,
-                                                                                 total, T, F, T + 2 * pt, pitch, pf, pt);
+  if (fmt == MPA_FMT_BF16)
+    pool3_res_cp8_kernel<MPA_FMT_BF16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)y_cp8, (const uint4*)res_cp8,
+                                                                                                 (uint4*)out_cp8, total, T, F, T + 2 * pt, pitch, pf, pt);
+  else
+    pool3_res_cp8_kernel<MPA_FMT_F16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)y_cp8, (const uint4*)res_cp8,
+                                                                                                (uint4*)out_cp8, total, T, F, T + 2 * pt, pitch, pf, pt);
   MPA_CHECK_LAUNCH("pool3_res_cp8");
   return MPA_OK;
 }
 
-int mpa_nchw_to_cp8(const float* x, void* out_cp8, int B, int C, int T, int F, int pitch, int pf, int pt, void* stream) {
+int mpa_nchw_to_cp8(const float* x, void* out_cp8, int B, int C, int T, int F, int pitch, int pf, int pt, int fmt, void* stream) {
   MPA_CHECK_ARCH();
   MPA_REQUIRE(x && out_cp8 && B > 0 && C > 0 && pitch >= pf + F, "nchw_to_cp8: bad argument");
   const int NCk = (C + 7) / 8;
   long long total = (long long)B * NCk * T * F;
-  nchw_to_cp8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out_cp8, total, C, T, F, NCk, T + 2 * pt,
-                                                                               pitch, pf, pt);
+  nchw_to_cp8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (uint16_t*)out_cp8, total, C, T, F, NCk, T + 2 * pt,
+                                                                               pitch, pf, pt, fmt);
   MPA_CHECK_LAUNCH("nchw_to_cp8");
   return MPA_OK;
 }
 
-int mpa_cp8_to_nchw(const void* in_cp8, float* out, int B, int C, int T, int F, int pitch, int pf, int pt, void* stream) {
+int mpa_cp8_to_nchw(const void* in_cp8, float* out, int B, int C, int T, int F, int pitch, int pf, int pt, int fmt, void* stream) {
   MPA_CHECK_ARCH();
   MPA_REQUIRE(in_cp8 && out && B > 0 && C > 0 && pitch >= pf + F, "cp8_to_nchw: bad argument");
   const int NCk = (C + 7) / 8;
   long long total = (long long)B * C * T * F;
-  cp8_to_nchw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in_cp8, out, total, C, T, F, NCk,
-                                                                               T + 2 * pt, pitch, pf, pt);
+  cp8_to_nchw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint16_t*)in_cp8, out, total, C, T, F, NCk,
+                                                                               T + 2 * pt, pitch, pf, pt, fmt);
   MPA_CHECK_LAUNCH("cp8_to_nchw");
   return MPA_OK;
 }

@@ -2,6 +2,7 @@
 // concat, BatchNorm statistics/apply, BCE loss.  fp32 NCHW.  All kernels are grid-stride / row-per-block with
 // coalesced accesses along F (the contiguous axis).
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace mpa {
 
@@ -69,8 +70,8 @@ __global__ void __launch_bounds__(128) layernorm_cf_kernel(const float* __restri
 template <int MAXV>
 __global__ void __launch_bounds__(128) layernorm_frames_kernel(const float* __restrict__ frames, const float* __restrict__ w,
                                                                const float* __restrict__ bsh, float* __restrict__ out_f32,
-                                                               __nv_bfloat16* __restrict__ out_cp8, int C, int N, int F, int lead,
-                                                               int trail, int pitch, int pf, float eps, float gamma_log) {
+                                                               uint16_t* __restrict__ out_cp8, int C, int N, int F, int lead,
+                                                               int trail, int pitch, int pf, float eps, float gamma_log, int fmt) {
   __shared__ float sh[8];
   const int s = blockIdx.x;
   const int NT = lead + N + trail;
@@ -109,7 +110,9 @@ __global__ void __launch_bounds__(128) layernorm_frames_kernel(const float* __re
       int c = e / F, f = e - c * F;
       float r = (v[i] - mean) * rstd * w[e] + bsh[e];
       if (out_f32) out_f32[((size_t)c * NT + s) * F + f] = r;
-      if (out_cp8) out_cp8[((size_t)s * pitch + pf + f) * 8 + c] = __float2bfloat16(r);
+      if (out_cp8)
+        out_cp8[((size_t)s * pitch + pf + f) * 8 + c] =
+            fmt == MPA_FMT_BF16 ? __bfloat16_as_ushort(__float2bfloat16(r)) : __half_as_ushort(__float2half_rn(r));
     }
   }
 }
@@ -280,7 +283,7 @@ int mpa_layernorm_cf_f32(const float* x, const float* ln_w, const float* ln_b, f
 }
 
 int mpa_layernorm_frames(const float* frames, const float* ln_w, const float* ln_b, float* out_f32, void* out_cp8, int C,
-                         int N, int F, int lead, int trail, int cp8_pitch, int cp8_pf, float eps, float gamma_log,
+                         int N, int F, int lead, int trail, int cp8_pitch, int cp8_pf, float eps, float gamma_log, int fmt,
                          void* stream) {
   MPA_CHECK_ARCH();
   MPA_REQUIRE(frames && ln_w && ln_b && (out_f32 || out_cp8) && C > 0 && N > 0 && F > 0 && lead >= 0 && trail >= 0,
@@ -288,7 +291,7 @@ int mpa_layernorm_frames(const float* frames, const float* ln_w, const float* ln
   MPA_REQUIRE(C * F <= 128 * 11, "layernorm_frames: C*F=%d exceeds 1408", C * F);
   MPA_REQUIRE(!out_cp8 || (C <= 8 && cp8_pitch >= F + cp8_pf), "layernorm_frames: CP8 output needs C<=8 and pitch>=F+pf");
   layernorm_frames_kernel<11><<<lead + N + trail, 128, 0, (cudaStream_t)stream>>>(
-      frames, ln_w, ln_b, out_f32, (__nv_bfloat16*)out_cp8, C, N, F, lead, trail, cp8_pitch, cp8_pf, eps, gamma_log);
+      frames, ln_w, ln_b, out_f32, (uint16_t*)out_cp8, C, N, F, lead, trail, cp8_pitch, cp8_pf, eps, gamma_log, fmt);
   MPA_CHECK_LAUNCH("layernorm_frames");
   return MPA_OK;
 }

@@ -18,16 +18,21 @@ HALF = CONTEXT // 2
 
 
 class CnnStreamEngine:
-    """DRCNN / DCNN / CNN inference over a whole recording with the tcgen05 (bf16) convolution stack."""
+    """DRCNN / DCNN / CNN inference over a whole recording with the tcgen05 convolution stack (model.precision
+    'fp16' or 'bf16')."""
 
-    def __init__(self, model, chunk=592, compression=10.0):
+    def __init__(self, model, chunk=646, compression=10.0):
         if not isinstance(model, (basic_cnn_segm_sigmoid, deep_cnn_segm_sigmoid)):
             raise TypeError('CnnStreamEngine serves the CNN / DCNN / DRCNN family')
         self.model, self.chunk, self.compression = model, int(chunk), float(compression)
         self.dev = next(model.parameters()).device
         if self.dev.type != 'cuda':
             raise _lib.MpaError('the engine needs the model on a CUDA (sm_100a) device')
-        self.blocks = [('conv1', model.conv1[0])] + [(f'prefilt_list.{i}', m[0]) for i, m in enumerate(getattr(model, 'prefilt_list', []))]
+        if not _exec.tc_eligible(model, model.n_bins_in):
+            raise _lib.MpaError("CnnStreamEngine needs precision 'fp16' or 'bf16' and <=128 channels per layer; "
+                                "use predict_patchwise for the fp32 path")
+        self.fmt = ops.fmt_of(model.precision)
+        self.blocks = _exec.cnn_blocks(model)
         self.residual = getattr(model, 'residual', False)
         self.F = model.n_bins_in
         self.C0 = self.blocks[0][1].weight.shape[0]
@@ -35,10 +40,10 @@ class CnnStreamEngine:
         self._bufs = None
         self.timers = None          # optional: list collecting (tag, start_event, end_event)
 
-    # -- buffers are allocated once (zero borders are never written again)
+    # -- buffers are allocated once (their zero borders are never written)
     def _buffers(self):
         if self._bufs is None:
-            mk = lambda: ops.CP8(self.chunk, self.C0, CONTEXT, self.F, self.pitch, self.pf, self.pt, self.dev)
+            mk = lambda: ops.CP8(self.chunk, self.C0, CONTEXT, self.F, self.pitch, self.pf, self.pt, self.dev, fmt=self.fmt)
             self._bufs = (mk(), mk(), mk())
         return self._bufs
 
@@ -61,54 +66,41 @@ class CnnStreamEngine:
         hcqt = hcqt.contiguous().float()
         lead, trail = self.pt + HALF, HALF + self.pt + 1
         rows = lead + N + trail
-        plane = torch.zeros(rows, self.pitch, 8, dtype=torch.bfloat16, device=self.dev)
-        _lib.call('layernorm_frames', hcqt, m.layernorm.weight, m.layernorm.bias, None, plane, C, N, F, lead, trail, self.pitch,
-                  self.pf, float(m.layernorm.eps), self.compression, _lib.stream_ptr())
+        plane = torch.zeros(rows, self.pitch, 8, dtype=ops._FMT_DTYPE[self.fmt], device=self.dev)
+        self._timed('layernorm_frames', lambda: _lib.call(
+            'layernorm_frames', hcqt, m.layernorm.weight, m.layernorm.bias, None, plane, C, N, F, lead, trail, self.pitch, self.pf,
+            float(m.layernorm.eps), self.compression, self.fmt, _lib.stream_ptr()))
         ya, za, zb = self._buffers()
-        n_out = m.conv4[3].weight.shape[0] * ((F // 3) - m.conv4[3].weight.shape[3] + 1)
-        out = torch.empty(N, n_out, dtype=torch.float32, device=self.dev)
+        outs = []
         for i0 in range(0, N, self.chunk):
             n = min(self.chunk, N - i0)
             z_prev = None
             for li, (name, conv) in enumerate(self.blocks):
                 w = conv.weight
-                wp = cache.get(name + ':wtc', [w], lambda: ops.conv_tc_pack(w, self.dev))
+                wp = cache.get(f'{name}:wtc{self.fmt}', [w], lambda: ops.conv_tc_pack(w, self.dev, self.fmt))
                 if li == 0:
                     src = ops.CP8.__new__(ops.CP8)
-                    src.B, src.C, src.T, src.F, src.pitch, src.pf, src.pt, src.NC = n, C, CONTEXT, F, self.pitch, self.pf, self.pt, 1
+                    src.B, src.C, src.T, src.F, src.pitch, src.pf, src.pt, src.NC, src.fmt = n, C, CONTEXT, F, self.pitch, self.pf, self.pt, 1, self.fmt
                     src.buf = plane[i0:]
-                    self._timed('conv_tc_first', lambda: ops.conv_tc(src, wp, conv.bias, self.C0, (15, 15), ops.ACT_LRELU, a, out=ya,
-                                                                    n_patches=n, patch_stride_rows=1, T=CONTEXT))
+                    self._timed('conv_tc_first', lambda: ops.conv_tc(src, wp, conv.bias, self.C0, tuple(conv.kernel_size), ops.ACT_LRELU, a,
+                                                                    out=ya.first(n), n_patches=n, patch_stride_rows=1, T=CONTEXT))
                     cur = za
-                    self._timed('pool3', lambda: ops.pool3_res_cp8(_view(ya, n), None, out=_view(cur, n)))
+                    self._timed('pool3', lambda: ops.pool3_res_cp8(ya.first(n), None, out=cur.first(n)))
                 else:
-                    self._timed('conv_tc', lambda: ops.conv_tc(_view(z_prev, n), wp, conv.bias, self.C0, (15, 15), ops.ACT_LRELU, a,
-                                                              out=ya, n_patches=n))
+                    self._timed('conv_tc', lambda: ops.conv_tc(z_prev.first(n), wp, conv.bias, self.C0, tuple(conv.kernel_size), ops.ACT_LRELU,
+                                                              a, out=ya.first(n), n_patches=n))
                     cur = zb if z_prev is za else za
-                    self._timed('pool3', lambda: ops.pool3_res_cp8(_view(ya, n), _view(z_prev, n) if self.residual else None,
-                                                                  out=_view(cur, n)))
+                    self._timed('pool3', lambda: ops.pool3_res_cp8(ya.first(n), z_prev.first(n) if self.residual else None,
+                                                                  out=cur.first(n)))
                 z_prev = cur
-            def head():
-                z = ops.cp8_to_nchw(_view(z_prev, n))
-                return _exec.head_f32(cache, m, z, a)
-            y = self._timed('head', head)
-            out[i0:i0 + n] = y.reshape(n, n_out)
-        return out
+            y = self._timed('head', lambda: _exec.head_tc(cache, m, z_prev.first(n), a))
+            outs.append(y.reshape(n, -1))
+        return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
 
     def predict_audio(self, y, plan):
         """y: 1-D float32 CUDA audio; plan: HCQTPlan.  -> ([N, 72] activations, tuning index tensor)."""
         hcqt, tun = self._timed('hcqt', lambda: plan.run(y))
         return self.predict_hcqt(hcqt), tun
-
-
-def _view(cp8, n):
-    """First n patches of a chunk-sized CP8 buffer (no copy)."""
-    if n == cp8.B:
-        return cp8
-    v = ops.CP8.__new__(ops.CP8)
-    v.B, v.C, v.T, v.F, v.pitch, v.pf, v.pt, v.NC = n, cp8.C, cp8.T, cp8.F, cp8.pitch, cp8.pf, cp8.pt, cp8.NC
-    v.buf = cp8.buf[:n]
-    return v
 
 
 def predict_patchwise(model, hcqt, batch=50):

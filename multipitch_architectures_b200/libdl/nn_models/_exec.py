@@ -11,7 +11,7 @@ import torch
 from ... import ops
 from ..._lib import MpaError
 
-PRECISIONS = ('fp32', 'bf16')
+PRECISIONS = ('fp32', 'fp16', 'bf16')     # fp16 / bf16: tcgen05 tensor-core path (16-bit operands, fp32 accumulate)
 
 
 class ParamCache:
@@ -78,27 +78,56 @@ def head_f32(cache, model, x, a):
     return conv_f32(cache, 'conv4.3', model.conv4[3], y, ops.ACT_SIGMOID)
 
 
+def head_tc(cache, model, zc, a):
+    """Head on a CP8 activation: conv2 (3x3, stride (1,3)) runs on the tensor cores as the stride-1 3x3 convolution
+    whose epilogue keeps columns 1, 4, 7, ... (exactly the strided outputs), then maxpool(13,1) and the fused tail."""
+    conv2, conv3, c40, c43 = model.conv2[0], model.conv3[0], model.conv4[0], model.conv4[3]
+    ok2 = (tuple(conv2.kernel_size) == (3, 3) and tuple(conv2.stride) == (1, 3) and tuple(conv2.padding) == (1, 0)
+           and conv2.weight.shape[0] <= 128 and zc.F % 3 == 0)
+    if not ok2:
+        return head_f32(cache, model, ops.cp8_to_nchw(zc), a)
+    w2 = conv2.weight
+    wp = cache.get(f'conv2:wtc{zc.fmt}', [w2], lambda: ops.conv_tc_pack(w2, zc.buf.device, zc.fmt))
+    y = ops.conv_tc(zc, wp, conv2.bias, w2.shape[0], (3, 3), ops.ACT_LRELU, a, subsample=(3, 1))
+    y = ops.maxpool_time(y, 13)
+    fused = (conv3.kernel_size[0] == zc.T and conv3.kernel_size[1] == 1 and tuple(c43.kernel_size) == (1, 1)
+             and conv3.weight.shape[0] <= 32 and c40.weight.shape[0] <= 16 and c43.weight.shape[0] == 1 and y.shape[3] <= 256)
+    if fused:
+        o = ops.head_tail(y, conv3.weight, conv3.bias, c40.weight, c40.bias, c43.weight, c43.bias, a)
+        return o.reshape(o.shape[0], 1, 1, o.shape[1])
+    y = conv_f32(cache, 'conv3', conv3, y, ops.ACT_LRELU, a)
+    y = conv_f32(cache, 'conv4.0', c40, y, ops.ACT_LRELU, a)
+    return conv_f32(cache, 'conv4.3', c43, y, ops.ACT_SIGMOID)
+
+
+def cnn_blocks(model):
+    return [('conv1', model.conv1[0])] + [(f'prefilt_list.{i}', m[0]) for i, m in enumerate(getattr(model, 'prefilt_list', []))]
+
+
+def tc_eligible(model, F):
+    return (model.precision in ('fp16', 'bf16') and F + 8 <= 256
+            and all(c.weight.shape[0] <= 128 and c.kernel_size[0] % 2 == 1 and c.kernel_size[1] % 2 == 1 for _, c in cnn_blocks(model)))
+
+
 def cnn_forward(model, x):
     """basic_cnn_segm_sigmoid / deep_cnn_segm_sigmoid inference forward."""
     cache, a = model._cache, model.a_lrelu
-    blocks = [('conv1', model.conv1[0])] + [(f'prefilt_list.{i}', m[0]) for i, m in enumerate(getattr(model, 'prefilt_list', []))]
+    blocks = cnn_blocks(model)
     residual = getattr(model, 'residual', False)
     z = ops.layernorm_cf(x, model.layernorm.weight, model.layernorm.bias, model.layernorm.eps)
-    use_tc = (model.precision == 'bf16' and all(c.weight.shape[0] <= 128 and c.kernel_size[0] % 2 == 1 for _, c in blocks)
-              and x.shape[3] + 8 <= 256)
-    if not use_tc:
+    if not tc_eligible(model, x.shape[3]):
         for i, (name, conv) in enumerate(blocks):
             y = conv_f32(cache, name, conv, z, ops.ACT_LRELU, a)
             z = ops.maxpool_time(y, 3, res=z if (residual and i > 0) else None)
-    else:
-        zc = ops.nchw_to_cp8(z)
-        for i, (name, conv) in enumerate(blocks):
-            w = conv.weight
-            wp = cache.get(name + ':wtc', [w], lambda: ops.conv_tc_pack(w, x.device))
-            yc = ops.conv_tc(zc, wp, conv.bias, w.shape[0], tuple(conv.kernel_size), ops.ACT_LRELU, a)
-            zc = ops.pool3_res_cp8(yc, res=zc if (residual and i > 0) else None)
-        z = ops.cp8_to_nchw(zc)
-    return head_f32(cache, model, z, a)
+        return head_f32(cache, model, z, a)
+    fmt = ops.fmt_of(model.precision)
+    zc = ops.nchw_to_cp8(z, fmt=fmt)
+    for i, (name, conv) in enumerate(blocks):
+        w = conv.weight
+        wp = cache.get(f'{name}:wtc{fmt}', [w], lambda: ops.conv_tc_pack(w, x.device, fmt))
+        yc = ops.conv_tc(zc, wp, conv.bias, w.shape[0], tuple(conv.kernel_size), ops.ACT_LRELU, a)
+        zc = ops.pool3_res_cp8(yc, res=zc if (residual and i > 0) else None)
+    return head_tc(cache, model, zc, a)
 
 
 def double_conv_f32(cache, name, dc, x, train, x2=None):

@@ -90,38 +90,55 @@ def bce_fwd_bwd(y_pred, y_true, want_grad=True):
 
 
 # ------------------------------------------------------------------------------------------------------
-# tcgen05 path: bf16 channel-chunk planes ("CP8", see include/mpa.h)
-class CP8:
-    """bf16 planes [B][ceil(C/8)][T+2*pt][pitch][8] with zero borders; real pixel (t,f) at [pt+t][pf+f]."""
+# tcgen05 path: 16-bit channel-chunk planes ("CP8", see include/mpa.h)
+FMT_F16, FMT_BF16 = 0, 1
+_FMT_DTYPE = {FMT_F16: torch.float16, FMT_BF16: torch.bfloat16}
 
-    def __init__(self, B, C, T, F, pitch=None, pf=8, pt=1, device='cuda', buf=None):
+
+def fmt_of(precision):
+    return {'fp16': FMT_F16, 'bf16': FMT_BF16}[precision]
+
+
+class CP8:
+    """16-bit planes [B][ceil(C/8)][T+2*pt][pitch][8] with zero borders; real pixel (t,f) at [pt+t][pf+f]."""
+
+    def __init__(self, B, C, T, F, pitch=None, pf=8, pt=1, device='cuda', buf=None, fmt=FMT_F16):
         if pitch is None:
             pitch = (F + pf + 15) // 16 * 16
-        self.B, self.C, self.T, self.F, self.pitch, self.pf, self.pt = B, C, T, F, pitch, pf, pt
+        self.B, self.C, self.T, self.F, self.pitch, self.pf, self.pt, self.fmt = B, C, T, F, pitch, pf, pt, fmt
         self.NC = (C + 7) // 8
         shape = (B, self.NC, T + 2 * pt, pitch, 8)
-        self.buf = buf if buf is not None else torch.zeros(shape, dtype=torch.bfloat16, device=device)
+        self.buf = buf if buf is not None else torch.zeros(shape, dtype=_FMT_DTYPE[fmt], device=device)
         assert tuple(self.buf.shape) == shape
 
     def like(self, C=None):
-        return CP8(self.B, self.C if C is None else C, self.T, self.F, self.pitch, self.pf, self.pt, self.buf.device)
+        return CP8(self.B, self.C if C is None else C, self.T, self.F, self.pitch, self.pf, self.pt, self.buf.device, fmt=self.fmt)
+
+    def first(self, n):
+        """First n patches (no copy)."""
+        if n == self.B:
+            return self
+        v = CP8.__new__(CP8)
+        v.__dict__.update(self.__dict__)
+        v.B, v.buf = n, self.buf[:n]
+        return v
 
 
-def nchw_to_cp8(x, pitch=None, pf=8, pt=1, out=None):
+def nchw_to_cp8(x, pitch=None, pf=8, pt=1, out=None, fmt=FMT_F16):
     B, C, T, F = x.shape
-    out = out if out is not None else CP8(B, C, T, F, pitch, pf, pt, x.device)
-    call('nchw_to_cp8', _f32(x), out.buf, B, C, T, F, out.pitch, out.pf, out.pt, stream_ptr())
+    out = out if out is not None else CP8(B, C, T, F, pitch, pf, pt, x.device, fmt=fmt)
+    call('nchw_to_cp8', _f32(x), out.buf, B, C, T, F, out.pitch, out.pf, out.pt, out.fmt, stream_ptr())
     return out
 
 
 def cp8_to_nchw(a):
     out = torch.empty(a.B, a.C, a.T, a.F, dtype=torch.float32, device=a.buf.device)
-    call('cp8_to_nchw', a.buf, out, a.B, a.C, a.T, a.F, a.pitch, a.pf, a.pt, stream_ptr())
+    call('cp8_to_nchw', a.buf, out, a.B, a.C, a.T, a.F, a.pitch, a.pf, a.pt, a.fmt, stream_ptr())
     return out
 
 
-def conv_tc_pack(w, device):
-    """[Cout,Cin,KH,KW] fp32 (any device) -> packed bf16 A-operand tiles on `device` (host-side one-off)."""
+def conv_tc_pack(w, device, fmt=FMT_F16):
+    """[Cout,Cin,KH,KW] fp32 (any device) -> packed 16-bit A-operand tiles on `device` (host-side one-off)."""
     import ctypes
     import numpy as np
     wh = np.ascontiguousarray(w.detach().float().cpu().numpy())
@@ -131,26 +148,44 @@ def conv_tc_pack(w, device):
         raise _lib.MpaError(f'conv_tc cannot pack Cin={Cin} Cout={Cout} K={KH}x{KW}')
     packed = np.zeros(nbytes, dtype=np.uint8)
     rc = _lib.lib().mpa_conv_tc_pack_weights(wh.ctypes.data_as(ctypes.c_void_p), packed.ctypes.data_as(ctypes.c_void_p),
-                                             Cin, Cout, KH, KW)
+                                             Cin, Cout, KH, KW, fmt)
     if rc != 0:
         raise _lib.MpaError('mpa_conv_tc_pack_weights: ' + _lib.last_error())
     return torch.from_numpy(packed).to(device)
 
 
 def conv_tc(a, w_packed, bias, Cout, ksize, act=ACT_NONE, act_param=0.0, out=None, n_patches=None,
-            patch_stride_rows=0, T=None):
-    """a: CP8 input (materialised patches) or, with patch_stride_rows>0, one shared frame-major plane."""
+            patch_stride_rows=0, T=None, subsample=None):
+    """a: CP8 input (materialised patches) or, with patch_stride_rows>0, one shared frame-major plane.
+    subsample=(stride, offset): write NCHW fp32 [n, Cout, T, F_out] keeping columns offset + k*stride only."""
     T = a.T if T is None else T
     n = a.B if n_patches is None else n_patches
+    if subsample is None:
+        if out is None:
+            out = CP8(n, Cout, T, a.F, a.pitch, a.pf, a.pt, a.buf.device, fmt=a.fmt)
+        call('conv_tc_f16', a.buf, w_packed, bias, out.buf, 0, 1, 0, n, a.C, Cout, T, a.F, ksize[0], ksize[1], a.pitch, a.pf, a.pt,
+             _lib.i64(patch_stride_rows), act, float(act_param), a.fmt, stream_ptr())
+        return out
+    stride, offset = subsample
+    F_out = (a.F - offset + stride - 1) // stride
     if out is None:
-        out = CP8(n, Cout, T, a.F, a.pitch, a.pf, a.pt, a.buf.device)
-    call('conv_tc_bf16', a.buf, w_packed, bias, out.buf, n, a.C, Cout, T, a.F, ksize[0], ksize[1], a.pitch, a.pf, a.pt,
-         _lib.i64(patch_stride_rows), act, float(act_param), stream_ptr())
+        out = torch.empty(n, Cout, T, F_out, dtype=torch.float32, device=a.buf.device)
+    call('conv_tc_f16', a.buf, w_packed, bias, out, 1, stride, offset, n, a.C, Cout, T, a.F, ksize[0], ksize[1], a.pitch, a.pf, a.pt,
+         _lib.i64(patch_stride_rows), act, float(act_param), a.fmt, stream_ptr())
     return out
 
 
 def pool3_res_cp8(y, res=None, out=None):
     out = out if out is not None else y.like()
-    call('pool3_res_cp8', y.buf, None if res is None else res.buf, out.buf, y.B, y.C, y.T, y.F, y.pitch, y.pf, y.pt,
+    call('pool3_res_cp8', y.buf, None if res is None else res.buf, out.buf, y.B, y.C, y.T, y.F, y.pitch, y.pf, y.pt, y.fmt,
          stream_ptr())
+    return out
+
+
+def head_tail(x, w3, b3, w40, b40, w43, b43, a_lrelu):
+    """x [B,C1,T,Fo] fp32 -> [B,Fo]; conv3 (T x 1) + LReLU + 1x1 + LReLU + 1x1 + sigmoid in one kernel."""
+    B, C1, T, Fo = x.shape
+    C2, C3 = w3.shape[0], w40.shape[0]
+    out = torch.empty(B, Fo, dtype=torch.float32, device=x.device)
+    call('head_tail_f32', _f32(x), w3, b3, w40, b40, w43, b43, out, B, C1, T, Fo, C2, C3, float(a_lrelu), stream_ptr())
     return out

@@ -37,7 +37,7 @@ def test_weight_packing_layout():
     rng = np.random.default_rng(0)
     Cin, Cout, KH, KW = 24, 40, 3, 3
     w = torch.from_numpy(rng.standard_normal((Cout, Cin, KH, KW)).astype(np.float32))
-    packed = ops.conv_tc_pack(w, 'cpu').numpy().view(np.uint16).reshape(KH + 2, -1, 2, 128, 8)
+    packed = ops.conv_tc_pack(w, 'cpu', ops.FMT_BF16).numpy().view(np.uint16).reshape(KH + 2, -1, 2, 128, 8)
     wb = w.to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
     mpr = (3 // 2) * KW + (KW + 1) // 2
     assert packed.shape[1] == mpr
@@ -58,6 +58,13 @@ def test_weight_packing_layout():
                     exp = wb[:, 16:24, kh, df] if (0 <= kh < KH and df < KW) else np.zeros((Cout, 8), np.uint16)
                     assert np.array_equal(got, exp)
     assert not packed[:, :, :, 120:, :].any()
+    ph = ops.conv_tc_pack(w, 'cpu', ops.FMT_F16).numpy().view(np.uint16).reshape(KH + 2, -1, 2, 128, 8)
+    wh = w.half().view(torch.int16).numpy().view(np.uint16)
+    assert np.array_equal(ph[1, 0, 1, 40:80, :], wh[:, 8:16, 0, 0])          # row r=1, j=1 -> kh=0, tap df=0, chunk 1
+    tiny = torch.tensor([1e-6, -3e-7, 65504.0, 1e5, 0.0, 6.1e-5, 5.97e-8, 2.0 ** -25]).reshape(8, 1, 1, 1)
+    pt = ops.conv_tc_pack(tiny.expand(8, 1, 1, 1).contiguous(), 'cpu', ops.FMT_F16).numpy().view(np.uint16).reshape(-1, 2, 128, 8)
+    exp = tiny.reshape(8).half().view(torch.int16).numpy().view(np.uint16)          # host RNE incl. subnormals / overflow
+    assert np.array_equal(pt[0, 0, 0:8, 0], exp)
 
 
 def test_no_cpu_fallback():

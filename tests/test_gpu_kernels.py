@@ -102,39 +102,67 @@ def test_pools_upsample_bn_bce(ops):
     assert (grad.cpu() - ypr.grad).abs().max() <= 1e-5 * ypr.grad.abs().max()
 
 
-def test_cp8_roundtrip_and_pool(ops):
+FMTS = [('fp16', torch.float16), ('bf16', torch.bfloat16)]
+
+
+@pytest.mark.parametrize('prec,dt', FMTS)
+def test_cp8_roundtrip_and_pool(ops, prec, dt):
+    fmt = ops.fmt_of(prec)
     x = rnd(3, 40, 75, 216, seed=1)
-    xc = ops.nchw_to_cp8(x.cuda())
-    assert xc.buf.shape == (3, 5, 77, 224, 8)
+    xc = ops.nchw_to_cp8(x.cuda(), fmt=fmt)
+    assert xc.buf.shape == (3, 5, 77, 224, 8) and xc.buf.dtype == dt
     back = ops.cp8_to_nchw(xc).cpu()
-    xb = x.to(torch.bfloat16).float()
+    xb = x.to(dt).float()
     assert torch.equal(back, xb)
     # borders stay zero
     assert float(xc.buf[:, :, 0].abs().max()) == 0 and float(xc.buf[:, :, :, :8].abs().max()) == 0
     r = rnd(3, 40, 75, 216, seed=2)
-    rc = ops.nchw_to_cp8(r.cuda())
+    rc = ops.nchw_to_cp8(r.cuda(), fmt=fmt)
     got = ops.cp8_to_nchw(ops.pool3_res_cp8(xc, rc)).cpu()
-    ref = (F.max_pool2d(xb, (3, 1), (1, 1), (1, 0)) + r.to(torch.bfloat16).float()).to(torch.bfloat16).float()
+    ref = (F.max_pool2d(xb, (3, 1), (1, 1), (1, 0)) + r.to(dt).float()).to(dt).float()
     assert torch.equal(got, ref)
 
 
+@pytest.mark.parametrize('prec,dt', FMTS)
 @pytest.mark.parametrize('cfg', [
     (2, 8, 40, 6, 24, 1, 1), (2, 16, 40, 7, 24, 3, 3), (3, 24, 40, 9, 40, 3, 3), (3, 6, 40, 20, 216, 15, 15),
     (3, 40, 40, 75, 216, 15, 15), (2, 20, 20, 75, 216, 15, 15), (2, 64, 128, 9, 27, 5, 5), (1, 40, 40, 75, 216, 15, 15),
+    (2, 8, 16, 37, 108, 15, 15), (5, 32, 8, 18, 54, 9, 9),
 ])
-def test_conv_tc_bf16(ops, cfg):
-    """tcgen05 path vs an fp64 convolution of the SAME bf16-rounded operands: only fp32 accumulation order and the
-    final bf16 rounding of the output (2^-9 relative) may differ."""
+def test_conv_tc(ops, cfg, prec, dt):
+    """tcgen05 path vs an fp64 convolution of the SAME 16-bit-rounded operands: only fp32 accumulation order and the
+    final rounding of the output to the storage format (half an ulp) may differ."""
     B, Cin, Cout, T, Fq, KH, KW = cfg
+    fmt = ops.fmt_of(prec)
     x, w, b = rnd(B, Cin, T, Fq, seed=4), rnd(Cout, Cin, KH, KW, seed=5, scale=(Cin * KH * KW) ** -0.5), rnd(Cout, seed=6, scale=0.1)
-    xr, wr = x.to(torch.bfloat16).double(), w.to(torch.bfloat16).double()
+    xr, wr = x.to(dt).double(), w.to(dt).double()
     ref = F.leaky_relu(F.conv2d(xr, wr, b.double(), padding=(KH // 2, KW // 2)), 0.3).float()
-    xc = ops.nchw_to_cp8(x.cuda())
-    yc = ops.conv_tc(xc, ops.conv_tc_pack(w, 'cuda'), b.cuda(), Cout, (KH, KW), ops.ACT_LRELU, 0.3)
+    xc = ops.nchw_to_cp8(x.cuda(), fmt=fmt)
+    yc = ops.conv_tc(xc, ops.conv_tc_pack(w, 'cuda', fmt), b.cuda(), Cout, (KH, KW), ops.ACT_LRELU, 0.3)
     got = ops.cp8_to_nchw(yc).cpu()
-    tol = 2 ** -8 * ref.abs().max().item() + 1e-4
-    assert (got - ref).abs().max() < tol
+    ulp = 2.0 ** -8 if prec == 'bf16' else 2.0 ** -11
+    assert (got - ref).abs().max() < ulp * ref.abs().max().item() + 1e-4
     assert float(yc.buf[:, :, 0].abs().max()) == 0 and float(yc.buf[:, :, :, :8].abs().max()) == 0     # borders untouched
+
+
+def test_conv_tc_subsampled_fp32_output_and_head_tail(ops):
+    """conv2 of the head: 3x3 stride (1,3) pad (1,0) == stride-1 'same' conv sampled at columns 1,4,7,...; then the
+    fused conv3/conv4 tail against torch."""
+    B, C0, C1, C2, C3, T, Fq = 3, 40, 40, 30, 10, 75, 216
+    x, w2, b2 = rnd(B, C0, T, Fq, seed=1), rnd(C1, C0, 3, 3, seed=2, scale=(C0 * 9) ** -0.5), rnd(C1, seed=3, scale=0.1)
+    xr, wr = x.half().double(), w2.half().double()
+    ref2 = F.leaky_relu(F.conv2d(xr, wr, b2.double(), stride=(1, 3), padding=(1, 0)), 0.3).float()
+    xc = ops.nchw_to_cp8(x.cuda(), fmt=ops.FMT_F16)
+    got2 = ops.conv_tc(xc, ops.conv_tc_pack(w2, 'cuda', ops.FMT_F16), b2.cuda(), C1, (3, 3), ops.ACT_LRELU, 0.3, subsample=(3, 1))
+    assert tuple(got2.shape) == (B, C1, T, 72)
+    assert (got2.cpu() - ref2).abs().max() < 2e-5 * max(1.0, ref2.abs().max().item())       # fp32 output: no storage rounding
+    w3, b3 = rnd(C2, C1, T, 1, seed=4, scale=(C1 * T) ** -0.5), rnd(C2, seed=5, scale=0.1)
+    w40, b40 = rnd(C3, C2, 1, 1, seed=6, scale=C2 ** -0.5), rnd(C3, seed=7, scale=0.1)
+    w43, b43 = rnd(1, C3, 1, 1, seed=8, scale=C3 ** -0.5), rnd(1, seed=9, scale=0.1)
+    y = F.max_pool2d(ref2, (13, 1), (1, 1), (6, 0))
+    ref = torch.sigmoid(F.conv2d(F.leaky_relu(F.conv2d(F.leaky_relu(F.conv2d(y, w3, b3), 0.3), w40, b40), 0.3), w43, b43))
+    got = ops.head_tail(y.cuda(), w3.cuda(), b3.cuda(), w40.cuda(), b40.cuda(), w43.cuda(), b43.cuda(), 0.3)
+    assert (got.cpu() - ref.reshape(B, 72)).abs().max() < 1e-5
 
 
 def test_encoder_layer(ops):

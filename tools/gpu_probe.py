@@ -1,6 +1,6 @@
 """GPU-side diagnostics (not a test): runs the tcgen05 convolution on progressively harder shapes, each in its
 own subprocess with a timeout (a device trap poisons the CUDA context), and prints max-abs errors against a torch
-fp32 reference on bf16-rounded operands.  Usage on the GPU box:  python tools/gpu_probe.py [case ...]"""
+fp32 reference on fp16-rounded operands.  Usage on the GPU box:  python tools/gpu_probe.py [case ...]"""
 import json
 import os
 import subprocess
@@ -35,8 +35,8 @@ def run_case(name):
     x = torch.randn(B, Cin, T, Fq, generator=g)
     w = torch.randn(Cout, Cin, KH, KW, generator=g) / (Cin * KH * KW) ** 0.5
     b = torch.randn(Cout, generator=g) * 0.1
-    xr = x.to(torch.bfloat16).float()
-    wr = w.to(torch.bfloat16).float()
+    xr = x.half().float()
+    wr = w.half().float()
     nref = min(B, 3)
     ref = F.leaky_relu(F.conv2d(xr[:nref].double(), wr.double(), b.double(), padding=(KH // 2, KW // 2)), 0.3).float()
     dev = 'cuda'
@@ -50,7 +50,7 @@ def run_case(name):
     xr = xr[:nref]
     err = (y - ref).abs()
     res = dict(case=name, roundtrip=float((back - xr).abs().max()), max_err=float(err.max()), mean_err=float(err.mean()),
-               ref_absmax=float(ref.abs().max()), bf16_eps_bound=float(ref.abs().max()) * 2 ** -8)
+               ref_absmax=float(ref.abs().max()), f16_eps_bound=float(ref.abs().max()) * 2 ** -11)
     # where are the errors? per output row / per channel maxima help localise descriptor mistakes
     res['err_by_row'] = [round(float(v), 4) for v in err.amax(dim=(0, 1, 3))[:12]]
     res['err_by_cout'] = [round(float(v), 4) for v in err.amax(dim=(0, 2, 3))[:8]]
