@@ -114,15 +114,17 @@ size_t mpa_conv_tc_packed_bytes(int Cin, int Cout, int KH, int KW);
 /* HOST function: w [Cout][Cin][KH][KW] fp32 (host) -> packed 16-bit A-operand tiles (host buffer), fmt = MPA_FMT_*. */
 int mpa_conv_tc_pack_weights(const float* w_host, void* packed_host, int Cin, int Cout, int KH, int KW, int fmt);
 /* out_mode 0: `out` is a CP8 plane set [n_patches][ceil(Cout/8)][T+2pt][pitch][8] (16-bit, same fmt);
- * out_mode 1: `out` is NCHW fp32 [n_patches][Cout][T][F_out] holding columns f = sub_offset + k*sub_stride only
- *             (a stride-(1,s) convolution evaluated as the stride-1 one and sub-sampled in the epilogue). */
+ * out_mode 1: `out` is the compact plane set [n_patches][ceil(Cout/8)][T][F_out][8] holding only the columns
+ *             f = sub_offset + k*sub_stride (a stride-(1,s) convolution evaluated as the stride-1 "same" convolution and
+ *             sub-sampled in the epilogue), F_out = ceil((F - sub_offset)/sub_stride). */
 int mpa_conv_tc_f16(const void* in_cp8, const void* w_packed, const float* bias, void* out, int out_mode,
                     int sub_stride, int sub_offset, int n_patches, int Cin, int Cout, int T, int F, int KH, int KW,
                     int pitch, int pf, int pt, long long in_patch_stride_rows, int act, float act_param, int fmt,
                     void* stream);
-/* out = maxpool_time3(y) + res (res may be NULL), CP8 in/out, per patch. */
-int mpa_pool3_res_cp8(const void* y_cp8, const void* res_cp8, void* out_cp8, int n_patches, int C, int T, int F,
-                      int pitch, int pf, int pt, int fmt, void* stream);
+/* out = maxpool_time_k(y) + res (res may be NULL; k odd, -inf padding), CP8 in/out; with pitch=F, pf=pt=0 it serves
+ * the compact out_mode-1 planes too. */
+int mpa_pool_time_res_cp8(const void* y_cp8, const void* res_cp8, void* out_cp8, int n_patches, int C, int T, int F,
+                          int pitch, int pf, int pt, int k, int fmt, void* stream);
 /* layout converters (tests, and the seams between the fp32 and the 16-bit paths). */
 int mpa_nchw_to_cp8(const float* x, void* out_cp8, int B, int C, int T, int F, int pitch, int pf, int pt, int fmt,
                     void* stream);
@@ -130,11 +132,12 @@ int mpa_cp8_to_nchw(const void* in_cp8, float* out, int B, int C, int T, int F, 
                     void* stream);
 
 /* Fused head tail for the patch-wise case (T == conv3 kernel height, conv4.3 kernel 1x1; basic_cnns.py:396-408):
- * x NCHW fp32 [B,C1,T,Fo] (max-pooled conv2 output) -> out [B,Fo] = sigmoid(conv4.3(lrelu(conv4.0(lrelu(conv3(x)))))).
- * w3 [C2][C1][T], w40 [C3][C2], w43 [C3] in state_dict layout.  C2 <= 32, C3 <= 16, Fo <= 256. */
-int mpa_head_tail_f32(const float* x, const float* w3, const float* b3, const float* w40, const float* b40,
+ * x compact 16-bit planes [B][ceil(C1/8)][T][Fo][8] (max-pooled conv2 output) -> out [B,Fo] fp32 =
+ * sigmoid(conv4.3(lrelu(conv4.0(lrelu(conv3(x)))))).  w3 [C2][C1][T], w40 [C3][C2], w43 [C3] in state_dict layout.
+ * C2 <= 32, C3 <= 16, Fo <= 256. */
+int mpa_head_tail_cp8(const void* x_cp8, const float* w3, const float* b3, const float* w40, const float* b40,
                       const float* w43, const float* b43, float* out, int B, int C1, int T, int Fo, int C2, int C3,
-                      float a_lrelu, void* stream);
+                      float a_lrelu, int fmt, void* stream);
 
 /* ---- HCQT (H1-H3): batched multirate constant-Q filterbank ---------------------------------------------
  * replaces librosa.cqt x3 + librosa.estimate_tuning as driven by libdl/data_preprocessing/hcqt.py:122,157-162;

@@ -15,11 +15,14 @@
 //   Zero padding in frequency is physical (zero gap columns between rows of the CP8 plane); zero padding in
 //   time is realised by skipping the K steps of out-of-range input rows.
 //
-// Pipeline (one CTA per SM, persistent over work units = (patch pair, row group)):
+// Pipeline (one CTA per SM, persistent over work units = (patch, row group)):
 //   warp 0  producer : cp.async.bulk (1-D TMA) of activation row slabs and packed weight stages -> mbarriers
-//   warp 1  MMA      : one thread issues tcgen05.mma (kind::f16, bf16 in, fp32 accumulate in TMEM);
-//                      each weight stage feeds TWO accumulators (two patches) to halve weight traffic
-//   warps 2-5 epilogue: tcgen05.ld -> +bias -> activation -> bf16 -> CP8 global store
+//   warp 1  MMA      : one thread issues tcgen05.mma (kind::f16, fp16/bf16 in, fp32 accumulate in TMEM) from a
+//                      pre-built shared-memory table of B descriptors
+//   warps 2-5 epilogue: tcgen05.ld -> +bias -> activation -> 16-bit -> transposed through shared memory ->
+//                      16-byte coalesced CP8 stores
+//   The accumulator is double buffered in TMEM (2 x 224 of 512 columns): the epilogue of unit k overlaps the
+//   main loop of unit k+1.  Weights stream from L2 once per unit (36 B/clk/SM, ~30 % of L2 throughput).
 #include "common.cuh"
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -31,8 +34,8 @@ namespace mpa {
 constexpr int kStageMMAs = 4;                 // MMAs (K=16 steps) per weight stage
 constexpr int kATileBytes = 2 * 128 * 16;     // one MMA's A tile: [2 k-slices][128 rows][16 B]
 constexpr int kAStageBytes = kStageMMAs * kATileBytes;
-constexpr int kNumAStages = 6;
-constexpr int kNumBStages = 2;
+constexpr int kNumAStages = 8;
+constexpr int kNumBStages = 3;
 constexpr int kThreads = 192;
 constexpr int kEpiPitch = 40;                 // 80-byte rows: conflict-free 16-byte reads in the transposing epilogue
 constexpr unsigned long long kWaitTimeoutNs = 4000000000ull;   // bounded waits: a protocol bug traps instead of hanging the GPU
@@ -41,8 +44,7 @@ struct ConvTcParams {
   const uint8_t* in;        // CP8 bf16 planes
   const uint8_t* w;         // packed weights
   const float* bias;        // [Cout]
-  uint16_t* out;            // CP8 16-bit planes [n_patches][NCo][TP][P][8]   (out_mode 0)
-  float* out32;             // NCHW fp32 [n_patches][Cout][T][F_out], column-subsampled (out_mode 1)
+  uint16_t* out;            // out_mode 0: CP8 planes [n][NCo][T+2pt][P][8]; out_mode 1: compact [n][NCo][T][F_out][8] (sub-sampled columns)
   int out_mode, sub_stride, sub_offset, F_out, fmt;
   long long in_patch_stride;   // bytes between patches in `in`
   long long in_chunk_stride;   // bytes between channel chunks in `in`
@@ -139,17 +141,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
   extern __shared__ __align__(1024) uint8_t smem[];
   const int slab_plane_bytes = p.slab_px * 16;
   const int slab_bytes = p.NC * slab_plane_bytes;        // one patch, one input row
-  const int bstage_bytes = 2 * slab_bytes;               // two patches
+  const int bstage_bytes = slab_bytes;
   uint8_t* a_smem = smem;                                // [kNumAStages][kAStageBytes]
-  uint8_t* b_smem = smem + kNumAStages * kAStageBytes;   // [kNumBStages][2][NC][slab_px][16B]
+  uint8_t* b_smem = smem + kNumAStages * kAStageBytes;   // [kNumBStages][NC][slab_px][16B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + kNumBStages * bstage_bytes);
   uint64_t* a_full = bars;
   uint64_t* a_empty = bars + kNumAStages;
   uint64_t* b_full = bars + 2 * kNumAStages;
   uint64_t* b_empty = b_full + kNumBStages;
-  uint64_t* acc_full = b_empty + kNumBStages;
-  uint64_t* acc_empty = acc_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+  uint64_t* acc_full = b_empty + kNumBStages;            // [2]
+  uint64_t* acc_empty = acc_full + 2;                    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   uint32_t* btab = tmem_slot + 2;                                          // [mmas_per_row] B-descriptor low words
   uint16_t* epi_smem = reinterpret_cast<uint16_t*>(smem + p.epi_off);      // 4 warps x [32][32] 16-bit staging
 
@@ -164,8 +166,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
       mbar_init(&b_full[i], 1);
       mbar_init(&b_empty[i], 1);
     }
-    mbar_init(acc_full, 1);
-    mbar_init(acc_empty, 128);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 128);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -179,8 +183,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
 
   const int ph = p.KH / 2, pw = p.KW / 2;
   const int rows_in = p.KH + p.J - 1;
-  const int n_pairs = (p.n_patches + 1) / 2;
-  (void)n_pairs;
 
   if (warp == 0) {
     // ===================================================== producer
@@ -188,19 +190,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
       int a_stage = 0, b_stage = 0;
       uint32_t a_phase = 0, b_phase = 0;
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-        const int pair = u / p.n_groups, g = u % p.n_groups;
+        const int b0 = u / p.n_groups, g = u % p.n_groups;
         const int t0 = g * p.J;
-        const int b0 = pair * 2;
-        const int np = (b0 + 1 < p.n_patches) ? 2 : 1;
         for (int r = 0; r < rows_in; ++r) {
           const int row = t0 - ph + r;
           if (row < 0 || row >= p.T) continue;
-          // activation slabs of this input row (both patches)
+          // activation slab of this input row
           mbar_wait(&b_empty[b_stage], b_phase ^ 1);
-          mbar_expect_tx(&b_full[b_stage], (uint32_t)(np * slab_bytes));
-          for (int q = 0; q < np; ++q) {
-            const uint8_t* src = p.in + p.in_row0 + (long long)(b0 + q) * p.in_patch_stride + ((long long)row * p.P - pw) * 16;
-            uint8_t* dst = b_smem + b_stage * bstage_bytes + q * slab_bytes;
+          mbar_expect_tx(&b_full[b_stage], (uint32_t)slab_bytes);
+          {
+            const uint8_t* src = p.in + p.in_row0 + (long long)b0 * p.in_patch_stride + ((long long)row * p.P - pw) * 16;
+            uint8_t* dst = b_smem + b_stage * bstage_bytes;
             for (int c = 0; c < p.NC; ++c)
               bulk_g2s(dst + c * slab_plane_bytes, src + (long long)c * p.in_chunk_stride, (uint32_t)slab_plane_bytes, &b_full[b_stage]);
           }
@@ -239,16 +239,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
     }
     if (lane == 0) {
       int a_stage = 0, b_stage = 0;
-      uint32_t a_phase = 0, b_phase = 0, acc_phase = 0;
+      uint32_t a_phase = 0, b_phase = 0;
       constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);                 // SBO = 128 B, descriptor version 1
       constexpr uint32_t kALoFixed = ((128u * 16u) >> 4) << 16;              // A: LBO = 2048 B between the two k-slices
-      const uint32_t slab16 = (uint32_t)slab_bytes >> 4;
-      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-        const int pair = u / p.n_groups, g = u % p.n_groups;
+      uint32_t k_unit = 0;
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++k_unit) {
+        const int g = u % p.n_groups;
         const int t0 = g * p.J;
-        const bool two = (pair * 2 + 1 < p.n_patches);
-        mbar_wait(acc_empty, acc_phase ^ 1);     // epilogue has drained the accumulators of the previous unit
+        const uint32_t buf = k_unit & 1u, acc_par = (k_unit >> 1) & 1u;
+        mbar_wait(&acc_empty[buf], acc_par ^ 1);     // epilogue has drained this accumulator (two units ago)
         tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * 256;
         uint32_t accum = 0;
         for (int r = 0; r < rows_in; ++r) {
           const int row = t0 - ph + r;
@@ -263,22 +264,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
 #pragma unroll
             for (int i = 0; i < kStageMMAs; ++i) {
               if (i < nm) {
-                const uint32_t e = btab[m0 + i];
                 const uint64_t adesc = ((uint64_t)kDescHi << 32) | (uint64_t)((abase16 + i * (kATileBytes >> 4)) | kALoFixed);
-                const uint64_t bdesc0 = ((uint64_t)kDescHi << 32) | (uint64_t)(bbase16 + e);
-                tc_mma_f16(tmem_base, adesc, bdesc0, p.idesc, accum);
-                if (two) tc_mma_f16(tmem_base + 256, adesc, bdesc0 + slab16, p.idesc, accum);
+                const uint64_t bdesc = ((uint64_t)kDescHi << 32) | (uint64_t)(bbase16 + btab[m0 + i]);
+                tc_mma_f16(tmem_d, adesc, bdesc, p.idesc, accum);
                 accum = 1;
               }
             }
             tc_commit(&a_empty[a_stage]);       // frees the weight stage when its MMAs have retired
             if (++a_stage == kNumAStages) { a_stage = 0; a_phase ^= 1; }
           }
-          tc_commit(&b_empty[b_stage]);         // frees the activation slabs of this row
+          tc_commit(&b_empty[b_stage]);         // frees the activation slab of this row
           if (++b_stage == kNumBStages) { b_stage = 0; b_phase ^= 1; }
         }
-        tc_commit(acc_full);                    // accumulators complete -> epilogue
-        acc_phase ^= 1;
+        tc_commit(&acc_full[buf]);              // accumulator complete -> epilogue
       }
     }
     __syncwarp();
@@ -290,67 +288,72 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
     const bool row_valid = (j < p.J);
     const float bias = row_valid ? p.bias[co] : 0.f;
     // coalesced path: 8 consecutive lanes = the 8 channels of one chunk of one output row (needs Cout % 8 == 0)
-    const bool staged = (p.out_mode == 0) && ((p.Cout & 7) == 0);
+    const bool staged = ((p.Cout & 7) == 0);
     uint16_t* stile = epi_smem + (warp - 2) * (32 * kEpiPitch);     // [32 columns][kEpiPitch >= 32 lanes] 16-bit
-    uint32_t acc_phase = 0;
-    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-      const int pair = u / p.n_groups, g = u % p.n_groups;
+    uint32_t k_unit = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++k_unit) {
+      const int b = u / p.n_groups, g = u % p.n_groups;
       const int t = g * p.J + j;
-      const int np = (pair * 2 + 1 < p.n_patches) ? 2 : 1;
-      mbar_wait(acc_full, acc_phase);
+      const uint32_t buf = k_unit & 1u, acc_par = (k_unit >> 1) & 1u;
+      mbar_wait(&acc_full[buf], acc_par);
       tc_fence_after();
-      for (int pq = 0; pq < np; ++pq) {
-        const int b = pair * 2 + pq;
-        for (int c0 = 0; c0 < p.P; c0 += 32) {
-          uint32_t v[32];
-          tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(pq * 256 + c0), v);
-          tc_wait_ld();
-          if (staged) {
+      for (int c0 = 0; c0 < p.P; c0 += 32) {
+        uint32_t v[32];
+        tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256 + c0), v);
+        tc_wait_ld();
+        if (staged) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float x = apply_act(__uint_as_float(v[i]) + bias, p.act, p.act_param);
-              stile[i * kEpiPitch + lane] = cvt16(x, p.fmt);
+          for (int i = 0; i < 32; ++i) {
+            const float x = apply_act(__uint_as_float(v[i]) + bias, p.act, p.act_param);
+            stile[i * kEpiPitch + lane] = cvt16(x, p.fmt);
+          }
+          __syncwarp();
+          // lane -> column c0+lane; pass k -> the k-th 8-lane group (= one channel chunk of one output row) of this warp
+          const int n = c0 + lane;
+          int fo = n - p.pf;
+          bool col_ok = (fo >= 0 && fo < p.F);
+          if (p.out_mode == 1) {
+            fo -= p.sub_offset;
+            col_ok = col_ok && fo >= 0 && (fo % p.sub_stride) == 0;
+            fo /= p.sub_stride;
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int mg = quad * 32 + k * 8;                  // first accumulator row of the group
+            const int jg = mg / p.Cout, cog = mg - jg * p.Cout;
+            const int tg = g * p.J + jg;
+            if (col_ok && jg < p.J && tg < p.T) {
+              const uint4 val = *reinterpret_cast<const uint4*>(stile + lane * kEpiPitch + k * 8);
+              uint16_t* dst = (p.out_mode == 0)
+                                  ? p.out + ((((size_t)b * p.NCo + (cog >> 3)) * p.TP_out + p.pt_out + tg) * p.P + n) * 8
+                                  : p.out + ((((size_t)b * p.NCo + (cog >> 3)) * p.T + tg) * p.F_out + fo) * 8;
+              *reinterpret_cast<uint4*>(dst) = val;
             }
-            __syncwarp();
-            // lane -> column c0+lane; pass k -> the k-th 8-lane group of this warp
-            const int n = c0 + lane;
-            const bool col_ok = (n >= p.pf && n < p.pf + p.F);
+          }
+          __syncwarp();
+        } else if (row_valid && t < p.T) {
+          // scalar fallback (Cout not a multiple of 8): same destinations, one 16-bit store per value
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int mg = quad * 32 + k * 8;                  // first accumulator row of the group
-              const int jg = mg / p.Cout, cog = mg - jg * p.Cout;
-              const int tg = g * p.J + jg;
-              if (col_ok && jg < p.J && tg < p.T) {
-                const uint4 val = *reinterpret_cast<const uint4*>(stile + lane * kEpiPitch + k * 8);
-                uint16_t* dst = p.out + ((((size_t)b * p.NCo + (cog >> 3)) * p.TP_out + p.pt_out + tg) * p.P + n) * 8;
-                *reinterpret_cast<uint4*>(dst) = val;
-              }
+          for (int i = 0; i < 32; ++i) {
+            const int n = c0 + i;
+            int fo = n - p.pf;
+            bool ok = (fo >= 0 && fo < p.F);
+            if (p.out_mode == 1) {
+              fo -= p.sub_offset;
+              ok = ok && fo >= 0 && (fo % p.sub_stride) == 0;
+              fo /= p.sub_stride;
             }
-            __syncwarp();
-          } else if (row_valid && t < p.T) {
-            if (p.out_mode == 0) {
-              uint16_t* orow = p.out + ((((size_t)b * p.NCo + (co >> 3)) * p.TP_out + p.pt_out + t) * p.P) * 8 + (co & 7);
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const int n = c0 + i;
-                if (n >= p.pf && n < p.pf + p.F)
-                  orow[(size_t)n * 8] = cvt16(apply_act(__uint_as_float(v[i]) + bias, p.act, p.act_param), p.fmt);
-              }
-            } else {
-              float* orow = p.out32 + (((size_t)b * p.Cout + co) * p.T + t) * p.F_out;
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const int f = c0 + i - p.pf - p.sub_offset;
-                if (f >= 0 && f < p.F_out * p.sub_stride && (f % p.sub_stride) == 0)
-                  orow[f / p.sub_stride] = apply_act(__uint_as_float(v[i]) + bias, p.act, p.act_param);
-              }
+            if (ok) {
+              uint16_t* dst = (p.out_mode == 0)
+                                  ? p.out + ((((size_t)b * p.NCo + (co >> 3)) * p.TP_out + p.pt_out + t) * p.P + n) * 8 + (co & 7)
+                                  : p.out + ((((size_t)b * p.NCo + (co >> 3)) * p.T + t) * p.F_out + fo) * 8 + (co & 7);
+              *dst = cvt16(apply_act(__uint_as_float(v[i]) + bias, p.act, p.act_param), p.fmt);
             }
           }
         }
       }
       tc_fence_before();
-      mbar_arrive(acc_empty);
-      acc_phase ^= 1;
+      mbar_arrive(&acc_empty[buf]);
     }
   }
   tc_fence_before();
@@ -466,8 +469,8 @@ __device__ __forceinline__ void add8(uint4& c, const uint4& r) {
   }
 }
 template <int FMT>
-__global__ void pool3_res_cp8_kernel(const uint4* __restrict__ y, const uint4* __restrict__ res, uint4* __restrict__ out,
-                                     long long total, int T, int F, int TP, int P, int pf, int pt) {
+__global__ void pool_time_res_cp8_kernel(const uint4* __restrict__ y, const uint4* __restrict__ res, uint4* __restrict__ out,
+                                         long long total, int T, int F, int TP, int P, int pf, int pt, int half) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int f = (int)(i % F);
     long long r = i / F;
@@ -475,8 +478,9 @@ __global__ void pool3_res_cp8_kernel(const uint4* __restrict__ y, const uint4* _
     long long plane = r / T;
     const size_t base = ((size_t)plane * TP + pt + t) * P + pf + f;
     uint4 c = y[base];
-    if (t > 0) max8<FMT>(c, y[base - P]);
-    if (t < T - 1) max8<FMT>(c, y[base + P]);
+    const int lo = max(-half, -t), hi = min(half, T - 1 - t);
+    for (int d = lo; d <= hi; ++d)
+      if (d != 0) max8<FMT>(c, y[base + (long long)d * P]);
     if (res) add8<FMT>(c, res[base]);
     out[base] = c;
   }
@@ -557,7 +561,6 @@ int mpa_conv_tc_f16(const void* in_cp8, const void* w_packed, const float* bias,
   p.w = (const uint8_t*)w_packed;
   p.bias = bias;
   p.out = (uint16_t*)out;
-  p.out32 = (float*)out;
   p.out_mode = out_mode;
   p.sub_stride = out_mode ? sub_stride : 1;
   p.sub_offset = out_mode ? sub_offset : 0;
@@ -586,13 +589,13 @@ int mpa_conv_tc_f16(const void* in_cp8, const void* w_packed, const float* bias,
   }
   p.mmas_per_row = mmas_per_row(p.NC, KW);
   p.n_groups = (T + p.J - 1) / p.J;
-  p.n_units = ((n_patches + 1) / 2) * p.n_groups;
+  p.n_units = n_patches * p.n_groups;
   p.slab_px = (pitch + 2 * (KW / 2) + 1 + 7) / 8 * 8;
   p.act = act;
   p.act_param = act_param;
   const uint32_t f = (fmt == MPA_FMT_BF16) ? 1u : 0u;
   p.idesc = (1u << 4) | (f << 7) | (f << 10) | ((uint32_t)(pitch >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  size_t off = (size_t)kNumAStages * kAStageBytes + (size_t)kNumBStages * 2 * p.NC * p.slab_px * 16;
+  size_t off = (size_t)kNumAStages * kAStageBytes + (size_t)kNumBStages * p.NC * p.slab_px * 16;
   off += 256 + (size_t)p.mmas_per_row * 4;      // barriers + tmem slot, descriptor table
   off = (off + 127) / 128 * 128;
   p.epi_off = (int)off;
@@ -617,19 +620,19 @@ int mpa_conv_tc_f16(const void* in_cp8, const void* w_packed, const float* bias,
   return MPA_OK;
 }
 
-int mpa_pool3_res_cp8(const void* y_cp8, const void* res_cp8, void* out_cp8, int n_patches, int C, int T, int F, int pitch, int pf,
-                      int pt, int fmt, void* stream) {
+int mpa_pool_time_res_cp8(const void* y_cp8, const void* res_cp8, void* out_cp8, int n_patches, int C, int T, int F, int pitch, int pf,
+                          int pt, int k, int fmt, void* stream) {
   MPA_CHECK_ARCH();
-  MPA_REQUIRE(y_cp8 && out_cp8 && n_patches > 0 && C > 0, "pool3_res_cp8: bad argument");
+  MPA_REQUIRE(y_cp8 && out_cp8 && n_patches > 0 && C > 0 && k >= 1 && (k & 1) && pitch >= pf + F, "pool_time_res_cp8: bad argument");
   const int NCk = (C + 7) / 8;
   long long total = (long long)n_patches * NCk * T * F;
   if (fmt == MPA_FMT_BF16)
-    pool3_res_cp8_kernel<MPA_FMT_BF16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)y_cp8, (const uint4*)res_cp8,
-                                                                                                 (uint4*)out_cp8, total, T, F, T + 2 * pt, pitch, pf, pt);
+    pool_time_res_cp8_kernel<MPA_FMT_BF16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)y_cp8, (const uint4*)res_cp8, (uint4*)out_cp8, total, T, F, T + 2 * pt, pitch, pf, pt, k / 2);
   else
-    pool3_res_cp8_kernel<MPA_FMT_F16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)y_cp8, (const uint4*)res_cp8,
-                                                                                                (uint4*)out_cp8, total, T, F, T + 2 * pt, pitch, pf, pt);
-  MPA_CHECK_LAUNCH("pool3_res_cp8");
+    pool_time_res_cp8_kernel<MPA_FMT_F16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)y_cp8, (const uint4*)res_cp8, (uint4*)out_cp8, total, T, F, T + 2 * pt, pitch, pf, pt, k / 2);
+  MPA_CHECK_LAUNCH("pool_time_res_cp8");
   return MPA_OK;
 }
 

@@ -88,13 +88,14 @@ def head_tc(cache, model, zc, a):
         return head_f32(cache, model, ops.cp8_to_nchw(zc), a)
     w2 = conv2.weight
     wp = cache.get(f'conv2:wtc{zc.fmt}', [w2], lambda: ops.conv_tc_pack(w2, zc.buf.device, zc.fmt))
-    y = ops.conv_tc(zc, wp, conv2.bias, w2.shape[0], (3, 3), ops.ACT_LRELU, a, subsample=(3, 1))
-    y = ops.maxpool_time(y, 13)
+    yc = ops.conv_tc(zc, wp, conv2.bias, w2.shape[0], (3, 3), ops.ACT_LRELU, a, subsample=(3, 1))
+    yc = ops.pool_time_res_cp8(yc, 13)
     fused = (conv3.kernel_size[0] == zc.T and conv3.kernel_size[1] == 1 and tuple(c43.kernel_size) == (1, 1)
-             and conv3.weight.shape[0] <= 32 and c40.weight.shape[0] <= 16 and c43.weight.shape[0] == 1 and y.shape[3] <= 256)
+             and conv3.weight.shape[0] <= 32 and c40.weight.shape[0] <= 16 and c43.weight.shape[0] == 1 and yc.F <= 256)
     if fused:
-        o = ops.head_tail(y, conv3.weight, conv3.bias, c40.weight, c40.bias, c43.weight, c43.bias, a)
+        o = ops.head_tail(yc, conv3.weight, conv3.bias, c40.weight, c40.bias, c43.weight, c43.bias, a)
         return o.reshape(o.shape[0], 1, 1, o.shape[1])
+    y = ops.cp8_to_nchw(yc)
     y = conv_f32(cache, 'conv3', conv3, y, ops.ACT_LRELU, a)
     y = conv_f32(cache, 'conv4.0', c40, y, ops.ACT_LRELU, a)
     return conv_f32(cache, 'conv4.3', c43, y, ops.ACT_SIGMOID)

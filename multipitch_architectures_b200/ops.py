@@ -112,6 +112,10 @@ class CP8:
         assert tuple(self.buf.shape) == shape
 
     def like(self, C=None):
+        if self.pt == 0 and self.pf == 0 and self.pitch == self.F:      # compact planes need no zero borders
+            return CP8(self.B, self.C if C is None else C, self.T, self.F, self.pitch, 0, 0, self.buf.device, fmt=self.fmt,
+                       buf=torch.empty(self.B, ((self.C if C is None else C) + 7) // 8, self.T, self.pitch, 8,
+                                       dtype=_FMT_DTYPE[self.fmt], device=self.buf.device))
         return CP8(self.B, self.C if C is None else C, self.T, self.F, self.pitch, self.pf, self.pt, self.buf.device, fmt=self.fmt)
 
     def first(self, n):
@@ -157,35 +161,39 @@ def conv_tc_pack(w, device, fmt=FMT_F16):
 def conv_tc(a, w_packed, bias, Cout, ksize, act=ACT_NONE, act_param=0.0, out=None, n_patches=None,
             patch_stride_rows=0, T=None, subsample=None):
     """a: CP8 input (materialised patches) or, with patch_stride_rows>0, one shared frame-major plane.
-    subsample=(stride, offset): write NCHW fp32 [n, Cout, T, F_out] keeping columns offset + k*stride only."""
+    subsample=(stride, offset): compact output CP8 (pitch = F_out, no padding) keeping columns offset + k*stride."""
     T = a.T if T is None else T
     n = a.B if n_patches is None else n_patches
     if subsample is None:
         if out is None:
             out = CP8(n, Cout, T, a.F, a.pitch, a.pf, a.pt, a.buf.device, fmt=a.fmt)
-        call('conv_tc_f16', a.buf, w_packed, bias, out.buf, 0, 1, 0, n, a.C, Cout, T, a.F, ksize[0], ksize[1], a.pitch, a.pf, a.pt,
-             _lib.i64(patch_stride_rows), act, float(act_param), a.fmt, stream_ptr())
-        return out
-    stride, offset = subsample
-    F_out = (a.F - offset + stride - 1) // stride
-    if out is None:
-        out = torch.empty(n, Cout, T, F_out, dtype=torch.float32, device=a.buf.device)
-    call('conv_tc_f16', a.buf, w_packed, bias, out, 1, stride, offset, n, a.C, Cout, T, a.F, ksize[0], ksize[1], a.pitch, a.pf, a.pt,
-         _lib.i64(patch_stride_rows), act, float(act_param), a.fmt, stream_ptr())
+        mode, stride, offset = 0, 1, 0
+    else:
+        stride, offset = subsample
+        F_out = (a.F - offset + stride - 1) // stride
+        if out is None:
+            out = CP8(n, Cout, T, F_out, F_out, 0, 0, a.buf.device, fmt=a.fmt,
+                      buf=torch.empty(n, (Cout + 7) // 8, T, F_out, 8, dtype=_FMT_DTYPE[a.fmt], device=a.buf.device))
+        mode = 1
+    call('conv_tc_f16', a.buf, w_packed, bias, out.buf, mode, stride, offset, n, a.C, Cout, T, a.F, ksize[0], ksize[1], a.pitch, a.pf,
+         a.pt, _lib.i64(patch_stride_rows), act, float(act_param), a.fmt, stream_ptr())
     return out
 
 
-def pool3_res_cp8(y, res=None, out=None):
+def pool_time_res_cp8(y, k, res=None, out=None):
     out = out if out is not None else y.like()
-    call('pool3_res_cp8', y.buf, None if res is None else res.buf, out.buf, y.B, y.C, y.T, y.F, y.pitch, y.pf, y.pt, y.fmt,
+    call('pool_time_res_cp8', y.buf, None if res is None else res.buf, out.buf, y.B, y.C, y.T, y.F, y.pitch, y.pf, y.pt, k, y.fmt,
          stream_ptr())
     return out
 
 
+def pool3_res_cp8(y, res=None, out=None):
+    return pool_time_res_cp8(y, 3, res, out)
+
+
 def head_tail(x, w3, b3, w40, b40, w43, b43, a_lrelu):
-    """x [B,C1,T,Fo] fp32 -> [B,Fo]; conv3 (T x 1) + LReLU + 1x1 + LReLU + 1x1 + sigmoid in one kernel."""
-    B, C1, T, Fo = x.shape
+    """x: compact CP8 [B][NC1][T][Fo][8] -> [B,Fo] fp32; conv3 (T x 1) + LReLU + 1x1 + LReLU + 1x1 + sigmoid in one kernel."""
     C2, C3 = w3.shape[0], w40.shape[0]
-    out = torch.empty(B, Fo, dtype=torch.float32, device=x.device)
-    call('head_tail_f32', _f32(x), w3, b3, w40, b40, w43, b43, out, B, C1, T, Fo, C2, C3, float(a_lrelu), stream_ptr())
+    out = torch.empty(x.B, x.F, dtype=torch.float32, device=x.buf.device)
+    call('head_tail_cp8', x.buf, w3, b3, w40, b40, w43, b43, out, x.B, x.C, x.T, x.F, C2, C3, float(a_lrelu), x.fmt, stream_ptr())
     return out

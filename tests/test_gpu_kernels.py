@@ -145,23 +145,29 @@ def test_conv_tc(ops, cfg, prec, dt):
     assert float(yc.buf[:, :, 0].abs().max()) == 0 and float(yc.buf[:, :, :, :8].abs().max()) == 0     # borders untouched
 
 
-def test_conv_tc_subsampled_fp32_output_and_head_tail(ops):
-    """conv2 of the head: 3x3 stride (1,3) pad (1,0) == stride-1 'same' conv sampled at columns 1,4,7,...; then the
-    fused conv3/conv4 tail against torch."""
+@pytest.mark.parametrize('prec,dt', FMTS)
+def test_conv_tc_subsampled_output_pool13_and_head_tail(ops, prec, dt):
+    """conv2 of the head: 3x3 stride (1,3) pad (1,0) == stride-1 'same' conv sampled at columns 1,4,7,... written as
+    compact 16-bit planes; then maxpool(13,1) on those planes and the fused conv3/conv4 tail, each against torch."""
+    fmt = ops.fmt_of(prec)
     B, C0, C1, C2, C3, T, Fq = 3, 40, 40, 30, 10, 75, 216
     x, w2, b2 = rnd(B, C0, T, Fq, seed=1), rnd(C1, C0, 3, 3, seed=2, scale=(C0 * 9) ** -0.5), rnd(C1, seed=3, scale=0.1)
-    xr, wr = x.half().double(), w2.half().double()
+    xr, wr = x.to(dt).double(), w2.to(dt).double()
     ref2 = F.leaky_relu(F.conv2d(xr, wr, b2.double(), stride=(1, 3), padding=(1, 0)), 0.3).float()
-    xc = ops.nchw_to_cp8(x.cuda(), fmt=ops.FMT_F16)
-    got2 = ops.conv_tc(xc, ops.conv_tc_pack(w2, 'cuda', ops.FMT_F16), b2.cuda(), C1, (3, 3), ops.ACT_LRELU, 0.3, subsample=(3, 1))
-    assert tuple(got2.shape) == (B, C1, T, 72)
-    assert (got2.cpu() - ref2).abs().max() < 2e-5 * max(1.0, ref2.abs().max().item())       # fp32 output: no storage rounding
+    xc = ops.nchw_to_cp8(x.cuda(), fmt=fmt)
+    y2 = ops.conv_tc(xc, ops.conv_tc_pack(w2, 'cuda', fmt), b2.cuda(), C1, (3, 3), ops.ACT_LRELU, 0.3, subsample=(3, 1))
+    assert tuple(y2.buf.shape) == (B, 5, T, 72, 8)
+    got2 = ops.cp8_to_nchw(y2).cpu()
+    ulp = 2.0 ** -8 if prec == 'bf16' else 2.0 ** -11
+    assert (got2 - ref2).abs().max() < ulp * ref2.abs().max().item() + 1e-4
+    p13 = ops.pool_time_res_cp8(y2, 13)
+    assert torch.equal(ops.cp8_to_nchw(p13).cpu(), F.max_pool2d(got2, (13, 1), (1, 1), (6, 0)))
     w3, b3 = rnd(C2, C1, T, 1, seed=4, scale=(C1 * T) ** -0.5), rnd(C2, seed=5, scale=0.1)
     w40, b40 = rnd(C3, C2, 1, 1, seed=6, scale=C2 ** -0.5), rnd(C3, seed=7, scale=0.1)
     w43, b43 = rnd(1, C3, 1, 1, seed=8, scale=C3 ** -0.5), rnd(1, seed=9, scale=0.1)
-    y = F.max_pool2d(ref2, (13, 1), (1, 1), (6, 0))
+    y = ops.cp8_to_nchw(p13).cpu()
     ref = torch.sigmoid(F.conv2d(F.leaky_relu(F.conv2d(F.leaky_relu(F.conv2d(y, w3, b3), 0.3), w40, b40), 0.3), w43, b43))
-    got = ops.head_tail(y.cuda(), w3.cuda(), b3.cuda(), w40.cuda(), b40.cuda(), w43.cuda(), b43.cuda(), 0.3)
+    got = ops.head_tail(p13, w3.cuda(), b3.cuda(), w40.cuda(), b40.cuda(), w43.cuda(), b43.cuda(), 0.3)
     assert (got.cpu() - ref.reshape(B, 72)).abs().max() < 1e-5
 
 
