@@ -31,11 +31,11 @@
 
 namespace mpa {
 
-constexpr int kStageMMAs = 4;                 // MMAs (K=16 steps) per weight stage
+constexpr int kStageMMAs = 8;                 // MMAs (K=16 steps) per weight stage
 constexpr int kATileBytes = 2 * 128 * 16;     // one MMA's A tile: [2 k-slices][128 rows][16 B]
 constexpr int kAStageBytes = kStageMMAs * kATileBytes;
-constexpr int kNumAStages = 8;
-constexpr int kNumBStages = 3;
+constexpr int kNumAStages = 5;
+constexpr int kNumBStages = 2;
 constexpr int kThreads = 192;
 constexpr int kEpiPitch = 40;                 // 80-byte rows: conflict-free 16-byte reads in the transposing epilogue
 constexpr unsigned long long kWaitTimeoutNs = 4000000000ull;   // bounded waits: a protocol bug traps instead of hanging the GPU
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
   uint64_t* acc_full = b_empty + kNumBStages;            // [2]
   uint64_t* acc_empty = acc_full + 2;                    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  uint32_t* btab = tmem_slot + 2;                                          // [mmas_per_row] B-descriptor low words
+  uint32_t* btab = reinterpret_cast<uint32_t*>(bars) + 64;                 // 256 B after the barriers: [mmas_per_row padded to 8]
   uint16_t* epi_smem = reinterpret_cast<uint16_t*>(smem + p.epi_off);      // 4 warps x [32][32] 16-bit staging
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -223,8 +223,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
     // B-descriptor table of one K row (identical for every row): low word = (offset>>4) | (LBO>>4)<<16
     {
       const int n_paired = (p.NC / 2) * p.KW;
-      for (int q = lane; q < p.mmas_per_row; q += 32) {
+      const int n_tab = (p.mmas_per_row + 7) / 8 * 8;
+      for (int q = lane; q < n_tab; q += 32) {
         uint32_t boff, lbo;
+        if (q >= p.mmas_per_row) { btab[q] = 0; continue; }
         if (q < n_paired) {
           const int cp = q / p.KW, df = q - cp * p.KW;
           boff = (uint32_t)(2 * cp * slab_plane_bytes + df * 16);
@@ -258,6 +260,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
           const uint32_t bbase16 = smem_u32(b_smem + b_stage * bstage_bytes) >> 4;
           for (int m0 = 0; m0 < p.mmas_per_row; m0 += kStageMMAs) {
             const int nm = min(kStageMMAs, p.mmas_per_row - m0);
+            // descriptor words of the whole stage are fetched before blocking on the barrier (btab is padded to 8)
+            const uint4 e0 = *reinterpret_cast<const uint4*>(btab + m0);
+            const uint4 e1 = *reinterpret_cast<const uint4*>(btab + m0 + 4);
+            const uint32_t ent[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
             mbar_wait(&a_full[a_stage], a_phase);
             tc_fence_after();
             const uint32_t abase16 = smem_u32(a_smem + a_stage * kAStageBytes) >> 4;
@@ -265,7 +271,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
             for (int i = 0; i < kStageMMAs; ++i) {
               if (i < nm) {
                 const uint64_t adesc = ((uint64_t)kDescHi << 32) | (uint64_t)((abase16 + i * (kATileBytes >> 4)) | kALoFixed);
-                const uint64_t bdesc = ((uint64_t)kDescHi << 32) | (uint64_t)(bbase16 + btab[m0 + i]);
+                const uint64_t bdesc = ((uint64_t)kDescHi << 32) | (uint64_t)(bbase16 + ent[i]);
                 tc_mma_f16(tmem_d, adesc, bdesc, p.idesc, accum);
                 accum = 1;
               }
@@ -596,7 +602,7 @@ int mpa_conv_tc_f16(const void* in_cp8, const void* w_packed, const float* bias,
   const uint32_t f = (fmt == MPA_FMT_BF16) ? 1u : 0u;
   p.idesc = (1u << 4) | (f << 7) | (f << 10) | ((uint32_t)(pitch >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   size_t off = (size_t)kNumAStages * kAStageBytes + (size_t)kNumBStages * p.NC * p.slab_px * 16;
-  off += 256 + (size_t)p.mmas_per_row * 4;      // barriers + tmem slot, descriptor table
+  off += 256 + (size_t)(p.mmas_per_row + 8) * 4;      // barriers + tmem slot (256 B), descriptor table
   off = (off + 127) / 128 * 128;
   p.epi_off = (int)off;
   const size_t smem = off + 4 * 32 * kEpiPitch * 2;
