@@ -57,8 +57,9 @@ class CnnStreamEngine:
         self.timers.append((tag, e0, e1))
         return r
 
-    def predict_hcqt(self, hcqt):
-        """hcqt: [C, N, F] fp32 CUDA, linear magnitudes (the reference's .npy transposed (2,1,0)) -> [N, n_out] fp32."""
+    def predict_hcqt(self, hcqt, lo=0, hi=None):
+        """hcqt: [C, N, F] fp32 CUDA, linear magnitudes (the reference's .npy transposed (2,1,0)) -> [hi-lo, n_out] fp32
+        for the patches centred on frames lo..hi-1 (default: all N); frames beyond the array's ends are zero padding."""
         m, cache, a = self.model, self.model._cache, self.model.a_lrelu
         C, N, F = hcqt.shape
         if C != m.n_chan_input or F != self.F:
@@ -72,8 +73,11 @@ class CnnStreamEngine:
             float(m.layernorm.eps), self.compression, self.fmt, _lib.stream_ptr()))
         ya, za, zb = self._buffers()
         outs = []
-        for i0 in range(0, N, self.chunk):
-            n = min(self.chunk, N - i0)
+        hi = N if hi is None else hi
+        if not (0 <= lo <= hi <= N):
+            raise ValueError('bad frame range')
+        for i0 in range(lo, hi, self.chunk):
+            n = min(self.chunk, hi - i0)
             z_prev = None
             for li, (name, conv) in enumerate(self.blocks):
                 w = conv.weight
@@ -95,6 +99,8 @@ class CnnStreamEngine:
                 z_prev = cur
             y = self._timed('head', lambda: _exec.head_tc(cache, m, z_prev.first(n), a))
             outs.append(y.reshape(n, -1))
+        if not outs:
+            return torch.empty(0, 0, dtype=torch.float32, device=self.dev)
         return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
 
     def predict_audio(self, y, plan):
