@@ -96,3 +96,17 @@ def test_audio_to_activations_end_to_end():
     ref = oracle_patchwise(sd, np.transpose(f, (2, 1, 0)).astype(np.float32), True)
     assert abs((-0.5 + 0.01 * int(tun.item())) - Q.estimate_tuning(y, bins_per_octave=36)) < 1e-9
     assert np.abs(act.cpu().numpy() - ref).max() < TOL['fp16']
+
+
+def test_frame_range_sharding_matches_unsharded_engine():
+    """Two emulated ranks (sequentially on one GPU): halo'd frame ranges reproduce the unsharded result bit for bit."""
+    from multipitch_architectures_b200.engine import CnnStreamEngine
+    from multipitch_architectures_b200.parallel import predict_sharded
+    m = build_model('drcnn_tiny', precision='fp16')
+    m.load_state_dict(fill_state_dict(m.state_dict(), 24))
+    m = m.cuda().eval()
+    eng = CnnStreamEngine(m, chunk=48)
+    h = torch.from_numpy(fake_hcqt(131, 5)).cuda()
+    full = eng.predict_hcqt(h)
+    parts = [predict_sharded(eng.predict_hcqt, h, world=3, rank=r, gather=False) for r in range(3)]
+    assert torch.equal(torch.cat(parts, 0), full)
