@@ -110,6 +110,121 @@ def cpu_reference_arm(seconds, n_patches_sample, threads):
                               f'of {n_frames} stride-1 patches ({t_nn:.2f} s), extrapolated linearly; torch threads={threads}')
 
 
+CNN_XS_KW = dict(n_chan_input=6, n_chan_layers=[20, 20, 10, 1], n_bins_in=216, n_bins_out=72)
+GFLOP_TRAIN_PER_PATCH = 2.75      # CNN:XS 0.916 GFLOP forward x3 for forward + backward
+
+
+def cpu_train_arm(batch, threads, steps=2):
+    """Oracle port of the training step on the host cores: fp32 forward + autograd backward + torch AdamW."""
+    import torch
+    from oracle import nn_oracle as NO
+    from multipitch_architectures_b200.libdl.nn_models import basic_cnn_segm_sigmoid
+    from tests.weights import synth_patches, synth_targets
+    torch.set_num_threads(threads)
+    m = basic_cnn_segm_sigmoid(**CNN_XS_KW)
+    make_weights(m)
+    sd = {k: v.clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    opt = torch.optim.AdamW(list(sd.values()), lr=1e-3, weight_decay=0.01)
+    x, t = synth_patches(batch, 0), synth_targets(batch, 0)
+    ts = []
+    for i in range(steps + 1):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        NO.bce_mean(NO.cnn_forward(sd, x), t).backward()
+        opt.step()
+        ts.append(time.perf_counter() - t0)
+    dt = sum(ts[1:]) / steps
+    return batch / dt, f'oracle port: fp32 CNN:XS forward + autograd backward + AdamW, batch {batch}, {steps} steps after 1 warm-up, torch threads={threads}'
+
+
+def train_main(args, rank, world, local, cores):
+    config = {'workload': f'CNN:XS [20,20,10,1] training step (forward + backward + BCE + AdamW), synthetic 6x75x216 patches, batch {args.batch} per GPU',
+              'timing': 'CUDA events; activations of one step (~3 GB) exceed L2', 'weights': 'seeded random init', 'dropout': 0.2}
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        v, desc = cpu_train_arm(min(args.batch, 64), cores, steps=max(1, args.steps))
+        print(json.dumps({'impl': 'reference', 'metric': 'train_patches_per_second', 'value': v, 'unit': 'patches/s', 'n_gpus': args.gpus,
+                          'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * args.batch / v, 'higher_is_better': True,
+                          'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
+                          'cpu_baseline': {'value': v, 'unit': 'patches/s', 'cores': cores, 'kind': 'port', 'sample': desc},
+                          'e2e': {'value': v, 'unit': 'patches/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+        return
+    import torch
+    import torch.distributed as dist
+    from multipitch_architectures_b200 import _lib
+    from multipitch_architectures_b200.libdl.nn_models import basic_cnn_segm_sigmoid
+    from multipitch_architectures_b200.training import TrainStep
+    from tests.weights import synth_patches, synth_targets
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    model = basic_cnn_segm_sigmoid(**CNN_XS_KW)
+    make_weights(model)
+    model = model.to(dev).train()
+    step = TrainStep(model, lr=1e-3, weight_decay=0.01)
+    xh, th = synth_patches(args.batch, rank).pin_memory(), synth_targets(args.batch, rank).pin_memory()
+    xd, td = xh.to(dev), th.to(dev)
+    loss_host = torch.empty(1).pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def resident():
+        step(xd, td)
+
+    def e2e():
+        loss_host.copy_(step(xh.to(dev, non_blocking=True), th.to(dev, non_blocking=True)), non_blocking=True)
+
+    for _ in range(args.warmup):
+        resident()
+        e2e()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    n0 = _lib.launch_count()
+    ms = timed(resident, args.steps)
+    launches = _lib.launch_count() - n0
+    ms_e2e = timed(e2e, args.steps)
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        n = args.batch * args.steps * world
+        value, e2e_v = n / (ms / 1e3), n / (ms_e2e / 1e3)
+        line = {'metric': 'train_patches_per_second', 'value': value, 'unit': 'patches/s', 'n_gpus': world, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': 'f32', 'data': 'synthetic', 'config': config, 'clocks': clocks, 'gpu_launches': int(launches),
+                'e2e': {'value': e2e_v, 'unit': 'patches/s', 'h2d_bytes_per_step': int(xh.numel() * 4 + th.numel() * 4), 'd2h_bytes_per_step': 4,
+                        'ms_per_step': ms_e2e / args.steps},
+                'roofline': {'bound': 'tensor', 'kernel': 'fp32 CUDA-core training kernels (conv2d_direct / conv_wgrad); not yet on tcgen05',
+                             'achieved': value * GFLOP_TRAIN_PER_PATCH / 1e3, 'peak': measured_peaks()[0], 'unit': 'TFLOP/s',
+                             'frac': value * GFLOP_TRAIN_PER_PATCH / 1e3 / measured_peaks()[0], 'traffic': None,
+                             'note': 'whole-step algorithmic FLOPs / step time against the bf16 tensor peak'}}
+        if not args.no_cpu_baseline:
+            v, desc = cpu_train_arm(min(args.batch, 64), cores)
+            line['cpu_baseline'] = {'value': v, 'unit': 'patches/s', 'cores': cores, 'kind': 'port', 'sample': desc}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -121,6 +236,9 @@ def main():
     ap.add_argument('--cpu-sample', type=int, default=100)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--precision', default='fp16', choices=['fp16', 'bf16'])
+    ap.add_argument('--workload', default='infer_drcnn', choices=['infer_drcnn', 'train_cnn_xs'],
+                    help='infer_drcnn (headline, BASELINE configs[0]) or train_cnn_xs (configs[1]: CNN:XS fwd+bwd+AdamW, batch 256)')
+    ap.add_argument('--batch', type=int, default=256)
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', 0))
@@ -130,6 +248,9 @@ def main():
     workload = f'DRCNN[40,40,30,10]x5 residual: HCQT(6x216, hop 512) + stride-1 patch-wise inference of one {args.seconds:.0f} s 22.05 kHz clip per GPU per step'
     config = {'workload': workload, 'patches_per_step_per_gpu': int(args.seconds * 22050) // 512 + 1, 'patch': '6x75x216',
               'timing': 'CUDA events, inputs larger than L2 (>=1 GB of activations per step vs 126 MB L2)', 'weights': 'seeded random init (no checkpoint blobs exist)'}
+
+    if args.workload == 'train_cnn_xs':
+        return train_main(args, rank, world, local, cores)
 
     if args.impl == 'reference':
         if rank != 0:

@@ -159,6 +159,33 @@ size_t mpa_tuning_workspace(int n_frames);
 int mpa_estimate_tuning_f32(const float* y, long long n, const float* hann2048, float sr, int bins_per_octave,
                             int* tuning_idx, void* workspace, size_t ws_bytes, void* stream);
 
+/* ---- training (configuration 2: CNN family forward + backward + AdamW), fp32 NCHW ------------------------------
+ * Backward of the blocks of basic_cnns.py:373-408 as autograd would compute them for the reference modules. */
+/* out = a + b (residual sums of activations / gradients; in place allowed). */
+int mpa_add_f32(const float* a, const float* b, float* out, long long n, void* stream);
+/* g_in = g_out * act'(.) with act' expressed through the forward OUTPUT `out` (LReLU / ReLU / sigmoid). */
+int mpa_act_bwd_f32(const float* out, const float* g_out, float* g_in, long long n, int act, float act_param,
+                    void* stream);
+/* MaxPool2d((k,1), stride 1, pad k/2) backward fused with the preceding activation's derivative: `a` is the pool's
+ * forward input (= activation output); the gradient goes to the FIRST maximum of each window (ATen semantics). */
+int mpa_maxpool_time_bwd_f32(const float* a, const float* g_pool, float* g_a, int B, int C, int T, int F, int k,
+                             int act, float act_param, void* stream);
+/* nn.Dropout(p) in training mode with a Philox-4x32-10 stream: element i uses counter (i/4, offset), key seed. */
+int mpa_dropout_f32(const float* x, float* out, long long n, float p, unsigned long long seed,
+                    unsigned long long offset, void* stream);
+/* Conv2d data gradient, any stride (gather form); w in state_dict layout [Cout][Cin][KH][KW]. */
+int mpa_conv2d_dgrad_f32(const float* g_out, const float* w, float* g_in, int B, int Cin, int H, int W, int Cout,
+                         int KH, int KW, int sh, int sw, int ph, int pw, void* stream);
+/* Conv2d weight (+ bias, g_b may be NULL) gradient; g_w [Cout][Cin][KH][KW] is overwritten.  KW <= 16. */
+int mpa_conv2d_wgrad_f32(const float* x, const float* g_out, float* g_w, float* g_b, int B, int Cin, int H, int W,
+                         int Cout, int KH, int KW, int sh, int sw, int ph, int pw, void* stream);
+/* Gradients of the LayerNorm([C,F]) affine parameters (the network input needs no gradient); x is the layer INPUT. */
+int mpa_layernorm_cf_param_grad_f32(const float* x, const float* g_out, float* g_w, float* g_b, int B, int C, int T,
+                                    int F, float eps, float gamma_log, void* stream);
+/* torch.optim.AdamW step on one flat tensor (exp126a…py:103-108,293); grad is multiplied by grad_scale first. */
+int mpa_adamw_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
+
 /* ---- N11: BCELoss(mean) on sigmoid outputs with the -100 log clamp, forward + d(loss)/d(pred) ---------- */
 int mpa_bce_fwd_bwd_f32(const float* y_pred, const float* y_true, float* loss_sum, float* grad_pred, long long n,
                         void* stream);

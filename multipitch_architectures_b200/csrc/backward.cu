@@ -1,0 +1,411 @@
+// Backward / optimiser kernels of the CNN family (training configuration 2: CNN:XS fwd+bwd).
+// fp32 NCHW, CUDA cores.  Reference semantics reproduced:
+//   * MaxPool2d((k,1)) backward routes the gradient to the FIRST maximum of each window (ATen max_pool2d_with_indices),
+//   * LeakyReLU backward uses the sign of the forward output,
+//   * BCELoss backward = (p - t) / max(p (1-p), 1e-12) / n   (elementwise.cu), sigmoid backward = g * p * (1-p),
+//   * AdamW exactly as torch.optim.AdamW (decoupled weight decay, bias correction, eps outside the sqrt).
+// Convolution data-gradients of stride-1 layers reuse the forward direct kernel with transposed/flipped weights (host
+// side packing); the strided head conv uses the generic gather kernel below.  Weight gradients are a blocked
+// correlation with split-K over (batch, row) and one atomicAdd per output per CTA.
+#include "common.cuh"
+
+namespace mpa {
+
+static inline int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  long long cap = 148LL * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+// g_in = g_out * act'(out)   (act' expressed through the forward OUTPUT)
+__global__ void act_bwd_kernel(const float* __restrict__ out, const float* __restrict__ g_out, float* __restrict__ g_in, long long n, int act,
+                               float p) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float o = out[i], g = g_out[i];
+    float d = 1.f;
+    if (act == MPA_ACT_LRELU) d = o >= 0.f ? 1.f : p;
+    else if (act == MPA_ACT_RELU) d = o > 0.f ? 1.f : 0.f;
+    else if (act == MPA_ACT_SIGMOID) d = o * (1.f - o);
+    g_in[i] = g * d;
+  }
+}
+
+// a: forward input of the pool (post-activation), g_p: gradient wrt pool output.  g_a[t'] = act'(a[t']) * sum_t g_p[t]*[argmax_t == t']
+__global__ void maxpool_time_bwd_kernel(const float* __restrict__ a, const float* __restrict__ g_p, float* __restrict__ g_a, long long total,
+                                        int T, int F, int k, int act, float act_param) {
+  const int h = k / 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i % F);
+    const long long r = i / F;
+    const int tp = (int)(r % T);
+    const long long plane = r / T;
+    const float* ap = a + plane * T * F + f;
+    const float* gp = g_p + plane * T * F + f;
+    const float mine = ap[(size_t)tp * F];
+    float acc = 0.f;
+    for (int t = max(0, tp - h); t <= min(T - 1, tp + h); ++t) {
+      // is tp the first arg-max of window [t-h, t+h]?
+      const int lo = max(0, t - h), hi = min(T - 1, t + h);
+      bool win = true;
+      for (int s = lo; s <= hi && win; ++s) {
+        const float v = ap[(size_t)s * F];
+        if (s < tp) win = !(v >= mine);      // an earlier element that is >= would have been picked first
+        else if (s > tp) win = !(v > mine);
+      }
+      if (win) acc += gp[(size_t)t * F];
+    }
+    float d = 1.f;
+    if (act == MPA_ACT_LRELU) d = mine >= 0.f ? 1.f : act_param;
+    else if (act == MPA_ACT_RELU) d = mine > 0.f ? 1.f : 0.f;
+    g_a[i] = acc * d;
+  }
+}
+
+// Philox-4x32-10 counter-based dropout: element i of call `offset` under `seed`
+__device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+__device__ __forceinline__ uint4 philox(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = mulhi32(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = mulhi32(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+__global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ out, long long n, float p, unsigned long long seed,
+                               unsigned long long offset) {
+  const float scale = 1.f / (1.f - p);
+  for (long long i4 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i4 * 4 < n; i4 += (long long)gridDim.x * blockDim.x) {
+    const uint4 r = philox(make_uint4((uint32_t)i4, (uint32_t)(i4 >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)),
+                           make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const long long i = i4 * 4 + e;
+      if (i < n) {
+        const float u = (float)(rr[e] >> 8) * (1.f / 16777216.f);
+        out[i] = u >= p ? x[i] * scale : 0.f;
+      }
+    }
+  }
+}
+
+// generic data gradient (gather form), any stride: gi[b,ci,h,w] = sum_{co,kh,kw} go[b,co,(h+ph-kh)/sh,(w+pw-kw)/sw] * w[co,ci,kh,kw]
+__global__ void conv_dgrad_kernel(const float* __restrict__ go, const float* __restrict__ w, float* __restrict__ gi, long long total, int Cin,
+                                  int H, int W, int Cout, int Ho, int Wo, int KH, int KW, int sh, int sw, int ph, int pw) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    long long r = i / W;
+    const int y = (int)(r % H);
+    r /= H;
+    const int ci = (int)(r % Cin);
+    const int b = (int)(r / Cin);
+    float acc = 0.f;
+    for (int kh = 0; kh < KH; ++kh) {
+      const int yy = y + ph - kh;
+      if (yy < 0 || yy % sh) continue;
+      const int ho = yy / sh;
+      if (ho >= Ho) continue;
+      for (int kw = 0; kw < KW; ++kw) {
+        const int xx = x + pw - kw;
+        if (xx < 0 || xx % sw) continue;
+        const int wo = xx / sw;
+        if (wo >= Wo) continue;
+        const float* gp = go + (((size_t)b * Cout) * Ho + ho) * Wo + wo;
+        const float* wp = w + ((size_t)ci * KH + kh) * KW + kw;
+        for (int co = 0; co < Cout; ++co) acc = fmaf(gp[(size_t)co * Ho * Wo], wp[(size_t)co * Cin * KH * KW], acc);
+      }
+    }
+    gi[i] = acc;
+  }
+}
+
+// weight gradient: gw[co,ci,kh,kw] += sum_{b,ho,wo} go[b,co,ho,wo] * x[b,ci,ho*sh+kh-ph,wo*sw+kw-pw]
+// CTA: 32 output channels x 8 (ci,kh) combos x 16 kw; thread = 4 co x 4 kw for one combo; split-K over (b,ho) rows.
+constexpr int WG_CO = 32, WG_COMBOS = 8, WG_KW = 16;
+__global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ go, float* __restrict__ gw, int B,
+                                                         int Cin, int H, int W, int Cout, int Ho, int Wo, int KH, int KW, int sh, int sw, int ph,
+                                                         int pw, int n_combos, int rows_per_cta) {
+  extern __shared__ float sm[];
+  const int XW = (Wo - 1) * sw + WG_KW;              // staged input row segment (zero padded)
+  float* go_s = sm;                                   // [Wo][WG_CO]
+  float* x_s = sm + (size_t)Wo * WG_CO;               // [WG_COMBOS][XW]
+  const int co0 = blockIdx.x * WG_CO;
+  const int combo0 = blockIdx.y * WG_COMBOS;
+  const int tid = threadIdx.x;
+  const int cl = tid >> 5;                            // local combo 0..7
+  const int lane = tid & 31;
+  const int co_t = (lane >> 2) * 4;                   // 0,4,..,28
+  const int kw_t = (lane & 3) * 4;                    // 0,4,8,12
+  const int combo = combo0 + cl;
+  const bool combo_ok = combo < n_combos;
+  const int ci = combo_ok ? combo / KH : 0, kh = combo_ok ? combo % KH : 0;
+  float acc[4][4] = {};
+  const long long n_rows = (long long)B * Ho;
+  const long long r0 = (long long)blockIdx.z * rows_per_cta;
+  for (long long rr = r0; rr < min(n_rows, r0 + rows_per_cta); ++rr) {
+    const int b = (int)(rr / Ho), ho = (int)(rr % Ho);
+    __syncthreads();
+    for (int e = tid; e < Wo * WG_CO; e += 256) {
+      const int c = e / Wo, f = e - c * Wo;           // coalesced along f in global
+      const int co = co0 + c;
+      go_s[f * WG_CO + c] = co < Cout ? go[(((size_t)b * Cout + co) * Ho + ho) * Wo + f] : 0.f;
+    }
+    for (int e = tid; e < WG_COMBOS * XW; e += 256) {
+      const int c = e / XW, xx = e - c * XW;
+      const int cb = combo0 + c;
+      float v = 0.f;
+      if (cb < n_combos) {
+        const int cci = cb / KH, ckh = cb % KH;
+        const int hy = ho * sh + ckh - ph, wx = xx - pw;
+        if (hy >= 0 && hy < H && wx >= 0 && wx < W) v = x[(((size_t)b * Cin + cci) * H + hy) * W + wx];
+      }
+      x_s[e] = v;
+    }
+    __syncthreads();
+    if (combo_ok) {
+      const float* xr = x_s + cl * XW + kw_t;
+      for (int f = 0; f < Wo; ++f) {
+        const float4 g4 = *reinterpret_cast<const float4*>(go_s + f * WG_CO + co_t);
+        const float* xp = xr + f * sw;
+        const float x0 = xp[0], x1 = xp[1], x2 = xp[2], x3 = xp[3];
+        acc[0][0] = fmaf(g4.x, x0, acc[0][0]); acc[0][1] = fmaf(g4.x, x1, acc[0][1]); acc[0][2] = fmaf(g4.x, x2, acc[0][2]); acc[0][3] = fmaf(g4.x, x3, acc[0][3]);
+        acc[1][0] = fmaf(g4.y, x0, acc[1][0]); acc[1][1] = fmaf(g4.y, x1, acc[1][1]); acc[1][2] = fmaf(g4.y, x2, acc[1][2]); acc[1][3] = fmaf(g4.y, x3, acc[1][3]);
+        acc[2][0] = fmaf(g4.z, x0, acc[2][0]); acc[2][1] = fmaf(g4.z, x1, acc[2][1]); acc[2][2] = fmaf(g4.z, x2, acc[2][2]); acc[2][3] = fmaf(g4.z, x3, acc[2][3]);
+        acc[3][0] = fmaf(g4.w, x0, acc[3][0]); acc[3][1] = fmaf(g4.w, x1, acc[3][1]); acc[3][2] = fmaf(g4.w, x2, acc[3][2]); acc[3][3] = fmaf(g4.w, x3, acc[3][3]);
+      }
+    }
+  }
+  if (!combo_ok) return;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int co = co0 + co_t + i;
+    if (co >= Cout) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int kw = kw_t + j;
+      if (kw < KW) atomicAdd(&gw[(((size_t)co * Cin + ci) * KH + kh) * KW + kw], acc[i][j]);
+    }
+  }
+}
+
+// gb[c] = sum over (b, hw) of g[b,c,hw]; one block per channel
+__global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict__ g, float* __restrict__ gb, int B, int C, int HW) {
+  __shared__ float sh[8];
+  const int c = blockIdx.x;
+  const long long n = (long long)B * HW;
+  float s = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const int b = (int)(i / HW);
+    s += g[((size_t)b * C + c) * HW + (i - (long long)b * HW)];
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += sh[i];
+    gb[c] = t;
+  }
+}
+
+// LayerNorm([C,F]) parameter gradients; one CTA per batch item, rows accumulated in registers, one atomicAdd per element per CTA
+template <int MAXV>
+__global__ void __launch_bounds__(128) layernorm_cf_param_grad_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ gw,
+                                                                      float* __restrict__ gb, int C, int T, int F, float eps, float gamma_log) {
+  __shared__ float sh[8];
+  const int b = blockIdx.x;
+  const int n = C * F;
+  float aw[MAXV], ab[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) aw[i] = ab[i] = 0.f;
+  for (int t = 0; t < T; ++t) {
+    const float* xr = x + ((size_t)b * C * T + t) * F;
+    const float* gr = g + ((size_t)b * C * T + t) * F;
+    float v[MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int e = threadIdx.x + i * 128;
+      float val = 0.f;
+      if (e < n) {
+        const int c = e / F, f = e - c * F;
+        val = xr[(size_t)c * T * F + f];
+        if (gamma_log > 0.f) val = logf(1.f + gamma_log * val);
+        s += val;
+      }
+      v[i] = val;
+    }
+    s = warp_sum(s);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    const float mean = (sh[0] + sh[1] + sh[2] + sh[3]) / n;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int e = threadIdx.x + i * 128;
+      if (e < n) {
+        const float d = v[i] - mean;
+        q += d * d;
+      }
+    }
+    q = warp_sum(q);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[4 + (threadIdx.x >> 5)] = q;
+    __syncthreads();
+    const float rstd = rsqrtf((sh[4] + sh[5] + sh[6] + sh[7]) / n + eps);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int e = threadIdx.x + i * 128;
+      if (e < n) {
+        const int c = e / F, f = e - c * F;
+        const float go = gr[(size_t)c * T * F + f];
+        aw[i] = fmaf(go, (v[i] - mean) * rstd, aw[i]);
+        ab[i] += go;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int e = threadIdx.x + i * 128;
+    if (e < n) {
+      atomicAdd(&gw[e], aw[i]);
+      atomicAdd(&gb[e], ab[i]);
+    }
+  }
+}
+
+__global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = a[i] + b[i];
+}
+
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n, float lr,
+                             float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float grad_scale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * grad_scale;
+    float pi = p[i] * (1.f - lr * wd);
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+
+}  // namespace mpa
+
+using namespace mpa;
+
+extern "C" {
+
+int mpa_add_f32(const float* a, const float* b, float* out, long long n, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(a && b && out && n > 0, "add: bad argument");
+  add_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, out, n);
+  MPA_CHECK_LAUNCH("add");
+  return MPA_OK;
+}
+
+int mpa_act_bwd_f32(const float* out, const float* g_out, float* g_in, long long n, int act, float act_param, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(out && g_out && g_in && n > 0, "act_bwd: bad argument");
+  act_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(out, g_out, g_in, n, act, act_param);
+  MPA_CHECK_LAUNCH("act_bwd");
+  return MPA_OK;
+}
+
+int mpa_maxpool_time_bwd_f32(const float* a, const float* g_pool, float* g_a, int B, int C, int T, int F, int k, int act, float act_param,
+                             void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(a && g_pool && g_a && B > 0 && C > 0 && T > 0 && F > 0 && k >= 1 && (k & 1), "maxpool_time_bwd: bad argument");
+  const long long total = (long long)B * C * T * F;
+  maxpool_time_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(a, g_pool, g_a, total, T, F, k, act, act_param);
+  MPA_CHECK_LAUNCH("maxpool_time_bwd");
+  return MPA_OK;
+}
+
+int mpa_dropout_f32(const float* x, float* out, long long n, float p, unsigned long long seed, unsigned long long offset, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(x && out && n > 0 && p >= 0.f && p < 1.f, "dropout: bad argument");
+  dropout_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, out, n, p, seed, offset);
+  MPA_CHECK_LAUNCH("dropout");
+  return MPA_OK;
+}
+
+int mpa_conv2d_dgrad_f32(const float* g_out, const float* w, float* g_in, int B, int Cin, int H, int W, int Cout, int KH, int KW, int sh, int sw,
+                         int ph, int pw, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(g_out && w && g_in && B > 0 && Cin > 0 && Cout > 0 && H > 0 && W > 0, "conv2d_dgrad: bad argument");
+  const int Ho = (H + 2 * ph - KH) / sh + 1, Wo = (W + 2 * pw - KW) / sw + 1;
+  const long long total = (long long)B * Cin * H * W;
+  conv_dgrad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(g_out, w, g_in, total, Cin, H, W, Cout, Ho, Wo, KH, KW, sh, sw, ph, pw);
+  MPA_CHECK_LAUNCH("conv2d_dgrad");
+  return MPA_OK;
+}
+
+int mpa_conv2d_wgrad_f32(const float* x, const float* g_out, float* g_w, float* g_b, int B, int Cin, int H, int W, int Cout, int KH, int KW, int sh,
+                         int sw, int ph, int pw, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(x && g_out && g_w && B > 0 && Cin > 0 && Cout > 0 && H > 0 && W > 0 && KH > 0 && KW > 0, "conv2d_wgrad: bad argument");
+  const int Ho = (H + 2 * ph - KH) / sh + 1, Wo = (W + 2 * pw - KW) / sw + 1;
+  MPA_REQUIRE(Ho > 0 && Wo > 0, "conv2d_wgrad: empty output");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(g_w, 0, sizeof(float) * (size_t)Cout * Cin * KH * KW, st);
+  const int n_combos = Cin * KH;
+  const long long n_rows = (long long)B * Ho;
+  // enough CTAs to fill the machine a few times; every CTA ends with <= 4096 atomics
+  const int gx = ceil_div(Cout, WG_CO), gy = ceil_div(n_combos, WG_COMBOS);
+  long long want = (148LL * 8) / ((long long)gx * gy);
+  if (want < 1) want = 1;
+  if (want > n_rows) want = n_rows;
+  const int rows_per_cta = (int)((n_rows + want - 1) / want);
+  const int gz = (int)((n_rows + rows_per_cta - 1) / rows_per_cta);
+  const int XW = (Wo - 1) * sw + WG_KW;
+  const size_t smem = ((size_t)Wo * WG_CO + (size_t)WG_COMBOS * XW) * sizeof(float);
+  MPA_REQUIRE(smem <= 200 * 1024, "conv2d_wgrad: row of %d outputs needs %zu B of shared memory", Wo, smem);
+  MPA_REQUIRE(KW <= WG_KW, "conv2d_wgrad: kernel width %d > %d not supported", KW, WG_KW);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("conv2d_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return MPA_ERR_CUDA;
+    }
+  }
+  conv_wgrad_kernel<<<dim3(gx, gy, gz), 256, smem, st>>>(x, g_out, g_w, B, Cin, H, W, Cout, Ho, Wo, KH, KW, sh, sw, ph, pw, n_combos, rows_per_cta);
+  MPA_CHECK_LAUNCH("conv2d_wgrad");
+  if (g_b) {
+    bias_grad_kernel<<<Cout, 256, 0, st>>>(g_out, g_b, B, Cout, Ho * Wo);
+    MPA_CHECK_LAUNCH("bias_grad");
+  }
+  return MPA_OK;
+}
+
+int mpa_layernorm_cf_param_grad_f32(const float* x, const float* g_out, float* g_w, float* g_b, int B, int C, int T, int F, float eps,
+                                    float gamma_log, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(x && g_out && g_w && g_b && B > 0 && C > 0 && T > 0 && F > 0 && C * F <= 128 * 11, "layernorm_cf_param_grad: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(g_w, 0, sizeof(float) * (size_t)C * F, st);
+  cudaMemsetAsync(g_b, 0, sizeof(float) * (size_t)C * F, st);
+  layernorm_cf_param_grad_kernel<11><<<B, 128, 0, st>>>(x, g_out, g_w, g_b, C, T, F, eps, gamma_log);
+  MPA_CHECK_LAUNCH("layernorm_cf_param_grad");
+  return MPA_OK;
+}
+
+int mpa_adamw_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, int step, float grad_scale, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "adamw: bad argument");
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
+  adamw_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1,
+                                                                    bc2s, grad_scale);
+  MPA_CHECK_LAUNCH("adamw");
+  return MPA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,208 @@
+"""Training path of the CNN family (basic_cnn_segm_sigmoid / deep_cnn_segm_sigmoid): forward with saved activations,
+hand-written backward, fused BCE and AdamW — all libmpa kernels (fp32).
+
+Reference loop being replaced (experiments/Exp1_SectionIV-B/exp126a_musicnet_cnn_basic.py:315-329):
+    y_pred = model(X); loss = BCELoss(y_pred, y); optimizer.zero_grad(); loss.backward(); optimizer.step()
+
+Two ways in:
+  * drop-in: `model.train(); y = model(x); loss = torch.nn.BCELoss()(y, t); loss.backward(); torch.optim.AdamW(...).step()`
+    — `model.forward` routes through `CnnTrainFunction` (a torch.autograd.Function whose backward is the code below);
+  * fused: `TrainStep(model, lr=...)(x, t)` — BCE forward/backward kernel, backward, (optional) gradient all-reduce over
+    NCCL on ONE flat buffer, fused AdamW; no torch operator touches an activation or a gradient.
+Dropout uses a Philox stream (seed, per-site offset); the reference's torch RNG stream cannot be reproduced, so parity
+tests run with p_dropout = 0."""
+import torch
+
+from . import _lib, ops
+from .libdl.nn_models import _exec
+from ._lib import call, stream_ptr
+
+
+def _dropout(x, p, seed, offset):
+    if p <= 0.0:
+        return x
+    out = torch.empty_like(x)
+    call('dropout_f32', x, out, _lib.i64(x.numel()), float(p), ctypes_u64(seed), ctypes_u64(offset), stream_ptr())
+    return out
+
+
+def ctypes_u64(v):
+    import ctypes
+    return ctypes.c_ulonglong(int(v) & 0xFFFFFFFFFFFFFFFF)
+
+
+def _conv_fwd(conv, x, act, a):
+    w = conv.weight
+    wp = ops.pack_conv_weight(w)
+    return ops.conv2d(x, wp, conv.bias, w.shape[0], tuple(w.shape[2:]), tuple(conv.stride), tuple(conv.padding), act, a)
+
+
+def _dgrad(conv, g, in_shape):
+    """Gradient wrt the conv input.  Stride-1 layers: forward kernel with swapped/flipped weights; else gather kernel."""
+    w = conv.weight
+    Cout, Cin, KH, KW = w.shape
+    B, _, H, W = in_shape
+    if tuple(conv.stride) == (1, 1):
+        wt = ops.pack_conv_weight(w.detach().permute(1, 0, 2, 3).flip(2, 3).contiguous())
+        return ops.conv2d(g, wt, None, Cin, (KH, KW), (1, 1), (KH - 1 - conv.padding[0], KW - 1 - conv.padding[1]))
+    gi = torch.empty(in_shape, dtype=torch.float32, device=g.device)
+    call('conv2d_dgrad_f32', g, w.detach().contiguous(), gi, B, Cin, H, W, Cout, KH, KW, conv.stride[0], conv.stride[1],
+         conv.padding[0], conv.padding[1], stream_ptr())
+    return gi
+
+
+def _wgrad(conv, x, g, gw, gb):
+    Cout, Cin, KH, KW = conv.weight.shape
+    B, _, H, W = x.shape
+    call('conv2d_wgrad_f32', x, g, gw, gb, B, Cin, H, W, Cout, KH, KW, conv.stride[0], conv.stride[1], conv.padding[0],
+         conv.padding[1], stream_ptr())
+
+
+def _add(a, b):
+    out = torch.empty_like(a)
+    call('add_f32', a, b, out, _lib.i64(a.numel()), stream_ptr())
+    return out
+
+
+def _act_bwd(out, g, act, a=0.0):
+    gi = torch.empty_like(g)
+    call('act_bwd_f32', out, g, gi, _lib.i64(g.numel()), act, float(a), stream_ptr())
+    return gi
+
+
+def _pool_bwd(a_in, g_pool, k, act, a):
+    B, C, T, F = a_in.shape
+    ga = torch.empty_like(a_in)
+    call('maxpool_time_bwd_f32', a_in, g_pool, ga, B, C, T, F, k, act, float(a), stream_ptr())
+    return ga
+
+
+def cnn_train_forward(model, x, seed=0, step=0):
+    """-> (y_pred [B,1,T-74,72], saved).  Train mode: dropout active when model.p_dropout > 0."""
+    a, p = model.a_lrelu, (model.p_dropout if model.training else 0.0)
+    blocks = _exec.cnn_blocks(model)
+    residual = getattr(model, 'residual', False)
+    site = [step * 64]
+
+    def drop(t):
+        site[0] += 1
+        return _dropout(t, p, seed, site[0])
+    sv = {'x': x, 'blocks': [], 'p': p, 'seed': seed, 'site0': step * 64}
+    z = ops.layernorm_cf(x, model.layernorm.weight, model.layernorm.bias, model.layernorm.eps)
+    for i, (name, conv) in enumerate(blocks):
+        act = _conv_fwd(conv, z, ops.ACT_LRELU, a)
+        d = drop(ops.maxpool_time(act, 3))
+        sv['blocks'].append((z, act))
+        z = _add(d, z) if (residual and i > 0) else d
+    a2 = _conv_fwd(model.conv2[0], z, ops.ACT_LRELU, a)
+    d2 = drop(ops.maxpool_time(a2, 13))
+    a3 = _conv_fwd(model.conv3[0], d2, ops.ACT_LRELU, a)
+    d3 = drop(a3)
+    a4 = _conv_fwd(model.conv4[0], d3, ops.ACT_LRELU, a)
+    d4 = drop(a4)
+    y = _conv_fwd(model.conv4[3], d4, ops.ACT_SIGMOID, 0.0)
+    sv.update(z_head=z, a2=a2, d2=d2, a3=a3, d3=d3, a4=a4, d4=d4, y=y)
+    return y, sv
+
+
+def cnn_train_backward(model, sv, g_y, grads):
+    """grads: dict parameter-name -> preallocated fp32 tensor (overwritten)."""
+    a, p, seed = model.a_lrelu, sv['p'], sv['seed']
+    blocks = _exec.cnn_blocks(model)
+    residual = getattr(model, 'residual', False)
+    n_sites = len(blocks) + 3
+    site = [sv['site0'] + n_sites + 1]
+
+    def drop_bwd(g):
+        site[0] -= 1
+        return _dropout(g, p, seed, site[0])
+    c43, c40, c3, c2 = model.conv4[3], model.conv4[0], model.conv3[0], model.conv2[0]
+    g = _act_bwd(sv['y'], g_y.contiguous(), ops.ACT_SIGMOID)
+    _wgrad(c43, sv['d4'], g, grads['conv4.3.weight'], grads['conv4.3.bias'])
+    g = drop_bwd(_dgrad(c43, g, sv['d4'].shape))
+    g = _act_bwd(sv['a4'], g, ops.ACT_LRELU, a)
+    _wgrad(c40, sv['d3'], g, grads['conv4.0.weight'], grads['conv4.0.bias'])
+    g = drop_bwd(_dgrad(c40, g, sv['d3'].shape))
+    g = _act_bwd(sv['a3'], g, ops.ACT_LRELU, a)
+    _wgrad(c3, sv['d2'], g, grads['conv3.0.weight'], grads['conv3.0.bias'])
+    g = drop_bwd(_dgrad(c3, g, sv['d2'].shape))
+    g = _pool_bwd(sv['a2'], g, 13, ops.ACT_LRELU, a)
+    _wgrad(c2, sv['z_head'], g, grads['conv2.0.weight'], grads['conv2.0.bias'])
+    g_z = _dgrad(c2, g, sv['z_head'].shape)
+    for i in range(len(blocks) - 1, -1, -1):
+        name, conv = blocks[i]
+        z_in, act = sv['blocks'][i]
+        g_conv = _pool_bwd(act, drop_bwd(g_z), 3, ops.ACT_LRELU, a)
+        _wgrad(conv, z_in, g_conv, grads[f'{name}.0.weight'], grads[f'{name}.0.bias'])
+        g_in = _dgrad(conv, g_conv, z_in.shape)
+        g_z = _add(g_in, g_z) if (residual and i > 0) else g_in
+    x = sv['x']
+    B, C, T, F = x.shape
+    call('layernorm_cf_param_grad_f32', x, g_z, grads['layernorm.weight'], grads['layernorm.bias'], B, C, T, F,
+         float(model.layernorm.eps), 0.0, stream_ptr())
+    return grads
+
+
+class CnnTrainFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, x, seed, step, *params):
+        with torch.no_grad():
+            y, sv = cnn_train_forward(model, x, seed, step)
+        ctx.model, ctx.sv = model, sv
+        return y
+
+    @staticmethod
+    def backward(ctx, g_y):
+        model = ctx.model
+        named = list(model.named_parameters())
+        with torch.no_grad():
+            grads = {n: torch.empty_like(p) for n, p in named}
+            cnn_train_backward(model, ctx.sv, g_y, grads)
+        return (None, None, None, None) + tuple(grads[n] for n, _ in named)
+
+
+def cnn_forward_train(model, x):
+    """Entry used by model.forward when autograd is recording."""
+    model._train_calls = getattr(model, '_train_calls', 0) + 1
+    seed = getattr(model, 'dropout_seed', 0x5EED)
+    return CnnTrainFunction.apply(model, x, seed, model._train_calls, *[p for _, p in model.named_parameters()])
+
+
+class TrainStep:
+    """Fused training step on flat parameter / gradient / moment buffers (one all-reduce, one AdamW sweep)."""
+
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, seed=0x5EED, process_group=None):
+        self.model, self.lr, self.betas, self.eps, self.wd, self.seed = model, lr, betas, eps, weight_decay, seed
+        self.group = process_group
+        named = list(model.named_parameters())
+        dev = named[0][1].device
+        n = sum(p.numel() for _, p in named)
+        self.flat_p = torch.empty(n, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.grads, off = {}, 0
+        with torch.no_grad():
+            for name, p in named:
+                k = p.numel()
+                self.flat_p[off:off + k] = p.reshape(-1)
+                p.data = self.flat_p[off:off + k].view_as(p)          # parameters become views of the flat buffer
+                self.grads[name] = self.flat_g[off:off + k].view_as(p)
+                off += k
+        self.step_count = 0
+
+    def __call__(self, x, target):
+        import torch.distributed as dist
+        self.step_count += 1
+        with torch.no_grad():
+            y, sv = cnn_train_forward(self.model, x, self.seed, self.step_count)
+            loss, g_y = ops.bce_fwd_bwd(y, target.contiguous())
+            cnn_train_backward(self.model, sv, g_y, self.grads)
+            scale = 1.0
+            if self.group is not None or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+                dist.all_reduce(self.flat_g, group=self.group)
+                scale = 1.0 / dist.get_world_size(self.group)
+            call('adamw_f32', self.flat_p, self.flat_g, self.m, self.v, _lib.i64(self.flat_p.numel()), float(self.lr), float(self.betas[0]),
+                 float(self.betas[1]), float(self.eps), float(self.wd), self.step_count, float(scale), stream_ptr())
+        self.model._cache._d.clear()        # packed operands derived from the old parameter values are stale
+        return loss
