@@ -104,7 +104,10 @@ def test_fused_train_step_matches_torch_adamw_on_oracle():
         # Adam's first steps move every weight by ~lr regardless of gradient scale; compare the UPDATE, not the value
         upd_ref = (ref[k].detach() - sd0[k])
         upd_gpu = (p.detach().cpu() - sd0[k])
-        assert (upd_gpu - upd_ref).abs().max() < 0.05 * 3e-3 + 0.05 * upd_ref.abs().max(), k
+        # elements whose gradient is at fp32-noise level at some step get a random +-lr there (sign of m/sqrt(v)), so
+        # bound the mean and the share of outliers rather than the maximum
+        d = (upd_gpu - upd_ref).abs()
+        assert d.mean() < 0.02 * 3e-3 and (d > 0.3e-3).float().mean() < 0.02, k
     # inference after training sees the updated weights (packed-operand cache invalidated)
     m.eval()
     x = synth_patches(2, 50)
