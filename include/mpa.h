@@ -119,17 +119,28 @@ int mpa_conv_tc_pack_weights(const float* w_host, void* packed_host, int Cin, in
  *             sub-sampled in the epilogue), F_out = ceil((F - sub_offset)/sub_stride). */
 int mpa_conv_tc_f16(const void* in_cp8, const void* w_packed, const float* bias, void* out, int out_mode,
                     int sub_stride, int sub_offset, int n_patches, int Cin, int Cout, int T, int F, int KH, int KW,
-                    int pitch, int pf, int pt, long long in_patch_stride_rows, int act, float act_param, int fmt,
-                    void* stream);
+                    int pitch, int pf, int pt, long long in_patch_stride_rows, int in_nc_stride, int out_nc_stride,
+                    int act, float act_param, int fmt, void* stream);
+/* Chunk-strided views: every CP8 entry point takes the number of channel chunks per item of the UNDERLYING buffer
+ * (`*_nc_stride` / `ncs_*`, 0 = the tensor's own chunk count) and a pointer already advanced to the view's first chunk.
+ * This is how U-Net skip connections are concatenated without a copy: the producer of the skip writes chunks [0, Cs/8) and
+ * the up-sampler writes chunks [Cs/8, (Cs+Cl)/8) of one buffer (unet_cnns.py:96-104). */
 /* out = maxpool_time_k(y) + res (res may be NULL; k odd, -inf padding), CP8 in/out; with pitch=F, pf=pt=0 it serves
  * the compact out_mode-1 planes too. */
 int mpa_pool_time_res_cp8(const void* y_cp8, const void* res_cp8, void* out_cp8, int n_patches, int C, int T, int F,
-                          int pitch, int pf, int pt, int k, int fmt, void* stream);
+                          int pitch, int pf, int pt, int k, int fmt, int ncs_y, int ncs_res, int ncs_out, void* stream);
+/* nn.MaxPool2d((2,2)) (floor) between two CP8 geometries (unet_cnns.py:349-361). */
+int mpa_maxpool2x2_cp8(const void* in_cp8, void* out_cp8, int n, int C, int T, int F, int pitch_in, int pf_in,
+                       int pt_in, int ncs_in, int pitch_out, int pf_out, int pt_out, int ncs_out, int fmt, void* stream);
+/* nn.Upsample(x2, bilinear, align_corners=True) + F.pad to the skip's size, written at `out_cp8` (already advanced to the
+ * first up-sampled chunk of the concat buffer). */
+int mpa_upsample2x_cp8(const void* low_cp8, void* out_cp8, int n, int C, int Tl, int Fl, int pitch_l, int pf_l, int pt_l,
+                       int ncs_l, int Ts, int Fs, int pitch_s, int pf_s, int pt_s, int ncs_out, int fmt, void* stream);
 /* layout converters (tests, and the seams between the fp32 and the 16-bit paths). */
 int mpa_nchw_to_cp8(const float* x, void* out_cp8, int B, int C, int T, int F, int pitch, int pf, int pt, int fmt,
-                    void* stream);
+                    int ncs_out, void* stream);
 int mpa_cp8_to_nchw(const void* in_cp8, float* out, int B, int C, int T, int F, int pitch, int pf, int pt, int fmt,
-                    void* stream);
+                    int ncs_in, void* stream);
 
 /* Fused head tail for the patch-wise case (T == conv3 kernel height, conv4.3 kernel 1x1; basic_cnns.py:396-408):
  * x compact 16-bit planes [B][ceil(C1/8)][T][Fo][8] (max-pooled conv2 output) -> out [B,Fo] fp32 =

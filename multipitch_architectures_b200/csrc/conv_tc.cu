@@ -34,7 +34,7 @@ namespace mpa {
 constexpr int kStageMMAs = 8;                 // MMAs (K=16 steps) per weight stage
 constexpr int kATileBytes = 2 * 128 * 16;     // one MMA's A tile: [2 k-slices][128 rows][16 B]
 constexpr int kAStageBytes = kStageMMAs * kATileBytes;
-constexpr int kNumAStages = 5;
+constexpr int kMaxAStages = 5;             // weight stages: as many as fit next to the activation slabs (>= 2)
 constexpr int kNumBStages = 2;
 constexpr int kThreads = 192;
 constexpr int kEpiPitch = 40;                 // 80-byte rows: conflict-free 16-byte reads in the transposing epilogue
@@ -50,7 +50,8 @@ struct ConvTcParams {
   long long in_chunk_stride;   // bytes between channel chunks in `in`
   long long in_row0;           // byte offset of (row 0, column 0) of patch 0 chunk 0
   int n_patches, NC, Cout, J, T, F, KH, KW, P, pf, pt_out, TP_out, NCo;
-  int mmas_per_row, n_groups, n_units, slab_px, epi_off;
+  int mmas_per_row, n_groups, n_units, slab_px, epi_off, a_stages, btab_off;
+  long long out_patch_stride;  // elements (16-bit) between patches in `out`
   int act;
   float act_param;
   uint32_t idesc;
@@ -142,17 +143,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
   const int slab_plane_bytes = p.slab_px * 16;
   const int slab_bytes = p.NC * slab_plane_bytes;        // one patch, one input row
   const int bstage_bytes = slab_bytes;
-  uint8_t* a_smem = smem;                                // [kNumAStages][kAStageBytes]
+  const int kNumAStages = p.a_stages;
+  uint8_t* a_smem = smem;                                // [a_stages][kAStageBytes]
   uint8_t* b_smem = smem + kNumAStages * kAStageBytes;   // [kNumBStages][NC][slab_px][16B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + kNumBStages * bstage_bytes);
   uint64_t* a_full = bars;
-  uint64_t* a_empty = bars + kNumAStages;
-  uint64_t* b_full = bars + 2 * kNumAStages;
+  uint64_t* a_empty = bars + kMaxAStages;
+  uint64_t* b_full = bars + 2 * kMaxAStages;
   uint64_t* b_empty = b_full + kNumBStages;
   uint64_t* acc_full = b_empty + kNumBStages;            // [2]
   uint64_t* acc_empty = acc_full + 2;                    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  uint32_t* btab = reinterpret_cast<uint32_t*>(bars) + 64;                 // 256 B after the barriers: [mmas_per_row padded to 8]
+  uint32_t* btab = reinterpret_cast<uint32_t*>(smem + p.btab_off);         // [mmas_per_row padded to 8] B-descriptor low words
   uint16_t* epi_smem = reinterpret_cast<uint16_t*>(smem + p.epi_off);      // 4 warps x [32][32] 16-bit staging
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -331,8 +333,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
             if (col_ok && jg < p.J && tg < p.T) {
               const uint4 val = *reinterpret_cast<const uint4*>(stile + lane * kEpiPitch + k * 8);
               uint16_t* dst = (p.out_mode == 0)
-                                  ? p.out + ((((size_t)b * p.NCo + (cog >> 3)) * p.TP_out + p.pt_out + tg) * p.P + n) * 8
-                                  : p.out + ((((size_t)b * p.NCo + (cog >> 3)) * p.T + tg) * p.F_out + fo) * 8;
+                                  ? p.out + (size_t)b * p.out_patch_stride + ((((size_t)(cog >> 3)) * p.TP_out + p.pt_out + tg) * p.P + n) * 8
+                                  : p.out + (size_t)b * p.out_patch_stride + ((((size_t)(cog >> 3)) * p.T + tg) * p.F_out + fo) * 8;
               *reinterpret_cast<uint4*>(dst) = val;
             }
           }
@@ -351,8 +353,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
             }
             if (ok) {
               uint16_t* dst = (p.out_mode == 0)
-                                  ? p.out + ((((size_t)b * p.NCo + (co >> 3)) * p.TP_out + p.pt_out + t) * p.P + n) * 8 + (co & 7)
-                                  : p.out + ((((size_t)b * p.NCo + (co >> 3)) * p.T + t) * p.F_out + fo) * 8 + (co & 7);
+                                  ? p.out + (size_t)b * p.out_patch_stride + ((((size_t)(co >> 3)) * p.TP_out + p.pt_out + t) * p.P + n) * 8 + (co & 7)
+                                  : p.out + (size_t)b * p.out_patch_stride + ((((size_t)(co >> 3)) * p.T + t) * p.F_out + fo) * 8 + (co & 7);
               *dst = cvt16(apply_act(__uint_as_float(v[i]) + bias, p.act, p.act_param), p.fmt);
             }
           }
@@ -407,7 +409,7 @@ static inline uint16_t f32_to_bf16_rne(float f) {
 
 // CP8 <-> NCHW converters ------------------------------------------------------------------------------
 __global__ void nchw_to_cp8_kernel(const float* __restrict__ x, uint16_t* __restrict__ out, long long total, int C, int T,
-                                   int F, int NCk, int TP, int P, int pf, int pt, int fmt) {
+                                   int F, int NCk, int NCs, int TP, int P, int pf, int pt, int fmt) {
   // one thread per (b, chunk, t, f): gathers 8 channels -> one 16-byte store
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int f = (int)(i % F);
@@ -422,12 +424,12 @@ __global__ void nchw_to_cp8_kernel(const float* __restrict__ x, uint16_t* __rest
       int c = ck * 8 + e;
       v[e] = cvt16(c < C ? x[(((size_t)b * C + c) * T + t) * F + f] : 0.f, fmt);
     }
-    *reinterpret_cast<uint4*>(out + ((((size_t)b * NCk + ck) * TP + pt + t) * P + pf + f) * 8) = *reinterpret_cast<uint4*>(v);
+    *reinterpret_cast<uint4*>(out + ((((size_t)b * NCs + ck) * TP + pt + t) * P + pf + f) * 8) = *reinterpret_cast<uint4*>(v);
   }
 }
 
 __global__ void cp8_to_nchw_kernel(const uint16_t* __restrict__ in, float* __restrict__ out, long long total, int C, int T,
-                                   int F, int NCk, int TP, int P, int pf, int pt, int fmt) {
+                                   int F, int NCs, int TP, int P, int pf, int pt, int fmt) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int f = (int)(i % F);
     long long r = i / F;
@@ -435,7 +437,7 @@ __global__ void cp8_to_nchw_kernel(const uint16_t* __restrict__ in, float* __res
     r /= T;
     int c = (int)(r % C);
     int b = (int)(r / C);
-    out[i] = cvt32(in[((((size_t)b * NCk + (c >> 3)) * TP + pt + t) * P + pf + f) * 8 + (c & 7)], fmt);
+    out[i] = cvt32(in[((((size_t)b * NCs + (c >> 3)) * TP + pt + t) * P + pf + f) * 8 + (c & 7)], fmt);
   }
 }
 
@@ -476,19 +478,90 @@ __device__ __forceinline__ void add8(uint4& c, const uint4& r) {
 }
 template <int FMT>
 __global__ void pool_time_res_cp8_kernel(const uint4* __restrict__ y, const uint4* __restrict__ res, uint4* __restrict__ out,
-                                         long long total, int T, int F, int TP, int P, int pf, int pt, int half) {
+                                         long long total, int NCk, int ncs_y, int ncs_res, int ncs_out, int T, int F, int TP, int P, int pf,
+                                         int pt, int half) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int f = (int)(i % F);
     long long r = i / F;
     int t = (int)(r % T);
-    long long plane = r / T;
-    const size_t base = ((size_t)plane * TP + pt + t) * P + pf + f;
+    r /= T;
+    const int ck = (int)(r % NCk);
+    const long long b = r / NCk;
+    const size_t in_plane = ((size_t)b * ncs_y + ck);
+    const size_t base = (in_plane * TP + pt + t) * P + pf + f;
     uint4 c = y[base];
     const int lo = max(-half, -t), hi = min(half, T - 1 - t);
     for (int d = lo; d <= hi; ++d)
       if (d != 0) max8<FMT>(c, y[base + (long long)d * P]);
-    if (res) add8<FMT>(c, res[base]);
-    out[base] = c;
+    if (res) add8<FMT>(c, res[((((size_t)b * ncs_res + ck) * TP + pt + t) * P) + pf + f]);
+    out[((((size_t)b * ncs_out + ck) * TP + pt + t) * P) + pf + f] = c;
+  }
+}
+
+// MaxPool2d((2,2)) floor mode between two CP8 geometries
+template <int FMT>
+__global__ void maxpool2x2_cp8_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, long long total, int NCk, int ncs_in, int ncs_out,
+                                      int To, int Fo, int TPi, int Pi, int pfi, int pti, int TPo, int Po, int pfo, int pto) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int f = (int)(i % Fo);
+    long long r = i / Fo;
+    int t = (int)(r % To);
+    r /= To;
+    const int ck = (int)(r % NCk);
+    const long long b = r / NCk;
+    const size_t ib = ((((size_t)b * ncs_in + ck) * TPi + pti + 2 * t) * Pi) + pfi + 2 * f;
+    uint4 c = in[ib];
+    max8<FMT>(c, in[ib + 1]);
+    max8<FMT>(c, in[ib + Pi]);
+    max8<FMT>(c, in[ib + Pi + 1]);
+    out[((((size_t)b * ncs_out + ck) * TPo + pto + t) * Po) + pfo + f] = c;
+  }
+}
+
+// nn.Upsample(x2, bilinear, align_corners=True) + zero pad to (Ts,Fs) (unet_up_concat_padding), written into the chunk range of the
+// concat buffer that follows the skip channels
+template <int FMT>
+__global__ void upsample2x_cp8_kernel(const uint16_t* __restrict__ low, uint16_t* __restrict__ out, long long total, int NCk, int ncs_in,
+                                      int ncs_out, int Tl, int Fl, int TPl, int Pl, int pfl, int ptl, int Ts, int Fs, int TPs, int Ps, int pfs,
+                                      int pts) {
+  const int Tu = 2 * Tl, Fu = 2 * Fl;
+  const int top = (Ts - Tu) / 2, left = (Fs - Fu) / 2;
+  const float ry = Tu > 1 ? (float)(Tl - 1) / (float)(Tu - 1) : 0.f;
+  const float rx = Fu > 1 ? (float)(Fl - 1) / (float)(Fu - 1) : 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int f = (int)(i % Fs);
+    long long r = i / Fs;
+    int t = (int)(r % Ts);
+    r /= Ts;
+    const int ck = (int)(r % NCk);
+    const long long b = r / NCk;
+    __align__(16) uint16_t o[8];
+    const int tu = t - top, fu = f - left;
+    if (tu < 0 || tu >= Tu || fu < 0 || fu >= Fu) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = 0;
+    } else {
+      const float sy = ry * tu, sx = rx * fu;
+      const int y0 = (int)sy, x0 = (int)sx;
+      const int y1 = min(y0 + 1, Tl - 1), x1 = min(x0 + 1, Fl - 1);
+      const float ly = sy - y0, lx = sx - x0;
+      const size_t pb = (((size_t)b * ncs_in + ck) * TPl + ptl);
+      const uint4 q00 = *reinterpret_cast<const uint4*>(low + ((pb + y0) * Pl + pfl + x0) * 8);
+      const uint4 q01 = *reinterpret_cast<const uint4*>(low + ((pb + y0) * Pl + pfl + x1) * 8);
+      const uint4 q10 = *reinterpret_cast<const uint4*>(low + ((pb + y1) * Pl + pfl + x0) * 8);
+      const uint4 q11 = *reinterpret_cast<const uint4*>(low + ((pb + y1) * Pl + pfl + x1) * 8);
+      const uint16_t* a00 = reinterpret_cast<const uint16_t*>(&q00);
+      const uint16_t* a01 = reinterpret_cast<const uint16_t*>(&q01);
+      const uint16_t* a10 = reinterpret_cast<const uint16_t*>(&q10);
+      const uint16_t* a11 = reinterpret_cast<const uint16_t*>(&q11);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float v = (1.f - ly) * ((1.f - lx) * cvt32(a00[e], FMT) + lx * cvt32(a01[e], FMT)) +
+                        ly * ((1.f - lx) * cvt32(a10[e], FMT) + lx * cvt32(a11[e], FMT));
+        o[e] = cvt16(v, FMT);
+      }
+    }
+    *reinterpret_cast<uint4*>(out + (((((size_t)b * ncs_out + ck) * TPs + pts + t) * Ps) + pfs + f) * 8) = *reinterpret_cast<const uint4*>(o);
   }
 }
 
@@ -551,7 +624,8 @@ int mpa_conv_tc_pack_weights(const float* w, void* packed, int Cin, int Cout, in
 
 int mpa_conv_tc_f16(const void* in_cp8, const void* w_packed, const float* bias, void* out, int out_mode, int sub_stride,
                     int sub_offset, int n_patches, int Cin, int Cout, int T, int F, int KH, int KW, int pitch, int pf, int pt,
-                    long long in_patch_stride_rows, int act, float act_param, int fmt, void* stream) {
+                    long long in_patch_stride_rows, int in_nc_stride, int out_nc_stride, int act, float act_param, int fmt,
+                    void* stream) {
   MPA_CHECK_ARCH();
   MPA_REQUIRE(in_cp8 && w_packed && bias && out && n_patches > 0, "conv_tc: null argument");
   MPA_REQUIRE(Cout > 0 && Cout <= 128 && Cin > 0, "conv_tc: Cout must be in 1..128 (got %d)", Cout);
@@ -584,7 +658,7 @@ int mpa_conv_tc_f16(const void* in_cp8, const void* w_packed, const float* bias,
   if (in_patch_stride_rows <= 0) {
     // materialised patches: [n_patches][NC][TP][P][8]
     p.in_chunk_stride = TP * pitch * 16;
-    p.in_patch_stride = p.in_chunk_stride * p.NC;
+    p.in_patch_stride = p.in_chunk_stride * (in_nc_stride > 0 ? in_nc_stride : p.NC);
     p.in_row0 = (long long)pt * pitch * 16;
   } else {
     // streaming: one shared frame-major plane [rows][P][8]; patch b starts at row b*stride (after pt guard rows)
@@ -593,6 +667,10 @@ int mpa_conv_tc_f16(const void* in_cp8, const void* w_packed, const float* bias,
     p.in_patch_stride = in_patch_stride_rows * pitch * 16;
     p.in_row0 = (long long)pt * pitch * 16;
   }
+  MPA_REQUIRE(in_nc_stride == 0 || in_nc_stride >= p.NC, "conv_tc: in_nc_stride %d < %d input chunks", in_nc_stride, p.NC);
+  MPA_REQUIRE(out_nc_stride == 0 || out_nc_stride >= p.NCo, "conv_tc: out_nc_stride %d < %d output chunks", out_nc_stride, p.NCo);
+  MPA_REQUIRE((Cout & 7) == 0 || out_nc_stride == 0 || out_nc_stride == p.NCo, "conv_tc: writing into a wider buffer needs Cout %% 8 == 0");
+  p.out_patch_stride = (long long)(out_nc_stride > 0 ? out_nc_stride : p.NCo) * (out_mode == 0 ? (long long)p.TP_out * pitch : (long long)T * p.F_out) * 8;
   p.mmas_per_row = mmas_per_row(p.NC, KW);
   p.n_groups = (T + p.J - 1) / p.J;
   p.n_units = n_patches * p.n_groups;
@@ -601,13 +679,18 @@ int mpa_conv_tc_f16(const void* in_cp8, const void* w_packed, const float* bias,
   p.act_param = act_param;
   const uint32_t f = (fmt == MPA_FMT_BF16) ? 1u : 0u;
   p.idesc = (1u << 4) | (f << 7) | (f << 10) | ((uint32_t)(pitch >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  size_t off = (size_t)kNumAStages * kAStageBytes + (size_t)kNumBStages * p.NC * p.slab_px * 16;
+  const size_t b_bytes = (size_t)kNumBStages * p.NC * p.slab_px * 16;
+  const size_t tail = 256 + (size_t)(p.mmas_per_row + 8) * 4 + 128 + 4 * 32 * kEpiPitch * 2;   // barriers, table, staging
+  int a_stages = kMaxAStages;
+  while (a_stages > 2 && (size_t)a_stages * kAStageBytes + b_bytes + tail > 227 * 1024) --a_stages;
+  p.a_stages = a_stages;
+  size_t off = (size_t)a_stages * kAStageBytes + b_bytes;
+  p.btab_off = (int)(off + 256);
   off += 256 + (size_t)(p.mmas_per_row + 8) * 4;      // barriers + tmem slot (256 B), descriptor table
   off = (off + 127) / 128 * 128;
   p.epi_off = (int)off;
   const size_t smem = off + 4 * 32 * kEpiPitch * 2;
   MPA_REQUIRE(smem <= 227 * 1024, "conv_tc: needs %zu B of shared memory (Cin=%d pitch=%d)", smem, Cin, pitch);
-  MPA_REQUIRE(p.mmas_per_row * 4 <= 4096, "conv_tc: K row too long");
   static thread_local size_t attr_set = 0;
   if (smem > attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -627,39 +710,85 @@ int mpa_conv_tc_f16(const void* in_cp8, const void* w_packed, const float* bias,
 }
 
 int mpa_pool_time_res_cp8(const void* y_cp8, const void* res_cp8, void* out_cp8, int n_patches, int C, int T, int F, int pitch, int pf,
-                          int pt, int k, int fmt, void* stream) {
+                          int pt, int k, int fmt, int ncs_y, int ncs_res, int ncs_out, void* stream) {
   MPA_CHECK_ARCH();
   MPA_REQUIRE(y_cp8 && out_cp8 && n_patches > 0 && C > 0 && k >= 1 && (k & 1) && pitch >= pf + F, "pool_time_res_cp8: bad argument");
   const int NCk = (C + 7) / 8;
+  if (ncs_y <= 0) ncs_y = NCk;
+  if (ncs_res <= 0) ncs_res = NCk;
+  if (ncs_out <= 0) ncs_out = NCk;
   long long total = (long long)n_patches * NCk * T * F;
   if (fmt == MPA_FMT_BF16)
     pool_time_res_cp8_kernel<MPA_FMT_BF16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const uint4*)y_cp8, (const uint4*)res_cp8, (uint4*)out_cp8, total, T, F, T + 2 * pt, pitch, pf, pt, k / 2);
+        (const uint4*)y_cp8, (const uint4*)res_cp8, (uint4*)out_cp8, total, NCk, ncs_y, ncs_res, ncs_out, T, F, T + 2 * pt, pitch, pf, pt, k / 2);
   else
     pool_time_res_cp8_kernel<MPA_FMT_F16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const uint4*)y_cp8, (const uint4*)res_cp8, (uint4*)out_cp8, total, T, F, T + 2 * pt, pitch, pf, pt, k / 2);
+        (const uint4*)y_cp8, (const uint4*)res_cp8, (uint4*)out_cp8, total, NCk, ncs_y, ncs_res, ncs_out, T, F, T + 2 * pt, pitch, pf, pt, k / 2);
   MPA_CHECK_LAUNCH("pool_time_res_cp8");
   return MPA_OK;
 }
 
-int mpa_nchw_to_cp8(const float* x, void* out_cp8, int B, int C, int T, int F, int pitch, int pf, int pt, int fmt, void* stream) {
+int mpa_maxpool2x2_cp8(const void* in_cp8, void* out_cp8, int n, int C, int T, int F, int pitch_in, int pf_in, int pt_in, int ncs_in,
+                       int pitch_out, int pf_out, int pt_out, int ncs_out, int fmt, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(in_cp8 && out_cp8 && n > 0 && C > 0 && T >= 2 && F >= 2, "maxpool2x2_cp8: bad argument");
+  const int NCk = (C + 7) / 8, To = T / 2, Fo = F / 2;
+  MPA_REQUIRE(pitch_in >= pf_in + F && pitch_out >= pf_out + Fo, "maxpool2x2_cp8: pitch too small");
+  if (ncs_in <= 0) ncs_in = NCk;
+  if (ncs_out <= 0) ncs_out = NCk;
+  long long total = (long long)n * NCk * To * Fo;
+  if (fmt == MPA_FMT_BF16)
+    maxpool2x2_cp8_kernel<MPA_FMT_BF16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)in_cp8, (uint4*)out_cp8, total, NCk, ncs_in, ncs_out, To, Fo, T + 2 * pt_in, pitch_in, pf_in, pt_in, To + 2 * pt_out, pitch_out,
+        pf_out, pt_out);
+  else
+    maxpool2x2_cp8_kernel<MPA_FMT_F16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)in_cp8, (uint4*)out_cp8, total, NCk, ncs_in, ncs_out, To, Fo, T + 2 * pt_in, pitch_in, pf_in, pt_in, To + 2 * pt_out, pitch_out,
+        pf_out, pt_out);
+  MPA_CHECK_LAUNCH("maxpool2x2_cp8");
+  return MPA_OK;
+}
+
+int mpa_upsample2x_cp8(const void* low_cp8, void* out_cp8, int n, int C, int Tl, int Fl, int pitch_l, int pf_l, int pt_l, int ncs_l, int Ts,
+                       int Fs, int pitch_s, int pf_s, int pt_s, int ncs_out, int fmt, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(low_cp8 && out_cp8 && n > 0 && C > 0 && (C & 7) == 0 && Ts >= 2 * Tl && Fs >= 2 * Fl, "upsample2x_cp8: bad argument (C %% 8 == 0 required)");
+  const int NCk = C / 8;
+  if (ncs_l <= 0) ncs_l = NCk;
+  MPA_REQUIRE(ncs_out >= NCk, "upsample2x_cp8: destination chunk stride too small");
+  long long total = (long long)n * NCk * Ts * Fs;
+  if (fmt == MPA_FMT_BF16)
+    upsample2x_cp8_kernel<MPA_FMT_BF16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint16_t*)low_cp8, (uint16_t*)out_cp8, total, NCk, ncs_l, ncs_out, Tl, Fl, Tl + 2 * pt_l, pitch_l, pf_l, pt_l, Ts, Fs, Ts + 2 * pt_s,
+        pitch_s, pf_s, pt_s);
+  else
+    upsample2x_cp8_kernel<MPA_FMT_F16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint16_t*)low_cp8, (uint16_t*)out_cp8, total, NCk, ncs_l, ncs_out, Tl, Fl, Tl + 2 * pt_l, pitch_l, pf_l, pt_l, Ts, Fs, Ts + 2 * pt_s,
+        pitch_s, pf_s, pt_s);
+  MPA_CHECK_LAUNCH("upsample2x_cp8");
+  return MPA_OK;
+}
+
+int mpa_nchw_to_cp8(const float* x, void* out_cp8, int B, int C, int T, int F, int pitch, int pf, int pt, int fmt, int ncs_out, void* stream) {
   MPA_CHECK_ARCH();
   MPA_REQUIRE(x && out_cp8 && B > 0 && C > 0 && pitch >= pf + F, "nchw_to_cp8: bad argument");
   const int NCk = (C + 7) / 8;
+  if (ncs_out <= 0) ncs_out = NCk;
   long long total = (long long)B * NCk * T * F;
-  nchw_to_cp8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (uint16_t*)out_cp8, total, C, T, F, NCk, T + 2 * pt,
+  nchw_to_cp8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (uint16_t*)out_cp8, total, C, T, F, NCk, ncs_out, T + 2 * pt,
                                                                                pitch, pf, pt, fmt);
   MPA_CHECK_LAUNCH("nchw_to_cp8");
   return MPA_OK;
 }
 
-int mpa_cp8_to_nchw(const void* in_cp8, float* out, int B, int C, int T, int F, int pitch, int pf, int pt, int fmt, void* stream) {
+int mpa_cp8_to_nchw(const void* in_cp8, float* out, int B, int C, int T, int F, int pitch, int pf, int pt, int fmt, int ncs_in, void* stream) {
   MPA_CHECK_ARCH();
   MPA_REQUIRE(in_cp8 && out && B > 0 && C > 0 && pitch >= pf + F, "cp8_to_nchw: bad argument");
   const int NCk = (C + 7) / 8;
+  if (ncs_in <= 0) ncs_in = NCk;
   long long total = (long long)B * C * T * F;
-  cp8_to_nchw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint16_t*)in_cp8, out, total, C, T, F, NCk,
-                                                                               T + 2 * pt, pitch, pf, pt, fmt);
+  cp8_to_nchw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint16_t*)in_cp8, out, total, C, T, F, ncs_in, T + 2 * pt,
+                                                                               pitch, pf, pt, fmt);
   MPA_CHECK_LAUNCH("cp8_to_nchw");
   return MPA_OK;
 }

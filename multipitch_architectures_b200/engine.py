@@ -85,6 +85,7 @@ class CnnStreamEngine:
                 if li == 0:
                     src = ops.CP8.__new__(ops.CP8)
                     src.B, src.C, src.T, src.F, src.pitch, src.pf, src.pt, src.NC, src.fmt = n, C, CONTEXT, F, self.pitch, self.pf, self.pt, 1, self.fmt
+                    src.ncs, src.chunk0 = 1, 0
                     src.buf = plane[i0:]
                     self._timed('conv_tc_first', lambda: ops.conv_tc(src, wp, conv.bias, self.C0, tuple(conv.kernel_size), ops.ACT_LRELU, a,
                                                                     out=ya.first(n), n_patches=n, patch_stride_rows=1, T=CONTEXT))

@@ -82,13 +82,13 @@ def head_tc(cache, model, zc, a):
     """Head on a CP8 activation: conv2 (3x3, stride (1,3)) runs on the tensor cores as the stride-1 3x3 convolution
     whose epilogue keeps columns 1, 4, 7, ... (exactly the strided outputs), then maxpool(13,1) and the fused tail."""
     conv2, conv3, c40, c43 = model.conv2[0], model.conv3[0], model.conv4[0], model.conv4[3]
-    ok2 = (tuple(conv2.kernel_size) == (3, 3) and tuple(conv2.stride) == (1, 3) and tuple(conv2.padding) == (1, 0)
-           and conv2.weight.shape[0] <= 128 and zc.F % 3 == 0)
+    ok2 = (tuple(conv2.kernel_size) == (3, 3) and tuple(conv2.stride) == (1, 3) and tuple(conv2.padding) == (1, 0) and zc.F % 3 == 0)
     if not ok2:
         return head_f32(cache, model, ops.cp8_to_nchw(zc), a)
-    w2 = conv2.weight
-    wp = cache.get(f'conv2:wtc{zc.fmt}', [w2], lambda: ops.conv_tc_pack(w2, zc.buf.device, zc.fmt))
-    yc = ops.conv_tc(zc, wp, conv2.bias, w2.shape[0], (3, 3), ops.ACT_LRELU, a, subsample=(3, 1))
+    C1 = conv2.weight.shape[0]
+    yc = ops.CP8(zc.B, C1, zc.T, zc.F // 3, zc.F // 3, 0, 0, zc.buf.device, fmt=zc.fmt, zero=False)
+    for wp, b, c0, c in _folded_tc(cache, 'conv2', conv2, None, zc.fmt, zc.buf.device):
+        ops.conv_tc(zc, wp, b, c, (3, 3), ops.ACT_LRELU, a, subsample=(3, 1), out=yc.channels(c0, c))
     yc = ops.pool_time_res_cp8(yc, 13)
     fused = (conv3.kernel_size[0] == zc.T and conv3.kernel_size[1] == 1 and tuple(c43.kernel_size) == (1, 1)
              and conv3.weight.shape[0] <= 32 and c40.weight.shape[0] <= 16 and c43.weight.shape[0] == 1 and yc.F <= 256)
@@ -157,6 +157,101 @@ def unet_up_f32(model, x5, skips, train):
     u = double_conv_f32(cache, 'upconv3', model.upconv3, ops.upsample2x_concat(u, x2), train)
     u = double_conv_f32(cache, 'upconv4', model.upconv4, ops.upsample2x_concat(u, x1), train)
     return u
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# U-Net family on the tcgen05 path (eval mode: BatchNorm folded into the packed weights / bias)
+LEVEL_PF = 8
+
+
+def level_geometry(T0, F0, n_levels=5):
+    """(T, F, pitch) of every U-Net level: MaxPool(2,2) floor sizes; pitch = multiple of 16 >= F + 8 (zero gap >= 7)."""
+    geo, T, F = [], T0, F0
+    for _ in range(n_levels):
+        geo.append((T, F, (F + LEVEL_PF + 15) // 16 * 16))
+        T, F = T // 2, F // 2
+    return geo
+
+
+def unet_tc_eligible(model, x):
+    if model.precision not in ('fp16', 'bf16') or model.training:
+        return False
+    chans = [model.inc.double_conv[0].weight.shape[0]] + [getattr(model, f'down{i}')[1].double_conv[0].weight.shape[0] for i in (1, 2, 3, 4)]
+    ups = [getattr(model, f'upconv{i}').double_conv[4].weight.shape[0] for i in (1, 2, 3)]
+    return all(c % 8 == 0 for c in chans + ups) and x.shape[3] + LEVEL_PF <= 256 and x.shape[2] >= 32
+
+
+def _folded_tc(cache, name, conv, bn, fmt, dev):
+    """Packed operand(s) of conv (+ eval BatchNorm folded): list of (packed weights, bias, cout0, cout) per <=128 block."""
+    params = [conv.weight, conv.bias] + ([bn.weight, bn.bias, bn.running_mean, bn.running_var] if bn is not None else [])
+
+    def build():
+        w, b = conv.weight.detach().float(), conv.bias.detach().float()
+        if bn is not None:
+            s = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+            w = w * s[:, None, None, None]
+            b = (b - bn.running_mean) * s + bn.bias
+        out = []
+        for c0 in range(0, w.shape[0], 128):
+            c1 = min(w.shape[0], c0 + 128)
+            out.append((ops.conv_tc_pack(w[c0:c1].contiguous(), dev, fmt), b[c0:c1].contiguous(), c0, c1 - c0))
+        return out
+    return cache.get(f'{name}:tcfold{fmt}', params, build)
+
+
+def conv_bn_relu_tc(cache, name, conv, bn, src, dst, act=ops.ACT_RELU, a=0.0):
+    k = tuple(conv.kernel_size)
+    for wp, b, c0, c in _folded_tc(cache, name, conv, bn, src.fmt, src.buf.device):
+        ops.conv_tc(src, wp, b, c, k, act, a, out=dst.channels(c0, c))
+    return dst
+
+
+def double_conv_tc(cache, name, dc, src, dst, scratch):
+    seq = dc.double_conv
+    conv_bn_relu_tc(cache, name + '.0', seq[0], seq[1], src, scratch)
+    return conv_bn_relu_tc(cache, name + '.4', seq[4], seq[5], scratch, dst)
+
+
+def unet_forward_tc(model, x):
+    """simple_u_net_largekernels / _doubleselfattn / _polyphony_classif_softmax, eval mode, tensor-core path.
+    Skip connections are written straight into the first chunks of the decoder's concat buffers; the bilinear
+    up-sampler fills the remaining chunks, so torch.cat never happens."""
+    cache, a = model._cache, model.a_lrelu
+    fmt = ops.fmt_of(model.precision)
+    B, C, T, F = x.shape
+    dev = x.device
+    geo = level_geometry(T, F)
+    c = [model.inc.double_conv[4].weight.shape[0]] + [getattr(model, f'down{i}')[1].double_conv[4].weight.shape[0] for i in (1, 2, 3, 4)]
+    up_out = [getattr(model, f'upconv{i}').double_conv[4].weight.shape[0] for i in (1, 2, 3, 4)]
+
+    def buf(level, ch):
+        Tl, Fl, P = geo[level]
+        return ops.CP8(B, ch, Tl, Fl, P, LEVEL_PF, 1, dev, fmt=fmt)
+    z = ops.nchw_to_cp8(ops.layernorm_cf(x, model.layernorm.weight, model.layernorm.bias, model.layernorm.eps),
+                        pitch=geo[0][2], pf=LEVEL_PF, pt=1, fmt=fmt)
+    # concat buffers of the decoder: level 3 (x4|up x5), level 2 (x3|up u1), level 1 (x2|up u2), level 0 (x1|up u3)
+    cat = {3: buf(3, c[3] + c[4]), 2: buf(2, c[2] + up_out[0]), 1: buf(1, c[1] + up_out[1]), 0: buf(0, c[0] + up_out[2])}
+    skips = {lv: cat[lv].channels(0, c[lv]) for lv in (0, 1, 2, 3)}
+    # encoder
+    double_conv_tc(cache, 'inc', model.inc, z, skips[0], buf(0, model.inc.double_conv[0].weight.shape[0]))
+    cur = skips[0]
+    for lv in (1, 2, 3, 4):
+        dc = getattr(model, f'down{lv}')[1]
+        pooled = ops.maxpool2x2_cp8(cur, buf(lv, c[lv - 1]))
+        dst = skips[lv] if lv < 4 else buf(4, c[4])
+        cur = double_conv_tc(cache, f'down{lv}', dc, pooled, dst, buf(lv, dc.double_conv[0].weight.shape[0]))
+    x5 = cur
+    if hasattr(model, 'attention1'):
+        t5 = model.attention2.run(model.attention1.run(ops.cp8_to_nchw(x5)))
+        x5 = ops.nchw_to_cp8(t5, pitch=geo[4][2], pf=LEVEL_PF, pt=1, fmt=fmt)
+    # decoder
+    low = x5
+    for i, lv in enumerate((3, 2, 1, 0)):
+        dc = getattr(model, f'upconv{i + 1}')
+        ops.upsample2x_cp8(low, cat[lv].channels(c[lv], low.C))
+        low = double_conv_tc(cache, f'upconv{i + 1}', dc, cat[lv], buf(lv, up_out[i]), buf(lv, dc.double_conv[0].weight.shape[0]))
+    y = head_tc(cache, model, low, a)
+    return y, x5
 
 
 def sinusoidal_pe(n, E, device):

@@ -119,6 +119,9 @@ class _UnetBase(_MpaModel):
             raise NotImplementedError('U-Net training (backward) is not part of this round; wrap inference in torch.no_grad()')
         self._guard_training()
         train = self._bn_train()
+        if _exec.unet_tc_eligible(self, x):
+            y, x5c = _exec.unet_forward_tc(self, x)
+            return y, (ops.cp8_to_nchw(x5c) if hasattr(self, 'convP') else None)
         x1, x2, x3, x4, x5 = _exec.unet_trunk_f32(self, x, train)
         x5 = self._bottleneck(x5)
         u = _exec.unet_up_f32(self, x5, (x1, x2, x3, x4), train)

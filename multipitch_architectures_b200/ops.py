@@ -100,26 +100,46 @@ def fmt_of(precision):
 
 
 class CP8:
-    """16-bit planes [B][ceil(C/8)][T+2*pt][pitch][8] with zero borders; real pixel (t,f) at [pt+t][pf+f]."""
+    """16-bit planes [B][ncs][T+2*pt][pitch][8] with zero borders; real pixel (t,f) at [pt+t][pf+f].
+    A CP8 may be a VIEW of `C` channels starting at chunk `chunk0` of a wider buffer with `ncs` chunks per item
+    (U-Net concat buffers): kernels receive the advanced pointer and the underlying chunk stride."""
 
-    def __init__(self, B, C, T, F, pitch=None, pf=8, pt=1, device='cuda', buf=None, fmt=FMT_F16):
+    def __init__(self, B, C, T, F, pitch=None, pf=8, pt=1, device='cuda', buf=None, fmt=FMT_F16, ncs=None, chunk0=0, zero=True):
         if pitch is None:
             pitch = (F + pf + 15) // 16 * 16
         self.B, self.C, self.T, self.F, self.pitch, self.pf, self.pt, self.fmt = B, C, T, F, pitch, pf, pt, fmt
         self.NC = (C + 7) // 8
-        shape = (B, self.NC, T + 2 * pt, pitch, 8)
-        self.buf = buf if buf is not None else torch.zeros(shape, dtype=_FMT_DTYPE[fmt], device=device)
-        assert tuple(self.buf.shape) == shape
+        self.ncs = self.NC if ncs is None else ncs
+        self.chunk0 = chunk0
+        shape = (B, self.ncs, T + 2 * pt, pitch, 8)
+        if buf is None:
+            buf = (torch.zeros if zero else torch.empty)(shape, dtype=_FMT_DTYPE[fmt], device=device)
+        self.buf = buf
+        assert tuple(self.buf.shape)[1:] == shape[1:] and self.buf.shape[0] >= B, (tuple(self.buf.shape), shape)
+
+    def ptr(self):
+        import ctypes
+        plane_bytes = (self.T + 2 * self.pt) * self.pitch * 16
+        return ctypes.c_void_p(self.buf.data_ptr() + self.chunk0 * plane_bytes)
+
+    @property
+    def compact(self):
+        return self.pt == 0 and self.pf == 0 and self.pitch == self.F
 
     def like(self, C=None):
-        if self.pt == 0 and self.pf == 0 and self.pitch == self.F:      # compact planes need no zero borders
-            return CP8(self.B, self.C if C is None else C, self.T, self.F, self.pitch, 0, 0, self.buf.device, fmt=self.fmt,
-                       buf=torch.empty(self.B, ((self.C if C is None else C) + 7) // 8, self.T, self.pitch, 8,
-                                       dtype=_FMT_DTYPE[self.fmt], device=self.buf.device))
-        return CP8(self.B, self.C if C is None else C, self.T, self.F, self.pitch, self.pf, self.pt, self.buf.device, fmt=self.fmt)
+        C = self.C if C is None else C
+        return CP8(self.B, C, self.T, self.F, self.pitch, self.pf, self.pt, self.buf.device, fmt=self.fmt, zero=not self.compact)
+
+    def channels(self, c0, C):
+        """View of channels [c0, c0+C) (both multiples of 8) of this buffer."""
+        assert c0 % 8 == 0 and (C % 8 == 0 or c0 + C == self.C)
+        v = CP8.__new__(CP8)
+        v.__dict__.update(self.__dict__)
+        v.C, v.NC, v.chunk0 = C, (C + 7) // 8, self.chunk0 + c0 // 8
+        return v
 
     def first(self, n):
-        """First n patches (no copy)."""
+        """First n items (no copy)."""
         if n == self.B:
             return self
         v = CP8.__new__(CP8)
@@ -131,13 +151,13 @@ class CP8:
 def nchw_to_cp8(x, pitch=None, pf=8, pt=1, out=None, fmt=FMT_F16):
     B, C, T, F = x.shape
     out = out if out is not None else CP8(B, C, T, F, pitch, pf, pt, x.device, fmt=fmt)
-    call('nchw_to_cp8', _f32(x), out.buf, B, C, T, F, out.pitch, out.pf, out.pt, out.fmt, stream_ptr())
+    call('nchw_to_cp8', _f32(x), out.ptr(), B, C, T, F, out.pitch, out.pf, out.pt, out.fmt, out.ncs, stream_ptr())
     return out
 
 
 def cp8_to_nchw(a):
     out = torch.empty(a.B, a.C, a.T, a.F, dtype=torch.float32, device=a.buf.device)
-    call('cp8_to_nchw', a.buf, out, a.B, a.C, a.T, a.F, a.pitch, a.pf, a.pt, a.fmt, stream_ptr())
+    call('cp8_to_nchw', a.ptr(), out, a.B, a.C, a.T, a.F, a.pitch, a.pf, a.pt, a.fmt, a.ncs, stream_ptr())
     return out
 
 
@@ -172,18 +192,17 @@ def conv_tc(a, w_packed, bias, Cout, ksize, act=ACT_NONE, act_param=0.0, out=Non
         stride, offset = subsample
         F_out = (a.F - offset + stride - 1) // stride
         if out is None:
-            out = CP8(n, Cout, T, F_out, F_out, 0, 0, a.buf.device, fmt=a.fmt,
-                      buf=torch.empty(n, (Cout + 7) // 8, T, F_out, 8, dtype=_FMT_DTYPE[a.fmt], device=a.buf.device))
+            out = CP8(n, Cout, T, F_out, F_out, 0, 0, a.buf.device, fmt=a.fmt, zero=False)
         mode = 1
-    call('conv_tc_f16', a.buf, w_packed, bias, out.buf, mode, stride, offset, n, a.C, Cout, T, a.F, ksize[0], ksize[1], a.pitch, a.pf,
-         a.pt, _lib.i64(patch_stride_rows), act, float(act_param), a.fmt, stream_ptr())
+    call('conv_tc_f16', a.ptr(), w_packed, bias, out.ptr(), mode, stride, offset, n, a.C, Cout, T, a.F, ksize[0], ksize[1], a.pitch,
+         a.pf, a.pt, _lib.i64(patch_stride_rows), 0 if patch_stride_rows else a.ncs, out.ncs, act, float(act_param), a.fmt, stream_ptr())
     return out
 
 
 def pool_time_res_cp8(y, k, res=None, out=None):
     out = out if out is not None else y.like()
-    call('pool_time_res_cp8', y.buf, None if res is None else res.buf, out.buf, y.B, y.C, y.T, y.F, y.pitch, y.pf, y.pt, k, y.fmt,
-         stream_ptr())
+    call('pool_time_res_cp8', y.ptr(), None if res is None else res.ptr(), out.ptr(), y.B, y.C, y.T, y.F, y.pitch, y.pf, y.pt, k, y.fmt,
+         y.ncs, 0 if res is None else res.ncs, out.ncs, stream_ptr())
     return out
 
 
@@ -191,9 +210,23 @@ def pool3_res_cp8(y, res=None, out=None):
     return pool_time_res_cp8(y, 3, res, out)
 
 
+def maxpool2x2_cp8(a, out):
+    call('maxpool2x2_cp8', a.ptr(), out.ptr(), a.B, a.C, a.T, a.F, a.pitch, a.pf, a.pt, a.ncs, out.pitch, out.pf, out.pt, out.ncs, a.fmt,
+         stream_ptr())
+    return out
+
+
+def upsample2x_cp8(low, out):
+    """bilinear x2 (align_corners) of `low` + zero pad to out's (T, F), written into the view `out` (C == low.C)."""
+    call('upsample2x_cp8', low.ptr(), out.ptr(), low.B, low.C, low.T, low.F, low.pitch, low.pf, low.pt, low.ncs, out.T, out.F, out.pitch,
+         out.pf, out.pt, out.ncs, low.fmt, stream_ptr())
+    return out
+
+
 def head_tail(x, w3, b3, w40, b40, w43, b43, a_lrelu):
     """x: compact CP8 [B][NC1][T][Fo][8] -> [B,Fo] fp32; conv3 (T x 1) + LReLU + 1x1 + LReLU + 1x1 + sigmoid in one kernel."""
     C2, C3 = w3.shape[0], w40.shape[0]
     out = torch.empty(x.B, x.F, dtype=torch.float32, device=x.buf.device)
-    call('head_tail_cp8', x.buf, w3, b3, w40, b40, w43, b43, out, x.B, x.C, x.T, x.F, C2, C3, float(a_lrelu), x.fmt, stream_ptr())
+    assert x.ncs == x.NC and x.chunk0 == 0
+    call('head_tail_cp8', x.ptr(), w3, b3, w40, b40, w43, b43, out, x.B, x.C, x.T, x.F, C2, C3, float(a_lrelu), x.fmt, stream_ptr())
     return out

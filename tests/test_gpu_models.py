@@ -67,6 +67,48 @@ def test_tensor_core_path(nn_golden, name, prec):
     assert not flips.any()
 
 
+@pytest.mark.parametrize('name,tol', [('unet_m', 2e-2), ('punet', 2e-2), ('saunet_l', 2e-2)])
+def test_unet_family_tensor_core_path(nn_golden, name, tol):
+    """Eval-mode U-Nets on the tcgen05 path (BN folded, concat-free skip buffers, CP8 pooling / bilinear up-sampling)."""
+    tag = f'{name}__eval'
+    B, seed, _ = nn_golden[tag + '__meta']
+    B, seed = int(B), int(seed)
+    m = _load(name, seed, 'eval', precision='fp16')
+    from multipitch_architectures_b200.libdl.nn_models import _exec
+    x = synth_patches(B, seed).cuda()
+    assert _exec.unet_tc_eligible(m, x)
+    with torch.no_grad():
+        y = m(x)
+    if isinstance(y, tuple):
+        en = np.abs(y[1].cpu().numpy() - nn_golden[tag + '__n']).max()
+        print(f'{tag} fp16: polyphony logits max|diff| = {en:.2e}')
+        assert en < 10 * tol * max(1.0, np.abs(nn_golden[tag + '__n']).max())
+        y = y[0]
+    err = np.abs(y.cpu().numpy() - nn_golden[tag + '__y']).max()
+    print(f'{tag} fp16: max|diff| vs reference golden = {err:.2e}')
+    assert err < tol
+
+
+def test_cp8_pool2x2_and_upsample_concat():
+    import torch.nn.functional as F
+    from multipitch_architectures_b200 import ops
+    from oracle import nn_oracle as NO
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 16, 37, 108, generator=g)
+    xc = ops.nchw_to_cp8(x.cuda(), pitch=128)
+    pooled = ops.maxpool2x2_cp8(xc, ops.CP8(2, 16, 18, 54, 64, 8, 1))
+    assert torch.equal(ops.cp8_to_nchw(pooled).cpu(), F.max_pool2d(x.half().float(), (2, 2)))
+    low = torch.randn(2, 24, 18, 54, generator=g)
+    cat = ops.CP8(2, 16 + 24, 37, 108, 128, 8, 1)
+    ops.nchw_to_cp8(x.cuda(), out=cat.channels(0, 16))
+    ops.upsample2x_cp8(ops.nchw_to_cp8(low.cuda(), pitch=64), cat.channels(16, 24))
+    ref = NO.upconcat(low.half().float(), x.half().float())
+    got = ops.cp8_to_nchw(cat).cpu()
+    assert torch.equal(got[:, :16], ref[:, :16])
+    assert (got[:, 16:] - ref[:, 16:]).abs().max() < 2e-3 * ref.abs().max()          # fp16 rounding of the interpolated value
+    assert float(cat.buf[:, :, :, :8].abs().max()) == 0
+
+
 def test_tensor_core_path_longer_input():
     from oracle import nn_oracle as NO
     m = _load('drcnn_tiny', 5, 'eval', precision='fp16')
