@@ -669,7 +669,6 @@ int mpa_conv_tc_f16(const void* in_cp8, const void* w_packed, const float* bias,
   }
   MPA_REQUIRE(in_nc_stride == 0 || in_nc_stride >= p.NC, "conv_tc: in_nc_stride %d < %d input chunks", in_nc_stride, p.NC);
   MPA_REQUIRE(out_nc_stride == 0 || out_nc_stride >= p.NCo, "conv_tc: out_nc_stride %d < %d output chunks", out_nc_stride, p.NCo);
-  MPA_REQUIRE((Cout & 7) == 0 || out_nc_stride == 0 || out_nc_stride == p.NCo, "conv_tc: writing into a wider buffer needs Cout %% 8 == 0");
   p.out_patch_stride = (long long)(out_nc_stride > 0 ? out_nc_stride : p.NCo) * (out_mode == 0 ? (long long)p.TP_out * pitch : (long long)T * p.F_out) * 8;
   p.mmas_per_row = mmas_per_row(p.NC, KW);
   p.n_groups = (T + p.J - 1) / p.J;
