@@ -110,9 +110,9 @@ int mpa_encoder_layer_f32(const float* x, float* out, int B, int E, int Th, int 
  * (host side, one-off).  out = act(conv + bias) in CP8 (pool / residual are applied by mpa_pool3_res_cp8).
  * in_patch_stride_rows: 0 for materialised patches [n][NC][T+2pt][pitch][8];
  * 1 for the streaming engine where patch i is rows [i, i+T) of one shared frame-major plane. */
-size_t mpa_conv_tc_packed_bytes(int Cin, int Cout, int KH, int KW);
+size_t mpa_conv_tc_packed_bytes(int Cin, int Cout, int KH, int KW, int J);
 /* HOST function: w [Cout][Cin][KH][KW] fp32 (host) -> packed 16-bit A-operand tiles (host buffer), fmt = MPA_FMT_*. */
-int mpa_conv_tc_pack_weights(const float* w_host, void* packed_host, int Cin, int Cout, int KH, int KW, int fmt);
+int mpa_conv_tc_pack_weights(const float* w_host, void* packed_host, int Cin, int Cout, int KH, int KW, int fmt, int J);
 /* out_mode 0: `out` is a CP8 plane set [n_patches][ceil(Cout/8)][T+2pt][pitch][8] (16-bit, same fmt);
  * out_mode 1: `out` is the compact plane set [n_patches][ceil(Cout/8)][T][F_out][8] holding only the columns
  *             f = sub_offset + k*sub_stride (a stride-(1,s) convolution evaluated as the stride-1 "same" convolution and
@@ -120,7 +120,12 @@ int mpa_conv_tc_pack_weights(const float* w_host, void* packed_host, int Cin, in
 int mpa_conv_tc_f16(const void* in_cp8, const void* w_packed, const float* bias, void* out, int out_mode,
                     int sub_stride, int sub_offset, int n_patches, int Cin, int Cout, int T, int F, int KH, int KW,
                     int pitch, int pf, int pt, long long in_patch_stride_rows, int in_nc_stride, int out_nc_stride,
-                    int act, float act_param, int fmt, void* stream);
+                    int J, int row0, int n_rows, int act, float act_param, int fmt, void* stream);
+/* J: output rows per work unit (0 = floor(128/Cout)); must match the J the weights were packed with.
+ * row0 / n_rows: compute output rows [row0, row0+n_rows) only (n_rows 0 = to the end) and store them as rows 0.. of `out`;
+ * a VALID (KH x 1) convolution such as conv3 (75 x 1, basic_cnns.py:398) is the "same" convolution restricted to
+ * row0 = KH/2, n_rows = T-KH+1.  With KW == 1 the row pitch need not be a multiple of 16 and pt may be 0 (compact planes),
+ * but the caller must leave >= 512 B of slack after the last input row. */
 /* Chunk-strided views: every CP8 entry point takes the number of channel chunks per item of the UNDERLYING buffer
  * (`*_nc_stride` / `ncs_*`, 0 = the tensor's own chunk count) and a pointer already advanced to the view's first chunk.
  * This is how U-Net skip connections are concatenated without a copy: the producer of the skip writes chunks [0, Cs/8) and
@@ -149,6 +154,11 @@ int mpa_cp8_to_nchw(const void* in_cp8, float* out, int B, int C, int T, int F, 
 int mpa_head_tail_cp8(const void* x_cp8, const float* w3, const float* b3, const float* w40, const float* b40,
                       const float* w43, const float* b43, float* out, int B, int C1, int T, int Fo, int C2, int C3,
                       float a_lrelu, int fmt, void* stream);
+
+/* conv4.0 (1x1) + LeakyReLU + conv4.3 (1x1) + sigmoid on the activated conv3 output h [B][ceil(C2/8)][R][Fo][8] (compact 16-bit
+ * planes, any widths) -> out [B][R][Fo] fp32 (basic_cnns.py:403-408). */
+int mpa_head_tail2_cp8(const void* h_cp8, const float* w40, const float* b40, const float* w43, const float* b43,
+                       float* out, int B, int R, int Fo, int C2, int C3, float a_lrelu, int fmt, void* stream);
 
 /* ---- HCQT (H1-H3): batched multirate constant-Q filterbank ---------------------------------------------
  * replaces librosa.cqt x3 + librosa.estimate_tuning as driven by libdl/data_preprocessing/hcqt.py:122,157-162;

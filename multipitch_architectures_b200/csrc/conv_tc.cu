@@ -49,7 +49,7 @@ struct ConvTcParams {
   long long in_patch_stride;   // bytes between patches in `in`
   long long in_chunk_stride;   // bytes between channel chunks in `in`
   long long in_row0;           // byte offset of (row 0, column 0) of patch 0 chunk 0
-  int n_patches, NC, Cout, J, T, F, KH, KW, P, pf, pt_out, TP_out, NCo;
+  int n_patches, NC, Cout, J, T, F, KH, KW, P, N, pf, pt_out, TP_out, T_out, row0, row_end, NCo;
   int mmas_per_row, n_groups, n_units, slab_px, epi_off, a_stages, btab_off;
   long long out_patch_stride;  // elements (16-bit) between patches in `out`
   int act;
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
       uint32_t a_phase = 0, b_phase = 0;
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
         const int b0 = u / p.n_groups, g = u % p.n_groups;
-        const int t0 = g * p.J;
+        const int t0 = p.row0 + g * p.J;
         for (int r = 0; r < rows_in; ++r) {
           const int row = t0 - ph + r;
           if (row < 0 || row >= p.T) continue;
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
       uint32_t k_unit = 0;
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++k_unit) {
         const int g = u % p.n_groups;
-        const int t0 = g * p.J;
+        const int t0 = p.row0 + g * p.J;
         const uint32_t buf = k_unit & 1u, acc_par = (k_unit >> 1) & 1u;
         mbar_wait(&acc_empty[buf], acc_par ^ 1);     // epilogue has drained this accumulator (two units ago)
         tc_fence_after();
@@ -301,11 +301,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
     uint32_t k_unit = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++k_unit) {
       const int b = u / p.n_groups, g = u % p.n_groups;
-      const int t = g * p.J + j;
+      const int t = p.row0 + g * p.J + j;
       const uint32_t buf = k_unit & 1u, acc_par = (k_unit >> 1) & 1u;
       mbar_wait(&acc_full[buf], acc_par);
       tc_fence_after();
-      for (int c0 = 0; c0 < p.P; c0 += 32) {
+      for (int c0 = 0; c0 < p.N; c0 += 32) {
         uint32_t v[32];
         tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256 + c0), v);
         tc_wait_ld();
@@ -329,17 +329,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
           for (int k = 0; k < 4; ++k) {
             const int mg = quad * 32 + k * 8;                  // first accumulator row of the group
             const int jg = mg / p.Cout, cog = mg - jg * p.Cout;
-            const int tg = g * p.J + jg;
-            if (col_ok && jg < p.J && tg < p.T) {
+            const int tg = p.row0 + g * p.J + jg;
+            if (col_ok && jg < p.J && tg < p.row_end) {
               const uint4 val = *reinterpret_cast<const uint4*>(stile + lane * kEpiPitch + k * 8);
               uint16_t* dst = (p.out_mode == 0)
-                                  ? p.out + (size_t)b * p.out_patch_stride + ((((size_t)(cog >> 3)) * p.TP_out + p.pt_out + tg) * p.P + n) * 8
-                                  : p.out + (size_t)b * p.out_patch_stride + ((((size_t)(cog >> 3)) * p.T + tg) * p.F_out + fo) * 8;
+                                  ? p.out + (size_t)b * p.out_patch_stride + ((((size_t)(cog >> 3)) * p.TP_out + p.pt_out + tg - p.row0) * p.P + n) * 8
+                                  : p.out + (size_t)b * p.out_patch_stride + ((((size_t)(cog >> 3)) * p.T_out + tg - p.row0) * p.F_out + fo) * 8;
               *reinterpret_cast<uint4*>(dst) = val;
             }
           }
           __syncwarp();
-        } else if (row_valid && t < p.T) {
+        } else if (row_valid && t < p.row_end) {
           // scalar fallback (Cout not a multiple of 8): same destinations, one 16-bit store per value
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -353,8 +353,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
             }
             if (ok) {
               uint16_t* dst = (p.out_mode == 0)
-                                  ? p.out + (size_t)b * p.out_patch_stride + ((((size_t)(co >> 3)) * p.TP_out + p.pt_out + t) * p.P + n) * 8 + (co & 7)
-                                  : p.out + (size_t)b * p.out_patch_stride + ((((size_t)(co >> 3)) * p.T + t) * p.F_out + fo) * 8 + (co & 7);
+                                  ? p.out + (size_t)b * p.out_patch_stride + ((((size_t)(co >> 3)) * p.TP_out + p.pt_out + t - p.row0) * p.P + n) * 8 + (co & 7)
+                                  : p.out + (size_t)b * p.out_patch_stride + ((((size_t)(co >> 3)) * p.T_out + t - p.row0) * p.F_out + fo) * 8 + (co & 7);
               *dst = cvt16(apply_act(__uint_as_float(v[i]) + bias, p.act, p.act_param), p.fmt);
             }
           }
@@ -577,18 +577,21 @@ using namespace mpa;
 
 extern "C" {
 
-size_t mpa_conv_tc_packed_bytes(int Cin, int Cout, int KH, int KW) {
-  if (Cin <= 0 || Cout <= 0 || Cout > 128 || KH <= 0 || KW <= 0) return 0;
-  const int NC = (Cin + 7) / 8, J = j_blocks(Cout);
+size_t mpa_conv_tc_packed_bytes(int Cin, int Cout, int KH, int KW, int J) {
+  if (Cin <= 0 || Cout <= 0 || Cout > 128 || KH <= 0 || KW <= 0 || J < 0 || J * Cout > 128) return 0;
+  const int NC = (Cin + 7) / 8;
+  if (J == 0) J = j_blocks(Cout);
   return (size_t)(KH + J - 1) * mmas_per_row(NC, KW) * kATileBytes;
 }
 
-int mpa_conv_tc_pack_weights(const float* w, void* packed, int Cin, int Cout, int KH, int KW, int fmt) {
+int mpa_conv_tc_pack_weights(const float* w, void* packed, int Cin, int Cout, int KH, int KW, int fmt, int J) {
   MPA_REQUIRE(w && packed && Cin > 0 && Cout > 0 && Cout <= 128 && KH > 0 && KW > 0, "conv_tc_pack_weights: bad argument (Cout must be <= 128)");
-  const int NC = (Cin + 7) / 8, J = j_blocks(Cout), mpr = mmas_per_row(NC, KW);
+  MPA_REQUIRE(J >= 0 && J * Cout <= 128, "conv_tc_pack_weights: J*Cout must be <= 128");
+  if (J == 0) J = j_blocks(Cout);
+  const int NC = (Cin + 7) / 8, mpr = mmas_per_row(NC, KW);
   const int n_paired = (NC / 2) * KW;
   uint16_t* o = (uint16_t*)packed;
-  memset(o, 0, mpa_conv_tc_packed_bytes(Cin, Cout, KH, KW));
+  memset(o, 0, mpa_conv_tc_packed_bytes(Cin, Cout, KH, KW, J));
   for (int r = 0; r < KH + J - 1; ++r) {
     for (int q = 0; q < mpr; ++q) {
       uint16_t* tile = o + ((size_t)r * mpr + q) * (kATileBytes / 2);
@@ -624,16 +627,18 @@ int mpa_conv_tc_pack_weights(const float* w, void* packed, int Cin, int Cout, in
 
 int mpa_conv_tc_f16(const void* in_cp8, const void* w_packed, const float* bias, void* out, int out_mode, int sub_stride,
                     int sub_offset, int n_patches, int Cin, int Cout, int T, int F, int KH, int KW, int pitch, int pf, int pt,
-                    long long in_patch_stride_rows, int in_nc_stride, int out_nc_stride, int act, float act_param, int fmt,
-                    void* stream) {
+                    long long in_patch_stride_rows, int in_nc_stride, int out_nc_stride, int J, int row0, int n_rows, int act,
+                    float act_param, int fmt, void* stream) {
   MPA_CHECK_ARCH();
   MPA_REQUIRE(in_cp8 && w_packed && bias && out && n_patches > 0, "conv_tc: null argument");
   MPA_REQUIRE(Cout > 0 && Cout <= 128 && Cin > 0, "conv_tc: Cout must be in 1..128 (got %d)", Cout);
   MPA_REQUIRE((KH & 1) && (KW & 1), "conv_tc: odd kernel sizes only");
   MPA_REQUIRE(fmt == MPA_FMT_F16 || fmt == MPA_FMT_BF16, "conv_tc: fmt must be MPA_FMT_F16 or MPA_FMT_BF16");
-  MPA_REQUIRE(pitch % 16 == 0 && pitch >= 16 && pitch <= 256, "conv_tc: row pitch must be a multiple of 16 in 16..256 (got %d)", pitch);
+  const int N = (pitch + 15) / 16 * 16;      // MMA N: one padded image row (columns >= pitch are never stored)
+  MPA_REQUIRE(N >= 16 && N <= 256 && (pitch % 16 == 0 || KW == 1), "conv_tc: row pitch %d must be a multiple of 16 (<= 256) unless KW == 1", pitch);
   MPA_REQUIRE(pf >= KW / 2 && pitch - F >= KW / 2 && pitch >= pf + F, "conv_tc: pitch %d / left pad %d too small for F=%d KW=%d", pitch, pf, F, KW);
-  MPA_REQUIRE(pt >= 1, "conv_tc: at least one guard row above and below each plane is required");
+  MPA_REQUIRE(pt >= 1 || KW == 1, "conv_tc: at least one guard row above and below each plane is required (KW > 1)");
+  MPA_REQUIRE(J >= 0 && J * Cout <= 128 && row0 >= 0 && n_rows >= 0 && row0 + n_rows <= T, "conv_tc: bad J / row window");
   MPA_REQUIRE(((uintptr_t)in_cp8 & 15) == 0 && ((uintptr_t)w_packed & 15) == 0 && ((uintptr_t)out & 15) == 0, "conv_tc: 16-byte alignment required");
   MPA_REQUIRE(out_mode == 0 || (out_mode == 1 && sub_stride >= 1 && sub_offset >= 0 && sub_offset < sub_stride), "conv_tc: bad output mode");
   ConvTcParams p;
@@ -649,10 +654,13 @@ int mpa_conv_tc_f16(const void* in_cp8, const void* w_packed, const float* bias,
   p.n_patches = n_patches;
   p.NC = (Cin + 7) / 8;
   p.Cout = Cout;
-  p.J = j_blocks(Cout);
-  p.T = T; p.F = F; p.KH = KH; p.KW = KW; p.P = pitch; p.pf = pf;
+  p.J = J > 0 ? J : j_blocks(Cout);
+  p.T = T; p.F = F; p.KH = KH; p.KW = KW; p.P = pitch; p.N = N; p.pf = pf;
+  p.row0 = row0;
+  p.T_out = n_rows > 0 ? n_rows : T - row0;
+  p.row_end = row0 + p.T_out;
   p.pt_out = pt;
-  p.TP_out = T + 2 * pt;
+  p.TP_out = p.T_out + 2 * pt;
   p.NCo = (Cout + 7) / 8;
   const long long TP = T + 2 * pt;
   if (in_patch_stride_rows <= 0) {
@@ -669,15 +677,15 @@ int mpa_conv_tc_f16(const void* in_cp8, const void* w_packed, const float* bias,
   }
   MPA_REQUIRE(in_nc_stride == 0 || in_nc_stride >= p.NC, "conv_tc: in_nc_stride %d < %d input chunks", in_nc_stride, p.NC);
   MPA_REQUIRE(out_nc_stride == 0 || out_nc_stride >= p.NCo, "conv_tc: out_nc_stride %d < %d output chunks", out_nc_stride, p.NCo);
-  p.out_patch_stride = (long long)(out_nc_stride > 0 ? out_nc_stride : p.NCo) * (out_mode == 0 ? (long long)p.TP_out * pitch : (long long)T * p.F_out) * 8;
+  p.out_patch_stride = (long long)(out_nc_stride > 0 ? out_nc_stride : p.NCo) * (out_mode == 0 ? (long long)p.TP_out * pitch : (long long)p.T_out * p.F_out) * 8;
   p.mmas_per_row = mmas_per_row(p.NC, KW);
-  p.n_groups = (T + p.J - 1) / p.J;
+  p.n_groups = (p.T_out + p.J - 1) / p.J;
   p.n_units = n_patches * p.n_groups;
-  p.slab_px = (pitch + 2 * (KW / 2) + 1 + 7) / 8 * 8;
+  p.slab_px = (N + 2 * (KW / 2) + 1 + 7) / 8 * 8;
   p.act = act;
   p.act_param = act_param;
   const uint32_t f = (fmt == MPA_FMT_BF16) ? 1u : 0u;
-  p.idesc = (1u << 4) | (f << 7) | (f << 10) | ((uint32_t)(pitch >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  p.idesc = (1u << 4) | (f << 7) | (f << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   const size_t b_bytes = (size_t)kNumBStages * p.NC * p.slab_px * 16;
   const size_t tail = 256 + (size_t)(p.mmas_per_row + 8) * 4 + 128 + 4 * 32 * kEpiPitch * 2;   // barriers, table, staging
   int a_stages = kMaxAStages;

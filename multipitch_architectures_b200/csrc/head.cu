@@ -14,6 +14,11 @@ namespace mpa {
 constexpr int kC2Max = 32, kC3Max = 16, kTBlk = 15;
 
 template <int FMT>
+__device__ __forceinline__ float cvt_in(uint16_t v) {
+  return FMT == MPA_FMT_BF16 ? __bfloat162float(__ushort_as_bfloat16(v)) : __half2float(__ushort_as_half(v));
+}
+
+template <int FMT>
 __device__ __forceinline__ void unpack8(const uint4& q, float* v) {
   if (FMT == MPA_FMT_BF16) {
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
@@ -114,6 +119,37 @@ __global__ void __launch_bounds__(256) head_tail_kernel(const uint4* __restrict_
   out[(size_t)b * Fo + f] = 1.f / (1.f + expf(-o));
 }
 
+// conv4.0 (1x1, C2 -> C3) + LeakyReLU + conv4.3 (1x1, C3 -> 1) + sigmoid on the (already activated) conv3 output held in compact
+// 16-bit planes [B][ceil(C2/8)][R][Fo][8]; any C2 / C3; one CTA per (patch, row), hidden vector staged in shared memory.
+template <int FMT>
+__global__ void __launch_bounds__(128) head_tail2_kernel(const uint16_t* __restrict__ h, const float* __restrict__ w40, const float* __restrict__ b40,
+                                                         const float* __restrict__ w43, const float* __restrict__ b43, float* __restrict__ out, int R,
+                                                         int Fo, int C2, int C3, float a) {
+  extern __shared__ float sm[];
+  float* hs = sm;                          // [C2][Fo]
+  float* ws = sm + (size_t)C2 * Fo;        // [C3][C2]
+  const int b = blockIdx.x / R, r = blockIdx.x % R;
+  const int NC2 = (C2 + 7) / 8;
+  for (int e = threadIdx.x; e < NC2 * Fo * 8; e += blockDim.x) {
+    const int c8 = e & 7, f = (e >> 3) % Fo, ck = e / (8 * Fo);
+    const int co = ck * 8 + c8;
+    if (co < C2) hs[co * Fo + f] = cvt_in<FMT>(h[((((size_t)b * NC2 + ck) * R + r) * Fo + f) * 8 + c8]);
+  }
+  for (int e = threadIdx.x; e < C3 * C2; e += blockDim.x) ws[e] = w40[e];
+  __syncthreads();
+  for (int f = threadIdx.x; f < Fo; f += blockDim.x) {
+    float o = b43[0];
+    for (int c3 = 0; c3 < C3; ++c3) {
+      float g = b40[c3];
+      const float* wr = ws + (size_t)c3 * C2;
+      for (int co = 0; co < C2; ++co) g = fmaf(wr[co], hs[co * Fo + f], g);
+      g = g >= 0.f ? g : a * g;
+      o = fmaf(w43[c3], g, o);
+    }
+    out[((size_t)b * R + r) * Fo + f] = 1.f / (1.f + expf(-o));
+  }
+}
+
 }  // namespace mpa
 
 using namespace mpa;
@@ -134,5 +170,22 @@ extern "C" int mpa_head_tail_cp8(const void* x_cp8, const float* w3, const float
     head_tail_kernel<MPA_FMT_F16><<<ceil_div(B, pb), 256, smem, (cudaStream_t)stream>>>((const uint4*)x_cp8, w3, b3, w40, b40, w43, b43, out, B,
                                                                                         C1, T, Fo, C2, C3, pb, a_lrelu);
   MPA_CHECK_LAUNCH("head_tail");
+  return MPA_OK;
+}
+
+extern "C" int mpa_head_tail2_cp8(const void* h_cp8, const float* w40, const float* b40, const float* w43, const float* b43, float* out, int B,
+                                  int R, int Fo, int C2, int C3, float a_lrelu, int fmt, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(h_cp8 && w40 && b40 && w43 && b43 && out && B > 0 && R > 0 && Fo > 0 && C2 > 0 && C3 > 0, "head_tail2: bad argument");
+  const size_t smem = ((size_t)C2 * Fo + (size_t)C3 * C2) * sizeof(float);
+  MPA_REQUIRE(smem <= 200 * 1024, "head_tail2: C2=%d C3=%d Fo=%d need %zu B of shared memory", C2, C3, Fo, smem);
+  if (fmt == MPA_FMT_BF16) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(head_tail2_kernel<MPA_FMT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    head_tail2_kernel<MPA_FMT_BF16><<<B * R, 128, smem, (cudaStream_t)stream>>>((const uint16_t*)h_cp8, w40, b40, w43, b43, out, R, Fo, C2, C3, a_lrelu);
+  } else {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(head_tail2_kernel<MPA_FMT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    head_tail2_kernel<MPA_FMT_F16><<<B * R, 128, smem, (cudaStream_t)stream>>>((const uint16_t*)h_cp8, w40, b40, w43, b43, out, R, Fo, C2, C3, a_lrelu);
+  }
+  MPA_CHECK_LAUNCH("head_tail2");
   return MPA_OK;
 }

@@ -79,26 +79,38 @@ def head_f32(cache, model, x, a):
 
 
 def head_tc(cache, model, zc, a):
-    """Head on a CP8 activation: conv2 (3x3, stride (1,3)) runs on the tensor cores as the stride-1 3x3 convolution
-    whose epilogue keeps columns 1, 4, 7, ... (exactly the strided outputs), then maxpool(13,1) and the fused tail."""
+    """Head on a CP8 activation, all on the tensor cores:
+      conv2 (3x3, stride (1,3), pad (1,0)) = the stride-1 3x3 convolution whose epilogue keeps columns 1, 4, 7, ...;
+      maxpool(13,1); conv3 (75x1, VALID) = the 'same' 75x1 convolution restricted to the rows whose window fits;
+      conv4.0 / conv4.3 / sigmoid in one small kernel.  Channel counts are padded to multiples of 8 with zero weights."""
     conv2, conv3, c40, c43 = model.conv2[0], model.conv3[0], model.conv4[0], model.conv4[3]
-    ok2 = (tuple(conv2.kernel_size) == (3, 3) and tuple(conv2.stride) == (1, 3) and tuple(conv2.padding) == (1, 0) and zc.F % 3 == 0)
-    if not ok2:
+    KH3 = conv3.kernel_size[0]
+    ok = (tuple(conv2.kernel_size) == (3, 3) and tuple(conv2.stride) == (1, 3) and tuple(conv2.padding) == (1, 0) and zc.F % 3 == 0
+          and conv3.kernel_size[1] == 1 and (KH3 & 1) and tuple(conv3.padding) == (0, 0) and zc.T >= KH3
+          and tuple(c40.kernel_size) == (1, 1) and tuple(c43.kernel_size) == (1, 1) and c43.weight.shape[0] == 1)
+    if not ok:
         return head_f32(cache, model, ops.cp8_to_nchw(zc), a)
-    C1 = conv2.weight.shape[0]
-    yc = ops.CP8(zc.B, C1, zc.T, zc.F // 3, zc.F // 3, 0, 0, zc.buf.device, fmt=zc.fmt, zero=False)
-    for wp, b, c0, c in _folded_tc(cache, 'conv2', conv2, None, zc.fmt, zc.buf.device):
+    dev, fmt = zc.buf.device, zc.fmt
+    C1p = (conv2.weight.shape[0] + 7) // 8 * 8
+    yc = ops.compact_cp8(zc.B, C1p, zc.T, zc.F // 3, dev, fmt)
+    for wp, b, c0, c in _folded_tc(cache, 'conv2', conv2, None, fmt, dev):
         ops.conv_tc(zc, wp, b, c, (3, 3), ops.ACT_LRELU, a, subsample=(3, 1), out=yc.channels(c0, c))
     yc = ops.pool_time_res_cp8(yc, 13)
-    fused = (conv3.kernel_size[0] == zc.T and conv3.kernel_size[1] == 1 and tuple(c43.kernel_size) == (1, 1)
-             and conv3.weight.shape[0] <= 32 and c40.weight.shape[0] <= 16 and c43.weight.shape[0] == 1 and yc.F <= 256)
-    if fused:
-        o = ops.head_tail(yc, conv3.weight, conv3.bias, c40.weight, c40.bias, c43.weight, c43.bias, a)
-        return o.reshape(o.shape[0], 1, 1, o.shape[1])
-    y = ops.cp8_to_nchw(yc)
-    y = conv_f32(cache, 'conv3', conv3, y, ops.ACT_LRELU, a)
-    y = conv_f32(cache, 'conv4.0', c40, y, ops.ACT_LRELU, a)
-    return conv_f32(cache, 'conv4.3', c43, y, ops.ACT_SIGMOID)
+    C2p = (conv3.weight.shape[0] + 7) // 8 * 8
+    n_rows = zc.T - KH3 + 1
+    hc = ops.compact_cp8(zc.B, C2p, n_rows, yc.F, dev, fmt)
+    for wp, b, c0, c in _folded_tc(cache, 'conv3', conv3, None, fmt, dev, cin_pad=C1p, J=1):
+        ops.conv_tc(yc, wp, b, c, (KH3, 1), ops.ACT_LRELU, a, out=hc.channels(c0, c), J=1, rows=(KH3 // 2, n_rows))
+    o = ops.head_tail2(hc, _pad_cols(c40.weight.reshape(c40.weight.shape[0], -1), C2p), c40.bias, c43.weight, c43.bias, a)
+    return o.reshape(zc.B, 1, n_rows, yc.F)
+
+
+def _pad_cols(w, n):
+    if w.shape[1] == n:
+        return w
+    out = torch.zeros(w.shape[0], n, dtype=w.dtype, device=w.device)
+    out[:, :w.shape[1]] = w.detach()
+    return out
 
 
 def cnn_blocks(model):
@@ -181,8 +193,10 @@ def unet_tc_eligible(model, x):
     return all(c % 8 == 0 for c in chans + ups) and x.shape[3] + LEVEL_PF <= 256 and x.shape[2] >= 32
 
 
-def _folded_tc(cache, name, conv, bn, fmt, dev):
-    """Packed operand(s) of conv (+ eval BatchNorm folded): list of (packed weights, bias, cout0, cout) per <=128 block."""
+def _folded_tc(cache, name, conv, bn, fmt, dev, cin_pad=None, J=0):
+    """Packed operand(s) of conv (+ eval BatchNorm folded): list of (packed weights, bias, cout0, cout) per <=128 block.
+    The output channels are padded to a multiple of 8 (zero weights / bias) so that every block ends on a chunk
+    boundary; `cin_pad` appends zero input channels (when the producer padded its outputs the same way)."""
     params = [conv.weight, conv.bias] + ([bn.weight, bn.bias, bn.running_mean, bn.running_var] if bn is not None else [])
 
     def build():
@@ -191,12 +205,21 @@ def _folded_tc(cache, name, conv, bn, fmt, dev):
             s = bn.weight / torch.sqrt(bn.running_var + bn.eps)
             w = w * s[:, None, None, None]
             b = (b - bn.running_mean) * s + bn.bias
+        Cout, Cin = w.shape[0], w.shape[1]
+        Cp = (Cout + 7) // 8 * 8
+        Ci = Cin if cin_pad is None else cin_pad
+        if Cp != Cout or Ci != Cin:
+            w2 = torch.zeros(Cp, Ci, w.shape[2], w.shape[3], dtype=w.dtype, device=w.device)
+            w2[:Cout, :Cin] = w
+            b2 = torch.zeros(Cp, dtype=b.dtype, device=b.device)
+            b2[:Cout] = b
+            w, b = w2, b2
         out = []
-        for c0 in range(0, w.shape[0], 128):
-            c1 = min(w.shape[0], c0 + 128)
-            out.append((ops.conv_tc_pack(w[c0:c1].contiguous(), dev, fmt), b[c0:c1].contiguous(), c0, c1 - c0))
+        for c0 in range(0, Cp, 128):
+            c1 = min(Cp, c0 + 128)
+            out.append((ops.conv_tc_pack(w[c0:c1].contiguous(), dev, fmt, J), b[c0:c1].contiguous(), c0, c1 - c0))
         return out
-    return cache.get(f'{name}:tcfold{fmt}', params, build)
+    return cache.get(f'{name}:tcfold{fmt}:{cin_pad}:{J}', params, build)
 
 
 def conv_bn_relu_tc(cache, name, conv, bn, src, dst, act=ops.ACT_RELU, a=0.0):

@@ -128,7 +128,9 @@ class CP8:
 
     def like(self, C=None):
         C = self.C if C is None else C
-        return CP8(self.B, C, self.T, self.F, self.pitch, self.pf, self.pt, self.buf.device, fmt=self.fmt, zero=not self.compact)
+        if self.compact:
+            return compact_cp8(self.B, C, self.T, self.F, self.buf.device, self.fmt)
+        return CP8(self.B, C, self.T, self.F, self.pitch, self.pf, self.pt, self.buf.device, fmt=self.fmt)
 
     def channels(self, c0, C):
         """View of channels [c0, c0+C) (both multiples of 8) of this buffer."""
@@ -161,41 +163,52 @@ def cp8_to_nchw(a):
     return out
 
 
-def conv_tc_pack(w, device, fmt=FMT_F16):
-    """[Cout,Cin,KH,KW] fp32 (any device) -> packed 16-bit A-operand tiles on `device` (host-side one-off)."""
+def conv_tc_pack(w, device, fmt=FMT_F16, J=0):
+    """[Cout,Cin,KH,KW] fp32 (any device) -> packed 16-bit A-operand tiles on `device` (host-side one-off).
+    J = output rows per work unit (0: floor(128/Cout)); pass the same J to conv_tc."""
     import ctypes
     import numpy as np
     wh = np.ascontiguousarray(w.detach().float().cpu().numpy())
     Cout, Cin, KH, KW = wh.shape
-    nbytes = _lib.lib().mpa_conv_tc_packed_bytes(Cin, Cout, KH, KW)
+    nbytes = _lib.lib().mpa_conv_tc_packed_bytes(Cin, Cout, KH, KW, J)
     if nbytes == 0:
         raise _lib.MpaError(f'conv_tc cannot pack Cin={Cin} Cout={Cout} K={KH}x{KW}')
     packed = np.zeros(nbytes, dtype=np.uint8)
     rc = _lib.lib().mpa_conv_tc_pack_weights(wh.ctypes.data_as(ctypes.c_void_p), packed.ctypes.data_as(ctypes.c_void_p),
-                                             Cin, Cout, KH, KW, fmt)
+                                             Cin, Cout, KH, KW, fmt, J)
     if rc != 0:
         raise _lib.MpaError('mpa_conv_tc_pack_weights: ' + _lib.last_error())
     return torch.from_numpy(packed).to(device)
 
 
+def compact_cp8(n, C, T, F, device, fmt):
+    """Un-padded planes [n][C/8][T][F][8]; one spare item of slack so that KW == 1 convolutions may over-read the last row."""
+    buf = torch.empty(n + 1, (C + 7) // 8, T, F, 8, dtype=_FMT_DTYPE[fmt], device=device)
+    return CP8(n, C, T, F, F, 0, 0, device, fmt=fmt, buf=buf)
+
+
 def conv_tc(a, w_packed, bias, Cout, ksize, act=ACT_NONE, act_param=0.0, out=None, n_patches=None,
-            patch_stride_rows=0, T=None, subsample=None):
+            patch_stride_rows=0, T=None, subsample=None, J=0, rows=None):
     """a: CP8 input (materialised patches) or, with patch_stride_rows>0, one shared frame-major plane.
-    subsample=(stride, offset): compact output CP8 (pitch = F_out, no padding) keeping columns offset + k*stride."""
+    subsample=(stride, offset): compact output CP8 (pitch = F_out, no padding) keeping columns offset + k*stride.
+    rows=(row0, n_rows): compute / store only that window of output rows (a VALID KHx1 conv = window (KH//2, T-KH+1))."""
     T = a.T if T is None else T
     n = a.B if n_patches is None else n_patches
+    row0, n_rows = rows if rows is not None else (0, T)
     if subsample is None:
         if out is None:
-            out = CP8(n, Cout, T, a.F, a.pitch, a.pf, a.pt, a.buf.device, fmt=a.fmt)
-        mode, stride, offset = 0, 1, 0
+            out = CP8(n, Cout, n_rows, a.F, a.pitch, a.pf, a.pt, a.buf.device, fmt=a.fmt) if not a.compact else \
+                compact_cp8(n, Cout, n_rows, a.F, a.buf.device, a.fmt)
+        mode, stride, offset = (0, 1, 0) if not out.compact else (1, 1, 0)
     else:
         stride, offset = subsample
         F_out = (a.F - offset + stride - 1) // stride
         if out is None:
-            out = CP8(n, Cout, T, F_out, F_out, 0, 0, a.buf.device, fmt=a.fmt, zero=False)
+            out = compact_cp8(n, Cout, n_rows, F_out, a.buf.device, a.fmt)
         mode = 1
     call('conv_tc_f16', a.ptr(), w_packed, bias, out.ptr(), mode, stride, offset, n, a.C, Cout, T, a.F, ksize[0], ksize[1], a.pitch,
-         a.pf, a.pt, _lib.i64(patch_stride_rows), 0 if patch_stride_rows else a.ncs, out.ncs, act, float(act_param), a.fmt, stream_ptr())
+         a.pf, a.pt, _lib.i64(patch_stride_rows), 0 if patch_stride_rows else a.ncs, out.ncs, J, row0, n_rows, act, float(act_param), a.fmt,
+         stream_ptr())
     return out
 
 
@@ -229,4 +242,15 @@ def head_tail(x, w3, b3, w40, b40, w43, b43, a_lrelu):
     out = torch.empty(x.B, x.F, dtype=torch.float32, device=x.buf.device)
     assert x.ncs == x.NC and x.chunk0 == 0
     call('head_tail_cp8', x.ptr(), w3, b3, w40, b40, w43, b43, out, x.B, x.C, x.T, x.F, C2, C3, float(a_lrelu), x.fmt, stream_ptr())
+    return out
+
+
+def head_tail2(h, w40, b40, w43, b43, a_lrelu):
+    """h: compact CP8 [B][NC2][R][Fo][8] (activated conv3 output) -> [B,R,Fo] fp32 = sigmoid(conv4.3(lrelu(conv4.0(h))))."""
+    C3 = w40.shape[0]
+    out = torch.empty(h.B, h.T, h.F, dtype=torch.float32, device=h.buf.device)
+    assert h.ncs == h.NC and h.chunk0 == 0
+    w40f = w40.reshape(C3, -1)
+    call('head_tail2_cp8', h.ptr(), w40f[:, :h.C].contiguous() if w40f.shape[1] != h.C else w40f.contiguous(), b40, w43.reshape(-1).contiguous(),
+         b43, out, h.B, h.T, h.F, h.C, C3, float(a_lrelu), h.fmt, stream_ptr())
     return out

@@ -24,9 +24,11 @@ def test_every_declared_symbol_is_exported(lib):
 
 def test_version_and_pure_host_entry_points(lib):
     assert lib.mpa_version() >= 100
-    assert lib.mpa_conv_tc_packed_bytes(40, 40, 15, 15) == 17 * 38 * 4096
-    assert lib.mpa_conv_tc_packed_bytes(6, 40, 15, 15) == 17 * 8 * 4096
-    assert lib.mpa_conv_tc_packed_bytes(40, 200, 15, 15) == 0
+    assert lib.mpa_conv_tc_packed_bytes(40, 40, 15, 15, 0) == 17 * 38 * 4096
+    assert lib.mpa_conv_tc_packed_bytes(6, 40, 15, 15, 0) == 17 * 8 * 4096
+    assert lib.mpa_conv_tc_packed_bytes(40, 200, 15, 15, 0) == 0
+    assert lib.mpa_conv_tc_packed_bytes(40, 30, 75, 1, 1) == 75 * 3 * 4096       # conv3 as a J=1 'same' 75x1 convolution
+    assert lib.mpa_conv_tc_packed_bytes(40, 80, 3, 3, 2) == 0                    # J*Cout > 128
 
 
 def test_weight_packing_layout():

@@ -171,6 +171,37 @@ def test_conv_tc_subsampled_output_pool13_and_head_tail(ops, prec, dt):
     assert (got.cpu() - ref.reshape(B, 72)).abs().max() < 1e-5
 
 
+@pytest.mark.parametrize('C1,C2,C3,T', [(40, 30, 10, 75), (100, 80, 50, 75), (180, 150, 100, 75), (20, 10, 1, 90)])
+def test_conv3_on_tensor_cores_and_general_tail(ops, C1, C2, C3, T):
+    """conv3 (75x1 VALID) as the row-windowed 'same' convolution on compact planes (KW == 1, pitch 72 -> MMA N 80), with
+    channel padding to multiples of 8 and co-blocks of 128, then the general conv4 tail; against torch fp64/fp32."""
+    from multipitch_architectures_b200.libdl.nn_models import _exec
+    import torch.nn as nn
+    B, Fo = 3, 72
+    y = rnd(B, C1, T, Fo, seed=1)
+    conv3, c40, c43 = nn.Conv2d(C1, C2, (75, 1)), nn.Conv2d(C2, C3, (1, 1)), nn.Conv2d(C3, 1, (1, 1))
+    yr = y.half().double()
+    h_ref = F.leaky_relu(F.conv2d(yr, conv3.weight.detach().half().double(), conv3.bias.detach().double()), 0.3).float()
+    C1p, C2p = (C1 + 7) // 8 * 8, (C2 + 7) // 8 * 8
+    yc = ops.compact_cp8(B, C1p, T, Fo, 'cuda', ops.FMT_F16)
+    yc.buf.zero_()
+    ops.nchw_to_cp8(y.cuda(), out=yc.channels(0, C1))
+    conv3, c40, c43 = conv3.cuda(), c40.cuda(), c43.cuda()
+    cache = _exec.ParamCache()
+    n_rows = T - 74
+    hc = ops.compact_cp8(B, C2p, n_rows, Fo, 'cuda', ops.FMT_F16)
+    for wp, b, c0, c in _exec._folded_tc(cache, 'conv3', conv3, None, ops.FMT_F16, 'cuda', cin_pad=C1p, J=1):
+        ops.conv_tc(yc, wp, b, c, (75, 1), ops.ACT_LRELU, 0.3, out=hc.channels(c0, c), J=1, rows=(37, n_rows))
+    h = ops.cp8_to_nchw(hc).cpu()
+    assert tuple(h.shape) == (B, C2p, n_rows, Fo)
+    assert (h[:, :C2] - h_ref).abs().max() < 2.0 ** -11 * h_ref.abs().max().item() + 1e-4
+    assert float(h[:, C2:].abs().max() if C2p > C2 else 0.0) == 0.0
+    o = ops.head_tail2(hc, _exec._pad_cols(c40.weight.reshape(C3, -1), C2p), c40.bias, c43.weight, c43.bias, 0.3).cpu()
+    hq = h[:, :C2]
+    ref = torch.sigmoid(F.conv2d(F.leaky_relu(F.conv2d(hq, c40.weight.cpu(), c40.bias.cpu()), 0.3), c43.weight.cpu(), c43.bias.cpu()))
+    assert (o - ref.reshape(B, n_rows, Fo)).abs().max() < 1e-5
+
+
 def test_encoder_layer(ops):
     from oracle import nn_oracle as NO
     from tests.refshapes import build_model
