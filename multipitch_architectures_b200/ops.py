@@ -133,8 +133,8 @@ class CP8:
         return CP8(self.B, C, self.T, self.F, self.pitch, self.pf, self.pt, self.buf.device, fmt=self.fmt)
 
     def channels(self, c0, C):
-        """View of channels [c0, c0+C) (both multiples of 8) of this buffer."""
-        assert c0 % 8 == 0 and (C % 8 == 0 or c0 + C == self.C)
+        """View of channels [c0, c0+C) of this buffer (c0 a multiple of 8; a trailing partial chunk is allowed)."""
+        assert c0 % 8 == 0 and c0 + C <= (self.C + 7) // 8 * 8
         v = CP8.__new__(CP8)
         v.__dict__.update(self.__dict__)
         v.C, v.NC, v.chunk0 = C, (C + 7) // 8, self.chunk0 + c0 // 8
