@@ -19,8 +19,8 @@
 //   warp 0  producer : cp.async.bulk (1-D TMA) of activation row slabs and packed weight stages -> mbarriers
 //   warp 1  MMA      : one thread issues tcgen05.mma (kind::f16, fp16/bf16 in, fp32 accumulate in TMEM) from a
 //                      pre-built shared-memory table of B descriptors
-//   warps 2-5 epilogue: tcgen05.ld -> +bias -> activation -> 16-bit -> transposed through shared memory ->
-//                      16-byte coalesced CP8 stores
+//   warps 2-9 epilogue: two warps per TMEM lane quadrant, alternating 32-column chunks: tcgen05.ld -> +bias ->
+//                      activation -> 16-bit -> transposed through shared memory -> 16-byte coalesced CP8 stores
 //   The accumulator is double buffered in TMEM (2 x 224 of 512 columns): the epilogue of unit k overlaps the
 //   main loop of unit k+1.  Weights stream from L2 once per unit (36 B/clk/SM, ~30 % of L2 throughput).
 #include "common.cuh"
@@ -36,7 +36,7 @@ constexpr int kATileBytes = 2 * 128 * 16;     // one MMA's A tile: [2 k-slices][
 constexpr int kAStageBytes = kStageMMAs * kATileBytes;
 constexpr int kMaxAStages = 5;             // weight stages: as many as fit next to the activation slabs (>= 2)
 constexpr int kNumBStages = 2;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;                 // producer warp, MMA warp, 8 epilogue warps
 constexpr int kEpiPitch = 40;                 // 80-byte rows: conflict-free 16-byte reads in the transposing epilogue
 constexpr unsigned long long kWaitTimeoutNs = 4000000000ull;   // bounded waits: a protocol bug traps instead of hanging the GPU
 
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 128);
+      mbar_init(&acc_empty[i], kThreads - 64);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -297,7 +297,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
     const float bias = row_valid ? p.bias[co] : 0.f;
     // coalesced path: 8 consecutive lanes = the 8 channels of one chunk of one output row (needs Cout % 8 == 0)
     const bool staged = ((p.Cout & 7) == 0);
-    uint16_t* stile = epi_smem + (warp - 2) * (32 * kEpiPitch);     // [32 columns][kEpiPitch >= 32 lanes] 16-bit
+    const int ewarp = warp - 2;                                       // 0..7: two warps per TMEM lane quadrant
+    const int ehalf = ewarp >> 2;                                     // which half of the 32-column chunks this warp drains
+    uint16_t* stile = epi_smem + ewarp * (32 * kEpiPitch);            // [32 columns][kEpiPitch >= 32 lanes] 16-bit
+    // per-thread constants of the transposed store phase: the 4 channel-chunk groups of this warp's 32 accumulator rows
+    int grp_j[4], grp_plane[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int mg = quad * 32 + k * 8;
+      grp_j[k] = mg / p.Cout;
+      grp_plane[k] = (mg - grp_j[k] * p.Cout) >> 3;
+    }
+    const size_t plane_elems = (p.out_mode == 0) ? (size_t)p.TP_out * p.P * 8 : (size_t)p.T_out * p.F_out * 8;
+    const int row_pitch = (p.out_mode == 0) ? p.P : p.F_out;
     uint32_t k_unit = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++k_unit) {
       const int b = u / p.n_groups, g = u % p.n_groups;
@@ -305,37 +317,40 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
       const uint32_t buf = k_unit & 1u, acc_par = (k_unit >> 1) & 1u;
       mbar_wait(&acc_full[buf], acc_par);
       tc_fence_after();
-      for (int c0 = 0; c0 < p.N; c0 += 32) {
+      uint16_t* out_b = p.out + (size_t)b * p.out_patch_stride;
+      for (int c0 = ehalf * 32; c0 < p.N; c0 += 64) {
+        // which of the 32 columns of this chunk are stored at all (real, and selected by the sub-sampling)?
+        const int n = c0 + lane;
+        int fo = n - p.pf;
+        bool col_ok = (fo >= 0 && fo < p.F);
+        int col_out = n;
+        if (p.out_mode == 1) {
+          fo -= p.sub_offset;
+          col_ok = col_ok && fo >= 0 && (fo % p.sub_stride) == 0;
+          col_out = fo / p.sub_stride;
+        }
+        const uint32_t keep = __ballot_sync(0xffffffffu, col_ok);
+        if (keep == 0) continue;
         uint32_t v[32];
         tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256 + c0), v);
         tc_wait_ld();
         if (staged) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const float x = apply_act(__uint_as_float(v[i]) + bias, p.act, p.act_param);
-            stile[i * kEpiPitch + lane] = cvt16(x, p.fmt);
+            if ((keep >> i) & 1u) {
+              const float x = apply_act(__uint_as_float(v[i]) + bias, p.act, p.act_param);
+              stile[i * kEpiPitch + lane] = cvt16(x, p.fmt);
+            }
           }
           __syncwarp();
           // lane -> column c0+lane; pass k -> the k-th 8-lane group (= one channel chunk of one output row) of this warp
-          const int n = c0 + lane;
-          int fo = n - p.pf;
-          bool col_ok = (fo >= 0 && fo < p.F);
-          if (p.out_mode == 1) {
-            fo -= p.sub_offset;
-            col_ok = col_ok && fo >= 0 && (fo % p.sub_stride) == 0;
-            fo /= p.sub_stride;
-          }
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const int mg = quad * 32 + k * 8;                  // first accumulator row of the group
-            const int jg = mg / p.Cout, cog = mg - jg * p.Cout;
-            const int tg = p.row0 + g * p.J + jg;
-            if (col_ok && jg < p.J && tg < p.row_end) {
+            const int tg = p.row0 + g * p.J + grp_j[k];
+            if (col_ok && grp_j[k] < p.J && tg < p.row_end) {
               const uint4 val = *reinterpret_cast<const uint4*>(stile + lane * kEpiPitch + k * 8);
-              uint16_t* dst = (p.out_mode == 0)
-                                  ? p.out + (size_t)b * p.out_patch_stride + ((((size_t)(cog >> 3)) * p.TP_out + p.pt_out + tg - p.row0) * p.P + n) * 8
-                                  : p.out + (size_t)b * p.out_patch_stride + ((((size_t)(cog >> 3)) * p.T_out + tg - p.row0) * p.F_out + fo) * 8;
-              *reinterpret_cast<uint4*>(dst) = val;
+              const int orow = (p.out_mode == 0 ? p.pt_out : 0) + tg - p.row0;
+              *reinterpret_cast<uint4*>(out_b + (size_t)grp_plane[k] * plane_elems + ((size_t)orow * row_pitch + col_out) * 8) = val;
             }
           }
           __syncwarp();
@@ -490,9 +505,14 @@ __global__ void pool_time_res_cp8_kernel(const uint4* __restrict__ y, const uint
     const size_t in_plane = ((size_t)b * ncs_y + ck);
     const size_t base = (in_plane * TP + pt + t) * P + pf + f;
     uint4 c = y[base];
-    const int lo = max(-half, -t), hi = min(half, T - 1 - t);
-    for (int d = lo; d <= hi; ++d)
-      if (d != 0) max8<FMT>(c, y[base + (long long)d * P]);
+    if (half == 1) {
+      if (t > 0) max8<FMT>(c, y[base - P]);
+      if (t < T - 1) max8<FMT>(c, y[base + P]);
+    } else {
+      const int lo = max(-half, -t), hi = min(half, T - 1 - t);
+      for (int d = lo; d <= hi; ++d)
+        if (d != 0) max8<FMT>(c, y[base + (long long)d * P]);
+    }
     if (res) add8<FMT>(c, res[((((size_t)b * ncs_res + ck) * TP + pt + t) * P) + pf + f]);
     out[((((size_t)b * ncs_out + ck) * TP + pt + t) * P) + pf + f] = c;
   }
@@ -687,7 +707,7 @@ int mpa_conv_tc_f16(const void* in_cp8, const void* w_packed, const float* bias,
   const uint32_t f = (fmt == MPA_FMT_BF16) ? 1u : 0u;
   p.idesc = (1u << 4) | (f << 7) | (f << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   const size_t b_bytes = (size_t)kNumBStages * p.NC * p.slab_px * 16;
-  const size_t tail = 256 + (size_t)(p.mmas_per_row + 8) * 4 + 128 + 4 * 32 * kEpiPitch * 2;   // barriers, table, staging
+  const size_t tail = 256 + (size_t)(p.mmas_per_row + 8) * 4 + 128 + 8 * 32 * kEpiPitch * 2;   // barriers, table, staging
   int a_stages = kMaxAStages;
   while (a_stages > 2 && (size_t)a_stages * kAStageBytes + b_bytes + tail > 227 * 1024) --a_stages;
   p.a_stages = a_stages;
@@ -696,7 +716,7 @@ int mpa_conv_tc_f16(const void* in_cp8, const void* w_packed, const float* bias,
   off += 256 + (size_t)(p.mmas_per_row + 8) * 4;      // barriers + tmem slot (256 B), descriptor table
   off = (off + 127) / 128 * 128;
   p.epi_off = (int)off;
-  const size_t smem = off + 4 * 32 * kEpiPitch * 2;
+  const size_t smem = off + 8 * 32 * kEpiPitch * 2;
   MPA_REQUIRE(smem <= 227 * 1024, "conv_tc: needs %zu B of shared memory (Cin=%d pitch=%d)", smem, Cin, pitch);
   static thread_local size_t attr_set = 0;
   if (smem > attr_set) {
