@@ -60,7 +60,9 @@ def build_reference_model(name):
 
 def nn_goldens():
     torch.set_num_threads(8)
-    cases = [  # (model, batch, seed, mode)
+    cases = [  # (model, batch, seed, mode); mode 'default' = eval with the reference's default-init weight distribution
+        ('cnn_xs', 4, 111, 'default'), ('drcnn', 2, 114, 'default'), ('unet_m', 2, 116, 'default'), ('punet', 2, 118, 'default'),
+        ('saunet_l', 4, 120, 'default'),
         ('cnn_xs', 4, 11, 'eval'), ('drcnn_tiny', 3, 12, 'eval'), ('dcnn_tiny', 3, 13, 'eval'),
         ('drcnn', 2, 14, 'eval'), ('unet_tiny', 3, 15, 'eval'), ('unet_tiny', 3, 15, 'train'),
         ('unet_m', 2, 16, 'eval'), ('punet_tiny', 3, 17, 'eval'), ('punet', 2, 18, 'eval'),
@@ -69,7 +71,7 @@ def nn_goldens():
     out = {}
     for name, B, seed, mode in cases:
         m = build_reference_model(name)
-        sd = fill_state_dict(m.state_dict(), seed)
+        sd = fill_state_dict(m.state_dict(), seed, scheme='torch_default' if mode == 'default' else 'adversarial')
         m.load_state_dict(sd)
         for mod in m.modules():                                # dropout off: RNG-free parity
             if isinstance(mod, torch.nn.Dropout):

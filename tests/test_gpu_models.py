@@ -15,14 +15,15 @@ TOL_FP32 = 1e-3      # north_star bound for the exact path; observed values are 
 # the adversarial-gain test weights (logits up to +-18): fp16 has the operand precision of TF32 (11-bit significand).
 TOL_TC = {'fp16': 1.5e-2, 'bf16': 1.2e-1}
 
-CASES = [('cnn_xs', 'eval'), ('drcnn_tiny', 'eval'), ('dcnn_tiny', 'eval'), ('drcnn', 'eval'), ('unet_tiny', 'eval'),
+CASES = [('cnn_xs', 'default'), ('drcnn', 'default'), ('unet_m', 'default'), ('punet', 'default'), ('saunet_l', 'default'),
+         ('cnn_xs', 'eval'), ('drcnn_tiny', 'eval'), ('dcnn_tiny', 'eval'), ('drcnn', 'eval'), ('unet_tiny', 'eval'),
          ('unet_tiny', 'train'), ('unet_m', 'eval'), ('punet_tiny', 'eval'), ('punet', 'eval'), ('saunet_tiny', 'eval'),
          ('saunet_l', 'eval'), ('saunet_tiny', 'train')]
 
 
 def _load(name, seed, mode, **extra):
     m = build_model(name, **extra)
-    m.load_state_dict(fill_state_dict(m.state_dict(), seed))
+    m.load_state_dict(fill_state_dict(m.state_dict(), seed, scheme='torch_default' if mode == 'default' else 'adversarial'))
     m.p_dropout = 0.0
     for mod in m.modules():
         if hasattr(mod, 'p_dropout'):
@@ -47,6 +48,25 @@ def test_fp32_path_matches_reference_golden(nn_golden, name, mode):
     err = np.abs(y.cpu().numpy() - nn_golden[tag + '__y']).max()
     print(f'{tag}: max|diff| vs reference golden = {err:.2e}')
     assert err < TOL_FP32
+
+
+@pytest.mark.parametrize('prec', ['fp16', 'bf16'])
+@pytest.mark.parametrize('name', ['cnn_xs', 'drcnn', 'unet_m', 'punet', 'saunet_l'])
+def test_tensor_core_path_meets_1e3_on_default_init(nn_golden, name, prec):
+    """The north-star tolerance (1e-3 abs) on the prescribed parity setup (the reference constructors' default
+    weight initialisation): every BASELINE model, both 16-bit tensor-core formats, against the reference's own outputs."""
+    tag = f'{name}__default'
+    B, seed, _ = nn_golden[tag + '__meta']
+    B, seed = int(B), int(seed)
+    m = _load(name, seed, 'default', precision=prec)
+    with torch.no_grad():
+        y = m(synth_patches(B, seed).cuda())
+    if isinstance(y, tuple):
+        assert np.abs(y[1].cpu().numpy() - nn_golden[tag + '__n']).max() < 1e-3
+        y = y[0]
+    err = np.abs(y.cpu().numpy() - nn_golden[tag + '__y']).max()
+    print(f'{tag} {prec}: max|diff| vs reference golden = {err:.2e}')
+    assert err < 1e-3
 
 
 @pytest.mark.parametrize('prec', ['fp16', 'bf16'])

@@ -12,7 +12,8 @@ from oracle import nn_oracle as NO
 from tests.weights import MODEL_SPECS, fill_state_dict, synth_patches, synth_targets
 from tests.refshapes import reference_state_shapes
 
-NN_CASES = [('cnn_xs', 'eval'), ('drcnn_tiny', 'eval'), ('dcnn_tiny', 'eval'), ('drcnn', 'eval'),
+NN_CASES = [('cnn_xs', 'default'), ('drcnn', 'default'), ('unet_m', 'default'), ('punet', 'default'), ('saunet_l', 'default'),
+            ('cnn_xs', 'eval'), ('drcnn_tiny', 'eval'), ('dcnn_tiny', 'eval'), ('drcnn', 'eval'),
             ('unet_tiny', 'eval'), ('unet_tiny', 'train'), ('unet_m', 'eval'), ('punet_tiny', 'eval'),
             ('punet', 'eval'), ('saunet_tiny', 'eval'), ('saunet_l', 'eval'), ('saunet_tiny', 'train')]
 
@@ -31,7 +32,7 @@ def test_nn_oracle_matches_reference_golden(nn_golden, name, mode):
     B, seed, wsum = nn_golden[tag + '__meta']
     B, seed = int(B), int(seed)
     shapes = reference_state_shapes(name)
-    sd = fill_state_dict(shapes, seed)
+    sd = fill_state_dict(shapes, seed, scheme='torch_default' if mode == 'default' else 'adversarial')
     assert abs(float(sum(v.double().sum() for v in sd.values())) - wsum) < 1e-6 * max(1.0, abs(wsum))
     n_par = sum(v.numel() for k, v in sd.items() if not k.endswith(('running_mean', 'running_var', 'num_batches_tracked')))
     assert n_par == int(nn_golden[tag + '__nparams'][0])

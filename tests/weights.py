@@ -5,9 +5,15 @@ import numpy as np
 import torch
 
 
-def fill_state_dict(sd, seed):
-    """Return a new state_dict with the same keys/shapes/dtypes as `sd`, filled from default_rng(seed)
-    in key order.  Conv/linear weights ~ U(+-1.4*sqrt(3/fan_in)); norm scales ~ U(.5,1.5); biases small."""
+def fill_state_dict(sd, seed, scheme='adversarial'):
+    """Return a new state_dict with the same keys/shapes/dtypes as `sd`, filled from default_rng(seed) in key order.
+
+    scheme 'adversarial' (default): conv/linear weights ~ U(+-1.4*sqrt(3/fan_in)) (2.4x the PyTorch default gain: logits reach
+    +-18, outputs span 0..1), norm scales ~ U(.5,1.5), small biases — a deliberately harsh numerical test.
+    scheme 'torch_default': the distribution of the reference constructors' own initialisation ("reference
+    constructor default init"): weights and biases ~ U(+-1/sqrt(fan_in)), norm weight 1 / bias 0, running stats 0 / 1."""
+    if scheme == 'torch_default':
+        return _fill_torch_default(sd, seed)
     rng = np.random.default_rng(seed)
     out = {}
     for k, v in sd.items():
@@ -32,6 +38,34 @@ def fill_state_dict(sd, seed):
             a = rng.uniform(-0.1, 0.1, size=shape)
         out[k] = torch.from_numpy(np.asarray(a, dtype=np.float32)).to(v.dtype)
     return out
+
+
+def _fill_torch_default(sd, seed):
+    rng = np.random.default_rng(seed)
+    out, last_fan_in = {}, 1
+    for k, v in sd.items():
+        shape = tuple(v.shape)
+        if k.endswith('num_batches_tracked'):
+            out[k] = torch.tensor(0, dtype=v.dtype)
+            continue
+        if k.endswith('running_var'):
+            a = np.ones(shape)
+        elif k.endswith('running_mean'):
+            a = np.zeros(shape)
+        elif ('layernorm' in k) or (k.endswith('weight') and len(shape) == 1) or (k.endswith('bias') and _is_norm_bias(k, sd)):
+            a = np.ones(shape) if k.endswith('weight') else np.zeros(shape)
+        elif k.endswith('weight'):
+            last_fan_in = int(np.prod(shape[1:]))
+            a = rng.uniform(-1.0, 1.0, size=shape) / np.sqrt(last_fan_in)
+        else:
+            a = rng.uniform(-1.0, 1.0, size=shape) / np.sqrt(last_fan_in)
+        out[k] = torch.from_numpy(np.asarray(a, dtype=np.float32)).to(v.dtype)
+    return out
+
+
+def _is_norm_bias(k, sd):
+    w = k[:-4] + 'weight'
+    return w in sd and sd[w].dim() == 1 and (k[:-4] + 'running_mean') in sd
 
 
 def synth_patches(B, seed, T=75, C=6, F=216):
