@@ -164,8 +164,8 @@ extern "C" {
 
 size_t mpa_encoder_layer_workspace(int B, int E, int S, int mlp_dim) {
   size_t n = (size_t)B * S;
-  // tok, qkv(3E), att, proj, h1, mlp hidden, mlp out
-  return sizeof(float) * n * ((size_t)E * 7 + (size_t)mlp_dim) + 256;
+  // tok (E), qkv (3E), att (E), proj (E), h1 (E), mlp out (E) = 8E, plus the MLP hidden layer
+  return sizeof(float) * n * ((size_t)E * 8 + (size_t)mlp_dim) + 256;
 }
 
 int mpa_encoder_layer_f32(const float* x, float* out, int B, int E, int Th, int Fw, int num_heads, int mlp_dim, const float* pe,
