@@ -29,6 +29,7 @@ DRCNN_KW = dict(n_chan_input=6, n_chan_layers=[40, 40, 30, 10], n_prefilt_layers
 HCQT_KW = dict(fs=22050, fs_hcqt_target=50, bins_per_octave=36, num_octaves=6, num_harmonics=5, num_subharmonics=1)
 GFLOP_PER_PATCH = 48.574          # SURVEY 8a row N3 (2*MAC of every Conv2d at T=75)
 GFLOP_PREFILT_LAYER = 11.664      # one 40->40 15x15 layer per patch
+DRAM_BYTES_PER_PATCH_LAYER = (875.0e6 + 800.8e6) / 646     # measured by ncu for conv_tc_kernel (see profiles/README.md)
 
 
 def measured_peaks():
@@ -361,7 +362,9 @@ def main():
                 'e2e': {'value': e2e, 'unit': 'audio-s/s', 'h2d_bytes_per_step': int(clips_host[0].numel() * 4),
                         'd2h_bytes_per_step': int(n_frames * 72 * 4), 'ms_per_step': ms_e2e / args.steps},
                 'roofline': {'bound': 'tensor', 'kernel': 'conv_tc_kernel (tcgen05 15x15 40->40, bias+LeakyReLU epilogue)', 'achieved': achieved,
-                             'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': (achieved / peak_tf) if achieved else None, 'traffic': None,
+                             'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': (achieved / peak_tf) if achieved else None,
+                             'traffic': DRAM_BYTES_PER_PATCH_LAYER * per_launch_patches,
+                             'traffic_source': 'ncu --set full (profiles/r01_conv_tc_prefilt_ncu_raw.csv): dram__bytes_read.sum 0.875 GB + dram__bytes_write.sum 0.801 GB per 646-patch launch; algorithmic 0.89 + 0.84 GB',
                              'peak_source': peak_src, 'launches_timed': len(conv), 'avg_launch_ms': avg_ms,
                              'algorithmic_flops_per_launch': flops_launch, 'time_share_by_stage': shares},
                 'effective_tflops': value * FPS * GFLOP_PER_PATCH / 1e3}
