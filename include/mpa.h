@@ -207,6 +207,38 @@ int mpa_layernorm_cf_param_grad_f32(const float* x, const float* g_out, float* g
 int mpa_adamw_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                   float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
 
+/* ---- training of the U-Net / SAUnet family (configuration 5), fp32 NCHW ------------------------------------------------
+ * BatchNorm2d(train) [+ ReLU] backward (unet_cnns.py:50-57): x = conv output (BN input), out = block output (ReLU mask),
+ * stats = [mean | biased var] from mpa_bn_stats_f32; scratch2c: 2*C floats. */
+int mpa_bn_relu_bwd_f32(const float* x, const float* out, const float* dy, const float* stats, const float* w, float* dx,
+                        float* dw, float* db, float* scratch2c, int B, int C, int HW, float eps, int relu, void* stream);
+/* MaxPool2d((kh,kw), stride (sh,sw)) backward, floor mode, gradient to the first maximum of each window. */
+int mpa_maxpool2d_bwd_f32(const float* x, const float* g_out, float* g_in, int B, int C, int H, int W, int kh, int kw,
+                          int sh, int sw, void* stream);
+/* unet_up_concat_padding backward: g_cat [B,Cs+Cl,Hs,Ws] -> g_skip (= or +=) and g_low [B,Cl,Hl,Wl]. */
+int mpa_upsample2x_concat_bwd_f32(const float* g_cat, float* g_skip, int accumulate_skip, float* g_low, int B, int Cl,
+                                  int Hl, int Wl, int Cs, int Hs, int Ws, void* stream);
+/* encoder-layer stages as separate calls (transformer_enc_layer, unet_cnns.py:148-159) and their backward pieces. */
+int mpa_enc_gather_f32(const float* x, const float* pe, float* tok, int B, int E, int S, void* stream);
+int mpa_gemm_nt_f32(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, int relu, void* stream);
+int mpa_batch_axis_attention_f32(const float* qkv, float* out, int B, int S, int E, int num_heads, void* stream);
+int mpa_add_layernorm_tok_f32(const float* a, const float* b, const float* w, const float* bias, float* out_tok,
+                              float* out_nchw, long long n_tok, int E, int S, float eps, void* stream);
+/* C[M,N] (=|+=) A*B with mode 0: A [M,K] B [K,N]; mode 1: A [K,M] (transposed) B [K,N]. */
+int mpa_gemm_f32(const float* A, const float* B, float* C, int M, int N, int K, int mode, int accumulate, void* stream);
+int mpa_colsum_f32(const float* A, float* out, int M, int N, void* stream);
+/* y = LayerNorm_E(u)*w+b backward per token: g_u, and g_w / g_b (overwritten). */
+int mpa_layernorm_tok_bwd_f32(const float* u, const float* g_y, const float* w, float* g_u, float* g_w, float* g_b,
+                              long long n_tok, int E, float eps, void* stream);
+int mpa_batch_axis_attention_bwd_f32(const float* qkv, const float* g_o, float* g_qkv, int B, int S, int E, int num_heads,
+                                     void* stream);
+/* tokens [(b*S+s)][E] <-> NCHW [B,E,S] */
+int mpa_nchw_tokens_f32(const float* src, float* dst, int B, int E, int S, int to_tokens, void* stream);
+/* PUnet degree-of-polyphony loss (RETRAIN4_exp195f...rerun1.py:343-345): scale * CrossEntropyLoss(mean)(logits [B,K],
+ * class = (long) sum_p y_true[b,p]) forward (added to *loss_sum when accumulate_loss, else overwriting) + d/d logits. */
+int mpa_ce_count_fwd_bwd_f32(const float* logits, const float* y_true, float* loss_sum, float* grad_logits, int B, int K,
+                             int P, float scale, int accumulate_loss, void* stream);
+
 /* ---- N11: BCELoss(mean) on sigmoid outputs with the -100 log clamp, forward + d(loss)/d(pred) ---------- */
 int mpa_bce_fwd_bwd_f32(const float* y_pred, const float* y_true, float* loss_sum, float* grad_pred, long long n,
                         void* stream);

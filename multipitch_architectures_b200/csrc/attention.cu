@@ -213,3 +213,43 @@ int mpa_encoder_layer_f32(const float* x, float* out, int B, int E, int Th, int 
 }
 
 }  // extern "C"
+
+// ---- the same stages as separate entry points (the training path interleaves dropout and keeps every intermediate) --------
+extern "C" {
+
+int mpa_enc_gather_f32(const float* x, const float* pe, float* tok, int B, int E, int S, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(x && tok && B > 0 && E > 0 && S > 0, "enc_gather: bad argument");
+  const long long n = (long long)B * S * E;
+  enc_gather_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, pe, tok, n, E, S);
+  MPA_CHECK_LAUNCH("enc_gather");
+  return MPA_OK;
+}
+
+int mpa_gemm_nt_f32(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, int relu, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(A && W && C && M > 0 && N > 0 && K > 0, "gemm_nt: bad argument");
+  gemm_nt_kernel<<<dim3(ceil_div(N, 64), ceil_div(M, 64)), 256, 0, (cudaStream_t)stream>>>(A, W, bias, C, M, N, K, relu);
+  MPA_CHECK_LAUNCH("gemm_nt");
+  return MPA_OK;
+}
+
+int mpa_batch_axis_attention_f32(const float* qkv, float* out, int B, int S, int E, int num_heads, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(qkv && out && B > 0 && S > 0 && E > 0 && num_heads > 0 && E % num_heads == 0 && E / num_heads <= 64, "attention: bad argument");
+  const int hd = E / num_heads;
+  batch_axis_attention_kernel<<<S * num_heads, 64, 2 * (size_t)B * hd * sizeof(float), (cudaStream_t)stream>>>(qkv, out, B, S, E, num_heads);
+  MPA_CHECK_LAUNCH("batch_axis_attention");
+  return MPA_OK;
+}
+
+int mpa_add_layernorm_tok_f32(const float* a, const float* b, const float* w, const float* bias, float* out_tok, float* out_nchw, long long n_tok,
+                              int E, int S, float eps, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(a && b && w && bias && (out_tok || out_nchw) && n_tok > 0 && E > 0 && E <= 1024 && S > 0, "add_layernorm_tok: bad argument");
+  add_ln_kernel<<<(unsigned)n_tok, 128, 0, (cudaStream_t)stream>>>(a, b, w, bias, out_tok, out_nchw, E, S, eps);
+  MPA_CHECK_LAUNCH("add_ln");
+  return MPA_OK;
+}
+
+}  // extern "C"

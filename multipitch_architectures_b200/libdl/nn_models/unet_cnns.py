@@ -115,9 +115,17 @@ class _UnetBase(_MpaModel):
         x = _exec._check_input(x, self.n_chan_input, self.n_bins_in)
         if x.shape[2] < 75:
             raise ValueError('U-Net models need at least 75 frames of context')
-        if torch.is_grad_enabled() and self.training:
-            raise NotImplementedError('U-Net training (backward) is not part of this round; wrap inference in torch.no_grad()')
-        self._guard_training()
+        if self.training:
+            # train mode (BatchNorm batch statistics, dropout): the tape-driven training path, with or without autograd recording
+            from ...training_unet import unet_forward_train, unet_train_forward
+            if torch.is_grad_enabled():
+                out = unet_forward_train(self, x)
+                return out if isinstance(out, tuple) else (out, None)
+            self._train_calls = getattr(self, '_train_calls', 0) + 1
+            y, n_pred, _ = unet_train_forward(self, x, {}, getattr(self, 'dropout_seed', 0x5EED), self._train_calls)
+            return y.d, (n_pred.d if n_pred is not None else None)
+        if torch.is_grad_enabled() and x.requires_grad:
+            raise NotImplementedError('eval-mode forward does not record gradients; call .train() (reference scripts train in train mode)')
         train = self._bn_train()
         if _exec.unet_tc_eligible(self, x):
             y, x5c = _exec.unet_forward_tc(self, x)
@@ -159,10 +167,6 @@ class simple_u_net_doubleselfattn(_UnetBase):
         self._build_up(n_chan_layers, scalefac, **kw)
         _head(self, n_chan_layers[0], n_chan_layers, n_bins_in, n_bins_out, a_lrelu, p_dropout)
 
-    def _guard_training(self):
-        if self.training and (self.p_dropout > 0 or self.attention1.p_dropout > 0):
-            raise NotImplementedError('train-mode forward with dropout>0 is not available; call .eval() for inference')
-
     def _bottleneck(self, x5):
         return self.attention2.run(self.attention1.run(x5))
 
@@ -186,6 +190,8 @@ class simple_u_net_polyphony_classif_softmax(_UnetBase):
 
     def forward(self, x):
         y, x5 = self._run(x)
+        if self.training:
+            return y, x5                     # the training path evaluates convP itself (x5 slot = n_pred)
         p = _exec.conv_f32(self._cache, 'convP.0', self.convP[0], x5, ops.ACT_LRELU, self.a_lrelu)
         p = ops.maxpool2d(p, (2, 5), (1, 2))
         n_pred = _exec.conv_f32(self._cache, 'convP.4', self.convP[4], p)

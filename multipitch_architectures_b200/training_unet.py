@@ -1,0 +1,379 @@
+"""Training path of the U-Net family (simple_u_net_largekernels / _doubleselfattn / _polyphony_classif_softmax):
+train-mode forward (BatchNorm batch statistics, dropout, batch-axis attention) with saved activations and the
+hand-written backward of every stage — all libmpa kernels (fp32), sequenced by a small reverse-mode tape.
+
+Reference loop being replaced (experiments/Exp2_SectionIV-C/RETRAIN4_exp180d_..._doubleselfattn_moresamples.py, same
+shape as exp126a...py:315-329; PUnet: RETRAIN4_exp195f..._rerun1.py:337-350):
+    y_pred[, n_pred] = model(X); loss = BCELoss(y_pred, y) [+ CrossEntropyLoss(n_pred, sum(y).long())/25]
+    optimizer.zero_grad(); loss.backward(); optimizer.step()
+
+Semantics kept from the reference modules (unet_cnns.py:30-159):
+  * double_conv = (Conv -> BatchNorm2d(train: batch mean / biased variance, running stats updated) -> ReLU -> Dropout(0)) x 2
+  * MaxPool2d(2) floor mode, gradient to the first maximum; bilinear x2 (align_corners) + pad + concat
+  * transformer_enc_layer: q/k/v Linear -> nn.MultiheadAttention over the BATCH axis -> o Linear -> add&LN -> MLP -> add&LN,
+    dropout after the positional encoding, the attention branch and the MLP branch (p = 0.2, the layer's own default)
+The q/k/v (and o/out_proj) Linear pairs are evaluated as ONE folded matrix each (W_in.W_q, W_o.W_out); the tape
+back-propagates through the fold to the reference's separate parameters."""
+import torch
+
+from . import _lib, ops
+from ._lib import call, stream_ptr
+from .libdl.nn_models import _exec
+from .training import _act_bwd, _add, _conv_fwd, _dgrad, _dropout, _pool_bwd, _wgrad
+
+
+class Node:
+    """An activation and its (lazily accumulated) gradient."""
+    __slots__ = ('d', 'g')
+
+    def __init__(self, d):
+        self.d, self.g = d, None
+
+    def acc(self, g):
+        self.g = g if self.g is None else _add(self.g, g)
+
+
+class Tape:
+    def __init__(self, grads, seed, step):
+        self.ops, self.grads, self.seed, self.site = [], grads, seed, step * 256
+
+    def push(self, fn):
+        self.ops.append(fn)
+
+    def backward(self):
+        for fn in reversed(self.ops):
+            fn()
+        self.ops = []
+
+    # ---------------------------------------------------------------------------------------------- stages
+    def dropout(self, x, p):
+        if p <= 0.0:
+            return x
+        self.site += 1
+        off = self.site
+        out = Node(_dropout(x.d, p, self.seed, off))
+        self.push(lambda: x.acc(_dropout(out.g, p, self.seed, off)))
+        return out
+
+    def conv(self, name, conv, x, act=ops.ACT_NONE, a=0.0, need_dx=True):
+        """Conv2d (+ bias, + fused pointwise activation)."""
+        out = Node(_conv_fwd(conv, x.d, act, a))
+
+        def bwd():
+            g = out.g if act == ops.ACT_NONE else _act_bwd(out.d, out.g, act, a)
+            _wgrad(conv, x.d, g, self.grads[name + '.weight'], self.grads[name + '.bias'])
+            if need_dx:
+                x.acc(_dgrad(conv, g, x.d.shape))
+        self.push(bwd)
+        return out
+
+    def conv_act_pool_time(self, name, conv, x, k, a):
+        """Conv2d -> LeakyReLU -> MaxPool((k,1), stride 1, pad k//2)  (head conv2, basic_cnns.py:391-393)."""
+        act = Node(_conv_fwd(conv, x.d, ops.ACT_LRELU, a))
+        out = Node(ops.maxpool_time(act.d, k))
+
+        def bwd():
+            g = _pool_bwd(act.d, out.g, k, ops.ACT_LRELU, a)
+            _wgrad(conv, x.d, g, self.grads[name + '.weight'], self.grads[name + '.bias'])
+            x.acc(_dgrad(conv, g, x.d.shape))
+        self.push(bwd)
+        return out
+
+    def bn_relu(self, name, bn, y):
+        """BatchNorm2d in training mode (batch statistics) + ReLU; running statistics updated as nn.BatchNorm2d does."""
+        B, C, H, W = y.d.shape
+        stats = ops.bn_stats(y.d)
+        if bn.track_running_stats:
+            n = B * H * W
+            m = bn.momentum if bn.momentum is not None else 0.1
+            bn.running_mean.mul_(1 - m).add_(stats[:C], alpha=m)
+            bn.running_var.mul_(1 - m).add_(stats[C:] * (n / max(n - 1, 1)), alpha=m)
+            bn.num_batches_tracked += 1
+        out = Node(ops.bn_apply(y.d, stats, bn.weight, bn.bias, bn.eps, ops.ACT_RELU, 0.0))
+
+        def bwd():
+            dx = torch.empty_like(y.d)
+            scratch = torch.empty(2 * C, dtype=torch.float32, device=y.d.device)
+            call('bn_relu_bwd_f32', y.d, out.d, out.g, stats, bn.weight, dx, self.grads[name + '.weight'], self.grads[name + '.bias'],
+                 scratch, B, C, H * W, float(bn.eps), 1, stream_ptr())
+            y.acc(dx)
+        self.push(bwd)
+        return out
+
+    def double_conv(self, name, dc, x, need_dx=True):
+        seq = dc.double_conv
+        y = self.bn_relu(name + '.double_conv.1', seq[1], self.conv(name + '.double_conv.0', seq[0], x, need_dx=need_dx))
+        return self.bn_relu(name + '.double_conv.5', seq[5], self.conv(name + '.double_conv.4', seq[4], y))
+
+    def maxpool2d(self, x, k, s):
+        out = Node(ops.maxpool2d(x.d, k, s))
+
+        def bwd():
+            B, C, H, W = x.d.shape
+            gi = torch.empty_like(x.d)
+            call('maxpool2d_bwd_f32', x.d, out.g, gi, B, C, H, W, k[0], k[1], s[0], s[1], stream_ptr())
+            x.acc(gi)
+        self.push(bwd)
+        return out
+
+    def upconcat(self, low, skip):
+        out = Node(ops.upsample2x_concat(low.d, skip.d))
+
+        def bwd():
+            B, Cl, Hl, Wl = low.d.shape
+            _, Cs, Hs, Ws = skip.d.shape
+            g_skip, g_low = torch.empty_like(skip.d), torch.empty_like(low.d)
+            call('upsample2x_concat_bwd_f32', out.g, g_skip, 0, g_low, B, Cl, Hl, Wl, Cs, Hs, Ws, stream_ptr())
+            skip.acc(g_skip)
+            low.acc(g_low)
+        self.push(bwd)
+        return out
+
+    def layernorm_cf(self, ln, x):
+        """LayerNorm([C,F]) on the network input: only the affine parameters receive gradients."""
+        out = Node(ops.layernorm_cf(x, ln.weight, ln.bias, ln.eps))
+
+        def bwd():
+            B, C, T, F = x.shape
+            call('layernorm_cf_param_grad_f32', x, out.g, self.grads['layernorm.weight'], self.grads['layernorm.bias'], B, C, T, F,
+                 float(ln.eps), 0.0, stream_ptr())
+        self.push(bwd)
+        return out
+
+    # ---------------------------------------------------------------------------------------------- encoder layer
+    def encoder_layer(self, name, layer, x, p_drop):
+        """transformer_enc_layer.forward (unet_cnns.py:148-159) on [B,E,Th,Fw]; tokens are rows (b*S+s) of [B*S, E]."""
+        B, E, Th, Fw = x.d.shape
+        S, H, dev = Th * Fw, layer.num_heads, x.d.device
+        M = B * S
+        at = layer.attn
+        Wi, bi = at.in_proj_weight, at.in_proj_bias
+        Wq, Wk, Wv, Wo, Wout, bout = (layer.q_linear.weight, layer.k_linear.weight, layer.v_linear.weight, layer.o_linear.weight,
+                                      at.out_proj.weight, at.out_proj.bias)
+        f32 = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
+
+        def gemm(A, Bm, Mm, Nn, Kk, mode, out=None, accumulate=0):
+            out = f32(Mm, Nn) if out is None else out
+            call('gemm_f32', A, Bm, out, Mm, Nn, Kk, mode, accumulate, stream_ptr())
+            return out
+
+        def gemm_nt(A, W, bias, Mm, Nn, Kk, relu=0):
+            out = f32(Mm, Nn)
+            call('gemm_nt_f32', A, W, bias, out, Mm, Nn, Kk, relu, stream_ptr())
+            return out
+
+        def colsum(A, Mm, Nn, out=None):
+            out = f32(Nn) if out is None else out
+            call('colsum_f32', A, out, Mm, Nn, stream_ptr())
+            return out
+        # folded projections (one-off E x E products of parameters)
+        w_qkv = f32(3 * E, E)
+        for i, Wx in enumerate((Wq, Wk, Wv)):
+            gemm(Wi[i * E:(i + 1) * E], Wx, E, E, E, 0, out=w_qkv[i * E:(i + 1) * E])
+        w_proj = gemm(Wo, Wout, E, E, E, 0)
+        b_proj = gemm(Wo, bout, E, 1, E, 0).reshape(E)
+
+        G = self.grads
+        pe = _exec.sinusoidal_pe(S, E, dev).contiguous() if layer.pos_encoding == 'sinusoidal' else None
+        W1, b1, W2, b2 = layer.mlp[0].weight, layer.mlp[0].bias, layer.mlp[2].weight, layer.mlp[2].bias
+        Dm = W1.shape[0]
+        # Closures are pushed in forward order (the tape runs them in reverse); they only dereference nodes when they run.
+        tok0 = f32(M, E)
+        call('enc_gather_f32', x.d, pe, tok0, B, E, S, stream_ptr())
+        tok = Node(tok0)
+        self.push(lambda: x.acc(self._tok_to_nchw(tok.g, B, E, S, Th, Fw)))
+        t = self.dropout(tok, p_drop) if pe is not None else tok
+
+        # -- attention branch: qkv -> batch-axis attention -> folded out_proj . o_linear
+        qkv = Node(gemm_nt(t.d, w_qkv, bi, M, 3 * E, E))
+        att = f32(M, E)
+        call('batch_axis_attention_f32', qkv.d, att, B, S, E, H, stream_ptr())
+        att = Node(att)
+        proj = Node(gemm_nt(att.d, w_proj, b_proj, M, E, E))
+
+        def bwd_attn():
+            g_p = proj.g
+            dWp = gemm(g_p, att.d, E, E, M, 1)                      # [E,E] = g_p^T att
+            dbp = colsum(g_p, M, E)
+            # w_proj = Wo @ Wout, b_proj = Wo @ bout
+            call('gemm_nt_f32', dWp, Wout, None, G[name + '.o_linear.weight'], E, E, E, 0, stream_ptr())          # dWp @ Wout^T
+            gemm(dbp, bout, E, E, 1, 0, out=G[name + '.o_linear.weight'], accumulate=1)                           # + dbp bout^T
+            gemm(Wo, dWp, E, E, E, 1, out=G[name + '.attn.out_proj.weight'])                                       # Wo^T dWp
+            gemm(Wo, dbp, E, 1, E, 1, out=G[name + '.attn.out_proj.bias'])                                         # Wo^T dbp
+            g_att = gemm(g_p, w_proj, M, E, E, 0)
+            g_qkv = f32(M, 3 * E)
+            call('batch_axis_attention_bwd_f32', qkv.d, g_att, g_qkv, B, S, E, H, stream_ptr())
+            dWf = gemm(g_qkv, t.d, 3 * E, E, M, 1)                  # [3E,E]
+            colsum(g_qkv, M, 3 * E, out=G[name + '.attn.in_proj_bias'])
+            gWi = G[name + '.attn.in_proj_weight']
+            for i, (Wx, nm) in enumerate(((Wq, 'q'), (Wk, 'k'), (Wv, 'v'))):
+                blk = dWf[i * E:(i + 1) * E]
+                call('gemm_nt_f32', blk, Wx, None, gWi[i * E:(i + 1) * E], E, E, E, 0, stream_ptr())            # dWf_i @ Wx^T
+                gemm(Wi[i * E:(i + 1) * E], blk, E, E, E, 1, out=G[f'{name}.{nm}_linear.weight'])                 # Wi_i^T dWf_i
+            t.acc(gemm(g_qkv, w_qkv, M, E, 3 * E, 0))
+        self.push(bwd_attn)
+        d1 = self.dropout(proj, p_drop)
+
+        # -- add & LayerNorm 1
+        u1 = _add(t.d, d1.d)
+        h1 = f32(M, E)
+        call('add_layernorm_tok_f32', t.d, d1.d, layer.layernorm1.weight, layer.layernorm1.bias, h1, None, _lib.i64(M), E, S,
+             float(layer.layernorm1.eps), stream_ptr())
+        h1 = Node(h1)
+
+        def bwd_ln1():
+            g_u1 = f32(M, E)
+            call('layernorm_tok_bwd_f32', u1, h1.g, layer.layernorm1.weight, g_u1, G[name + '.layernorm1.weight'],
+                 G[name + '.layernorm1.bias'], _lib.i64(M), E, float(layer.layernorm1.eps), stream_ptr())
+            t.acc(g_u1)
+            d1.acc(g_u1)
+        self.push(bwd_ln1)
+
+        # -- MLP
+        hid = Node(gemm_nt(h1.d, W1, b1, M, Dm, E, relu=1))
+        m2 = Node(gemm_nt(hid.d, W2, b2, M, E, Dm))
+
+        def bwd_mlp():
+            g_m2 = m2.g
+            gemm(g_m2, hid.d, E, Dm, M, 1, out=G[name + '.mlp.2.weight'])
+            colsum(g_m2, M, E, out=G[name + '.mlp.2.bias'])
+            g_hid = _act_bwd(hid.d, gemm(g_m2, W2, M, Dm, E, 0), ops.ACT_RELU)
+            gemm(g_hid, h1.d, Dm, E, M, 1, out=G[name + '.mlp.0.weight'])
+            colsum(g_hid, M, Dm, out=G[name + '.mlp.0.bias'])
+            h1.acc(gemm(g_hid, W1, M, E, Dm, 0))
+        self.push(bwd_mlp)
+        d2 = self.dropout(m2, p_drop)
+
+        # -- add & LayerNorm 2, back to NCHW
+        u2 = _add(h1.d, d2.d)
+        out = f32(B, E, Th, Fw)
+        call('add_layernorm_tok_f32', h1.d, d2.d, layer.layernorm2.weight, layer.layernorm2.bias, None, out, _lib.i64(M), E, S,
+             float(layer.layernorm2.eps), stream_ptr())
+        out = Node(out)
+
+        def bwd_ln2():
+            g_tok = f32(M, E)
+            call('nchw_tokens_f32', out.g, g_tok, B, E, S, 1, stream_ptr())
+            g_u2 = f32(M, E)
+            call('layernorm_tok_bwd_f32', u2, g_tok, layer.layernorm2.weight, g_u2, G[name + '.layernorm2.weight'],
+                 G[name + '.layernorm2.bias'], _lib.i64(M), E, float(layer.layernorm2.eps), stream_ptr())
+            h1.acc(g_u2)
+            d2.acc(g_u2)
+        self.push(bwd_ln2)
+        return out
+
+    @staticmethod
+    def _tok_to_nchw(g_tok, B, E, S, Th, Fw):
+        out = torch.empty(B, E, Th, Fw, dtype=torch.float32, device=g_tok.device)
+        call('nchw_tokens_f32', g_tok, out, B, E, S, 0, stream_ptr())
+        return out
+
+
+def unet_train_forward(model, x, grads, seed=0, step=0):
+    """-> (y_pred [B,1,T-74,72], n_pred or None, tape).  Train mode: BatchNorm batch statistics, dropout when p > 0."""
+    a, p = model.a_lrelu, (model.p_dropout if model.training else 0.0)
+    tp = Tape(grads, seed, step)
+    z = tp.layernorm_cf(model.layernorm, x)
+    x1 = tp.double_conv('inc', model.inc, z)
+    xs = [x1]
+    for lv in (1, 2, 3, 4):
+        xs.append(tp.double_conv(f'down{lv}.1', getattr(model, f'down{lv}')[1], tp.maxpool2d(xs[-1], (2, 2), (2, 2))))
+    x5 = xs[4]
+    if hasattr(model, 'attention1'):
+        for nm in ('attention1', 'attention2'):
+            layer = getattr(model, nm)
+            x5 = tp.encoder_layer(nm, layer, x5, layer.p_dropout if model.training else 0.0)
+    u = x5
+    for i, lv in enumerate((3, 2, 1, 0)):
+        u = tp.double_conv(f'upconv{i + 1}', getattr(model, f'upconv{i + 1}'), tp.upconcat(u, xs[lv]))
+    h = tp.dropout(tp.conv_act_pool_time('conv2.0', model.conv2[0], u, 13, a), p)
+    h = tp.dropout(tp.conv('conv3.0', model.conv3[0], h, ops.ACT_LRELU, a), p)
+    h = tp.dropout(tp.conv('conv4.0', model.conv4[0], h, ops.ACT_LRELU, a), p)
+    y = tp.conv('conv4.3', model.conv4[3], h, ops.ACT_SIGMOID)
+    n_pred = None
+    if hasattr(model, 'convP'):
+        q = tp.conv('convP.0', model.convP[0], x5, ops.ACT_LRELU, a)
+        q = tp.dropout(tp.maxpool2d(q, (2, 5), (1, 2)), p)
+        n_pred = tp.conv('convP.4', model.convP[4], q)
+    return y, n_pred, tp
+
+
+class UnetTrainFunction(torch.autograd.Function):
+    """Drop-in autograd bridge: `model.train(); y = model(x); loss.backward()` runs the tape above."""
+
+    @staticmethod
+    def forward(ctx, model, x, seed, step, *params):
+        named = list(model.named_parameters())
+        with torch.no_grad():
+            grads = {n: torch.zeros_like(p) for n, p in named}
+            y, n_pred, tape = unet_train_forward(model, x, grads, seed, step)
+        ctx.model, ctx.tape, ctx.grads, ctx.nodes = model, tape, grads, (y, n_pred)
+        if n_pred is None:
+            return y.d
+        return y.d, n_pred.d
+
+    @staticmethod
+    def backward(ctx, g_y, g_n=None):
+        y, n_pred = ctx.nodes
+        with torch.no_grad():
+            y.g = g_y.contiguous()
+            if n_pred is not None:
+                n_pred.g = g_n.contiguous() if g_n is not None else torch.zeros_like(n_pred.d)
+            ctx.tape.backward()
+        named = list(ctx.model.named_parameters())
+        return (None, None, None, None) + tuple(ctx.grads[n] for n, _ in named)
+
+
+def unet_forward_train(model, x):
+    model._train_calls = getattr(model, '_train_calls', 0) + 1
+    seed = getattr(model, 'dropout_seed', 0x5EED)
+    return UnetTrainFunction.apply(model, x, seed, model._train_calls, *[p for _, p in model.named_parameters()])
+
+
+class UnetTrainStep:
+    """Fused training step of a U-Net-family model on flat parameter / gradient / moment buffers:
+    forward, BCE (+ CE/25 for the PUnet), backward, ONE gradient all-reduce (NCCL, when a process group is active), fused AdamW."""
+
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, seed=0x5EED, process_group=None, ce_scale=1.0 / 25.0):
+        self.model, self.lr, self.betas, self.eps, self.wd, self.seed = model, lr, betas, eps, weight_decay, seed
+        self.group, self.ce_scale = process_group, ce_scale
+        named = list(model.named_parameters())
+        dev = named[0][1].device
+        n = sum(p.numel() for _, p in named)
+        self.flat_p = torch.empty(n, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.grads, off = {}, 0
+        with torch.no_grad():
+            for name, p in named:
+                k = p.numel()
+                self.flat_p[off:off + k] = p.reshape(-1)
+                p.data = self.flat_p[off:off + k].view_as(p)
+                self.grads[name] = self.flat_g[off:off + k].view_as(p)
+                off += k
+        self.step_count = 0
+
+    def __call__(self, x, target):
+        import torch.distributed as dist
+        self.step_count += 1
+        with torch.no_grad():
+            y, n_pred, tape = unet_train_forward(self.model, x, self.grads, self.seed, self.step_count)
+            target = target.contiguous()
+            loss, y.g = ops.bce_fwd_bwd(y.d, target)
+            if n_pred is not None:
+                B, K = n_pred.d.shape[0], n_pred.d.shape[1]
+                n_pred.g = torch.empty_like(n_pred.d)
+                call('ce_count_fwd_bwd_f32', n_pred.d, target, loss, n_pred.g, B, K, target.numel() // B, float(self.ce_scale), 1, stream_ptr())
+            tape.backward()
+            scale = 1.0
+            if self.group is not None or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+                dist.all_reduce(self.flat_g, group=self.group)
+                scale = 1.0 / dist.get_world_size(self.group)
+            call('adamw_f32', self.flat_p, self.flat_g, self.m, self.v, _lib.i64(self.flat_p.numel()), float(self.lr), float(self.betas[0]),
+                 float(self.betas[1]), float(self.eps), float(self.wd), self.step_count, float(scale), stream_ptr())
+        self.model._cache._d.clear()
+        for nm in ('attention1', 'attention2'):
+            if hasattr(self.model, nm):
+                getattr(self.model, nm)._cache._d.clear()
+        return loss

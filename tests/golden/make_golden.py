@@ -188,6 +188,47 @@ def host_goldens():
     print('annot sha1', bytes(out['annot_sha1']).hex(), 'nnz', len(out['annot_nnz']), 'shape', A.shape)
 
 
+def train_goldens():
+    """Loss + parameter gradients of the REFERENCE U-Net-family modules in train mode (BatchNorm batch statistics, dropout p=0):
+    BCELoss(mean) and, for the PUnet, + CrossEntropyLoss(n_pred, sum(labels).long())/25 (RETRAIN4_exp195f...rerun1.py:343-346)."""
+    torch.set_num_threads(8)
+    out = {}
+    for name, B, seed in (('unet_tiny', 3, 15), ('saunet_tiny', 5, 19), ('punet_tiny', 3, 17)):
+        m = build_reference_model(name)
+        sd = fill_state_dict(m.state_dict(), seed)
+        m.load_state_dict(sd)
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+        m.train(True)
+        x, yt = synth_patches(B, seed), synth_targets(B, seed)
+        m.zero_grad()
+        y = m(x)
+        tag = f'{name}__train'
+        if isinstance(y, tuple):
+            y, n_pred = y
+            n_target = torch.sum(yt, dim=-1, keepdims=True).long().squeeze(3)
+            loss = torch.nn.BCELoss(reduction='mean')(y, yt) + torch.nn.CrossEntropyLoss(reduction='mean')(n_pred, n_target) / 25.0
+            out[tag + '__n'] = n_pred.detach().numpy()
+        else:
+            loss = torch.nn.BCELoss(reduction='mean')(y, yt)
+        loss.backward()
+        out[tag + '__y'] = y.detach().numpy()
+        out[tag + '__loss'] = np.array([loss.item()])
+        out[tag + '__meta'] = np.array([B, seed])
+        for k, p in m.named_parameters():
+            out[tag + '__grad__' + k] = p.grad.numpy().copy()
+        for k, v in m.state_dict().items():
+            if 'running_' in k:
+                out[tag + '__stat__' + k] = v.numpy().copy()
+        print(tag, 'loss', loss.item())
+    np.savez_compressed(os.path.join(HERE, 'nn_train_golden.npz'), **out)
+
+
 if __name__ == '__main__':
+    if 'train' in sys.argv[1:]:
+        train_goldens()
+        sys.exit(0)
     host_goldens()
     nn_goldens()
+    train_goldens()

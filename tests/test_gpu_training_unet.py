@@ -1,0 +1,209 @@
+"""`-m gpu`: training path of the U-Net family (configuration 5).  Backward kernels against torch autograd
+of the same op; whole-model loss / gradients / BatchNorm running statistics against the REFERENCE goldens
+(tests/golden/nn_train_golden.npz: loss.backward() on the unmodified reference modules in train mode); the fused
+UnetTrainStep (BCE [+ CE/25] + backward + AdamW kernels) against torch.optim.AdamW driving the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.refshapes import build_model
+from tests.weights import MODEL_SPECS, fill_state_dict, synth_patches, synth_targets
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def train_golden():
+    return np.load(os.path.join(ROOT, 'tests', 'golden', 'nn_train_golden.npz'))
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+def _call(name, *a):
+    from multipitch_architectures_b200 import _lib
+    _lib.call(name, *a, _lib.stream_ptr())
+
+
+def test_bn_relu_bwd():
+    B, C, H, W = 3, 5, 9, 13
+    x = rnd(B, C, H, W, seed=1).requires_grad_(True)
+    w, b = (1 + 0.2 * rnd(C, seed=2)).requires_grad_(True), (0.1 * rnd(C, seed=3)).requires_grad_(True)
+    y = torch.relu(F.batch_norm(x, None, None, w, b, training=True, eps=1e-5))
+    g = rnd(B, C, H, W, seed=4)
+    y.backward(g)
+    from multipitch_architectures_b200 import ops
+    xc = x.detach().cuda()
+    stats = ops.bn_stats(xc)
+    out = ops.bn_apply(xc, stats, w.detach().cuda(), b.detach().cuda(), 1e-5, ops.ACT_RELU, 0.0)
+    assert (out.cpu() - y.detach()).abs().max() < 1e-5
+    dx, dw, db, scr = torch.empty_like(xc), torch.empty(C).cuda(), torch.empty(C).cuda(), torch.empty(2 * C).cuda()
+    _call('bn_relu_bwd_f32', xc, out, g.cuda(), stats, w.detach().cuda(), dx, dw, db, scr, B, C, H * W, 1e-5, 1)
+    assert (dx.cpu() - x.grad).abs().max() < 2e-5
+    assert (dw.cpu() - w.grad).abs().max() < 1e-4 and (db.cpu() - b.grad).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize('k,s,shape', [((2, 2), (2, 2), (2, 3, 9, 27)), ((2, 2), (2, 2), (2, 3, 75, 216)), ((2, 5), (1, 2), (3, 4, 3, 9))])
+def test_maxpool2d_bwd(k, s, shape):
+    x = rnd(*shape, seed=5).requires_grad_(True)
+    y = F.max_pool2d(x, k, s)
+    g = rnd(*y.shape, seed=6)
+    y.backward(g)
+    gi = torch.empty(*shape).cuda()
+    B, C, H, W = shape
+    _call('maxpool2d_bwd_f32', x.detach().cuda(), g.cuda(), gi, B, C, H, W, k[0], k[1], s[0], s[1])
+    assert (gi.cpu() - x.grad).abs().max() < 1e-6
+
+
+@pytest.mark.parametrize('lo,sk', [((2, 3, 4, 13), (2, 5, 9, 27)), ((2, 4, 9, 27), (2, 2, 18, 54)), ((1, 2, 37, 108), (1, 3, 75, 216))])
+def test_upsample_concat_bwd(lo, sk):
+    from oracle import nn_oracle as NO
+    low, skip = rnd(*lo, seed=7).requires_grad_(True), rnd(*sk, seed=8).requires_grad_(True)
+    cat = NO.upconcat(low, skip)
+    g = rnd(*cat.shape, seed=9)
+    cat.backward(g)
+    g_skip, g_low = torch.empty(*sk).cuda(), torch.empty(*lo).cuda()
+    _call('upsample2x_concat_bwd_f32', g.cuda(), g_skip, 0, g_low, lo[0], lo[1], lo[2], lo[3], sk[1], sk[2], sk[3])
+    assert (g_skip.cpu() - skip.grad).abs().max() < 1e-6
+    assert (g_low.cpu() - low.grad).abs().max() < 1e-5
+
+
+def test_attention_and_layernorm_bwd():
+    B, S, E, H = 5, 7, 32, 8
+    hd = E // H
+    qkv = rnd(B * S, 3 * E, seed=10).requires_grad_(True)
+    q, k, v = [qkv[:, i * E:(i + 1) * E].reshape(B, S, H, hd).permute(1, 2, 0, 3) for i in range(3)]
+    att = torch.softmax((q @ k.transpose(-1, -2)) / hd ** 0.5, dim=-1)
+    o = (att @ v).permute(2, 0, 1, 3).reshape(B * S, E)
+    g = rnd(B * S, E, seed=11)
+    o.backward(g)
+    oc, gq = torch.empty(B * S, E).cuda(), torch.empty(B * S, 3 * E).cuda()
+    _call('batch_axis_attention_f32', qkv.detach().cuda(), oc, B, S, E, H)
+    assert (oc.cpu() - o.detach()).abs().max() < 1e-5
+    _call('batch_axis_attention_bwd_f32', qkv.detach().cuda(), g.cuda(), gq, B, S, E, H)
+    assert (gq.cpu() - qkv.grad).abs().max() < 1e-5
+    from multipitch_architectures_b200 import _lib
+    u = rnd(B * S, E, seed=12).requires_grad_(True)
+    w, b = (1 + 0.1 * rnd(E, seed=13)).requires_grad_(True), (0.1 * rnd(E, seed=14)).requires_grad_(True)
+    F.layer_norm(u, (E,), w, b, 1e-5).backward(g)
+    gu, gw, gb = torch.empty(B * S, E).cuda(), torch.empty(E).cuda(), torch.empty(E).cuda()
+    _lib.call('layernorm_tok_bwd_f32', u.detach().cuda(), g.cuda(), w.detach().cuda(), gu, gw, gb, _lib.i64(B * S), E, 1e-5, _lib.stream_ptr())
+    assert (gu.cpu() - u.grad).abs().max() < 1e-5
+    assert (gw.cpu() - w.grad).abs().max() < 1e-4 and (gb.cpu() - b.grad).abs().max() < 1e-4
+
+
+def test_gemm_modes_colsum_ce():
+    A, Bm = rnd(37, 19, seed=15), rnd(19, 70, seed=16)
+    C = torch.empty(37, 70).cuda()
+    _call('gemm_f32', A.cuda(), Bm.cuda(), C, 37, 70, 19, 0, 0)
+    assert (C.cpu() - A @ Bm).abs().max() < 1e-4
+    At = rnd(19, 37, seed=17)
+    _call('gemm_f32', At.cuda(), Bm.cuda(), C, 37, 70, 19, 1, 1)
+    assert (C.cpu() - (A @ Bm + At.T @ Bm)).abs().max() < 1e-4
+    s = torch.empty(70).cuda()
+    _call('colsum_f32', Bm.cuda(), s, 19, 70)
+    assert (s.cpu() - Bm.sum(0)).abs().max() < 1e-5
+    logits = rnd(6, 24, seed=18).requires_grad_(True)
+    yt = synth_targets(6, 3).reshape(6, 72)
+    yt[0, :30] = 1.0                                              # class index clamps at K-1 (the reference would raise)
+    cls = yt.sum(-1).long().clamp(max=23)
+    loss = F.cross_entropy(logits, cls) / 25.0
+    loss.backward()
+    ls, gl = torch.zeros(1).cuda(), torch.empty(6, 24).cuda()
+    _call('ce_count_fwd_bwd_f32', logits.detach().cuda(), yt.cuda(), ls, gl, 6, 24, 72, 1.0 / 25.0, 0)
+    assert abs(ls.item() - loss.item()) < 1e-6 and (gl.cpu() - logits.grad).abs().max() < 1e-7
+
+
+def _zero_dropout(m):
+    m.p_dropout = 0.0
+    for mod in m.modules():
+        if hasattr(mod, 'p_dropout'):
+            mod.p_dropout = 0.0
+
+
+@pytest.mark.parametrize('name', ['unet_tiny', 'saunet_tiny', 'punet_tiny'])
+def test_model_loss_grads_and_running_stats_match_reference_golden(train_golden, name):
+    tag = f'{name}__train'
+    B, seed = [int(v) for v in train_golden[tag + '__meta']]
+    m = build_model(name)
+    m.load_state_dict(fill_state_dict(m.state_dict(), seed))
+    _zero_dropout(m)
+    m = m.cuda().train()
+    x, t = synth_patches(B, seed).cuda(), synth_targets(B, seed).cuda()
+    y = m(x)                                                    # autograd path (UnetTrainFunction)
+    if isinstance(y, tuple):
+        y, n_pred = y
+        assert np.abs(n_pred.detach().cpu().numpy() - train_golden[tag + '__n']).max() < 1e-3
+        n_target = torch.sum(t, dim=-1, keepdims=True).long().squeeze(3)
+        loss = torch.nn.BCELoss(reduction='mean')(y, t) + torch.nn.CrossEntropyLoss(reduction='mean')(n_pred, n_target) / 25.0
+    else:
+        loss = torch.nn.BCELoss(reduction='mean')(y, t)
+    assert np.abs(y.detach().cpu().numpy() - train_golden[tag + '__y']).max() < 1e-3
+    loss.backward()
+    assert abs(loss.item() - float(train_golden[tag + '__loss'][0])) < 2e-5
+    worst = 0.0
+    # conv biases in front of a train-mode BatchNorm have a mathematically zero gradient (rounding noise on both sides): every
+    # tensor is judged against max(its own scale, 1e-3 of the largest gradient in the model)
+    gmax = max(np.abs(train_golden[tag + '__grad__' + k]).max() for k, _ in m.named_parameters())
+    for k, p in m.named_parameters():
+        g = train_golden[tag + '__grad__' + k]
+        d = np.abs(p.grad.cpu().numpy() - g)
+        scale = max(np.abs(g).max(), 1e-3 * gmax)
+        worst = max(worst, d.max() / scale)
+        # fp32 summation-order noise + rare max-pool / ReLU near-tie flips: bound the maximum loosely and the mean tightly
+        assert d.max() <= 2e-2 * scale and (d.mean() <= 4e-3 * scale or d.size < 64), (k, d.max() / scale, d.mean() / scale)
+    print(f'{tag}: worst relative gradient deviation {worst:.2e}')
+    for k, v in m.state_dict().items():
+        if 'running_' in k:
+            assert np.abs(v.cpu().numpy() - train_golden[tag + '__stat__' + k]).max() < 1e-4, k
+
+
+@pytest.mark.parametrize('name', ['saunet_tiny', 'punet_tiny'])
+def test_fused_train_step_matches_torch_adamw_on_oracle(name):
+    from oracle import nn_oracle as NO
+    from multipitch_architectures_b200.training_unet import UnetTrainStep
+    m = build_model(name)
+    sd0 = fill_state_dict(m.state_dict(), 33)
+    m.load_state_dict(sd0)
+    _zero_dropout(m)
+    m = m.cuda().train()
+    step = UnetTrainStep(m, lr=1e-3, weight_decay=0.01)
+    ref = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'running_' not in k else v.clone()) for k, v in sd0.items()}
+    params = [v for v in ref.values() if v.requires_grad]
+    opt = torch.optim.AdamW(params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+    pe = MODEL_SPECS[name]['kw'].get('pos_encoding')
+    for it in range(2):
+        x, t = synth_patches(4, 60 + it), synth_targets(4, 60 + it)
+        l_gpu = step(x.cuda(), t.cuda()).item()
+        opt.zero_grad()
+        y = NO.unet_forward(ref, x, train=True, pos_encoding=pe)
+        if isinstance(y, tuple):
+            y, n_pred = y
+            l_ref = NO.bce_mean(y, t) + F.cross_entropy(n_pred, t.sum(-1, keepdim=True).long().squeeze(3)) / 25.0
+        else:
+            l_ref = NO.bce_mean(y, t)
+        l_ref.backward()
+        opt.step()
+        assert abs(l_gpu - l_ref.item()) < 5e-4 * max(1.0, abs(l_ref.item())), (it, l_gpu, l_ref.item())
+    # inference after training sees the updated weights
+    m.eval()
+
+
+def test_train_mode_dropout_is_active_and_deterministic():
+    m = build_model('saunet_tiny')
+    m.load_state_dict(fill_state_dict(m.state_dict(), 35))
+    m = m.cuda().train()
+    x = synth_patches(3, 70).cuda()
+    with torch.no_grad():
+        m._train_calls = 0
+        y1 = m(x)
+        m._train_calls = 0
+        y2 = m(x)
+        y3 = m(x)
+    assert torch.equal(y1, y2) and not torch.equal(y1, y3)

@@ -1,6 +1,7 @@
 """`-m "not gpu"`: pins the oracle restatements against fixtures produced by the reference itself
 (tests/golden/make_golden.py).  No CUDA, no /root/reference at run time."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -148,3 +149,34 @@ def test_resample_halfband_properties():
     z = Q.resample_2to1(y)
     assert len(z) == 2001 and z[-1] == 0.0
     assert abs(z[1000] - np.sqrt(2.0)) < 2e-3            # DC gain 1 then x sqrt(2)
+
+
+@pytest.mark.parametrize('name', ['unet_tiny', 'saunet_tiny', 'punet_tiny'])
+def test_oracle_train_mode_loss_and_grads_match_reference(name):
+    """The oracle's train-mode forward (BatchNorm batch statistics, batch-axis attention) differentiated by autograd must give
+    the loss and parameter gradients of the unmodified reference modules (tests/golden/nn_train_golden.npz)."""
+    import torch.nn.functional as F
+    from tests.weights import MODEL_SPECS, synth_targets
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'nn_train_golden.npz'))
+    tag = f'{name}__train'
+    B, seed = [int(v) for v in g[tag + '__meta']]
+    sd = fill_state_dict(reference_state_shapes(name), seed)
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'running_' not in k else v) for k, v in sd.items()}
+    x, t = synth_patches(B, seed), synth_targets(B, seed)
+    y = NO.unet_forward(sd, x, train=True, pos_encoding=MODEL_SPECS[name]['kw'].get('pos_encoding'))
+    if isinstance(y, tuple):
+        y, n_pred = y
+        loss = NO.bce_mean(y, t) + F.cross_entropy(n_pred, t.sum(-1, keepdim=True).long().squeeze(3)) / 25.0
+    else:
+        loss = NO.bce_mean(y, t)
+    loss.backward()
+    assert abs(loss.item() - float(g[tag + '__loss'][0])) < 1e-5
+    # conv biases in front of a train-mode BatchNorm have a mathematically zero gradient (pure rounding noise in both
+    # implementations): every tensor is judged against max(its own scale, 1e-3 of the largest gradient in the model)
+    gmax = max(np.abs(g[tag + '__grad__' + k]).max() for k, v in sd.items() if v.requires_grad)
+    for k, v in sd.items():
+        if v.requires_grad:
+            ref = g[tag + '__grad__' + k]
+            d = np.abs(v.grad.numpy() - ref)
+            scale = max(np.abs(ref).max(), 1e-3 * gmax)
+            assert d.max() <= 2e-2 * scale and (d.mean() <= 4e-3 * scale or d.size < 64), (k, d.max() / scale, d.mean() / scale)
