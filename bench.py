@@ -237,6 +237,8 @@ def main():
     ap.add_argument('--cpu-sample', type=int, default=100)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--precision', default='fp16', choices=['fp16', 'bf16'])
+    ap.add_argument('--no-ring', action='store_true', help='fused schedule with ready-made weight tiles instead of ring pieces')
+    ap.add_argument('--plain', action='store_true', help='per-patch conv_tc + separate pool kernels (no fusion / de-duplication)')
     ap.add_argument('--workload', default='infer_drcnn', choices=['infer_drcnn', 'train_cnn_xs'],
                     help='infer_drcnn (headline, BASELINE configs[0]) or train_cnn_xs (configs[1]: CNN:XS fwd+bwd+AdamW, batch 256)')
     ap.add_argument('--batch', type=int, default=256)
@@ -289,7 +291,7 @@ def main():
     model = deep_cnn_segm_sigmoid(**DRCNN_KW, precision=args.precision)
     make_weights(model)
     model = model.to(dev).eval()
-    eng = CnnStreamEngine(model, chunk=args.chunk)
+    eng = CnnStreamEngine(model, chunk=args.chunk, fused=not args.plain, ring=not args.no_ring)
     fmin = C1_HZ / 2 ** ((3 - 1) / (2 * 36))
     plan = get_plan(22050, float(fmin), 512, 36, 6, 5, 1, str(dev))
     n_clips = 2
@@ -346,15 +348,21 @@ def main():
     e2e = audio_s / (ms_e2e / 1e3)
     if rank == 0:
         # roofline of the dominant kernel from the events recorded inside the timed region
-        by = {}
-        for tag, a, b in timers:
+        by, work = {}, {}
+        for tag, a, b, w in timers:
             by.setdefault(tag, []).append(a.elapsed_time(b))
+            work[tag] = work.get(tag, 0) + w
         conv = by.get('conv_tc', [])
         peak_tf, peak_bw, peak_src = measured_peaks()
-        per_launch_patches = n_frames / max(1, (n_frames + args.chunk - 1) // args.chunk)
-        flops_launch = GFLOP_PREFILT_LAYER * 1e9 * per_launch_patches
-        avg_ms = sum(conv) / max(1, len(conv))
-        achieved = flops_launch / (avg_ms * 1e-3) / 1e12 if conv else None
+        # executed algorithmic FLOPs of the 40->40 launches: output rows actually produced x 2*Cin*Cout*KH*KW*F per row
+        # (rows shared between overlapping patches are counted ONCE — the de-duplicated schedule does less work than the
+        # patch-wise 11.664 GFLOP per patch-layer; `patchwise_equivalent_tflops` below uses the reference's patch-wise count)
+        flops_row = GFLOP_PREFILT_LAYER * 1e9 / 75.0
+        conv_ms = sum(conv)
+        flops_launch = flops_row * work.get('conv_tc', 0) / max(1, len(conv))
+        avg_ms = conv_ms / max(1, len(conv))
+        achieved = flops_row * work.get('conv_tc', 0) / (conv_ms * 1e-3) / 1e12 if conv else None
+        per_launch_rows = work.get('conv_tc', 0) / max(1, len(conv))
         shares = {k: round(sum(v) / (ms) , 4) for k, v in by.items()}
         line = {'metric': 'audio_seconds_per_second', 'value': value, 'unit': 'audio-s/s', 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -363,11 +371,12 @@ def main():
                         'd2h_bytes_per_step': int(n_frames * 72 * 4), 'ms_per_step': ms_e2e / args.steps},
                 'roofline': {'bound': 'tensor', 'kernel': 'conv_tc_kernel (tcgen05 15x15 40->40, bias+LeakyReLU epilogue)', 'achieved': achieved,
                              'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': (achieved / peak_tf) if achieved else None,
-                             'traffic': DRAM_BYTES_PER_PATCH_LAYER * per_launch_patches,
+                             'traffic': DRAM_BYTES_PER_PATCH_LAYER * per_launch_rows / 75.0,
                              'traffic_source': 'ncu --set full (profiles/r01_conv_tc_prefilt_ncu_raw.csv): dram__bytes_read.sum 0.875 GB + dram__bytes_write.sum 0.801 GB per 646-patch launch; algorithmic 0.89 + 0.84 GB',
                              'peak_source': peak_src, 'launches_timed': len(conv), 'avg_launch_ms': avg_ms,
-                             'algorithmic_flops_per_launch': flops_launch, 'time_share_by_stage': shares},
-                'effective_tflops': value * FPS * GFLOP_PER_PATCH / 1e3}
+                             'algorithmic_flops_per_launch': flops_launch, 'output_rows_per_launch': per_launch_rows, 'time_share_by_stage': shares,
+                             'schedule': 'fused conv+LReLU+pool3+residual, interior rows shared across patches' if eng.fused else 'plain per-patch'},
+                'patchwise_equivalent_tflops': value * FPS * GFLOP_PER_PATCH / 1e3}
         if not args.no_cpu_baseline:
             v, desc = cpu_reference_arm(args.seconds, args.cpu_sample, cores)
             line['cpu_baseline'] = {'value': v, 'unit': 'audio-s/s', 'cores': cores, 'kind': 'port', 'sample': desc}

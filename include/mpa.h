@@ -121,6 +121,43 @@ int mpa_conv_tc_f16(const void* in_cp8, const void* w_packed, const float* bias,
                     int sub_stride, int sub_offset, int n_patches, int Cin, int Cout, int T, int F, int KH, int KW,
                     int pitch, int pf, int pt, long long in_patch_stride_rows, int in_nc_stride, int out_nc_stride,
                     int J, int row0, int n_rows, int act, float act_param, int fmt, void* stream);
+/* Fused variant for the CNN / DCNN / DRCNN blocks (basic_cnns.py:373-378, 412-419): z = MaxPool((3,1), s1, p(1,0))(act(conv + bias))
+ * [+ the layer input, residual] in ONE kernel, with "virtual" patch rows on both sides so that rows whose receptive field has
+ * not reached the zero padding at the patch edges are computed ONCE PER FRAME instead of once per patch:
+ *   row r of patch b = rows [0,e) and [T-e,T): per-patch edge planes [patch][chunk][2e rows][pitch][8] (row r at index r, resp. r-(T-2e));
+ *                      every other row: the shared stream [chunk][rows][pitch][8] at row b*stream_patch_rows + r.
+ * e == T means a fully materialised patch (index r), e == 0 a pure stream.  All pointers address (row 0, column 0) of patch 0, chunk 0;
+ * the caller provides at least one readable row before and after every plane and zeroed gap columns, as for mpa_conv_tc_f16.
+ * z rows [z_lo[s], z_hi[s]) of every patch are produced for each of the n_seg (1 or 2) segments; the conv rows one above / below
+ * each segment are evaluated on the fly (the pool's halo).  workspace >= mpa_conv_tc_pool_workspace() bytes (L2-resident scratch). */
+typedef struct mpa_conv_tc_desc {
+  const void* in_edge;
+  const void* in_stream;
+  long long in_edge_patch_stride, in_edge_chunk_stride, in_stream_chunk_stride; /* bytes */
+  long long in_stream_patch_rows;
+  int in_e;
+  const void* w_packed;
+  const float* bias;
+  void* out_edge;
+  void* out_stream;
+  long long out_edge_patch_stride, out_edge_chunk_stride, out_stream_chunk_stride; /* bytes */
+  long long out_stream_patch_rows;
+  int out_e;
+  int n_patches, Cin, Cout, T, F, KH, KW, pitch, pf, J;
+  int n_seg;
+  int z_lo[2], z_hi[2];
+  int residual, act;
+  float act_param;
+  int fmt;
+  int weights_layout; /* 0: tiles of mpa_conv_tc_pack_weights; 1: ring pieces of mpa_conv_tc_ring_pack_weights (3x less L2->SM traffic at J = 3) */
+  void* workspace;
+  size_t ws_bytes;
+} mpa_conv_tc_desc;
+size_t mpa_conv_tc_pool_workspace(int Cout, int pitch, int J);
+/* HOST functions: un-duplicated weight pieces for weights_layout 1 (one filter row per piece; Cout a multiple of 8). */
+size_t mpa_conv_tc_ring_packed_bytes(int Cin, int Cout, int KH, int KW, int J);
+int mpa_conv_tc_ring_pack_weights(const float* w_host, void* packed_host, int Cin, int Cout, int KH, int KW, int fmt, int J);
+int mpa_conv_tc_pool_f16(const mpa_conv_tc_desc* desc, void* stream);
 /* J: output rows per work unit (0 = floor(128/Cout)); must match the J the weights were packed with.
  * row0 / n_rows: compute output rows [row0, row0+n_rows) only (n_rows 0 = to the end) and store them as rows 0.. of `out`;
  * a VALID (KH x 1) convolution such as conv3 (75 x 1, basic_cnns.py:398) is the "same" convolution restricted to

@@ -37,24 +37,43 @@ constexpr int kAStageBytes = kStageMMAs * kATileBytes;
 constexpr int kMaxAStages = 5;             // weight stages: as many as fit next to the activation slabs (>= 2)
 constexpr int kNumBStages = 2;
 constexpr int kThreads = 320;                 // producer warp, MMA warp, 8 epilogue warps
+constexpr int kMaxRingS = 24;                // ring positions (<= J + 4, J <= 16) and activation stages of the ring main loop
+constexpr int kMaxRingB = 8;
+constexpr int kMaxGrid = 160;                 // upper bound of the persistent grid (scratch-ring sizing)
 constexpr int kEpiPitch = 40;                 // 80-byte rows: conflict-free 16-byte reads in the transposing epilogue
 constexpr unsigned long long kWaitTimeoutNs = 4000000000ull;   // bounded waits: a protocol bug traps instead of hanging the GPU
 
 struct ConvTcParams {
-  const uint8_t* in;        // CP8 bf16 planes
+  // ---- input: virtual patch rows.  Rows [0,in_e) and [T-in_e,T) of patch b live in per-patch "edge" planes (in_e == T: the whole
+  // patch is materialised), every other row r in ONE shared stream at row b*in_stream_patch_rows + r (patch-independent rows are
+  // stored once per frame instead of once per patch).  All pointers address (row 0, column 0) of patch 0, chunk 0.
+  const uint8_t* in_edge;
+  const uint8_t* in_stream;
+  long long in_edge_patch_stride, in_edge_chunk_stride, in_stream_chunk_stride;   // bytes
+  long long in_stream_patch_rows;
+  int in_e;
   const uint8_t* w;         // packed weights
   const float* bias;        // [Cout]
-  uint16_t* out;            // out_mode 0: CP8 planes [n][NCo][T+2pt][P][8]; out_mode 1: compact [n][NCo][T][F_out][8] (sub-sampled columns)
+  // ---- output, legacy epilogue (pool == 0)
+  uint16_t* out;            // out_mode 0: CP8 planes [n][NCo][T_out+2pt][P][8]; out_mode 1: compact [n][NCo][T_out][F_out][8] (sub-sampled columns)
   int out_mode, sub_stride, sub_offset, F_out, fmt;
-  long long in_patch_stride;   // bytes between patches in `in`
-  long long in_chunk_stride;   // bytes between channel chunks in `in`
-  long long in_row0;           // byte offset of (row 0, column 0) of patch 0 chunk 0
-  int n_patches, NC, Cout, J, T, F, KH, KW, P, N, pf, pt_out, TP_out, T_out, row0, row_end, NCo;
-  int mmas_per_row, n_groups, n_units, slab_px, epi_off, a_stages, btab_off;
+  // ---- output, fused epilogue (pool == 3): z = maxpool_time3(act(conv + bias)) (+ input row) written with the same virtual row scheme
+  uint8_t* out_edge;
+  uint8_t* out_stream;
+  long long out_edge_patch_stride, out_edge_chunk_stride, out_stream_chunk_stride, out_stream_patch_rows;
+  int out_e, pool, residual;
+  uint8_t* ring;            // per-CTA scratch of activated conv rows: [grid][2 banks][J][NCo][P][16 B]
+  // ---- geometry
+  int n_patches, NC, Cout, J, T, F, KH, KW, P, N, pf, pt_out, TP_out, T_out, row0, NCo;
+  int n_seg, y_lo[2], y_hi[2], z_lo[2], z_hi[2], seg_groups[2], groups_per_patch;
+  int mmas_per_row, n_units, slab_px, epi_off, a_stages, btab_off;
   long long out_patch_stride;  // elements (16-bit) between patches in `out`
   int act;
   float act_param;
   uint32_t idesc;
+  uint32_t btab[128];       // tile main loop: B-descriptor low words of one K row, (offset >> 4) | (LBO >> 4) << 16
+  // ---- ring main loop (conv_tc_ring_kernel): un-duplicated weight pieces, see below
+  int ring_on, ring_S, ring_npos, ring_ps, ring_sbo, ring_nb, ring_b_off, ring_bar_off;
 };
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
@@ -124,6 +143,11 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint16_t cvt16(float x, int fmt) {
   return fmt == MPA_FMT_BF16 ? __bfloat16_as_ushort(__float2bfloat16(x)) : __half_as_ushort(__float2half_rn(x));
 }
@@ -137,159 +161,93 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
 
-// ------------------------------------------------------------------------------------------ kernel
-__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  const int slab_plane_bytes = p.slab_px * 16;
-  const int slab_bytes = p.NC * slab_plane_bytes;        // one patch, one input row
-  const int bstage_bytes = slab_bytes;
-  const int kNumAStages = p.a_stages;
-  uint8_t* a_smem = smem;                                // [a_stages][kAStageBytes]
-  uint8_t* b_smem = smem + kNumAStages * kAStageBytes;   // [kNumBStages][NC][slab_px][16B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + kNumBStages * bstage_bytes);
-  uint64_t* a_full = bars;
-  uint64_t* a_empty = bars + kMaxAStages;
-  uint64_t* b_full = bars + 2 * kMaxAStages;
-  uint64_t* b_empty = b_full + kNumBStages;
-  uint64_t* acc_full = b_empty + kNumBStages;            // [2]
-  uint64_t* acc_empty = acc_full + 2;                    // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  uint32_t* btab = reinterpret_cast<uint32_t*>(smem + p.btab_off);         // [mmas_per_row padded to 8] B-descriptor low words
-  uint16_t* epi_smem = reinterpret_cast<uint16_t*>(smem + p.epi_off);      // 4 warps x [32][32] 16-bit staging
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < kNumAStages; ++i) {
-      mbar_init(&a_full[i], 1);
-      mbar_init(&a_empty[i], 1);
-    }
-    for (int i = 0; i < kNumBStages; ++i) {
-      mbar_init(&b_full[i], 1);
-      mbar_init(&b_empty[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], kThreads - 64);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+// ------------------------------------------------------------------------------------------ unit decoding
+struct UnitInfo {
+  int b, seg, t0;        // patch, segment, first conv row of the unit
+  bool first_in_seg;
+};
+__device__ __forceinline__ UnitInfo decode_unit(const ConvTcParams& p, int u) {
+  UnitInfo ui;
+  ui.b = u / p.groups_per_patch;
+  int g = u - ui.b * p.groups_per_patch;
+  ui.seg = 0;
+  if (g >= p.seg_groups[0]) { g -= p.seg_groups[0]; ui.seg = 1; }
+  ui.t0 = p.y_lo[ui.seg] + g * p.J;
+  ui.first_in_seg = (g == 0);
+  return ui;
+}
+// Work units are dealt to CTAs in CONTIGUOUS ranges (a CTA walks down the rows of a patch, so the fused pool finds the
+// neighbouring conv rows in its own scratch ring).  In pool mode a range that starts in the middle of a segment is preceded
+// by one warm-up unit (the previous row group) whose pooled output is suppressed.
+__device__ __forceinline__ void unit_range(const ConvTcParams& p, int& u_begin, int& u_end, int& u_first_real) {
+  const long long U = p.n_units;
+  u_first_real = (int)(U * blockIdx.x / gridDim.x);
+  u_end = (int)(U * (blockIdx.x + 1) / gridDim.x);
+  u_begin = u_first_real;
+  if (p.pool && u_first_real < u_end && !decode_unit(p, u_first_real).first_in_seg) u_begin = u_first_real - 1;
+}
+// byte address of (patch b, row, column 0, chunk 0) of the virtual input and the chunk stride that goes with it
+__device__ __forceinline__ const uint8_t* in_row_ptr(const ConvTcParams& p, int b, int row, long long& chunk_stride) {
+  if (row < p.in_e || row >= p.T - p.in_e) {
+    const int idx = row < p.in_e ? row : row - (p.T - 2 * p.in_e);
+    chunk_stride = p.in_edge_chunk_stride;
+    return p.in_edge + (long long)b * p.in_edge_patch_stride + (long long)idx * p.P * 16;
   }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  chunk_stride = p.in_stream_chunk_stride;
+  return p.in_stream + ((long long)b * p.in_stream_patch_rows + row) * p.P * 16;
+}
+__device__ __forceinline__ uint8_t* out_row_ptr(const ConvTcParams& p, int b, int row, long long& chunk_stride) {
+  if (row < p.out_e || row >= p.T - p.out_e) {
+    const int idx = row < p.out_e ? row : row - (p.T - 2 * p.out_e);
+    chunk_stride = p.out_edge_chunk_stride;
+    return p.out_edge + (long long)b * p.out_edge_patch_stride + (long long)idx * p.P * 16;
   }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  chunk_stride = p.out_stream_chunk_stride;
+  return p.out_stream + ((long long)b * p.out_stream_patch_rows + row) * p.P * 16;
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-  const int ph = p.KH / 2, pw = p.KW / 2;
-  const int rows_in = p.KH + p.J - 1;
-
-  if (warp == 0) {
-    // ===================================================== producer
-    if (lane == 0) {
-      int a_stage = 0, b_stage = 0;
-      uint32_t a_phase = 0, b_phase = 0;
-      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-        const int b0 = u / p.n_groups, g = u % p.n_groups;
-        const int t0 = p.row0 + g * p.J;
-        for (int r = 0; r < rows_in; ++r) {
-          const int row = t0 - ph + r;
-          if (row < 0 || row >= p.T) continue;
-          // activation slab of this input row
-          mbar_wait(&b_empty[b_stage], b_phase ^ 1);
-          mbar_expect_tx(&b_full[b_stage], (uint32_t)slab_bytes);
-          {
-            const uint8_t* src = p.in + p.in_row0 + (long long)b0 * p.in_patch_stride + ((long long)row * p.P - pw) * 16;
-            uint8_t* dst = b_smem + b_stage * bstage_bytes;
-            for (int c = 0; c < p.NC; ++c)
-              bulk_g2s(dst + c * slab_plane_bytes, src + (long long)c * p.in_chunk_stride, (uint32_t)slab_plane_bytes, &b_full[b_stage]);
-          }
-          if (++b_stage == kNumBStages) { b_stage = 0; b_phase ^= 1; }
-          // weight stages of this K row
-          const uint8_t* wrow = p.w + (size_t)r * p.mmas_per_row * kATileBytes;
-          for (int m0 = 0; m0 < p.mmas_per_row; m0 += kStageMMAs) {
-            const int nm = min(kStageMMAs, p.mmas_per_row - m0);
-            mbar_wait(&a_empty[a_stage], a_phase ^ 1);
-            mbar_expect_tx(&a_full[a_stage], (uint32_t)(nm * kATileBytes));
-            bulk_g2s(a_smem + a_stage * kAStageBytes, wrow + (size_t)m0 * kATileBytes, (uint32_t)(nm * kATileBytes), &a_full[a_stage]);
-            if (++a_stage == kNumAStages) { a_stage = 0; a_phase ^= 1; }
-          }
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    // ===================================================== MMA issuer
-    // B-descriptor table of one K row (identical for every row): low word = (offset>>4) | (LBO>>4)<<16
-    {
-      const int n_paired = (p.NC / 2) * p.KW;
-      const int n_tab = (p.mmas_per_row + 7) / 8 * 8;
-      for (int q = lane; q < n_tab; q += 32) {
-        uint32_t boff, lbo;
-        if (q >= p.mmas_per_row) { btab[q] = 0; continue; }
-        if (q < n_paired) {
-          const int cp = q / p.KW, df = q - cp * p.KW;
-          boff = (uint32_t)(2 * cp * slab_plane_bytes + df * 16);
-          lbo = (uint32_t)slab_plane_bytes;
-        } else {
-          boff = (uint32_t)((p.NC - 1) * slab_plane_bytes + 2 * (q - n_paired) * 16);
-          lbo = 16u;
-        }
-        btab[q] = (boff >> 4) | ((lbo >> 4) << 16);
-      }
-      __syncwarp();
-    }
-    if (lane == 0) {
-      int a_stage = 0, b_stage = 0;
-      uint32_t a_phase = 0, b_phase = 0;
-      constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);                 // SBO = 128 B, descriptor version 1
-      constexpr uint32_t kALoFixed = ((128u * 16u) >> 4) << 16;              // A: LBO = 2048 B between the two k-slices
-      uint32_t k_unit = 0;
-      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++k_unit) {
-        const int g = u % p.n_groups;
-        const int t0 = p.row0 + g * p.J;
-        const uint32_t buf = k_unit & 1u, acc_par = (k_unit >> 1) & 1u;
-        mbar_wait(&acc_empty[buf], acc_par ^ 1);     // epilogue has drained this accumulator (two units ago)
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + buf * 256;
-        uint32_t accum = 0;
-        for (int r = 0; r < rows_in; ++r) {
-          const int row = t0 - ph + r;
-          if (row < 0 || row >= p.T) continue;
-          mbar_wait(&b_full[b_stage], b_phase);
-          const uint32_t bbase16 = smem_u32(b_smem + b_stage * bstage_bytes) >> 4;
-          for (int m0 = 0; m0 < p.mmas_per_row; m0 += kStageMMAs) {
-            const int nm = min(kStageMMAs, p.mmas_per_row - m0);
-            // descriptor words of the whole stage are fetched before blocking on the barrier (btab is padded to 8)
-            const uint4 e0 = *reinterpret_cast<const uint4*>(btab + m0);
-            const uint4 e1 = *reinterpret_cast<const uint4*>(btab + m0 + 4);
-            const uint32_t ent[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
-            mbar_wait(&a_full[a_stage], a_phase);
-            tc_fence_after();
-            const uint32_t abase16 = smem_u32(a_smem + a_stage * kAStageBytes) >> 4;
+__device__ __forceinline__ uint4 max8_rt(uint4 c, const uint4 a, int fmt) {
+  if (fmt == MPA_FMT_BF16) {
+    __nv_bfloat162* cm = reinterpret_cast<__nv_bfloat162*>(&c);
+    const __nv_bfloat162* am = reinterpret_cast<const __nv_bfloat162*>(&a);
 #pragma unroll
-            for (int i = 0; i < kStageMMAs; ++i) {
-              if (i < nm) {
-                const uint64_t adesc = ((uint64_t)kDescHi << 32) | (uint64_t)((abase16 + i * (kATileBytes >> 4)) | kALoFixed);
-                const uint64_t bdesc = ((uint64_t)kDescHi << 32) | (uint64_t)(bbase16 + ent[i]);
-                tc_mma_f16(tmem_d, adesc, bdesc, p.idesc, accum);
-                accum = 1;
-              }
-            }
-            tc_commit(&a_empty[a_stage]);       // frees the weight stage when its MMAs have retired
-            if (++a_stage == kNumAStages) { a_stage = 0; a_phase ^= 1; }
-          }
-          tc_commit(&b_empty[b_stage]);         // frees the activation slab of this row
-          if (++b_stage == kNumBStages) { b_stage = 0; b_phase ^= 1; }
-        }
-        tc_commit(&acc_full[buf]);              // accumulator complete -> epilogue
-      }
-    }
-    __syncwarp();
+    for (int e = 0; e < 4; ++e) cm[e] = __hmax2(cm[e], am[e]);
   } else {
-    // ===================================================== epilogue (warps 2..5 -> TMEM lane quadrants 2,3,0,1)
+    __half2* cm = reinterpret_cast<__half2*>(&c);
+    const __half2* am = reinterpret_cast<const __half2*>(&a);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) cm[e] = __hmax2(cm[e], am[e]);
+  }
+  return c;
+}
+__device__ __forceinline__ uint4 add8_rt(uint4 c, const uint4 r, int fmt) {
+  if (fmt == MPA_FMT_BF16) {
+    __nv_bfloat162* cm = reinterpret_cast<__nv_bfloat162*>(&c);
+    const __nv_bfloat162* rm = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float2 a = __bfloat1622float2(cm[e]), b2 = __bfloat1622float2(rm[e]);
+      cm[e] = __floats2bfloat162_rn(a.x + b2.x, a.y + b2.y);
+    }
+  } else {
+    __half2* cm = reinterpret_cast<__half2*>(&c);
+    const __half2* rm = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float2 a = __half22float2(cm[e]), b2 = __half22float2(rm[e]);
+      cm[e] = __floats2half2_rn(a.x + b2.x, a.y + b2.y);
+    }
+  }
+  return c;
+}
+
+// ------------------------------------------------------------------------------------------ epilogue role (warps 2..9)
+__device__ __forceinline__ void epilogue_role(const ConvTcParams& p, uint32_t tmem_base, uint16_t* epi_smem, uint64_t* acc_full, uint64_t* acc_empty,
+                                              int u_begin, int u_end, int u_first_real) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
+    // ===================================================== epilogue (warps 2..9: two warps per TMEM lane quadrant)
     const int quad = warp & 3;
     const int m = quad * 32 + lane;             // accumulator row = (j, co)
     const int j = m / p.Cout, co = m - j * p.Cout;
@@ -297,8 +255,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
     const float bias = row_valid ? p.bias[co] : 0.f;
     // coalesced path: 8 consecutive lanes = the 8 channels of one chunk of one output row (needs Cout % 8 == 0)
     const bool staged = ((p.Cout & 7) == 0);
-    const int ewarp = warp - 2;                                       // 0..7: two warps per TMEM lane quadrant
+    const int ewarp = warp - 2;                                       // 0..7
     const int ehalf = ewarp >> 2;                                     // which half of the 32-column chunks this warp drains
+    const int etid = threadIdx.x - 64;                                // 0..255 within the epilogue group
     uint16_t* stile = epi_smem + ewarp * (32 * kEpiPitch);            // [32 columns][kEpiPitch >= 32 lanes] 16-bit
     // per-thread constants of the transposed store phase: the 4 channel-chunk groups of this warp's 32 accumulator rows
     int grp_j[4], grp_plane[4];
@@ -310,11 +269,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
     }
     const size_t plane_elems = (p.out_mode == 0) ? (size_t)p.TP_out * p.P * 8 : (size_t)p.T_out * p.F_out * 8;
     const int row_pitch = (p.out_mode == 0) ? p.P : p.F_out;
+    const size_t ring_row_bytes = (size_t)p.NCo * p.P * 16;
+    uint8_t* ring_cta = p.pool ? p.ring + (size_t)blockIdx.x * 2 * p.J * ring_row_bytes : nullptr;
     uint32_t k_unit = 0;
-    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++k_unit) {
-      const int b = u / p.n_groups, g = u % p.n_groups;
-      const int t = p.row0 + g * p.J + j;
+    for (int u = u_begin; u < u_end; ++u, ++k_unit) {
+      const UnitInfo ui = decode_unit(p, u);
+      const int b = ui.b, t0 = ui.t0;
+      const int y_hi = p.y_hi[ui.seg];
+      const int t = t0 + j;
       const uint32_t buf = k_unit & 1u, acc_par = (k_unit >> 1) & 1u;
+      uint8_t* ring_bank = p.pool ? ring_cta + (size_t)(k_unit & 1u) * p.J * ring_row_bytes : nullptr;
       mbar_wait(&acc_full[buf], acc_par);
       tc_fence_after();
       uint16_t* out_b = p.out + (size_t)b * p.out_patch_stride;
@@ -346,30 +310,34 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
           // lane -> column c0+lane; pass k -> the k-th 8-lane group (= one channel chunk of one output row) of this warp
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const int tg = p.row0 + g * p.J + grp_j[k];
-            if (col_ok && grp_j[k] < p.J && tg < p.row_end) {
+            const int tg = t0 + grp_j[k];
+            if (col_ok && grp_j[k] < p.J && tg < y_hi) {
               const uint4 val = *reinterpret_cast<const uint4*>(stile + lane * kEpiPitch + k * 8);
-              const int orow = (p.out_mode == 0 ? p.pt_out : 0) + tg - p.row0;
-              *reinterpret_cast<uint4*>(out_b + (size_t)grp_plane[k] * plane_elems + ((size_t)orow * row_pitch + col_out) * 8) = val;
+              if (p.pool) {
+                *reinterpret_cast<uint4*>(ring_bank + ((size_t)grp_j[k] * p.NCo + grp_plane[k]) * p.P * 16 + (size_t)n * 16) = val;
+              } else {
+                const int orow = (p.out_mode == 0 ? p.pt_out : 0) + tg - p.row0;
+                *reinterpret_cast<uint4*>(out_b + (size_t)grp_plane[k] * plane_elems + ((size_t)orow * row_pitch + col_out) * 8) = val;
+              }
             }
           }
           __syncwarp();
-        } else if (row_valid && t < p.row_end) {
-          // scalar fallback (Cout not a multiple of 8): same destinations, one 16-bit store per value
+        } else if (row_valid && t < y_hi) {
+          // scalar fallback (Cout not a multiple of 8; never used with the fused pool): one 16-bit store per value
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const int n = c0 + i;
-            int fo = n - p.pf;
-            bool ok = (fo >= 0 && fo < p.F);
+            const int n2 = c0 + i;
+            int fo2 = n2 - p.pf;
+            bool ok = (fo2 >= 0 && fo2 < p.F);
             if (p.out_mode == 1) {
-              fo -= p.sub_offset;
-              ok = ok && fo >= 0 && (fo % p.sub_stride) == 0;
-              fo /= p.sub_stride;
+              fo2 -= p.sub_offset;
+              ok = ok && fo2 >= 0 && (fo2 % p.sub_stride) == 0;
+              fo2 /= p.sub_stride;
             }
             if (ok) {
               uint16_t* dst = (p.out_mode == 0)
-                                  ? p.out + (size_t)b * p.out_patch_stride + ((((size_t)(co >> 3)) * p.TP_out + p.pt_out + t - p.row0) * p.P + n) * 8 + (co & 7)
-                                  : p.out + (size_t)b * p.out_patch_stride + ((((size_t)(co >> 3)) * p.T_out + t - p.row0) * p.F_out + fo) * 8 + (co & 7);
+                                  ? p.out + (size_t)b * p.out_patch_stride + ((((size_t)(co >> 3)) * p.TP_out + p.pt_out + t - p.row0) * p.P + n2) * 8 + (co & 7)
+                                  : p.out + (size_t)b * p.out_patch_stride + ((((size_t)(co >> 3)) * p.T_out + t - p.row0) * p.F_out + fo2) * 8 + (co & 7);
               *dst = cvt16(apply_act(__uint_as_float(v[i]) + bias, p.act, p.act_param), p.fmt);
             }
           }
@@ -377,7 +345,379 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[buf]);
+      if (p.pool) {
+        // ---- fused MaxPool((3,1), stride 1, pad (1,0)) + residual.  The activated conv rows of this unit are in the current
+        // ring bank, the two rows above them in the other bank (written by this CTA one unit ago).
+        epi_bar_sync();
+        if (u >= u_first_real) {
+          const int t_last = min(t0 + p.J, y_hi) - 1;
+          int ze_lo = max(ui.first_in_seg ? p.z_lo[ui.seg] : t0 - 1, p.z_lo[ui.seg]);
+          int ze_hi = min(t_last == p.T - 1 ? t_last : t_last - 1, p.z_hi[ui.seg] - 1);
+          const uint8_t* ring_prev = ring_cta + (size_t)((k_unit & 1u) ^ 1u) * p.J * ring_row_bytes;
+          const int n_items = (ze_hi - ze_lo + 1) * p.NCo * p.F;
+          for (int it = etid; it < n_items; it += 256) {
+            const int f = it % p.F;
+            int r = it / p.F;
+            const int ck = r % p.NCo;
+            const int tz = ze_lo + r / p.NCo;
+            const size_t col_off = (size_t)ck * p.P * 16 + (size_t)(p.pf + f) * 16;
+            auto yrow = [&](int ty) -> uint4 {
+              const uint8_t* base = ty >= t0 ? ring_bank + (size_t)(ty - t0) * ring_row_bytes : ring_prev + (size_t)(p.J + ty - t0) * ring_row_bytes;
+              return *reinterpret_cast<const uint4*>(base + col_off);
+            };
+            uint4 c = yrow(tz);
+            if (tz > 0) c = max8_rt(c, yrow(tz - 1), p.fmt);
+            if (tz < p.T - 1) c = max8_rt(c, yrow(tz + 1), p.fmt);
+            if (p.residual) {
+              long long cs;
+              const uint8_t* rp = in_row_ptr(p, b, tz, cs);
+              c = add8_rt(c, *reinterpret_cast<const uint4*>(rp + (long long)ck * cs + (size_t)(p.pf + f) * 16), p.fmt);
+            }
+            long long ocs;
+            uint8_t* op = out_row_ptr(p, b, tz, ocs);
+            *reinterpret_cast<uint4*>(op + (long long)ck * ocs + (size_t)(p.pf + f) * 16) = c;
+          }
+        }
+        epi_bar_sync();
+      }
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int slab_plane_bytes = p.slab_px * 16;
+  const int slab_bytes = p.NC * slab_plane_bytes;        // one patch, one input row
+  const int bstage_bytes = slab_bytes;
+  const int kNumAStages = p.a_stages;
+  uint8_t* a_smem = smem;                                // [a_stages][kAStageBytes]
+  uint8_t* b_smem = smem + kNumAStages * kAStageBytes;   // [kNumBStages][NC][slab_px][16B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + kNumBStages * bstage_bytes);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = bars + kMaxAStages;
+  uint64_t* b_full = bars + 2 * kMaxAStages;
+  uint64_t* b_empty = b_full + kNumBStages;
+  uint64_t* acc_full = b_empty + kNumBStages;            // [2]
+  uint64_t* acc_empty = acc_full + 2;                    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint32_t* btab = reinterpret_cast<uint32_t*>(smem + p.btab_off);         // [mmas_per_row padded to 8] B-descriptor low words
+  uint16_t* epi_smem = reinterpret_cast<uint16_t*>(smem + p.epi_off);      // 8 warps x [32][kEpiPitch] 16-bit staging
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kNumAStages; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < kNumBStages; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], kThreads - 64);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int ph = p.KH / 2, pw = p.KW / 2;
+  const int rows_in = p.KH + p.J - 1;
+  int u_begin, u_end, u_first_real;
+  unit_range(p, u_begin, u_end, u_first_real);
+
+  if (warp == 0) {
+    // ===================================================== producer
+    if (lane == 0) {
+      int a_stage = 0, b_stage = 0;
+      uint32_t a_phase = 0, b_phase = 0;
+      for (int u = u_begin; u < u_end; ++u) {
+        const UnitInfo ui = decode_unit(p, u);
+        for (int r = 0; r < rows_in; ++r) {
+          const int row = ui.t0 - ph + r;
+          if (row < 0 || row >= p.T) continue;
+          // activation slab of this input row
+          mbar_wait(&b_empty[b_stage], b_phase ^ 1);
+          mbar_expect_tx(&b_full[b_stage], (uint32_t)slab_bytes);
+          {
+            long long cs;
+            const uint8_t* src = in_row_ptr(p, ui.b, row, cs) - pw * 16;
+            uint8_t* dst = b_smem + b_stage * bstage_bytes;
+            for (int c = 0; c < p.NC; ++c)
+              bulk_g2s(dst + c * slab_plane_bytes, src + (long long)c * cs, (uint32_t)slab_plane_bytes, &b_full[b_stage]);
+          }
+          if (++b_stage == kNumBStages) { b_stage = 0; b_phase ^= 1; }
+          // weight stages of this K row
+          const uint8_t* wrow = p.w + (size_t)r * p.mmas_per_row * kATileBytes;
+          for (int m0 = 0; m0 < p.mmas_per_row; m0 += kStageMMAs) {
+            const int nm = min(kStageMMAs, p.mmas_per_row - m0);
+            mbar_wait(&a_empty[a_stage], a_phase ^ 1);
+            mbar_expect_tx(&a_full[a_stage], (uint32_t)(nm * kATileBytes));
+            bulk_g2s(a_smem + a_stage * kAStageBytes, wrow + (size_t)m0 * kATileBytes, (uint32_t)(nm * kATileBytes), &a_full[a_stage]);
+            if (++a_stage == kNumAStages) { a_stage = 0; a_phase ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    // The whole warp walks the loops and waits (warp-uniform control flow and operands); one elected lane issues.  The B-descriptor
+    // words of one K row come from the kernel parameters (constant bank -> uniform registers), so an MMA costs a constant load
+    // and two uniform adds in the issuing thread (the per-MMA cost of that thread bounds the kernel once L2 keeps up).
+    {
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      int a_stage = 0, b_stage = 0;
+      uint32_t a_phase = 0, b_phase = 0;
+      constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);                 // SBO = 128 B, descriptor version 1
+      constexpr uint32_t kALoFixed = ((128u * 16u) >> 4) << 16;              // A: LBO = 2048 B between the two k-slices
+      const uint32_t asm16 = smem_u32(a_smem) >> 4, bsm16 = smem_u32(b_smem) >> 4, bst16 = (uint32_t)bstage_bytes >> 4;
+      uint32_t k_unit = 0;
+      for (int u = u_begin; u < u_end; ++u, ++k_unit) {
+        const UnitInfo ui = decode_unit(p, u);
+        const uint32_t buf = k_unit & 1u, acc_par = (k_unit >> 1) & 1u;
+        mbar_wait(&acc_empty[buf], acc_par ^ 1);     // epilogue has drained this accumulator (two units ago)
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_u + buf * 256;
+        uint32_t accum = 0;
+        for (int r = 0; r < rows_in; ++r) {
+          const int row = ui.t0 - ph + r;
+          if (row < 0 || row >= p.T) continue;
+          mbar_wait(&b_full[b_stage], b_phase);
+          const uint32_t bbase16 = bsm16 + (uint32_t)b_stage * bst16;
+          for (int m0 = 0; m0 < p.mmas_per_row; m0 += kStageMMAs) {
+            const int nm = min(kStageMMAs, p.mmas_per_row - m0);
+            mbar_wait(&a_full[a_stage], a_phase);
+            tc_fence_after();
+            const uint32_t a_lo = (asm16 + (uint32_t)a_stage * (kAStageBytes >> 4)) | kALoFixed;
+            if (elect_one_sync()) {
+              if (nm == kStageMMAs) {
+                tc_mma_f16(tmem_d, ((uint64_t)kDescHi << 32) | (uint64_t)a_lo, ((uint64_t)kDescHi << 32) | (uint64_t)(bbase16 + p.btab[m0]), p.idesc, accum);
+#pragma unroll
+                for (int i = 1; i < kStageMMAs; ++i)
+                  tc_mma_f16(tmem_d, ((uint64_t)kDescHi << 32) | (uint64_t)(a_lo + (uint32_t)i * (kATileBytes >> 4)),
+                             ((uint64_t)kDescHi << 32) | (uint64_t)(bbase16 + p.btab[m0 + i]), p.idesc, 1u);
+              } else {
+                for (int i = 0; i < nm; ++i)
+                  tc_mma_f16(tmem_d, ((uint64_t)kDescHi << 32) | (uint64_t)(a_lo + (uint32_t)i * (kATileBytes >> 4)),
+                             ((uint64_t)kDescHi << 32) | (uint64_t)(bbase16 + p.btab[m0 + i]), p.idesc, (i == 0) ? accum : 1u);
+              }
+              tc_commit(&a_empty[a_stage]);       // frees the weight stage when its MMAs have retired
+            }
+            __syncwarp();
+            accum = 1;
+            if (++a_stage == kNumAStages) { a_stage = 0; a_phase ^= 1; }
+          }
+          if (elect_one_sync()) tc_commit(&b_empty[b_stage]);         // frees the activation slab of this row
+          __syncwarp();
+          if (++b_stage == kNumBStages) { b_stage = 0; b_phase ^= 1; }
+        }
+        if (elect_one_sync()) tc_commit(&acc_full[buf]);              // accumulator complete -> epilogue
+        __syncwarp();
+      }
+    }
+    __syncwarp();
+  } else {
+    epilogue_role(p, tmem_base, epi_smem, acc_full, acc_empty, u_begin, u_end, u_first_real);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
+// ------------------------------------------------------------------------------------------ ring main loop
+// The J row blocks of the A operand hold the SAME filter rows shifted by one input row (block j of the tile of input row r =
+// filter row r-j), so streaming ready-made 128-row tiles moves every weight J times through L2->SM (36 B/clk/SM at J = 3: the
+// measured limiter of conv_tc_kernel).  Here the weights travel as "pieces" = one filter row, all Cout channels, for the K
+// slices of one channel-chunk GROUP (two chunks x KW taps, or the odd last chunk with taps paired), laid out
+//     ring[position][row group of 8 channels][q][k-slice][8 rows][16 B]        (SBO = Q*256 B between row groups, LBO = 128 B)
+// in a shared-memory ring whose positions DESCEND as r grows: the tile of input row r is simply the J pieces starting at the
+// position of filter row r (block j = the next position = filter row r-1 ...), i.e. a descriptor start address — nothing is
+// copied twice except the J-1 pieces that wrap (mirrored behind the ring's end).  The K loop runs group-major (all input rows
+// of a unit for chunk pair 0, then pair 1, ...), so only one group's pieces are resident: J+2..J+4 positions.
+// Q MMAs of one tile: A descriptors step by 256 B (next q of the piece), B descriptors by BSTEP pixels (16 B each)
+template <int Q, int BSTEP>
+__device__ __forceinline__ void issue_tile(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t first) {
+  tc_mma_f16(tmem_d, ((uint64_t)a_hi << 32) | (uint64_t)a_lo, ((uint64_t)b_hi << 32) | (uint64_t)b_lo, idesc, first ? 0u : 1u);
+#pragma unroll
+  for (int q = 1; q < Q; ++q)
+    tc_mma_f16(tmem_d, ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)q * 16u), ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + (uint32_t)(q * BSTEP)), idesc, 1u);
+}
+__device__ __forceinline__ void ring_group(const ConvTcParams& p, int g, int& Q, int& planes, int& chunk0) {
+  if (g < p.NC / 2) { Q = p.KW; planes = 2; chunk0 = 2 * g; }
+  else { Q = (p.KW + 1) / 2; planes = 1; chunk0 = p.NC - 1; }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_ring_kernel(const ConvTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int slab_plane_bytes = p.slab_px * 16;
+  const int bstage_bytes = 2 * slab_plane_bytes;
+  const int S = p.ring_S, NB = p.ring_nb;
+  uint8_t* ring = smem;                                   // [ring_npos][ring_ps]
+  uint8_t* b_smem = smem + p.ring_b_off;                  // [NB][2 planes][slab_px][16 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.ring_bar_off);
+  uint64_t* w_full = bars;                                // [S]
+  uint64_t* w_empty = bars + kMaxRingS;                   // [S]
+  uint64_t* b_full = bars + 2 * kMaxRingS;                // [NB]
+  uint64_t* b_empty = b_full + kMaxRingB;
+  uint64_t* acc_full = b_empty + kMaxRingB;               // [2]
+  uint64_t* acc_empty = acc_full + 2;                     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint32_t* btab = reinterpret_cast<uint32_t*>(smem + p.btab_off);         // [group][16] B-descriptor low words
+  uint16_t* epi_smem = reinterpret_cast<uint16_t*>(smem + p.epi_off);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kThreads - 64); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int ph = p.KH / 2, pw = p.KW / 2;
+  const int rows_in = p.KH + p.J - 1;
+  const int NG = (p.NC + 1) / 2;
+  const int G8 = p.Cout >> 3;
+  const int n_kh = p.KH + 2 * (p.J - 1);                  // filter-row pieces per group in the packed array (zero pieces at both ends)
+  int u_begin, u_end, u_first_real;
+  unit_range(p, u_begin, u_end, u_first_real);
+
+  if (warp == 0) {
+    // ===================================================== producer: weight pieces + activation slabs, in consumption order
+    if (lane == 0) {
+      uint32_t n_piece = 0;                                 // running piece counter: position = S-1 - n % S
+      int b_stage = 0;
+      uint32_t b_phase = 0;
+      for (int u = u_begin; u < u_end; ++u) {
+        const UnitInfo ui = decode_unit(p, u);
+        const int r_first = max(0, ph - ui.t0), r_last = min(rows_in - 1, p.T - 1 - ui.t0 + ph);
+        size_t g_off = 0;
+        for (int g = 0; g < NG; ++g) {
+          int Q, planes, chunk0;
+          ring_group(p, g, Q, planes, chunk0);
+          const uint32_t row_bytes = (uint32_t)Q * 256u;                     // one row group of 8 channels, all q, both k-slices
+          const uint8_t* wg = p.w + g_off;
+          for (int kh = r_first - (p.J - 1); kh <= r_last; ++kh, ++n_piece) {
+            const int pos = S - 1 - (int)(n_piece % (uint32_t)S);
+            const uint32_t round = n_piece / (uint32_t)S;
+            const bool mirror = pos <= p.J - 2;
+            mbar_wait(&w_empty[pos], (round & 1u) ^ 1u);
+            const bool mir = mirror;
+            mbar_expect_tx(&w_full[pos], (uint32_t)G8 * row_bytes * (mir ? 2u : 1u));
+            const uint8_t* src = wg + (size_t)(kh + p.J - 1) * G8 * row_bytes;
+            uint8_t* dst = ring + (size_t)pos * p.ring_ps;
+            if (row_bytes == (uint32_t)p.ring_sbo) {
+              // the piece is contiguous in shared memory as well: one bulk copy (plus its mirror)
+              bulk_g2s(dst, src, (uint32_t)G8 * row_bytes, &w_full[pos]);
+              if (mir) bulk_g2s(dst + (size_t)S * p.ring_ps, src, (uint32_t)G8 * row_bytes, &w_full[pos]);
+            } else {
+              for (int g8 = 0; g8 < G8; ++g8) {
+                bulk_g2s(dst + (size_t)g8 * p.ring_sbo, src + (size_t)g8 * row_bytes, row_bytes, &w_full[pos]);
+                if (mir) bulk_g2s(dst + (size_t)S * p.ring_ps + (size_t)g8 * p.ring_sbo, src + (size_t)g8 * row_bytes, row_bytes, &w_full[pos]);
+              }
+            }
+            if (kh >= r_first) {
+              // activation slab (this group's planes) of input row kh
+              const int row = ui.t0 - ph + kh;
+              mbar_wait(&b_empty[b_stage], b_phase ^ 1);
+              mbar_expect_tx(&b_full[b_stage], (uint32_t)(planes * slab_plane_bytes));
+              long long cs;
+              const uint8_t* bsrc = in_row_ptr(p, ui.b, row, cs) - pw * 16 + (long long)chunk0 * cs;
+              uint8_t* bdst = b_smem + b_stage * bstage_bytes;
+              for (int c = 0; c < planes; ++c)
+                bulk_g2s(bdst + c * slab_plane_bytes, bsrc + (long long)c * cs, (uint32_t)slab_plane_bytes, &b_full[b_stage]);
+              if (++b_stage == NB) { b_stage = 0; b_phase ^= 1; }
+            }
+          }
+          g_off += (size_t)n_kh * G8 * row_bytes;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    // The whole warp walks the loops and waits on the barriers (warp-uniform control flow, every operand of the issue path
+    // derived from kernel parameters / uniform values); one elected lane issues the MMAs and commits.  The issue sequence is
+    // kept to two integer adds per MMA: the per-MMA cost of the single issuing thread is what bounds this kernel next to L2.
+    {
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      uint32_t n_piece = 0;
+      int b_stage = 0;
+      uint32_t b_phase = 0;
+      const uint32_t kDescHiB = (128u >> 4) | (1u << 14);                            // B: SBO = 128 B
+      const uint32_t kDescHiA = ((uint32_t)p.ring_sbo >> 4) | (1u << 14);            // A: SBO = Q*256 B between 8-row groups
+      constexpr uint32_t kALoFixed = (128u >> 4) << 16;                              // A: LBO = 128 B between the two k-slices
+      const uint32_t ring16 = smem_u32(ring) >> 4, ps16 = (uint32_t)p.ring_ps >> 4;
+      const uint32_t bsm16 = smem_u32(b_smem) >> 4, bst16 = (uint32_t)bstage_bytes >> 4;
+      const uint32_t plane16 = (uint32_t)slab_plane_bytes >> 4;
+      uint32_t k_unit = 0;
+      for (int u = u_begin; u < u_end; ++u, ++k_unit) {
+        const UnitInfo ui = decode_unit(p, u);
+        const int r_first = max(0, ph - ui.t0), r_last = min(rows_in - 1, p.T - 1 - ui.t0 + ph);
+        const uint32_t buf = k_unit & 1u, acc_par = (k_unit >> 1) & 1u;
+        mbar_wait(&acc_empty[buf], acc_par ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_u + buf * 256;
+        uint32_t first = 1;                                 // the unit's very first MMA overwrites the accumulator
+        for (int g = 0; g < NG; ++g) {
+          const bool pair = g < p.NC / 2;
+          const int Q = pair ? p.KW : (p.KW + 1) / 2;
+          const uint32_t b_lo_fixed = pair ? (plane16 << 16) : (1u << 16);           // LBO: the other chunk's plane / the next tap
+          for (int kh = r_first - (p.J - 1); kh <= r_last; ++kh, ++n_piece) {
+            const int pos = S - 1 - (int)(n_piece % (uint32_t)S);
+            mbar_wait(&w_full[pos], (n_piece / (uint32_t)S) & 1u);
+            if (kh < r_first) continue;                    // pre-loaded pieces of the first tile
+            mbar_wait(&b_full[b_stage], b_phase);
+            tc_fence_after();
+            const uint32_t a_lo = (ring16 + (uint32_t)pos * ps16) | kALoFixed;
+            const uint32_t b_lo = (bsm16 + (uint32_t)b_stage * bst16) | b_lo_fixed;
+            const uint32_t n_old = n_piece - (uint32_t)(p.J - 1);
+            if (elect_one_sync()) {
+              if (pair && Q == 15) issue_tile<15, 1>(tmem_d, a_lo, kDescHiA, b_lo, kDescHiB, p.idesc, first);
+              else if (!pair && Q == 8) issue_tile<8, 2>(tmem_d, a_lo, kDescHiA, b_lo, kDescHiB, p.idesc, first);
+              else {
+                const uint32_t bstep = pair ? 1u : 2u;
+                for (int q = 0; q < Q; ++q)
+                  tc_mma_f16(tmem_d, ((uint64_t)kDescHiA << 32) | (uint64_t)(a_lo + (uint32_t)q * 16u), ((uint64_t)kDescHiB << 32) | (uint64_t)(b_lo + (uint32_t)q * bstep),
+                             p.idesc, (q == 0 && first) ? 0u : 1u);
+              }
+              tc_commit(&b_empty[b_stage]);
+              // the oldest piece of this tile (filter row kh-(J-1)) is done; after the group's last row so are the J-1 others
+              tc_commit(&w_empty[S - 1 - (int)(n_old % (uint32_t)S)]);
+              if (kh == r_last)
+                for (int jj = p.J - 2; jj >= 0; --jj) tc_commit(&w_empty[S - 1 - (int)((n_piece - (uint32_t)jj) % (uint32_t)S)]);
+            }
+            __syncwarp();
+            first = 0;
+            if (++b_stage == NB) { b_stage = 0; b_phase ^= 1; }
+          }
+        }
+        if (elect_one_sync()) tc_commit(&acc_full[buf]);
+        __syncwarp();
+      }
+    }
+  } else {
+    epilogue_role(p, tmem_base, epi_smem, acc_full, acc_empty, u_begin, u_end, u_first_real);
   }
   tc_fence_before();
   __syncthreads();
@@ -645,6 +985,135 @@ int mpa_conv_tc_pack_weights(const float* w, void* packed, int Cin, int Cout, in
   return MPA_OK;
 }
 
+size_t mpa_conv_tc_ring_packed_bytes(int Cin, int Cout, int KH, int KW, int J) {
+  if (Cin <= 0 || Cout <= 0 || Cout > 128 || (Cout & 7) || KH <= 0 || KW <= 0 || KW > 16 || J < 0 || J * Cout > 128) return 0;
+  const int NC = (Cin + 7) / 8;
+  if (J == 0) J = j_blocks(Cout);
+  const size_t n_kh = (size_t)KH + 2 * (J - 1);
+  const size_t q_total = (size_t)(NC / 2) * KW + ((NC & 1) ? (KW + 1) / 2 : 0);
+  return n_kh * (Cout / 8) * q_total * 256;
+}
+
+/* Ring layout (conv_tc_ring_kernel): [group][filter row -(J-1) .. KH-1+(J-1)][row group of 8 channels][q][k-slice][8][8] 16-bit;
+ * group g < NC/2: chunks (2g, 2g+1), q = tap; last group when NC is odd: chunk NC-1, q-th MMA = taps (2q, 2q+1).  Filter rows outside
+ * [0, KH) are zero pieces (the shifted row blocks of the first / last tiles). */
+int mpa_conv_tc_ring_pack_weights(const float* w, void* packed, int Cin, int Cout, int KH, int KW, int fmt, int J) {
+  MPA_REQUIRE(w && packed && Cin > 0 && Cout > 0 && Cout <= 128 && (Cout & 7) == 0 && KH > 0 && KW > 0 && KW <= 16,
+              "conv_tc_ring_pack_weights: bad argument (Cout multiple of 8, <= 128; KW <= 16)");
+  MPA_REQUIRE(J >= 0 && J * Cout <= 128, "conv_tc_ring_pack_weights: J*Cout must be <= 128");
+  if (J == 0) J = j_blocks(Cout);
+  const int NC = (Cin + 7) / 8, NG = (NC + 1) / 2, G8 = Cout / 8, n_kh = KH + 2 * (J - 1);
+  uint16_t* o = (uint16_t*)packed;
+  memset(o, 0, mpa_conv_tc_ring_packed_bytes(Cin, Cout, KH, KW, J));
+  size_t g_off = 0;   // in 16-bit elements
+  for (int g = 0; g < NG; ++g) {
+    const bool pair = g < NC / 2;
+    const int Q = pair ? KW : (KW + 1) / 2;
+    for (int khi = 0; khi < n_kh; ++khi) {
+      const int kh = khi - (J - 1);
+      if (kh < 0 || kh >= KH) continue;
+      for (int g8 = 0; g8 < G8; ++g8)
+        for (int q = 0; q < Q; ++q)
+          for (int ks = 0; ks < 2; ++ks) {
+            const int c = pair ? 2 * g + ks : NC - 1;
+            const int df = pair ? q : 2 * q + ks;
+            if (df >= KW) continue;
+            for (int row = 0; row < 8; ++row) {
+              const int co = g8 * 8 + row;
+              for (int e = 0; e < 8; ++e) {
+                const int ci = c * 8 + e;
+                if (ci >= Cin) continue;
+                const float wv = w[(((size_t)co * Cin + ci) * KH + kh) * KW + df];
+                o[g_off + ((((size_t)khi * G8 + g8) * Q + q) * 2 + ks) * 64 + row * 8 + e] = fmt == MPA_FMT_BF16 ? f32_to_bf16_rne(wv) : f32_to_f16_rne(wv);
+              }
+            }
+          }
+    }
+    g_off += (size_t)n_kh * G8 * Q * 128;
+  }
+  return MPA_OK;
+}
+
+// smem layout, grid and launch shared by both entry points (p: everything but the smem offsets filled in)
+static int launch_conv_tc(ConvTcParams& p, int Cin, cudaStream_t stream, int* grid_out) {
+  p.mmas_per_row = mmas_per_row(p.NC, p.KW);
+  p.slab_px = (p.N + 2 * (p.KW / 2) + 1 + 7) / 8 * 8;
+  size_t smem = 0;
+  if (p.ring_on) {
+    const int qmax = p.NC >= 2 ? p.KW : (p.KW + 1) / 2;
+    MPA_REQUIRE(p.KW <= 16 && (p.Cout & 7) == 0 && p.NC <= 16, "conv_tc(ring): KW <= 16, Cout %% 8 == 0, Cin <= 128 required");
+    p.ring_sbo = qmax * 256;
+    p.ring_ps = (p.Cout / 8) * p.ring_sbo;
+    p.ring_nb = 4;
+    const size_t bstage = 2 * (size_t)p.slab_px * 16;
+    const size_t fixed = (size_t)p.ring_nb * bstage + 640 + 512 + 128 + 8 * 32 * kEpiPitch * 2;
+    int S = p.J + 4;
+    while (S > p.J + 1 && (size_t)(S + p.J - 1) * p.ring_ps + fixed > 227 * 1024) --S;
+    MPA_REQUIRE(S >= p.J + 1 && S <= kMaxRingS, "conv_tc(ring): the weight ring does not fit (Cout=%d J=%d)", p.Cout, p.J);
+    p.ring_S = S;
+    p.ring_npos = S + p.J - 1;
+    p.ring_b_off = p.ring_npos * p.ring_ps;
+    p.ring_bar_off = p.ring_b_off + (int)(p.ring_nb * bstage);
+    p.btab_off = p.ring_bar_off + 640;
+    size_t off = (size_t)p.btab_off + 512;
+    off = (off + 127) / 128 * 128;
+    p.epi_off = (int)off;
+    smem = off + 8 * 32 * kEpiPitch * 2;
+  } else {
+    const size_t b_bytes = (size_t)kNumBStages * p.NC * p.slab_px * 16;
+    const size_t tail = 256 + (size_t)(p.mmas_per_row + 8) * 4 + 128 + 8 * 32 * kEpiPitch * 2;   // barriers, table, staging
+    int a_stages = kMaxAStages;
+    while (a_stages > 2 && (size_t)a_stages * kAStageBytes + b_bytes + tail > 227 * 1024) --a_stages;
+    p.a_stages = a_stages;
+    MPA_REQUIRE(p.mmas_per_row <= 128, "conv_tc: too many K steps per row (%d)", p.mmas_per_row);
+    {
+      const uint32_t plane = (uint32_t)p.slab_px * 16u;
+      const int n_paired = (p.NC / 2) * p.KW;
+      for (int q = 0; q < p.mmas_per_row; ++q) {
+        uint32_t boff, lbo;
+        if (q < n_paired) {
+          const int cp = q / p.KW, df = q - cp * p.KW;
+          boff = (uint32_t)(2 * cp) * plane + (uint32_t)df * 16u;
+          lbo = plane;
+        } else {
+          boff = (uint32_t)(p.NC - 1) * plane + 2u * (uint32_t)(q - n_paired) * 16u;
+          lbo = 16u;
+        }
+        p.btab[q] = (boff >> 4) | ((lbo >> 4) << 16);
+      }
+    }
+    size_t off = (size_t)a_stages * kAStageBytes + b_bytes;
+    p.btab_off = (int)(off + 256);
+    off += 256 + (size_t)(p.mmas_per_row + 8) * 4;      // barriers + tmem slot (256 B), descriptor table
+    off = (off + 127) / 128 * 128;
+    p.epi_off = (int)off;
+    smem = off + 8 * 32 * kEpiPitch * 2;
+  }
+  MPA_REQUIRE(smem <= 227 * 1024, "conv_tc: needs %zu B of shared memory (Cin=%d pitch=%d)", smem, Cin, p.P);
+  static thread_local size_t attr_set[2] = {0, 0};
+  if (smem > attr_set[p.ring_on ? 1 : 0]) {
+    cudaError_t e = p.ring_on ? cudaFuncSetAttribute(conv_tc_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                              : cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("conv_tc: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+      return MPA_ERR_CUDA;
+    }
+    attr_set[p.ring_on ? 1 : 0] = smem;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms > kMaxGrid) sms = kMaxGrid;
+  const int grid = p.n_units < sms ? p.n_units : sms;
+  if (grid_out) *grid_out = grid;
+  if (p.ring_on)
+    conv_tc_ring_kernel<<<grid, kThreads, smem, stream>>>(p);
+  else
+    conv_tc_kernel<<<grid, kThreads, smem, stream>>>(p);
+  MPA_CHECK_LAUNCH("conv_tc");
+  return MPA_OK;
+}
+
 int mpa_conv_tc_f16(const void* in_cp8, const void* w_packed, const float* bias, void* out, int out_mode, int sub_stride,
                     int sub_offset, int n_patches, int Cin, int Cout, int T, int F, int KH, int KW, int pitch, int pf, int pt,
                     long long in_patch_stride_rows, int in_nc_stride, int out_nc_stride, int J, int row0, int n_rows, int act,
@@ -662,7 +1131,7 @@ int mpa_conv_tc_f16(const void* in_cp8, const void* w_packed, const float* bias,
   MPA_REQUIRE(((uintptr_t)in_cp8 & 15) == 0 && ((uintptr_t)w_packed & 15) == 0 && ((uintptr_t)out & 15) == 0, "conv_tc: 16-byte alignment required");
   MPA_REQUIRE(out_mode == 0 || (out_mode == 1 && sub_stride >= 1 && sub_offset >= 0 && sub_offset < sub_stride), "conv_tc: bad output mode");
   ConvTcParams p;
-  p.in = (const uint8_t*)in_cp8;
+  memset(&p, 0, sizeof(p));
   p.w = (const uint8_t*)w_packed;
   p.bias = bias;
   p.out = (uint16_t*)out;
@@ -678,62 +1147,121 @@ int mpa_conv_tc_f16(const void* in_cp8, const void* w_packed, const float* bias,
   p.T = T; p.F = F; p.KH = KH; p.KW = KW; p.P = pitch; p.N = N; p.pf = pf;
   p.row0 = row0;
   p.T_out = n_rows > 0 ? n_rows : T - row0;
-  p.row_end = row0 + p.T_out;
   p.pt_out = pt;
   p.TP_out = p.T_out + 2 * pt;
   p.NCo = (Cout + 7) / 8;
   const long long TP = T + 2 * pt;
+  const uint8_t* in0 = (const uint8_t*)in_cp8 + (long long)pt * pitch * 16;   // (row 0, column 0) of patch 0, chunk 0
   if (in_patch_stride_rows <= 0) {
     // materialised patches: [n_patches][NC][TP][P][8]
-    p.in_chunk_stride = TP * pitch * 16;
-    p.in_patch_stride = p.in_chunk_stride * (in_nc_stride > 0 ? in_nc_stride : p.NC);
-    p.in_row0 = (long long)pt * pitch * 16;
+    p.in_e = T;
+    p.in_edge = in0;
+    p.in_edge_chunk_stride = TP * pitch * 16;
+    p.in_edge_patch_stride = p.in_edge_chunk_stride * (in_nc_stride > 0 ? in_nc_stride : p.NC);
   } else {
     // streaming: one shared frame-major plane [rows][P][8]; patch b starts at row b*stride (after pt guard rows)
     MPA_REQUIRE(p.NC == 1, "conv_tc: streaming input supports a single channel chunk");
-    p.in_chunk_stride = 0;
-    p.in_patch_stride = in_patch_stride_rows * pitch * 16;
-    p.in_row0 = (long long)pt * pitch * 16;
+    p.in_e = 0;
+    p.in_stream = in0;
+    p.in_stream_chunk_stride = 0;
+    p.in_stream_patch_rows = in_patch_stride_rows;
   }
   MPA_REQUIRE(in_nc_stride == 0 || in_nc_stride >= p.NC, "conv_tc: in_nc_stride %d < %d input chunks", in_nc_stride, p.NC);
   MPA_REQUIRE(out_nc_stride == 0 || out_nc_stride >= p.NCo, "conv_tc: out_nc_stride %d < %d output chunks", out_nc_stride, p.NCo);
   p.out_patch_stride = (long long)(out_nc_stride > 0 ? out_nc_stride : p.NCo) * (out_mode == 0 ? (long long)p.TP_out * pitch : (long long)p.T_out * p.F_out) * 8;
-  p.mmas_per_row = mmas_per_row(p.NC, KW);
-  p.n_groups = (p.T_out + p.J - 1) / p.J;
-  p.n_units = n_patches * p.n_groups;
-  p.slab_px = (N + 2 * (KW / 2) + 1 + 7) / 8 * 8;
+  p.n_seg = 1;
+  p.y_lo[0] = p.z_lo[0] = row0;
+  p.y_hi[0] = p.z_hi[0] = row0 + p.T_out;
+  p.seg_groups[0] = (p.T_out + p.J - 1) / p.J;
+  p.seg_groups[1] = 0;
+  p.groups_per_patch = p.seg_groups[0];
+  p.n_units = n_patches * p.groups_per_patch;
   p.act = act;
   p.act_param = act_param;
   const uint32_t f = (fmt == MPA_FMT_BF16) ? 1u : 0u;
   p.idesc = (1u << 4) | (f << 7) | (f << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  const size_t b_bytes = (size_t)kNumBStages * p.NC * p.slab_px * 16;
-  const size_t tail = 256 + (size_t)(p.mmas_per_row + 8) * 4 + 128 + 8 * 32 * kEpiPitch * 2;   // barriers, table, staging
-  int a_stages = kMaxAStages;
-  while (a_stages > 2 && (size_t)a_stages * kAStageBytes + b_bytes + tail > 227 * 1024) --a_stages;
-  p.a_stages = a_stages;
-  size_t off = (size_t)a_stages * kAStageBytes + b_bytes;
-  p.btab_off = (int)(off + 256);
-  off += 256 + (size_t)(p.mmas_per_row + 8) * 4;      // barriers + tmem slot (256 B), descriptor table
-  off = (off + 127) / 128 * 128;
-  p.epi_off = (int)off;
-  const size_t smem = off + 8 * 32 * kEpiPitch * 2;
-  MPA_REQUIRE(smem <= 227 * 1024, "conv_tc: needs %zu B of shared memory (Cin=%d pitch=%d)", smem, Cin, pitch);
-  static thread_local size_t attr_set = 0;
-  if (smem > attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      set_error("conv_tc: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
-      return MPA_ERR_CUDA;
-    }
-    attr_set = smem;
+  return launch_conv_tc(p, Cin, (cudaStream_t)stream, nullptr);
+}
+
+size_t mpa_conv_tc_pool_workspace(int Cout, int pitch, int J) {
+  if (Cout <= 0 || Cout > 128 || pitch <= 0) return 0;
+  if (J <= 0) J = j_blocks(Cout);
+  return (size_t)kMaxGrid * 2 * J * ((Cout + 7) / 8) * pitch * 16;
+}
+
+int mpa_conv_tc_pool_f16(const mpa_conv_tc_desc* d, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(d && d->w_packed && d->bias && d->workspace && d->n_patches > 0, "conv_tc_pool: null argument");
+  MPA_REQUIRE(d->Cout > 0 && d->Cout <= 64 && (d->Cout & 7) == 0 && d->Cin > 0, "conv_tc_pool: Cout must be a multiple of 8, <= 64 (got %d)", d->Cout);
+  MPA_REQUIRE((d->KH & 1) && (d->KW & 1), "conv_tc_pool: odd kernel sizes only");
+  MPA_REQUIRE(d->fmt == MPA_FMT_F16 || d->fmt == MPA_FMT_BF16, "conv_tc_pool: fmt must be MPA_FMT_F16 or MPA_FMT_BF16");
+  const int pitch = d->pitch, KW = d->KW, F = d->F, pf = d->pf, T = d->T;
+  MPA_REQUIRE(pitch >= 16 && pitch <= 256 && pitch % 16 == 0, "conv_tc_pool: row pitch %d must be a multiple of 16 (<= 256)", pitch);
+  MPA_REQUIRE(pf >= KW / 2 && pitch - F >= KW / 2 && pitch >= pf + F, "conv_tc_pool: pitch %d / left pad %d too small for F=%d KW=%d", pitch, pf, F, KW);
+  const int J = d->J > 0 ? d->J : j_blocks(d->Cout);
+  MPA_REQUIRE(J >= 2 && J * d->Cout <= 128, "conv_tc_pool: needs 2 <= J and J*Cout <= 128");
+  MPA_REQUIRE(d->in_e == T || (d->in_e >= 0 && 2 * d->in_e <= T), "conv_tc_pool: in_e must be T or <= T/2");
+  MPA_REQUIRE(d->out_e == T || (d->out_e >= 0 && 2 * d->out_e <= T), "conv_tc_pool: out_e must be T or <= T/2");
+  MPA_REQUIRE((d->in_e == 0 || d->in_edge) && (d->in_e == T || d->in_stream), "conv_tc_pool: missing input plane");
+  MPA_REQUIRE((d->out_e == 0 || d->out_edge) && (d->out_e == T || d->out_stream), "conv_tc_pool: missing output plane");
+  MPA_REQUIRE(d->n_seg == 1 || d->n_seg == 2, "conv_tc_pool: 1 or 2 row segments");
+  ConvTcParams p;
+  memset(&p, 0, sizeof(p));
+  p.in_edge = (const uint8_t*)d->in_edge;
+  p.in_stream = (const uint8_t*)d->in_stream;
+  p.in_edge_patch_stride = d->in_edge_patch_stride;
+  p.in_edge_chunk_stride = d->in_edge_chunk_stride;
+  p.in_stream_chunk_stride = d->in_stream_chunk_stride;
+  p.in_stream_patch_rows = d->in_stream_patch_rows;
+  p.in_e = d->in_e;
+  p.out_edge = (uint8_t*)d->out_edge;
+  p.out_stream = (uint8_t*)d->out_stream;
+  p.out_edge_patch_stride = d->out_edge_patch_stride;
+  p.out_edge_chunk_stride = d->out_edge_chunk_stride;
+  p.out_stream_chunk_stride = d->out_stream_chunk_stride;
+  p.out_stream_patch_rows = d->out_stream_patch_rows;
+  p.out_e = d->out_e;
+  MPA_REQUIRE((((uintptr_t)p.in_edge | (uintptr_t)p.in_stream | (uintptr_t)p.out_edge | (uintptr_t)p.out_stream | (uintptr_t)d->w_packed |
+                (uintptr_t)d->workspace) & 15) == 0, "conv_tc_pool: 16-byte alignment required");
+  MPA_REQUIRE(((p.in_edge_patch_stride | p.in_edge_chunk_stride | p.in_stream_chunk_stride | p.out_edge_patch_stride | p.out_edge_chunk_stride |
+                p.out_stream_chunk_stride) & 15) == 0, "conv_tc_pool: strides must be multiples of 16 bytes");
+  p.pool = 3;
+  p.ring_on = d->weights_layout == 1 ? 1 : 0;
+  MPA_REQUIRE(d->weights_layout == 0 || d->weights_layout == 1, "conv_tc_pool: weights_layout must be 0 (tiles) or 1 (ring pieces)");
+  p.residual = d->residual ? 1 : 0;
+  p.w = (const uint8_t*)d->w_packed;
+  p.bias = d->bias;
+  p.fmt = d->fmt;
+  p.n_patches = d->n_patches;
+  p.NC = (d->Cin + 7) / 8;
+  p.Cout = d->Cout;
+  p.NCo = d->Cout / 8;
+  MPA_REQUIRE(!p.residual || p.NC == p.NCo, "conv_tc_pool: the residual needs Cin == Cout");
+  p.J = J;
+  p.T = T; p.F = F; p.KH = d->KH; p.KW = KW; p.P = pitch; p.N = pitch; p.pf = pf;
+  p.sub_stride = 1;
+  p.F_out = F;
+  p.n_seg = d->n_seg;
+  p.groups_per_patch = 0;
+  for (int s = 0; s < 2; ++s) {
+    if (s >= d->n_seg) { p.seg_groups[s] = 0; continue; }
+    MPA_REQUIRE(d->z_lo[s] >= 0 && d->z_lo[s] < d->z_hi[s] && d->z_hi[s] <= T, "conv_tc_pool: bad row segment %d: [%d,%d)", s, d->z_lo[s], d->z_hi[s]);
+    p.z_lo[s] = d->z_lo[s];
+    p.z_hi[s] = d->z_hi[s];
+    p.y_lo[s] = d->z_lo[s] > 0 ? d->z_lo[s] - 1 : 0;
+    p.y_hi[s] = d->z_hi[s] < T ? d->z_hi[s] + 1 : T;
+    p.seg_groups[s] = (p.y_hi[s] - p.y_lo[s] + J - 1) / J;
+    p.groups_per_patch += p.seg_groups[s];
   }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = p.n_units < sms ? p.n_units : sms;
-  conv_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
-  MPA_CHECK_LAUNCH("conv_tc");
-  return MPA_OK;
+  MPA_REQUIRE(d->n_seg == 1 || p.y_hi[0] <= p.y_lo[1], "conv_tc_pool: row segments overlap");
+  p.n_units = d->n_patches * p.groups_per_patch;
+  p.ring = (uint8_t*)d->workspace;
+  MPA_REQUIRE(d->ws_bytes >= mpa_conv_tc_pool_workspace(d->Cout, pitch, J), "conv_tc_pool: workspace too small (%zu B)", d->ws_bytes);
+  p.act = d->act;
+  p.act_param = d->act_param;
+  const uint32_t f = (d->fmt == MPA_FMT_BF16) ? 1u : 0u;
+  p.idesc = (1u << 4) | (f << 7) | (f << 10) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  return launch_conv_tc(p, d->Cin, (cudaStream_t)stream, nullptr);
 }
 
 int mpa_pool_time_res_cp8(const void* y_cp8, const void* res_cp8, void* out_cp8, int n_patches, int C, int T, int F, int pitch, int pf,

@@ -21,7 +21,7 @@ class CnnStreamEngine:
     """DRCNN / DCNN / CNN inference over a whole recording with the tcgen05 convolution stack (model.precision
     'fp16' or 'bf16')."""
 
-    def __init__(self, model, chunk=646, compression=10.0):
+    def __init__(self, model, chunk=646, compression=10.0, fused=True, dedup=True, ring=True):
         if not isinstance(model, (basic_cnn_segm_sigmoid, deep_cnn_segm_sigmoid)):
             raise TypeError('CnnStreamEngine serves the CNN / DCNN / DRCNN family')
         self.model, self.chunk, self.compression = model, int(chunk), float(compression)
@@ -39,6 +39,12 @@ class CnnStreamEngine:
         self.pitch, self.pf, self.pt = (self.F + 8 + 15) // 16 * 16, 8, 1
         self._bufs = None
         self.timers = None          # optional: list collecting (tag, start_event, end_event)
+        # Fused / de-duplicated schedule (mpa_conv_tc_pool_f16): needs chunk-aligned channel counts and J >= 2
+        ks = {tuple(c.kernel_size) for _, c in self.blocks}
+        self.fused = bool(fused) and self.C0 % 8 == 0 and self.C0 <= 64 and len(ks) == 1 and all(k % 2 == 1 for k in next(iter(ks)))
+        self.KH, self.KW = next(iter(ks)) if len(ks) == 1 else (0, 0)
+        self._vbufs = None
+        self.dedup, self.ring = bool(dedup), bool(ring)      # (test knobs) share interior rows across patches / ring weight pieces
 
     # -- buffers are allocated once (their zero borders are never written)
     def _buffers(self):
@@ -47,14 +53,15 @@ class CnnStreamEngine:
             self._bufs = (mk(), mk(), mk())
         return self._bufs
 
-    def _timed(self, tag, fn):
+    def _timed(self, tag, fn, work=0):
+        """work: output rows x patches of a convolution launch (for FLOP accounting by the caller)."""
         if self.timers is None:
             return fn()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         r = fn()
         e1.record()
-        self.timers.append((tag, e0, e1))
+        self.timers.append((tag, e0, e1, work))
         return r
 
     def predict_hcqt(self, hcqt, lo=0, hi=None):
@@ -71,11 +78,13 @@ class CnnStreamEngine:
         self._timed('layernorm_frames', lambda: _lib.call(
             'layernorm_frames', hcqt, m.layernorm.weight, m.layernorm.bias, None, plane, C, N, F, lead, trail, self.pitch, self.pf,
             float(m.layernorm.eps), self.compression, self.fmt, _lib.stream_ptr()))
-        ya, za, zb = self._buffers()
-        outs = []
         hi = N if hi is None else hi
         if not (0 <= lo <= hi <= N):
             raise ValueError('bad frame range')
+        if self.fused:
+            return self._predict_fused(plane, N, lo, hi)
+        ya, za, zb = self._buffers()
+        outs = []
         for i0 in range(lo, hi, self.chunk):
             n = min(self.chunk, hi - i0)
             z_prev = None
@@ -93,12 +102,78 @@ class CnnStreamEngine:
                     self._timed('pool3', lambda: ops.pool3_res_cp8(ya.first(n), None, out=cur.first(n)))
                 else:
                     self._timed('conv_tc', lambda: ops.conv_tc(z_prev.first(n), wp, conv.bias, self.C0, tuple(conv.kernel_size), ops.ACT_LRELU,
-                                                              a, out=ya.first(n), n_patches=n))
+                                                              a, out=ya.first(n), n_patches=n), work=n * CONTEXT)
                     cur = zb if z_prev is za else za
                     self._timed('pool3', lambda: ops.pool3_res_cp8(ya.first(n), z_prev.first(n) if self.residual else None,
                                                                   out=cur.first(n)))
                 z_prev = cur
             y = self._timed('head', lambda: _exec.head_tc(cache, m, z_prev.first(n), a))
+            outs.append(y.reshape(n, -1))
+        if not outs:
+            return torch.empty(0, 0, dtype=torch.float32, device=self.dev)
+        return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # Fused, de-duplicated schedule.  Block i (1-based) = conv KHxKW -> LeakyReLU -> MaxPool((3,1)) (+ residual): row r of its
+    # output depends on input rows r-h .. r+h, h = KH//2 + 1.  Rows r in [i*h, T - i*h) of patch p therefore never see the zero
+    # padding at the patch edges and equal row p+r of ONE clip-long "stream" computed once per frame; only the 2*i*h edge rows
+    # are evaluated per patch (exactly the reference's patch-wise arithmetic, SURVEY 0.8 — the same MMA sequence per row).
+    def _edges(self):
+        h, L = self.KH // 2 + 1, len(self.blocks)
+        e = []
+        for i in range(1, L + 1):
+            ei = i * h
+            e.append(ei if (self.dedup and i < L and 2 * ei + 2 <= CONTEXT) else CONTEXT)     # the last block feeds the head: materialised
+        return e
+
+    def _virtual_buffers(self, R):
+        e = self._edges()
+        key = (R, tuple(e))
+        if self._vbufs is None or self._vbufs[0] != key:
+            dt, dev, NC = ops._FMT_DTYPE[self.fmt], self.dev, self.C0 // 8
+            streams = [torch.zeros(NC, R + 8, self.pitch, 8, dtype=dt, device=dev) if ei < CONTEXT else None for ei in e]
+            edges = [torch.zeros(self.chunk + (1 if ei == CONTEXT else 0), NC, (2 * ei if ei < CONTEXT else CONTEXT) + 2, self.pitch, 8,
+                                 dtype=dt, device=dev) for ei in e]
+            ws = ops.conv_tc_pool_workspace(self.C0, self.pitch, dev)
+            self._vbufs = (key, streams, edges, ws)
+        return self._vbufs[1:]
+
+    def _predict_fused(self, plane, N, lo, hi):
+        m, cache, a = self.model, self.model._cache, self.model.a_lrelu
+        T, F, C = CONTEXT, self.F, m.n_chan_input
+        R = N + T - 1                                   # stream rows: row s of the stream = row s - p of patch p
+        e = self._edges()
+        streams, edges, ws = self._virtual_buffers(R)
+        packed = []
+        for name, conv in self.blocks:
+            w = conv.weight
+            packed.append(cache.get(f'{name}:wtc{self.fmt}:{int(self.ring)}', [w], lambda: ops.conv_tc_pack(w, self.dev, self.fmt, ring=self.ring)))
+        plane_stream = plane.unsqueeze(0)               # [1][rows][P][8]: 1 guard row, then stream rows 0..R-1
+
+        def run(i, src, dst, n, segments, tag):
+            conv = self.blocks[i][1]
+            cin = C if i == 0 else self.C0
+            self._timed(tag, lambda: ops.conv_tc_pool(src, dst, packed[i], conv.bias, n, cin, self.C0, F, (self.KH, self.KW), self.pitch, self.pf,
+                                                      segments, self.residual and i > 0, ops.ACT_LRELU, a, self.fmt, ws, ring=self.ring),
+                        work=n * sum(hi_ - lo_ for lo_, hi_ in segments))
+        # 1) clip-long streams of the patch-independent rows
+        for i, ei in enumerate(e):
+            if ei == T:
+                break
+            src = ops.VRows(R, 0, stream=plane_stream if i == 0 else streams[i - 1])
+            run(i, src, ops.VRows(R, 0, stream=streams[i]), 1, [(ei, R - ei)], 'conv_tc_stream')
+        # 2) per patch: the edge rows of every block, the last block in full, then the head
+        outs = []
+        for i0 in range(lo, hi, self.chunk):
+            n = min(self.chunk, hi - i0)
+            prev = ops.VRows(T, 0, stream=plane_stream, row0=i0)
+            for i, ei in enumerate(e):
+                dst = ops.VRows(T, ei, edge=edges[i], stream=streams[i], row0=i0)
+                segs = [(0, ei), (T - ei, T)] if ei < T else [(0, T)]
+                run(i, prev, dst, n, segs, 'conv_tc_first' if i == 0 else 'conv_tc')
+                prev = dst
+            zc = ops.CP8(n, self.C0, T, F, self.pitch, self.pf, 1, self.dev, buf=edges[-1], fmt=self.fmt)
+            y = self._timed('head', lambda: _exec.head_tc(cache, m, zc, a))
             outs.append(y.reshape(n, -1))
         if not outs:
             return torch.empty(0, 0, dtype=torch.float32, device=self.dev)

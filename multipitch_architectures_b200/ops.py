@@ -163,27 +163,30 @@ def cp8_to_nchw(a):
     return out
 
 
-def conv_tc_pack(w, device, fmt=FMT_F16, J=0):
+def conv_tc_pack(w, device, fmt=FMT_F16, J=0, ring=False):
     """[Cout,Cin,KH,KW] fp32 (any device) -> packed 16-bit A-operand tiles on `device` (host-side one-off).
-    J = output rows per work unit (0: floor(128/Cout)); pass the same J to conv_tc."""
+    J = output rows per work unit (0: floor(128/Cout)); pass the same J to conv_tc.
+    ring=True: the un-duplicated "piece" layout of the ring main loop (conv_tc_pool(..., ring=True))."""
     import ctypes
     import numpy as np
     wh = np.ascontiguousarray(w.detach().float().cpu().numpy())
     Cout, Cin, KH, KW = wh.shape
-    nbytes = _lib.lib().mpa_conv_tc_packed_bytes(Cin, Cout, KH, KW, J)
+    L = _lib.lib()
+    nbytes = (L.mpa_conv_tc_ring_packed_bytes if ring else L.mpa_conv_tc_packed_bytes)(Cin, Cout, KH, KW, J)
     if nbytes == 0:
         raise _lib.MpaError(f'conv_tc cannot pack Cin={Cin} Cout={Cout} K={KH}x{KW}')
     packed = np.zeros(nbytes, dtype=np.uint8)
-    rc = _lib.lib().mpa_conv_tc_pack_weights(wh.ctypes.data_as(ctypes.c_void_p), packed.ctypes.data_as(ctypes.c_void_p),
-                                             Cin, Cout, KH, KW, fmt, J)
+    rc = (L.mpa_conv_tc_ring_pack_weights if ring else L.mpa_conv_tc_pack_weights)(
+        wh.ctypes.data_as(ctypes.c_void_p), packed.ctypes.data_as(ctypes.c_void_p), Cin, Cout, KH, KW, fmt, J)
     if rc != 0:
-        raise _lib.MpaError('mpa_conv_tc_pack_weights: ' + _lib.last_error())
+        raise _lib.MpaError('conv_tc weight packing: ' + _lib.last_error())
     return torch.from_numpy(packed).to(device)
 
 
 def compact_cp8(n, C, T, F, device, fmt):
     """Un-padded planes [n][C/8][T][F][8]; one spare item of slack so that KW == 1 convolutions may over-read the last row."""
     buf = torch.empty(n + 1, (C + 7) // 8, T, F, 8, dtype=_FMT_DTYPE[fmt], device=device)
+    buf[n:].zero_()     # the over-read meets zero weights (dummy K slice): it must be finite, or NaN * 0 poisons the last column
     return CP8(n, C, T, F, F, 0, 0, device, fmt=fmt, buf=buf)
 
 
@@ -254,3 +257,69 @@ def head_tail2(h, w40, b40, w43, b43, a_lrelu):
     call('head_tail2_cp8', h.ptr(), w40f[:, :h.C].contiguous() if w40f.shape[1] != h.C else w40f.contiguous(), b40, w43.reshape(-1).contiguous(),
          b43, out, h.B, h.T, h.F, h.C, C3, float(a_lrelu), h.fmt, stream_ptr())
     return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# fused conv + LeakyReLU + MaxPool((3,1)) + residual on "virtual" patch rows (mpa_conv_tc_pool_f16, include/mpa.h)
+import ctypes as _ct
+
+
+class ConvTcDesc(_ct.Structure):
+    _fields_ = [('in_edge', _ct.c_void_p), ('in_stream', _ct.c_void_p),
+                ('in_edge_patch_stride', _ct.c_longlong), ('in_edge_chunk_stride', _ct.c_longlong), ('in_stream_chunk_stride', _ct.c_longlong),
+                ('in_stream_patch_rows', _ct.c_longlong), ('in_e', _ct.c_int),
+                ('w_packed', _ct.c_void_p), ('bias', _ct.c_void_p),
+                ('out_edge', _ct.c_void_p), ('out_stream', _ct.c_void_p),
+                ('out_edge_patch_stride', _ct.c_longlong), ('out_edge_chunk_stride', _ct.c_longlong), ('out_stream_chunk_stride', _ct.c_longlong),
+                ('out_stream_patch_rows', _ct.c_longlong), ('out_e', _ct.c_int),
+                ('n_patches', _ct.c_int), ('Cin', _ct.c_int), ('Cout', _ct.c_int), ('T', _ct.c_int), ('F', _ct.c_int), ('KH', _ct.c_int),
+                ('KW', _ct.c_int), ('pitch', _ct.c_int), ('pf', _ct.c_int), ('J', _ct.c_int),
+                ('n_seg', _ct.c_int), ('z_lo', _ct.c_int * 2), ('z_hi', _ct.c_int * 2),
+                ('residual', _ct.c_int), ('act', _ct.c_int), ('act_param', _ct.c_float), ('fmt', _ct.c_int), ('weights_layout', _ct.c_int),
+                ('workspace', _ct.c_void_p), ('ws_bytes', _ct.c_size_t)]
+
+
+class VRows:
+    """Virtual patch rows (see mpa_conv_tc_desc): per-patch edge planes [n][NC][2e+2][pitch][8] (one guard row on each side; e == T: a
+    plain CP8 buffer with pt = 1) and / or a shared stream [NC][rows+guard][pitch][8] whose row `row0 + b*patch_rows + r` is row r of patch b."""
+
+    def __init__(self, T, e, edge=None, stream=None, row0=0, patch_rows=1):
+        self.T, self.e, self.edge, self.stream, self.row0, self.patch_rows = T, e, edge, stream, row0, patch_rows
+
+    def fields(self, pitch):
+        row = pitch * 16
+        ed = (0, 0, 0)
+        if self.edge is not None:
+            n, NC, RE = self.edge.shape[0], self.edge.shape[1], self.edge.shape[2]
+            ed = (self.edge.data_ptr() + row, NC * RE * row, RE * row)
+        st = (0, 0)
+        if self.stream is not None:
+            st = (self.stream.data_ptr() + (1 + self.row0) * row, self.stream.shape[1] * row)
+        return ed, st
+
+
+def conv_tc_pool_workspace(Cout, pitch, device, J=0):
+    n = _lib.lib().mpa_conv_tc_pool_workspace(Cout, pitch, J)
+    return torch.empty(n, dtype=torch.uint8, device=device)
+
+
+def conv_tc_pool(src, dst, w_packed, bias, n_patches, Cin, Cout, F, ksize, pitch, pf, segments, residual, act, act_param, fmt, workspace, J=0,
+                 ring=False):
+    """dst rows [z_lo, z_hi) of every segment = maxpool_time3(act(conv(src) + bias)) (+ src row when residual); src / dst: VRows."""
+    d = ConvTcDesc()
+    (d.in_edge, d.in_edge_patch_stride, d.in_edge_chunk_stride), (d.in_stream, d.in_stream_chunk_stride) = src.fields(pitch)
+    d.in_stream_patch_rows, d.in_e = src.patch_rows, src.e
+    (d.out_edge, d.out_edge_patch_stride, d.out_edge_chunk_stride), (d.out_stream, d.out_stream_chunk_stride) = dst.fields(pitch)
+    d.out_stream_patch_rows, d.out_e = dst.patch_rows, dst.e
+    d.w_packed, d.bias = w_packed.data_ptr(), bias.data_ptr()
+    d.n_patches, d.Cin, d.Cout, d.T, d.F, d.KH, d.KW, d.pitch, d.pf, d.J = n_patches, Cin, Cout, src.T, F, ksize[0], ksize[1], pitch, pf, J
+    d.n_seg = len(segments)
+    for i, (lo, hi) in enumerate(segments):
+        d.z_lo[i], d.z_hi[i] = lo, hi
+    d.residual, d.act, d.act_param, d.fmt = int(bool(residual)), act, float(act_param), fmt
+    d.weights_layout = 1 if ring else 0
+    d.workspace, d.ws_bytes = workspace.data_ptr(), workspace.numel()
+    rc = _lib.lib().mpa_conv_tc_pool_f16(_ct.byref(d), stream_ptr())
+    if rc != 0:
+        raise _lib.MpaError(f'mpa_conv_tc_pool_f16 failed ({rc}): {_lib.last_error()}')
+    return dst

@@ -110,3 +110,32 @@ def test_frame_range_sharding_matches_unsharded_engine():
     full = eng.predict_hcqt(h)
     parts = [predict_sharded(eng.predict_hcqt, h, world=3, rank=r, gather=False) for r in range(3)]
     assert torch.equal(torch.cat(parts, 0), full)
+
+
+@pytest.mark.parametrize('name,N,chunk,prec', [('drcnn_tiny', 90, 64, 'fp16'), ('drcnn_tiny', 131, 40, 'bf16'), ('dcnn_tiny', 60, 64, 'fp16'),
+                                               ('drcnn', 100, 37, 'fp16'), ('drcnn', 80, 80, 'bf16')])
+def test_fused_deduplicated_schedule_equals_plain_schedule(name, N, chunk, prec):
+    """Fused conv+pool+residual kernel with frame-shared interior rows (mpa_conv_tc_pool_f16) vs the plain per-patch
+    sequence conv_tc -> pool_time_res.
+    (a) same main loop (tile weights): the same MMA sequence per output row and the same 16-bit roundings -> bit for bit;
+    (b) ring main loop (un-duplicated weight pieces, K walked group-major): de-duplicated vs fully per-patch -> bit for bit
+        (this is what makes sharing rows across patches legal), and vs (a) within fp32 summation-order noise."""
+    from multipitch_architectures_b200.engine import CnnStreamEngine
+    m = build_model(name, precision=prec)
+    m.load_state_dict(fill_state_dict(m.state_dict(), 27))
+    m = m.cuda().eval()
+    h = torch.from_numpy(fake_hcqt(N, 6)).cuda()
+    plain = CnnStreamEngine(m, chunk=chunk, fused=False).predict_hcqt(h)
+    tiles = CnnStreamEngine(m, chunk=chunk, fused=True, ring=False)
+    assert tiles.fused
+    fused = tiles.predict_hcqt(h)
+    assert fused.shape == plain.shape == (N, 72)
+    assert torch.equal(fused, plain), (fused - plain).abs().max().item()
+    ring_eng = CnnStreamEngine(m, chunk=chunk, fused=True, ring=True)
+    ring = ring_eng.predict_hcqt(h)
+    ring_full = CnnStreamEngine(m, chunk=chunk, fused=True, ring=True, dedup=False).predict_hcqt(h)
+    assert torch.equal(ring, ring_full), (ring - ring_full).abs().max().item()
+    assert (ring - plain).abs().max().item() < (2e-3 if prec == 'fp16' else 2e-2)
+    # a sub-range of frames (what a rank of the sharded run evaluates)
+    part = ring_eng.predict_hcqt(h, lo=11, hi=N - 7)
+    assert torch.equal(part, ring[11:N - 7])
