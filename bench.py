@@ -29,7 +29,7 @@ DRCNN_KW = dict(n_chan_input=6, n_chan_layers=[40, 40, 30, 10], n_prefilt_layers
 HCQT_KW = dict(fs=22050, fs_hcqt_target=50, bins_per_octave=36, num_octaves=6, num_harmonics=5, num_subharmonics=1)
 GFLOP_PER_PATCH = 48.574          # SURVEY 8a row N3 (2*MAC of every Conv2d at T=75)
 GFLOP_PREFILT_LAYER = 11.664      # one 40->40 15x15 layer per patch
-DRAM_BYTES_PER_PATCH_LAYER = (875.0e6 + 800.8e6) / 646     # measured by ncu for conv_tc_kernel (see profiles/README.md)
+DRAM_BYTES_PER_PATCH_LAYER = (951.8e6 + 938.2e6) / 646     # measured by ncu for the fused conv_tc_kernel, 75 rows per patch (profiles/README.md)
 
 
 def measured_peaks():
@@ -237,7 +237,7 @@ def main():
     ap.add_argument('--cpu-sample', type=int, default=100)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--precision', default='fp16', choices=['fp16', 'bf16'])
-    ap.add_argument('--no-ring', action='store_true', help='fused schedule with ready-made weight tiles instead of ring pieces')
+    ap.add_argument('--ring', action='store_true', help='fused schedule with the ring main loop (un-duplicated weight pieces) instead of ready-made tiles')
     ap.add_argument('--plain', action='store_true', help='per-patch conv_tc + separate pool kernels (no fusion / de-duplication)')
     ap.add_argument('--workload', default='infer_drcnn', choices=['infer_drcnn', 'train_cnn_xs'],
                     help='infer_drcnn (headline, BASELINE configs[0]) or train_cnn_xs (configs[1]: CNN:XS fwd+bwd+AdamW, batch 256)')
@@ -291,7 +291,7 @@ def main():
     model = deep_cnn_segm_sigmoid(**DRCNN_KW, precision=args.precision)
     make_weights(model)
     model = model.to(dev).eval()
-    eng = CnnStreamEngine(model, chunk=args.chunk, fused=not args.plain, ring=not args.no_ring)
+    eng = CnnStreamEngine(model, chunk=args.chunk, fused=not args.plain, ring=args.ring)
     fmin = C1_HZ / 2 ** ((3 - 1) / (2 * 36))
     plan = get_plan(22050, float(fmin), 512, 36, 6, 5, 1, str(dev))
     n_clips = 2
@@ -369,10 +369,10 @@ def main():
                 'dtype': args.precision, 'data': 'synthetic', 'config': config, 'clocks': clocks, 'gpu_launches': int(launches),
                 'e2e': {'value': e2e, 'unit': 'audio-s/s', 'h2d_bytes_per_step': int(clips_host[0].numel() * 4),
                         'd2h_bytes_per_step': int(n_frames * 72 * 4), 'ms_per_step': ms_e2e / args.steps},
-                'roofline': {'bound': 'tensor', 'kernel': 'conv_tc_kernel (tcgen05 15x15 40->40, bias+LeakyReLU epilogue)', 'achieved': achieved,
+                'roofline': {'bound': 'tensor', 'kernel': 'conv_tc_kernel (tcgen05 15x15 40->40; bias + LeakyReLU + MaxPool(3,1) + residual epilogue)', 'achieved': achieved,
                              'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': (achieved / peak_tf) if achieved else None,
                              'traffic': DRAM_BYTES_PER_PATCH_LAYER * per_launch_rows / 75.0,
-                             'traffic_source': 'ncu --set full (profiles/r01_conv_tc_prefilt_ncu_raw.csv): dram__bytes_read.sum 0.875 GB + dram__bytes_write.sum 0.801 GB per 646-patch launch; algorithmic 0.89 + 0.84 GB',
+                             'traffic_source': 'ncu --set full (profiles/r01_conv_tc_fused_ncu_raw.csv): dram__bytes_read.sum 0.952 GB + dram__bytes_write.sum 0.938 GB per 646-patch x 75-row launch (algorithmic 0.89 + 0.89 GB), scaled by the rows per launch',
                              'peak_source': peak_src, 'launches_timed': len(conv), 'avg_launch_ms': avg_ms,
                              'algorithmic_flops_per_launch': flops_launch, 'output_rows_per_launch': per_launch_rows, 'time_share_by_stage': shares,
                              'schedule': 'fused conv+LReLU+pool3+residual, interior rows shared across patches' if eng.fused else 'plain per-patch'},

@@ -21,7 +21,7 @@ class CnnStreamEngine:
     """DRCNN / DCNN / CNN inference over a whole recording with the tcgen05 convolution stack (model.precision
     'fp16' or 'bf16')."""
 
-    def __init__(self, model, chunk=646, compression=10.0, fused=True, dedup=True, ring=True):
+    def __init__(self, model, chunk=646, compression=10.0, fused=True, dedup=True, ring=False):
         if not isinstance(model, (basic_cnn_segm_sigmoid, deep_cnn_segm_sigmoid)):
             raise TypeError('CnnStreamEngine serves the CNN / DCNN / DRCNN family')
         self.model, self.chunk, self.compression = model, int(chunk), float(compression)
@@ -44,7 +44,9 @@ class CnnStreamEngine:
         self.fused = bool(fused) and self.C0 % 8 == 0 and self.C0 <= 64 and len(ks) == 1 and all(k % 2 == 1 for k in next(iter(ks)))
         self.KH, self.KW = next(iter(ks)) if len(ks) == 1 else (0, 0)
         self._vbufs = None
-        self.dedup, self.ring = bool(dedup), bool(ring)      # (test knobs) share interior rows across patches / ring weight pieces
+        # dedup: share interior rows across patches (test knob; off = every row per patch).  ring: main loop that streams
+        # un-duplicated weight pieces (2.2x less L2->SM traffic, measured SLOWER than ready-made tiles: 626 vs 729 audio-s/s)
+        self.dedup, self.ring = bool(dedup), bool(ring)
 
     # -- buffers are allocated once (their zero borders are never written)
     def _buffers(self):

@@ -1,6 +1,6 @@
 #!/bin/bash
 # A/B timing inside ONE gpurun call (boxes differ by several %): alternates the variants given as "name:ENV=..;flags" arguments.
-# usage: tools/ab_bench.sh rounds "ring:;" "tiles:;--no-ring" "half:MPA_DEBUG_WSHIFT=1;--no-ring"
+# usage: tools/ab_bench.sh rounds "tiles:;" "ring:;--ring" "plain:;--plain"
 rounds=$1; shift
 for r in $(seq 1 $rounds); do
   for v in "$@"; do
