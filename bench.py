@@ -112,41 +112,69 @@ def cpu_reference_arm(seconds, n_patches_sample, threads):
 
 
 CNN_XS_KW = dict(n_chan_input=6, n_chan_layers=[20, 20, 10, 1], n_bins_in=216, n_bins_out=72)
-GFLOP_TRAIN_PER_PATCH = 2.75      # CNN:XS 0.916 GFLOP forward x3 for forward + backward
+SAUNET_L_KW = dict(n_chan_input=6, n_chan_layers=[128, 80, 50, 30], n_bins_in=216, n_bins_out=72, scalefac=4, embed_dim=128, num_heads=8,
+                   mlp_dim=8192, pos_encoding='sinusoidal')
+UNET_M_KW = dict(n_chan_input=6, n_chan_layers=[128, 100, 80, 50], n_bins_in=216, n_bins_out=72, scalefac=8)
+PUNET_KW = dict(n_chan_input=6, n_chan_layers=[128, 180, 150, 100], n_bins_in=216, n_bins_out=72, scalefac=2, num_polyphony_steps=24)
+# 2*MAC of every Conv2d / Linear at T=75 (forward); training = 3x forward
+TRAIN_SPECS = {
+    'train_cnn_xs': dict(cls='basic_cnn_segm_sigmoid', kw=CNN_XS_KW, gflop_fwd=0.916, batch=256, lr=1e-3, cpu_batch=64,
+                         label='CNN:XS [20,20,10,1] (BASELINE configs[1])'),
+    'train_saunet': dict(cls='simple_u_net_doubleselfattn', kw=SAUNET_L_KW, gflop_fwd=29.110, batch=25, lr=1e-3, cpu_batch=25,
+                         label='SAUnet:L [128,80,50,30] sc=4 E=128 mlp=8192 (BASELINE configs[4]; per-rank batch = the reference batch of 25: '
+                               'batch-axis attention and BatchNorm statistics are per batch)'),
+}
+INFER_SPECS = {
+    'infer_unet_m': dict(cls='simple_u_net_largekernels', kw=UNET_M_KW, gflop=12.144, label='Unet:M [128,100,80,50] sc=8 (BASELINE configs[2])'),
+    'infer_punet': dict(cls='simple_u_net_polyphony_classif_softmax', kw=PUNET_KW, gflop=81.777,
+                        label='PUnet [128,180,150,100] sc=2, 24 polyphony steps (BASELINE configs[3])'),
+}
 
 
-def cpu_train_arm(batch, threads, steps=2):
+def cpu_train_arm(spec, batch, threads, steps=2):
     """Oracle port of the training step on the host cores: fp32 forward + autograd backward + torch AdamW."""
     import torch
+    import torch.nn.functional as F
     from oracle import nn_oracle as NO
-    from multipitch_architectures_b200.libdl.nn_models import basic_cnn_segm_sigmoid
+    from multipitch_architectures_b200.libdl import nn_models as M
     from tests.weights import synth_patches, synth_targets
     torch.set_num_threads(threads)
-    m = basic_cnn_segm_sigmoid(**CNN_XS_KW)
+    m = getattr(M, spec['cls'])(**spec['kw'])
     make_weights(m)
-    sd = {k: v.clone().requires_grad_(True) for k, v in m.state_dict().items()}
-    opt = torch.optim.AdamW(list(sd.values()), lr=1e-3, weight_decay=0.01)
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'running_' not in k else v.clone()) for k, v in m.state_dict().items()}
+    opt = torch.optim.AdamW([v for v in sd.values() if v.requires_grad], lr=spec['lr'], weight_decay=0.01)
     x, t = synth_patches(batch, 0), synth_targets(batch, 0)
+    cnn = spec['cls'].startswith(('basic_cnn', 'deep_cnn'))
     ts = []
     for i in range(steps + 1):
         t0 = time.perf_counter()
         opt.zero_grad()
-        NO.bce_mean(NO.cnn_forward(sd, x), t).backward()
+        y = NO.cnn_forward(sd, x) if cnn else NO.unet_forward(sd, x, train=True, pos_encoding=spec['kw'].get('pos_encoding'))
+        if isinstance(y, tuple):
+            loss = NO.bce_mean(y[0], t) + F.cross_entropy(y[1], t.sum(-1, keepdim=True).long().squeeze(3)) / 25.0
+        else:
+            loss = NO.bce_mean(y, t)
+        loss.backward()
         opt.step()
         ts.append(time.perf_counter() - t0)
     dt = sum(ts[1:]) / steps
-    return batch / dt, f'oracle port: fp32 CNN:XS forward + autograd backward + AdamW, batch {batch}, {steps} steps after 1 warm-up, torch threads={threads}'
+    return batch / dt, (f"oracle port: fp32 {spec['cls']} forward + autograd backward + AdamW, batch {batch}, {steps} steps after 1 warm-up, "
+                        f'torch threads={threads}')
 
 
 def train_main(args, rank, world, local, cores):
-    config = {'workload': f'CNN:XS [20,20,10,1] training step (forward + backward + BCE + AdamW), synthetic 6x75x216 patches, batch {args.batch} per GPU',
-              'timing': 'CUDA events; activations of one step (~3 GB) exceed L2', 'weights': 'seeded random init', 'dropout': 0.2}
+    spec = TRAIN_SPECS[args.workload]
+    batch = args.batch if args.batch > 0 else spec['batch']
+    gflop_step = 3.0 * spec['gflop_fwd']
+    config = {'workload': f"{spec['label']}: training step (forward + backward + loss + AdamW), synthetic 6x75x216 patches, batch {batch} per GPU",
+              'timing': 'CUDA events; the activations of one step exceed L2', 'weights': 'seeded random init', 'dropout': 0.2,
+              'parallelism': f'dp{world} (replicas, one flat NCCL gradient all-reduce per step)' if world > 1 else 'single GPU'}
     if args.impl == 'reference':
         if rank != 0:
             return
-        v, desc = cpu_train_arm(min(args.batch, 64), cores, steps=max(1, args.steps))
+        v, desc = cpu_train_arm(spec, min(batch, spec['cpu_batch']), cores, steps=max(1, min(args.steps, 2)))
         print(json.dumps({'impl': 'reference', 'metric': 'train_patches_per_second', 'value': v, 'unit': 'patches/s', 'n_gpus': args.gpus,
-                          'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * args.batch / v, 'higher_is_better': True,
+                          'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * batch / v, 'higher_is_better': True,
                           'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
                           'cpu_baseline': {'value': v, 'unit': 'patches/s', 'cores': cores, 'kind': 'port', 'sample': desc},
                           'e2e': {'value': v, 'unit': 'patches/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
@@ -154,18 +182,22 @@ def train_main(args, rank, world, local, cores):
     import torch
     import torch.distributed as dist
     from multipitch_architectures_b200 import _lib
-    from multipitch_architectures_b200.libdl.nn_models import basic_cnn_segm_sigmoid
-    from multipitch_architectures_b200.training import TrainStep
+    from multipitch_architectures_b200.libdl import nn_models as M
     from tests.weights import synth_patches, synth_targets
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    model = basic_cnn_segm_sigmoid(**CNN_XS_KW)
+    model = getattr(M, spec['cls'])(**spec['kw'], precision=args.train_precision)
     make_weights(model)
     model = model.to(dev).train()
-    step = TrainStep(model, lr=1e-3, weight_decay=0.01)
-    xh, th = synth_patches(args.batch, rank).pin_memory(), synth_targets(args.batch, rank).pin_memory()
+    if spec['cls'].startswith(('basic_cnn', 'deep_cnn')):
+        from multipitch_architectures_b200.training import TrainStep
+        step = TrainStep(model, lr=spec['lr'], weight_decay=0.01)
+    else:
+        from multipitch_architectures_b200.training_unet import UnetTrainStep
+        step = UnetTrainStep(model, lr=spec['lr'], weight_decay=0.01)
+    xh, th = synth_patches(batch, rank).pin_memory(), synth_targets(batch, rank).pin_memory()
     xd, td = xh.to(dev), th.to(dev)
     loss_host = torch.empty(1).pin_memory()
 
@@ -206,20 +238,155 @@ def train_main(args, rank, world, local, cores):
     ms_e2e = timed(e2e, args.steps)
     clocks = sampler.stop() if sampler else None
     if rank == 0:
-        n = args.batch * args.steps * world
+        n = batch * args.steps * world
         value, e2e_v = n / (ms / 1e3), n / (ms_e2e / 1e3)
+        tc = args.train_precision != 'fp32'
         line = {'metric': 'train_patches_per_second', 'value': value, 'unit': 'patches/s', 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-                'dtype': 'f32', 'data': 'synthetic', 'config': config, 'clocks': clocks, 'gpu_launches': int(launches),
+                'dtype': 'bf16' if tc else 'f32', 'data': 'synthetic', 'config': config, 'clocks': clocks, 'gpu_launches': int(launches),
                 'e2e': {'value': e2e_v, 'unit': 'patches/s', 'h2d_bytes_per_step': int(xh.numel() * 4 + th.numel() * 4), 'd2h_bytes_per_step': 4,
                         'ms_per_step': ms_e2e / args.steps},
-                'roofline': {'bound': 'tensor', 'kernel': 'fp32 CUDA-core training kernels (conv2d_direct / conv_wgrad); not yet on tcgen05',
-                             'achieved': value * GFLOP_TRAIN_PER_PATCH / 1e3, 'peak': measured_peaks()[0], 'unit': 'TFLOP/s',
-                             'frac': value * GFLOP_TRAIN_PER_PATCH / 1e3 / measured_peaks()[0], 'traffic': None,
-                             'note': 'whole-step algorithmic FLOPs / step time against the bf16 tensor peak'}}
+                'roofline': {'bound': 'tensor', 'kernel': ('tcgen05 forward / dgrad / wgrad convolutions + fp32 element-wise kernels' if tc else
+                                                           'fp32 CUDA-core training kernels (conv2d_direct / conv_wgrad)') + ': whole step',
+                             'achieved': value * gflop_step / 1e3, 'peak': measured_peaks()[0], 'unit': 'TFLOP/s',
+                             'frac': value * gflop_step / 1e3 / measured_peaks()[0], 'traffic': None,
+                             'note': f'whole-step algorithmic FLOPs ({gflop_step:.3f} GFLOP per patch = 3 x forward) / step time against the bf16 tensor peak'}}
         if not args.no_cpu_baseline:
-            v, desc = cpu_train_arm(min(args.batch, 64), cores)
+            v, desc = cpu_train_arm(spec, min(batch, spec['cpu_batch']), cores)
             line['cpu_baseline'] = {'value': v, 'unit': 'patches/s', 'cores': cores, 'kind': 'port', 'sample': desc}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_unet_infer_arm(spec, seconds, n_patches_sample, threads):
+    """Oracle port: NumPy HCQT of the clip + the fp32 U-Net on a bounded sample of stride-1 patches (batches of 50)."""
+    import numpy as np
+    import torch
+    from oracle import hcqt_oracle as HO
+    from oracle import host_oracle as PO
+    from oracle import nn_oracle as NO
+    from multipitch_architectures_b200.libdl import nn_models as M
+    torch.set_num_threads(threads)
+    m = getattr(M, spec['cls'])(**spec['kw'])
+    make_weights(m)
+    sd = m.state_dict()
+    y = HO.synth_clip(0, seconds=seconds)
+    t0 = time.perf_counter()
+    f, _, _ = HO.compute_efficient_hcqt(y, **HCQT_KW)
+    t_hcqt = time.perf_counter() - t0
+    n_frames = f.shape[1]
+    ip, _ = PO.pad_for_inference(np.transpose(f, (2, 1, 0)), np.zeros((n_frames, 72)))
+    n = min(n_patches_sample, n_frames)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for b0 in range(0, n, 50):
+            nb = min(50, n - b0)
+            X = torch.from_numpy(np.stack([PO.context_item(ip, np.zeros((ip.shape[1], 72)), b0 + i)[0] for i in range(nb)]))
+            NO.unet_forward(sd, X)
+    t_nn = time.perf_counter() - t0
+    t_clip = t_hcqt + t_nn * (n_frames / n)
+    return seconds / t_clip, (f"oracle port: NumPy HCQT of the full {seconds:.0f} s clip ({t_hcqt:.2f} s) + fp32 {spec['cls']} on the first {n} of "
+                              f'{n_frames} stride-1 patches ({t_nn:.2f} s), extrapolated linearly; torch threads={threads}')
+
+
+def unet_infer_main(args, rank, world, local, cores):
+    """BASELINE configs[2] / [3]: HCQT + patch-wise U-Net inference (tcgen05 path), clips sharded across the GPUs (one 30 s clip per GPU
+    per step, weak scaling; the 10 h of configs[2] are 1,200 such clips), final activations on the host."""
+    spec = INFER_SPECS[args.workload]
+    config = {'workload': f"{spec['label']}: HCQT(6x216, hop 512) + stride-1 patch-wise inference of one {args.seconds:.0f} s 22.05 kHz clip per GPU per step "
+                          f'(batches of {args.infer_batch} materialised patches)',
+              'patches_per_step_per_gpu': int(args.seconds * 22050) // 512 + 1, 'patch': '6x75x216',
+              'timing': 'CUDA events, activations larger than L2', 'weights': 'seeded random init (no checkpoint blobs exist)',
+              'parallelism': f'{world} independent clip shards, no data-path collective'}
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        v, desc = cpu_unet_infer_arm(spec, args.seconds, 50, cores)
+        print(json.dumps({'impl': 'reference', 'metric': 'audio_seconds_per_second', 'value': v, 'unit': 'audio-s/s', 'n_gpus': args.gpus,
+                          'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * args.seconds / v, 'higher_is_better': True,
+                          'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
+                          'cpu_baseline': {'value': v, 'unit': 'audio-s/s', 'cores': cores, 'kind': 'port', 'sample': desc},
+                          'e2e': {'value': v, 'unit': 'audio-s/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+        return
+    import torch
+    import torch.distributed as dist
+    from multipitch_architectures_b200 import _lib
+    from multipitch_architectures_b200.engine import predict_patchwise
+    from multipitch_architectures_b200.libdl import nn_models as M
+    from multipitch_architectures_b200.libdl.data_preprocessing.hcqt import get_plan, C1_HZ
+    from oracle import hcqt_oracle as HO       # synthetic-clip generator only
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    model = getattr(M, spec['cls'])(**spec['kw'], precision=args.precision)
+    make_weights(model)
+    model = model.to(dev).eval()
+    plan = get_plan(22050, float(C1_HZ / 2 ** ((3 - 1) / (2 * 36))), 512, 36, 6, 5, 1, str(dev))
+    clips_host = [torch.from_numpy(HO.synth_clip(1000 * rank + i, seconds=args.seconds)).pin_memory() for i in range(2)]
+    clips_dev = [c.to(dev) for c in clips_host]
+    n_frames = clips_host[0].numel() // 512 + 1
+    out_host = torch.empty(n_frames, 72, dtype=torch.float32).pin_memory()
+
+    def run(y):
+        with torch.no_grad():
+            hcqt, _ = plan.run(y)
+            out = predict_patchwise(model, hcqt, batch=args.infer_batch)
+        return out[0] if isinstance(out, tuple) else out
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def resident(i):
+        run(clips_dev[i % 2])
+
+    def e2e(i):
+        out_host.copy_(run(clips_host[i % 2].to(dev, non_blocking=True)), non_blocking=True)
+
+    for i in range(args.warmup):
+        resident(i)
+        e2e(i)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    n0 = _lib.launch_count()
+    ms = timed(resident, args.steps)
+    launches = _lib.launch_count() - n0
+    ms_e2e = timed(e2e, args.steps)
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        audio_s = args.seconds * args.steps * world
+        value, e2e_v = audio_s / (ms / 1e3), audio_s / (ms_e2e / 1e3)
+        tf = value * FPS * spec['gflop'] / 1e3
+        line = {'metric': 'audio_seconds_per_second', 'value': value, 'unit': 'audio-s/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+                'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.precision,
+                'data': 'synthetic', 'config': config, 'clocks': clocks, 'gpu_launches': int(launches),
+                'e2e': {'value': e2e_v, 'unit': 'audio-s/s', 'h2d_bytes_per_step': int(clips_host[0].numel() * 4),
+                        'd2h_bytes_per_step': int(n_frames * 72 * 4), 'ms_per_step': ms_e2e / args.steps},
+                'roofline': {'bound': 'tensor', 'kernel': 'conv_tc_kernel over all U-Net levels (whole step)', 'achieved': tf, 'peak': measured_peaks()[0],
+                             'unit': 'TFLOP/s', 'frac': tf / measured_peaks()[0], 'traffic': None,
+                             'note': f"whole-step patch-wise algorithmic FLOPs ({spec['gflop']} GFLOP per patch) / step time"}}
+        if not args.no_cpu_baseline:
+            v, desc = cpu_unet_infer_arm(spec, args.seconds, 50, cores)
+            line['cpu_baseline'] = {'value': v, 'unit': 'audio-s/s', 'cores': cores, 'kind': 'port', 'sample': desc}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -239,9 +406,12 @@ def main():
     ap.add_argument('--precision', default='fp16', choices=['fp16', 'bf16'])
     ap.add_argument('--ring', action='store_true', help='fused schedule with the ring main loop (un-duplicated weight pieces) instead of ready-made tiles')
     ap.add_argument('--plain', action='store_true', help='per-patch conv_tc + separate pool kernels (no fusion / de-duplication)')
-    ap.add_argument('--workload', default='infer_drcnn', choices=['infer_drcnn', 'train_cnn_xs'],
-                    help='infer_drcnn (headline, BASELINE configs[0]) or train_cnn_xs (configs[1]: CNN:XS fwd+bwd+AdamW, batch 256)')
-    ap.add_argument('--batch', type=int, default=256)
+    ap.add_argument('--workload', default='infer_drcnn', choices=['infer_drcnn', 'train_cnn_xs', 'infer_unet_m', 'infer_punet', 'train_saunet'],
+                    help='infer_drcnn (headline, BASELINE configs[0]); train_cnn_xs (configs[1], batch 256); infer_unet_m (configs[2]); '
+                         'infer_punet (configs[3]); train_saunet (configs[4]: SAUnet:L data-parallel training, batch 25 per GPU)')
+    ap.add_argument('--batch', type=int, default=0, help='training batch per GPU (0 = the workload default)')
+    ap.add_argument('--train-precision', default='fp32', choices=['fp32', 'bf16'])
+    ap.add_argument('--infer-batch', type=int, default=100)
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', 0))
@@ -252,8 +422,10 @@ def main():
     config = {'workload': workload, 'patches_per_step_per_gpu': int(args.seconds * 22050) // 512 + 1, 'patch': '6x75x216',
               'timing': 'CUDA events, inputs larger than L2 (>=1 GB of activations per step vs 126 MB L2)', 'weights': 'seeded random init (no checkpoint blobs exist)'}
 
-    if args.workload == 'train_cnn_xs':
+    if args.workload in TRAIN_SPECS:
         return train_main(args, rank, world, local, cores)
+    if args.workload in INFER_SPECS:
+        return unet_infer_main(args, rank, world, local, cores)
 
     if args.impl == 'reference':
         if rank != 0:
