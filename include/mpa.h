@@ -244,6 +244,17 @@ int mpa_layernorm_cf_param_grad_f32(const float* x, const float* g_out, float* g
 int mpa_adamw_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                   float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
 
+/* ---- tensor-core training convolutions (bf16 / fp16 CP8 operands, fp32 accumulate) -------------------------------------
+ * Weight gradient of a stride-1 "same" KHxKW convolution (nn.Conv2d backward): gw[co0+co][ci0+ci][kh][kw] +=
+ * sum_{b,t,f} g[b,co,t,f] * x[b,ci,t+kh-KH/2,f+kw-KW/2]; x / g are CP8 planes of the same geometry (zero gap columns!), gw is the
+ * fp32 gradient in state_dict layout [Cout_total][Cin_total][KH][KW] and must be ZEROED by the caller (results are accumulated with
+ * atomicAdd).  zero_row: >= ceil(Cout/8)*pitch*16 bytes of zeros (rows outside the patch).  Cout <= 128 per call (use channel-block views). */
+int mpa_conv_wgrad_tc(const void* x_cp8, const void* g_cp8, const void* zero_row, float* gw, int n_items, int Cin, int Cout, int T,
+                      int F, int KH, int KW, int pitch, int pf, int pt, int x_nc_stride, int g_nc_stride, int Cin_total, int ci0,
+                      int Cout_total, int co0, int fmt, void* stream);
+/* out[c] = sum_{b,hw} x[b][c][hw] (bias gradient of a convolution). */
+int mpa_channel_sum_f32(const float* x, float* out, int B, int C, int HW, void* stream);
+
 /* ---- training of the U-Net / SAUnet family (configuration 5), fp32 NCHW ------------------------------------------------
  * BatchNorm2d(train) [+ ReLU] backward (unet_cnns.py:50-57): x = conv output (BN input), out = block output (ReLU mask),
  * stats = [mean | biased var] from mpa_bn_stats_f32; scratch2c: 2*C floats. */

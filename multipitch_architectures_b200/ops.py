@@ -323,3 +323,38 @@ def conv_tc_pool(src, dst, w_packed, bias, n_patches, Cin, Cout, F, ksize, pitch
     if rc != 0:
         raise _lib.MpaError(f'mpa_conv_tc_pool_f16 failed ({rc}): {_lib.last_error()}')
     return dst
+
+
+# ------------------------------------------------------------------------------------------------------
+# tensor-core training convolutions
+_ZERO_ROWS = {}
+
+
+def _zero_row(device, nbytes):
+    key = str(device)
+    z = _ZERO_ROWS.get(key)
+    if z is None or z.numel() < nbytes:
+        z = torch.zeros(max(nbytes, 16 * 256 * 16), dtype=torch.uint8, device=device)
+        _ZERO_ROWS[key] = z
+    return z
+
+
+def conv_wgrad_tc(x, g, gw, ksize):
+    """gw [Cout, Cin, KH, KW] fp32 (overwritten) = weight gradient of the stride-1 'same' convolution; x, g: CP8 of one geometry."""
+    Cout_t, Cin_t, KH, KW = gw.shape
+    assert (KH, KW) == tuple(ksize) and x.B == g.B and (x.T, x.F, x.pitch, x.pf, x.pt) == (g.T, g.F, g.pitch, g.pf, g.pt)
+    gw.zero_()
+    for co0 in range(0, g.C, 128):
+        co = min(128, g.C - co0)
+        gv = g.channels(co0, co) if (co0 or co != g.C) else g
+        z = _zero_row(gw.device, ((co + 7) // 8) * x.pitch * 16)
+        call('conv_wgrad_tc', x.ptr(), gv.ptr(), z, gw, x.B, x.C, co, x.T, x.F, KH, KW, x.pitch, x.pf, x.pt, x.ncs, gv.ncs, Cin_t, 0, Cout_t, co0,
+             x.fmt, stream_ptr())
+    return gw
+
+
+def channel_sum(x, out=None):
+    B, C = x.shape[0], x.shape[1]
+    out = out if out is not None else torch.empty(C, dtype=torch.float32, device=x.device)
+    call('channel_sum_f32', _f32(x), out, B, C, x.numel() // (B * C), stream_ptr())
+    return out

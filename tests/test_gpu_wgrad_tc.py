@@ -1,0 +1,40 @@
+"""`-m gpu`: tcgen05 weight-gradient kernel (mpa_conv_wgrad_tc) against torch autograd of nn.Conv2d on the same 16-bit-rounded
+operands (fp32 accumulate on both sides: only the summation order differs), and the bias-gradient reduction."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+@pytest.mark.parametrize('fmt', ['bf16', 'fp16'])
+@pytest.mark.parametrize('cfg', [
+    # B, Cin, Cout, T, F, K
+    (3, 6, 20, 75, 216, 15), (2, 40, 40, 75, 216, 15), (2, 16, 8, 37, 108, 15), (2, 64, 32, 18, 54, 9), (2, 128, 128, 9, 27, 5),
+    (3, 256, 128, 4, 13, 3), (2, 32, 200, 9, 27, 3), (5, 8, 16, 75, 216, 15), (1, 6, 40, 75, 216, 15),
+])
+def test_wgrad_tc_matches_autograd(cfg, fmt):
+    from multipitch_architectures_b200 import ops
+    B, Cin, Cout, T, Fq, K = cfg
+    dt = torch.bfloat16 if fmt == 'bf16' else torch.float16
+    x = rnd(B, Cin, T, Fq, seed=1).to(dt).float()
+    g = rnd(B, Cout, T, Fq, seed=2, scale=0.05).to(dt).float()
+    w = torch.zeros(Cout, Cin, K, K, requires_grad=True)
+    F.conv2d(x, w, padding=K // 2).backward(g)
+    f = ops.fmt_of(fmt)
+    pitch = (Fq + 8 + 15) // 16 * 16
+    xc = ops.nchw_to_cp8(x.cuda(), pitch=pitch, fmt=f)
+    gc = ops.nchw_to_cp8(g.cuda(), pitch=pitch, fmt=f)
+    gw = torch.full((Cout, Cin, K, K), 7.0, device='cuda')
+    ops.conv_wgrad_tc(xc, gc, gw, (K, K))
+    ref = w.grad
+    err = (gw.cpu() - ref).abs().max().item()
+    print(f'{cfg} {fmt}: max|diff| = {err:.3e} of max|gw| = {ref.abs().max().item():.3e}')
+    assert err <= 2e-4 * max(1.0, ref.abs().max().item())
+    gb = ops.channel_sum(g.cuda())
+    assert (gb.cpu() - g.sum(dim=(0, 2, 3))).abs().max() < 1e-3
