@@ -57,4 +57,18 @@ __device__ __forceinline__ float warp_max(float v) {
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Opt a kernel into the maximum dynamic shared memory once per (kernel, device) for the whole PROCESS.  (The attribute is a
+// property of the function on the device, not of the calling thread: per-thread bookkeeping lets an autograd worker thread
+// lower what the main thread believes it has set.)  `flags`: one static array per kernel.
+template <typename K>
+static inline cudaError_t opt_in_max_smem(K kernel, unsigned char* flags /*[64]*/) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (__atomic_load_n(&flags[dev], __ATOMIC_ACQUIRE)) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess) __atomic_store_n(&flags[dev], (unsigned char)1, __ATOMIC_RELEASE);
+  return e;
+}
+
 }  // namespace mpa

@@ -925,6 +925,37 @@ __global__ void upsample2x_cp8_kernel(const uint16_t* __restrict__ low, uint16_t
   }
 }
 
+// Device-side packing of the A-operand tiles (same layout as mpa_conv_tc_pack_weights) for the training path, where the weights
+// change every step.  transpose_flip: pack the DATA-GRADIENT convolution w'[co'][ci'][kh][kw] = w[ci'][co'][KH-1-kh][KW-1-kw].
+__global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, long long total, int Cin, int Cout, int KH, int KW,
+                                    int J, int NC, int mpr, int fmt, int transpose_flip, int Cout_total, int co0) {
+  const int n_paired = (NC / 2) * KW;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(idx & 7);
+    const int mrow = (int)((idx >> 3) & 127);
+    const int kc = (int)((idx >> 10) & 1);
+    const long long tile = idx >> 11;
+    const int q = (int)(tile % mpr), r = (int)(tile / mpr);
+    int df, c;
+    if (q < n_paired) {
+      const int cp = q / KW;
+      df = q - cp * KW;
+      c = 2 * cp + kc;
+    } else {
+      df = 2 * (q - n_paired) + kc;
+      c = NC - 1;
+    }
+    const int j = mrow / Cout, co = mrow - j * Cout;
+    const int kh = r - j, ci = c * 8 + e;
+    float v = 0.f;
+    if (df < KW && j < J && kh >= 0 && kh < KH && ci < Cin) {
+      v = transpose_flip ? w[(((size_t)ci * Cout_total + co0 + co) * KH + (KH - 1 - kh)) * KW + (KW - 1 - df)]
+                         : w[(((size_t)(co0 + co) * Cin + ci) * KH + kh) * KW + df];
+    }
+    out[idx] = cvt16(v, fmt);
+  }
+}
+
 static inline int grid_for(long long total, int block) {
   long long g = (total + block - 1) / block;
   long long cap = 148LL * 16;
@@ -982,6 +1013,20 @@ int mpa_conv_tc_pack_weights(const float* w, void* packed, int Cin, int Cout, in
       }
     }
   }
+  return MPA_OK;
+}
+
+int mpa_conv_tc_pack_weights_dev(const float* w_dev, void* packed_dev, int Cin, int Cout, int KH, int KW, int fmt, int J, int transpose_flip,
+                                 int Cout_total, int co0, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(w_dev && packed_dev && Cin > 0 && Cout > 0 && Cout <= 128 && KH > 0 && KW > 0, "conv_tc_pack_weights_dev: bad argument (Cout <= 128 per block)");
+  MPA_REQUIRE(J >= 0 && J * Cout <= 128 && co0 >= 0 && co0 + Cout <= Cout_total, "conv_tc_pack_weights_dev: bad J / channel block");
+  if (J == 0) J = j_blocks(Cout);
+  const int NC = (Cin + 7) / 8, mpr = mmas_per_row(NC, KW);
+  const long long total = (long long)(KH + J - 1) * mpr * (kATileBytes / 2);
+  pack_weights_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w_dev, (uint16_t*)packed_dev, total, Cin, Cout, KH, KW, J, NC, mpr, fmt,
+                                                                              transpose_flip, Cout_total, co0);
+  MPA_CHECK_LAUNCH("conv_tc_pack_weights_dev");
   return MPA_OK;
 }
 
@@ -1090,15 +1135,13 @@ static int launch_conv_tc(ConvTcParams& p, int Cin, cudaStream_t stream, int* gr
     smem = off + 8 * 32 * kEpiPitch * 2;
   }
   MPA_REQUIRE(smem <= 227 * 1024, "conv_tc: needs %zu B of shared memory (Cin=%d pitch=%d)", smem, Cin, p.P);
-  static thread_local size_t attr_set[2] = {0, 0};
-  if (smem > attr_set[p.ring_on ? 1 : 0]) {
-    cudaError_t e = p.ring_on ? cudaFuncSetAttribute(conv_tc_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                              : cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {
+    static unsigned char flags_tile[64], flags_ring[64];
+    cudaError_t e = p.ring_on ? opt_in_max_smem(conv_tc_ring_kernel, flags_ring) : opt_in_max_smem(conv_tc_kernel, flags_tile);
     if (e != cudaSuccess) {
-      set_error("conv_tc: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+      set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return MPA_ERR_CUDA;
     }
-    attr_set[p.ring_on ? 1 : 0] = smem;
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

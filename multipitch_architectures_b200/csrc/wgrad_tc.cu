@@ -348,10 +348,13 @@ int mpa_conv_wgrad_tc(const void* x_cp8, const void* g_cp8, const void* zero_row
   MPA_REQUIRE(slots >= p.RS + 1 && slots <= kWgMaxSlots && (size_t)(slots + p.RS - 1) * p.slot_bytes + fixed <= 227 * 1024,
               "conv_wgrad_tc: the row ring does not fit in shared memory (Cout=%d pitch=%d)", Cout, pitch);
   p.slots = slots;
-  // the unused lanes of the last stacked row group may read one slot beyond the mirror: keep that inside the x stages
   p.x_off = (slots + p.RS - 1) * p.slot_bytes;
   p.bar_off = p.x_off + kWgXStages * p.xstage_bytes;
-  const size_t smem = (size_t)p.bar_off + 1024;
+  // M = 128 always reads 16 row groups from the tile start; when RS*NCo < 16 the surplus groups (ignored lanes) reach past the ring
+  size_t smem = (size_t)p.bar_off + 1024;
+  const size_t reach = (size_t)(slots - 1) * p.slot_bytes + 16 * (size_t)p.gslab_bytes;
+  if (smem < reach) smem = reach;
+  MPA_REQUIRE(smem <= 227 * 1024, "conv_wgrad_tc: needs %zu B of shared memory", smem);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -365,14 +368,13 @@ int mpa_conv_wgrad_tc(const void* x_cp8, const void* g_cp8, const void* zero_row
   const uint32_t f = (fmt == MPA_FMT_BF16) ? 1u : 0u;
   const int N = (KW * 8 + 15) / 16 * 16;                   // M = 128 needs N % 16 == 0: the extra taps land in ignored columns
   p.idesc = (1u << 4) | (f << 7) | (f << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  static thread_local size_t attr_set = 0;
-  if (smem > attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {
+    static unsigned char flags[64];
+    cudaError_t e = opt_in_max_smem(wgrad_tc_kernel, flags);
     if (e != cudaSuccess) {
-      set_error("conv_wgrad_tc: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+      set_error("conv_wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return MPA_ERR_CUDA;
     }
-    attr_set = smem;
   }
   const int grid = p.n_items < sms ? p.n_items : sms;
   wgrad_tc_kernel<<<grid, kWgThreads, smem, (cudaStream_t)stream>>>(p);

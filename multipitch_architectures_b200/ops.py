@@ -358,3 +358,16 @@ def channel_sum(x, out=None):
     out = out if out is not None else torch.empty(C, dtype=torch.float32, device=x.device)
     call('channel_sum_f32', _f32(x), out, B, C, x.numel() // (B * C), stream_ptr())
     return out
+
+
+def conv_tc_pack_dev(w, Cin, Cout, ksize, fmt, transpose_flip=False, Cout_total=None, co0=0, J=0):
+    """Device-side packing of conv_tc A-operand tiles from the fp32 weight tensor `w` (state_dict layout, on the GPU).
+    transpose_flip: pack the data-gradient convolution of the forward weight `w` (see mpa_conv_tc_pack_weights_dev)."""
+    KH, KW = ksize
+    nbytes = _lib.lib().mpa_conv_tc_packed_bytes(Cin, Cout, KH, KW, J)
+    if nbytes == 0:
+        raise _lib.MpaError(f'conv_tc cannot pack Cin={Cin} Cout={Cout} K={KH}x{KW}')
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    call('conv_tc_pack_weights_dev', _f32(w.detach()), packed, Cin, Cout, KH, KW, fmt, J, int(bool(transpose_flip)),
+         Cout if Cout_total is None else Cout_total, co0, stream_ptr())
+    return packed

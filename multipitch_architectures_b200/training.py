@@ -77,6 +77,64 @@ def _pool_bwd(a_in, g_pool, k, act, a):
     return ga
 
 
+class TcConv:
+    """bf16 tensor-core forward / backward of a stride-1 'same' nn.Conv2d inside the fp32 NCHW training graph:
+    forward = mpa_conv_tc_f16 on CP8 planes, data gradient = the same kernel with the transposed / flipped weights, weight gradient =
+    mpa_conv_wgrad_tc, bias gradient = a channel reduction.  Activations and gradients cross the boundary through nchw<->CP8 converters
+    (16-bit operands, fp32 accumulation; the optimiser state and every element-wise stage stay fp32)."""
+    PF, PT = 8, 1
+    _pool = {}
+
+    @staticmethod
+    def eligible(model, conv, F):
+        KH, KW = conv.kernel_size
+        return (getattr(model, 'precision', 'fp32') == 'bf16' and tuple(conv.stride) == (1, 1) and KH % 2 == 1 and KW % 2 == 1 and 3 <= KW <= 15 and KH >= 3
+                and tuple(conv.padding) == (KH // 2, KW // 2) and F + TcConv.PF + 15 < 272 and conv.bias is not None)
+
+    @classmethod
+    def _buf(cls, tag, B, C, T, F, dev, fmt):
+        """CP8 scratch reused across steps (zero gap columns are never written, so they stay zero)."""
+        pitch = (F + cls.PF + 15) // 16 * 16
+        key = (tag, B, C, T, F, str(dev), fmt)
+        b = cls._pool.get(key)
+        if b is None:
+            b = ops.CP8(B, C, T, F, pitch, cls.PF, cls.PT, dev, fmt=fmt)
+            cls._pool[key] = b
+        return b
+
+    @classmethod
+    def forward(cls, tag, conv, x, act, a):
+        fmt = ops.FMT_BF16
+        B, Cin, T, F = x.shape
+        Cout, _, KH, KW = conv.weight.shape
+        xc = ops.nchw_to_cp8(x, out=cls._buf(tag + ':x', B, Cin, T, F, x.device, fmt), fmt=fmt)
+        yc = cls._buf(tag + ':y', B, Cout, T, F, x.device, fmt)
+        for c0 in range(0, Cout, 128):
+            c = min(128, Cout - c0)
+            wp = ops.conv_tc_pack_dev(conv.weight, Cin, c, (KH, KW), fmt, False, Cout, c0)
+            ops.conv_tc(xc, wp, conv.bias[c0:c0 + c], c, (KH, KW), act, a, out=yc.channels(c0, c))
+        return ops.cp8_to_nchw(yc), xc
+
+    @classmethod
+    def backward(cls, tag, conv, xc, g, gw, gb, need_dx):
+        """g: fp32 gradient wrt the convolution output (before the activation has been differentiated away by the caller)."""
+        fmt = ops.FMT_BF16
+        B, Cout, T, F = g.shape
+        _, Cin, KH, KW = conv.weight.shape
+        gc = ops.nchw_to_cp8(g, out=cls._buf(tag + ':g', B, Cout, T, F, g.device, fmt), fmt=fmt)
+        ops.conv_wgrad_tc(xc, gc, gw, (KH, KW))
+        ops.channel_sum(g, out=gb)
+        if not need_dx:
+            return None
+        gxc = cls._buf(tag + ':gx', B, Cin, T, F, g.device, fmt)
+        zb = torch.zeros(min(Cin, 128), dtype=torch.float32, device=g.device)
+        for c0 in range(0, Cin, 128):
+            c = min(128, Cin - c0)
+            wp = ops.conv_tc_pack_dev(conv.weight, Cout, c, (KH, KW), fmt, True, Cin, c0)
+            ops.conv_tc(gc, wp, zb[:c], c, (KH, KW), ops.ACT_NONE, 0.0, out=gxc.channels(c0, c))
+        return ops.cp8_to_nchw(gxc)
+
+
 def cnn_train_forward(model, x, seed=0, step=0):
     """-> (y_pred [B,1,T-74,72], saved).  Train mode: dropout active when model.p_dropout > 0."""
     a, p = model.a_lrelu, (model.p_dropout if model.training else 0.0)
@@ -90,9 +148,12 @@ def cnn_train_forward(model, x, seed=0, step=0):
     sv = {'x': x, 'blocks': [], 'p': p, 'seed': seed, 'site0': step * 64}
     z = ops.layernorm_cf(x, model.layernorm.weight, model.layernorm.bias, model.layernorm.eps)
     for i, (name, conv) in enumerate(blocks):
-        act = _conv_fwd(conv, z, ops.ACT_LRELU, a)
+        if TcConv.eligible(model, conv, z.shape[3]):
+            act, xc = TcConv.forward(name, conv, z, ops.ACT_LRELU, a)
+        else:
+            act, xc = _conv_fwd(conv, z, ops.ACT_LRELU, a), None
         d = drop(ops.maxpool_time(act, 3))
-        sv['blocks'].append((z, act))
+        sv['blocks'].append((z, act, xc))
         z = _add(d, z) if (residual and i > 0) else d
     a2 = _conv_fwd(model.conv2[0], z, ops.ACT_LRELU, a)
     d2 = drop(ops.maxpool_time(a2, 13))
@@ -131,10 +192,13 @@ def cnn_train_backward(model, sv, g_y, grads):
     g_z = _dgrad(c2, g, sv['z_head'].shape)
     for i in range(len(blocks) - 1, -1, -1):
         name, conv = blocks[i]
-        z_in, act = sv['blocks'][i]
+        z_in, act, xc = sv['blocks'][i]
         g_conv = _pool_bwd(act, drop_bwd(g_z), 3, ops.ACT_LRELU, a)
-        _wgrad(conv, z_in, g_conv, grads[f'{name}.0.weight'], grads[f'{name}.0.bias'])
-        g_in = _dgrad(conv, g_conv, z_in.shape)
+        if xc is not None:
+            g_in = TcConv.backward(name, conv, xc, g_conv, grads[f'{name}.0.weight'], grads[f'{name}.0.bias'], need_dx=True)
+        else:
+            _wgrad(conv, z_in, g_conv, grads[f'{name}.0.weight'], grads[f'{name}.0.bias'])
+            g_in = _dgrad(conv, g_conv, z_in.shape)
         g_z = _add(g_in, g_z) if (residual and i > 0) else g_in
     x = sv['x']
     B, C, T, F = x.shape

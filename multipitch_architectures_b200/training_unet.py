@@ -19,7 +19,7 @@ import torch
 from . import _lib, ops
 from ._lib import call, stream_ptr
 from .libdl.nn_models import _exec
-from .training import _act_bwd, _add, _conv_fwd, _dgrad, _dropout, _pool_bwd, _wgrad
+from .training import TcConv, _act_bwd, _add, _conv_fwd, _dgrad, _dropout, _pool_bwd, _wgrad
 
 
 class Node:
@@ -34,8 +34,8 @@ class Node:
 
 
 class Tape:
-    def __init__(self, grads, seed, step):
-        self.ops, self.grads, self.seed, self.site = [], grads, seed, step * 256
+    def __init__(self, grads, seed, step, model=None):
+        self.ops, self.grads, self.seed, self.site, self.model = [], grads, seed, step * 256, model
 
     def push(self, fn):
         self.ops.append(fn)
@@ -56,7 +56,18 @@ class Tape:
         return out
 
     def conv(self, name, conv, x, act=ops.ACT_NONE, a=0.0, need_dx=True):
-        """Conv2d (+ bias, + fused pointwise activation)."""
+        """Conv2d (+ bias, + fused pointwise activation); stride-1 'same' convolutions of a bf16 model run on the tensor cores."""
+        if self.model is not None and TcConv.eligible(self.model, conv, x.d.shape[3]) and x.d.shape[2] >= 2:
+            y, xc = TcConv.forward(name, conv, x.d, act, a)
+            out = Node(y)
+
+            def bwd_tc():
+                g = out.g if act == ops.ACT_NONE else _act_bwd(out.d, out.g, act, a)
+                gx = TcConv.backward(name, conv, xc, g, self.grads[name + '.weight'], self.grads[name + '.bias'], need_dx)
+                if need_dx:
+                    x.acc(gx)
+            self.push(bwd_tc)
+            return out
         out = Node(_conv_fwd(conv, x.d, act, a))
 
         def bwd():
@@ -272,9 +283,9 @@ class Tape:
 def unet_train_forward(model, x, grads, seed=0, step=0):
     """-> (y_pred [B,1,T-74,72], n_pred or None, tape).  Train mode: BatchNorm batch statistics, dropout when p > 0."""
     a, p = model.a_lrelu, (model.p_dropout if model.training else 0.0)
-    tp = Tape(grads, seed, step)
+    tp = Tape(grads, seed, step, model)
     z = tp.layernorm_cf(model.layernorm, x)
-    x1 = tp.double_conv('inc', model.inc, z)
+    x1 = tp.double_conv('inc', model.inc, z)       # (the gradient wrt z feeds the LayerNorm parameter gradients)
     xs = [x1]
     for lv in (1, 2, 3, 4):
         xs.append(tp.double_conv(f'down{lv}.1', getattr(model, f'down{lv}')[1], tp.maxpool2d(xs[-1], (2, 2), (2, 2))))

@@ -38,3 +38,34 @@ def test_wgrad_tc_matches_autograd(cfg, fmt):
     assert err <= 2e-4 * max(1.0, ref.abs().max().item())
     gb = ops.channel_sum(g.cuda())
     assert (gb.cpu() - g.sum(dim=(0, 2, 3))).abs().max() < 1e-3
+
+
+@pytest.mark.parametrize('cfg', [
+    # B, Cin, Cout, T, F, K   (shapes of the U-Net levels, incl. channel counts that are not multiples of 8 and > 128)
+    (3, 6, 4, 75, 216, 15), (3, 4, 4, 75, 216, 15), (3, 4, 8, 37, 108, 15), (3, 8, 16, 18, 54, 9), (3, 16, 32, 9, 27, 5),
+    (3, 32, 32, 4, 13, 3), (3, 64, 16, 9, 27, 3), (3, 32, 8, 18, 54, 5), (3, 16, 4, 37, 108, 9), (3, 8, 4, 75, 216, 15),
+    (2, 40, 40, 75, 216, 15), (2, 256, 192, 9, 27, 3), (2, 24, 136, 18, 54, 9),
+])
+def test_tc_conv_forward_backward_matches_fp32_conv(cfg):
+    """TcConv (bf16 tensor-core forward / dgrad / wgrad used by the training paths) against torch's fp32 convolution on
+    bf16-rounded operands: the only differences left are the 16-bit rounding of outputs and the summation order."""
+    import torch.nn as nn
+    from multipitch_architectures_b200.training import TcConv
+    from multipitch_architectures_b200 import ops
+    B, Cin, Cout, T, Fq, K = cfg
+    conv = nn.Conv2d(Cin, Cout, (K, K), padding=K // 2)
+    with torch.no_grad():
+        conv.weight.copy_(conv.weight.to(torch.bfloat16).float())
+    x = rnd(B, Cin, T, Fq, seed=3).to(torch.bfloat16).float().requires_grad_(True)
+    y = conv(x)
+    g = rnd(*y.shape, seed=4, scale=1e-4).to(torch.bfloat16).float()
+    y.backward(g)
+    cc = nn.Conv2d(Cin, Cout, (K, K), padding=K // 2).cuda()
+    cc.load_state_dict(conv.state_dict())
+    yt, xc = TcConv.forward('t', cc, x.detach().cuda(), ops.ACT_NONE, 0.0)
+    gw, gb = torch.empty_like(cc.weight), torch.empty_like(cc.bias)
+    gx = TcConv.backward('t', cc, xc, g.cuda(), gw, gb, True)
+    rel = lambda a, b: ((a.cpu() - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+    e = (rel(yt, y.detach()), rel(gx, x.grad), rel(gw, conv.weight.grad), rel(gb, conv.bias.grad))
+    print(f'{cfg}: rel err y {e[0]:.2e} gx {e[1]:.2e} gw {e[2]:.2e} gb {e[3]:.2e}')
+    assert e[0] < 8e-3 and e[1] < 8e-3 and e[2] < 2e-3 and e[3] < 1e-4
