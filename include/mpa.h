@@ -186,6 +186,10 @@ int mpa_upsample2x_cp8(const void* low_cp8, void* out_cp8, int n, int C, int Tl,
 /* layout converters (tests, and the seams between the fp32 and the 16-bit paths). */
 int mpa_nchw_to_cp8(const float* x, void* out_cp8, int B, int C, int T, int F, int pitch, int pf, int pt, int fmt,
                     int ncs_out, void* stream);
+/* x [B][C][T][Fs] fp32 -> CP8 planes of width F with source column f on column offset + f*stride; the other real columns are NOT
+ * written (they must hold the zeros of the initial allocation): zero-inserted gradient of a stride-(1,stride) convolution. */
+int mpa_nchw_to_cp8_strided(const float* x, void* out_cp8, int B, int C, int T, int Fs, int F, int stride, int offset, int pitch,
+                            int pf, int pt, int fmt, int ncs_out, void* stream);
 int mpa_cp8_to_nchw(const void* in_cp8, float* out, int B, int C, int T, int F, int pitch, int pf, int pt, int fmt,
                     int ncs_in, void* stream);
 

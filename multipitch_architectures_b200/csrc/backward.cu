@@ -31,33 +31,43 @@ __global__ void act_bwd_kernel(const float* __restrict__ out, const float* __res
 }
 
 // a: forward input of the pool (post-activation), g_p: gradient wrt pool output.  g_a[t'] = act'(a[t']) * sum_t g_p[t]*[argmax_t == t']
-__global__ void maxpool_time_bwd_kernel(const float* __restrict__ a, const float* __restrict__ g_p, float* __restrict__ g_a, long long total,
-                                        int T, int F, int k, int act, float act_param) {
+// One CTA per (plane, 64 columns): the column tile of `a` is staged in shared memory, every thread owns one column and walks the T
+// windows in order — the first arg-max of a window takes its gradient (ATen semantics) — accumulating into its own column of the tile.
+constexpr int kPoolBwdCols = 64;
+__global__ void __launch_bounds__(kPoolBwdCols) maxpool_time_bwd_kernel(const float* __restrict__ a, const float* __restrict__ g_p, float* __restrict__ g_a,
+                                                                        int T, int F, int k, int act, float act_param) {
+  extern __shared__ float sm[];
+  float* av = sm;                               // [T][64]
+  float* acc = sm + (size_t)T * kPoolBwdCols;    // [T][64]
   const int h = k / 2;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int f = (int)(i % F);
-    const long long r = i / F;
-    const int tp = (int)(r % T);
-    const long long plane = r / T;
-    const float* ap = a + plane * T * F + f;
-    const float* gp = g_p + plane * T * F + f;
-    const float mine = ap[(size_t)tp * F];
-    float acc = 0.f;
-    for (int t = max(0, tp - h); t <= min(T - 1, tp + h); ++t) {
-      // is tp the first arg-max of window [t-h, t+h]?
-      const int lo = max(0, t - h), hi = min(T - 1, t + h);
-      bool win = true;
-      for (int s = lo; s <= hi && win; ++s) {
-        const float v = ap[(size_t)s * F];
-        if (s < tp) win = !(v >= mine);      // an earlier element that is >= would have been picked first
-        else if (s > tp) win = !(v > mine);
-      }
-      if (win) acc += gp[(size_t)t * F];
+  const long long plane = blockIdx.x;
+  const int f = blockIdx.y * kPoolBwdCols + threadIdx.x;
+  const bool ok = f < F;
+  const float* ap = a + plane * T * F + f;
+  const float* gp = g_p + plane * T * F + f;
+  for (int t = 0; t < T; ++t) {
+    av[t * kPoolBwdCols + threadIdx.x] = ok ? ap[(size_t)t * F] : 0.f;
+    acc[t * kPoolBwdCols + threadIdx.x] = 0.f;
+  }
+  // (each thread touches only its own column: no synchronisation needed)
+  if (!ok) return;
+  for (int t = 0; t < T; ++t) {
+    const int lo = max(0, t - h), hi = min(T - 1, t + h);
+    int am = lo;
+    float best = av[lo * kPoolBwdCols + threadIdx.x];
+    for (int s = lo + 1; s <= hi; ++s) {
+      const float v = av[s * kPoolBwdCols + threadIdx.x];
+      if (v > best) { best = v; am = s; }          // strict: the first maximum wins
     }
+    acc[am * kPoolBwdCols + threadIdx.x] += gp[(size_t)t * F];
+  }
+  float* op = g_a + plane * T * F + f;
+  for (int t = 0; t < T; ++t) {
+    const float mine = av[t * kPoolBwdCols + threadIdx.x];
     float d = 1.f;
     if (act == MPA_ACT_LRELU) d = mine >= 0.f ? 1.f : act_param;
     else if (act == MPA_ACT_RELU) d = mine > 0.f ? 1.f : 0.f;
-    g_a[i] = acc * d;
+    op[(size_t)t * F] = acc[t * kPoolBwdCols + threadIdx.x] * d;
   }
 }
 
@@ -191,26 +201,6 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict
   }
 }
 
-// gb[c] = sum over (b, hw) of g[b,c,hw]; one block per channel
-__global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict__ g, float* __restrict__ gb, int B, int C, int HW) {
-  __shared__ float sh[8];
-  const int c = blockIdx.x;
-  const long long n = (long long)B * HW;
-  float s = 0.f;
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-    const int b = (int)(i / HW);
-    s += g[((size_t)b * C + c) * HW + (i - (long long)b * HW)];
-  }
-  s = warp_sum(s);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int i = 0; i < 8; ++i) t += sh[i];
-    gb[c] = t;
-  }
-}
-
 // LayerNorm([C,F]) parameter gradients; one CTA per batch item, rows accumulated in registers, one atomicAdd per element per CTA
 template <int MAXV>
 __global__ void __launch_bounds__(128) layernorm_cf_param_grad_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ gw,
@@ -322,8 +312,10 @@ int mpa_maxpool_time_bwd_f32(const float* a, const float* g_pool, float* g_a, in
                              void* stream) {
   MPA_CHECK_ARCH();
   MPA_REQUIRE(a && g_pool && g_a && B > 0 && C > 0 && T > 0 && F > 0 && k >= 1 && (k & 1), "maxpool_time_bwd: bad argument");
-  const long long total = (long long)B * C * T * F;
-  maxpool_time_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(a, g_pool, g_a, total, T, F, k, act, act_param);
+  const size_t smem = 2 * (size_t)T * kPoolBwdCols * sizeof(float);
+  MPA_REQUIRE(smem <= 160 * 1024, "maxpool_time_bwd: T = %d too long for the column tile", T);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(maxpool_time_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  maxpool_time_bwd_kernel<<<dim3(B * C, ceil_div(F, kPoolBwdCols)), kPoolBwdCols, smem, (cudaStream_t)stream>>>(a, g_pool, g_a, T, F, k, act, act_param);
   MPA_CHECK_LAUNCH("maxpool_time_bwd");
   return MPA_OK;
 }
@@ -378,7 +370,8 @@ int mpa_conv2d_wgrad_f32(const float* x, const float* g_out, float* g_w, float* 
   conv_wgrad_kernel<<<dim3(gx, gy, gz), 256, smem, st>>>(x, g_out, g_w, B, Cin, H, W, Cout, Ho, Wo, KH, KW, sh, sw, ph, pw, n_combos, rows_per_cta);
   MPA_CHECK_LAUNCH("conv2d_wgrad");
   if (g_b) {
-    bias_grad_kernel<<<Cout, 256, 0, st>>>(g_out, g_b, B, Cout, Ho * Wo);
+    int rc = channel_sum_launch(g_out, g_b, B, Cout, Ho * Wo, st);
+    if (rc != MPA_OK) return rc;
     MPA_CHECK_LAUNCH("bias_grad");
   }
   return MPA_OK;

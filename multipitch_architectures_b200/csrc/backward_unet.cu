@@ -23,32 +23,6 @@ __device__ __forceinline__ float block_sum256(float v, float* sh) {
 }
 
 // ---- BatchNorm2d(train) + ReLU backward -------------------------------------------------------------------------
-// pass 1 (one block per channel): s1 = sum dy', s2 = sum dy' * xhat, dy' = dy * (out > 0); also dw = s2, db = s1
-__global__ void __launch_bounds__(256) bn_relu_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ out, const float* __restrict__ dy,
-                                                                 const float* __restrict__ stats, float eps, float* __restrict__ sums, float* __restrict__ dw,
-                                                                 float* __restrict__ db, int B, int C, int HW, int relu) {
-  __shared__ float sh[8];
-  const int c = blockIdx.x;
-  const float mean = stats[c], rstd = rsqrtf(stats[C + c] + eps);
-  const long long n = (long long)B * HW;
-  float s1 = 0.f, s2 = 0.f;
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-    const int b = (int)(i / HW);
-    const size_t idx = ((size_t)b * C + c) * HW + (i - (long long)b * HW);
-    float g = dy[idx];
-    if (relu && !(out[idx] > 0.f)) g = 0.f;
-    s1 += g;
-    s2 += g * (x[idx] - mean) * rstd;
-  }
-  s1 = block_sum256(s1, sh);
-  s2 = block_sum256(s2, sh);
-  if (threadIdx.x == 0) {
-    sums[c] = s1;
-    sums[C + c] = s2;
-    db[c] = s1;
-    dw[c] = s2;
-  }
-}
 // pass 2: dx = w * rstd * (dy' - s1/N - xhat * s2/N)
 __global__ void bn_relu_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ out, const float* __restrict__ dy,
                                          const float* __restrict__ stats, const float* __restrict__ w, const float* __restrict__ sums, float eps,
@@ -398,7 +372,10 @@ int mpa_bn_relu_bwd_f32(const float* x, const float* out, const float* dy, const
   MPA_CHECK_ARCH();
   MPA_REQUIRE(x && out && dy && stats && w && dx && dw && db && scratch2c && B > 0 && C > 0 && HW > 0, "bn_relu_bwd: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
-  bn_relu_bwd_reduce_kernel<<<C, 256, 0, st>>>(x, out, dy, stats, eps, scratch2c, dw, db, B, C, HW, relu);
+  {
+    int rc = bn_bwd_sums_launch(x, out, dy, stats, eps, scratch2c, dw, db, B, C, HW, relu, st);
+    if (rc != MPA_OK) return rc;
+  }
   MPA_CHECK_LAUNCH("bn_relu_bwd_reduce");
   const long long total = (long long)B * C * HW;
   bn_relu_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, st>>>(x, out, dy, stats, w, scratch2c, eps, dx, total, C, HW, 1.f / ((float)B * HW), relu);

@@ -12,6 +12,11 @@ namespace mpa {
 void set_error(const char* fmt, ...);
 int check_arch();
 void count_launch(int n = 1);
+// reduce.cu: parallel, order-stable per-channel reductions (launch only; the caller checks the launch)
+int channel_sum_launch(const float* x, float* out, int B, int C, int HW, cudaStream_t st);
+int bn_bwd_sums_launch(const float* x, const float* out_act, const float* dy, const float* stats, float eps, float* sums2c, float* dw, float* db,
+                       int B, int C, int HW, int relu, cudaStream_t st);
+int bn_stats_launch(const float* x, float* stats, int B, int C, int HW, cudaStream_t st);
 
 #define MPA_REQUIRE(cond, ...)                 \
   do {                                         \

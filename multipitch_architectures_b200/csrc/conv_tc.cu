@@ -783,6 +783,27 @@ __global__ void nchw_to_cp8_kernel(const float* __restrict__ x, uint16_t* __rest
   }
 }
 
+// x [B][C][T][Fs] -> CP8 planes of width F: source column f lands on column offset + f*stride (every other real column keeps the
+// zero it was initialised with): the zero-inserted gradient of a stride-(1,s) convolution evaluated as a sub-sampled stride-1 one
+__global__ void nchw_to_cp8_strided_kernel(const float* __restrict__ x, uint16_t* __restrict__ out, long long total, int C, int T, int Fs, int NCk,
+                                           int NCs, int TP, int P, int pf, int pt, int fmt, int stride, int offset) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int f = (int)(i % Fs);
+    long long r = i / Fs;
+    int t = (int)(r % T);
+    r /= T;
+    int ck = (int)(r % NCk);
+    int b = (int)(r / NCk);
+    __align__(16) uint16_t v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      int c = ck * 8 + e;
+      v[e] = cvt16(c < C ? x[(((size_t)b * C + c) * T + t) * Fs + f] : 0.f, fmt);
+    }
+    *reinterpret_cast<uint4*>(out + ((((size_t)b * NCs + ck) * TP + pt + t) * P + pf + offset + f * stride) * 8) = *reinterpret_cast<uint4*>(v);
+  }
+}
+
 __global__ void cp8_to_nchw_kernel(const uint16_t* __restrict__ in, float* __restrict__ out, long long total, int C, int T,
                                    int F, int NCs, int TP, int P, int pf, int pt, int fmt) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -1376,6 +1397,20 @@ int mpa_nchw_to_cp8(const float* x, void* out_cp8, int B, int C, int T, int F, i
   nchw_to_cp8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (uint16_t*)out_cp8, total, C, T, F, NCk, ncs_out, T + 2 * pt,
                                                                                pitch, pf, pt, fmt);
   MPA_CHECK_LAUNCH("nchw_to_cp8");
+  return MPA_OK;
+}
+
+int mpa_nchw_to_cp8_strided(const float* x, void* out_cp8, int B, int C, int T, int Fs, int F, int stride, int offset, int pitch, int pf, int pt,
+                            int fmt, int ncs_out, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(x && out_cp8 && B > 0 && C > 0 && stride >= 1 && offset >= 0 && offset + (Fs - 1) * stride < F && pitch >= pf + F,
+              "nchw_to_cp8_strided: bad argument");
+  const int NCk = (C + 7) / 8;
+  if (ncs_out <= 0) ncs_out = NCk;
+  long long total = (long long)B * NCk * T * Fs;
+  nchw_to_cp8_strided_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (uint16_t*)out_cp8, total, C, T, Fs, NCk, ncs_out, T + 2 * pt,
+                                                                                       pitch, pf, pt, fmt, stride, offset);
+  MPA_CHECK_LAUNCH("nchw_to_cp8_strided");
   return MPA_OK;
 }
 

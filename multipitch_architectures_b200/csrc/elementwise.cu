@@ -186,32 +186,6 @@ __global__ void upsample_concat_kernel(const float* __restrict__ low, const floa
   }
 }
 
-// one block per channel; two-pass mean / biased variance over (B, HW)
-__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ x, float* __restrict__ stats, int B, int C, int HW) {
-  __shared__ float sh[8];
-  const int c = blockIdx.x;
-  const long long n = (long long)B * HW;
-  float s = 0.f;
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-    int b = (int)(i / HW);
-    int p = (int)(i - (long long)b * HW);
-    s += x[((size_t)b * C + c) * HW + p];
-  }
-  float mean = block_sum(s, sh) / (float)n;
-  float q = 0.f;
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-    int b = (int)(i / HW);
-    int p = (int)(i - (long long)b * HW);
-    float d = x[((size_t)b * C + c) * HW + p] - mean;
-    q += d * d;
-  }
-  float var = block_sum(q, sh) / (float)n;
-  if (threadIdx.x == 0) {
-    stats[c] = mean;
-    stats[C + c] = var;
-  }
-}
-
 __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ w,
                                 const float* __restrict__ b, float* __restrict__ out, long long total, int C, int HW, float eps,
                                 int act, float act_param) {
@@ -339,7 +313,10 @@ int mpa_upsample2x_concat_f32(const float* low, const float* skip, float* out, i
 int mpa_bn_stats_f32(const float* x, float* stats, int B, int C, int HW, void* stream) {
   MPA_CHECK_ARCH();
   MPA_REQUIRE(x && stats && B > 0 && C > 0 && HW > 0, "bn_stats: bad argument");
-  bn_stats_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(x, stats, B, C, HW);
+  {
+    int rc = bn_stats_launch(x, stats, B, C, HW, (cudaStream_t)stream);
+    if (rc != MPA_OK) return rc;
+  }
   MPA_CHECK_LAUNCH("bn_stats");
   return MPA_OK;
 }

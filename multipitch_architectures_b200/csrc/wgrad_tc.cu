@@ -281,26 +281,6 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgradPara
   }
 }
 
-// out[c] = sum over (b, hw) of x[b][c][hw]  (bias gradient); one block per channel
-__global__ void __launch_bounds__(256) channel_sum_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int C, int HW) {
-  __shared__ float sh[8];
-  const int c = blockIdx.x;
-  float s = 0.f;
-  const long long n = (long long)B * HW;
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-    const int b = (int)(i / HW);
-    s += x[((size_t)b * C + c) * HW + (i - (long long)b * HW)];
-  }
-  s = warp_sum(s);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int i = 0; i < 8; ++i) t += sh[i];
-    out[c] = t;
-  }
-}
-
 }  // namespace mpa
 
 using namespace mpa;
@@ -379,14 +359,6 @@ int mpa_conv_wgrad_tc(const void* x_cp8, const void* g_cp8, const void* zero_row
   const int grid = p.n_items < sms ? p.n_items : sms;
   wgrad_tc_kernel<<<grid, kWgThreads, smem, (cudaStream_t)stream>>>(p);
   MPA_CHECK_LAUNCH("conv_wgrad_tc");
-  return MPA_OK;
-}
-
-int mpa_channel_sum_f32(const float* x, float* out, int B, int C, int HW, void* stream) {
-  MPA_CHECK_ARCH();
-  MPA_REQUIRE(x && out && B > 0 && C > 0 && HW > 0, "channel_sum: bad argument");
-  channel_sum_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(x, out, B, C, HW);
-  MPA_CHECK_LAUNCH("channel_sum");
   return MPA_OK;
 }
 

@@ -135,6 +135,43 @@ class TcConv:
         return ops.cp8_to_nchw(gxc)
 
 
+def _tc_s3_eligible(model, conv, F):
+    """The head's 3x3 / stride (1,3) / pad (1,0) convolution (basic_cnns.py:391) = the stride-1 'same' 3x3 convolution sampled at
+    columns 1, 4, 7, ... ; its backward is the stride-1 backward of the zero-inserted output gradient."""
+    return (getattr(model, 'precision', 'fp32') == 'bf16' and tuple(conv.kernel_size) == (3, 3) and tuple(conv.stride) == (1, 3)
+            and tuple(conv.padding) == (1, 0) and F % 3 == 0 and F + TcConv.PF + 15 < 272 and conv.bias is not None)
+
+
+def _tc_s3_forward(tag, conv, x, act, a):
+    fmt = ops.FMT_BF16
+    B, Cin, T, F = x.shape
+    Cout = conv.weight.shape[0]
+    xc = ops.nchw_to_cp8(x, out=TcConv._buf(tag + ':x', B, Cin, T, F, x.device, fmt), fmt=fmt)
+    yc = ops.compact_cp8(B, Cout, T, F // 3, x.device, fmt)
+    for c0 in range(0, Cout, 128):
+        c = min(128, Cout - c0)
+        wp = ops.conv_tc_pack_dev(conv.weight, Cin, c, (3, 3), fmt, False, Cout, c0)
+        ops.conv_tc(xc, wp, conv.bias[c0:c0 + c], c, (3, 3), act, a, subsample=(3, 1), out=yc.channels(c0, c))
+    return ops.cp8_to_nchw(yc), xc
+
+
+def _tc_s3_backward(tag, conv, xc, g, gw, gb):
+    fmt = ops.FMT_BF16
+    B, Cout, T, Fo = g.shape
+    Cin, F = conv.weight.shape[1], xc.F
+    gc = TcConv._buf(tag + ':g3', B, Cout, T, F, g.device, fmt)
+    call('nchw_to_cp8_strided', g, gc.ptr(), B, Cout, T, Fo, F, 3, 1, gc.pitch, gc.pf, gc.pt, fmt, gc.ncs, stream_ptr())
+    ops.conv_wgrad_tc(xc, gc, gw, (3, 3))
+    ops.channel_sum(g, out=gb)
+    gxc = TcConv._buf(tag + ':gx', B, Cin, T, F, g.device, fmt)
+    zb = torch.zeros(min(Cin, 128), dtype=torch.float32, device=g.device)
+    for c0 in range(0, Cin, 128):
+        c = min(128, Cin - c0)
+        wp = ops.conv_tc_pack_dev(conv.weight, Cout, c, (3, 3), fmt, True, Cin, c0)
+        ops.conv_tc(gc, wp, zb[:c], c, (3, 3), ops.ACT_NONE, 0.0, out=gxc.channels(c0, c))
+    return ops.cp8_to_nchw(gxc)
+
+
 def cnn_train_forward(model, x, seed=0, step=0):
     """-> (y_pred [B,1,T-74,72], saved).  Train mode: dropout active when model.p_dropout > 0."""
     a, p = model.a_lrelu, (model.p_dropout if model.training else 0.0)
@@ -155,14 +192,17 @@ def cnn_train_forward(model, x, seed=0, step=0):
         d = drop(ops.maxpool_time(act, 3))
         sv['blocks'].append((z, act, xc))
         z = _add(d, z) if (residual and i > 0) else d
-    a2 = _conv_fwd(model.conv2[0], z, ops.ACT_LRELU, a)
+    if _tc_s3_eligible(model, model.conv2[0], z.shape[3]):
+        a2, x2c = _tc_s3_forward('conv2', model.conv2[0], z, ops.ACT_LRELU, a)
+    else:
+        a2, x2c = _conv_fwd(model.conv2[0], z, ops.ACT_LRELU, a), None
     d2 = drop(ops.maxpool_time(a2, 13))
     a3 = _conv_fwd(model.conv3[0], d2, ops.ACT_LRELU, a)
     d3 = drop(a3)
     a4 = _conv_fwd(model.conv4[0], d3, ops.ACT_LRELU, a)
     d4 = drop(a4)
     y = _conv_fwd(model.conv4[3], d4, ops.ACT_SIGMOID, 0.0)
-    sv.update(z_head=z, a2=a2, d2=d2, a3=a3, d3=d3, a4=a4, d4=d4, y=y)
+    sv.update(z_head=z, a2=a2, d2=d2, a3=a3, d3=d3, a4=a4, d4=d4, y=y, x2c=x2c)
     return y, sv
 
 
@@ -188,8 +228,11 @@ def cnn_train_backward(model, sv, g_y, grads):
     _wgrad(c3, sv['d2'], g, grads['conv3.0.weight'], grads['conv3.0.bias'])
     g = drop_bwd(_dgrad(c3, g, sv['d2'].shape))
     g = _pool_bwd(sv['a2'], g, 13, ops.ACT_LRELU, a)
-    _wgrad(c2, sv['z_head'], g, grads['conv2.0.weight'], grads['conv2.0.bias'])
-    g_z = _dgrad(c2, g, sv['z_head'].shape)
+    if sv.get('x2c') is not None:
+        g_z = _tc_s3_backward('conv2', c2, sv['x2c'], g, grads['conv2.0.weight'], grads['conv2.0.bias'])
+    else:
+        _wgrad(c2, sv['z_head'], g, grads['conv2.0.weight'], grads['conv2.0.bias'])
+        g_z = _dgrad(c2, g, sv['z_head'].shape)
     for i in range(len(blocks) - 1, -1, -1):
         name, conv = blocks[i]
         z_in, act, xc = sv['blocks'][i]

@@ -19,7 +19,8 @@ import torch
 from . import _lib, ops
 from ._lib import call, stream_ptr
 from .libdl.nn_models import _exec
-from .training import TcConv, _act_bwd, _add, _conv_fwd, _dgrad, _dropout, _pool_bwd, _wgrad
+from .training import (TcConv, _act_bwd, _add, _conv_fwd, _dgrad, _dropout, _pool_bwd, _tc_s3_backward, _tc_s3_eligible, _tc_s3_forward,
+                       _wgrad)
 
 
 class Node:
@@ -80,11 +81,19 @@ class Tape:
 
     def conv_act_pool_time(self, name, conv, x, k, a):
         """Conv2d -> LeakyReLU -> MaxPool((k,1), stride 1, pad k//2)  (head conv2, basic_cnns.py:391-393)."""
-        act = Node(_conv_fwd(conv, x.d, ops.ACT_LRELU, a))
+        xc = None
+        if self.model is not None and _tc_s3_eligible(self.model, conv, x.d.shape[3]):
+            y, xc = _tc_s3_forward(name, conv, x.d, ops.ACT_LRELU, a)
+            act = Node(y)
+        else:
+            act = Node(_conv_fwd(conv, x.d, ops.ACT_LRELU, a))
         out = Node(ops.maxpool_time(act.d, k))
 
         def bwd():
             g = _pool_bwd(act.d, out.g, k, ops.ACT_LRELU, a)
+            if xc is not None:
+                x.acc(_tc_s3_backward(name, conv, xc, g, self.grads[name + '.weight'], self.grads[name + '.bias']))
+                return
             _wgrad(conv, x.d, g, self.grads[name + '.weight'], self.grads[name + '.bias'])
             x.acc(_dgrad(conv, g, x.d.shape))
         self.push(bwd)

@@ -243,7 +243,7 @@ def _cosines(ga, gb):
 
 
 @pytest.mark.parametrize('name,scheme,min_cos,min_worst', [
-    ('cnn_xs', 'adversarial', 0.999, 0.99), ('drcnn_tiny', 'adversarial', 0.999, 0.99),
+    ('cnn_xs', 'adversarial', 0.999, 0.98), ('drcnn_tiny', 'adversarial', 0.999, 0.98),
     ('unet_tiny', 'torch_default', 0.95, 0.80), ('saunet_tiny', 'torch_default', 0.96, 0.80), ('punet_tiny', 'torch_default', 0.90, 0.80),
     ('unet_tiny', 'adversarial', 0.83, 0.60), ('saunet_tiny', 'adversarial', 0.95, 0.80), ('punet_tiny', 'adversarial', 0.87, 0.75)])
 def test_bf16_tensor_core_training_tracks_the_fp32_path(name, scheme, min_cos, min_worst):
