@@ -155,7 +155,8 @@ typedef struct mpa_conv_tc_desc {
 } mpa_conv_tc_desc;
 size_t mpa_conv_tc_pool_workspace(int Cout, int pitch, int J);
 /* DEVICE-side packing (training: the weights change every step): w_dev fp32 in state_dict layout.  Packs output channels
- * [co0, co0+Cout) of a convolution with Cout_total output channels.  transpose_flip = 1 packs the data-gradient convolution
+ * [co0, co0+Cout) of a convolution with Cout_total output channels (channels >= Cout_total are packed as zeros, so a block may be
+ * padded to a multiple of 8).  transpose_flip = 1 packs the data-gradient convolution
  * w'[co'][ci'][kh][kw] = w[ci'][co'][KH-1-kh][KW-1-kw] of a forward weight w [Cin][Cout_total][KH][KW] (Cin = forward Cout). */
 int mpa_conv_tc_pack_weights_dev(const float* w_dev, void* packed_dev, int Cin, int Cout, int KH, int KW, int fmt, int J,
                                  int transpose_flip, int Cout_total, int co0, void* stream);

@@ -23,6 +23,15 @@ __global__ void enc_gather_kernel(const float* __restrict__ x, const float* __re
   }
 }
 
+__device__ __forceinline__ int ceil_div_dev(int a, int b) { return (a + b - 1) / b; }
+static inline int pick_ksplit(int blocks, int K, int allow) {
+  if (!allow || blocks >= 148 || K < 512) return 1;
+  int ks = 296 / (blocks < 1 ? 1 : blocks);
+  if (ks > K / 128) ks = K / 128;
+  if (ks > 32) ks = 32;
+  return ks < 1 ? 1 : ks;
+}
+
 // C[M,N] = act(A[M,K] * W[N,K]^T + bias[N]); 64x64 tile, 256 threads, 4x4 register tile, K step 16
 __global__ void __launch_bounds__(256) gemm_nt_kernel(const float* __restrict__ A, const float* __restrict__ W, const float* __restrict__ bias,
                                                       float* __restrict__ C, int M, int N, int K, int relu) {
@@ -31,12 +40,15 @@ __global__ void __launch_bounds__(256) gemm_nt_kernel(const float* __restrict__ 
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += 16) {
+  // split-K over blockIdx.z (wide-K, small-output products: the slices are combined with atomicAdd into a pre-zeroed C)
+  const int kchunk = (ceil_div_dev(K, (int)gridDim.z) + 15) / 16 * 16;
+  const int k_begin = blockIdx.z * kchunk, k_end = min(K, k_begin + kchunk);
+  for (int k0 = k_begin; k0 < k_end; k0 += 16) {
     for (int e = threadIdx.x; e < 64 * 16; e += 256) {
       int kk = e & 15, r = e >> 4;
       int m = m0 + r, n = n0 + r, k = k0 + kk;
-      As[kk][r] = (m < M && k < K) ? A[(size_t)m * K + k] : 0.f;
-      Ws[kk][r] = (n < N && k < K) ? W[(size_t)n * K + k] : 0.f;
+      As[kk][r] = (m < M && k < k_end) ? A[(size_t)m * K + k] : 0.f;
+      Ws[kk][r] = (n < N && k < k_end) ? W[(size_t)n * K + k] : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -61,8 +73,9 @@ __global__ void __launch_bounds__(256) gemm_nt_kernel(const float* __restrict__ 
     for (int j = 0; j < 4; ++j) {
       int n = n0 + tx * 4 + j;
       if (n >= N) continue;
-      float v = acc[i][j] + (bias ? bias[n] : 0.f);
-      C[(size_t)m * N + n] = relu ? fmaxf(v, 0.f) : v;
+      float v = acc[i][j] + ((bias && blockIdx.z == 0) ? bias[n] : 0.f);
+      if (gridDim.z > 1) atomicAdd(&C[(size_t)m * N + n], v);
+      else C[(size_t)m * N + n] = relu ? fmaxf(v, 0.f) : v;
     }
   }
 }
@@ -205,7 +218,11 @@ int mpa_encoder_layer_f32(const float* x, float* out, int B, int E, int Th, int 
   MPA_CHECK_LAUNCH("add_ln1");
   gemm_nt_kernel<<<dim3(ceil_div(mlp_dim, 64), ceil_div(n, 64)), 256, 0, st>>>(h1, mlp0_w, mlp0_b, hid, (int)n, mlp_dim, E, 1);
   MPA_CHECK_LAUNCH("gemm_mlp0");
-  gemm_nt_kernel<<<dim3(ceil_div(E, 64), ceil_div(n, 64)), 256, 0, st>>>(hid, mlp2_w, mlp2_b, mo, (int)n, E, mlp_dim, 0);
+  {
+    const int ks = pick_ksplit(ceil_div(E, 64) * ceil_div(n, 64), mlp_dim, 1);
+    if (ks > 1) cudaMemsetAsync(mo, 0, sizeof(float) * (size_t)n * E, st);
+    gemm_nt_kernel<<<dim3(ceil_div(E, 64), ceil_div(n, 64), ks), 256, 0, st>>>(hid, mlp2_w, mlp2_b, mo, (int)n, E, mlp_dim, 0);
+  }
   MPA_CHECK_LAUNCH("gemm_mlp2");
   add_ln_kernel<<<(unsigned)n, 128, 0, st>>>(h1, mo, ln2_w, ln2_b, nullptr, out, E, S, eps);
   MPA_CHECK_LAUNCH("add_ln2");
@@ -229,7 +246,11 @@ int mpa_enc_gather_f32(const float* x, const float* pe, float* tok, int B, int E
 int mpa_gemm_nt_f32(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, int relu, void* stream) {
   MPA_CHECK_ARCH();
   MPA_REQUIRE(A && W && C && M > 0 && N > 0 && K > 0, "gemm_nt: bad argument");
-  gemm_nt_kernel<<<dim3(ceil_div(N, 64), ceil_div(M, 64)), 256, 0, (cudaStream_t)stream>>>(A, W, bias, C, M, N, K, relu);
+  {
+    const int ks = pick_ksplit(ceil_div(N, 64) * ceil_div(M, 64), K, !relu);
+    if (ks > 1) cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, (cudaStream_t)stream);
+    gemm_nt_kernel<<<dim3(ceil_div(N, 64), ceil_div(M, 64), ks), 256, 0, (cudaStream_t)stream>>>(A, W, bias, C, M, N, K, relu);
+  }
   MPA_CHECK_LAUNCH("gemm_nt");
   return MPA_OK;
 }

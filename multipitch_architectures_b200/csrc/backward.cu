@@ -33,41 +33,46 @@ __global__ void act_bwd_kernel(const float* __restrict__ out, const float* __res
 // a: forward input of the pool (post-activation), g_p: gradient wrt pool output.  g_a[t'] = act'(a[t']) * sum_t g_p[t]*[argmax_t == t']
 // One CTA per (plane, 64 columns): the column tile of `a` is staged in shared memory, every thread owns one column and walks the T
 // windows in order — the first arg-max of a window takes its gradient (ATen semantics) — accumulating into its own column of the tile.
-constexpr int kPoolBwdCols = 64;
-__global__ void __launch_bounds__(kPoolBwdCols) maxpool_time_bwd_kernel(const float* __restrict__ a, const float* __restrict__ g_p, float* __restrict__ g_a,
-                                                                        int T, int F, int k, int act, float act_param) {
+constexpr int kPoolBwdCols = 64, kPoolBwdRowGroups = 4;
+__global__ void __launch_bounds__(kPoolBwdCols * kPoolBwdRowGroups) maxpool_time_bwd_kernel(const float* __restrict__ a, const float* __restrict__ g_p,
+                                                                                            float* __restrict__ g_a, int T, int F, int k, int act,
+                                                                                            float act_param) {
   extern __shared__ float sm[];
   float* av = sm;                               // [T][64]
   float* acc = sm + (size_t)T * kPoolBwdCols;    // [T][64]
   const int h = k / 2;
   const long long plane = blockIdx.x;
-  const int f = blockIdx.y * kPoolBwdCols + threadIdx.x;
+  const int col = threadIdx.x % kPoolBwdCols, rg = threadIdx.x / kPoolBwdCols;
+  const int f = blockIdx.y * kPoolBwdCols + col;
   const bool ok = f < F;
   const float* ap = a + plane * T * F + f;
   const float* gp = g_p + plane * T * F + f;
-  for (int t = 0; t < T; ++t) {
-    av[t * kPoolBwdCols + threadIdx.x] = ok ? ap[(size_t)t * F] : 0.f;
-    acc[t * kPoolBwdCols + threadIdx.x] = 0.f;
+  for (int t = rg; t < T; t += kPoolBwdRowGroups) {
+    av[t * kPoolBwdCols + col] = ok ? ap[(size_t)t * F] : 0.f;
+    acc[t * kPoolBwdCols + col] = 0.f;
   }
-  // (each thread touches only its own column: no synchronisation needed)
-  if (!ok) return;
-  for (int t = 0; t < T; ++t) {
-    const int lo = max(0, t - h), hi = min(T - 1, t + h);
-    int am = lo;
-    float best = av[lo * kPoolBwdCols + threadIdx.x];
-    for (int s = lo + 1; s <= hi; ++s) {
-      const float v = av[s * kPoolBwdCols + threadIdx.x];
-      if (v > best) { best = v; am = s; }          // strict: the first maximum wins
+  __syncthreads();
+  if (ok) {
+    for (int t = rg; t < T; t += kPoolBwdRowGroups) {
+      const int lo = max(0, t - h), hi = min(T - 1, t + h);
+      int am = lo;
+      float best = av[lo * kPoolBwdCols + col];
+      for (int s = lo + 1; s <= hi; ++s) {
+        const float v = av[s * kPoolBwdCols + col];
+        if (v > best) { best = v; am = s; }          // strict: the first maximum wins
+      }
+      atomicAdd(&acc[am * kPoolBwdCols + col], gp[(size_t)t * F]);   // <= k windows share an arg-max row
     }
-    acc[am * kPoolBwdCols + threadIdx.x] += gp[(size_t)t * F];
   }
+  __syncthreads();
+  if (!ok) return;
   float* op = g_a + plane * T * F + f;
-  for (int t = 0; t < T; ++t) {
-    const float mine = av[t * kPoolBwdCols + threadIdx.x];
+  for (int t = rg; t < T; t += kPoolBwdRowGroups) {
+    const float mine = av[t * kPoolBwdCols + col];
     float d = 1.f;
     if (act == MPA_ACT_LRELU) d = mine >= 0.f ? 1.f : act_param;
     else if (act == MPA_ACT_RELU) d = mine > 0.f ? 1.f : 0.f;
-    op[(size_t)t * F] = acc[t * kPoolBwdCols + threadIdx.x] * d;
+    op[(size_t)t * F] = acc[t * kPoolBwdCols + col] * d;
   }
 }
 
@@ -315,7 +320,7 @@ int mpa_maxpool_time_bwd_f32(const float* a, const float* g_pool, float* g_a, in
   const size_t smem = 2 * (size_t)T * kPoolBwdCols * sizeof(float);
   MPA_REQUIRE(smem <= 160 * 1024, "maxpool_time_bwd: T = %d too long for the column tile", T);
   if (smem > 48 * 1024) cudaFuncSetAttribute(maxpool_time_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  maxpool_time_bwd_kernel<<<dim3(B * C, ceil_div(F, kPoolBwdCols)), kPoolBwdCols, smem, (cudaStream_t)stream>>>(a, g_pool, g_a, T, F, k, act, act_param);
+  maxpool_time_bwd_kernel<<<dim3(B * C, ceil_div(F, kPoolBwdCols)), kPoolBwdCols * kPoolBwdRowGroups, smem, (cudaStream_t)stream>>>(a, g_pool, g_a, T, F, k, act, act_param);
   MPA_CHECK_LAUNCH("maxpool_time_bwd");
   return MPA_OK;
 }

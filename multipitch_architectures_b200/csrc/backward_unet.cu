@@ -136,20 +136,23 @@ __global__ void __launch_bounds__(256) gemm_generic_kernel(const float* __restri
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += 16) {
+  // split-K over blockIdx.z: the slices are combined with atomicAdd (C pre-zeroed unless accumulating)
+  const int kchunk = (((K + (int)gridDim.z - 1) / (int)gridDim.z) + 15) / 16 * 16;
+  const int k_begin = blockIdx.z * kchunk, k_end = min(K, k_begin + kchunk);
+  for (int k0 = k_begin; k0 < k_end; k0 += 16) {
     for (int e = threadIdx.x; e < 64 * 16; e += 256) {
       if (mode == 0) {
         const int kk = e & 15, r = e >> 4;
         const int m = m0 + r, k = k0 + kk;
-        As[kk][r] = (m < M && k < K) ? A[(size_t)m * K + k] : 0.f;
+        As[kk][r] = (m < M && k < k_end) ? A[(size_t)m * K + k] : 0.f;
       } else {
         const int r = e & 63, kk = e >> 6;
         const int m = m0 + r, k = k0 + kk;
-        As[kk][r] = (m < M && k < K) ? A[(size_t)k * M + m] : 0.f;
+        As[kk][r] = (m < M && k < k_end) ? A[(size_t)k * M + m] : 0.f;
       }
       const int r = e & 63, kk = e >> 6;
       const int n = n0 + r, k = k0 + kk;
-      Bs[kk][r] = (n < N && k < K) ? Bm[(size_t)k * N + n] : 0.f;
+      Bs[kk][r] = (n < N && k < k_end) ? Bm[(size_t)k * N + n] : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -175,7 +178,8 @@ __global__ void __launch_bounds__(256) gemm_generic_kernel(const float* __restri
       const int n = n0 + tx * 4 + j;
       if (n >= N) continue;
       const size_t idx = (size_t)m * N + n;
-      C[idx] = accumulate ? C[idx] + acc[i][j] : acc[i][j];
+      if (gridDim.z > 1) atomicAdd(&C[idx], acc[i][j]);
+      else C[idx] = accumulate ? C[idx] + acc[i][j] : acc[i][j];
     }
   }
 }
@@ -410,7 +414,18 @@ int mpa_upsample2x_concat_bwd_f32(const float* g_cat, float* g_skip, int accumul
 int mpa_gemm_f32(const float* A, const float* Bm, float* C, int M, int N, int K, int mode, int accumulate, void* stream) {
   MPA_CHECK_ARCH();
   MPA_REQUIRE(A && Bm && C && M > 0 && N > 0 && K > 0 && (mode == 0 || mode == 1), "gemm: bad argument");
-  gemm_generic_kernel<<<dim3(ceil_div(N, 64), ceil_div(M, 64)), 256, 0, (cudaStream_t)stream>>>(A, Bm, C, M, N, K, mode, accumulate);
+  {
+    const int blocks = ceil_div(N, 64) * ceil_div(M, 64);
+    int ks = 1;
+    if (blocks < 148 && K >= 512) {
+      ks = 296 / blocks;
+      if (ks > K / 128) ks = K / 128;
+      if (ks > 32) ks = 32;
+      if (ks < 1) ks = 1;
+    }
+    if (ks > 1 && !accumulate) cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, (cudaStream_t)stream);
+    gemm_generic_kernel<<<dim3(ceil_div(N, 64), ceil_div(M, 64), ks), 256, 0, (cudaStream_t)stream>>>(A, Bm, C, M, N, K, mode, accumulate);
+  }
   MPA_CHECK_LAUNCH("gemm_generic");
   return MPA_OK;
 }

@@ -969,7 +969,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __res
     const int j = mrow / Cout, co = mrow - j * Cout;
     const int kh = r - j, ci = c * 8 + e;
     float v = 0.f;
-    if (df < KW && j < J && kh >= 0 && kh < KH && ci < Cin) {
+    if (df < KW && j < J && kh >= 0 && kh < KH && ci < Cin && co0 + co < Cout_total) {
       v = transpose_flip ? w[(((size_t)ci * Cout_total + co0 + co) * KH + (KH - 1 - kh)) * KW + (KW - 1 - df)]
                          : w[(((size_t)(co0 + co) * Cin + ci) * KH + kh) * KW + df];
     }
@@ -1041,7 +1041,7 @@ int mpa_conv_tc_pack_weights_dev(const float* w_dev, void* packed_dev, int Cin, 
                                  int Cout_total, int co0, void* stream) {
   MPA_CHECK_ARCH();
   MPA_REQUIRE(w_dev && packed_dev && Cin > 0 && Cout > 0 && Cout <= 128 && KH > 0 && KW > 0, "conv_tc_pack_weights_dev: bad argument (Cout <= 128 per block)");
-  MPA_REQUIRE(J >= 0 && J * Cout <= 128 && co0 >= 0 && co0 + Cout <= Cout_total, "conv_tc_pack_weights_dev: bad J / channel block");
+  MPA_REQUIRE(J >= 0 && J * Cout <= 128 && co0 >= 0 && co0 < Cout_total, "conv_tc_pack_weights_dev: bad J / channel block");
   if (J == 0) J = j_blocks(Cout);
   const int NC = (Cin + 7) / 8, mpr = mmas_per_row(NC, KW);
   const long long total = (long long)(KH + J - 1) * mpr * (kATileBytes / 2);

@@ -42,7 +42,8 @@ def _dgrad(conv, g, in_shape):
     w = conv.weight
     Cout, Cin, KH, KW = w.shape
     B, _, H, W = in_shape
-    if tuple(conv.stride) == (1, 1):
+    if tuple(conv.stride) == (1, 1) and tuple(conv.padding) == (KH // 2, KW // 2) and KH % 2 == 1 and KW % 2 == 1:
+        # 'same' convolutions only: for a VALID one (conv3, 75x1) the flipped full correlation multiplies 75x more zeros than data
         wt = ops.pack_conv_weight(w.detach().permute(1, 0, 2, 3).flip(2, 3).contiguous())
         return ops.conv2d(g, wt, None, Cin, (KH, KW), (1, 1), (KH - 1 - conv.padding[0], KW - 1 - conv.padding[1]))
     gi = torch.empty(in_shape, dtype=torch.float32, device=g.device)
@@ -102,6 +103,13 @@ class TcConv:
             cls._pool[key] = b
         return b
 
+    @staticmethod
+    def _pad8(v, n):
+        """bias (or zeros) padded to n entries: the padded output channels of a block carry zero weights and zero bias."""
+        out = torch.zeros(n, dtype=torch.float32, device=v.device)
+        out[:v.numel()] = v.detach()
+        return out
+
     @classmethod
     def forward(cls, tag, conv, x, act, a):
         fmt = ops.FMT_BF16
@@ -111,8 +119,9 @@ class TcConv:
         yc = cls._buf(tag + ':y', B, Cout, T, F, x.device, fmt)
         for c0 in range(0, Cout, 128):
             c = min(128, Cout - c0)
-            wp = ops.conv_tc_pack_dev(conv.weight, Cin, c, (KH, KW), fmt, False, Cout, c0)
-            ops.conv_tc(xc, wp, conv.bias[c0:c0 + c], c, (KH, KW), act, a, out=yc.channels(c0, c))
+            cp = (c + 7) // 8 * 8                        # whole chunks: the coalesced epilogue needs Cout % 8 == 0
+            wp = ops.conv_tc_pack_dev(conv.weight, Cin, cp, (KH, KW), fmt, False, Cout, c0)
+            ops.conv_tc(xc, wp, cls._pad8(conv.bias[c0:c0 + c], cp), cp, (KH, KW), act, a, out=yc.channels(c0, cp))
         return ops.cp8_to_nchw(yc), xc
 
     @classmethod
@@ -127,11 +136,12 @@ class TcConv:
         if not need_dx:
             return None
         gxc = cls._buf(tag + ':gx', B, Cin, T, F, g.device, fmt)
-        zb = torch.zeros(min(Cin, 128), dtype=torch.float32, device=g.device)
+        zb = torch.zeros(128, dtype=torch.float32, device=g.device)
         for c0 in range(0, Cin, 128):
             c = min(128, Cin - c0)
-            wp = ops.conv_tc_pack_dev(conv.weight, Cout, c, (KH, KW), fmt, True, Cin, c0)
-            ops.conv_tc(gc, wp, zb[:c], c, (KH, KW), ops.ACT_NONE, 0.0, out=gxc.channels(c0, c))
+            cp = (c + 7) // 8 * 8
+            wp = ops.conv_tc_pack_dev(conv.weight, Cout, cp, (KH, KW), fmt, True, Cin, c0)
+            ops.conv_tc(gc, wp, zb[:cp], cp, (KH, KW), ops.ACT_NONE, 0.0, out=gxc.channels(c0, cp))
         return ops.cp8_to_nchw(gxc)
 
 
@@ -150,8 +160,9 @@ def _tc_s3_forward(tag, conv, x, act, a):
     yc = ops.compact_cp8(B, Cout, T, F // 3, x.device, fmt)
     for c0 in range(0, Cout, 128):
         c = min(128, Cout - c0)
-        wp = ops.conv_tc_pack_dev(conv.weight, Cin, c, (3, 3), fmt, False, Cout, c0)
-        ops.conv_tc(xc, wp, conv.bias[c0:c0 + c], c, (3, 3), act, a, subsample=(3, 1), out=yc.channels(c0, c))
+        cp = (c + 7) // 8 * 8
+        wp = ops.conv_tc_pack_dev(conv.weight, Cin, cp, (3, 3), fmt, False, Cout, c0)
+        ops.conv_tc(xc, wp, TcConv._pad8(conv.bias[c0:c0 + c], cp), cp, (3, 3), act, a, subsample=(3, 1), out=yc.channels(c0, cp))
     return ops.cp8_to_nchw(yc), xc
 
 
@@ -164,11 +175,12 @@ def _tc_s3_backward(tag, conv, xc, g, gw, gb):
     ops.conv_wgrad_tc(xc, gc, gw, (3, 3))
     ops.channel_sum(g, out=gb)
     gxc = TcConv._buf(tag + ':gx', B, Cin, T, F, g.device, fmt)
-    zb = torch.zeros(min(Cin, 128), dtype=torch.float32, device=g.device)
+    zb = torch.zeros(128, dtype=torch.float32, device=g.device)
     for c0 in range(0, Cin, 128):
         c = min(128, Cin - c0)
-        wp = ops.conv_tc_pack_dev(conv.weight, Cout, c, (3, 3), fmt, True, Cin, c0)
-        ops.conv_tc(gc, wp, zb[:c], c, (3, 3), ops.ACT_NONE, 0.0, out=gxc.channels(c0, c))
+        cp = (c + 7) // 8 * 8
+        wp = ops.conv_tc_pack_dev(conv.weight, Cout, cp, (3, 3), fmt, True, Cin, c0)
+        ops.conv_tc(gc, wp, zb[:cp], cp, (3, 3), ops.ACT_NONE, 0.0, out=gxc.channels(c0, cp))
     return ops.cp8_to_nchw(gxc)
 
 

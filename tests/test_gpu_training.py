@@ -50,7 +50,7 @@ def test_pool_act_bwd_and_dropout(k):
     g = rnd(*p.shape, seed=4)
     p.backward(g)
     got = TR._pool_bwd(a.detach().cuda(), g.cuda(), k, ops.ACT_LRELU, 0.3).cpu()
-    assert (got - y.grad).abs().max() < 1e-6
+    assert (got - y.grad).abs().max() < 1e-5      # up to k windows add into one row in arbitrary order
     x = torch.ones(100003).cuda()
     d = TR._dropout(x, 0.2, 7, 3)
     keep = (d != 0).float().mean().item()
