@@ -411,7 +411,7 @@ def main():
                          'infer_punet (configs[3]); train_saunet (configs[4]: SAUnet:L data-parallel training, batch 25 per GPU)')
     ap.add_argument('--batch', type=int, default=0, help='training batch per GPU (0 = the workload default)')
     ap.add_argument('--train-precision', default='fp32', choices=['fp32', 'bf16'])
-    ap.add_argument('--infer-batch', type=int, default=100)
+    ap.add_argument('--infer-batch', type=int, default=400, help='patches per forward of the U-Net inference workloads (any size is legal: eval-mode patches are independent)')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', 0))
