@@ -67,6 +67,7 @@ struct ConvTcParams {
   int n_patches, NC, Cout, J, T, F, KH, KW, P, N, pf, pt_out, TP_out, T_out, row0, NCo;
   int n_seg, y_lo[2], y_hi[2], z_lo[2], z_hi[2], seg_groups[2], groups_per_patch;
   int mmas_per_row, n_units, slab_px, epi_off, a_stages, btab_off;
+  int resident;             // tile main loop: the whole weight set fits in the A stages -> loaded once per CTA, never re-streamed
   long long out_patch_stride;  // elements (16-bit) between patches in `out`
   int act;
   float act_param;
@@ -440,6 +441,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
     if (lane == 0) {
       int a_stage = 0, b_stage = 0;
       uint32_t a_phase = 0, b_phase = 0;
+      if (p.resident && u_begin < u_end) {
+        // small filters (the head's 3x3): every weight stage has its own slot and is loaded exactly once
+        const int spr = (p.mmas_per_row + kStageMMAs - 1) / kStageMMAs;
+        for (int r = 0; r < rows_in; ++r)
+          for (int m0 = 0; m0 < p.mmas_per_row; m0 += kStageMMAs) {
+            const int nm = min(kStageMMAs, p.mmas_per_row - m0), idx = r * spr + m0 / kStageMMAs;
+            mbar_expect_tx(&a_full[idx], (uint32_t)(nm * kATileBytes));
+            bulk_g2s(a_smem + idx * kAStageBytes, p.w + ((size_t)r * p.mmas_per_row + m0) * kATileBytes, (uint32_t)(nm * kATileBytes), &a_full[idx]);
+          }
+      }
       for (int u = u_begin; u < u_end; ++u) {
         const UnitInfo ui = decode_unit(p, u);
         for (int r = 0; r < rows_in; ++r) {
@@ -457,6 +468,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
           }
           if (++b_stage == kNumBStages) { b_stage = 0; b_phase ^= 1; }
           // weight stages of this K row
+          if (p.resident) continue;
           const uint8_t* wrow = p.w + (size_t)r * p.mmas_per_row * kATileBytes;
           for (int m0 = 0; m0 < p.mmas_per_row; m0 += kStageMMAs) {
             const int nm = min(kStageMMAs, p.mmas_per_row - m0);
@@ -482,6 +494,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
       constexpr uint32_t kALoFixed = ((128u * 16u) >> 4) << 16;              // A: LBO = 2048 B between the two k-slices
       const uint32_t asm16 = smem_u32(a_smem) >> 4, bsm16 = smem_u32(b_smem) >> 4, bst16 = (uint32_t)bstage_bytes >> 4;
       uint32_t k_unit = 0;
+      const int spr = (p.mmas_per_row + kStageMMAs - 1) / kStageMMAs;
+      if (p.resident && u_begin < u_end)
+        for (int i = 0; i < rows_in * spr; ++i) mbar_wait(&a_full[i], 0);     // the resident weight set has landed
       for (int u = u_begin; u < u_end; ++u, ++k_unit) {
         const UnitInfo ui = decode_unit(p, u);
         const uint32_t buf = k_unit & 1u, acc_par = (k_unit >> 1) & 1u;
@@ -496,7 +511,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
           const uint32_t bbase16 = bsm16 + (uint32_t)b_stage * bst16;
           for (int m0 = 0; m0 < p.mmas_per_row; m0 += kStageMMAs) {
             const int nm = min(kStageMMAs, p.mmas_per_row - m0);
-            mbar_wait(&a_full[a_stage], a_phase);
+            if (p.resident) a_stage = r * spr + m0 / kStageMMAs;
+            else mbar_wait(&a_full[a_stage], a_phase);
             tc_fence_after();
             const uint32_t a_lo = (asm16 + (uint32_t)a_stage * (kAStageBytes >> 4)) | kALoFixed;
             if (elect_one_sync()) {
@@ -511,11 +527,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
                   tc_mma_f16(tmem_d, ((uint64_t)kDescHi << 32) | (uint64_t)(a_lo + (uint32_t)i * (kATileBytes >> 4)),
                              ((uint64_t)kDescHi << 32) | (uint64_t)(bbase16 + p.btab[m0 + i]), p.idesc, (i == 0) ? accum : 1u);
               }
-              tc_commit(&a_empty[a_stage]);       // frees the weight stage when its MMAs have retired
+              if (!p.resident) tc_commit(&a_empty[a_stage]);       // frees the weight stage when its MMAs have retired
             }
             __syncwarp();
             accum = 1;
-            if (++a_stage == kNumAStages) { a_stage = 0; a_phase ^= 1; }
+            if (!p.resident && ++a_stage == kNumAStages) { a_stage = 0; a_phase ^= 1; }
           }
           if (elect_one_sync()) tc_commit(&b_empty[b_stage]);         // frees the activation slab of this row
           __syncwarp();
@@ -879,6 +895,41 @@ __global__ void pool_time_res_cp8_kernel(const uint4* __restrict__ y, const uint
   }
 }
 
+// Wide time pools (k = 13 of the head): one thread per (item, chunk, column) walks down the T rows with the last k values in
+// registers — one 16-byte load per output instead of k
+template <int FMT, int K>
+__global__ void pool_time_col_cp8_kernel(const uint4* __restrict__ y, const uint4* __restrict__ res, uint4* __restrict__ out, long long total,
+                                         int NCk, int ncs_y, int ncs_res, int ncs_out, int T, int F, int TP, int P, int pf, int pt) {
+  constexpr int H = K / 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i % F);
+    long long r = i / F;
+    const int ck = (int)(r % NCk);
+    const long long b = r / NCk;
+    const size_t yb = (((size_t)b * ncs_y + ck) * TP + pt) * P + pf + f;
+    const size_t ob = (((size_t)b * ncs_out + ck) * TP + pt) * P + pf + f;
+    const size_t rb = (((size_t)b * ncs_res + ck) * TP + pt) * P + pf + f;
+    uint4 win[K];                                  // win[j] = row t - H + j (rows outside [0,T) hold a copy of a valid row: max-neutral)
+    const uint4 first = y[yb];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const int t = j - H - 1;                     // window of the (virtual) output row -1
+      win[j] = (t >= 0 && t < T) ? y[yb + (size_t)t * P] : first;
+    }
+    for (int t = 0; t < T; ++t) {
+#pragma unroll
+      for (int j = 0; j < K - 1; ++j) win[j] = win[j + 1];
+      const int tn = t + H;
+      win[K - 1] = tn < T ? y[yb + (size_t)tn * P] : win[K - 2];
+      uint4 c = win[0];
+#pragma unroll
+      for (int j = 1; j < K; ++j) max8<FMT>(c, win[j]);
+      if (res) add8<FMT>(c, res[rb + (size_t)t * P]);
+      out[ob + (size_t)t * P] = c;
+    }
+  }
+}
+
 // MaxPool2d((2,2)) floor mode between two CP8 geometries
 template <int FMT>
 __global__ void maxpool2x2_cp8_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, long long total, int NCk, int ncs_in, int ncs_out,
@@ -1131,6 +1182,7 @@ static int launch_conv_tc(ConvTcParams& p, int Cin, cudaStream_t stream, int* gr
     int a_stages = kMaxAStages;
     while (a_stages > 2 && (size_t)a_stages * kAStageBytes + b_bytes + tail > 227 * 1024) --a_stages;
     p.a_stages = a_stages;
+    p.resident = ((p.KH + p.J - 1) * ((p.mmas_per_row + kStageMMAs - 1) / kStageMMAs) <= a_stages) ? 1 : 0;
     MPA_REQUIRE(p.mmas_per_row <= 128, "conv_tc: too many K steps per row (%d)", p.mmas_per_row);
     {
       const uint32_t plane = (uint32_t)p.slab_px * 16u;
@@ -1337,7 +1389,15 @@ int mpa_pool_time_res_cp8(const void* y_cp8, const void* res_cp8, void* out_cp8,
   if (ncs_res <= 0) ncs_res = NCk;
   if (ncs_out <= 0) ncs_out = NCk;
   long long total = (long long)n_patches * NCk * T * F;
-  if (fmt == MPA_FMT_BF16)
+  if (k == 13 && T >= 13) {
+    const long long cols = (long long)n_patches * NCk * F;
+    if (fmt == MPA_FMT_BF16)
+      pool_time_col_cp8_kernel<MPA_FMT_BF16, 13><<<grid_for(cols, 128), 128, 0, (cudaStream_t)stream>>>(
+          (const uint4*)y_cp8, (const uint4*)res_cp8, (uint4*)out_cp8, cols, NCk, ncs_y, ncs_res, ncs_out, T, F, T + 2 * pt, pitch, pf, pt);
+    else
+      pool_time_col_cp8_kernel<MPA_FMT_F16, 13><<<grid_for(cols, 128), 128, 0, (cudaStream_t)stream>>>(
+          (const uint4*)y_cp8, (const uint4*)res_cp8, (uint4*)out_cp8, cols, NCk, ncs_y, ncs_res, ncs_out, T, F, T + 2 * pt, pitch, pf, pt);
+  } else if (fmt == MPA_FMT_BF16)
     pool_time_res_cp8_kernel<MPA_FMT_BF16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
         (const uint4*)y_cp8, (const uint4*)res_cp8, (uint4*)out_cp8, total, NCk, ncs_y, ncs_res, ncs_out, T, F, T + 2 * pt, pitch, pf, pt, k / 2);
   else
