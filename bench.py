@@ -57,7 +57,7 @@ class ClockSampler(threading.Thread):
                 self.rows.append([c.strip() for c in r.stdout.strip().split(',')])
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.05)
 
     def stop(self):
         self._stop_evt.set()
