@@ -267,6 +267,10 @@ def unet_forward_tc(model, x):
     if hasattr(model, 'attention1'):
         t5 = model.attention2.run(model.attention1.run(ops.cp8_to_nchw(x5)))
         x5 = ops.nchw_to_cp8(t5, pitch=geo[4][2], pf=LEVEL_PF, pt=1, fmt=fmt)
+    if hasattr(model, 'attention3'):
+        # SAUSnet: the lowest skip connection passes two encoder layers too (x5 above was computed from the un-attended x4)
+        t4 = model.attention4.run(model.attention3.run(ops.cp8_to_nchw(skips[3])))
+        ops.nchw_to_cp8(t4, out=skips[3], fmt=fmt)
     # decoder
     low = x5
     for i, lv in enumerate((3, 2, 1, 0)):

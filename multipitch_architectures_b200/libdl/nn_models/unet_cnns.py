@@ -132,11 +132,15 @@ class _UnetBase(_MpaModel):
             return y, (ops.cp8_to_nchw(x5c) if hasattr(self, 'convP') else None)
         x1, x2, x3, x4, x5 = _exec.unet_trunk_f32(self, x, train)
         x5 = self._bottleneck(x5)
+        x4 = self._skip4(x4)                  # (SAUSnet: attention on the lowest skip, after x5 was taken from the original x4)
         u = _exec.unet_up_f32(self, x5, (x1, x2, x3, x4), train)
         return _exec.head_f32(self._cache, self, u, self.a_lrelu), x5
 
     def _bottleneck(self, x5):
         return x5
+
+    def _skip4(self, x4):
+        return x4
 
 
 class simple_u_net_largekernels(_UnetBase):
@@ -169,6 +173,35 @@ class simple_u_net_doubleselfattn(_UnetBase):
 
     def _bottleneck(self, x5):
         return self.attention2.run(self.attention1.run(x5))
+
+    def forward(self, x):
+        return self._run(x)[0]
+
+
+class simple_u_net_doubleselfattn_twolayers(_UnetBase):
+    """SAUSnet (unet_cnns.py:670-754): two encoder layers at the bottleneck AND two on the lowest skip connection x4.  The reference
+    hands its own p_dropout to the encoder layers here (the SAUnet above leaves them at their default 0.2)."""
+
+    def __init__(self, n_chan_input=6, n_chan_layers=[64, 30, 20, 10], n_bins_in=216, n_bins_out=12, a_lrelu=0.3, p_dropout=0.2,
+                 convdrop=0, residual=False, scalefac=16, embed_dim=4 * 8, num_heads=8, mlp_dim=512, pos_encoding=None, precision='fp32'):
+        super().__init__()
+        self._init_common(n_chan_input, n_bins_in, a_lrelu, p_dropout, precision)
+        kw = dict(convdrop=convdrop, residual=residual)
+        self.layernorm = nn.LayerNorm(normalized_shape=[n_chan_input, n_bins_in])
+        self._build_trunk(n_chan_input, n_chan_layers, scalefac, **kw)
+        enc = dict(embed_dim=embed_dim, num_heads=num_heads, mlp_dim=mlp_dim, p_dropout=p_dropout)
+        self.attention1 = transformer_enc_layer(pos_encoding=pos_encoding, **enc)
+        self.attention2 = transformer_enc_layer(**enc)
+        self.attention3 = transformer_enc_layer(pos_encoding=pos_encoding, **enc)
+        self.attention4 = transformer_enc_layer(**enc)
+        self._build_up(n_chan_layers, scalefac, **kw)
+        _head(self, n_chan_layers[0], n_chan_layers, n_bins_in, n_bins_out, a_lrelu, p_dropout)
+
+    def _bottleneck(self, x5):
+        return self.attention2.run(self.attention1.run(x5))
+
+    def _skip4(self, x4):
+        return self.attention4.run(self.attention3.run(x4))
 
     def forward(self, x):
         return self._run(x)[0]

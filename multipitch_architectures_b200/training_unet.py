@@ -303,6 +303,10 @@ def unet_train_forward(model, x, grads, seed=0, step=0):
         for nm in ('attention1', 'attention2'):
             layer = getattr(model, nm)
             x5 = tp.encoder_layer(nm, layer, x5, layer.p_dropout if model.training else 0.0)
+    if hasattr(model, 'attention3'):                    # SAUSnet: the lowest skip passes two encoder layers (after x5 was taken from it)
+        for nm in ('attention3', 'attention4'):
+            layer = getattr(model, nm)
+            xs[3] = tp.encoder_layer(nm, layer, xs[3], layer.p_dropout if model.training else 0.0)
     u = x5
     for i, lv in enumerate((3, 2, 1, 0)):
         u = tp.double_conv(f'upconv{i + 1}', getattr(model, f'upconv{i + 1}'), tp.upconcat(u, xs[lv]))
@@ -393,7 +397,7 @@ class UnetTrainStep:
             call('adamw_f32', self.flat_p, self.flat_g, self.m, self.v, _lib.i64(self.flat_p.numel()), float(self.lr), float(self.betas[0]),
                  float(self.betas[1]), float(self.eps), float(self.wd), self.step_count, float(scale), stream_ptr())
         self.model._cache._d.clear()
-        for nm in ('attention1', 'attention2'):
+        for nm in ('attention1', 'attention2', 'attention3', 'attention4'):
             if hasattr(self.model, nm):
                 getattr(self.model, nm)._cache._d.clear()
         return loss

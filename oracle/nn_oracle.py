@@ -18,7 +18,7 @@ Reference sites restated here (all relative to /root/reference):
   * double_conv (Conv+BN+ReLU x2, opt. 1x1 res) . libdl/nn_models/unet_cnns.py:30-82
   * bilinear x2 upsample + pad + concat ......... libdl/nn_models/unet_cnns.py:85-104
   * transformer_enc_layer (batch-axis MHA) ...... libdl/nn_models/unet_cnns.py:107-159
-  * Unet / SAUnet / PUnet forward ............... libdl/nn_models/unet_cnns.py:333-407, 496-575, 2251-2335
+  * Unet / SAUnet / SAUSnet / PUnet forward ..... libdl/nn_models/unet_cnns.py:333-407, 496-575, 670-754, 2251-2335
   * BCELoss(mean) with -100 log clamp ........... experiments/Exp1_SectionIV-B/exp126a_musicnet_cnn_basic.py:87
 """
 import math
@@ -183,6 +183,9 @@ def unet_forward(sd, x, a_lrelu=0.3, train=False, num_heads=8, pos_encoding=None
     if 'attention1.q_linear.weight' in sd:
         x5 = encoder_layer(x5, sd, 'attention1', num_heads, pos_encoding == 'sinusoidal')
         x5 = encoder_layer(x5, sd, 'attention2', num_heads, False)
+    if 'attention3.q_linear.weight' in sd:                       # SAUSnet (unet_cnns.py:744-745): attention on the lowest skip
+        x4 = encoder_layer(x4, sd, 'attention3', num_heads, pos_encoding == 'sinusoidal')
+        x4 = encoder_layer(x4, sd, 'attention4', num_heads, False)
     u = double_conv(upconcat(x5, x4), sd, 'upconv1', train)
     u = double_conv(upconcat(u, x3), sd, 'upconv2', train)
     u = double_conv(upconcat(u, x2), sd, 'upconv3', train)

@@ -193,7 +193,7 @@ def train_goldens():
     BCELoss(mean) and, for the PUnet, + CrossEntropyLoss(n_pred, sum(labels).long())/25 (RETRAIN4_exp195f...rerun1.py:343-346)."""
     torch.set_num_threads(8)
     out = {}
-    for name, B, seed in (('unet_tiny', 3, 15), ('saunet_tiny', 5, 19), ('punet_tiny', 3, 17)):
+    for name, B, seed in (('unet_tiny', 3, 15), ('saunet_tiny', 5, 19), ('punet_tiny', 3, 17), ('sausnet_tiny', 5, 23)):
         m = build_reference_model(name)
         sd = fill_state_dict(m.state_dict(), seed)
         m.load_state_dict(sd)
@@ -221,6 +221,11 @@ def train_goldens():
         for k, v in m.state_dict().items():
             if 'running_' in k:
                 out[tag + '__stat__' + k] = v.numpy().copy()
+        m.load_state_dict(sd)                               # (the train-mode pass above moved the BatchNorm running statistics)
+        m.eval()
+        with torch.no_grad():
+            ye = m(x)
+        out[tag + '__eval_y'] = (ye[0] if isinstance(ye, tuple) else ye).numpy()
         print(tag, 'loss', loss.item())
     np.savez_compressed(os.path.join(HERE, 'nn_train_golden.npz'), **out)
 

@@ -127,7 +127,7 @@ def _zero_dropout(m):
             mod.p_dropout = 0.0
 
 
-@pytest.mark.parametrize('name', ['unet_tiny', 'saunet_tiny', 'punet_tiny'])
+@pytest.mark.parametrize('name', ['unet_tiny', 'saunet_tiny', 'punet_tiny', 'sausnet_tiny'])
 def test_model_loss_grads_and_running_stats_match_reference_golden(train_golden, name):
     tag = f'{name}__train'
     B, seed = [int(v) for v in train_golden[tag + '__meta']]
@@ -245,7 +245,8 @@ def _cosines(ga, gb):
 @pytest.mark.parametrize('name,scheme,min_cos,min_worst', [
     ('cnn_xs', 'adversarial', 0.999, 0.98), ('drcnn_tiny', 'adversarial', 0.999, 0.98),
     ('unet_tiny', 'torch_default', 0.95, 0.80), ('saunet_tiny', 'torch_default', 0.96, 0.80), ('punet_tiny', 'torch_default', 0.90, 0.80),
-    ('unet_tiny', 'adversarial', 0.83, 0.60), ('saunet_tiny', 'adversarial', 0.95, 0.80), ('punet_tiny', 'adversarial', 0.87, 0.75)])
+    ('unet_tiny', 'adversarial', 0.83, 0.60), ('saunet_tiny', 'adversarial', 0.95, 0.80), ('punet_tiny', 'adversarial', 0.87, 0.75),
+    ('sausnet_tiny', 'torch_default', 0.90, 0.75)])
 def test_bf16_tensor_core_training_tracks_the_fp32_path(name, scheme, min_cos, min_worst):
     """precision='bf16': every stride-1 'same' convolution runs forward / data-gradient / weight-gradient on the tensor cores
     (16-bit operands, fp32 accumulate; layer-level parity <= 4e-3 is in test_gpu_wgrad_tc.py).  Model-level stated bound against the
@@ -261,3 +262,25 @@ def test_bf16_tensor_core_training_tracks_the_fp32_path(name, scheme, min_cos, m
     print(f'{name}/{scheme}: loss bf16 {l16:.5f} fp32 {l32:.5f}; gradient cosine {cos:.5f}; worst tensor {worst[1]} {worst[0]:.4f}')
     assert abs(l16 - l32) < 2e-2 * max(1.0, abs(l32))
     assert cos >= min_cos and worst[0] >= min_worst
+
+
+def test_sausnet_eval_fp32_matches_reference_and_tensor_core_path_matches_fp32(train_golden):
+    """simple_u_net_doubleselfattn_twolayers (SAUSnet): eval output of the fp32 path against the reference's own output; the tcgen05
+    path (BatchNorm folded, attention on the bottleneck and on the lowest skip) against the fp32 path on a chunk-aligned variant."""
+    tag = 'sausnet_tiny__train'
+    B, seed = [int(v) for v in train_golden[tag + '__meta']]
+    m = build_model('sausnet_tiny')
+    m.load_state_dict(fill_state_dict(m.state_dict(), seed))
+    m = m.cuda().eval()
+    with torch.no_grad():
+        y = m(synth_patches(B, seed).cuda())
+    assert np.abs(y.cpu().numpy() - train_golden[tag + '__eval_y']).max() < 1e-3
+    x = synth_patches(4, 77).cuda()
+    outs = {}
+    for prec in ('fp32', 'fp16'):
+        m = build_model('sausnet_s8', precision=prec)
+        m.load_state_dict(fill_state_dict(m.state_dict(), 78, scheme='torch_default'))
+        m = m.cuda().eval()
+        with torch.no_grad():
+            outs[prec] = m(x)
+    assert (outs['fp16'] - outs['fp32']).abs().max().item() < 1e-3

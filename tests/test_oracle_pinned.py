@@ -151,7 +151,7 @@ def test_resample_halfband_properties():
     assert abs(z[1000] - np.sqrt(2.0)) < 2e-3            # DC gain 1 then x sqrt(2)
 
 
-@pytest.mark.parametrize('name', ['unet_tiny', 'saunet_tiny', 'punet_tiny'])
+@pytest.mark.parametrize('name', ['unet_tiny', 'saunet_tiny', 'punet_tiny', 'sausnet_tiny'])
 def test_oracle_train_mode_loss_and_grads_match_reference(name):
     """The oracle's train-mode forward (BatchNorm batch statistics, batch-axis attention) differentiated by autograd must give
     the loss and parameter gradients of the unmodified reference modules (tests/golden/nn_train_golden.npz)."""
@@ -180,3 +180,14 @@ def test_oracle_train_mode_loss_and_grads_match_reference(name):
             d = np.abs(v.grad.numpy() - ref)
             scale = max(np.abs(ref).max(), 1e-3 * gmax)
             assert d.max() <= 2e-2 * scale and (d.mean() <= 4e-3 * scale or d.size < 64), (k, d.max() / scale, d.mean() / scale)
+
+
+def test_oracle_sausnet_eval_matches_reference():
+    """simple_u_net_doubleselfattn_twolayers (attention also on the lowest skip) in eval mode against the reference's output."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'nn_train_golden.npz'))
+    tag = 'sausnet_tiny__train'
+    B, seed = [int(v) for v in g[tag + '__meta']]
+    sd = fill_state_dict(reference_state_shapes('sausnet_tiny'), seed)
+    with torch.no_grad():
+        y = NO.unet_forward(sd, synth_patches(B, seed), pos_encoding='sinusoidal')
+    assert np.abs(y.numpy() - g[tag + '__eval_y']).max() < 1e-5

@@ -92,5 +92,7 @@ MODEL_SPECS = {
     'punet':      dict(cls='simple_u_net_polyphony_classif_softmax', kw=dict(n_chan_input=6, n_chan_layers=[128, 180, 150, 100], n_bins_in=216, n_bins_out=72, scalefac=2, num_polyphony_steps=24)),
     'punet_tiny': dict(cls='simple_u_net_polyphony_classif_softmax', kw=dict(n_chan_input=6, n_chan_layers=[16, 10, 8, 5], n_bins_in=216, n_bins_out=72, scalefac=16, num_polyphony_steps=24)),
     'saunet_l':   dict(cls='simple_u_net_doubleselfattn', kw=dict(n_chan_input=6, n_chan_layers=[128, 80, 50, 30], n_bins_in=216, n_bins_out=72, scalefac=4, embed_dim=128, num_heads=8, mlp_dim=8192, pos_encoding='sinusoidal')),
+    'sausnet_tiny': dict(cls='simple_u_net_doubleselfattn_twolayers', kw=dict(n_chan_input=6, n_chan_layers=[16, 10, 8, 5], n_bins_in=216, n_bins_out=72, scalefac=16, embed_dim=32, num_heads=8, mlp_dim=64, pos_encoding='sinusoidal')),
+    'sausnet_s8': dict(cls='simple_u_net_doubleselfattn_twolayers', kw=dict(n_chan_input=6, n_chan_layers=[16, 10, 8, 5], n_bins_in=216, n_bins_out=72, scalefac=8, embed_dim=64, num_heads=8, mlp_dim=128, pos_encoding='sinusoidal')),
     'saunet_tiny': dict(cls='simple_u_net_doubleselfattn', kw=dict(n_chan_input=6, n_chan_layers=[16, 10, 8, 5], n_bins_in=216, n_bins_out=72, scalefac=16, embed_dim=32, num_heads=8, mlp_dim=64, pos_encoding='sinusoidal')),
 }
