@@ -254,6 +254,15 @@ int mpa_layernorm_cf_param_grad_f32(const float* x, const float* g_out, float* g
 int mpa_adamw_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                   float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
 
+/* ---- tcgen05 GEMM for the token-wise Linear layers of transformer_enc_layer (unet_cnns.py:131-157) ------------------------
+ * Y[M,N] fp32 row-major = act(X[M,K] * W[N,K]^T + bias[N]) with 16-bit operands in the chunk layout [ceil(K/64)*8][rows padded][8]
+ * produced by mpa_gemm_tc_to_chunks (row_tile 256 for X = tokens, 128 for W = nn.Linear.weight); fp32 accumulate in TMEM.
+ * Wide-K products with few output tiles are split over K and combined with atomicAdd (not with relu). */
+size_t mpa_gemm_tc_chunked_bytes(int rows, int K, int row_tile);
+int mpa_gemm_tc_to_chunks(const float* x_rows, void* out_chunks, int rows, int K, int row_tile, int fmt, void* stream);
+int mpa_gemm_tc_f16(const void* x_chunks, const void* w_chunks, const float* bias, float* y, int M, int N, int K, int relu, int fmt,
+                    void* stream);
+
 /* ---- tensor-core training convolutions (bf16 / fp16 CP8 operands, fp32 accumulate) -------------------------------------
  * Weight gradient of a stride-1 "same" KHxKW convolution (nn.Conv2d backward): gw[co0+co][ci0+ci][kh][kw] +=
  * sum_{b,t,f} g[b,co,t,f] * x[b,ci,t+kh-KH/2,f+kw-KW/2]; x / g are CP8 planes of the same geometry (zero gap columns!), gw is the

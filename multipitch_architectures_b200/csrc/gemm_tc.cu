@@ -1,0 +1,328 @@
+// tcgen05 GEMM for the token-wise Linear layers of transformer_enc_layer (unet_cnns.py:131-157: the MLP E -> mlp_dim -> E holds
+// > 95 % of the layer's FLOPs):      Y[M, N] = act(X[M, K] * W[N, K]^T + bias[N])        (nn.Linear)
+//
+// Both operands are pre-arranged in the channel-chunk layout the convolutions use, [K/8][rows][8] 16-bit, which IS the K-major
+// SWIZZLE_NONE canonical operand layout: a tile (128 weight rows or 256 tokens) x one 8-wide K chunk is one contiguous bulk copy.
+//   D[n (128 TMEM lanes = output features), m (256 columns = tokens)] += W_tile[n, k] * X_tile[k, m]
+// so the fp32 epilogue writes Y row-major with 32 consecutive features per warp store (coalesced), adding bias / ReLU, or — for
+// split-K (wide K, few tiles: the second MLP layer) — accumulates with atomicAdd into a pre-initialised Y.
+// Warp roles as in conv_tc.cu: TMA producer, single-lane MMA issue from a warp-uniform loop, 4 epilogue warps; the accumulator is
+// double buffered in TMEM (2 x 256 columns) so the epilogue of tile k overlaps the main loop of tile k+1.
+#include "common.cuh"
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <string.h>
+
+namespace mpa {
+
+constexpr int kGmThreads = 192;              // producer warp, MMA warp, 4 epilogue warps
+constexpr int kGmStages = 4;
+constexpr int kGmChunksPerStage = 8;         // K = 64 per stage = 4 MMAs
+constexpr int kGmTileN = 128, kGmTileM = 256;
+constexpr int kGmWBytes = kGmChunksPerStage * kGmTileN * 16;     // 16 KB
+constexpr int kGmXBytes = kGmChunksPerStage * kGmTileM * 16;     // 32 KB
+constexpr unsigned long long kGmTimeoutNs = 4000000000ull;
+
+struct GemmTcParams {
+  const uint8_t* x;          // [KC][Mpad][8] 16-bit
+  const uint8_t* w;          // [KC][Npad][8] 16-bit
+  const float* bias;         // [N] or null
+  float* y;                  // [M][N] fp32 row-major
+  int M, N, KC, Mpad, Npad, relu, ksplit, n_tiles_n, n_tiles_m, n_units;
+  uint32_t idesc;
+};
+
+__device__ __forceinline__ uint32_t gm_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void gm_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gm_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void gm_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gm_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void gm_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gm_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool gm_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(gm_smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void gm_wait(uint64_t* bar, uint32_t parity) {
+  if (gm_try_wait(bar, parity)) return;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  uint32_t spins = 0;
+  while (!gm_try_wait(bar, parity)) {
+    if ((++spins & 255u) == 0) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > kGmTimeoutNs) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void gm_bulk(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(gm_smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(gm_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ bool gm_elect() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void gm_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(gm_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void gm_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void gm_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+
+struct GmUnit {
+  int n0, m0, kc0, kc1;
+};
+__device__ __forceinline__ GmUnit gm_decode(const GemmTcParams& p, int u) {
+  GmUnit g;
+  const int ks = u % p.ksplit;
+  int t = u / p.ksplit;
+  const int tn = t % p.n_tiles_n, tm = t / p.n_tiles_n;
+  g.n0 = tn * kGmTileN;
+  g.m0 = tm * kGmTileM;
+  const int per = (p.KC / kGmChunksPerStage + p.ksplit - 1) / p.ksplit;      // stages per K slice (KC is a multiple of 8 chunks)
+  g.kc0 = ks * per * kGmChunksPerStage;
+  g.kc1 = min(p.KC, g.kc0 + per * kGmChunksPerStage);
+  return g;
+}
+
+__global__ void __launch_bounds__(kGmThreads, 1) gemm_tc_kernel(const GemmTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* w_smem = smem;                                        // [stages][8 chunks][128 rows][16 B]
+  uint8_t* x_smem = smem + kGmStages * kGmWBytes;                 // [stages][8 chunks][256 rows][16 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(x_smem + kGmStages * kGmXBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kGmStages;
+  uint64_t* acc_full = empty + kGmStages;      // [2]
+  uint64_t* acc_empty = acc_full + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kGmStages; ++i) { gm_mbar_init(&full[i], 1); gm_mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { gm_mbar_init(&acc_full[i], 1); gm_mbar_init(&acc_empty[i], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(gm_smem_u32(tmem_slot)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+        const GmUnit g = gm_decode(p, u);
+        for (int kc = g.kc0; kc < g.kc1; kc += kGmChunksPerStage) {
+          gm_wait(&empty[st], ph ^ 1);
+          gm_expect_tx(&full[st], (uint32_t)(kGmWBytes + kGmXBytes));
+          for (int c = 0; c < kGmChunksPerStage; ++c) {
+            gm_bulk(w_smem + st * kGmWBytes + c * (kGmTileN * 16), p.w + ((size_t)(kc + c) * p.Npad + g.n0) * 16, kGmTileN * 16, &full[st]);
+            gm_bulk(x_smem + st * kGmXBytes + c * (kGmTileM * 16), p.x + ((size_t)(kc + c) * p.Mpad + g.m0) * 16, kGmTileM * 16, &full[st]);
+          }
+          if (++st == kGmStages) { st = 0; ph ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t w16 = gm_smem_u32(w_smem) >> 4, x16 = gm_smem_u32(x_smem) >> 4;
+    constexpr uint32_t kHi = (128u >> 4) | (1u << 14);                               // SBO = 128 B
+    constexpr uint32_t kWLo = ((uint32_t)(kGmTileN * 16) >> 4) << 16;                // LBO = next K chunk of the weight tile
+    constexpr uint32_t kXLo = ((uint32_t)(kGmTileM * 16) >> 4) << 16;
+    int st = 0;
+    uint32_t ph = 0, k_unit = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++k_unit) {
+      const GmUnit g = gm_decode(p, u);
+      const uint32_t buf = k_unit & 1u;
+      gm_wait(&acc_empty[buf], ((k_unit >> 1) & 1u) ^ 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tmem_d = tmem_u + buf * 256;
+      uint32_t first = 1;
+      for (int kc = g.kc0; kc < g.kc1; kc += kGmChunksPerStage) {
+        gm_wait(&full[st], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_lo = (w16 + (uint32_t)st * (kGmWBytes >> 4)) | kWLo;
+        const uint32_t b_lo = (x16 + (uint32_t)st * (kGmXBytes >> 4)) | kXLo;
+        if (gm_elect()) {
+          gm_mma(tmem_d, ((uint64_t)kHi << 32) | a_lo, ((uint64_t)kHi << 32) | b_lo, p.idesc, first ? 0u : 1u);
+#pragma unroll
+          for (int i = 1; i < kGmChunksPerStage / 2; ++i)
+            gm_mma(tmem_d, ((uint64_t)kHi << 32) | (uint64_t)(a_lo + (uint32_t)i * (2 * kGmTileN * 16 >> 4)),
+                   ((uint64_t)kHi << 32) | (uint64_t)(b_lo + (uint32_t)i * (2 * kGmTileM * 16 >> 4)), p.idesc, 1u);
+          gm_commit(&empty[st]);
+        }
+        __syncwarp();
+        first = 0;
+        if (++st == kGmStages) { st = 0; ph ^= 1; }
+      }
+      if (gm_elect()) gm_commit(&acc_full[buf]);
+      __syncwarp();
+    }
+  } else {
+    const int quad = warp & 3;
+    uint32_t k_unit = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++k_unit) {
+      const GmUnit g = gm_decode(p, u);
+      const uint32_t buf = k_unit & 1u;
+      gm_wait(&acc_full[buf], (k_unit >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int n = g.n0 + quad * 32 + lane;
+      const bool n_ok = n < p.N;
+      const float b = (n_ok && p.bias && g.kc0 == 0) ? p.bias[n] : 0.f;
+      const int m_hi = min(kGmTileM, p.M - g.m0);
+      for (int c0 = 0; c0 < m_hi; c0 += 32) {
+        uint32_t v[32];
+        gm_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256 + c0), v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (n_ok) {
+          float* yp = p.y + (size_t)(g.m0 + c0) * p.N + n;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (c0 + i < m_hi) {
+              float val = __uint_as_float(v[i]) + b;
+              if (p.ksplit > 1) atomicAdd(yp + (size_t)i * p.N, val);
+              else yp[(size_t)i * p.N] = p.relu ? fmaxf(val, 0.f) : val;
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      gm_arrive(&acc_empty[buf]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
+// fp32 row-major [R][K] -> 16-bit chunk layout [KCpad][Rpad][8] (zero padded rows / columns); optional ReLU'd source is NOT applied here
+__global__ void rows_to_chunks_kernel(const float* __restrict__ x, uint16_t* __restrict__ out, long long total, int R, int K, int Rpad, int fmt) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i % Rpad);
+    const int kc = (int)(i / Rpad);
+    __align__(16) uint16_t v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = kc * 8 + e;
+      const float f = (r < R && k < K) ? x[(size_t)r * K + k] : 0.f;
+      v[e] = fmt == MPA_FMT_BF16 ? __bfloat16_as_ushort(__float2bfloat16(f)) : __half_as_ushort(__float2half_rn(f));
+    }
+    *reinterpret_cast<uint4*>(out + (size_t)i * 8) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
+}  // namespace mpa
+
+using namespace mpa;
+
+extern "C" {
+
+size_t mpa_gemm_tc_chunked_bytes(int rows, int K, int row_tile) {
+  if (rows <= 0 || K <= 0 || row_tile <= 0) return 0;
+  const size_t rpad = (size_t)(rows + row_tile - 1) / row_tile * row_tile;
+  const size_t kc = (size_t)(K + 63) / 64 * 8;
+  return kc * rpad * 16;
+}
+
+int mpa_gemm_tc_to_chunks(const float* x, void* out, int rows, int K, int row_tile, int fmt, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(x && out && rows > 0 && K > 0 && (row_tile == kGmTileN || row_tile == kGmTileM), "gemm_tc_to_chunks: bad argument (row_tile 128 or 256)");
+  const int rpad = (rows + row_tile - 1) / row_tile * row_tile, kc = (K + 63) / 64 * 8;
+  const long long total = (long long)kc * rpad;
+  long long g = (total + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  rows_to_chunks_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(x, (uint16_t*)out, total, rows, K, rpad, fmt);
+  MPA_CHECK_LAUNCH("gemm_tc_to_chunks");
+  return MPA_OK;
+}
+
+int mpa_gemm_tc_f16(const void* x_chunks, const void* w_chunks, const float* bias, float* y, int M, int N, int K, int relu, int fmt, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(x_chunks && w_chunks && y && M > 0 && N > 0 && K > 0, "gemm_tc: bad argument");
+  MPA_REQUIRE(fmt == MPA_FMT_F16 || fmt == MPA_FMT_BF16, "gemm_tc: fmt must be MPA_FMT_F16 or MPA_FMT_BF16");
+  MPA_REQUIRE((((uintptr_t)x_chunks | (uintptr_t)w_chunks) & 15) == 0, "gemm_tc: 16-byte alignment required");
+  GemmTcParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = (const uint8_t*)x_chunks;
+  p.w = (const uint8_t*)w_chunks;
+  p.bias = bias;
+  p.y = y;
+  p.M = M; p.N = N;
+  p.KC = (K + 63) / 64 * 8;
+  p.Mpad = (M + kGmTileM - 1) / kGmTileM * kGmTileM;
+  p.Npad = (N + kGmTileN - 1) / kGmTileN * kGmTileN;
+  p.relu = relu;
+  p.n_tiles_n = p.Npad / kGmTileN;
+  p.n_tiles_m = p.Mpad / kGmTileM;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles = p.n_tiles_n * p.n_tiles_m, stages = p.KC / kGmChunksPerStage;
+  int ks = 1;
+  if (!relu && tiles < sms && stages >= 8) {
+    ks = sms / tiles;
+    if (ks > stages / 4) ks = stages / 4;
+    if (ks < 1) ks = 1;
+    const int per = (stages + ks - 1) / ks;
+    ks = (stages + per - 1) / per;                       // every K slice non-empty
+  }
+  p.ksplit = ks;
+  p.n_units = tiles * ks;
+  const uint32_t f = (fmt == MPA_FMT_BF16) ? 1u : 0u;
+  p.idesc = (1u << 4) | (f << 7) | (f << 10) | ((uint32_t)(kGmTileM >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  if (ks > 1) cudaMemsetAsync(y, 0, sizeof(float) * (size_t)M * N, (cudaStream_t)stream);
+  const size_t smem = (size_t)kGmStages * (kGmWBytes + kGmXBytes) + 256;
+  {
+    static unsigned char flags[64];
+    cudaError_t e = opt_in_max_smem(gemm_tc_kernel, flags);
+    if (e != cudaSuccess) {
+      set_error("gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return MPA_ERR_CUDA;
+    }
+  }
+  const int grid = p.n_units < sms ? p.n_units : sms;
+  gemm_tc_kernel<<<grid, kGmThreads, smem, (cudaStream_t)stream>>>(p);
+  MPA_CHECK_LAUNCH("gemm_tc");
+  return MPA_OK;
+}
+
+}  // extern "C"

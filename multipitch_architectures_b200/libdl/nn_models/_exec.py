@@ -265,11 +265,11 @@ def unet_forward_tc(model, x):
         cur = double_conv_tc(cache, f'down{lv}', dc, pooled, dst, buf(lv, dc.double_conv[0].weight.shape[0]))
     x5 = cur
     if hasattr(model, 'attention1'):
-        t5 = model.attention2.run(model.attention1.run(ops.cp8_to_nchw(x5)))
+        t5 = model.attention2.run(model.attention1.run(ops.cp8_to_nchw(x5), fmt), fmt)
         x5 = ops.nchw_to_cp8(t5, pitch=geo[4][2], pf=LEVEL_PF, pt=1, fmt=fmt)
     if hasattr(model, 'attention3'):
         # SAUSnet: the lowest skip connection passes two encoder layers too (x5 above was computed from the un-attended x4)
-        t4 = model.attention4.run(model.attention3.run(ops.cp8_to_nchw(skips[3])))
+        t4 = model.attention4.run(model.attention3.run(ops.cp8_to_nchw(skips[3]), fmt), fmt)
         ops.nchw_to_cp8(t4, out=skips[3], fmt=fmt)
     # decoder
     low = x5

@@ -371,3 +371,23 @@ def conv_tc_pack_dev(w, Cin, Cout, ksize, fmt, transpose_flip=False, Cout_total=
     call('conv_tc_pack_weights_dev', _f32(w.detach()), packed, Cin, Cout, KH, KW, fmt, J, int(bool(transpose_flip)),
          Cout if Cout_total is None else Cout_total, co0, stream_ptr())
     return packed
+
+
+# ------------------------------------------------------------------------------------------------------
+# tcgen05 GEMM (token-wise nn.Linear layers)
+def gemm_tc_chunks(x, row_tile, fmt):
+    """fp32 [rows, K] -> 16-bit chunk layout for mpa_gemm_tc_f16 (row_tile 256: activations / tokens, 128: nn.Linear weights)."""
+    rows, K = x.shape
+    nbytes = _lib.lib().mpa_gemm_tc_chunked_bytes(rows, K, row_tile)
+    out = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    call('gemm_tc_to_chunks', _f32(x.detach()), out, rows, K, row_tile, fmt, stream_ptr())
+    return out
+
+
+def gemm_tc(x, w_chunks, bias, N, relu, fmt):
+    """y [M, N] fp32 = act(x [M, K] @ W^T + bias) on the tensor cores; w_chunks = gemm_tc_chunks(W [N, K], 128, fmt)."""
+    M, K = x.shape
+    xc = gemm_tc_chunks(x, 256, fmt)
+    y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    call('gemm_tc_f16', xc, w_chunks, bias, y, M, N, K, int(bool(relu)), fmt, stream_ptr())
+    return y

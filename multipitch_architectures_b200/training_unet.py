@@ -250,8 +250,13 @@ class Tape:
         self.push(bwd_ln1)
 
         # -- MLP
-        hid = Node(gemm_nt(h1.d, W1, b1, M, Dm, E, relu=1))
-        m2 = Node(gemm_nt(hid.d, W2, b2, M, E, Dm))
+        if self.model is not None and getattr(self.model, 'precision', 'fp32') == 'bf16':
+            # the MLP's forward products on the tensor cores (bf16 operands, fp32 accumulate); the backward stays fp32
+            hid = Node(ops.gemm_tc(h1.d, ops.gemm_tc_chunks(W1, 128, ops.FMT_BF16), b1, Dm, True, ops.FMT_BF16))
+            m2 = Node(ops.gemm_tc(hid.d, ops.gemm_tc_chunks(W2, 128, ops.FMT_BF16), b2, E, False, ops.FMT_BF16))
+        else:
+            hid = Node(gemm_nt(h1.d, W1, b1, M, Dm, E, relu=1))
+            m2 = Node(gemm_nt(hid.d, W2, b2, M, E, Dm))
 
         def bwd_mlp():
             g_m2 = m2.g

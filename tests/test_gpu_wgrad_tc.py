@@ -69,3 +69,23 @@ def test_tc_conv_forward_backward_matches_fp32_conv(cfg):
     e = (rel(yt, y.detach()), rel(gx, x.grad), rel(gw, conv.weight.grad), rel(gb, conv.bias.grad))
     print(f'{cfg}: rel err y {e[0]:.2e} gx {e[1]:.2e} gw {e[2]:.2e} gb {e[3]:.2e}')
     assert e[0] < 8e-3 and e[1] < 8e-3 and e[2] < 2e-3 and e[3] < 1e-4
+
+
+@pytest.mark.parametrize('fmt', ['fp16', 'bf16'])
+@pytest.mark.parametrize('M,N,K,relu', [(1300, 8192, 128, True), (1300, 128, 8192, False), (52, 64, 32, True), (2600, 384, 128, False),
+                                        (300, 200, 72, False), (257, 129, 8200, False)])
+def test_gemm_tc_matches_linear(M, N, K, relu, fmt):
+    """mpa_gemm_tc_f16 (the encoder MLP's nn.Linear layers on tcgen05) against torch on the same 16-bit-rounded operands."""
+    from multipitch_architectures_b200 import ops
+    dt = torch.bfloat16 if fmt == 'bf16' else torch.float16
+    x = rnd(M, K, seed=5).to(dt).float()
+    w = (rnd(N, K, seed=6) / K ** 0.5).to(dt).float()
+    b = rnd(N, seed=7)
+    ref = x @ w.T + b
+    if relu:
+        ref = torch.relu(ref)
+    f = ops.fmt_of(fmt)
+    y = ops.gemm_tc(x.cuda(), ops.gemm_tc_chunks(w.cuda(), 128, f), b.cuda(), N, relu, f).cpu()
+    err = (y - ref).abs().max().item()
+    print(f'gemm_tc {M}x{N}x{K} {fmt}: max|diff| = {err:.2e}')
+    assert err < 2e-4 * max(1.0, ref.abs().max().item())
