@@ -259,7 +259,8 @@ int mpa_adamw_f32(float* param, const float* grad, float* exp_avg, float* exp_av
  * produced by mpa_gemm_tc_to_chunks (row_tile 256 for X = tokens, 128 for W = nn.Linear.weight); fp32 accumulate in TMEM.
  * Wide-K products with few output tiles are split over K and combined with atomicAdd (not with relu). */
 size_t mpa_gemm_tc_chunked_bytes(int rows, int K, int row_tile);
-int mpa_gemm_tc_to_chunks(const float* x_rows, void* out_chunks, int rows, int K, int row_tile, int fmt, void* stream);
+/* transposed = 1: the source is stored [K][rows] (the operand is the transpose of a row-major matrix: weight / activation gradients). */
+int mpa_gemm_tc_to_chunks(const float* x_rows, void* out_chunks, int rows, int K, int row_tile, int fmt, int transposed, void* stream);
 int mpa_gemm_tc_f16(const void* x_chunks, const void* w_chunks, const float* bias, float* y, int M, int N, int K, int relu, int fmt,
                     void* stream);
 

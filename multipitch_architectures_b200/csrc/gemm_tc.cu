@@ -234,8 +234,9 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemm_tc_kernel(const GemmTcPara
   }
 }
 
-// fp32 row-major [R][K] -> 16-bit chunk layout [KCpad][Rpad][8] (zero padded rows / columns); optional ReLU'd source is NOT applied here
-__global__ void rows_to_chunks_kernel(const float* __restrict__ x, uint16_t* __restrict__ out, long long total, int R, int K, int Rpad, int fmt) {
+// fp32 row-major [R][K] (or, transposed, [K][R]) -> 16-bit chunk layout [KCpad][Rpad][8] (zero padded rows / columns)
+__global__ void rows_to_chunks_kernel(const float* __restrict__ x, uint16_t* __restrict__ out, long long total, int R, int K, int Rpad, int fmt,
+                                      int transposed) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i % Rpad);
     const int kc = (int)(i / Rpad);
@@ -243,7 +244,7 @@ __global__ void rows_to_chunks_kernel(const float* __restrict__ x, uint16_t* __r
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int k = kc * 8 + e;
-      const float f = (r < R && k < K) ? x[(size_t)r * K + k] : 0.f;
+      const float f = (r < R && k < K) ? (transposed ? x[(size_t)k * R + r] : x[(size_t)r * K + k]) : 0.f;
       v[e] = fmt == MPA_FMT_BF16 ? __bfloat16_as_ushort(__float2bfloat16(f)) : __half_as_ushort(__float2half_rn(f));
     }
     *reinterpret_cast<uint4*>(out + (size_t)i * 8) = *reinterpret_cast<const uint4*>(v);
@@ -263,14 +264,14 @@ size_t mpa_gemm_tc_chunked_bytes(int rows, int K, int row_tile) {
   return kc * rpad * 16;
 }
 
-int mpa_gemm_tc_to_chunks(const float* x, void* out, int rows, int K, int row_tile, int fmt, void* stream) {
+int mpa_gemm_tc_to_chunks(const float* x, void* out, int rows, int K, int row_tile, int fmt, int transposed, void* stream) {
   MPA_CHECK_ARCH();
   MPA_REQUIRE(x && out && rows > 0 && K > 0 && (row_tile == kGmTileN || row_tile == kGmTileM), "gemm_tc_to_chunks: bad argument (row_tile 128 or 256)");
   const int rpad = (rows + row_tile - 1) / row_tile * row_tile, kc = (K + 63) / 64 * 8;
   const long long total = (long long)kc * rpad;
   long long g = (total + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
-  rows_to_chunks_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(x, (uint16_t*)out, total, rows, K, rpad, fmt);
+  rows_to_chunks_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(x, (uint16_t*)out, total, rows, K, rpad, fmt, transposed);
   MPA_CHECK_LAUNCH("gemm_tc_to_chunks");
   return MPA_OK;
 }

@@ -375,19 +375,20 @@ def conv_tc_pack_dev(w, Cin, Cout, ksize, fmt, transpose_flip=False, Cout_total=
 
 # ------------------------------------------------------------------------------------------------------
 # tcgen05 GEMM (token-wise nn.Linear layers)
-def gemm_tc_chunks(x, row_tile, fmt):
-    """fp32 [rows, K] -> 16-bit chunk layout for mpa_gemm_tc_f16 (row_tile 256: activations / tokens, 128: nn.Linear weights)."""
-    rows, K = x.shape
+def gemm_tc_chunks(x, row_tile, fmt, transposed=False):
+    """fp32 [rows, K] (transposed: stored [K, rows]) -> 16-bit chunk layout for mpa_gemm_tc_f16 (row_tile 256: the X operand, 128: W)."""
+    rows, K = (x.shape[1], x.shape[0]) if transposed else x.shape
     nbytes = _lib.lib().mpa_gemm_tc_chunked_bytes(rows, K, row_tile)
     out = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
-    call('gemm_tc_to_chunks', _f32(x.detach()), out, rows, K, row_tile, fmt, stream_ptr())
+    call('gemm_tc_to_chunks', _f32(x.detach()), out, rows, K, row_tile, fmt, int(bool(transposed)), stream_ptr())
     return out
 
 
-def gemm_tc(x, w_chunks, bias, N, relu, fmt):
-    """y [M, N] fp32 = act(x [M, K] @ W^T + bias) on the tensor cores; w_chunks = gemm_tc_chunks(W [N, K], 128, fmt)."""
-    M, K = x.shape
-    xc = gemm_tc_chunks(x, 256, fmt)
-    y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+def gemm_tc(x, w_chunks, bias, N, relu, fmt, x_transposed=False, out=None):
+    """y [M, N] fp32 = act(X @ W^T + bias) on the tensor cores; X = x [M, K] (or x^T when x_transposed: x stored [K, M]);
+    w_chunks = gemm_tc_chunks(W [N, K], 128, fmt) (or of the [K, N]-stored transpose)."""
+    M, K = (x.shape[1], x.shape[0]) if x_transposed else x.shape
+    xc = gemm_tc_chunks(x, 256, fmt, x_transposed)
+    y = out if out is not None else torch.empty(M, N, dtype=torch.float32, device=x.device)
     call('gemm_tc_f16', xc, w_chunks, bias, y, M, N, K, int(bool(relu)), fmt, stream_ptr())
     return y

@@ -258,7 +258,20 @@ class Tape:
             hid = Node(gemm_nt(h1.d, W1, b1, M, Dm, E, relu=1))
             m2 = Node(gemm_nt(hid.d, W2, b2, M, E, Dm))
 
+        def bwd_mlp_tc():
+            # the four products of the MLP backward as X @ W'^T on tcgen05 (bf16 operands): transposes are taken by the chunking pass
+            fm = ops.FMT_BF16
+            g_m2 = m2.g
+            ops.gemm_tc(g_m2, ops.gemm_tc_chunks(hid.d, 128, fm, True), None, Dm, False, fm, x_transposed=True, out=G[name + '.mlp.2.weight'])
+            colsum(g_m2, M, E, out=G[name + '.mlp.2.bias'])
+            g_hid = _act_bwd(hid.d, ops.gemm_tc(g_m2, ops.gemm_tc_chunks(W2, 128, fm, True), None, Dm, False, fm), ops.ACT_RELU)
+            ops.gemm_tc(g_hid, ops.gemm_tc_chunks(h1.d, 128, fm, True), None, E, False, fm, x_transposed=True, out=G[name + '.mlp.0.weight'])
+            colsum(g_hid, M, Dm, out=G[name + '.mlp.0.bias'])
+            h1.acc(ops.gemm_tc(g_hid, ops.gemm_tc_chunks(W1, 128, fm, True), None, E, False, fm))
+
         def bwd_mlp():
+            if self.model is not None and getattr(self.model, 'precision', 'fp32') == 'bf16':
+                return bwd_mlp_tc()
             g_m2 = m2.g
             gemm(g_m2, hid.d, E, Dm, M, 1, out=G[name + '.mlp.2.weight'])
             colsum(g_m2, M, E, out=G[name + '.mlp.2.bias'])
