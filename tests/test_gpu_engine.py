@@ -113,7 +113,8 @@ def test_frame_range_sharding_matches_unsharded_engine():
 
 
 @pytest.mark.parametrize('name,N,chunk,prec', [('drcnn_tiny', 90, 64, 'fp16'), ('drcnn_tiny', 131, 40, 'bf16'), ('dcnn_tiny', 60, 64, 'fp16'),
-                                               ('drcnn', 100, 37, 'fp16'), ('drcnn', 80, 80, 'bf16')])
+                                               ('drcnn', 100, 37, 'fp16'), ('drcnn', 80, 80, 'bf16'),
+                                               ('drcnn', 1292, 646, 'fp16')])      # BASELINE configs[0] at full size: one 30 s clip
 def test_fused_deduplicated_schedule_equals_plain_schedule(name, N, chunk, prec):
     """Fused conv+pool+residual kernel with frame-shared interior rows (mpa_conv_tc_pool_f16) vs the plain per-patch
     sequence conv_tc -> pool_time_res.
