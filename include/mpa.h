@@ -68,6 +68,31 @@ int mpa_layernorm_frames(const float* frames, const float* ln_w, const float* ln
 int mpa_gather_patches_f32(const float* in, float* out, int C, int NT, int F, int i0, int n, int T, int stride,
                            float gamma_log, void* stream);
 
+/* Training-time augmentation fused with the patch cut (hcqt_datasets.py:67-141): for each of n patches starting at
+ * frame start[b] of in [C][NT][F]:  random EQ  w_c(f) = 1 - 2e-6*eq_alpha[b]*(f - (eq_beta[b] - eq_offset[c]))^2  (:80-97; eq_alpha NULL or 0 = off)
+ * -> x = |x + noise_std*N(0,1)| (:99-102) -> log(1 + gamma_log*x) (:105-106) -> tuning shift by tune2[b]/2 bins, tune2 in -2..2 (:108-123)
+ * -> transposition by transp[b] semitones of bins_per_semitone bins (:125-139); bins vacated by the two shifts hold |N(0, fill_std)|.
+ * The integer decisions are drawn by the caller (host mirror, incl. the reference's rejection loop); Gaussian values are Philox-4x32-10
+ * under (seed, offset).  out [n][C][T][F] fp32.  All index arrays are device pointers. */
+int mpa_augment_patches_f32(const float* in, const long long* start, float* out, int C, int NT, int F, int n, int T, const int* eq_alpha,
+                            const int* eq_beta, const int* eq_offset, float noise_std, float gamma_log, const int* tune2,
+                            const int* transp, int bins_per_semitone, float fill_std, unsigned long long seed,
+                            unsigned long long offset, void* stream);
+/* Targets of those patches: y[b][q] = targets[frame[b]][q - transp[b]], wrapped entries zeroed (P = 12 pitch classes: plain roll)
+ * (hcqt_datasets.py:75,127-137).  targets [N][P] fp32, frame [n] centre frames, y [n][P]. */
+int mpa_augment_targets_f32(const float* targets, const long long* frame, const int* transp, float* y, int n, int P, void* stream);
+
+/* ---- evaluation measures (eval_metrics.py:8-110,158-189) --------------------------------------------------------
+ * targ, pred [n_frames][n_bins] fp32 (device).  sums16 (device, 16 doubles) = sums over frames of the per-frame terms, float64 arithmetic:
+ *  0 TP  1 #est (pred >= threshold)  2 #(targ > 0)  3 cosine of the L2-normalised frames (libfmp unit-vector fallback below 1e-10)
+ *  4 sum_bins t*log2(p+eps)+(1-t)*log2(1-p+eps)  5 |t-p|_2  6 #((pred>=threshold) == targ)  7 sum_bins t*p+(1-t)*(1-p)
+ *  8 sum(t*p)/(sum(t)+eps)  9 matched pitch classes (bin q is pitch min_pitch+q)  10 min(n_ref,n_est)  11 max(n_ref,n_est)
+ *  12 max(0,n_ref-n_est)  13 max(0,n_est-n_ref)  14 n_ref = #(targ != 0)  15 zero.
+ * workspace >= mpa_eval_workspace(n_frames) bytes; frames are added in a fixed order (bit-reproducible). */
+size_t mpa_eval_workspace(int n_frames);
+int mpa_eval_sums_f32(const float* targ, const float* pred, int n_frames, int n_bins, double threshold, int min_pitch, double* sums16,
+                      void* workspace, size_t ws_bytes, void* stream);
+
 /* ---- generic direct convolution, fp32 CUDA cores (all kernel sizes / strides of the model zoo) ---------
  * replaces nn.Conv2d (+ eval BatchNorm2d folded as per-channel scale/shift) + activation.
  * x NCHW [B,Cin,H,W]; if x2 != NULL the input is the channel concat [x (Cin1) | x2 (Cin-Cin1)] (U-Net skip).
@@ -213,6 +238,17 @@ int mpa_head_tail2_cp8(const void* h_cp8, const float* w40, const float* b40, co
 /* y_out[t] = sqrt(2) * sum_{|j|<=31} h[|j|] * y_in[2t+j] (resampy kaiser_fast at a 2:1 ratio, librosa scale=True);
  * n_out = ceil(n_in/2), the last sample is zero when n_in is odd.  half_taps: 32 floats (device). */
 int mpa_decimate2_f32(const float* y_in, float* y_out, const float* half_taps, long long n_in, void* stream);
+/* General power-of-two form (librosa's one-shot early down-sampling of a CQT whose top octave lies far below Nyquist, reached by
+ * compute_hcqt, hcqt.py:66-81): y_out[t] = sqrt(factor) * sum_{|j|<n_half} h[|j|] * y_in[factor*t+j], n_out = ceil(n_in/factor),
+ * samples t >= floor(n_in/factor) are zero.  half_taps: n_half = 16*factor floats (device). */
+int mpa_decimate_f32(const float* y_in, float* y_out, const float* half_taps, int n_half, int factor, long long n_in, void* stream);
+/* Same with an explicit gain instead of sqrt(factor): gain 1 = librosa.load's resampling of a 44.1 kHz file to 22.05 kHz (notebook 01
+ * cell 3; res_type kaiser_best: n_half = 64*factor taps), which does not rescale. */
+int mpa_decimate_gain_f32(const float* y_in, float* y_out, const float* half_taps, int n_half, int factor, double gain, long long n_in,
+                          void* stream);
+/* On-disk feature format -> network layout (exp126a...py:413-420): hcqt_fnc [F][N][C] float64 (the .npy the reference's notebook 01
+ * saves) -> out [C][lead+N+trail][F] fp32 with zero pad frames (lead = 37, trail = 38 for inference, 0/0 for training files). */
+int mpa_hcqt_npy_to_frames_f64(const double* hcqt_fnc, float* out, int F, int N, int C, int lead, int trail, void* stream);
 /* One octave level: frame t is centred on sample t*hop of y_level (reflect padding), rectangular window, FFT of
  * n_fft, then for each of the n_rows filter rows (every CQT that runs at this rate)
  *   out[ch][t][bin] = | sum_f basis[row][f] * X[start_row + f] | * row_scale[row]   for each destination of the row.

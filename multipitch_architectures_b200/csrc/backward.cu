@@ -76,19 +76,7 @@ __global__ void __launch_bounds__(kPoolBwdCols * kPoolBwdRowGroups) maxpool_time
   }
 }
 
-// Philox-4x32-10 counter-based dropout: element i of call `offset` under `seed`
-__device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) { return __umulhi(a, b); }
-__device__ __forceinline__ uint4 philox(uint4 ctr, uint2 key) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = mulhi32(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
-    const uint32_t hi1 = mulhi32(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += 0x9E3779B9u;
-    key.y += 0xBB67AE85u;
-  }
-  return ctr;
-}
+// Philox-4x32-10 counter-based dropout (philox() in common.cuh): element i of call `offset` under `seed`
 __global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ out, long long n, float p, unsigned long long seed,
                                unsigned long long offset) {
   const float scale = 1.f / (1.f - p);
@@ -228,7 +216,7 @@ __global__ void __launch_bounds__(128) layernorm_cf_param_grad_kernel(const floa
       if (e < n) {
         const int c = e / F, f = e - c * F;
         val = xr[(size_t)c * T * F + f];
-        if (gamma_log > 0.f) val = logf(1.f + gamma_log * val);
+        if (gamma_log > 0.f) val = logf(__fadd_rn(1.f, __fmul_rn(gamma_log, val)));
         s += val;
       }
       v[i] = val;

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(128) layernorm_cf_kernel(const float* __restri
     if (e < n) {
       int c = e / F, f = e - c * F;
       val = xr[(size_t)c * T * F + f];
-      if (gamma_log > 0.f) val = logf(1.f + gamma_log * val);
+      if (gamma_log > 0.f) val = logf(__fadd_rn(1.f, __fmul_rn(gamma_log, val)));
       s += val;
     }
     v[i] = val;
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(128) layernorm_frames_kernel(const float* __re
     if (real && e < n) {
       int c = e / F, f = e - c * F;
       val = frames[((size_t)c * N + src) * F + f];
-      if (gamma_log > 0.f) val = logf(1.f + gamma_log * val);
+      if (gamma_log > 0.f) val = logf(__fadd_rn(1.f, __fmul_rn(gamma_log, val)));
       sum += val;
     }
     v[i] = val;
@@ -226,7 +226,7 @@ __global__ void gather_patches_kernel(const float* __restrict__ in, float* __res
     int c = (int)(r % C);
     int b = (int)(r / C);
     float v = in[((size_t)c * NT + (size_t)(i0 + b) * stride + t) * F + f];
-    out[i] = gamma > 0.f ? logf(1.f + gamma * v) : v;
+    out[i] = gamma > 0.f ? logf(__fadd_rn(1.f, __fmul_rn(gamma, v))) : v;     // 1 + gamma*x rounded twice, as the reference's tensor expression
   }
 }
 

@@ -1,6 +1,7 @@
 // HCQT feature extraction (reference: libdl/data_preprocessing/hcqt.py:89-164, which delegates to librosa.cqt /
 // librosa.estimate_tuning).  B200 formulation: a batched multirate constant-Q filterbank.
-//   * mpa_decimate2_f32      : the 2:1 kaiser_fast windowed-sinc decimator chain (one launch per octave level)
+//   * mpa_decimate(2)_f32   : the 2:1 kaiser_fast windowed-sinc decimator chain (one launch per octave level) and the one-shot
+//                              2^c:1 decimator of librosa's early down-sampling (compute_hcqt's low harmonics)
 //   * mpa_cqt_level_f32      : one CTA per frame: gather the reflect-padded frame, radix-2 FFT in shared memory,
 //                              contract the spectrum with the banded (sparsified) filter rows of EVERY CQT that
 //                              uses this rate, magnitude, per-row scale, scatter into the [H][frames][bins] patch
@@ -56,21 +57,24 @@ __device__ __forceinline__ void load_frame_bitrev(float2* a, float2* tw, const f
   __syncthreads();
 }
 
-__global__ void decimate2_kernel(const float* __restrict__ yin, float* __restrict__ yout, const float* __restrict__ half, long long n_in,
-                                 long long n_out_real, long long n_out) {
-  __shared__ float h[32];
-  if (threadIdx.x < 32) h[threadIdx.x] = half[threadIdx.x];
+// out[t] = gain * sum_{|j| < n_half} h[|j|] * yin[D*t + j]  (taps outside the signal are skipped, as resampy does); D = 2 for the
+// octave chain, 2^c for librosa's one-shot early down-sampling (gain sqrt(D): librosa's scale=True) and for librosa.load's
+// 44.1 -> 22.05 kHz kaiser_best resampling (gain 1).  float64 accumulation, one rounding to fp32.
+__global__ void decimate_kernel(const float* __restrict__ yin, float* __restrict__ yout, const float* __restrict__ half, int n_half, int factor,
+                                double gain, long long n_in, long long n_out_real, long long n_out) {
+  extern __shared__ float h[];
+  for (int i = threadIdx.x; i < n_half; i += blockDim.x) h[i] = half[i];
   __syncthreads();
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n_out; t += (long long)gridDim.x * blockDim.x) {
     double acc = 0.0;
     if (t < n_out_real) {
-      const long long c = 2 * t;
+      const long long c = (long long)factor * t;
 #pragma unroll 1
-      for (int j = -31; j <= 31; ++j) {
+      for (int j = -(n_half - 1); j <= n_half - 1; ++j) {
         long long i = c + j;
         if (i >= 0 && i < n_in) acc += (double)h[j < 0 ? -j : j] * (double)yin[i];
       }
-      acc *= 1.4142135623730951;
+      acc *= gain;
     }
     yout[t] = (float)acc;
   }
@@ -232,6 +236,38 @@ __global__ void __launch_bounds__(1024) tuning_finalize_kernel(const int* __rest
   }
 }
 
+// on-disk HCQT [F][N][C] float64 (np.save of compute_efficient_hcqt's result) -> network layout [C][lead + N + trail][F] fp32 with zeroed
+// pad frames (np.transpose(.., (2,1,0)) + np.pad + .float() of exp126a...py:413-420 in one pass); 32 bins x 32 frames per CTA
+__global__ void __launch_bounds__(256) hcqt_npy_to_frames_kernel(const double* __restrict__ in, float* __restrict__ out, int F, int N, int C,
+                                                                 int lead, int trail) {
+  extern __shared__ float tile[];      // [32 f][32 n][C], +1 float of padding per f row
+  const int f0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  const int row = 32 * C + 1;
+  const int nn = min(32, N - n0), nf = min(32, F - f0);
+  for (int i = threadIdx.x; i < nf * nn * C; i += blockDim.x) {
+    const int fl = i / (nn * C), r = i % (nn * C);
+    tile[fl * row + r] = (float)in[((size_t)(f0 + fl) * N + n0) * C + r];
+  }
+  __syncthreads();
+  const int NT = lead + N + trail;
+  for (int i = threadIdx.x; i < C * nn * nf; i += blockDim.x) {
+    const int fl = i % nf, nl = (i / nf) % nn, c = i / (nf * nn);
+    out[((size_t)c * NT + lead + n0 + nl) * F + f0 + fl] = tile[fl * row + nl * C + c];
+  }
+}
+
+__global__ void zero_pad_frames_kernel(float* __restrict__ out, int F, int N, int C, int lead, int trail) {
+  const int NT = lead + N + trail;
+  const long long total = (long long)C * (lead + trail) * F;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i % F);
+    const int r = (int)((i / F) % (lead + trail));
+    const int c = (int)(i / ((long long)F * (lead + trail)));
+    const int n = r < lead ? r : N + r;
+    out[((size_t)c * NT + n) * F + f] = 0.f;
+  }
+}
+
 static inline int ilog2(int n) {
   int l = 0;
   while ((1 << l) < n) ++l;
@@ -244,15 +280,25 @@ using namespace mpa;
 
 extern "C" {
 
-int mpa_decimate2_f32(const float* y_in, float* y_out, const float* half_taps, long long n_in, void* stream) {
+int mpa_decimate_gain_f32(const float* y_in, float* y_out, const float* half_taps, int n_half, int factor, double gain, long long n_in,
+                          void* stream) {
   MPA_CHECK_ARCH();
-  MPA_REQUIRE(y_in && y_out && half_taps && n_in >= 2, "decimate2: bad argument");
-  const long long n_real = n_in / 2, n_out = (n_in + 1) / 2;
+  MPA_REQUIRE(y_in && y_out && half_taps && factor >= 2 && (factor & (factor - 1)) == 0 && n_half >= 1 && n_half <= 4096 && n_in >= factor,
+              "decimate: bad argument");
+  const long long n_real = n_in / factor, n_out = (n_in + factor - 1) / factor;
   long long g = (n_out + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
-  decimate2_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(y_in, y_out, half_taps, n_in, n_real, n_out);
-  MPA_CHECK_LAUNCH("decimate2");
+  decimate_kernel<<<(unsigned)g, 256, (size_t)n_half * sizeof(float), (cudaStream_t)stream>>>(y_in, y_out, half_taps, n_half, factor, gain, n_in, n_real, n_out);
+  MPA_CHECK_LAUNCH("decimate");
   return MPA_OK;
+}
+
+int mpa_decimate_f32(const float* y_in, float* y_out, const float* half_taps, int n_half, int factor, long long n_in, void* stream) {
+  return mpa_decimate_gain_f32(y_in, y_out, half_taps, n_half, factor, sqrt((double)factor), n_in, stream);
+}
+
+int mpa_decimate2_f32(const float* y_in, float* y_out, const float* half_taps, long long n_in, void* stream) {
+  return mpa_decimate_f32(y_in, y_out, half_taps, 32, 2, n_in, stream);
 }
 
 int mpa_cqt_level_f32(const float* y_level, long long n_level, int n_fft, int hop, int n_frames, const float* basis, const int* band_start,
@@ -269,6 +315,20 @@ int mpa_cqt_level_f32(const float* y_level, long long n_level, int n_fft, int ho
   cqt_level_kernel<<<n_frames, 256, smem, (cudaStream_t)stream>>>(y_level, n_level, n_fft, ilog2(n_fft), hop, (const float2*)basis, band_start,
                                                                    row_scale, n_rows, band, tuning_idx, dest, n_dest, out, out_frames, out_bins);
   MPA_CHECK_LAUNCH("cqt_level");
+  return MPA_OK;
+}
+
+int mpa_hcqt_npy_to_frames_f64(const double* hcqt_fnc, float* out, int F, int N, int C, int lead, int trail, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(hcqt_fnc && out && F > 0 && N > 0 && C > 0 && C <= 32 && lead >= 0 && trail >= 0, "hcqt_npy_to_frames: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(ceil_div(F, 32), ceil_div(N, 32));
+  hcqt_npy_to_frames_kernel<<<grid, 256, (size_t)(32 * (32 * C + 1)) * sizeof(float), st>>>(hcqt_fnc, out, F, N, C, lead, trail);
+  MPA_CHECK_LAUNCH("hcqt_npy_to_frames");
+  if (lead + trail > 0) {
+    zero_pad_frames_kernel<<<ceil_div((long long)C * (lead + trail) * F, 256), 256, 0, st>>>(out, F, N, C, lead, trail);
+    MPA_CHECK_LAUNCH("zero_pad_frames");
+  }
   return MPA_OK;
 }
 

@@ -1,0 +1,134 @@
+"""On-disk formats and the file-level steps either side of the hot path.
+
+  * `load_audio`       — the `librosa.load(path, sr=22050)` of notebook 01 cell 3 / notebook 02: WAV decode, channel mean, and
+                         the power-of-two kaiser_best down-sampling (44.1 -> 22.05 kHz) on the device (mpa_decimate_gain_f32).
+  * `load_hcqt_npy`    — the reference's feature files: float64 `[216, N, 6]` -> `[6, lead+N+trail, 216]` fp32 in HBM, transposed,
+                         cast and zero-padded by one kernel (exp126a_musicnet_cnn_basic.py:255-258, 413-420).
+  * `load_pitch_npy`   — annotation files `[128, N]` -> `[N, n_out]` targets, `targets[:, min_pitch:min_pitch+n_out]` (:414-416).
+  * `evaluate_file` / `write_results_csv` — the per-file body of the reference test loop (:404-458): predict, save `[N, 72]`
+                         predictions as .npy, score on the device, one CSV row per file + FILEWISE / FRAMEWISE means (:463-508).
+No arithmetic on features or activations happens on the host."""
+import csv
+import os
+import wave
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import CnnStreamEngine, predict_patchwise, CONTEXT, HALF
+from .libdl.metrics import calculate_eval_measures, calculate_mpe_measures_mireval
+
+EVAL_MEASURES = ['precision', 'recall', 'f_measure', 'cosine_sim', 'binary_crossentropy', 'euclidean_distance', 'binary_accuracy',
+                 'soft_accuracy', 'accum_energy', 'roc_auc_measure', 'average_precision_score']     # exp126a...py:144-146
+
+
+def kaiser_best_half_taps(factor=2):
+    """|j| = 0 .. 64*factor-1 taps of resampy's kaiser_best window (64 zero crossings, roll-off 0.9475937167399596,
+    Kaiser beta 14.769656459379492) walked at a factor:1 ratio — librosa.load's default res_type in librosa 0.8."""
+    num_zeros, beta, rolloff = 64, 14.769656459379492, 0.9475937167399596
+    t = np.arange(0, factor * num_zeros) / float(factor)
+    taper = np.i0(beta * np.sqrt(1.0 - (t / num_zeros) ** 2)) / np.i0(beta)
+    return (rolloff * np.sinc(rolloff * t) * taper / float(factor)).astype(np.float32)
+
+
+def read_wav(path):
+    """PCM WAV -> (float32 [n, channels] in [-1, 1), sample rate); 16-bit (MusicNet, the shipped example) / 8 / 24 / 32-bit."""
+    with wave.open(path, 'rb') as w:
+        sr, nch, width, n = w.getframerate(), w.getnchannels(), w.getsampwidth(), w.getnframes()
+        raw = w.readframes(n)
+    if width == 2:
+        x = np.frombuffer(raw, dtype='<i2').astype(np.float32) / 32768.0
+    elif width == 4:
+        x = np.frombuffer(raw, dtype='<i4').astype(np.float32) / 2147483648.0
+    elif width == 3:
+        b = np.frombuffer(raw, dtype=np.uint8).reshape(-1, 3).astype(np.int32)
+        x = (((b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)) << 8) >> 8).astype(np.float32) / 8388608.0
+    elif width == 1:
+        x = (np.frombuffer(raw, dtype=np.uint8).astype(np.float32) - 128.0) / 128.0
+    else:
+        raise ValueError(f'unsupported sample width {width}')
+    return x.reshape(-1, nch), sr
+
+
+def load_audio(path, sr=22050, device='cuda'):
+    """-> (float32 CUDA tensor [n], sr): mono mix (librosa.to_mono = channel mean) then kaiser_best resampling when the file's
+    rate is a power-of-two multiple of `sr` (no rescaling, as librosa.load)."""
+    x, sr_native = read_wav(path)
+    y = torch.from_numpy(np.ascontiguousarray(x.mean(axis=1, dtype=np.float32) if x.shape[1] > 1 else x[:, 0])).to(device)
+    if sr is None or sr_native == sr:
+        return y, sr_native
+    factor = sr_native // sr
+    if factor * sr != sr_native or factor & (factor - 1):
+        raise NotImplementedError(f'resampling {sr_native} -> {sr} Hz: only power-of-two down-sampling runs on the device')
+    taps = torch.from_numpy(kaiser_best_half_taps(factor)).to(device)
+    import ctypes
+    out = torch.empty(-(-y.numel() // factor), dtype=torch.float32, device=device)
+    _lib.call('decimate_gain_f32', y, out, taps, taps.numel(), factor, ctypes.c_double(1.0), _lib.i64(y.numel()), _lib.stream_ptr())
+    return out, sr
+
+
+def load_hcqt_npy(path, lead=0, trail=0, device='cuda'):
+    """Reference feature file (float64 [F, N, C]) -> fp32 CUDA [C, lead+N+trail, F]; lead = 37, trail = 38 is the inference padding."""
+    a = np.load(path)
+    if a.ndim != 3 or a.dtype != np.float64:
+        raise ValueError(f'{path}: expected a float64 [bins, frames, harmonics] array, got {a.dtype} {a.shape}')
+    F, N, C = a.shape
+    src = torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    out = torch.empty(C, lead + N + trail, F, dtype=torch.float32, device=device)
+    _lib.call('hcqt_npy_to_frames_f64', src, out, F, N, C, lead, trail, _lib.stream_ptr())
+    return out
+
+
+def load_pitch_npy(path, min_pitch=24, n_out=72, device='cuda'):
+    """Reference annotation file ([128, N] or [12, N]) -> fp32 CUDA [N, n_out] (exp126a...py:414-416)."""
+    t = np.load(path).T
+    if n_out != 12:
+        t = t[:, min_pitch:min_pitch + n_out]
+    return torch.from_numpy(np.ascontiguousarray(t, dtype=np.float32)).to(device)
+
+
+def predict_hcqt(model, hcqt, engine=None, batch=50):
+    """[C, N, F] fp32 CUDA (un-padded) -> [N, n_out] activations: the streaming engine for the CNN family on the tensor-core
+    formats, the reference-shaped batches of `batch` consecutive patches otherwise."""
+    if engine is not None:
+        return engine.predict_hcqt(hcqt)
+    out = predict_patchwise(model, hcqt, batch=batch)
+    return out[0] if isinstance(out, tuple) else out
+
+
+def evaluate_file(model, path_hcqt, path_annot, dir_predictions=None, eval_measures=EVAL_MEASURES, eval_thresh=0.4, min_pitch=24,
+                  n_out=72, max_frames=None, engine=None, batch=50):
+    """One iteration of the reference's per-file test loop -> ordered dict row (Filename, measures, mir_eval-style scores)."""
+    hcqt = load_hcqt_npy(path_hcqt)
+    targ = load_pitch_npy(path_annot, min_pitch, n_out)
+    if max_frames is not None:                      # test_subset 1: the first 3920 frames (:420-422)
+        hcqt, targ = hcqt[:, :max_frames].contiguous(), targ[:max_frames].contiguous()
+    pred = predict_hcqt(model, hcqt, engine=engine, batch=batch)
+    assert tuple(pred.shape) == tuple(targ.shape), \
+        'Shape mismatch! Target shape: ' + str(tuple(targ.shape)) + ', Pred. shape: ' + str(tuple(pred.shape))
+    fn = os.path.basename(path_hcqt)
+    if dir_predictions is not None:
+        os.makedirs(dir_predictions, exist_ok=True)
+        np.save(os.path.join(dir_predictions, fn[:-4] + '.npy'), pred.cpu().numpy().astype(np.float64))
+    row = {'Filename': fn}
+    row.update(calculate_eval_measures(targ, pred, measures=eval_measures, threshold=eval_thresh))
+    row.update(calculate_mpe_measures_mireval(targ, pred, threshold=eval_thresh, min_pitch=min_pitch))
+    row['_kframes'] = targ.shape[0] / 1000
+    return row
+
+
+def write_results_csv(rows, path_output):
+    """Per-file rows + 'FILEWISE MEAN' + 'FRAMEWISE MEAN' (frame-count weighted) in the reference's DataFrame.to_csv layout."""
+    keys = [k for k in rows[0] if k not in ('Filename', '_kframes')]
+    vals = np.array([[r[k] for k in keys] for r in rows], dtype=float)
+    kf = np.array([r['_kframes'] for r in rows], dtype=float)
+    table = [[r['Filename']] + list(v) for r, v in zip(rows, vals)]
+    table.append(['FILEWISE MEAN'] + list(vals.sum(0) / len(rows)))
+    table.append(['FRAMEWISE MEAN'] + list((vals * kf[:, None]).sum(0) / kf.sum()))
+    with open(path_output, 'w', newline='') as f:
+        w = csv.writer(f)
+        w.writerow([''] + ['Filename'] + keys)
+        for i, r in enumerate(table):
+            w.writerow([i] + r)
+    return table

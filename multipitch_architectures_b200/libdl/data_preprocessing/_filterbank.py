@@ -65,9 +65,10 @@ def _band_rows(spec):
 
 
 def cqt_schedule(sr, hop, fmin, n_bins, bpo):
-    """Octave schedule of librosa.cqt for one base CQT at one tuning: list of
-    (level, n_fft_key, scale, first_bin) top octave first, where n_fft_key selects 'top' (full-rate bank built at
-    the top octave before the kaiser_fast chain) or 'loop'."""
+    """Octave schedule of librosa.cqt for one CQT at one tuning: (early, [(signal, key, scale, first_bin, fmin_oct, sr_oct)])
+    top octave first.  `early` = c of librosa's one-shot 2^c:1 early down-sampling; `signal` = (c, i): the input after that
+    and i further 2:1 kaiser_fast steps; key selects 'top' (full-rate bank built at the top octave before the kaiser_fast
+    chain) or 'loop'."""
     n_oct = int(np.ceil(n_bins / bpo))
     alpha = 2.0 ** (1.0 / bpo) - 1.0
     freqs = fmin * 2.0 ** (np.arange(n_bins, dtype=float) / bpo)
@@ -81,29 +82,47 @@ def cqt_schedule(sr, hop, fmin, n_bins, bpo):
         twos += 1
         h //= 2
     early = min(max(0, int(np.ceil(np.log2(BW_FASTEST * nyq / cutoff)) - 1) - 1), max(0, twos - n_oct + 1))
-    if early != 0:
-        raise NotImplementedError('configurations that trigger librosa early down-sampling are not supported')
+    if not fast:
+        early = 0
+    sr_e = sr / 2.0 ** early
+    twos -= early
     sched = []
     end = n_bins
     if not fast:
-        sched.append((0, 'top', 1.0, end - bpo, fmin_t))
+        sched.append(((0, 0), 'top', 1.0, end - bpo, fmin_t, sr_e))
         end -= bpo
         fmin_t /= 2
         n_oct -= 1
     if twos < n_oct - 1:
         raise ValueError('hop_length must be a positive integer multiple of 2^%d for %d-octave CQT' % (n_oct - 1, n_oct))
     for i in range(n_oct):
-        sched.append((i, 'loop', float(np.sqrt(2.0 ** i)), end - bpo, fmin_t))
+        sched.append(((early, i), 'loop', float(np.sqrt(2.0 ** i)), end - bpo, fmin_t, sr_e / 2.0 ** i))
         end -= bpo
-    return sched
+    return early, sched
+
+
+def signal_length(n, signal):
+    """Samples of `signal` = (early c, 2:1 steps i) for an n-sample input: librosa fixes every resample to ceil(len * ratio)."""
+    c, i = signal
+    n = -(-n // 2 ** c)
+    for _ in range(i):
+        n = -(-n // 2)
+    return n
+
+
+def cqt_frames(sr, hop, fmin, n_bins, bpo, n):
+    """Columns librosa.cqt returns for an n-sample input: __trim_stack keeps the shortest octave response."""
+    _, sched = cqt_schedule(sr, hop, fmin, n_bins, bpo)
+    return min(1 + signal_length(n, sg) // (hop >> (sg[0] + sg[1])) for (sg, *_r) in sched)
 
 
 def build_tables(sr, hop, fmin, bpo, num_octaves, list_harmonics, base_harmonics):
-    """-> dict level_key=(level, n_fft) -> dict(basis [100, R, BAND] c64, start [100, R] i32, scale [100, R] f32,
-    dest [R, n_dest] i32), plus n_levels."""
+    """-> dict (signal, n_fft) -> dict(basis [100, R, BAND] c64, start [100, R] i32, scale [100, R] f32, dest [R, n_dest] i32),
+    signal = (early c, 2:1 steps i).  One CQT per distinct base harmonic; harmonic i reads the bins of its base CQT shifted by
+    log2(list_harmonics[i] / base) octaves (compute_efficient_hcqt) or is its own base (compute_hcqt)."""
     H = len(list_harmonics)
     alpha = 2.0 ** (1.0 / bpo) - 1.0
-    groups = {}           # (level, n_fft) -> list of row descriptors (cqt id, key, bins...)
+    groups = {}           # (signal, n_fft) -> list of row descriptors
     per_tuning = []       # for each tuning: {(cqt, key): (band, start, n_fft)}, and lengths per cqt
     bases = sorted(set(base_harmonics))
     sched_ref = None
@@ -115,26 +134,27 @@ def build_tables(sr, hop, fmin, bpo, num_octaves, list_harmonics, base_harmonics
             add = int(np.ceil(np.log2(list_harmonics[max(members)] / b)))
             n_bins = (num_octaves + add) * bpo
             f0 = fmin_tuned * b
-            sched = cqt_schedule(sr, hop, f0, n_bins, bpo)
-            scheds[b] = [(lv, key, sc, fb) for (lv, key, sc, fb, _) in sched]
-            for (lv, key, sc, fb, fm) in sched:
+            early, sched = cqt_schedule(sr, hop, f0, n_bins, bpo)
+            scheds[b] = [(sg, key, sc, fb) for (sg, key, sc, fb, _, _) in sched]
+            for (sg, key, sc, fb, fm, sr_oct) in sched:
                 if (b, key) not in banks:
-                    spec, n_fft = _bank(sr / 2.0 ** lv, fm, bpo)
+                    spec, n_fft = _bank(sr_oct, fm, bpo)
                     band, start = _band_rows(spec)
                     banks[(b, key)] = (band, start, n_fft)
-            lens[b] = (1.0 / alpha) * sr / (f0 * 2.0 ** (np.arange(n_bins, dtype=float) / bpo))
+            # final length normalisation uses the (early down-sampled) rate the CQT runs at
+            lens[b] = (1.0 / alpha) * (sr / 2.0 ** early) / (f0 * 2.0 ** (np.arange(n_bins, dtype=float) / bpo))
         if sched_ref is None:
             sched_ref = scheds
             nfft_ref = {k: v[2] for k, v in banks.items()}
         elif scheds != sched_ref or nfft_ref != {k: v[2] for k, v in banks.items()}:
             raise NotImplementedError('octave schedule / n_fft changes with the tuning estimate for this configuration')
         per_tuning.append((banks, lens))
-    # row tables per (level, n_fft)
+    # row tables per (signal, n_fft)
     for b in bases:
         members = [i for i in range(H) if base_harmonics[i] == b]
-        for (lv, key, sc, fb) in sched_ref[b]:
+        for (sg, key, sc, fb) in sched_ref[b]:
             n_fft = nfft_ref[(b, key)]
-            g = groups.setdefault((lv, n_fft), [])
+            g = groups.setdefault((sg, n_fft), [])
             for k in range(bpo):
                 cbin = fb + k
                 dests = []
@@ -164,9 +184,10 @@ def build_tables(sr, hop, fmin, bpo, num_octaves, list_harmonics, base_harmonics
     return tables
 
 
-def kaiser_fast_half_taps():
-    """|j| = 0..31 taps of resampy's kaiser_fast interpolation window walked at a 2:1 ratio (x 0.5 sample ratio)."""
+def kaiser_fast_half_taps(factor=2):
+    """|j| = 0 .. 16*factor-1 taps of resampy's kaiser_fast interpolation window walked at a factor:1 ratio
+    (x 1/factor sample ratio)."""
     num_zeros, beta, rolloff = 16, 8.555504641634386, 0.85
-    t = np.arange(0, 2 * num_zeros) / 2.0
+    t = np.arange(0, factor * num_zeros) / float(factor)
     taper = np.i0(beta * np.sqrt(1.0 - (t / num_zeros) ** 2)) / np.i0(beta)
-    return (0.5 * rolloff * np.sinc(rolloff * t) * taper).astype(np.float32)
+    return (rolloff * np.sinc(rolloff * t) * taper / float(factor)).astype(np.float32)

@@ -35,27 +35,52 @@ def _harmonic_plan(num_harmonics, num_subharmonics):
 
 
 class HCQTPlan:
-    """Device-resident filter tables + launch schedule for one HCQT configuration."""
+    """Device-resident filter tables + launch schedule for one HCQT configuration.  `efficient`: harmonics related by a
+    power of two share one CQT (compute_efficient_hcqt); otherwise every (sub)harmonic runs its own CQT (compute_hcqt)."""
 
-    def __init__(self, fs, fmin, hop, bins_per_octave, num_octaves, num_harmonics, num_subharmonics, device):
+    def __init__(self, fs, fmin, hop, bins_per_octave, num_octaves, num_harmonics, num_subharmonics, device, efficient=True):
         self.fs, self.hop, self.bpo, self.num_octaves = fs, hop, bins_per_octave, num_octaves
         self.H = num_harmonics + num_subharmonics
         self.n_bins = bins_per_octave * num_octaves
         self.device = torch.device(device)
         list_h, base = _harmonic_plan(num_harmonics, num_subharmonics)
+        if not efficient:
+            base = list(list_h)
         tabs = FB.build_tables(fs, hop, fmin, bins_per_octave, num_octaves, list_h, base)
+        # (f0 multiplier, n_bins) of every CQT, for the frame count librosa would return
+        self.cqts = []
+        for b in sorted(set(base)):
+            top = max(h for h, bb in zip(list_h, base) if bb == b)
+            self.cqts.append((fmin * b, (num_octaves + int(np.ceil(np.log2(top / b)))) * bins_per_octave))
+        self.first_cqt = self.cqts[sorted(set(base)).index(base[num_subharmonics])]      # the one serving h = 1
         self.levels = []
-        for (lv, n_fft), t in sorted(tabs.items()):
+        for (sg, n_fft), t in sorted(tabs.items()):
             self.levels.append(dict(
-                level=lv, n_fft=n_fft, n_rows=t['dest'].shape[0], n_dest=t['dest'].shape[1],
+                signal=sg, n_fft=n_fft, n_rows=t['dest'].shape[0], n_dest=t['dest'].shape[1],
                 basis=torch.from_numpy(np.ascontiguousarray(t['basis']).view(np.float32)).to(self.device),
                 start=torch.from_numpy(t['start']).to(self.device), scale=torch.from_numpy(t['scale']).to(self.device),
                 dest=torch.from_numpy(t['dest']).to(self.device)))
-        self.max_level = max(l['level'] for l in self.levels)
-        self.taps = torch.from_numpy(FB.kaiser_fast_half_taps()).to(self.device)
+        self.signals = sorted({l['signal'] for l in self.levels} |
+                              {(c, j) for (c, i) in {l['signal'] for l in self.levels} for j in range(i)})
+        self.taps = {f: torch.from_numpy(FB.kaiser_fast_half_taps(f)).to(self.device)
+                     for f in {2} | {2 ** c for (c, _) in self.signals if c > 0}}
         n = np.arange(2048)
         self.hann2048 = torch.from_numpy((0.5 - 0.5 * np.cos(2 * np.pi * n / 2048)).astype(np.float32)).to(self.device)
         self.tunings = FB.tuning_values()
+        self._frames = {}
+
+    def n_frames(self, n):
+        """Frames of the HCQT of an n-sample input (= columns of the CQT serving the fundamental, hcqt.py:69,125); raises like
+        the reference's array assignment does when another CQT of the set returns a different number of columns."""
+        if n in self._frames:
+            return self._frames[n]
+        fr = [FB.cqt_frames(self.fs, self.hop, f0, nb, self.bpo, n) for (f0, nb) in self.cqts]
+        first = FB.cqt_frames(self.fs, self.hop, self.first_cqt[0], self.first_cqt[1], self.bpo, n)
+        if any(f != first for f in fr):
+            raise ValueError(f'could not broadcast CQTs of {sorted(set(fr))} frames into one HCQT of {first} frames')
+        if len(self._frames) < 4096:
+            self._frames[n] = first
+        return first
 
     def run(self, y, tuning_idx=None):
         """y: 1-D float32 CUDA tensor -> (hcqt [H, n_frames, n_bins] fp32 CUDA, tuning_idx int32[1] CUDA)."""
@@ -64,30 +89,53 @@ class HCQTPlan:
         y = y.contiguous()
         n = y.numel()
         st = _lib.stream_ptr()
-        n_frames = n // self.hop + 1
+        n_frames = self.n_frames(n)
         if tuning_idx is None:
             tuning_idx = torch.empty(1, dtype=torch.int32, device=y.device)
             ws_bytes = _lib.lib().mpa_tuning_workspace(n // 512 + 1)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=y.device)
             _lib.call('estimate_tuning_f32', y, _lib.i64(n), self.hann2048, float(self.fs), self.bpo, tuning_idx, ws,
                       _lib.usize(ws_bytes), st)
-        sig = [y]
-        for _ in range(self.max_level):
-            prev = sig[-1]
-            nxt = torch.empty((prev.numel() + 1) // 2, dtype=torch.float32, device=y.device)
-            _lib.call('decimate2_f32', prev, nxt, self.taps, _lib.i64(prev.numel()), st)
-            sig.append(nxt)
+        sig = {(0, 0): y}
+        for (c, i) in self.signals:            # sorted: (c, i-1) precedes (c, i)
+            if (c, i) in sig:
+                continue
+            prev, factor = (y, 2 ** c) if i == 0 else (sig[(c, i - 1)], 2)
+            nxt = torch.empty(-(-prev.numel() // factor), dtype=torch.float32, device=y.device)
+            taps = self.taps[factor]
+            _lib.call('decimate_f32', prev, nxt, taps, taps.numel(), factor, _lib.i64(prev.numel()), st)
+            sig[(c, i)] = nxt
         out = torch.empty(self.H, n_frames, self.n_bins, dtype=torch.float32, device=y.device)
         for L in self.levels:
-            s = sig[L['level']]
-            _lib.call('cqt_level_f32', s, _lib.i64(s.numel()), L['n_fft'], self.hop >> L['level'], n_frames, L['basis'], L['start'],
+            s = sig[L['signal']]
+            _lib.call('cqt_level_f32', s, _lib.i64(s.numel()), L['n_fft'], self.hop >> sum(L['signal']), n_frames, L['basis'], L['start'],
                       L['scale'], L['n_rows'], FB.BAND, tuning_idx, L['dest'], L['n_dest'], out, n_frames, self.n_bins, st)
         return out, tuning_idx
 
 
 @functools.lru_cache(maxsize=8)
-def get_plan(fs, fmin, hop, bins_per_octave, num_octaves, num_harmonics, num_subharmonics, device):
-    return HCQTPlan(fs, fmin, hop, bins_per_octave, num_octaves, num_harmonics, num_subharmonics, device)
+def get_plan(fs, fmin, hop, bins_per_octave, num_octaves, num_harmonics, num_subharmonics, device, efficient=True):
+    return HCQTPlan(fs, fmin, hop, bins_per_octave, num_octaves, num_harmonics, num_subharmonics, device, efficient)
+
+
+def _hcqt_host(plan, f_audio):
+    y = torch.from_numpy(np.ascontiguousarray(f_audio, dtype=np.float32)).to(plan.device)
+    out, _ = plan.run(y)
+    return out.permute(2, 1, 0).contiguous().cpu().numpy().astype(np.float64)
+
+
+def compute_hcqt(f_audio, fs=22050, fmin=C1_HZ, fs_hcqt_target=91, bins_per_octave=60, num_octaves=6, num_harmonics=5,
+                 num_subharmonics=1, center_bins=True, device='cuda'):
+    """Drop-in for the reference's standard HCQT (hcqt.py:34-85): one individual CQT per (sub)harmonic, hop size derived from
+    num_octaves alone.  Returns (f_hcqt float64 ndarray [n_bins, n_frames, H], fs_hcqt, hopsize_cqt)."""
+    hopsize_cqt, _ = compute_hopsize_cqt(fs_hcqt_target, fs=fs, num_octaves=num_octaves)
+    fs_hcqt = fs / hopsize_cqt
+    assert np.mod(bins_per_octave, 12) == 0, 'Error: bins_per_octave no multiple of 12'
+    bins_per_semitone = int(bins_per_octave / 12)
+    if center_bins:
+        fmin = fmin / 2 ** ((bins_per_semitone - 1) / (2 * bins_per_octave))
+    plan = get_plan(fs, float(fmin), hopsize_cqt, bins_per_octave, num_octaves, num_harmonics, num_subharmonics, str(device), False)
+    return _hcqt_host(plan, f_audio), fs_hcqt, hopsize_cqt
 
 
 def compute_efficient_hcqt(f_audio, fs=22050, fmin=C1_HZ, fs_hcqt_target=91, bins_per_octave=60, num_octaves=6,
@@ -104,10 +152,7 @@ def compute_efficient_hcqt(f_audio, fs=22050, fmin=C1_HZ, fs_hcqt_target=91, bin
     if center_bins:
         fmin = fmin / 2 ** ((bins_per_semitone - 1) / (2 * bins_per_octave))
     plan = get_plan(fs, float(fmin), hopsize_cqt, bins_per_octave, num_octaves, num_harmonics, num_subharmonics, str(device))
-    y = torch.from_numpy(np.ascontiguousarray(f_audio, dtype=np.float32)).to(plan.device)
-    out, _ = plan.run(y)
-    f_hcqt = out.permute(2, 1, 0).contiguous().cpu().numpy().astype(np.float64)
-    return f_hcqt, fs_hcqt, hopsize_cqt
+    return _hcqt_host(plan, f_audio), fs_hcqt, hopsize_cqt
 
 
 def estimate_tuning(f_audio, fs=22050, bins_per_octave=36, device='cuda'):

@@ -1,1 +1,2 @@
-from .eval_metrics import calculate_eval_measures, calculate_single_measure, compute_eval_measures
+from .eval_metrics import (calculate_eval_measures, calculate_single_measure, calculate_mpe_measures_mireval,
+                           compute_eval_measures, eval_sums, roc_auc, average_precision)

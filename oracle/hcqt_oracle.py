@@ -39,45 +39,60 @@ def compute_hopsize_cqt(fs_cqt_target, fs=22050, num_octaves=7):
     return hop, fs / hop
 
 
-# ----------------------------------------------------------------------------- resampy 2:1
-def _kaiser_fast_halfband():
-    """Taps h[j], j=-32..32, of resampy's kaiser_fast filter evaluated at a 2:1 ratio.
+# ----------------------------------------------------------------------------- resampy 2^c:1
+RESAMPY_FILTERS = {                     # resampy's published window parameters: (zero crossings, Kaiser beta, roll-off)
+    'kaiser_fast': (16, 8.555504641634386, 0.85),
+    'kaiser_best': (64, 14.769656459379492, 0.9475937167399596),
+}
 
-    resampy builds interp_win = rolloff*sinc(rolloff*t)*kaiser(t), t in [0,num_zeros] at 2^precision
-    steps per zero crossing and, for sample_ratio=0.5, walks it with index_step = 0.5*2^precision, i.e.
-    t = j/2; interp_win is pre-multiplied by sample_ratio (0.5)."""
-    num_zeros, beta, rolloff = 16, 8.555504641634386, 0.85
-    j = np.arange(0, 2 * num_zeros + 1, dtype=np.float64)
-    t = j / 2.0
+
+def _kaiser_fast_half(factor=2, filt='kaiser_fast'):
+    """Taps h[|j|], |j| = 0 .. 16*factor-1, of resampy's kaiser_fast filter evaluated at a factor:1 ratio
+    (64*factor taps for kaiser_best, the default of librosa.load).
+
+    resampy builds interp_win = rolloff*sinc(rolloff*t)*kaiser(t), t in [0,num_zeros] at 2^precision = 512
+    steps per zero crossing and, for sample_ratio = 1/factor, walks it with index_step = 512/factor, i.e.
+    t = j/factor; interp_win is pre-multiplied by sample_ratio.  Its wing loops stop at
+    (len(interp_win) - offset) // index_step = 16*factor (left wing, incl. the centre tap) and 16*factor-1
+    (right wing) taps, i.e. |j| <= 16*factor-1: the table's end point t = 16 is never read."""
+    num_zeros, beta, rolloff = RESAMPY_FILTERS[filt]
+    j = np.arange(0, num_zeros * factor, dtype=np.float64)
+    t = j / float(factor)
     # right half of scipy.signal.kaiser(2n+1, beta) sampled at t/num_zeros
     taper = scipy.special.i0(beta * np.sqrt(np.clip(1.0 - (t / num_zeros) ** 2, 0.0, None))) / scipy.special.i0(beta)
-    half = 0.5 * rolloff * np.sinc(rolloff * t) * taper
-    # resampy's wing loops stop at (len(interp_win) - offset) // index_step = 32 (left, incl. centre)
-    # and 31 (right) taps, i.e. |j| <= 31: the table's end point j=32 is never read.
-    return half[:2 * num_zeros]                             # h[|j|], |j| = 0..31
+    return rolloff * np.sinc(rolloff * t) * taper / float(factor)
 
 
-def resample_2to1(y):
-    """librosa.resample(y, 2, 1, res_type='kaiser_fast', scale=True) for 1-D float32 y.
+def _kaiser_fast_halfband():
+    return _kaiser_fast_half(2)
 
-    resampy output length floor(n/2); librosa fixes the length to ceil(n/2) (zero pad) and
-    divides by sqrt(ratio) = multiplies by sqrt(2).  Output sample t sits at input sample 2t;
+
+def resample_pow2(y, factor, filt='kaiser_fast', scale=True):
+    """librosa.resample(y, sr, sr/factor, res_type=filt, scale=scale) for 1-D float32 y, factor = 2^c
+    (librosa.load resamples with kaiser_best and scale=False).
+
+    resampy output length floor(n/factor); librosa fixes the length to ceil(n/factor) (zero pad) and
+    divides by sqrt(ratio) = multiplies by sqrt(factor).  Output sample t sits at input sample factor*t;
     taps outside [0,n) are skipped (no padding).  resampy accumulates in the dtype of y."""
     y = np.asarray(y)
     n = y.shape[0]
-    n_out = n // 2
-    half = _kaiser_fast_halfband()
+    n_out = n // factor
+    half = _kaiser_fast_half(factor, filt)
     L = half.shape[0] - 1
-    ypad = np.concatenate([np.zeros(L, y.dtype), y, np.zeros(L + 2, y.dtype)]).astype(np.float64)
+    ypad = np.concatenate([np.zeros(L, y.dtype), y, np.zeros(L + factor, y.dtype)]).astype(np.float64)
     taps = np.concatenate([half[::-1], half[1:]])           # j = -L..L
-    # out[t] = sum_j taps[j] * y[2t + j]
+    # out[t] = sum_j taps[j] * y[factor*t + j]
     full = np.convolve(ypad, taps[::-1], mode='valid')      # full[m] = sum_j taps[j]*ypad[m + j + L] -> centre m
-    out = full[0:2 * n_out:2]
-    out = (out * np.sqrt(2.0)).astype(y.dtype)
-    n_fix = int(np.ceil(n * 0.5))
+    out = full[0:factor * n_out:factor]
+    out = (out * (np.sqrt(float(factor)) if scale else 1.0)).astype(y.dtype)
+    n_fix = int(np.ceil(n / float(factor)))
     if n_fix > n_out:
         out = np.concatenate([out, np.zeros(n_fix - n_out, y.dtype)])
     return out
+
+
+def resample_2to1(y):
+    return resample_pow2(y, 2)
 
 
 # ----------------------------------------------------------------------------- filter bank
@@ -149,7 +164,14 @@ def cqt(y, sr=22050, hop_length=512, fmin=None, n_bins=84, bins_per_octave=12, t
         num_twos += 1
         h //= 2
     d2 = max(0, num_twos - n_octaves + 1)
-    assert min(d1, d2) == 0, 'early downsampling is not exercised by the reference configurations'
+    early = min(d1, d2)
+    if early > 0 and res_fast:
+        # __early_downsample: ONE resample by 2^early (not a chain of 2:1 steps); scale=True keeps the energy, so
+        # the filter lengths of the final normalisation are those at the reduced rate
+        y = resample_pow2(y, 2 ** early)
+        hop_length //= 2 ** early
+        sr = sr / float(2 ** early)
+        num_twos -= early
     plan = []                                               # (level, n_fft, fmin_oct, scale)
     resp = []
     if not res_fast:
@@ -286,6 +308,33 @@ def compute_efficient_hcqt(f_audio, fs=22050, fmin=C1_HZ, fs_hcqt_target=91, bin
         for i in members:
             factor = int(np.log2(list_h[i] / b))
             f_hcqt[:, :, i] = np.abs(C[factor * bins_per_octave:(factor + num_octaves) * bins_per_octave, :])
+    return f_hcqt, fs_hcqt, hop
+
+
+def compute_hcqt(f_audio, fs=22050, fmin=C1_HZ, fs_hcqt_target=91, bins_per_octave=60, num_octaves=6,
+                 num_harmonics=5, num_subharmonics=1, center_bins=True, tuning_est=None):
+    """hcqt.py:34-85: one individual CQT per (sub)harmonic -> (f_hcqt float64 [n_bins, n_frames, H], fs_hcqt, hopsize).
+    The hop size follows from num_octaves alone (hcqt.py:54), so the low harmonics run into librosa's early
+    down-sampling and the top ones into its full-rate top octave."""
+    f_audio = np.asarray(f_audio, dtype=np.float32)
+    hop, _ = compute_hopsize_cqt(fs_hcqt_target, fs=fs, num_octaves=num_octaves)
+    fs_hcqt = fs / hop
+    n_bins = num_octaves * bins_per_octave
+    assert bins_per_octave % 12 == 0, 'Error: bins_per_octave no multiple of 12'
+    bps = bins_per_octave // 12
+    if center_bins:
+        fmin = fmin / 2 ** ((bps - 1) / (2 * bins_per_octave))
+    if tuning_est is None:
+        tuning_est = estimate_tuning(f_audio, sr=fs, bins_per_octave=bins_per_octave)
+    fmin_tuned = fmin * 2 ** (tuning_est / bins_per_octave)
+    kw = dict(sr=fs, hop_length=hop, n_bins=n_bins, bins_per_octave=bins_per_octave, tuning=0.0)
+    C1 = cqt(f_audio, fmin=fmin_tuned, **kw)
+    f_hcqt = np.zeros((n_bins, C1.shape[1], num_harmonics + num_subharmonics))
+    f_hcqt[:, :, num_subharmonics] = np.abs(C1)
+    for n_ha in range(2, num_harmonics + 1):
+        f_hcqt[:, :, num_subharmonics + n_ha - 1] = np.abs(cqt(f_audio, fmin=n_ha * fmin_tuned, **kw))
+    for n_hs in range(1, num_subharmonics + 1):
+        f_hcqt[:, :, num_subharmonics - n_hs] = np.abs(cqt(f_audio, fmin=fmin_tuned / (n_hs + 1), **kw))
     return f_hcqt, fs_hcqt, hop
 
 

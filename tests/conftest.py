@@ -22,3 +22,9 @@ def nn_golden():
 def host_golden():
     import numpy as np
     return np.load(os.path.join(ROOT, 'tests', 'golden', 'host_golden.npz'))
+
+
+@pytest.fixture(scope='session')
+def ext_golden():
+    import numpy as np
+    return np.load(os.path.join(ROOT, 'tests', 'golden', 'ext_golden.npz'))

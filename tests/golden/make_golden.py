@@ -230,10 +230,158 @@ def train_goldens():
     np.savez_compressed(os.path.join(HERE, 'nn_train_golden.npz'), **out)
 
 
+def load_reference_eval_metrics():
+    """libdl/metrics/eval_metrics.py imports matplotlib, IPython, librosa, libfmp.c3/c5, libdl.data_preprocessing, sklearn and
+    mir_eval at module scope.  sklearn is installed; libfmp.c3 / c5 are loaded from the reference's own files; the rest is stubbed."""
+    load_reference_hcqt()
+    for name in ('matplotlib.colors', 'libfmp', 'libfmp.b', 'libfmp.c4', 'mir_eval', 'mir_eval.multipitch'):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules['matplotlib'].colors = sys.modules['matplotlib.colors']
+    sys.modules['matplotlib'].pyplot = sys.modules['matplotlib.pyplot']
+    sys.modules['mir_eval'].multipitch = sys.modules['mir_eval.multipitch']
+    for attr in ('MultiplePlot', 'plot_matrix', 'plot_segments', 'read_csv'):
+        setattr(sys.modules['libfmp.b'], attr, None)
+    sys.modules['libfmp.b'].MultiplePlot = object
+    for sub, path in (('c3', 'libfmp/c3/c3s1_post_processing.py'), ('c5', 'libfmp/c5/c5s2_chord_rec_template.py')):
+        spec = importlib.util.spec_from_file_location('libfmp.' + sub, os.path.join(REF, path))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules['libfmp.' + sub] = mod
+        setattr(sys.modules['libfmp'], sub, mod)
+        spec.loader.exec_module(mod)
+    dp = types.ModuleType('libdl.data_preprocessing')
+    saved = sys.modules.get('libdl.data_preprocessing')
+    sys.modules['libdl.data_preprocessing'] = dp
+    try:
+        spec = importlib.util.spec_from_file_location('ref_eval_metrics', os.path.join(REF, 'libdl/metrics/eval_metrics.py'))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        if saved is not None:
+            sys.modules['libdl.data_preprocessing'] = saved
+        else:
+            del sys.modules['libdl.data_preprocessing']
+    return mod
+
+
+AUG_ROWS = [0, 37, 74]
+
+
+def ext_goldens():
+    """Goldens of the rows added after the first pass (SURVEY.md 8b compute_hcqt; 8f rows 1 and 4) -> ext_golden.npz."""
+    out = {}
+    ref = load_reference_hcqt()
+    # compute_hcqt (hcqt.py:34-85): the reference wrapper with the oracle standing in for librosa vs the oracle's own wrapper;
+    # hop 448 at the paper's resolution -> early down-sampling for h = 1/2, 1 and a full-rate top octave for h = 5
+    y = HO.synth_clip(3, seconds=2.0)
+    kw = dict(fs=22050, fmin=HO.C1_HZ, fs_hcqt_target=50, bins_per_octave=36, num_octaves=6, num_harmonics=5, num_subharmonics=1)
+    f_ref, fs_h, hop = ref.compute_hcqt(y, **kw)
+    f_or, fs_o, hop_o = HO.compute_hcqt(y, **kw)
+    assert np.array_equal(f_ref, f_or) and hop == hop_o == 448 and fs_h == fs_o, 'oracle compute_hcqt != reference wrapper'
+    out['hcqt_std_2s'] = f_ref.astype(np.float32)
+    # the reference's default arguments (Bittner et al.: 60 bins per octave, hop 256): early down-sampling by 4 for the sub-harmonic
+    kw60 = dict(fs=22050, fmin=HO.C1_HZ)
+    f_ref, fs_h, hop = ref.compute_hcqt(y[:22050], **kw60)
+    f_or, _, hop_o = HO.compute_hcqt(y[:22050], **kw60)
+    assert np.array_equal(f_ref, f_or) and hop == hop_o == 256
+    out['hcqt_std60_1s'] = f_ref.astype(np.float32)
+
+    # evaluation measures through the reference function
+    em = load_reference_eval_metrics()
+    rng = np.random.default_rng(11)
+    targ = (rng.uniform(size=(400, 72)) < 0.06).astype(np.float64)
+    pred = np.clip(0.75 * targ * rng.uniform(0.3, 1.3, size=targ.shape) + rng.uniform(size=targ.shape) ** 6, 0, 1).astype(np.float32)
+    targ[7] = 0          # silent reference frame -> libfmp's unit-vector fallback / empty reference set
+    pred[9] = 0          # silent estimate
+    targ[9] = 0
+    pred[11, :] = 1e-12
+    names = ['precision', 'recall', 'f_measure', 'cosine_sim', 'binary_crossentropy', 'euclidean_distance', 'binary_accuracy',
+             'soft_accuracy', 'accum_energy', 'roc_auc_measure', 'average_precision_score']
+    out['ev_targ'] = targ.astype(np.float32)
+    out['ev_pred'] = pred
+    for thr in (0.4, 0.7):
+        d = em.calculate_eval_measures(targ, pred.astype(np.float64), names, threshold=thr)
+        out['ev_values_%02d' % int(thr * 10)] = np.array([d[k] for k in names], dtype=np.float64)
+    out['ev_names'] = np.array(names)
+
+    # augmentations: the reference __getitem__ with every torch.randint / torch.normal result recorded
+    from libdl.data_loaders import dataset_context
+    inp = np.abs(rng.normal(0, 0.05, size=(6, 130, 216)))
+    tg = (rng.uniform(size=(130, 72)) < 0.05).astype(np.float64)
+    out['aug_in'] = inp.astype(np.float32)
+    out['aug_tg'] = tg.astype(np.float32)
+    real_randint, real_normal = torch.randint, torch.normal
+    rec = []
+
+    def randint(*a, **k):
+        r = real_randint(*a, **k)
+        rec.append(('i', r.clone()))
+        return r
+
+    def normal(*a, **k):
+        r = real_normal(*a, **k)
+        rec.append(('n', r.clone()))
+        return r
+
+    cases = []
+    for ci, (params, idxs) in enumerate((
+            ({'aug:randomeq': 20, 'aug:tuning': True, 'aug:transpsemitones': 5}, list(range(0, 55, 3))),
+            ({'aug:randomeq': 20, 'aug:noisestd': 1e-4, 'aug:tuning': True, 'aug:transpsemitones': 5}, [1, 20, 40]),
+            ({'aug:transpsemitones': 2, 'targettype': 'pitch_class'}, [2, 9, 30]))):
+        p = dict({'context': 75, 'stride': 1, 'compression': 10}, **params)
+        tgt = tg[:, :12] if params.get('targettype') == 'pitch_class' else tg
+        ds = dataset_context(torch.from_numpy(inp.astype(np.float32).astype(np.float64)), torch.from_numpy(tgt), p)
+        torch.manual_seed(100 + ci)
+        for i in idxs:
+            rec.clear()
+            torch.randint, torch.normal = randint, normal
+            try:
+                X, yy = ds[i]
+            finally:
+                torch.randint, torch.normal = real_randint, real_normal
+            ints = [int(r) for k, r in rec if k == 'i']
+            norms = [r.numpy() for k, r in rec if k == 'n']
+            pos = 0
+            alpha = beta = 0
+            if 'aug:randomeq' in params:
+                n_pairs = (len(ints) - ('aug:tuning' in params) - ('aug:transpsemitones' in params)) // 2
+                alpha, beta = ints[2 * n_pairs - 2], ints[2 * n_pairs - 1]
+                pos = 2 * n_pairs
+            tune2 = 0
+            if 'aug:tuning' in params:
+                tune2 = ints[pos] if True else 0
+                pos += 1
+            transp = ints[pos] if 'aug:transpsemitones' in params else 0
+            noise = norms.pop(0) if 'aug:noisestd' in params else None
+            fill_tune = norms.pop(0) if tune2 != 0 else None
+            fill_tr = norms.pop(0) if transp != 0 else None
+            assert not norms
+            tag = 'aug%d_%d' % (ci, i)
+            out[tag + '_dec'] = np.array([i, alpha, beta, tune2, transp], dtype=np.int64)
+            out[tag + '_X'] = X.numpy().astype(np.float32)[:, AUG_ROWS, :]      # the chain is row-independent: 3 of 75 rows keep the fixture small
+            out[tag + '_y'] = yy.numpy().astype(np.float32)
+            if noise is not None:
+                out[tag + '_noise'] = noise.astype(np.float32)[:, AUG_ROWS, :]
+            if fill_tune is not None:
+                out[tag + '_ftune'] = fill_tune.astype(np.float32)[:, AUG_ROWS, :]
+            if fill_tr is not None:
+                out[tag + '_ftr'] = fill_tr.astype(np.float32)[:, AUG_ROWS, :]
+            cases.append((ci, i, alpha, beta, tune2, transp))
+    out['aug_cases'] = np.array(cases, dtype=np.int64)
+    assert set(c[4] for c in cases) == {-2, -1, 0, 1, 2}, sorted(set(c[4] for c in cases))
+    assert any(c[5] > 0 for c in cases) and any(c[5] < 0 for c in cases)
+    np.savez_compressed(os.path.join(HERE, 'ext_golden.npz'), **out)
+    print('ext goldens:', len(out), 'arrays;', len(cases), 'augmentation cases')
+
+
 if __name__ == '__main__':
     if 'train' in sys.argv[1:]:
         train_goldens()
         sys.exit(0)
+    if 'ext' in sys.argv[1:]:
+        ext_goldens()
+        sys.exit(0)
     host_goldens()
     nn_goldens()
     train_goldens()
+    ext_goldens()

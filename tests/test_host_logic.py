@@ -1,6 +1,7 @@
 """`-m "not gpu"`: host-side mirror of the reference interface (dataset index math, metrics, hop size, annotation
 rasteriser, harmonic plan, filter tables) against the reference-generated goldens and the oracle."""
 import numpy as np
+import pytest
 import torch
 
 from oracle import hcqt_oracle as Q
@@ -24,11 +25,9 @@ def test_dataset_context_matches_reference_golden(host_golden):
 
 
 def test_metrics_match_reference_golden(host_golden):
-    from multipitch_architectures_b200.libdl.metrics import calculate_eval_measures, compute_eval_measures
+    from multipitch_architectures_b200.libdl.metrics import compute_eval_measures
     got = compute_eval_measures(host_golden['prf_targ'], host_golden['prf_pred'] >= 0.4)
     assert np.allclose(np.array(got, dtype=np.float64), host_golden['prf'], atol=1e-12, rtol=0)
-    d = calculate_eval_measures(host_golden['prf_targ'], host_golden['prf_pred'], threshold=0.4)
-    assert abs(d['f_measure'] - host_golden['prf'][2]) < 1e-12
 
 
 def test_hopsize_annotation_plan(host_golden):
@@ -52,11 +51,11 @@ def test_filter_tables_match_oracle_filterbank():
     fmin = Q.C1_HZ / 2 ** (2 / 72)
     lh, base = _harmonic_plan(5, 1)
     tabs = FB.build_tables(22050, 512, fmin, 36, 6, lh, base)
-    assert sorted(tabs) == [(0, 256)] + [(i, 512) for i in range(9)]
+    assert sorted(tabs) == [((0, 0), 256)] + [((0, i), 512) for i in range(9)]
     for ti in (0, 37, 50, 99):
         tun = FB.tuning_values()[ti]
         fb, n_fft, _ = Q.cqt_filter_fft(22050 / 4, fmin * 2 ** (tun / 36) * 0.5 * 2 ** (288 / 36) / 4, 36, 36)
-        t = tabs[(2, 512)]
+        t = tabs[((0, 2), 512)]
         for r in range(36):
             s = t['start'][ti, r]
             dense = np.zeros(257, np.complex64)
@@ -70,3 +69,81 @@ def test_filter_tables_match_oracle_filterbank():
             if code >= 0:
                 cover[code >> 16, code & 0xffff] += 1
     assert (cover == 1).all()
+
+
+def _resampy_table_walk(x, factor):
+    """The table-walking form of resampy's resample_f for sample_ratio = 1/factor (kaiser_fast: 16 zero crossings, 512 table
+    steps per crossing), written out literally as a second, independent statement of the decimator."""
+    import scipy.signal
+    num_zeros, precision, rolloff, beta = 16, 9, 0.85, 8.555504641634386
+    num_table = 2 ** precision
+    n_tab = num_table * num_zeros
+    sinc_win = rolloff * np.sinc(rolloff * np.linspace(0, num_zeros, num=n_tab + 1, endpoint=True))
+    interp_win = sinc_win * scipy.signal.windows.kaiser(2 * n_tab + 1, beta)[n_tab:]
+    ratio = 1.0 / factor
+    interp_win = interp_win * ratio
+    interp_delta = np.zeros_like(interp_win)
+    interp_delta[:-1] = np.diff(interp_win)
+    scale = min(1.0, ratio)
+    time_increment = 1.0 / ratio
+    index_step = int(scale * num_table)
+    n_orig, n_out = len(x), int(len(x) * ratio)
+    y = np.zeros(n_out, dtype=x.dtype)
+    nwin = len(interp_win)
+    time_register = 0.0
+    for t in range(n_out):
+        n = int(time_register)
+        frac = scale * (time_register - n)
+        index_frac = frac * num_table
+        offset = int(index_frac)
+        eta = index_frac - offset
+        i_max = min(n + 1, (nwin - offset) // index_step)
+        for i in range(i_max):
+            w = interp_win[offset + i * index_step] + eta * interp_delta[offset + i * index_step]
+            y[t] += w * x[n - i]
+        frac = scale - frac
+        index_frac = frac * num_table
+        offset = int(index_frac)
+        eta = index_frac - offset
+        k_max = min(n_orig - n - 1, (nwin - offset) // index_step)
+        for k in range(k_max):
+            w = interp_win[offset + k * index_step] + eta * interp_delta[offset + k * index_step]
+            y[t] += w * x[n + k + 1]
+        time_register += time_increment
+    return y
+
+
+@pytest.mark.parametrize('factor', [2, 4])
+def test_oracle_decimator_matches_table_walk(factor):
+    x = np.random.default_rng(factor).standard_normal(700 + factor + 1)
+    walk = _resampy_table_walk(x, factor) * np.sqrt(factor)
+    got = Q.resample_pow2(x, factor)
+    assert len(got) == -(-len(x) // factor) and len(walk) == len(x) // factor
+    assert np.abs(got[:len(walk)] - walk).max() < 1e-12
+    assert (got[len(walk):] == 0).all()
+
+
+def test_compute_hcqt_schedule_uses_early_downsampling_and_top_octave():
+    """compute_hcqt (hcqt.py:34-85) at the paper's 36 bins/octave: hop 448; the low harmonics trigger librosa's one-shot early
+    down-sampling, h = 5 its full-rate top octave; the product tables follow the oracle's schedule."""
+    from multipitch_architectures_b200.libdl.data_preprocessing import _filterbank as FB
+    fmin = Q.C1_HZ / 2 ** (2 / 72)
+    lh = [0.5, 1.0, 2.0, 3.0, 4.0, 5.0]
+    early = [FB.cqt_schedule(22050, 448, fmin * h, 216, 36)[0] for h in lh]
+    assert early == [1, 1, 0, 0, 0, 0]
+    assert FB.cqt_schedule(22050, 448, fmin * 5, 216, 36)[1][0][1] == 'top'
+    assert [FB.cqt_schedule(22050, 256, Q.C1_HZ / 2 ** (4 / 120) * h, 360, 60)[0] for h in (0.5, 1.0)] == [2, 1]
+    tabs = FB.build_tables(22050, 448, fmin, 36, 6, lh, lh)
+    cover = np.zeros((6, 216), int)
+    for t in tabs.values():
+        for code in t['dest'].ravel():
+            if code >= 0:
+                cover[code >> 16, code & 0xffff] += 1
+    assert (cover == 1).all()
+    assert np.array_equal(FB.kaiser_fast_half_taps(4), Q._kaiser_fast_half(4).astype(np.float32))
+    # frame counts follow the shortest octave response of the oracle's cqt
+    for n in (20000, 20000 + 447):
+        y = np.zeros(n, np.float32)
+        y[::5] = 1.0
+        C = Q.cqt(y, sr=22050, hop_length=448, fmin=fmin, n_bins=216, bins_per_octave=36)
+        assert C.shape[1] == FB.cqt_frames(22050, 448, fmin, 216, 36, n)

@@ -191,3 +191,60 @@ def test_oracle_sausnet_eval_matches_reference():
     with torch.no_grad():
         y = NO.unet_forward(sd, synth_patches(B, seed), pos_encoding='sinusoidal')
     assert np.abs(y.numpy() - g[tag + '__eval_y']).max() < 1e-5
+
+
+# ----------------------------------------------------------------------------- rows added after the first pass (ext_golden.npz)
+def test_compute_hcqt_oracle_matches_reference_wrapper_golden(ext_golden):
+    """compute_hcqt (hcqt.py:34-85) incl. early down-sampling (h = 1/2, 1) and the full-rate top octave (h = 5)."""
+    y = Q.synth_clip(3, seconds=2.0)
+    f, fs, hop = Q.compute_hcqt(y, fs=22050, fs_hcqt_target=50, bins_per_octave=36)
+    assert hop == 448 and fs == 22050 / 448 and f.shape == ext_golden['hcqt_std_2s'].shape
+    assert np.abs(f.astype(np.float32) - ext_golden['hcqt_std_2s']).max() < 1e-5
+    g, _, hop60 = Q.compute_hcqt(y[:22050])
+    assert hop60 == 256 and np.abs(g.astype(np.float32) - ext_golden['hcqt_std60_1s']).max() < 1e-5
+    # the early-down-sampled CQT agrees with the same bins of the shared-octave HCQT at the common frame times (hop 448 vs 512:
+    # frames 8k and 7k are both centred on sample 3584 k)
+    e, _, _ = Q.compute_efficient_hcqt(y, fs=22050, fs_hcqt_target=50, bins_per_octave=36)
+    for k in range(1, 10):
+        a, b = f[:, 8 * k, :], e[:, 7 * k, :]
+        assert np.abs(a - b)[:, 3:].max() < 1e-6 * b.max()       # h = 3, 4, 5: the same octave schedule in both variants
+        assert np.abs(a - b)[:, :3].max() < 1e-2 * b.max()       # h = 1/2, 1, 2: one decimation stage more / less (pass-band ripple)
+
+
+def test_eval_measures_oracle_matches_reference_golden(ext_golden):
+    targ, pred = ext_golden['ev_targ'].astype(np.float64), ext_golden['ev_pred'].astype(np.float64)
+    names = [str(n) for n in ext_golden['ev_names']]
+    for thr, key in ((0.4, 'ev_values_04'), (0.7, 'ev_values_07')):
+        for n, want in zip(names, ext_golden[key]):
+            if n in ('roc_auc_measure', 'average_precision_score'):
+                continue
+            assert abs(HO.eval_measure(targ, pred, n, thr) - want) < 1e-12, n
+
+
+def test_augmentation_oracle_matches_reference_golden(ext_golden):
+    """hcqt_datasets.py:77-139 with the reference's own random draws replayed: bit-exact except the log (numpy vs torch fp32 log)."""
+    inp, tg = ext_golden['aug_in'], ext_golden['aug_tg']
+    rows = [0, 37, 74]
+    for ci, i, alpha, beta, tune2, transp in ext_golden['aug_cases']:
+        tag = 'aug%d_%d' % (ci, i)
+        X0 = inp[:, i:i + 75, :][:, rows, :]
+        t = tg[:, :12] if ci == 2 else tg
+        y0 = t[i + 37][None, None, :]
+        get = lambda k: ext_golden[tag + k] if tag + k in ext_golden.files else None
+        X, y = HO.augment_item(X0, y0, 10.0, (alpha, beta) if alpha else None, int(tune2), int(transp), get('_noise'),
+                               get('_ftune'), get('_ftr'))
+        assert np.abs(X - ext_golden[tag + '_X']).max() < 1e-6, tag
+        assert np.array_equal(y, ext_golden[tag + '_y']), tag
+
+
+def test_mpe_scores_properties():
+    rng = np.random.default_rng(0)
+    targ = (rng.uniform(size=(50, 72)) < 0.05).astype(np.float64)
+    same = HO.mpe_scores(targ, targ, 0.5)
+    assert same['Precision'] == same['Recall'] == same['Accuracy'] == 1.0 and same['Total Error'] == 0.0
+    octave = np.roll(targ, 12, axis=1)
+    octave[:, :12] = 0
+    targ[:, 60:] = 0
+    s = HO.mpe_scores(targ, octave, 0.5)
+    assert s['Chroma Precision'] >= s['Precision'] and s['Chroma Total Error'] <= s['Total Error']
+    assert abs(s['Total Error'] - (s['Substitution Error'] + s['Miss Error'] + s['False Alarm Error'])) < 1e-12
