@@ -82,6 +82,17 @@ int mpa_augment_patches_f32(const float* in, const long long* start, float* out,
  * (hcqt_datasets.py:75,127-137).  targets [N][P] fp32, frame [n] centre frames, y [n][P]. */
 int mpa_augment_targets_f32(const float* targets, const long long* frame, const int* transp, float* y, int n, int P, void* stream);
 
+/* ---- BLUnet bottleneck: bidirectional LSTM over the time axis (unet_cnns.py:220-243, 1000-1101) -------------------
+ * One nn.LSTM layer, batch_first: x [B][T][I] -> out [B][T][D*H] (forward direction in [0,H), reverse in [H,2H)), zero initial state.
+ * w_ih [D][4H][I], w_hh [D][4H][H], b_ih, b_hh [D][4H] = weight_ih_l{k}(_reverse) ... stacked per direction; gate order i, f, g, o.
+ * workspace >= mpa_lstm_layer_workspace() bytes. */
+size_t mpa_lstm_layer_workspace(int B, int T, int H, int D);
+int mpa_lstm_layer_f32(const float* x, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, float* out, int B,
+                       int T, int I, int H, int D, void* workspace, size_t ws_bytes, void* stream);
+/* blstm_temporal_enc_layer's layout changes: x NCHW [B,C,T,F] <-> seq [B][T][C*F] (feature = c*F + f). */
+int mpa_lstm_seq_from_nchw_f32(const float* x, float* seq, int B, int C, int T, int F, void* stream);
+int mpa_lstm_seq_to_nchw_f32(const float* seq, float* x, int B, int C, int T, int F, void* stream);
+
 /* ---- evaluation measures (eval_metrics.py:8-110,158-189) --------------------------------------------------------
  * targ, pred [n_frames][n_bins] fp32 (device).  sums16 (device, 16 doubles) = sums over frames of the per-frame terms, float64 arithmetic:
  *  0 TP  1 #est (pred >= threshold)  2 #(targ > 0)  3 cosine of the L2-normalised frames (libfmp unit-vector fallback below 1e-10)

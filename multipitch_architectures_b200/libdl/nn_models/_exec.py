@@ -267,6 +267,11 @@ def unet_forward_tc(model, x):
     if hasattr(model, 'attention1'):
         t5 = model.attention2.run(model.attention1.run(ops.cp8_to_nchw(x5), fmt), fmt)
         x5 = ops.nchw_to_cp8(t5, pitch=geo[4][2], pf=LEVEL_PF, pt=1, fmt=fmt)
+    if getattr(model, 'lstm_depth', 0) > 0:
+        # BLUnet: BLSTM over time at the bottleneck (fp32 kernels; < 1 % of the model's FLOPs)
+        x5 = ops.nchw_to_cp8(model.lstm5.run(ops.cp8_to_nchw(x5)), pitch=geo[4][2], pf=LEVEL_PF, pt=1, fmt=fmt)
+    if getattr(model, 'lstm_depth', 0) > 1:
+        ops.nchw_to_cp8(model.lstm4.run(ops.cp8_to_nchw(skips[3])), out=skips[3], fmt=fmt)
     if hasattr(model, 'attention3'):
         # SAUSnet: the lowest skip connection passes two encoder layers too (x5 above was computed from the un-attended x4)
         t4 = model.attention4.run(model.attention3.run(ops.cp8_to_nchw(skips[3]), fmt), fmt)

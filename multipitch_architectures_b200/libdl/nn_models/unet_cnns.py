@@ -1,5 +1,5 @@
-"""Unet / SAUnet / SAUSnet / PUnet multi-pitch networks with the reference's constructor signatures and
-state_dict layout (/root/reference/libdl/nn_models/unet_cnns.py:30-159, 333-407, 496-575, 670-754,
+"""Unet / SAUnet / SAUSnet / PUnet / BLUnet multi-pitch networks with the reference's constructor signatures and
+state_dict layout (/root/reference/libdl/nn_models/unet_cnns.py:30-159, 220-243, 333-407, 496-575, 670-754, 1000-1101,
 2251-2335), executed by libmpa CUDA kernels (see _exec.py).  torch.nn layers are parameter holders only."""
 import ctypes
 
@@ -120,6 +120,42 @@ def _enc_run_tc(self, x, fmt, pe, w_qkv, b_qkv, w_proj, b_proj):
 
 
 transformer_enc_layer._run_tc = _enc_run_tc
+
+
+class blstm_temporal_enc_layer(nn.Module):
+    """BLSTM over the time axis of a U-Net level (unet_cnns.py:220-243): the (channel, bin) plane of every frame is one
+    input vector; `num_layers` stacked bidirectional nn.LSTM layers (parameter holder: `blstm`), zero initial state."""
+
+    def __init__(self, embed_dim=32, hidden_size=512, num_layers=1, batch_first=True, bidirectional=True):
+        super().__init__()
+        self.embed_dim, self.hidden_size, self.num_layers = embed_dim, hidden_size, num_layers
+        self.blstm = nn.LSTM(input_size=embed_dim, hidden_size=hidden_size, num_layers=num_layers, batch_first=True, bidirectional=True)
+        self._cache = _exec.ParamCache()
+
+    def run(self, x):
+        B, C, T, F = x.shape
+        H, I = self.hidden_size, C * F
+        if I != self.embed_dim:
+            raise RuntimeError(f'input.size(-1) must be equal to input_size. Expected {self.embed_dim}, got {I}')
+        c_out = self.embed_dim // F                      # embed_dim_scaled of the reference's .view
+        if 2 * H != c_out * F:
+            raise RuntimeError(f'shape [-1, {c_out}, {F}, {T}] is invalid for the BLSTM output of {2 * H} features per frame')
+        sp, dev = _lib.stream_ptr, x.device
+        seq = torch.empty(B, T, I, dtype=torch.float32, device=dev)
+        _lib.call('lstm_seq_from_nchw_f32', x, seq, B, C, T, F, sp())
+        ws_bytes = _lib.lib().mpa_lstm_layer_workspace(B, T, H, 2)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        for l in range(self.num_layers):
+            names = [f'{p}_l{l}{sfx}' for p in ('weight_ih', 'weight_hh', 'bias_ih', 'bias_hh') for sfx in ('', '_reverse')]
+            params = [getattr(self.blstm, n) for n in names]
+            w_ih, w_hh, b_ih, b_hh = self._cache.get(f'l{l}', params, lambda: tuple(
+                torch.stack([params[2 * i].detach().float(), params[2 * i + 1].detach().float()]).contiguous() for i in range(4)))
+            out = torch.empty(B, T, 2 * H, dtype=torch.float32, device=dev)
+            _lib.call('lstm_layer_f32', seq, w_ih, w_hh, b_ih, b_hh, out, B, T, seq.shape[2], H, 2, ws, _lib.usize(ws_bytes), sp())
+            seq = out
+        y = torch.empty(B, c_out, T, F, dtype=torch.float32, device=dev)
+        _lib.call('lstm_seq_to_nchw_f32', seq, y, B, c_out, T, F, sp())
+        return y
 
 
 def _down(cin, cout, k, **kw):
@@ -263,3 +299,35 @@ class simple_u_net_polyphony_classif_softmax(_UnetBase):
         p = ops.maxpool2d(p, (2, 5), (1, 2))
         n_pred = _exec.conv_f32(self._cache, 'convP.4', self.convP[4], p)
         return y, n_pred
+
+
+class u_net_blstm_varlayers(_UnetBase):
+    """BLUnet (unet_cnns.py:1000-1101; experiments exp186b/d/e): the large-kernel U-Net with `lstm_number` stacked BLSTM layers over
+    time at the bottleneck (lstm_depth 1) and, for lstm_depth > 1, on the skip connections from the bottom up.  Inference only
+    (the BLSTM has no hand-written backward yet)."""
+
+    def __init__(self, n_chan_input=6, n_chan_layers=[64, 30, 20, 10], n_bins_in=216, n_bins_out=12, a_lrelu=0.3, p_dropout=0.2,
+                 scalefac=8, embed_dim=4 * 16, hidden_size=512, lstm_depth=0, lstm_number=2, precision='fp32'):
+        super().__init__()
+        self._init_common(n_chan_input, n_bins_in, a_lrelu, p_dropout, precision)
+        self.lstm_depth, self.lstm_number = lstm_depth, lstm_number
+        self.layernorm = nn.LayerNorm(normalized_shape=[n_chan_input, n_bins_in])
+        self._build_trunk(n_chan_input, n_chan_layers, scalefac)
+        for depth, name in enumerate(('lstm5', 'lstm4', 'lstm3', 'lstm2', 'lstm1')):
+            if lstm_depth > depth:
+                setattr(self, name, blstm_temporal_enc_layer(embed_dim=embed_dim, hidden_size=hidden_size, num_layers=lstm_number))
+        self._build_up(n_chan_layers, scalefac)
+        _head(self, n_chan_layers[0], n_chan_layers, n_bins_in, n_bins_out, a_lrelu, p_dropout)
+
+    def _bottleneck(self, x5):
+        return self.lstm5.run(x5) if self.lstm_depth > 0 else x5
+
+    def _skip4(self, x4):
+        return self.lstm4.run(x4) if self.lstm_depth > 1 else x4
+
+    def forward(self, x):
+        if self.training:
+            raise NotImplementedError('u_net_blstm_varlayers: only the eval-mode forward is implemented (no BLSTM backward kernels)')
+        if self.lstm_depth > 2:
+            raise NotImplementedError('BLSTM layers on the upper skip connections (lstm_depth > 2) are not used by any experiment')
+        return self._run(x)[0]

@@ -19,6 +19,7 @@ Reference sites restated here (all relative to /root/reference):
   * bilinear x2 upsample + pad + concat ......... libdl/nn_models/unet_cnns.py:85-104
   * transformer_enc_layer (batch-axis MHA) ...... libdl/nn_models/unet_cnns.py:107-159
   * Unet / SAUnet / SAUSnet / PUnet forward ..... libdl/nn_models/unet_cnns.py:333-407, 496-575, 670-754, 2251-2335
+  * blstm_temporal_enc_layer / BLUnet forward ... libdl/nn_models/unet_cnns.py:220-243, 1000-1101
   * BCELoss(mean) with -100 log clamp ........... experiments/Exp1_SectionIV-B/exp126a_musicnet_cnn_basic.py:87
 """
 import math
@@ -171,6 +172,31 @@ def encoder_layer(x, sd, pre, num_heads, use_pe):
     return h2.transpose(1, 2).reshape(B, E, Th, Fw)
 
 
+def blstm_layer(x, sd, pre):
+    """blstm_temporal_enc_layer: stacked bidirectional LSTM over time, written out gate by gate (PyTorch order i, f, g, o)."""
+    B, C, T, Fw = x.shape
+    seq = x.permute(0, 2, 1, 3).reshape(B, T, C * Fw)            # [B,T,(c,f)]
+    layer = 0
+    while f'{pre}.blstm.weight_ih_l{layer}' in sd:
+        outs = []
+        for sfx in ('', '_reverse'):
+            w_ih, w_hh = sd[f'{pre}.blstm.weight_ih_l{layer}{sfx}'], sd[f'{pre}.blstm.weight_hh_l{layer}{sfx}']
+            b = sd[f'{pre}.blstm.bias_ih_l{layer}{sfx}'] + sd[f'{pre}.blstm.bias_hh_l{layer}{sfx}']
+            H = w_hh.shape[1]
+            h, c = torch.zeros(B, H), torch.zeros(B, H)
+            hs = [None] * T
+            for t in (range(T) if sfx == '' else range(T - 1, -1, -1)):
+                g = seq[:, t] @ w_ih.T + h @ w_hh.T + b
+                i, f, gg, o = torch.sigmoid(g[:, :H]), torch.sigmoid(g[:, H:2 * H]), torch.tanh(g[:, 2 * H:3 * H]), torch.sigmoid(g[:, 3 * H:])
+                c = f * c + i * gg
+                h = o * torch.tanh(c)
+                hs[t] = h
+            outs.append(torch.stack(hs, 1))
+        seq = torch.cat(outs, 2)                                 # [B,T,2H]
+        layer += 1
+    return seq.reshape(B, T, -1, Fw).permute(0, 2, 1, 3).contiguous()
+
+
 def unet_forward(sd, x, a_lrelu=0.3, train=False, num_heads=8, pos_encoding=None):
     """simple_u_net_largekernels / _doubleselfattn / _polyphony_classif_softmax.
     Returns y_pred, or (y_pred, n_pred) when the state_dict holds the convP head."""
@@ -180,6 +206,10 @@ def unet_forward(sd, x, a_lrelu=0.3, train=False, num_heads=8, pos_encoding=None
     x3 = double_conv(maxpool2x2(x2), sd, 'down2.1', train)
     x4 = double_conv(maxpool2x2(x3), sd, 'down3.1', train)
     x5 = double_conv(maxpool2x2(x4), sd, 'down4.1', train)
+    if 'lstm5.blstm.weight_ih_l0' in sd:                         # BLUnet (unet_cnns.py:1083-1086)
+        x5 = blstm_layer(x5, sd, 'lstm5')
+    if 'lstm4.blstm.weight_ih_l0' in sd:
+        x4 = blstm_layer(x4, sd, 'lstm4')
     if 'attention1.q_linear.weight' in sd:
         x5 = encoder_layer(x5, sd, 'attention1', num_heads, pos_encoding == 'sinusoidal')
         x5 = encoder_layer(x5, sd, 'attention2', num_heads, False)

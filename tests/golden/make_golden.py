@@ -367,6 +367,17 @@ def ext_goldens():
             if fill_tr is not None:
                 out[tag + '_ftr'] = fill_tr.astype(np.float32)[:, AUG_ROWS, :]
             cases.append((ci, i, alpha, beta, tune2, transp))
+    # BLUnet (u_net_blstm_varlayers, exp186b/d/e): eval-mode outputs of the reference class
+    for name, B, seed, scheme in (('blunet_tiny', 3, 41, 'adversarial'), ('blunet_d', 2, 42, 'torch_default')):
+        m = build_reference_model(name)
+        sd = fill_state_dict(m.state_dict(), seed, scheme=scheme)
+        m.load_state_dict(sd)
+        m.eval()
+        with torch.no_grad():
+            yb = m(synth_patches(B, seed))
+        out[name + '__y'] = yb.numpy()
+        out[name + '__meta'] = np.array([B, seed, float(sum(v.double().sum() for v in sd.values())), sum(p.numel() for p in m.parameters())])
+        print(name, 'params', int(out[name + '__meta'][3]), 'y', out[name + '__y'].reshape(-1)[:3])
     out['aug_cases'] = np.array(cases, dtype=np.int64)
     assert set(c[4] for c in cases) == {-2, -1, 0, 1, 2}, sorted(set(c[4] for c in cases))
     assert any(c[5] > 0 for c in cases) and any(c[5] < 0 for c in cases)

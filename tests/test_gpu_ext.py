@@ -293,3 +293,46 @@ def test_evaluate_file_and_results_csv(tmp_path):
     assert [l[1] for l in lines[1:]] == ['f0_hcqt.npy', 'f1_hcqt.npy', 'FILEWISE MEAN', 'FRAMEWISE MEAN']
     fm = (60 * rows[0]['cosine_sim'] + 45 * rows[1]['cosine_sim']) / 105
     assert abs(float(lines[4][2 + 3]) - fm) < 1e-12 and abs(table[2][1 + 3] - (rows[0]['cosine_sim'] + rows[1]['cosine_sim']) / 2) < 1e-12
+
+
+# ----------------------------------------------------------------------------- BLUnet
+@pytest.mark.parametrize('B,T,I,H', [(5, 4, 416, 208), (50, 4, 832, 416), (3, 9, 40, 12), (33, 1, 64, 32)])
+def test_lstm_layer_matches_oracle(B, T, I, H):
+    from multipitch_architectures_b200 import _lib
+    from oracle import nn_oracle as NO
+    rng = np.random.default_rng(B * 1000 + T)
+    sd = {}
+    for sfx in ('', '_reverse'):
+        sd['l.blstm.weight_ih_l0' + sfx] = torch.from_numpy((rng.uniform(-1, 1, size=(4 * H, I)) / np.sqrt(H)).astype(np.float32))
+        sd['l.blstm.weight_hh_l0' + sfx] = torch.from_numpy((rng.uniform(-1, 1, size=(4 * H, H)) / np.sqrt(H)).astype(np.float32))
+        sd['l.blstm.bias_ih_l0' + sfx] = torch.from_numpy((rng.uniform(-1, 1, size=4 * H) / np.sqrt(H)).astype(np.float32))
+        sd['l.blstm.bias_hh_l0' + sfx] = torch.from_numpy((rng.uniform(-1, 1, size=4 * H) / np.sqrt(H)).astype(np.float32))
+    x = torch.from_numpy(rng.standard_normal((B, T, I)).astype(np.float32))
+    # the oracle takes NCHW [B, C, T, F] with features (c, f): use C = I, F = 1
+    ref = NO.blstm_layer(x.permute(0, 2, 1)[:, :, :, None].contiguous(), sd, 'l')          # [B, 2H, T, 1]
+    ref = ref[:, :, :, 0].permute(0, 2, 1)
+    st = lambda k: torch.stack([sd[f'l.blstm.{k}_l0'], sd[f'l.blstm.{k}_l0_reverse']]).contiguous().cuda()
+    out = torch.empty(B, T, 2 * H, dtype=torch.float32, device='cuda')
+    ws_bytes = _lib.lib().mpa_lstm_layer_workspace(B, T, H, 2)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device='cuda')
+    _lib.call('lstm_layer_f32', x.cuda(), st('weight_ih'), st('weight_hh'), st('bias_ih'), st('bias_hh'), out, B, T, I, H, 2, ws,
+              _lib.usize(ws_bytes), _lib.stream_ptr())
+    assert np.abs(out.cpu().numpy() - ref.numpy()).max() < 2e-5
+
+
+@pytest.mark.parametrize('name,B,seed,scheme,prec,tol', [
+    ('blunet_tiny', 3, 41, 'adversarial', 'fp32', 1e-3), ('blunet_d', 2, 42, 'torch_default', 'fp32', 1e-3),
+    ('blunet_d', 2, 42, 'torch_default', 'fp16', 1e-3), ('blunet_tiny', 3, 41, 'adversarial', 'fp16', 2e-2)])
+def test_blunet_matches_reference_golden(ext_golden, name, B, seed, scheme, prec, tol):
+    from tests.refshapes import build_model
+    from tests.weights import fill_state_dict, synth_patches
+    m = build_model(name, precision=prec)
+    m.load_state_dict(fill_state_dict(m.state_dict(), seed, scheme=scheme))
+    m = m.cuda().eval()
+    with torch.no_grad():
+        y = m(synth_patches(B, seed).cuda())
+    err = np.abs(y.cpu().numpy() - ext_golden[name + '__y']).max()
+    print(f'{name} {prec}: max|diff| vs reference = {err:.2e}')
+    assert y.shape == (B, 1, 1, 72) and err < tol
+    with pytest.raises(NotImplementedError):
+        m.train()(synth_patches(B, seed).cuda())

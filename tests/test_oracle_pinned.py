@@ -248,3 +248,22 @@ def test_mpe_scores_properties():
     s = HO.mpe_scores(targ, octave, 0.5)
     assert s['Chroma Precision'] >= s['Precision'] and s['Chroma Total Error'] <= s['Total Error']
     assert abs(s['Total Error'] - (s['Substitution Error'] + s['Miss Error'] + s['False Alarm Error'])) < 1e-12
+
+
+@pytest.mark.parametrize('name,B,seed,scheme', [('blunet_tiny', 3, 41, 'adversarial'), ('blunet_d', 2, 42, 'torch_default')])
+def test_blunet_oracle_matches_reference_golden(ext_golden, name, B, seed, scheme):
+    """u_net_blstm_varlayers (unet_cnns.py:1000-1101): state_dict layout, parameter count (exp186d log: 9,649,003) and eval output."""
+    import torch
+    from oracle import nn_oracle as NO
+    from tests.refshapes import build_model
+    from tests.weights import fill_state_dict, synth_patches
+    m = build_model(name)
+    sd = fill_state_dict(m.state_dict(), seed, scheme=scheme)
+    meta = ext_golden[name + '__meta']
+    assert abs(float(sum(v.double().sum() for v in sd.values())) - meta[2]) < 1e-6        # same keys, shapes and order as the reference
+    assert sum(p.numel() for p in m.parameters()) == int(meta[3])
+    if name == 'blunet_d':
+        assert int(meta[3]) == 9649003
+    with torch.no_grad():
+        y = NO.unet_forward(sd, synth_patches(B, seed))
+    assert np.abs(y.numpy() - ext_golden[name + '__y']).max() < 1e-5
