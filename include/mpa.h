@@ -82,6 +82,14 @@ int mpa_augment_patches_f32(const float* in, const long long* start, float* out,
  * (hcqt_datasets.py:75,127-137).  targets [N][P] fp32, frame [n] centre frames, y [n][P]. */
 int mpa_augment_targets_f32(const float* targets, const long long* frame, const int* transp, float* y, int n, int P, void* stream);
 
+/* ---- full-height VALID convolution = the head's 75x1 "time reduction" conv3 (basic_cnns.py:396-401) as GEMMs -----------------------
+ * H == KH, KW == 1, one output row: Y[co][(b,w)] = sum_(ci,h) w[co][ci][h] * x[b][ci][h][w].  x [B][Cin][H][W], w [Cout][Cin][H][1]
+ * (state_dict layout), out / g_out [B][Cout][1][W].  Forward fuses bias + activation; wgrad overwrites g_w (split-K, fp32 atomics). */
+int mpa_conv_rows_fwd_f32(const float* x, const float* w, const float* bias, float* out, int B, int Cin, int H, int W, int Cout, int act,
+                          float act_param, void* stream);
+int mpa_conv_rows_dgrad_f32(const float* g_out, const float* w, float* g_in, int B, int Cin, int H, int W, int Cout, void* stream);
+int mpa_conv_rows_wgrad_f32(const float* x, const float* g_out, float* g_w, int B, int Cin, int H, int W, int Cout, void* stream);
+
 /* ---- BLUnet bottleneck: bidirectional LSTM over the time axis (unet_cnns.py:220-243, 1000-1101) -------------------
  * One nn.LSTM layer, batch_first: x [B][T][I] -> out [B][T][D*H] (forward direction in [0,H), reverse in [H,2H)), zero initial state.
  * w_ih [D][4H][I], w_hh [D][4H][H], b_ih, b_hh [D][4H] = weight_ih_l{k}(_reverse) ... stacked per direction; gate order i, f, g, o.

@@ -9,6 +9,7 @@ import math
 import torch
 
 from ... import ops
+from ... import _lib
 from ..._lib import MpaError
 
 PRECISIONS = ('fp32', 'fp16', 'bf16')     # fp16 / bf16: tcgen05 tensor-core path (16-bit operands, fp32 accumulate)
@@ -45,8 +46,14 @@ def conv_f32(cache, name, conv, x, act=ops.ACT_NONE, act_param=0.0, bn=None, bn_
     """nn.Conv2d (+ BatchNorm2d + activation) through mpa_conv2d_f32."""
     w = conv.weight
     Cout, Cin, KH, KW = w.shape
-    wp = cache.get(name + ':w32', [w], lambda: ops.pack_conv_weight(w))
     stride, padding = tuple(conv.stride), tuple(conv.padding)
+    if bn is None and x2 is None and (KH, KW) == (x.shape[2], 1) and stride == (1, 1) and padding == (0, 0):
+        # full-height VALID convolution (conv3 on a 75-frame patch): GEMM kernel instead of 16-row output tiles
+        B, _, H, W = x.shape
+        out = torch.empty(B, Cout, 1, W, dtype=torch.float32, device=x.device)
+        _lib.call('conv_rows_fwd_f32', x, w.detach().contiguous(), conv.bias, out, B, Cin, H, W, Cout, act, float(act_param), _lib.stream_ptr())
+        return out
+    wp = cache.get(name + ':w32', [w], lambda: ops.pack_conv_weight(w))
     if bn is None:
         return ops.conv2d(x, wp, conv.bias, Cout, (KH, KW), stride, padding, act, act_param, x2=x2)
     if not bn_train:

@@ -31,8 +31,19 @@ def ctypes_u64(v):
     return ctypes.c_ulonglong(int(v) & 0xFFFFFFFFFFFFFFFF)
 
 
+def _is_rows_conv(conv, H):
+    """Full-height VALID convolution with one output row (conv3, 75x1 on a 75-frame patch): served by the GEMM kernels of conv_rows.cu."""
+    return (tuple(conv.kernel_size) == (H, 1) and tuple(conv.stride) == (1, 1) and tuple(conv.padding) == (0, 0)
+            and tuple(conv.dilation) == (1, 1))
+
+
 def _conv_fwd(conv, x, act, a):
     w = conv.weight
+    if _is_rows_conv(conv, x.shape[2]):
+        B, Cin, H, W = x.shape
+        out = torch.empty(B, w.shape[0], 1, W, dtype=torch.float32, device=x.device)
+        call('conv_rows_fwd_f32', x, w.detach().contiguous(), conv.bias, out, B, Cin, H, W, w.shape[0], act, float(a), stream_ptr())
+        return out
     wp = ops.pack_conv_weight(w)
     return ops.conv2d(x, wp, conv.bias, w.shape[0], tuple(w.shape[2:]), tuple(conv.stride), tuple(conv.padding), act, a)
 
@@ -47,6 +58,9 @@ def _dgrad(conv, g, in_shape):
         wt = ops.pack_conv_weight(w.detach().permute(1, 0, 2, 3).flip(2, 3).contiguous())
         return ops.conv2d(g, wt, None, Cin, (KH, KW), (1, 1), (KH - 1 - conv.padding[0], KW - 1 - conv.padding[1]))
     gi = torch.empty(in_shape, dtype=torch.float32, device=g.device)
+    if _is_rows_conv(conv, H):
+        call('conv_rows_dgrad_f32', g, w.detach().contiguous(), gi, B, Cin, H, W, Cout, stream_ptr())
+        return gi
     call('conv2d_dgrad_f32', g, w.detach().contiguous(), gi, B, Cin, H, W, Cout, KH, KW, conv.stride[0], conv.stride[1],
          conv.padding[0], conv.padding[1], stream_ptr())
     return gi
@@ -55,6 +69,10 @@ def _dgrad(conv, g, in_shape):
 def _wgrad(conv, x, g, gw, gb):
     Cout, Cin, KH, KW = conv.weight.shape
     B, _, H, W = x.shape
+    if _is_rows_conv(conv, H):
+        call('conv_rows_wgrad_f32', x, g, gw, B, Cin, H, W, Cout, stream_ptr())
+        ops.channel_sum(g, out=gb)
+        return
     call('conv2d_wgrad_f32', x, g, gw, gb, B, Cin, H, W, Cout, KH, KW, conv.stride[0], conv.stride[1], conv.padding[0],
          conv.padding[1], stream_ptr())
 

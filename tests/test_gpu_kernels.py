@@ -215,3 +215,29 @@ def test_encoder_layer(ops):
         got = m.attention1.run(x5.cuda()).cpu()
         ref = NO.encoder_layer(x5, sd, 'attention1', 8, True)
     assert (got - ref).abs().max() < 5e-5
+
+
+@pytest.mark.parametrize('B,Cin,H,W,Cout', [(25, 80, 75, 72, 50), (256, 20, 75, 72, 10), (3, 7, 75, 72, 5), (2, 100, 9, 13, 80)])
+def test_conv_rows_gemm_kernels_match_torch(B, Cin, H, W, Cout):
+    """conv3 (75x1 VALID, one output row) forward / data gradient / weight gradient as GEMMs vs torch fp32 conv2d + autograd."""
+    import torch.nn.functional as F
+    from multipitch_architectures_b200 import _lib
+    g = torch.Generator().manual_seed(B * 7 + Cin)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, H, 1, generator=g) / (Cin * H) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    gy = torch.randn(B, Cout, 1, W, generator=g)
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    pre = F.conv2d(xr, wr, b)
+    pre.backward(gy)
+    ref = torch.where(pre >= 0, pre, 0.3 * pre).detach()
+    xc, wc, bc, gc = x.cuda(), w.cuda(), b.cuda(), gy.cuda()
+    out = torch.empty(B, Cout, 1, W, device='cuda')
+    _lib.call('conv_rows_fwd_f32', xc, wc, bc, out, B, Cin, H, W, Cout, 1, 0.3, _lib.stream_ptr())
+    assert (out.cpu() - ref).abs().max() < 2e-5
+    gi = torch.empty_like(xc)
+    _lib.call('conv_rows_dgrad_f32', gc, wc, gi, B, Cin, H, W, Cout, _lib.stream_ptr())
+    assert (gi.cpu() - xr.grad).abs().max() < 2e-5
+    gw = torch.full_like(wc, 7.0)           # must be overwritten, not accumulated
+    _lib.call('conv_rows_wgrad_f32', xc, gc, gw, B, Cin, H, W, Cout, _lib.stream_ptr())
+    assert (gw.cpu() - wr.grad).abs().max() < 2e-4 * max(1.0, wr.grad.abs().max().item())
