@@ -296,6 +296,10 @@ int mpa_maxpool_time_bwd_f32(const float* a, const float* g_pool, float* g_a, in
 /* nn.Dropout(p) in training mode with a Philox-4x32-10 stream: element i uses counter (i/4, offset), key seed. */
 int mpa_dropout_f32(const float* x, float* out, long long n, float p, unsigned long long seed,
                     unsigned long long offset, void* stream);
+/* Same with offset = step_dev[0] * step_mul + site, the step counter read from DEVICE memory: a training step captured in a CUDA graph
+ * (UnetTrainStep(graph=True)) then draws fresh masks on every replay, identical to the eager step of the same number. */
+int mpa_dropout_dev_f32(const float* x, float* out, long long n, float p, unsigned long long seed, unsigned long long site,
+                        const long long* step_dev, unsigned long long step_mul, void* stream);
 /* Conv2d data gradient, any stride (gather form); w in state_dict layout [Cout][Cin][KH][KW]. */
 int mpa_conv2d_dgrad_f32(const float* g_out, const float* w, float* g_in, int B, int Cin, int H, int W, int Cout,
                          int KH, int KW, int sh, int sw, int ph, int pw, void* stream);

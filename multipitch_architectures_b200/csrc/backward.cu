@@ -76,9 +76,69 @@ __global__ void __launch_bounds__(kPoolBwdCols * kPoolBwdRowGroups) maxpool_time
   }
 }
 
+// Same result without shared memory or atomics for the two window lengths the models use (3 and 13): one thread owns one column and walks
+// down the T rows with the window's k activations and the k pending gradient sums in registers; row t-h is final once window t is done.
+// Loads / stores are coalesced across the threads of a row; HBM-bound (reads a and g_p once, writes g_a once).
+template <int K>
+__global__ void __launch_bounds__(128) maxpool_time_bwd_col_kernel(const float* __restrict__ a, const float* __restrict__ g_p, float* __restrict__ g_a,
+                                                                   int T, int F, int act, float act_param) {
+  constexpr int H = K / 2;
+  const int f = blockIdx.y * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  const size_t base = (size_t)blockIdx.x * T * F + f;
+  const float* ap = a + base;
+  const float* gp = g_p + base;
+  float* op = g_a + base;
+  float win[K], acc[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    const int r = j - H;
+    win[j] = (r >= 0 && r < T) ? ap[(size_t)r * F] : -INFINITY;
+    acc[j] = 0.f;
+  }
+  for (int t = 0; t < T; ++t) {
+    const float g = gp[(size_t)t * F];
+    int am = 0;
+    float best = win[0];
+#pragma unroll
+    for (int j = 1; j < K; ++j)
+      if (win[j] > best) { best = win[j]; am = j; }        // strict: the first maximum of the window wins (ATen semantics)
+#pragma unroll
+    for (int j = 0; j < K; ++j) acc[j] += (j == am) ? g : 0.f;
+    if (t - H >= 0) {
+      float d = 1.f;
+      if (act == MPA_ACT_LRELU) d = win[0] >= 0.f ? 1.f : act_param;
+      else if (act == MPA_ACT_RELU) d = win[0] > 0.f ? 1.f : 0.f;
+      op[(size_t)(t - H) * F] = acc[0] * d;
+    }
+#pragma unroll
+    for (int j = 0; j < K - 1; ++j) {
+      win[j] = win[j + 1];
+      acc[j] = acc[j + 1];
+    }
+    const int r = t + H + 1;
+    win[K - 1] = r < T ? ap[(size_t)r * F] : -INFINITY;
+    acc[K - 1] = 0.f;
+  }
+  // rows T-H .. T-1 are now win[0..H-1]
+#pragma unroll
+  for (int j = 0; j < H; ++j) {
+    const int r = T - H + j;
+    if (r >= 0) {
+      float d = 1.f;
+      if (act == MPA_ACT_LRELU) d = win[j] >= 0.f ? 1.f : act_param;
+      else if (act == MPA_ACT_RELU) d = win[j] > 0.f ? 1.f : 0.f;
+      op[(size_t)r * F] = acc[j] * d;
+    }
+  }
+}
+
 // Philox-4x32-10 counter-based dropout (philox() in common.cuh): element i of call `offset` under `seed`
+// step_dev != nullptr: offset = step_dev[0] * step_mul + offset (the step counter lives in device memory so that a captured CUDA graph of
+// the training step draws fresh masks on every replay)
 __global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ out, long long n, float p, unsigned long long seed,
-                               unsigned long long offset) {
+                               unsigned long long offset, const long long* __restrict__ step_dev, unsigned long long step_mul) {
+  if (step_dev) offset += (unsigned long long)step_dev[0] * step_mul;
   const float scale = 1.f / (1.f - p);
   for (long long i4 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i4 * 4 < n; i4 += (long long)gridDim.x * blockDim.x) {
     const uint4 r = philox(make_uint4((uint32_t)i4, (uint32_t)(i4 >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)),
@@ -204,7 +264,10 @@ __global__ void __launch_bounds__(128) layernorm_cf_param_grad_kernel(const floa
   float aw[MAXV], ab[MAXV];
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) aw[i] = ab[i] = 0.f;
-  for (int t = 0; t < T; ++t) {
+  // gridDim.y time slices per item (parallelism for small batches); the slices meet in the atomics below
+  const int t_per = (T + (int)gridDim.y - 1) / (int)gridDim.y;
+  const int t_begin = blockIdx.y * t_per, t_end = min(T, t_begin + t_per);
+  for (int t = t_begin; t < t_end; ++t) {
     const float* xr = x + ((size_t)b * C * T + t) * F;
     const float* gr = g + ((size_t)b * C * T + t) * F;
     float v[MAXV];
@@ -305,6 +368,13 @@ int mpa_maxpool_time_bwd_f32(const float* a, const float* g_pool, float* g_a, in
                              void* stream) {
   MPA_CHECK_ARCH();
   MPA_REQUIRE(a && g_pool && g_a && B > 0 && C > 0 && T > 0 && F > 0 && k >= 1 && (k & 1), "maxpool_time_bwd: bad argument");
+  if ((k == 3 || k == 13) && T > k / 2) {
+    const dim3 grid(B * C, ceil_div(F, 128));
+    if (k == 3) maxpool_time_bwd_col_kernel<3><<<grid, 128, 0, (cudaStream_t)stream>>>(a, g_pool, g_a, T, F, act, act_param);
+    else maxpool_time_bwd_col_kernel<13><<<grid, 128, 0, (cudaStream_t)stream>>>(a, g_pool, g_a, T, F, act, act_param);
+    MPA_CHECK_LAUNCH("maxpool_time_bwd_col");
+    return MPA_OK;
+  }
   const size_t smem = 2 * (size_t)T * kPoolBwdCols * sizeof(float);
   MPA_REQUIRE(smem <= 160 * 1024, "maxpool_time_bwd: T = %d too long for the column tile", T);
   if (smem > 48 * 1024) cudaFuncSetAttribute(maxpool_time_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -316,7 +386,16 @@ int mpa_maxpool_time_bwd_f32(const float* a, const float* g_pool, float* g_a, in
 int mpa_dropout_f32(const float* x, float* out, long long n, float p, unsigned long long seed, unsigned long long offset, void* stream) {
   MPA_CHECK_ARCH();
   MPA_REQUIRE(x && out && n > 0 && p >= 0.f && p < 1.f, "dropout: bad argument");
-  dropout_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, out, n, p, seed, offset);
+  dropout_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, out, n, p, seed, offset, nullptr, 0);
+  MPA_CHECK_LAUNCH("dropout");
+  return MPA_OK;
+}
+
+int mpa_dropout_dev_f32(const float* x, float* out, long long n, float p, unsigned long long seed, unsigned long long site,
+                        const long long* step_dev, unsigned long long step_mul, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(x && out && step_dev && n > 0 && p >= 0.f && p < 1.f, "dropout_dev: bad argument");
+  dropout_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, out, n, p, seed, site, step_dev, step_mul);
   MPA_CHECK_LAUNCH("dropout");
   return MPA_OK;
 }
@@ -377,7 +456,9 @@ int mpa_layernorm_cf_param_grad_f32(const float* x, const float* g_out, float* g
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(g_w, 0, sizeof(float) * (size_t)C * F, st);
   cudaMemsetAsync(g_b, 0, sizeof(float) * (size_t)C * F, st);
-  layernorm_cf_param_grad_kernel<11><<<B, 128, 0, st>>>(x, g_out, g_w, g_b, C, T, F, eps, gamma_log);
+  int slices = ceil_div(148 * 8, B);
+  slices = slices < 1 ? 1 : (slices > T ? T : slices);
+  layernorm_cf_param_grad_kernel<11><<<dim3(B, slices), 128, 0, st>>>(x, g_out, g_w, g_b, C, T, F, eps, gamma_log);
   MPA_CHECK_LAUNCH("layernorm_cf_param_grad");
   return MPA_OK;
 }

@@ -250,9 +250,12 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const float* __restrict__ u
   }
 }
 
-// batch-axis attention backward; one block per (s, head).  qkv [(b*S+s)][3E], g_o [(b*S+s)][E] -> g_qkv
-__global__ void __launch_bounds__(64) batch_axis_attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ g_o,
-                                                                      float* __restrict__ g_qkv, int B, int S, int E, int H) {
+// batch-axis attention backward; one block per (s, head).  qkv [(b*S+s)][3E], g_o [(b*S+s)][E] -> g_qkv.
+// The B x B score matrix of one (token position, head) lives in shared memory; every stage is a data-parallel pass over (b1, b2) pairs or
+// (b, k) outputs with a fixed summation order — no atomics, bit-reproducible:
+//   P = softmax_b2(Q K^T / sqrt(hd));  dP = dO V^T;  dS = P * (dP - rowsum(P * dP)) / sqrt(hd);  dQ = dS K;  dK = dS^T Q;  dV = P^T dO.
+__global__ void __launch_bounds__(256) batch_axis_attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ g_o,
+                                                                       float* __restrict__ g_qkv, int B, int S, int E, int H) {
   extern __shared__ float sm[];
   const int hd = E / H;
   const int s = blockIdx.x / H, h = blockIdx.x % H;
@@ -260,30 +263,34 @@ __global__ void __launch_bounds__(64) batch_axis_attention_bwd_kernel(const floa
   float* Km = Q + (size_t)B * hd;
   float* V = Km + (size_t)B * hd;
   float* dO = V + (size_t)B * hd;
-  float* P = dO + (size_t)B * hd;      // [B][B] probabilities, then dS
-  float* dQ = P + (size_t)B * B;
-  float* dK = dQ + (size_t)B * hd;
-  float* dV = dK + (size_t)B * hd;
-  for (int e = threadIdx.x; e < B * hd; e += blockDim.x) {
+  float* P = dO + (size_t)B * hd;      // [B][B] probabilities
+  float* dS = P + (size_t)B * B;       // [B][B] dP, then dS
+  float* rowv = dS + (size_t)B * B;    // [B]
+  const int nt = blockDim.x;
+  for (int e = threadIdx.x; e < B * hd; e += nt) {
     const int b = e / hd, d = e - b * hd;
     const float* row = qkv + ((size_t)b * S + s) * 3 * E + h * hd + d;
     Q[e] = row[0];
     Km[e] = row[E];
     V[e] = row[2 * E];
     dO[e] = g_o[((size_t)b * S + s) * E + h * hd + d];
-    dK[e] = 0.f;
-    dV[e] = 0.f;
   }
   __syncthreads();
   const float sc = rsqrtf((float)hd);
-  for (int b1 = threadIdx.x; b1 < B; b1 += blockDim.x) {
-    float mx = -INFINITY;
-    for (int b2 = 0; b2 < B; ++b2) {
-      float d = 0.f;
-      for (int k = 0; k < hd; ++k) d = fmaf(Q[b1 * hd + k], Km[b2 * hd + k], d);
-      P[b1 * B + b2] = d * sc;
-      mx = fmaxf(mx, d * sc);
+  for (int e = threadIdx.x; e < B * B; e += nt) {
+    const int b1 = e / B, b2 = e - b1 * B;
+    float d = 0.f, dp = 0.f;
+    for (int k = 0; k < hd; ++k) {
+      d = fmaf(Q[b1 * hd + k], Km[b2 * hd + k], d);
+      dp = fmaf(dO[b1 * hd + k], V[b2 * hd + k], dp);
     }
+    P[e] = d * sc;
+    dS[e] = dp;
+  }
+  __syncthreads();
+  for (int b1 = threadIdx.x; b1 < B; b1 += nt) {
+    float mx = -INFINITY;
+    for (int b2 = 0; b2 < B; ++b2) mx = fmaxf(mx, P[b1 * B + b2]);
     float den = 0.f;
     for (int b2 = 0; b2 < B; ++b2) {
       const float pr = expf(P[b1 * B + b2] - mx);
@@ -293,31 +300,26 @@ __global__ void __launch_bounds__(64) batch_axis_attention_bwd_kernel(const floa
     float dot = 0.f;     // sum_b2 P * dP
     for (int b2 = 0; b2 < B; ++b2) {
       const float pr = P[b1 * B + b2] / den;
-      float dp = 0.f;
-      for (int k = 0; k < hd; ++k) dp = fmaf(dO[b1 * hd + k], V[b2 * hd + k], dp);
       P[b1 * B + b2] = pr;
-      dot = fmaf(pr, dp, dot);
+      dot = fmaf(pr, dS[b1 * B + b2], dot);
     }
-    for (int k = 0; k < hd; ++k) dQ[b1 * hd + k] = 0.f;
-    for (int b2 = 0; b2 < B; ++b2) {
-      const float pr = P[b1 * B + b2];
-      float dp = 0.f;
-      for (int k = 0; k < hd; ++k) dp = fmaf(dO[b1 * hd + k], V[b2 * hd + k], dp);
-      const float ds = pr * (dp - dot) * sc;
-      for (int k = 0; k < hd; ++k) {
-        dQ[b1 * hd + k] = fmaf(ds, Km[b2 * hd + k], dQ[b1 * hd + k]);
-        atomicAdd(&dK[b2 * hd + k], ds * Q[b1 * hd + k]);
-        atomicAdd(&dV[b2 * hd + k], pr * dO[b1 * hd + k]);
-      }
-    }
+    rowv[b1] = dot;
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < B * hd; e += blockDim.x) {
-    const int b = e / hd, d = e - b * hd;
-    float* row = g_qkv + ((size_t)b * S + s) * 3 * E + h * hd + d;
-    row[0] = dQ[e];
-    row[E] = dK[e];
-    row[2 * E] = dV[e];
+  for (int e = threadIdx.x; e < B * B; e += nt) dS[e] = P[e] * (dS[e] - rowv[e / B]) * sc;
+  __syncthreads();
+  for (int e = threadIdx.x; e < B * hd; e += nt) {
+    const int b = e / hd, k = e - b * hd;
+    float dq = 0.f, dk = 0.f, dv = 0.f;
+    for (int o = 0; o < B; ++o) {
+      dq = fmaf(dS[b * B + o], Km[o * hd + k], dq);
+      dk = fmaf(dS[o * B + b], Q[o * hd + k], dk);
+      dv = fmaf(P[o * B + b], dO[o * hd + k], dv);
+    }
+    float* row = g_qkv + ((size_t)b * S + s) * 3 * E + h * hd + k;
+    row[0] = dq;
+    row[E] = dk;
+    row[2 * E] = dv;
   }
 }
 
@@ -454,9 +456,9 @@ int mpa_batch_axis_attention_bwd_f32(const float* qkv, const float* g_o, float* 
   MPA_CHECK_ARCH();
   MPA_REQUIRE(qkv && g_o && g_qkv && B > 0 && S > 0 && E > 0 && num_heads > 0 && E % num_heads == 0, "attention_bwd: bad argument");
   const int hd = E / num_heads;
-  const size_t smem = ((size_t)7 * B * hd + (size_t)B * B) * sizeof(float);
+  const size_t smem = ((size_t)4 * B * hd + (size_t)2 * B * B + B) * sizeof(float);
   MPA_REQUIRE(smem <= 48 * 1024, "attention_bwd: batch %d too large for the shared-memory tile", B);
-  batch_axis_attention_bwd_kernel<<<S * num_heads, 64, smem, (cudaStream_t)stream>>>(qkv, g_o, g_qkv, B, S, E, num_heads);
+  batch_axis_attention_bwd_kernel<<<S * num_heads, 256, smem, (cudaStream_t)stream>>>(qkv, g_o, g_qkv, B, S, E, num_heads);
   MPA_CHECK_LAUNCH("attention_bwd");
   return MPA_OK;
 }

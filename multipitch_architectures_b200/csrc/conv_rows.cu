@@ -30,49 +30,50 @@ struct RowsGemm {
   int a_k_fast, b_k_fast;   // which index is the unit-stride one (coalescing of the tile loads)
 };
 
+// TM x TN output tile per CTA of 256 threads (16 x 16 threads, (TM/16) x (TN/16) outputs each), K step 16.
+template <int TM, int TN>
 __global__ void __launch_bounds__(256) rows_gemm_kernel(RowsGemm p) {
-  __shared__ float As[16][64 + 4];
-  __shared__ float Bs[16][64 + 4];
-  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  constexpr int RM = TM / 16, RN = TN / 16;
+  __shared__ float As[16][TM + 4];
+  __shared__ float Bs[16][TN + 4];
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  float acc[4][4] = {};
+  float acc[RM][RN] = {};
   const int kchunk = (((p.K + (int)gridDim.z - 1) / (int)gridDim.z) + 15) / 16 * 16;
   const int k_begin = blockIdx.z * kchunk, k_end = min(p.K, k_begin + kchunk);
   for (int k0 = k_begin; k0 < k_end; k0 += 16) {
-    for (int e = threadIdx.x; e < 64 * 16; e += 256) {
-      {
-        const int kk = p.a_k_fast ? (e & 15) : (e >> 6), r = p.a_k_fast ? (e >> 4) : (e & 63);
-        const int m = m0 + r, k = k0 + kk;
-        As[kk][r] = (m < p.M && k < k_end) ? p.A[p.am.off(m) + p.ak.off(k)] : 0.f;
-      }
-      {
-        const int kk = p.b_k_fast ? (e & 15) : (e >> 6), r = p.b_k_fast ? (e >> 4) : (e & 63);
-        const int n = n0 + r, k = k0 + kk;
-        Bs[kk][r] = (n < p.N && k < k_end) ? p.B[p.bk.off(k) + p.bn.off(n)] : 0.f;
-      }
+    for (int e = threadIdx.x; e < TM * 16; e += 256) {
+      const int kk = p.a_k_fast ? (e & 15) : (e / TM), r = p.a_k_fast ? (e >> 4) : (e % TM);
+      const int m = m0 + r, k = k0 + kk;
+      As[kk][r] = (m < p.M && k < k_end) ? p.A[p.am.off(m) + p.ak.off(k)] : 0.f;
+    }
+    for (int e = threadIdx.x; e < TN * 16; e += 256) {
+      const int kk = p.b_k_fast ? (e & 15) : (e / TN), r = p.b_k_fast ? (e >> 4) : (e % TN);
+      const int n = n0 + r, k = k0 + kk;
+      Bs[kk][r] = (n < p.N && k < k_end) ? p.B[p.bk.off(k) + p.bn.off(n)] : 0.f;
     }
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) {
-      float a[4], b[4];
+      float a[RM], b[RN];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+      for (int i = 0; i < RM; ++i) a[i] = As[kk][ty * RM + i];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+      for (int j = 0; j < RN; ++j) b[j] = Bs[kk][tx * RN + j];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < RM; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < RN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
+  for (int i = 0; i < RM; ++i) {
+    const int m = m0 + ty * RM + i;
     if (m >= p.M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
+    for (int j = 0; j < RN; ++j) {
+      const int n = n0 + tx * RN + j;
       if (n >= p.N) continue;
       float* c = p.C + p.cm.off(m) + p.cn.off(n);
       if (gridDim.z > 1) {
@@ -86,8 +87,14 @@ __global__ void __launch_bounds__(256) rows_gemm_kernel(RowsGemm p) {
   }
 }
 
+// tile choice: few output rows (Cout of a small head) -> 16-row tiles; too few 64 x 64 tiles to fill the chip -> 32 x 32 tiles
 static int launch_rows_gemm(RowsGemm& p, int ks, cudaStream_t st) {
-  rows_gemm_kernel<<<dim3(ceil_div(p.N, 64), ceil_div(p.M, 64), ks), 256, 0, st>>>(p);
+  if (p.M <= 16)
+    rows_gemm_kernel<16, 64><<<dim3(ceil_div(p.N, 64), ceil_div(p.M, 16), ks), 256, 0, st>>>(p);
+  else if ((long long)ceil_div(p.N, 64) * ceil_div(p.M, 64) * ks < 120)
+    rows_gemm_kernel<32, 32><<<dim3(ceil_div(p.N, 32), ceil_div(p.M, 32), ks), 256, 0, st>>>(p);
+  else
+    rows_gemm_kernel<64, 64><<<dim3(ceil_div(p.N, 64), ceil_div(p.M, 64), ks), 256, 0, st>>>(p);
   return MPA_OK;
 }
 

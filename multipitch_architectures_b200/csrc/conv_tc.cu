@@ -820,16 +820,23 @@ __global__ void nchw_to_cp8_strided_kernel(const float* __restrict__ x, uint16_t
   }
 }
 
+// one thread per (b, chunk, t, f): one 16-byte load -> 8 channel planes (each store coalesced across the threads of a row)
 __global__ void cp8_to_nchw_kernel(const uint16_t* __restrict__ in, float* __restrict__ out, long long total, int C, int T,
-                                   int F, int NCs, int TP, int P, int pf, int pt, int fmt) {
+                                   int F, int NCk, int NCs, int TP, int P, int pf, int pt, int fmt) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int f = (int)(i % F);
     long long r = i / F;
     int t = (int)(r % T);
     r /= T;
-    int c = (int)(r % C);
-    int b = (int)(r / C);
-    out[i] = cvt32(in[((((size_t)b * NCs + (c >> 3)) * TP + pt + t) * P + pf + f) * 8 + (c & 7)], fmt);
+    int ck = (int)(r % NCk);
+    int b = (int)(r / NCk);
+    __align__(16) uint16_t v[8];
+    *reinterpret_cast<uint4*>(v) = *reinterpret_cast<const uint4*>(in + ((((size_t)b * NCs + ck) * TP + pt + t) * P + pf + f) * 8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = ck * 8 + e;
+      if (c < C) out[(((size_t)b * C + c) * T + t) * F + f] = cvt32(v[e], fmt);
+    }
   }
 }
 
@@ -1479,8 +1486,8 @@ int mpa_cp8_to_nchw(const void* in_cp8, float* out, int B, int C, int T, int F, 
   MPA_REQUIRE(in_cp8 && out && B > 0 && C > 0 && pitch >= pf + F, "cp8_to_nchw: bad argument");
   const int NCk = (C + 7) / 8;
   if (ncs_in <= 0) ncs_in = NCk;
-  long long total = (long long)B * C * T * F;
-  cp8_to_nchw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint16_t*)in_cp8, out, total, C, T, F, ncs_in, T + 2 * pt,
+  long long total = (long long)B * NCk * T * F;
+  cp8_to_nchw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint16_t*)in_cp8, out, total, C, T, F, NCk, ncs_in, T + 2 * pt,
                                                                                pitch, pf, pt, fmt);
   MPA_CHECK_LAUNCH("cp8_to_nchw");
   return MPA_OK;

@@ -134,6 +134,29 @@ __global__ void maxpool_time_kernel(const float* __restrict__ x, const float* __
   }
 }
 
+// F % 4 == 0: four neighbouring bins per thread, 16-byte loads / stores
+__global__ void maxpool_time_vec4_kernel(const float4* __restrict__ x, const float4* __restrict__ res, float4* __restrict__ out, long long total4,
+                                         int T, int F4, int k) {
+  const int h = k / 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i % F4);
+    const long long r = i / F4;
+    const int t = (int)(r % T);
+    const float4* xp = x + (r - t) * F4 + f;
+    const int lo = max(0, t - h), hi = min(T - 1, t + h);
+    float4 m = xp[(size_t)lo * F4];
+    for (int tt = lo + 1; tt <= hi; ++tt) {
+      const float4 v = xp[(size_t)tt * F4];
+      m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+    }
+    if (res) {
+      const float4 q = res[i];
+      m.x += q.x; m.y += q.y; m.z += q.z; m.w += q.w;
+    }
+    out[i] = m;
+  }
+}
+
 __global__ void maxpool2d_kernel(const float* __restrict__ x, float* __restrict__ out, long long total, int H, int W,
                                  int Ho, int Wo, int kh, int kw, int sh, int sw) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -285,6 +308,13 @@ int mpa_maxpool_time_f32(const float* x, const float* res, float* out, int B, in
   MPA_CHECK_ARCH();
   MPA_REQUIRE(x && out && B > 0 && C > 0 && T > 0 && F > 0 && k >= 1 && (k & 1), "maxpool_time: bad argument");
   long long total = (long long)B * C * T * F;
+  if (F % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)res & 15) == 0) {
+    long long g = (total / 4 + 255) / 256;
+    maxpool_time_vec4_kernel<<<(unsigned)(g > 148LL * 64 ? 148LL * 64 : g), 256, 0, (cudaStream_t)stream>>>(
+        (const float4*)x, (const float4*)res, (float4*)out, total / 4, T, F / 4, k);
+    MPA_CHECK_LAUNCH("maxpool_time_vec4");
+    return MPA_OK;
+  }
   maxpool_time_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, res, out, total, T, F, k);
   MPA_CHECK_LAUNCH("maxpool_time");
   return MPA_OK;

@@ -18,10 +18,19 @@ from .libdl.nn_models import _exec
 from ._lib import call, stream_ptr
 
 
+# Device-resident step counter (int64[1]) while a training step is being captured into a CUDA graph: dropout offsets are then formed on
+# the device as step * 256 + site instead of being baked into the kernel arguments.
+_step_dev = None
+
+
 def _dropout(x, p, seed, offset):
     if p <= 0.0:
         return x
     out = torch.empty_like(x)
+    if _step_dev is not None:
+        call('dropout_dev_f32', x, out, _lib.i64(x.numel()), float(p), ctypes_u64(seed), ctypes_u64(offset), _step_dev, ctypes_u64(256),
+             stream_ptr())
+        return out
     call('dropout_f32', x, out, _lib.i64(x.numel()), float(p), ctypes_u64(seed), ctypes_u64(offset), stream_ptr())
     return out
 

@@ -376,7 +376,11 @@ class UnetTrainStep:
     """Fused training step of a U-Net-family model on flat parameter / gradient / moment buffers:
     forward, BCE (+ CE/25 for the PUnet), backward, ONE gradient all-reduce (NCCL, when a process group is active), fused AdamW."""
 
-    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, seed=0x5EED, process_group=None, ce_scale=1.0 / 25.0):
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, seed=0x5EED, process_group=None, ce_scale=1.0 / 25.0,
+                 graph=False):
+        """graph=True: after two eager steps the forward + loss + backward sequence (~3,500 kernel launches for the SAUnet:L, more host
+        launch time than GPU time) is captured ONCE into a CUDA graph and replayed; the all-reduce and AdamW stay eager.  Inputs must keep
+        their shape.  The replayed step is the eager step of the same number (dropout offsets come from a device-side step counter)."""
         self.model, self.lr, self.betas, self.eps, self.wd, self.seed = model, lr, betas, eps, weight_decay, seed
         self.group, self.ce_scale = process_group, ce_scale
         named = list(model.named_parameters())
@@ -395,19 +399,46 @@ class UnetTrainStep:
                 self.grads[name] = self.flat_g[off:off + k].view_as(p)
                 off += k
         self.step_count = 0
+        self.use_graph, self._graph = bool(graph), None
+
+    def _forward_backward(self, x, target, tape_step):
+        y, n_pred, tape = unet_train_forward(self.model, x, self.grads, self.seed, tape_step)
+        target = target.contiguous()
+        loss, y.g = ops.bce_fwd_bwd(y.d, target)
+        if n_pred is not None:
+            B, K = n_pred.d.shape[0], n_pred.d.shape[1]
+            n_pred.g = torch.empty_like(n_pred.d)
+            call('ce_count_fwd_bwd_f32', n_pred.d, target, loss, n_pred.g, B, K, target.numel() // B, float(self.ce_scale), 1, stream_ptr())
+        tape.backward()
+        return loss
+
+    def _capture(self, x, target):
+        from . import training as T
+        self._xs, self._ts = x.clone(), target.contiguous().clone()
+        self._step_dev = torch.zeros(1, dtype=torch.int64, device=x.device)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._step_dev += 1
+            T._step_dev = self._step_dev
+            try:
+                self._loss = self._forward_backward(self._xs, self._ts, 0)
+            finally:
+                T._step_dev = None
+        self._step_dev.fill_(self.step_count - 1)
 
     def __call__(self, x, target):
         import torch.distributed as dist
         self.step_count += 1
         with torch.no_grad():
-            y, n_pred, tape = unet_train_forward(self.model, x, self.grads, self.seed, self.step_count)
-            target = target.contiguous()
-            loss, y.g = ops.bce_fwd_bwd(y.d, target)
-            if n_pred is not None:
-                B, K = n_pred.d.shape[0], n_pred.d.shape[1]
-                n_pred.g = torch.empty_like(n_pred.d)
-                call('ce_count_fwd_bwd_f32', n_pred.d, target, loss, n_pred.g, B, K, target.numel() // B, float(self.ce_scale), 1, stream_ptr())
-            tape.backward()
+            if self.use_graph and self.step_count > 2:
+                if self._graph is None:
+                    self._capture(x, target)
+                self._xs.copy_(x)
+                self._ts.copy_(target)
+                self._graph.replay()
+                loss = self._loss
+            else:
+                loss = self._forward_backward(x, target, self.step_count)
             scale = 1.0
             if self.group is not None or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
                 dist.all_reduce(self.flat_g, group=self.group)
