@@ -196,7 +196,7 @@ def train_main(args, rank, world, local, cores):
         step = TrainStep(model, lr=spec['lr'], weight_decay=0.01)
     else:
         from multipitch_architectures_b200.training_unet import UnetTrainStep
-        step = UnetTrainStep(model, lr=spec['lr'], weight_decay=0.01)
+        step = UnetTrainStep(model, lr=spec['lr'], weight_decay=0.01, graph=not args.no_train_graph)
     xh, th = synth_patches(batch, rank).pin_memory(), synth_targets(batch, rank).pin_memory()
     xd, td = xh.to(dev), th.to(dev)
     loss_host = torch.empty(1).pin_memory()
@@ -232,9 +232,10 @@ def train_main(args, rank, world, local, cores):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    n0 = _lib.launch_count()
+    n0, r0 = _lib.launch_count(), getattr(step, 'replays', 0)
     ms = timed(resident, args.steps)
-    launches = _lib.launch_count() - n0
+    # kernels launched inside the timed region: the host-side counter plus the kernel nodes of every CUDA-graph replay
+    launches = _lib.launch_count() - n0 + (getattr(step, 'replays', 0) - r0) * getattr(step, 'launches_per_replay', 0)
     ms_e2e = timed(e2e, args.steps)
     clocks = sampler.stop() if sampler else None
     if rank == 0:
@@ -411,6 +412,7 @@ def main():
                          'infer_punet (configs[3]); train_saunet (configs[4]: SAUnet:L data-parallel training, batch 25 per GPU)')
     ap.add_argument('--batch', type=int, default=0, help='training batch per GPU (0 = the workload default)')
     ap.add_argument('--train-precision', default='fp32', choices=['fp32', 'bf16'])
+    ap.add_argument('--no-train-graph', action='store_true', help='U-Net training workloads: launch every kernel eagerly instead of replaying the captured forward+backward CUDA graph')
     ap.add_argument('--infer-batch', type=int, default=400, help='patches per forward of the U-Net inference workloads (any size is legal: eval-mode patches are independent)')
     args = ap.parse_args()
 

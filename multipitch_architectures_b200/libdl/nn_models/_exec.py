@@ -293,7 +293,19 @@ def unet_forward_tc(model, x):
     return y, x5
 
 
+_PE_TABLES = {}
+
+
 def sinusoidal_pe(n, E, device):
+    """The reference's sinusoidal table (unet_cnns.py:118-125), built once per (length, width, device): a constant, and a host->device
+    copy per call would also be illegal inside a CUDA-graph capture of the training step."""
+    key = (int(n), int(E), str(device))
+    if key not in _PE_TABLES:
+        _PE_TABLES[key] = _sinusoidal_pe(n, E, device)
+    return _PE_TABLES[key]
+
+
+def _sinusoidal_pe(n, E, device):
     position = torch.arange(n, dtype=torch.float32).unsqueeze(1)
     div_term = torch.exp(torch.arange(0, E, 2, dtype=torch.float32) * (-math.log(10000.0) / E))
     pe = torch.zeros(n, E)

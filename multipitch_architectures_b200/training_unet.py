@@ -417,6 +417,7 @@ class UnetTrainStep:
         self._xs, self._ts = x.clone(), target.contiguous().clone()
         self._step_dev = torch.zeros(1, dtype=torch.int64, device=x.device)
         self._graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
         with torch.cuda.graph(self._graph):
             self._step_dev += 1
             T._step_dev = self._step_dev
@@ -424,6 +425,8 @@ class UnetTrainStep:
                 self._loss = self._forward_backward(self._xs, self._ts, 0)
             finally:
                 T._step_dev = None
+        self.launches_per_replay = _lib.launch_count() - n0      # libmpa kernels inside the graph (the host counter does not see replays)
+        self.replays = 0
         self._step_dev.fill_(self.step_count - 1)
 
     def __call__(self, x, target):
@@ -436,6 +439,7 @@ class UnetTrainStep:
                 self._xs.copy_(x)
                 self._ts.copy_(target)
                 self._graph.replay()
+                self.replays += 1
                 loss = self._loss
             else:
                 loss = self._forward_backward(x, target, self.step_count)

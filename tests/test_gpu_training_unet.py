@@ -284,3 +284,32 @@ def test_sausnet_eval_fp32_matches_reference_and_tensor_core_path_matches_fp32(t
         with torch.no_grad():
             outs[prec] = m(x)
     assert (outs['fp16'] - outs['fp32']).abs().max().item() < 1e-3
+
+
+def test_graph_replayed_step_equals_eager_step():
+    """UnetTrainStep(graph=True): steps 3.. replay ONE captured forward+backward CUDA graph; with dropout on, every replayed step must be the
+    eager step of the same number (dropout offsets come from the device-side step counter).  The learning rate is tiny so that the fp32-atomic
+    noise of the weight-gradient kernels is not amplified through the parameters: the loss of step k then depends on the data and the
+    dropout masks of step k only (a wrong mask moves it by ~1e-2)."""
+    from multipitch_architectures_b200.training_unet import UnetTrainStep
+    from tests.refshapes import build_model
+    from tests.weights import fill_state_dict, synth_patches, synth_targets
+    res = {}
+    for mode in (False, True):
+        m = build_model('saunet_tiny', precision='bf16')
+        m.load_state_dict(fill_state_dict(m.state_dict(), 5, scheme='torch_default'))
+        m = m.cuda().train()
+        assert m.p_dropout > 0
+        step = UnetTrainStep(m, lr=1e-6, graph=mode)
+        losses = []
+        for i in range(6):
+            x, y = synth_patches(5, 50 + i).cuda(), synth_targets(5, 50 + i).cuda()
+            losses.append(float(step(x, y).item()))
+        res[mode] = (losses, step.flat_p.clone())
+        if mode:
+            assert step.replays == 4 and step.launches_per_replay > 100
+    le, lg = res[False][0], res[True][0]
+    print('eager', le, 'graph', lg)
+    assert all(abs(a - b) <= 2e-4 * max(1.0, abs(a)) for a, b in zip(le, lg))
+    assert len(set(round(v, 4) for v in lg)) == len(lg)                   # every step saw its own data / masks
+    assert (res[False][1] - res[True][1]).abs().max().item() < 1e-5       # fp32 atomics (split-K, wgrad flush) are not order-stable
