@@ -160,7 +160,11 @@ int mpa_conv_tc_pack_weights(const float* w_host, void* packed_host, int Cin, in
 /* out_mode 0: `out` is a CP8 plane set [n_patches][ceil(Cout/8)][T+2pt][pitch][8] (16-bit, same fmt);
  * out_mode 1: `out` is the compact plane set [n_patches][ceil(Cout/8)][T][F_out][8] holding only the columns
  *             f = sub_offset + k*sub_stride (a stride-(1,s) convolution evaluated as the stride-1 "same" convolution and
- *             sub-sampled in the epilogue), F_out = ceil((F - sub_offset)/sub_stride). */
+ *             sub-sampled in the epilogue), F_out = ceil((F - sub_offset)/sub_stride);
+ * out_mode 2: phase-split planes for a following stride-(1,s) convolution (s = sub_stride, sub_offset = 0, Cout % 8 == 0):
+ *             `out` is [n_patches][s][out_nc_stride/s][T+2pt][P2][8], column f of the result lands in phase set f % s at column
+ *             8 + f/s, P2 = ceil((8 + F_out)/16)*16.  The strided KHxs convolution then is a stride-1 KHx1 convolution over s*Cin
+ *             channels of width F_out: s times fewer MMA columns than the sub-sampled stride-1 form. */
 int mpa_conv_tc_f16(const void* in_cp8, const void* w_packed, const float* bias, void* out, int out_mode,
                     int sub_stride, int sub_offset, int n_patches, int Cin, int Cout, int T, int F, int KH, int KW,
                     int pitch, int pf, int pt, long long in_patch_stride_rows, int in_nc_stride, int out_nc_stride,

@@ -57,6 +57,9 @@ struct ConvTcParams {
   // ---- output, legacy epilogue (pool == 0)
   uint16_t* out;            // out_mode 0: CP8 planes [n][NCo][T_out+2pt][P][8]; out_mode 1: compact [n][NCo][T_out][F_out][8] (sub-sampled columns)
   int out_mode, sub_stride, sub_offset, F_out, fmt;
+  // out_mode 2 (phase split): column f goes to phase plane set f % sub_stride, column pf2 + f / sub_stride of CP8 planes of pitch P2;
+  // the phase plane sets are `phase_planes` chunk planes apart: [n][sub_stride][phase_planes][T_out+2pt][P2][8]
+  int P2, pf2, phase_planes;
   // ---- output, fused epilogue (pool == 3): z = maxpool_time3(act(conv + bias)) (+ input row) written with the same virtual row scheme
   uint8_t* out_edge;
   uint8_t* out_stream;
@@ -268,8 +271,8 @@ __device__ __forceinline__ void epilogue_role(const ConvTcParams& p, uint32_t tm
       grp_j[k] = mg / p.Cout;
       grp_plane[k] = (mg - grp_j[k] * p.Cout) >> 3;
     }
-    const size_t plane_elems = (p.out_mode == 0) ? (size_t)p.TP_out * p.P * 8 : (size_t)p.T_out * p.F_out * 8;
-    const int row_pitch = (p.out_mode == 0) ? p.P : p.F_out;
+    const size_t plane_elems = (p.out_mode == 0) ? (size_t)p.TP_out * p.P * 8 : (p.out_mode == 2) ? (size_t)p.TP_out * p.P2 * 8 : (size_t)p.T_out * p.F_out * 8;
+    const int row_pitch = (p.out_mode == 0) ? p.P : (p.out_mode == 2) ? p.P2 : p.F_out;
     const size_t ring_row_bytes = (size_t)p.NCo * p.P * 16;
     uint8_t* ring_cta = p.pool ? p.ring + (size_t)blockIdx.x * 2 * p.J * ring_row_bytes : nullptr;
     uint32_t k_unit = 0;
@@ -288,11 +291,15 @@ __device__ __forceinline__ void epilogue_role(const ConvTcParams& p, uint32_t tm
         const int n = c0 + lane;
         int fo = n - p.pf;
         bool col_ok = (fo >= 0 && fo < p.F);
-        int col_out = n;
+        int col_out = n, ph_plane = 0;
         if (p.out_mode == 1) {
           fo -= p.sub_offset;
           col_ok = col_ok && fo >= 0 && (fo % p.sub_stride) == 0;
           col_out = fo / p.sub_stride;
+        } else if (p.out_mode == 2 && col_ok) {
+          const int q = fo / p.sub_stride;
+          ph_plane = (fo - q * p.sub_stride) * p.phase_planes;
+          col_out = p.pf2 + q;
         }
         const uint32_t keep = __ballot_sync(0xffffffffu, col_ok);
         if (keep == 0) continue;
@@ -317,8 +324,8 @@ __device__ __forceinline__ void epilogue_role(const ConvTcParams& p, uint32_t tm
               if (p.pool) {
                 *reinterpret_cast<uint4*>(ring_bank + ((size_t)grp_j[k] * p.NCo + grp_plane[k]) * p.P * 16 + (size_t)n * 16) = val;
               } else {
-                const int orow = (p.out_mode == 0 ? p.pt_out : 0) + tg - p.row0;
-                *reinterpret_cast<uint4*>(out_b + (size_t)grp_plane[k] * plane_elems + ((size_t)orow * row_pitch + col_out) * 8) = val;
+                const int orow = (p.out_mode != 1 ? p.pt_out : 0) + tg - p.row0;
+                *reinterpret_cast<uint4*>(out_b + (size_t)(ph_plane + grp_plane[k]) * plane_elems + ((size_t)orow * row_pitch + col_out) * 8) = val;
               }
             }
           }
@@ -1252,7 +1259,9 @@ int mpa_conv_tc_f16(const void* in_cp8, const void* w_packed, const float* bias,
   MPA_REQUIRE(pt >= 1 || KW == 1, "conv_tc: at least one guard row above and below each plane is required (KW > 1)");
   MPA_REQUIRE(J >= 0 && J * Cout <= 128 && row0 >= 0 && n_rows >= 0 && row0 + n_rows <= T, "conv_tc: bad J / row window");
   MPA_REQUIRE(((uintptr_t)in_cp8 & 15) == 0 && ((uintptr_t)w_packed & 15) == 0 && ((uintptr_t)out & 15) == 0, "conv_tc: 16-byte alignment required");
-  MPA_REQUIRE(out_mode == 0 || (out_mode == 1 && sub_stride >= 1 && sub_offset >= 0 && sub_offset < sub_stride), "conv_tc: bad output mode");
+  MPA_REQUIRE(out_mode == 0 || (out_mode == 1 && sub_stride >= 1 && sub_offset >= 0 && sub_offset < sub_stride) ||
+                  (out_mode == 2 && sub_stride >= 2 && sub_offset == 0 && (Cout & 7) == 0 && out_nc_stride > 0 && out_nc_stride % sub_stride == 0),
+              "conv_tc: bad output mode");
   ConvTcParams p;
   memset(&p, 0, sizeof(p));
   p.w = (const uint8_t*)w_packed;
@@ -1262,6 +1271,9 @@ int mpa_conv_tc_f16(const void* in_cp8, const void* w_packed, const float* bias,
   p.sub_stride = out_mode ? sub_stride : 1;
   p.sub_offset = out_mode ? sub_offset : 0;
   p.F_out = out_mode ? (F - p.sub_offset + p.sub_stride - 1) / p.sub_stride : F;
+  p.pf2 = 8;
+  p.P2 = (p.pf2 + p.F_out + 15) / 16 * 16;
+  p.phase_planes = out_mode == 2 ? out_nc_stride / sub_stride : 0;
   p.fmt = fmt;
   p.n_patches = n_patches;
   p.NC = (Cin + 7) / 8;
@@ -1291,7 +1303,9 @@ int mpa_conv_tc_f16(const void* in_cp8, const void* w_packed, const float* bias,
   }
   MPA_REQUIRE(in_nc_stride == 0 || in_nc_stride >= p.NC, "conv_tc: in_nc_stride %d < %d input chunks", in_nc_stride, p.NC);
   MPA_REQUIRE(out_nc_stride == 0 || out_nc_stride >= p.NCo, "conv_tc: out_nc_stride %d < %d output chunks", out_nc_stride, p.NCo);
-  p.out_patch_stride = (long long)(out_nc_stride > 0 ? out_nc_stride : p.NCo) * (out_mode == 0 ? (long long)p.TP_out * pitch : (long long)p.T_out * p.F_out) * 8;
+  p.out_patch_stride = (long long)(out_nc_stride > 0 ? out_nc_stride : p.NCo) *
+                       (out_mode == 0 ? (long long)p.TP_out * pitch : out_mode == 2 ? (long long)p.TP_out * p.P2 : (long long)p.T_out * p.F_out) * 8;
+  MPA_REQUIRE(out_mode != 2 || p.phase_planes >= p.NCo, "conv_tc: %d chunk planes per phase < %d output chunks", p.phase_planes, p.NCo);
   p.n_seg = 1;
   p.y_lo[0] = p.z_lo[0] = row0;
   p.y_hi[0] = p.z_hi[0] = row0 + p.T_out;

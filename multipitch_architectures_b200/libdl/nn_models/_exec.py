@@ -85,23 +85,53 @@ def head_f32(cache, model, x, a):
     return conv_f32(cache, 'conv4.3', model.conv4[3], y, ops.ACT_SIGMOID)
 
 
-def head_tc(cache, model, zc, a):
+def head_split_factor(model, F):
+    """3 when the head's conv2 is the reference's 3x3 / stride (1,3) / pad (1,0) binning convolution and F is a multiple of 3: its producer
+    may then write phase-split planes (conv_tc out_mode 2) and conv2 runs as a stride-1 3x1 convolution over 3*Cin channels of width F/3."""
+    conv2 = model.conv2[0]
+    ok = tuple(conv2.kernel_size) == (3, 3) and tuple(conv2.stride) == (1, 3) and tuple(conv2.padding) == (1, 0) and F % 3 == 0
+    return 3 if ok else None
+
+
+def _split_conv2_blocks(cache, conv2, C0p, fmt, dev):
+    """conv2's weights re-laid for the phase-split input: w'[co][ph*C0p + ci][kh][0] = w[co][ci][kh][ph]."""
+    def build():
+        w = conv2.weight.detach().float()
+        Cout, C0 = w.shape[0], w.shape[1]
+        w2 = torch.zeros(Cout, 3 * C0p, 3, 1, dtype=w.dtype, device=w.device)
+        for ph in range(3):
+            w2[:, ph * C0p:ph * C0p + C0, :, 0] = w[:, :, :, ph]
+        import types
+        return types.SimpleNamespace(weight=w2, bias=conv2.bias, kernel_size=(3, 1))
+    shim = cache.get(f'conv2:splitw:{C0p}', [conv2.weight, conv2.bias], build)
+    return _folded_tc(cache, f'conv2split{C0p}', shim, None, fmt, dev)
+
+
+def head_tc(cache, model, zc, a, split=None):
     """Head on a CP8 activation, all on the tensor cores:
       conv2 (3x3, stride (1,3), pad (1,0)) = the stride-1 3x3 convolution whose epilogue keeps columns 1, 4, 7, ...;
       maxpool(13,1); conv3 (75x1, VALID) = the 'same' 75x1 convolution restricted to the rows whose window fits;
       conv4.0 / conv4.3 / sigmoid in one small kernel.  Channel counts are padded to multiples of 8 with zero weights."""
     conv2, conv3, c40, c43 = model.conv2[0], model.conv3[0], model.conv4[0], model.conv4[3]
     KH3 = conv3.kernel_size[0]
-    ok = (tuple(conv2.kernel_size) == (3, 3) and tuple(conv2.stride) == (1, 3) and tuple(conv2.padding) == (1, 0) and zc.F % 3 == 0
+    Fin = zc.F * split if split else zc.F
+    ok = (tuple(conv2.kernel_size) == (3, 3) and tuple(conv2.stride) == (1, 3) and tuple(conv2.padding) == (1, 0) and Fin % 3 == 0
           and conv3.kernel_size[1] == 1 and (KH3 & 1) and tuple(conv3.padding) == (0, 0) and zc.T >= KH3
           and tuple(c40.kernel_size) == (1, 1) and tuple(c43.kernel_size) == (1, 1) and c43.weight.shape[0] == 1)
     if not ok:
+        if split:
+            raise MpaError('head_tc: phase-split input needs the tensor-core head')
         return head_f32(cache, model, ops.cp8_to_nchw(zc), a)
     dev, fmt = zc.buf.device, zc.fmt
     C1p = (conv2.weight.shape[0] + 7) // 8 * 8
-    yc = ops.compact_cp8(zc.B, C1p, zc.T, zc.F // 3, dev, fmt)
-    for wp, b, c0, c in _folded_tc(cache, 'conv2', conv2, None, fmt, dev):
-        ops.conv_tc(zc, wp, b, c, (3, 3), ops.ACT_LRELU, a, subsample=(3, 1), out=yc.channels(c0, c))
+    yc = ops.compact_cp8(zc.B, C1p, zc.T, Fin // 3, dev, fmt)
+    if split:
+        # producer wrote phase-split planes: conv2 = stride-1 3x1 convolution over 3*C0p channels of width F/3 (3x fewer MMA columns)
+        for wp, b, c0, c in _split_conv2_blocks(cache, conv2, zc.C // 3, fmt, dev):
+            ops.conv_tc(zc, wp, b, c, (3, 1), ops.ACT_LRELU, a, subsample=(1, 0), out=yc.channels(c0, c))
+    else:
+        for wp, b, c0, c in _folded_tc(cache, 'conv2', conv2, None, fmt, dev):
+            ops.conv_tc(zc, wp, b, c, (3, 3), ops.ACT_LRELU, a, subsample=(3, 1), out=yc.channels(c0, c))
     yc = ops.pool_time_res_cp8(yc, 13)
     C2p = (conv3.weight.shape[0] + 7) // 8 * 8
     n_rows = zc.T - KH3 + 1
@@ -229,17 +259,18 @@ def _folded_tc(cache, name, conv, bn, fmt, dev, cin_pad=None, J=0):
     return cache.get(f'{name}:tcfold{fmt}:{cin_pad}:{J}', params, build)
 
 
-def conv_bn_relu_tc(cache, name, conv, bn, src, dst, act=ops.ACT_RELU, a=0.0):
+def conv_bn_relu_tc(cache, name, conv, bn, src, dst, act=ops.ACT_RELU, a=0.0, split=None):
+    """split = s: `dst` is an ops.split_cp8 buffer (s phase sets); co-block c0 starts at chunk c0/8 of every phase set."""
     k = tuple(conv.kernel_size)
     for wp, b, c0, c in _folded_tc(cache, name, conv, bn, src.fmt, src.buf.device):
-        ops.conv_tc(src, wp, b, c, k, act, a, out=dst.channels(c0, c))
+        ops.conv_tc(src, wp, b, c, k, act, a, out=dst.channels(c0, c), split=split)
     return dst
 
 
-def double_conv_tc(cache, name, dc, src, dst, scratch):
+def double_conv_tc(cache, name, dc, src, dst, scratch, split=None):
     seq = dc.double_conv
     conv_bn_relu_tc(cache, name + '.0', seq[0], seq[1], src, scratch)
-    return conv_bn_relu_tc(cache, name + '.4', seq[4], seq[5], scratch, dst)
+    return conv_bn_relu_tc(cache, name + '.4', seq[4], seq[5], scratch, dst, split=split)
 
 
 def unet_forward_tc(model, x):
@@ -254,11 +285,23 @@ def unet_forward_tc(model, x):
     c = [model.inc.double_conv[4].weight.shape[0]] + [getattr(model, f'down{i}')[1].double_conv[4].weight.shape[0] for i in (1, 2, 3, 4)]
     up_out = [getattr(model, f'upconv{i}').double_conv[4].weight.shape[0] for i in (1, 2, 3, 4)]
 
+    # Activation planes are allocated (and zeroed) once per (batch, shape) and reused by later forwards: kernels write real pixels only,
+    # so the zero borders survive, and re-zeroing ~25 buffers per forward cost 9 % of the Unet:M step.  The n-th request of a forward
+    # always gets the n-th buffer, so two live buffers never alias.
+    pool = model.__dict__.setdefault('_plane_pool', {})
+    if pool.get('key') != (B, T, F, fmt, str(dev)):
+        pool.clear()
+        pool['key'] = (B, T, F, fmt, str(dev))
+    counter = [0]
+
     def buf(level, ch):
         Tl, Fl, P = geo[level]
-        return ops.CP8(B, ch, Tl, Fl, P, LEVEL_PF, 1, dev, fmt=fmt)
-    z = ops.nchw_to_cp8(ops.layernorm_cf(x, model.layernorm.weight, model.layernorm.bias, model.layernorm.eps),
-                        pitch=geo[0][2], pf=LEVEL_PF, pt=1, fmt=fmt)
+        counter[0] += 1
+        k = (counter[0], level, ch)
+        if k not in pool:
+            pool[k] = ops.CP8(B, ch, Tl, Fl, P, LEVEL_PF, 1, dev, fmt=fmt)
+        return pool[k]
+    z = ops.nchw_to_cp8(ops.layernorm_cf(x, model.layernorm.weight, model.layernorm.bias, model.layernorm.eps), out=buf(0, C))
     # concat buffers of the decoder: level 3 (x4|up x5), level 2 (x3|up u1), level 1 (x2|up u2), level 0 (x1|up u3)
     cat = {3: buf(3, c[3] + c[4]), 2: buf(2, c[2] + up_out[0]), 1: buf(1, c[1] + up_out[1]), 0: buf(0, c[0] + up_out[2])}
     skips = {lv: cat[lv].channels(0, c[lv]) for lv in (0, 1, 2, 3)}
@@ -285,11 +328,20 @@ def unet_forward_tc(model, x):
         ops.nchw_to_cp8(t4, out=skips[3], fmt=fmt)
     # decoder
     low = x5
+    split = head_split_factor(model, F) if up_out[3] % 8 == 0 else None
     for i, lv in enumerate((3, 2, 1, 0)):
         dc = getattr(model, f'upconv{i + 1}')
         ops.upsample2x_cp8(low, cat[lv].channels(c[lv], low.C))
-        low = double_conv_tc(cache, f'upconv{i + 1}', dc, cat[lv], buf(lv, up_out[i]), buf(lv, dc.double_conv[0].weight.shape[0]))
-    y = head_tc(cache, model, low, a)
+        if lv == 0 and split:
+            # the last convolution feeds the head's stride-(1,3) conv2: write its output phase-split
+            counter[0] += 1
+            k = (counter[0], 'split', up_out[i])
+            if k not in pool:
+                pool[k] = ops.split_cp8(B, up_out[i], T, F, split, dev, fmt)
+            low = double_conv_tc(cache, f'upconv{i + 1}', dc, cat[lv], pool[k], buf(lv, dc.double_conv[0].weight.shape[0]), split=split)
+        else:
+            low = double_conv_tc(cache, f'upconv{i + 1}', dc, cat[lv], buf(lv, up_out[i]), buf(lv, dc.double_conv[0].weight.shape[0]))
+    y = head_tc(cache, model, low, a, split=split)
     return y, x5
 
 

@@ -190,15 +190,25 @@ def compact_cp8(n, C, T, F, device, fmt):
     return CP8(n, C, T, F, F, 0, 0, device, fmt=fmt, buf=buf)
 
 
+def split_cp8(n, C, T, F, s, device, fmt, pt=1):
+    """Phase-split planes (conv_tc out_mode 2): s phase sets of ceil(C/8) chunk planes, each of width ceil(F/s); as a CP8 of s*C8 channels
+    it is the input of the stride-1 KHx1 form of a stride-(1,s) convolution."""
+    C8, Fo = (C + 7) // 8 * 8, (F + s - 1) // s
+    return CP8(n, s * C8, T, Fo, (8 + Fo + 15) // 16 * 16, 8, pt, device, fmt=fmt)
+
+
 def conv_tc(a, w_packed, bias, Cout, ksize, act=ACT_NONE, act_param=0.0, out=None, n_patches=None,
-            patch_stride_rows=0, T=None, subsample=None, J=0, rows=None):
+            patch_stride_rows=0, T=None, subsample=None, J=0, rows=None, split=None):
     """a: CP8 input (materialised patches) or, with patch_stride_rows>0, one shared frame-major plane.
     subsample=(stride, offset): compact output CP8 (pitch = F_out, no padding) keeping columns offset + k*stride.
     rows=(row0, n_rows): compute / store only that window of output rows (a VALID KHx1 conv = window (KH//2, T-KH+1))."""
     T = a.T if T is None else T
     n = a.B if n_patches is None else n_patches
     row0, n_rows = rows if rows is not None else (0, T)
-    if subsample is None:
+    if split is not None:
+        # `out`: a split_cp8 buffer, or a view of it advanced to this co-block's first chunk (out.ncs = s * chunks per phase)
+        mode, stride, offset = 2, int(split), 0
+    elif subsample is None:
         if out is None:
             out = CP8(n, Cout, n_rows, a.F, a.pitch, a.pf, a.pt, a.buf.device, fmt=a.fmt) if not a.compact else \
                 compact_cp8(n, Cout, n_rows, a.F, a.buf.device, a.fmt)
