@@ -7,7 +7,8 @@
 // transposition) are drawn by the host mirror (incl. the reference's rejection loop on the EQ curve) and passed in as int arrays, so the
 // deterministic part of the transform is bit-comparable with the reference; the Gaussian values come from Philox-4x32-10 keyed on the
 // SOURCE element, so the two neighbours averaged by a half-bin tuning shift see the same noisy value, as in the reference.
-// HBM-bound: 5.2 kB read (L2-resident re-reads) + 388.8 kB written per 6x75x216 patch.
+// HBM-bound without noise: 5.2 kB read (L2-resident re-reads) + 388.8 kB written per 6x75x216 patch; with additive noise the Philox +
+// Box-Muller arithmetic per element dominates.
 #include "common.cuh"
 
 namespace mpa {
@@ -51,14 +52,14 @@ __device__ __forceinline__ float aug_source(const AugParams& p, const float* __r
   return v;
 }
 
+// one CTA per (patch, channel) plane: 256 threads sweep its T x F elements (16,200 per plane: enough work per CTA to amortise the
+// per-patch parameter loads; consecutive threads write consecutive bins)
 __global__ void __launch_bounds__(256) augment_patches_kernel(AugParams p) {
-  const long long row_id = blockIdx.x;          // (b, c, t)
-  const int t = (int)(row_id % p.T);
-  const int c = (int)((row_id / p.T) % p.C);
-  const int b = (int)(row_id / ((long long)p.T * p.C));
+  const int c = blockIdx.x % p.C;
+  const int b = blockIdx.x / p.C;
   const int F = p.F;
-  const float* row = p.in + ((size_t)c * p.NT + (size_t)(p.start[b] + t)) * F;
-  const long long elem_row = row_id * F;
+  const float* plane = p.in + ((size_t)c * p.NT + (size_t)p.start[b]) * F;
+  const long long elem_plane = (long long)blockIdx.x * p.T * F;
   const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
   const int alpha = p.eq_alpha ? p.eq_alpha[b] : 0;
   const float a_eq = alpha ? __fmul_rn(2e-6f, (float)alpha) : 0.f;
@@ -66,16 +67,27 @@ __global__ void __launch_bounds__(256) augment_patches_kernel(AugParams p) {
   const int ts = p.tune2 ? p.tune2[b] : 0;
   const int tr = p.transp ? p.transp[b] : 0;
   const int shift = tr * p.bins_per_semitone;
-  float* orow = p.out + elem_row;
-  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+  const bool plain = (alpha == 0 && ts == 0 && tr == 0 && p.noise_std == 0.f);
+  float* oplane = p.out + elem_plane;
+  const int total = p.T * F;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int t = e / F, f = e - t * F;
+    const float* row = plane + (size_t)t * F;
+    const long long elem_row = elem_plane + (long long)t * F;
+    float v;
+    if (plain) {
+      v = row[f];
+      if (p.gamma_log > 0.f) v = logf(__fadd_rn(1.f, __fmul_rn(p.gamma_log, v)));
+      oplane[e] = v;
+      continue;
+    }
     const bool fill_tr = (tr > 0 && f < shift) || (tr < 0 && f >= F + shift);
     int s = (f - shift) % F;
     if (s < 0) s += F;
     const bool fill_tu = (ts > 0 && s == 0) || (ts < 0 && s == F - 1);
-    float v;
     if (fill_tr || fill_tu) {
-      const unsigned long long e = (unsigned long long)(elem_row + (fill_tr ? f : s));
-      const uint4 r = philox(make_uint4((uint32_t)e, (uint32_t)(e >> 32), (uint32_t)p.offset,
+      const unsigned long long q = (unsigned long long)(elem_row + (fill_tr ? f : s));
+      const uint4 r = philox(make_uint4((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)p.offset,
                                         (uint32_t)(p.offset >> 32) ^ (fill_tr ? 0x30000000u : 0x20000000u)), key);
       v = fabsf(__fmul_rn(p.fill_std, gauss_from(r.x, r.y)));
     } else if (ts == 0) {
@@ -88,7 +100,7 @@ __global__ void __launch_bounds__(256) augment_patches_kernel(AugParams p) {
       const int s0 = ts == 1 ? s - 1 : s;
       v = __fmul_rn(0.5f, __fadd_rn(aug_source(p, row, elem_row, s0, a_eq, apex, key), aug_source(p, row, elem_row, s0 + 1, a_eq, apex, key)));
     }
-    orow[f] = v;
+    oplane[e] = v;
   }
 }
 
@@ -123,9 +135,8 @@ int mpa_augment_patches_f32(const float* in, const long long* start, float* out,
   p.in = in; p.start = start; p.out = out; p.eq_alpha = eq_alpha; p.eq_beta = eq_beta; p.eq_offset = eq_offset; p.tune2 = tune2;
   p.transp = transp; p.C = C; p.NT = NT; p.F = F; p.n = n; p.T = T; p.bins_per_semitone = bins_per_semitone;
   p.noise_std = noise_std; p.gamma_log = gamma_log; p.fill_std = fill_std; p.seed = seed; p.offset = offset;
-  const long long rows = (long long)n * C * T;
-  MPA_REQUIRE(rows < 2147483647LL, "augment_patches: too many rows for one launch");
-  augment_patches_kernel<<<(unsigned)rows, 224, 0, (cudaStream_t)stream>>>(p);
+  MPA_REQUIRE((long long)n * C < 2147483647LL && (long long)T * F < 2147483647LL, "augment_patches: too many planes for one launch");
+  augment_patches_kernel<<<(unsigned)(n * C), 256, 0, (cudaStream_t)stream>>>(p);
   MPA_CHECK_LAUNCH("augment_patches");
   return MPA_OK;
 }

@@ -77,21 +77,19 @@ __global__ void __launch_bounds__(128) eval_frame_stats_kernel(const float* __re
   s[14] = nref; s[15] = 0.0;
 }
 
-// out[k] = sum_n stats[n][k], fixed order: thread i adds frames i, i+1024, ...; then a shared-memory tree
+// out[k] = sum_n stats[n][k], fixed order: CTA k, thread i adds frames i, i+1024, ...; then a shared-memory tree
 __global__ void __launch_bounds__(1024) eval_reduce_kernel(const double* __restrict__ stats, int N, double* __restrict__ out) {
   __shared__ double sm[1024];
-  for (int k = 0; k < kEvalStats; ++k) {
-    double a = 0.0;
-    for (int n = threadIdx.x; n < N; n += 1024) a += stats[(size_t)n * kEvalStats + k];
-    sm[threadIdx.x] = a;
-    __syncthreads();
-    for (int o = 512; o > 0; o >>= 1) {
-      if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) out[k] = sm[0];
+  const int k = blockIdx.x;
+  double a = 0.0;
+  for (int n = threadIdx.x; n < N; n += 1024) a += stats[(size_t)n * kEvalStats + k];
+  sm[threadIdx.x] = a;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
     __syncthreads();
   }
+  if (threadIdx.x == 0) out[k] = sm[0];
 }
 
 }  // namespace mpa
@@ -113,7 +111,7 @@ int mpa_eval_sums_f32(const float* targ, const float* pred, int n_frames, int n_
   cudaStream_t st = (cudaStream_t)stream;
   eval_frame_stats_kernel<<<ceil_div(n_frames, 4), 128, 0, st>>>(targ, pred, n_frames, n_bins, threshold, min_pitch, (double*)workspace);
   MPA_CHECK_LAUNCH("eval_frame_stats");
-  eval_reduce_kernel<<<1, 1024, 0, st>>>((const double*)workspace, n_frames, sums16);
+  eval_reduce_kernel<<<kEvalStats, 1024, 0, st>>>((const double*)workspace, n_frames, sums16);
   MPA_CHECK_LAUNCH("eval_reduce");
   return MPA_OK;
 }

@@ -120,8 +120,18 @@ class dataset_context(torch.utils.data.Dataset):
             raise IndexError('dataset_context.gather: patch index out of range')
         if decisions is None:
             decisions = self.draw(n) if self.augmenting else {}
-        start = (idx * self.stride).to(dev)
-        dd = {k: torch.from_numpy(np.ascontiguousarray(v, dtype=np.int32)).to(dev) for k, v in decisions.items()}
+        # ONE host->device copy for the per-patch integers: row 0 = start frames (int64), rows 1-2 = the four int32 decision arrays
+        pack = np.zeros((3, n), dtype=np.int64)
+        pack[0] = idx.numpy() * self.stride
+        dec32 = pack[1:].view(np.int32).reshape(4, n)
+        names = ('eq_alpha', 'eq_beta', 'tune2', 'transp')
+        for r, k in enumerate(names):
+            if k in decisions:
+                dec32[r] = np.asarray(decisions[k], dtype=np.int32)
+        pack_d = torch.from_numpy(pack).to(dev)
+        start = pack_d[0]
+        dec_d = pack_d[1:].view(torch.int32).view(4, n)
+        dd = {k: dec_d[r] for r, k in enumerate(names) if k in decisions}
         X = torch.empty(n, C, self.context, F, dtype=torch.float32, device=dev)
         gamma = float(self.compression) if self.compression is not None else 0.0
         if noise_offset is None:
