@@ -97,6 +97,16 @@ int mpa_conv_rows_wgrad_f32(const float* x, const float* g_out, float* g_w, int 
 size_t mpa_lstm_layer_workspace(int B, int T, int H, int D);
 int mpa_lstm_layer_f32(const float* x, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, float* out, int B,
                        int T, int I, int H, int D, void* workspace, size_t ws_bytes, void* stream);
+/* Training: the forward keeps the activated gates [D][B*T][4H] and all cell states [D][B][T][H]; the backward consumes them (gates holds
+ * the pre-activation gradients afterwards) and overwrites g_x [B][T][I] (may be NULL), g_w_ih [D][4H][I], g_w_hh [D][4H][H] and
+ * g_b [D][4H] (the gradient of bias_ih and of bias_hh).  Forward workspace >= D*B*H floats; backward >= mpa_lstm_layer_bwd_workspace(). */
+int mpa_lstm_layer_train_f32(const float* x, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, float* out,
+                             float* gates, float* c_all, int B, int T, int I, int H, int D, void* workspace, size_t ws_bytes,
+                             void* stream);
+size_t mpa_lstm_layer_bwd_workspace(int B, int T, int H, int D);
+int mpa_lstm_layer_bwd_f32(const float* x, const float* w_ih, const float* w_hh, float* gates, const float* c_all, const float* out,
+                           const float* g_out, float* g_x, float* g_w_ih, float* g_w_hh, float* g_b, int B, int T, int I, int H, int D,
+                           void* workspace, size_t ws_bytes, void* stream);
 /* blstm_temporal_enc_layer's layout changes: x NCHW [B,C,T,F] <-> seq [B][T][C*F] (feature = c*F + f). */
 int mpa_lstm_seq_from_nchw_f32(const float* x, float* seq, int B, int C, int T, int F, void* stream);
 int mpa_lstm_seq_to_nchw_f32(const float* seq, float* x, int B, int C, int T, int F, void* stream);

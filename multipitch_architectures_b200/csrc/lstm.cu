@@ -71,8 +71,10 @@ constexpr int kLstmUnits = 8, kLstmBatch = 32;
 
 // one time step of both directions: direction d handles t = step (d = 0) or T-1-step (d = 1).
 // CTA = kLstmUnits hidden units x 4 gates (32 weight rows) x kLstmBatch sequences; h_prev is read from `out` (the previous step's slot).
-__global__ void __launch_bounds__(256) lstm_step_kernel(const float* __restrict__ G, const float* __restrict__ w_hh, float* __restrict__ cstate,
-                                                        float* __restrict__ out, int B, int T, int H, int D, int step) {
+// c_all != nullptr (training): the activated gates overwrite their pre-activations in G and every cell state is kept in
+// c_all [D][B][T][H] — what the backward pass needs.
+__global__ void __launch_bounds__(256) lstm_step_kernel(float* __restrict__ G, const float* __restrict__ w_hh, float* __restrict__ cstate,
+                                                        float* __restrict__ out, float* __restrict__ c_all, int B, int T, int H, int D, int step) {
   __shared__ float Wt[32][33], Ht[kLstmBatch][33], gates[32][kLstmBatch + 1];
   const int d = blockIdx.y, j0 = blockIdx.x * kLstmUnits, b0 = blockIdx.z * kLstmBatch;
   const int t = d == 0 ? step : T - 1 - step;
@@ -120,7 +122,62 @@ __global__ void __launch_bounds__(256) lstm_step_kernel(const float* __restrict_
       const float c = (step > 0 ? gf * cp[0] : 0.f) + gi * gg;
       cp[0] = c;
       out[((size_t)b * T + t) * D * H + (size_t)d * H + j] = go * tanhf(c);
+      if (c_all) {
+        c_all[(((size_t)d * B + b) * T + t) * H + j] = c;
+        float* gs = G + ((size_t)d * M + (size_t)b * T + t) * N + j;
+        gs[0] = gi; gs[H] = gf; gs[2 * (size_t)H] = gg; gs[3 * (size_t)H] = go;
+      }
     }
+  }
+}
+
+// One backward time step of both directions (run in the reverse of the forward order).  Thread per (d, b, j):
+//   dh = g_out[b][t][d*H+j] + sum_n dgate[d][(b, t_later)][n] * w_hh[d][n][j]     (the recurrent term, absent at the first backward step)
+//   dc = dc_carry + dh * o * (1 - tanh(c)^2);   di, df, dg, do = ... * sigma' / tanh';   dc_carry = dc * f
+// gates [D][B*T][4H] holds the activated gates and is overwritten in place by the pre-activation gradients.
+__global__ void __launch_bounds__(128) lstm_step_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_all, const float* __restrict__ w_hh,
+                                                            const float* __restrict__ g_out, float* __restrict__ dc_carry, int B, int T, int H, int D,
+                                                            int bstep) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y, d = blockIdx.z;
+  if (j >= H) return;
+  const int fstep = T - 1 - bstep;                       // forward step index being undone
+  const int t = d == 0 ? fstep : T - 1 - fstep;
+  const int t_later = d == 0 ? t + 1 : t - 1;            // the time index processed one forward step later
+  const int t_prev = d == 0 ? t - 1 : t + 1;
+  const size_t M = (size_t)B * T, N = 4 * (size_t)H;
+  float dh = g_out[((size_t)b * T + t) * D * H + (size_t)d * H + j];
+  if (bstep > 0) {
+    const float* dg_later = gates + ((size_t)d * M + (size_t)b * T + t_later) * N;
+    const float* W = w_hh + (size_t)d * N * H + j;
+    float acc = 0.f;
+    for (int n = 0; n < (int)N; ++n) acc = fmaf(dg_later[n], W[(size_t)n * H], acc);
+    dh += acc;
+  }
+  float* gs = gates + ((size_t)d * M + (size_t)b * T + t) * N + j;
+  const float gi = gs[0], gf = gs[H], gg = gs[2 * (size_t)H], go = gs[3 * (size_t)H];
+  const float c = c_all[(((size_t)d * B + b) * T + t) * H + j];
+  const float c_prev = fstep > 0 ? c_all[(((size_t)d * B + b) * T + t_prev) * H + j] : 0.f;
+  const float tc = tanhf(c);
+  float* dcp = dc_carry + ((size_t)d * B + b) * H + j;
+  const float dc = (bstep > 0 ? dcp[0] : 0.f) + dh * go * (1.f - tc * tc);
+  dcp[0] = dc * gf;
+  // (no cross-thread hazard on gs: each thread owns its four entries; the dg_later rows belong to another time index)
+  gs[0] = dc * gg * gi * (1.f - gi);
+  gs[H] = dc * c_prev * gf * (1.f - gf);
+  gs[2 * (size_t)H] = dc * gi * (1.f - gg * gg);
+  gs[3 * (size_t)H] = dh * tc * go * (1.f - go);
+}
+
+// hprev[d][(b,t)][k] = h of the previous forward step of direction d (zero at the first one), from out [B][T][D*H]
+__global__ void lstm_hprev_kernel(const float* __restrict__ out, float* __restrict__ hprev, long long total, int B, int T, int H, int D) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % H);
+    const int t = (int)((i / H) % T);
+    const int b = (int)((i / ((long long)H * T)) % B);
+    const int d = (int)(i / ((long long)H * T * B));
+    const int tp = d == 0 ? t - 1 : t + 1;
+    hprev[i] = (tp >= 0 && tp < T) ? out[((size_t)b * T + tp) * D * H + (size_t)d * H + k] : 0.f;
   }
 }
 
@@ -152,6 +209,70 @@ size_t mpa_lstm_layer_workspace(int B, int T, int H, int D) {
   return ((size_t)D * B * T * 4 * H + (size_t)D * B * H) * sizeof(float);
 }
 
+static int lstm_forward(const float* x, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, float* out, int B, int T,
+                        int I, int H, int D, float* G, float* cstate, float* c_all, cudaStream_t st) {
+  const int M = B * T, N = 4 * H;
+  lstm_pregate_kernel<<<dim3(ceil_div(N, 64), ceil_div(M, 64), D), 256, 0, st>>>(x, w_ih, b_ih, b_hh, G, M, N, I);
+  MPA_CHECK_LAUNCH("lstm_pregate");
+  for (int s = 0; s < T; ++s) {
+    lstm_step_kernel<<<dim3(ceil_div(H, kLstmUnits), D, ceil_div(B, kLstmBatch)), 256, 0, st>>>(G, w_hh, cstate, out, c_all, B, T, H, D, s);
+    MPA_CHECK_LAUNCH("lstm_step");
+  }
+  return MPA_OK;
+}
+
+/* training forward: `gates` [D][B*T][4H] and `c_all` [D][B][T][H] are kept for mpa_lstm_layer_bwd_f32; workspace >= D*B*H floats */
+int mpa_lstm_layer_train_f32(const float* x, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, float* out, float* gates,
+                             float* c_all, int B, int T, int I, int H, int D, void* workspace, size_t ws_bytes, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(x && w_ih && w_hh && b_ih && b_hh && out && gates && c_all && workspace, "lstm_layer_train: null argument");
+  MPA_REQUIRE(B > 0 && T > 0 && I > 0 && H > 0 && (D == 1 || D == 2), "lstm_layer_train: bad shape");
+  MPA_REQUIRE(ws_bytes >= (size_t)D * B * H * sizeof(float), "lstm_layer_train: workspace too small");
+  return lstm_forward(x, w_ih, w_hh, b_ih, b_hh, out, B, T, I, H, D, gates, (float*)workspace, c_all, (cudaStream_t)stream);
+}
+
+size_t mpa_lstm_layer_bwd_workspace(int B, int T, int H, int D) { return ((size_t)D * B * H + (size_t)D * B * T * H) * sizeof(float); }
+
+/* backward of one layer.  gates / c_all / out from mpa_lstm_layer_train_f32 (gates is consumed: it holds the pre-activation gradients
+ * afterwards); g_out [B][T][D*H].  Outputs (overwritten): g_x [B][T][I] (may be NULL), g_w_ih [D][4H][I], g_w_hh [D][4H][H], g_b [D][4H]
+ * (= the gradient of both bias vectors). */
+int mpa_lstm_layer_bwd_f32(const float* x, const float* w_ih, const float* w_hh, float* gates, const float* c_all, const float* out,
+                           const float* g_out, float* g_x, float* g_w_ih, float* g_w_hh, float* g_b, int B, int T, int I, int H, int D,
+                           void* workspace, size_t ws_bytes, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(x && w_ih && w_hh && gates && c_all && out && g_out && g_w_ih && g_w_hh && g_b && workspace, "lstm_layer_bwd: null argument");
+  MPA_REQUIRE(B > 0 && T > 0 && I > 0 && H > 0 && (D == 1 || D == 2), "lstm_layer_bwd: bad shape");
+  if (ws_bytes < mpa_lstm_layer_bwd_workspace(B, T, H, D)) {
+    set_error("lstm_layer_bwd: workspace %zu < %zu bytes", ws_bytes, mpa_lstm_layer_bwd_workspace(B, T, H, D));
+    return MPA_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  float* dc_carry = (float*)workspace;
+  float* hprev = dc_carry + (size_t)D * B * H;
+  const int M = B * T, N = 4 * H;
+  for (int s = 0; s < T; ++s) {
+    lstm_step_bwd_kernel<<<dim3(ceil_div(H, 128), B, D), 128, 0, st>>>(gates, c_all, w_hh, g_out, dc_carry, B, T, H, D, s);
+    MPA_CHECK_LAUNCH("lstm_step_bwd");
+  }
+  const long long total = (long long)D * M * H;
+  lstm_hprev_kernel<<<ceil_div(total, 256) > 2368 ? 2368 : ceil_div(total, 256), 256, 0, st>>>(out, hprev, total, B, T, H, D);
+  MPA_CHECK_LAUNCH("lstm_hprev");
+  for (int d = 0; d < D; ++d) {
+    const float* dg = gates + (size_t)d * M * N;
+    int rc = mpa_gemm_f32(dg, x, g_w_ih + (size_t)d * N * I, N, I, M, 1, 0, stream);                       // dW_ih = dgates^T x
+    if (rc != MPA_OK) return rc;
+    rc = mpa_gemm_f32(dg, hprev + (size_t)d * M * H, g_w_hh + (size_t)d * N * H, N, H, M, 1, 0, stream);   // dW_hh = dgates^T h_prev
+    if (rc != MPA_OK) return rc;
+    rc = mpa_colsum_f32(dg, g_b + (size_t)d * N, M, N, stream);
+    if (rc != MPA_OK) return rc;
+    if (g_x) {
+      rc = mpa_gemm_f32(dg, w_ih + (size_t)d * N * I, g_x, M, I, N, 0, d > 0 ? 1 : 0, stream);             // dx (+)= dgates W_ih
+      if (rc != MPA_OK) return rc;
+    }
+  }
+  return MPA_OK;
+}
+
 int mpa_lstm_layer_f32(const float* x, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, float* out, int B, int T,
                        int I, int H, int D, void* workspace, size_t ws_bytes, void* stream) {
   MPA_CHECK_ARCH();
@@ -161,17 +282,9 @@ int mpa_lstm_layer_f32(const float* x, const float* w_ih, const float* w_hh, con
     set_error("lstm_layer: workspace %zu < %zu bytes", ws_bytes, mpa_lstm_layer_workspace(B, T, H, D));
     return MPA_ERR_WORKSPACE;
   }
-  cudaStream_t st = (cudaStream_t)stream;
   float* G = (float*)workspace;
   float* cstate = G + (size_t)D * B * T * 4 * H;
-  const int M = B * T, N = 4 * H;
-  lstm_pregate_kernel<<<dim3(ceil_div(N, 64), ceil_div(M, 64), D), 256, 0, st>>>(x, w_ih, b_ih, b_hh, G, M, N, I);
-  MPA_CHECK_LAUNCH("lstm_pregate");
-  for (int s = 0; s < T; ++s) {
-    lstm_step_kernel<<<dim3(ceil_div(H, kLstmUnits), D, ceil_div(B, kLstmBatch)), 256, 0, st>>>(G, w_hh, cstate, out, B, T, H, D, s);
-    MPA_CHECK_LAUNCH("lstm_step");
-  }
-  return MPA_OK;
+  return lstm_forward(x, w_ih, w_hh, b_ih, b_hh, out, B, T, I, H, D, G, cstate, nullptr, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -303,8 +303,7 @@ class simple_u_net_polyphony_classif_softmax(_UnetBase):
 
 class u_net_blstm_varlayers(_UnetBase):
     """BLUnet (unet_cnns.py:1000-1101; experiments exp186b/d/e): the large-kernel U-Net with `lstm_number` stacked BLSTM layers over
-    time at the bottleneck (lstm_depth 1) and, for lstm_depth > 1, on the skip connections from the bottom up.  Inference only
-    (the BLSTM has no hand-written backward yet)."""
+    time at the bottleneck (lstm_depth 1) and, for lstm_depth > 1, on the skip connections from the bottom up."""
 
     def __init__(self, n_chan_input=6, n_chan_layers=[64, 30, 20, 10], n_bins_in=216, n_bins_out=12, a_lrelu=0.3, p_dropout=0.2,
                  scalefac=8, embed_dim=4 * 16, hidden_size=512, lstm_depth=0, lstm_number=2, precision='fp32'):
@@ -326,8 +325,6 @@ class u_net_blstm_varlayers(_UnetBase):
         return self.lstm4.run(x4) if self.lstm_depth > 1 else x4
 
     def forward(self, x):
-        if self.training:
-            raise NotImplementedError('u_net_blstm_varlayers: only the eval-mode forward is implemented (no BLSTM backward kernels)')
         if self.lstm_depth > 2:
             raise NotImplementedError('BLSTM layers on the upper skip connections (lstm_depth > 2) are not used by any experiment')
         return self._run(x)[0]

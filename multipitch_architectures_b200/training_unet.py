@@ -300,6 +300,55 @@ class Tape:
         self.push(bwd_ln2)
         return out
 
+    # ---------------------------------------------------------------------------------------------- BLSTM (BLUnet bottleneck)
+    def blstm(self, name, layer, x):
+        """blstm_temporal_enc_layer.forward (unet_cnns.py:233-243) on [B,C,T,F] with the backward through time of every stacked
+        bidirectional layer (mpa_lstm_layer_train_f32 / mpa_lstm_layer_bwd_f32)."""
+        B, C, T, F = x.d.shape
+        H, I0, dev = layer.hidden_size, C * F, x.d.device
+        if I0 != layer.embed_dim or 2 * H != (layer.embed_dim // F) * F:
+            raise RuntimeError(f'BLSTM of input size {layer.embed_dim} / hidden {H} does not fit a [{C},{F}] plane per frame')
+        c_out = layer.embed_dim // F
+        f32 = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
+        seq = f32(B, T, I0)
+        call('lstm_seq_from_nchw_f32', x.d, seq, B, C, T, F, stream_ptr())
+        saved = []
+        ws = f32(2 * B * H)
+        for l in range(layer.num_layers):
+            stk = lambda p: torch.stack([getattr(layer.blstm, f'{p}_l{l}').detach(), getattr(layer.blstm, f'{p}_l{l}_reverse').detach()]).contiguous()
+            w_ih, w_hh, b_ih, b_hh = stk('weight_ih'), stk('weight_hh'), stk('bias_ih'), stk('bias_hh')
+            I = seq.shape[2]
+            out, gates, c_all = f32(B, T, 2 * H), f32(2, B * T, 4 * H), f32(2, B, T, H)
+            call('lstm_layer_train_f32', seq, w_ih, w_hh, b_ih, b_hh, out, gates, c_all, B, T, I, H, 2, ws, _lib.usize(ws.numel() * 4), stream_ptr())
+            saved.append((seq, w_ih, w_hh, gates, c_all, out, I))
+            seq = out
+        y = f32(B, c_out, T, F)
+        call('lstm_seq_to_nchw_f32', seq, y, B, c_out, T, F, stream_ptr())
+        res = Node(y)
+        G = self.grads
+
+        def bwd():
+            g = f32(B, T, 2 * H)
+            call('lstm_seq_from_nchw_f32', res.g, g, B, c_out, T, F, stream_ptr())
+            wsb_bytes = _lib.lib().mpa_lstm_layer_bwd_workspace(B, T, H, 2)
+            wsb = torch.empty(wsb_bytes, dtype=torch.uint8, device=dev)
+            for l in range(layer.num_layers - 1, -1, -1):
+                xin, w_ih, w_hh, gates, c_all, out, I = saved[l]
+                g_x, g_wih, g_whh, g_b = f32(B, T, I), f32(2, 4 * H, I), f32(2, 4 * H, H), f32(2, 4 * H)
+                call('lstm_layer_bwd_f32', xin, w_ih, w_hh, gates, c_all, out, g, g_x, g_wih, g_whh, g_b, B, T, I, H, 2, wsb, _lib.usize(wsb_bytes),
+                     stream_ptr())
+                for d, sfx in enumerate(('', '_reverse')):
+                    G[f'{name}.blstm.weight_ih_l{l}{sfx}'].copy_(g_wih[d])
+                    G[f'{name}.blstm.weight_hh_l{l}{sfx}'].copy_(g_whh[d])
+                    G[f'{name}.blstm.bias_ih_l{l}{sfx}'].copy_(g_b[d])
+                    G[f'{name}.blstm.bias_hh_l{l}{sfx}'].copy_(g_b[d])
+                g = g_x
+            gx = f32(B, C, T, F)
+            call('lstm_seq_to_nchw_f32', g, gx, B, C, T, F, stream_ptr())
+            x.acc(gx)
+        self.push(bwd)
+        return res
+
     @staticmethod
     def _tok_to_nchw(g_tok, B, E, S, Th, Fw):
         out = torch.empty(B, E, Th, Fw, dtype=torch.float32, device=g_tok.device)
@@ -317,6 +366,10 @@ def unet_train_forward(model, x, grads, seed=0, step=0):
     for lv in (1, 2, 3, 4):
         xs.append(tp.double_conv(f'down{lv}.1', getattr(model, f'down{lv}')[1], tp.maxpool2d(xs[-1], (2, 2), (2, 2))))
     x5 = xs[4]
+    if getattr(model, 'lstm_depth', 0) > 0:             # BLUnet: BLSTM over time at the bottleneck (and on the lowest skip for depth 2)
+        x5 = tp.blstm('lstm5', model.lstm5, x5)
+    if getattr(model, 'lstm_depth', 0) > 1:
+        xs[3] = tp.blstm('lstm4', model.lstm4, xs[3])
     if hasattr(model, 'attention1'):
         for nm in ('attention1', 'attention2'):
             layer = getattr(model, nm)

@@ -378,6 +378,28 @@ def ext_goldens():
         out[name + '__y'] = yb.numpy()
         out[name + '__meta'] = np.array([B, seed, float(sum(v.double().sum() for v in sd.values())), sum(p.numel() for p in m.parameters())])
         print(name, 'params', int(out[name + '__meta'][3]), 'y', out[name + '__y'].reshape(-1)[:3])
+    # BLUnet training: loss + gradients of the reference class in train mode (BatchNorm batch statistics, dropout p = 0);
+    # tensors above 20k elements (the LSTM matrices) are stored as every 5th element
+    name, B, seed = 'blunet_s32', 3, 43
+    m = build_reference_model(name)
+    sd = fill_state_dict(m.state_dict(), seed)
+    m.load_state_dict(sd)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    m.train(True)
+    xb, yt = synth_patches(B, seed), synth_targets(B, seed)
+    m.zero_grad()
+    yb = m(xb)
+    loss = torch.nn.BCELoss(reduction='mean')(yb, yt)
+    loss.backward()
+    out[name + '__train__y'] = yb.detach().numpy()
+    out[name + '__train__loss'] = np.array([loss.item()])
+    out[name + '__train__meta'] = np.array([B, seed])
+    for k, p in m.named_parameters():
+        g = p.grad.numpy().reshape(-1)
+        out[name + '__train__grad__' + k] = (g[::5] if g.size > 20000 else g).copy()
+    print(name, 'train loss', loss.item())
     out['aug_cases'] = np.array(cases, dtype=np.int64)
     assert set(c[4] for c in cases) == {-2, -1, 0, 1, 2}, sorted(set(c[4] for c in cases))
     assert any(c[5] > 0 for c in cases) and any(c[5] < 0 for c in cases)

@@ -334,5 +334,63 @@ def test_blunet_matches_reference_golden(ext_golden, name, B, seed, scheme, prec
     err = np.abs(y.cpu().numpy() - ext_golden[name + '__y']).max()
     print(f'{name} {prec}: max|diff| vs reference = {err:.2e}')
     assert y.shape == (B, 1, 1, 72) and err < tol
-    with pytest.raises(NotImplementedError):
-        m.train()(synth_patches(B, seed).cuda())
+
+
+def test_blunet_training_loss_and_gradients_match_reference_golden(ext_golden):
+    """u_net_blstm_varlayers in train mode: loss.backward() through the tape incl. the BLSTM backward through time, against
+    loss.backward() on the unmodified reference module (gradients of the large LSTM matrices are pinned on every 5th element)."""
+    from tests.refshapes import build_model
+    from tests.weights import fill_state_dict, synth_patches, synth_targets
+    name = 'blunet_s32'
+    B, seed = [int(v) for v in ext_golden[name + '__train__meta']]
+    m = build_model(name)
+    m.load_state_dict(fill_state_dict(m.state_dict(), seed))
+    for mod in m.modules():
+        if hasattr(mod, 'p_dropout'):
+            mod.p_dropout = 0.0
+    m = m.cuda().train()
+    x, t = synth_patches(B, seed).cuda(), synth_targets(B, seed).cuda()
+    y = m(x)
+    loss = torch.nn.BCELoss(reduction='mean')(y, t)
+    assert np.abs(y.detach().cpu().numpy() - ext_golden[name + '__train__y']).max() < 1e-3
+    loss.backward()
+    assert abs(loss.item() - float(ext_golden[name + '__train__loss'][0])) < 2e-5
+    gmax = max(np.abs(ext_golden[name + '__train__grad__' + k]).max() for k, _ in m.named_parameters())
+    worst = 0.0
+    for k, p in m.named_parameters():
+        g = ext_golden[name + '__train__grad__' + k]
+        mine = p.grad.cpu().numpy().reshape(-1)
+        mine = mine[::5] if mine.size > 20000 else mine
+        d = np.abs(mine - g)
+        scale = max(np.abs(g).max(), 1e-3 * gmax)
+        worst = max(worst, d.max() / scale)
+        assert d.max() <= 0.25 * scale and (d.mean() <= 1e-2 * scale or d.size < 64), (k, d.max() / scale, d.mean() / scale)
+    print(f'{name} train: worst relative gradient deviation {worst:.2e}')
+
+
+@pytest.mark.parametrize('B,T,I,H', [(5, 4, 208, 104), (25, 4, 832, 416), (3, 6, 40, 12)])
+def test_lstm_layer_backward_matches_torch_autograd(B, T, I, H):
+    from multipitch_architectures_b200 import _lib
+    torch.manual_seed(B + T)
+    lstm = torch.nn.LSTM(input_size=I, hidden_size=H, num_layers=1, batch_first=True, bidirectional=True)
+    x = torch.randn(B, T, I, requires_grad=True)
+    gy = torch.randn(B, T, 2 * H)
+    out_ref, _ = lstm(x)
+    out_ref.backward(gy)
+    st = lambda k: torch.stack([getattr(lstm, k + '_l0').detach(), getattr(lstm, k + '_l0_reverse').detach()]).contiguous().cuda()
+    w_ih, w_hh, b_ih, b_hh = st('weight_ih'), st('weight_hh'), st('bias_ih'), st('bias_hh')
+    f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device='cuda')
+    xc = x.detach().cuda()
+    out, gates, c_all, ws = f32(B, T, 2 * H), f32(2, B * T, 4 * H), f32(2, B, T, H), f32(2 * B * H)
+    _lib.call('lstm_layer_train_f32', xc, w_ih, w_hh, b_ih, b_hh, out, gates, c_all, B, T, I, H, 2, ws, _lib.usize(ws.numel() * 4), _lib.stream_ptr())
+    assert (out.cpu() - out_ref.detach()).abs().max() < 2e-5
+    wsb_bytes = _lib.lib().mpa_lstm_layer_bwd_workspace(B, T, H, 2)
+    wsb = torch.empty(wsb_bytes, dtype=torch.uint8, device='cuda')
+    g_x, g_wih, g_whh, g_b = f32(B, T, I), f32(2, 4 * H, I), f32(2, 4 * H, H), f32(2, 4 * H)
+    _lib.call('lstm_layer_bwd_f32', xc, w_ih, w_hh, gates, c_all, out, gy.cuda(), g_x, g_wih, g_whh, g_b, B, T, I, H, 2, wsb, _lib.usize(wsb_bytes),
+              _lib.stream_ptr())
+    assert (g_x.cpu() - x.grad).abs().max() < 5e-5
+    for d, sfx in enumerate(('', '_reverse')):
+        for mine, k in ((g_wih, 'weight_ih'), (g_whh, 'weight_hh'), (g_b, 'bias_ih'), (g_b, 'bias_hh')):
+            ref = getattr(lstm, k + '_l0' + sfx).grad
+            assert (mine[d].cpu() - ref).abs().max() < 2e-4 * max(1.0, ref.abs().max().item()), (k, sfx)

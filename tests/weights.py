@@ -95,6 +95,7 @@ MODEL_SPECS = {
     'sausnet_tiny': dict(cls='simple_u_net_doubleselfattn_twolayers', kw=dict(n_chan_input=6, n_chan_layers=[16, 10, 8, 5], n_bins_in=216, n_bins_out=72, scalefac=16, embed_dim=32, num_heads=8, mlp_dim=64, pos_encoding='sinusoidal')),
     'sausnet_s8': dict(cls='simple_u_net_doubleselfattn_twolayers', kw=dict(n_chan_input=6, n_chan_layers=[16, 10, 8, 5], n_bins_in=216, n_bins_out=72, scalefac=8, embed_dim=64, num_heads=8, mlp_dim=128, pos_encoding='sinusoidal')),
     'blunet_tiny': dict(cls='u_net_blstm_varlayers', kw=dict(n_chan_input=6, n_chan_layers=[16, 10, 8, 5], n_bins_in=216, n_bins_out=72, scalefac=16, embed_dim=416, hidden_size=208, lstm_depth=1, lstm_number=2)),
+    'blunet_s32': dict(cls='u_net_blstm_varlayers', kw=dict(n_chan_input=6, n_chan_layers=[16, 10, 8, 5], n_bins_in=216, n_bins_out=72, scalefac=32, embed_dim=208, hidden_size=104, lstm_depth=1, lstm_number=2)),
     'blunet_d':   dict(cls='u_net_blstm_varlayers', kw=dict(n_chan_input=6, n_chan_layers=[128, 80, 50, 30], n_bins_in=216, n_bins_out=72, scalefac=8, embed_dim=832, hidden_size=416, lstm_depth=1, lstm_number=2)),
     'saunet_tiny': dict(cls='simple_u_net_doubleselfattn', kw=dict(n_chan_input=6, n_chan_layers=[16, 10, 8, 5], n_bins_in=216, n_bins_out=72, scalefac=16, embed_dim=32, num_heads=8, mlp_dim=64, pos_encoding='sinusoidal')),
 }
