@@ -279,6 +279,12 @@ int mpa_decimate_f32(const float* y_in, float* y_out, const float* half_taps, in
  * cell 3; res_type kaiser_best: n_half = 64*factor taps), which does not rescale. */
 int mpa_decimate_gain_f32(const float* y_in, float* y_out, const float* half_taps, int n_half, int factor, double gain, long long n_in,
                           void* stream);
+/* General-ratio resampling (resampy's table walk; librosa.load of a file whose rate is not a power-of-two multiple of the target):
+ * interp_win = the resampy window (float64, n_win = num_zeros*num_table + 1 entries) pre-multiplied by min(1, ratio), interp_delta its
+ * forward differences; output sample t sits at input time time_register[t] (resampy's sequentially accumulated float64 register, >=
+ * floor(n_in*ratio) entries; NULL = t/ratio); samples t >= floor(n_in*ratio) are zero (librosa's length fix). */
+int mpa_resample_f32(const float* y_in, float* y_out, const double* interp_win, const double* interp_delta, const double* time_register,
+                     int n_win, int num_table, double ratio, double gain, long long n_in, long long n_out, void* stream);
 /* On-disk feature format -> network layout (exp126a...py:413-420): hcqt_fnc [F][N][C] float64 (the .npy the reference's notebook 01
  * saves) -> out [C][lead+N+trail][F] fp32 with zero pad frames (lead = 37, trail = 38 for inference, 0/0 for training files). */
 int mpa_hcqt_npy_to_frames_f64(const double* hcqt_fnc, float* out, int F, int N, int C, int lead, int trail, void* stream);

@@ -236,6 +236,51 @@ __global__ void __launch_bounds__(1024) tuning_finalize_kernel(const int* __rest
   }
 }
 
+// General-ratio band-limited resampling = resampy's table walk (resample_f) with one thread per output sample: output t sits at input
+// time t / ratio; both filter wings walk the interpolation window `win` (float64, num_zeros * 2^precision + 1 entries, already multiplied
+// by min(1, ratio)) in steps of index_step = int(min(1, ratio) * 2^precision) with linear interpolation between table entries
+// (`delta` = forward differences).  float64 accumulation, one rounding to fp32.  Serves librosa.load(path, sr=22050) for files whose rate
+// is not a power-of-two multiple of 22.05 kHz (48 kHz, 16 kHz, ...).
+// `times` (optional): resampy's time register of every output sample, i.e. the SEQUENTIALLY accumulated sum of 1/ratio in float64 —
+// resampy truncates index_step to an integer, so its output is discontinuous where the register crosses an integer and the accumulated
+// rounding decides the side; without it the register is t * (1/ratio).
+__global__ void resample_table_walk_kernel(const float* __restrict__ x, float* __restrict__ y, const double* __restrict__ win,
+                                           const double* __restrict__ delta, const double* __restrict__ times, int nwin, int num_table,
+                                           double ratio, long long n_in, long long n_out_real, long long n_out, double gain) {
+  const double scale = ratio < 1.0 ? ratio : 1.0;
+  const int index_step = (int)(scale * num_table);
+  const double time_increment = 1.0 / ratio;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n_out; t += (long long)gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    if (t < n_out_real) {
+      const double time_register = times ? times[t] : (double)t * time_increment;
+      const long long n = (long long)time_register;
+      double frac = scale * (time_register - (double)n);
+      double index_frac = frac * num_table;
+      int offset = (int)index_frac;
+      double eta = index_frac - offset;
+      long long i_max = (nwin - offset) / index_step;
+      if (i_max > n + 1) i_max = n + 1;
+      for (long long i = 0; i < i_max; ++i) {
+        const int idx = offset + (int)i * index_step;
+        acc += (win[idx] + eta * delta[idx]) * (double)x[n - i];
+      }
+      frac = scale - frac;
+      index_frac = frac * num_table;
+      offset = (int)index_frac;
+      eta = index_frac - offset;
+      long long k_max = (nwin - offset) / index_step;
+      if (k_max > n_in - n - 1) k_max = n_in - n - 1;
+      for (long long k = 0; k < k_max; ++k) {
+        const int idx = offset + (int)k * index_step;
+        acc += (win[idx] + eta * delta[idx]) * (double)x[n + k + 1];
+      }
+      acc *= gain;
+    }
+    y[t] = (float)acc;
+  }
+}
+
 // on-disk HCQT [F][N][C] float64 (np.save of compute_efficient_hcqt's result) -> network layout [C][lead + N + trail][F] fp32 with zeroed
 // pad frames (np.transpose(.., (2,1,0)) + np.pad + .float() of exp126a...py:413-420 in one pass); 32 bins x 32 frames per CTA
 __global__ void __launch_bounds__(256) hcqt_npy_to_frames_kernel(const double* __restrict__ in, float* __restrict__ out, int F, int N, int C,
@@ -315,6 +360,23 @@ int mpa_cqt_level_f32(const float* y_level, long long n_level, int n_fft, int ho
   cqt_level_kernel<<<n_frames, 256, smem, (cudaStream_t)stream>>>(y_level, n_level, n_fft, ilog2(n_fft), hop, (const float2*)basis, band_start,
                                                                    row_scale, n_rows, band, tuning_idx, dest, n_dest, out, out_frames, out_bins);
   MPA_CHECK_LAUNCH("cqt_level");
+  return MPA_OK;
+}
+
+int mpa_resample_f32(const float* y_in, float* y_out, const double* interp_win, const double* interp_delta, const double* time_register,
+                     int n_win, int num_table, double ratio, double gain, long long n_in, long long n_out, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(y_in && y_out && interp_win && interp_delta && n_win > 1 && num_table > 0 && ratio > 0.0 && n_in > 0 && n_out > 0,
+              "resample: bad argument");
+  const double scale = ratio < 1.0 ? ratio : 1.0;
+  MPA_REQUIRE((int)(scale * num_table) >= 1, "resample: ratio %g too small for a table of %d steps per zero crossing", ratio, num_table);
+  long long n_real = (long long)((double)n_in * ratio);       // resampy's output length; librosa pads / trims to n_out
+  if (n_real > n_out) n_real = n_out;
+  long long g = (n_out + 127) / 128;
+  if (g > 148 * 32) g = 148 * 32;
+  resample_table_walk_kernel<<<(unsigned)g, 128, 0, (cudaStream_t)stream>>>(y_in, y_out, interp_win, interp_delta, time_register, n_win, num_table, ratio,
+                                                                             n_in, n_real, n_out, gain);
+  MPA_CHECK_LAUNCH("resample");
   return MPA_OK;
 }
 

@@ -53,19 +53,59 @@ def read_wav(path):
 
 def load_audio(path, sr=22050, device='cuda'):
     """-> (float32 CUDA tensor [n], sr): mono mix (librosa.to_mono = channel mean) then kaiser_best resampling when the file's
-    rate is a power-of-two multiple of `sr` (no rescaling, as librosa.load)."""
+    rate is a power-of-two multiple of `sr`, resampy's general table walk otherwise (no rescaling, as librosa.load)."""
     x, sr_native = read_wav(path)
     y = torch.from_numpy(np.ascontiguousarray(x.mean(axis=1, dtype=np.float32) if x.shape[1] > 1 else x[:, 0])).to(device)
     if sr is None or sr_native == sr:
         return y, sr_native
     factor = sr_native // sr
     if factor * sr != sr_native or factor & (factor - 1):
-        raise NotImplementedError(f'resampling {sr_native} -> {sr} Hz: only power-of-two down-sampling runs on the device')
+        return resample(y, sr_native, sr), sr
     taps = torch.from_numpy(kaiser_best_half_taps(factor)).to(device)
     import ctypes
     out = torch.empty(-(-y.numel() // factor), dtype=torch.float32, device=device)
     _lib.call('decimate_gain_f32', y, out, taps, taps.numel(), factor, ctypes.c_double(1.0), _lib.i64(y.numel()), _lib.stream_ptr())
     return out, sr
+
+
+_WINDOWS = {}
+
+
+def resampy_window(filt='kaiser_best', precision=9):
+    """resampy's interpolation window (sinc_window): 64 zero crossings x 2^9 table steps for kaiser_best -> float64 [32769]."""
+    key = (filt, precision)
+    if key not in _WINDOWS:
+        num_zeros, beta, rolloff = {'kaiser_best': (64, 14.769656459379492, 0.9475937167399596), 'kaiser_fast': (16, 8.555504641634386, 0.85)}[filt]
+        n = (2 ** precision) * num_zeros
+        t = np.linspace(0, num_zeros, num=n + 1, endpoint=True)
+        taper = np.i0(beta * np.sqrt(np.clip(1.0 - (t / num_zeros) ** 2, 0.0, None))) / np.i0(beta)
+        _WINDOWS[key] = (rolloff * np.sinc(rolloff * t) * taper, 2 ** precision)
+    return _WINDOWS[key]
+
+
+def resample(y, sr_orig, sr_new, res_type='kaiser_best', scale=False):
+    """librosa.resample for any ratio on the device (mpa_resample_f32: resampy's table walk, one thread per output sample).
+    y: 1-D float32 CUDA tensor -> float32 CUDA tensor of ceil(n * sr_new / sr_orig) samples."""
+    import ctypes
+    ratio = float(sr_new) / float(sr_orig)
+    win, num_table = resampy_window(res_type)
+    if ratio < 1:
+        win = win * ratio
+    delta = np.zeros_like(win)
+    delta[:-1] = np.diff(win)
+    dev = y.device
+    n_out = int(np.ceil(y.numel() * ratio))
+    out = torch.empty(n_out, dtype=torch.float32, device=dev)
+    gain = 1.0 / np.sqrt(ratio) if scale else 1.0
+    # resampy's time register: 1/ratio accumulated sequentially in float64 (np.cumsum adds in order) — see the kernel's comment
+    n_real = int(y.numel() * ratio)
+    times = np.zeros(max(n_real, 1), dtype=np.float64)
+    if n_real > 1:
+        times[1:] = np.cumsum(np.full(n_real - 1, 1.0 / ratio, dtype=np.float64))
+    _lib.call('resample_f32', y.contiguous(), out, torch.from_numpy(win).to(dev), torch.from_numpy(delta).to(dev), torch.from_numpy(times).to(dev),
+              len(win), num_table,
+              ctypes.c_double(ratio), ctypes.c_double(gain), _lib.i64(y.numel()), _lib.i64(n_out), _lib.stream_ptr())
+    return out
 
 
 def load_hcqt_npy(path, lead=0, trail=0, device='cuda'):

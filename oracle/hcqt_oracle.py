@@ -91,6 +91,60 @@ def resample_pow2(y, factor, filt='kaiser_fast', scale=True):
     return out
 
 
+def resampy_window(filt='kaiser_best', precision=9):
+    """resampy.filters.sinc_window for the published kaiser_fast / kaiser_best parameters -> (interp_win float64, 2^precision)."""
+    num_zeros, beta, rolloff = RESAMPY_FILTERS[filt]
+    num_bits = 2 ** precision
+    n = num_bits * num_zeros
+    sinc_win = rolloff * np.sinc(rolloff * np.linspace(0, num_zeros, num=n + 1, endpoint=True))
+    taper = scipy.signal.windows.kaiser(2 * n + 1, beta)[n:]
+    return sinc_win * taper, num_bits
+
+
+def resample_general(y, sr_orig, sr_new, filt='kaiser_best', scale=False):
+    """librosa.resample(y, sr_orig, sr_new, res_type=filt, scale=scale) for any ratio: resampy's table walk (resample_f) vectorised over
+    the output samples (one pass per tap); float64 accumulation, output length fixed to ceil(n * ratio)."""
+    y = np.asarray(y)
+    ratio = float(sr_new) / float(sr_orig)
+    interp_win, num_table = resampy_window(filt)
+    if ratio < 1:
+        interp_win = interp_win * ratio
+    delta = np.zeros_like(interp_win)
+    delta[:-1] = np.diff(interp_win)
+    sc = min(1.0, ratio)
+    index_step = int(sc * num_table)
+    n_in = y.shape[0]
+    n_real = int(n_in * ratio)
+    # resampy's time register is ACCUMULATED (time_register += 1/ratio per output sample); np.cumsum adds sequentially, so this is
+    # the same float64 sequence.  It matters: index_step is truncated to an integer, which makes the output discontinuous where the
+    # register crosses an integer.
+    t = np.zeros(n_real, dtype=np.float64)
+    if n_real > 1:
+        t[1:] = np.cumsum(np.full(n_real - 1, 1.0 / ratio, dtype=np.float64))
+    n = t.astype(np.int64)
+    out = np.zeros(n_real, dtype=np.float64)
+    nwin = len(interp_win)
+    yd = y.astype(np.float64)
+    for wing in (0, 1):
+        frac = sc * (t - n) if wing == 0 else sc - sc * (t - n)
+        index_frac = frac * num_table
+        offset = index_frac.astype(np.int64)
+        eta = index_frac - offset
+        lim = (nwin - offset) // index_step
+        cnt = np.minimum(n + 1, lim) if wing == 0 else np.minimum(n_in - n - 1, lim)
+        for i in range(int(cnt.max()) if len(cnt) else 0):
+            m = cnt > i
+            idx = offset[m] + i * index_step
+            src = n[m] - i if wing == 0 else n[m] + i + 1
+            out[m] += (interp_win[idx] + eta[m] * delta[idx]) * yd[src]
+    if scale:
+        out /= np.sqrt(ratio)
+    n_fix = int(np.ceil(n_in * ratio))
+    res = np.zeros(n_fix, dtype=y.dtype)
+    res[:min(n_fix, n_real)] = out[:n_fix].astype(y.dtype)
+    return res
+
+
 def resample_2to1(y):
     return resample_pow2(y, 2)
 

@@ -247,8 +247,27 @@ def test_load_audio_wav_downsampling_matches_oracle(tmp_path):
     assert np.abs(y.cpu().numpy() - want).max() < 1e-6
     y0, sr0 = io.load_audio(path, sr=None)
     assert sr0 == 44100 and np.array_equal(y0.cpu().numpy(), mono)
-    with pytest.raises(NotImplementedError):
-        io.load_audio(path, sr=16000)
+    # a rate that is not a power-of-two multiple: resampy's general table walk (44.1 kHz -> 16 kHz, ratio 160/441)
+    y16, sr16 = io.load_audio(path, sr=16000)
+    want16 = Q.resample_general(mono, 44100, 16000, 'kaiser_best', False)
+    assert sr16 == 16000 and y16.numel() == len(want16) and np.abs(y16.cpu().numpy() - want16).max() < 1e-6
+
+
+@pytest.mark.parametrize('sr_from,sr_to,filt,scale', [(48000, 22050, 'kaiser_best', False), (16000, 22050, 'kaiser_best', False),
+                                                      (22050, 11025, 'kaiser_fast', True), (32000, 22050, 'kaiser_fast', True)])
+def test_general_resampler_matches_oracle(sr_from, sr_to, filt, scale):
+    from multipitch_architectures_b200 import io
+    n = 20000 + 13
+    x = (0.5 * np.sin(2 * np.pi * 700 * np.arange(n) / sr_from) + 0.1 * np.random.default_rng(sr_from).standard_normal(n)).astype(np.float32)
+    want = Q.resample_general(x, sr_from, sr_to, filt, scale)
+    got = io.resample(torch.from_numpy(x).cuda(), sr_from, sr_to, filt, scale).cpu().numpy()
+    assert got.shape == want.shape and np.abs(got - want).max() < 2e-6
+    # a pure in-band tone survives with its amplitude (up to librosa's sqrt(ratio) energy rescaling when scale=True)
+    tone = (0.5 * np.sin(2 * np.pi * 700 * np.arange(n) / sr_from)).astype(np.float32)
+    r = io.resample(torch.from_numpy(tone).cuda(), sr_from, sr_to, filt, scale).cpu().numpy()
+    mid = r[len(r) // 4: 3 * len(r) // 4]
+    gain = 1.0 / np.sqrt(sr_to / sr_from) if scale else 1.0
+    assert abs(np.abs(mid).max() / gain - 0.5) < 0.01
 
 
 def test_evaluate_file_and_results_csv(tmp_path):

@@ -147,3 +147,40 @@ def test_compute_hcqt_schedule_uses_early_downsampling_and_top_octave():
         y[::5] = 1.0
         C = Q.cqt(y, sr=22050, hop_length=448, fmin=fmin, n_bins=216, bins_per_octave=36)
         assert C.shape[1] == FB.cqt_frames(22050, 448, fmin, 216, 36, n)
+
+
+def test_oracle_general_resampler_matches_literal_table_walk():
+    """Q.resample_general (vectorised over outputs) vs the literal per-output loops of resampy's resample_f for a non-trivial ratio."""
+    import scipy.signal
+    ratio_from, ratio_to = 48000, 22050
+    ratio = ratio_to / ratio_from
+    x = np.random.default_rng(1).standard_normal(900)
+    win, num_table = Q.resampy_window('kaiser_best')
+    win = win * ratio
+    delta = np.zeros_like(win)
+    delta[:-1] = np.diff(win)
+    scale = min(1.0, ratio)
+    index_step = int(scale * num_table)
+    n_out = int(len(x) * ratio)
+    y = np.zeros(n_out)
+    time_register = 0.0
+    for t in range(n_out):
+        n = int(time_register)
+        frac = scale * (time_register - n)
+        index_frac = frac * num_table
+        offset = int(index_frac)
+        eta = index_frac - offset
+        for i in range(min(n + 1, (len(win) - offset) // index_step)):
+            y[t] += (win[offset + i * index_step] + eta * delta[offset + i * index_step]) * x[n - i]
+        frac = scale - frac
+        index_frac = frac * num_table
+        offset = int(index_frac)
+        eta = index_frac - offset
+        for k in range(min(len(x) - n - 1, (len(win) - offset) // index_step)):
+            y[t] += (win[offset + k * index_step] + eta * delta[offset + k * index_step]) * x[n + k + 1]
+        time_register += 1.0 / ratio
+    got = Q.resample_general(x, ratio_from, ratio_to, 'kaiser_best', False)
+    assert len(got) == int(np.ceil(len(x) * ratio)) and np.abs(got[:n_out] - y).max() < 1e-9
+    # identical to the dedicated power-of-two oracle where both apply
+    xf = x.astype(np.float32)
+    assert np.array_equal(Q.resample_general(xf, 44100, 22050, 'kaiser_fast', True), Q.resample_pow2(xf, 2, 'kaiser_fast', True))
