@@ -400,6 +400,21 @@ def ext_goldens():
         g = p.grad.numpy().reshape(-1)
         out[name + '__train__grad__' + k] = (g[::5] if g.size > 20000 else g).copy()
     print(name, 'train loss', loss.item())
+    # early_stopping (libdl/metrics/monitoring.py): stop decisions of the reference class over noisy metric sequences
+    spec = importlib.util.spec_from_file_location('ref_monitoring', os.path.join(REF, 'libdl/metrics/monitoring.py'))
+    mon = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mon)
+    es_cfg = [('min', 1e-5, 12, False), ('max', 0.01, 3, False), ('min', 2.0, 4, True), ('max', 1.0, 2, True), ('min', 0, 0, False)]
+    seqs = np.stack([np.linspace(1.0, 0.5, 60) + 0.05 * rng.standard_normal(60) * (np.arange(60) > 15), 0.5 + 0.4 * rng.uniform(size=60)])
+    seqs[1, 40] = np.nan
+    flags = np.zeros((len(es_cfg), 2, 60), dtype=np.int8)
+    for ci, (mode, md, pat, pct) in enumerate(es_cfg):
+        for si in range(2):
+            es = mon.early_stopping(mode=mode, min_delta=md, patience=pat, percentage=pct)
+            for k, v in enumerate(seqs[si]):
+                flags[ci, si, k] = int(bool(es.step(float(v))))
+    out['es_seqs'] = seqs
+    out['es_flags'] = flags
     out['aug_cases'] = np.array(cases, dtype=np.int64)
     assert set(c[4] for c in cases) == {-2, -1, 0, 1, 2}, sorted(set(c[4] for c in cases))
     assert any(c[5] > 0 for c in cases) and any(c[5] < 0 for c in cases)

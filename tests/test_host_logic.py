@@ -184,3 +184,17 @@ def test_oracle_general_resampler_matches_literal_table_walk():
     # identical to the dedicated power-of-two oracle where both apply
     xf = x.astype(np.float32)
     assert np.array_equal(Q.resample_general(xf, 44100, 22050, 'kaiser_fast', True), Q.resample_pow2(xf, 2, 'kaiser_fast', True))
+
+
+def test_early_stopping_matches_reference_golden():
+    import os
+    from multipitch_architectures_b200.libdl.metrics import early_stopping
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'ext_golden.npz'))
+    cfg = [('min', 1e-5, 12, False), ('max', 0.01, 3, False), ('min', 2.0, 4, True), ('max', 1.0, 2, True), ('min', 0, 0, False)]
+    for ci, (mode, md, pat, pct) in enumerate(cfg):
+        for si in range(2):
+            es = early_stopping(mode=mode, min_delta=md, patience=pat, percentage=pct)
+            got = [int(bool(es.step(float(v)))) for v in g['es_seqs'][si]]
+            assert got == list(g['es_flags'][ci, si]), (ci, si)
+    with pytest.raises(ValueError):
+        early_stopping(mode='median')
