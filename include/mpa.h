@@ -210,6 +210,9 @@ typedef struct mpa_conv_tc_desc {
   int weights_layout; /* 0: tiles of mpa_conv_tc_pack_weights; 1: ring pieces of mpa_conv_tc_ring_pack_weights (3x less L2->SM traffic at J = 3) */
   void* workspace;
   size_t ws_bytes;
+  int out_split;      /* 0, or s >= 2 (needs out_e == T, n_seg == 1): z is written phase-split for a following stride-(1,s) convolution,
+                         out_edge = [patch][s][Cout/8][T+2][P2][8] with column f at phase f % s, column 8 + f/s, P2 = ceil((8 + ceil(F/s))/16)*16;
+                         out_edge_chunk_stride / out_edge_patch_stride describe THAT buffer (see mpa_conv_tc_f16 out_mode 2) */
 } mpa_conv_tc_desc;
 size_t mpa_conv_tc_pool_workspace(int Cout, int pitch, int J);
 /* DEVICE-side packing (training: the weights change every step): w_dev fp32 in state_dict layout.  Packs output channels

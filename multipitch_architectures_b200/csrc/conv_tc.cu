@@ -60,6 +60,7 @@ struct ConvTcParams {
   // out_mode 2 (phase split): column f goes to phase plane set f % sub_stride, column pf2 + f / sub_stride of CP8 planes of pitch P2;
   // the phase plane sets are `phase_planes` chunk planes apart: [n][sub_stride][phase_planes][T_out+2pt][P2][8]
   int P2, pf2, phase_planes;
+  int out_split;            // fused epilogue (pool == 3, out_e == T): z written phase-split with sub_stride = out_split phases
   // ---- output, fused epilogue (pool == 3): z = maxpool_time3(act(conv + bias)) (+ input row) written with the same virtual row scheme
   uint8_t* out_edge;
   uint8_t* out_stream;
@@ -381,9 +382,17 @@ __device__ __forceinline__ void epilogue_role(const ConvTcParams& p, uint32_t tm
               const uint8_t* rp = in_row_ptr(p, b, tz, cs);
               c = add8_rt(c, *reinterpret_cast<const uint4*>(rp + (long long)ck * cs + (size_t)(p.pf + f) * 16), p.fmt);
             }
-            long long ocs;
-            uint8_t* op = out_row_ptr(p, b, tz, ocs);
-            *reinterpret_cast<uint4*>(op + (long long)ck * ocs + (size_t)(p.pf + f) * 16) = c;
+            if (p.out_split) {
+              // materialised output in phase-split planes [patch][phase][chunk][T+2][P2][8] (the input of the head's stride-(1,s) conv2)
+              const int q = f / p.out_split, ph = f - q * p.out_split;
+              uint8_t* op = p.out_edge + (long long)b * p.out_edge_patch_stride + (long long)(ph * p.NCo + ck) * p.out_edge_chunk_stride +
+                            ((long long)tz * p.P2 + p.pf2 + q) * 16;
+              *reinterpret_cast<uint4*>(op) = c;
+            } else {
+              long long ocs;
+              uint8_t* op = out_row_ptr(p, b, tz, ocs);
+              *reinterpret_cast<uint4*>(op + (long long)ck * ocs + (size_t)(p.pf + f) * 16) = c;
+            }
           }
         }
         epi_bar_sync();
@@ -1358,6 +1367,10 @@ int mpa_conv_tc_pool_f16(const mpa_conv_tc_desc* d, void* stream) {
   p.out_stream_chunk_stride = d->out_stream_chunk_stride;
   p.out_stream_patch_rows = d->out_stream_patch_rows;
   p.out_e = d->out_e;
+  p.out_split = d->out_split;
+  MPA_REQUIRE(d->out_split == 0 || (d->out_split >= 2 && d->out_e == T && d->n_seg == 1), "conv_tc_pool: out_split needs a materialised single-segment output");
+  p.pf2 = 8;
+  p.P2 = d->out_split ? (8 + (F + d->out_split - 1) / d->out_split + 15) / 16 * 16 : 0;
   MPA_REQUIRE((((uintptr_t)p.in_edge | (uintptr_t)p.in_stream | (uintptr_t)p.out_edge | (uintptr_t)p.out_stream | (uintptr_t)d->w_packed |
                 (uintptr_t)d->workspace) & 15) == 0, "conv_tc_pool: 16-byte alignment required");
   MPA_REQUIRE(((p.in_edge_patch_stride | p.in_edge_chunk_stride | p.in_stream_chunk_stride | p.out_edge_patch_stride | p.out_edge_chunk_stride |

@@ -21,7 +21,7 @@ class CnnStreamEngine:
     """DRCNN / DCNN / CNN inference over a whole recording with the tcgen05 convolution stack (model.precision
     'fp16' or 'bf16')."""
 
-    def __init__(self, model, chunk=646, compression=10.0, fused=True, dedup=True, ring=False):
+    def __init__(self, model, chunk=646, compression=10.0, fused=True, dedup=True, ring=False, split_head=True):
         if not isinstance(model, (basic_cnn_segm_sigmoid, deep_cnn_segm_sigmoid)):
             raise TypeError('CnnStreamEngine serves the CNN / DCNN / DRCNN family')
         self.model, self.chunk, self.compression = model, int(chunk), float(compression)
@@ -44,6 +44,8 @@ class CnnStreamEngine:
         self.fused = bool(fused) and self.C0 % 8 == 0 and self.C0 <= 64 and len(ks) == 1 and all(k % 2 == 1 for k in next(iter(ks)))
         self.KH, self.KW = next(iter(ks)) if len(ks) == 1 else (0, 0)
         self._vbufs = None
+        # phase-split hand-over to the head (see _virtual_buffers); needs >= 2 blocks so that the last block is a 40->40 one
+        self.split = (_exec.head_split_factor(model, self.F) if (self.fused and len(self.blocks) >= 1 and split_head) else None)
         # dedup: share interior rows across patches (test knob; off = every row per patch).  ring: main loop that streams
         # un-duplicated weight pieces (2.2x less L2->SM traffic, measured SLOWER than ready-made tiles: 626 vs 729 audio-s/s)
         self.dedup, self.ring = bool(dedup), bool(ring)
@@ -136,6 +138,10 @@ class CnnStreamEngine:
             streams = [torch.zeros(NC, R + 8, self.pitch, 8, dtype=dt, device=dev) if ei < CONTEXT else None for ei in e]
             edges = [torch.zeros(self.chunk + (1 if ei == CONTEXT else 0), NC, (2 * ei if ei < CONTEXT else CONTEXT) + 2, self.pitch, 8,
                                  dtype=dt, device=dev) for ei in e]
+            if self.split:
+                # the last block feeds the head's stride-(1,3) conv2: its output is written phase-split (3 sets of NC chunk planes of
+                # width F/3), conv2 then is a stride-1 3x1 convolution with resident weights (see _exec.head_tc)
+                edges[-1] = ops.split_cp8(self.chunk + 1, self.C0, CONTEXT, self.F, self.split, dev, self.fmt).buf
             ws = ops.conv_tc_pool_workspace(self.C0, self.pitch, dev)
             self._vbufs = (key, streams, edges, ws)
         return self._vbufs[1:]
@@ -152,11 +158,12 @@ class CnnStreamEngine:
             packed.append(cache.get(f'{name}:wtc{self.fmt}:{int(self.ring)}', [w], lambda: ops.conv_tc_pack(w, self.dev, self.fmt, ring=self.ring)))
         plane_stream = plane.unsqueeze(0)               # [1][rows][P][8]: 1 guard row, then stream rows 0..R-1
 
-        def run(i, src, dst, n, segments, tag):
+        def run(i, src, dst, n, segments, tag, out_split=0):
             conv = self.blocks[i][1]
             cin = C if i == 0 else self.C0
             self._timed(tag, lambda: ops.conv_tc_pool(src, dst, packed[i], conv.bias, n, cin, self.C0, F, (self.KH, self.KW), self.pitch, self.pf,
-                                                      segments, self.residual and i > 0, ops.ACT_LRELU, a, self.fmt, ws, ring=self.ring),
+                                                      segments, self.residual and i > 0, ops.ACT_LRELU, a, self.fmt, ws, ring=self.ring,
+                                                      out_split=out_split),
                         work=n * sum(hi_ - lo_ for lo_, hi_ in segments))
         # 1) clip-long streams of the patch-independent rows
         for i, ei in enumerate(e):
@@ -172,10 +179,15 @@ class CnnStreamEngine:
             for i, ei in enumerate(e):
                 dst = ops.VRows(T, ei, edge=edges[i], stream=streams[i], row0=i0)
                 segs = [(0, ei), (T - ei, T)] if ei < T else [(0, T)]
-                run(i, prev, dst, n, segs, 'conv_tc_first' if i == 0 else 'conv_tc')
+                last = i == len(e) - 1
+                run(i, prev, dst, n, segs, 'conv_tc_first' if i == 0 else 'conv_tc', out_split=self.split if (last and self.split) else 0)
                 prev = dst
-            zc = ops.CP8(n, self.C0, T, F, self.pitch, self.pf, 1, self.dev, buf=edges[-1], fmt=self.fmt)
-            y = self._timed('head', lambda: _exec.head_tc(cache, m, zc, a))
+            if self.split:
+                sb = edges[-1]
+                zc = ops.CP8(n, self.split * self.C0, T, F // self.split, sb.shape[3], 8, 1, self.dev, buf=sb, fmt=self.fmt)
+            else:
+                zc = ops.CP8(n, self.C0, T, F, self.pitch, self.pf, 1, self.dev, buf=edges[-1], fmt=self.fmt)
+            y = self._timed('head', lambda: _exec.head_tc(cache, m, zc, a, split=self.split))
             outs.append(y.reshape(n, -1))
         if not outs:
             return torch.empty(0, 0, dtype=torch.float32, device=self.dev)

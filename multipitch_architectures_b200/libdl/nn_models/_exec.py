@@ -93,7 +93,13 @@ def head_split_factor(model, F):
     return 3 if ok else None
 
 
-def _split_conv2_blocks(cache, conv2, C0p, fmt, dev):
+def _split_conv2_J(C0p, C1p):
+    """Output rows per work unit for the phase-split conv2: 3 when the whole weight set ((3 + J - 1) K rows of one 8-MMA stage each) then
+    stays resident in the kernel's 5 weight stages (CNN family: 3*C0p <= 128 channels), else the kernel's default."""
+    return 3 if (3 * C0p // 8 + 1) // 2 <= 8 and 3 * C1p <= 128 else 0
+
+
+def _split_conv2_blocks(cache, conv2, C0p, fmt, dev, J=0):
     """conv2's weights re-laid for the phase-split input: w'[co][ph*C0p + ci][kh][0] = w[co][ci][kh][ph]."""
     def build():
         w = conv2.weight.detach().float()
@@ -104,7 +110,7 @@ def _split_conv2_blocks(cache, conv2, C0p, fmt, dev):
         import types
         return types.SimpleNamespace(weight=w2, bias=conv2.bias, kernel_size=(3, 1))
     shim = cache.get(f'conv2:splitw:{C0p}', [conv2.weight, conv2.bias], build)
-    return _folded_tc(cache, f'conv2split{C0p}', shim, None, fmt, dev)
+    return _folded_tc(cache, f'conv2split{C0p}', shim, None, fmt, dev, J=J)
 
 
 def head_tc(cache, model, zc, a, split=None):
@@ -127,8 +133,9 @@ def head_tc(cache, model, zc, a, split=None):
     yc = ops.compact_cp8(zc.B, C1p, zc.T, Fin // 3, dev, fmt)
     if split:
         # producer wrote phase-split planes: conv2 = stride-1 3x1 convolution over 3*C0p channels of width F/3 (3x fewer MMA columns)
-        for wp, b, c0, c in _split_conv2_blocks(cache, conv2, zc.C // 3, fmt, dev):
-            ops.conv_tc(zc, wp, b, c, (3, 1), ops.ACT_LRELU, a, subsample=(1, 0), out=yc.channels(c0, c))
+        J2 = _split_conv2_J(zc.C // 3, C1p)
+        for wp, b, c0, c in _split_conv2_blocks(cache, conv2, zc.C // 3, fmt, dev, J=J2):
+            ops.conv_tc(zc, wp, b, c, (3, 1), ops.ACT_LRELU, a, subsample=(1, 0), out=yc.channels(c0, c), J=J2)
     else:
         for wp, b, c0, c in _folded_tc(cache, 'conv2', conv2, None, fmt, dev):
             ops.conv_tc(zc, wp, b, c, (3, 3), ops.ACT_LRELU, a, subsample=(3, 1), out=yc.channels(c0, c))

@@ -286,7 +286,7 @@ class ConvTcDesc(_ct.Structure):
                 ('KW', _ct.c_int), ('pitch', _ct.c_int), ('pf', _ct.c_int), ('J', _ct.c_int),
                 ('n_seg', _ct.c_int), ('z_lo', _ct.c_int * 2), ('z_hi', _ct.c_int * 2),
                 ('residual', _ct.c_int), ('act', _ct.c_int), ('act_param', _ct.c_float), ('fmt', _ct.c_int), ('weights_layout', _ct.c_int),
-                ('workspace', _ct.c_void_p), ('ws_bytes', _ct.c_size_t)]
+                ('workspace', _ct.c_void_p), ('ws_bytes', _ct.c_size_t), ('out_split', _ct.c_int)]
 
 
 class VRows:
@@ -314,12 +314,15 @@ def conv_tc_pool_workspace(Cout, pitch, device, J=0):
 
 
 def conv_tc_pool(src, dst, w_packed, bias, n_patches, Cin, Cout, F, ksize, pitch, pf, segments, residual, act, act_param, fmt, workspace, J=0,
-                 ring=False):
-    """dst rows [z_lo, z_hi) of every segment = maxpool_time3(act(conv(src) + bias)) (+ src row when residual); src / dst: VRows."""
+                 ring=False, out_split=0):
+    """dst rows [z_lo, z_hi) of every segment = maxpool_time3(act(conv(src) + bias)) (+ src row when residual); src / dst: VRows.
+    out_split = s: dst.edge is a split_cp8 buffer (s phase sets of Cout/8 chunk planes of pitch P2), see mpa_conv_tc_desc.out_split."""
     d = ConvTcDesc()
     (d.in_edge, d.in_edge_patch_stride, d.in_edge_chunk_stride), (d.in_stream, d.in_stream_chunk_stride) = src.fields(pitch)
     d.in_stream_patch_rows, d.in_e = src.patch_rows, src.e
-    (d.out_edge, d.out_edge_patch_stride, d.out_edge_chunk_stride), (d.out_stream, d.out_stream_chunk_stride) = dst.fields(pitch)
+    d.out_split = int(out_split)
+    (d.out_edge, d.out_edge_patch_stride, d.out_edge_chunk_stride), (d.out_stream, d.out_stream_chunk_stride) = \
+        dst.fields(dst.edge.shape[3] if out_split else pitch)
     d.out_stream_patch_rows, d.out_e = dst.patch_rows, dst.e
     d.w_packed, d.bias = w_packed.data_ptr(), bias.data_ptr()
     d.n_patches, d.Cin, d.Cout, d.T, d.F, d.KH, d.KW, d.pitch, d.pf, d.J = n_patches, Cin, Cout, src.T, F, ksize[0], ksize[1], pitch, pf, J

@@ -127,11 +127,19 @@ def test_fused_deduplicated_schedule_equals_plain_schedule(name, N, chunk, prec)
     m = m.cuda().eval()
     h = torch.from_numpy(fake_hcqt(N, 6)).cuda()
     plain = CnnStreamEngine(m, chunk=chunk, fused=False).predict_hcqt(h)
-    tiles = CnnStreamEngine(m, chunk=chunk, fused=True, ring=False)
+    tiles = CnnStreamEngine(m, chunk=chunk, fused=True, ring=False, split_head=False)
     assert tiles.fused
     fused = tiles.predict_hcqt(h)
     assert fused.shape == plain.shape == (N, 72)
     assert torch.equal(fused, plain), (fused - plain).abs().max().item()
+    # default engine: the last block hands its output to the head phase-split and conv2 runs as a 3x1 convolution over 3*C0 channels:
+    # another K order in conv2 (fp32 summation-order noise vs (a)), but still bit-identical between the de-duplicated and the
+    # fully per-patch schedule
+    split_eng = CnnStreamEngine(m, chunk=chunk, fused=True)
+    assert split_eng.split == 3
+    sp = split_eng.predict_hcqt(h)
+    assert (sp - plain).abs().max().item() < (2e-3 if prec == 'fp16' else 2e-2)
+    assert torch.equal(sp, CnnStreamEngine(m, chunk=chunk, fused=True, dedup=False).predict_hcqt(h))
     ring_eng = CnnStreamEngine(m, chunk=chunk, fused=True, ring=True)
     ring = ring_eng.predict_hcqt(h)
     ring_full = CnnStreamEngine(m, chunk=chunk, fused=True, ring=True, dedup=False).predict_hcqt(h)
