@@ -193,7 +193,7 @@ def train_main(args, rank, world, local, cores):
     model = model.to(dev).train()
     if spec['cls'].startswith(('basic_cnn', 'deep_cnn')):
         from multipitch_architectures_b200.training import TrainStep
-        step = TrainStep(model, lr=spec['lr'], weight_decay=0.01)
+        step = TrainStep(model, lr=spec['lr'], weight_decay=0.01, graph=not args.no_train_graph)
     else:
         from multipitch_architectures_b200.training_unet import UnetTrainStep
         step = UnetTrainStep(model, lr=spec['lr'], weight_decay=0.01, graph=not args.no_train_graph)
@@ -223,8 +223,20 @@ def train_main(args, rank, world, local, cores):
     def resident():
         step(xd, td)
 
+    # end to end: every step's batch travels from pinned host memory inside the timed region, double-buffered on a side stream
+    # (io.HostPrefetcher: the copy of batch k+1 overlaps the step on batch k), and the loss is read back
+    from multipitch_architectures_b200.io import HostPrefetcher
+
+    def host_batches():
+        while True:
+            yield (xh, th)
+    feed = [None]
+
     def e2e():
-        loss_host.copy_(step(xh.to(dev, non_blocking=True), th.to(dev, non_blocking=True)), non_blocking=True)
+        if feed[0] is None:
+            feed[0] = HostPrefetcher(host_batches(), dev)
+        xb, tb = next(feed[0])
+        loss_host.copy_(step(xb, tb), non_blocking=True)
 
     for _ in range(args.warmup):
         resident()
@@ -412,7 +424,7 @@ def main():
                          'infer_punet (configs[3]); train_saunet (configs[4]: SAUnet:L data-parallel training, batch 25 per GPU)')
     ap.add_argument('--batch', type=int, default=0, help='training batch per GPU (0 = the workload default)')
     ap.add_argument('--train-precision', default='fp32', choices=['fp32', 'bf16'])
-    ap.add_argument('--no-train-graph', action='store_true', help='U-Net training workloads: launch every kernel eagerly instead of replaying the captured forward+backward CUDA graph')
+    ap.add_argument('--no-train-graph', action='store_true', help='training workloads: launch every kernel eagerly instead of replaying the captured forward+backward CUDA graph')
     ap.add_argument('--infer-batch', type=int, default=400, help='patches per forward of the U-Net inference workloads (any size is legal: eval-mode patches are independent)')
     args = ap.parse_args()
 

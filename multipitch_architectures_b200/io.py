@@ -172,3 +172,46 @@ def write_results_csv(rows, path_output):
         for i, r in enumerate(table):
             w.writerow([i] + r)
     return table
+
+
+class HostPrefetcher:
+    """Double-buffered host -> device feed for the training loop (the reference copies every batch synchronously on the compute stream,
+    exp126a...py:317-319).  `batches`: an iterable of tuples of PINNED host tensors; iteration yields the same tuples as CUDA tensors
+    while the NEXT batch is already being copied on a side stream.  A yielded batch stays valid until the one after the next is requested
+    (two device buffers per tensor, reused)."""
+
+    def __init__(self, batches, device='cuda'):
+        self.it, self.dev = iter(batches), torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.dev)
+        self.slots, self.k, self.next = [None, None], 0, None
+        self._issue()
+
+    def _issue(self):
+        try:
+            host = next(self.it)
+        except StopIteration:
+            self.next = None
+            return
+        slot = self.slots[self.k]
+        if slot is None or any(d.shape != h.shape or d.dtype != h.dtype for d, h in zip(slot[0], host)):
+            slot = ([torch.empty(h.shape, dtype=h.dtype, device=self.dev) for h in host], torch.cuda.Event())
+            self.slots[self.k] = slot
+        bufs, ev = slot
+        self.stream.wait_stream(torch.cuda.current_stream(self.dev))     # the consumer of this slot's previous contents has been enqueued
+        with torch.cuda.stream(self.stream):
+            for d, h in zip(bufs, host):
+                d.copy_(h, non_blocking=True)
+            ev.record(self.stream)
+        self.next = (bufs, ev)
+        self.k ^= 1
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self.next is None:
+            raise StopIteration
+        bufs, ev = self.next
+        torch.cuda.current_stream(self.dev).wait_event(ev)
+        self._issue()
+        return tuple(bufs)

@@ -21,6 +21,7 @@ from ._lib import call, stream_ptr
 # Device-resident step counter (int64[1]) while a training step is being captured into a CUDA graph: dropout offsets are then formed on
 # the device as step * 256 + site instead of being baked into the kernel arguments.
 _step_dev = None
+_step_mul = 256        # offset = step * _step_mul + site (256 sites per step in the U-Net tape, 64 in the CNN path)
 
 
 def _dropout(x, p, seed, offset):
@@ -28,7 +29,7 @@ def _dropout(x, p, seed, offset):
         return x
     out = torch.empty_like(x)
     if _step_dev is not None:
-        call('dropout_dev_f32', x, out, _lib.i64(x.numel()), float(p), ctypes_u64(seed), ctypes_u64(offset), _step_dev, ctypes_u64(256),
+        call('dropout_dev_f32', x, out, _lib.i64(x.numel()), float(p), ctypes_u64(seed), ctypes_u64(offset), _step_dev, ctypes_u64(_step_mul),
              stream_ptr())
         return out
     call('dropout_f32', x, out, _lib.i64(x.numel()), float(p), ctypes_u64(seed), ctypes_u64(offset), stream_ptr())
@@ -317,7 +318,9 @@ def cnn_forward_train(model, x):
 class TrainStep:
     """Fused training step on flat parameter / gradient / moment buffers (one all-reduce, one AdamW sweep)."""
 
-    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, seed=0x5EED, process_group=None):
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, seed=0x5EED, process_group=None, graph=False):
+        """graph=True: from the third step on, forward + loss + backward replay ONE captured CUDA graph (fixed input shape; dropout offsets
+        come from a device-side step counter, so a replayed step equals the eager step of the same number); all-reduce and AdamW stay eager."""
         self.model, self.lr, self.betas, self.eps, self.wd, self.seed = model, lr, betas, eps, weight_decay, seed
         self.group = process_group
         named = list(model.named_parameters())
@@ -336,14 +339,45 @@ class TrainStep:
                 self.grads[name] = self.flat_g[off:off + k].view_as(p)
                 off += k
         self.step_count = 0
+        self.use_graph, self._graph = bool(graph), None
+
+    def _forward_backward(self, x, target, tape_step):
+        y, sv = cnn_train_forward(self.model, x, self.seed, tape_step)
+        loss, g_y = ops.bce_fwd_bwd(y, target.contiguous())
+        cnn_train_backward(self.model, sv, g_y, self.grads)
+        return loss
+
+    def _capture(self, x, target):
+        global _step_dev, _step_mul
+        self._xs, self._ts = x.clone(), target.contiguous().clone()
+        self._step_dev = torch.zeros(1, dtype=torch.int64, device=x.device)
+        self._graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(self._graph):
+            self._step_dev += 1
+            _step_dev, _step_mul = self._step_dev, 64
+            try:
+                self._loss = self._forward_backward(self._xs, self._ts, 0)
+            finally:
+                _step_dev, _step_mul = None, 256
+        self.launches_per_replay = _lib.launch_count() - n0
+        self.replays = 0
+        self._step_dev.fill_(self.step_count - 1)
 
     def __call__(self, x, target):
         import torch.distributed as dist
         self.step_count += 1
         with torch.no_grad():
-            y, sv = cnn_train_forward(self.model, x, self.seed, self.step_count)
-            loss, g_y = ops.bce_fwd_bwd(y, target.contiguous())
-            cnn_train_backward(self.model, sv, g_y, self.grads)
+            if self.use_graph and self.step_count > 2:
+                if self._graph is None:
+                    self._capture(x, target)
+                self._xs.copy_(x)
+                self._ts.copy_(target)
+                self._graph.replay()
+                self.replays += 1
+                loss = self._loss
+            else:
+                loss = self._forward_backward(x, target, self.step_count)
             scale = 1.0
             if self.group is not None or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
                 dist.all_reduce(self.flat_g, group=self.group)

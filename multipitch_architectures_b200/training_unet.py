@@ -473,7 +473,7 @@ class UnetTrainStep:
         n0 = _lib.launch_count()
         with torch.cuda.graph(self._graph):
             self._step_dev += 1
-            T._step_dev = self._step_dev
+            T._step_dev, T._step_mul = self._step_dev, 256
             try:
                 self._loss = self._forward_backward(self._xs, self._ts, 0)
             finally:

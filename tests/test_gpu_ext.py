@@ -413,3 +413,16 @@ def test_lstm_layer_backward_matches_torch_autograd(B, T, I, H):
         for mine, k in ((g_wih, 'weight_ih'), (g_whh, 'weight_hh'), (g_b, 'bias_ih'), (g_b, 'bias_hh')):
             ref = getattr(lstm, k + '_l0' + sfx).grad
             assert (mine[d].cpu() - ref).abs().max() < 2e-4 * max(1.0, ref.abs().max().item()), (k, sfx)
+
+
+def test_host_prefetcher_delivers_batches_in_order():
+    from multipitch_architectures_b200.io import HostPrefetcher
+    rng = np.random.default_rng(0)
+    host = [(torch.from_numpy(rng.standard_normal((4, 6, 75, 216)).astype(np.float32)).pin_memory(),
+             torch.from_numpy(rng.uniform(size=(4, 1, 1, 72)).astype(np.float32)).pin_memory()) for _ in range(5)]
+    seen = 0
+    for k, (x, y) in enumerate(HostPrefetcher(host)):
+        assert x.is_cuda and torch.equal(x.cpu(), host[k][0]) and torch.equal(y.cpu(), host[k][1])
+        (x * 2).sum()        # consumer work on the compute stream
+        seen += 1
+    assert seen == 5

@@ -115,3 +115,27 @@ def test_fused_train_step_matches_torch_adamw_on_oracle():
         y = m(x.cuda()).cpu()
         yr = NO.cnn_forward({k: v.detach() for k, v in ref.items()}, x)
     assert (y - yr).abs().max() < 1e-3
+
+
+def test_cnn_graph_replayed_step_equals_eager_step():
+    """TrainStep(graph=True): steps 3.. replay one captured forward+backward CUDA graph with dropout on; tiny learning rate so that the
+    loss of step k depends on the data and the dropout masks of step k only."""
+    from multipitch_architectures_b200.training import TrainStep
+    from tests.refshapes import build_model
+    from tests.weights import fill_state_dict, synth_patches, synth_targets
+    res = {}
+    for mode in (False, True):
+        m = build_model('drcnn_tiny', precision='bf16')
+        m.load_state_dict(fill_state_dict(m.state_dict(), 5, scheme='torch_default'))
+        m = m.cuda().train()
+        assert m.p_dropout > 0
+        step = TrainStep(m, lr=1e-6, graph=mode)
+        losses = []
+        for i in range(6):
+            losses.append(float(step(synth_patches(6, 70 + i).cuda(), synth_targets(6, 70 + i).cuda()).item()))
+        res[mode] = losses
+        if mode:
+            assert step.replays == 4 and step.launches_per_replay > 20
+    print('eager', res[False], 'graph', res[True])
+    assert all(abs(a - b) <= 2e-4 * max(1.0, abs(a)) for a, b in zip(res[False], res[True]))
+    assert len(set(round(v, 4) for v in res[True])) == 6
