@@ -84,9 +84,11 @@ int mpa_augment_targets_f32(const float* targets, const long long* frame, const 
 
 /* ---- full-height VALID convolution = the head's 75x1 "time reduction" conv3 (basic_cnns.py:396-401) as GEMMs -----------------------
  * H == KH, KW == 1, one output row: Y[co][(b,w)] = sum_(ci,h) w[co][ci][h] * x[b][ci][h][w].  x [B][Cin][H][W], w [Cout][Cin][H][1]
- * (state_dict layout), out / g_out [B][Cout][1][W].  Forward fuses bias + activation; wgrad overwrites g_w (split-K, fp32 atomics). */
+ * (state_dict layout), out / g_out [B][Cout][1][W].  Forward fuses bias + activation (K is split across CTAs; the slices are kept apart in the workspace and added in order:
+ * deterministic); the gradients overwrite their outputs (split-K, fp32 atomics). */
+size_t mpa_conv_rows_fwd_workspace(int B, int Cin, int H, int W, int Cout);   /* split-K partial sums of the forward (may be 0) */
 int mpa_conv_rows_fwd_f32(const float* x, const float* w, const float* bias, float* out, int B, int Cin, int H, int W, int Cout, int act,
-                          float act_param, void* stream);
+                          float act_param, void* workspace, size_t ws_bytes, void* stream);
 int mpa_conv_rows_dgrad_f32(const float* g_out, const float* w, float* g_in, int B, int Cin, int H, int W, int Cout, void* stream);
 int mpa_conv_rows_wgrad_f32(const float* x, const float* g_out, float* g_w, int B, int Cin, int H, int W, int Cout, void* stream);
 

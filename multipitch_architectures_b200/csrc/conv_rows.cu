@@ -28,6 +28,7 @@ struct RowsGemm {
   int act;
   float act_param;
   int a_k_fast, b_k_fast;   // which index is the unit-stride one (coalescing of the tile loads)
+  float* partial;           // split-K forward: per-slice partial sums [ks][M][N], reduced IN ORDER by the second pass (deterministic)
 };
 
 // TM x TN output tile per CTA of 256 threads (16 x 16 threads, (TM/16) x (TN/16) outputs each), K step 16.
@@ -76,7 +77,9 @@ __global__ void __launch_bounds__(256) rows_gemm_kernel(RowsGemm p) {
       const int n = n0 + tx * RN + j;
       if (n >= p.N) continue;
       float* c = p.C + p.cm.off(m) + p.cn.off(n);
-      if (gridDim.z > 1) {
+      if (gridDim.z > 1 && p.partial) {
+        p.partial[((size_t)blockIdx.z * p.M + m) * p.N + n] = acc[i][j];
+      } else if (gridDim.z > 1) {
         atomicAdd(c, acc[i][j]);
       } else {
         float v = acc[i][j];
@@ -87,14 +90,54 @@ __global__ void __launch_bounds__(256) rows_gemm_kernel(RowsGemm p) {
   }
 }
 
+// second pass of a split-K forward: C = act(sum_z partial[z] + bias[m]), slices added in order
+__global__ void rows_bias_act_kernel(RowsGemm p, int ks) {
+  const long long total = (long long)p.M * p.N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(i / p.N), n = (int)(i % p.N);
+    float v = 0.f;
+    for (int z = 0; z < ks; ++z) v += p.partial[(size_t)z * total + i];
+    if (p.bias) v += p.bias[m];
+    p.C[p.cm.off(m) + p.cn.off(n)] = apply_act(v, p.act, p.act_param);
+  }
+}
+
+// Split-K factor: these GEMMs are short and wide in K (Cin*75 up to 11,250) with few output tiles; one CTA per tile would walk hundreds of
+// latency-bound K steps on a mostly idle chip (measured 0.32 ms for the SAUnet:L conv3 forward), so K is cut until every SM holds
+// several CTAs; the slices meet in fp32 atomics.
+static int split_k_for(const RowsGemm& p, int tm, int tn) {
+  const long long tiles = (long long)ceil_div(p.N, tn) * ceil_div(p.M, tm);
+  int ks = 1;
+  while (tiles * ks < 148 * 4 && p.K / (ks * 2) >= 128 && ks < 64) ks *= 2;
+  return ks;
+}
+
 // tile choice: few output rows (Cout of a small head) -> 16-row tiles; too few 64 x 64 tiles to fill the chip -> 32 x 32 tiles
-static int launch_rows_gemm(RowsGemm& p, int ks, cudaStream_t st) {
-  if (p.M <= 16)
+static void tile_for(const RowsGemm& p, int& tm, int& tn) {
+  tm = tn = 64;
+  if (p.M <= 16) tm = 16;
+  else if ((long long)ceil_div(p.N, 64) * ceil_div(p.M, 64) < 120) tm = tn = 32;
+}
+
+// c_bytes: size of the (dense) output buffer, zeroed when the K slices meet in atomics (gradients).  The forward (p.partial set by the
+// caller from its workspace) keeps the slices apart and adds them in order together with bias and activation.
+static int launch_rows_gemm(RowsGemm& p, size_t c_bytes, cudaStream_t st) {
+  int tm, tn;
+  tile_for(p, tm, tn);
+  const int ks = split_k_for(p, tm, tn);
+  if (ks == 1) p.partial = nullptr;
+  if (ks > 1 && !p.partial) cudaMemsetAsync(p.C, 0, c_bytes, st);
+  if (tm == 16)
     rows_gemm_kernel<16, 64><<<dim3(ceil_div(p.N, 64), ceil_div(p.M, 16), ks), 256, 0, st>>>(p);
-  else if ((long long)ceil_div(p.N, 64) * ceil_div(p.M, 64) * ks < 120)
+  else if (tm == 32)
     rows_gemm_kernel<32, 32><<<dim3(ceil_div(p.N, 32), ceil_div(p.M, 32), ks), 256, 0, st>>>(p);
   else
     rows_gemm_kernel<64, 64><<<dim3(ceil_div(p.N, 64), ceil_div(p.M, 64), ks), 256, 0, st>>>(p);
+  if (ks > 1 && p.partial) {
+    const long long total = (long long)p.M * p.N;
+    rows_bias_act_kernel<<<ceil_div(total, 256) > 1184 ? 1184 : ceil_div(total, 256), 256, 0, st>>>(p, ks);
+    count_launch();
+  }
   return MPA_OK;
 }
 
@@ -107,18 +150,33 @@ using namespace mpa;
 extern "C" {
 
 /* x [B][Cin][H][W], w [Cout][Cin][H][1] (state_dict layout), out [B][Cout][1][W] = act(conv + bias) */
+size_t mpa_conv_rows_fwd_workspace(int B, int Cin, int H, int W, int Cout) {
+  RowsGemm p{};
+  p.M = Cout; p.N = B * W; p.K = Cin * H;
+  int tm, tn;
+  tile_for(p, tm, tn);
+  const int ks = split_k_for(p, tm, tn);
+  return ks > 1 ? (size_t)ks * p.M * p.N * sizeof(float) : 0;
+}
+
 int mpa_conv_rows_fwd_f32(const float* x, const float* w, const float* bias, float* out, int B, int Cin, int H, int W, int Cout, int act,
-                          float act_param, void* stream) {
+                          float act_param, void* workspace, size_t ws_bytes, void* stream) {
   MPA_CHECK_ARCH();
   MPA_REQUIRE(x && w && out && B > 0 && Cin > 0 && H > 0 && W > 0 && Cout > 0, "conv_rows_fwd: bad argument");
+  const size_t need = mpa_conv_rows_fwd_workspace(B, Cin, H, W, Cout);
+  if (need > 0 && (!workspace || ws_bytes < need)) {
+    set_error("conv_rows_fwd: workspace %zu < %zu bytes", ws_bytes, need);
+    return MPA_ERR_WORKSPACE;
+  }
   RowsGemm p{};
+  p.partial = need > 0 ? (float*)workspace : nullptr;
   const int K = Cin * H;
   p.A = w; p.B = x; p.C = out; p.bias = bias; p.M = Cout; p.N = B * W; p.K = K;
   p.am = flat(K); p.ak = flat(1); p.a_k_fast = 1;
   p.bk = flat(W); p.bn = Idx2{W, (long long)K * W, 1}; p.b_k_fast = 0;
   p.cm = flat(W); p.cn = Idx2{W, (long long)Cout * W, 1};
   p.act = act; p.act_param = act_param;
-  launch_rows_gemm(p, 1, (cudaStream_t)stream);
+  launch_rows_gemm(p, sizeof(float) * (size_t)B * Cout * W, (cudaStream_t)stream);
   MPA_CHECK_LAUNCH("conv_rows_fwd");
   return MPA_OK;
 }
@@ -134,7 +192,7 @@ int mpa_conv_rows_dgrad_f32(const float* g_out, const float* w, float* g_in, int
   p.bk = flat(W); p.bn = Idx2{W, (long long)Cout * W, 1}; p.b_k_fast = 0;
   p.cm = flat(W); p.cn = Idx2{W, (long long)K * W, 1};
   p.act = MPA_ACT_NONE; p.act_param = 0.f;
-  launch_rows_gemm(p, 1, (cudaStream_t)stream);
+  launch_rows_gemm(p, sizeof(float) * (size_t)B * K * W, (cudaStream_t)stream);
   MPA_CHECK_LAUNCH("conv_rows_dgrad");
   return MPA_OK;
 }
@@ -150,12 +208,7 @@ int mpa_conv_rows_wgrad_f32(const float* x, const float* g_out, float* g_w, int 
   p.bn = flat(W); p.bk = Idx2{W, (long long)K * W, 1}; p.b_k_fast = 1;
   p.cm = flat(K); p.cn = flat(1);
   p.act = MPA_ACT_NONE; p.act_param = 0.f;
-  const int tiles = ceil_div(p.N, 64) * ceil_div(p.M, 64);
-  int ks = 1;
-  while (tiles * ks < 296 && (p.K / (ks * 2)) >= 256) ks *= 2;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (ks > 1) cudaMemsetAsync(g_w, 0, sizeof(float) * (size_t)Cout * K, st);
-  launch_rows_gemm(p, ks, st);
+  launch_rows_gemm(p, sizeof(float) * (size_t)Cout * K, (cudaStream_t)stream);
   MPA_CHECK_LAUNCH("conv_rows_wgrad");
   return MPA_OK;
 }

@@ -51,7 +51,10 @@ def conv_f32(cache, name, conv, x, act=ops.ACT_NONE, act_param=0.0, bn=None, bn_
         # full-height VALID convolution (conv3 on a 75-frame patch): GEMM kernel instead of 16-row output tiles
         B, _, H, W = x.shape
         out = torch.empty(B, Cout, 1, W, dtype=torch.float32, device=x.device)
-        _lib.call('conv_rows_fwd_f32', x, w.detach().contiguous(), conv.bias, out, B, Cin, H, W, Cout, act, float(act_param), _lib.stream_ptr())
+        ws_bytes = _lib.lib().mpa_conv_rows_fwd_workspace(B, Cin, H, W, Cout)
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=x.device)
+        _lib.call('conv_rows_fwd_f32', x, w.detach().contiguous(), conv.bias, out, B, Cin, H, W, Cout, act, float(act_param), ws,
+                  _lib.usize(ws_bytes), _lib.stream_ptr())
         return out
     wp = cache.get(name + ':w32', [w], lambda: ops.pack_conv_weight(w))
     if bn is None:

@@ -52,7 +52,10 @@ def _conv_fwd(conv, x, act, a):
     if _is_rows_conv(conv, x.shape[2]):
         B, Cin, H, W = x.shape
         out = torch.empty(B, w.shape[0], 1, W, dtype=torch.float32, device=x.device)
-        call('conv_rows_fwd_f32', x, w.detach().contiguous(), conv.bias, out, B, Cin, H, W, w.shape[0], act, float(a), stream_ptr())
+        ws_bytes = _lib.lib().mpa_conv_rows_fwd_workspace(B, Cin, H, W, w.shape[0])
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=x.device)
+        call('conv_rows_fwd_f32', x, w.detach().contiguous(), conv.bias, out, B, Cin, H, W, w.shape[0], act, float(a), ws, _lib.usize(ws_bytes),
+             stream_ptr())
         return out
     wp = ops.pack_conv_weight(w)
     return ops.conv2d(x, wp, conv.bias, w.shape[0], tuple(w.shape[2:]), tuple(conv.stride), tuple(conv.padding), act, a)

@@ -233,7 +233,12 @@ def test_conv_rows_gemm_kernels_match_torch(B, Cin, H, W, Cout):
     ref = torch.where(pre >= 0, pre, 0.3 * pre).detach()
     xc, wc, bc, gc = x.cuda(), w.cuda(), b.cuda(), gy.cuda()
     out = torch.empty(B, Cout, 1, W, device='cuda')
-    _lib.call('conv_rows_fwd_f32', xc, wc, bc, out, B, Cin, H, W, Cout, 1, 0.3, _lib.stream_ptr())
+    ws_bytes = _lib.lib().mpa_conv_rows_fwd_workspace(B, Cin, H, W, Cout)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device='cuda')
+    _lib.call('conv_rows_fwd_f32', xc, wc, bc, out, B, Cin, H, W, Cout, 1, 0.3, ws, _lib.usize(ws_bytes), _lib.stream_ptr())
+    out2 = torch.empty_like(out)
+    _lib.call('conv_rows_fwd_f32', xc, wc, bc, out2, B, Cin, H, W, Cout, 1, 0.3, ws, _lib.usize(ws_bytes), _lib.stream_ptr())
+    assert torch.equal(out, out2)          # split-K forward: slices added in order, bit-reproducible
     assert (out.cpu() - ref).abs().max() < 2e-5
     gi = torch.empty_like(xc)
     _lib.call('conv_rows_dgrad_f32', gc, wc, gi, B, Cin, H, W, Cout, _lib.stream_ptr())
