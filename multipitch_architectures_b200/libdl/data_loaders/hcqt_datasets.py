@@ -7,7 +7,8 @@ ONE kernel launch (`batch` / `gather`: mpa_gather_patches_f32, mpa_augment_patch
 in 16 DataLoader worker processes.  The random DECISIONS of the augmentations (EQ curve incl. the reference's rejection
 loop, tuning step, transposition) are drawn on the host from a torch generator, the Gaussian values on the device (Philox),
 so the distributions — not the random streams — match the reference.  `__getitem__` keeps the
-per-item Dataset protocol: host tensors take the un-augmented reference path (index math + log), CUDA tensors the kernels."""
+per-item Dataset protocol on top of the same kernels (host tensors are moved to the GPU on first use; no CPU arithmetic path);
+`patch_frames` is the integer index math on its own."""
 import numpy as np
 import torch
 import torch.utils.data
@@ -65,21 +66,24 @@ class dataset_context(torch.utils.data.Dataset):
     def __len__(self):
         return (self.inputs.size()[1] - self.context) // self.stride
 
-    def __getitem__(self, index):
-        if self.scalingfactor:
-            assert False, 'Scaling not implemented for dataset_context!'
-        if self.inputs.is_cuda:
-            X, y = self.gather([int(index)])
-            return X[0], y[0]
-        if self.augmenting:
-            raise _lib.MpaError('augmentations run in the libmpa kernels: move the dataset tensors to the GPU (there is no CPU path)')
+    def patch_frames(self, index):
+        """Integer index math of the reference's __getitem__ (hcqt_datasets.py:67-75): -> (first frame, last frame + 1, target frame)."""
         half = self.context // 2
         centre = index * self.stride + half
-        X = self.inputs[:, centre - half:centre + half + 1, :].type(torch.FloatTensor)
-        y = self.targets[centre, :].type(torch.FloatTensor)[None, None, :]
-        if self.compression is not None:
-            X = torch.log(1 + self.compression * X)
-        return X, y
+        return centre - half, centre + half + 1, centre
+
+    def __getitem__(self, index):
+        """(X [C,context,F], y [1,1,P]) as CUDA tensors.  Host tensors are moved to the GPU on first use: the cut, the log compression and
+        the augmentations run in the libmpa kernels only — there is no CPU arithmetic path."""
+        if self.scalingfactor:
+            assert False, 'Scaling not implemented for dataset_context!'
+        if not self.inputs.is_cuda:
+            if not torch.cuda.is_available():
+                raise _lib.MpaError('dataset_context items are produced by the libmpa kernels: a CUDA (sm_100a) device is required '
+                                    '(there is no CPU path)')
+            self.inputs, self.targets = self.inputs.cuda(), self.targets.cuda()
+        X, y = self.gather([int(index)])
+        return X[0], y[0]
 
     # ------------------------------------------------------------------ device path
     def _resident(self):

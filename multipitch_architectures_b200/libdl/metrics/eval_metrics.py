@@ -20,11 +20,14 @@ _EPS = np.finfo(float).eps
 
 
 def compute_eval_measures(I_ref, I_est):
-    """libfmp.c5.compute_eval_measures (libfmp/c5/c5s2_chord_rec_template.py:238-261) for host arrays: integer counting."""
-    assert I_ref.shape == I_est.shape, 'Dimension of input matrices must agree'
-    TP = np.sum(np.logical_and(I_ref, I_est))
-    FP = np.sum(I_est > 0, axis=None) - TP
-    FN = np.sum(I_ref > 0, axis=None) - TP
+    """libfmp.c5.compute_eval_measures (libfmp/c5/c5s2_chord_rec_template.py:238-261): P, R, F, TP, FP, FN of two binary matrices,
+    counted by the same device kernel as everything else (mpa_eval_sums_f32; the counts are exact integers in float64)."""
+    assert tuple(I_ref.shape) == tuple(I_est.shape), 'Dimension of input matrices must agree'
+    ref = I_ref if isinstance(I_ref, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(I_ref))
+    est = I_est if isinstance(I_est, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(I_est))
+    ref2, est2 = ref.reshape(ref.shape[0], -1).float(), (est.reshape(est.shape[0], -1) > 0).float()
+    s = eval_sums(ref2, est2, 0.5)
+    TP, FP, FN = int(s[0]), int(s[1] - s[0]), int(s[2] - s[0])
     P = R = F = 0
     if TP > 0:
         P = TP / (TP + FP)

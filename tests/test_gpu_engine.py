@@ -78,6 +78,16 @@ def test_dataset_context_batch_kernel(host_golden):
     for j, i in enumerate(host_golden['ds_idx']):
         assert np.abs(X[int(i)].cpu().numpy() - host_golden['ds_X'][j]).max() < 1e-6
         assert np.array_equal(y[int(i)].cpu().numpy(), host_golden['ds_y'][j])
+    # the per-item Dataset protocol on HOST tensors (what the reference scripts construct): items come back from the same kernels
+    dh = dataset_context(torch.from_numpy(ip.astype(np.float64)), torch.from_numpy(tp.astype(np.float64)), {'context': 75, 'stride': 1, 'compression': 10})
+    assert len(dh) == int(host_golden['ds_len'][0])
+    for j, i in enumerate(host_golden['ds_idx']):
+        Xi, yi = dh[int(i)]
+        assert Xi.is_cuda and Xi.dtype == torch.float32 and tuple(Xi.shape) == (6, 75, 216) and tuple(yi.shape) == (1, 1, 72)
+        assert np.abs(Xi.cpu().numpy() - host_golden['ds_X'][j]).max() < 1e-6 and np.array_equal(yi.cpu().numpy(), host_golden['ds_y'][j])
+    d3 = dataset_context(torch.from_numpy(ip.astype(np.float64)), torch.from_numpy(tp.astype(np.float64)), {'context': 75, 'stride': 3, 'compression': None})
+    X5, y5 = d3[5]
+    assert abs(float(X5.double().sum()) - float(host_golden['ds3_X5_sum'][0])) < 1e-3 and np.array_equal(y5.cpu().numpy(), host_golden['ds3_y5'])
 
 
 def test_audio_to_activations_end_to_end():

@@ -72,7 +72,9 @@ def test_eval_measures_match_reference_golden(ext_golden):
 
 
 def test_prf_matches_host_golden_and_large_random(host_golden):
-    from multipitch_architectures_b200.libdl.metrics import calculate_eval_measures
+    from multipitch_architectures_b200.libdl.metrics import calculate_eval_measures, compute_eval_measures
+    got = compute_eval_measures(host_golden['prf_targ'], host_golden['prf_pred'] >= 0.4)       # the libfmp-shaped entry point
+    assert np.allclose(np.array(got, dtype=np.float64), host_golden['prf'], atol=1e-12, rtol=0)
     d = calculate_eval_measures(host_golden['prf_targ'], host_golden['prf_pred'], threshold=0.4)
     assert abs(d['precision'] - host_golden['prf'][0]) < 1e-12 and abs(d['recall'] - host_golden['prf'][1]) < 1e-12
     assert abs(d['f_measure'] - host_golden['prf'][2]) < 1e-12
