@@ -334,7 +334,7 @@ def unet_infer_main(args, rank, world, local, cores):
     from multipitch_architectures_b200.engine import predict_patchwise
     from multipitch_architectures_b200.libdl import nn_models as M
     from multipitch_architectures_b200.libdl.data_preprocessing.hcqt import get_plan, C1_HZ
-    from oracle import hcqt_oracle as HO       # synthetic-clip generator only
+    from tests import synth as HO              # synthetic-clip generator (workload data)
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
@@ -478,7 +478,7 @@ def main():
     from multipitch_architectures_b200.engine import CnnStreamEngine
     from multipitch_architectures_b200.libdl.data_preprocessing.hcqt import get_plan, C1_HZ
     from multipitch_architectures_b200.libdl.nn_models import deep_cnn_segm_sigmoid
-    from oracle import hcqt_oracle as HO       # synthetic-clip generator only (test infrastructure, not the measured path)
+    from tests import synth as HO              # synthetic-clip generator (workload data; the product arm never imports oracle/)
 
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)

@@ -35,7 +35,7 @@ def main():
     from multipitch_architectures_b200.libdl.data_loaders import dataset_context
     from multipitch_architectures_b200.libdl.metrics import eval_sums
     from multipitch_architectures_b200.libdl.data_preprocessing.hcqt import get_plan, C1_HZ
-    from oracle import hcqt_oracle as Q          # synthetic clip generator only
+    from tests import synth as Q                 # synthetic clip generator (workload data)
     peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else {}
     bw = peaks.get('hbm_gbs', 6541.5)
     dev = 'cuda'

@@ -14,7 +14,7 @@ def main():
     from multipitch_architectures_b200.engine import CnnStreamEngine
     from multipitch_architectures_b200.libdl.data_preprocessing.hcqt import get_plan, C1_HZ
     from multipitch_architectures_b200.libdl.nn_models import deep_cnn_segm_sigmoid
-    from oracle import hcqt_oracle as HO
+    from tests import synth as HO
     dev = torch.device('cuda', 0)
     model = deep_cnn_segm_sigmoid(**bench.DRCNN_KW, precision='fp16')
     bench.make_weights(model)
