@@ -199,3 +199,43 @@ def test_early_stopping_matches_reference_golden():
             assert got == list(g['es_flags'][ci, si]), (ci, si)
     with pytest.raises(ValueError):
         early_stopping(mode='median')
+
+
+@pytest.mark.parametrize('width', [1, 2, 3, 4])
+def test_read_wav_decodes_every_pcm_width(tmp_path, width):
+    """Host-side WAV decode of io.load_audio (integer PCM -> float32 in [-1, 1)); resampling itself is a kernel (GPU tests)."""
+    import wave
+    from multipitch_architectures_b200.io import read_wav
+    rng = np.random.default_rng(width)
+    n, nch = 257, 2
+    full = 2 ** (8 * width - 1)
+    ints = rng.integers(-full, full, size=(n, nch))
+    ints[0] = (-full, full - 1)
+    if width == 1:
+        raw = (ints + 128).astype(np.uint8).tobytes()
+    elif width == 3:
+        u = ints.astype(np.int64) & 0xFFFFFF
+        raw = np.stack([u & 255, (u >> 8) & 255, (u >> 16) & 255], -1).astype(np.uint8).tobytes()
+    else:
+        raw = ints.astype('<i2' if width == 2 else '<i4').tobytes()
+    path = str(tmp_path / f'w{width}.wav')
+    with wave.open(path, 'wb') as w:
+        w.setnchannels(nch)
+        w.setsampwidth(width)
+        w.setframerate(44100)
+        w.writeframes(raw)
+    x, sr = read_wav(path)
+    assert sr == 44100 and x.shape == (n, nch) and x.dtype == np.float32
+    assert np.array_equal(x, (ints / float(full)).astype(np.float32))
+
+
+def test_results_csv_layout(tmp_path):
+    import csv
+    from multipitch_architectures_b200.io import write_results_csv
+    rows = [{'Filename': 'a.npy', 'precision': 0.5, 'recall': 0.25, '_kframes': 1.0}, {'Filename': 'b.npy', 'precision': 1.0, 'recall': 0.75, '_kframes': 3.0}]
+    table = write_results_csv(rows, str(tmp_path / 'r.csv'))
+    lines = list(csv.reader(open(str(tmp_path / 'r.csv'))))
+    assert lines[0] == ['', 'Filename', 'precision', 'recall']
+    assert lines[3][1] == 'FILEWISE MEAN' and float(lines[3][2]) == 0.75 and float(lines[3][3]) == 0.5
+    assert lines[4][1] == 'FRAMEWISE MEAN' and float(lines[4][2]) == 0.875 and float(lines[4][3]) == 0.625
+    assert table[3][0] == 'FRAMEWISE MEAN'
