@@ -321,6 +321,15 @@ int mpa_maxpool_time_bwd_f32(const float* a, const float* g_pool, float* g_a, in
 /* nn.Dropout(p) in training mode with a Philox-4x32-10 stream: element i uses counter (i/4, offset), key seed. */
 int mpa_dropout_f32(const float* x, float* out, long long n, float p, unsigned long long seed,
                     unsigned long long offset, void* stream);
+/* MaxPool((k,1)) -> Dropout(p) (-> + res) of a CNN block in one pass, and its backward (g_out = the gradient behind the dropout layer; its
+ * mask is re-drawn on the fly).  The masks are those of mpa_dropout_f32 / mpa_dropout_dev_f32 for the same (seed, offset[, step_dev]).
+ * Forward: F % 4 == 0; backward: k = 3 or 13. */
+int mpa_maxpool_time_dropout_f32(const float* x, const float* res, float* out, int B, int C, int T, int F, int k, float p,
+                                 unsigned long long seed, unsigned long long offset, const long long* step_dev,
+                                 unsigned long long step_mul, void* stream);
+int mpa_maxpool_time_bwd_dropout_f32(const float* a, const float* g_out, float* g_a, int B, int C, int T, int F, int k, int act,
+                                     float act_param, float p, unsigned long long seed, unsigned long long offset,
+                                     const long long* step_dev, unsigned long long step_mul, void* stream);
 /* Same with offset = step_dev[0] * step_mul + site, the step counter read from DEVICE memory: a training step captured in a CUDA graph
  * (UnetTrainStep(graph=True)) then draws fresh masks on every replay, identical to the eager step of the same number. */
 int mpa_dropout_dev_f32(const float* x, float* out, long long n, float p, unsigned long long seed, unsigned long long site,

@@ -80,8 +80,9 @@ __global__ void __launch_bounds__(kPoolBwdCols * kPoolBwdRowGroups) maxpool_time
 // down the T rows with the window's k activations and the k pending gradient sums in registers; row t-h is final once window t is done.
 // Loads / stores are coalesced across the threads of a row; HBM-bound (reads a and g_p once, writes g_a once).
 template <int K>
+// d.p > 0: g_p is the gradient BEHIND a dropout layer that followed the pool; its mask (same convention as dropout_kernel) is applied on the fly
 __global__ void __launch_bounds__(128) maxpool_time_bwd_col_kernel(const float* __restrict__ a, const float* __restrict__ g_p, float* __restrict__ g_a,
-                                                                   int T, int F, int act, float act_param) {
+                                                                   int T, int F, int act, float act_param, DropoutArgs d) {
   constexpr int H = K / 2;
   const int f = blockIdx.y * blockDim.x + threadIdx.x;
   if (f >= F) return;
@@ -89,6 +90,8 @@ __global__ void __launch_bounds__(128) maxpool_time_bwd_col_kernel(const float* 
   const float* ap = a + base;
   const float* gp = g_p + base;
   float* op = g_a + base;
+  const unsigned long long d_off = d.p > 0.f ? dropout_offset(d) : 0ull;
+  const float d_scale = d.p > 0.f ? 1.f / (1.f - d.p) : 1.f;
   float win[K], acc[K];
 #pragma unroll
   for (int j = 0; j < K; ++j) {
@@ -97,7 +100,8 @@ __global__ void __launch_bounds__(128) maxpool_time_bwd_col_kernel(const float* 
     acc[j] = 0.f;
   }
   for (int t = 0; t < T; ++t) {
-    const float g = gp[(size_t)t * F];
+    float g = gp[(size_t)t * F];
+    if (d.p > 0.f) g = __fmul_rn(g, dropout_factor_at((long long)(base + (size_t)t * F), d.p, d_scale, d.seed, d_off));
     int am = 0;
     float best = win[0];
 #pragma unroll
@@ -370,8 +374,9 @@ int mpa_maxpool_time_bwd_f32(const float* a, const float* g_pool, float* g_a, in
   MPA_REQUIRE(a && g_pool && g_a && B > 0 && C > 0 && T > 0 && F > 0 && k >= 1 && (k & 1), "maxpool_time_bwd: bad argument");
   if ((k == 3 || k == 13) && T > k / 2) {
     const dim3 grid(B * C, ceil_div(F, 128));
-    if (k == 3) maxpool_time_bwd_col_kernel<3><<<grid, 128, 0, (cudaStream_t)stream>>>(a, g_pool, g_a, T, F, act, act_param);
-    else maxpool_time_bwd_col_kernel<13><<<grid, 128, 0, (cudaStream_t)stream>>>(a, g_pool, g_a, T, F, act, act_param);
+    const DropoutArgs nod{0.f, 0ull, 0ull, nullptr, 0ull};
+    if (k == 3) maxpool_time_bwd_col_kernel<3><<<grid, 128, 0, (cudaStream_t)stream>>>(a, g_pool, g_a, T, F, act, act_param, nod);
+    else maxpool_time_bwd_col_kernel<13><<<grid, 128, 0, (cudaStream_t)stream>>>(a, g_pool, g_a, T, F, act, act_param, nod);
     MPA_CHECK_LAUNCH("maxpool_time_bwd_col");
     return MPA_OK;
   }
@@ -446,6 +451,20 @@ int mpa_conv2d_wgrad_f32(const float* x, const float* g_out, float* g_w, float* 
     if (rc != MPA_OK) return rc;
     MPA_CHECK_LAUNCH("bias_grad");
   }
+  return MPA_OK;
+}
+
+int mpa_maxpool_time_bwd_dropout_f32(const float* a, const float* g_out, float* g_a, int B, int C, int T, int F, int k, int act, float act_param,
+                                     float p, unsigned long long seed, unsigned long long offset, const long long* step_dev,
+                                     unsigned long long step_mul, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(a && g_out && g_a && B > 0 && C > 0 && F > 0 && (k == 3 || k == 13) && T > k / 2 && p >= 0.f && p < 1.f,
+              "maxpool_time_bwd_dropout: bad argument (k must be 3 or 13)");
+  const dim3 grid(B * C, ceil_div(F, 128));
+  const DropoutArgs d{p, seed, offset, step_dev, step_mul};
+  if (k == 3) maxpool_time_bwd_col_kernel<3><<<grid, 128, 0, (cudaStream_t)stream>>>(a, g_out, g_a, T, F, act, act_param, d);
+  else maxpool_time_bwd_col_kernel<13><<<grid, 128, 0, (cudaStream_t)stream>>>(a, g_out, g_a, T, F, act, act_param, d);
+  MPA_CHECK_LAUNCH("maxpool_time_bwd_dropout");
   return MPA_OK;
 }
 

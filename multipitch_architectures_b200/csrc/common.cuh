@@ -74,6 +74,29 @@ __device__ __forceinline__ uint4 philox(uint4 ctr, uint2 key) {
   return ctr;
 }
 
+// nn.Dropout keep factor of element i of a tensor under (seed, offset): the convention of dropout_kernel (counter i/4, lane i%4)
+struct DropoutArgs {
+  float p;                        // 0 = no dropout
+  unsigned long long seed, offset;
+  const long long* step_dev;      // optional device-side step counter: offset += step_dev[0] * step_mul
+  unsigned long long step_mul;
+};
+__device__ __forceinline__ unsigned long long dropout_offset(const DropoutArgs& d) {
+  return d.step_dev ? d.offset + (unsigned long long)d.step_dev[0] * d.step_mul : d.offset;
+}
+__device__ __forceinline__ uint4 dropout_bits(long long i4, unsigned long long seed, unsigned long long offset) {
+  return philox(make_uint4((uint32_t)i4, (uint32_t)(i4 >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)),
+                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+}
+__device__ __forceinline__ float dropout_factor(uint32_t bits, float p, float scale) {
+  return (float)(bits >> 8) * (1.f / 16777216.f) >= p ? scale : 0.f;
+}
+__device__ __forceinline__ float dropout_factor_at(long long i, float p, float scale, unsigned long long seed, unsigned long long offset) {
+  const uint4 r = dropout_bits(i >> 2, seed, offset);
+  const int e = (int)(i & 3);
+  return dropout_factor(e == 0 ? r.x : e == 1 ? r.y : e == 2 ? r.z : r.w, p, scale);
+}
+
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // Opt a kernel into the maximum dynamic shared memory once per (kernel, device) for the whole PROCESS.  (The attribute is a

@@ -157,6 +157,36 @@ __global__ void maxpool_time_vec4_kernel(const float4* __restrict__ x, const flo
   }
 }
 
+// out = dropout(maxpool_time(x)) + res  — the CNN block's MaxPool -> Dropout (-> residual add) in one pass (basic_cnns.py:376-377, 415-417);
+// the mask is the one mpa_dropout_f32 draws for the same (seed, offset): counter i/4, lane i%4 of the element index
+__global__ void maxpool_time_dropout_vec4_kernel(const float4* __restrict__ x, const float4* __restrict__ res, float4* __restrict__ out,
+                                                 long long total4, int T, int F4, int k, DropoutArgs d) {
+  const int h = k / 2;
+  const unsigned long long offset = dropout_offset(d);
+  const float scale = 1.f / (1.f - d.p);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i % F4);
+    const long long r = i / F4;
+    const int t = (int)(r % T);
+    const float4* xp = x + (r - t) * F4 + f;
+    const int lo = max(0, t - h), hi = min(T - 1, t + h);
+    float4 m = xp[(size_t)lo * F4];
+    for (int tt = lo + 1; tt <= hi; ++tt) {
+      const float4 v = xp[(size_t)tt * F4];
+      m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+    }
+    const uint4 bits = dropout_bits(i, d.seed, offset);
+    // __fmul_rn: the product is rounded before the residual is added, exactly like the separate dropout and add kernels (no FMA contraction)
+    m.x = __fmul_rn(m.x, dropout_factor(bits.x, d.p, scale)); m.y = __fmul_rn(m.y, dropout_factor(bits.y, d.p, scale));
+    m.z = __fmul_rn(m.z, dropout_factor(bits.z, d.p, scale)); m.w = __fmul_rn(m.w, dropout_factor(bits.w, d.p, scale));
+    if (res) {
+      const float4 q = res[i];
+      m.x += q.x; m.y += q.y; m.z += q.z; m.w += q.w;
+    }
+    out[i] = m;
+  }
+}
+
 __global__ void maxpool2d_kernel(const float* __restrict__ x, float* __restrict__ out, long long total, int H, int W,
                                  int Ho, int Wo, int kh, int kw, int sh, int sw) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -317,6 +347,22 @@ int mpa_maxpool_time_f32(const float* x, const float* res, float* out, int B, in
   }
   maxpool_time_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, res, out, total, T, F, k);
   MPA_CHECK_LAUNCH("maxpool_time");
+  return MPA_OK;
+}
+
+int mpa_maxpool_time_dropout_f32(const float* x, const float* res, float* out, int B, int C, int T, int F, int k, float p,
+                                 unsigned long long seed, unsigned long long offset, const long long* step_dev, unsigned long long step_mul,
+                                 void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(x && out && B > 0 && C > 0 && T > 0 && F > 0 && k >= 1 && (k & 1) && p >= 0.f && p < 1.f, "maxpool_time_dropout: bad argument");
+  MPA_REQUIRE(F % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)res & 15) == 0,
+              "maxpool_time_dropout: F must be a multiple of 4 and the tensors 16-byte aligned");
+  const long long total = (long long)B * C * T * F;
+  long long g = (total / 4 + 255) / 256;
+  DropoutArgs d{p, seed, offset, step_dev, step_mul};
+  maxpool_time_dropout_vec4_kernel<<<(unsigned)(g > 148LL * 64 ? 148LL * 64 : g), 256, 0, (cudaStream_t)stream>>>(
+      (const float4*)x, (const float4*)res, (float4*)out, total / 4, T, F / 4, k, d);
+  MPA_CHECK_LAUNCH("maxpool_time_dropout");
   return MPA_OK;
 }
 

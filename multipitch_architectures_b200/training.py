@@ -102,6 +102,37 @@ def _act_bwd(out, g, act, a=0.0):
     return gi
 
 
+FUSE_POOL_DROPOUT = True      # test knob: False = separate pool / dropout (/ add) kernels; the results are identical
+
+
+def _step_args():
+    return _step_dev, ctypes_u64(_step_mul if _step_dev is not None else 0)
+
+
+def _pool_dropout(act_t, k, res, p, seed, offset):
+    """dropout(maxpool_time(act_t, k)) (+ res): one kernel when dropout is on (same mask as _dropout(., p, seed, offset))."""
+    B, C, T, F = act_t.shape
+    if p > 0.0 and FUSE_POOL_DROPOUT and F % 4 == 0:
+        out = torch.empty_like(act_t)
+        sd, sm = _step_args()
+        call('maxpool_time_dropout_f32', act_t, res, out, B, C, T, F, k, float(p), ctypes_u64(seed), ctypes_u64(offset), sd, sm, stream_ptr())
+        return out
+    d = _dropout(ops.maxpool_time(act_t, k), p, seed, offset)
+    return _add(d, res) if res is not None else d
+
+
+def _pool_bwd_dropout(a_in, g_out, k, act, a, p, seed, offset):
+    """Gradient wrt the pool input of dropout(maxpool_time(.)): the dropout mask is applied to g_out on the fly."""
+    if p > 0.0 and FUSE_POOL_DROPOUT and k in (3, 13) and a_in.shape[2] > k // 2:
+        B, C, T, F = a_in.shape
+        ga = torch.empty_like(a_in)
+        sd, sm = _step_args()
+        call('maxpool_time_bwd_dropout_f32', a_in, g_out, ga, B, C, T, F, k, act, float(a), float(p), ctypes_u64(seed), ctypes_u64(offset), sd, sm,
+             stream_ptr())
+        return ga
+    return _pool_bwd(a_in, _dropout(g_out, p, seed, offset), k, act, a)
+
+
 def _pool_bwd(a_in, g_pool, k, act, a):
     B, C, T, F = a_in.shape
     ga = torch.empty_like(a_in)
@@ -232,14 +263,15 @@ def cnn_train_forward(model, x, seed=0, step=0):
             act, xc = TcConv.forward(name, conv, z, ops.ACT_LRELU, a)
         else:
             act, xc = _conv_fwd(conv, z, ops.ACT_LRELU, a), None
-        d = drop(ops.maxpool_time(act, 3))
+        site[0] += 1
         sv['blocks'].append((z, act, xc))
-        z = _add(d, z) if (residual and i > 0) else d
+        z = _pool_dropout(act, 3, z if (residual and i > 0) else None, p, seed, site[0])
     if _tc_s3_eligible(model, model.conv2[0], z.shape[3]):
         a2, x2c = _tc_s3_forward('conv2', model.conv2[0], z, ops.ACT_LRELU, a)
     else:
         a2, x2c = _conv_fwd(model.conv2[0], z, ops.ACT_LRELU, a), None
-    d2 = drop(ops.maxpool_time(a2, 13))
+    site[0] += 1
+    d2 = _pool_dropout(a2, 13, None, p, seed, site[0])
     a3 = _conv_fwd(model.conv3[0], d2, ops.ACT_LRELU, a)
     d3 = drop(a3)
     a4 = _conv_fwd(model.conv4[0], d3, ops.ACT_LRELU, a)
@@ -269,8 +301,8 @@ def cnn_train_backward(model, sv, g_y, grads):
     g = drop_bwd(_dgrad(c40, g, sv['d3'].shape))
     g = _act_bwd(sv['a3'], g, ops.ACT_LRELU, a)
     _wgrad(c3, sv['d2'], g, grads['conv3.0.weight'], grads['conv3.0.bias'])
-    g = drop_bwd(_dgrad(c3, g, sv['d2'].shape))
-    g = _pool_bwd(sv['a2'], g, 13, ops.ACT_LRELU, a)
+    site[0] -= 1
+    g = _pool_bwd_dropout(sv['a2'], _dgrad(c3, g, sv['d2'].shape), 13, ops.ACT_LRELU, a, p, seed, site[0])
     if sv.get('x2c') is not None:
         g_z = _tc_s3_backward('conv2', c2, sv['x2c'], g, grads['conv2.0.weight'], grads['conv2.0.bias'])
     else:
@@ -279,7 +311,8 @@ def cnn_train_backward(model, sv, g_y, grads):
     for i in range(len(blocks) - 1, -1, -1):
         name, conv = blocks[i]
         z_in, act, xc = sv['blocks'][i]
-        g_conv = _pool_bwd(act, drop_bwd(g_z), 3, ops.ACT_LRELU, a)
+        site[0] -= 1
+        g_conv = _pool_bwd_dropout(act, g_z, 3, ops.ACT_LRELU, a, p, seed, site[0])
         if xc is not None:
             g_in = TcConv.backward(name, conv, xc, g_conv, grads[f'{name}.0.weight'], grads[f'{name}.0.bias'], need_dx=True)
         else:

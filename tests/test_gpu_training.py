@@ -139,3 +139,31 @@ def test_cnn_graph_replayed_step_equals_eager_step():
     print('eager', res[False], 'graph', res[True])
     assert all(abs(a - b) <= 2e-4 * max(1.0, abs(a)) for a, b in zip(res[False], res[True]))
     assert len(set(round(v, 4) for v in res[True])) == 6
+
+
+def test_fused_pool_dropout_kernels_equal_the_separate_kernels():
+    """MaxPool -> Dropout (-> + residual) in one kernel and its backward with the mask re-drawn on the fly: bit-identical to
+    maxpool_time -> dropout -> add and dropout -> maxpool_time_bwd (same Philox convention), through a whole training step."""
+    from multipitch_architectures_b200 import training as TR
+    from tests.refshapes import build_model
+    from tests.weights import fill_state_dict, synth_patches, synth_targets
+    res = {}
+    for fuse in (True, False):
+        TR.FUSE_POOL_DROPOUT = fuse
+        try:
+            m = build_model('drcnn_tiny')
+            m.load_state_dict(fill_state_dict(m.state_dict(), 9, scheme='torch_default'))
+            m = m.cuda().train()
+            assert m.p_dropout > 0
+            x, t = synth_patches(4, 81).cuda(), synth_targets(4, 81).cuda()
+            m.dropout_seed, m._train_calls = 1234, 0
+            y = m(x)
+            loss = torch.nn.BCELoss()(y, t)
+            loss.backward()
+            res[fuse] = (y.detach().clone(), {k: p.grad.clone() for k, p in m.named_parameters()})
+        finally:
+            TR.FUSE_POOL_DROPOUT = True
+    assert torch.equal(res[True][0], res[False][0])
+    for k in res[True][1]:
+        a, b = res[True][1][k], res[False][1][k]
+        assert (a - b).abs().max().item() <= 1e-6 * max(1.0, b.abs().max().item()), k       # weight gradients meet in fp32 atomics
