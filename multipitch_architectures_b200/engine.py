@@ -38,7 +38,8 @@ class CnnStreamEngine:
         self.C0 = self.blocks[0][1].weight.shape[0]
         self.pitch, self.pf, self.pt = (self.F + 8 + 15) // 16 * 16, 8, 1
         self._bufs = None
-        self.timers = None          # optional: list collecting (tag, start_event, end_event)
+        self.timers = None          # optional: list collecting (tag, start_event, end_event, work)
+        self.timer_tags = None      # optional: only these stage tags are timed (None = every stage)
         # Fused / de-duplicated schedule (mpa_conv_tc_pool_f16): needs chunk-aligned channel counts and J >= 2
         ks = {tuple(c.kernel_size) for _, c in self.blocks}
         self.fused = bool(fused) and self.C0 % 8 == 0 and self.C0 <= 64 and len(ks) == 1 and all(k % 2 == 1 for k in next(iter(ks)))
@@ -59,7 +60,7 @@ class CnnStreamEngine:
 
     def _timed(self, tag, fn, work=0):
         """work: output rows x patches of a convolution launch (for FLOP accounting by the caller)."""
-        if self.timers is None:
+        if self.timers is None or (self.timer_tags is not None and tag not in self.timer_tags):
             return fn()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
