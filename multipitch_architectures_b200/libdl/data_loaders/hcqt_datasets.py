@@ -108,9 +108,10 @@ class dataset_context(torch.utils.data.Dataset):
             d['transp'] = torch.randint(-t, t + 1, (n,), generator=g).numpy().astype(np.int32)
         return d
 
-    def gather(self, indices, decisions=None, noise_offset=None):
+    def gather(self, indices, decisions=None, noise_offset=None, out=None):
         """Patches `indices` (any order) in one launch for CUDA-resident inputs -> (X [n,C,context,F], y [n,1,1,P]).
-        `decisions`: output of `draw` (drawn here when None and augmentations are configured)."""
+        `decisions`: output of `draw` (drawn here when None and augmentations are configured); `out` = (X, y) contiguous
+        tensors (e.g. slices of a larger batch) to write into."""
         if not self.inputs.is_cuda:
             raise _lib.MpaError('dataset_context.gather needs CUDA-resident inputs')
         if self.scalingfactor:
@@ -136,7 +137,7 @@ class dataset_context(torch.utils.data.Dataset):
         start = pack_d[0]
         dec_d = pack_d[1:].view(torch.int32).view(4, n)
         dd = {k: dec_d[r] for r, k in enumerate(names) if k in decisions}
-        X = torch.empty(n, C, self.context, F, dtype=torch.float32, device=dev)
+        X = out[0] if out is not None else torch.empty(n, C, self.context, F, dtype=torch.float32, device=dev)
         gamma = float(self.compression) if self.compression is not None else 0.0
         if noise_offset is None:
             noise_offset = self._calls
@@ -146,7 +147,7 @@ class dataset_context(torch.utils.data.Dataset):
                   float(self.noisestd or 0.0), gamma, dd.get('tune2'), dd.get('transp'), 3, 1e-4,
                   _lib.u64(self._seed), _lib.u64(noise_offset), st)
         P = tg.shape[1]
-        y = torch.empty(n, 1, 1, P, dtype=torch.float32, device=dev)
+        y = out[1] if out is not None else torch.empty(n, 1, 1, P, dtype=torch.float32, device=dev)
         frame = start + self.context // 2
         _lib.call('augment_targets_f32', tg, frame, dd.get('transp'), y, n, P, st)
         return X, y

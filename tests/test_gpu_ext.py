@@ -428,3 +428,40 @@ def test_host_prefetcher_delivers_batches_in_order():
         (x * 2).sum()        # consumer work on the compute stream
         seen += 1
     assert seen == 5
+
+
+# ----------------------------------------------------------------------------- the scripts' training loop on top of the pieces
+def _toy_sets(n_files, n_frames, seed, params):
+    """HCQT-like inputs whose fundamental channel carries the labels: learnable in a few dozen steps."""
+    from multipitch_architectures_b200.libdl.data_loaders import dataset_context
+    rng = np.random.default_rng(seed)
+    sets = []
+    for _ in range(n_files):
+        roll = (rng.uniform(size=(n_frames, 72)) < 0.06).astype(np.float32)
+        roll = np.maximum.reduce([np.roll(roll, s, axis=0) for s in range(6)])          # notes last 6 frames
+        x = 0.02 * np.abs(rng.standard_normal((6, n_frames, 216))).astype(np.float32)
+        x[1, :, 1::3] += 0.8 * roll
+        x[2, :, 37::3][:, :60] += 0.4 * roll[:, :60]
+        sets.append(dataset_context(torch.from_numpy(x).cuda(), torch.from_numpy(roll).cuda(), dict({'context': 75, 'stride': 1, 'compression': 10}, **params)))
+    return sets
+
+
+@pytest.mark.parametrize('name,graph', [('cnn_xs', True), ('unet_tiny', False)])
+def test_fit_loop_trains_validates_schedules_and_checkpoints(tmp_path, name, graph):
+    from multipitch_architectures_b200.loop import fit
+    from tests.refshapes import build_model
+    torch.manual_seed(0)
+    m = build_model(name, precision='bf16').cuda()
+    aug = {'aug:randomeq': 20, 'aug:noisestd': 1e-4, 'aug:tuning': True, 'aug:transpsemitones': 5}
+    train, val = _toy_sets(3, 160, 1, aug), _toy_sets(1, 120, 2, {})
+    path = str(tmp_path / 'best.pt')
+    logs = []
+    hist = fit(m, train, val, batch_size=16, val_batch_size=25, lr=2e-3, max_epochs=4, max_batches_per_epoch=12, seed=3, save_path=path, graph=graph,
+               scheduler=dict(factor=0.5, patience=0, threshold=0.5), early=dict(patience=3, min_delta=1e-5), log=logs.append)
+    assert 1 <= len(hist) <= 4 and len(logs) == len(hist) and all(np.isfinite(h['train_loss']) and np.isfinite(h['val_loss']) for h in hist)
+    assert hist[-1]['train_loss'] < hist[0]['train_loss']                     # it learns
+    assert hist[-1]['lr'] < 2e-3                                              # a 50 % improvement threshold forces the scheduler to act
+    sd = torch.load(path)
+    assert set(sd) == set(m.state_dict()) and all(torch.isfinite(v.float()).all() for v in sd.values())
+    m2 = build_model(name, precision='bf16')
+    m2.load_state_dict(sd)

@@ -239,3 +239,54 @@ def test_results_csv_layout(tmp_path):
     assert lines[3][1] == 'FILEWISE MEAN' and float(lines[3][2]) == 0.75 and float(lines[3][3]) == 0.5
     assert lines[4][1] == 'FRAMEWISE MEAN' and float(lines[4][2]) == 0.875 and float(lines[4][3]) == 0.625
     assert table[3][0] == 'FRAMEWISE MEAN'
+
+
+def test_reduce_lr_on_plateau_matches_torch():
+    """loop.ReduceLROnPlateau (drives the `lr` attribute of the fused train steps) vs torch.optim.lr_scheduler.ReduceLROnPlateau with the
+    scripts' settings (mode min, factor 0.5, patience 5, threshold 1e-4 rel, min_lr 1e-6, exp126a...py:118-130)."""
+    import types
+    from multipitch_architectures_b200.loop import ReduceLROnPlateau
+    rng = np.random.default_rng(0)
+    for trial in range(4):
+        seq = np.concatenate([np.linspace(1.0, 0.6, 15), 0.6 + 0.01 * rng.standard_normal(70)]) * (1 + 0.002 * rng.standard_normal(85))
+        p = torch.nn.Parameter(torch.zeros(1))
+        opt = torch.optim.SGD([p], lr=1e-3)
+        ref = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, mode='min', factor=0.5, patience=5 - trial, threshold=1e-4, threshold_mode='rel',
+                                                         cooldown=trial % 2, eps=1e-8, min_lr=1e-6)
+        holder = types.SimpleNamespace(lr=1e-3)
+        mine = ReduceLROnPlateau(holder, factor=0.5, patience=5 - trial, threshold=1e-4, cooldown=trial % 2, min_lr=1e-6, eps=1e-8)
+        for v in seq:
+            ref.step(float(v))
+            mine.step(float(v))
+            assert holder.lr == opt.param_groups[0]['lr']
+        assert holder.lr < 1e-3
+
+
+def test_patch_sampler_covers_every_patch_once_per_epoch():
+    """ConcatDataset + DataLoader(shuffle=True) semantics on stand-in datasets: every (file, patch) pair exactly once per epoch, batches
+    straddle files, items land in the batch positions the sampler assigned."""
+    from multipitch_architectures_b200.loop import PatchSampler
+
+    class Fake:
+        def __init__(self, n, tag):
+            self.inputs, self.targets, self.context, self.n, self.tag = torch.zeros(2, n + 5, 4), torch.zeros(n + 5, 3), 5, n, tag
+
+        def __len__(self):
+            return self.n
+
+        def gather(self, idx, out=None):
+            for j, i in enumerate(idx):
+                out[0][j] = 1000 * self.tag + int(i)
+                out[1][j] = self.tag
+    sets = [Fake(7, 1), Fake(12, 2), Fake(3, 3)]
+    smp = PatchSampler(sets, batch_size=5, shuffle=True, seed=1)
+    assert len(smp) == 5
+    for _ in range(2):
+        seen = []
+        for X, y in smp.epoch():
+            assert X.shape[1:] == (2, 5, 4) and y.shape[1:] == (1, 1, 3) and X.shape[0] in (5, 2)
+            ids = X[:, 0, 0, 0].long().tolist()
+            assert [int(v) // 1000 for v in ids] == y[:, 0, 0, 0].long().tolist()
+            seen += ids
+        assert sorted(seen) == sorted([1000 + i for i in range(7)] + [2000 + i for i in range(12)] + [3000 + i for i in range(3)])
+    assert len(PatchSampler(sets, 5, max_batches=2)) == 2
