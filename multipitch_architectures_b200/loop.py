@@ -45,19 +45,29 @@ class PatchSampler:
     """Batches over the concatenation of several dataset_context objects: (dataset id, patch index) pairs in one shuffled permutation
     per epoch, cut into batches of `batch_size` (the last one may be short), each gathered into ONE [n,C,T,F] tensor."""
 
-    def __init__(self, datasets, batch_size, shuffle=True, seed=0, max_batches=None):
+    def __init__(self, datasets, batch_size, shuffle=True, seed=0, max_batches=None, rank=0, world=1):
+        """Data-parallel runs: every rank draws the SAME permutation (same seed) and keeps the items rank, rank+world, ... of it, so the
+        ranks see disjoint patches and together cover the epoch (torch's DistributedSampler scheme); all ranks run the same number of
+        batches (the tail is padded by wrapping around), which the per-step gradient all-reduce needs."""
         self.datasets, self.batch_size, self.shuffle, self.max_batches = list(datasets), int(batch_size), shuffle, max_batches
+        self.rank, self.world = int(rank), int(world)
         self.rng = np.random.default_rng(seed)
         self.lengths = np.array([len(d) for d in self.datasets], dtype=np.int64)
         self.offsets = np.concatenate([[0], np.cumsum(self.lengths)])
 
+    def _per_rank(self):
+        return int(-(-int(self.offsets[-1]) // self.world))
+
     def __len__(self):
-        n = int(-(-self.offsets[-1] // self.batch_size))
+        n = int(-(-self._per_rank() // self.batch_size))
         return n if self.max_batches is None else min(n, int(self.max_batches))
 
     def epoch(self):
         total = int(self.offsets[-1])
         order = self.rng.permutation(total) if self.shuffle else np.arange(total)
+        if self.world > 1:
+            padded = np.concatenate([order, order[:self._per_rank() * self.world - total]])
+            order = padded[self.rank::self.world]
         for k in range(len(self)):
             yield self.gather(order[k * self.batch_size:(k + 1) * self.batch_size])
 
@@ -107,11 +117,24 @@ def fit(model, train_sets, val_sets=None, batch_size=25, val_batch_size=50, lr=1
     model.train()
     cnn = isinstance(model, (basic_cnn_segm_sigmoid, deep_cnn_segm_sigmoid))
     step = (TrainStep if cnn else UnetTrainStep)(model, lr=lr, weight_decay=weight_decay, graph=graph)
-    sampler = PatchSampler(train_sets, batch_size, shuffle=True, seed=seed, max_batches=max_batches_per_epoch)
-    vsampler = PatchSampler(val_sets, val_batch_size, shuffle=False) if val_sets else None
+    import torch.distributed as dist
+    world, rank = (dist.get_world_size(), dist.get_rank()) if (dist.is_available() and dist.is_initialized()) else (1, 0)
+    sampler = PatchSampler(train_sets, batch_size, shuffle=True, seed=seed, max_batches=max_batches_per_epoch, rank=rank, world=world)
+    vsampler = PatchSampler(val_sets, val_batch_size, shuffle=False) if val_sets else None       # every rank validates on the whole set
     sched = None if scheduler is False or vsampler is None else ReduceLROnPlateau(step, **(scheduler or {}))
     es = None if early is False or vsampler is None else early_stopping(**dict(dict(mode='min', min_delta=1e-5, patience=12, percentage=False),
                                                                                 **(early or {})))
+    if world > 1:
+        dist.broadcast(step.flat_p, src=0)              # replicas start from rank 0's parameters
+
+    def across_ranks(v):
+        """Mean over the ranks: scheduler and early-stopping decisions must be identical everywhere (a rank that stopped alone would
+        leave the others waiting in the gradient all-reduce)."""
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=step.flat_p.device)
+        dist.all_reduce(t)
+        return float(t.item()) / world
     history = []
     full = None
     for epoch in range(max_epochs):
@@ -123,23 +146,24 @@ def fit(model, train_sets, val_sets=None, batch_size=25, val_batch_size=50, lr=1
                 continue                                  # a short last batch does not fit the captured graph: skipped (drop_last)
             acc += step(X, y).reshape(())
             n_batches += 1
-        rec = {'epoch': epoch, 'train_loss': float(acc.item()) / max(1, n_batches), 'lr': step.lr}
+        rec = {'epoch': epoch, 'train_loss': across_ranks(float(acc.item()) / max(1, n_batches)), 'lr': step.lr}
         if vsampler is not None:
             vacc, n_val = torch.zeros_like(acc), 0
             for X, y in vsampler.epoch():
                 vacc += _train_mode_loss(model, step, X, y).reshape(())
                 n_val += 1
-            rec['val_loss'] = float(vacc.item()) / max(1, n_val)
+            rec['val_loss'] = across_ranks(float(vacc.item()) / max(1, n_val))
             if sched is not None:
                 sched.step(rec['val_loss'])
         history.append(rec)
-        log('Epoch #%d finished. Train Loss: %.4f%s with lr: %.5f' % (epoch, rec['train_loss'],
-                                                                      (', Val Loss: %.4f' % rec['val_loss']) if 'val_loss' in rec else '', rec['lr']))
+        if rank == 0:
+            log('Epoch #%d finished. Train Loss: %.4f%s with lr: %.5f' % (epoch, rec['train_loss'],
+                                                                          (', Val Loss: %.4f' % rec['val_loss']) if 'val_loss' in rec else '', rec['lr']))
         if es is not None:
-            if save_path and (epoch == 0 or es.curr_is_better(rec['val_loss'])):
+            if save_path and rank == 0 and (epoch == 0 or es.curr_is_better(rec['val_loss'])):
                 torch.save(model.state_dict(), save_path)
             if es.step(rec['val_loss']):
                 break
-    if save_path and es is None:
+    if save_path and es is None and rank == 0:
         torch.save(model.state_dict(), save_path)
     return history

@@ -290,3 +290,31 @@ def test_patch_sampler_covers_every_patch_once_per_epoch():
             seen += ids
         assert sorted(seen) == sorted([1000 + i for i in range(7)] + [2000 + i for i in range(12)] + [3000 + i for i in range(3)])
     assert len(PatchSampler(sets, 5, max_batches=2)) == 2
+
+
+def test_patch_sampler_ranks_partition_the_epoch():
+    """Data-parallel sampling: with the same seed the ranks' items are disjoint, cover every patch, and every rank runs the same number
+    of batches (the gradient all-reduce needs matching step counts)."""
+    from multipitch_architectures_b200.loop import PatchSampler
+
+    class Fake:
+        def __init__(self, n, tag):
+            self.inputs, self.targets, self.context, self.n, self.tag = torch.zeros(1, n + 3, 2), torch.zeros(n + 3, 1), 3, n, tag
+
+        def __len__(self):
+            return self.n
+
+        def gather(self, idx, out=None):
+            for j, i in enumerate(idx):
+                out[0][j] = 100 * self.tag + int(i)
+    for world in (2, 3, 8):
+        per_rank = []
+        for r in range(world):
+            smp = PatchSampler([Fake(11, 1), Fake(20, 2)], batch_size=4, shuffle=True, seed=7, rank=r, world=world)
+            items = [int(v) for X, _ in smp.epoch() for v in X[:, 0, 0, 0]]
+            per_rank.append(items)
+            assert len(smp) == -(-(-(-31 // world)) // 4)
+        assert len({len(p) for p in per_rank}) == 1
+        flat = [v for p in per_rank for v in p]
+        assert set(flat) == set([100 + i for i in range(11)] + [200 + i for i in range(20)])
+        assert len(flat) - len(set(flat)) == (-(-31 // world)) * world - 31          # only the wrap-around padding repeats
