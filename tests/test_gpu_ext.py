@@ -465,3 +465,25 @@ def test_fit_loop_trains_validates_schedules_and_checkpoints(tmp_path, name, gra
     assert set(sd) == set(m.state_dict()) and all(torch.isfinite(v.float()).all() for v in sd.values())
     m2 = build_model(name, precision='bf16')
     m2.load_state_dict(sd)
+
+
+def test_example_predict_wav_runs_the_notebook_flow(tmp_path):
+    """examples/predict_wav.py (notebook 02 of the reference): WAV -> 22.05 kHz -> HCQT -> DRCNN -> [n_frames, 72]."""
+    import importlib.util
+    import os
+    import wave
+    spec = importlib.util.spec_from_file_location('predict_wav', os.path.join(os.path.dirname(os.path.dirname(__file__)), 'examples', 'predict_wav.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    y = Q.synth_clip(4, seconds=1.5, sr=44100)
+    path = str(tmp_path / 'clip.wav')
+    with wave.open(path, 'wb') as w:
+        w.setnchannels(1)
+        w.setsampwidth(2)
+        w.setframerate(44100)
+        w.writeframes(np.round(y * 32767).astype('<i2').tobytes())
+    torch.manual_seed(0)
+    act, roll, fs_hcqt = mod.predict(path)
+    n22 = (len(y) + 1) // 2
+    assert act.shape == (n22 // 512 + 1, 72) and roll.shape == act.shape and roll.dtype == torch.bool
+    assert abs(fs_hcqt - 22050 / 512) < 1e-12 and torch.isfinite(act).all() and (act >= 0).all() and (act <= 1).all()
