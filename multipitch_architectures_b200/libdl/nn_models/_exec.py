@@ -298,10 +298,13 @@ def unet_forward_tc(model, x):
     # Activation planes are allocated (and zeroed) once per (batch, shape) and reused by later forwards: kernels write real pixels only,
     # so the zero borders survive, and re-zeroing ~25 buffers per forward cost 9 % of the Unet:M step.  The n-th request of a forward
     # always gets the n-th buffer, so two live buffers never alias.
-    pool = model.__dict__.setdefault('_plane_pool', {})
-    if pool.get('key') != (B, T, F, fmt, str(dev)):
-        pool.clear()
-        pool['key'] = (B, T, F, fmt, str(dev))
+    pools = model.__dict__.setdefault('_plane_pools', {})
+    key = (B, T, F, fmt, str(dev))
+    if key not in pools:
+        while len(pools) >= 3:                          # e.g. the full batch and the ragged last batch of a recording
+            pools.pop(next(iter(pools)))
+        pools[key] = {}
+    pool = pools[key]
     counter = [0]
 
     def buf(level, ch):
