@@ -437,7 +437,7 @@ def main():
     ap.add_argument('--batch', type=int, default=0, help='training batch per GPU (0 = the workload default)')
     ap.add_argument('--train-precision', default='fp32', choices=['fp32', 'bf16'])
     ap.add_argument('--no-train-graph', action='store_true', help='training workloads: launch every kernel eagerly instead of replaying the captured forward+backward CUDA graph')
-    ap.add_argument('--infer-batch', type=int, default=400, help='patches per forward of the U-Net inference workloads (any size is legal: eval-mode patches are independent)')
+    ap.add_argument('--infer-batch', type=int, default=646, help='patches per forward of the U-Net inference workloads (any size is legal: eval-mode patches are independent)')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', 0))
