@@ -330,6 +330,21 @@ int mpa_maxpool_time_dropout_f32(const float* x, const float* res, float* out, i
 int mpa_maxpool_time_bwd_dropout_f32(const float* a, const float* g_out, float* g_a, int B, int C, int T, int F, int k, int act,
                                      float act_param, float p, unsigned long long seed, unsigned long long offset,
                                      const long long* step_dev, unsigned long long step_mul, void* stream);
+/* The same two stages (k = 3) and the bias-gradient reduction directly on 16-bit CP8 planes [B][ceil(C/8)][T+2*pt][pitch][8]
+ * (geometry as mpa_nchw_to_cp8): a training step of the CNN family then runs conv -> pool+dropout -> conv and
+ * dgrad -> pool backward -> wgrad / dgrad without any nchw<->CP8 converter in between.  The dropout mask is the one the fp32
+ * kernels above draw for the NCHW element index of the same (b, c, t, f); sums are formed in fp32 and rounded once on the store, so the
+ * planes equal mpa_nchw_to_cp8 of the fp32 kernels' results bit for bit.  Replaces, for the bf16 training mode, the reference's
+ * nn.MaxPool2d((3,1),(1,1),(1,0)) + nn.Dropout forward / backward (libdl/nn_models/basic_cnns.py:172-175, 376-377) and the bias
+ * gradient of the following nn.Conv2d.  F % 4 == 0.  mpa_channel_sum_cp8: out[c] = sum over (b, t, f) of channel c, fixed order. */
+int mpa_pool3_dropout_cp8(const void* a_cp8, void* out_cp8, int B, int C, int T, int F, int pitch, int pf, int pt, int fmt, float p,
+                          unsigned long long seed, unsigned long long offset, const long long* step_dev, unsigned long long step_mul,
+                          void* stream);
+int mpa_pool3_bwd_dropout_cp8(const void* a_cp8, const void* g_out_cp8, void* g_a_cp8, int B, int C, int T, int F, int pitch, int pf,
+                              int pt, int fmt, int act, float act_param, float p, unsigned long long seed, unsigned long long offset,
+                              const long long* step_dev, unsigned long long step_mul, void* stream);
+int mpa_channel_sum_cp8(const void* g_cp8, float* out, int B, int C, int T, int F, int pitch, int pf, int pt, int fmt, int ncs,
+                        void* stream);
 /* Same with offset = step_dev[0] * step_mul + site, the step counter read from DEVICE memory: a training step captured in a CUDA graph
  * (UnetTrainStep(graph=True)) then draws fresh masks on every replay, identical to the eager step of the same number. */
 int mpa_dropout_dev_f32(const float* x, float* out, long long n, float p, unsigned long long seed, unsigned long long site,

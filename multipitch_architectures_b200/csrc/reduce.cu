@@ -92,6 +92,42 @@ __global__ void channel_final_kernel(const float* __restrict__ partial, float* _
   if (out2) out2[k] = t;
 }
 
+// Per-channel sums of a 16-bit CP8 tensor (bias gradient of a tensor-core convolution whose output gradient never leaves the CP8 layout):
+// grid (chunk, slice); a thread adds the 8 channels of its pixels in fp32, the block's 8 sums go to partial[(chunk*8 + e)][slice]
+template <int FMT>
+__global__ void __launch_bounds__(kRedThreads) channel_partial_cp8_kernel(const uint4* __restrict__ g, float* __restrict__ partial, int B, int T, int F,
+                                                                          int TP, int P, int pf, int pt, int ncs, int S) {
+  __shared__ float sh[kRedThreads / 32];
+  const int ck = blockIdx.x, s = blockIdx.y;
+  const unsigned n = (unsigned)B * T * F;
+  const unsigned i0 = (unsigned)((unsigned long long)n * s / S), i1 = (unsigned)((unsigned long long)n * (s + 1) / S);
+  float a[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) a[e] = 0.f;
+  for (unsigned i = i0 + threadIdx.x; i < i1; i += kRedThreads) {
+    const unsigned row = i / F, f = i - row * F;
+    const unsigned b = row / T, t = row - b * T;
+    const uint4 u = g[(((size_t)b * ncs + ck) * TP + pt + t) * P + pf + f];
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (FMT == MPA_FMT_BF16) {
+        a[2 * e] += __uint_as_float(w[e] << 16);
+        a[2 * e + 1] += __uint_as_float(w[e] & 0xFFFF0000u);
+      } else {
+        const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
+        a[2 * e] += f2.x;
+        a[2 * e + 1] += f2.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float r = block_sum_red(a[e], sh);
+    if (threadIdx.x == 0) partial[(size_t)(ck * 8 + e) * S + s] = r;
+  }
+}
+
 // BatchNorm batch statistics: per slice (n, mean, M2) with a two-pass mean / squared deviation inside the slice, merged in slice
 // order with Chan's parallel-variance update (robust against |mean| >> std; biased variance = M2 / n as nn.BatchNorm2d normalises)
 __global__ void __launch_bounds__(kRedThreads) bn_stats_partial_kernel(const float* __restrict__ x, float* __restrict__ partial, int B, int C, int HW,
@@ -140,6 +176,23 @@ int channel_sum_launch(const float* x, float* out, int B, int C, int HW, cudaStr
   const int S = pick_slices((long long)B * HW, C);
   if ((size_t)C * S > kRedScratchFloats) { set_error("channel_sum: too many channels (%d)", C); return MPA_ERR_ARG; }
   channel_partial_kernel<<<dim3(C, S), kRedThreads, 0, st>>>(x, nullptr, nullptr, nullptr, 0.f, scratch, B, C, HW, S, 0, 0);
+  channel_final_kernel<<<ceil_div(C, 128), 128, 0, st>>>(scratch, out, nullptr, C, S);
+  return MPA_OK;
+}
+int channel_sum_cp8_launch(const uint4* g, float* out, int B, int C, int T, int F, int TP, int P, int pf, int pt, int ncs, int fmt, cudaStream_t st) {
+  float* scratch = reduce_scratch();
+  if (!scratch) { set_error("channel_sum_cp8: scratch allocation failed"); return MPA_ERR_CUDA; }
+  if ((long long)B * T * F >= (1LL << 31)) { set_error("channel_sum_cp8: tensor too large"); return MPA_ERR_ARG; }
+  const int NCk = (C + 7) / 8;
+  // few chunk planes: more slices than pick_slices allows (about 8 CTAs per SM in total, at least ~2k pixels per CTA)
+  long long S_ = (148LL * 8 + NCk - 1) / NCk, by_work = ((long long)B * T * F + 2047) / 2048;
+  S_ = S_ < by_work ? S_ : by_work;
+  const int S = (int)(S_ < 1 ? 1 : (S_ > 512 ? 512 : S_));
+  if ((size_t)NCk * 8 * S > kRedScratchFloats) { set_error("channel_sum_cp8: too many channels (%d)", C); return MPA_ERR_ARG; }
+  if (fmt == MPA_FMT_BF16)
+    channel_partial_cp8_kernel<MPA_FMT_BF16><<<dim3(NCk, S), kRedThreads, 0, st>>>(g, scratch, B, T, F, TP, P, pf, pt, ncs, S);
+  else
+    channel_partial_cp8_kernel<MPA_FMT_F16><<<dim3(NCk, S), kRedThreads, 0, st>>>(g, scratch, B, T, F, TP, P, pf, pt, ncs, S);
   channel_final_kernel<<<ceil_div(C, 128), 128, 0, st>>>(scratch, out, nullptr, C, S);
   return MPA_OK;
 }

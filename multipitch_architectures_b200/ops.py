@@ -373,6 +373,13 @@ def channel_sum(x, out=None):
     return out
 
 
+def channel_sum_cp8(g, out=None):
+    """out[c] = sum over (b, t, f) of channel c of the CP8 tensor g (fp32 accumulation, fixed order)."""
+    out = out if out is not None else torch.empty(g.C, dtype=torch.float32, device=g.buf.device)
+    call('channel_sum_cp8', g.ptr(), out, g.B, g.C, g.T, g.F, g.pitch, g.pf, g.pt, g.fmt, g.ncs, stream_ptr())
+    return out
+
+
 def conv_tc_pack_dev(w, Cin, Cout, ksize, fmt, transpose_flip=False, Cout_total=None, co0=0, J=0):
     """Device-side packing of conv_tc A-operand tiles from the fp32 weight tensor `w` (state_dict layout, on the GPU).
     transpose_flip: pack the data-gradient convolution of the forward weight `w` (see mpa_conv_tc_pack_weights_dev)."""

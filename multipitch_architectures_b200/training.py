@@ -176,35 +176,54 @@ class TcConv:
     def forward(cls, tag, conv, x, act, a):
         fmt = ops.FMT_BF16
         B, Cin, T, F = x.shape
-        Cout, _, KH, KW = conv.weight.shape
         xc = ops.nchw_to_cp8(x, out=cls._buf(tag + ':x', B, Cin, T, F, x.device, fmt), fmt=fmt)
-        yc = cls._buf(tag + ':y', B, Cout, T, F, x.device, fmt)
+        return ops.cp8_to_nchw(cls.forward_cp8(tag, conv, xc, act, a)), xc
+
+    @classmethod
+    def forward_cp8(cls, tag, conv, xc, act, a):
+        """CP8 in -> CP8 out (pooled buffer `tag:y`)."""
+        fmt = ops.FMT_BF16
+        B, Cin, T, F = xc.B, xc.C, xc.T, xc.F
+        Cout, _, KH, KW = conv.weight.shape
+        yc = cls._buf(tag + ':y', B, Cout, T, F, xc.buf.device, fmt)
         for c0 in range(0, Cout, 128):
             c = min(128, Cout - c0)
             cp = (c + 7) // 8 * 8                        # whole chunks: the coalesced epilogue needs Cout % 8 == 0
             wp = ops.conv_tc_pack_dev(conv.weight, Cin, cp, (KH, KW), fmt, False, Cout, c0)
             ops.conv_tc(xc, wp, cls._pad8(conv.bias[c0:c0 + c], cp), cp, (KH, KW), act, a, out=yc.channels(c0, cp))
-        return ops.cp8_to_nchw(yc), xc
+        return yc
 
     @classmethod
     def backward(cls, tag, conv, xc, g, gw, gb, need_dx):
         """g: fp32 gradient wrt the convolution output (before the activation has been differentiated away by the caller)."""
         fmt = ops.FMT_BF16
         B, Cout, T, F = g.shape
-        _, Cin, KH, KW = conv.weight.shape
         gc = ops.nchw_to_cp8(g, out=cls._buf(tag + ':g', B, Cout, T, F, g.device, fmt), fmt=fmt)
-        ops.conv_wgrad_tc(xc, gc, gw, (KH, KW))
         ops.channel_sum(g, out=gb)
+        gxc = cls.backward_cp8(tag, conv, xc, gc, gw, None, need_dx)
+        return ops.cp8_to_nchw(gxc) if need_dx else None
+
+    @classmethod
+    def backward_cp8(cls, tag, conv, xc, gc, gw, gb, need_dx):
+        """gc: CP8 gradient wrt the convolution output; -> CP8 gradient wrt its input (pooled buffer `tag:gx`).  gb (optional): bias
+        gradient summed from the 16-bit planes."""
+        fmt = ops.FMT_BF16
+        B, Cout, T, F = gc.B, gc.C, gc.T, gc.F
+        _, Cin, KH, KW = conv.weight.shape
+        dev = gc.buf.device
+        ops.conv_wgrad_tc(xc, gc, gw, (KH, KW))
+        if gb is not None:
+            ops.channel_sum_cp8(gc, out=gb)
         if not need_dx:
             return None
-        gxc = cls._buf(tag + ':gx', B, Cin, T, F, g.device, fmt)
-        zb = torch.zeros(128, dtype=torch.float32, device=g.device)
+        gxc = cls._buf(tag + ':gx', B, Cin, T, F, dev, fmt)
+        zb = torch.zeros(128, dtype=torch.float32, device=dev)
         for c0 in range(0, Cin, 128):
             c = min(128, Cin - c0)
             cp = (c + 7) // 8 * 8
             wp = ops.conv_tc_pack_dev(conv.weight, Cout, cp, (KH, KW), fmt, True, Cin, c0)
             ops.conv_tc(gc, wp, zb[:cp], cp, (KH, KW), ops.ACT_NONE, 0.0, out=gxc.channels(c0, cp))
-        return ops.cp8_to_nchw(gxc)
+        return gxc
 
 
 def _tc_s3_eligible(model, conv, F):
@@ -215,11 +234,16 @@ def _tc_s3_eligible(model, conv, F):
 
 
 def _tc_s3_forward(tag, conv, x, act, a):
+    """x: fp32 NCHW or the CP8 planes a preceding CP8-resident block left behind."""
     fmt = ops.FMT_BF16
-    B, Cin, T, F = x.shape
+    if isinstance(x, ops.CP8):
+        xc = x
+    else:
+        B, Cin, T, F = x.shape
+        xc = ops.nchw_to_cp8(x, out=TcConv._buf(tag + ':x', B, Cin, T, F, x.device, fmt), fmt=fmt)
+    B, Cin, T, F = xc.B, xc.C, xc.T, xc.F
     Cout = conv.weight.shape[0]
-    xc = ops.nchw_to_cp8(x, out=TcConv._buf(tag + ':x', B, Cin, T, F, x.device, fmt), fmt=fmt)
-    yc = ops.compact_cp8(B, Cout, T, F // 3, x.device, fmt)
+    yc = ops.compact_cp8(B, Cout, T, F // 3, xc.buf.device, fmt)
     for c0 in range(0, Cout, 128):
         c = min(128, Cout - c0)
         cp = (c + 7) // 8 * 8
@@ -228,7 +252,7 @@ def _tc_s3_forward(tag, conv, x, act, a):
     return ops.cp8_to_nchw(yc), xc
 
 
-def _tc_s3_backward(tag, conv, xc, g, gw, gb):
+def _tc_s3_backward(tag, conv, xc, g, gw, gb, keep_cp8=False):
     fmt = ops.FMT_BF16
     B, Cout, T, Fo = g.shape
     Cin, F = conv.weight.shape[1], xc.F
@@ -243,7 +267,43 @@ def _tc_s3_backward(tag, conv, xc, g, gw, gb):
         cp = (c + 7) // 8 * 8
         wp = ops.conv_tc_pack_dev(conv.weight, Cout, cp, (3, 3), fmt, True, Cin, c0)
         ops.conv_tc(gc, wp, zb[:cp], cp, (3, 3), ops.ACT_NONE, 0.0, out=gxc.channels(c0, cp))
-    return ops.cp8_to_nchw(gxc)
+    return gxc if keep_cp8 else ops.cp8_to_nchw(gxc)
+
+
+CP8_RESIDENT = True          # test knob: False = every block crosses nchw<->CP8 converters and pools in fp32 NCHW (identical results)
+
+
+def _cp8_resident(model, blocks, F):
+    """bf16 mode, no residual path: activations and gradients stay in the CP8 planes between the convolutions of the blocks
+    (pool + dropout forward / backward and the bias gradients run on the planes, train_cp8.cu)."""
+    return (CP8_RESIDENT and not getattr(model, 'residual', False) and F % 4 == 0 and all(TcConv.eligible(model, c, F) for _, c in blocks)
+            and _tc_s3_eligible(model, model.conv2[0], F))
+
+
+def _cnn_train_forward_cp8(model, blocks, z, sv, site, drop):
+    a, p, seed = model.a_lrelu, sv['p'], sv['seed']
+    fmt = ops.FMT_BF16
+    B, C0, T, F = z.shape
+    xc = ops.nchw_to_cp8(z, out=TcConv._buf(blocks[0][0] + ':x', B, C0, T, F, z.device, fmt), fmt=fmt)
+    sd, sm = _step_args()
+    for name, conv in blocks:
+        yc = TcConv.forward_cp8(name, conv, xc, ops.ACT_LRELU, a)
+        site[0] += 1
+        zc = TcConv._buf(name + ':z', B, yc.C, T, F, z.device, fmt)
+        call('pool3_dropout_cp8', yc.ptr(), zc.ptr(), B, yc.C, T, F, yc.pitch, yc.pf, yc.pt, fmt, float(p), ctypes_u64(seed), ctypes_u64(site[0]),
+             sd, sm, stream_ptr())
+        sv['blocks'].append((None, yc, xc))
+        xc = zc
+    a2, x2c = _tc_s3_forward('conv2', model.conv2[0], xc, ops.ACT_LRELU, a)
+    site[0] += 1
+    d2 = _pool_dropout(a2, 13, None, p, seed, site[0])
+    a3 = _conv_fwd(model.conv3[0], d2, ops.ACT_LRELU, a)
+    d3 = drop(a3)
+    a4 = _conv_fwd(model.conv4[0], d3, ops.ACT_LRELU, a)
+    d4 = drop(a4)
+    y = _conv_fwd(model.conv4[3], d4, ops.ACT_SIGMOID, 0.0)
+    sv.update(z_head=None, a2=a2, d2=d2, a3=a3, d3=d3, a4=a4, d4=d4, y=y, x2c=x2c, cp8=True)
+    return y, sv
 
 
 def cnn_train_forward(model, x, seed=0, step=0):
@@ -258,6 +318,8 @@ def cnn_train_forward(model, x, seed=0, step=0):
         return _dropout(t, p, seed, site[0])
     sv = {'x': x, 'blocks': [], 'p': p, 'seed': seed, 'site0': step * 64}
     z = ops.layernorm_cf(x, model.layernorm.weight, model.layernorm.bias, model.layernorm.eps)
+    if _cp8_resident(model, blocks, z.shape[3]):
+        return _cnn_train_forward_cp8(model, blocks, z, sv, site, drop)
     for i, (name, conv) in enumerate(blocks):
         if TcConv.eligible(model, conv, z.shape[3]):
             act, xc = TcConv.forward(name, conv, z, ops.ACT_LRELU, a)
@@ -303,12 +365,25 @@ def cnn_train_backward(model, sv, g_y, grads):
     _wgrad(c3, sv['d2'], g, grads['conv3.0.weight'], grads['conv3.0.bias'])
     site[0] -= 1
     g = _pool_bwd_dropout(sv['a2'], _dgrad(c3, g, sv['d2'].shape), 13, ops.ACT_LRELU, a, p, seed, site[0])
-    if sv.get('x2c') is not None:
+    if sv.get('cp8'):
+        fmt = ops.FMT_BF16
+        gzc = _tc_s3_backward('conv2', c2, sv['x2c'], g, grads['conv2.0.weight'], grads['conv2.0.bias'], keep_cp8=True)
+        sd, sm = _step_args()
+        for i in range(len(blocks) - 1, -1, -1):
+            name, conv = blocks[i]
+            _, yc, xc = sv['blocks'][i]
+            site[0] -= 1
+            gc = TcConv._buf(name + ':g', yc.B, yc.C, yc.T, yc.F, yc.buf.device, fmt)
+            call('pool3_bwd_dropout_cp8', yc.ptr(), gzc.ptr(), gc.ptr(), yc.B, yc.C, yc.T, yc.F, yc.pitch, yc.pf, yc.pt, fmt, ops.ACT_LRELU, float(a),
+                 float(p), ctypes_u64(seed), ctypes_u64(site[0]), sd, sm, stream_ptr())
+            gzc = TcConv.backward_cp8(name, conv, xc, gc, grads[f'{name}.0.weight'], grads[f'{name}.0.bias'], need_dx=True)
+        g_z = ops.cp8_to_nchw(gzc)
+    elif sv.get('x2c') is not None:
         g_z = _tc_s3_backward('conv2', c2, sv['x2c'], g, grads['conv2.0.weight'], grads['conv2.0.bias'])
     else:
         _wgrad(c2, sv['z_head'], g, grads['conv2.0.weight'], grads['conv2.0.bias'])
         g_z = _dgrad(c2, g, sv['z_head'].shape)
-    for i in range(len(blocks) - 1, -1, -1):
+    for i in range(len(blocks) - 1, -1, -1) if not sv.get('cp8') else ():
         name, conv = blocks[i]
         z_in, act, xc = sv['blocks'][i]
         site[0] -= 1

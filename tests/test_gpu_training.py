@@ -167,3 +167,86 @@ def test_fused_pool_dropout_kernels_equal_the_separate_kernels():
     for k in res[True][1]:
         a, b = res[True][1][k], res[False][1][k]
         assert (a - b).abs().max().item() <= 1e-6 * max(1.0, b.abs().max().item()), k       # weight gradients meet in fp32 atomics
+
+
+def _bf16_valued(*shape, seed=0, scale=1.0):
+    return (rnd(*shape, seed=seed, scale=scale).bfloat16().float()).cuda()
+
+
+@pytest.mark.parametrize('B,C,T,F,p', [(1, 5, 75, 216, 0.2), (3, 20, 75, 216, 0.2), (2, 8, 2, 40, 0.5), (2, 11, 1, 8, 0.2), (2, 20, 30, 216, 0.0)])
+def test_cp8_pool_dropout_kernels_equal_the_nchw_kernels(B, C, T, F, p):
+    """train_cp8.cu: MaxPool(3,1)+Dropout forward / backward and the bias-gradient sum on the 16-bit CP8 planes = the fp32 NCHW kernels
+    behind the converters, bit for bit (same Philox element indexing, fp32 sums in the same order, one rounding on the store)."""
+    from multipitch_architectures_b200 import _lib, ops
+    from multipitch_architectures_b200.training import ctypes_u64
+    fmt = ops.FMT_BF16
+    seed, off = 0x1234, 77
+    a = torch.where(_bf16_valued(B, C, T, F, seed=1) > 0.5, _bf16_valued(B, C, T, F, seed=1), torch.zeros(()).cuda()) - 0.25   # many ties
+    a = a.bfloat16().float().contiguous()
+    ac = ops.nchw_to_cp8(a, fmt=fmt)
+    # forward
+    want = torch.empty_like(a)
+    if p > 0:
+        _lib.call('maxpool_time_dropout_f32', a, None, want, B, C, T, F, 3, float(p), ctypes_u64(seed), ctypes_u64(off), None, ctypes_u64(0),
+                  _lib.stream_ptr())
+    else:
+        want = ops.maxpool_time(a, 3)
+    zc = ac.like()
+    _lib.call('pool3_dropout_cp8', ac.ptr(), zc.ptr(), B, C, T, F, ac.pitch, ac.pf, ac.pt, fmt, float(p), ctypes_u64(seed), ctypes_u64(off), None,
+              ctypes_u64(0), _lib.stream_ptr())
+    assert torch.equal(ops.cp8_to_nchw(zc), want.bfloat16().float())
+    assert torch.equal(zc.buf[..., :zc.pf, :], torch.zeros_like(zc.buf[..., :zc.pf, :])) and (zc.buf[:, :, 0] == 0).all()     # borders stay zero
+    # backward
+    g = _bf16_valued(B, C, T, F, seed=2)
+    gc = ops.nchw_to_cp8(g, fmt=fmt)
+    want = torch.empty_like(a)
+    if T > 1:
+        _lib.call('maxpool_time_bwd_dropout_f32', a, g, want, B, C, T, F, 3, ops.ACT_LRELU, 0.3, float(p), ctypes_u64(seed), ctypes_u64(off), None,
+                  ctypes_u64(0), _lib.stream_ptr())
+    else:
+        keep = torch.empty_like(g)
+        _lib.call('dropout_f32', g, keep, _lib.i64(g.numel()), float(p), ctypes_u64(seed), ctypes_u64(off), _lib.stream_ptr())
+        want = keep * torch.where(a >= 0, 1.0, 0.3)
+    gac = ac.like()
+    _lib.call('pool3_bwd_dropout_cp8', ac.ptr(), gc.ptr(), gac.ptr(), B, C, T, F, ac.pitch, ac.pf, ac.pt, fmt, ops.ACT_LRELU, 0.3, float(p),
+              ctypes_u64(seed), ctypes_u64(off), None, ctypes_u64(0), _lib.stream_ptr())
+    got = ops.cp8_to_nchw(gac)
+    assert torch.equal(got, want.bfloat16().float())
+    # bias gradient from the planes
+    s = ops.channel_sum_cp8(gac)
+    ref = got.double().sum(dim=(0, 2, 3))
+    assert s.shape == (C,) and (s.double() - ref).abs().max().item() <= 1e-5 * max(1.0, got.double().abs().sum(dim=(0, 2, 3)).max().item())
+
+
+@pytest.mark.parametrize('name,p', [('cnn_xs', None), ('dcnn_tiny', None), ('dcnn_tiny', 0.0)])
+def test_cp8_resident_training_step_equals_the_converter_path(name, p):
+    """bf16 CNN training with activations / gradients resident in CP8 between the convolutions (no nchw<->CP8 converters, pools on the
+    planes) against the same step through the converters and the fp32 NCHW pool kernels: same outputs bit for bit; gradients up to
+    the order of the fp32 atomics, block bias gradients up to the 16-bit rounding of the summed gradient."""
+    from multipitch_architectures_b200 import training as TR
+    res = {}
+    for resident in (True, False):
+        TR.CP8_RESIDENT = resident
+        try:
+            m = build_model(name, precision='bf16')
+            m.load_state_dict(fill_state_dict(m.state_dict(), 9, scheme='torch_default'))
+            if p is not None:
+                m.p_dropout = p
+            m = m.cuda().train()
+            x, t = synth_patches(5, 83).cuda(), synth_targets(5, 83).cuda()
+            m.dropout_seed, m._train_calls = 4321, 0
+            n0 = TR._lib.launch_count()
+            y = m(x)
+            loss = torch.nn.BCELoss()(y, t)
+            loss.backward()
+            res[resident] = (y.detach().clone(), {k: q.grad.clone() for k, q in m.named_parameters()}, TR._lib.launch_count() - n0)
+        finally:
+            TR.CP8_RESIDENT = True
+    assert torch.equal(res[True][0], res[False][0])
+    assert res[True][2] < res[False][2]                        # fewer launches: the converters are gone
+    n_blocks = 1 if name == 'cnn_xs' else 3
+    block_bias = {'conv1.0.bias'} | {f'prefilt_list.{i}.0.bias' for i in range(n_blocks - 1)}
+    for k in res[True][1]:
+        a, b = res[True][1][k], res[False][1][k]
+        tol = 2e-2 if k in block_bias else 1e-5
+        assert (a - b).abs().max().item() <= tol * max(1e-6, b.abs().max().item()), (k, (a - b).abs().max().item(), b.abs().max().item())
