@@ -6,7 +6,7 @@
 // NCHW kernels of elementwise.cu / backward.cu see behind the converters, every sum is formed in fp32 in the same order and rounded
 // once on the store, and the dropout mask uses the SAME convention (Philox counter i/4, lane i%4 of the NCHW element index
 // i = ((b*C + c)*T + t)*F + f) — outputs are bit-identical to the converter path (tests/test_gpu_training.py).
-// One thread owns the 8 channels of a pixel; the 4 threads of a quad (f = 4q..4q+3) share 8 Philox draws (2 each, exchanged by shuffles).
+// One thread owns 4 neighbouring bins x 8 channels (64 contiguous bytes per row): one Philox draw per channel serves its 4 bins.
 // HBM-bound: forward reads a once (rows re-read from L1/L2) and writes z; backward reads a and g once and writes ga.
 #include "common.cuh"
 
@@ -46,172 +46,220 @@ __device__ __forceinline__ uint4 pack8(const float v[8]) {
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-__device__ __forceinline__ uint32_t comp4(const uint4& r, int j) { return j == 0 ? r.x : j == 1 ? r.y : j == 2 ? r.z : r.w; }
-
-// Dropout keep factors of channels c0..c0+7 at pixel (t, f) for the 4 lanes of a quad (lane j holds f = 4q + j; all 32 lanes of the warp
-// must call).  i_quad = NCHW element index of channel c0 at (t, 4q) — a multiple of 4 because F % 4 == 0; plane = T*F.
-__device__ __forceinline__ void quad_dropout8(float fac[8], long long i_quad, long long plane, int j, float p, float scale,
-                                              unsigned long long seed, unsigned long long offset) {
-  uint32_t v[4][2];                                   // v[r][e]: bits of channel 2*(j^r)+e at my column
+// Dropout keep factors of the 8 channels ck*8 .. ck*8+7 at the 4 pixels (t, 4q .. 4q+3): one Philox draw per channel (the 4 lanes of a
+// draw are the 4 neighbouring bins — F % 4 == 0 makes the NCHW element index of bin 4q a multiple of 4).  Padded channels (>= C) keep 1.
+__device__ __forceinline__ void dropout_quad8(float fac[4][8], long long i_quad /* element index of channel ck*8 at (t, 4q) */, long long plane,
+                                              int c_real /* C - ck*8 */, float p, float scale, unsigned long long seed,
+                                              unsigned long long offset) {
 #pragma unroll
-  for (int e = 0; e < 2; ++e) {
-    const uint4 mine = dropout_bits((i_quad + (long long)(2 * j + e) * plane) >> 2, seed, offset);   // channel 2j+e, columns 4q..4q+3
-    v[0][e] = comp4(mine, j);
-#pragma unroll
-    for (int r = 1; r < 4; ++r) v[r][e] = __shfl_xor_sync(0xffffffffu, comp4(mine, j ^ r), r);
-  }
-#pragma unroll
-  for (int s = 0; s < 4; ++s) {
-    const int r = s ^ j;
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const uint32_t bits = r == 0 ? v[0][e] : r == 1 ? v[1][e] : r == 2 ? v[2][e] : v[3][e];
-      fac[2 * s + e] = dropout_factor(bits, p, scale);
+  for (int e = 0; e < 8; ++e) {
+    if (e < c_real) {
+      const uint4 r = dropout_bits((i_quad + (long long)e * plane) >> 2, seed, offset);
+      fac[0][e] = dropout_factor(r.x, p, scale);
+      fac[1][e] = dropout_factor(r.y, p, scale);
+      fac[2][e] = dropout_factor(r.z, p, scale);
+      fac[3][e] = dropout_factor(r.w, p, scale);
+    } else {
+      fac[0][e] = fac[1][e] = fac[2][e] = fac[3][e] = 1.f;
     }
+  }
+}
+
+template <int FMT>
+__device__ __forceinline__ void max8(uint4& c, const uint4& u) {
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    if (FMT == MPA_FMT_BF16)
+      reinterpret_cast<__nv_bfloat162*>(&c)[e] = __hmax2(reinterpret_cast<__nv_bfloat162*>(&c)[e], reinterpret_cast<const __nv_bfloat162*>(&u)[e]);
+    else
+      reinterpret_cast<__half2*>(&c)[e] = __hmax2(reinterpret_cast<__half2*>(&c)[e], reinterpret_cast<const __half2*>(&u)[e]);
   }
 }
 
 constexpr int kCp8Threads = 128;
 
-// grid (B * NCk * T, ceil(F / 128)); thread = one pixel of one chunk plane
+// thread = 4 neighbouring bins x 8 channels of one row of one chunk plane (64 contiguous bytes per row); total = B * NCk * T * F/4
 template <int FMT>
-__global__ void __launch_bounds__(kCp8Threads) pool3_dropout_cp8_kernel(const uint4* __restrict__ a, uint4* __restrict__ out, int C, int NCk, int T,
-                                                                        int F, int TP, int P, int pf, int pt, DropoutArgs d) {
-  const int f = blockIdx.y * kCp8Threads + threadIdx.x;
-  int r = blockIdx.x;
-  const int t = r % T;
+__global__ void __launch_bounds__(kCp8Threads) pool3_dropout_cp8_kernel(const uint4* __restrict__ a, uint4* __restrict__ out, long long total, int C,
+                                                                        int NCk, int T, int F4, int TP, int P, int pf, int pt, DropoutArgs d) {
+  const long long i = blockIdx.x * (long long)kCp8Threads + threadIdx.x;
+  if (i >= total) return;
+  const int q = (int)(i % F4);
+  long long r = i / F4;
+  const int t = (int)(r % T);
   r /= T;
-  const int ck = r % NCk;
-  const int b = r / NCk;
-  const bool ok = f < F;
-  const size_t base = (((size_t)b * NCk + ck) * TP + pt + t) * P + pf + (ok ? f : 0);
-  float m[8];
-  if (ok) {
-    uint4 c = a[base];
-    __nv_bfloat162* cm = reinterpret_cast<__nv_bfloat162*>(&c);
-    __half2* ch = reinterpret_cast<__half2*>(&c);
-    if (t > 0) {
-      const uint4 u = a[base - P];
+  const int ck = (int)(r % NCk);
+  const long long b = r / NCk;
+  const size_t base = (((size_t)b * NCk + ck) * TP + pt + t) * P + pf + 4 * q;
+  uint4 c[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        if (FMT == MPA_FMT_BF16) cm[e] = __hmax2(cm[e], reinterpret_cast<const __nv_bfloat162*>(&u)[e]);
-        else ch[e] = __hmax2(ch[e], reinterpret_cast<const __half2*>(&u)[e]);
-      }
-    }
-    if (t < T - 1) {
-      const uint4 u = a[base + P];
+  for (int x = 0; x < 4; ++x) c[x] = a[base + x];
+  if (t > 0) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        if (FMT == MPA_FMT_BF16) cm[e] = __hmax2(cm[e], reinterpret_cast<const __nv_bfloat162*>(&u)[e]);
-        else ch[e] = __hmax2(ch[e], reinterpret_cast<const __half2*>(&u)[e]);
-      }
-    }
-    if (d.p <= 0.f) {
-      out[base] = c;
-      return;
-    }
-    unpack8<FMT>(c, m);
+    for (int x = 0; x < 4; ++x) max8<FMT>(c[x], a[base - P + x]);
   }
-  if (d.p <= 0.f) return;
-  // dropout: every lane of the warp takes part in the shuffles (F % 4 == 0: quads are entirely inside or outside the row)
-  float fac[8];
-  const long long plane = (long long)T * F;
-  const long long i_quad = (((long long)b * C + ck * 8) * T + t) * F + (f & ~3);
-  quad_dropout8(fac, i_quad, plane, f & 3, d.p, 1.f / (1.f - d.p), d.seed, dropout_offset(d));
-  if (!ok) return;
+  if (t < T - 1) {
 #pragma unroll
-  for (int e = 0; e < 8; ++e) m[e] = __fmul_rn(m[e], fac[e]);
-  out[base] = pack8<FMT>(m);
+    for (int x = 0; x < 4; ++x) max8<FMT>(c[x], a[base + P + x]);
+  }
+  if (d.p > 0.f) {
+    float fac[4][8];
+    const long long plane = (long long)T * (4 * F4);
+    dropout_quad8(fac, ((b * C + ck * 8) * T + t) * (long long)(4 * F4) + 4 * q, plane, C - ck * 8, d.p, 1.f / (1.f - d.p), d.seed,
+                  dropout_offset(d));
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+      float m[8];
+      unpack8<FMT>(c[x], m);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) m[e] = __fmul_rn(m[e], fac[x][e]);
+      c[x] = pack8<FMT>(m);
+    }
+  }
+#pragma unroll
+  for (int x = 0; x < 4; ++x) out[base + x] = c[x];
 }
 
-// grid (B * NCk, ceil(F / 128), row segments); thread = one column of one chunk plane, walking down its segment of the T rows with the
-// window's 3 activation rows and 3 pending gradient sums (x 8 channels) in registers — the register version of maxpool_time_bwd_col_kernel<3>
 template <int FMT>
-__global__ void __launch_bounds__(kCp8Threads) pool3_bwd_dropout_cp8_kernel(const uint4* __restrict__ a, const uint4* __restrict__ g_p,
-                                                                            uint4* __restrict__ g_a, int C, int NCk, int T, int F, int TP, int P,
-                                                                            int pf, int pt, int act, float act_param, DropoutArgs d) {
-  const int f = blockIdx.y * kCp8Threads + threadIdx.x;
-  const int ck = blockIdx.x % NCk, b = blockIdx.x / NCk;
-  const bool ok = f < F;
+__device__ __forceinline__ float elem2(const uint2& u, int e) {       // channel e (0..3, compile-time) of half a packed pixel
+  const uint32_t w = (e >> 1) == 0 ? u.x : u.y;
+  if (FMT == MPA_FMT_BF16) return (e & 1) ? __uint_as_float(w & 0xFFFF0000u) : __uint_as_float(w << 16);
+  const __half2 h = *reinterpret_cast<const __half2*>(&w);
+  return (e & 1) ? __high2float(h) : __low2float(h);
+}
+template <int FMT>
+__device__ __forceinline__ uint2 pack4(const float v[4]) {
+  uint32_t w[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    if (FMT == MPA_FMT_BF16) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+      w[e] = *reinterpret_cast<const uint32_t*>(&h);
+    } else {
+      const __half2 h = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+      w[e] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+  }
+  return make_uint2(w[0], w[1]);
+}
+
+// thread = 4 neighbouring bins x 4 channels (half a chunk: 8-byte loads, the two halves of a pixel sit in neighbouring threads) of one
+// chunk plane, walking down a segment of the T rows with the window's 3 activation rows (packed 16-bit) and the 3 pending gradient sums
+// (fp32) in registers — the register version of maxpool_time_bwd_col_kernel<3>.  total = B * NCk * segs * F/4 * 2; a segment re-reads
+// one halo window above and below.
+template <int FMT>
+__global__ void __launch_bounds__(kCp8Threads) pool3_bwd_dropout_cp8_kernel(const uint2* __restrict__ a, const uint2* __restrict__ g_p,
+                                                                            uint2* __restrict__ g_a, long long total, int C, int NCk, int segs, int T,
+                                                                            int F4, int TP, int P, int pf, int pt, int act, float act_param,
+                                                                            DropoutArgs d) {
+  const long long i = blockIdx.x * (long long)kCp8Threads + threadIdx.x;
+  if (i >= total) return;
+  const int half = (int)(i & 1);
+  long long r = i >> 1;
+  const int q = (int)(r % F4);
+  r /= F4;
+  const int sg = (int)(r % segs);
+  r /= segs;
+  const int ck = (int)(r % NCk);
+  const long long b = r / NCk;
   // output rows [r0, r1) of this segment; windows r0-1 .. r1 contribute to them
-  const int seg = (T + (int)gridDim.z - 1) / (int)gridDim.z;
-  const int r0 = blockIdx.z * seg, r1 = min(T, r0 + seg);
+  const int seg = (T + segs - 1) / segs;
+  const int r0 = sg * seg, r1 = min(T, r0 + seg);
   if (r0 >= r1) return;
-  const size_t base = (((size_t)b * NCk + ck) * TP + pt) * P + pf + (ok ? f : 0);
+  const size_t base = ((((size_t)b * NCk + ck) * TP + pt) * P + pf + 4 * q) * 2 + half;      // in 8-byte units; next bin: + 2, next row: + 2 P
+  const size_t P2 = 2 * (size_t)P;
   const bool drop = d.p > 0.f;
   const unsigned long long d_off = drop ? dropout_offset(d) : 0ull;
   const float d_scale = drop ? 1.f / (1.f - d.p) : 1.f;
+  const int F = 4 * F4;
   const long long plane = (long long)T * F;
-  const long long i_col = ((long long)b * C + ck * 8) * plane + (f & ~3);
-  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+  const int c_first = ck * 8 + half * 4;
+  const long long i_col = (b * C + c_first) * plane + 4 * q;
+  const uint2 zero2 = make_uint2(0u, 0u);
 
-  float win[3][8], acc[3][8];      // win[j] = activation row w - 1 + j of window w; acc[j] = pending gradient of that row
+  uint2 win[3][4];                 // win[j][x] = activation row w - 1 + j of window w, bin 4q + x
+  float acc[3][4][4];              // pending gradient of those rows [row][bin][channel]
   bool valid[3];
-  // first window of the segment: w = r0 - 1 (only its contribution to row r0 matters; it exists when r0 >= 1)
-  int w = r0 >= 1 ? r0 - 1 : 0;
+  int w = r0 >= 1 ? r0 - 1 : 0;    // first window of the segment (for r0 >= 1 only its contribution to row r0 matters)
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
     const int row = w - 1 + j;
     valid[j] = row >= 0 && row < T;
-    unpack8<FMT>((ok && valid[j]) ? a[base + (size_t)row * P] : zero4, win[j]);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
+    for (int x = 0; x < 4; ++x) {
+      win[j][x] = valid[j] ? a[base + (size_t)row * P2 + 2 * x] : zero2;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[j][x][e] = 0.f;
+    }
   }
   const int w_last = min(T - 1, r1);
+  uint2 graw[4];
+#pragma unroll
+  for (int x = 0; x < 4; ++x) graw[x] = g_p[base + (size_t)w * P2 + 2 * x];
   for (; w <= w_last; ++w) {
-    float g[8];
-    unpack8<FMT>(ok ? g_p[base + (size_t)w * P] : zero4, g);
-    if (drop) {
-      float fac[8];
-      quad_dropout8(fac, i_col + (long long)w * F, plane, f & 3, d.p, d_scale, d.seed, d_off);
+    // the next rows are requested before this window's arithmetic
+    uint2 gnext[4], anext[4];
+    const bool more_g = w + 1 <= w_last, more_a = w + 2 < T;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) g[e] = __fmul_rn(g[e], fac[e]);
+    for (int x = 0; x < 4; ++x) {
+      gnext[x] = more_g ? g_p[base + (size_t)(w + 1) * P2 + 2 * x] : zero2;
+      anext[x] = more_a ? a[base + (size_t)(w + 2) * P2 + 2 * x] : zero2;
     }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      // strict '>': the first maximum of the window wins (ATen semantics); rows outside [0, T) never win
-      int am = valid[0] ? 0 : 1;
-      float best = valid[0] ? win[0][e] : win[1][e];
-      if (valid[0] && win[1][e] > best) { best = win[1][e]; am = 1; }
-      if (valid[2] && win[2][e] > best) { am = 2; }
-      acc[0][e] += am == 0 ? g[e] : 0.f;
-      acc[1][e] += am == 1 ? g[e] : 0.f;
-      acc[2][e] += am == 2 ? g[e] : 0.f;
-    }
-    // row w - 1 has now seen its three windows (w - 2, w - 1, w)
-    const int done = w - 1;
-    if (ok && done >= r0 && done < r1) {
-      float o[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        float dd = 1.f;
-        if (act == MPA_ACT_LRELU) dd = win[0][e] >= 0.f ? 1.f : act_param;
-        else if (act == MPA_ACT_RELU) dd = win[0][e] > 0.f ? 1.f : 0.f;
-        o[e] = acc[0][e] * dd;
+    for (int e = 0; e < 4; ++e) {
+      float fac[4] = {1.f, 1.f, 1.f, 1.f};
+      if (drop && c_first + e < C) {         // one Philox draw per channel serves its 4 bins; padded channels carry zeros anyway
+        const uint4 rb = dropout_bits((i_col + (long long)e * plane + (long long)w * F) >> 2, d.seed, d_off);
+        fac[0] = dropout_factor(rb.x, d.p, d_scale);
+        fac[1] = dropout_factor(rb.y, d.p, d_scale);
+        fac[2] = dropout_factor(rb.z, d.p, d_scale);
+        fac[3] = dropout_factor(rb.w, d.p, d_scale);
       }
-      g_a[base + (size_t)done * P] = pack8<FMT>(o);
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        float g = elem2<FMT>(graw[x], e);
+        if (drop) g = __fmul_rn(g, fac[x]);
+        const float a0 = elem2<FMT>(win[0][x], e), a1 = elem2<FMT>(win[1][x], e), a2 = elem2<FMT>(win[2][x], e);
+        // strict '>': the first maximum of the window wins (ATen semantics); rows outside [0, T) never win
+        int am = valid[0] ? 0 : 1;
+        float best = valid[0] ? a0 : a1;
+        if (valid[0] && a1 > best) { best = a1; am = 1; }
+        if (valid[2] && a2 > best) am = 2;
+        acc[0][x][e] += am == 0 ? g : 0.f;
+        acc[1][x][e] += am == 1 ? g : 0.f;
+        acc[2][x][e] += am == 2 ? g : 0.f;
+      }
+    }
+    // row w - 1 has now seen its three windows (w - 2, w - 1, w); after the last window of the tensor row T - 1 is final as well
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int done = w - 1 + j;
+      if (done >= r0 && done < r1 && (j == 0 || w == T - 1)) {
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float mine = elem2<FMT>(win[j][x], e);
+            float dd = 1.f;
+            if (act == MPA_ACT_LRELU) dd = mine >= 0.f ? 1.f : act_param;
+            else if (act == MPA_ACT_RELU) dd = mine > 0.f ? 1.f : 0.f;
+            o[e] = acc[j][x][e] * dd;
+          }
+          g_a[base + (size_t)done * P2 + 2 * x] = pack4<FMT>(o);
+        }
+      }
     }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      win[0][e] = win[1][e]; win[1][e] = win[2][e];
-      acc[0][e] = acc[1][e]; acc[1][e] = acc[2][e]; acc[2][e] = 0.f;
-    }
-    valid[0] = valid[1]; valid[1] = valid[2];
-    const int nrow = w + 2;
-    valid[2] = nrow < T;
-    unpack8<FMT>((ok && valid[2]) ? a[base + (size_t)nrow * P] : zero4, win[2]);
-  }
-  // the last row of the tensor has no window below it: it is final after window T - 1
-  if (ok && r1 == T && w == T) {
-    float o[8];
+    for (int x = 0; x < 4; ++x) {
+      win[0][x] = win[1][x]; win[1][x] = win[2][x]; win[2][x] = anext[x];
+      graw[x] = gnext[x];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float dd = 1.f;
-      if (act == MPA_ACT_LRELU) dd = win[0][e] >= 0.f ? 1.f : act_param;
-      else if (act == MPA_ACT_RELU) dd = win[0][e] > 0.f ? 1.f : 0.f;
-      o[e] = acc[0][e] * dd;
+      for (int e = 0; e < 4; ++e) {
+        acc[0][x][e] = acc[1][x][e]; acc[1][x][e] = acc[2][x][e]; acc[2][x][e] = 0.f;
+      }
     }
-    g_a[base + (size_t)(T - 1) * P] = pack8<FMT>(o);
+    valid[0] = valid[1]; valid[1] = valid[2]; valid[2] = more_a;
   }
 }
 
@@ -229,14 +277,15 @@ int mpa_pool3_dropout_cp8(const void* a_cp8, void* out_cp8, int B, int C, int T,
                   (fmt == MPA_FMT_BF16 || fmt == MPA_FMT_F16),
               "pool3_dropout_cp8: bad argument (F must be a multiple of 4)");
   const int NCk = (C + 7) / 8;
-  const dim3 grid(B * NCk * T, ceil_div(F, kCp8Threads));
+  const long long total = (long long)B * NCk * T * (F / 4);
+  const int grid = ceil_div(total, kCp8Threads);
   const DropoutArgs d{p, seed, offset, step_dev, step_mul};
   if (fmt == MPA_FMT_BF16)
-    pool3_dropout_cp8_kernel<MPA_FMT_BF16><<<grid, kCp8Threads, 0, (cudaStream_t)stream>>>((const uint4*)a_cp8, (uint4*)out_cp8, C, NCk, T, F,
-                                                                                          T + 2 * pt, pitch, pf, pt, d);
+    pool3_dropout_cp8_kernel<MPA_FMT_BF16><<<grid, kCp8Threads, 0, (cudaStream_t)stream>>>((const uint4*)a_cp8, (uint4*)out_cp8, total, C, NCk, T,
+                                                                                          F / 4, T + 2 * pt, pitch, pf, pt, d);
   else
-    pool3_dropout_cp8_kernel<MPA_FMT_F16><<<grid, kCp8Threads, 0, (cudaStream_t)stream>>>((const uint4*)a_cp8, (uint4*)out_cp8, C, NCk, T, F,
-                                                                                         T + 2 * pt, pitch, pf, pt, d);
+    pool3_dropout_cp8_kernel<MPA_FMT_F16><<<grid, kCp8Threads, 0, (cudaStream_t)stream>>>((const uint4*)a_cp8, (uint4*)out_cp8, total, C, NCk, T,
+                                                                                         F / 4, T + 2 * pt, pitch, pf, pt, d);
   MPA_CHECK_LAUNCH("pool3_dropout_cp8");
   return MPA_OK;
 }
@@ -249,18 +298,19 @@ int mpa_pool3_bwd_dropout_cp8(const void* a_cp8, const void* g_out_cp8, void* g_
                   p < 1.f && (fmt == MPA_FMT_BF16 || fmt == MPA_FMT_F16),
               "pool3_bwd_dropout_cp8: bad argument (F must be a multiple of 4)");
   const int NCk = (C + 7) / 8;
-  // enough CTAs to fill the GPU: split the T rows into segments when there are few planes (each segment re-reads 2 halo rows)
-  const int cols = ceil_div(F, kCp8Threads);
-  int segs = ceil_div(148 * 16, (long long)B * NCk * cols);
+  // enough threads to fill the GPU: split the T rows into segments (each segment re-reads 2 halo rows)
+  const long long cols = (long long)B * NCk * (F / 4);
+  int segs = ceil_div(148LL * 8 * kCp8Threads, cols * 2);
   segs = segs < 1 ? 1 : (segs > ceil_div(T, 8) ? ceil_div(T, 8) : segs);
-  const dim3 grid(B * NCk, cols, segs);
+  const long long total = cols * segs * 2;
+  const int grid = ceil_div(total, kCp8Threads);
   const DropoutArgs d{p, seed, offset, step_dev, step_mul};
   if (fmt == MPA_FMT_BF16)
     pool3_bwd_dropout_cp8_kernel<MPA_FMT_BF16><<<grid, kCp8Threads, 0, (cudaStream_t)stream>>>(
-        (const uint4*)a_cp8, (const uint4*)g_out_cp8, (uint4*)g_a_cp8, C, NCk, T, F, T + 2 * pt, pitch, pf, pt, act, act_param, d);
+        (const uint2*)a_cp8, (const uint2*)g_out_cp8, (uint2*)g_a_cp8, total, C, NCk, segs, T, F / 4, T + 2 * pt, pitch, pf, pt, act, act_param, d);
   else
     pool3_bwd_dropout_cp8_kernel<MPA_FMT_F16><<<grid, kCp8Threads, 0, (cudaStream_t)stream>>>(
-        (const uint4*)a_cp8, (const uint4*)g_out_cp8, (uint4*)g_a_cp8, C, NCk, T, F, T + 2 * pt, pitch, pf, pt, act, act_param, d);
+        (const uint2*)a_cp8, (const uint2*)g_out_cp8, (uint2*)g_a_cp8, total, C, NCk, segs, T, F / 4, T + 2 * pt, pitch, pf, pt, act, act_param, d);
   MPA_CHECK_LAUNCH("pool3_bwd_dropout_cp8");
   return MPA_OK;
 }
