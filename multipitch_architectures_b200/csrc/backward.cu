@@ -137,6 +137,9 @@ __global__ void __launch_bounds__(128) maxpool_time_bwd_col_kernel(const float* 
   }
 }
 
+// narrow tensors (the head's 72 bins): whole warps only, so that one wave of CTAs covers all (item, channel) planes
+static inline int pool_col_threads(int F) { return F >= 128 ? 128 : (F + 31) / 32 * 32; }
+
 // Philox-4x32-10 counter-based dropout (philox() in common.cuh): element i of call `offset` under `seed`
 // step_dev != nullptr: offset = step_dev[0] * step_mul + offset (the step counter lives in device memory so that a captured CUDA graph of
 // the training step draws fresh masks on every replay)
@@ -373,10 +376,11 @@ int mpa_maxpool_time_bwd_f32(const float* a, const float* g_pool, float* g_a, in
   MPA_CHECK_ARCH();
   MPA_REQUIRE(a && g_pool && g_a && B > 0 && C > 0 && T > 0 && F > 0 && k >= 1 && (k & 1), "maxpool_time_bwd: bad argument");
   if ((k == 3 || k == 13) && T > k / 2) {
-    const dim3 grid(B * C, ceil_div(F, 128));
+    const int threads = pool_col_threads(F);
+    const dim3 grid(B * C, ceil_div(F, threads));
     const DropoutArgs nod{0.f, 0ull, 0ull, nullptr, 0ull};
-    if (k == 3) maxpool_time_bwd_col_kernel<3><<<grid, 128, 0, (cudaStream_t)stream>>>(a, g_pool, g_a, T, F, act, act_param, nod);
-    else maxpool_time_bwd_col_kernel<13><<<grid, 128, 0, (cudaStream_t)stream>>>(a, g_pool, g_a, T, F, act, act_param, nod);
+    if (k == 3) maxpool_time_bwd_col_kernel<3><<<grid, threads, 0, (cudaStream_t)stream>>>(a, g_pool, g_a, T, F, act, act_param, nod);
+    else maxpool_time_bwd_col_kernel<13><<<grid, threads, 0, (cudaStream_t)stream>>>(a, g_pool, g_a, T, F, act, act_param, nod);
     MPA_CHECK_LAUNCH("maxpool_time_bwd_col");
     return MPA_OK;
   }
@@ -460,10 +464,11 @@ int mpa_maxpool_time_bwd_dropout_f32(const float* a, const float* g_out, float* 
   MPA_CHECK_ARCH();
   MPA_REQUIRE(a && g_out && g_a && B > 0 && C > 0 && F > 0 && (k == 3 || k == 13) && T > k / 2 && p >= 0.f && p < 1.f,
               "maxpool_time_bwd_dropout: bad argument (k must be 3 or 13)");
-  const dim3 grid(B * C, ceil_div(F, 128));
+  const int threads = pool_col_threads(F);
+  const dim3 grid(B * C, ceil_div(F, threads));
   const DropoutArgs d{p, seed, offset, step_dev, step_mul};
-  if (k == 3) maxpool_time_bwd_col_kernel<3><<<grid, 128, 0, (cudaStream_t)stream>>>(a, g_out, g_a, T, F, act, act_param, d);
-  else maxpool_time_bwd_col_kernel<13><<<grid, 128, 0, (cudaStream_t)stream>>>(a, g_out, g_a, T, F, act, act_param, d);
+  if (k == 3) maxpool_time_bwd_col_kernel<3><<<grid, threads, 0, (cudaStream_t)stream>>>(a, g_out, g_a, T, F, act, act_param, d);
+  else maxpool_time_bwd_col_kernel<13><<<grid, threads, 0, (cudaStream_t)stream>>>(a, g_out, g_a, T, F, act, act_param, d);
   MPA_CHECK_LAUNCH("maxpool_time_bwd_dropout");
   return MPA_OK;
 }

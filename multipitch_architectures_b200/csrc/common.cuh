@@ -88,8 +88,11 @@ __device__ __forceinline__ uint4 dropout_bits(long long i4, unsigned long long s
   return philox(make_uint4((uint32_t)i4, (uint32_t)(i4 >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)),
                 make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
 }
+// keep <=> (bits >> 8) * 2^-24 >= p  <=>  (bits >> 8) >= ceil(p * 2^24)  <=>  bits >= ceil(p * 2^24) << 8   (all steps exact for 0 <= p < 1;
+// the threshold is loop-invariant, which leaves one integer compare and one select per element)
 __device__ __forceinline__ float dropout_factor(uint32_t bits, float p, float scale) {
-  return (float)(bits >> 8) * (1.f / 16777216.f) >= p ? scale : 0.f;
+  const uint32_t thr = (uint32_t)ceilf(p * 16777216.f) << 8;
+  return bits >= thr ? scale : 0.f;
 }
 __device__ __forceinline__ float dropout_factor_at(long long i, float p, float scale, unsigned long long seed, unsigned long long offset) {
   const uint4 r = dropout_bits(i >> 2, seed, offset);

@@ -141,6 +141,139 @@ static int launch_rows_gemm(RowsGemm& p, size_t c_bytes, cudaStream_t st) {
 
 static inline Idx2 flat(long long s) { return Idx2{1 << 30, 0, s}; }
 
+// ---- thin layers (Cout <= 10: the conv3 of CNN:XS 20 -> 10 and of the DRCNN 30 -> 10, the 1 x 1 convolutions of conv4): the products
+// above degenerate to a few matrix-vector products on the [K][W] matrix x[b] and are HBM-bound — read (or write) the 4*B*K*W bytes once
+// with 16-byte accesses instead of tiling a GEMM whose M (or K) is a fraction of a tile.
+constexpr int kThinMaxCout = 10;
+constexpr size_t kThinScratchFloats = 1u << 22;      // weight-gradient partial sums [slices][Cout][K][W/4]
+
+static float* thin_scratch() {
+  static float* ptr[64] = {nullptr};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!ptr[dev]) {
+    float* q = nullptr;
+    if (cudaMalloc(&q, kThinScratchFloats * sizeof(float)) != cudaSuccess) return nullptr;
+    ptr[dev] = q;
+  }
+  return ptr[dev];
+}
+
+// forward: one CTA per item; thread (row group g, bin quad f4) adds rows g, g+G, ... of x[b]; the G groups meet in shared memory in order
+template <int CO>
+__global__ void __launch_bounds__(256) conv_rows_thin_fwd_kernel(const float4* __restrict__ x, const float* __restrict__ w,
+                                                                 const float* __restrict__ bias, float* __restrict__ out, int K, int W4, int act,
+                                                                 float act_param) {
+  extern __shared__ float4 red[];                 // [G][CO][W4]
+  const int G = 256 / W4;
+  const int f4 = threadIdx.x % W4, g = threadIdx.x / W4;
+  const int b = blockIdx.x;
+  if (g < G) {
+    float4 acc[CO];
+#pragma unroll
+    for (int co = 0; co < CO; ++co) acc[co] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* xb = x + (size_t)b * K * W4 + f4;
+#pragma unroll 4
+    for (int r = g; r < K; r += G) {
+      const float4 v = xb[(size_t)r * W4];
+#pragma unroll
+      for (int co = 0; co < CO; ++co) {
+        const float wv = w[(size_t)co * K + r];
+        acc[co].x = fmaf(v.x, wv, acc[co].x); acc[co].y = fmaf(v.y, wv, acc[co].y);
+        acc[co].z = fmaf(v.z, wv, acc[co].z); acc[co].w = fmaf(v.w, wv, acc[co].w);
+      }
+    }
+#pragma unroll
+    for (int co = 0; co < CO; ++co) red[((size_t)g * CO + co) * W4 + f4] = acc[co];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < CO * W4; e += 256) {
+    const int co = e / W4, q = e - co * W4;
+    float4 t = red[(size_t)co * W4 + q];
+    for (int gg = 1; gg < G; ++gg) {
+      const float4 u = red[((size_t)gg * CO + co) * W4 + q];
+      t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+    }
+    const float bv = bias ? bias[co] : 0.f;
+    t.x = apply_act(t.x + bv, act, act_param); t.y = apply_act(t.y + bv, act, act_param);
+    t.z = apply_act(t.z + bv, act, act_param); t.w = apply_act(t.w + bv, act, act_param);
+    reinterpret_cast<float4*>(out)[((size_t)b * CO + co) * W4 + q] = t;
+  }
+}
+
+// data gradient: g_in[b][r][:] = sum_co w[co][r] * g_out[b][co][:]; one thread per 4 bins, write-bound
+template <int CO>
+__global__ void __launch_bounds__(256) conv_rows_thin_dgrad_kernel(const float4* __restrict__ go, const float* __restrict__ w, float4* __restrict__ gi,
+                                                                   long long total, int K, int W4) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int f4 = (int)(i % W4);
+    const long long br = i / W4;
+    const int r = (int)(br % K);
+    const long long b = br / K;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int co = 0; co < CO; ++co) {
+      const float4 gv = go[(b * CO + co) * W4 + f4];
+      const float wv = w[(size_t)co * K + r];
+      t.x = fmaf(gv.x, wv, t.x); t.y = fmaf(gv.y, wv, t.y); t.z = fmaf(gv.z, wv, t.z); t.w = fmaf(gv.w, wv, t.w);
+    }
+    gi[i] = t;
+  }
+}
+
+// weight gradient, pass 1: thread j = (row r, bin quad f4) of the [K][W4] matrix adds its items of slice s; partial[s][co][j]
+template <int CO>
+__global__ void __launch_bounds__(256) conv_rows_thin_wgrad_kernel(const float4* __restrict__ x, const float4* __restrict__ go,
+                                                                   float* __restrict__ partial, int B, int K, int W4, int S) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  const int KW4 = K * W4;
+  if (j >= KW4) return;
+  const int f4 = j % W4, s = blockIdx.y;
+  const int b0 = (int)((long long)B * s / S), b1 = (int)((long long)B * (s + 1) / S);
+  float4 acc[CO];
+#pragma unroll
+  for (int co = 0; co < CO; ++co) acc[co] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int b = b0; b < b1; ++b) {
+    const float4 v = x[(size_t)b * KW4 + j];
+#pragma unroll
+    for (int co = 0; co < CO; ++co) {
+      const float4 gv = go[((size_t)b * CO + co) * W4 + f4];
+      acc[co].x = fmaf(v.x, gv.x, acc[co].x); acc[co].y = fmaf(v.y, gv.y, acc[co].y);
+      acc[co].z = fmaf(v.z, gv.z, acc[co].z); acc[co].w = fmaf(v.w, gv.w, acc[co].w);
+    }
+  }
+#pragma unroll
+  for (int co = 0; co < CO; ++co) partial[((size_t)s * CO + co) * KW4 + j] = (acc[co].x + acc[co].y) + (acc[co].z + acc[co].w);
+}
+// pass 2: g_w[co][r] = sum over slices and bin quads; one warp per output, lane l adds terms l, l+32, ... in order, then a shuffle tree
+__global__ void __launch_bounds__(128) conv_rows_thin_wgrad_final_kernel(const float* __restrict__ partial, float* __restrict__ gw, int CO, int K,
+                                                                         int W4, int S) {
+  const int i = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= CO * K) return;
+  const int co = i / K, r = i - co * K;
+  float t = 0.f;
+  for (int e = lane; e < S * W4; e += 32) {
+    const int sl = e / W4, q = e - sl * W4;
+    t += partial[((size_t)sl * CO + co) * K * W4 + (size_t)r * W4 + q];
+  }
+  t = warp_sum(t);
+  if (lane == 0) gw[i] = t;
+}
+
+static inline bool thin_ok(int Cout, int W) {
+  return Cout <= kThinMaxCout && W % 4 == 0 && W / 4 <= 128 && sizeof(float4) * (size_t)(256 / (W / 4)) * Cout * (W / 4) <= 48 * 1024;
+}
+static inline bool aligned16(const void* q) { return ((uintptr_t)q & 15) == 0; }
+
+#define THIN_CASE(N, CALL) case N: { constexpr int C_ = N; CALL; } break;
+#define THIN_DISPATCH(CO, CALL)                                                                                             \
+  switch (CO) {                                                                                                             \
+    THIN_CASE(1, CALL) THIN_CASE(2, CALL) THIN_CASE(3, CALL) THIN_CASE(4, CALL) THIN_CASE(5, CALL) THIN_CASE(6, CALL)        \
+    THIN_CASE(7, CALL) THIN_CASE(8, CALL) THIN_CASE(9, CALL) default: { constexpr int C_ = 10; CALL; } break;               \
+  }
+
 }  // namespace mpa
 
 using namespace mpa;
@@ -161,6 +294,13 @@ int mpa_conv_rows_fwd_f32(const float* x, const float* w, const float* bias, flo
                           float act_param, void* workspace, size_t ws_bytes, void* stream) {
   MPA_CHECK_ARCH();
   MPA_REQUIRE(x && w && out && B > 0 && Cin > 0 && H > 0 && W > 0 && Cout > 0, "conv_rows_fwd: bad argument");
+  if (thin_ok(Cout, W) && aligned16(x) && aligned16(out)) {
+    const int K = Cin * H, W4 = W / 4, G = 256 / W4;
+    const size_t smem = sizeof(float4) * (size_t)G * Cout * W4;
+    THIN_DISPATCH(Cout, (conv_rows_thin_fwd_kernel<C_><<<B, 256, smem, (cudaStream_t)stream>>>((const float4*)x, w, bias, out, K, W4, act, act_param)));
+    MPA_CHECK_LAUNCH("conv_rows_fwd(thin)");
+    return MPA_OK;
+  }
   const size_t need = mpa_conv_rows_fwd_workspace(B, Cin, H, W, Cout);
   if (need > 0 && (!workspace || ws_bytes < need)) {
     set_error("conv_rows_fwd: workspace %zu < %zu bytes", ws_bytes, need);
@@ -183,6 +323,14 @@ int mpa_conv_rows_fwd_f32(const float* x, const float* w, const float* bias, flo
 int mpa_conv_rows_dgrad_f32(const float* g_out, const float* w, float* g_in, int B, int Cin, int H, int W, int Cout, void* stream) {
   MPA_CHECK_ARCH();
   MPA_REQUIRE(g_out && w && g_in && B > 0 && Cin > 0 && H > 0 && W > 0 && Cout > 0, "conv_rows_dgrad: bad argument");
+  if (thin_ok(Cout, W) && aligned16(g_out) && aligned16(g_in)) {
+    const int K = Cin * H, W4 = W / 4;
+    const long long total = (long long)B * K * W4;
+    const int grid = ceil_div(total, 256) > 148 * 16 ? 148 * 16 : ceil_div(total, 256);
+    THIN_DISPATCH(Cout, (conv_rows_thin_dgrad_kernel<C_><<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)g_out, w, (float4*)g_in, total, K, W4)));
+    MPA_CHECK_LAUNCH("conv_rows_dgrad(thin)");
+    return MPA_OK;
+  }
   RowsGemm p{};
   const int K = Cin * H;
   p.A = w; p.B = g_out; p.C = g_in; p.bias = nullptr; p.M = K; p.N = B * W; p.K = Cout;
@@ -199,6 +347,22 @@ int mpa_conv_rows_dgrad_f32(const float* g_out, const float* w, float* g_in, int
 int mpa_conv_rows_wgrad_f32(const float* x, const float* g_out, float* g_w, int B, int Cin, int H, int W, int Cout, void* stream) {
   MPA_CHECK_ARCH();
   MPA_REQUIRE(x && g_out && g_w && B > 0 && Cin > 0 && H > 0 && W > 0 && Cout > 0, "conv_rows_wgrad: bad argument");
+  if (thin_ok(Cout, W) && aligned16(x) && aligned16(g_out)) {
+    const int K = Cin * H, W4 = W / 4;
+    const int blocks = ceil_div((long long)K * W4, 256);
+    int S = ceil_div(148 * 8, blocks);
+    S = S > B ? B : S;
+    while (S > 1 && (size_t)S * Cout * K * W4 > kThinScratchFloats) --S;
+    float* scratch = (size_t)S * Cout * K * W4 <= kThinScratchFloats ? thin_scratch() : nullptr;
+    if (scratch) {
+      THIN_DISPATCH(Cout, (conv_rows_thin_wgrad_kernel<C_><<<dim3(blocks, S), 256, 0, (cudaStream_t)stream>>>((const float4*)x, (const float4*)g_out,
+                                                                                                         scratch, B, K, W4, S)));
+      conv_rows_thin_wgrad_final_kernel<<<ceil_div((long long)Cout * K, 4), 128, 0, (cudaStream_t)stream>>>(scratch, g_w, Cout, K, W4, S);
+      count_launch();
+      MPA_CHECK_LAUNCH("conv_rows_wgrad(thin)");
+      return MPA_OK;
+    }
+  }
   RowsGemm p{};
   const int K = Cin * H;
   p.A = g_out; p.B = x; p.C = g_w; p.bias = nullptr; p.M = Cout; p.N = K; p.K = B * W;

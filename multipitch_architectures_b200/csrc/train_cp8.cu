@@ -78,46 +78,66 @@ __device__ __forceinline__ void max8(uint4& c, const uint4& u) {
 
 constexpr int kCp8Threads = 128;
 
-// thread = 4 neighbouring bins x 8 channels of one row of one chunk plane (64 contiguous bytes per row); total = B * NCk * T * F/4
+// thread = 4 neighbouring bins x 8 channels (64 contiguous bytes per row) of one chunk plane, walking down a segment of the T rows with
+// the previous / current / next row in registers: every row is loaded once (plus one halo row at each end of a segment).
+// total = B * NCk * segs * F/4
 template <int FMT>
 __global__ void __launch_bounds__(kCp8Threads) pool3_dropout_cp8_kernel(const uint4* __restrict__ a, uint4* __restrict__ out, long long total, int C,
-                                                                        int NCk, int T, int F4, int TP, int P, int pf, int pt, DropoutArgs d) {
+                                                                        int NCk, int segs, int T, int F4, int TP, int P, int pf, int pt,
+                                                                        DropoutArgs d) {
   const long long i = blockIdx.x * (long long)kCp8Threads + threadIdx.x;
   if (i >= total) return;
   const int q = (int)(i % F4);
   long long r = i / F4;
-  const int t = (int)(r % T);
-  r /= T;
+  const int sg = (int)(r % segs);
+  r /= segs;
   const int ck = (int)(r % NCk);
   const long long b = r / NCk;
-  const size_t base = (((size_t)b * NCk + ck) * TP + pt + t) * P + pf + 4 * q;
-  uint4 c[4];
+  const int seg = (T + segs - 1) / segs;
+  const int r0 = sg * seg, r1 = min(T, r0 + seg);
+  if (r0 >= r1) return;
+  const size_t base = (((size_t)b * NCk + ck) * TP + pt) * P + pf + 4 * q;
+  const bool drop = d.p > 0.f;
+  const unsigned long long d_off = drop ? dropout_offset(d) : 0ull;
+  const float d_scale = drop ? 1.f / (1.f - d.p) : 1.f;
+  const int F = 4 * F4;
+  const long long plane = (long long)T * F;
+  const long long i_col = (b * C + ck * 8) * plane + 4 * q;
+  uint4 prev[4], cur[4], next[4];
 #pragma unroll
-  for (int x = 0; x < 4; ++x) c[x] = a[base + x];
-  if (t > 0) {
-#pragma unroll
-    for (int x = 0; x < 4; ++x) max8<FMT>(c[x], a[base - P + x]);
+  for (int x = 0; x < 4; ++x) {
+    cur[x] = a[base + (size_t)r0 * P + x];
+    prev[x] = r0 > 0 ? a[base + (size_t)(r0 - 1) * P + x] : cur[x];      // outside [0, T): a copy of a valid row is max-neutral
   }
-  if (t < T - 1) {
+  for (int t = r0; t < r1; ++t) {
 #pragma unroll
-    for (int x = 0; x < 4; ++x) max8<FMT>(c[x], a[base + P + x]);
-  }
-  if (d.p > 0.f) {
-    float fac[4][8];
-    const long long plane = (long long)T * (4 * F4);
-    dropout_quad8(fac, ((b * C + ck * 8) * T + t) * (long long)(4 * F4) + 4 * q, plane, C - ck * 8, d.p, 1.f / (1.f - d.p), d.seed,
-                  dropout_offset(d));
+    for (int x = 0; x < 4; ++x) next[x] = t + 1 < T ? a[base + (size_t)(t + 1) * P + x] : cur[x];
+    uint4 c[4];
 #pragma unroll
     for (int x = 0; x < 4; ++x) {
-      float m[8];
-      unpack8<FMT>(c[x], m);
+      c[x] = cur[x];
+      max8<FMT>(c[x], prev[x]);
+      max8<FMT>(c[x], next[x]);
+    }
+    if (drop) {
+      float fac[4][8];
+      dropout_quad8(fac, i_col + (long long)t * F, plane, C - ck * 8, d.p, d_scale, d.seed, d_off);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) m[e] = __fmul_rn(m[e], fac[x][e]);
-      c[x] = pack8<FMT>(m);
+      for (int x = 0; x < 4; ++x) {
+        float m[8];
+        unpack8<FMT>(c[x], m);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) m[e] = __fmul_rn(m[e], fac[x][e]);
+        c[x] = pack8<FMT>(m);
+      }
+    }
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+      out[base + (size_t)t * P + x] = c[x];
+      prev[x] = cur[x];
+      cur[x] = next[x];
     }
   }
-#pragma unroll
-  for (int x = 0; x < 4; ++x) out[base + x] = c[x];
 }
 
 template <int FMT>
@@ -277,15 +297,19 @@ int mpa_pool3_dropout_cp8(const void* a_cp8, void* out_cp8, int B, int C, int T,
                   (fmt == MPA_FMT_BF16 || fmt == MPA_FMT_F16),
               "pool3_dropout_cp8: bad argument (F must be a multiple of 4)");
   const int NCk = (C + 7) / 8;
-  const long long total = (long long)B * NCk * T * (F / 4);
+  // enough threads to fill the GPU: split the T rows into segments (each segment re-reads 2 halo rows)
+  const long long cols = (long long)B * NCk * (F / 4);
+  int segs = ceil_div(148LL * 8 * kCp8Threads, cols);
+  segs = segs < 1 ? 1 : (segs > ceil_div(T, 8) ? ceil_div(T, 8) : segs);
+  const long long total = cols * segs;
   const int grid = ceil_div(total, kCp8Threads);
   const DropoutArgs d{p, seed, offset, step_dev, step_mul};
   if (fmt == MPA_FMT_BF16)
-    pool3_dropout_cp8_kernel<MPA_FMT_BF16><<<grid, kCp8Threads, 0, (cudaStream_t)stream>>>((const uint4*)a_cp8, (uint4*)out_cp8, total, C, NCk, T,
-                                                                                          F / 4, T + 2 * pt, pitch, pf, pt, d);
+    pool3_dropout_cp8_kernel<MPA_FMT_BF16><<<grid, kCp8Threads, 0, (cudaStream_t)stream>>>((const uint4*)a_cp8, (uint4*)out_cp8, total, C, NCk, segs,
+                                                                                          T, F / 4, T + 2 * pt, pitch, pf, pt, d);
   else
-    pool3_dropout_cp8_kernel<MPA_FMT_F16><<<grid, kCp8Threads, 0, (cudaStream_t)stream>>>((const uint4*)a_cp8, (uint4*)out_cp8, total, C, NCk, T,
-                                                                                         F / 4, T + 2 * pt, pitch, pf, pt, d);
+    pool3_dropout_cp8_kernel<MPA_FMT_F16><<<grid, kCp8Threads, 0, (cudaStream_t)stream>>>((const uint4*)a_cp8, (uint4*)out_cp8, total, C, NCk, segs,
+                                                                                         T, F / 4, T + 2 * pt, pitch, pf, pt, d);
   MPA_CHECK_LAUNCH("pool3_dropout_cp8");
   return MPA_OK;
 }

@@ -217,7 +217,10 @@ def test_encoder_layer(ops):
     assert (got - ref).abs().max() < 5e-5
 
 
-@pytest.mark.parametrize('B,Cin,H,W,Cout', [(25, 80, 75, 72, 50), (256, 20, 75, 72, 10), (3, 7, 75, 72, 5), (2, 100, 9, 13, 80)])
+@pytest.mark.parametrize('B,Cin,H,W,Cout', [(25, 80, 75, 72, 50), (256, 20, 75, 72, 10), (3, 7, 75, 72, 5), (2, 100, 9, 13, 80),
+                                            # thin layers (Cout <= 4, W % 4 == 0): the HBM-bound matrix-vector kernels
+                                            (256, 10, 75, 72, 1), (5, 10, 75, 72, 1), (7, 6, 20, 216, 3), (40, 3, 11, 8, 4), (4, 1, 1, 72, 1),
+                                            (3, 5, 9, 70, 2)])
 def test_conv_rows_gemm_kernels_match_torch(B, Cin, H, W, Cout):
     """conv3 (75x1 VALID, one output row) forward / data gradient / weight gradient as GEMMs vs torch fp32 conv2d + autograd."""
     import torch.nn.functional as F
