@@ -250,3 +250,21 @@ def test_cp8_resident_training_step_equals_the_converter_path(name, p):
         a, b = res[True][1][k], res[False][1][k]
         tol = 2e-2 if k in block_bias else 1e-5
         assert (a - b).abs().max().item() <= tol * max(1e-6, b.abs().max().item()), (k, (a - b).abs().max().item(), b.abs().max().item())
+
+
+@pytest.mark.parametrize('B,C,T,F', [(2, 5, 75, 72), (1, 3, 75, 216), (2, 2, 9, 8), (1, 2, 30, 40)])
+def test_pool13_bwd_with_dropout_equals_dropout_then_pool_bwd(B, C, T, F):
+    """k = 13 backward with the dropout mask re-drawn on the fly == dropout_kernel followed by the plain backward == torch autograd of
+    max_pool2d on the masked gradient (plateaus in the input: the first maximum of a window must win)."""
+    from multipitch_architectures_b200 import training as TR, ops
+    a = torch.where(rnd(B, C, T, F, seed=5) > 0.3, rnd(B, C, T, F, seed=5), torch.zeros(())) - 0.2        # plateaus: ties inside the windows
+    g = rnd(B, C, T, F, seed=6)
+    ac, gc = a.cuda().contiguous(), g.cuda().contiguous()
+    fused = TR._pool_bwd_dropout(ac, gc, 13, ops.ACT_LRELU, 0.3, 0.25, 99, 5)
+    gm = TR._dropout(gc, 0.25, 99, 5)
+    assert torch.equal(fused, TR._pool_bwd(ac, gm, 13, ops.ACT_LRELU, 0.3))
+    # torch reference: `a` is the pool input (post-activation); the activation derivative is applied from its sign
+    ar = a.clone().requires_grad_(True)
+    torch.nn.functional.max_pool2d(ar, (13, 1), (1, 1), (6, 0)).backward(gm.cpu())
+    want = ar.grad * torch.where(a >= 0, 1.0, 0.3)
+    assert (fused.cpu() - want).abs().max() < 1e-5
