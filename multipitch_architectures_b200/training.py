@@ -9,6 +9,9 @@ Two ways in:
     — `model.forward` routes through `CnnTrainFunction` (a torch.autograd.Function whose backward is the code below);
   * fused: `TrainStep(model, lr=...)(x, t)` — BCE forward/backward kernel, backward, (optional) gradient all-reduce over
     NCCL on ONE flat buffer, fused AdamW; no torch operator touches an activation or a gradient.
+With `precision='bf16'` the convolutions run on the tensor cores (TcConv) and, for the models without the residual path, activations and
+gradients stay in the 16-bit CP8 planes between the block convolutions (`_cp8_resident`: pool + dropout forward / backward and the bias
+gradients are train_cp8.cu kernels; bit-identical to crossing the nchw<->CP8 converters around the fp32 kernels).
 Dropout uses a Philox stream (seed, per-site offset); the reference's torch RNG stream cannot be reproduced, so parity
 tests run with p_dropout = 0."""
 import torch
