@@ -37,6 +37,31 @@ __global__ void bn_relu_bwd_apply_kernel(const float* __restrict__ x, const floa
   }
 }
 
+// HW % 4 == 0 and 16-byte aligned tensors: 16-byte accesses, one index division per 4 elements (same arithmetic per element)
+__global__ void bn_relu_bwd_apply_vec4_kernel(const float4* __restrict__ x, const float4* __restrict__ out, const float4* __restrict__ dy,
+                                              const float* __restrict__ stats, const float* __restrict__ w, const float* __restrict__ sums,
+                                              float eps, float4* __restrict__ dx, long long total4, int C, int HW4, float inv_n, int relu) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)((i / HW4) % C);
+    const float mean = stats[c], rstd = rsqrtf(stats[C + c] + eps), wc = w[c], s1 = sums[c], s2 = sums[C + c];
+    const float4 xv = x[i];
+    float4 g = dy[i];
+    if (relu) {
+      const float4 o = out[i];
+      if (!(o.x > 0.f)) g.x = 0.f;
+      if (!(o.y > 0.f)) g.y = 0.f;
+      if (!(o.z > 0.f)) g.z = 0.f;
+      if (!(o.w > 0.f)) g.w = 0.f;
+    }
+    float4 r;
+    r.x = wc * rstd * (g.x - s1 * inv_n - (xv.x - mean) * rstd * s2 * inv_n);
+    r.y = wc * rstd * (g.y - s1 * inv_n - (xv.y - mean) * rstd * s2 * inv_n);
+    r.z = wc * rstd * (g.z - s1 * inv_n - (xv.z - mean) * rstd * s2 * inv_n);
+    r.w = wc * rstd * (g.w - s1 * inv_n - (xv.w - mean) * rstd * s2 * inv_n);
+    dx[i] = r;
+  }
+}
+
 // ---- MaxPool2d backward, any kernel / stride, no padding, floor mode; first arg-max in row-major window order ---------
 __global__ void maxpool2d_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g_out, float* __restrict__ g_in, long long total, int H,
                                      int W, int Ho, int Wo, int kh, int kw, int sh, int sw) {
@@ -384,7 +409,11 @@ int mpa_bn_relu_bwd_f32(const float* x, const float* out, const float* dy, const
   }
   MPA_CHECK_LAUNCH("bn_relu_bwd_reduce");
   const long long total = (long long)B * C * HW;
-  bn_relu_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, st>>>(x, out, dy, stats, w, scratch2c, eps, dx, total, C, HW, 1.f / ((float)B * HW), relu);
+  if (HW % 4 == 0 && ((((uintptr_t)x | (uintptr_t)out | (uintptr_t)dy | (uintptr_t)dx) & 15) == 0))
+    bn_relu_bwd_apply_vec4_kernel<<<grid_for(total / 4, 256), 256, 0, st>>>((const float4*)x, (const float4*)out, (const float4*)dy, stats, w, scratch2c,
+                                                                             eps, (float4*)dx, total / 4, C, HW / 4, 1.f / ((float)B * HW), relu);
+  else
+    bn_relu_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, st>>>(x, out, dy, stats, w, scratch2c, eps, dx, total, C, HW, 1.f / ((float)B * HW), relu);
   MPA_CHECK_LAUNCH("bn_relu_bwd_apply");
   return MPA_OK;
 }

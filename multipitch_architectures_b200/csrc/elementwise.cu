@@ -249,6 +249,23 @@ __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __rest
   }
 }
 
+// HW % 4 == 0 and 16-byte aligned tensors: 4 neighbouring elements share their channel — 16-byte accesses, one index division per 4
+__global__ void bn_apply_vec4_kernel(const float4* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ w,
+                                     const float* __restrict__ b, float4* __restrict__ out, long long total4, int C, int HW4, float eps, int act,
+                                     float act_param) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)((i / HW4) % C);
+    const float mean = stats[c], rstd = rsqrtf(stats[C + c] + eps), wc = w[c], bc = b[c];
+    const float4 v = x[i];
+    float4 o;
+    o.x = apply_act((v.x - mean) * rstd * wc + bc, act, act_param);
+    o.y = apply_act((v.y - mean) * rstd * wc + bc, act, act_param);
+    o.z = apply_act((v.z - mean) * rstd * wc + bc, act, act_param);
+    o.w = apply_act((v.w - mean) * rstd * wc + bc, act, act_param);
+    out[i] = o;
+  }
+}
+
 __global__ void __launch_bounds__(256) bce_kernel(const float* __restrict__ yp, const float* __restrict__ yt, float* __restrict__ loss_sum,
                                                   float* __restrict__ grad, long long n) {
   __shared__ float sh[8];
@@ -402,7 +419,11 @@ int mpa_bn_apply_f32(const float* x, const float* stats, const float* w, const f
   MPA_CHECK_ARCH();
   MPA_REQUIRE(x && stats && w && b && out && B > 0 && C > 0 && HW > 0, "bn_apply: bad argument");
   long long total = (long long)B * C * HW;
-  bn_apply_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, stats, w, b, out, total, C, HW, eps, act, act_param);
+  if (HW % 4 == 0 && ((((uintptr_t)x | (uintptr_t)out) & 15) == 0))
+    bn_apply_vec4_kernel<<<grid_for(total / 4, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)x, stats, w, b, (float4*)out, total / 4, C, HW / 4,
+                                                                                      eps, act, act_param);
+  else
+    bn_apply_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, stats, w, b, out, total, C, HW, eps, act, act_param);
   MPA_CHECK_LAUNCH("bn_apply");
   return MPA_OK;
 }
