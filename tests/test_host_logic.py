@@ -318,3 +318,21 @@ def test_patch_sampler_ranks_partition_the_epoch():
         flat = [v for p in per_rank for v in p]
         assert set(flat) == set([100 + i for i in range(11)] + [200 + i for i in range(20)])
         assert len(flat) - len(set(flat)) == (-(-31 // world)) * world - 31          # only the wrap-around padding repeats
+
+
+def test_cp8_resident_training_path_eligibility():
+    """Host decision only: which CNN models keep activations / gradients in the CP8 planes between the block convolutions of a bf16
+    training step (training._cp8_resident) — tensor-core mode, no residual path, whole bin quads per row."""
+    from multipitch_architectures_b200 import training as TR
+    from multipitch_architectures_b200.libdl.nn_models import _exec
+    from tests.refshapes import build_model
+    for name, prec, want in [('cnn_xs', 'bf16', True), ('dcnn_tiny', 'bf16', True), ('drcnn_tiny', 'bf16', False), ('cnn_xs', 'fp32', False)]:
+        m = build_model(name, precision=prec)
+        assert TR._cp8_resident(m, _exec.cnn_blocks(m), 216) is want, (name, prec)
+    m = build_model('cnn_xs', precision='bf16')
+    assert TR._cp8_resident(m, _exec.cnn_blocks(m), 218) is False          # rows must be whole bin quads (Philox draws serve 4 bins)
+    TR.CP8_RESIDENT = False
+    try:
+        assert TR._cp8_resident(m, _exec.cnn_blocks(m), 216) is False
+    finally:
+        TR.CP8_RESIDENT = True
