@@ -42,6 +42,11 @@ extern "C" {
 /* 16-bit storage / tensor-core operand formats of the CP8 planes (fp32 accumulation in both cases) */
 #define MPA_FMT_F16 0     /* IEEE half: 11-bit significand, the default (same operand precision as TF32) */
 #define MPA_FMT_BF16 1    /* bfloat16: 8-bit significand */
+#define MPA_FMT_F16X3 2   /* split precision: every value is a pair of fp16 planes (hi = fp16(x), lo = fp16(x - hi), ~22-bit significand);
+                             a convolution is three tensor-core passes (W_hi x_hi + W_lo x_hi + W_hi x_lo) into one fp32 accumulator.
+                             A buffer with `ncs` chunk planes per item holds its hi planes in chunks [0, ncs/2) and its lo planes in
+                             [ncs/2, ncs); every CP8 entry point accepts this format with the same arguments (ncs even).  This is the
+                             tensor-core mode that meets the reference's fp32 results to ~1e-5 (the north star's 1e-3 with margin). */
 
 int mpa_version(void);
 const char* mpa_last_error(void);
@@ -167,6 +172,8 @@ int mpa_encoder_layer_f32(const float* x, float* out, int B, int E, int Th, int 
  * in_patch_stride_rows: 0 for materialised patches [n][NC][T+2pt][pitch][8];
  * 1 for the streaming engine where patch i is rows [i, i+T) of one shared frame-major plane. */
 size_t mpa_conv_tc_packed_bytes(int Cin, int Cout, int KH, int KW, int J);
+/* the same for any fmt (MPA_FMT_F16X3: three tile passes + per-output-channel inverse scales) */
+size_t mpa_conv_tc_packed_bytes_fmt(int Cin, int Cout, int KH, int KW, int J, int fmt);
 /* HOST function: w [Cout][Cin][KH][KW] fp32 (host) -> packed 16-bit A-operand tiles (host buffer), fmt = MPA_FMT_*. */
 int mpa_conv_tc_pack_weights(const float* w_host, void* packed_host, int Cin, int Cout, int KH, int KW, int fmt, int J);
 /* out_mode 0: `out` is a CP8 plane set [n_patches][ceil(Cout/8)][T+2pt][pitch][8] (16-bit, same fmt);
@@ -217,6 +224,7 @@ typedef struct mpa_conv_tc_desc {
                          out_edge_chunk_stride / out_edge_patch_stride describe THAT buffer (see mpa_conv_tc_f16 out_mode 2) */
 } mpa_conv_tc_desc;
 size_t mpa_conv_tc_pool_workspace(int Cout, int pitch, int J);
+size_t mpa_conv_tc_pool_workspace_fmt(int Cout, int pitch, int J, int fmt);
 /* DEVICE-side packing (training: the weights change every step): w_dev fp32 in state_dict layout.  Packs output channels
  * [co0, co0+Cout) of a convolution with Cout_total output channels (channels >= Cout_total are packed as zeros, so a block may be
  * padded to a multiple of 8).  transpose_flip = 1 packs the data-gradient convolution

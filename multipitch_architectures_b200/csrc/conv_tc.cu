@@ -28,6 +28,7 @@
 #include <cuda_fp16.h>
 #include <vector>
 #include <string.h>
+#include <math.h>
 
 namespace mpa {
 
@@ -76,7 +77,14 @@ struct ConvTcParams {
   int act;
   float act_param;
   uint32_t idesc;
-  uint32_t btab[128];       // tile main loop: B-descriptor low words of one K row, (offset >> 4) | (LBO >> 4) << 16
+  // ---- split-precision mode (MPA_FMT_F16X3): every tensor is a (hi, lo) pair of fp16 planes, x = hi + lo (hi = fp16(x), lo = fp16(x - hi));
+  // the lo planes of a buffer sit `*_lo_off` chunk planes after its hi planes.  One input row is two B stages (hi planes, then lo planes) and
+  // three passes of A tiles: W_hi x_hi, W_lo x_hi (same B stage), W_hi x_lo — 3 MMAs per product, ~2^-21 relative operand error.
+  // The weights are pre-scaled per output channel by a power of two (so that W_lo stays clear of the fp16 subnormals); the epilogue
+  // multiplies the accumulator by inv_scale[co].
+  int x3, in_lo_off, out_lo_off, tiles_per_row;
+  const float* inv_scale;
+  uint32_t btab[256];       // tile main loop: B-descriptor low words of one K row, (offset >> 4) | (LBO >> 4) << 16 (x3: the row twice)
   // ---- ring main loop (conv_tc_ring_kernel): un-duplicated weight pieces, see below
   int ring_on, ring_S, ring_npos, ring_ps, ring_sbo, ring_nb, ring_b_off, ring_bar_off;
 };
@@ -158,6 +166,32 @@ __device__ __forceinline__ uint16_t cvt16(float x, int fmt) {
 }
 __device__ __forceinline__ float cvt32(uint16_t v, int fmt) {
   return fmt == MPA_FMT_BF16 ? __bfloat162float(__ushort_as_bfloat16(v)) : __half2float(__ushort_as_half(v));
+}
+
+// split-precision halves of an fp32 value: part 0 = fp16(x), part 1 = fp16(x - fp16(x))
+__device__ __forceinline__ uint16_t split16(float x, int part) {
+  const __half h = __float2half_rn(x);
+  return __half_as_ushort(part == 0 ? h : __float2half_rn(x - __half2float(h)));
+}
+__device__ __forceinline__ void join8(const uint4& hi, const uint4& lo, float* v) {
+  const __half2* h = reinterpret_cast<const __half2*>(&hi);
+  const __half2* l = reinterpret_cast<const __half2*>(&lo);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 a = __half22float2(h[e]), b = __half22float2(l[e]);
+    v[2 * e] = a.x + b.x;
+    v[2 * e + 1] = a.y + b.y;
+  }
+}
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+  __half2* h = reinterpret_cast<__half2*>(&hi);
+  __half2* l = reinterpret_cast<__half2*>(&lo);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    h[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+    const float2 r = __half22float2(h[e]);
+    l[e] = __floats2half2_rn(v[2 * e] - r.x, v[2 * e + 1] - r.y);
+  }
 }
 
 // K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout)
@@ -248,6 +282,7 @@ __device__ __forceinline__ uint4 add8_rt(uint4 c, const uint4 r, int fmt) {
 }
 
 // ------------------------------------------------------------------------------------------ epilogue role (warps 2..9)
+template <bool X3>
 __device__ __forceinline__ void epilogue_role(const ConvTcParams& p, uint32_t tmem_base, uint16_t* epi_smem, uint64_t* acc_full, uint64_t* acc_empty,
                                               int u_begin, int u_end, int u_first_real) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -258,6 +293,9 @@ __device__ __forceinline__ void epilogue_role(const ConvTcParams& p, uint32_t tm
     const int j = m / p.Cout, co = m - j * p.Cout;
     const bool row_valid = (j < p.J);
     const float bias = row_valid ? p.bias[co] : 0.f;
+    const float inv_scale = (X3 && row_valid) ? p.inv_scale[co] : 1.f;
+    constexpr int n_parts = X3 ? 2 : 1;
+    const int NCoP = n_parts * p.NCo;                                 // chunk planes of one activated conv row in the scratch ring
     // coalesced path: 8 consecutive lanes = the 8 channels of one chunk of one output row (needs Cout % 8 == 0)
     const bool staged = ((p.Cout & 7) == 0);
     const int ewarp = warp - 2;                                       // 0..7
@@ -274,7 +312,7 @@ __device__ __forceinline__ void epilogue_role(const ConvTcParams& p, uint32_t tm
     }
     const size_t plane_elems = (p.out_mode == 0) ? (size_t)p.TP_out * p.P * 8 : (p.out_mode == 2) ? (size_t)p.TP_out * p.P2 * 8 : (size_t)p.T_out * p.F_out * 8;
     const int row_pitch = (p.out_mode == 0) ? p.P : (p.out_mode == 2) ? p.P2 : p.F_out;
-    const size_t ring_row_bytes = (size_t)p.NCo * p.P * 16;
+    const size_t ring_row_bytes = (size_t)NCoP * p.P * 16;
     uint8_t* ring_cta = p.pool ? p.ring + (size_t)blockIdx.x * 2 * p.J * ring_row_bytes : nullptr;
     uint32_t k_unit = 0;
     for (int u = u_begin; u < u_end; ++u, ++k_unit) {
@@ -308,29 +346,32 @@ __device__ __forceinline__ void epilogue_role(const ConvTcParams& p, uint32_t tm
         tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256 + c0), v);
         tc_wait_ld();
         if (staged) {
+          for (int part = 0; part < n_parts; ++part) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if ((keep >> i) & 1u) {
-              const float x = apply_act(__uint_as_float(v[i]) + bias, p.act, p.act_param);
-              stile[i * kEpiPitch + lane] = cvt16(x, p.fmt);
-            }
-          }
-          __syncwarp();
-          // lane -> column c0+lane; pass k -> the k-th 8-lane group (= one channel chunk of one output row) of this warp
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int tg = t0 + grp_j[k];
-            if (col_ok && grp_j[k] < p.J && tg < y_hi) {
-              const uint4 val = *reinterpret_cast<const uint4*>(stile + lane * kEpiPitch + k * 8);
-              if (p.pool) {
-                *reinterpret_cast<uint4*>(ring_bank + ((size_t)grp_j[k] * p.NCo + grp_plane[k]) * p.P * 16 + (size_t)n * 16) = val;
-              } else {
-                const int orow = (p.out_mode != 1 ? p.pt_out : 0) + tg - p.row0;
-                *reinterpret_cast<uint4*>(out_b + (size_t)(ph_plane + grp_plane[k]) * plane_elems + ((size_t)orow * row_pitch + col_out) * 8) = val;
+            for (int i = 0; i < 32; ++i) {
+              if ((keep >> i) & 1u) {
+                const float x = apply_act(fmaf(__uint_as_float(v[i]), inv_scale, bias), p.act, p.act_param);
+                stile[i * kEpiPitch + lane] = X3 ? split16(x, part) : cvt16(x, p.fmt);
               }
             }
+            __syncwarp();
+            // lane -> column c0+lane; pass k -> the k-th 8-lane group (= one channel chunk of one output row) of this warp
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int tg = t0 + grp_j[k];
+              if (col_ok && grp_j[k] < p.J && tg < y_hi) {
+                const uint4 val = *reinterpret_cast<const uint4*>(stile + lane * kEpiPitch + k * 8);
+                if (p.pool) {
+                  *reinterpret_cast<uint4*>(ring_bank + ((size_t)grp_j[k] * NCoP + part * p.NCo + grp_plane[k]) * p.P * 16 + (size_t)n * 16) = val;
+                } else {
+                  const int orow = (p.out_mode != 1 ? p.pt_out : 0) + tg - p.row0;
+                  *reinterpret_cast<uint4*>(out_b + (size_t)(part * p.out_lo_off + ph_plane + grp_plane[k]) * plane_elems +
+                                            ((size_t)orow * row_pitch + col_out) * 8) = val;
+                }
+              }
+            }
+            __syncwarp();
           }
-          __syncwarp();
         } else if (row_valid && t < y_hi) {
           // scalar fallback (Cout not a multiple of 8; never used with the fused pool): one 16-bit store per value
 #pragma unroll
@@ -364,6 +405,53 @@ __device__ __forceinline__ void epilogue_role(const ConvTcParams& p, uint32_t tm
           int ze_hi = min(t_last == p.T - 1 ? t_last : t_last - 1, p.z_hi[ui.seg] - 1);
           const uint8_t* ring_prev = ring_cta + (size_t)((k_unit & 1u) ^ 1u) * p.J * ring_row_bytes;
           const int n_items = (ze_hi - ze_lo + 1) * p.NCo * p.F;
+          if (X3) {
+            // split precision: max and residual add on the joined fp32 values (hi + lo is exact in fp32), re-split on the way out
+            for (int it = etid; it < n_items; it += 256) {
+              const int f = it % p.F;
+              int r = it / p.F;
+              const int ck = r % p.NCo;
+              const int tz = ze_lo + r / p.NCo;
+              const size_t col_off = (size_t)ck * p.P * 16 + (size_t)(p.pf + f) * 16;
+              const size_t lo_off = (size_t)p.NCo * p.P * 16;
+              auto yrow = [&](int ty, float* o) {
+                const uint8_t* base = ty >= t0 ? ring_bank + (size_t)(ty - t0) * ring_row_bytes : ring_prev + (size_t)(p.J + ty - t0) * ring_row_bytes;
+                join8(*reinterpret_cast<const uint4*>(base + col_off), *reinterpret_cast<const uint4*>(base + col_off + lo_off), o);
+              };
+              float c[8], o[8];
+              yrow(tz, c);
+              if (tz > 0) {
+                yrow(tz - 1, o);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) c[e] = fmaxf(c[e], o[e]);
+              }
+              if (tz < p.T - 1) {
+                yrow(tz + 1, o);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) c[e] = fmaxf(c[e], o[e]);
+              }
+              if (p.residual) {
+                long long cs;
+                const uint8_t* rp = in_row_ptr(p, b, tz, cs) + (size_t)(p.pf + f) * 16;
+                join8(*reinterpret_cast<const uint4*>(rp + (long long)ck * cs), *reinterpret_cast<const uint4*>(rp + (long long)(p.in_lo_off + ck) * cs), o);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) c[e] += o[e];
+              }
+              uint4 hi, lo;
+              split8(c, hi, lo);
+              if (p.out_split) {
+                const int q = f / p.out_split, ph = f - q * p.out_split;
+                uint8_t* op = p.out_edge + (long long)b * p.out_edge_patch_stride + ((long long)tz * p.P2 + p.pf2 + q) * 16;
+                *reinterpret_cast<uint4*>(op + (long long)(ph * p.NCo + ck) * p.out_edge_chunk_stride) = hi;
+                *reinterpret_cast<uint4*>(op + (long long)(p.out_lo_off + ph * p.NCo + ck) * p.out_edge_chunk_stride) = lo;
+              } else {
+                long long ocs;
+                uint8_t* op = out_row_ptr(p, b, tz, ocs) + (size_t)(p.pf + f) * 16;
+                *reinterpret_cast<uint4*>(op + (long long)ck * ocs) = hi;
+                *reinterpret_cast<uint4*>(op + (long long)(p.out_lo_off + ck) * ocs) = lo;
+              }
+            }
+          } else
           for (int it = etid; it < n_items; it += 256) {
             const int f = it % p.F;
             int r = it / p.F;
@@ -402,6 +490,7 @@ __device__ __forceinline__ void epilogue_role(const ConvTcParams& p, uint32_t tm
 }
 
 // ------------------------------------------------------------------------------------------ kernel
+template <bool X3>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int slab_plane_bytes = p.slab_px * 16;
@@ -449,6 +538,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
 
   const int ph = p.KH / 2, pw = p.KW / 2;
   const int rows_in = p.KH + p.J - 1;
+  constexpr int n_parts = X3 ? 2 : 1;
   int u_begin, u_end, u_first_real;
   unit_range(p, u_begin, u_end, u_first_real);
 
@@ -472,26 +562,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
         for (int r = 0; r < rows_in; ++r) {
           const int row = ui.t0 - ph + r;
           if (row < 0 || row >= p.T) continue;
-          // activation slab of this input row
-          mbar_wait(&b_empty[b_stage], b_phase ^ 1);
-          mbar_expect_tx(&b_full[b_stage], (uint32_t)slab_bytes);
-          {
-            long long cs;
-            const uint8_t* src = in_row_ptr(p, ui.b, row, cs) - pw * 16;
-            uint8_t* dst = b_smem + b_stage * bstage_bytes;
-            for (int c = 0; c < p.NC; ++c)
-              bulk_g2s(dst + c * slab_plane_bytes, src + (long long)c * cs, (uint32_t)slab_plane_bytes, &b_full[b_stage]);
-          }
-          if (++b_stage == kNumBStages) { b_stage = 0; b_phase ^= 1; }
-          // weight stages of this K row
-          if (p.resident) continue;
-          const uint8_t* wrow = p.w + (size_t)r * p.mmas_per_row * kATileBytes;
-          for (int m0 = 0; m0 < p.mmas_per_row; m0 += kStageMMAs) {
-            const int nm = min(kStageMMAs, p.mmas_per_row - m0);
-            mbar_wait(&a_empty[a_stage], a_phase ^ 1);
-            mbar_expect_tx(&a_full[a_stage], (uint32_t)(nm * kATileBytes));
-            bulk_g2s(a_smem + a_stage * kAStageBytes, wrow + (size_t)m0 * kATileBytes, (uint32_t)(nm * kATileBytes), &a_full[a_stage]);
-            if (++a_stage == kNumAStages) { a_stage = 0; a_phase ^= 1; }
+          for (int part = 0; part < n_parts; ++part) {
+            // activation slab of this input row (split precision: the hi planes, then the lo planes)
+            mbar_wait(&b_empty[b_stage], b_phase ^ 1);
+            mbar_expect_tx(&b_full[b_stage], (uint32_t)slab_bytes);
+            {
+              long long cs;
+              const uint8_t* src = in_row_ptr(p, ui.b, row, cs) - pw * 16;
+              if (part) src += (long long)p.in_lo_off * cs;
+              uint8_t* dst = b_smem + b_stage * bstage_bytes;
+              for (int c = 0; c < p.NC; ++c)
+                bulk_g2s(dst + c * slab_plane_bytes, src + (long long)c * cs, (uint32_t)slab_plane_bytes, &b_full[b_stage]);
+            }
+            if (++b_stage == kNumBStages) { b_stage = 0; b_phase ^= 1; }
+            // weight stages of this K row (split precision: W_hi and W_lo tiles against the hi planes, W_hi tiles against the lo planes)
+            if (p.resident) continue;
+            const int n_tiles = (X3 && part == 0) ? 2 * p.mmas_per_row : p.mmas_per_row;
+            const uint8_t* wrow = p.w + ((size_t)r * p.tiles_per_row + (part ? 2 * p.mmas_per_row : 0)) * kATileBytes;
+            for (int m0 = 0; m0 < n_tiles; m0 += kStageMMAs) {
+              const int nm = min(kStageMMAs, n_tiles - m0);
+              mbar_wait(&a_empty[a_stage], a_phase ^ 1);
+              mbar_expect_tx(&a_full[a_stage], (uint32_t)(nm * kATileBytes));
+              bulk_g2s(a_smem + a_stage * kAStageBytes, wrow + (size_t)m0 * kATileBytes, (uint32_t)(nm * kATileBytes), &a_full[a_stage]);
+              if (++a_stage == kNumAStages) { a_stage = 0; a_phase ^= 1; }
+            }
           }
         }
       }
@@ -523,10 +617,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
         for (int r = 0; r < rows_in; ++r) {
           const int row = ui.t0 - ph + r;
           if (row < 0 || row >= p.T) continue;
+          for (int part = 0; part < n_parts; ++part) {
+          const int n_tiles = (X3 && part == 0) ? 2 * p.mmas_per_row : p.mmas_per_row;
           mbar_wait(&b_full[b_stage], b_phase);
           const uint32_t bbase16 = bsm16 + (uint32_t)b_stage * bst16;
-          for (int m0 = 0; m0 < p.mmas_per_row; m0 += kStageMMAs) {
-            const int nm = min(kStageMMAs, p.mmas_per_row - m0);
+          for (int m0 = 0; m0 < n_tiles; m0 += kStageMMAs) {
+            const int nm = min(kStageMMAs, n_tiles - m0);
             if (p.resident) a_stage = r * spr + m0 / kStageMMAs;
             else mbar_wait(&a_full[a_stage], a_phase);
             tc_fence_after();
@@ -552,6 +648,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
           if (elect_one_sync()) tc_commit(&b_empty[b_stage]);         // frees the activation slab of this row
           __syncwarp();
           if (++b_stage == kNumBStages) { b_stage = 0; b_phase ^= 1; }
+          }
         }
         if (elect_one_sync()) tc_commit(&acc_full[buf]);              // accumulator complete -> epilogue
         __syncwarp();
@@ -559,7 +656,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
     }
     __syncwarp();
   } else {
-    epilogue_role(p, tmem_base, epi_smem, acc_full, acc_empty, u_begin, u_end, u_first_real);
+    epilogue_role<X3>(p, tmem_base, epi_smem, acc_full, acc_empty, u_begin, u_end, u_first_real);
   }
   tc_fence_before();
   __syncthreads();
@@ -749,7 +846,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_ring_kernel(const ConvTcP
       }
     }
   } else {
-    epilogue_role(p, tmem_base, epi_smem, acc_full, acc_empty, u_begin, u_end, u_first_real);
+    epilogue_role<false>(p, tmem_base, epi_smem, acc_full, acc_empty, u_begin, u_end, u_first_real);
   }
   tc_fence_before();
   __syncthreads();
@@ -786,6 +883,27 @@ static inline uint16_t f32_to_f16_rne(float f) {
   return (uint16_t)(sign | h);
 }
 
+static inline float f16_to_f32(uint16_t h) {
+  const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+  const int exp = (h >> 10) & 0x1f;
+  const uint32_t man = h & 0x3ffu;
+  float f;
+  if (exp == 0) {
+    f = ldexpf((float)man, -24);
+  } else if (exp == 31) {
+    uint32_t u = 0x7f800000u | (man << 13);
+    memcpy(&f, &u, 4);
+  } else {
+    uint32_t u = ((uint32_t)(exp - 15 + 127) << 23) | (man << 13);
+    memcpy(&f, &u, 4);
+  }
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  u |= sign;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
 static inline uint16_t f32_to_bf16_rne(float f) {
   uint32_t u;
   memcpy(&u, &f, 4);
@@ -806,6 +924,19 @@ __global__ void nchw_to_cp8_kernel(const float* __restrict__ x, uint16_t* __rest
     int ck = (int)(r % NCk);
     int b = (int)(r / NCk);
     __align__(16) uint16_t v[8];
+    if (fmt == MPA_FMT_F16X3) {
+      __align__(16) uint16_t lo[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        int c = ck * 8 + e;
+        const float xv = c < C ? x[(((size_t)b * C + c) * T + t) * F + f] : 0.f;
+        v[e] = split16(xv, 0);
+        lo[e] = split16(xv, 1);
+      }
+      *reinterpret_cast<uint4*>(out + ((((size_t)b * NCs + ck) * TP + pt + t) * P + pf + f) * 8) = *reinterpret_cast<uint4*>(v);
+      *reinterpret_cast<uint4*>(out + ((((size_t)b * NCs + NCs / 2 + ck) * TP + pt + t) * P + pf + f) * 8) = *reinterpret_cast<uint4*>(lo);
+      continue;
+    }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       int c = ck * 8 + e;
@@ -848,6 +979,16 @@ __global__ void cp8_to_nchw_kernel(const uint16_t* __restrict__ in, float* __res
     int b = (int)(r / NCk);
     __align__(16) uint16_t v[8];
     *reinterpret_cast<uint4*>(v) = *reinterpret_cast<const uint4*>(in + ((((size_t)b * NCs + ck) * TP + pt + t) * P + pf + f) * 8);
+    if (fmt == MPA_FMT_F16X3) {
+      float o[8];
+      join8(*reinterpret_cast<const uint4*>(v), *reinterpret_cast<const uint4*>(in + ((((size_t)b * NCs + NCs / 2 + ck) * TP + pt + t) * P + pf + f) * 8), o);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int c = ck * 8 + e;
+        if (c < C) out[(((size_t)b * C + c) * T + t) * F + f] = o[e];
+      }
+      continue;
+    }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int c = ck * 8 + e;
@@ -1020,6 +1161,108 @@ __global__ void upsample2x_cp8_kernel(const uint16_t* __restrict__ low, uint16_t
   }
 }
 
+// ---- split-precision (MPA_FMT_F16X3) forms of the element-wise CP8 kernels: values are joined to fp32 (exact), processed in fp32 and
+// re-split; the lo planes of a buffer with `ncs` chunk planes per item start at chunk ncs/2
+struct X3Plane {
+  const uint4* p;
+  size_t lo;     // distance (in 16-byte pixels) from a hi pixel to its lo pixel
+  __device__ __forceinline__ void load(size_t i, float* v) const { join8(p[i], p[i + lo], v); }
+};
+__device__ __forceinline__ void x3_store(uint4* p, size_t lo, size_t i, const float* v) {
+  uint4 h, l;
+  split8(v, h, l);
+  p[i] = h;
+  p[i + lo] = l;
+}
+__global__ void pool_time_res_x3_kernel(const uint4* __restrict__ y, const uint4* __restrict__ res, uint4* __restrict__ out, long long total, int NCk,
+                                        int ncs_y, int ncs_res, int ncs_out, int T, int F, int TP, int P, int pf, int pt, int half) {
+  const size_t plane = (size_t)TP * P;
+  const X3Plane Y{y, (size_t)(ncs_y / 2) * plane}, R{res, (size_t)(ncs_res / 2) * plane};
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int f = (int)(i % F);
+    long long r = i / F;
+    int t = (int)(r % T);
+    r /= T;
+    const int ck = (int)(r % NCk);
+    const long long b = r / NCk;
+    const size_t base = (((size_t)b * ncs_y + ck) * TP + pt + t) * P + pf + f;
+    float c[8], o[8];
+    Y.load(base, c);
+    const int lo = max(-half, -t), hi = min(half, T - 1 - t);
+    for (int d = lo; d <= hi; ++d)
+      if (d != 0) {
+        Y.load(base + (long long)d * P, o);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) c[e] = fmaxf(c[e], o[e]);
+      }
+    if (res) {
+      R.load((((size_t)b * ncs_res + ck) * TP + pt + t) * P + pf + f, o);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) c[e] += o[e];
+    }
+    x3_store(out, (size_t)(ncs_out / 2) * plane, (((size_t)b * ncs_out + ck) * TP + pt + t) * P + pf + f, c);
+  }
+}
+__global__ void maxpool2x2_x3_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, long long total, int NCk, int ncs_in, int ncs_out, int To,
+                                     int Fo, int TPi, int Pi, int pfi, int pti, int TPo, int Po, int pfo, int pto) {
+  const X3Plane I{in, (size_t)(ncs_in / 2) * TPi * Pi};
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int f = (int)(i % Fo);
+    long long r = i / Fo;
+    int t = (int)(r % To);
+    r /= To;
+    const int ck = (int)(r % NCk);
+    const long long b = r / NCk;
+    const size_t ib = ((((size_t)b * ncs_in + ck) * TPi + pti + 2 * t) * Pi) + pfi + 2 * f;
+    float c[8], o[8];
+    I.load(ib, c);
+    const size_t nb[3] = {ib + 1, ib + (size_t)Pi, ib + (size_t)Pi + 1};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      I.load(nb[k], o);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) c[e] = fmaxf(c[e], o[e]);
+    }
+    x3_store(out, (size_t)(ncs_out / 2) * TPo * Po, ((((size_t)b * ncs_out + ck) * TPo + pto + t) * Po) + pfo + f, c);
+  }
+}
+__global__ void upsample2x_x3_kernel(const uint4* __restrict__ low, uint4* __restrict__ out, long long total, int NCk, int ncs_in, int ncs_out, int Tl,
+                                     int Fl, int TPl, int Pl, int pfl, int ptl, int Ts, int Fs, int TPs, int Ps, int pfs, int pts) {
+  const int Tu = 2 * Tl, Fu = 2 * Fl;
+  const int top = (Ts - Tu) / 2, left = (Fs - Fu) / 2;
+  const float ry = Tu > 1 ? (float)(Tl - 1) / (float)(Tu - 1) : 0.f;
+  const float rx = Fu > 1 ? (float)(Fl - 1) / (float)(Fu - 1) : 0.f;
+  const X3Plane L{low, (size_t)(ncs_in / 2) * TPl * Pl};
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int f = (int)(i % Fs);
+    long long r = i / Fs;
+    int t = (int)(r % Ts);
+    r /= Ts;
+    const int ck = (int)(r % NCk);
+    const long long b = r / NCk;
+    float o[8];
+    const int tu = t - top, fu = f - left;
+    if (tu < 0 || tu >= Tu || fu < 0 || fu >= Fu) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = 0.f;
+    } else {
+      const float sy = ry * tu, sx = rx * fu;
+      const int y0 = (int)sy, x0 = (int)sx;
+      const int y1 = min(y0 + 1, Tl - 1), x1 = min(x0 + 1, Fl - 1);
+      const float ly = sy - y0, lx = sx - x0;
+      const size_t pb = (((size_t)b * ncs_in + ck) * TPl + ptl);
+      float a00[8], a01[8], a10[8], a11[8];
+      L.load((pb + y0) * Pl + pfl + x0, a00);
+      L.load((pb + y0) * Pl + pfl + x1, a01);
+      L.load((pb + y1) * Pl + pfl + x0, a10);
+      L.load((pb + y1) * Pl + pfl + x1, a11);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = (1.f - ly) * ((1.f - lx) * a00[e] + lx * a01[e]) + ly * ((1.f - lx) * a10[e] + lx * a11[e]);
+    }
+    x3_store(out, (size_t)(ncs_out / 2) * TPs * Ps, ((((size_t)b * ncs_out + ck) * TPs + pts + t) * Ps) + pfs + f, o);
+  }
+}
+
 // Device-side packing of the A-operand tiles (same layout as mpa_conv_tc_pack_weights) for the training path, where the weights
 // change every step.  transpose_flip: pack the DATA-GRADIENT convolution w'[co'][ci'][kh][kw] = w[ci'][co'][KH-1-kh][KW-1-kw].
 __global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, long long total, int Cin, int Cout, int KH, int KW,
@@ -1070,6 +1313,12 @@ size_t mpa_conv_tc_packed_bytes(int Cin, int Cout, int KH, int KW, int J) {
   return (size_t)(KH + J - 1) * mmas_per_row(NC, KW) * kATileBytes;
 }
 
+/* MPA_FMT_F16X3: three tile passes per K row (W_hi, W_lo, W_hi) + 128 floats of per-output-channel inverse scales */
+size_t mpa_conv_tc_packed_bytes_fmt(int Cin, int Cout, int KH, int KW, int J, int fmt) {
+  const size_t n = mpa_conv_tc_packed_bytes(Cin, Cout, KH, KW, J);
+  return (fmt == MPA_FMT_F16X3 && n) ? 3 * n + 128 * sizeof(float) : n;
+}
+
 int mpa_conv_tc_pack_weights(const float* w, void* packed, int Cin, int Cout, int KH, int KW, int fmt, int J) {
   MPA_REQUIRE(w && packed && Cin > 0 && Cout > 0 && Cout <= 128 && KH > 0 && KW > 0, "conv_tc_pack_weights: bad argument (Cout must be <= 128)");
   MPA_REQUIRE(J >= 0 && J * Cout <= 128, "conv_tc_pack_weights: J*Cout must be <= 128");
@@ -1077,10 +1326,34 @@ int mpa_conv_tc_pack_weights(const float* w, void* packed, int Cin, int Cout, in
   const int NC = (Cin + 7) / 8, mpr = mmas_per_row(NC, KW);
   const int n_paired = (NC / 2) * KW;
   uint16_t* o = (uint16_t*)packed;
-  memset(o, 0, mpa_conv_tc_packed_bytes(Cin, Cout, KH, KW, J));
+  const bool x3 = fmt == MPA_FMT_F16X3;
+  memset(o, 0, mpa_conv_tc_packed_bytes_fmt(Cin, Cout, KH, KW, J, fmt));
+  std::vector<float> scale(Cout, 1.f);
+  if (x3) {
+    // per-output-channel power-of-two scale: max |w| lands in [256, 512), so that the low halves of all but the tiniest weights are
+    // normal fp16 numbers; the epilogue multiplies by the (exact) inverse
+    float* inv = (float*)((uint8_t*)packed + 3 * mpa_conv_tc_packed_bytes(Cin, Cout, KH, KW, J));
+    for (int co = 0; co < Cout; ++co) {
+      float m = 0.f;
+      for (size_t i = 0; i < (size_t)Cin * KH * KW; ++i) m = fmaxf(m, fabsf(w[(size_t)co * Cin * KH * KW + i]));
+      int e = 0;
+      if (m > 0.f && m < 3.0e38f) {
+        frexpf(m, &e);               // m = f * 2^e, f in [0.5, 1)
+        e = 9 - e;                   // m * 2^e in [256, 512)
+        if (e > 60) e = 60;
+        if (e < -60) e = -60;
+      }
+      scale[co] = ldexpf(1.f, e);
+      inv[co] = ldexpf(1.f, -e);
+    }
+    for (int co = Cout; co < 128; ++co) inv[co] = 1.f;
+  }
+  const int tpr = x3 ? 3 * mpr : mpr;
   for (int r = 0; r < KH + J - 1; ++r) {
     for (int q = 0; q < mpr; ++q) {
-      uint16_t* tile = o + ((size_t)r * mpr + q) * (kATileBytes / 2);
+      uint16_t* tile = o + ((size_t)r * tpr + q) * (kATileBytes / 2);
+      uint16_t* tile_lo = tile + (size_t)mpr * (kATileBytes / 2);          // x3: the W_lo pass, then the second W_hi pass
+      uint16_t* tile_hi2 = tile + (size_t)2 * mpr * (kATileBytes / 2);
       for (int kc = 0; kc < 2; ++kc) {
         int df, c;
         if (q < n_paired) {
@@ -1101,7 +1374,15 @@ int mpa_conv_tc_pack_weights(const float* w, void* packed, int Cin, int Cout, in
               const int ci = c * 8 + e;
               if (ci >= Cin) continue;
               const float wv = w[(((size_t)co * Cin + ci) * KH + kh) * KW + df];
-              tile[((size_t)kc * 128 + mrow) * 8 + e] = fmt == MPA_FMT_BF16 ? f32_to_bf16_rne(wv) : f32_to_f16_rne(wv);
+              const size_t at = ((size_t)kc * 128 + mrow) * 8 + e;
+              if (x3) {
+                const float ws = wv * scale[co];
+                const uint16_t hi = f32_to_f16_rne(ws);
+                tile[at] = tile_hi2[at] = hi;
+                tile_lo[at] = f32_to_f16_rne(ws - f16_to_f32(hi));
+              } else {
+                tile[at] = fmt == MPA_FMT_BF16 ? f32_to_bf16_rne(wv) : f32_to_f16_rne(wv);
+              }
             }
           }
         }
@@ -1179,6 +1460,11 @@ static int launch_conv_tc(ConvTcParams& p, int Cin, cudaStream_t stream, int* gr
   p.mmas_per_row = mmas_per_row(p.NC, p.KW);
   p.slab_px = (p.N + 2 * (p.KW / 2) + 1 + 7) / 8 * 8;
   size_t smem = 0;
+  if (p.x3) {
+    MPA_REQUIRE(!p.ring_on, "conv_tc: the ring main loop has no split-precision variant");
+    MPA_REQUIRE((p.Cout & 7) == 0, "conv_tc(fp16x3): Cout must be a multiple of 8 (got %d)", p.Cout);
+    p.inv_scale = (const float*)(p.w + (size_t)3 * (p.KH + p.J - 1) * p.mmas_per_row * kATileBytes);
+  }
   if (p.ring_on) {
     const int qmax = p.NC >= 2 ? p.KW : (p.KW + 1) / 2;
     MPA_REQUIRE(p.KW <= 16 && (p.Cout & 7) == 0 && p.NC <= 16, "conv_tc(ring): KW <= 16, Cout %% 8 == 0, Cin <= 128 required");
@@ -1205,8 +1491,9 @@ static int launch_conv_tc(ConvTcParams& p, int Cin, cudaStream_t stream, int* gr
     int a_stages = kMaxAStages;
     while (a_stages > 2 && (size_t)a_stages * kAStageBytes + b_bytes + tail > 227 * 1024) --a_stages;
     p.a_stages = a_stages;
-    p.resident = ((p.KH + p.J - 1) * ((p.mmas_per_row + kStageMMAs - 1) / kStageMMAs) <= a_stages) ? 1 : 0;
+    p.resident = (!p.x3 && (p.KH + p.J - 1) * ((p.mmas_per_row + kStageMMAs - 1) / kStageMMAs) <= a_stages) ? 1 : 0;
     MPA_REQUIRE(p.mmas_per_row <= 128, "conv_tc: too many K steps per row (%d)", p.mmas_per_row);
+    p.tiles_per_row = p.x3 ? 3 * p.mmas_per_row : p.mmas_per_row;
     {
       const uint32_t plane = (uint32_t)p.slab_px * 16u;
       const int n_paired = (p.NC / 2) * p.KW;
@@ -1221,6 +1508,7 @@ static int launch_conv_tc(ConvTcParams& p, int Cin, cudaStream_t stream, int* gr
           lbo = 16u;
         }
         p.btab[q] = (boff >> 4) | ((lbo >> 4) << 16);
+        if (p.x3) p.btab[p.mmas_per_row + q] = p.btab[q];      // the W_lo pass walks the same (hi) slab again
       }
     }
     size_t off = (size_t)a_stages * kAStageBytes + b_bytes;
@@ -1232,8 +1520,10 @@ static int launch_conv_tc(ConvTcParams& p, int Cin, cudaStream_t stream, int* gr
   }
   MPA_REQUIRE(smem <= 227 * 1024, "conv_tc: needs %zu B of shared memory (Cin=%d pitch=%d)", smem, Cin, p.P);
   {
-    static unsigned char flags_tile[64], flags_ring[64];
-    cudaError_t e = p.ring_on ? opt_in_max_smem(conv_tc_ring_kernel, flags_ring) : opt_in_max_smem(conv_tc_kernel, flags_tile);
+    static unsigned char flags_tile[64], flags_ring[64], flags_x3[64];
+    cudaError_t e = p.ring_on ? opt_in_max_smem(conv_tc_ring_kernel, flags_ring)
+                    : p.x3    ? opt_in_max_smem(conv_tc_kernel<true>, flags_x3)
+                              : opt_in_max_smem(conv_tc_kernel<false>, flags_tile);
     if (e != cudaSuccess) {
       set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return MPA_ERR_CUDA;
@@ -1247,8 +1537,10 @@ static int launch_conv_tc(ConvTcParams& p, int Cin, cudaStream_t stream, int* gr
   if (grid_out) *grid_out = grid;
   if (p.ring_on)
     conv_tc_ring_kernel<<<grid, kThreads, smem, stream>>>(p);
+  else if (p.x3)
+    conv_tc_kernel<true><<<grid, kThreads, smem, stream>>>(p);
   else
-    conv_tc_kernel<<<grid, kThreads, smem, stream>>>(p);
+    conv_tc_kernel<false><<<grid, kThreads, smem, stream>>>(p);
   MPA_CHECK_LAUNCH("conv_tc");
   return MPA_OK;
 }
@@ -1261,7 +1553,9 @@ int mpa_conv_tc_f16(const void* in_cp8, const void* w_packed, const float* bias,
   MPA_REQUIRE(in_cp8 && w_packed && bias && out && n_patches > 0, "conv_tc: null argument");
   MPA_REQUIRE(Cout > 0 && Cout <= 128 && Cin > 0, "conv_tc: Cout must be in 1..128 (got %d)", Cout);
   MPA_REQUIRE((KH & 1) && (KW & 1), "conv_tc: odd kernel sizes only");
-  MPA_REQUIRE(fmt == MPA_FMT_F16 || fmt == MPA_FMT_BF16, "conv_tc: fmt must be MPA_FMT_F16 or MPA_FMT_BF16");
+  MPA_REQUIRE(fmt == MPA_FMT_F16 || fmt == MPA_FMT_BF16 || fmt == MPA_FMT_F16X3, "conv_tc: fmt must be MPA_FMT_F16, MPA_FMT_BF16 or MPA_FMT_F16X3");
+  const bool x3 = fmt == MPA_FMT_F16X3;
+  MPA_REQUIRE(!x3 || in_patch_stride_rows <= 0, "conv_tc(fp16x3): the streaming input goes through mpa_conv_tc_pool_f16");
   const int N = (pitch + 15) / 16 * 16;      // MMA N: one padded image row (columns >= pitch are never stored)
   MPA_REQUIRE(N >= 16 && N <= 256 && (pitch % 16 == 0 || KW == 1), "conv_tc: row pitch %d must be a multiple of 16 (<= 256) unless KW == 1", pitch);
   MPA_REQUIRE(pf >= KW / 2 && pitch - F >= KW / 2 && pitch >= pf + F, "conv_tc: pitch %d / left pad %d too small for F=%d KW=%d", pitch, pf, F, KW);
@@ -1282,8 +1576,9 @@ int mpa_conv_tc_f16(const void* in_cp8, const void* w_packed, const float* bias,
   p.F_out = out_mode ? (F - p.sub_offset + p.sub_stride - 1) / p.sub_stride : F;
   p.pf2 = 8;
   p.P2 = (p.pf2 + p.F_out + 15) / 16 * 16;
-  p.phase_planes = out_mode == 2 ? out_nc_stride / sub_stride : 0;
+  p.phase_planes = out_mode == 2 ? out_nc_stride / sub_stride / (x3 ? 2 : 1) : 0;
   p.fmt = fmt;
+  p.x3 = x3 ? 1 : 0;
   p.n_patches = n_patches;
   p.NC = (Cin + 7) / 8;
   p.Cout = Cout;
@@ -1301,7 +1596,8 @@ int mpa_conv_tc_f16(const void* in_cp8, const void* w_packed, const float* bias,
     p.in_e = T;
     p.in_edge = in0;
     p.in_edge_chunk_stride = TP * pitch * 16;
-    p.in_edge_patch_stride = p.in_edge_chunk_stride * (in_nc_stride > 0 ? in_nc_stride : p.NC);
+    p.in_edge_patch_stride = p.in_edge_chunk_stride * (in_nc_stride > 0 ? in_nc_stride : (x3 ? 2 : 1) * p.NC);
+    p.in_lo_off = in_nc_stride > 0 ? in_nc_stride / 2 : p.NC;
   } else {
     // streaming: one shared frame-major plane [rows][P][8]; patch b starts at row b*stride (after pt guard rows)
     MPA_REQUIRE(p.NC == 1, "conv_tc: streaming input supports a single channel chunk");
@@ -1312,7 +1608,9 @@ int mpa_conv_tc_f16(const void* in_cp8, const void* w_packed, const float* bias,
   }
   MPA_REQUIRE(in_nc_stride == 0 || in_nc_stride >= p.NC, "conv_tc: in_nc_stride %d < %d input chunks", in_nc_stride, p.NC);
   MPA_REQUIRE(out_nc_stride == 0 || out_nc_stride >= p.NCo, "conv_tc: out_nc_stride %d < %d output chunks", out_nc_stride, p.NCo);
-  p.out_patch_stride = (long long)(out_nc_stride > 0 ? out_nc_stride : p.NCo) *
+  MPA_REQUIRE(!x3 || ((in_nc_stride & 1) == 0 && (out_nc_stride & 1) == 0), "conv_tc(fp16x3): chunk strides must be even (hi planes, then lo planes)");
+  p.out_lo_off = out_nc_stride > 0 ? out_nc_stride / 2 : p.NCo;
+  p.out_patch_stride = (long long)(out_nc_stride > 0 ? out_nc_stride : (x3 ? 2 : 1) * p.NCo) *
                        (out_mode == 0 ? (long long)p.TP_out * pitch : out_mode == 2 ? (long long)p.TP_out * p.P2 : (long long)p.T_out * p.F_out) * 8;
   MPA_REQUIRE(out_mode != 2 || p.phase_planes >= p.NCo, "conv_tc: %d chunk planes per phase < %d output chunks", p.phase_planes, p.NCo);
   p.n_seg = 1;
@@ -1335,12 +1633,16 @@ size_t mpa_conv_tc_pool_workspace(int Cout, int pitch, int J) {
   return (size_t)kMaxGrid * 2 * J * ((Cout + 7) / 8) * pitch * 16;
 }
 
+size_t mpa_conv_tc_pool_workspace_fmt(int Cout, int pitch, int J, int fmt) {
+  return mpa_conv_tc_pool_workspace(Cout, pitch, J) * (fmt == MPA_FMT_F16X3 ? 2 : 1);
+}
+
 int mpa_conv_tc_pool_f16(const mpa_conv_tc_desc* d, void* stream) {
   MPA_CHECK_ARCH();
   MPA_REQUIRE(d && d->w_packed && d->bias && d->workspace && d->n_patches > 0, "conv_tc_pool: null argument");
   MPA_REQUIRE(d->Cout > 0 && d->Cout <= 64 && (d->Cout & 7) == 0 && d->Cin > 0, "conv_tc_pool: Cout must be a multiple of 8, <= 64 (got %d)", d->Cout);
   MPA_REQUIRE((d->KH & 1) && (d->KW & 1), "conv_tc_pool: odd kernel sizes only");
-  MPA_REQUIRE(d->fmt == MPA_FMT_F16 || d->fmt == MPA_FMT_BF16, "conv_tc_pool: fmt must be MPA_FMT_F16 or MPA_FMT_BF16");
+  MPA_REQUIRE(d->fmt == MPA_FMT_F16 || d->fmt == MPA_FMT_BF16 || d->fmt == MPA_FMT_F16X3, "conv_tc_pool: fmt must be MPA_FMT_F16, MPA_FMT_BF16 or MPA_FMT_F16X3");
   const int pitch = d->pitch, KW = d->KW, F = d->F, pf = d->pf, T = d->T;
   MPA_REQUIRE(pitch >= 16 && pitch <= 256 && pitch % 16 == 0, "conv_tc_pool: row pitch %d must be a multiple of 16 (<= 256)", pitch);
   MPA_REQUIRE(pf >= KW / 2 && pitch - F >= KW / 2 && pitch >= pf + F, "conv_tc_pool: pitch %d / left pad %d too small for F=%d KW=%d", pitch, pf, F, KW);
@@ -1382,6 +1684,11 @@ int mpa_conv_tc_pool_f16(const mpa_conv_tc_desc* d, void* stream) {
   p.w = (const uint8_t*)d->w_packed;
   p.bias = d->bias;
   p.fmt = d->fmt;
+  p.x3 = d->fmt == MPA_FMT_F16X3 ? 1 : 0;
+  // split precision: the lo planes follow the hi planes of every edge / stream buffer (2*NC chunk planes per row set); a phase-split
+  // output holds [part][phase][chunk] planes
+  p.in_lo_off = (d->Cin + 7) / 8;
+  p.out_lo_off = (d->out_split ? d->out_split : 1) * (d->Cout / 8);
   p.n_patches = d->n_patches;
   p.NC = (d->Cin + 7) / 8;
   p.Cout = d->Cout;
@@ -1406,7 +1713,7 @@ int mpa_conv_tc_pool_f16(const mpa_conv_tc_desc* d, void* stream) {
   MPA_REQUIRE(d->n_seg == 1 || p.y_hi[0] <= p.y_lo[1], "conv_tc_pool: row segments overlap");
   p.n_units = d->n_patches * p.groups_per_patch;
   p.ring = (uint8_t*)d->workspace;
-  MPA_REQUIRE(d->ws_bytes >= mpa_conv_tc_pool_workspace(d->Cout, pitch, J), "conv_tc_pool: workspace too small (%zu B)", d->ws_bytes);
+  MPA_REQUIRE(d->ws_bytes >= mpa_conv_tc_pool_workspace_fmt(d->Cout, pitch, J, d->fmt), "conv_tc_pool: workspace too small (%zu B)", d->ws_bytes);
   p.act = d->act;
   p.act_param = d->act_param;
   const uint32_t f = (d->fmt == MPA_FMT_BF16) ? 1u : 0u;
@@ -1423,7 +1730,14 @@ int mpa_pool_time_res_cp8(const void* y_cp8, const void* res_cp8, void* out_cp8,
   if (ncs_res <= 0) ncs_res = NCk;
   if (ncs_out <= 0) ncs_out = NCk;
   long long total = (long long)n_patches * NCk * T * F;
-  if (k == 13 && T >= 13) {
+  if (fmt == MPA_FMT_F16X3) {
+    if (ncs_y == NCk) ncs_y = 2 * NCk;
+    if (ncs_res == NCk) ncs_res = 2 * NCk;
+    if (ncs_out == NCk) ncs_out = 2 * NCk;
+    MPA_REQUIRE(!((ncs_y | ncs_res | ncs_out) & 1), "pool_time_res_cp8(fp16x3): chunk strides must be even");
+    pool_time_res_x3_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)y_cp8, (const uint4*)res_cp8, (uint4*)out_cp8, total, NCk,
+                                                                                     ncs_y, ncs_res, ncs_out, T, F, T + 2 * pt, pitch, pf, pt, k / 2);
+  } else if (k == 13 && T >= 13) {
     const long long cols = (long long)n_patches * NCk * F;
     if (fmt == MPA_FMT_BF16)
       pool_time_col_cp8_kernel<MPA_FMT_BF16, 13><<<grid_for(cols, 128), 128, 0, (cudaStream_t)stream>>>(
@@ -1450,7 +1764,13 @@ int mpa_maxpool2x2_cp8(const void* in_cp8, void* out_cp8, int n, int C, int T, i
   if (ncs_in <= 0) ncs_in = NCk;
   if (ncs_out <= 0) ncs_out = NCk;
   long long total = (long long)n * NCk * To * Fo;
-  if (fmt == MPA_FMT_BF16)
+  if (fmt == MPA_FMT_F16X3) {
+    if (ncs_in == NCk) ncs_in = 2 * NCk;
+    if (ncs_out == NCk) ncs_out = 2 * NCk;
+    MPA_REQUIRE(!((ncs_in | ncs_out) & 1), "maxpool2x2_cp8(fp16x3): chunk strides must be even");
+    maxpool2x2_x3_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)in_cp8, (uint4*)out_cp8, total, NCk, ncs_in, ncs_out, To, Fo,
+                                                                                  T + 2 * pt_in, pitch_in, pf_in, pt_in, To + 2 * pt_out, pitch_out, pf_out, pt_out);
+  } else if (fmt == MPA_FMT_BF16)
     maxpool2x2_cp8_kernel<MPA_FMT_BF16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
         (const uint4*)in_cp8, (uint4*)out_cp8, total, NCk, ncs_in, ncs_out, To, Fo, T + 2 * pt_in, pitch_in, pf_in, pt_in, To + 2 * pt_out, pitch_out,
         pf_out, pt_out);
@@ -1470,7 +1790,12 @@ int mpa_upsample2x_cp8(const void* low_cp8, void* out_cp8, int n, int C, int Tl,
   if (ncs_l <= 0) ncs_l = NCk;
   MPA_REQUIRE(ncs_out >= NCk, "upsample2x_cp8: destination chunk stride too small");
   long long total = (long long)n * NCk * Ts * Fs;
-  if (fmt == MPA_FMT_BF16)
+  if (fmt == MPA_FMT_F16X3) {
+    if (ncs_l == NCk) ncs_l = 2 * NCk;
+    MPA_REQUIRE(!((ncs_l | ncs_out) & 1) && ncs_out >= 2 * NCk, "upsample2x_cp8(fp16x3): chunk strides must be even (hi planes, then lo planes)");
+    upsample2x_x3_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)low_cp8, (uint4*)out_cp8, total, NCk, ncs_l, ncs_out, Tl, Fl,
+                                                                                  Tl + 2 * pt_l, pitch_l, pf_l, pt_l, Ts, Fs, Ts + 2 * pt_s, pitch_s, pf_s, pt_s);
+  } else if (fmt == MPA_FMT_BF16)
     upsample2x_cp8_kernel<MPA_FMT_BF16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
         (const uint16_t*)low_cp8, (uint16_t*)out_cp8, total, NCk, ncs_l, ncs_out, Tl, Fl, Tl + 2 * pt_l, pitch_l, pf_l, pt_l, Ts, Fs, Ts + 2 * pt_s,
         pitch_s, pf_s, pt_s);
@@ -1486,7 +1811,8 @@ int mpa_nchw_to_cp8(const float* x, void* out_cp8, int B, int C, int T, int F, i
   MPA_CHECK_ARCH();
   MPA_REQUIRE(x && out_cp8 && B > 0 && C > 0 && pitch >= pf + F, "nchw_to_cp8: bad argument");
   const int NCk = (C + 7) / 8;
-  if (ncs_out <= 0) ncs_out = NCk;
+  if (ncs_out <= 0) ncs_out = (fmt == MPA_FMT_F16X3 ? 2 : 1) * NCk;
+  MPA_REQUIRE(fmt != MPA_FMT_F16X3 || !(ncs_out & 1), "nchw_to_cp8(fp16x3): the chunk stride must be even");
   long long total = (long long)B * NCk * T * F;
   nchw_to_cp8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (uint16_t*)out_cp8, total, C, T, F, NCk, ncs_out, T + 2 * pt,
                                                                                pitch, pf, pt, fmt);
@@ -1512,7 +1838,8 @@ int mpa_cp8_to_nchw(const void* in_cp8, float* out, int B, int C, int T, int F, 
   MPA_CHECK_ARCH();
   MPA_REQUIRE(in_cp8 && out && B > 0 && C > 0 && pitch >= pf + F, "cp8_to_nchw: bad argument");
   const int NCk = (C + 7) / 8;
-  if (ncs_in <= 0) ncs_in = NCk;
+  if (ncs_in <= 0) ncs_in = (fmt == MPA_FMT_F16X3 ? 2 : 1) * NCk;
+  MPA_REQUIRE(fmt != MPA_FMT_F16X3 || !(ncs_in & 1), "cp8_to_nchw(fp16x3): the chunk stride must be even");
   long long total = (long long)B * NCk * T * F;
   cp8_to_nchw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint16_t*)in_cp8, out, total, C, T, F, NCk, ncs_in, T + 2 * pt,
                                                                                pitch, pf, pt, fmt);

@@ -110,9 +110,17 @@ __global__ void __launch_bounds__(128) layernorm_frames_kernel(const float* __re
       int c = e / F, f = e - c * F;
       float r = (v[i] - mean) * rstd * w[e] + bsh[e];
       if (out_f32) out_f32[((size_t)c * NT + s) * F + f] = r;
-      if (out_cp8)
-        out_cp8[((size_t)s * pitch + pf + f) * 8 + c] =
-            fmt == MPA_FMT_BF16 ? __bfloat16_as_ushort(__float2bfloat16(r)) : __half_as_ushort(__float2half_rn(r));
+      if (out_cp8) {
+        const size_t at = ((size_t)s * pitch + pf + f) * 8 + c;
+        if (fmt == MPA_FMT_F16X3) {
+          // split precision: hi plane, then the lo plane [NT][pitch][8] right behind it
+          const __half hi = __float2half_rn(r);
+          out_cp8[at] = __half_as_ushort(hi);
+          out_cp8[(size_t)NT * pitch * 8 + at] = __half_as_ushort(__float2half_rn(r - __half2float(hi)));
+        } else {
+          out_cp8[at] = fmt == MPA_FMT_BF16 ? __bfloat16_as_ushort(__float2bfloat16(r)) : __half_as_ushort(__float2half_rn(r));
+        }
+      }
     }
   }
 }

@@ -124,16 +124,21 @@ __global__ void __launch_bounds__(256) head_tail_kernel(const uint4* __restrict_
 template <int FMT>
 __global__ void __launch_bounds__(128) head_tail2_kernel(const uint16_t* __restrict__ h, const float* __restrict__ w40, const float* __restrict__ b40,
                                                          const float* __restrict__ w43, const float* __restrict__ b43, float* __restrict__ out, int R,
-                                                         int Fo, int C2, int C3, float a) {
+                                                         int Fo, int C2, int C3, float a, int x3) {
   extern __shared__ float sm[];
   float* hs = sm;                          // [C2][Fo]
   float* ws = sm + (size_t)C2 * Fo;        // [C3][C2]
   const int b = blockIdx.x / R, r = blockIdx.x % R;
   const int NC2 = (C2 + 7) / 8;
+  const int ncs = x3 ? 2 * NC2 : NC2;      // split precision: hi planes, then lo planes
   for (int e = threadIdx.x; e < NC2 * Fo * 8; e += blockDim.x) {
     const int c8 = e & 7, f = (e >> 3) % Fo, ck = e / (8 * Fo);
     const int co = ck * 8 + c8;
-    if (co < C2) hs[co * Fo + f] = cvt_in<FMT>(h[((((size_t)b * NC2 + ck) * R + r) * Fo + f) * 8 + c8]);
+    if (co < C2) {
+      float v = cvt_in<FMT>(h[((((size_t)b * ncs + ck) * R + r) * Fo + f) * 8 + c8]);
+      if (x3) v += cvt_in<FMT>(h[((((size_t)b * ncs + NC2 + ck) * R + r) * Fo + f) * 8 + c8]);
+      hs[co * Fo + f] = v;
+    }
   }
   for (int e = threadIdx.x; e < C3 * C2; e += blockDim.x) ws[e] = w40[e];
   __syncthreads();
@@ -181,10 +186,11 @@ extern "C" int mpa_head_tail2_cp8(const void* h_cp8, const float* w40, const flo
   MPA_REQUIRE(smem <= 200 * 1024, "head_tail2: C2=%d C3=%d Fo=%d need %zu B of shared memory", C2, C3, Fo, smem);
   if (fmt == MPA_FMT_BF16) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(head_tail2_kernel<MPA_FMT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    head_tail2_kernel<MPA_FMT_BF16><<<B * R, 128, smem, (cudaStream_t)stream>>>((const uint16_t*)h_cp8, w40, b40, w43, b43, out, R, Fo, C2, C3, a_lrelu);
+    head_tail2_kernel<MPA_FMT_BF16><<<B * R, 128, smem, (cudaStream_t)stream>>>((const uint16_t*)h_cp8, w40, b40, w43, b43, out, R, Fo, C2, C3, a_lrelu, 0);
   } else {
     if (smem > 48 * 1024) cudaFuncSetAttribute(head_tail2_kernel<MPA_FMT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    head_tail2_kernel<MPA_FMT_F16><<<B * R, 128, smem, (cudaStream_t)stream>>>((const uint16_t*)h_cp8, w40, b40, w43, b43, out, R, Fo, C2, C3, a_lrelu);
+    head_tail2_kernel<MPA_FMT_F16><<<B * R, 128, smem, (cudaStream_t)stream>>>((const uint16_t*)h_cp8, w40, b40, w43, b43, out, R, Fo, C2, C3, a_lrelu,
+                                                                               fmt == MPA_FMT_F16X3 ? 1 : 0);
   }
   MPA_CHECK_LAUNCH("head_tail2");
   return MPA_OK;

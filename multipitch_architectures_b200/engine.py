@@ -29,13 +29,16 @@ class CnnStreamEngine:
         if self.dev.type != 'cuda':
             raise _lib.MpaError('the engine needs the model on a CUDA (sm_100a) device')
         if not _exec.tc_eligible(model, model.n_bins_in):
-            raise _lib.MpaError("CnnStreamEngine needs precision 'fp16' or 'bf16' and <=128 channels per layer; "
+            raise _lib.MpaError("CnnStreamEngine needs precision 'fp16', 'bf16' or 'fp16x3' and <=128 channels per layer; "
                                 "use predict_patchwise for the fp32 path")
         self.fmt = ops.fmt_of(model.precision)
+        self.x3 = self.fmt == ops.FMT_F16X3
         self.blocks = _exec.cnn_blocks(model)
         self.residual = getattr(model, 'residual', False)
         self.F = model.n_bins_in
         self.C0 = self.blocks[0][1].weight.shape[0]
+        if self.x3:
+            self.C0 = (self.C0 + 7) // 8 * 8          # split precision stores whole channel chunks: the block width is zero-padded
         self.pitch, self.pf, self.pt = (self.F + 8 + 15) // 16 * 16, 8, 1
         self._bufs = None
         self.timers = None          # optional: list collecting (tag, start_event, end_event, work)
@@ -50,6 +53,10 @@ class CnnStreamEngine:
         # dedup: share interior rows across patches (test knob; off = every row per patch).  ring: main loop that streams
         # un-duplicated weight pieces (2.2x less L2->SM traffic, measured SLOWER than ready-made tiles: 626 vs 729 audio-s/s)
         self.dedup, self.ring = bool(dedup), bool(ring)
+        if self.x3 and not self.fused:
+            raise _lib.MpaError("CnnStreamEngine(precision='fp16x3') runs the fused schedule only (block width <= 64 channels, odd kernels)")
+        if self.x3 and self.ring:
+            raise _lib.MpaError('the ring main loop has no split-precision variant')
 
     # -- buffers are allocated once (their zero borders are never written)
     def _buffers(self):
@@ -79,7 +86,7 @@ class CnnStreamEngine:
         hcqt = hcqt.contiguous().float()
         lead, trail = self.pt + HALF, HALF + self.pt + 1
         rows = lead + N + trail
-        plane = torch.zeros(rows, self.pitch, 8, dtype=ops._FMT_DTYPE[self.fmt], device=self.dev)
+        plane = torch.zeros(ops.planes_per_chunk(self.fmt), rows, self.pitch, 8, dtype=ops._FMT_DTYPE[self.fmt], device=self.dev)
         self._timed('layernorm_frames', lambda: _lib.call(
             'layernorm_frames', hcqt, m.layernorm.weight, m.layernorm.bias, None, plane, C, N, F, lead, trail, self.pitch, self.pf,
             float(m.layernorm.eps), self.compression, self.fmt, _lib.stream_ptr()))
@@ -100,7 +107,7 @@ class CnnStreamEngine:
                     src = ops.CP8.__new__(ops.CP8)
                     src.B, src.C, src.T, src.F, src.pitch, src.pf, src.pt, src.NC, src.fmt = n, C, CONTEXT, F, self.pitch, self.pf, self.pt, 1, self.fmt
                     src.ncs, src.chunk0 = 1, 0
-                    src.buf = plane[i0:]
+                    src.buf = plane[0, i0:]
                     self._timed('conv_tc_first', lambda: ops.conv_tc(src, wp, conv.bias, self.C0, tuple(conv.kernel_size), ops.ACT_LRELU, a,
                                                                     out=ya.first(n), n_patches=n, patch_stride_rows=1, T=CONTEXT))
                     cur = za
@@ -135,7 +142,7 @@ class CnnStreamEngine:
         e = self._edges()
         key = (R, tuple(e))
         if self._vbufs is None or self._vbufs[0] != key:
-            dt, dev, NC = ops._FMT_DTYPE[self.fmt], self.dev, self.C0 // 8
+            dt, dev, NC = ops._FMT_DTYPE[self.fmt], self.dev, self.C0 // 8 * ops.planes_per_chunk(self.fmt)
             streams = [torch.zeros(NC, R + 8, self.pitch, 8, dtype=dt, device=dev) if ei < CONTEXT else None for ei in e]
             edges = [torch.zeros(self.chunk + (1 if ei == CONTEXT else 0), NC, (2 * ei if ei < CONTEXT else CONTEXT) + 2, self.pitch, 8,
                                  dtype=dt, device=dev) for ei in e]
@@ -143,7 +150,7 @@ class CnnStreamEngine:
                 # the last block feeds the head's stride-(1,3) conv2: its output is written phase-split (3 sets of NC chunk planes of
                 # width F/3), conv2 then is a stride-1 3x1 convolution with resident weights (see _exec.head_tc)
                 edges[-1] = ops.split_cp8(self.chunk + 1, self.C0, CONTEXT, self.F, self.split, dev, self.fmt).buf
-            ws = ops.conv_tc_pool_workspace(self.C0, self.pitch, dev)
+            ws = ops.conv_tc_pool_workspace(self.C0, self.pitch, dev, fmt=self.fmt)
             self._vbufs = (key, streams, edges, ws)
         return self._vbufs[1:]
 
@@ -153,16 +160,21 @@ class CnnStreamEngine:
         R = N + T - 1                                   # stream rows: row s of the stream = row s - p of patch p
         e = self._edges()
         streams, edges, ws = self._virtual_buffers(R)
-        packed = []
-        for name, conv in self.blocks:
+        packed, biases = [], []
+        for i, (name, conv) in enumerate(self.blocks):
             w = conv.weight
-            packed.append(cache.get(f'{name}:wtc{self.fmt}:{int(self.ring)}', [w], lambda: ops.conv_tc_pack(w, self.dev, self.fmt, ring=self.ring)))
-        plane_stream = plane.unsqueeze(0)               # [1][rows][P][8]: 1 guard row, then stream rows 0..R-1
+            if self.x3:
+                wp, b = _exec.block_operands(cache, name, conv, self.fmt, self.dev, C if i == 0 else self.C0, self.C0)
+            else:
+                wp = cache.get(f'{name}:wtc{self.fmt}:{int(self.ring)}', [w], lambda: ops.conv_tc_pack(w, self.dev, self.fmt, ring=self.ring))
+                b = conv.bias
+            packed.append(wp)
+            biases.append(b)
+        plane_stream = plane                            # [planes][rows][P][8]: 1 guard row, then stream rows 0..R-1
 
         def run(i, src, dst, n, segments, tag, out_split=0):
-            conv = self.blocks[i][1]
             cin = C if i == 0 else self.C0
-            self._timed(tag, lambda: ops.conv_tc_pool(src, dst, packed[i], conv.bias, n, cin, self.C0, F, (self.KH, self.KW), self.pitch, self.pf,
+            self._timed(tag, lambda: ops.conv_tc_pool(src, dst, packed[i], biases[i], n, cin, self.C0, F, (self.KH, self.KW), self.pitch, self.pf,
                                                       segments, self.residual and i > 0, ops.ACT_LRELU, a, self.fmt, ws, ring=self.ring,
                                                       out_split=out_split),
                         work=n * sum(hi_ - lo_ for lo_, hi_ in segments))

@@ -9,6 +9,8 @@ loop, tuning step, transposition) are drawn on the host from a torch generator, 
 so the distributions — not the random streams — match the reference.  `__getitem__` keeps the
 per-item Dataset protocol on top of the same kernels (host tensors are moved to the GPU on first use; no CPU arithmetic path);
 `patch_frames` is the integer index math on its own."""
+import itertools
+
 import numpy as np
 import torch
 import torch.utils.data
@@ -34,6 +36,9 @@ def draw_eq(randomeq, n_chan, generator=None, n_bins=216):
             return alpha, beta
 
 
+_DATASET_IDS = itertools.count()
+
+
 class dataset_context(torch.utils.data.Dataset):
     def __init__(self, inputs, targets, params):
         self.inputs = inputs if isinstance(inputs, torch.Tensor) else torch.as_tensor(inputs)
@@ -55,7 +60,9 @@ class dataset_context(torch.utils.data.Dataset):
             t /= np.max(t)
             self.targets = torch.from_numpy(t).to(self.targets.device)
         self.generator = None          # torch.Generator for the augmentation decisions (None = global RNG)
-        self._seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+        # Philox stream of the additive / fill noise: every dataset object owns its own key (the reference draws independent noise per
+        # item; with one shared seed, call k of file A and call k of file B would produce bit-identical noise fields)
+        self._seed = (int(torch.initial_seed()) + 0x9E3779B97F4A7C15 * (1 + next(_DATASET_IDS))) & 0xFFFFFFFFFFFFFFFF
         self._calls = 0
         self._dev = {}
 

@@ -12,7 +12,10 @@ from ... import ops
 from ... import _lib
 from ..._lib import MpaError
 
-PRECISIONS = ('fp32', 'fp16', 'bf16')     # fp16 / bf16: tcgen05 tensor-core path (16-bit operands, fp32 accumulate)
+# fp16 / bf16: tcgen05 tensor-core path (16-bit operands and storage, fp32 accumulate); fp16x3: the same kernels in split precision
+# (hi/lo fp16 pairs, three MMA passes per product: fp32-class results at a third of the fp16 rate); fp32: exact CUDA-core path
+PRECISIONS = ('fp32', 'fp16', 'bf16', 'fp16x3')
+TC_PRECISIONS = ('fp16', 'bf16', 'fp16x3')
 
 
 class ParamCache:
@@ -29,6 +32,15 @@ class ParamCache:
                 hit = (sig, build())
             self._d[key] = hit
         return hit[1]
+
+
+def invalidate_caches(model):
+    """Clear every ParamCache of the module tree.  Needed after an in-place update through raw pointers (the fused AdamW kernel), which
+    changes neither data_ptr nor _version of a parameter."""
+    for m in model.modules():
+        c = getattr(m, '_cache', None)
+        if isinstance(c, ParamCache):
+            c._d.clear()
 
 
 def _check_input(x, n_chan, n_bins, min_T=1):
@@ -140,7 +152,8 @@ def head_tc(cache, model, zc, a, split=None):
         for wp, b, c0, c in _split_conv2_blocks(cache, conv2, zc.C // 3, fmt, dev, J=J2):
             ops.conv_tc(zc, wp, b, c, (3, 1), ops.ACT_LRELU, a, subsample=(1, 0), out=yc.channels(c0, c), J=J2)
     else:
-        for wp, b, c0, c in _folded_tc(cache, 'conv2', conv2, None, fmt, dev):
+        cin_pad = zc.C if zc.C != conv2.weight.shape[1] else None          # the producer padded its channels to whole chunks
+        for wp, b, c0, c in _folded_tc(cache, 'conv2', conv2, None, fmt, dev, cin_pad=cin_pad):
             ops.conv_tc(zc, wp, b, c, (3, 3), ops.ACT_LRELU, a, subsample=(3, 1), out=yc.channels(c0, c))
     yc = ops.pool_time_res_cp8(yc, 13)
     C2p = (conv3.weight.shape[0] + 7) // 8 * 8
@@ -165,7 +178,7 @@ def cnn_blocks(model):
 
 
 def tc_eligible(model, F):
-    return (model.precision in ('fp16', 'bf16') and F + 8 <= 256
+    return (model.precision in TC_PRECISIONS and F + 8 <= 256
             and all(c.weight.shape[0] <= 128 and c.kernel_size[0] % 2 == 1 and c.kernel_size[1] % 2 == 1 for _, c in cnn_blocks(model)))
 
 
@@ -184,10 +197,31 @@ def cnn_forward(model, x):
     zc = ops.nchw_to_cp8(z, fmt=fmt)
     for i, (name, conv) in enumerate(blocks):
         w = conv.weight
-        wp = cache.get(f'{name}:wtc{fmt}', [w], lambda: ops.conv_tc_pack(w, x.device, fmt))
-        yc = ops.conv_tc(zc, wp, conv.bias, w.shape[0], tuple(conv.kernel_size), ops.ACT_LRELU, a)
+        if fmt == ops.FMT_F16X3:
+            # split precision stores whole channel chunks: pad the block width with zero filters (LeakyReLU / pool / residual keep zeros)
+            cout = (w.shape[0] + 7) // 8 * 8
+            wp, bias = block_operands(cache, name, conv, fmt, x.device, w.shape[1] if i == 0 else zc.C, cout)
+        else:
+            cout, bias = w.shape[0], conv.bias
+            wp = cache.get(f'{name}:wtc{fmt}', [w], lambda: ops.conv_tc_pack(w, x.device, fmt))
+        yc = ops.conv_tc(zc, wp, bias, cout, tuple(conv.kernel_size), ops.ACT_LRELU, a)
         zc = ops.pool3_res_cp8(yc, res=zc if (residual and i > 0) else None)
     return head_tc(cache, model, zc, a)
+
+
+def block_operands(cache, name, conv, fmt, dev, cin_pad, cout_pad, ring=False):
+    """(packed weights, bias) of one CNN block with its channel counts zero-padded to (cin_pad, cout_pad)."""
+    def build():
+        w, b = conv.weight.detach().float(), conv.bias.detach().float()
+        Cout, Cin = w.shape[0], w.shape[1]
+        if (Cout, Cin) != (cout_pad, cin_pad):
+            w2 = torch.zeros(cout_pad, cin_pad, w.shape[2], w.shape[3], dtype=w.dtype, device=w.device)
+            w2[:Cout, :Cin] = w
+            b2 = torch.zeros(cout_pad, dtype=b.dtype, device=b.device)
+            b2[:Cout] = b
+            w, b = w2, b2
+        return ops.conv_tc_pack(w, dev, fmt, ring=ring), b.contiguous().to(dev)
+    return cache.get(f'{name}:wtcpad{fmt}:{cin_pad}:{cout_pad}:{int(ring)}', [conv.weight, conv.bias], build)
 
 
 def double_conv_f32(cache, name, dc, x, train, x2=None):
@@ -233,7 +267,7 @@ def level_geometry(T0, F0, n_levels=5):
 
 
 def unet_tc_eligible(model, x):
-    if model.precision not in ('fp16', 'bf16') or model.training:
+    if model.precision not in TC_PRECISIONS or model.training:
         return False
     chans = [model.inc.double_conv[0].weight.shape[0]] + [getattr(model, f'down{i}')[1].double_conv[0].weight.shape[0] for i in (1, 2, 3, 4)]
     ups = [getattr(model, f'upconv{i}').double_conv[4].weight.shape[0] for i in (1, 2, 3)]
@@ -327,8 +361,9 @@ def unet_forward_tc(model, x):
         dst = skips[lv] if lv < 4 else buf(4, c[4])
         cur = double_conv_tc(cache, f'down{lv}', dc, pooled, dst, buf(lv, dc.double_conv[0].weight.shape[0]))
     x5 = cur
+    afmt = None if fmt == ops.FMT_F16X3 else fmt        # split precision: the encoder layers run their fp32 sequence
     if hasattr(model, 'attention1'):
-        t5 = model.attention2.run(model.attention1.run(ops.cp8_to_nchw(x5), fmt), fmt)
+        t5 = model.attention2.run(model.attention1.run(ops.cp8_to_nchw(x5), afmt), afmt)
         x5 = ops.nchw_to_cp8(t5, pitch=geo[4][2], pf=LEVEL_PF, pt=1, fmt=fmt)
     if getattr(model, 'lstm_depth', 0) > 0:
         # BLUnet: BLSTM over time at the bottleneck (fp32 kernels; < 1 % of the model's FLOPs)
@@ -337,7 +372,7 @@ def unet_forward_tc(model, x):
         ops.nchw_to_cp8(model.lstm4.run(ops.cp8_to_nchw(skips[3])), out=skips[3], fmt=fmt)
     if hasattr(model, 'attention3'):
         # SAUSnet: the lowest skip connection passes two encoder layers too (x5 above was computed from the un-attended x4)
-        t4 = model.attention4.run(model.attention3.run(ops.cp8_to_nchw(skips[3]), fmt), fmt)
+        t4 = model.attention4.run(model.attention3.run(ops.cp8_to_nchw(skips[3]), afmt), afmt)
         ops.nchw_to_cp8(t4, out=skips[3], fmt=fmt)
     # decoder
     low = x5

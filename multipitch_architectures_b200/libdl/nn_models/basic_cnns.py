@@ -48,10 +48,19 @@ class _MpaModel(nn.Module):
         self.a_lrelu, self.p_dropout, self.precision = a_lrelu, p_dropout, precision
         self._cache = _exec.ParamCache()
 
-    def _guard_training(self):
-        if self.training and self.p_dropout > 0:
-            raise NotImplementedError('train-mode forward with dropout>0 runs through the training engine '
-                                      '(multipitch_architectures_b200.training); call .eval() for inference')
+
+
+def _dispatch(model, x):
+    """Autograd recording -> the training tape; train mode under no_grad -> the training forward with its tape discarded (dropout stays
+    active exactly as in the reference, whose validation pass runs in train mode: exp126a...py:333-345); eval -> inference path."""
+    if torch.is_grad_enabled() and (model.training or x.requires_grad):
+        from ...training import cnn_forward_train
+        return cnn_forward_train(model, x)
+    if model.training and model.p_dropout > 0:
+        from ...training import cnn_train_forward
+        model._train_calls = getattr(model, '_train_calls', 0) + 1
+        return cnn_train_forward(model, x, getattr(model, 'dropout_seed', 0x5EED), model._train_calls)[0]
+    return _exec.cnn_forward(model, x)
 
 
 class basic_cnn_segm_sigmoid(_MpaModel):
@@ -69,10 +78,7 @@ class basic_cnn_segm_sigmoid(_MpaModel):
 
     def forward(self, x):
         x = _exec._check_input(x, self.n_chan_input, self.n_bins_in)
-        if torch.is_grad_enabled() and (self.training or x.requires_grad):
-            from ...training import cnn_forward_train
-            return cnn_forward_train(self, x)
-        return _exec.cnn_forward(self, x)
+        return _dispatch(self, x)
 
 
 class deep_cnn_segm_sigmoid(_MpaModel):
@@ -92,7 +98,4 @@ class deep_cnn_segm_sigmoid(_MpaModel):
 
     def forward(self, x):
         x = _exec._check_input(x, self.n_chan_input, self.n_bins_in)
-        if torch.is_grad_enabled() and (self.training or x.requires_grad):
-            from ...training import cnn_forward_train
-            return cnn_forward_train(self, x)
-        return _exec.cnn_forward(self, x)
+        return _dispatch(self, x)

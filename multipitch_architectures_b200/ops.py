@@ -91,12 +91,18 @@ def bce_fwd_bwd(y_pred, y_true, want_grad=True):
 
 # ------------------------------------------------------------------------------------------------------
 # tcgen05 path: 16-bit channel-chunk planes ("CP8", see include/mpa.h)
-FMT_F16, FMT_BF16 = 0, 1
-_FMT_DTYPE = {FMT_F16: torch.float16, FMT_BF16: torch.bfloat16}
+FMT_F16, FMT_BF16, FMT_F16X3 = 0, 1, 2
+# FMT_F16X3 (precision 'fp16x3'): split precision, every value a (hi, lo) pair of fp16 planes; a buffer holds its hi planes in the first half
+# of its chunk planes and the lo planes in the second half (include/mpa.h, MPA_FMT_F16X3)
+_FMT_DTYPE = {FMT_F16: torch.float16, FMT_BF16: torch.bfloat16, FMT_F16X3: torch.float16}
 
 
 def fmt_of(precision):
-    return {'fp16': FMT_F16, 'bf16': FMT_BF16}[precision]
+    return {'fp16': FMT_F16, 'bf16': FMT_BF16, 'fp16x3': FMT_F16X3}[precision]
+
+
+def planes_per_chunk(fmt):
+    return 2 if fmt == FMT_F16X3 else 1
 
 
 class CP8:
@@ -109,7 +115,7 @@ class CP8:
             pitch = (F + pf + 15) // 16 * 16
         self.B, self.C, self.T, self.F, self.pitch, self.pf, self.pt, self.fmt = B, C, T, F, pitch, pf, pt, fmt
         self.NC = (C + 7) // 8
-        self.ncs = self.NC if ncs is None else ncs
+        self.ncs = self.NC * planes_per_chunk(fmt) if ncs is None else ncs
         self.chunk0 = chunk0
         shape = (B, self.ncs, T + 2 * pt, pitch, 8)
         if buf is None:
@@ -172,7 +178,9 @@ def conv_tc_pack(w, device, fmt=FMT_F16, J=0, ring=False):
     wh = np.ascontiguousarray(w.detach().float().cpu().numpy())
     Cout, Cin, KH, KW = wh.shape
     L = _lib.lib()
-    nbytes = (L.mpa_conv_tc_ring_packed_bytes if ring else L.mpa_conv_tc_packed_bytes)(Cin, Cout, KH, KW, J)
+    if ring and fmt == FMT_F16X3:
+        raise _lib.MpaError('the ring main loop has no split-precision variant')
+    nbytes = L.mpa_conv_tc_ring_packed_bytes(Cin, Cout, KH, KW, J) if ring else L.mpa_conv_tc_packed_bytes_fmt(Cin, Cout, KH, KW, J, fmt)
     if nbytes == 0:
         raise _lib.MpaError(f'conv_tc cannot pack Cin={Cin} Cout={Cout} K={KH}x{KW}')
     packed = np.zeros(nbytes, dtype=np.uint8)
@@ -185,7 +193,7 @@ def conv_tc_pack(w, device, fmt=FMT_F16, J=0, ring=False):
 
 def compact_cp8(n, C, T, F, device, fmt):
     """Un-padded planes [n][C/8][T][F][8]; one spare item of slack so that KW == 1 convolutions may over-read the last row."""
-    buf = torch.empty(n + 1, (C + 7) // 8, T, F, 8, dtype=_FMT_DTYPE[fmt], device=device)
+    buf = torch.empty(n + 1, (C + 7) // 8 * planes_per_chunk(fmt), T, F, 8, dtype=_FMT_DTYPE[fmt], device=device)
     buf[n:].zero_()     # the over-read meets zero weights (dummy K slice): it must be finite, or NaN * 0 poisons the last column
     return CP8(n, C, T, F, F, 0, 0, device, fmt=fmt, buf=buf)
 
@@ -262,7 +270,7 @@ def head_tail2(h, w40, b40, w43, b43, a_lrelu):
     """h: compact CP8 [B][NC2][R][Fo][8] (activated conv3 output) -> [B,R,Fo] fp32 = sigmoid(conv4.3(lrelu(conv4.0(h))))."""
     C3 = w40.shape[0]
     out = torch.empty(h.B, h.T, h.F, dtype=torch.float32, device=h.buf.device)
-    assert h.ncs == h.NC and h.chunk0 == 0
+    assert h.ncs == h.NC * planes_per_chunk(h.fmt) and h.chunk0 == 0
     w40f = w40.reshape(C3, -1)
     call('head_tail2_cp8', h.ptr(), w40f[:, :h.C].contiguous() if w40f.shape[1] != h.C else w40f.contiguous(), b40, w43.reshape(-1).contiguous(),
          b43, out, h.B, h.T, h.F, h.C, C3, float(a_lrelu), h.fmt, stream_ptr())
@@ -308,8 +316,8 @@ class VRows:
         return ed, st
 
 
-def conv_tc_pool_workspace(Cout, pitch, device, J=0):
-    n = _lib.lib().mpa_conv_tc_pool_workspace(Cout, pitch, J)
+def conv_tc_pool_workspace(Cout, pitch, device, J=0, fmt=FMT_F16):
+    n = _lib.lib().mpa_conv_tc_pool_workspace_fmt(Cout, pitch, J, fmt)
     return torch.empty(n, dtype=torch.uint8, device=device)
 
 

@@ -157,11 +157,38 @@ class TcConv:
         return (getattr(model, 'precision', 'fp32') == 'bf16' and tuple(conv.stride) == (1, 1) and KH % 2 == 1 and KW % 2 == 1 and 3 <= KW <= 15 and KH >= 3
                 and tuple(conv.padding) == (KH // 2, KW // 2) and F + TcConv.PF + 15 < 272 and conv.bias is not None)
 
+    _scope = None           # owner of the pooled buffers (a TrainStep); None = allocate per call
+
+    @classmethod
+    def scope(cls, owner):
+        """Context manager: inside it `_buf` hands out buffers pooled under `owner` (a fused train step, which runs forward and backward
+        atomically, so reusing the SAVED activation planes across steps is safe).  Outside any scope — the autograd bridge, where a
+        second forward may run before the first backward (gradient accumulation, two losses, two same-shape models) — every call gets
+        fresh planes, because the planes are what the backward reads."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def cm():
+            prev, cls._scope = cls._scope, id(owner)
+            try:
+                yield
+            finally:
+                cls._scope = prev
+        return cm()
+
+    @classmethod
+    def release(cls, owner):
+        """Drop every pooled buffer of `owner`."""
+        for k in [k for k in cls._pool if k[0] == id(owner)]:
+            del cls._pool[k]
+
     @classmethod
     def _buf(cls, tag, B, C, T, F, dev, fmt):
-        """CP8 scratch reused across steps (zero gap columns are never written, so they stay zero)."""
+        """CP8 scratch reused across the steps of one owner (zero gap columns are never written, so they stay zero)."""
         pitch = (F + cls.PF + 15) // 16 * 16
-        key = (tag, B, C, T, F, str(dev), fmt)
+        if cls._scope is None:
+            return ops.CP8(B, C, T, F, pitch, cls.PF, cls.PT, dev, fmt=fmt)
+        key = (cls._scope, tag, B, C, T, F, str(dev), fmt)
         b = cls._pool.get(key)
         if b is None:
             b = ops.CP8(B, C, T, F, pitch, cls.PF, cls.PT, dev, fmt=fmt)
@@ -456,10 +483,16 @@ class TrainStep:
         self.use_graph, self._graph = bool(graph), None
 
     def _forward_backward(self, x, target, tape_step):
-        y, sv = cnn_train_forward(self.model, x, self.seed, tape_step)
-        loss, g_y = ops.bce_fwd_bwd(y, target.contiguous())
-        cnn_train_backward(self.model, sv, g_y, self.grads)
+        with TcConv.scope(self):
+            y, sv = cnn_train_forward(self.model, x, self.seed, tape_step)
+            loss, g_y = ops.bce_fwd_bwd(y, target.contiguous())
+            cnn_train_backward(self.model, sv, g_y, self.grads)
         return loss
+
+    def release(self):
+        """Free the pooled activation planes of this step (and the captured graph that points into them)."""
+        self._graph = None
+        TcConv.release(self)
 
     def _capture(self, x, target):
         global _step_dev, _step_mul
@@ -498,5 +531,5 @@ class TrainStep:
                 scale = 1.0 / dist.get_world_size(self.group)
             call('adamw_f32', self.flat_p, self.flat_g, self.m, self.v, _lib.i64(self.flat_p.numel()), float(self.lr), float(self.betas[0]),
                  float(self.betas[1]), float(self.eps), float(self.wd), self.step_count, float(scale), stream_ptr())
-        self.model._cache._d.clear()        # packed operands derived from the old parameter values are stale
+        _exec.invalidate_caches(self.model)   # packed operands derived from the old parameter values are stale
         return loss

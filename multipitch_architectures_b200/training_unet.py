@@ -455,15 +455,21 @@ class UnetTrainStep:
         self.use_graph, self._graph = bool(graph), None
 
     def _forward_backward(self, x, target, tape_step):
-        y, n_pred, tape = unet_train_forward(self.model, x, self.grads, self.seed, tape_step)
-        target = target.contiguous()
-        loss, y.g = ops.bce_fwd_bwd(y.d, target)
-        if n_pred is not None:
-            B, K = n_pred.d.shape[0], n_pred.d.shape[1]
-            n_pred.g = torch.empty_like(n_pred.d)
-            call('ce_count_fwd_bwd_f32', n_pred.d, target, loss, n_pred.g, B, K, target.numel() // B, float(self.ce_scale), 1, stream_ptr())
-        tape.backward()
+        with TcConv.scope(self):
+            y, n_pred, tape = unet_train_forward(self.model, x, self.grads, self.seed, tape_step)
+            target = target.contiguous()
+            loss, y.g = ops.bce_fwd_bwd(y.d, target)
+            if n_pred is not None:
+                B, K = n_pred.d.shape[0], n_pred.d.shape[1]
+                n_pred.g = torch.empty_like(n_pred.d)
+                call('ce_count_fwd_bwd_f32', n_pred.d, target, loss, n_pred.g, B, K, target.numel() // B, float(self.ce_scale), 1, stream_ptr())
+            tape.backward()
         return loss
+
+    def release(self):
+        """Free the pooled activation planes of this step (and the captured graph that points into them)."""
+        self._graph = None
+        TcConv.release(self)
 
     def _capture(self, x, target):
         from . import training as T
@@ -502,8 +508,7 @@ class UnetTrainStep:
                 scale = 1.0 / dist.get_world_size(self.group)
             call('adamw_f32', self.flat_p, self.flat_g, self.m, self.v, _lib.i64(self.flat_p.numel()), float(self.lr), float(self.betas[0]),
                  float(self.betas[1]), float(self.eps), float(self.wd), self.step_count, float(scale), stream_ptr())
-        self.model._cache._d.clear()
-        for nm in ('attention1', 'attention2', 'attention3', 'attention4'):
-            if hasattr(self.model, nm):
-                getattr(self.model, nm)._cache._d.clear()
+        # the raw-pointer AdamW leaves data_ptr / _version unchanged: every ParamCache of the module tree (model, encoder layers, BLSTM
+        # layers) is stale now
+        _exec.invalidate_caches(self.model)
         return loss

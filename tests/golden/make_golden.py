@@ -422,7 +422,79 @@ def ext_goldens():
     print('ext goldens:', len(out), 'arrays;', len(cases), 'augmentation cases')
 
 
+REALISTIC = ('cnn_xs', 'drcnn', 'unet_m')
+REALISTIC_CLIP = dict(seed=777, seconds=30.0)
+HCQT_KW = dict(fs=22050, fs_hcqt_target=50, bins_per_octave=36, num_octaves=6, num_harmonics=5, num_subharmonics=1)
+
+
+def realistic_goldens(src=os.path.join(ROOT, 'gpurun_out', 'realistic')):
+    """The REALISTIC weight set: state_dicts trained by tools/train_realistic.py (this repo's own loop.fit on labelled synthetic audio, on
+    the GPU) are committed as tests/golden/realistic_weights.npz, and the UNMODIFIED reference classes are run on them through the
+    reference's own test loop (exp126a...py:413-436: np.pad -> dataset_context(stride 1, compression 10) -> DataLoader(batch 50) ->
+    model(batch)) over the whole held-out 30 s clip.  Input = the oracle HCQT of tests.synth clip 777 (regenerated by the tests)."""
+    import time
+    from libdl.data_loaders import dataset_context
+    import libdl.nn_models  # noqa: F401
+    from tests import synth
+    torch.set_num_threads(os.cpu_count() or 8)
+    y, notes = synth.synth_clip_labeled(**REALISTIC_CLIP)
+    f, _, _ = HO.compute_efficient_hcqt(y, **HCQT_KW)                      # [216, N, 6] float64, linear magnitudes
+    inputs = np.transpose(f, (2, 1, 0))
+    n_frames = inputs.shape[1]
+    roll = synth.piano_roll(notes, n_frames)
+    out = {'hcqt_sum': np.array([f.sum(dtype=np.float64)]), 'hcqt_probe': np.asarray(f[::37, ::101, :], dtype=np.float64),
+           'roll': np.packbits(roll.astype(np.uint8)), 'n_frames': np.array([n_frames])}
+    weights = {}
+    half = 75 // 2
+    for name in REALISTIC:
+        sd = torch.load(os.path.join(src, name + '.pt'))
+        m = build_reference_model(name)
+        m.load_state_dict(sd)                                               # strict: names, shapes, dtypes of the reference
+        m.eval()
+        ic = torch.from_numpy(np.pad(inputs, ((0, 0), (half, half + 1), (0, 0))))
+        tc = torch.from_numpy(np.pad(roll, ((half, half + 1), (0, 0))))
+        gen = torch.utils.data.DataLoader(dataset_context(ic, tc, {'context': 75, 'stride': 1, 'compression': 10}), batch_size=50, shuffle=False)
+        t0 = time.time()
+        preds = []
+        with torch.no_grad():
+            for xb, _ in gen:
+                yp = m(xb)
+                preds.append(torch.squeeze(torch.squeeze(yp, 2), 1).numpy())
+        pred = np.concatenate(preds, 0).astype(np.float32)
+        assert pred.shape == (n_frames, 72)
+        out[name + '__y'] = pred
+        est = pred >= 0.4
+        tp = int((est & (roll > 0)).sum())
+        out[name + '__counts'] = np.array([tp, int(est.sum()) - tp, int((roll > 0).sum()) - tp])
+        for k, v in sd.items():
+            weights[name + '/' + k] = v.numpy()
+        print(f'realistic {name}: {n_frames} patches in {time.time() - t0:.1f} s; outputs span {pred.min():.3g}..{pred.max():.3g}, '
+              f'{int(est.sum())} active cells, TP/FP/FN = {out[name + "__counts"].tolist()}', flush=True)
+    np.savez_compressed(os.path.join(HERE, 'realistic_golden.npz'), **out)
+    np.savez_compressed(os.path.join(HERE, 'realistic_weights.npz'), **weights)
+
+
+def state_dict_key_fixture():
+    """Names, shapes and dtypes (in order) of the state_dict of every reference model class / size the tests use: the drop-in contract
+    `model.load_state_dict(torch.load(pt))` (exp126a...py:388) is a contract on NAMES, so they are pinned as text."""
+    import json
+    out = {}
+    for name in MODEL_SPECS:
+        m = build_reference_model(name)
+        out[name] = [[k, list(v.shape), str(v.dtype).replace('torch.', '')] for k, v in m.state_dict().items()]
+    with open(os.path.join(HERE, 'state_dict_keys.json'), 'w') as f:
+        json.dump(out, f, indent=0)
+    print('state_dict key lists:', {k: len(v) for k, v in out.items()})
+
+
 if __name__ == '__main__':
+    if 'keys' in sys.argv[1:]:
+        state_dict_key_fixture()
+        sys.exit(0)
+    if 'realistic' in sys.argv[1:]:
+        realistic_goldens()
+        state_dict_key_fixture()
+        sys.exit(0)
     if 'train' in sys.argv[1:]:
         train_goldens()
         sys.exit(0)
