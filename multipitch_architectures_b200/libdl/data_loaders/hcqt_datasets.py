@@ -92,6 +92,19 @@ class dataset_context(torch.utils.data.Dataset):
         X, y = self.gather([int(index)])
         return X[0], y[0]
 
+    def __getitems__(self, indices):
+        """Batched fetch hook of torch.utils.data.DataLoader (one kernel launch per batch instead of one per item): the reference's
+        `DataLoader(dataset_context(...), batch_size=50)` loop then costs one cut per batch.  Items are views of one [n,C,T,F] tensor."""
+        if self.scalingfactor:
+            assert False, 'Scaling not implemented for dataset_context!'
+        if not self.inputs.is_cuda:
+            if not torch.cuda.is_available():
+                raise _lib.MpaError('dataset_context items are produced by the libmpa kernels: a CUDA (sm_100a) device is required '
+                                    '(there is no CPU path)')
+            self.inputs, self.targets = self.inputs.cuda(), self.targets.cuda()
+        X, y = self.gather([int(i) for i in indices])
+        return [(X[i], y[i]) for i in range(X.shape[0])]
+
     # ------------------------------------------------------------------ device path
     def _resident(self):
         if 'inp' not in self._dev:

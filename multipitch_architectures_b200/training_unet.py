@@ -504,7 +504,14 @@ class UnetTrainStep:
                 loss = self._forward_backward(x, target, self.step_count)
             scale = 1.0
             if self.group is not None or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+                ev = getattr(self, 'comm_events', None)
+                if ev is not None:                    # bench.py: CUDA events around the collective (time of the all-reduce per step)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
                 dist.all_reduce(self.flat_g, group=self.group)
+                if ev is not None:
+                    e1.record()
+                    ev.append((e0, e1))
                 scale = 1.0 / dist.get_world_size(self.group)
             call('adamw_f32', self.flat_p, self.flat_g, self.m, self.v, _lib.i64(self.flat_p.numel()), float(self.lr), float(self.betas[0]),
                  float(self.betas[1]), float(self.eps), float(self.wd), self.step_count, float(scale), stream_ptr())
