@@ -4,7 +4,10 @@ The nn.Module classes in this package own parameters with exactly the reference'
 `forward` never calls a torch operator on activations — every stage below is a libmpa kernel
 (include/mpa.h).  torch is used to hold memory and to do one-off parameter preparation (weight packing,
 BatchNorm folding)."""
+import logging
 import math
+import os
+import warnings
 
 import torch
 
@@ -16,6 +19,19 @@ from ..._lib import MpaError
 # (hi/lo fp16 pairs, three MMA passes per product: fp32-class results at a third of the fp16 rate); fp32: exact CUDA-core path
 PRECISIONS = ('fp32', 'fp16', 'bf16', 'fp16x3')
 TC_PRECISIONS = ('fp16', 'bf16', 'fp16x3')
+# precision of a model constructed without the keyword (the reference's constructors have none): see install_as_libdl / set_default_precision
+DEFAULT_PRECISION = os.environ.get('MPA_PRECISION', 'fp32')
+log = logging.getLogger('multipitch_architectures_b200')
+_warned = set()
+
+
+def note_path(model, what):
+    """Say ONCE per (model class, reason) which kernel path a tensor-core model actually takes when it cannot take the tcgen05 one."""
+    key = (type(model).__name__, what)
+    if key not in _warned:
+        _warned.add(key)
+        warnings.warn(f'{type(model).__name__}(precision={model.precision!r}): {what}', RuntimeWarning, stacklevel=3)
+        log.warning('%s(precision=%r): %s', type(model).__name__, model.precision, what)
 
 
 class ParamCache:
@@ -189,6 +205,9 @@ def cnn_forward(model, x):
     residual = getattr(model, 'residual', False)
     z = ops.layernorm_cf(x, model.layernorm.weight, model.layernorm.bias, model.layernorm.eps)
     if not tc_eligible(model, x.shape[3]):
+        if model.precision in TC_PRECISIONS:
+            note_path(model, 'this configuration runs on the fp32 CUDA-core kernels, not on the tensor cores (the tcgen05 path needs <= 128 '
+                             'channels per block, odd kernel sizes and n_bins_in <= 248)')
         for i, (name, conv) in enumerate(blocks):
             y = conv_f32(cache, name, conv, z, ops.ACT_LRELU, a)
             z = ops.maxpool_time(y, 3, res=z if (residual and i > 0) else None)
@@ -271,7 +290,11 @@ def unet_tc_eligible(model, x):
         return False
     chans = [model.inc.double_conv[0].weight.shape[0]] + [getattr(model, f'down{i}')[1].double_conv[0].weight.shape[0] for i in (1, 2, 3, 4)]
     ups = [getattr(model, f'upconv{i}').double_conv[4].weight.shape[0] for i in (1, 2, 3)]
-    return all(c % 8 == 0 for c in chans + ups) and x.shape[3] + LEVEL_PF <= 256 and x.shape[2] >= 32
+    ok = all(c % 8 == 0 for c in chans + ups) and x.shape[3] + LEVEL_PF <= 256 and x.shape[2] >= 32
+    if not ok:
+        note_path(model, 'this configuration runs on the fp32 CUDA-core kernels, not on the tensor cores (the tcgen05 U-Net path needs every '
+                         f'level width to be a multiple of 8 channels: {chans + ups}, n_bins_in <= 248 and >= 32 frames)')
+    return ok
 
 
 def _folded_tc(cache, name, conv, bn, fmt, dev, cin_pad=None, J=0):

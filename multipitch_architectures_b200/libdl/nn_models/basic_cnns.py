@@ -42,6 +42,8 @@ def _head(model, c0, n_ch, n_bins_in, n_bins_out, a, p):
 
 class _MpaModel(nn.Module):
     def _init_common(self, n_chan_input, n_bins_in, a_lrelu, p_dropout, precision):
+        if precision is None:
+            precision = _exec.DEFAULT_PRECISION          # the reference's constructors take no such keyword: package-level default
         if precision not in _exec.PRECISIONS:
             raise ValueError(f'precision must be one of {_exec.PRECISIONS}')
         self.n_chan_input, self.n_bins_in = n_chan_input, n_bins_in
@@ -68,7 +70,7 @@ class basic_cnn_segm_sigmoid(_MpaModel):
     a_lrelu, p_dropout."""
 
     def __init__(self, n_chan_input=6, n_chan_layers=[20, 20, 10, 1], n_bins_in=216, n_bins_out=12, a_lrelu=0.3,
-                 p_dropout=0.2, precision='fp32'):
+                 p_dropout=0.2, precision=None):
         super().__init__()
         self._init_common(n_chan_input, n_bins_in, a_lrelu, p_dropout, precision)
         n_ch = n_chan_layers
@@ -85,7 +87,7 @@ class deep_cnn_segm_sigmoid(_MpaModel):
     """DCNN / DRCNN: n_prefilt_layers 15x15 blocks, optional residual connections."""
 
     def __init__(self, n_chan_input=6, n_chan_layers=[20, 20, 10, 1], n_prefilt_layers=1, residual=False, n_bins_in=216,
-                 n_bins_out=12, a_lrelu=0.3, p_dropout=0.2, precision='fp32'):
+                 n_bins_out=12, a_lrelu=0.3, p_dropout=0.2, precision=None):
         super().__init__()
         self._init_common(n_chan_input, n_bins_in, a_lrelu, p_dropout, precision)
         n_ch = n_chan_layers

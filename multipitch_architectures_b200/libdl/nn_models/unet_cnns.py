@@ -215,7 +215,7 @@ class _UnetBase(_MpaModel):
 
 class simple_u_net_largekernels(_UnetBase):
     def __init__(self, n_chan_input=6, n_chan_layers=[64, 30, 20, 10], n_bins_in=216, n_bins_out=12, a_lrelu=0.3, p_dropout=0.2,
-                 scalefac=16, precision='fp32'):
+                 scalefac=16, precision=None):
         super().__init__()
         self._init_common(n_chan_input, n_bins_in, a_lrelu, p_dropout, precision)
         self.layernorm = nn.LayerNorm(normalized_shape=[n_chan_input, n_bins_in])
@@ -230,7 +230,7 @@ class simple_u_net_largekernels(_UnetBase):
 class simple_u_net_doubleselfattn(_UnetBase):
     def __init__(self, n_chan_input=6, n_chan_layers=[64, 30, 20, 10], n_bins_in=216, n_bins_out=12, a_lrelu=0.3, p_dropout=0.2,
                  convdrop=0, residual=False, alt_order=False, scalefac=16, embed_dim=4 * 8, num_heads=8, mlp_dim=512,
-                 pos_encoding=None, precision='fp32'):
+                 pos_encoding=None, precision=None):
         super().__init__()
         self._init_common(n_chan_input, n_bins_in, a_lrelu, p_dropout, precision)
         kw = dict(convdrop=convdrop, residual=residual, alt_order=alt_order)
@@ -253,7 +253,7 @@ class simple_u_net_doubleselfattn_twolayers(_UnetBase):
     hands its own p_dropout to the encoder layers here (the SAUnet above leaves them at their default 0.2)."""
 
     def __init__(self, n_chan_input=6, n_chan_layers=[64, 30, 20, 10], n_bins_in=216, n_bins_out=12, a_lrelu=0.3, p_dropout=0.2,
-                 convdrop=0, residual=False, scalefac=16, embed_dim=4 * 8, num_heads=8, mlp_dim=512, pos_encoding=None, precision='fp32'):
+                 convdrop=0, residual=False, scalefac=16, embed_dim=4 * 8, num_heads=8, mlp_dim=512, pos_encoding=None, precision=None):
         super().__init__()
         self._init_common(n_chan_input, n_bins_in, a_lrelu, p_dropout, precision)
         kw = dict(convdrop=convdrop, residual=residual)
@@ -279,7 +279,7 @@ class simple_u_net_doubleselfattn_twolayers(_UnetBase):
 
 class simple_u_net_polyphony_classif_softmax(_UnetBase):
     def __init__(self, n_chan_input=6, n_chan_layers=[64, 30, 20, 10], n_bins_in=216, n_bins_out=12, a_lrelu=0.3, p_dropout=0.2,
-                 scalefac=16, num_polyphony_steps=24, precision='fp32'):
+                 scalefac=16, num_polyphony_steps=24, precision=None):
         super().__init__()
         self._init_common(n_chan_input, n_bins_in, a_lrelu, p_dropout, precision)
         sc = scalefac
@@ -306,7 +306,7 @@ class u_net_blstm_varlayers(_UnetBase):
     time at the bottleneck (lstm_depth 1) and, for lstm_depth > 1, on the skip connections from the bottom up."""
 
     def __init__(self, n_chan_input=6, n_chan_layers=[64, 30, 20, 10], n_bins_in=216, n_bins_out=12, a_lrelu=0.3, p_dropout=0.2,
-                 scalefac=8, embed_dim=4 * 16, hidden_size=512, lstm_depth=0, lstm_number=2, precision='fp32'):
+                 scalefac=8, embed_dim=4 * 16, hidden_size=512, lstm_depth=0, lstm_number=2, precision=None):
         super().__init__()
         self._init_common(n_chan_input, n_bins_in, a_lrelu, p_dropout, precision)
         self.lstm_depth, self.lstm_number = lstm_depth, lstm_number

@@ -46,10 +46,16 @@ def test_stream_engine_matches_oracle_patchwise(name, N, chunk, prec):
     assert got.shape == (N, 72) and err < TOL[prec]
     targ = np.random.default_rng(1).uniform(size=(N, 72)) < 0.3
     p_ref, p_got = HO.eval_prf(targ, ref, 0.4), HO.eval_prf(targ, got, 0.4)
+    flips = (got >= 0.4) != (ref >= 0.4)
     near = np.abs(ref - 0.4) < TOL[prec]
-    assert not (((got >= 0.4) != (ref >= 0.4)) & ~near).any()
-    if not near.any():
-        assert all(round(a, 3) == round(b, 3) for a, b in zip(p_ref[:3], p_got[:3]))
+    print(f'{name} {prec}: {int(flips.sum())} threshold flips of {flips.size} cells ({int(near.sum())} cells within the {TOL[prec]} bound of 0.4); '
+          f'P/R/F {tuple(round(v, 4) for v in p_got[:3])} vs {tuple(round(v, 4) for v in p_ref[:3])}')
+    assert not (flips & ~near).any()                 # a decision may only change where the reference sits within the format's bound of 0.4
+    # P/R/F: every flip moves one of TP / FP / FN by one, so the measures may move by at most flips / (smallest denominator); these are
+    # the ADVERSARIAL-gain random weights (the format's worst case) — the 3-decimal identity is asserted unconditionally on the
+    # trained weights in tests/test_gpu_realistic.py and, for the split-precision mode, on these weights in tests/test_gpu_x3.py
+    denom = max(1, min(p_ref[3] + p_ref[4], p_ref[3] + p_ref[5]) - int(flips.sum()))
+    assert all(abs(a - b) <= 2.0 * flips.sum() / denom + 1e-12 for a, b in zip(p_ref[:3], p_got[:3]))
 
 
 def test_patchwise_loop_fp32_matches_oracle_and_prf():
@@ -64,9 +70,8 @@ def test_patchwise_loop_fp32_matches_oracle_and_prf():
     assert np.abs(got - ref).max() < 1e-3
     targ = np.random.default_rng(2).uniform(size=ref.shape) < 0.3
     flips = (got >= 0.4) != (ref >= 0.4)
-    assert not (flips & (np.abs(ref - 0.4) > 1e-3)).any()
-    if not flips.any():
-        assert HO.eval_prf(targ, got, 0.4) == HO.eval_prf(targ, ref, 0.4)
+    assert not flips.any(), f'{int(flips.sum())} thresholded cells differ (closest reference value to 0.4: {np.abs(ref - 0.4).min():.2e})'
+    assert HO.eval_prf(targ, got, 0.4) == HO.eval_prf(targ, ref, 0.4)          # unconditional: identical counts, hence identical P/R/F
 
 
 def test_dataset_context_batch_kernel(host_golden):

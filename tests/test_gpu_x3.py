@@ -151,10 +151,9 @@ def test_x3_stream_engine_matches_oracle_and_prf(name, N, chunk):
     print(f'{name}: streaming fp16x3 engine vs oracle max|diff| = {err:.2e}')
     assert got.shape == (N, 72) and err < TOL_X3
     flips = (got >= 0.4) != (ref >= 0.4)
-    assert not flips.any() or np.abs(ref - 0.4)[flips].max() < TOL_X3
+    assert not flips.any(), f'{int(flips.sum())} thresholded cells differ (closest reference value to 0.4: {np.abs(ref - 0.4).min():.2e})'
     targ = np.random.default_rng(1).uniform(size=(N, 72)) < 0.3
-    if not flips.any():
-        assert HO.eval_prf(targ, got, 0.4) == HO.eval_prf(targ, ref, 0.4)
+    assert HO.eval_prf(targ, got, 0.4) == HO.eval_prf(targ, ref, 0.4)          # unconditional: identical counts, hence identical P/R/F
     # the un-deduplicated schedule (every row per patch) gives the same numbers: the same MMA sequence produces each row
     got2 = CnnStreamEngine(m, chunk=chunk, dedup=False).predict_hcqt(torch.from_numpy(h).cuda()).cpu().numpy()
     assert np.array_equal(got, got2)
