@@ -399,7 +399,7 @@ def run_infer(ctx, name, precision, steps, warmup, preload, detail=False, e2e_fi
         with torch.no_grad():
             if cnn:
                 return eng.predict_audio(y, plan)[0]
-            hcqt, _ = plan.run(y)
+            hcqt, _ = plan.run_graph(y)
             out = predict_patchwise(model, hcqt, batch=args.infer_batch)
             return out[0] if isinstance(out, tuple) else out
 
@@ -429,9 +429,9 @@ def run_infer(ctx, name, precision, steps, warmup, preload, detail=False, e2e_fi
     # idle time); the per-stage time shares come from two extra, untimed steps afterwards
     if eng is not None and detail:
         eng.timers, eng.timer_tags = [], {'conv_tc'}
-    n0 = _lib.launch_count()
+    n0, g0 = _lib.launch_count(), plan.graph_launches
     ms = ctx.timed(step_resident, steps)
-    launches = _lib.launch_count() - n0
+    launches = _lib.launch_count() - n0 + (plan.graph_launches - g0)      # host-side counter + the kernel nodes of the replayed HCQT graphs
     timers, share_timers = [], []
     if eng is not None and detail:
         timers, eng.timers, eng.timer_tags = eng.timers, [], None

@@ -84,6 +84,11 @@ struct ConvTcParams {
   // multiplies the accumulator by inv_scale[co].
   int x3, in_lo_off, out_lo_off, tiles_per_row;
   const float* inv_scale;
+  // ---- wide-K / row-merged mode of the tile main loop (KW == 1 convolutions with many input chunks, e.g. the phase-split conv2 of the
+  // U-Net heads, 384 -> 104 channels): (a) R consecutive image rows form ONE operand row of N = R * pitch columns (rows are contiguous in
+  // memory and a KH x 1 filter has no horizontal taps), so every weight tile is used for R output rows instead of one; (b) an activation
+  // stage holds G of the NC input chunks (the K loop of an input row walks ceil(NC / G) stages), which keeps the stages inside 227 KB.
+  int R, G, n_groups;
   uint32_t btab[256];       // tile main loop: B-descriptor low words of one K row, (offset >> 4) | (LBO >> 4) << 16 (x3: the row twice)
   // ---- ring main loop (conv_tc_ring_kernel): un-duplicated weight pieces, see below
   int ring_on, ring_S, ring_npos, ring_ps, ring_sbo, ring_nb, ring_b_off, ring_bar_off;
@@ -211,7 +216,7 @@ __device__ __forceinline__ UnitInfo decode_unit(const ConvTcParams& p, int u) {
   int g = u - ui.b * p.groups_per_patch;
   ui.seg = 0;
   if (g >= p.seg_groups[0]) { g -= p.seg_groups[0]; ui.seg = 1; }
-  ui.t0 = p.y_lo[ui.seg] + g * p.J;
+  ui.t0 = p.y_lo[ui.seg] + g * p.J * p.R;
   ui.first_in_seg = (g == 0);
   return ui;
 }
@@ -328,9 +333,11 @@ __device__ __forceinline__ void epilogue_role(const ConvTcParams& p, uint32_t tm
       for (int c0 = ehalf * 32; c0 < p.N; c0 += 64) {
         // which of the 32 columns of this chunk are stored at all (real, and selected by the sub-sampling)?
         const int n = c0 + lane;
-        int fo = n - p.pf;
-        bool col_ok = (fo >= 0 && fo < p.F);
-        int col_out = n, ph_plane = 0;
+        int rr = 0, nn = n;                      // row-merged operand rows: column n = row rr of the unit, column nn of that row
+        if (p.R > 1) { rr = n / p.P; nn = n - rr * p.P; }
+        int fo = nn - p.pf;
+        bool col_ok = (fo >= 0 && fo < p.F && rr < p.R);
+        int col_out = nn, ph_plane = 0;
         if (p.out_mode == 1) {
           fo -= p.sub_offset;
           col_ok = col_ok && fo >= 0 && (fo % p.sub_stride) == 0;
@@ -358,7 +365,7 @@ __device__ __forceinline__ void epilogue_role(const ConvTcParams& p, uint32_t tm
             // lane -> column c0+lane; pass k -> the k-th 8-lane group (= one channel chunk of one output row) of this warp
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const int tg = t0 + grp_j[k];
+              const int tg = t0 + grp_j[k] + rr;
               if (col_ok && grp_j[k] < p.J && tg < y_hi) {
                 const uint4 val = *reinterpret_cast<const uint4*>(stile + lane * kEpiPitch + k * 8);
                 if (p.pool) {
@@ -494,8 +501,7 @@ template <bool X3>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int slab_plane_bytes = p.slab_px * 16;
-  const int slab_bytes = p.NC * slab_plane_bytes;        // one patch, one input row
-  const int bstage_bytes = slab_bytes;
+  const int bstage_bytes = min(p.G, p.NC) * slab_plane_bytes;   // one patch, one input row, one chunk group
   const int kNumAStages = p.a_stages;
   uint8_t* a_smem = smem;                                // [a_stages][kAStageBytes]
   uint8_t* b_smem = smem + kNumAStages * kAStageBytes;   // [kNumBStages][NC][slab_px][16B]
@@ -561,24 +567,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
         const UnitInfo ui = decode_unit(p, u);
         for (int r = 0; r < rows_in; ++r) {
           const int row = ui.t0 - ph + r;
-          if (row < 0 || row >= p.T) continue;
+          if (p.R == 1 && (row < 0 || row >= p.T)) continue;      // row-merged mode: the zero guard rows stand in for the time padding
           for (int part = 0; part < n_parts; ++part) {
-            // activation slab of this input row (split precision: the hi planes, then the lo planes)
+           for (int gi = 0; gi < p.n_groups; ++gi) {
+            // activation slab of this input row: chunk group gi (split precision: the hi planes, then the lo planes)
+            const int planes = min(p.G, p.NC - gi * p.G);
             mbar_wait(&b_empty[b_stage], b_phase ^ 1);
-            mbar_expect_tx(&b_full[b_stage], (uint32_t)slab_bytes);
+            mbar_expect_tx(&b_full[b_stage], (uint32_t)(planes * slab_plane_bytes));
             {
               long long cs;
               const uint8_t* src = in_row_ptr(p, ui.b, row, cs) - pw * 16;
-              if (part) src += (long long)p.in_lo_off * cs;
+              src += (long long)((part ? p.in_lo_off : 0) + gi * p.G) * cs;
               uint8_t* dst = b_smem + b_stage * bstage_bytes;
-              for (int c = 0; c < p.NC; ++c)
+              for (int c = 0; c < planes; ++c)
                 bulk_g2s(dst + c * slab_plane_bytes, src + (long long)c * cs, (uint32_t)slab_plane_bytes, &b_full[b_stage]);
             }
             if (++b_stage == kNumBStages) { b_stage = 0; b_phase ^= 1; }
             // weight stages of this K row (split precision: W_hi and W_lo tiles against the hi planes, W_hi tiles against the lo planes)
             if (p.resident) continue;
-            const int n_tiles = (X3 && part == 0) ? 2 * p.mmas_per_row : p.mmas_per_row;
-            const uint8_t* wrow = p.w + ((size_t)r * p.tiles_per_row + (part ? 2 * p.mmas_per_row : 0)) * kATileBytes;
+            const int q0 = gi * (p.G / 2) * p.KW;
+            const int n_tiles = (X3 && part == 0) ? 2 * p.mmas_per_row : (gi == p.n_groups - 1 ? p.mmas_per_row : (gi + 1) * (p.G / 2) * p.KW) - q0;
+            const uint8_t* wrow = p.w + ((size_t)r * p.tiles_per_row + (part ? 2 * p.mmas_per_row : 0) + q0) * kATileBytes;
             for (int m0 = 0; m0 < n_tiles; m0 += kStageMMAs) {
               const int nm = min(kStageMMAs, n_tiles - m0);
               mbar_wait(&a_empty[a_stage], a_phase ^ 1);
@@ -586,6 +595,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
               bulk_g2s(a_smem + a_stage * kAStageBytes, wrow + (size_t)m0 * kATileBytes, (uint32_t)(nm * kATileBytes), &a_full[a_stage]);
               if (++a_stage == kNumAStages) { a_stage = 0; a_phase ^= 1; }
             }
+           }
           }
         }
       }
@@ -616,9 +626,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
         uint32_t accum = 0;
         for (int r = 0; r < rows_in; ++r) {
           const int row = ui.t0 - ph + r;
-          if (row < 0 || row >= p.T) continue;
+          if (p.R == 1 && (row < 0 || row >= p.T)) continue;
           for (int part = 0; part < n_parts; ++part) {
-          const int n_tiles = (X3 && part == 0) ? 2 * p.mmas_per_row : p.mmas_per_row;
+          for (int gi = 0; gi < p.n_groups; ++gi) {
+          const int q0 = gi * (p.G / 2) * p.KW;
+          const int n_tiles = (X3 && part == 0) ? 2 * p.mmas_per_row : (gi == p.n_groups - 1 ? p.mmas_per_row : (gi + 1) * (p.G / 2) * p.KW) - q0;
           mbar_wait(&b_full[b_stage], b_phase);
           const uint32_t bbase16 = bsm16 + (uint32_t)b_stage * bst16;
           for (int m0 = 0; m0 < n_tiles; m0 += kStageMMAs) {
@@ -628,16 +640,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
             tc_fence_after();
             const uint32_t a_lo = (asm16 + (uint32_t)a_stage * (kAStageBytes >> 4)) | kALoFixed;
             if (elect_one_sync()) {
+              const int qb = q0 + m0;
               if (nm == kStageMMAs) {
-                tc_mma_f16(tmem_d, ((uint64_t)kDescHi << 32) | (uint64_t)a_lo, ((uint64_t)kDescHi << 32) | (uint64_t)(bbase16 + p.btab[m0]), p.idesc, accum);
+                tc_mma_f16(tmem_d, ((uint64_t)kDescHi << 32) | (uint64_t)a_lo, ((uint64_t)kDescHi << 32) | (uint64_t)(bbase16 + p.btab[qb]), p.idesc, accum);
 #pragma unroll
                 for (int i = 1; i < kStageMMAs; ++i)
                   tc_mma_f16(tmem_d, ((uint64_t)kDescHi << 32) | (uint64_t)(a_lo + (uint32_t)i * (kATileBytes >> 4)),
-                             ((uint64_t)kDescHi << 32) | (uint64_t)(bbase16 + p.btab[m0 + i]), p.idesc, 1u);
+                             ((uint64_t)kDescHi << 32) | (uint64_t)(bbase16 + p.btab[qb + i]), p.idesc, 1u);
               } else {
                 for (int i = 0; i < nm; ++i)
                   tc_mma_f16(tmem_d, ((uint64_t)kDescHi << 32) | (uint64_t)(a_lo + (uint32_t)i * (kATileBytes >> 4)),
-                             ((uint64_t)kDescHi << 32) | (uint64_t)(bbase16 + p.btab[m0 + i]), p.idesc, (i == 0) ? accum : 1u);
+                             ((uint64_t)kDescHi << 32) | (uint64_t)(bbase16 + p.btab[qb + i]), p.idesc, (i == 0) ? accum : 1u);
               }
               if (!p.resident) tc_commit(&a_empty[a_stage]);       // frees the weight stage when its MMAs have retired
             }
@@ -648,6 +661,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
           if (elect_one_sync()) tc_commit(&b_empty[b_stage]);         // frees the activation slab of this row
           __syncwarp();
           if (++b_stage == kNumBStages) { b_stage = 0; b_phase ^= 1; }
+          }
           }
         }
         if (elect_one_sync()) tc_commit(&acc_full[buf]);              // accumulator complete -> epilogue
@@ -1459,6 +1473,7 @@ int mpa_conv_tc_ring_pack_weights(const float* w, void* packed, int Cin, int Cou
 static int launch_conv_tc(ConvTcParams& p, int Cin, cudaStream_t stream, int* grid_out) {
   p.mmas_per_row = mmas_per_row(p.NC, p.KW);
   p.slab_px = (p.N + 2 * (p.KW / 2) + 1 + 7) / 8 * 8;
+  if (p.R < 1) p.R = 1;
   size_t smem = 0;
   if (p.x3) {
     MPA_REQUIRE(!p.ring_on, "conv_tc: the ring main loop has no split-precision variant");
@@ -1476,6 +1491,8 @@ static int launch_conv_tc(ConvTcParams& p, int Cin, cudaStream_t stream, int* gr
     int S = p.J + 4;
     while (S > p.J + 1 && (size_t)(S + p.J - 1) * p.ring_ps + fixed > 227 * 1024) --S;
     MPA_REQUIRE(S >= p.J + 1 && S <= kMaxRingS, "conv_tc(ring): the weight ring does not fit (Cout=%d J=%d)", p.Cout, p.J);
+    p.G = p.NC;
+    p.n_groups = 1;
     p.ring_S = S;
     p.ring_npos = S + p.J - 1;
     p.ring_b_off = p.ring_npos * p.ring_ps;
@@ -1486,12 +1503,19 @@ static int launch_conv_tc(ConvTcParams& p, int Cin, cudaStream_t stream, int* gr
     p.epi_off = (int)off;
     smem = off + 8 * 32 * kEpiPitch * 2;
   } else {
-    const size_t b_bytes = (size_t)kNumBStages * p.NC * p.slab_px * 16;
     const size_t tail = 256 + (size_t)(p.mmas_per_row + 8) * 4 + 128 + 8 * 32 * kEpiPitch * 2;   // barriers, table, staging
+    // chunks per activation stage: all of them when two stages fit next to >= 2 weight stages, else the largest even group that does
+    // (wide-K layers; one group = G/2 * KW consecutive MMAs of the row)
+    p.G = p.NC;
+    if (!p.x3)
+      while (p.G > 2 && (size_t)kNumBStages * p.G * p.slab_px * 16 + 2 * (size_t)kAStageBytes + tail > 227 * 1024) p.G = (p.G - 1) / 2 * 2;
+    if (p.G < p.NC && p.G >= 16) p.G = p.G / 16 * 16;      // whole weight stages (8 MMAs) per group when KW == 1
+    p.n_groups = (p.NC + p.G - 1) / p.G;
+    const size_t b_bytes = (size_t)kNumBStages * p.G * p.slab_px * 16;
     int a_stages = kMaxAStages;
     while (a_stages > 2 && (size_t)a_stages * kAStageBytes + b_bytes + tail > 227 * 1024) --a_stages;
     p.a_stages = a_stages;
-    p.resident = (!p.x3 && (p.KH + p.J - 1) * ((p.mmas_per_row + kStageMMAs - 1) / kStageMMAs) <= a_stages) ? 1 : 0;
+    p.resident = (!p.x3 && p.n_groups == 1 && (p.KH + p.J - 1) * ((p.mmas_per_row + kStageMMAs - 1) / kStageMMAs) <= a_stages) ? 1 : 0;
     MPA_REQUIRE(p.mmas_per_row <= 128, "conv_tc: too many K steps per row (%d)", p.mmas_per_row);
     p.tiles_per_row = p.x3 ? 3 * p.mmas_per_row : p.mmas_per_row;
     {
@@ -1501,10 +1525,10 @@ static int launch_conv_tc(ConvTcParams& p, int Cin, cudaStream_t stream, int* gr
         uint32_t boff, lbo;
         if (q < n_paired) {
           const int cp = q / p.KW, df = q - cp * p.KW;
-          boff = (uint32_t)(2 * cp) * plane + (uint32_t)df * 16u;
+          boff = (uint32_t)((2 * cp) % p.G) * plane + (uint32_t)df * 16u;          // offset inside the chunk group's stage
           lbo = plane;
         } else {
-          boff = (uint32_t)(p.NC - 1) * plane + 2u * (uint32_t)(q - n_paired) * 16u;
+          boff = (uint32_t)((p.NC - 1) % p.G) * plane + 2u * (uint32_t)(q - n_paired) * 16u;
           lbo = 16u;
         }
         p.btab[q] = (boff >> 4) | ((lbo >> 4) << 16);
@@ -1613,17 +1637,25 @@ int mpa_conv_tc_f16(const void* in_cp8, const void* w_packed, const float* bias,
   p.out_patch_stride = (long long)(out_nc_stride > 0 ? out_nc_stride : (x3 ? 2 : 1) * p.NCo) *
                        (out_mode == 0 ? (long long)p.TP_out * pitch : out_mode == 2 ? (long long)p.TP_out * p.P2 : (long long)p.T_out * p.F_out) * 8;
   MPA_REQUIRE(out_mode != 2 || p.phase_planes >= p.NCo, "conv_tc: %d chunk planes per phase < %d output chunks", p.phase_planes, p.NCo);
+  // row-merged operand rows (see ConvTcParams::R): KH x 1 filters on materialised patches whose zero guard rows cover the time padding
+  p.R = 1;
+  if (KW == 1 && KH / 2 <= pt && pt >= 1 && in_patch_stride_rows <= 0 && p.J == 1 && !x3 && pitch % 16 == 0 && out_mode != 2) {
+    int R = 256 / pitch;
+    while (R > 1 && (p.T_out % R)) --R;
+    p.R = R;
+    p.N = R * pitch;
+  }
   p.n_seg = 1;
   p.y_lo[0] = p.z_lo[0] = row0;
   p.y_hi[0] = p.z_hi[0] = row0 + p.T_out;
-  p.seg_groups[0] = (p.T_out + p.J - 1) / p.J;
+  p.seg_groups[0] = (p.T_out + p.J * p.R - 1) / (p.J * p.R);
   p.seg_groups[1] = 0;
   p.groups_per_patch = p.seg_groups[0];
   p.n_units = n_patches * p.groups_per_patch;
   p.act = act;
   p.act_param = act_param;
   const uint32_t f = (fmt == MPA_FMT_BF16) ? 1u : 0u;
-  p.idesc = (1u << 4) | (f << 7) | (f << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  p.idesc = (1u << 4) | (f << 7) | (f << 10) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   return launch_conv_tc(p, Cin, (cudaStream_t)stream, nullptr);
 }
 

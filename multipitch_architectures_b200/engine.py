@@ -206,9 +206,10 @@ class CnnStreamEngine:
             return torch.empty(0, 0, dtype=torch.float32, device=self.dev)
         return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
 
-    def predict_audio(self, y, plan):
-        """y: 1-D float32 CUDA audio; plan: HCQTPlan.  -> ([N, 72] activations, tuning index tensor)."""
-        hcqt, tun = self._timed('hcqt', lambda: plan.run(y))
+    def predict_audio(self, y, plan, graph=True):
+        """y: 1-D float32 CUDA audio; plan: HCQTPlan.  -> ([N, 72] activations, tuning index tensor).
+        graph: replay the HCQT's launch sequence from a CUDA graph (plan.run_graph; the HCQT is consumed at once on this stream)."""
+        hcqt, tun = self._timed('hcqt', lambda: plan.run_graph(y) if graph else plan.run(y))
         return self.predict_hcqt(hcqt), tun
 
 
@@ -217,6 +218,9 @@ def predict_patchwise(model, hcqt, batch=50):
     consecutive frames (the batch composition matters for the SAUnet's batch-axis attention)."""
     C, N, F = hcqt.shape
     dev = hcqt.device
+    if (hasattr(model, 'predict_frames') and not model.training and model.precision in ('fp16', 'bf16') and C <= 8
+            and _exec.unet_tc_eligible(model, torch.empty(0, C, CONTEXT, F, device='meta'))):
+        return _predict_patchwise_frames(model, hcqt.contiguous().float(), batch)
     padded = torch.zeros(C, N + CONTEXT, F, dtype=torch.float32, device=dev)
     padded[:, HALF:HALF + N] = hcqt
     outs, npreds = [], []
@@ -231,4 +235,28 @@ def predict_patchwise(model, hcqt, batch=50):
             y = y[0]
         outs.append(y.reshape(n, -1))
     out = torch.cat(outs, 0)
+    return (out, torch.cat(npreds, 0)) if npreds else out
+
+
+def _predict_patchwise_frames(model, hcqt, batch):
+    """U-Net family on the tcgen05 path: LayerNorm (+ log compression) once per FRAME into a 16-bit frame-major plane; every batch of
+    `batch` consecutive patches reads its 75-row windows straight from it (the reference pads 37 / 38 zero frames: they come out of
+    LayerNorm as its bias, which is what the pad rows of mpa_layernorm_frames hold).  No patch is materialised on the input side."""
+    C, N, F = hcqt.shape
+    dev, fmt = hcqt.device, ops.fmt_of(model.precision)
+    pitch, pf, pt = (F + _exec.LEVEL_PF + 15) // 16 * 16, _exec.LEVEL_PF, 1
+    lead, trail = pt + HALF, HALF + pt + 1
+    plane = torch.zeros(lead + N + trail, pitch, 8, dtype=ops._FMT_DTYPE[fmt], device=dev)
+    ln = model.layernorm
+    _lib.call('layernorm_frames', hcqt, ln.weight, ln.bias, None, plane, C, N, F, lead, trail, pitch, pf, float(ln.eps), 10.0, fmt, _lib.stream_ptr())
+    outs, npreds = [], []
+    with torch.no_grad():
+        for i0 in range(0, N, batch):
+            n = min(batch, N - i0)
+            y = model.predict_frames(plane, i0, n)
+            if isinstance(y, tuple):
+                npreds.append(y[1].reshape(n, -1))
+                y = y[0]
+            outs.append(y.reshape(n, -1))
+    out = torch.cat(outs, 0) if len(outs) > 1 else outs[0]
     return (out, torch.cat(npreds, 0)) if npreds else out

@@ -68,6 +68,7 @@ class HCQTPlan:
         self.hann2048 = torch.from_numpy((0.5 - 0.5 * np.cos(2 * np.pi * n / 2048)).astype(np.float32)).to(self.device)
         self.tunings = FB.tuning_values()
         self._frames = {}
+        self._graphs, self.graph_replays, self.graph_launches = {}, 0, 0     # run_graph: captured launch sequences per input length
 
     def n_frames(self, n):
         """Frames of the HCQT of an n-sample input (= columns of the CQT serving the fundamental, hcqt.py:69,125); raises like
@@ -81,6 +82,33 @@ class HCQTPlan:
         if len(self._frames) < 4096:
             self._frames[n] = first
         return first
+
+    def run_graph(self, y):
+        """plan.run(y) replayed from a CUDA graph captured once per input length: the ~25 small dependent launches of one clip (tuning
+        estimate, decimator chain, one CQT launch per octave / rate) become ONE graph launch (the launch-bound 0.56 ms of a 30 s clip is
+        mostly host launch latency).  The result lives in buffers OWNED BY THE PLAN and is overwritten by the next call of the same
+        length: for consumers that use it at once on the same stream (the inference engines); plan.run returns fresh tensors."""
+        if y.dim() != 1 or not y.is_cuda or y.dtype != torch.float32:
+            raise _lib.MpaError('HCQTPlan.run_graph expects a 1-D float32 CUDA tensor')
+        n = y.numel()
+        g = self._graphs.get(n)
+        if g is None:
+            if len(self._graphs) >= 4:
+                self._graphs.pop(next(iter(self._graphs)))
+            y_static = y.contiguous().clone()
+            self.run(y_static)                                  # warm-up outside the capture (lazy module loading, workspace sizes)
+            torch.cuda.current_stream().synchronize()
+            graph = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(graph):
+                out, tun = self.run(y_static)
+            g = self._graphs[n] = (graph, y_static, out, tun, _lib.launch_count() - n0)
+        graph, y_static, out, tun, n_launches = g
+        y_static.copy_(y)
+        graph.replay()
+        self.graph_replays += 1
+        self.graph_launches += n_launches
+        return out, tun
 
     def run(self, y, tuning_idx=None):
         """y: 1-D float32 CUDA tensor -> (hcqt [H, n_frames, n_bins] fp32 CUDA, tuning_idx int32[1] CUDA)."""

@@ -126,8 +126,9 @@ def head_split_factor(model, F):
 
 def _split_conv2_J(C0p, C1p):
     """Output rows per work unit for the phase-split conv2: 3 when the whole weight set ((3 + J - 1) K rows of one 8-MMA stage each) then
-    stays resident in the kernel's 5 weight stages (CNN family: 3*C0p <= 128 channels), else the kernel's default."""
-    return 3 if (3 * C0p // 8 + 1) // 2 <= 8 and 3 * C1p <= 128 else 0
+    stays resident in the kernel's 5 weight stages (CNN family: 3*C0p <= 128 channels); else 1, which lets the kernel merge R = 3 image
+    rows into one operand row of N = 240 columns (every streamed weight tile then serves 3 output rows; J > 1 would disable that)."""
+    return 3 if (3 * C0p // 8 + 1) // 2 <= 8 and 3 * C1p <= 128 else 1
 
 
 def _split_conv2_blocks(cache, conv2, C0p, fmt, dev, J=0):
@@ -327,11 +328,40 @@ def _folded_tc(cache, name, conv, bn, fmt, dev, cin_pad=None, J=0):
 
 
 def conv_bn_relu_tc(cache, name, conv, bn, src, dst, act=ops.ACT_RELU, a=0.0, split=None):
-    """split = s: `dst` is an ops.split_cp8 buffer (s phase sets); co-block c0 starts at chunk c0/8 of every phase set."""
+    """split = s: `dst` is an ops.split_cp8 buffer (s phase sets); co-block c0 starts at chunk c0/8 of every phase set.
+    src may be a frame window (ops.frame_window): patch b = rows [b, b+T) of one shared frame-major plane."""
     k = tuple(conv.kernel_size)
+    stream = dict(n_patches=src.B, patch_stride_rows=1, T=src.T) if getattr(src, 'streaming', False) else {}
     for wp, b, c0, c in _folded_tc(cache, name, conv, bn, src.fmt, src.buf.device):
-        ops.conv_tc(src, wp, b, c, k, act, a, out=dst.channels(c0, c), split=split)
+        ops.conv_tc(src, wp, b, c, k, act, a, out=dst.channels(c0, c), split=split, **stream)
     return dst
+
+
+def conv_even_valid_tc(cache, name, conv, src, act, a):
+    """A VALID convolution with an EVEN kernel height (the PUnet's convP.0, (2,5) on the 4x13 bottleneck) on the tcgen05 kernel: it
+    equals the odd (KH+1) x KW 'same' convolution whose first filter row is zero, restricted to output rows [0, T-KH] and columns
+    [KW//2, F-1-KW//2].  src: CP8 -> fp32 NCHW [B, Cout, T-KH+1, F-KW+1].  (The fp32 direct kernel spent 5.3 ms per 400 patches on
+    these 7 GFLOP: its 16-row output tiles hold 3 real rows.)"""
+    Cout, Cin, KH, KW = conv.weight.shape
+    assert KH % 2 == 0 and KW % 2 == 1 and tuple(conv.stride) == (1, 1) and tuple(conv.padding) == (0, 0)
+    fmt, dev = src.fmt, src.buf.device
+
+    def build():
+        import types
+        w = conv.weight.detach().float()
+        w3 = torch.zeros(Cout, Cin, KH + 1, KW, dtype=w.dtype, device=w.device)
+        w3[:, :, 1:, :] = w
+        return types.SimpleNamespace(weight=w3, bias=conv.bias, kernel_size=(KH + 1, KW))
+    shim = cache.get(f'{name}:oddw', [conv.weight, conv.bias], build)
+    rows = src.T - KH + 1
+    out = ops.CP8(src.B, (Cout + 7) // 8 * 8, rows, src.F, src.pitch, src.pf, src.pt, dev, fmt=fmt)
+    for wp, b, c0, c in _folded_tc(cache, name + ':odd', shim, None, fmt, dev):
+        ops.conv_tc(src, wp, b, c, (KH + 1, KW), act, a, out=out.channels(c0, c), rows=(0, rows))
+    # un-pad: columns [KW//2, F-1-KW//2] of the 'same' result, read by the converter through a shifted left pad
+    Fo = src.F - KW + 1
+    y = torch.empty(src.B, Cout, rows, Fo, dtype=torch.float32, device=dev)
+    _lib.call('cp8_to_nchw', out.ptr(), y, src.B, Cout, rows, Fo, out.pitch, out.pf + KW // 2, out.pt, fmt, out.ncs, _lib.stream_ptr())
+    return y
 
 
 def double_conv_tc(cache, name, dc, src, dst, scratch, split=None):
@@ -340,14 +370,18 @@ def double_conv_tc(cache, name, dc, src, dst, scratch, split=None):
     return conv_bn_relu_tc(cache, name + '.4', seq[4], seq[5], scratch, dst, split=split)
 
 
-def unet_forward_tc(model, x):
+def unet_forward_tc(model, x, frames=None):
     """simple_u_net_largekernels / _doubleselfattn / _polyphony_classif_softmax, eval mode, tensor-core path.
     Skip connections are written straight into the first chunks of the decoder's concat buffers; the bilinear
     up-sampler fills the remaining chunks, so torch.cat never happens."""
     cache, a = model._cache, model.a_lrelu
     fmt = ops.fmt_of(model.precision)
-    B, C, T, F = x.shape
-    dev = x.device
+    if frames is not None:
+        plane, i0, B = frames
+        C, T, F, dev = model.n_chan_input, 75, model.n_bins_in, plane.device
+    else:
+        B, C, T, F = x.shape
+        dev = x.device
     geo = level_geometry(T, F)
     c = [model.inc.double_conv[4].weight.shape[0]] + [getattr(model, f'down{i}')[1].double_conv[4].weight.shape[0] for i in (1, 2, 3, 4)]
     up_out = [getattr(model, f'upconv{i}').double_conv[4].weight.shape[0] for i in (1, 2, 3, 4)]
@@ -371,7 +405,10 @@ def unet_forward_tc(model, x):
         if k not in pool:
             pool[k] = ops.CP8(B, ch, Tl, Fl, P, LEVEL_PF, 1, dev, fmt=fmt)
         return pool[k]
-    z = ops.nchw_to_cp8(ops.layernorm_cf(x, model.layernorm.weight, model.layernorm.bias, model.layernorm.eps), out=buf(0, C))
+    if frames is not None:
+        z = ops.frame_window(plane, i0, B, C, T, F, geo[0][2], LEVEL_PF, 1, fmt)      # LayerNorm was evaluated once per frame
+    else:
+        z = ops.nchw_to_cp8(ops.layernorm_cf(x, model.layernorm.weight, model.layernorm.bias, model.layernorm.eps), out=buf(0, C))
     # concat buffers of the decoder: level 3 (x4|up x5), level 2 (x3|up u1), level 1 (x2|up u2), level 0 (x1|up u3)
     cat = {3: buf(3, c[3] + c[4]), 2: buf(2, c[2] + up_out[0]), 1: buf(1, c[1] + up_out[1]), 0: buf(0, c[0] + up_out[2])}
     skips = {lv: cat[lv].channels(0, c[lv]) for lv in (0, 1, 2, 3)}

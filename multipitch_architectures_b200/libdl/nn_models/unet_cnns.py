@@ -181,6 +181,17 @@ class _UnetBase(_MpaModel):
     def _bn_train(self):
         return self.training
 
+    def predict_frames(self, plane, i0, n):
+        """Eval-mode forward of the n stride-1 patches starting at frames i0.. of a recording whose LayerNorm'ed (+ log-compressed) frames
+        sit in the 16-bit frame-major `plane` [rows][pitch][8] (mpa_layernorm_frames; engine.predict_patchwise builds it once per
+        recording).  The first convolution gathers its 75-row windows straight from the plane: no patch is materialised.  Same result as
+        forward() on the materialised patches (same kernels, same operand values)."""
+        y, x5 = _exec.unet_forward_tc(self, None, frames=(plane, int(i0), int(n)))
+        return self._finish(y, x5 if hasattr(self, 'convP') else None)
+
+    def _finish(self, y, x5):
+        return y
+
     def _run(self, x):
         x = _exec._check_input(x, self.n_chan_input, self.n_bins_in)
         if x.shape[2] < 75:
@@ -199,7 +210,7 @@ class _UnetBase(_MpaModel):
         train = self._bn_train()
         if _exec.unet_tc_eligible(self, x):
             y, x5c = _exec.unet_forward_tc(self, x)
-            return y, (ops.cp8_to_nchw(x5c) if hasattr(self, 'convP') else None)
+            return y, (x5c if hasattr(self, 'convP') else None)          # PUnet: the bottleneck stays in its CP8 planes for convP
         x1, x2, x3, x4, x5 = _exec.unet_trunk_f32(self, x, train)
         x5 = self._bottleneck(x5)
         x4 = self._skip4(x4)                  # (SAUSnet: attention on the lowest skip, after x5 was taken from the original x4)
@@ -295,9 +306,22 @@ class simple_u_net_polyphony_classif_softmax(_UnetBase):
         y, x5 = self._run(x)
         if self.training:
             return y, x5                     # the training path evaluates convP itself (x5 slot = n_pred)
-        p = _exec.conv_f32(self._cache, 'convP.0', self.convP[0], x5, ops.ACT_LRELU, self.a_lrelu)
+        return self._finish(y, x5)
+
+    def _finish(self, y, x5):
+        if isinstance(x5, ops.CP8):
+            p = _exec.conv_even_valid_tc(self._cache, 'convP.0', self.convP[0], x5, ops.ACT_LRELU, self.a_lrelu)
+        else:
+            p = _exec.conv_f32(self._cache, 'convP.0', self.convP[0], x5, ops.ACT_LRELU, self.a_lrelu)
         p = ops.maxpool2d(p, (2, 5), (1, 2))
-        n_pred = _exec.conv_f32(self._cache, 'convP.4', self.convP[4], p)
+        c4 = self.convP[4]
+        if tuple(p.shape[2:]) == tuple(c4.kernel_size):
+            # the (2,3) VALID convolution covers its whole input: one GEMM row per item
+            n_pred = torch.empty(p.shape[0], c4.weight.shape[0], 1, 1, dtype=torch.float32, device=p.device)
+            w = self._cache.get('convP.4:flat', [c4.weight], lambda: c4.weight.detach().reshape(c4.weight.shape[0], -1).contiguous())
+            _lib.call('gemm_nt_f32', p, w, c4.bias, n_pred, p.shape[0], w.shape[0], w.shape[1], 0, _lib.stream_ptr())
+        else:
+            n_pred = _exec.conv_f32(self._cache, 'convP.4', c4, p)
         return y, n_pred
 
 

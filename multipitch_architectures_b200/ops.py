@@ -156,6 +156,17 @@ class CP8:
         return v
 
 
+def frame_window(plane, i0, n, C, T, F, pitch, pf, pt, fmt):
+    """n stride-1 patches of T frames starting at frame i0 of a frame-major 16-bit plane [rows][pitch][8] (C <= 8 channels: one chunk;
+    row 0 is a zero guard row) as a conv_tc input: patch b = rows [i0 + b, i0 + b + T) (conv_tc(..., patch_stride_rows=1))."""
+    v = CP8.__new__(CP8)
+    v.B, v.C, v.T, v.F, v.pitch, v.pf, v.pt, v.NC, v.fmt = n, C, T, F, pitch, pf, pt, 1, fmt
+    v.ncs, v.chunk0 = 1, 0
+    v.buf = plane[i0:]
+    v.streaming = True
+    return v
+
+
 def nchw_to_cp8(x, pitch=None, pf=8, pt=1, out=None, fmt=FMT_F16):
     B, C, T, F = x.shape
     out = out if out is not None else CP8(B, C, T, F, pitch, pf, pt, x.device, fmt=fmt)

@@ -128,6 +128,8 @@ def test_cp8_roundtrip_and_pool(ops, prec, dt):
     (2, 8, 40, 6, 24, 1, 1), (2, 16, 40, 7, 24, 3, 3), (3, 24, 40, 9, 40, 3, 3), (3, 6, 40, 20, 216, 15, 15),
     (3, 40, 40, 75, 216, 15, 15), (2, 20, 20, 75, 216, 15, 15), (2, 64, 128, 9, 27, 5, 5), (1, 40, 40, 75, 216, 15, 15),
     (2, 8, 16, 37, 108, 15, 15), (5, 32, 8, 18, 54, 9, 9),
+    # KH x 1 filters with many input chunks: row-merged operand rows (R = 256 // pitch rows per MMA) and chunk-group activation stages
+    (2, 384, 104, 75, 72, 3, 1), (3, 48, 128, 12, 40, 3, 1), (2, 136, 80, 10, 72, 1, 1), (2, 392, 128, 14, 72, 3, 1), (1, 16, 128, 7, 100, 3, 1),
 ])
 def test_conv_tc(ops, cfg, prec, dt):
     """tcgen05 path vs an fp64 convolution of the SAME 16-bit-rounded operands: only fp32 accumulation order and the
