@@ -565,6 +565,37 @@ def run_train(ctx, name, precision, steps, warmup, preload):
     return res
 
 
+def run_infer_saunet_sharded(ctx, steps, warmup):
+    """ONE recording sharded across the ranks for the SAUnet (whose attention mixes the items of a batch): contiguous frame
+    ranges on multiples of the reference batch (50 consecutive frames), 37-frame halos of real frames, final NCCL all-gather of [N, 72].
+    Strong scaling of a single 30 s clip: value = clip seconds / step time (not multiplied by the number of ranks)."""
+    import torch
+    from multipitch_architectures_b200.engine import predict_patchwise
+    from multipitch_architectures_b200.libdl.data_preprocessing.hcqt import get_plan, C1_HZ
+    from multipitch_architectures_b200.parallel import predict_sharded
+    from tests import synth as HO
+    args, dev = ctx.args, ctx.dev
+    model = build_model('train_saunet', 'fp16', dev).eval()
+    plan = get_plan(22050, float(C1_HZ / 2 ** ((3 - 1) / (2 * 36))), 512, 36, 6, 5, 1, str(dev))
+    clip = torch.from_numpy(HO.synth_clip(4242, seconds=args.seconds)).to(dev)      # the SAME recording on every rank
+
+    def step(i):
+        with torch.no_grad():
+            hcqt, _ = plan.run_graph(clip)
+            return predict_sharded(lambda h, lo, hi: predict_patchwise(model, h, batch=50, lo=lo, hi=hi), hcqt, ctx.world, ctx.rank, multiple=50, gather=True)
+    for i in range(warmup):
+        out = step(i)
+    ms = ctx.timed(step, steps)
+    n_frames = int(out.shape[0])
+    per_gpu_tf = args.seconds * steps / (ms / 1e3) / ctx.world * FPS * WORKLOADS['train_saunet']['gflop'] / 1e3
+    del model
+    torch.cuda.empty_cache()
+    return {'config': f'SAUnet:L inference of ONE {args.seconds:.0f} s clip ({n_frames} patches) sharded across {ctx.world} GPU(s) on multiples of 50 frames '
+                      '(batch-axis attention: reference batches of 50 consecutive frames stay on one rank), HCQT on every rank, NCCL all-gather of the activations',
+            'value': args.seconds * steps / (ms / 1e3), 'unit': 'audio-s/s', 'scaling': 'strong', 'n_gpus': ctx.world, 'steps': steps, 'warmup': warmup,
+            'ms_per_step': ms / steps, 'dtype': 'fp16', 'roofline_frac_per_gpu': per_gpu_tf / measured_peaks()[0]}
+
+
 def parity_block(ctx, modes):
     """Each tensor-core mode of the HEADLINE model on the realistic (trained) weights vs the outputs of the UNMODIFIED reference class
     over the whole held-out 30 s clip (tests/golden/realistic_golden.npz), outside every timed region.  The oracle is used here as the
@@ -727,6 +758,7 @@ def main():
                                      'warmup': sub_warm, 'ms_per_step': o['ms_per_step'], 'dtype': o['dtype'], 'e2e': o['e2e'],
                                      'roofline_frac_per_gpu': o['roofline']['frac'], 'gpu_launches': o['gpu_launches'],
                                      **({'allreduce': o['allreduce'], 'parallelism': o['parallelism']} if 'allreduce' in o else {})}
+        line['workloads']['infer_saunet_sharded'] = run_infer_saunet_sharded(ctx, sub_steps, sub_warm)
         if rank == 0:
             line['dropin_e2e'] = dropin_e2e(ctx, line['dtype'], 2)
         if world > 1:

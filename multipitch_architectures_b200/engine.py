@@ -40,7 +40,7 @@ class CnnStreamEngine:
         if self.x3:
             self.C0 = (self.C0 + 7) // 8 * 8          # split precision stores whole channel chunks: the block width is zero-padded
         self.pitch, self.pf, self.pt = (self.F + 8 + 15) // 16 * 16, 8, 1
-        self._bufs = None
+        self._bufs, self._plane, self._head_pool = None, None, {}
         self.timers = None          # optional: list collecting (tag, start_event, end_event, work)
         self.timer_tags = None      # optional: only these stage tags are timed (None = every stage)
         # Fused / de-duplicated schedule (mpa_conv_tc_pool_f16): needs chunk-aligned channel counts and J >= 2
@@ -86,7 +86,10 @@ class CnnStreamEngine:
         hcqt = hcqt.contiguous().float()
         lead, trail = self.pt + HALF, HALF + self.pt + 1
         rows = lead + N + trail
-        plane = torch.zeros(ops.planes_per_chunk(self.fmt), rows, self.pitch, 8, dtype=ops._FMT_DTYPE[self.fmt], device=self.dev)
+        # the frame plane is kept between calls (every row, pad rows included, is rewritten by the kernel; the zero gap columns never are)
+        if self._plane is None or self._plane.shape[1] != rows:
+            self._plane = torch.zeros(ops.planes_per_chunk(self.fmt), rows, self.pitch, 8, dtype=ops._FMT_DTYPE[self.fmt], device=self.dev)
+        plane = self._plane
         self._timed('layernorm_frames', lambda: _lib.call(
             'layernorm_frames', hcqt, m.layernorm.weight, m.layernorm.bias, None, plane, C, N, F, lead, trail, self.pitch, self.pf,
             float(m.layernorm.eps), self.compression, self.fmt, _lib.stream_ptr()))
@@ -184,7 +187,9 @@ class CnnStreamEngine:
                 break
             src = ops.VRows(R, 0, stream=plane_stream if i == 0 else streams[i - 1])
             run(i, src, ops.VRows(R, 0, stream=streams[i]), 1, [(ei, R - ei)], 'conv_tc_stream')
-        # 2) per patch: the edge rows of every block, the last block in full, then the head
+        # 2) per patch: the edge rows of every block, the last block in full, then the head (which writes straight into the result)
+        direct = _exec.head_tc_supported(m, T, F) and T == m.conv3[0].kernel_size[0]      # one output row of F/3 bins per patch
+        result = torch.empty(hi - lo, F // 3, dtype=torch.float32, device=self.dev) if direct else None
         outs = []
         for i0 in range(lo, hi, self.chunk):
             n = min(self.chunk, hi - i0)
@@ -200,10 +205,14 @@ class CnnStreamEngine:
                 zc = ops.CP8(n, self.split * self.C0, T, F // self.split, sb.shape[3], 8, 1, self.dev, buf=sb, fmt=self.fmt)
             else:
                 zc = ops.CP8(n, self.C0, T, F, self.pitch, self.pf, 1, self.dev, buf=edges[-1], fmt=self.fmt)
-            y = self._timed('head', lambda: _exec.head_tc(cache, m, zc, a, split=self.split))
-            outs.append(y.reshape(n, -1))
-        if not outs:
+            y = self._timed('head', lambda: _exec.head_tc(cache, m, zc, a, split=self.split, pool=self._head_pool,
+                                                          out=result[i0 - lo:i0 - lo + n] if direct else None))
+            if not direct:
+                outs.append(y.reshape(n, -1))
+        if hi == lo:
             return torch.empty(0, 0, dtype=torch.float32, device=self.dev)
+        if direct:
+            return result
         return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
 
     def predict_audio(self, y, plan, graph=True):
@@ -213,19 +222,23 @@ class CnnStreamEngine:
         return self.predict_hcqt(hcqt), tun
 
 
-def predict_patchwise(model, hcqt, batch=50):
-    """Reference-shaped loop for any model (U-Nets included): materialised stride-1 patches in batches of `batch`
-    consecutive frames (the batch composition matters for the SAUnet's batch-axis attention)."""
+def predict_patchwise(model, hcqt, batch=50, lo=0, hi=None):
+    """Reference-shaped loop for any model (U-Nets included): stride-1 patches in batches of `batch` consecutive frames (the batch
+    composition matters for the SAUnet's batch-axis attention), for the patches centred on frames lo..hi-1 (default: all); frames
+    beyond the array's ends are zero padding (multi-GPU sharding hands every rank its range plus a halo of real frames)."""
     C, N, F = hcqt.shape
     dev = hcqt.device
+    hi = N if hi is None else hi
+    if not (0 <= lo <= hi <= N):
+        raise ValueError('bad frame range')
     if (hasattr(model, 'predict_frames') and not model.training and model.precision in ('fp16', 'bf16') and C <= 8
             and _exec.unet_tc_eligible(model, torch.empty(0, C, CONTEXT, F, device='meta'))):
-        return _predict_patchwise_frames(model, hcqt.contiguous().float(), batch)
+        return _predict_patchwise_frames(model, hcqt.contiguous().float(), batch, lo, hi)
     padded = torch.zeros(C, N + CONTEXT, F, dtype=torch.float32, device=dev)
     padded[:, HALF:HALF + N] = hcqt
     outs, npreds = [], []
-    for i0 in range(0, N, batch):
-        n = min(batch, N - i0)
+    for i0 in range(lo, hi, batch):
+        n = min(batch, hi - i0)
         x = torch.empty(n, C, CONTEXT, F, dtype=torch.float32, device=dev)
         _lib.call('gather_patches_f32', padded, x, C, N + CONTEXT, F, i0, n, CONTEXT, 1, 10.0, _lib.stream_ptr())
         with torch.no_grad():
@@ -234,11 +247,13 @@ def predict_patchwise(model, hcqt, batch=50):
             npreds.append(y[1].reshape(n, -1))
             y = y[0]
         outs.append(y.reshape(n, -1))
+    if not outs:
+        return torch.empty(0, 0, dtype=torch.float32, device=dev)
     out = torch.cat(outs, 0)
     return (out, torch.cat(npreds, 0)) if npreds else out
 
 
-def _predict_patchwise_frames(model, hcqt, batch):
+def _predict_patchwise_frames(model, hcqt, batch, lo, hi):
     """U-Net family on the tcgen05 path: LayerNorm (+ log compression) once per FRAME into a 16-bit frame-major plane; every batch of
     `batch` consecutive patches reads its 75-row windows straight from it (the reference pads 37 / 38 zero frames: they come out of
     LayerNorm as its bias, which is what the pad rows of mpa_layernorm_frames hold).  No patch is materialised on the input side."""
@@ -246,17 +261,25 @@ def _predict_patchwise_frames(model, hcqt, batch):
     dev, fmt = hcqt.device, ops.fmt_of(model.precision)
     pitch, pf, pt = (F + _exec.LEVEL_PF + 15) // 16 * 16, _exec.LEVEL_PF, 1
     lead, trail = pt + HALF, HALF + pt + 1
-    plane = torch.zeros(lead + N + trail, pitch, 8, dtype=ops._FMT_DTYPE[fmt], device=dev)
+    # the frame plane is kept with the model between calls (every row is rewritten by the kernel; the zero gap columns never are)
+    planes = model.__dict__.setdefault('_frame_planes', {})
+    key = (lead + N + trail, pitch, fmt, str(dev))
+    if key not in planes:
+        planes.clear()
+        planes[key] = torch.zeros(lead + N + trail, pitch, 8, dtype=ops._FMT_DTYPE[fmt], device=dev)
+    plane = planes[key]
     ln = model.layernorm
     _lib.call('layernorm_frames', hcqt, ln.weight, ln.bias, None, plane, C, N, F, lead, trail, pitch, pf, float(ln.eps), 10.0, fmt, _lib.stream_ptr())
     outs, npreds = [], []
     with torch.no_grad():
-        for i0 in range(0, N, batch):
-            n = min(batch, N - i0)
+        for i0 in range(lo, hi, batch):
+            n = min(batch, hi - i0)
             y = model.predict_frames(plane, i0, n)
             if isinstance(y, tuple):
                 npreds.append(y[1].reshape(n, -1))
                 y = y[0]
             outs.append(y.reshape(n, -1))
+    if not outs:
+        return torch.empty(0, 0, dtype=torch.float32, device=dev)
     out = torch.cat(outs, 0) if len(outs) > 1 else outs[0]
     return (out, torch.cat(npreds, 0)) if npreds else out

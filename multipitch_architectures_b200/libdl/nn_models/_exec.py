@@ -145,7 +145,17 @@ def _split_conv2_blocks(cache, conv2, C0p, fmt, dev, J=0):
     return _folded_tc(cache, f'conv2split{C0p}', shim, None, fmt, dev, J=J)
 
 
-def head_tc(cache, model, zc, a, split=None):
+def head_tc_supported(model, T, Fin):
+    """The head shape the tensor-core sequence covers: the reference's 3x3 / stride (1,3) binning conv2, a full-height odd conv3 and 1x1
+    convolutions in conv4 (n_bins_out == n_bins_in // 3, as in every experiment script)."""
+    conv2, conv3, c40, c43 = model.conv2[0], model.conv3[0], model.conv4[0], model.conv4[3]
+    KH3 = conv3.kernel_size[0]
+    return (tuple(conv2.kernel_size) == (3, 3) and tuple(conv2.stride) == (1, 3) and tuple(conv2.padding) == (1, 0) and Fin % 3 == 0
+            and conv3.kernel_size[1] == 1 and (KH3 & 1) and tuple(conv3.padding) == (0, 0) and T >= KH3
+            and tuple(c40.kernel_size) == (1, 1) and tuple(c43.kernel_size) == (1, 1) and c43.weight.shape[0] == 1)
+
+
+def head_tc(cache, model, zc, a, split=None, out=None, pool=None):
     """Head on a CP8 activation, all on the tensor cores:
       conv2 (3x3, stride (1,3), pad (1,0)) = the stride-1 3x3 convolution whose epilogue keeps columns 1, 4, 7, ...;
       maxpool(13,1); conv3 (75x1, VALID) = the 'same' 75x1 convolution restricted to the rows whose window fits;
@@ -153,16 +163,16 @@ def head_tc(cache, model, zc, a, split=None):
     conv2, conv3, c40, c43 = model.conv2[0], model.conv3[0], model.conv4[0], model.conv4[3]
     KH3 = conv3.kernel_size[0]
     Fin = zc.F * split if split else zc.F
-    ok = (tuple(conv2.kernel_size) == (3, 3) and tuple(conv2.stride) == (1, 3) and tuple(conv2.padding) == (1, 0) and Fin % 3 == 0
-          and conv3.kernel_size[1] == 1 and (KH3 & 1) and tuple(conv3.padding) == (0, 0) and zc.T >= KH3
-          and tuple(c40.kernel_size) == (1, 1) and tuple(c43.kernel_size) == (1, 1) and c43.weight.shape[0] == 1)
-    if not ok:
+    if not head_tc_supported(model, zc.T, Fin):
         if split:
             raise MpaError('head_tc: phase-split input needs the tensor-core head')
-        return head_f32(cache, model, ops.cp8_to_nchw(zc), a)
+        y = head_f32(cache, model, ops.cp8_to_nchw(zc), a)
+        if out is not None:
+            out.copy_(y.reshape(out.shape))
+        return y
     dev, fmt = zc.buf.device, zc.fmt
     C1p = (conv2.weight.shape[0] + 7) // 8 * 8
-    yc = ops.compact_cp8(zc.B, C1p, zc.T, Fin // 3, dev, fmt)
+    yc = ops.compact_cp8(zc.B, C1p, zc.T, Fin // 3, dev, fmt, pool, 'head:y')
     if split:
         # producer wrote phase-split planes: conv2 = stride-1 3x1 convolution over 3*C0p channels of width F/3 (3x fewer MMA columns)
         J2 = _split_conv2_J(zc.C // 3, C1p)
@@ -172,13 +182,14 @@ def head_tc(cache, model, zc, a, split=None):
         cin_pad = zc.C if zc.C != conv2.weight.shape[1] else None          # the producer padded its channels to whole chunks
         for wp, b, c0, c in _folded_tc(cache, 'conv2', conv2, None, fmt, dev, cin_pad=cin_pad):
             ops.conv_tc(zc, wp, b, c, (3, 3), ops.ACT_LRELU, a, subsample=(3, 1), out=yc.channels(c0, c))
-    yc = ops.pool_time_res_cp8(yc, 13)
+    yc = ops.pool_time_res_cp8(yc, 13, out=ops.compact_cp8(zc.B, C1p, zc.T, Fin // 3, dev, fmt, pool, 'head:p') if pool is not None else None)
     C2p = (conv3.weight.shape[0] + 7) // 8 * 8
     n_rows = zc.T - KH3 + 1
-    hc = ops.compact_cp8(zc.B, C2p, n_rows, yc.F, dev, fmt)
+    hc = ops.compact_cp8(zc.B, C2p, n_rows, yc.F, dev, fmt, pool, 'head:h')
     for wp, b, c0, c in _folded_tc(cache, 'conv3', conv3, None, fmt, dev, cin_pad=C1p, J=1):
         ops.conv_tc(yc, wp, b, c, (KH3, 1), ops.ACT_LRELU, a, out=hc.channels(c0, c), J=1, rows=(KH3 // 2, n_rows))
-    o = ops.head_tail2(hc, _pad_cols(c40.weight.reshape(c40.weight.shape[0], -1), C2p), c40.bias, c43.weight, c43.bias, a)
+    w40 = cache.get(f'conv4.0:padded{C2p}', [c40.weight], lambda: _pad_cols(c40.weight.detach().reshape(c40.weight.shape[0], -1), C2p).contiguous())
+    o = ops.head_tail2(hc, w40, c40.bias, c43.weight, c43.bias, a, out=out)
     return o.reshape(zc.B, 1, n_rows, yc.F)
 
 
@@ -449,7 +460,7 @@ def unet_forward_tc(model, x, frames=None):
             low = double_conv_tc(cache, f'upconv{i + 1}', dc, cat[lv], pool[k], buf(lv, dc.double_conv[0].weight.shape[0]), split=split)
         else:
             low = double_conv_tc(cache, f'upconv{i + 1}', dc, cat[lv], buf(lv, up_out[i]), buf(lv, dc.double_conv[0].weight.shape[0]))
-    y = head_tc(cache, model, low, a, split=split)
+    y = head_tc(cache, model, low, a, split=split, pool=pool)
     return y, x5
 
 

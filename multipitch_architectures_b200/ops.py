@@ -202,10 +202,16 @@ def conv_tc_pack(w, device, fmt=FMT_F16, J=0, ring=False):
     return torch.from_numpy(packed).to(device)
 
 
-def compact_cp8(n, C, T, F, device, fmt):
-    """Un-padded planes [n][C/8][T][F][8]; one spare item of slack so that KW == 1 convolutions may over-read the last row."""
-    buf = torch.empty(n + 1, (C + 7) // 8 * planes_per_chunk(fmt), T, F, 8, dtype=_FMT_DTYPE[fmt], device=device)
-    buf[n:].zero_()     # the over-read meets zero weights (dummy K slice): it must be finite, or NaN * 0 poisons the last column
+def compact_cp8(n, C, T, F, device, fmt, pool=None, tag=None):
+    """Un-padded planes [n][C/8][T][F][8]; one spare item of slack so that KW == 1 convolutions may over-read the last row.
+    pool (dict) + tag: reuse the buffer of an earlier call with the same geometry (steady-state inference allocates and fills nothing)."""
+    key = (tag, n, C, T, F, str(device), fmt)
+    buf = pool.get(key) if pool is not None else None
+    if buf is None:
+        buf = torch.empty(n + 1, (C + 7) // 8 * planes_per_chunk(fmt), T, F, 8, dtype=_FMT_DTYPE[fmt], device=device)
+        buf[n:].zero_()     # the over-read meets zero weights (dummy K slice): it must be finite, or NaN * 0 poisons the last column
+        if pool is not None:
+            pool[key] = buf
     return CP8(n, C, T, F, F, 0, 0, device, fmt=fmt, buf=buf)
 
 
@@ -277,10 +283,12 @@ def head_tail(x, w3, b3, w40, b40, w43, b43, a_lrelu):
     return out
 
 
-def head_tail2(h, w40, b40, w43, b43, a_lrelu):
+def head_tail2(h, w40, b40, w43, b43, a_lrelu, out=None):
     """h: compact CP8 [B][NC2][R][Fo][8] (activated conv3 output) -> [B,R,Fo] fp32 = sigmoid(conv4.3(lrelu(conv4.0(h))))."""
     C3 = w40.shape[0]
-    out = torch.empty(h.B, h.T, h.F, dtype=torch.float32, device=h.buf.device)
+    if out is None:
+        out = torch.empty(h.B, h.T, h.F, dtype=torch.float32, device=h.buf.device)
+    assert out.is_contiguous() and out.numel() == h.B * h.T * h.F
     assert h.ncs == h.NC * planes_per_chunk(h.fmt) and h.chunk0 == 0
     w40f = w40.reshape(C3, -1)
     call('head_tail2_cp8', h.ptr(), w40f[:, :h.C].contiguous() if w40f.shape[1] != h.C else w40f.contiguous(), b40, w43.reshape(-1).contiguous(),
