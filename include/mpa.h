@@ -166,6 +166,15 @@ int mpa_encoder_layer_f32(const float* x, float* out, int B, int E, int Th, int 
                           const float* mlp0_b, const float* mlp2_w, const float* mlp2_b, const float* ln2_w,
                           const float* ln2_b, float eps, void* workspace, size_t ws_bytes, void* stream);
 
+/* Fused attention half of the encoder layer (unet_cnns.py:131-153), eval mode, ONE launch on the tensor cores: token gather (+ pe [S,E]
+ * or NULL) -> folded q/k/v in-projection (tcgen05) -> batch-axis softmax attention (fp32) -> folded out-projection (tcgen05) -> + residual
+ * -> LayerNorm1.  w_qkv_chunks / w_proj_chunks: the folded [3E,E] / [E,E] matrices of mpa_encoder_layer_f32 in the chunk layout of
+ * mpa_gemm_tc_to_chunks (row tile 128).  h1 [B*S, E] fp32 tokens; h1_chunks (optional): the same tokens as the 16-bit X operand of
+ * mpa_gemm_tc_f16 (row tile 256).  Needs B <= 64, E a multiple of 16 with 64 <= E <= 128; other shapes use the separate stages. */
+int mpa_enc_attn_block_tc(const float* x, const float* pe, const void* w_qkv_chunks, const float* b_qkv, const void* w_proj_chunks,
+                          const float* b_proj, const float* ln_w, const float* ln_b, float* h1, void* h1_chunks, int B, int E, int S,
+                          int num_heads, float eps, int fmt, void* stream);
+
 /* ---- tcgen05 implicit-GEMM convolution (the hot op: 96 % of DRCNN FLOPs) ------------------------------
  * KHxKW "same" convolution, stride 1, on CP8 bf16 planes.  Weights pre-packed by mpa_conv_tc_pack_weights
  * (host side, one-off).  out = act(conv + bias) in CP8 (pool / residual are applied by mpa_pool3_res_cp8).

@@ -97,21 +97,30 @@ def _enc_run_tc(self, x, fmt, pe, w_qkv, b_qkv, w_proj, b_proj):
     S, M, dev = Th * Fw, B * Th * Fw, x.device
     f32 = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
     sp = _lib.stream_ptr
-    tok = f32(M, E)
-    _lib.call('enc_gather_f32', x, pe, tok, B, E, S, sp())
-    qkv = f32(M, 3 * E)
-    _lib.call('gemm_nt_f32', tok, w_qkv, b_qkv, qkv, M, 3 * E, E, 0, sp())
-    att = f32(M, E)
-    _lib.call('batch_axis_attention_f32', qkv, att, B, S, E, self.num_heads, sp())
-    proj = f32(M, E)
-    _lib.call('gemm_nt_f32', att, w_proj, b_proj, proj, M, E, E, 0, sp())
-    h1 = f32(M, E)
-    _lib.call('add_layernorm_tok_f32', tok, proj, self.layernorm1.weight, self.layernorm1.bias, h1, None, _lib.i64(M), E, S,
-              float(self.layernorm1.eps), sp())
+    h1, h1c = f32(M, E), None
+    if B <= 64 and E % 16 == 0 and 64 <= E <= 128 and 2 * E + 128 <= (3 * E + 127) // 128 * 128:
+        # the attention half in ONE launch: gather + PE, folded q/k/v and out-projection on tcgen05, batch-axis softmax, residual, LayerNorm1
+        wqc = self._cache.get(f'wqkvc{fmt}', [self.attn.in_proj_weight, self.q_linear.weight, self.k_linear.weight, self.v_linear.weight],
+                              lambda: ops.gemm_tc_chunks(w_qkv, 128, fmt))
+        wpc = self._cache.get(f'wprojc{fmt}', [self.o_linear.weight, self.attn.out_proj.weight], lambda: ops.gemm_tc_chunks(w_proj, 128, fmt))
+        h1c = torch.empty(_lib.lib().mpa_gemm_tc_chunked_bytes(M, E, 256), dtype=torch.uint8, device=dev)
+        _lib.call('enc_attn_block_tc', x, pe, wqc, b_qkv, wpc, b_proj, self.layernorm1.weight, self.layernorm1.bias, h1, h1c, B, E, S,
+                  self.num_heads, float(self.layernorm1.eps), fmt, sp())
+    else:
+        tok = f32(M, E)
+        _lib.call('enc_gather_f32', x, pe, tok, B, E, S, sp())
+        qkv = f32(M, 3 * E)
+        _lib.call('gemm_nt_f32', tok, w_qkv, b_qkv, qkv, M, 3 * E, E, 0, sp())
+        att = f32(M, E)
+        _lib.call('batch_axis_attention_f32', qkv, att, B, S, E, self.num_heads, sp())
+        proj = f32(M, E)
+        _lib.call('gemm_nt_f32', att, w_proj, b_proj, proj, M, E, E, 0, sp())
+        _lib.call('add_layernorm_tok_f32', tok, proj, self.layernorm1.weight, self.layernorm1.bias, h1, None, _lib.i64(M), E, S,
+                  float(self.layernorm1.eps), sp())
     W1, W2 = self.mlp[0].weight, self.mlp[2].weight
     w1c = self._cache.get(f'w1c{fmt}', [W1], lambda: ops.gemm_tc_chunks(W1, 128, fmt))
     w2c = self._cache.get(f'w2c{fmt}', [W2], lambda: ops.gemm_tc_chunks(W2, 128, fmt))
-    hid = ops.gemm_tc(h1, w1c, self.mlp[0].bias, self.mlp_dim, True, fmt)
+    hid = ops.gemm_tc(h1, w1c, self.mlp[0].bias, self.mlp_dim, True, fmt, x_chunks=h1c)
     mo = ops.gemm_tc(hid, w2c, self.mlp[2].bias, E, False, fmt)
     out = torch.empty_like(x)
     _lib.call('add_layernorm_tok_f32', h1, mo, self.layernorm2.weight, self.layernorm2.bias, None, out, _lib.i64(M), E, S,

@@ -431,11 +431,11 @@ def gemm_tc_chunks(x, row_tile, fmt, transposed=False):
     return out
 
 
-def gemm_tc(x, w_chunks, bias, N, relu, fmt, x_transposed=False, out=None):
+def gemm_tc(x, w_chunks, bias, N, relu, fmt, x_transposed=False, out=None, x_chunks=None):
     """y [M, N] fp32 = act(X @ W^T + bias) on the tensor cores; X = x [M, K] (or x^T when x_transposed: x stored [K, M]);
-    w_chunks = gemm_tc_chunks(W [N, K], 128, fmt) (or of the [K, N]-stored transpose)."""
+    w_chunks = gemm_tc_chunks(W [N, K], 128, fmt) (or of the [K, N]-stored transpose); x_chunks: X already in the operand layout."""
     M, K = (x.shape[1], x.shape[0]) if x_transposed else x.shape
-    xc = gemm_tc_chunks(x, 256, fmt, x_transposed)
+    xc = x_chunks if x_chunks is not None else gemm_tc_chunks(x, 256, fmt, x_transposed)
     y = out if out is not None else torch.empty(M, N, dtype=torch.float32, device=x.device)
     call('gemm_tc_f16', xc, w_chunks, bias, y, M, N, K, int(bool(relu)), fmt, stream_ptr())
     return y

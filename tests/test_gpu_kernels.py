@@ -251,3 +251,32 @@ def test_conv_rows_gemm_kernels_match_torch(B, Cin, H, W, Cout):
     gw = torch.full_like(wc, 7.0)           # must be overwritten, not accumulated
     _lib.call('conv_rows_wgrad_f32', xc, gc, gw, B, Cin, H, W, Cout, _lib.stream_ptr())
     assert (gw.cpu() - wr.grad).abs().max() < 2e-4 * max(1.0, wr.grad.abs().max().item())
+
+
+@pytest.mark.parametrize('B,E,S,H,prec', [(50, 128, 52, 8, 'fp16'), (25, 128, 52, 8, 'bf16'), (64, 64, 12, 8, 'fp16'), (3, 128, 5, 4, 'fp16'), (1, 96, 7, 6, 'fp16')])
+def test_fused_attention_block_tc_matches_the_separate_fp32_stages(ops, B, E, S, H, prec):
+    """mpa_enc_attn_block_tc (gather + PE, q/k/v and out-projection on tcgen05, batch-axis softmax, residual, LayerNorm1 in ONE launch)
+    vs the five separate fp32 launches it replaces; the difference is the 16-bit rounding of the two GEMMs' operands."""
+    from multipitch_architectures_b200 import _lib
+    fmt = ops.fmt_of(prec)
+    x, pe = rnd(B, E, S, seed=1).cuda(), rnd(S, E, seed=2, scale=0.5).cuda()
+    w_qkv, b_qkv = rnd(3 * E, E, seed=3, scale=E ** -0.5).cuda(), rnd(3 * E, seed=4, scale=0.1).cuda()
+    w_proj, b_proj = rnd(E, E, seed=5, scale=E ** -0.5).cuda(), rnd(E, seed=6, scale=0.1).cuda()
+    ln_w, ln_b = (1 + 0.1 * rnd(E, seed=7)).cuda(), (0.1 * rnd(E, seed=8)).cuda()
+    M, sp = B * S, _lib.stream_ptr
+    f32 = lambda *sh: torch.empty(*sh, dtype=torch.float32, device='cuda')
+    tok, qkv, att, proj, ref = f32(M, E), f32(M, 3 * E), f32(M, E), f32(M, E), f32(M, E)
+    _lib.call('enc_gather_f32', x, pe, tok, B, E, S, sp())
+    _lib.call('gemm_nt_f32', tok, w_qkv, b_qkv, qkv, M, 3 * E, E, 0, sp())
+    _lib.call('batch_axis_attention_f32', qkv, att, B, S, E, H, sp())
+    _lib.call('gemm_nt_f32', att, w_proj, b_proj, proj, M, E, E, 0, sp())
+    _lib.call('add_layernorm_tok_f32', tok, proj, ln_w, ln_b, ref, None, _lib.i64(M), E, S, 1e-5, sp())
+    h1 = f32(M, E)
+    h1c = torch.zeros(_lib.lib().mpa_gemm_tc_chunked_bytes(M, E, 256), dtype=torch.uint8, device='cuda')
+    _lib.call('enc_attn_block_tc', x, pe, ops.gemm_tc_chunks(w_qkv, 128, fmt), b_qkv, ops.gemm_tc_chunks(w_proj, 128, fmt), b_proj, ln_w, ln_b,
+              h1, h1c, B, E, S, H, 1e-5, fmt, sp())
+    err = (h1 - ref).abs().max().item()
+    print(f'fused attention block B={B} E={E} {prec}: max|diff| vs fp32 stages = {err:.2e}')
+    assert err < (4e-2 if prec == 'bf16' else 6e-3)
+    # the 16-bit operand copy of h1 equals what the converter makes of it
+    assert torch.equal(h1c, ops.gemm_tc_chunks(h1, 256, fmt)[:h1c.numel()]) or (E % 64 != 0)
