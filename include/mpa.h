@@ -318,6 +318,21 @@ int mpa_hcqt_npy_to_frames_f64(const double* hcqt_fnc, float* out, int F, int N,
 int mpa_cqt_level_f32(const float* y_level, long long n_level, int n_fft, int hop, int n_frames, const float* basis,
                       const int* band_start, const float* row_scale, int n_rows, int band, const int* tuning_idx,
                       const int* dest, int n_dest, float* out, int out_frames, int out_bins, void* stream);
+/* All levels of one HCQT in ONE launch (grid = frames x levels; same arithmetic per (level, frame) as mpa_cqt_level_f32, so the results
+ * are bit-identical to the per-level calls).  `levels`: HOST array of n_levels <= 16 descriptors holding device pointers. */
+typedef struct mpa_cqt_level {
+  const float* y;            /* the level's (decimated) signal */
+  long long n;               /* its length in samples */
+  int n_fft, hop;            /* FFT size and hop at this rate */
+  const float* basis;        /* complex64 interleaved [n_tunings][n_rows][band] */
+  const int* band_start;     /* [n_tunings][n_rows] */
+  const float* row_scale;    /* [n_tunings][n_rows] */
+  int n_rows;
+  const int* dest;           /* [n_rows][n_dest] = (channel << 16 | bin) or -1 */
+  int n_dest;
+} mpa_cqt_level;
+int mpa_cqt_levels_f32(const mpa_cqt_level* levels, int n_levels, int n_frames, int band, const int* tuning_idx, float* out,
+                       int out_frames, int out_bins, void* stream);
 /* librosa.estimate_tuning(y, sr, bins_per_octave) with n_fft=2048, hop=512, fmin=150, fmax=4000, threshold=0.1,
  * resolution=0.01: writes tuning_idx[0] in [0,100), tuning = -0.5 + 0.01*idx.  hann2048: periodic hann window. */
 size_t mpa_tuning_workspace(int n_frames);

@@ -11,6 +11,7 @@
 //                              stays on the device as an index into the pre-built per-tuning filter banks.
 // HBM-bound by design: per 30 s clip the algorithmic traffic is 2.65 MB in + 6.7 MB out.
 #include "common.cuh"
+#include <string.h>
 
 namespace mpa {
 
@@ -114,6 +115,54 @@ __global__ void __launch_bounds__(256) cqt_level_kernel(const float* __restrict_
     for (int d = 0; d < n_dest; ++d) {
       const int code = dest[r * n_dest + d];
       if (code >= 0) out[((size_t)(code >> 16) * out_frames + t) * out_bins + (code & 0xffff)] = mag;
+    }
+  }
+}
+
+// Every (rate, FFT size) level of one HCQT in ONE launch: blockIdx.y selects the level, blockIdx.x the frame.  The levels are independent
+// of each other (each reads its own decimated signal and scatters into its own rows of the output), and a single level (1,292 CTAs of
+// one small FFT) does not fill the chip.  The per-level arguments travel in the kernel parameters.
+constexpr int kMaxCqtLevels = 16;
+struct CqtLevelsParams {
+  mpa_cqt_level lv[kMaxCqtLevels];
+  int log2n[kMaxCqtLevels];
+  int n_frames, band, out_frames, out_bins;
+  const int* tuning_idx;
+  float* out;
+};
+__global__ void __launch_bounds__(256) cqt_levels_kernel(const __grid_constant__ CqtLevelsParams p) {
+  extern __shared__ float2 sm2[];
+  const mpa_cqt_level& L = p.lv[blockIdx.y];
+  const int n_fft = L.n_fft, log2n = p.log2n[blockIdx.y];
+  float2* a = sm2;              // [n_fft]
+  float2* tw = sm2 + n_fft;     // [n_fft/2]
+  const int t = blockIdx.x;
+  load_frame_bitrev(a, tw, L.y, L.n, nullptr, (long long)t * L.hop - n_fft / 2, n_fft, log2n);
+  fft_smem(a, tw, n_fft, log2n);
+  const int tune = p.tuning_idx ? p.tuning_idx[0] : 0;
+  const int n_rows = L.n_rows, band = p.band;
+  const float2* bs = reinterpret_cast<const float2*>(L.basis) + (size_t)tune * n_rows * band;
+  const int* st = L.band_start + (size_t)tune * n_rows;
+  const float* sc = L.row_scale + (size_t)tune * n_rows;
+  const int nb = n_fft / 2 + 1;
+  for (int r = threadIdx.x; r < n_rows; r += blockDim.x) {
+    const int s0 = st[r];
+    const float2* br = bs + (size_t)r * band;
+    float re = 0.f, im = 0.f;
+    for (int f = 0; f < band; ++f) {
+      const int bin = s0 + f;
+      if (bin < nb) {
+        const float2 b = br[f], x = a[bin];
+        re = fmaf(b.x, x.x, re);
+        re = fmaf(-b.y, x.y, re);
+        im = fmaf(b.x, x.y, im);
+        im = fmaf(b.y, x.x, im);
+      }
+    }
+    const float mag = sqrtf(re * re + im * im) * sc[r];
+    for (int d = 0; d < L.n_dest; ++d) {
+      const int code = L.dest[r * L.n_dest + d];
+      if (code >= 0) p.out[((size_t)(code >> 16) * p.out_frames + t) * p.out_bins + (code & 0xffff)] = mag;
     }
   }
 }
@@ -360,6 +409,31 @@ int mpa_cqt_level_f32(const float* y_level, long long n_level, int n_fft, int ho
   cqt_level_kernel<<<n_frames, 256, smem, (cudaStream_t)stream>>>(y_level, n_level, n_fft, ilog2(n_fft), hop, (const float2*)basis, band_start,
                                                                    row_scale, n_rows, band, tuning_idx, dest, n_dest, out, out_frames, out_bins);
   MPA_CHECK_LAUNCH("cqt_level");
+  return MPA_OK;
+}
+
+int mpa_cqt_levels_f32(const mpa_cqt_level* levels, int n_levels, int n_frames, int band, const int* tuning_idx, float* out, int out_frames,
+                       int out_bins, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(levels && out && n_levels >= 1 && n_levels <= kMaxCqtLevels, "cqt_levels: 1..%d levels", kMaxCqtLevels);
+  MPA_REQUIRE(n_frames >= 1 && n_frames <= out_frames && band >= 1 && out_bins < 65536, "cqt_levels: bad shape");
+  CqtLevelsParams p;
+  memset(&p, 0, sizeof(p));
+  int max_fft = 0;
+  for (int i = 0; i < n_levels; ++i) {
+    const mpa_cqt_level& L = levels[i];
+    MPA_REQUIRE(L.y && L.basis && L.band_start && L.row_scale && L.dest, "cqt_levels: null argument in level %d", i);
+    MPA_REQUIRE(L.n_fft >= 64 && L.n_fft <= 4096 && (L.n_fft & (L.n_fft - 1)) == 0, "cqt_levels: n_fft must be a power of two in 64..4096");
+    MPA_REQUIRE(L.n >= 2 && L.hop >= 1 && L.n_rows >= 1 && L.n_dest >= 1, "cqt_levels: bad level %d", i);
+    MPA_REQUIRE((long long)(n_frames - 1) * L.hop <= L.n, "cqt_levels: %d frames at hop %d exceed the signal (%lld samples)", n_frames, L.hop, L.n);
+    p.lv[i] = L;
+    p.log2n[i] = ilog2(L.n_fft);
+    if (L.n_fft > max_fft) max_fft = L.n_fft;
+  }
+  p.n_frames = n_frames; p.band = band; p.out_frames = out_frames; p.out_bins = out_bins;
+  p.tuning_idx = tuning_idx; p.out = out;
+  cqt_levels_kernel<<<dim3(n_frames, n_levels), 256, (size_t)max_fft * 12, (cudaStream_t)stream>>>(p);
+  MPA_CHECK_LAUNCH("cqt_levels");
   return MPA_OK;
 }
 

@@ -1,6 +1,7 @@
 """HCQT feature extraction with the reference's API (/root/reference/libdl/data_preprocessing/hcqt.py:9-164,
 205-272) on a B200: audio in, `[n_bins, n_frames, n_harmonics]` float64 out; all signal arithmetic runs in the
 libmpa CUDA kernels (decimator chain, fused FFT + constant-Q contraction, tuning estimate)."""
+import ctypes
 import functools
 
 import numpy as np
@@ -32,6 +33,13 @@ def _harmonic_plan(num_harmonics, num_subharmonics):
         else:
             base.append(h)
     return list_h, base
+
+
+class CqtLevel(ctypes.Structure):
+    """mpa_cqt_level (include/mpa.h)"""
+    _fields_ = [('y', ctypes.c_void_p), ('n', ctypes.c_longlong), ('n_fft', ctypes.c_int), ('hop', ctypes.c_int), ('basis', ctypes.c_void_p),
+                ('band_start', ctypes.c_void_p), ('row_scale', ctypes.c_void_p), ('n_rows', ctypes.c_int), ('dest', ctypes.c_void_p),
+                ('n_dest', ctypes.c_int)]
 
 
 class HCQTPlan:
@@ -68,6 +76,7 @@ class HCQTPlan:
         self.hann2048 = torch.from_numpy((0.5 - 0.5 * np.cos(2 * np.pi * n / 2048)).astype(np.float32)).to(self.device)
         self.tunings = FB.tuning_values()
         self._frames = {}
+        self._side = None
         self._graphs, self.graph_replays, self.graph_launches = {}, 0, 0     # run_graph: captured launch sequences per input length
 
     def n_frames(self, n):
@@ -118,12 +127,22 @@ class HCQTPlan:
         n = y.numel()
         st = _lib.stream_ptr()
         n_frames = self.n_frames(n)
+        side = None
         if tuning_idx is None:
-            tuning_idx = torch.empty(1, dtype=torch.int32, device=y.device)
-            ws_bytes = _lib.lib().mpa_tuning_workspace(n // 512 + 1)
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=y.device)
-            _lib.call('estimate_tuning_f32', y, _lib.i64(n), self.hann2048, float(self.fs), self.bpo, tuning_idx, ws,
-                      _lib.usize(ws_bytes), st)
+            # the tuning estimate (STFT-2048 + peak statistics) needs only y: it runs on a side stream next to the decimator chain and
+            # joins before the filterbank launch that reads it
+            cur = torch.cuda.current_stream(y.device)
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=y.device)
+            side = self._side
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                tuning_idx = torch.empty(1, dtype=torch.int32, device=y.device)
+                ws_bytes = _lib.lib().mpa_tuning_workspace(n // 512 + 1)
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=y.device)
+                _lib.call('estimate_tuning_f32', y, _lib.i64(n), self.hann2048, float(self.fs), self.bpo, tuning_idx, ws,
+                          _lib.usize(ws_bytes), _lib.stream_ptr())
+            tuning_idx.record_stream(cur)
         sig = {(0, 0): y}
         for (c, i) in self.signals:            # sorted: (c, i-1) precedes (c, i)
             if (c, i) in sig:
@@ -134,6 +153,18 @@ class HCQTPlan:
             _lib.call('decimate_f32', prev, nxt, taps, taps.numel(), factor, _lib.i64(prev.numel()), st)
             sig[(c, i)] = nxt
         out = torch.empty(self.H, n_frames, self.n_bins, dtype=torch.float32, device=y.device)
+        if side is not None:
+            torch.cuda.current_stream(y.device).wait_stream(side)
+        if len(self.levels) <= 16:
+            # every (rate, FFT size) level in ONE launch: the levels are independent and a single one does not fill the chip
+            arr = (CqtLevel * len(self.levels))()
+            for d, L in zip(arr, self.levels):
+                s = sig[L['signal']]
+                d.y, d.n, d.n_fft, d.hop = s.data_ptr(), s.numel(), L['n_fft'], self.hop >> sum(L['signal'])
+                d.basis, d.band_start, d.row_scale = L['basis'].data_ptr(), L['start'].data_ptr(), L['scale'].data_ptr()
+                d.n_rows, d.dest, d.n_dest = L['n_rows'], L['dest'].data_ptr(), L['n_dest']
+            _lib.call('cqt_levels_f32', arr, len(self.levels), n_frames, FB.BAND, tuning_idx, out, n_frames, self.n_bins, st)
+            return out, tuning_idx
         for L in self.levels:
             s = sig[L['signal']]
             _lib.call('cqt_level_f32', s, _lib.i64(s.numel()), L['n_fft'], self.hop >> sum(L['signal']), n_frames, L['basis'], L['start'],
