@@ -474,6 +474,41 @@ def realistic_goldens(src=os.path.join(ROOT, 'gpurun_out', 'realistic')):
     np.savez_compressed(os.path.join(HERE, 'realistic_weights.npz'), **weights)
 
 
+def grad_sample_index(numel, k=256):
+    """Deterministic sample of a flattened tensor: every element when it has <= k, else k evenly spread positions."""
+    return np.arange(numel) if numel <= k else (np.arange(k, dtype=np.int64) * numel) // k
+
+
+def saunet_l_train_golden():
+    """FULL-SIZE SAUnet:L (BASELINE configs[4]) in train mode on the reference class: loss, outputs, BatchNorm statistics and, per
+    parameter, the gradient's L2 norm plus a 256-element sample (the 8.1 M gradient values themselves would be 32 MB)."""
+    torch.set_num_threads(os.cpu_count() or 8)
+    name, B, seed = 'saunet_l', 4, 31
+    m = build_reference_model(name)
+    sd = fill_state_dict(m.state_dict(), seed, scheme='torch_default')
+    m.load_state_dict(sd)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    m.train(True)
+    x, yt = synth_patches(B, seed), synth_targets(B, seed)
+    m.zero_grad()
+    y = m(x)
+    loss = torch.nn.BCELoss(reduction='mean')(y, yt)
+    loss.backward()
+    tag = f'{name}__train'
+    out = {tag + '__y': y.detach().numpy(), tag + '__loss': np.array([loss.item()]), tag + '__meta': np.array([B, seed])}
+    for k, p in m.named_parameters():
+        g = p.grad.numpy().reshape(-1)
+        out[tag + '__gnorm__' + k] = np.array([np.sqrt((g.astype(np.float64) ** 2).sum())])
+        out[tag + '__gsamp__' + k] = g[grad_sample_index(g.size)].copy()
+    for k, v in m.state_dict().items():
+        if 'running_' in k:
+            out[tag + '__stat__' + k] = v.numpy().copy()
+    np.savez_compressed(os.path.join(HERE, 'saunet_l_train_golden.npz'), **out)
+    print(tag, 'loss', loss.item(), 'tensors', sum(1 for k in out if '__gnorm__' in k))
+
+
 def state_dict_key_fixture():
     """Names, shapes and dtypes (in order) of the state_dict of every reference model class / size the tests use: the drop-in contract
     `model.load_state_dict(torch.load(pt))` (exp126a...py:388) is a contract on NAMES, so they are pinned as text."""
@@ -488,6 +523,9 @@ def state_dict_key_fixture():
 
 
 if __name__ == '__main__':
+    if 'saunet_l_train' in sys.argv[1:]:
+        saunet_l_train_golden()
+        sys.exit(0)
     if 'keys' in sys.argv[1:]:
         state_dict_key_fixture()
         sys.exit(0)

@@ -313,3 +313,85 @@ def test_graph_replayed_step_equals_eager_step():
     assert all(abs(a - b) <= 2e-4 * max(1.0, abs(a)) for a, b in zip(le, lg))
     assert len(set(round(v, 4) for v in lg)) == len(lg)                   # every step saw its own data / masks
     assert (res[False][1] - res[True][1]).abs().max().item() < 1e-5       # fp32 atomics (split-K, wgrad flush) are not order-stable
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# full-size SAUnet:L (BASELINE configs[4]): the reference's loss.backward() and a bf16-vs-fp32 training run
+def _sample_index(numel, k=256):
+    return np.arange(numel) if numel <= k else (np.arange(k, dtype=np.int64) * numel) // k
+
+
+@pytest.fixture(scope='module')
+def saunet_l_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'saunet_l_train_golden.npz'))
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_full_size_saunet_l_loss_and_gradients_vs_reference(saunet_l_golden, precision):
+    """SAUnet:L [128,80,50,30] sc=4 E=128 mlp=8192 (8.1 M parameters), train mode, batch 4: loss, outputs, BatchNorm running statistics and
+    every parameter gradient (norm + a 256-element sample per tensor) against the REFERENCE class's loss.backward()
+    (tests/golden/make_golden.py saunet_l_train).  fp32 path: 1e-3 relative; bf16 tensor-core path: its stated looser bound."""
+    g = saunet_l_golden
+    tag = 'saunet_l__train'
+    B, seed = [int(v) for v in g[tag + '__meta']]
+    m = build_model('saunet_l', precision=precision)
+    m.load_state_dict(fill_state_dict(m.state_dict(), seed, scheme='torch_default'))
+    _zero_dropout(m)
+    m = m.cuda().train()
+    x, t = synth_patches(B, seed).cuda(), synth_targets(B, seed).cuda()
+    y = m(x)
+    loss = torch.nn.BCELoss(reduction='mean')(y, t)
+    loss.backward()
+    fp32 = precision == 'fp32'
+    assert abs(loss.item() - float(g[tag + '__loss'][0])) < (1e-5 if fp32 else 2e-3)
+    assert np.abs(y.detach().cpu().numpy() - g[tag + '__y']).max() < (1e-4 if fp32 else 5e-3)
+    dots = n1 = n2 = 0.0
+    gnorm_total = sum(float(g[k][0]) ** 2 for k in g.files if '__gnorm__' in k) ** 0.5
+    worst = (1.0, '')
+    for k, p in m.named_parameters():
+        got = p.grad.detach().float().cpu().numpy().reshape(-1)
+        ref_norm, ref_s = float(g[tag + '__gnorm__' + k][0]), g[tag + '__gsamp__' + k]
+        got_s = got[_sample_index(got.size)]
+        assert np.isfinite(got).all(), k
+        if fp32 and ref_norm > 1e-3 * gnorm_total:
+            assert abs(np.sqrt((got.astype(np.float64) ** 2).sum()) - ref_norm) < 1e-2 * ref_norm, k
+            # element-wise: train-mode BatchNorm over a batch of 4 amplifies the fp32 summation-order differences between the two
+            # implementations to ~1 % of a tensor's largest gradient entry; the cosine below is the tight check
+            assert np.abs(got_s - ref_s).max() < 5e-2 * max(np.abs(ref_s).max(), 1e-12) + 1e-7, k
+        dg, dd, gg = float((got_s * ref_s).sum()), float((got_s ** 2).sum()), float((ref_s ** 2).sum())
+        dots += dg; n1 += dd; n2 += gg
+        if ref_norm > 1e-2 * gnorm_total:
+            worst = min(worst, (dg / max(dd ** 0.5 * gg ** 0.5, 1e-30), k))
+    cos = dots / (n1 ** 0.5 * n2 ** 0.5)
+    print(f'SAUnet:L {precision}: loss {loss.item():.6f} (reference {float(g[tag + "__loss"][0]):.6f}); sampled-gradient cosine {cos:.5f}; worst tensor {worst[1]} {worst[0]:.4f}')
+    assert cos > (0.9999 if fp32 else 0.97) and worst[0] > (0.999 if fp32 else 0.80)      # bf16 observed: 0.998 / 0.857
+    if fp32:
+        for k, v in m.state_dict().items():
+            if 'running_' in k:
+                assert np.abs(v.cpu().numpy() - g[tag + '__stat__' + k]).max() < 1e-4, k
+
+
+def test_saunet_l_bf16_training_run_follows_the_fp32_run():
+    """60 optimiser steps of the full-size SAUnet:L on the same 6 cycling batches of 25 patches (dropout on, same masks: the Philox offsets
+    depend on the step number only), once on the fp32 CUDA-core path and once on the bf16 tensor-core path: the two loss curves must
+    stay together (the model memorises the batches: the loss falls by > 25 %; smoothed curves within 8 % of the initial loss
+    of each other everywhere and within 4 % on the plateau)."""
+    from multipitch_architectures_b200.training_unet import UnetTrainStep
+    curves = {}
+    data = [(synth_patches(25, 900 + i).cuda(), synth_targets(25, 900 + i).cuda()) for i in range(6)]
+    for precision in ('fp32', 'bf16'):
+        m = build_model('saunet_l', precision=precision)
+        m.load_state_dict(fill_state_dict(m.state_dict(), 3, scheme='torch_default'))
+        m = m.cuda().train()
+        step = UnetTrainStep(m, lr=1e-3, weight_decay=0.01, graph=(precision == 'bf16'))
+        curves[precision] = [float(step(*data[i % 6]).item()) for i in range(60)]
+        step.release()
+    a, b = np.array(curves['fp32']), np.array(curves['bf16'])
+    sm = lambda v: np.convolve(v, np.ones(6) / 6, mode='valid')
+    print('fp32 loss', np.round(sm(a)[::9], 4), 'bf16 loss', np.round(sm(b)[::9], 4))
+    assert np.isfinite(a).all() and np.isfinite(b).all()
+    assert sm(a)[-1] < 0.75 * sm(a)[0] and sm(b)[-1] < 0.75 * sm(b)[0]
+    assert np.abs(sm(a) - sm(b)).max() < 0.08 * sm(a).max()           # steep first steps: observed <= 0.02 of 0.29
+    assert abs(a[-12:].mean() - b[-12:].mean()) < 0.04 * a[-12:].mean()   # plateau: observed 0.162 vs 0.159
+    assert abs(a[0] - b[0]) < 2e-3 * a[0]
