@@ -89,6 +89,12 @@ struct ConvTcParams {
   // memory and a KH x 1 filter has no horizontal taps), so every weight tile is used for R output rows instead of one; (b) an activation
   // stage holds G of the NC input chunks (the K loop of an input row walks ceil(NC / G) stages), which keeps the stages inside 227 KB.
   int R, G, n_groups;
+  // Rs: image rows between two merged rows.  1: the R rows are consecutive (one bulk copy; needs J == 1).  J: merged row rr holds image
+  // row (r + J*rr), so that row block j of the A tile and merged row rr together produce output row t0 + j + J*rr: R*J output rows
+  // per unit with the J-fold weight reuse of the stacked filters kept (the head's 40-channel conv2: 9 rows per unit instead of 3; its
+  // work units were so small that fixed per-unit costs, not the tensor pipe, set the pace).  The R rows arrive as R separate copies;
+  // rows outside the plane (+ guard rows) are skipped, their columns only feed outputs that are never stored.
+  int Rs, pt_in;
   uint32_t btab[256];       // tile main loop: B-descriptor low words of one K row, (offset >> 4) | (LBO >> 4) << 16 (x3: the row twice)
   // ---- ring main loop (conv_tc_ring_kernel): un-duplicated weight pieces, see below
   int ring_on, ring_S, ring_npos, ring_ps, ring_sbo, ring_nb, ring_b_off, ring_bar_off;
@@ -300,6 +306,9 @@ __device__ __forceinline__ void epilogue_role(const ConvTcParams& p, uint32_t tm
     const float bias = row_valid ? p.bias[co] : 0.f;
     const float inv_scale = (X3 && row_valid) ? p.inv_scale[co] : 1.f;
     constexpr int n_parts = X3 ? 2 : 1;
+    // activations of the form max(x, slope * x): none (slope 1), ReLU (0), LeakyReLU with 0 <= slope <= 1
+    const float act_slope = p.act == MPA_ACT_NONE ? 1.f : p.act == MPA_ACT_RELU ? 0.f : p.act_param;
+    const bool fast_act = p.act != MPA_ACT_SIGMOID && act_slope >= 0.f && act_slope <= 1.f;
     const int NCoP = n_parts * p.NCo;                                 // chunk planes of one activated conv row in the scratch ring
     // coalesced path: 8 consecutive lanes = the 8 channels of one chunk of one output row (needs Cout % 8 == 0)
     const bool staged = ((p.Cout & 7) == 0);
@@ -354,18 +363,36 @@ __device__ __forceinline__ void epilogue_role(const ConvTcParams& p, uint32_t tm
         tc_wait_ld();
         if (staged) {
           for (int part = 0; part < n_parts; ++part) {
+            if (!X3 && fast_act) {
+              // the common case, branch-free per element: none / ReLU / LeakyReLU(0 <= slope <= 1) are all max(x, slope * x); columns
+              // that are not kept are converted too (finite accumulators; their staging slots are never read)
+              if (p.fmt == MPA_FMT_BF16) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              if ((keep >> i) & 1u) {
-                const float x = apply_act(fmaf(__uint_as_float(v[i]), inv_scale, bias), p.act, p.act_param);
-                stile[i * kEpiPitch + lane] = X3 ? split16(x, part) : cvt16(x, p.fmt);
+                for (int i = 0; i < 32; ++i) {
+                  const float x = fmaf(__uint_as_float(v[i]), inv_scale, bias);
+                  stile[i * kEpiPitch + lane] = __bfloat16_as_ushort(__float2bfloat16(fmaxf(x, x * act_slope)));
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  const float x = fmaf(__uint_as_float(v[i]), inv_scale, bias);
+                  stile[i * kEpiPitch + lane] = __half_as_ushort(__float2half_rn(fmaxf(x, x * act_slope)));
+                }
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                if ((keep >> i) & 1u) {
+                  const float x = apply_act(fmaf(__uint_as_float(v[i]), inv_scale, bias), p.act, p.act_param);
+                  stile[i * kEpiPitch + lane] = X3 ? split16(x, part) : cvt16(x, p.fmt);
+                }
               }
             }
             __syncwarp();
             // lane -> column c0+lane; pass k -> the k-th 8-lane group (= one channel chunk of one output row) of this warp
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const int tg = t0 + grp_j[k] + rr;
+              const int tg = t0 + grp_j[k] + rr * p.Rs;
               if (col_ok && grp_j[k] < p.J && tg < y_hi) {
                 const uint4 val = *reinterpret_cast<const uint4*>(stile + lane * kEpiPitch + k * 8);
                 if (p.pool) {
@@ -533,6 +560,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (p.Rs > 1) {
+    // skipped rows and the over-read tail of a stage are never written by a copy: they must hold finite values (their columns feed
+    // outputs that are discarded, or meet zero weights)
+    for (int i = threadIdx.x; i < kNumBStages * bstage_bytes / 16; i += kThreads) reinterpret_cast<uint4*>(b_smem)[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -550,10 +583,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
 
   if (warp == 0) {
     // ===================================================== producer
-    if (lane == 0) {
+    // The whole warp walks the (warp-uniform) loops; lane 0 waits on / arms the barriers and issues the weight copies, the activation
+    // copies of a stage — one per chunk plane (x merged row) — are issued by 32 lanes at once.  (A single thread needs ~170 clocks per
+    // bulk copy for the address arithmetic and the issue; wide-K stages of 16-45 copies per ~1,000 tensor-clocks were bound by that.)
+    {
       int a_stage = 0, b_stage = 0;
       uint32_t a_phase = 0, b_phase = 0;
-      if (p.resident && u_begin < u_end) {
+      if (lane == 0 && p.resident && u_begin < u_end) {
         // small filters (the head's 3x3): every weight stage has its own slot and is loaded exactly once
         const int spr = (p.mmas_per_row + kStageMMAs - 1) / kStageMMAs;
         for (int r = 0; r < rows_in; ++r)
@@ -563,6 +599,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
             bulk_g2s(a_smem + idx * kAStageBytes, p.w + ((size_t)r * p.mmas_per_row + m0) * kATileBytes, (uint32_t)(nm * kATileBytes), &a_full[idx]);
           }
       }
+      __syncwarp();
       for (int u = u_begin; u < u_end; ++u) {
         const UnitInfo ui = decode_unit(p, u);
         for (int r = 0; r < rows_in; ++r) {
@@ -572,16 +609,41 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
            for (int gi = 0; gi < p.n_groups; ++gi) {
             // activation slab of this input row: chunk group gi (split precision: the hi planes, then the lo planes)
             const int planes = min(p.G, p.NC - gi * p.G);
-            mbar_wait(&b_empty[b_stage], b_phase ^ 1);
-            mbar_expect_tx(&b_full[b_stage], (uint32_t)(planes * slab_plane_bytes));
-            {
+            uint8_t* dst = b_smem + b_stage * bstage_bytes;
+            if (p.Rs > 1) {
+              // spaced merged rows: one copy of `pitch` pixels per (plane, merged row); rows beyond the guard rows are left out
+              int n_ok = 0;
+              for (int rr = 0; rr < p.R; ++rr) {
+                const int rw = row + rr * p.Rs;
+                n_ok += (rw >= -p.pt_in && rw < p.T + p.pt_in) ? 1 : 0;
+              }
+              if (lane == 0) {
+                mbar_wait(&b_empty[b_stage], b_phase ^ 1);
+                mbar_expect_tx(&b_full[b_stage], (uint32_t)(planes * n_ok * p.P * 16));
+              }
+              __syncwarp();
+              long long cs;
+              const uint8_t* src = in_row_ptr(p, ui.b, 0, cs) + (long long)(gi * p.G) * cs;       // materialised patches: row r at r * pitch
+              for (int i = lane; i < planes * p.R; i += 32) {
+                const int rr = i / planes, c = i - rr * planes;
+                const int rw = row + rr * p.Rs;
+                if (rw < -p.pt_in || rw >= p.T + p.pt_in) continue;
+                bulk_g2s(dst + c * slab_plane_bytes + rr * p.P * 16, src + (long long)c * cs + (long long)rw * p.P * 16, (uint32_t)(p.P * 16),
+                         &b_full[b_stage]);
+              }
+            } else {
+              if (lane == 0) {
+                mbar_wait(&b_empty[b_stage], b_phase ^ 1);
+                mbar_expect_tx(&b_full[b_stage], (uint32_t)(planes * slab_plane_bytes));
+              }
+              __syncwarp();
               long long cs;
               const uint8_t* src = in_row_ptr(p, ui.b, row, cs) - pw * 16;
               src += (long long)((part ? p.in_lo_off : 0) + gi * p.G) * cs;
-              uint8_t* dst = b_smem + b_stage * bstage_bytes;
-              for (int c = 0; c < planes; ++c)
+              for (int c = lane; c < planes; c += 32)
                 bulk_g2s(dst + c * slab_plane_bytes, src + (long long)c * cs, (uint32_t)slab_plane_bytes, &b_full[b_stage]);
             }
+            __syncwarp();
             if (++b_stage == kNumBStages) { b_stage = 0; b_phase ^= 1; }
             // weight stages of this K row (split precision: W_hi and W_lo tiles against the hi planes, W_hi tiles against the lo planes)
             if (p.resident) continue;
@@ -590,9 +652,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
             const uint8_t* wrow = p.w + ((size_t)r * p.tiles_per_row + (part ? 2 * p.mmas_per_row : 0) + q0) * kATileBytes;
             for (int m0 = 0; m0 < n_tiles; m0 += kStageMMAs) {
               const int nm = min(kStageMMAs, n_tiles - m0);
-              mbar_wait(&a_empty[a_stage], a_phase ^ 1);
-              mbar_expect_tx(&a_full[a_stage], (uint32_t)(nm * kATileBytes));
-              bulk_g2s(a_smem + a_stage * kAStageBytes, wrow + (size_t)m0 * kATileBytes, (uint32_t)(nm * kATileBytes), &a_full[a_stage]);
+              if (lane == 0) {
+                mbar_wait(&a_empty[a_stage], a_phase ^ 1);
+                mbar_expect_tx(&a_full[a_stage], (uint32_t)(nm * kATileBytes));
+                bulk_g2s(a_smem + a_stage * kAStageBytes, wrow + (size_t)m0 * kATileBytes, (uint32_t)(nm * kATileBytes), &a_full[a_stage]);
+              }
               if (++a_stage == kNumAStages) { a_stage = 0; a_phase ^= 1; }
             }
            }
@@ -1474,6 +1538,7 @@ static int launch_conv_tc(ConvTcParams& p, int Cin, cudaStream_t stream, int* gr
   p.mmas_per_row = mmas_per_row(p.NC, p.KW);
   p.slab_px = (p.N + 2 * (p.KW / 2) + 1 + 7) / 8 * 8;
   if (p.R < 1) p.R = 1;
+  if (p.Rs < 1) p.Rs = 1;
   size_t smem = 0;
   if (p.x3) {
     MPA_REQUIRE(!p.ring_on, "conv_tc: the ring main loop has no split-precision variant");
@@ -1639,11 +1704,18 @@ int mpa_conv_tc_f16(const void* in_cp8, const void* w_packed, const float* bias,
   MPA_REQUIRE(out_mode != 2 || p.phase_planes >= p.NCo, "conv_tc: %d chunk planes per phase < %d output chunks", p.phase_planes, p.NCo);
   // row-merged operand rows (see ConvTcParams::R): KH x 1 filters on materialised patches whose zero guard rows cover the time padding
   p.R = 1;
+  p.Rs = 1;
+  p.pt_in = pt;
   if (KW == 1 && KH / 2 <= pt && pt >= 1 && in_patch_stride_rows <= 0 && p.J == 1 && !x3 && pitch % 16 == 0 && out_mode != 2) {
     int R = 256 / pitch;
     while (R > 1 && (p.T_out % R)) --R;
     p.R = R;
     p.N = R * pitch;
+  } else if (KW == 1 && KH / 2 <= pt && pt >= 1 && in_patch_stride_rows <= 0 && p.J > 1 && !x3 && pitch % 16 == 0 && out_mode != 2 && 256 / pitch >= 2 &&
+             p.T_out >= 2 * p.J) {
+    p.R = 256 / pitch;
+    p.Rs = p.J;
+    p.N = p.R * pitch;
   }
   p.n_seg = 1;
   p.y_lo[0] = p.z_lo[0] = row0;

@@ -142,20 +142,28 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemm_tc_kernel(const GemmTcPara
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int st = 0;
-      uint32_t ph = 0;
-      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-        const GmUnit g = gm_decode(p, u);
-        for (int kc = g.kc0; kc < g.kc1; kc += kGmChunksPerStage) {
+    // the whole warp walks the loops: lane 0 waits on / arms the stage barrier, then 16 lanes issue the stage's 16 bulk copies at once
+    // (one thread needs ~170 clocks per copy for address arithmetic + issue: 16 copies per stage of 4 MMAs = 512 tensor-clocks made
+    // the single-thread producer the limiter of this kernel)
+    int st = 0;
+    uint32_t ph = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const GmUnit g = gm_decode(p, u);
+      for (int kc = g.kc0; kc < g.kc1; kc += kGmChunksPerStage) {
+        if (lane == 0) {
           gm_wait(&empty[st], ph ^ 1);
           gm_expect_tx(&full[st], (uint32_t)(kGmWBytes + kGmXBytes));
-          for (int c = 0; c < kGmChunksPerStage; ++c) {
-            gm_bulk(w_smem + st * kGmWBytes + c * (kGmTileN * 16), p.w + ((size_t)(kc + c) * p.Npad + g.n0) * 16, kGmTileN * 16, &full[st]);
-            gm_bulk(x_smem + st * kGmXBytes + c * (kGmTileM * 16), p.x + ((size_t)(kc + c) * p.Mpad + g.m0) * 16, kGmTileM * 16, &full[st]);
-          }
-          if (++st == kGmStages) { st = 0; ph ^= 1; }
         }
+        __syncwarp();
+        if (lane < 2 * kGmChunksPerStage) {
+          const int c = lane >> 1;
+          if (lane & 1)
+            gm_bulk(x_smem + st * kGmXBytes + c * (kGmTileM * 16), p.x + ((size_t)(kc + c) * p.Mpad + g.m0) * 16, kGmTileM * 16, &full[st]);
+          else
+            gm_bulk(w_smem + st * kGmWBytes + c * (kGmTileN * 16), p.w + ((size_t)(kc + c) * p.Npad + g.n0) * 16, kGmTileN * 16, &full[st]);
+        }
+        __syncwarp();
+        if (++st == kGmStages) { st = 0; ph ^= 1; }
       }
     }
     __syncwarp();

@@ -156,7 +156,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgradPara
 
   if (warp == 0) {
     // ===================================================== producer: g rows (ring, ascending t) and x row slabs
-    if (lane == 0) {
+    // the whole warp walks the (warp-uniform) loops; lane 0 waits on / arms the barriers, the copies of a ring slot (one per output
+    // chunk, plus its mirror) and of an x stage are issued by the lanes in parallel (one thread needs ~170 clocks per bulk copy)
+    {
       uint32_t n_row = 0;
       int xst = 0;
       uint32_t xph = 0;
@@ -170,23 +172,32 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgradPara
             const int t = t_new - k;
             const int pos = (int)(n_row % (uint32_t)S);
             const bool mirror = pos < p.RS - 1;
-            wg_mbar_wait(&g_empty[pos], ((n_row / (uint32_t)S) & 1u) ^ 1u);
-            wg_mbar_expect_tx(&g_full[pos], (uint32_t)(p.NCo * p.gslab_bytes) * (mirror ? 2u : 1u));
+            if (lane == 0) {
+              wg_mbar_wait(&g_empty[pos], ((n_row / (uint32_t)S) & 1u) ^ 1u);
+              wg_mbar_expect_tx(&g_full[pos], (uint32_t)(p.NCo * p.gslab_bytes) * (mirror ? 2u : 1u));
+            }
+            __syncwarp();
             uint8_t* dst = ring + (size_t)pos * p.slot_bytes;
             const bool inside = (t >= 0 && t < p.T);
-            for (int ck = 0; ck < p.NCo; ++ck) {
+            const int n_copies = p.NCo * (mirror ? 2 : 1);
+            for (int i = lane; i < n_copies; i += 32) {
+              const int ck = i % p.NCo, mir = i / p.NCo;
               const uint8_t* src = inside ? p.g + (long long)b * p.g_item_stride + (long long)ck * p.g_chunk_stride + (long long)t * p.P * 16
                                           : p.zero_row + (size_t)ck * p.gslab_bytes;
-              wg_bulk_g2s(dst + (size_t)ck * p.gslab_bytes, src, (uint32_t)p.gslab_bytes, &g_full[pos]);
-              if (mirror) wg_bulk_g2s(dst + (size_t)S * p.slot_bytes + (size_t)ck * p.gslab_bytes, src, (uint32_t)p.gslab_bytes, &g_full[pos]);
+              wg_bulk_g2s(dst + (mir ? (size_t)S * p.slot_bytes : 0) + (size_t)ck * p.gslab_bytes, src, (uint32_t)p.gslab_bytes, &g_full[pos]);
             }
+            __syncwarp();
           }
-          wg_mbar_wait(&x_empty[xst], xph ^ 1);
-          wg_mbar_expect_tx(&x_full[xst], (uint32_t)(it.nchunks * p.xslab_bytes));
+          if (lane == 0) {
+            wg_mbar_wait(&x_empty[xst], xph ^ 1);
+            wg_mbar_expect_tx(&x_full[xst], (uint32_t)(it.nchunks * p.xslab_bytes));
+          }
+          __syncwarp();
           const uint8_t* xsrc = p.x + (long long)b * p.x_item_stride + ((long long)s * p.P - p.pw) * 16;
-          for (int c = 0; c < it.nchunks; ++c)
+          for (int c = lane; c < it.nchunks; c += 32)
             wg_bulk_g2s(xs + (size_t)xst * p.xstage_bytes + (size_t)c * p.xslab_bytes, xsrc + (long long)(it.c0 + c) * p.x_chunk_stride,
                         (uint32_t)p.xslab_bytes, &x_full[xst]);
+          __syncwarp();
           if (++xst == kWgXStages) { xst = 0; xph ^= 1; }
         }
       }

@@ -130,6 +130,8 @@ def test_cp8_roundtrip_and_pool(ops, prec, dt):
     (2, 8, 16, 37, 108, 15, 15), (5, 32, 8, 18, 54, 9, 9),
     # KH x 1 filters with many input chunks: row-merged operand rows (R = 256 // pitch rows per MMA) and chunk-group activation stages
     (2, 384, 104, 75, 72, 3, 1), (3, 48, 128, 12, 40, 3, 1), (2, 136, 80, 10, 72, 1, 1), (2, 392, 128, 14, 72, 3, 1), (1, 16, 128, 7, 100, 3, 1),
+    # ... and with J > 1 row blocks (Cout <= 64): merged rows J apart, R * J output rows per unit (the DRCNN head's 120 -> 40 conv2)
+    (2, 120, 40, 75, 72, 3, 1), (3, 24, 16, 20, 40, 3, 1), (2, 64, 56, 11, 72, 3, 1), (5, 8, 32, 9, 24, 1, 1),
 ])
 def test_conv_tc(ops, cfg, prec, dt):
     """tcgen05 path vs an fp64 convolution of the SAME 16-bit-rounded operands: only fp32 accumulation order and the
