@@ -377,6 +377,33 @@ int mpa_pool3_bwd_dropout_cp8(const void* a_cp8, const void* g_out_cp8, void* g_
                               const long long* step_dev, unsigned long long step_mul, void* stream);
 int mpa_channel_sum_cp8(const void* g_cp8, float* out, int B, int C, int T, int F, int pitch, int pf, int pt, int fmt, int ncs,
                         void* stream);
+/* U-Net family, bf16 training mode, CP8-resident (train_unet_cp8.cu): the element-wise stages between two tensor-core convolutions of a
+ * training step on the 16-bit planes themselves.  Geometry arguments as mpa_nchw_to_cp8; every `ncs_*` is the chunk-plane stride per item
+ * of that buffer (0 = C/8; larger for a channel view of a concat buffer); C % 8 == 0; fmt = MPA_FMT_BF16 | MPA_FMT_F16.
+ *   mpa_bn_stats_cp8       stats[0..C) = batch mean, stats[C..2C) = biased batch variance of y (two-pass per slice + Chan merge in a fixed
+ *                          order); running_mean / running_var (optional) <- (1-m)*running + m*(mean | var*n/(n-1)), num_batches_tracked += 1:
+ *                          nn.BatchNorm2d in training mode (libdl/nn_models/unet_cnns.py:39,44 — double_conv's BatchNorm2d layers)
+ *   mpa_bn_relu_apply_cp8  out = max(0, (y - mean) * rsqrt(var + eps) * weight + bias)        (unet_cnns.py:39-41: BatchNorm2d -> ReLU)
+ *   mpa_bn_relu_bwd_cp8    the backward of that pair: g' = g * [out > 0] (out recomputed from y), g_bias = sum g', g_weight = sum g' * xhat,
+ *                          dy = weight * rstd * (g' - mean(g') - xhat * mean(g' * xhat)) written as CP8 (the operand of the preceding
+ *                          convolution's weight / data gradient), g_conv_bias (optional) = sum dy — what loss.backward() leaves in
+ *                          BatchNorm2d.weight.grad / .bias.grad and Conv2d.bias.grad
+ *   mpa_maxpool2x2_bwd_cp8 out = addend (optional) + MaxPool2d(2) backward of g_pool: the gradient goes to the first maximum of each 2x2 window
+ *                          in row-major order (ATen); `a` is the un-pooled activation, pooled level = (T/2, F/2)   (unet_cnns.py:60-61 `down`)
+ *   mpa_upsample2x_bwd_cp8 g_low = adjoint of mpa_upsample2x_cp8 (bilinear x2, align_corners=True, zero pad to (Ts, Fs)) applied to g_up
+ *                          (unet_cnns.py:83-101 `unet_up_concat_padding`) */
+int mpa_bn_stats_cp8(const void* y_cp8, float* stats, int B, int C, int T, int F, int pitch, int pf, int pt, int ncs, int fmt,
+                     float* running_mean, float* running_var, float momentum, long long* num_batches_tracked, void* stream);
+int mpa_bn_relu_apply_cp8(const void* y_cp8, void* out_cp8, const float* stats, const float* weight, const float* bias, float eps, int B,
+                          int C, int T, int F, int pitch, int pf, int pt, int ncs_y, int ncs_out, int fmt, void* stream);
+int mpa_bn_relu_bwd_cp8(const void* g_cp8, const void* y_cp8, void* dy_cp8, const float* stats, const float* weight, const float* bias,
+                        float eps, float* g_weight, float* g_bias, float* g_conv_bias, int B, int C, int T, int F, int pitch, int pf, int pt,
+                        int ncs_g, int ncs_y, int ncs_dy, int fmt, void* stream);
+int mpa_maxpool2x2_bwd_cp8(const void* a_cp8, const void* g_pool_cp8, const void* addend_cp8, void* out_cp8, int B, int C, int T, int F,
+                           int pitch, int pf, int pt, int ncs_a, int ncs_add, int ncs_out, int pitch_o, int pf_o, int pt_o, int ncs_gp,
+                           int fmt, void* stream);
+int mpa_upsample2x_bwd_cp8(const void* g_up_cp8, void* g_low_cp8, int B, int C, int Tl, int Fl, int pitch_l, int pf_l, int pt_l,
+                           int ncs_low, int Ts, int Fs, int pitch_s, int pf_s, int pt_s, int ncs_up, int fmt, void* stream);
 /* Same with offset = step_dev[0] * step_mul + site, the step counter read from DEVICE memory: a training step captured in a CUDA graph
  * (UnetTrainStep(graph=True)) then draws fresh masks on every replay, identical to the eager step of the same number. */
 int mpa_dropout_dev_f32(const float* x, float* out, long long n, float p, unsigned long long seed, unsigned long long site,

@@ -11,42 +11,12 @@
 // every row is loaded once: forward reads a and writes z, backward reads a and g and writes ga.  Measured (profiles/README.md): forward
 // 124 us, backward 230 us for 256 x 20 x 75 x 216 (the backward is bound by the compare / select arithmetic of the arg-max routing).
 #include "common.cuh"
+#include "cp8.cuh"
 
 namespace mpa {
 
 int channel_sum_cp8_launch(const uint4* g, float* out, int B, int C, int T, int F, int TP, int P, int pf, int pt, int ncs, int fmt,
                            cudaStream_t st);   // reduce.cu
-
-template <int FMT>
-__device__ __forceinline__ void unpack8(const uint4& u, float v[8]) {
-  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    if (FMT == MPA_FMT_BF16) {
-      v[2 * e] = __uint_as_float(w[e] << 16);
-      v[2 * e + 1] = __uint_as_float(w[e] & 0xFFFF0000u);
-    } else {
-      const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
-      v[2 * e] = f2.x;
-      v[2 * e + 1] = f2.y;
-    }
-  }
-}
-template <int FMT>
-__device__ __forceinline__ uint4 pack8(const float v[8]) {
-  uint32_t w[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    if (FMT == MPA_FMT_BF16) {
-      const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-      w[e] = *reinterpret_cast<const uint32_t*>(&h);
-    } else {
-      const __half2 h = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
-      w[e] = *reinterpret_cast<const uint32_t*>(&h);
-    }
-  }
-  return make_uint4(w[0], w[1], w[2], w[3]);
-}
 
 // Dropout keep factors of the 8 channels ck*8 .. ck*8+7 at the 4 pixels (t, 4q .. 4q+3): one Philox draw per channel (the 4 lanes of a
 // draw are the 4 neighbouring bins — F % 4 == 0 makes the NCHW element index of bin 4q a multiple of 4).  Padded channels (>= C) keep 1.

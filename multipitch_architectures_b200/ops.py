@@ -274,6 +274,50 @@ def upsample2x_cp8(low, out):
     return out
 
 
+# ---- U-Net training stages on the planes (train_unet_cp8.cu) -----------------------------------------
+def bn_stats_cp8(y, bn=None, update_running=True):
+    """[2C] fp32 = (batch mean | biased batch variance) of the CP8 tensor y; with `bn` (nn.BatchNorm2d, train mode) its running
+    statistics and num_batches_tracked are updated in the same launch pair."""
+    stats = torch.empty(2 * y.C, dtype=torch.float32, device=y.buf.device)
+    rm = rv = nbt = None
+    mom = 0.1
+    if bn is not None and update_running and bn.track_running_stats:
+        rm, rv, nbt = bn.running_mean, bn.running_var, bn.num_batches_tracked
+        mom = bn.momentum if bn.momentum is not None else 0.1
+    call('bn_stats_cp8', y.ptr(), stats, y.B, y.C, y.T, y.F, y.pitch, y.pf, y.pt, y.ncs, y.fmt, rm, rv, float(mom), nbt, stream_ptr())
+    return stats
+
+
+def bn_relu_apply_cp8(y, stats, bn, out):
+    assert (y.B, y.C, y.T, y.F, y.pitch, y.pf, y.pt) == (out.B, out.C, out.T, out.F, out.pitch, out.pf, out.pt)
+    call('bn_relu_apply_cp8', y.ptr(), out.ptr(), stats, bn.weight, bn.bias, float(bn.eps), y.B, y.C, y.T, y.F, y.pitch, y.pf, y.pt, y.ncs, out.ncs,
+         y.fmt, stream_ptr())
+    return out
+
+
+def bn_relu_bwd_cp8(g, y, stats, bn, dy, g_weight, g_bias, g_conv_bias=None):
+    """dy (CP8, written) = gradient wrt the BatchNorm input of relu(bn(y)) given g wrt its output; g_weight / g_bias / g_conv_bias overwritten."""
+    assert (y.B, y.C, y.T, y.F, y.pitch, y.pf, y.pt) == (g.B, g.C, g.T, g.F, g.pitch, g.pf, g.pt) == (dy.B, dy.C, dy.T, dy.F, dy.pitch, dy.pf, dy.pt)
+    call('bn_relu_bwd_cp8', g.ptr(), y.ptr(), dy.ptr(), stats, bn.weight, bn.bias, float(bn.eps), g_weight, g_bias, g_conv_bias, y.B, y.C, y.T, y.F,
+         y.pitch, y.pf, y.pt, g.ncs, y.ncs, dy.ncs, y.fmt, stream_ptr())
+    return dy
+
+
+def maxpool2x2_bwd_cp8(a, g_pool, addend, out):
+    """out = (addend or 0) + MaxPool2d(2) backward of g_pool through the un-pooled activation a."""
+    assert (g_pool.T, g_pool.F) == (a.T // 2, a.F // 2) and g_pool.C == a.C
+    call('maxpool2x2_bwd_cp8', a.ptr(), g_pool.ptr(), None if addend is None else addend.ptr(), out.ptr(), a.B, a.C, a.T, a.F, a.pitch, a.pf, a.pt,
+         a.ncs, 0 if addend is None else addend.ncs, out.ncs, g_pool.pitch, g_pool.pf, g_pool.pt, g_pool.ncs, a.fmt, stream_ptr())
+    return out
+
+
+def upsample2x_bwd_cp8(g_up, g_low):
+    """g_low (written) = adjoint of upsample2x_cp8 applied to the channel view g_up of the concat buffer's gradient."""
+    call('upsample2x_bwd_cp8', g_up.ptr(), g_low.ptr(), g_low.B, g_low.C, g_low.T, g_low.F, g_low.pitch, g_low.pf, g_low.pt, g_low.ncs, g_up.T,
+         g_up.F, g_up.pitch, g_up.pf, g_up.pt, g_up.ncs, g_low.fmt, stream_ptr())
+    return g_low
+
+
 def head_tail(x, w3, b3, w40, b40, w43, b43, a_lrelu):
     """x: compact CP8 [B][NC1][T][Fo][8] -> [B,Fo] fp32; conv3 (T x 1) + LReLU + 1x1 + LReLU + 1x1 + sigmoid in one kernel."""
     C2, C3 = w3.shape[0], w40.shape[0]

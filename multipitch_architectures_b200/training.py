@@ -198,9 +198,21 @@ class TcConv:
     @staticmethod
     def _pad8(v, n):
         """bias (or zeros) padded to n entries: the padded output channels of a block carry zero weights and zero bias."""
+        if v.numel() == n:
+            return v.detach()
         out = torch.zeros(n, dtype=torch.float32, device=v.device)
         out[:v.numel()] = v.detach()
         return out
+
+    _zeros = {}
+
+    @classmethod
+    def _zero_bias(cls, dev):
+        """128 fp32 zeros (the bias operand of a data-gradient convolution), allocated once per device."""
+        z = cls._zeros.get(str(dev))
+        if z is None:
+            z = cls._zeros[str(dev)] = torch.zeros(128, dtype=torch.float32, device=dev)
+        return z
 
     @classmethod
     def forward(cls, tag, conv, x, act, a):
@@ -247,7 +259,7 @@ class TcConv:
         if not need_dx:
             return None
         gxc = cls._buf(tag + ':gx', B, Cin, T, F, dev, fmt)
-        zb = torch.zeros(128, dtype=torch.float32, device=dev)
+        zb = cls._zero_bias(dev)
         for c0 in range(0, Cin, 128):
             c = min(128, Cin - c0)
             cp = (c + 7) // 8 * 8
@@ -291,7 +303,7 @@ def _tc_s3_backward(tag, conv, xc, g, gw, gb, keep_cp8=False):
     ops.conv_wgrad_tc(xc, gc, gw, (3, 3))
     ops.channel_sum(g, out=gb)
     gxc = TcConv._buf(tag + ':gx', B, Cin, T, F, g.device, fmt)
-    zb = torch.zeros(128, dtype=torch.float32, device=g.device)
+    zb = TcConv._zero_bias(g.device)
     for c0 in range(0, Cin, 128):
         c = min(128, Cin - c0)
         cp = (c + 7) // 8 * 8

@@ -160,6 +160,98 @@ class Tape:
         self.push(bwd)
         return out
 
+    # ---------------------------------------------------------------------------------------------- CP8-resident stages (bf16)
+    # Nodes whose .d / .g are ops.CP8 planes: between two tensor-core convolutions nothing leaves the 16-bit planes (train_unet_cp8.cu).
+    # Every such node has ONE consumer, except the skip connections (max-pool + concat), whose two gradients meet in maxpool_cp8's backward.
+    def conv_cp8(self, name, conv, x, need_dx=True):
+        """Conv2d (+ bias) on the planes -> the raw (pre-BatchNorm) output; the bias gradient is left to the BatchNorm backward."""
+        out = Node(TcConv.forward_cp8(name, conv, x.d, ops.ACT_NONE, 0.0))
+
+        def bwd():
+            gx = TcConv.backward_cp8(name, conv, x.d, out.g, self.grads[name + '.weight'], None, need_dx)
+            if need_dx:
+                x.g = gx
+        self.push(bwd)
+        return out
+
+    def bn_relu_cp8(self, name, bn, y, dst, conv_bias_name):
+        """BatchNorm2d (train mode, running statistics updated) + ReLU on the planes, written into `dst` (a buffer or a channel view of a
+        concat buffer)."""
+        stats = ops.bn_stats_cp8(y.d, bn)
+        out = Node(ops.bn_relu_apply_cp8(y.d, stats, bn, dst))
+
+        def bwd():
+            yc = y.d
+            dy = TcConv._buf(name + ':dy', yc.B, yc.C, yc.T, yc.F, yc.buf.device, yc.fmt)
+            y.g = ops.bn_relu_bwd_cp8(out.g, yc, stats, bn, dy, self.grads[name + '.weight'], self.grads[name + '.bias'],
+                                        self.grads[conv_bias_name])
+        self.push(bwd)
+        return out
+
+    def double_conv_cp8(self, name, dc, x, dst=None, need_dx=True):
+        seq = dc.double_conv
+        n0, n1, n4, n5 = (f'{name}.double_conv.{i}' for i in (0, 1, 4, 5))
+        xc = x.d
+        mid = TcConv._buf(n1 + ':a', xc.B, seq[0].weight.shape[0], xc.T, xc.F, xc.buf.device, xc.fmt)
+        a1 = self.bn_relu_cp8(n1, seq[1], self.conv_cp8(n0, seq[0], x, need_dx), mid, n0 + '.bias')
+        if dst is None:
+            dst = TcConv._buf(n5 + ':a', xc.B, seq[4].weight.shape[0], xc.T, xc.F, xc.buf.device, xc.fmt)
+        return self.bn_relu_cp8(n5, seq[5], self.conv_cp8(n4, seq[4], a1), dst, n4 + '.bias')
+
+    def maxpool_cp8(self, tag, x):
+        xc = x.d
+        out = Node(ops.maxpool2x2_cp8(xc, TcConv._buf(tag + ':pool', xc.B, xc.C, xc.T // 2, xc.F // 2, xc.buf.device, xc.fmt)))
+
+        def bwd():
+            # x.g: the gradient the skip connection already delivered (decoder side runs first in the backward), or None
+            x.g = ops.maxpool2x2_bwd_cp8(xc, out.g, x.g, TcConv._buf(tag + ':gpool', xc.B, xc.C, xc.T, xc.F, xc.buf.device, xc.fmt))
+        self.push(bwd)
+        return out
+
+    def upcat_cp8(self, tag, low, skip, cat, c_skip):
+        """`skip` already sits in channels [0, c_skip) of `cat`; the bilinear x2 up-sampling of `low` fills the rest."""
+        lc = low.d
+        ops.upsample2x_cp8(lc, cat.channels(c_skip, lc.C))
+        out = Node(cat)
+
+        def bwd():
+            g = out.g
+            skip.g = g.channels(0, c_skip)
+            low.g = ops.upsample2x_bwd_cp8(g.channels(c_skip, lc.C), TcConv._buf(tag + ':glow', lc.B, lc.C, lc.T, lc.F, lc.buf.device, lc.fmt))
+        self.push(bwd)
+        return out
+
+    def cp8_to_f32(self, tag, x):
+        """planes -> fp32 NCHW node (the encoder layers and the 72-bin head stay fp32)."""
+        xc = x.d
+        out = Node(ops.cp8_to_nchw(xc))
+
+        def bwd():
+            x.g = ops.nchw_to_cp8(out.g, out=TcConv._buf(tag + ':g16', xc.B, xc.C, xc.T, xc.F, xc.buf.device, xc.fmt), fmt=xc.fmt)
+        self.push(bwd)
+        return out
+
+    def f32_to_cp8(self, tag, x, fmt):
+        B, C, T, F = x.d.shape
+        out = Node(ops.nchw_to_cp8(x.d, out=TcConv._buf(tag + ':x16', B, C, T, F, x.d.device, fmt), fmt=fmt))
+
+        def bwd():
+            x.acc(ops.cp8_to_nchw(out.g))
+        self.push(bwd)
+        return out
+
+    def head_conv2_cp8(self, name, conv, u, k, a):
+        """Head conv2 (3x3, stride (1,3)) on the planes -> LeakyReLU -> MaxPool((k,1)) in fp32 NCHW (72 bins)."""
+        y, xc = _tc_s3_forward(name, conv, u.d, ops.ACT_LRELU, a)
+        act = Node(y)
+        out = Node(ops.maxpool_time(act.d, k))
+
+        def bwd():
+            g = _pool_bwd(act.d, out.g, k, ops.ACT_LRELU, a)
+            u.g = _tc_s3_backward(name, conv, xc, g, self.grads[name + '.weight'], self.grads[name + '.bias'], keep_cp8=True)
+        self.push(bwd)
+        return out
+
     # ---------------------------------------------------------------------------------------------- encoder layer
     def encoder_layer(self, name, layer, x, p_drop):
         """transformer_enc_layer.forward (unet_cnns.py:148-159) on [B,E,Th,Fw]; tokens are rows (b*S+s) of [B*S, E]."""
@@ -356,8 +448,68 @@ class Tape:
         return out
 
 
+CP8_TAPE = True            # test knob: False = the fp32 NCHW tape with converters around every tensor-core convolution
+
+
+def cp8_tape_eligible(model, x):
+    """bf16 U-Net / SAUnet whose every double_conv convolution runs on the tensor cores with whole channel chunks: the training step keeps
+    activations and gradients on the CP8 planes between the convolutions."""
+    if not CP8_TAPE or getattr(model, 'precision', 'fp32') != 'bf16':
+        return False
+    if hasattr(model, 'convP') or hasattr(model, 'attention3') or getattr(model, 'lstm_depth', 0) > 0:
+        return False
+    T, F = x.shape[2], x.shape[3]
+    geo = _exec.level_geometry(T, F)
+    blocks = [(model.inc, 0)] + [(getattr(model, f'down{i}')[1], i) for i in (1, 2, 3, 4)] + \
+             [(getattr(model, f'upconv{i + 1}'), lv) for i, lv in enumerate((3, 2, 1, 0))]
+    for dc, lv in blocks:
+        Tl, Fl, _ = geo[lv]
+        for conv in (dc.double_conv[0], dc.double_conv[4]):
+            if not (TcConv.eligible(model, conv, Fl) and Tl >= 2 and conv.weight.shape[0] % 8 == 0):
+                return False
+    return geo[4][0] >= 1 and _tc_s3_eligible(model, model.conv2[0], F) and model.conv2[0].weight.shape[1] % 8 == 0
+
+
+def _unet_train_forward_cp8(model, x, grads, seed, step):
+    """The CP8-resident tape: LayerNorm -> planes -> [conv -> BN stats -> BN+ReLU]* with max-pool / up-sampling / concat on the planes ->
+    (encoder layers in fp32 tokens) -> head conv2 on the planes -> fp32 72-bin head."""
+    a, p = model.a_lrelu, (model.p_dropout if model.training else 0.0)
+    fmt = ops.FMT_BF16
+    tp = Tape(grads, seed, step, model)
+    B, C, T, F = x.shape
+    dev = x.device
+    geo = _exec.level_geometry(T, F)
+    c = [model.inc.double_conv[4].weight.shape[0]] + [getattr(model, f'down{i}')[1].double_conv[4].weight.shape[0] for i in (1, 2, 3, 4)]
+    up_out = [getattr(model, f'upconv{i}').double_conv[4].weight.shape[0] for i in (1, 2, 3, 4)]
+    buf = lambda tag, lv, ch: TcConv._buf(tag, B, ch, geo[lv][0], geo[lv][1], dev, fmt)
+    z = tp.f32_to_cp8('inc.in', tp.layernorm_cf(model.layernorm, x), fmt)
+    cat = {3: buf('cat3', 3, c[3] + c[4]), 2: buf('cat2', 2, c[2] + up_out[0]), 1: buf('cat1', 1, c[1] + up_out[1]),
+           0: buf('cat0', 0, c[0] + up_out[2])}
+    xs = [tp.double_conv_cp8('inc', model.inc, z, cat[0].channels(0, c[0]))]
+    for lv in (1, 2, 3, 4):
+        dst = cat[lv].channels(0, c[lv]) if lv < 4 else None
+        xs.append(tp.double_conv_cp8(f'down{lv}.1', getattr(model, f'down{lv}')[1], tp.maxpool_cp8(f'down{lv}', xs[-1]), dst))
+    x5 = xs[4]
+    if hasattr(model, 'attention1'):
+        t5 = tp.cp8_to_f32('x5', x5)
+        for nm in ('attention1', 'attention2'):
+            layer = getattr(model, nm)
+            t5 = tp.encoder_layer(nm, layer, t5, layer.p_dropout if model.training else 0.0)
+        x5 = tp.f32_to_cp8('x5a', t5, fmt)
+    u = x5
+    for i, lv in enumerate((3, 2, 1, 0)):
+        u = tp.double_conv_cp8(f'upconv{i + 1}', getattr(model, f'upconv{i + 1}'), tp.upcat_cp8(f'up{i + 1}', u, xs[lv], cat[lv], c[lv]))
+    h = tp.dropout(tp.head_conv2_cp8('conv2.0', model.conv2[0], u, 13, a), p)
+    h = tp.dropout(tp.conv('conv3.0', model.conv3[0], h, ops.ACT_LRELU, a), p)
+    h = tp.dropout(tp.conv('conv4.0', model.conv4[0], h, ops.ACT_LRELU, a), p)
+    y = tp.conv('conv4.3', model.conv4[3], h, ops.ACT_SIGMOID)
+    return y, None, tp
+
+
 def unet_train_forward(model, x, grads, seed=0, step=0):
     """-> (y_pred [B,1,T-74,72], n_pred or None, tape).  Train mode: BatchNorm batch statistics, dropout when p > 0."""
+    if cp8_tape_eligible(model, x):
+        return _unet_train_forward_cp8(model, x, grads, seed, step)
     a, p = model.a_lrelu, (model.p_dropout if model.training else 0.0)
     tp = Tape(grads, seed, step, model)
     z = tp.layernorm_cf(model.layernorm, x)
