@@ -404,6 +404,35 @@ int mpa_maxpool2x2_bwd_cp8(const void* a_cp8, const void* g_pool_cp8, const void
                            int fmt, void* stream);
 int mpa_upsample2x_bwd_cp8(const void* g_up_cp8, void* g_low_cp8, int B, int C, int Tl, int Fl, int pitch_l, int pf_l, int pt_l,
                            int ncs_low, int Ts, int Fs, int pitch_s, int pf_s, int pt_s, int ncs_up, int fmt, void* stream);
+/* Training path of the attention half of transformer_enc_layer (libdl/nn_models/unet_cnns.py:131-153: q/k/v Linear -> nn.MultiheadAttention over
+ * the BATCH axis -> o Linear -> Dropout -> add -> LayerNorm1), fp32, one CTA per bottleneck position (enc_train.cu).
+ *   mpa_enc_fold_f32        w_qkv [3E,E] (+ transpose w_qkvT [E,3E]) = in_proj_weight_z . {q,k,v}_linear.weight, w_proj [E,E] (+ w_projT) =
+ *                           o_linear.weight . out_proj.weight, b_proj = o_linear.weight . out_proj.bias  — one launch
+ *   mpa_enc_fold_bwd_f32    the chain rule through that fold: from d w_qkv / d w_proj / d b_proj to the gradients of the reference's seven
+ *                           parameters (all overwritten) — one launch
+ *   mpa_enc_attn_train_fwd_f32  x [B,E,S] (NCHW bottleneck) -> t = Dropout(tokens + PE) (only behind a positional encoding, as the reference),
+ *                           qkv, att, u1 = t + Dropout(att W_proj^T + b_proj), h1 = LayerNorm1(u1); all [B*S, .] token-major, saved for the backward.
+ *                           Dropout sites: element index of the [B*S,E] matrix, offset = site (+ step_dev[0] * step_mul), as mpa_dropout_f32.
+ *   mpa_enc_attn_train_bwd_f32  g_h1 -> g_x [B,E,S] (overwritten), g_p (gradient wrt the projection output) and g_qkv for the weight-gradient
+ *                           GEMMs, LayerNorm1 parameter gradients (overwritten)
+ *   mpa_enc_train_supported 1 when the shape fits (E % 32 == 0, E <= 128, head dim <= 16, the B x E tiles of one position in shared memory) */
+int mpa_enc_train_supported(int B, int E, int num_heads);
+int mpa_enc_fold_f32(const float* in_proj_weight, const float* wq, const float* wk, const float* wv, const float* wo,
+                     const float* out_proj_weight, const float* out_proj_bias, float* w_qkv, float* w_qkvT, float* w_proj, float* w_projT,
+                     float* b_proj, int E, void* stream);
+int mpa_enc_fold_bwd_f32(const float* d_w_qkv, const float* d_w_proj, const float* d_b_proj, const float* in_proj_weight, const float* wq,
+                         const float* wk, const float* wv, const float* wo, const float* out_proj_weight, const float* out_proj_bias,
+                         float* g_in_proj_weight, float* g_wq, float* g_wk, float* g_wv, float* g_wo, float* g_out_proj_weight,
+                         float* g_out_proj_bias, int E, void* stream);
+int mpa_enc_attn_train_fwd_f32(const float* x, const float* pe, const float* w_qkvT, const float* b_qkv, const float* w_projT,
+                               const float* b_proj, const float* ln_w, const float* ln_b, float eps, float* t, float* qkv, float* att,
+                               float* u1, float* h1, int B, int E, int S, int num_heads, float p_drop, unsigned long long seed,
+                               unsigned long long site_tok, unsigned long long site_att, const long long* step_dev,
+                               unsigned long long step_mul, void* stream);
+int mpa_enc_attn_train_bwd_f32(const float* g_h1, const float* u1, const float* qkv, const float* w_qkv, const float* w_proj,
+                               const float* ln_w, float eps, float* g_p, float* g_qkv, float* g_x, float* g_ln_w, float* g_ln_b, int B, int E,
+                               int S, int num_heads, int has_pe, float p_drop, unsigned long long seed, unsigned long long site_tok,
+                               unsigned long long site_att, const long long* step_dev, unsigned long long step_mul, void* stream);
 /* Same with offset = step_dev[0] * step_mul + site, the step counter read from DEVICE memory: a training step captured in a CUDA graph
  * (UnetTrainStep(graph=True)) then draws fresh masks on every replay, identical to the eager step of the same number. */
 int mpa_dropout_dev_f32(const float* x, float* out, long long n, float p, unsigned long long seed, unsigned long long site,

@@ -19,7 +19,7 @@ import torch
 from . import _lib, ops
 from ._lib import call, stream_ptr
 from .libdl.nn_models import _exec
-from .training import (TcConv, _act_bwd, _add, _conv_fwd, _dgrad, _dropout, _pool_bwd, _tc_s3_backward, _tc_s3_eligible, _tc_s3_forward,
+from .training import (TcConv, ctypes_u64, _act_bwd, _add, _conv_fwd, _dgrad, _dropout, _pool_bwd, _tc_s3_backward, _tc_s3_eligible, _tc_s3_forward,
                        _wgrad)
 
 
@@ -253,6 +253,52 @@ class Tape:
         return out
 
     # ---------------------------------------------------------------------------------------------- encoder layer
+    def _enc_attn_fused(self, name, layer, x, p_drop, pe, gemm, colsum):
+        """Attention half of the layer in one launch per direction (enc_train.cu): gather + PE + dropout + folded q/k/v + batch-axis attention
+        + folded out-projection + dropout + residual + LayerNorm1, one CTA per bottleneck position; the parameter folds and their chain rule
+        are one launch each.  Only the weight gradients (reductions over all B*S tokens) remain GEMM launches."""
+        B, E, Th, Fw = x.d.shape
+        S, H, dev = Th * Fw, layer.num_heads, x.d.device
+        M = B * S
+        at = layer.attn
+        G = self.grads
+        f32 = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
+        params = (at.in_proj_weight, layer.q_linear.weight, layer.k_linear.weight, layer.v_linear.weight, layer.o_linear.weight, at.out_proj.weight,
+                  at.out_proj.bias)
+        w_qkv, w_qkvT, w_proj, w_projT, b_proj = f32(3 * E, E), f32(E, 3 * E), f32(E, E), f32(E, E), f32(E)
+        call('enc_fold_f32', *params, w_qkv, w_qkvT, w_proj, w_projT, b_proj, E, stream_ptr())
+        site_tok = site_att = 0
+        if p_drop > 0.0:
+            if pe is not None:
+                self.site += 1
+                site_tok = self.site
+            self.site += 1
+            site_att = self.site
+        from . import training as T
+        sd, sm = T._step_dev, ctypes_u64(T._step_mul if T._step_dev is not None else 0)
+        t, qkv, att, u1, h1 = f32(M, E), f32(M, 3 * E), f32(M, E), f32(M, E), f32(M, E)
+        call('enc_attn_train_fwd_f32', x.d, pe, w_qkvT, at.in_proj_bias, w_projT, b_proj, layer.layernorm1.weight, layer.layernorm1.bias,
+             float(layer.layernorm1.eps), t, qkv, att, u1, h1, B, E, S, H, float(p_drop), ctypes_u64(self.seed), ctypes_u64(site_tok),
+             ctypes_u64(site_att), sd, sm, stream_ptr())
+        h1 = Node(h1)
+
+        def bwd():
+            g_p, g_qkv, g_x = f32(M, E), f32(M, 3 * E), f32(B, E, Th, Fw)
+            sd_b, sm_b = T._step_dev, ctypes_u64(T._step_mul if T._step_dev is not None else 0)
+            call('enc_attn_train_bwd_f32', h1.g, u1, qkv, w_qkv, w_proj, layer.layernorm1.weight, float(layer.layernorm1.eps), g_p, g_qkv, g_x,
+                 G[name + '.layernorm1.weight'], G[name + '.layernorm1.bias'], B, E, S, H, int(pe is not None), float(p_drop),
+                 ctypes_u64(self.seed), ctypes_u64(site_tok), ctypes_u64(site_att), sd_b, sm_b, stream_ptr())
+            x.acc(g_x)
+            dWp = gemm(g_p, att, E, E, M, 1)                        # [E,E] = g_p^T att
+            dbp = colsum(g_p, M, E)
+            dWf = gemm(g_qkv, t, 3 * E, E, M, 1)                    # [3E,E] = g_qkv^T t
+            colsum(g_qkv, M, 3 * E, out=G[name + '.attn.in_proj_bias'])
+            call('enc_fold_bwd_f32', dWf, dWp, dbp, *params, G[name + '.attn.in_proj_weight'], G[name + '.q_linear.weight'],
+                 G[name + '.k_linear.weight'], G[name + '.v_linear.weight'], G[name + '.o_linear.weight'], G[name + '.attn.out_proj.weight'],
+                 G[name + '.attn.out_proj.bias'], E, stream_ptr())
+        self.push(bwd)
+        return h1
+
     def encoder_layer(self, name, layer, x, p_drop):
         """transformer_enc_layer.forward (unet_cnns.py:148-159) on [B,E,Th,Fw]; tokens are rows (b*S+s) of [B*S, E]."""
         B, E, Th, Fw = x.d.shape
@@ -278,68 +324,71 @@ class Tape:
             out = f32(Nn) if out is None else out
             call('colsum_f32', A, out, Mm, Nn, stream_ptr())
             return out
-        # folded projections (one-off E x E products of parameters)
-        w_qkv = f32(3 * E, E)
-        for i, Wx in enumerate((Wq, Wk, Wv)):
-            gemm(Wi[i * E:(i + 1) * E], Wx, E, E, E, 0, out=w_qkv[i * E:(i + 1) * E])
-        w_proj = gemm(Wo, Wout, E, E, E, 0)
-        b_proj = gemm(Wo, bout, E, 1, E, 0).reshape(E)
-
         G = self.grads
         pe = _exec.sinusoidal_pe(S, E, dev).contiguous() if layer.pos_encoding == 'sinusoidal' else None
         W1, b1, W2, b2 = layer.mlp[0].weight, layer.mlp[0].bias, layer.mlp[2].weight, layer.mlp[2].bias
         Dm = W1.shape[0]
-        # Closures are pushed in forward order (the tape runs them in reverse); they only dereference nodes when they run.
-        tok0 = f32(M, E)
-        call('enc_gather_f32', x.d, pe, tok0, B, E, S, stream_ptr())
-        tok = Node(tok0)
-        self.push(lambda: x.acc(self._tok_to_nchw(tok.g, B, E, S, Th, Fw)))
-        t = self.dropout(tok, p_drop) if pe is not None else tok
+        if ENC_FUSED and _lib.lib().mpa_enc_train_supported(B, E, H):
+            h1 = self._enc_attn_fused(name, layer, x, p_drop, pe, gemm, colsum)
+        else:
+            # folded projections (one-off E x E products of parameters)
+            w_qkv = f32(3 * E, E)
+            for i, Wx in enumerate((Wq, Wk, Wv)):
+                gemm(Wi[i * E:(i + 1) * E], Wx, E, E, E, 0, out=w_qkv[i * E:(i + 1) * E])
+            w_proj = gemm(Wo, Wout, E, E, E, 0)
+            b_proj = gemm(Wo, bout, E, 1, E, 0).reshape(E)
 
-        # -- attention branch: qkv -> batch-axis attention -> folded out_proj . o_linear
-        qkv = Node(gemm_nt(t.d, w_qkv, bi, M, 3 * E, E))
-        att = f32(M, E)
-        call('batch_axis_attention_f32', qkv.d, att, B, S, E, H, stream_ptr())
-        att = Node(att)
-        proj = Node(gemm_nt(att.d, w_proj, b_proj, M, E, E))
+            # Closures are pushed in forward order (the tape runs them in reverse); they only dereference nodes when they run.
+            tok0 = f32(M, E)
+            call('enc_gather_f32', x.d, pe, tok0, B, E, S, stream_ptr())
+            tok = Node(tok0)
+            self.push(lambda: x.acc(self._tok_to_nchw(tok.g, B, E, S, Th, Fw)))
+            t = self.dropout(tok, p_drop) if pe is not None else tok
 
-        def bwd_attn():
-            g_p = proj.g
-            dWp = gemm(g_p, att.d, E, E, M, 1)                      # [E,E] = g_p^T att
-            dbp = colsum(g_p, M, E)
-            # w_proj = Wo @ Wout, b_proj = Wo @ bout
-            call('gemm_nt_f32', dWp, Wout, None, G[name + '.o_linear.weight'], E, E, E, 0, stream_ptr())          # dWp @ Wout^T
-            gemm(dbp, bout, E, E, 1, 0, out=G[name + '.o_linear.weight'], accumulate=1)                           # + dbp bout^T
-            gemm(Wo, dWp, E, E, E, 1, out=G[name + '.attn.out_proj.weight'])                                       # Wo^T dWp
-            gemm(Wo, dbp, E, 1, E, 1, out=G[name + '.attn.out_proj.bias'])                                         # Wo^T dbp
-            g_att = gemm(g_p, w_proj, M, E, E, 0)
-            g_qkv = f32(M, 3 * E)
-            call('batch_axis_attention_bwd_f32', qkv.d, g_att, g_qkv, B, S, E, H, stream_ptr())
-            dWf = gemm(g_qkv, t.d, 3 * E, E, M, 1)                  # [3E,E]
-            colsum(g_qkv, M, 3 * E, out=G[name + '.attn.in_proj_bias'])
-            gWi = G[name + '.attn.in_proj_weight']
-            for i, (Wx, nm) in enumerate(((Wq, 'q'), (Wk, 'k'), (Wv, 'v'))):
-                blk = dWf[i * E:(i + 1) * E]
-                call('gemm_nt_f32', blk, Wx, None, gWi[i * E:(i + 1) * E], E, E, E, 0, stream_ptr())            # dWf_i @ Wx^T
-                gemm(Wi[i * E:(i + 1) * E], blk, E, E, E, 1, out=G[f'{name}.{nm}_linear.weight'])                 # Wi_i^T dWf_i
-            t.acc(gemm(g_qkv, w_qkv, M, E, 3 * E, 0))
-        self.push(bwd_attn)
-        d1 = self.dropout(proj, p_drop)
+            # -- attention branch: qkv -> batch-axis attention -> folded out_proj . o_linear
+            qkv = Node(gemm_nt(t.d, w_qkv, bi, M, 3 * E, E))
+            att = f32(M, E)
+            call('batch_axis_attention_f32', qkv.d, att, B, S, E, H, stream_ptr())
+            att = Node(att)
+            proj = Node(gemm_nt(att.d, w_proj, b_proj, M, E, E))
 
-        # -- add & LayerNorm 1
-        u1 = _add(t.d, d1.d)
-        h1 = f32(M, E)
-        call('add_layernorm_tok_f32', t.d, d1.d, layer.layernorm1.weight, layer.layernorm1.bias, h1, None, _lib.i64(M), E, S,
-             float(layer.layernorm1.eps), stream_ptr())
-        h1 = Node(h1)
+            def bwd_attn():
+                g_p = proj.g
+                dWp = gemm(g_p, att.d, E, E, M, 1)                      # [E,E] = g_p^T att
+                dbp = colsum(g_p, M, E)
+                # w_proj = Wo @ Wout, b_proj = Wo @ bout
+                call('gemm_nt_f32', dWp, Wout, None, G[name + '.o_linear.weight'], E, E, E, 0, stream_ptr())          # dWp @ Wout^T
+                gemm(dbp, bout, E, E, 1, 0, out=G[name + '.o_linear.weight'], accumulate=1)                           # + dbp bout^T
+                gemm(Wo, dWp, E, E, E, 1, out=G[name + '.attn.out_proj.weight'])                                       # Wo^T dWp
+                gemm(Wo, dbp, E, 1, E, 1, out=G[name + '.attn.out_proj.bias'])                                         # Wo^T dbp
+                g_att = gemm(g_p, w_proj, M, E, E, 0)
+                g_qkv = f32(M, 3 * E)
+                call('batch_axis_attention_bwd_f32', qkv.d, g_att, g_qkv, B, S, E, H, stream_ptr())
+                dWf = gemm(g_qkv, t.d, 3 * E, E, M, 1)                  # [3E,E]
+                colsum(g_qkv, M, 3 * E, out=G[name + '.attn.in_proj_bias'])
+                gWi = G[name + '.attn.in_proj_weight']
+                for i, (Wx, nm) in enumerate(((Wq, 'q'), (Wk, 'k'), (Wv, 'v'))):
+                    blk = dWf[i * E:(i + 1) * E]
+                    call('gemm_nt_f32', blk, Wx, None, gWi[i * E:(i + 1) * E], E, E, E, 0, stream_ptr())            # dWf_i @ Wx^T
+                    gemm(Wi[i * E:(i + 1) * E], blk, E, E, E, 1, out=G[f'{name}.{nm}_linear.weight'])                 # Wi_i^T dWf_i
+                t.acc(gemm(g_qkv, w_qkv, M, E, 3 * E, 0))
+            self.push(bwd_attn)
+            d1 = self.dropout(proj, p_drop)
 
-        def bwd_ln1():
-            g_u1 = f32(M, E)
-            call('layernorm_tok_bwd_f32', u1, h1.g, layer.layernorm1.weight, g_u1, G[name + '.layernorm1.weight'],
-                 G[name + '.layernorm1.bias'], _lib.i64(M), E, float(layer.layernorm1.eps), stream_ptr())
-            t.acc(g_u1)
-            d1.acc(g_u1)
-        self.push(bwd_ln1)
+            # -- add & LayerNorm 1
+            u1 = _add(t.d, d1.d)
+            h1 = f32(M, E)
+            call('add_layernorm_tok_f32', t.d, d1.d, layer.layernorm1.weight, layer.layernorm1.bias, h1, None, _lib.i64(M), E, S,
+                 float(layer.layernorm1.eps), stream_ptr())
+            h1 = Node(h1)
+
+            def bwd_ln1():
+                g_u1 = f32(M, E)
+                call('layernorm_tok_bwd_f32', u1, h1.g, layer.layernorm1.weight, g_u1, G[name + '.layernorm1.weight'],
+                     G[name + '.layernorm1.bias'], _lib.i64(M), E, float(layer.layernorm1.eps), stream_ptr())
+                t.acc(g_u1)
+                d1.acc(g_u1)
+            self.push(bwd_ln1)
 
         # -- MLP
         if self.model is not None and getattr(self.model, 'precision', 'fp32') == 'bf16':
@@ -448,6 +497,7 @@ class Tape:
         return out
 
 
+ENC_FUSED = True           # test knob: False = the attention half of an encoder layer as separate GEMM / attention / LayerNorm launches
 CP8_TAPE = True            # test knob: False = the fp32 NCHW tape with converters around every tensor-core convolution
 
 

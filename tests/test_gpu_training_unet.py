@@ -396,3 +396,38 @@ def test_saunet_l_bf16_training_run_follows_the_fp32_run():
     assert np.abs(sm(a) - sm(b)).max() < 0.15 * sm(a).max()           # steep first steps: observed 0.02-0.028 of 0.285
     assert abs(a[-12:].mean() - b[-12:].mean()) < 0.04 * a[-12:].mean()   # plateau: observed 0.162 vs 0.159
     assert abs(a[0] - b[0]) < 2e-3 * a[0]
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_fused_attention_half_equals_the_stage_by_stage_path(precision):
+    """enc_train.cu (one CTA per bottleneck position; fold / fold-backward in one launch each) against the separate GEMM / attention /
+    LayerNorm launches, dropout ON (p = 0.2, same Philox sites): loss and every gradient agree to fp32 summation-order noise."""
+    from multipitch_architectures_b200 import training_unet
+    from multipitch_architectures_b200.libdl import nn_models as M
+    res = {}
+    for fused in (True, False):
+        m = M.simple_u_net_doubleselfattn(n_chan_input=6, n_chan_layers=[16, 10, 8, 5], n_bins_in=216, n_bins_out=72, scalefac=8, embed_dim=64,
+                                          num_heads=8, mlp_dim=128, pos_encoding='sinusoidal', precision=precision)
+        m.load_state_dict(fill_state_dict(m.state_dict(), 11, scheme='torch_default'))
+        m = m.cuda().train()
+        x, t = synth_patches(5, 11).cuda(), synth_targets(5, 11).cuda()
+        old = training_unet.ENC_FUSED
+        training_unet.ENC_FUSED = fused
+        try:
+            m._train_calls = 0
+            y = m(x)
+            loss = torch.nn.BCELoss(reduction='mean')(y, t)
+            loss.backward()
+        finally:
+            training_unet.ENC_FUSED = old
+        res[fused] = (loss.item(), y.detach().cpu().numpy(), {k: p.grad.cpu().numpy() for k, p in m.named_parameters()})
+    (la, ya, ga), (lb, yb, gb) = res[True], res[False]
+    tol = 1e-5 if precision == 'fp32' else 2e-3        # bf16: the MLP GEMMs round their (slightly different) inputs to 16 bits
+    assert abs(la - lb) < tol * abs(lb) and np.abs(ya - yb).max() < 10 * tol
+    cos, worst = _cosines(ga, gb)
+    print(f'fused vs staged ({precision}): gradient cosine {cos:.7f}, worst tensor {worst[1]} {worst[0]:.6f}')
+    assert cos > (0.99999 if precision == 'fp32' else 0.999) and worst[0] > (0.9999 if precision == 'fp32' else 0.99)
+    if precision == 'fp32':
+        for k in ga:
+            if 'attention' in k:
+                assert np.abs(ga[k] - gb[k]).max() < 1e-4 * max(np.abs(gb[k]).max(), 1e-6) + 1e-7, k
