@@ -459,6 +459,19 @@ size_t mpa_gemm_tc_chunked_bytes(int rows, int K, int row_tile);
 int mpa_gemm_tc_to_chunks(const float* x_rows, void* out_chunks, int rows, int K, int row_tile, int fmt, int transposed, void* stream);
 int mpa_gemm_tc_f16(const void* x_chunks, const void* w_chunks, const float* bias, float* y, int M, int N, int K, int relu, int fmt,
                     void* stream);
+/* The same product with operand-layout copies of the result written by the epilogue (no converter launch, no fp32 round trip of the
+ * [M, mlp_dim] tensors of the encoder MLP and its backward; only without K split):
+ *   y (optional here)    fp32 row-major result as above
+ *   y_tok                16-bit token-chunked copy [y_tok_chunks][y_tok_rows][8] = the operand of a later product that reduces over the M
+ *                        tokens (weight gradients dW = g^T x): chunk = 8 consecutive tokens, row = output feature; chunks past ceil(M/8)
+ *                        must be pre-zeroed by the caller, they are never written
+ *   y_feat               16-bit feature-chunked copy [ceil(N/128)*16][y_feat_rows][8] = the X operand of the next Linear layer (K = N)
+ *   mask_tok             a tensor in y_tok's layout (same strides): the result is zeroed where it is <= 0 — ReLU backward against the
+ *                        saved activation   colsum [N] += column sums of the (masked) result — the bias gradient (atomics; pre-zeroed)
+ *   x_rows / w_rows      row stride of the X / W operand buffers when they are padded further than this product needs (0 = default) */
+int mpa_gemm_tc_ex_f16(const void* x_chunks, const void* w_chunks, const float* bias, float* y, int M, int N, int K, int relu, int fmt,
+                       int x_rows, int w_rows, void* y_tok, int y_tok_rows, int y_tok_chunks, void* y_feat, int y_feat_rows,
+                       const void* mask_tok, float* colsum, void* stream);
 
 /* ---- tensor-core training convolutions (bf16 / fp16 CP8 operands, fp32 accumulate) -------------------------------------
  * Weight gradient of a stride-1 "same" KHxKW convolution (nn.Conv2d backward): gw[co0+co][ci0+ci][kh][kw] +=

@@ -209,20 +209,24 @@ __global__ void __launch_bounds__(256) gemm_generic_kernel(const float* __restri
   }
 }
 
-// column sums: out[n] = sum_m A[m,n]
+// column sums: out[n] = sum_m A[m,n].  grid (column blocks of 32, row slices): few-column matrices (E = 128 columns, B*S = 1300 rows) ran on 4
+// CTAs; the row slices meet in atomics (out pre-zeroed) when there is more than one
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ A, float* __restrict__ out, int M, int N) {
   const int n = blockIdx.x * 32 + (threadIdx.x & 31);
   const int slice = threadIdx.x >> 5;
   __shared__ float sh[8][33];
+  const int per = (M + gridDim.y - 1) / gridDim.y;
+  const int m0 = blockIdx.y * per, m1 = min(M, m0 + per);
   float s = 0.f;
   if (n < N)
-    for (int m = slice; m < M; m += 8) s += A[(size_t)m * N + n];
+    for (int m = m0 + slice; m < m1; m += 8) s += A[(size_t)m * N + n];
   sh[slice][threadIdx.x & 31] = s;
   __syncthreads();
   if (slice == 0 && n < N) {
     float t = 0.f;
     for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x & 31];
-    out[n] = t;
+    if (gridDim.y > 1) atomicAdd(&out[n], t);
+    else out[n] = t;
   }
 }
 
@@ -464,7 +468,11 @@ int mpa_gemm_f32(const float* A, const float* Bm, float* C, int M, int N, int K,
 int mpa_colsum_f32(const float* A, float* out, int M, int N, void* stream) {
   MPA_CHECK_ARCH();
   MPA_REQUIRE(A && out && M > 0 && N > 0, "colsum: bad argument");
-  colsum_kernel<<<ceil_div(N, 32), 256, 0, (cudaStream_t)stream>>>(A, out, M, N);
+  const int cb = ceil_div(N, 32);
+  int slices = cb >= 148 ? 1 : ceil_div(296, cb);
+  if (slices > ceil_div(M, 64)) slices = ceil_div(M, 64);
+  if (slices > 1) cudaMemsetAsync(out, 0, sizeof(float) * N, (cudaStream_t)stream);
+  colsum_kernel<<<dim3(cb, slices), 256, 0, (cudaStream_t)stream>>>(A, out, M, N);
   MPA_CHECK_LAUNCH("colsum");
   return MPA_OK;
 }

@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(256) enc_fold_bwd_kernel(const float* __restri
 }
 
 // ---- the per-position kernels ---------------------------------------------------------------------------------------------------------
-constexpr int kBC = 16;          // batch items per register block of the projection loops
+constexpr int kBC = 32;          // batch items per register block of the projection loops (B = 25: one pass over the weight column)
 
 // out[b][j] (+ global copy) = sum_k in[b][k] * WT[k*ldw + j] + bias[j] for all b < B, this thread's column j; in: shared [B][E]
 template <class Store>
@@ -134,7 +134,8 @@ __device__ __forceinline__ void project_column(const float* __restrict__ in, int
     float acc[kBC];
 #pragma unroll
     for (int bb = 0; bb < kBC; ++bb) acc[bb] = bias;
-    for (int k = 0; k < E; k += 4) {
+#pragma unroll 2
+    for (int k = 0; k < E; k += 4) {          // 8 independent weight loads in flight: the loop is bound by the L2 latency of WT otherwise
       const float w0 = WT[(size_t)k * ldw + j], w1 = WT[(size_t)(k + 1) * ldw + j], w2 = WT[(size_t)(k + 2) * ldw + j],
                   w3 = WT[(size_t)(k + 3) * ldw + j];
 #pragma unroll

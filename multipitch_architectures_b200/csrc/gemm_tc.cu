@@ -30,7 +30,16 @@ struct GemmTcParams {
   float* y;                  // [M][N] fp32 row-major
   int M, N, KC, Mpad, Npad, relu, ksplit, n_tiles_n, n_tiles_m, n_units;
   uint32_t idesc;
+  // optional 16-bit copies of the result in operand layouts (ksplit == 1 only), written by the epilogue instead of a converter launch:
+  uint16_t* y_tok;           // token-chunked [y_tok_chunks][y_tok_rows (features)][8]: the operand of a product that reduces over the tokens
+  int y_tok_rows, y_tok_chunks;
+  uint16_t* y_feat;          // feature-chunked [ceil(Npad/8)][y_feat_rows (tokens)][8]: the X operand of the next Linear layer
+  int y_feat_rows;
+  const uint16_t* mask_tok;  // layout of y_tok: the result is zeroed where this tensor is <= 0 (ReLU backward)
+  float* colsum;             // [N] += sum over the tokens of the (masked) result (bias gradient), atomics
+  int bf16;
 };
+constexpr int kGmTrBytes = 32 * 80;            // per epilogue warp: 32 tokens x (32 features x 2 B + 16 B pad) transposing tile
 
 __device__ __forceinline__ uint32_t gm_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void gm_mbar_init(uint64_t* bar, uint32_t count) {
@@ -125,6 +134,7 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemm_tc_kernel(const GemmTcPara
   uint64_t* acc_full = empty + kGmStages;      // [2]
   uint64_t* acc_empty = acc_full + 2;          // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint8_t* tr_smem = reinterpret_cast<uint8_t*>(bars) + 256;      // [4 epilogue warps][kGmTrBytes]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -214,22 +224,105 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemm_tc_kernel(const GemmTcPara
       const bool n_ok = n < p.N;
       const float b = (n_ok && p.bias && g.kc0 == 0) ? p.bias[n] : 0.f;
       const int m_hi = min(kGmTileM, p.M - g.m0);
-      for (int c0 = 0; c0 < m_hi; c0 += 32) {
+      const bool extra = p.y_tok || p.y_feat || p.mask_tok || p.colsum;
+      float csum = 0.f;
+      uint8_t* tr = tr_smem + quad * kGmTrBytes;
+      for (int c0 = 0; c0 < (extra ? kGmTileM : m_hi); c0 += 32) {
+        if (c0 >= m_hi) {
+          // token rows past M inside the padded tile: the feature-chunked copy must hold zeros there (the consumer's bulk copies read them)
+          if (p.y_feat) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(p.y_feat + ((size_t)((g.n0 + quad * 32) / 8 + j) * p.y_feat_rows + g.m0 + c0 + lane) * 8) = make_uint4(0, 0, 0, 0);
+          }
+          continue;
+        }
         uint32_t v[32];
         gm_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256 + c0), v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (n_ok) {
-          float* yp = p.y + (size_t)(g.m0 + c0) * p.N + n;
+        if (!extra) {
+          if (n_ok) {
+            float* yp = p.y + (size_t)(g.m0 + c0) * p.N + n;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (c0 + i < m_hi) {
-              float val = __uint_as_float(v[i]) + b;
-              if (p.ksplit > 1) atomicAdd(yp + (size_t)i * p.N, val);
-              else yp[(size_t)i * p.N] = p.relu ? fmaxf(val, 0.f) : val;
+            for (int i = 0; i < 32; ++i) {
+              if (c0 + i < m_hi) {
+                float val = __uint_as_float(v[i]) + b;
+                if (p.ksplit > 1) atomicAdd(yp + (size_t)i * p.N, val);
+                else yp[(size_t)i * p.N] = p.relu ? fmaxf(val, 0.f) : val;
+              }
+            }
+          }
+          continue;
+        }
+        // ---- epilogue with operand-layout copies (ksplit == 1)
+        const int ch0 = (g.m0 + c0) >> 3;                      // first token chunk of this block
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float val = __uint_as_float(v[i]) + b;
+          if (p.relu) val = fmaxf(val, 0.f);
+          if (!n_ok || c0 + i >= m_hi) val = 0.f;
+          v[i] = __float_as_uint(val);
+        }
+        if (p.mask_tok && n_ok) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (ch0 + q < p.y_tok_chunks) {
+              const uint4 mk = *reinterpret_cast<const uint4*>(p.mask_tok + ((size_t)(ch0 + q) * p.y_tok_rows + n) * 8);
+              const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const uint32_t h = (e & 1) ? (mw[e >> 1] >> 16) : (mw[e >> 1] & 0xFFFFu);
+                // > 0 in either 16-bit format: sign bit clear and magnitude non-zero
+                if ((h & 0x8000u) || (h & 0x7FFFu) == 0u) v[q * 8 + e] = 0u;
+              }
             }
           }
         }
+        if (p.colsum) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) csum += __uint_as_float(v[i]);
+        }
+        if (p.y && n_ok) {
+          float* yp = p.y + (size_t)(g.m0 + c0) * p.N + n;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i < m_hi) yp[(size_t)i * p.N] = __uint_as_float(v[i]);
+        }
+        uint32_t h16[16];                                      // the 32 values as 16-bit pairs (tokens 2i, 2i+1)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          if (p.bf16) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+            h16[i] = *reinterpret_cast<const uint32_t*>(&h);
+          } else {
+            const __half2 h = __floats2half2_rn(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+            h16[i] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+        }
+        if (p.y_tok && n < p.y_tok_rows) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (ch0 + q < p.y_tok_chunks)
+              *reinterpret_cast<uint4*>(p.y_tok + ((size_t)(ch0 + q) * p.y_tok_rows + n) * 8) =
+                  make_uint4(h16[4 * q], h16[4 * q + 1], h16[4 * q + 2], h16[4 * q + 3]);
+        }
+        if (p.y_feat) {
+          // transpose the warp's 32 features x 32 tokens through shared memory: row = token (80-byte stride: conflict-free 16-byte reads)
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            *reinterpret_cast<uint16_t*>(tr + (2 * i) * 80 + lane * 2) = (uint16_t)(h16[i] & 0xFFFFu);
+            *reinterpret_cast<uint16_t*>(tr + (2 * i + 1) * 80 + lane * 2) = (uint16_t)(h16[i] >> 16);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 piece = *reinterpret_cast<const uint4*>(tr + lane * 80 + j * 16);
+            *reinterpret_cast<uint4*>(p.y_feat + ((size_t)((g.n0 + quad * 32) / 8 + j) * p.y_feat_rows + g.m0 + c0 + lane) * 8) = piece;
+          }
+        }
       }
+      if (p.colsum && n_ok) atomicAdd(&p.colsum[n], csum);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       gm_arrive(&acc_empty[buf]);
     }
@@ -284,11 +377,15 @@ int mpa_gemm_tc_to_chunks(const float* x, void* out, int rows, int K, int row_ti
   return MPA_OK;
 }
 
-int mpa_gemm_tc_f16(const void* x_chunks, const void* w_chunks, const float* bias, float* y, int M, int N, int K, int relu, int fmt, void* stream) {
+int mpa_gemm_tc_ex_f16(const void* x_chunks, const void* w_chunks, const float* bias, float* y, int M, int N, int K, int relu, int fmt, int x_rows,
+                       int w_rows, void* y_tok, int y_tok_rows, int y_tok_chunks, void* y_feat, int y_feat_rows, const void* mask_tok, float* colsum,
+                       void* stream) {
   MPA_CHECK_ARCH();
-  MPA_REQUIRE(x_chunks && w_chunks && y && M > 0 && N > 0 && K > 0, "gemm_tc: bad argument");
+  const bool extra = y_tok || y_feat || mask_tok || colsum;
+  MPA_REQUIRE(x_chunks && w_chunks && (y || extra) && M > 0 && N > 0 && K > 0, "gemm_tc: bad argument");
   MPA_REQUIRE(fmt == MPA_FMT_F16 || fmt == MPA_FMT_BF16, "gemm_tc: fmt must be MPA_FMT_F16 or MPA_FMT_BF16");
-  MPA_REQUIRE((((uintptr_t)x_chunks | (uintptr_t)w_chunks) & 15) == 0, "gemm_tc: 16-byte alignment required");
+  MPA_REQUIRE((((uintptr_t)x_chunks | (uintptr_t)w_chunks | (uintptr_t)y_tok | (uintptr_t)y_feat | (uintptr_t)mask_tok) & 15) == 0,
+              "gemm_tc: 16-byte alignment required");
   GemmTcParams p;
   memset(&p, 0, sizeof(p));
   p.x = (const uint8_t*)x_chunks;
@@ -302,12 +399,22 @@ int mpa_gemm_tc_f16(const void* x_chunks, const void* w_chunks, const float* bia
   p.relu = relu;
   p.n_tiles_n = p.Npad / kGmTileN;
   p.n_tiles_m = p.Mpad / kGmTileM;
+  // row strides of the operand buffers (a buffer written by another product's epilogue may be padded further than this product needs)
+  MPA_REQUIRE((x_rows == 0 || x_rows >= p.Mpad) && (w_rows == 0 || w_rows >= p.Npad), "gemm_tc: operand row stride smaller than the padded tile range");
+  if (x_rows > 0) p.Mpad = x_rows;
+  if (w_rows > 0) p.Npad = w_rows;
+  if (y_tok || mask_tok) MPA_REQUIRE(y_tok_rows >= N && y_tok_chunks > 0, "gemm_tc: y_tok / mask_tok need their row stride and chunk count");
+  if (y_feat) MPA_REQUIRE(y_feat_rows >= p.n_tiles_m * kGmTileM, "gemm_tc: y_feat row stride must cover the padded token tiles");
+  p.y_tok = (uint16_t*)y_tok; p.y_tok_rows = y_tok_rows; p.y_tok_chunks = y_tok_chunks;
+  p.y_feat = (uint16_t*)y_feat; p.y_feat_rows = y_feat_rows;
+  p.mask_tok = (const uint16_t*)mask_tok; p.colsum = colsum;
+  p.bf16 = fmt == MPA_FMT_BF16;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int tiles = p.n_tiles_n * p.n_tiles_m, stages = p.KC / kGmChunksPerStage;
   int ks = 1;
-  if (!relu && tiles < sms && stages >= 8) {
+  if (!relu && !extra && tiles < sms && stages >= 8) {
     ks = sms / tiles;
     if (ks > stages / 4) ks = stages / 4;
     if (ks < 1) ks = 1;
@@ -319,7 +426,7 @@ int mpa_gemm_tc_f16(const void* x_chunks, const void* w_chunks, const float* bia
   const uint32_t f = (fmt == MPA_FMT_BF16) ? 1u : 0u;
   p.idesc = (1u << 4) | (f << 7) | (f << 10) | ((uint32_t)(kGmTileM >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   if (ks > 1) cudaMemsetAsync(y, 0, sizeof(float) * (size_t)M * N, (cudaStream_t)stream);
-  const size_t smem = (size_t)kGmStages * (kGmWBytes + kGmXBytes) + 256;
+  const size_t smem = (size_t)kGmStages * (kGmWBytes + kGmXBytes) + 256 + 4 * kGmTrBytes;
   {
     static unsigned char flags[64];
     cudaError_t e = opt_in_max_smem(gemm_tc_kernel, flags);
@@ -332,6 +439,10 @@ int mpa_gemm_tc_f16(const void* x_chunks, const void* w_chunks, const float* bia
   gemm_tc_kernel<<<grid, kGmThreads, smem, (cudaStream_t)stream>>>(p);
   MPA_CHECK_LAUNCH("gemm_tc");
   return MPA_OK;
+}
+
+int mpa_gemm_tc_f16(const void* x_chunks, const void* w_chunks, const float* bias, float* y, int M, int N, int K, int relu, int fmt, void* stream) {
+  return mpa_gemm_tc_ex_f16(x_chunks, w_chunks, bias, y, M, N, K, relu, fmt, 0, 0, nullptr, 0, 0, nullptr, 0, nullptr, nullptr, stream);
 }
 
 }  // extern "C"

@@ -483,3 +483,11 @@ def gemm_tc(x, w_chunks, bias, N, relu, fmt, x_transposed=False, out=None, x_chu
     y = out if out is not None else torch.empty(M, N, dtype=torch.float32, device=x.device)
     call('gemm_tc_f16', xc, w_chunks, bias, y, M, N, K, int(bool(relu)), fmt, stream_ptr())
     return y
+
+
+def gemm_tc_ex(x_chunks, w_chunks, bias, M, N, K, relu, fmt, y=None, x_rows=0, w_rows=0, y_tok=None, y_tok_rows=0, y_tok_chunks=0, y_feat=None,
+               y_feat_rows=0, mask_tok=None, colsum=None):
+    """mpa_gemm_tc_ex_f16: the tcgen05 product on pre-chunked operands with optional 16-bit operand-layout copies of the result."""
+    call('gemm_tc_ex_f16', x_chunks, w_chunks, bias, y, M, N, K, int(bool(relu)), fmt, int(x_rows), int(w_rows), y_tok, int(y_tok_rows),
+         int(y_tok_chunks), y_feat, int(y_feat_rows), mask_tok, colsum, stream_ptr())
+    return y

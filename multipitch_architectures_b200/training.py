@@ -195,6 +195,17 @@ class TcConv:
             cls._pool[key] = b
         return b
 
+    @classmethod
+    def _raw(cls, tag, nbytes, zero, dev):
+        """Byte scratch pooled like `_buf` (zero: zero-filled when it is created; the users never dirty the parts that must stay zero)."""
+        if cls._scope is None:
+            return (torch.zeros if zero else torch.empty)(nbytes, dtype=torch.uint8, device=dev)
+        key = (cls._scope, tag, nbytes, str(dev), bool(zero))
+        b = cls._pool.get(key)
+        if b is None:
+            b = cls._pool[key] = (torch.zeros if zero else torch.empty)(nbytes, dtype=torch.uint8, device=dev)
+        return b
+
     @staticmethod
     def _pad8(v, n):
         """bias (or zeros) padded to n entries: the padded output channels of a block carry zero weights and zero bias."""

@@ -391,27 +391,41 @@ class Tape:
             self.push(bwd_ln1)
 
         # -- MLP
-        if self.model is not None and getattr(self.model, 'precision', 'fp32') == 'bf16':
-            # the MLP's forward products on the tensor cores (bf16 operands, fp32 accumulate); the backward stays fp32
-            hid = Node(ops.gemm_tc(h1.d, ops.gemm_tc_chunks(W1, 128, ops.FMT_BF16), b1, Dm, True, ops.FMT_BF16))
-            m2 = Node(ops.gemm_tc(hid.d, ops.gemm_tc_chunks(W2, 128, ops.FMT_BF16), b2, E, False, ops.FMT_BF16))
+        tc_mlp = self.model is not None and getattr(self.model, 'precision', 'fp32') == 'bf16'
+        if tc_mlp:
+            # Both Linear layers and the four products of their backward on the tensor cores (bf16 operands, fp32 accumulate).  The hidden
+            # activation [M, mlp_dim] and its gradient exist ONLY as 16-bit operand-layout copies written by the GEMM epilogues
+            # (token-chunked for the weight-gradient products, feature-chunked for the next layer): no fp32 round trip, no converter pass,
+            # ReLU backward and the bias gradient inside the epilogue (mpa_gemm_tc_ex_f16).
+            fm = ops.FMT_BF16
+            Mp, KCt, rows_t, Np8 = (M + 255) // 256 * 256, (M + 63) // 64 * 8, (Dm + 255) // 256 * 256, (Dm + 127) // 128 * 16
+            hid_tok = TcConv._raw(name + ':hid_tok', KCt * rows_t * 16, True, dev)
+            hid_feat = TcConv._raw(name + ':hid_feat', Np8 * Mp * 16, False, dev)
+            ops.gemm_tc_ex(ops.gemm_tc_chunks(h1.d, 256, fm), ops.gemm_tc_chunks(W1, 128, fm), b1, M, Dm, E, True, fm, y_tok=hid_tok,
+                           y_tok_rows=rows_t, y_tok_chunks=KCt, y_feat=hid_feat, y_feat_rows=Mp)
+            m2 = Node(ops.gemm_tc_ex(hid_feat, ops.gemm_tc_chunks(W2, 128, fm), b2, M, E, Dm, False, fm, y=f32(M, E)))
         else:
             hid = Node(gemm_nt(h1.d, W1, b1, M, Dm, E, relu=1))
             m2 = Node(gemm_nt(hid.d, W2, b2, M, E, Dm))
 
         def bwd_mlp_tc():
-            # the four products of the MLP backward as X @ W'^T on tcgen05 (bf16 operands): transposes are taken by the chunking pass
-            fm = ops.FMT_BF16
             g_m2 = m2.g
-            ops.gemm_tc(g_m2, ops.gemm_tc_chunks(hid.d, 128, fm, True), None, Dm, False, fm, x_transposed=True, out=G[name + '.mlp.2.weight'])
+            # dW2 [E, Dm] = g_m2^T hid
+            ops.gemm_tc_ex(ops.gemm_tc_chunks(g_m2, 256, fm, True), hid_tok, None, E, Dm, M, False, fm, y=G[name + '.mlp.2.weight'], w_rows=rows_t)
             colsum(g_m2, M, E, out=G[name + '.mlp.2.bias'])
-            g_hid = _act_bwd(hid.d, ops.gemm_tc(g_m2, ops.gemm_tc_chunks(W2, 128, fm, True), None, Dm, False, fm), ops.ACT_RELU)
-            ops.gemm_tc(g_hid, ops.gemm_tc_chunks(h1.d, 128, fm, True), None, E, False, fm, x_transposed=True, out=G[name + '.mlp.0.weight'])
-            colsum(g_hid, M, Dm, out=G[name + '.mlp.0.bias'])
-            h1.acc(ops.gemm_tc(g_hid, ops.gemm_tc_chunks(W1, 128, fm, True), None, E, False, fm))
+            # g_hid = (g_m2 W2) * [hid > 0] -> both operand layouts, bias gradient = its column sums
+            ghid_tok = TcConv._raw(name + ':ghid_tok', KCt * rows_t * 16, True, dev)
+            ghid_feat = TcConv._raw(name + ':ghid_feat', Np8 * Mp * 16, False, dev)
+            gb1 = G[name + '.mlp.0.bias']
+            gb1.zero_()
+            ops.gemm_tc_ex(ops.gemm_tc_chunks(g_m2, 256, fm), ops.gemm_tc_chunks(W2, 128, fm, True), None, M, Dm, E, False, fm, y_tok=ghid_tok,
+                           y_tok_rows=rows_t, y_tok_chunks=KCt, y_feat=ghid_feat, y_feat_rows=Mp, mask_tok=hid_tok, colsum=gb1)
+            # dW1 [Dm, E] = g_hid^T h1;  g_h1 [M, E] = g_hid W1
+            ops.gemm_tc_ex(ghid_tok, ops.gemm_tc_chunks(h1.d, 128, fm, True), None, Dm, E, M, False, fm, y=G[name + '.mlp.0.weight'], x_rows=rows_t)
+            h1.acc(ops.gemm_tc_ex(ghid_feat, ops.gemm_tc_chunks(W1, 128, fm, True), None, M, E, Dm, False, fm, y=f32(M, E)))
 
         def bwd_mlp():
-            if self.model is not None and getattr(self.model, 'precision', 'fp32') == 'bf16':
+            if tc_mlp:
                 return bwd_mlp_tc()
             g_m2 = m2.g
             gemm(g_m2, hid.d, E, Dm, M, 1, out=G[name + '.mlp.2.weight'])
