@@ -176,9 +176,13 @@ struct EncTrainParams {
 __global__ void __launch_bounds__(384) enc_attn_train_fwd_kernel(const EncTrainParams p) {
   extern __shared__ __align__(16) float sm[];
   const int B = p.B, E = p.E, S = p.S, H = p.H, hd = E / H, E3 = 3 * E;
+  // q | k | v of one item in shared memory: [3 parts][H heads][hd + 4] — the 4-float pad per head spreads the heads over the banks
+  // (lanes of a warp differ in the head: with the dense layout the key / value reads of the attention loop were 4-way, the query reads
+  // 16-way bank conflicted and the attention step took ~100 us of this kernel)
+  const int HS = hd + 4, PS = H * HS, RS = 3 * PS;
   float* t = sm;                       // [B][E]
-  float* qkv = t + (size_t)B * E;      // [B][3E]
-  float* att = qkv + (size_t)B * E3;   // [B][E]
+  float* qkv = t + (size_t)B * E;      // [B][RS]
+  float* att = qkv + (size_t)B * RS;   // [B][E]
   float* u1 = att + (size_t)B * E;     // [B][E]
   const int s = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   const unsigned long long off_t = p.d_tok.p > 0.f ? dropout_offset(p.d_tok) : 0ull, off_a = p.d_att.p > 0.f ? dropout_offset(p.d_att) : 0ull;
@@ -198,36 +202,45 @@ __global__ void __launch_bounds__(384) enc_attn_train_fwd_kernel(const EncTrainP
   }
   __syncthreads();
   // 2. q | k | v
-  for (int j = tid; j < E3; j += nt)
+  for (int j = tid; j < E3; j += nt) {
+    const int part = j / E, c = j - part * E, hh = c / hd;
+    const int js = part * PS + hh * HS + (c - hh * hd);
     project_column(t, B, E, p.w_qkvT, E3, j, p.b_qkv[j], [&](int b, float v) {
-      qkv[(size_t)b * E3 + j] = v;
+      qkv[(size_t)b * RS + js] = v;
       p.qkv[((size_t)b * S + s) * E3 + j] = v;
     });
+  }
   __syncthreads();
   // 3. batch-axis attention: thread = (query item b1, head h); the same two-pass softmax as batch_axis_attention_kernel
   const float sc = rsqrtf((float)hd);
   for (int i = tid; i < B * H; i += nt) {
     const int b1 = i / H, h = i - b1 * H;
-    const float* q = qkv + (size_t)b1 * E3 + h * hd;
+    float q[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) q[k] = k < hd ? qkv[(size_t)b1 * RS + h * HS + k] : 0.f;
     float mx = -INFINITY;
     for (int b2 = 0; b2 < B; ++b2) {
-      const float* kr = qkv + (size_t)b2 * E3 + E + h * hd;
+      const float* kr = qkv + (size_t)b2 * RS + PS + h * HS;
       float d = 0.f;
-      for (int k = 0; k < hd; ++k) d = fmaf(q[k], kr[k], d);
+#pragma unroll
+      for (int k = 0; k < 16; ++k)
+        if (k < hd) d = fmaf(q[k], kr[k], d);
       mx = fmaxf(mx, d * sc);
     }
     float den = 0.f, o[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) o[k] = 0.f;
     for (int b2 = 0; b2 < B; ++b2) {
-      const float* kr = qkv + (size_t)b2 * E3 + E + h * hd;
+      const float* kr = qkv + (size_t)b2 * RS + PS + h * HS;
       float d = 0.f;
-      for (int k = 0; k < hd; ++k) d = fmaf(q[k], kr[k], d);
+#pragma unroll
+      for (int k = 0; k < 16; ++k)
+        if (k < hd) d = fmaf(q[k], kr[k], d);
       const float pr = expf(d * sc - mx);
       den += pr;
 #pragma unroll
       for (int k = 0; k < 16; ++k)
-        if (k < hd) o[k] = fmaf(pr, kr[E + k], o[k]);
+        if (k < hd) o[k] = fmaf(pr, kr[PS + k], o[k]);
     }
 #pragma unroll
     for (int k = 0; k < 16; ++k)
@@ -283,19 +296,19 @@ __global__ void __launch_bounds__(384) enc_attn_train_bwd_kernel(const EncTrainP
   const int B = p.B, E = p.E, S = p.S, H = p.H, hd = E / H, E3 = 3 * E;
   float* g_u1 = sm;                        // [B][E]
   float* xh = g_u1 + (size_t)B * E;        // [B][E]  LayerNorm xhat, then g_p
-  float* qkv = xh + (size_t)B * E;         // [B][3E]
-  float* g_att = qkv + (size_t)B * E3;     // [B][E]
+  float* g_att = xh + (size_t)B * E;       // [B][E]
   float* g_qkv = g_att + (size_t)B * E;    // [B][3E]
-  float* P = g_qkv + (size_t)B * E3;       // [B][B]
+  const int HP = hd + 1;                   // odd row stride of the per-head tiles: the (b1, b2) passes read them conflict-free
+  float* Qh = g_qkv + (size_t)B * E3;      // [B][HP] this head's q, k, v and dO
+  float* Kh = Qh + (size_t)B * HP;
+  float* Vh = Kh + (size_t)B * HP;
+  float* dOh = Vh + (size_t)B * HP;
+  float* P = dOh + (size_t)B * HP;         // [B][B]
   float* dS = P + (size_t)B * B;           // [B][B]
   float* rowv = dS + (size_t)B * B;        // [B]
   const int s = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   const unsigned long long off_t = p.d_tok.p > 0.f ? dropout_offset(p.d_tok) : 0ull, off_a = p.d_att.p > 0.f ? dropout_offset(p.d_att) : 0ull;
   const float sc_t = p.d_tok.p > 0.f ? 1.f / (1.f - p.d_tok.p) : 1.f, sc_a = p.d_att.p > 0.f ? 1.f / (1.f - p.d_att.p) : 1.f;
-  for (int i = tid; i < B * E3; i += nt) {
-    const int b = i / E3, j = i - b * E3;
-    qkv[i] = p.qkv[((size_t)b * S + s) * E3 + j];
-  }
   // 1. LayerNorm1 backward, one warp per token (the arithmetic of ln_bwd_kernel); xh keeps xhat, g_att (scratch) keeps g_y
   const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
   for (int b = warp; b < B; b += nw) {
@@ -368,16 +381,21 @@ __global__ void __launch_bounds__(384) enc_attn_train_bwd_kernel(const EncTrainP
   // 3. attention backward, head by head (the passes of batch_axis_attention_bwd_kernel on this CTA's shared tiles)
   const float sc = rsqrtf((float)hd);
   for (int h = 0; h < H; ++h) {
-    const float* Q = qkv + h * hd;               // row stride E3
-    const float* Km = Q + E;
-    const float* V = Q + 2 * E;
-    const float* dO = g_att + h * hd;            // row stride E
+    for (int e = tid; e < B * hd; e += nt) {
+      const int b = e / hd, k = e - b * hd;
+      const float* row = p.qkv + ((size_t)b * S + s) * E3 + h * hd + k;
+      Qh[b * HP + k] = row[0];
+      Kh[b * HP + k] = row[E];
+      Vh[b * HP + k] = row[2 * E];
+      dOh[b * HP + k] = g_att[(size_t)b * E + h * hd + k];
+    }
+    __syncthreads();
     for (int e = tid; e < B * B; e += nt) {
       const int b1 = e / B, b2 = e - b1 * B;
       float d = 0.f, dp = 0.f;
       for (int k = 0; k < hd; ++k) {
-        d = fmaf(Q[(size_t)b1 * E3 + k], Km[(size_t)b2 * E3 + k], d);
-        dp = fmaf(dO[(size_t)b1 * E + k], V[(size_t)b2 * E3 + k], dp);
+        d = fmaf(Qh[b1 * HP + k], Kh[b2 * HP + k], d);
+        dp = fmaf(dOh[b1 * HP + k], Vh[b2 * HP + k], dp);
       }
       P[e] = d * sc;
       dS[e] = dp;
@@ -407,9 +425,9 @@ __global__ void __launch_bounds__(384) enc_attn_train_bwd_kernel(const EncTrainP
       const int b = e / hd, k = e - b * hd;
       float dq = 0.f, dk = 0.f, dv = 0.f;
       for (int o = 0; o < B; ++o) {
-        dq = fmaf(dS[b * B + o], Km[(size_t)o * E3 + k], dq);
-        dk = fmaf(dS[o * B + b], Q[(size_t)o * E3 + k], dk);
-        dv = fmaf(P[o * B + b], dO[(size_t)o * E + k], dv);
+        dq = fmaf(dS[b * B + o], Kh[o * HP + k], dq);
+        dk = fmaf(dS[o * B + b], Qh[o * HP + k], dk);
+        dv = fmaf(P[o * B + b], dOh[o * HP + k], dv);
       }
       float* row = g_qkv + (size_t)b * E3 + h * hd + k;
       row[0] = dq;
@@ -434,8 +452,8 @@ __global__ void __launch_bounds__(384) enc_attn_train_bwd_kernel(const EncTrainP
     });
 }
 
-static size_t enc_fwd_smem(int B, int E) { return sizeof(float) * (size_t)B * E * 6; }
-static size_t enc_bwd_smem(int B, int E) { return sizeof(float) * ((size_t)B * E * 9 + 2 * (size_t)B * B + B); }
+static size_t enc_fwd_smem(int B, int E, int H) { return sizeof(float) * (size_t)B * (3 * E + 3 * (E + 4 * H)); }
+static size_t enc_bwd_smem(int B, int E, int H) { return sizeof(float) * ((size_t)B * E * 6 + 4 * (size_t)B * (E / H + 1) + 2 * (size_t)B * B + B); }
 
 }  // namespace mpa
 
@@ -445,7 +463,7 @@ extern "C" {
 
 int mpa_enc_train_supported(int B, int E, int num_heads) {
   return E % 32 == 0 && E <= 128 && num_heads > 0 && E % num_heads == 0 && E / num_heads <= 16 && B >= 1 &&
-         enc_bwd_smem(B, E) <= 220 * 1024 && enc_fwd_smem(B, E) <= 220 * 1024;
+         enc_bwd_smem(B, E, num_heads) <= 220 * 1024 && enc_fwd_smem(B, E, num_heads) <= 220 * 1024;
 }
 
 int mpa_enc_fold_f32(const float* in_proj_weight, const float* wq, const float* wk, const float* wv, const float* wo, const float* out_proj_weight,
@@ -494,7 +512,7 @@ int mpa_enc_attn_train_fwd_f32(const float* x, const float* pe, const float* w_q
   p.t = t; p.qkv = qkv; p.att = att; p.u1 = u1; p.h1 = h1; p.B = B; p.E = E; p.S = S; p.H = num_heads;
   p.d_tok = DropoutArgs{pe ? p_drop : 0.f, seed, site_tok, step_dev, step_mul};       // the reference drops the tokens only behind a positional encoding
   p.d_att = DropoutArgs{p_drop, seed, site_att, step_dev, step_mul};
-  enc_attn_train_fwd_kernel<<<S, 384, enc_fwd_smem(B, E), (cudaStream_t)stream>>>(p);
+  enc_attn_train_fwd_kernel<<<S, 384, enc_fwd_smem(B, E, num_heads), (cudaStream_t)stream>>>(p);
   MPA_CHECK_LAUNCH("enc_attn_train_fwd");
   return MPA_OK;
 }
@@ -519,7 +537,7 @@ int mpa_enc_attn_train_bwd_f32(const float* g_h1, const float* u1, const float* 
   p.g_p = g_p; p.g_qkv = g_qkv; p.g_x = g_x; p.g_ln_w = g_ln_w; p.g_ln_b = g_ln_b; p.B = B; p.E = E; p.S = S; p.H = num_heads;
   p.d_tok = DropoutArgs{has_pe ? p_drop : 0.f, seed, site_tok, step_dev, step_mul};
   p.d_att = DropoutArgs{p_drop, seed, site_att, step_dev, step_mul};
-  enc_attn_train_bwd_kernel<<<S, 384, enc_bwd_smem(B, E), st>>>(p);
+  enc_attn_train_bwd_kernel<<<S, 384, enc_bwd_smem(B, E, num_heads), st>>>(p);
   MPA_CHECK_LAUNCH("enc_attn_train_bwd");
   return MPA_OK;
 }
