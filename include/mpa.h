@@ -459,19 +459,43 @@ size_t mpa_gemm_tc_chunked_bytes(int rows, int K, int row_tile);
 int mpa_gemm_tc_to_chunks(const float* x_rows, void* out_chunks, int rows, int K, int row_tile, int fmt, int transposed, void* stream);
 int mpa_gemm_tc_f16(const void* x_chunks, const void* w_chunks, const float* bias, float* y, int M, int N, int K, int relu, int fmt,
                     void* stream);
-/* The same product with operand-layout copies of the result written by the epilogue (no converter launch, no fp32 round trip of the
- * [M, mlp_dim] tensors of the encoder MLP and its backward; only without K split):
- *   y (optional here)    fp32 row-major result as above
- *   y_tok                16-bit token-chunked copy [y_tok_chunks][y_tok_rows][8] = the operand of a later product that reduces over the M
- *                        tokens (weight gradients dW = g^T x): chunk = 8 consecutive tokens, row = output feature; chunks past ceil(M/8)
- *                        must be pre-zeroed by the caller, they are never written
- *   y_feat               16-bit feature-chunked copy [ceil(N/128)*16][y_feat_rows][8] = the X operand of the next Linear layer (K = N)
- *   mask_tok             a tensor in y_tok's layout (same strides): the result is zeroed where it is <= 0 — ReLU backward against the
- *                        saved activation   colsum [N] += column sums of the (masked) result — the bias gradient (atomics; pre-zeroed)
- *   x_rows / w_rows      row stride of the X / W operand buffers when they are padded further than this product needs (0 = default) */
-int mpa_gemm_tc_ex_f16(const void* x_chunks, const void* w_chunks, const float* bias, float* y, int M, int N, int K, int relu, int fmt,
-                       int x_rows, int w_rows, void* y_tok, int y_tok_rows, int y_tok_chunks, void* y_feat, int y_feat_rows,
-                       const void* mask_tok, float* colsum, void* stream);
+/* out[b][c][.] = act(x[b][c][.] + bias[c]) on NCHW fp32 (in place allowed; bias may be NULL): bias + activation of a convolution whose
+ * K slices met in atomics (the tensor-core form of the head's 75x1 convolution, nn.Conv2d + nn.LeakyReLU, unet_cnns.py:380-386). */
+int mpa_bias_act_f32(const float* x, const float* bias, float* out, int B, int C, int HW, int act, float act_param, void* stream);
+/* The same product described by a struct, with the options the training path needs:
+ *  - operand-layout copies of the result written by the epilogue (no converter launch, no fp32 round trip of the [M, mlp_dim] tensors of
+ *    the encoder MLP and its backward; only without K split):
+ *      y_tok     16-bit token-chunked copy [y_tok_chunks][y_tok_rows][8] = the operand of a later product that reduces over the M tokens
+ *                (weight gradients dW = g^T x): chunk = 8 consecutive tokens, row = output feature; chunks past ceil(M/8) must be
+ *                pre-zeroed by the caller, they are never written
+ *      y_feat    16-bit feature-chunked copy [ceil(N/128)*16][y_feat_rows][8] = the X operand of the next Linear layer (K = N)
+ *      mask_tok  a tensor in y_tok's layout (same strides): the result is zeroed where it is <= 0 — ReLU backward against the saved
+ *                activation;  colsum [N] += column sums of the (masked) result — the bias gradient (atomics; pre-zeroed)
+ *  - x_rows / w_rows: row stride of the X / W operand buffers when they are padded further than this product needs (0 = default)
+ *  - strided fp32 result: element (m, n) at y[moff(m) + noff(n)], moff(m) = (m / y_mn2) * y_ms1 + (m % y_mn2) * y_ms2 (y_mn2 == 0: m * y_ms2,
+ *    y_ms2 == 0: N), noff alike (default 1): the product writes straight into an NCHW tensor whose (item, bin) pair is one GEMM
+ *    dimension.  This is how the head's full-height 75x1 convolution (libdl/nn_models/unet_cnns.py:380-385, basic_cnns.py:396-401) and its
+ *    two gradients run on the tensor cores: operands chunked by mpa_gemm_tc_strided_to_chunks, which reads element (r, k) of a tensor at
+ *    (r / r_n2) * r_s1 + (r % r_n2) * r_s2 + (k / k_n2) * k_s1 + (k % k_n2) * k_s2.  With a strided result the K split (atomics) is used only
+ *    when the caller has zeroed y (y_zeroed = 1). */
+typedef struct mpa_gemm_tc_desc {
+  const void* x_chunks;
+  const void* w_chunks;
+  const float* bias;
+  float* y;
+  int M, N, K, relu, fmt, x_rows, w_rows;
+  void* y_tok;
+  int y_tok_rows, y_tok_chunks;
+  void* y_feat;
+  int y_feat_rows;
+  const void* mask_tok;
+  float* colsum;
+  int y_mn2, y_nn2, y_zeroed;
+  long long y_ms1, y_ms2, y_ns1, y_ns2;
+} mpa_gemm_tc_desc;
+int mpa_gemm_tc_run(const mpa_gemm_tc_desc* desc, void* stream);
+int mpa_gemm_tc_strided_to_chunks(const float* x, void* out_chunks, int rows, int K, int row_tile, int fmt, int r_n2, long long r_s1,
+                                  long long r_s2, int k_n2, long long k_s1, long long k_s2, void* stream);
 
 /* ---- tensor-core training convolutions (bf16 / fp16 CP8 operands, fp32 accumulate) -------------------------------------
  * Weight gradient of a stride-1 "same" KHxKW convolution (nn.Conv2d backward): gw[co0+co][ci0+ci][kh][kw] +=

@@ -274,6 +274,15 @@ __global__ void bn_apply_vec4_kernel(const float4* __restrict__ x, const float* 
   }
 }
 
+// out = act(x + bias[c]) on NCHW (in place allowed): the second pass of a split-K product whose slices met in atomics
+__global__ void bias_act_kernel(const float* __restrict__ x, const float* __restrict__ bias, float* __restrict__ out, long long total, int C, int HW,
+                                int act, float act_param) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)((i / HW) % C);
+    out[i] = apply_act(x[i] + (bias ? bias[c] : 0.f), act, act_param);
+  }
+}
+
 __global__ void __launch_bounds__(256) bce_kernel(const float* __restrict__ yp, const float* __restrict__ yt, float* __restrict__ loss_sum,
                                                   float* __restrict__ grad, long long n) {
   __shared__ float sh[8];
@@ -433,6 +442,15 @@ int mpa_bn_apply_f32(const float* x, const float* stats, const float* w, const f
   else
     bn_apply_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, stats, w, b, out, total, C, HW, eps, act, act_param);
   MPA_CHECK_LAUNCH("bn_apply");
+  return MPA_OK;
+}
+
+int mpa_bias_act_f32(const float* x, const float* bias, float* out, int B, int C, int HW, int act, float act_param, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(x && out && B > 0 && C > 0 && HW > 0, "bias_act: bad argument");
+  const long long total = (long long)B * C * HW;
+  bias_act_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, bias, out, total, C, HW, act, act_param);
+  MPA_CHECK_LAUNCH("bias_act");
   return MPA_OK;
 }
 

@@ -38,7 +38,14 @@ struct GemmTcParams {
   const uint16_t* mask_tok;  // layout of y_tok: the result is zeroed where this tensor is <= 0 (ReLU backward)
   float* colsum;             // [N] += sum over the tokens of the (masked) result (bias gradient), atomics
   int bf16;
+  // fp32 result address = y + moff(m) + noff(n), each a 2-level index (i / n2) * s1 + (i % n2) * s2 (n2 == 0: i * s2): lets a product write
+  // straight into an NCHW tensor whose (item, bin) pair is one GEMM dimension (the head's 75x1 convolution and its gradients)
+  int y_mn2, y_nn2;
+  long long y_ms1, y_ms2, y_ns1, y_ns2;
 };
+__device__ __forceinline__ long long gm_off(int i, int n2, long long s1, long long s2) {
+  return n2 > 0 ? (long long)(i / n2) * s1 + (long long)(i % n2) * s2 : (long long)i * s2;
+}
 constexpr int kGmTrBytes = 32 * 80;            // per epilogue warp: 32 tokens x (32 features x 2 B + 16 B pad) transposing tile
 
 __device__ __forceinline__ uint32_t gm_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -242,13 +249,14 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemm_tc_kernel(const GemmTcPara
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (!extra) {
           if (n_ok) {
-            float* yp = p.y + (size_t)(g.m0 + c0) * p.N + n;
+            float* yn = p.y + gm_off(n, p.y_nn2, p.y_ns1, p.y_ns2);
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               if (c0 + i < m_hi) {
                 float val = __uint_as_float(v[i]) + b;
-                if (p.ksplit > 1) atomicAdd(yp + (size_t)i * p.N, val);
-                else yp[(size_t)i * p.N] = p.relu ? fmaxf(val, 0.f) : val;
+                float* yp = yn + gm_off(g.m0 + c0 + i, p.y_mn2, p.y_ms1, p.y_ms2);
+                if (p.ksplit > 1) atomicAdd(yp, val);
+                else *yp = p.relu ? fmaxf(val, 0.f) : val;
               }
             }
           }
@@ -283,10 +291,10 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemm_tc_kernel(const GemmTcPara
           for (int i = 0; i < 32; ++i) csum += __uint_as_float(v[i]);
         }
         if (p.y && n_ok) {
-          float* yp = p.y + (size_t)(g.m0 + c0) * p.N + n;
+          float* yn = p.y + gm_off(n, p.y_nn2, p.y_ns1, p.y_ns2);
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (c0 + i < m_hi) yp[(size_t)i * p.N] = __uint_as_float(v[i]);
+            if (c0 + i < m_hi) yn[gm_off(g.m0 + c0 + i, p.y_mn2, p.y_ms1, p.y_ms2)] = __uint_as_float(v[i]);
         }
         uint32_t h16[16];                                      // the 32 values as 16-bit pairs (tokens 2i, 2i+1)
 #pragma unroll
@@ -352,11 +360,45 @@ __global__ void rows_to_chunks_kernel(const float* __restrict__ x, uint16_t* __r
   }
 }
 
+// element (r, k) at x[(r / r_n2) * r_s1 + (r % r_n2) * r_s2 + (k / k_n2) * k_s1 + (k % k_n2) * k_s2] -> the same chunk layout: any NCHW tensor whose
+// GEMM dimensions are pairs of its axes (the head's 75x1 convolution: tokens = (item, bin), K = (channel, frame))
+__global__ void strided_to_chunks_kernel(const float* __restrict__ x, uint16_t* __restrict__ out, long long total, int R, int K, int Rpad, int fmt,
+                                         int r_n2, long long r_s1, long long r_s2, int k_n2, long long k_s1, long long k_s2) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i % Rpad);
+    const int kc = (int)(i / Rpad);
+    __align__(16) uint16_t v[8];
+    const long long ro = r < R ? (long long)(r / r_n2) * r_s1 + (long long)(r % r_n2) * r_s2 : 0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = kc * 8 + e;
+      const float f = (r < R && k < K) ? x[ro + (long long)(k / k_n2) * k_s1 + (long long)(k % k_n2) * k_s2] : 0.f;
+      v[e] = fmt == MPA_FMT_BF16 ? __bfloat16_as_ushort(__float2bfloat16(f)) : __half_as_ushort(__float2half_rn(f));
+    }
+    *reinterpret_cast<uint4*>(out + (size_t)i * 8) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
 }  // namespace mpa
 
 using namespace mpa;
 
 extern "C" {
+
+int mpa_gemm_tc_strided_to_chunks(const float* x, void* out, int rows, int K, int row_tile, int fmt, int r_n2, long long r_s1, long long r_s2,
+                                  int k_n2, long long k_s1, long long k_s2, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(x && out && rows > 0 && K > 0 && row_tile > 0 && row_tile % kGmTileN == 0 && r_n2 > 0 && k_n2 > 0,
+              "gemm_tc_strided_to_chunks: bad argument (row_tile: a multiple of 128)");
+  const int rpad = (rows + row_tile - 1) / row_tile * row_tile, kc = (K + 63) / 64 * 8;
+  const long long total = (long long)kc * rpad;
+  long long g = (total + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  strided_to_chunks_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(x, (uint16_t*)out, total, rows, K, rpad, fmt, r_n2, r_s1, r_s2, k_n2, k_s1,
+                                                                     k_s2);
+  MPA_CHECK_LAUNCH("gemm_tc_strided_to_chunks");
+  return MPA_OK;
+}
 
 size_t mpa_gemm_tc_chunked_bytes(int rows, int K, int row_tile) {
   if (rows <= 0 || K <= 0 || row_tile <= 0) return 0;
@@ -377,10 +419,15 @@ int mpa_gemm_tc_to_chunks(const float* x, void* out, int rows, int K, int row_ti
   return MPA_OK;
 }
 
-int mpa_gemm_tc_ex_f16(const void* x_chunks, const void* w_chunks, const float* bias, float* y, int M, int N, int K, int relu, int fmt, int x_rows,
-                       int w_rows, void* y_tok, int y_tok_rows, int y_tok_chunks, void* y_feat, int y_feat_rows, const void* mask_tok, float* colsum,
-                       void* stream) {
+int mpa_gemm_tc_run(const mpa_gemm_tc_desc* d, void* stream) {
   MPA_CHECK_ARCH();
+  MPA_REQUIRE(d, "gemm_tc: null descriptor");
+  const void *x_chunks = d->x_chunks, *w_chunks = d->w_chunks, *mask_tok = d->mask_tok;
+  const float* bias = d->bias;
+  float *y = d->y, *colsum = d->colsum;
+  void *y_tok = d->y_tok, *y_feat = d->y_feat;
+  const int M = d->M, N = d->N, K = d->K, relu = d->relu, fmt = d->fmt, x_rows = d->x_rows, w_rows = d->w_rows, y_tok_rows = d->y_tok_rows,
+            y_tok_chunks = d->y_tok_chunks, y_feat_rows = d->y_feat_rows;
   const bool extra = y_tok || y_feat || mask_tok || colsum;
   MPA_REQUIRE(x_chunks && w_chunks && (y || extra) && M > 0 && N > 0 && K > 0, "gemm_tc: bad argument");
   MPA_REQUIRE(fmt == MPA_FMT_F16 || fmt == MPA_FMT_BF16, "gemm_tc: fmt must be MPA_FMT_F16 or MPA_FMT_BF16");
@@ -409,6 +456,8 @@ int mpa_gemm_tc_ex_f16(const void* x_chunks, const void* w_chunks, const float* 
   p.y_feat = (uint16_t*)y_feat; p.y_feat_rows = y_feat_rows;
   p.mask_tok = (const uint16_t*)mask_tok; p.colsum = colsum;
   p.bf16 = fmt == MPA_FMT_BF16;
+  p.y_mn2 = d->y_mn2; p.y_ms1 = d->y_ms1; p.y_ms2 = d->y_mn2 > 0 || d->y_ms2 != 0 ? d->y_ms2 : (long long)N;
+  p.y_nn2 = d->y_nn2; p.y_ns1 = d->y_ns1; p.y_ns2 = d->y_nn2 > 0 || d->y_ns2 != 0 ? d->y_ns2 : 1;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -425,7 +474,10 @@ int mpa_gemm_tc_ex_f16(const void* x_chunks, const void* w_chunks, const float* 
   p.n_units = tiles * ks;
   const uint32_t f = (fmt == MPA_FMT_BF16) ? 1u : 0u;
   p.idesc = (1u << 4) | (f << 7) | (f << 10) | ((uint32_t)(kGmTileM >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  if (ks > 1) cudaMemsetAsync(y, 0, sizeof(float) * (size_t)M * N, (cudaStream_t)stream);
+  // the K slices meet in atomics: a dense result is zeroed here, a strided one (y_mn2 / y_nn2 / explicit strides) by the caller
+  const bool dense_y = d->y_mn2 == 0 && d->y_nn2 == 0 && d->y_ms2 == 0 && d->y_ns2 == 0;
+  if (ks > 1 && dense_y) cudaMemsetAsync(y, 0, sizeof(float) * (size_t)M * N, (cudaStream_t)stream);
+  if (ks > 1 && !dense_y && !d->y_zeroed) ks = 1, p.ksplit = 1, p.n_units = tiles;
   const size_t smem = (size_t)kGmStages * (kGmWBytes + kGmXBytes) + 256 + 4 * kGmTrBytes;
   {
     static unsigned char flags[64];
@@ -442,7 +494,10 @@ int mpa_gemm_tc_ex_f16(const void* x_chunks, const void* w_chunks, const float* 
 }
 
 int mpa_gemm_tc_f16(const void* x_chunks, const void* w_chunks, const float* bias, float* y, int M, int N, int K, int relu, int fmt, void* stream) {
-  return mpa_gemm_tc_ex_f16(x_chunks, w_chunks, bias, y, M, N, K, relu, fmt, 0, 0, nullptr, 0, 0, nullptr, 0, nullptr, nullptr, stream);
+  mpa_gemm_tc_desc d;
+  memset(&d, 0, sizeof(d));
+  d.x_chunks = x_chunks; d.w_chunks = w_chunks; d.bias = bias; d.y = y; d.M = M; d.N = N; d.K = K; d.relu = relu; d.fmt = fmt;
+  return mpa_gemm_tc_run(&d, stream);
 }
 
 }  // extern "C"

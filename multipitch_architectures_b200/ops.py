@@ -485,9 +485,46 @@ def gemm_tc(x, w_chunks, bias, N, relu, fmt, x_transposed=False, out=None, x_chu
     return y
 
 
+class GemmTcDesc(_ct.Structure):
+    _fields_ = [('x_chunks', _ct.c_void_p), ('w_chunks', _ct.c_void_p), ('bias', _ct.c_void_p), ('y', _ct.c_void_p),
+                ('M', _ct.c_int), ('N', _ct.c_int), ('K', _ct.c_int), ('relu', _ct.c_int), ('fmt', _ct.c_int), ('x_rows', _ct.c_int),
+                ('w_rows', _ct.c_int), ('y_tok', _ct.c_void_p), ('y_tok_rows', _ct.c_int), ('y_tok_chunks', _ct.c_int), ('y_feat', _ct.c_void_p),
+                ('y_feat_rows', _ct.c_int), ('mask_tok', _ct.c_void_p), ('colsum', _ct.c_void_p), ('y_mn2', _ct.c_int), ('y_nn2', _ct.c_int),
+                ('y_zeroed', _ct.c_int), ('y_ms1', _ct.c_longlong), ('y_ms2', _ct.c_longlong), ('y_ns1', _ct.c_longlong), ('y_ns2', _ct.c_longlong)]
+
+
+def _dptr(t):
+    if t is None:
+        return None
+    if not t.is_cuda or not t.is_contiguous():
+        raise _lib.MpaError('libmpa operators take contiguous CUDA tensors')
+    return t.data_ptr()
+
+
 def gemm_tc_ex(x_chunks, w_chunks, bias, M, N, K, relu, fmt, y=None, x_rows=0, w_rows=0, y_tok=None, y_tok_rows=0, y_tok_chunks=0, y_feat=None,
-               y_feat_rows=0, mask_tok=None, colsum=None):
-    """mpa_gemm_tc_ex_f16: the tcgen05 product on pre-chunked operands with optional 16-bit operand-layout copies of the result."""
-    call('gemm_tc_ex_f16', x_chunks, w_chunks, bias, y, M, N, K, int(bool(relu)), fmt, int(x_rows), int(w_rows), y_tok, int(y_tok_rows),
-         int(y_tok_chunks), y_feat, int(y_feat_rows), mask_tok, colsum, stream_ptr())
+               y_feat_rows=0, mask_tok=None, colsum=None, y_m=None, y_n=None, y_zeroed=False):
+    """mpa_gemm_tc_run: the tcgen05 product on pre-chunked operands; optional 16-bit operand-layout copies of the result (y_tok / y_feat),
+    ReLU-backward mask and bias-gradient sums in the epilogue, and a strided fp32 result (y_m / y_n = (n2, s1, s2) two-level indices)."""
+    d = GemmTcDesc()
+    d.x_chunks, d.w_chunks, d.bias, d.y = _dptr(x_chunks), _dptr(w_chunks), _dptr(bias), _dptr(y)
+    d.M, d.N, d.K, d.relu, d.fmt, d.x_rows, d.w_rows = M, N, K, int(bool(relu)), fmt, int(x_rows), int(w_rows)
+    d.y_tok, d.y_tok_rows, d.y_tok_chunks, d.y_feat, d.y_feat_rows = _dptr(y_tok), int(y_tok_rows), int(y_tok_chunks), _dptr(y_feat), int(y_feat_rows)
+    d.mask_tok, d.colsum, d.y_zeroed = _dptr(mask_tok), _dptr(colsum), int(bool(y_zeroed))
+    if y_m is not None:
+        d.y_mn2, d.y_ms1, d.y_ms2 = y_m
+    if y_n is not None:
+        d.y_nn2, d.y_ns1, d.y_ns2 = y_n
+    rc = _lib.lib().mpa_gemm_tc_run(_ct.byref(d), stream_ptr())
+    if rc != 0:
+        raise _lib.MpaError(f'mpa_gemm_tc_run failed ({rc}): {_lib.last_error()}')
     return y
+
+
+def strided_chunks(x, rows, K, row_tile, fmt, r_idx, k_idx):
+    """16-bit chunk-layout operand [ceil(K/64)*8][rows padded to row_tile][8] of the matrix whose element (r, k) sits at
+    x.flat[(r // r_idx[0]) * r_idx[1] + (r % r_idx[0]) * r_idx[2] + (k // k_idx[0]) * k_idx[1] + (k % k_idx[0]) * k_idx[2]]."""
+    rpad, kc = (rows + row_tile - 1) // row_tile * row_tile, (K + 63) // 64 * 8
+    out = torch.empty(kc * rpad * 16, dtype=torch.uint8, device=x.device)
+    call('gemm_tc_strided_to_chunks', _f32(x), out, rows, K, row_tile, fmt, int(r_idx[0]), _lib.i64(r_idx[1]), _lib.i64(r_idx[2]), int(k_idx[0]),
+         _lib.i64(k_idx[1]), _lib.i64(k_idx[2]), stream_ptr())
+    return out

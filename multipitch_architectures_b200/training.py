@@ -93,6 +93,49 @@ def _wgrad(conv, x, g, gw, gb):
          conv.padding[1], stream_ptr())
 
 
+ROWS_TC = True             # test knob: False = conv3 of the bf16 models on the fp32 strided-GEMM kernels (conv_rows.cu)
+
+
+def _rows_tc_eligible(model, conv, x):
+    """The head's full-height 75x1 convolution of a bf16 model with more than 10 output channels (thinner ones are HBM-bound matrix-vector
+    products: conv_rows_thin_*): forward and both gradients as tcgen05 GEMMs."""
+    return (ROWS_TC and model is not None and getattr(model, 'precision', 'fp32') == 'bf16' and _is_rows_conv(conv, x.shape[2])
+            and conv.weight.shape[0] > 10 and x.shape[3] % 8 == 0 and conv.bias is not None)
+
+
+def _rows_tc_forward(conv, x, act, a):
+    """Y[b][co][w] = act(sum_k W[co][k] x[b][k][w] + bias[co]), k = (ci, frame): tokens (b, w) x K on the tensor cores (bf16 operands, fp32
+    accumulate, K slices in atomics), then bias + activation in place."""
+    fm = ops.FMT_BF16
+    B, Cin, H, W = x.shape
+    Cout, K, Mt = conv.weight.shape[0], Cin * H, B * W
+    xf = ops.strided_chunks(x, Mt, K, 256, fm, (W, K * W, 1), (K, 0, W))
+    wc = ops.gemm_tc_chunks(conv.weight.detach().reshape(Cout, K), 128, fm)
+    y = torch.zeros(B, Cout, 1, W, dtype=torch.float32, device=x.device)
+    ops.gemm_tc_ex(xf, wc, None, Mt, Cout, K, False, fm, y=y, y_m=(W, Cout * W, 1), y_n=(0, 0, W), y_zeroed=True)
+    call('bias_act_f32', y, conv.bias, y, B, Cout, W, act, float(a), stream_ptr())
+    return y
+
+
+def _rows_tc_backward(conv, x, g, gw, gb, need_dx):
+    """g: gradient wrt the convolution output (activation already differentiated away).  Weight gradient [Cout][K] = g^T x over the B*W
+    tokens, data gradient [b][k][w] = W^T g written straight into NCHW."""
+    fm = ops.FMT_BF16
+    B, Cin, H, W = x.shape
+    Cout, K, Mt = conv.weight.shape[0], Cin * H, B * W
+    gt = ops.strided_chunks(g, Cout, Mt, 256, fm, (Cout, 0, W), (W, Cout * W, 1))
+    xt = ops.strided_chunks(x, K, Mt, 128, fm, (K, 0, W), (W, K * W, 1))
+    ops.gemm_tc_ex(gt, xt, None, Cout, K, Mt, False, fm, y=gw.view(Cout, K))
+    ops.channel_sum(g, out=gb)
+    if not need_dx:
+        return None
+    gf = ops.strided_chunks(g, Mt, Cout, 128, fm, (W, Cout * W, 1), (Cout, 0, W))
+    wt = ops.gemm_tc_chunks(conv.weight.detach().reshape(Cout, K), 256, fm, True)
+    gi = torch.empty(B, Cin, H, W, dtype=torch.float32, device=x.device)
+    ops.gemm_tc_ex(wt, gf, None, K, Mt, Cout, False, fm, y=gi, y_m=(0, 0, W), y_n=(W, K * W, 1))
+    return gi
+
+
 def _add(a, b):
     out = torch.empty_like(a)
     call('add_f32', a, b, out, _lib.i64(a.numel()), stream_ptr())

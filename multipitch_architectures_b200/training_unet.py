@@ -19,7 +19,7 @@ import torch
 from . import _lib, ops
 from ._lib import call, stream_ptr
 from .libdl.nn_models import _exec
-from .training import (TcConv, ctypes_u64, _act_bwd, _add, _conv_fwd, _dgrad, _dropout, _pool_bwd, _tc_s3_backward, _tc_s3_eligible, _tc_s3_forward,
+from .training import (TcConv, ctypes_u64, _rows_tc_backward, _rows_tc_eligible, _rows_tc_forward, _act_bwd, _add, _conv_fwd, _dgrad, _dropout, _pool_bwd, _tc_s3_backward, _tc_s3_eligible, _tc_s3_forward,
                        _wgrad)
 
 
@@ -68,6 +68,16 @@ class Tape:
                 if need_dx:
                     x.acc(gx)
             self.push(bwd_tc)
+            return out
+        if _rows_tc_eligible(self.model, conv, x.d):
+            out = Node(_rows_tc_forward(conv, x.d, act, a))
+
+            def bwd_rows():
+                g = out.g if act == ops.ACT_NONE else _act_bwd(out.d, out.g, act, a)
+                gx = _rows_tc_backward(conv, x.d, g, self.grads[name + '.weight'], self.grads[name + '.bias'], need_dx)
+                if need_dx:
+                    x.acc(gx)
+            self.push(bwd_rows)
             return out
         out = Node(_conv_fwd(conv, x.d, act, a))
 

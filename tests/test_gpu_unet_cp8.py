@@ -197,3 +197,24 @@ def test_cp8_tape_forward_without_grad_equals_the_recorded_forward():
         y2 = m(x)
     y2 = y2[0] if isinstance(y2, tuple) else y2
     assert torch.equal(y1.detach(), y2)
+
+
+@pytest.mark.parametrize('B,Cin,Cout,W', [(25, 80, 50, 72), (3, 10, 16, 72), (5, 24, 11, 40)])
+def test_full_height_convolution_on_the_tensor_cores(B, Cin, Cout, W):
+    """conv3 (75 x 1, VALID, one output row; unet_cnns.py:380-385) forward / weight gradient / data gradient as tcgen05 GEMMs whose
+    operands and results are addressed inside the NCHW tensors, against torch on the bf16-rounded operands."""
+    from multipitch_architectures_b200 import ops, training
+    H = 75
+    conv = torch.nn.Conv2d(Cin, Cout, (H, 1)).cuda()
+    x = rnd(B, Cin, H, W, seed=20).cuda()
+    g = rnd(B, Cout, 1, W, seed=21).cuda()
+    xr, wr, gr = bf(x).requires_grad_(True), bf(conv.weight.detach()).requires_grad_(True), bf(g)
+    ref = F.leaky_relu(F.conv2d(xr, wr, conv.bias), 0.3)
+    y = training._rows_tc_forward(conv, x, ops.ACT_LRELU, 0.3)
+    assert (y - ref.detach()).abs().max() < 2e-3 * ref.abs().max()
+    F.conv2d(xr, wr, conv.bias).backward(gr)
+    gw, gb = torch.empty_like(conv.weight), torch.empty_like(conv.bias)
+    gx = training._rows_tc_backward(conv, x, g, gw, gb, True)
+    assert (gw - wr.grad).abs().max() < 2e-3 * wr.grad.abs().max()
+    assert (gx - xr.grad).abs().max() < 2e-3 * xr.grad.abs().max()
+    assert (gb - g.sum((0, 2, 3))).abs().max() < 1e-4 * g.abs().sum() / Cout
