@@ -240,6 +240,18 @@ size_t mpa_conv_tc_pool_workspace_fmt(int Cout, int pitch, int J, int fmt);
  * w'[co'][ci'][kh][kw] = w[ci'][co'][KH-1-kh][KW-1-kw] of a forward weight w [Cin][Cout_total][KH][KW] (Cin = forward Cout). */
 int mpa_conv_tc_pack_weights_dev(const float* w_dev, void* packed_dev, int Cin, int Cout, int KH, int KW, int fmt, int J,
                                  int transpose_flip, int Cout_total, int co0, void* stream);
+/* All packed operands of a training step in one launch: a table of mpa_conv_tc_pack_weights_dev jobs (same argument meaning) is turned
+ * into its device form on the host (mpa_conv_tc_pack_table_build writes mpa_conv_tc_pack_table_bytes(n) bytes into table_host and returns the
+ * number of thread blocks of the flattened grid, negative on error; the caller copies the table to the device once), then mpa_conv_tc_pack_weights_multi re-packs every job from the current weights — the per-step
+ * refresh of the A operands after the optimiser update (replaces 2 launches per nn.Conv2d and step). */
+typedef struct mpa_pack_job {
+  const float* w;
+  void* packed;
+  int Cin, Cout, KH, KW, fmt, J, transpose_flip, Cout_total, co0;
+} mpa_pack_job;
+size_t mpa_conv_tc_pack_table_bytes(int n_jobs);
+int mpa_conv_tc_pack_table_build(const mpa_pack_job* jobs, int n_jobs, void* table_host);
+int mpa_conv_tc_pack_weights_multi(const void* table_dev, int n_jobs, int n_blocks, void* stream);
 /* HOST functions: un-duplicated weight pieces for weights_layout 1 (one filter row per piece; Cout a multiple of 8). */
 size_t mpa_conv_tc_ring_packed_bytes(int Cin, int Cout, int KH, int KW, int J);
 int mpa_conv_tc_ring_pack_weights(const float* w_host, void* packed_host, int Cin, int Cout, int KH, int KW, int fmt, int J);

@@ -1343,10 +1343,11 @@ __global__ void upsample2x_x3_kernel(const uint4* __restrict__ low, uint4* __res
 
 // Device-side packing of the A-operand tiles (same layout as mpa_conv_tc_pack_weights) for the training path, where the weights
 // change every step.  transpose_flip: pack the DATA-GRADIENT convolution w'[co'][ci'][kh][kw] = w[ci'][co'][KH-1-kh][KW-1-kw].
-__global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, long long total, int Cin, int Cout, int KH, int KW,
-                                    int J, int NC, int mpr, int fmt, int transpose_flip, int Cout_total, int co0) {
+__device__ __forceinline__ void pack_weights_range(const float* __restrict__ w, uint16_t* __restrict__ out, long long total, int Cin, int Cout,
+                                                   int KH, int KW, int J, int NC, int mpr, int fmt, int transpose_flip, int Cout_total, int co0,
+                                                   long long first, long long step) {
   const int n_paired = (NC / 2) * KW;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+  for (long long idx = first; idx < total; idx += step) {
     const int e = (int)(idx & 7);
     const int mrow = (int)((idx >> 3) & 127);
     const int kc = (int)((idx >> 10) & 1);
@@ -1370,6 +1371,35 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __res
     }
     out[idx] = cvt16(v, fmt);
   }
+}
+__global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, long long total, int Cin, int Cout, int KH, int KW,
+                                    int J, int NC, int mpr, int fmt, int transpose_flip, int Cout_total, int co0) {
+  pack_weights_range(w, out, total, Cin, Cout, KH, KW, J, NC, mpr, fmt, transpose_flip, Cout_total, co0,
+                     blockIdx.x * (long long)blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
+}
+// Every packed operand of a training step (forward and data-gradient tiles of all convolutions) in ONE launch: blockIdx.y = job of a
+// device-resident table (the step's 39 separate 7-us launches were 3.6 % of the SAUnet:L step)
+struct PackJobDev {
+  const float* w;
+  uint16_t* out;
+  long long total;
+  int Cin, Cout, KH, KW, J, NC, mpr, fmt, transpose_flip, Cout_total, co0;
+  int block0;              // first block of this job in the flattened grid (2048 elements per block)
+};
+constexpr int kPackPerBlock = 2048;
+__global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackJobDev* __restrict__ jobs, int n_jobs) {
+  __shared__ int job;
+  if (threadIdx.x == 0) {
+    int j = 0;
+    while (j + 1 < n_jobs && (int)blockIdx.x >= jobs[j + 1].block0) ++j;
+    job = j;
+  }
+  __syncthreads();
+  const PackJobDev j = jobs[job];
+  const long long first = (long long)((int)blockIdx.x - j.block0) * kPackPerBlock;
+  const long long last = first + kPackPerBlock < j.total ? first + kPackPerBlock : j.total;
+  pack_weights_range(j.w, j.out, last, j.Cin, j.Cout, j.KH, j.KW, j.J, j.NC, j.mpr, j.fmt, j.transpose_flip, j.Cout_total, j.co0,
+                     first + threadIdx.x, 256);
 }
 
 static inline int grid_for(long long total, int block) {
@@ -1481,6 +1511,33 @@ int mpa_conv_tc_pack_weights_dev(const float* w_dev, void* packed_dev, int Cin, 
   pack_weights_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w_dev, (uint16_t*)packed_dev, total, Cin, Cout, KH, KW, J, NC, mpr, fmt,
                                                                               transpose_flip, Cout_total, co0);
   MPA_CHECK_LAUNCH("conv_tc_pack_weights_dev");
+  return MPA_OK;
+}
+
+size_t mpa_conv_tc_pack_table_bytes(int n_jobs) { return n_jobs > 0 ? (size_t)n_jobs * sizeof(PackJobDev) : 0; }
+
+int mpa_conv_tc_pack_table_build(const mpa_pack_job* jobs, int n_jobs, void* table_host) {
+  MPA_REQUIRE(jobs && table_host && n_jobs > 0, "conv_tc_pack_table_build: bad argument");
+  PackJobDev* t = (PackJobDev*)table_host;
+  int blocks = 0;
+  for (int i = 0; i < n_jobs; ++i) {
+    const mpa_pack_job& a = jobs[i];
+    MPA_REQUIRE(a.w && a.packed && a.Cin > 0 && a.Cout > 0 && a.Cout <= 128 && a.KH > 0 && a.KW > 0 && a.J >= 0 && a.J * a.Cout <= 128 &&
+                    a.co0 >= 0 && a.co0 < a.Cout_total && (a.fmt == MPA_FMT_F16 || a.fmt == MPA_FMT_BF16),
+                "conv_tc_pack_table_build: bad job");
+    const int J = a.J == 0 ? j_blocks(a.Cout) : a.J, NC = (a.Cin + 7) / 8, mpr = mmas_per_row(NC, a.KW);
+    const long long total = (long long)(a.KH + J - 1) * mpr * (kATileBytes / 2);
+    t[i] = PackJobDev{a.w, (uint16_t*)a.packed, total, a.Cin, a.Cout, a.KH, a.KW, J, NC, mpr, a.fmt, a.transpose_flip, a.Cout_total, a.co0, blocks};
+    blocks += (int)((total + kPackPerBlock - 1) / kPackPerBlock);
+  }
+  return blocks;
+}
+
+int mpa_conv_tc_pack_weights_multi(const void* table_dev, int n_jobs, int n_blocks, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(table_dev && n_jobs > 0 && n_blocks > 0, "conv_tc_pack_weights_multi: bad argument");
+  pack_weights_multi_kernel<<<n_blocks, 256, 0, (cudaStream_t)stream>>>((const PackJobDev*)table_dev, n_jobs);
+  MPA_CHECK_LAUNCH("conv_tc_pack_weights_multi");
   return MPA_OK;
 }
 

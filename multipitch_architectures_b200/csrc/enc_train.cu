@@ -124,23 +124,25 @@ __global__ void __launch_bounds__(256) enc_fold_bwd_kernel(const float* __restri
 }
 
 // ---- the per-position kernels ---------------------------------------------------------------------------------------------------------
-constexpr int kBC = 32;          // batch items per register block of the projection loops (B = 25: one pass over the weight column)
+constexpr int kBC = 32;          // batch items per register block of the q|k|v projection (B = 25: one pass over the weight column)
+constexpr int kBG = 12;          // ... of the E-column projections, whose items are split over blockDim / E thread groups
 
-// out[b][j] (+ global copy) = sum_k in[b][k] * WT[k*ldw + j] + bias[j] for all b < B, this thread's column j; in: shared [B][E]
-template <class Store>
-__device__ __forceinline__ void project_column(const float* __restrict__ in, int B, int E, const float* __restrict__ WT, int ldw, int j, float bias,
-                                               Store store) {
-  for (int b0 = 0; b0 < B; b0 += kBC) {
-    float acc[kBC];
+// out[b][j] = sum_k in[b][k] * WT[k*ldw + j] + bias for the items b_lo <= b < b_hi and this thread's column j; in: shared [B][E].
+// NB items per register block (one pass over the weight column per block).
+template <int NB, class Store>
+__device__ __forceinline__ void project_column(const float* __restrict__ in, int b_lo, int b_hi, int E, const float* __restrict__ WT, int ldw, int j,
+                                               float bias, Store store) {
+  for (int b0 = b_lo; b0 < b_hi; b0 += NB) {
+    float acc[NB];
 #pragma unroll
-    for (int bb = 0; bb < kBC; ++bb) acc[bb] = bias;
+    for (int bb = 0; bb < NB; ++bb) acc[bb] = bias;
 #pragma unroll 2
     for (int k = 0; k < E; k += 4) {          // 8 independent weight loads in flight: the loop is bound by the L2 latency of WT otherwise
       const float w0 = WT[(size_t)k * ldw + j], w1 = WT[(size_t)(k + 1) * ldw + j], w2 = WT[(size_t)(k + 2) * ldw + j],
                   w3 = WT[(size_t)(k + 3) * ldw + j];
 #pragma unroll
-      for (int bb = 0; bb < kBC; ++bb) {
-        const int b = min(b0 + bb, B - 1);
+      for (int bb = 0; bb < NB; ++bb) {
+        const int b = min(b0 + bb, b_hi - 1);
         const float4 v = *reinterpret_cast<const float4*>(in + (size_t)b * E + k);
         acc[bb] = fmaf(v.x, w0, acc[bb]);
         acc[bb] = fmaf(v.y, w1, acc[bb]);
@@ -149,9 +151,18 @@ __device__ __forceinline__ void project_column(const float* __restrict__ in, int
       }
     }
 #pragma unroll
-    for (int bb = 0; bb < kBC; ++bb)
-      if (b0 + bb < B) store(b0 + bb, acc[bb]);
+    for (int bb = 0; bb < NB; ++bb)
+      if (b0 + bb < b_hi) store(b0 + bb, acc[bb]);
   }
+}
+// The E-column projections use ALL threads: thread = (column tid % E, item group tid / E), each group a contiguous range of the B items
+// (with E = 128 columns on 128 of the 384 threads the other 8 warps waited at the next barrier: a third of the forward kernel's time)
+__device__ __forceinline__ void item_range(int B, int E, int& col, int& b_lo, int& b_hi) {
+  const int groups = max(1, (int)blockDim.x / E), grp = threadIdx.x / E;
+  col = threadIdx.x - grp * E;
+  const int per = (B + groups - 1) / groups;
+  b_lo = min(B, grp * per);
+  b_hi = grp < groups ? min(B, b_lo + per) : b_lo;
 }
 
 __device__ __forceinline__ float drop_fac(const DropoutArgs& d, unsigned long long off, float scale, long long i) {
@@ -205,7 +216,7 @@ __global__ void __launch_bounds__(384) enc_attn_train_fwd_kernel(const EncTrainP
   for (int j = tid; j < E3; j += nt) {
     const int part = j / E, c = j - part * E, hh = c / hd;
     const int js = part * PS + hh * HS + (c - hh * hd);
-    project_column(t, B, E, p.w_qkvT, E3, j, p.b_qkv[j], [&](int b, float v) {
+    project_column<kBC>(t, 0, B, E, p.w_qkvT, E3, j, p.b_qkv[j], [&](int b, float v) {
       qkv[(size_t)b * RS + js] = v;
       p.qkv[((size_t)b * S + s) * E3 + j] = v;
     });
@@ -252,8 +263,10 @@ __global__ void __launch_bounds__(384) enc_attn_train_fwd_kernel(const EncTrainP
   }
   __syncthreads();
   // 4. out-projection + dropout + residual
-  for (int e = tid; e < E; e += nt)
-    project_column(att, B, E, p.w_projT, E, e, p.b_proj[e], [&](int b, float v) {
+  int e, b_lo, b_hi;
+  item_range(B, E, e, b_lo, b_hi);
+  if (b_lo < b_hi)
+    project_column<kBG>(att, b_lo, b_hi, E, p.w_projT, E, e, p.b_proj[e], [&](int b, float v) {
       const long long gi = ((long long)b * S + s) * E + e;
       if (p.d_att.p > 0.f) {
         const float f = drop_fac(p.d_att, off_a, sc_a, gi);
@@ -354,16 +367,19 @@ __global__ void __launch_bounds__(384) enc_attn_train_bwd_kernel(const EncTrainP
   }
   __syncthreads();
   // LayerNorm parameter gradients of this position's B tokens, then g_p = dropout mask * g_u1 (xh is overwritten by g_p)
-  for (int e = tid; e < E; e += nt) {
+  int col, b_lo, b_hi;
+  item_range(B, E, col, b_lo, b_hi);
+  if (b_lo < b_hi) {
+    const int e = col;
     float gw = 0.f, gb = 0.f;
-    for (int b = 0; b < B; ++b) {
+    for (int b = b_lo; b < b_hi; ++b) {
       const float gy = g_att[(size_t)b * E + e];
       gw = fmaf(gy, xh[(size_t)b * E + e], gw);
       gb += gy;
     }
     atomicAdd(&p.g_ln_w[e], gw);
     atomicAdd(&p.g_ln_b[e], gb);
-    for (int b = 0; b < B; ++b) {
+    for (int b = b_lo; b < b_hi; ++b) {
       const long long gi = ((long long)b * S + s) * E + e;
       float v = g_u1[(size_t)b * E + e];
       if (p.d_att.p > 0.f) {
@@ -376,7 +392,7 @@ __global__ void __launch_bounds__(384) enc_attn_train_bwd_kernel(const EncTrainP
   }
   __syncthreads();
   // 2. g_att = g_p W_proj   (g_att[b][k] = sum_e g_p[b][e] w_proj[e][k])
-  for (int k = tid; k < E; k += nt) project_column(xh, B, E, p.w_proj, E, k, 0.f, [&](int b, float v) { g_att[(size_t)b * E + k] = v; });
+  if (b_lo < b_hi) project_column<kBG>(xh, b_lo, b_hi, E, p.w_proj, E, col, 0.f, [&](int b, float v) { g_att[(size_t)b * E + col] = v; });
   __syncthreads();
   // 3. attention backward, head by head (the passes of batch_axis_attention_bwd_kernel on this CTA's shared tiles)
   const float sc = rsqrtf((float)hd);
@@ -441,8 +457,9 @@ __global__ void __launch_bounds__(384) enc_attn_train_bwd_kernel(const EncTrainP
     p.g_qkv[((size_t)b * S + s) * E3 + j] = g_qkv[i];
   }
   // 4. g_t = g_qkv W_qkv + g_u1 (residual), through the token dropout mask, scattered back to NCHW
-  for (int e = tid; e < E; e += nt)
-    project_column(g_qkv, B, E3, p.w_qkv, E, e, 0.f, [&](int b, float v) {
+  const int e = col;
+  if (b_lo < b_hi)
+    project_column<kBG>(g_qkv, b_lo, b_hi, E3, p.w_qkv, E, e, 0.f, [&](int b, float v) {
       v += g_u1[(size_t)b * E + e];
       if (p.d_tok.p > 0.f) {
         const float f = drop_fac(p.d_tok, off_t, sc_t, ((long long)b * S + s) * E + e);

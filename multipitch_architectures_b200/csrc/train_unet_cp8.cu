@@ -18,6 +18,10 @@ namespace mpa {
 
 constexpr int kUT = 256;          // threads per block of every kernel here
 
+// 4 MB of partial sums per device + (in front of them) the arrival counter of the "last block finishes the reduction" pattern: the block
+// (one per chunk plane, <= 64 chunks = 512 channels) of the "last block finishes the reduction" pattern: the slice block of a chunk that
+// arrives last merges that chunk's partials (one warp per channel) and resets the counter, so a per-channel reduction is ONE launch (the
+// separate final kernels were 36 launches of ~5 us per SAUnet:L training step).  Kernels of one stream run in order: one set is enough.
 static float* unet_scratch() {
   static float* ptr[64] = {nullptr};
   int dev = 0;
@@ -25,10 +29,21 @@ static float* unet_scratch() {
   if (dev < 0 || dev >= 64) dev = 0;
   if (!ptr[dev]) {
     float* p = nullptr;
-    if (cudaMalloc(&p, sizeof(float) * (1u << 20)) != cudaSuccess) return nullptr;
+    if (cudaMalloc(&p, sizeof(float) * ((1u << 20) + 64)) != cudaSuccess) return nullptr;
+    if (cudaMemset(p, 0, sizeof(float) * 64) != cudaSuccess) return nullptr;
     ptr[dev] = p;
   }
-  return ptr[dev];
+  return ptr[dev] + 64;
+}
+// counter: one per chunk plane (blockIdx.x); the last of the gridDim.y slice blocks of a chunk finishes that chunk's channels
+__device__ __forceinline__ bool last_block_done(unsigned* counter) {
+  __shared__ bool last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(counter, 1u) == gridDim.y - 1;
+  __syncthreads();
+  if (last) __threadfence();
+  return last;
 }
 
 // v[e] <- sum over the block of v[e], e < N (every thread gets the result); sh: kUT/32 * N floats
@@ -63,12 +78,65 @@ struct Cp8Geo {
 
 __device__ __forceinline__ float bn_val(float y, float mean, float rstd, float w, float b) { return (y - mean) * rstd * w + b; }
 
+__device__ __forceinline__ void chan_merge(float& n, float& mean, float& m2, float ns, float ms, float qs) {
+  if (ns <= 0.f) return;
+  const float nn = n + ns, delta = ms - mean;
+  mean += delta * (ns / nn);
+  m2 += qs + delta * delta * (n * ns / nn);
+  n = nn;
+}
+struct BnStatsFinal {
+  float* stats;            // [2C] mean | biased variance
+  float *run_mean, *run_var;
+  float momentum;
+  long long* nbt;
+};
+// one warp per channel: lane l merges slices l, l+32, ... in order, the 32 lane results are merged by a shuffle tree (fixed order).
+// Also the running-statistics update of nn.BatchNorm2d (momentum m; unbiased variance).
+__device__ __forceinline__ void bn_stats_merge(const float* __restrict__ partial, float* __restrict__ stats, unsigned n_tot, int C, int S, int c,
+                                               float* __restrict__ run_mean, float* __restrict__ run_var, float momentum) {
+  const int lane = threadIdx.x & 31;
+  float n = 0.f, mean = 0.f, m2 = 0.f;
+  float2 pv[16];                                   // S <= 512: all of this lane's slices are requested before the (dependent) merges
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int s = lane + 32 * i;
+    pv[i] = s < S ? __ldcg(reinterpret_cast<const float2*>(partial) + (size_t)c * S + s) : make_float2(0.f, 0.f);   // L2: written by other CTAs
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int s = lane + 32 * i;
+    if (s < S) {
+      const float ns = (float)((unsigned)((unsigned long long)n_tot * (s + 1) / S) - (unsigned)((unsigned long long)n_tot * s / S));
+      chan_merge(n, mean, m2, ns, pv[i].x, pv[i].y);
+    }
+  }
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float n2 = __shfl_xor_sync(0xffffffffu, n, o), me2 = __shfl_xor_sync(0xffffffffu, mean, o), q2 = __shfl_xor_sync(0xffffffffu, m2, o);
+    // both partners apply the same merge (lower lane's triple first), so all lanes agree
+    float an = n, am = mean, aq = m2, bn = n2, bm = me2, bq = q2;
+    if (lane & o) { an = n2; am = me2; aq = q2; bn = n; bm = mean; bq = m2; }
+    chan_merge(an, am, aq, bn, bm, bq);
+    n = an; mean = am; m2 = aq;
+  }
+  if (lane == 0) {
+    const float var = m2 / (float)n_tot;
+    stats[c] = mean;
+    stats[C + c] = var;
+    if (run_mean) {
+      run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * mean;
+      run_var[c] = (1.f - momentum) * run_var[c] + momentum * (var * ((float)n_tot / fmaxf((float)n_tot - 1.f, 1.f)));
+    }
+  }
+}
+
 // ---- BatchNorm batch statistics -------------------------------------------------------------------------------------------------------
 // grid (chunk, slice): per channel of the chunk the slice's mean and sum of squared deviations (two passes over the slice, the second one
 // from L1/L2), merged in slice order by the final kernel with Chan's update
 template <int FMT>
 __global__ void __launch_bounds__(kUT) bn_stats_partial_cp8_kernel(const uint4* __restrict__ y, float* __restrict__ partial, unsigned n, Cp8Geo g,
-                                                                   int ncs, int S) {
+                                                                   int ncs, int S, BnStatsFinal f) {
   __shared__ float sh[kUT / 32 * 8];
   const int ck = blockIdx.x, s = blockIdx.y;
   const unsigned i0 = (unsigned)((unsigned long long)n * s / S), i1 = (unsigned)((unsigned long long)n * (s + 1) / S);
@@ -104,46 +172,12 @@ __global__ void __launch_bounds__(kUT) bn_stats_partial_cp8_kernel(const uint4* 
     partial[((size_t)(ck * 8 + e) * S + s) * 2] = mean[e];
     partial[((size_t)(ck * 8 + e) * S + s) * 2 + 1] = q[e];
   }
-}
-
-__device__ __forceinline__ void chan_merge(float& n, float& mean, float& m2, float ns, float ms, float qs) {
-  if (ns <= 0.f) return;
-  const float nn = n + ns, delta = ms - mean;
-  mean += delta * (ns / nn);
-  m2 += qs + delta * delta * (n * ns / nn);
-  n = nn;
-}
-
-// one warp per channel: lane l merges slices l, l+32, ... in order, the 32 lane results are merged by a shuffle tree (fixed order).
-// Also the running-statistics update of nn.BatchNorm2d (momentum m; unbiased variance) and num_batches_tracked += 1.
-__global__ void __launch_bounds__(128) bn_stats_final_cp8_kernel(const float* __restrict__ partial, float* __restrict__ stats, unsigned n_tot, int C,
-                                                                 int S, float* __restrict__ run_mean, float* __restrict__ run_var, float momentum,
-                                                                 long long* __restrict__ nbt) {
-  const int c = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (blockIdx.x == 0 && threadIdx.x == 0 && nbt) nbt[0] += 1;
-  if (c >= C) return;
-  float n = 0.f, mean = 0.f, m2 = 0.f;
-  for (int s = lane; s < S; s += 32) {
-    const float ns = (float)((unsigned)((unsigned long long)n_tot * (s + 1) / S) - (unsigned)((unsigned long long)n_tot * s / S));
-    chan_merge(n, mean, m2, ns, partial[((size_t)c * S + s) * 2], partial[((size_t)c * S + s) * 2 + 1]);
-  }
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const float n2 = __shfl_xor_sync(0xffffffffu, n, o), me2 = __shfl_xor_sync(0xffffffffu, mean, o), q2 = __shfl_xor_sync(0xffffffffu, m2, o);
-    // both partners apply the same symmetric merge (lower lane's triple first), so all lanes agree
-    float an = n, am = mean, aq = m2, bn = n2, bm = me2, bq = q2;
-    if (lane & o) { an = n2; am = me2; aq = q2; bn = n; bm = mean; bq = m2; }
-    chan_merge(an, am, aq, bn, bm, bq);
-    n = an; mean = am; m2 = aq;
-  }
-  if (lane == 0) {
-    const float var = m2 / (float)n_tot;
-    stats[c] = mean;
-    stats[C + c] = var;
-    if (run_mean) {
-      run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * mean;
-      run_var[c] = (1.f - momentum) * run_var[c] + momentum * (var * ((float)n_tot / fmaxf((float)n_tot - 1.f, 1.f)));
-    }
+  unsigned* counter = reinterpret_cast<unsigned*>(partial) - 64 + ck;
+  if (!last_block_done(counter)) return;
+  bn_stats_merge(partial, f.stats, n, gridDim.x * 8, S, ck * 8 + (threadIdx.x >> 5), f.run_mean, f.run_var, f.momentum);     // 8 warps = 8 channels
+  if (threadIdx.x == 0) {
+    if (f.nbt && ck == 0) f.nbt[0] += 1;
+    *counter = 0u;
   }
 }
 
@@ -178,12 +212,15 @@ __global__ void __launch_bounds__(kUT) bn_relu_apply_cp8_kernel(const uint4* __r
   }
 }
 
+struct BnBwdFinal {
+  float *sums2c, *dw, *db, *conv_gb;
+};
 // ---- backward: the two per-channel sums ----------------------------------------------------------------------------------------------
 template <int FMT>
 __global__ void __launch_bounds__(kUT) bn_relu_bwd_partial_cp8_kernel(const uint4* __restrict__ g, const uint4* __restrict__ y,
                                                                       const float* __restrict__ stats, const float* __restrict__ w,
                                                                       const float* __restrict__ bias, float eps, float* __restrict__ partial,
-                                                                      unsigned n, Cp8Geo geo, int C, int ncs_g, int ncs_y, int S) {
+                                                                      unsigned n, Cp8Geo geo, int C, int ncs_g, int ncs_y, int S, BnBwdFinal f) {
   __shared__ float sh[kUT / 32 * 16];
   const int ck = blockIdx.x, s = blockIdx.y;
   const unsigned i0 = (unsigned)((unsigned long long)n * s / S), i1 = (unsigned)((unsigned long long)n * (s + 1) / S);
@@ -213,21 +250,28 @@ __global__ void __launch_bounds__(kUT) bn_relu_bwd_partial_cp8_kernel(const uint
     const int e = threadIdx.x & 7, which = threadIdx.x >> 3;
     partial[(size_t)(which * C + ck * 8 + e) * S + s] = acc[threadIdx.x];
   }
-}
-// sums2c[k] = sum_s partial[k][s] (slice order); d beta = s1, d gamma = s2; the conv-bias gradient is zeroed for the apply kernel's atomics
-__global__ void bn_relu_bwd_final_cp8_kernel(const float* __restrict__ partial, float* __restrict__ sums2c, float* __restrict__ dw,
-                                             float* __restrict__ db, float* __restrict__ conv_gb, int C, int S) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= 2 * C) return;
-  float t = 0.f;
-  for (int s = 0; s < S; ++s) t += partial[(size_t)k * S + s];
-  sums2c[k] = t;
-  if (k < C) {
-    db[k] = t;
-    if (conv_gb) conv_gb[k] = 0.f;
-  } else {
-    dw[k - C] = t;
+  unsigned* counter = reinterpret_cast<unsigned*>(partial) - 64 + ck;
+  if (!last_block_done(counter)) return;
+  // sums2c[k] = sum_s partial[k][s] (lane-strided, then a shuffle tree: fixed order) for the 16 rows of this chunk, two per warp;
+  // d beta = s1, d gamma = s2; the conv-bias gradient is zeroed for the apply kernel's atomics
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int which = r, e = threadIdx.x >> 5;
+    const int k = which * C + ck * 8 + e;
+    float t = 0.f;
+    for (int sl = threadIdx.x & 31; sl < S; sl += 32) t += __ldcg(&partial[(size_t)k * S + sl]);
+    t = warp_sum(t);
+    if ((threadIdx.x & 31) == 0) {
+      f.sums2c[k] = t;
+      if (which == 0) {
+        f.db[k] = t;
+        if (f.conv_gb) f.conv_gb[k] = 0.f;
+      } else {
+        f.dw[k - C] = t;
+      }
+    }
   }
+  if (threadIdx.x == 0) *counter = 0u;
 }
 
 // ---- backward apply: dy (CP8) and the conv-bias gradient ------------------------------------------------------------------------------
@@ -390,16 +434,15 @@ int mpa_bn_stats_cp8(const void* y_cp8, float* stats, int B, int C, int T, int F
   if (ncs <= 0) ncs = NCk;
   const unsigned n = (unsigned)B * T * F;
   const int S = slices_for(n, NCk);
-  MPA_REQUIRE((size_t)C * S * 2 <= (1u << 20), "bn_stats_cp8: too many channels");
+  MPA_REQUIRE((size_t)C * S * 2 <= (1u << 20) && NCk <= 64, "bn_stats_cp8: too many channels (<= 512)");
   const Cp8Geo g{T, F, T + 2 * pt, pitch, pf, pt};
   cudaStream_t st = (cudaStream_t)stream;
+  const BnStatsFinal f{stats, running_mean, running_var, momentum, num_batches_tracked};
   if (fmt == MPA_FMT_BF16)
-    bn_stats_partial_cp8_kernel<MPA_FMT_BF16><<<dim3(NCk, S), kUT, 0, st>>>((const uint4*)y_cp8, scratch, n, g, ncs, S);
+    bn_stats_partial_cp8_kernel<MPA_FMT_BF16><<<dim3(NCk, S), kUT, 0, st>>>((const uint4*)y_cp8, scratch, n, g, ncs, S, f);
   else
-    bn_stats_partial_cp8_kernel<MPA_FMT_F16><<<dim3(NCk, S), kUT, 0, st>>>((const uint4*)y_cp8, scratch, n, g, ncs, S);
-  MPA_CHECK_LAUNCH("bn_stats_partial_cp8");
-  bn_stats_final_cp8_kernel<<<ceil_div(C, 4), 128, 0, st>>>(scratch, stats, n, C, S, running_mean, running_var, momentum, num_batches_tracked);
-  MPA_CHECK_LAUNCH("bn_stats_final_cp8");
+    bn_stats_partial_cp8_kernel<MPA_FMT_F16><<<dim3(NCk, S), kUT, 0, st>>>((const uint4*)y_cp8, scratch, n, g, ncs, S, f);
+  MPA_CHECK_LAUNCH("bn_stats_cp8");
   return MPA_OK;
 }
 
@@ -434,20 +477,19 @@ int mpa_bn_relu_bwd_cp8(const void* g_cp8, const void* y_cp8, void* dy_cp8, cons
   if (ncs_dy <= 0) ncs_dy = NCk;
   const unsigned n = (unsigned)B * T * F;
   const int S = slices_for(n, NCk);
-  MPA_REQUIRE((size_t)2 * C * S + 2 * C <= (1u << 20), "bn_relu_bwd_cp8: too many channels");
+  MPA_REQUIRE((size_t)2 * C * S + 2 * C <= (1u << 20) && NCk <= 64, "bn_relu_bwd_cp8: too many channels (<= 512)");
   float* sums = scratch + (size_t)2 * C * S;
   const Cp8Geo geo{T, F, T + 2 * pt, pitch, pf, pt};
   cudaStream_t st = (cudaStream_t)stream;
   const dim3 grid_a(ceil_div((long long)T * F, 4 * kUT), B * NCk);
+  const BnBwdFinal f{sums, g_weight, g_bias, g_conv_bias};
   if (fmt == MPA_FMT_BF16)
     bn_relu_bwd_partial_cp8_kernel<MPA_FMT_BF16><<<dim3(NCk, S), kUT, 0, st>>>((const uint4*)g_cp8, (const uint4*)y_cp8, stats, weight, bias, eps,
-                                                                              scratch, n, geo, C, ncs_g, ncs_y, S);
+                                                                              scratch, n, geo, C, ncs_g, ncs_y, S, f);
   else
     bn_relu_bwd_partial_cp8_kernel<MPA_FMT_F16><<<dim3(NCk, S), kUT, 0, st>>>((const uint4*)g_cp8, (const uint4*)y_cp8, stats, weight, bias, eps,
-                                                                             scratch, n, geo, C, ncs_g, ncs_y, S);
-  MPA_CHECK_LAUNCH("bn_relu_bwd_partial_cp8");
-  bn_relu_bwd_final_cp8_kernel<<<ceil_div(2 * C, 128), 128, 0, st>>>(scratch, sums, g_weight, g_bias, g_conv_bias, C, S);
-  MPA_CHECK_LAUNCH("bn_relu_bwd_final_cp8");
+                                                                             scratch, n, geo, C, ncs_g, ncs_y, S, f);
+  MPA_CHECK_LAUNCH("bn_relu_bwd_sums_cp8");
   const float inv_n = 1.f / (float)n;
   if (fmt == MPA_FMT_BF16)
     bn_relu_bwd_apply_cp8_kernel<MPA_FMT_BF16><<<grid_a, kUT, 0, st>>>((const uint4*)g_cp8, (const uint4*)y_cp8, (uint4*)dy_cp8, stats, weight, bias,

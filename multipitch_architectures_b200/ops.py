@@ -451,16 +451,60 @@ def channel_sum_cp8(g, out=None):
     return out
 
 
+class PackJob(_ct.Structure):
+    _fields_ = [('w', _ct.c_void_p), ('packed', _ct.c_void_p), ('Cin', _ct.c_int), ('Cout', _ct.c_int), ('KH', _ct.c_int), ('KW', _ct.c_int),
+                ('fmt', _ct.c_int), ('J', _ct.c_int), ('transpose_flip', _ct.c_int), ('Cout_total', _ct.c_int), ('co0', _ct.c_int)]
+
+
+class PackPlan:
+    """The conv_tc_pack_dev calls of one training step, recorded during the first step of their owner (a fused train step whose
+    parameters are views of one flat buffer: stable pointers) and from then on re-packed by ONE launch at the start of every step
+    (mpa_conv_tc_pack_weights_multi); the individual calls then just hand out their persistent buffer."""
+
+    def __init__(self):
+        self.index, self.jobs, self.table, self.fresh = {}, [], None, False
+
+    def refresh(self):
+        if self.table is not None:
+            call('conv_tc_pack_weights_multi', self.table, len(self.jobs), self.n_blocks, stream_ptr())
+            self.fresh = True
+
+    def build(self):
+        if self.table is not None or not self.jobs:
+            return
+        L = _lib.lib()
+        L.mpa_conv_tc_pack_table_bytes.restype = _ct.c_size_t
+        arr = (PackJob * len(self.jobs))(*self.jobs)
+        host = (_ct.c_ubyte * L.mpa_conv_tc_pack_table_bytes(len(self.jobs)))()
+        self.n_blocks = L.mpa_conv_tc_pack_table_build(arr, len(self.jobs), host)
+        if self.n_blocks <= 0:
+            raise _lib.MpaError('conv_tc_pack_table_build: ' + _lib.last_error())
+        dev = next(iter(self.index.values())).device
+        self.table = torch.frombuffer(bytearray(host), dtype=torch.uint8).to(dev)
+
+
+_PACK_PLAN = None
+
+
 def conv_tc_pack_dev(w, Cin, Cout, ksize, fmt, transpose_flip=False, Cout_total=None, co0=0, J=0):
     """Device-side packing of conv_tc A-operand tiles from the fp32 weight tensor `w` (state_dict layout, on the GPU).
     transpose_flip: pack the data-gradient convolution of the forward weight `w` (see mpa_conv_tc_pack_weights_dev)."""
     KH, KW = ksize
+    plan = _PACK_PLAN
+    Ct = Cout if Cout_total is None else Cout_total
+    key = (w.data_ptr(), Cin, Cout, KH, KW, fmt, int(bool(transpose_flip)), Ct, co0, J)
+    if plan is not None and plan.fresh and key in plan.index:
+        return plan.index[key]
     nbytes = _lib.lib().mpa_conv_tc_packed_bytes(Cin, Cout, KH, KW, J)
     if nbytes == 0:
         raise _lib.MpaError(f'conv_tc cannot pack Cin={Cin} Cout={Cout} K={KH}x{KW}')
-    packed = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
-    call('conv_tc_pack_weights_dev', _f32(w.detach()), packed, Cin, Cout, KH, KW, fmt, J, int(bool(transpose_flip)),
-         Cout if Cout_total is None else Cout_total, co0, stream_ptr())
+    packed = plan.index.get(key) if plan is not None else None
+    if packed is None:
+        packed = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+        if plan is not None and plan.table is None:
+            plan.index[key] = packed
+            plan.jobs.append(PackJob(w.data_ptr(), packed.data_ptr(), Cin, Cout, KH, KW, fmt, J, int(bool(transpose_flip)), Ct, co0))
+    call('conv_tc_pack_weights_dev', _f32(w.detach()), packed, Cin, Cout, KH, KW, fmt, J, int(bool(transpose_flip)), Ct, co0, stream_ptr())
     return packed
 
 

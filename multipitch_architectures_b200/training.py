@@ -93,6 +93,7 @@ def _wgrad(conv, x, g, gw, gb):
          conv.padding[1], stream_ptr())
 
 
+PACK_MULTI = True          # test knob: False = one weight-packing launch per convolution and direction
 ROWS_TC = True             # test knob: False = conv3 of the bf16 models on the fp32 strided-GEMM kernels (conv_rows.cu)
 
 
@@ -213,17 +214,30 @@ class TcConv:
         @contextlib.contextmanager
         def cm():
             prev, cls._scope = cls._scope, id(owner)
+            plan = cls._plans.get(id(owner))
+            if plan is None:
+                plan = cls._plans[id(owner)] = ops.PackPlan()
+            prev_plan, ops._PACK_PLAN = ops._PACK_PLAN, plan
+            plan.fresh = False
+            if PACK_MULTI:
+                plan.refresh()           # every packed operand of the step in one launch (from the second step on)
             try:
                 yield
+                if PACK_MULTI:
+                    plan.build()
             finally:
-                cls._scope = prev
+                cls._scope, ops._PACK_PLAN = prev, prev_plan
+                plan.fresh = False
         return cm()
+
+    _plans = {}
 
     @classmethod
     def release(cls, owner):
         """Drop every pooled buffer of `owner`."""
         for k in [k for k in cls._pool if k[0] == id(owner)]:
             del cls._pool[k]
+        cls._plans.pop(id(owner), None)
 
     @classmethod
     def _buf(cls, tag, B, C, T, F, dev, fmt):
