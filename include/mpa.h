@@ -61,6 +61,15 @@ long long mpa_launch_count(void);
 int mpa_layernorm_cf_f32(const float* x, const float* ln_w, const float* ln_b, float* out,
                          int B, int C, int T, int F, float eps, float gamma_log, void* stream);
 
+/* The same LayerNorm written straight into 16-bit CP8 planes (one chunk, C <= 8; geometry as mpa_nchw_to_cp8) — the input of the first
+ * tensor-core convolution of a training step, without the fp32 NCHW copy and its converter pass — and the matching parameter gradient
+ * that reads the gradient wrt the LayerNorm output from the CP8 planes the first convolution's data gradient wrote
+ * (nn.LayerNorm([C,F]).weight.grad / .bias.grad of basic_cnns.py:371 / unet_cnns.py:355 after loss.backward()). */
+int mpa_layernorm_cf_cp8(const float* x, const float* ln_w, const float* ln_b, void* out_cp8, int B, int C, int T, int F, int pitch, int pf,
+                         int pt, float eps, float gamma_log, int fmt, void* stream);
+int mpa_layernorm_cf_param_grad_cp8(const float* x, const void* g_cp8, float* g_w, float* g_b, int B, int C, int T, int F, int pitch, int pf,
+                                    int pt, int fmt, float eps, float gamma_log, void* stream);
+
 /* Frame-major variant used by the streaming inference engine: frames [C][N][F] (the HCQT layout) ->
  * normalised frames; rows s with s < lead or s >= lead+N are the patch zero padding and come out as ln_b
  * (LayerNorm of an all-zero row).  out_f32 [C][lead+N+trail][F] and/or out_cp8 CP8 plane (1 chunk). */

@@ -66,6 +66,58 @@ __global__ void __launch_bounds__(128) layernorm_cf_kernel(const float* __restri
   }
 }
 
+// The same row LayerNorm written straight into the 16-bit CP8 planes the first convolution reads (C <= 8: one chunk; channels >= C hold
+// zeros): the fp32 NCHW copy of the normalised input and its converter pass (2 x 100 MB per CNN:XS training step) disappear.  The row is
+// staged in shared memory as [F][8] 16-bit so that every pixel leaves as one 16-byte store.
+template <int MAXV>
+__global__ void __launch_bounds__(128) layernorm_cf_cp8_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                               const float* __restrict__ bsh, uint4* __restrict__ out, int C, int T, int F, int TP,
+                                                               int P, int pf, int pt, float eps, float gamma_log, int fmt) {
+  extern __shared__ __align__(16) uint16_t row16[];      // [F][8]
+  __shared__ float sh[8];
+  const int b = blockIdx.x / T, t = blockIdx.x % T;
+  const int n = C * F;
+  const float* xr = x + ((size_t)b * C * T + t) * F;
+  float v[MAXV];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < F * 4; i += 128) reinterpret_cast<uint32_t*>(row16)[i] = 0u;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int e = threadIdx.x + i * 128;
+    float val = 0.f;
+    if (e < n) {
+      const int c = e / F, f = e - c * F;
+      val = xr[(size_t)c * T * F + f];
+      if (gamma_log > 0.f) val = logf(__fadd_rn(1.f, __fmul_rn(gamma_log, val)));
+      s += val;
+    }
+    v[i] = val;
+  }
+  const float mean = block_sum(s, sh) / n;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int e = threadIdx.x + i * 128;
+    if (e < n) {
+      const float d = v[i] - mean;
+      q += d * d;
+    }
+  }
+  const float rstd = rsqrtf(block_sum(q, sh) / n + eps);      // (block_sum's barriers order the zero fill before the writes below)
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int e = threadIdx.x + i * 128;
+    if (e < n) {
+      const int c = e / F, f = e - c * F;
+      const float r = (v[i] - mean) * rstd * w[e] + bsh[e];
+      row16[f * 8 + c] = fmt == MPA_FMT_BF16 ? __bfloat16_as_ushort(__float2bfloat16(r)) : __half_as_ushort(__float2half_rn(r));
+    }
+  }
+  __syncthreads();
+  uint4* orow = out + ((size_t)b * TP + pt + t) * P + pf;
+  for (int f = threadIdx.x; f < F; f += 128) orow[f] = reinterpret_cast<const uint4*>(row16)[f];
+}
+
 // frame-major: frames [C][N][F]; output rows s in [0, lead+N+trail); pad rows -> bias
 template <int MAXV>
 __global__ void __launch_bounds__(128) layernorm_frames_kernel(const float* __restrict__ frames, const float* __restrict__ w,
@@ -340,6 +392,18 @@ int mpa_layernorm_cf_f32(const float* x, const float* ln_w, const float* ln_b, f
   else
     layernorm_cf_kernel<16><<<B * T, 128, 0, st>>>(x, ln_w, ln_b, out, C, T, F, eps, gamma_log);
   MPA_CHECK_LAUNCH("layernorm_cf");
+  return MPA_OK;
+}
+
+int mpa_layernorm_cf_cp8(const float* x, const float* ln_w, const float* ln_b, void* out_cp8, int B, int C, int T, int F, int pitch, int pf,
+                         int pt, float eps, float gamma_log, int fmt, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(x && ln_w && ln_b && out_cp8 && B > 0 && C > 0 && C <= 8 && T > 0 && F > 0 && pitch >= pf + F && pt >= 0 &&
+                  (fmt == MPA_FMT_BF16 || fmt == MPA_FMT_F16) && C * F <= 128 * 11,
+              "layernorm_cf_cp8: bad argument (C <= 8, C*F <= 1408, 16-bit formats)");
+  layernorm_cf_cp8_kernel<11><<<B * T, 128, (size_t)F * 16, (cudaStream_t)stream>>>(x, ln_w, ln_b, (uint4*)out_cp8, C, T, F, T + 2 * pt, pitch, pf,
+                                                                                   pt, eps, gamma_log, fmt);
+  MPA_CHECK_LAUNCH("layernorm_cf_cp8");
   return MPA_OK;
 }
 

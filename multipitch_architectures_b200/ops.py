@@ -31,6 +31,22 @@ def layernorm_cf(x, w, b, eps=1e-5, gamma_log=0.0):
     return out
 
 
+def layernorm_cf_cp8(x, w, b, eps, out, gamma_log=0.0):
+    """LayerNorm([C,F]) of x [B,C,T,F] fp32 written straight into the CP8 planes `out` (one chunk: C <= 8)."""
+    B, C, T, F = x.shape
+    assert (out.B, out.T, out.F) == (B, T, F) and out.NC == 1 and out.ncs == 1
+    call('layernorm_cf_cp8', _f32(x), _f32(w), _f32(b), out.ptr(), B, C, T, F, out.pitch, out.pf, out.pt, float(eps), float(gamma_log), out.fmt,
+         stream_ptr())
+    return out
+
+
+def layernorm_cf_param_grad_cp8(x, g, gw, gb, eps, gamma_log=0.0):
+    """gw / gb [C,F] (overwritten) = gradients of the LayerNorm([C,F]) affine parameters; g: CP8 gradient wrt the LayerNorm output."""
+    B, C, T, F = x.shape
+    assert (g.B, g.T, g.F) == (B, T, F) and g.ncs == 1
+    call('layernorm_cf_param_grad_cp8', _f32(x), g.ptr(), gw, gb, B, C, T, F, g.pitch, g.pf, g.pt, g.fmt, float(eps), float(gamma_log), stream_ptr())
+
+
 def conv2d(x, wp, bias, Cout, ksize, stride=(1, 1), padding=(0, 0), act=ACT_NONE, act_param=0.0,
            scale=None, shift=None, x2=None):
     B, C1, H, W = x.shape

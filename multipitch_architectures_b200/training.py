@@ -390,11 +390,14 @@ def _cp8_resident(model, blocks, F):
             and _tc_s3_eligible(model, model.conv2[0], F))
 
 
-def _cnn_train_forward_cp8(model, blocks, z, sv, site, drop):
+def _cnn_train_forward_cp8(model, blocks, x, sv, site, drop):
     a, p, seed = model.a_lrelu, sv['p'], sv['seed']
     fmt = ops.FMT_BF16
-    B, C0, T, F = z.shape
-    xc = ops.nchw_to_cp8(z, out=TcConv._buf(blocks[0][0] + ':x', B, C0, T, F, z.device, fmt), fmt=fmt)
+    B, C0, T, F = x.shape
+    z = x           # (device of the buffers below)
+    ln = model.layernorm
+    # LayerNorm writes the first convolution's input planes directly (no fp32 copy of the normalised patch, no converter pass)
+    xc = ops.layernorm_cf_cp8(x, ln.weight, ln.bias, ln.eps, TcConv._buf(blocks[0][0] + ':x', B, C0, T, F, x.device, fmt))
     sd, sm = _step_args()
     for name, conv in blocks:
         yc = TcConv.forward_cp8(name, conv, xc, ops.ACT_LRELU, a)
@@ -427,9 +430,9 @@ def cnn_train_forward(model, x, seed=0, step=0):
         site[0] += 1
         return _dropout(t, p, seed, site[0])
     sv = {'x': x, 'blocks': [], 'p': p, 'seed': seed, 'site0': step * 64}
+    if _cp8_resident(model, blocks, x.shape[3]) and x.shape[1] <= 8:
+        return _cnn_train_forward_cp8(model, blocks, x, sv, site, drop)
     z = ops.layernorm_cf(x, model.layernorm.weight, model.layernorm.bias, model.layernorm.eps)
-    if _cp8_resident(model, blocks, z.shape[3]):
-        return _cnn_train_forward_cp8(model, blocks, z, sv, site, drop)
     for i, (name, conv) in enumerate(blocks):
         if TcConv.eligible(model, conv, z.shape[3]):
             act, xc = TcConv.forward(name, conv, z, ops.ACT_LRELU, a)
@@ -487,7 +490,8 @@ def cnn_train_backward(model, sv, g_y, grads):
             call('pool3_bwd_dropout_cp8', yc.ptr(), gzc.ptr(), gc.ptr(), yc.B, yc.C, yc.T, yc.F, yc.pitch, yc.pf, yc.pt, fmt, ops.ACT_LRELU, float(a),
                  float(p), ctypes_u64(seed), ctypes_u64(site[0]), sd, sm, stream_ptr())
             gzc = TcConv.backward_cp8(name, conv, xc, gc, grads[f'{name}.0.weight'], grads[f'{name}.0.bias'], need_dx=True)
-        g_z = ops.cp8_to_nchw(gzc)
+        ops.layernorm_cf_param_grad_cp8(sv['x'], gzc, grads['layernorm.weight'], grads['layernorm.bias'], model.layernorm.eps)
+        return grads
     elif sv.get('x2c') is not None:
         g_z = _tc_s3_backward('conv2', c2, sv['x2c'], g, grads['conv2.0.weight'], grads['conv2.0.bias'])
     else:

@@ -170,6 +170,13 @@ class Tape:
         self.push(bwd)
         return out
 
+    def layernorm_cf_cp8(self, ln, x, dst):
+        """LayerNorm([C,F]) on the network input, written straight into the first convolution's planes; the parameter gradients read the
+        planes the first convolution's data gradient wrote."""
+        out = Node(ops.layernorm_cf_cp8(x, ln.weight, ln.bias, ln.eps, dst))
+        self.push(lambda: ops.layernorm_cf_param_grad_cp8(x, out.g, self.grads['layernorm.weight'], self.grads['layernorm.bias'], ln.eps))
+        return out
+
     # ---------------------------------------------------------------------------------------------- CP8-resident stages (bf16)
     # Nodes whose .d / .g are ops.CP8 planes: between two tensor-core convolutions nothing leaves the 16-bit planes (train_unet_cp8.cu).
     # Every such node has ONE consumer, except the skip connections (max-pool + concat), whose two gradients meet in maxpool_cp8's backward.
@@ -556,7 +563,8 @@ def _unet_train_forward_cp8(model, x, grads, seed, step):
     c = [model.inc.double_conv[4].weight.shape[0]] + [getattr(model, f'down{i}')[1].double_conv[4].weight.shape[0] for i in (1, 2, 3, 4)]
     up_out = [getattr(model, f'upconv{i}').double_conv[4].weight.shape[0] for i in (1, 2, 3, 4)]
     buf = lambda tag, lv, ch: TcConv._buf(tag, B, ch, geo[lv][0], geo[lv][1], dev, fmt)
-    z = tp.f32_to_cp8('inc.in', tp.layernorm_cf(model.layernorm, x), fmt)
+    z = tp.layernorm_cf_cp8(model.layernorm, x, TcConv._buf('inc.in:x16', B, C, T, F, dev, fmt)) if C <= 8 else \
+        tp.f32_to_cp8('inc.in', tp.layernorm_cf(model.layernorm, x), fmt)
     cat = {3: buf('cat3', 3, c[3] + c[4]), 2: buf('cat2', 2, c[2] + up_out[0]), 1: buf('cat1', 1, c[1] + up_out[1]),
            0: buf('cat0', 0, c[0] + up_out[2])}
     xs = [tp.double_conv_cp8('inc', model.inc, z, cat[0].channels(0, c[0]))]
