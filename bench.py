@@ -557,7 +557,12 @@ def run_train(ctx, name, precision, steps, warmup, preload):
         torch.cuda.synchronize()
         t = [a.elapsed_time(b) for a, b in comm]
         res['allreduce'] = {'ms_per_step': sum(t) / len(t), 'bytes': int(step.flat_g.numel() * 4), 'calls_timed': len(t),
-                            'share_of_step': (sum(t) / len(t)) / (ms / steps), 'how': 'CUDA events around dist.all_reduce(flat gradients) inside the timed steps'}
+                            'share_of_step': (sum(t) / len(t)) / (ms / steps),
+                            'overlapped_bytes': int((step.flat_g.numel() - getattr(step, 'n_trunk', step.flat_g.numel())) * 4)
+                            if getattr(step, 'overlap_comm', False) and getattr(step, 'n_trunk', 0) > 0 else 0,
+                            'how': 'CUDA events around the part of the gradient all-reduce the step waits for, inside the timed steps '
+                                   '(U-Net family: the gradients behind the encoder trunk are reduced on the NCCL stream while the trunk\'s backward '
+                                   'runs; `overlapped_bytes` of `bytes` are issued before it)'}
     if hasattr(step, 'release'):
         step.release()
     del step, model

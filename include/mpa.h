@@ -257,7 +257,14 @@ typedef struct mpa_pack_job {
   const float* w;
   void* packed;
   int Cin, Cout, KH, KW, fmt, J, transpose_flip, Cout_total, co0;
+  int split, C0;          /* 0, 0 or the phase-split form (mpa_conv_tc_pack_weights_split_dev) */
 } mpa_pack_job;
+/* Phase-split form of a KH x s convolution with stride (1, s) (the head's conv2, s = 3; real weights w[Cout][C0][KH][s]): packed as the
+ * stride-1 KH x 1 convolution over s * C0p logical input channels (channel ph * C0p + c = tap ph of real channel c; KW = 1, Cin = s * C0p),
+ * whose input are phase-split planes (mpa_conv_tc_f16 out_mode 2).  transpose_flip: its data gradient, Cout_total = s * C0p logical output
+ * channels (the gradient comes out phase-split), Cin = the real (padded) output channels.  Otherwise as mpa_conv_tc_pack_weights_dev. */
+int mpa_conv_tc_pack_weights_split_dev(const float* w_dev, void* packed_dev, int Cin, int Cout, int KH, int KW, int fmt, int J,
+                                       int transpose_flip, int Cout_total, int co0, int split, int C0, void* stream);
 size_t mpa_conv_tc_pack_table_bytes(int n_jobs);
 int mpa_conv_tc_pack_table_build(const mpa_pack_job* jobs, int n_jobs, void* table_host);
 int mpa_conv_tc_pack_weights_multi(const void* table_dev, int n_jobs, int n_blocks, void* stream);
@@ -398,6 +405,16 @@ int mpa_pool3_bwd_dropout_cp8(const void* a_cp8, const void* g_out_cp8, void* g_
                               const long long* step_dev, unsigned long long step_mul, void* stream);
 int mpa_channel_sum_cp8(const void* g_cp8, float* out, int B, int C, int T, int F, int pitch, int pf, int pt, int fmt, int ncs,
                         void* stream);
+/* The same pair with a phase-split hand-over (CNN family, head conv2 = 3x3 / stride (1,3)): the forward writes the pooled activation into
+ * phase-split planes (bin f -> phase set f % out_split, column f / out_split, pitch out_pitch; layout of mpa_conv_tc_f16 out_mode 2), the
+ * backward reads the gradient wrt the pool output from such planes (what the stride-1 form of conv2's data gradient writes). */
+int mpa_pool3_dropout_split_cp8(const void* a_cp8, void* out_cp8, int B, int C, int T, int F, int pitch, int pf, int pt, int fmt, float p,
+                                unsigned long long seed, unsigned long long offset, const long long* step_dev,
+                                unsigned long long step_mul, int out_split, int out_pitch, void* stream);
+int mpa_pool3_bwd_dropout_split_cp8(const void* a_cp8, const void* g_out_cp8, void* g_a_cp8, int B, int C, int T, int F, int pitch, int pf,
+                                    int pt, int fmt, int act, float act_param, float p, unsigned long long seed,
+                                    unsigned long long offset, const long long* step_dev, unsigned long long step_mul, int g_split,
+                                    int g_pitch, void* stream);
 /* U-Net family, bf16 training mode, CP8-resident (train_unet_cp8.cu): the element-wise stages between two tensor-core convolutions of a
  * training step on the 16-bit planes themselves.  Geometry arguments as mpa_nchw_to_cp8; every `ncs_*` is the chunk-plane stride per item
  * of that buffer (0 = C/8; larger for a channel view of a concat buffer); C % 8 == 0; fmt = MPA_FMT_BF16 | MPA_FMT_F16.
@@ -409,6 +426,9 @@ int mpa_channel_sum_cp8(const void* g_cp8, float* out, int B, int C, int T, int 
  *                          dy = weight * rstd * (g' - mean(g') - xhat * mean(g' * xhat)) written as CP8 (the operand of the preceding
  *                          convolution's weight / data gradient), g_conv_bias (optional) = sum dy — what loss.backward() leaves in
  *                          BatchNorm2d.weight.grad / .bias.grad and Conv2d.bias.grad
+ *                          out_split / g_split = s > 0 (with the split planes' pitch): the activation is written to / the gradient is read from
+ *                          PHASE-SPLIT planes (bin f -> phase set f % s, column f / s; mpa_conv_tc_f16 out_mode 2), the hand-over to the head's
+ *                          stride-(1, s) convolution in its stride-1 form and back from its data gradient
  *   mpa_maxpool2x2_bwd_cp8 out = addend (optional) + MaxPool2d(2) backward of g_pool: the gradient goes to the first maximum of each 2x2 window
  *                          in row-major order (ATen); `a` is the un-pooled activation, pooled level = (T/2, F/2)   (unet_cnns.py:60-61 `down`)
  *   mpa_upsample2x_bwd_cp8 g_low = adjoint of mpa_upsample2x_cp8 (bilinear x2, align_corners=True, zero pad to (Ts, Fs)) applied to g_up
@@ -416,10 +436,11 @@ int mpa_channel_sum_cp8(const void* g_cp8, float* out, int B, int C, int T, int 
 int mpa_bn_stats_cp8(const void* y_cp8, float* stats, int B, int C, int T, int F, int pitch, int pf, int pt, int ncs, int fmt,
                      float* running_mean, float* running_var, float momentum, long long* num_batches_tracked, void* stream);
 int mpa_bn_relu_apply_cp8(const void* y_cp8, void* out_cp8, const float* stats, const float* weight, const float* bias, float eps, int B,
-                          int C, int T, int F, int pitch, int pf, int pt, int ncs_y, int ncs_out, int fmt, void* stream);
+                          int C, int T, int F, int pitch, int pf, int pt, int ncs_y, int ncs_out, int out_split, int out_pitch, int fmt,
+                          void* stream);
 int mpa_bn_relu_bwd_cp8(const void* g_cp8, const void* y_cp8, void* dy_cp8, const float* stats, const float* weight, const float* bias,
                         float eps, float* g_weight, float* g_bias, float* g_conv_bias, int B, int C, int T, int F, int pitch, int pf, int pt,
-                        int ncs_g, int ncs_y, int ncs_dy, int fmt, void* stream);
+                        int ncs_g, int ncs_y, int ncs_dy, int g_split, int g_pitch, int fmt, void* stream);
 int mpa_maxpool2x2_bwd_cp8(const void* a_cp8, const void* g_pool_cp8, const void* addend_cp8, void* out_cp8, int B, int C, int T, int F,
                            int pitch, int pf, int pt, int ncs_a, int ncs_add, int ncs_out, int pitch_o, int pf_o, int pt_o, int ncs_gp,
                            int fmt, void* stream);

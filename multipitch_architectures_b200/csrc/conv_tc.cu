@@ -1345,7 +1345,7 @@ __global__ void upsample2x_x3_kernel(const uint4* __restrict__ low, uint4* __res
 // change every step.  transpose_flip: pack the DATA-GRADIENT convolution w'[co'][ci'][kh][kw] = w[ci'][co'][KH-1-kh][KW-1-kw].
 __device__ __forceinline__ void pack_weights_range(const float* __restrict__ w, uint16_t* __restrict__ out, long long total, int Cin, int Cout,
                                                    int KH, int KW, int J, int NC, int mpr, int fmt, int transpose_flip, int Cout_total, int co0,
-                                                   long long first, long long step) {
+                                                   long long first, long long step, int split = 0, int C0 = 0) {
   const int n_paired = (NC / 2) * KW;
   for (long long idx = first; idx < total; idx += step) {
     const int e = (int)(idx & 7);
@@ -1365,7 +1365,20 @@ __device__ __forceinline__ void pack_weights_range(const float* __restrict__ w, 
     const int j = mrow / Cout, co = mrow - j * Cout;
     const int kh = r - j, ci = c * 8 + e;
     float v = 0.f;
-    if (df < KW && j < J && kh >= 0 && kh < KH && ci < Cin && co0 + co < Cout_total) {
+    if (split) {
+      // phase-split form of a KH x split / stride (1, split) convolution with real weights w[Cout][C0][KH][split]: logical input channel
+      // ph * C0p + c = (tap ph, real channel c), one tap column.  Forward: Cin = split * C0p;  data gradient (transpose_flip): the logical
+      // OUTPUT channels are the split ones (Cout_total = split * C0p), rows flipped, the column tap is the phase itself
+      if (df < 1 && j < J && kh >= 0 && kh < KH) {
+        if (!transpose_flip) {
+          const int C0p = Cin / split, ph = ci / C0p, c0r = ci - ph * C0p;
+          if (ci < Cin && c0r < C0 && co0 + co < Cout_total) v = w[(((size_t)(co0 + co) * C0 + c0r) * KH + kh) * split + ph];
+        } else {
+          const int C0p = Cout_total / split, o = co0 + co, ph = o / C0p, c0r = o - ph * C0p;
+          if (o < Cout_total && c0r < C0 && ci < Cin) v = w[(((size_t)ci * C0 + c0r) * KH + (KH - 1 - kh)) * split + ph];
+        }
+      }
+    } else if (df < KW && j < J && kh >= 0 && kh < KH && ci < Cin && co0 + co < Cout_total) {
       v = transpose_flip ? w[(((size_t)ci * Cout_total + co0 + co) * KH + (KH - 1 - kh)) * KW + (KW - 1 - df)]
                          : w[(((size_t)(co0 + co) * Cin + ci) * KH + kh) * KW + df];
     }
@@ -1373,9 +1386,9 @@ __device__ __forceinline__ void pack_weights_range(const float* __restrict__ w, 
   }
 }
 __global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, long long total, int Cin, int Cout, int KH, int KW,
-                                    int J, int NC, int mpr, int fmt, int transpose_flip, int Cout_total, int co0) {
+                                    int J, int NC, int mpr, int fmt, int transpose_flip, int Cout_total, int co0, int split, int C0) {
   pack_weights_range(w, out, total, Cin, Cout, KH, KW, J, NC, mpr, fmt, transpose_flip, Cout_total, co0,
-                     blockIdx.x * (long long)blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
+                     blockIdx.x * (long long)blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x, split, C0);
 }
 // Every packed operand of a training step (forward and data-gradient tiles of all convolutions) in ONE launch: blockIdx.y = job of a
 // device-resident table (the step's 39 separate 7-us launches were 3.6 % of the SAUnet:L step)
@@ -1385,6 +1398,7 @@ struct PackJobDev {
   long long total;
   int Cin, Cout, KH, KW, J, NC, mpr, fmt, transpose_flip, Cout_total, co0;
   int block0;              // first block of this job in the flattened grid (2048 elements per block)
+  int split, C0;
 };
 constexpr int kPackPerBlock = 2048;
 __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackJobDev* __restrict__ jobs, int n_jobs) {
@@ -1399,7 +1413,7 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackJobDe
   const long long first = (long long)((int)blockIdx.x - j.block0) * kPackPerBlock;
   const long long last = first + kPackPerBlock < j.total ? first + kPackPerBlock : j.total;
   pack_weights_range(j.w, j.out, last, j.Cin, j.Cout, j.KH, j.KW, j.J, j.NC, j.mpr, j.fmt, j.transpose_flip, j.Cout_total, j.co0,
-                     first + threadIdx.x, 256);
+                     first + threadIdx.x, 256, j.split, j.C0);
 }
 
 static inline int grid_for(long long total, int block) {
@@ -1500,18 +1514,25 @@ int mpa_conv_tc_pack_weights(const float* w, void* packed, int Cin, int Cout, in
   return MPA_OK;
 }
 
-int mpa_conv_tc_pack_weights_dev(const float* w_dev, void* packed_dev, int Cin, int Cout, int KH, int KW, int fmt, int J, int transpose_flip,
-                                 int Cout_total, int co0, void* stream) {
+int mpa_conv_tc_pack_weights_split_dev(const float* w_dev, void* packed_dev, int Cin, int Cout, int KH, int KW, int fmt, int J, int transpose_flip,
+                                       int Cout_total, int co0, int split, int C0, void* stream) {
   MPA_CHECK_ARCH();
   MPA_REQUIRE(w_dev && packed_dev && Cin > 0 && Cout > 0 && Cout <= 128 && KH > 0 && KW > 0, "conv_tc_pack_weights_dev: bad argument (Cout <= 128 per block)");
   MPA_REQUIRE(J >= 0 && J * Cout <= 128 && co0 >= 0 && co0 < Cout_total, "conv_tc_pack_weights_dev: bad J / channel block");
+  MPA_REQUIRE(split == 0 || (split > 1 && KW == 1 && C0 > 0 && (transpose_flip ? Cout_total : Cin) % split == 0),
+              "conv_tc_pack_weights_dev: bad phase split (KW must be 1, the split channel count a multiple of split)");
   if (J == 0) J = j_blocks(Cout);
   const int NC = (Cin + 7) / 8, mpr = mmas_per_row(NC, KW);
   const long long total = (long long)(KH + J - 1) * mpr * (kATileBytes / 2);
   pack_weights_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w_dev, (uint16_t*)packed_dev, total, Cin, Cout, KH, KW, J, NC, mpr, fmt,
-                                                                              transpose_flip, Cout_total, co0);
+                                                                              transpose_flip, Cout_total, co0, split, C0);
   MPA_CHECK_LAUNCH("conv_tc_pack_weights_dev");
   return MPA_OK;
+}
+
+int mpa_conv_tc_pack_weights_dev(const float* w_dev, void* packed_dev, int Cin, int Cout, int KH, int KW, int fmt, int J, int transpose_flip,
+                                 int Cout_total, int co0, void* stream) {
+  return mpa_conv_tc_pack_weights_split_dev(w_dev, packed_dev, Cin, Cout, KH, KW, fmt, J, transpose_flip, Cout_total, co0, 0, 0, stream);
 }
 
 size_t mpa_conv_tc_pack_table_bytes(int n_jobs) { return n_jobs > 0 ? (size_t)n_jobs * sizeof(PackJobDev) : 0; }
@@ -1527,7 +1548,10 @@ int mpa_conv_tc_pack_table_build(const mpa_pack_job* jobs, int n_jobs, void* tab
                 "conv_tc_pack_table_build: bad job");
     const int J = a.J == 0 ? j_blocks(a.Cout) : a.J, NC = (a.Cin + 7) / 8, mpr = mmas_per_row(NC, a.KW);
     const long long total = (long long)(a.KH + J - 1) * mpr * (kATileBytes / 2);
-    t[i] = PackJobDev{a.w, (uint16_t*)a.packed, total, a.Cin, a.Cout, a.KH, a.KW, J, NC, mpr, a.fmt, a.transpose_flip, a.Cout_total, a.co0, blocks};
+    MPA_REQUIRE(a.split == 0 || (a.split > 1 && a.KW == 1 && a.C0 > 0 && (a.transpose_flip ? a.Cout_total : a.Cin) % a.split == 0),
+                "conv_tc_pack_table_build: bad phase split");
+    t[i] = PackJobDev{a.w, (uint16_t*)a.packed, total, a.Cin, a.Cout, a.KH, a.KW, J, NC, mpr, a.fmt, a.transpose_flip, a.Cout_total, a.co0, blocks,
+                      a.split, a.C0};
     blocks += (int)((total + kPackPerBlock - 1) / kPackPerBlock);
   }
   return blocks;

@@ -56,7 +56,7 @@ constexpr int kCp8Threads = 128;
 template <int FMT>
 __global__ void __launch_bounds__(kCp8Threads) pool3_dropout_cp8_kernel(const uint4* __restrict__ a, uint4* __restrict__ out, long long total, int C,
                                                                         int NCk, int segs, int T, int F4, int TP, int P, int pf, int pt,
-                                                                        DropoutArgs d) {
+                                                                        DropoutArgs d, int out_split, int P2) {
   const long long i = blockIdx.x * (long long)kCp8Threads + threadIdx.x;
   if (i >= total) return;
   const int q = (int)(i % F4);
@@ -105,7 +105,13 @@ __global__ void __launch_bounds__(kCp8Threads) pool3_dropout_cp8_kernel(const ui
     }
 #pragma unroll
     for (int x = 0; x < 4; ++x) {
-      out[base + (size_t)t * P + x] = c[x];
+      if (out_split) {
+        // phase-split hand-over to a stride-(1, s) convolution: bin f -> phase set f % s (s * NCk chunk planes per item), column f / s
+        const int f = 4 * q + x, ph = f % out_split;
+        out[((((size_t)b * out_split + ph) * NCk + ck) * TP + pt + t) * P2 + pf + f / out_split] = c[x];
+      } else {
+        out[base + (size_t)t * P + x] = c[x];
+      }
       prev[x] = cur[x];
       cur[x] = next[x];
     }
@@ -143,7 +149,7 @@ template <int FMT>
 __global__ void __launch_bounds__(kCp8Threads) pool3_bwd_dropout_cp8_kernel(const uint2* __restrict__ a, const uint2* __restrict__ g_p,
                                                                             uint2* __restrict__ g_a, long long total, int C, int NCk, int segs, int T,
                                                                             int F4, int TP, int P, int pf, int pt, int act, float act_param,
-                                                                            DropoutArgs d) {
+                                                                            DropoutArgs d, int g_split, int Pg) {
   const long long i = blockIdx.x * (long long)kCp8Threads + threadIdx.x;
   if (i >= total) return;
   const int half = (int)(i & 1);
@@ -185,16 +191,27 @@ __global__ void __launch_bounds__(kCp8Threads) pool3_bwd_dropout_cp8_kernel(cons
     }
   }
   const int w_last = min(T - 1, r1);
+  // gradient wrt the pool output: same planes as `a`, or (g_split = s) the phase-split planes a stride-(1, s) convolution's data gradient wrote
+  size_t gbase[4], grow = P2;
+#pragma unroll
+  for (int x = 0; x < 4; ++x) {
+    gbase[x] = base + 2 * x;
+    if (g_split) {
+      const int f = 4 * q + x, ph = f % g_split;
+      gbase[x] = (((((size_t)b * g_split + ph) * NCk + ck) * TP + pt) * Pg + pf + f / g_split) * 2 + half;
+      grow = 2 * (size_t)Pg;
+    }
+  }
   uint2 graw[4];
 #pragma unroll
-  for (int x = 0; x < 4; ++x) graw[x] = g_p[base + (size_t)w * P2 + 2 * x];
+  for (int x = 0; x < 4; ++x) graw[x] = g_p[gbase[x] + (size_t)w * grow];
   for (; w <= w_last; ++w) {
     // the next rows are requested before this window's arithmetic
     uint2 gnext[4], anext[4];
     const bool more_g = w + 1 <= w_last, more_a = w + 2 < T;
 #pragma unroll
     for (int x = 0; x < 4; ++x) {
-      gnext[x] = more_g ? g_p[base + (size_t)(w + 1) * P2 + 2 * x] : zero2;
+      gnext[x] = more_g ? g_p[gbase[x] + (size_t)(w + 1) * grow] : zero2;
       anext[x] = more_a ? a[base + (size_t)(w + 2) * P2 + 2 * x] : zero2;
     }
 #pragma unroll
@@ -261,10 +278,21 @@ using namespace mpa;
 
 extern "C" {
 
+int mpa_pool3_dropout_split_cp8(const void* a_cp8, void* out_cp8, int B, int C, int T, int F, int pitch, int pf, int pt, int fmt, float p,
+                                unsigned long long seed, unsigned long long offset, const long long* step_dev, unsigned long long step_mul,
+                                int out_split, int out_pitch, void* stream);
+
 int mpa_pool3_dropout_cp8(const void* a_cp8, void* out_cp8, int B, int C, int T, int F, int pitch, int pf, int pt, int fmt, float p,
                           unsigned long long seed, unsigned long long offset, const long long* step_dev, unsigned long long step_mul,
                           void* stream) {
+  return mpa_pool3_dropout_split_cp8(a_cp8, out_cp8, B, C, T, F, pitch, pf, pt, fmt, p, seed, offset, step_dev, step_mul, 0, 0, stream);
+}
+
+int mpa_pool3_dropout_split_cp8(const void* a_cp8, void* out_cp8, int B, int C, int T, int F, int pitch, int pf, int pt, int fmt, float p,
+                                unsigned long long seed, unsigned long long offset, const long long* step_dev, unsigned long long step_mul,
+                                int out_split, int out_pitch, void* stream) {
   MPA_CHECK_ARCH();
+  MPA_REQUIRE(out_split == 0 || (out_split > 1 && F % out_split == 0 && out_pitch >= pf + F / out_split), "pool3_dropout_cp8: bad phase split");
   MPA_REQUIRE(a_cp8 && out_cp8 && B > 0 && C > 0 && T > 0 && F > 0 && F % 4 == 0 && pitch >= pf + F && pt >= 0 && p >= 0.f && p < 1.f &&
                   (fmt == MPA_FMT_BF16 || fmt == MPA_FMT_F16),
               "pool3_dropout_cp8: bad argument (F must be a multiple of 4)");
@@ -278,18 +306,30 @@ int mpa_pool3_dropout_cp8(const void* a_cp8, void* out_cp8, int B, int C, int T,
   const DropoutArgs d{p, seed, offset, step_dev, step_mul};
   if (fmt == MPA_FMT_BF16)
     pool3_dropout_cp8_kernel<MPA_FMT_BF16><<<grid, kCp8Threads, 0, (cudaStream_t)stream>>>((const uint4*)a_cp8, (uint4*)out_cp8, total, C, NCk, segs,
-                                                                                          T, F / 4, T + 2 * pt, pitch, pf, pt, d);
+                                                                                          T, F / 4, T + 2 * pt, pitch, pf, pt, d, out_split, out_pitch);
   else
     pool3_dropout_cp8_kernel<MPA_FMT_F16><<<grid, kCp8Threads, 0, (cudaStream_t)stream>>>((const uint4*)a_cp8, (uint4*)out_cp8, total, C, NCk, segs,
-                                                                                         T, F / 4, T + 2 * pt, pitch, pf, pt, d);
+                                                                                         T, F / 4, T + 2 * pt, pitch, pf, pt, d, out_split, out_pitch);
   MPA_CHECK_LAUNCH("pool3_dropout_cp8");
   return MPA_OK;
 }
 
+int mpa_pool3_bwd_dropout_split_cp8(const void* a_cp8, const void* g_out_cp8, void* g_a_cp8, int B, int C, int T, int F, int pitch, int pf, int pt,
+                                    int fmt, int act, float act_param, float p, unsigned long long seed, unsigned long long offset,
+                                    const long long* step_dev, unsigned long long step_mul, int g_split, int g_pitch, void* stream);
+
 int mpa_pool3_bwd_dropout_cp8(const void* a_cp8, const void* g_out_cp8, void* g_a_cp8, int B, int C, int T, int F, int pitch, int pf, int pt,
                               int fmt, int act, float act_param, float p, unsigned long long seed, unsigned long long offset,
                               const long long* step_dev, unsigned long long step_mul, void* stream) {
+  return mpa_pool3_bwd_dropout_split_cp8(a_cp8, g_out_cp8, g_a_cp8, B, C, T, F, pitch, pf, pt, fmt, act, act_param, p, seed, offset, step_dev,
+                                         step_mul, 0, 0, stream);
+}
+
+int mpa_pool3_bwd_dropout_split_cp8(const void* a_cp8, const void* g_out_cp8, void* g_a_cp8, int B, int C, int T, int F, int pitch, int pf, int pt,
+                                    int fmt, int act, float act_param, float p, unsigned long long seed, unsigned long long offset,
+                                    const long long* step_dev, unsigned long long step_mul, int g_split, int g_pitch, void* stream) {
   MPA_CHECK_ARCH();
+  MPA_REQUIRE(g_split == 0 || (g_split > 1 && F % g_split == 0 && g_pitch >= pf + F / g_split), "pool3_bwd_dropout_cp8: bad phase split");
   MPA_REQUIRE(a_cp8 && g_out_cp8 && g_a_cp8 && B > 0 && C > 0 && T > 0 && F > 0 && F % 4 == 0 && pitch >= pf + F && pt >= 0 && p >= 0.f &&
                   p < 1.f && (fmt == MPA_FMT_BF16 || fmt == MPA_FMT_F16),
               "pool3_bwd_dropout_cp8: bad argument (F must be a multiple of 4)");
@@ -303,10 +343,12 @@ int mpa_pool3_bwd_dropout_cp8(const void* a_cp8, const void* g_out_cp8, void* g_
   const DropoutArgs d{p, seed, offset, step_dev, step_mul};
   if (fmt == MPA_FMT_BF16)
     pool3_bwd_dropout_cp8_kernel<MPA_FMT_BF16><<<grid, kCp8Threads, 0, (cudaStream_t)stream>>>(
-        (const uint2*)a_cp8, (const uint2*)g_out_cp8, (uint2*)g_a_cp8, total, C, NCk, segs, T, F / 4, T + 2 * pt, pitch, pf, pt, act, act_param, d);
+        (const uint2*)a_cp8, (const uint2*)g_out_cp8, (uint2*)g_a_cp8, total, C, NCk, segs, T, F / 4, T + 2 * pt, pitch, pf, pt, act, act_param, d,
+        g_split, g_pitch);
   else
     pool3_bwd_dropout_cp8_kernel<MPA_FMT_F16><<<grid, kCp8Threads, 0, (cudaStream_t)stream>>>(
-        (const uint2*)a_cp8, (const uint2*)g_out_cp8, (uint2*)g_a_cp8, total, C, NCk, segs, T, F / 4, T + 2 * pt, pitch, pf, pt, act, act_param, d);
+        (const uint2*)a_cp8, (const uint2*)g_out_cp8, (uint2*)g_a_cp8, total, C, NCk, segs, T, F / 4, T + 2 * pt, pitch, pf, pt, act, act_param, d,
+        g_split, g_pitch);
   MPA_CHECK_LAUNCH("pool3_bwd_dropout_cp8");
   return MPA_OK;
 }

@@ -74,6 +74,12 @@ struct Cp8Geo {
     const unsigned b = row / (unsigned)T, t = row - b * (unsigned)T;
     return (((size_t)b * ncs + ck) * TP + pt + t) * P + pf + f;
   }
+  // the same pixel in phase-split planes (s phase sets of NCk chunk planes per item, pitch P2): bin f -> phase f % s, column f / s
+  __device__ __forceinline__ size_t at_split(unsigned i, int NCk, int ck, int s, int P2) const {
+    const unsigned row = i / (unsigned)F, f = i - row * (unsigned)F;
+    const unsigned b = row / (unsigned)T, t = row - b * (unsigned)T;
+    return ((((size_t)b * s + f % s) * NCk + ck) * TP + pt + t) * P2 + pf + f / s;
+  }
 };
 
 __device__ __forceinline__ float bn_val(float y, float mean, float rstd, float w, float b) { return (y - mean) * rstd * w + b; }
@@ -186,7 +192,8 @@ __global__ void __launch_bounds__(kUT) bn_stats_partial_cp8_kernel(const uint4* 
 template <int FMT>
 __global__ void __launch_bounds__(kUT) bn_relu_apply_cp8_kernel(const uint4* __restrict__ y, uint4* __restrict__ out, const float* __restrict__ stats,
                                                                 const float* __restrict__ w, const float* __restrict__ bias, float eps, int C, int NCk,
-                                                                int T, int F, int TP, int P, int pf, int pt, int ncs_y, int ncs_out) {
+                                                                int T, int F, int TP, int P, int pf, int pt, int ncs_y, int ncs_out, int out_split,
+                                                                int P2) {
   const int ck = blockIdx.y % NCk, b = blockIdx.y / NCk;
   float mean[8], rstd[8], wc[8], bc[8];
 #pragma unroll
@@ -208,7 +215,10 @@ __global__ void __launch_bounds__(kUT) bn_relu_apply_cp8_kernel(const uint4* __r
     unpack8<FMT>(y[by + (size_t)t * P + f], v);
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = fmaxf(bn_val(v[e], mean[e], rstd[e], wc[e], bc[e]), 0.f);
-    out[bo + (size_t)t * P + f] = pack8<FMT>(v);
+    if (out_split)
+      out[((((size_t)b * out_split + f % out_split) * NCk + ck) * TP + pt + t) * P2 + pf + f / out_split] = pack8<FMT>(v);
+    else
+      out[bo + (size_t)t * P + f] = pack8<FMT>(v);
   }
 }
 
@@ -220,7 +230,8 @@ template <int FMT>
 __global__ void __launch_bounds__(kUT) bn_relu_bwd_partial_cp8_kernel(const uint4* __restrict__ g, const uint4* __restrict__ y,
                                                                       const float* __restrict__ stats, const float* __restrict__ w,
                                                                       const float* __restrict__ bias, float eps, float* __restrict__ partial,
-                                                                      unsigned n, Cp8Geo geo, int C, int ncs_g, int ncs_y, int S, BnBwdFinal f) {
+                                                                      unsigned n, Cp8Geo geo, int C, int ncs_g, int ncs_y, int S, BnBwdFinal f,
+                                                                      int g_split, int Pg) {
   __shared__ float sh[kUT / 32 * 16];
   const int ck = blockIdx.x, s = blockIdx.y;
   const unsigned i0 = (unsigned)((unsigned long long)n * s / S), i1 = (unsigned)((unsigned long long)n * (s + 1) / S);
@@ -236,7 +247,7 @@ __global__ void __launch_bounds__(kUT) bn_relu_bwd_partial_cp8_kernel(const uint
   }
   for (unsigned i = i0 + threadIdx.x; i < i1; i += kUT) {
     float gv[8], yv[8];
-    unpack8<FMT>(g[geo.at(i, ncs_g, ck)], gv);
+    unpack8<FMT>(g[g_split ? geo.at_split(i, gridDim.x, ck, g_split, Pg) : geo.at(i, ncs_g, ck)], gv);
     unpack8<FMT>(y[geo.at(i, ncs_y, ck)], yv);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -280,7 +291,7 @@ __global__ void __launch_bounds__(kUT) bn_relu_bwd_apply_cp8_kernel(const uint4*
                                                                     const float* __restrict__ stats, const float* __restrict__ w,
                                                                     const float* __restrict__ bias, const float* __restrict__ sums, float eps,
                                                                     float inv_n, float* __restrict__ conv_gb, int C, int NCk, int T, int F, int TP,
-                                                                    int P, int pf, int pt, int ncs_g, int ncs_y, int ncs_dy) {
+                                                                    int P, int pf, int pt, int ncs_g, int ncs_y, int ncs_dy, int g_split, int Pg) {
   __shared__ float sh[kUT / 32 * 8];
   const int ck = blockIdx.y % NCk, b = blockIdx.y / NCk;
   float mean[8], rstd[8], wc[8], bc[8], m1[8], m2[8], tot[8];
@@ -305,7 +316,7 @@ __global__ void __launch_bounds__(kUT) bn_relu_bwd_apply_cp8_kernel(const uint4*
     const unsigned t = i / (unsigned)F, f = i - t * (unsigned)F;
     const size_t o = (size_t)t * P + f;
     float gv[8], yv[8], r[8];
-    unpack8<FMT>(g[bg + o], gv);
+    unpack8<FMT>(g[g_split ? ((((size_t)b * g_split + f % g_split) * NCk + ck) * TP + pt + t) * Pg + pf + f / g_split : bg + o], gv);
     unpack8<FMT>(y[by + o], yv);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -447,28 +458,30 @@ int mpa_bn_stats_cp8(const void* y_cp8, float* stats, int B, int C, int T, int F
 }
 
 int mpa_bn_relu_apply_cp8(const void* y_cp8, void* out_cp8, const float* stats, const float* weight, const float* bias, float eps, int B, int C,
-                          int T, int F, int pitch, int pf, int pt, int ncs_y, int ncs_out, int fmt, void* stream) {
+                          int T, int F, int pitch, int pf, int pt, int ncs_y, int ncs_out, int out_split, int out_pitch, int fmt, void* stream) {
   UNET_CP8_COMMON("bn_relu_apply_cp8");
   MPA_REQUIRE(y_cp8 && out_cp8 && stats && weight && bias, "bn_relu_apply_cp8: null pointer");
+  MPA_REQUIRE(out_split == 0 || (out_split > 1 && F % out_split == 0 && out_pitch >= pf + F / out_split), "bn_relu_apply_cp8: bad phase split");
   const int NCk = C / 8;
   if (ncs_y <= 0) ncs_y = NCk;
   if (ncs_out <= 0) ncs_out = NCk;
   const dim3 grid(ceil_div((long long)T * F, 4 * kUT), B * NCk);
   if (fmt == MPA_FMT_BF16)
     bn_relu_apply_cp8_kernel<MPA_FMT_BF16><<<grid, kUT, 0, (cudaStream_t)stream>>>((const uint4*)y_cp8, (uint4*)out_cp8, stats, weight, bias, eps, C,
-                                                                                  NCk, T, F, T + 2 * pt, pitch, pf, pt, ncs_y, ncs_out);
+                                                                                  NCk, T, F, T + 2 * pt, pitch, pf, pt, ncs_y, ncs_out, out_split, out_pitch);
   else
     bn_relu_apply_cp8_kernel<MPA_FMT_F16><<<grid, kUT, 0, (cudaStream_t)stream>>>((const uint4*)y_cp8, (uint4*)out_cp8, stats, weight, bias, eps, C,
-                                                                                 NCk, T, F, T + 2 * pt, pitch, pf, pt, ncs_y, ncs_out);
+                                                                                 NCk, T, F, T + 2 * pt, pitch, pf, pt, ncs_y, ncs_out, out_split, out_pitch);
   MPA_CHECK_LAUNCH("bn_relu_apply_cp8");
   return MPA_OK;
 }
 
 int mpa_bn_relu_bwd_cp8(const void* g_cp8, const void* y_cp8, void* dy_cp8, const float* stats, const float* weight, const float* bias, float eps,
                         float* g_weight, float* g_bias, float* g_conv_bias, int B, int C, int T, int F, int pitch, int pf, int pt, int ncs_g,
-                        int ncs_y, int ncs_dy, int fmt, void* stream) {
+                        int ncs_y, int ncs_dy, int g_split, int g_pitch, int fmt, void* stream) {
   UNET_CP8_COMMON("bn_relu_bwd_cp8");
   MPA_REQUIRE(g_cp8 && y_cp8 && dy_cp8 && stats && weight && bias && g_weight && g_bias, "bn_relu_bwd_cp8: null pointer");
+  MPA_REQUIRE(g_split == 0 || (g_split > 1 && F % g_split == 0 && g_pitch >= pf + F / g_split), "bn_relu_bwd_cp8: bad phase split");
   float* scratch = unet_scratch();
   MPA_REQUIRE(scratch, "bn_relu_bwd_cp8: scratch allocation failed");
   const int NCk = C / 8;
@@ -485,20 +498,20 @@ int mpa_bn_relu_bwd_cp8(const void* g_cp8, const void* y_cp8, void* dy_cp8, cons
   const BnBwdFinal f{sums, g_weight, g_bias, g_conv_bias};
   if (fmt == MPA_FMT_BF16)
     bn_relu_bwd_partial_cp8_kernel<MPA_FMT_BF16><<<dim3(NCk, S), kUT, 0, st>>>((const uint4*)g_cp8, (const uint4*)y_cp8, stats, weight, bias, eps,
-                                                                              scratch, n, geo, C, ncs_g, ncs_y, S, f);
+                                                                              scratch, n, geo, C, ncs_g, ncs_y, S, f, g_split, g_pitch);
   else
     bn_relu_bwd_partial_cp8_kernel<MPA_FMT_F16><<<dim3(NCk, S), kUT, 0, st>>>((const uint4*)g_cp8, (const uint4*)y_cp8, stats, weight, bias, eps,
-                                                                             scratch, n, geo, C, ncs_g, ncs_y, S, f);
+                                                                             scratch, n, geo, C, ncs_g, ncs_y, S, f, g_split, g_pitch);
   MPA_CHECK_LAUNCH("bn_relu_bwd_sums_cp8");
   const float inv_n = 1.f / (float)n;
   if (fmt == MPA_FMT_BF16)
     bn_relu_bwd_apply_cp8_kernel<MPA_FMT_BF16><<<grid_a, kUT, 0, st>>>((const uint4*)g_cp8, (const uint4*)y_cp8, (uint4*)dy_cp8, stats, weight, bias,
                                                                       sums, eps, inv_n, g_conv_bias, C, NCk, T, F, T + 2 * pt, pitch, pf, pt, ncs_g,
-                                                                      ncs_y, ncs_dy);
+                                                                      ncs_y, ncs_dy, g_split, g_pitch);
   else
     bn_relu_bwd_apply_cp8_kernel<MPA_FMT_F16><<<grid_a, kUT, 0, st>>>((const uint4*)g_cp8, (const uint4*)y_cp8, (uint4*)dy_cp8, stats, weight, bias,
                                                                      sums, eps, inv_n, g_conv_bias, C, NCk, T, F, T + 2 * pt, pitch, pf, pt, ncs_g,
-                                                                     ncs_y, ncs_dy);
+                                                                     ncs_y, ncs_dy, g_split, g_pitch);
   MPA_CHECK_LAUNCH("bn_relu_bwd_apply_cp8");
   return MPA_OK;
 }

@@ -120,8 +120,15 @@ def _enc_run_tc(self, x, fmt, pe, w_qkv, b_qkv, w_proj, b_proj):
     W1, W2 = self.mlp[0].weight, self.mlp[2].weight
     w1c = self._cache.get(f'w1c{fmt}', [W1], lambda: ops.gemm_tc_chunks(W1, 128, fmt))
     w2c = self._cache.get(f'w2c{fmt}', [W2], lambda: ops.gemm_tc_chunks(W2, 128, fmt))
-    hid = ops.gemm_tc(h1, w1c, self.mlp[0].bias, self.mlp_dim, True, fmt, x_chunks=h1c)
-    mo = ops.gemm_tc(hid, w2c, self.mlp[2].bias, E, False, fmt)
+    # hidden activation [M, mlp_dim]: written by the first product's epilogue as the 16-bit X operand of the second one (no fp32 copy,
+    # no converter pass: at 646 patches the fp32 tensor alone was 1.1 GB per layer)
+    Dm = self.mlp_dim
+    Mp, Np8 = (M + 255) // 256 * 256, (Dm + 127) // 128 * 16
+    if h1c is None:
+        h1c = ops.gemm_tc_chunks(h1, 256, fmt)
+    hid_feat = torch.empty(Np8 * Mp * 16, dtype=torch.uint8, device=dev)
+    ops.gemm_tc_ex(h1c, w1c, self.mlp[0].bias, M, Dm, E, True, fmt, y_feat=hid_feat, y_feat_rows=Mp)
+    mo = ops.gemm_tc_ex(hid_feat, w2c, self.mlp[2].bias, M, E, Dm, False, fmt, y=f32(M, E))
     out = torch.empty_like(x)
     _lib.call('add_layernorm_tok_f32', h1, mo, self.layernorm2.weight, self.layernorm2.bias, None, out, _lib.i64(M), E, S,
               float(self.layernorm2.eps), sp())

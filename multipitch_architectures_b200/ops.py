@@ -304,18 +304,27 @@ def bn_stats_cp8(y, bn=None, update_running=True):
     return stats
 
 
-def bn_relu_apply_cp8(y, stats, bn, out):
-    assert (y.B, y.C, y.T, y.F, y.pitch, y.pf, y.pt) == (out.B, out.C, out.T, out.F, out.pitch, out.pf, out.pt)
+def bn_relu_apply_cp8(y, stats, bn, out, split=0):
+    """split = s: `out` is an ops.split_cp8 buffer (phase-split hand-over to a stride-(1, s) convolution)."""
+    if split:
+        assert (out.B, out.C, out.T, out.F) == (y.B, split * y.C, y.T, y.F // split) and y.C % 8 == 0
+    else:
+        assert (y.B, y.C, y.T, y.F, y.pitch, y.pf, y.pt) == (out.B, out.C, out.T, out.F, out.pitch, out.pf, out.pt)
     call('bn_relu_apply_cp8', y.ptr(), out.ptr(), stats, bn.weight, bn.bias, float(bn.eps), y.B, y.C, y.T, y.F, y.pitch, y.pf, y.pt, y.ncs, out.ncs,
-         y.fmt, stream_ptr())
+         int(split), out.pitch if split else 0, y.fmt, stream_ptr())
     return out
 
 
-def bn_relu_bwd_cp8(g, y, stats, bn, dy, g_weight, g_bias, g_conv_bias=None):
-    """dy (CP8, written) = gradient wrt the BatchNorm input of relu(bn(y)) given g wrt its output; g_weight / g_bias / g_conv_bias overwritten."""
-    assert (y.B, y.C, y.T, y.F, y.pitch, y.pf, y.pt) == (g.B, g.C, g.T, g.F, g.pitch, g.pf, g.pt) == (dy.B, dy.C, dy.T, dy.F, dy.pitch, dy.pf, dy.pt)
+def bn_relu_bwd_cp8(g, y, stats, bn, dy, g_weight, g_bias, g_conv_bias=None, split=0):
+    """dy (CP8, written) = gradient wrt the BatchNorm input of relu(bn(y)) given g wrt its output; g_weight / g_bias / g_conv_bias overwritten.
+    split = s: g comes in phase-split planes (the data gradient of the stride-1 form of a stride-(1, s) convolution)."""
+    assert (y.B, y.C, y.T, y.F, y.pitch, y.pf, y.pt) == (dy.B, dy.C, dy.T, dy.F, dy.pitch, dy.pf, dy.pt)
+    if split:
+        assert (g.B, g.C, g.T, g.F) == (y.B, split * y.C, y.T, y.F // split)
+    else:
+        assert (y.B, y.C, y.T, y.F, y.pitch, y.pf, y.pt) == (g.B, g.C, g.T, g.F, g.pitch, g.pf, g.pt)
     call('bn_relu_bwd_cp8', g.ptr(), y.ptr(), dy.ptr(), stats, bn.weight, bn.bias, float(bn.eps), g_weight, g_bias, g_conv_bias, y.B, y.C, y.T, y.F,
-         y.pitch, y.pf, y.pt, g.ncs, y.ncs, dy.ncs, y.fmt, stream_ptr())
+         y.pitch, y.pf, y.pt, g.ncs, y.ncs, dy.ncs, int(split), g.pitch if split else 0, y.fmt, stream_ptr())
     return dy
 
 
@@ -469,7 +478,8 @@ def channel_sum_cp8(g, out=None):
 
 class PackJob(_ct.Structure):
     _fields_ = [('w', _ct.c_void_p), ('packed', _ct.c_void_p), ('Cin', _ct.c_int), ('Cout', _ct.c_int), ('KH', _ct.c_int), ('KW', _ct.c_int),
-                ('fmt', _ct.c_int), ('J', _ct.c_int), ('transpose_flip', _ct.c_int), ('Cout_total', _ct.c_int), ('co0', _ct.c_int)]
+                ('fmt', _ct.c_int), ('J', _ct.c_int), ('transpose_flip', _ct.c_int), ('Cout_total', _ct.c_int), ('co0', _ct.c_int),
+                ('split', _ct.c_int), ('C0', _ct.c_int)]
 
 
 class PackPlan:
@@ -502,13 +512,14 @@ class PackPlan:
 _PACK_PLAN = None
 
 
-def conv_tc_pack_dev(w, Cin, Cout, ksize, fmt, transpose_flip=False, Cout_total=None, co0=0, J=0):
+def conv_tc_pack_dev(w, Cin, Cout, ksize, fmt, transpose_flip=False, Cout_total=None, co0=0, J=0, split=0, C0=0):
     """Device-side packing of conv_tc A-operand tiles from the fp32 weight tensor `w` (state_dict layout, on the GPU).
-    transpose_flip: pack the data-gradient convolution of the forward weight `w` (see mpa_conv_tc_pack_weights_dev)."""
+    transpose_flip: pack the data-gradient convolution of the forward weight `w` (see mpa_conv_tc_pack_weights_dev).
+    split = s, C0: the phase-split form of a KH x s / stride (1, s) convolution with C0 real input channels (mpa_conv_tc_pack_weights_split_dev)."""
     KH, KW = ksize
     plan = _PACK_PLAN
     Ct = Cout if Cout_total is None else Cout_total
-    key = (w.data_ptr(), Cin, Cout, KH, KW, fmt, int(bool(transpose_flip)), Ct, co0, J)
+    key = (w.data_ptr(), Cin, Cout, KH, KW, fmt, int(bool(transpose_flip)), Ct, co0, J, split, C0)
     if plan is not None and plan.fresh and key in plan.index:
         return plan.index[key]
     nbytes = _lib.lib().mpa_conv_tc_packed_bytes(Cin, Cout, KH, KW, J)
@@ -519,8 +530,9 @@ def conv_tc_pack_dev(w, Cin, Cout, ksize, fmt, transpose_flip=False, Cout_total=
         packed = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
         if plan is not None and plan.table is None:
             plan.index[key] = packed
-            plan.jobs.append(PackJob(w.data_ptr(), packed.data_ptr(), Cin, Cout, KH, KW, fmt, J, int(bool(transpose_flip)), Ct, co0))
-    call('conv_tc_pack_weights_dev', _f32(w.detach()), packed, Cin, Cout, KH, KW, fmt, J, int(bool(transpose_flip)), Ct, co0, stream_ptr())
+            plan.jobs.append(PackJob(w.data_ptr(), packed.data_ptr(), Cin, Cout, KH, KW, fmt, J, int(bool(transpose_flip)), Ct, co0, split, C0))
+    call('conv_tc_pack_weights_split_dev', _f32(w.detach()), packed, Cin, Cout, KH, KW, fmt, J, int(bool(transpose_flip)), Ct, co0, split, C0,
+         stream_ptr())
     return packed
 
 

@@ -204,7 +204,7 @@ class TcConv:
     _scope = None           # owner of the pooled buffers (a TrainStep); None = allocate per call
 
     @classmethod
-    def scope(cls, owner):
+    def scope(cls, owner, refresh=True):
         """Context manager: inside it `_buf` hands out buffers pooled under `owner` (a fused train step, which runs forward and backward
         atomically, so reusing the SAVED activation planes across steps is safe).  Outside any scope — the autograd bridge, where a
         second forward may run before the first backward (gradient accumulation, two losses, two same-shape models) — every call gets
@@ -218,9 +218,12 @@ class TcConv:
             if plan is None:
                 plan = cls._plans[id(owner)] = ops.PackPlan()
             prev_plan, ops._PACK_PLAN = ops._PACK_PLAN, plan
-            plan.fresh = False
-            if PACK_MULTI:
-                plan.refresh()           # every packed operand of the step in one launch (from the second step on)
+            if refresh:
+                plan.fresh = False
+                if PACK_MULTI:
+                    plan.refresh()       # every packed operand of the step in one launch (from the second step on)
+            else:
+                plan.fresh = plan.table is not None and PACK_MULTI      # second half of a step: the operands were refreshed by the first
             try:
                 yield
                 if PACK_MULTI:
@@ -380,6 +383,65 @@ def _tc_s3_backward(tag, conv, xc, g, gw, gb, keep_cp8=False):
     return gxc if keep_cp8 else ops.cp8_to_nchw(gxc)
 
 
+# Phase-split form of the head's stride-(1,3) conv2 in TRAINING (the inference path uses it).  Correct (tests/test_gpu_unet_cp8.py) but measured
+# slower than the stride-1 3x3 convolution on full-width / zero-inserted planes and therefore off: the forward gains (SAUnet:L 118 -> 65 us) are
+# lost in the weight gradient, whose KW = 1 form leaves wgrad_tc_kernel with N = 32 MMA columns per input-chunk group (298 -> 534 us; CNN:XS
+# 211 -> 406 us), and the phase-split reads / writes of the neighbouring element-wise kernels cost another ~100 us.
+S3_SPLIT = False
+
+
+def _s3_split_eligible(model, conv, F):
+    """CP8-resident training paths: the producer of conv2's input writes phase-split planes (bin f -> phase f % 3, column f / 3), conv2 runs
+    as the stride-1 3x1 convolution over 3 * C0p channels of width F / 3 — 3x fewer MMAs forward, no zero-inserted gradient planes backward,
+    its data gradient comes out phase-split for the producer's backward."""
+    return S3_SPLIT and _tc_s3_eligible(model, conv, F) and (F // 3 + TcConv.PF + 15) // 16 * 16 <= 256
+
+
+def _split_buf(tag, B, C, T, F, s, dev, fmt):
+    """Phase-split planes (ops.split_cp8) pooled like TcConv._buf."""
+    if TcConv._scope is None:
+        return ops.split_cp8(B, C, T, F, s, dev, fmt)
+    key = (TcConv._scope, tag, 'split', B, C, T, F, s, str(dev), fmt)
+    b = TcConv._pool.get(key)
+    if b is None:
+        b = TcConv._pool[key] = ops.split_cp8(B, C, T, F, s, dev, fmt)
+    return b
+
+
+def _tc_s3_forward_split(tag, conv, xs, act, a):
+    """xs: phase-split planes of conv2's input (3 * C0p channels, width F / 3) -> (fp32 NCHW activation [B, Cout, T, F/3], xs)."""
+    fmt = xs.fmt
+    Cout, C0 = conv.weight.shape[0], conv.weight.shape[1]
+    C0p, C1p = xs.C // 3, (Cout + 7) // 8 * 8
+    J = _exec._split_conv2_J(C0p, C1p)
+    yc = ops.compact_cp8(xs.B, Cout, xs.T, xs.F, xs.buf.device, fmt)
+    for c0 in range(0, Cout, 128):
+        c = min(128, Cout - c0)
+        cp = (c + 7) // 8 * 8
+        wp = ops.conv_tc_pack_dev(conv.weight, 3 * C0p, cp, (3, 1), fmt, False, Cout, c0, J=J, split=3, C0=C0)
+        ops.conv_tc(xs, wp, TcConv._pad8(conv.bias[c0:c0 + c], cp), cp, (3, 1), act, a, subsample=(1, 0), out=yc.channels(c0, cp), J=J)
+    return ops.cp8_to_nchw(yc), xs
+
+
+def _tc_s3_backward_split(tag, conv, xs, g, gw, gb):
+    """g: fp32 gradient wrt conv2's output [B, Cout, T, F/3] -> phase-split planes of the gradient wrt its input; gw / gb overwritten."""
+    fmt = xs.fmt
+    B, Cout, T, Fo = g.shape
+    C0, C0p, dev = conv.weight.shape[1], xs.C // 3, g.device
+    gc = ops.nchw_to_cp8(g, out=TcConv._buf(tag + ':g3s', B, Cout, T, Fo, dev, fmt), fmt=fmt)
+    gwp = TcConv._raw(tag + ':gwsplit', Cout * 3 * C0p * 3 * 4, False, dev).view(torch.float32).view(Cout, 3 * C0p, 3, 1)
+    ops.conv_wgrad_tc(xs, gc, gwp, (3, 1))
+    gw.copy_(gwp.view(Cout, 3, C0p, 3)[:, :, :C0, :].permute(0, 2, 3, 1))          # gw[co][ci][kh][ph] = gw'[co][ph * C0p + ci][kh]
+    ops.channel_sum(g, out=gb)
+    gxs = _split_buf(tag + ':gxs', B, C0p, T, 3 * Fo, 3, dev, fmt)
+    zb = TcConv._zero_bias(dev)
+    for c0 in range(0, 3 * C0p, 128):
+        cp = min(128, 3 * C0p - c0)
+        wp = ops.conv_tc_pack_dev(conv.weight, Cout, cp, (3, 1), fmt, True, 3 * C0p, c0, split=3, C0=C0)
+        ops.conv_tc(gc, wp, zb[:cp], cp, (3, 1), ops.ACT_NONE, 0.0, out=gxs.channels(c0, cp))
+    return gxs
+
+
 CP8_RESIDENT = True          # test knob: False = every block crosses nchw<->CP8 converters and pools in fp32 NCHW (identical results)
 
 
@@ -399,15 +461,21 @@ def _cnn_train_forward_cp8(model, blocks, x, sv, site, drop):
     # LayerNorm writes the first convolution's input planes directly (no fp32 copy of the normalised patch, no converter pass)
     xc = ops.layernorm_cf_cp8(x, ln.weight, ln.bias, ln.eps, TcConv._buf(blocks[0][0] + ':x', B, C0, T, F, x.device, fmt))
     sd, sm = _step_args()
-    for name, conv in blocks:
+    split = 3 if _s3_split_eligible(model, model.conv2[0], F) else 0
+    for bi, (name, conv) in enumerate(blocks):
         yc = TcConv.forward_cp8(name, conv, xc, ops.ACT_LRELU, a)
         site[0] += 1
-        zc = TcConv._buf(name + ':z', B, yc.C, T, F, z.device, fmt)
-        call('pool3_dropout_cp8', yc.ptr(), zc.ptr(), B, yc.C, T, F, yc.pitch, yc.pf, yc.pt, fmt, float(p), ctypes_u64(seed), ctypes_u64(site[0]),
-             sd, sm, stream_ptr())
+        sp = split if bi == len(blocks) - 1 else 0          # the last block hands over to conv2 in phase-split planes
+        zc = _split_buf(name + ':zs', B, (yc.C + 7) // 8 * 8, T, F, sp, z.device, fmt) if sp else TcConv._buf(name + ':z', B, yc.C, T, F, z.device, fmt)
+        call('pool3_dropout_split_cp8', yc.ptr(), zc.ptr(), B, yc.C, T, F, yc.pitch, yc.pf, yc.pt, fmt, float(p), ctypes_u64(seed),
+             ctypes_u64(site[0]), sd, sm, sp, zc.pitch if sp else 0, stream_ptr())
         sv['blocks'].append((None, yc, xc))
         xc = zc
-    a2, x2c = _tc_s3_forward('conv2', model.conv2[0], xc, ops.ACT_LRELU, a)
+    sv['split'] = split
+    if split:
+        a2, x2c = _tc_s3_forward_split('conv2', model.conv2[0], xc, ops.ACT_LRELU, a)
+    else:
+        a2, x2c = _tc_s3_forward('conv2', model.conv2[0], xc, ops.ACT_LRELU, a)
     site[0] += 1
     d2 = _pool_dropout(a2, 13, None, p, seed, site[0])
     a3 = _conv_fwd(model.conv3[0], d2, ops.ACT_LRELU, a)
@@ -480,15 +548,20 @@ def cnn_train_backward(model, sv, g_y, grads):
     g = _pool_bwd_dropout(sv['a2'], _dgrad(c3, g, sv['d2'].shape), 13, ops.ACT_LRELU, a, p, seed, site[0])
     if sv.get('cp8'):
         fmt = ops.FMT_BF16
-        gzc = _tc_s3_backward('conv2', c2, sv['x2c'], g, grads['conv2.0.weight'], grads['conv2.0.bias'], keep_cp8=True)
+        split = sv.get('split', 0)
+        if split:
+            gzc = _tc_s3_backward_split('conv2', c2, sv['x2c'], g, grads['conv2.0.weight'], grads['conv2.0.bias'])
+        else:
+            gzc = _tc_s3_backward('conv2', c2, sv['x2c'], g, grads['conv2.0.weight'], grads['conv2.0.bias'], keep_cp8=True)
         sd, sm = _step_args()
         for i in range(len(blocks) - 1, -1, -1):
             name, conv = blocks[i]
             _, yc, xc = sv['blocks'][i]
             site[0] -= 1
             gc = TcConv._buf(name + ':g', yc.B, yc.C, yc.T, yc.F, yc.buf.device, fmt)
-            call('pool3_bwd_dropout_cp8', yc.ptr(), gzc.ptr(), gc.ptr(), yc.B, yc.C, yc.T, yc.F, yc.pitch, yc.pf, yc.pt, fmt, ops.ACT_LRELU, float(a),
-                 float(p), ctypes_u64(seed), ctypes_u64(site[0]), sd, sm, stream_ptr())
+            sp = split if i == len(blocks) - 1 else 0       # conv2's data gradient arrives in phase-split planes
+            call('pool3_bwd_dropout_split_cp8', yc.ptr(), gzc.ptr(), gc.ptr(), yc.B, yc.C, yc.T, yc.F, yc.pitch, yc.pf, yc.pt, fmt, ops.ACT_LRELU,
+                 float(a), float(p), ctypes_u64(seed), ctypes_u64(site[0]), sd, sm, sp, gzc.pitch if sp else 0, stream_ptr())
             gzc = TcConv.backward_cp8(name, conv, xc, gc, grads[f'{name}.0.weight'], grads[f'{name}.0.bias'], need_dx=True)
         ops.layernorm_cf_param_grad_cp8(sv['x'], gzc, grads['layernorm.weight'], grads['layernorm.bias'], model.layernorm.eps)
         return grads

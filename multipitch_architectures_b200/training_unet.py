@@ -19,7 +19,7 @@ import torch
 from . import _lib, ops
 from ._lib import call, stream_ptr
 from .libdl.nn_models import _exec
-from .training import (TcConv, ctypes_u64, _rows_tc_backward, _rows_tc_eligible, _rows_tc_forward, _act_bwd, _add, _conv_fwd, _dgrad, _dropout, _pool_bwd, _tc_s3_backward, _tc_s3_eligible, _tc_s3_forward,
+from .training import (TcConv, ctypes_u64, _s3_split_eligible, _split_buf, _tc_s3_backward_split, _tc_s3_forward_split, _rows_tc_backward, _rows_tc_eligible, _rows_tc_forward, _act_bwd, _add, _conv_fwd, _dgrad, _dropout, _pool_bwd, _tc_s3_backward, _tc_s3_eligible, _tc_s3_forward,
                        _wgrad)
 
 
@@ -37,14 +37,18 @@ class Node:
 class Tape:
     def __init__(self, grads, seed, step, model=None):
         self.ops, self.grads, self.seed, self.site, self.model = [], grads, seed, step * 256, model
+        self.trunk_mark = 0
 
     def push(self, fn):
         self.ops.append(fn)
 
-    def backward(self):
-        for fn in reversed(self.ops):
+    def backward(self, lo=0, hi=None):
+        """Run the recorded stages ops[lo:hi] in reverse (default: all).  `trunk_mark` = number of stages of the encoder trunk: running
+        [trunk_mark, end) first and [0, trunk_mark) second splits the backward where the gradients of everything but the trunk are final."""
+        hi = len(self.ops) if hi is None else hi
+        for fn in reversed(self.ops[lo:hi]):
             fn()
-        self.ops = []
+        del self.ops[lo:hi]
 
     # ---------------------------------------------------------------------------------------------- stages
     def dropout(self, x, p):
@@ -191,21 +195,21 @@ class Tape:
         self.push(bwd)
         return out
 
-    def bn_relu_cp8(self, name, bn, y, dst, conv_bias_name):
+    def bn_relu_cp8(self, name, bn, y, dst, conv_bias_name, split=0):
         """BatchNorm2d (train mode, running statistics updated) + ReLU on the planes, written into `dst` (a buffer or a channel view of a
-        concat buffer)."""
+        concat buffer; split = s: phase-split planes, the hand-over to the head's stride-(1, s) convolution and back)."""
         stats = ops.bn_stats_cp8(y.d, bn)
-        out = Node(ops.bn_relu_apply_cp8(y.d, stats, bn, dst))
+        out = Node(ops.bn_relu_apply_cp8(y.d, stats, bn, dst, split))
 
         def bwd():
             yc = y.d
             dy = TcConv._buf(name + ':dy', yc.B, yc.C, yc.T, yc.F, yc.buf.device, yc.fmt)
             y.g = ops.bn_relu_bwd_cp8(out.g, yc, stats, bn, dy, self.grads[name + '.weight'], self.grads[name + '.bias'],
-                                        self.grads[conv_bias_name])
+                                        self.grads[conv_bias_name], split)
         self.push(bwd)
         return out
 
-    def double_conv_cp8(self, name, dc, x, dst=None, need_dx=True):
+    def double_conv_cp8(self, name, dc, x, dst=None, need_dx=True, split=0):
         seq = dc.double_conv
         n0, n1, n4, n5 = (f'{name}.double_conv.{i}' for i in (0, 1, 4, 5))
         xc = x.d
@@ -213,7 +217,7 @@ class Tape:
         a1 = self.bn_relu_cp8(n1, seq[1], self.conv_cp8(n0, seq[0], x, need_dx), mid, n0 + '.bias')
         if dst is None:
             dst = TcConv._buf(n5 + ':a', xc.B, seq[4].weight.shape[0], xc.T, xc.F, xc.buf.device, xc.fmt)
-        return self.bn_relu_cp8(n5, seq[5], self.conv_cp8(n4, seq[4], a1), dst, n4 + '.bias')
+        return self.bn_relu_cp8(n5, seq[5], self.conv_cp8(n4, seq[4], a1), dst, n4 + '.bias', split)
 
     def maxpool_cp8(self, tag, x):
         xc = x.d
@@ -257,15 +261,19 @@ class Tape:
         self.push(bwd)
         return out
 
-    def head_conv2_cp8(self, name, conv, u, k, a):
-        """Head conv2 (3x3, stride (1,3)) on the planes -> LeakyReLU -> MaxPool((k,1)) in fp32 NCHW (72 bins)."""
-        y, xc = _tc_s3_forward(name, conv, u.d, ops.ACT_LRELU, a)
+    def head_conv2_cp8(self, name, conv, u, k, a, split=0):
+        """Head conv2 (3x3, stride (1,3)) on the planes (split: phase-split input, stride-1 3x1 form) -> LeakyReLU -> MaxPool((k,1)) in fp32
+        NCHW (72 bins)."""
+        y, xc = (_tc_s3_forward_split if split else _tc_s3_forward)(name, conv, u.d, ops.ACT_LRELU, a)
         act = Node(y)
         out = Node(ops.maxpool_time(act.d, k))
 
         def bwd():
             g = _pool_bwd(act.d, out.g, k, ops.ACT_LRELU, a)
-            u.g = _tc_s3_backward(name, conv, xc, g, self.grads[name + '.weight'], self.grads[name + '.bias'], keep_cp8=True)
+            if split:
+                u.g = _tc_s3_backward_split(name, conv, xc, g, self.grads[name + '.weight'], self.grads[name + '.bias'])
+            else:
+                u.g = _tc_s3_backward(name, conv, xc, g, self.grads[name + '.weight'], self.grads[name + '.bias'], keep_cp8=True)
         self.push(bwd)
         return out
 
@@ -572,6 +580,7 @@ def _unet_train_forward_cp8(model, x, grads, seed, step):
         dst = cat[lv].channels(0, c[lv]) if lv < 4 else None
         xs.append(tp.double_conv_cp8(f'down{lv}.1', getattr(model, f'down{lv}')[1], tp.maxpool_cp8(f'down{lv}', xs[-1]), dst))
     x5 = xs[4]
+    tp.trunk_mark = len(tp.ops)
     if hasattr(model, 'attention1'):
         t5 = tp.cp8_to_f32('x5', x5)
         for nm in ('attention1', 'attention2'):
@@ -579,9 +588,13 @@ def _unet_train_forward_cp8(model, x, grads, seed, step):
             t5 = tp.encoder_layer(nm, layer, t5, layer.p_dropout if model.training else 0.0)
         x5 = tp.f32_to_cp8('x5a', t5, fmt)
     u = x5
+    split = 3 if _s3_split_eligible(model, model.conv2[0], F) else 0
     for i, lv in enumerate((3, 2, 1, 0)):
-        u = tp.double_conv_cp8(f'upconv{i + 1}', getattr(model, f'upconv{i + 1}'), tp.upcat_cp8(f'up{i + 1}', u, xs[lv], cat[lv], c[lv]))
-    h = tp.dropout(tp.head_conv2_cp8('conv2.0', model.conv2[0], u, 13, a), p)
+        last = lv == 0 and split
+        dst = _split_buf('upconv4:as', B, up_out[3], T, F, 3, dev, fmt) if last else None       # hand-over to conv2 in phase-split planes
+        u = tp.double_conv_cp8(f'upconv{i + 1}', getattr(model, f'upconv{i + 1}'), tp.upcat_cp8(f'up{i + 1}', u, xs[lv], cat[lv], c[lv]), dst,
+                               split=split if last else 0)
+    h = tp.dropout(tp.head_conv2_cp8('conv2.0', model.conv2[0], u, 13, a, split), p)
     h = tp.dropout(tp.conv('conv3.0', model.conv3[0], h, ops.ACT_LRELU, a), p)
     h = tp.dropout(tp.conv('conv4.0', model.conv4[0], h, ops.ACT_LRELU, a), p)
     y = tp.conv('conv4.3', model.conv4[3], h, ops.ACT_SIGMOID)
@@ -600,6 +613,7 @@ def unet_train_forward(model, x, grads, seed=0, step=0):
     for lv in (1, 2, 3, 4):
         xs.append(tp.double_conv(f'down{lv}.1', getattr(model, f'down{lv}')[1], tp.maxpool2d(xs[-1], (2, 2), (2, 2))))
     x5 = xs[4]
+    tp.trunk_mark = len(tp.ops)
     if getattr(model, 'lstm_depth', 0) > 0:             # BLUnet: BLSTM over time at the bottleneck (and on the lowest skip for depth 2)
         x5 = tp.blstm('lstm5', model.lstm5, x5)
     if getattr(model, 'lstm_depth', 0) > 1:
@@ -664,7 +678,7 @@ class UnetTrainStep:
     forward, BCE (+ CE/25 for the PUnet), backward, ONE gradient all-reduce (NCCL, when a process group is active), fused AdamW."""
 
     def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, seed=0x5EED, process_group=None, ce_scale=1.0 / 25.0,
-                 graph=False):
+                 graph=False, overlap_comm=True):
         """graph=True: after two eager steps the forward + loss + backward sequence (~3,500 kernel launches for the SAUnet:L, more host
         launch time than GPU time) is captured ONCE into a CUDA graph and replayed; the all-reduce and AdamW stay eager.  Inputs must keep
         their shape.  The replayed step is the eager step of the same number (dropout offsets come from a device-side step counter)."""
@@ -687,8 +701,24 @@ class UnetTrainStep:
                 off += k
         self.step_count = 0
         self.use_graph, self._graph = bool(graph), None
+        # Data-parallel runs overlap the gradient all-reduce with the backward: the parameters of the encoder trunk (layernorm, inc, down1-4)
+        # are a PREFIX of the flat buffer; everything behind it (attention, decoder, head: ~3/4 of the SAUnet:L's bytes) is final once the
+        # backward has reached the bottleneck, and is reduced on NCCL's stream while the trunk's backward still runs.
+        self.overlap_comm = bool(overlap_comm)
+        self.n_trunk, seen_other = 0, False
+        for name, p in named:
+            trunk = name.startswith(('layernorm.', 'inc.', 'down'))
+            if trunk and seen_other:
+                self.n_trunk = 0                       # not a prefix (unknown model layout): one flat all-reduce after the backward
+                break
+            if trunk:
+                self.n_trunk += p.numel()
+            else:
+                seen_other = True
+        self._tape = None
 
-    def _forward_backward(self, x, target, tape_step):
+    def _forward_backward(self, x, target, tape_step, split=False):
+        """split: stop the backward at the bottleneck (the trunk's part follows in _trunk_backward)."""
         with TcConv.scope(self):
             y, n_pred, tape = unet_train_forward(self.model, x, self.grads, self.seed, tape_step)
             target = target.contiguous()
@@ -697,28 +727,42 @@ class UnetTrainStep:
                 B, K = n_pred.d.shape[0], n_pred.d.shape[1]
                 n_pred.g = torch.empty_like(n_pred.d)
                 call('ce_count_fwd_bwd_f32', n_pred.d, target, loss, n_pred.g, B, K, target.numel() // B, float(self.ce_scale), 1, stream_ptr())
-            tape.backward()
+            if split:
+                tape.backward(lo=tape.trunk_mark)
+                self._tape = tape
+            else:
+                tape.backward()
         return loss
+
+    def _trunk_backward(self):
+        with TcConv.scope(self, refresh=False):
+            tape, self._tape = self._tape, None
+            tape.backward()
 
     def release(self):
         """Free the pooled activation planes of this step (and the captured graph that points into them)."""
-        self._graph = None
+        self._graph = self._graph2 = None
         TcConv.release(self)
 
-    def _capture(self, x, target):
+    def _capture(self, x, target, split):
         from . import training as T
         self._xs, self._ts = x.clone(), target.contiguous().clone()
         self._step_dev = torch.zeros(1, dtype=torch.int64, device=x.device)
         self._graph = torch.cuda.CUDAGraph()
+        self._graph2 = None
         n0 = _lib.launch_count()
-        with torch.cuda.graph(self._graph):
-            self._step_dev += 1
-            T._step_dev, T._step_mul = self._step_dev, 256
-            try:
-                self._loss = self._forward_backward(self._xs, self._ts, 0)
-            finally:
-                T._step_dev = None
-        self.launches_per_replay = _lib.launch_count() - n0      # libmpa kernels inside the graph (the host counter does not see replays)
+        T._step_dev, T._step_mul = self._step_dev, 256
+        try:
+            with torch.cuda.graph(self._graph):
+                self._step_dev += 1
+                self._loss = self._forward_backward(self._xs, self._ts, 0, split)
+            if split:                                  # the trunk's backward as a second graph (same memory pool): the all-reduce of the
+                self._graph2 = torch.cuda.CUDAGraph()  # finished gradients is issued between the two replays
+                with torch.cuda.graph(self._graph2, pool=self._graph.pool()):
+                    self._trunk_backward()
+        finally:
+            T._step_dev = None
+        self.launches_per_replay = _lib.launch_count() - n0      # libmpa kernels inside the graph(s) (the host counter does not see replays)
         self.replays = 0
         self._step_dev.fill_(self.step_count - 1)
 
@@ -726,23 +770,37 @@ class UnetTrainStep:
         import torch.distributed as dist
         self.step_count += 1
         with torch.no_grad():
-            if self.use_graph and self.step_count > 2:
+            multi = self.group is not None or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
+            split = bool(multi and self.overlap_comm and self.n_trunk > 0)
+            graphed = self.use_graph and self.step_count > 2
+            if graphed:
                 if self._graph is None:
-                    self._capture(x, target)
+                    self._capture(x, target, split)
                 self._xs.copy_(x)
                 self._ts.copy_(target)
                 self._graph.replay()
                 self.replays += 1
                 loss = self._loss
             else:
-                loss = self._forward_backward(x, target, self.step_count)
+                loss = self._forward_backward(x, target, self.step_count, split)
             scale = 1.0
-            if self.group is not None or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            if multi:
                 ev = getattr(self, 'comm_events', None)
-                if ev is not None:                    # bench.py: CUDA events around the collective (time of the all-reduce per step)
+                if split:
+                    w_a = dist.all_reduce(self.flat_g[self.n_trunk:], group=self.group, async_op=True)    # NCCL's stream waits for the work so far
+                    if graphed:
+                        self._graph2.replay()
+                    else:
+                        self._trunk_backward()
+                if ev is not None:                    # bench.py: CUDA events around the part of the collective the step waits for
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
-                dist.all_reduce(self.flat_g, group=self.group)
+                if split:
+                    w_b = dist.all_reduce(self.flat_g[:self.n_trunk], group=self.group, async_op=True)
+                    w_a.wait()
+                    w_b.wait()
+                else:
+                    dist.all_reduce(self.flat_g, group=self.group)
                 if ev is not None:
                     e1.record()
                     ev.append((e0, e1))

@@ -218,3 +218,47 @@ def test_full_height_convolution_on_the_tensor_cores(B, Cin, Cout, W):
     assert (gw - wr.grad).abs().max() < 2e-3 * wr.grad.abs().max()
     assert (gx - xr.grad).abs().max() < 2e-3 * xr.grad.abs().max()
     assert (gb - g.sum((0, 2, 3))).abs().max() < 1e-4 * g.abs().sum() / Cout
+
+
+@pytest.mark.parametrize('kind', ['unet', 'saunet', 'cnn'])
+def test_phase_split_conv2_equals_the_stride_emulation(kind):
+    """Head conv2 (3x3, stride (1,3); basic_cnns.py:391, unet_cnns.py:376) in training: phase-split hand-over (producer writes bin f to phase
+    f % 3, conv2 = stride-1 3x1 convolution over 3 * C0p channels, data gradient back in phase-split planes) against the stride-1 3x3
+    convolution with sub-sampled output / zero-inserted gradient.  Same bf16 operand values, different accumulation order."""
+    from multipitch_architectures_b200 import training
+    from multipitch_architectures_b200.libdl import nn_models as M
+    res = {}
+    for split in (True, False):
+        if kind == 'cnn':
+            m = M.basic_cnn_segm_sigmoid(n_chan_input=6, n_chan_layers=[20, 20, 10, 1], n_bins_in=216, n_bins_out=72, precision='bf16')
+        else:
+            m = _model(kind, 'bf16')
+        m.load_state_dict(fill_state_dict(m.state_dict(), 77, scheme='torch_default'))
+        m = m.cuda().train()
+        x, t = synth_patches(4, 77).cuda(), synth_targets(4, 77).cuda()
+        from multipitch_architectures_b200 import training_unet
+        calls = []
+        orig = training._tc_s3_forward_split
+
+        def spy(*a, **k):
+            calls.append(1)
+            return orig(*a, **k)
+        old = training.S3_SPLIT
+        training.S3_SPLIT = split
+        training._tc_s3_forward_split = training_unet._tc_s3_forward_split = spy
+        try:
+            m._train_calls = 0
+            y = m(x)
+            loss = torch.nn.BCELoss(reduction='mean')(y, t)
+            loss.backward()
+        finally:
+            training.S3_SPLIT = old
+            training._tc_s3_forward_split = training_unet._tc_s3_forward_split = orig
+        assert len(calls) == (1 if split else 0)             # the phase-split form really ran (or really did not)
+        res[split] = (loss.item(), y.detach().cpu().numpy(), {k: p.grad.cpu().numpy() for k, p in m.named_parameters()})
+    (la, ya, ga), (lb, yb, gb) = res[True], res[False]
+    cos, worst = _cos(ga, gb)
+    print(f'{kind}: loss split {la:.6f} emulated {lb:.6f}; max|dy| {np.abs(ya - yb).max():.2e}; gradient cosine {cos:.6f}, worst {worst[1]} {worst[0]:.5f}')
+    assert abs(la - lb) < 1e-3 * abs(lb) and np.abs(ya - yb).max() < 5e-3
+    assert cos > 0.995 and worst[0] > 0.98
+    assert np.abs(ga['conv2.0.weight'] - gb['conv2.0.weight']).max() < 2e-2 * np.abs(gb['conv2.0.weight']).max()
