@@ -98,8 +98,9 @@ ROWS_TC = True             # test knob: False = conv3 of the bf16 models on the 
 
 
 def _rows_tc_eligible(model, conv, x):
-    """The head's full-height 75x1 convolution of a bf16 model with more than 10 output channels (thinner ones are HBM-bound matrix-vector
-    products: conv_rows_thin_*): forward and both gradients as tcgen05 GEMMs."""
+    """The head's full-height 75x1 convolution of a bf16 model with more than 10 output channels: forward and both gradients as tcgen05
+    GEMMs.  Thinner ones (CNN:XS 20 -> 10, DRCNN 30 -> 10) are HBM-bound matrix-vector products and stay on the conv_rows_thin_* kernels (the
+    tensor-core form was measured at batch 256: 3.39 -> 3.48 ms per CNN:XS step — two operand-chunking passes over x outweigh the GEMMs)."""
     return (ROWS_TC and model is not None and getattr(model, 'precision', 'fp32') == 'bf16' and _is_rows_conv(conv, x.shape[2])
             and conv.weight.shape[0] > 10 and x.shape[3] % 8 == 0 and conv.bias is not None)
 
@@ -478,7 +479,8 @@ def _cnn_train_forward_cp8(model, blocks, x, sv, site, drop):
         a2, x2c = _tc_s3_forward('conv2', model.conv2[0], xc, ops.ACT_LRELU, a)
     site[0] += 1
     d2 = _pool_dropout(a2, 13, None, p, seed, site[0])
-    a3 = _conv_fwd(model.conv3[0], d2, ops.ACT_LRELU, a)
+    a3 = _rows_tc_forward(model.conv3[0], d2, ops.ACT_LRELU, a) if _rows_tc_eligible(model, model.conv3[0], d2) else \
+        _conv_fwd(model.conv3[0], d2, ops.ACT_LRELU, a)
     d3 = drop(a3)
     a4 = _conv_fwd(model.conv4[0], d3, ops.ACT_LRELU, a)
     d4 = drop(a4)
@@ -515,7 +517,8 @@ def cnn_train_forward(model, x, seed=0, step=0):
         a2, x2c = _conv_fwd(model.conv2[0], z, ops.ACT_LRELU, a), None
     site[0] += 1
     d2 = _pool_dropout(a2, 13, None, p, seed, site[0])
-    a3 = _conv_fwd(model.conv3[0], d2, ops.ACT_LRELU, a)
+    a3 = _rows_tc_forward(model.conv3[0], d2, ops.ACT_LRELU, a) if _rows_tc_eligible(model, model.conv3[0], d2) else \
+        _conv_fwd(model.conv3[0], d2, ops.ACT_LRELU, a)
     d3 = drop(a3)
     a4 = _conv_fwd(model.conv4[0], d3, ops.ACT_LRELU, a)
     d4 = drop(a4)
@@ -543,9 +546,13 @@ def cnn_train_backward(model, sv, g_y, grads):
     _wgrad(c40, sv['d3'], g, grads['conv4.0.weight'], grads['conv4.0.bias'])
     g = drop_bwd(_dgrad(c40, g, sv['d3'].shape))
     g = _act_bwd(sv['a3'], g, ops.ACT_LRELU, a)
-    _wgrad(c3, sv['d2'], g, grads['conv3.0.weight'], grads['conv3.0.bias'])
+    if _rows_tc_eligible(model, c3, sv['d2']):
+        g_d2 = _rows_tc_backward(c3, sv['d2'], g, grads['conv3.0.weight'], grads['conv3.0.bias'], True)
+    else:
+        _wgrad(c3, sv['d2'], g, grads['conv3.0.weight'], grads['conv3.0.bias'])
+        g_d2 = _dgrad(c3, g, sv['d2'].shape)
     site[0] -= 1
-    g = _pool_bwd_dropout(sv['a2'], _dgrad(c3, g, sv['d2'].shape), 13, ops.ACT_LRELU, a, p, seed, site[0])
+    g = _pool_bwd_dropout(sv['a2'], g_d2, 13, ops.ACT_LRELU, a, p, seed, site[0])
     if sv.get('cp8'):
         fmt = ops.FMT_BF16
         split = sv.get('split', 0)
