@@ -519,7 +519,10 @@ int mpa_bias_act_f32(const float* x, const float* bias, float* out, int B, int C
  *    dimension.  This is how the head's full-height 75x1 convolution (libdl/nn_models/unet_cnns.py:380-385, basic_cnns.py:396-401) and its
  *    two gradients run on the tensor cores: operands chunked by mpa_gemm_tc_strided_to_chunks, which reads element (r, k) of a tensor at
  *    (r / r_n2) * r_s1 + (r % r_n2) * r_s2 + (k / k_n2) * k_s1 + (k % k_n2) * k_s2.  With a strided result the K split (atomics) is used only
- *    when the caller has zeroed y (y_zeroed = 1). */
+ *    when the caller has zeroed y (y_zeroed = 1).
+ *  - residual add + LayerNorm epilogue (N <= 128, no K split, no other epilogue output): ln_out[b][n][s] (NCHW, s < ln_S) =
+ *    LayerNorm_n(result + bias + ln_res[m][n]) * ln_w + ln_b for token m = b * ln_S + s — the second add & LayerNorm of transformer_enc_layer
+ *    (unet_cnns.py:155-158) inside the MLP's second product, so that an encoder layer forward is 3 launches. */
 typedef struct mpa_gemm_tc_desc {
   const void* x_chunks;
   const void* w_chunks;
@@ -534,6 +537,10 @@ typedef struct mpa_gemm_tc_desc {
   float* colsum;
   int y_mn2, y_nn2, y_zeroed;
   long long y_ms1, y_ms2, y_ns1, y_ns2;
+  const float *ln_res, *ln_w, *ln_b;   /* residual + LayerNorm epilogue (see above); ln_out NULL = off */
+  float* ln_out;
+  float ln_eps;
+  int ln_S;
 } mpa_gemm_tc_desc;
 int mpa_gemm_tc_run(const mpa_gemm_tc_desc* desc, void* stream);
 int mpa_gemm_tc_strided_to_chunks(const float* x, void* out_chunks, int rows, int K, int row_tile, int fmt, int r_n2, long long r_s1,

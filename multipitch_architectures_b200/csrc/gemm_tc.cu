@@ -42,11 +42,20 @@ struct GemmTcParams {
   // straight into an NCHW tensor whose (item, bin) pair is one GEMM dimension (the head's 75x1 convolution and its gradients)
   int y_mn2, y_nn2;
   long long y_ms1, y_ms2, y_ns1, y_ns2;
+  // residual add + LayerNorm over the N features in the epilogue (N <= 128: one feature tile; no K split): out_nchw[b][n][s] =
+  // LN(result + bias + ln_res[m][n]) * ln_w + ln_b for token m = b * ln_S + s — the second add & LayerNorm of transformer_enc_layer
+  const float *ln_res, *ln_w, *ln_b;
+  float* ln_out;
+  float ln_eps;
+  int ln_S;
+  unsigned* ln_counters;     // K split: arrival counter per token tile (zero on entry, reset by the last arriver)
 };
 __device__ __forceinline__ long long gm_off(int i, int n2, long long s1, long long s2) {
   return n2 > 0 ? (long long)(i / n2) * s1 + (long long)(i % n2) * s2 : (long long)i * s2;
 }
 constexpr int kGmTrBytes = 32 * 80;            // per epilogue warp: 32 tokens x (32 features x 2 B + 16 B pad) transposing tile
+constexpr int kGmLnPitch = 129;                // fp32 staging tile of the LayerNorm epilogue: [32 tokens][128 features + 1]
+constexpr int kGmLnBytes = 32 * kGmLnPitch * 4 + 32 * 8;     // + (mean, rstd) per token
 
 __device__ __forceinline__ uint32_t gm_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void gm_mbar_init(uint64_t* bar, uint32_t count) {
@@ -231,7 +240,7 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemm_tc_kernel(const GemmTcPara
       const bool n_ok = n < p.N;
       const float b = (n_ok && p.bias && g.kc0 == 0) ? p.bias[n] : 0.f;
       const int m_hi = min(kGmTileM, p.M - g.m0);
-      const bool extra = p.y_tok || p.y_feat || p.mask_tok || p.colsum;
+      const bool extra = p.y_tok || p.y_feat || p.mask_tok || p.colsum || p.ln_out;
       float csum = 0.f;
       uint8_t* tr = tr_smem + quad * kGmTrBytes;
       for (int c0 = 0; c0 < (extra ? kGmTileM : m_hi); c0 += 32) {
@@ -247,7 +256,7 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemm_tc_kernel(const GemmTcPara
         uint32_t v[32];
         gm_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256 + c0), v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (!extra) {
+        if (!extra || (p.ln_out && p.ksplit > 1)) {
           if (n_ok) {
             float* yn = p.y + gm_off(n, p.y_nn2, p.y_ns1, p.y_ns2);
 #pragma unroll
@@ -270,6 +279,52 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemm_tc_kernel(const GemmTcPara
           if (p.relu) val = fmaxf(val, 0.f);
           if (!n_ok || c0 + i >= m_hi) val = 0.f;
           v[i] = __float_as_uint(val);
+        }
+        if (p.ln_out && p.ksplit == 1) {
+          // ---- residual + LayerNorm over the features (the four epilogue warps hold all N <= 128 features of these 32 tokens)
+          float* stage = reinterpret_cast<float*>(tr_smem);                    // [32][kGmLnPitch]
+          float2* tstat = reinterpret_cast<float2*>(tr_smem + 32 * kGmLnPitch * 4);
+          const int nloc = quad * 32 + lane;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float val = __uint_as_float(v[i]);
+            if (n_ok && c0 + i < m_hi) val += p.ln_res[(size_t)(g.m0 + c0 + i) * p.N + n];
+            stage[i * kGmLnPitch + nloc] = val;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          for (int t8 = 0; t8 < 8; ++t8) {                                    // warp `quad` owns tokens quad*8 .. quad*8+7
+            const int tok = quad * 8 + t8;
+            float x4[4], sum = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              x4[k] = lane + 32 * k < p.N ? stage[tok * kGmLnPitch + lane + 32 * k] : 0.f;
+              sum += x4[k];
+            }
+            const float mean = warp_sum(sum) / p.N;
+            float q = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (lane + 32 * k < p.N) {
+                const float d = x4[k] - mean;
+                q += d * d;
+              }
+            const float rstd = rsqrtf(warp_sum(q) / p.N + p.ln_eps);
+            if (lane == 0) tstat[tok] = make_float2(mean, rstd);
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          {
+            // lanes = tokens: consecutive lanes write consecutive bottleneck positions of one NCHW feature plane
+            const int m = g.m0 + c0 + lane;
+            const bool live = c0 + lane < m_hi;
+            const float2 st = tstat[lane];
+            const int bb = live ? m / p.ln_S : 0, ss = live ? m - bb * p.ln_S : 0;
+            for (int e = quad * 32; e < quad * 32 + 32 && e < p.N; ++e) {
+              const float r = (stage[lane * kGmLnPitch + e] - st.x) * st.y * p.ln_w[e] + p.ln_b[e];
+              if (live) p.ln_out[((size_t)bb * p.N + e) * p.ln_S + ss] = r;
+            }
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          continue;
         }
         if (p.mask_tok && n_ok) {
 #pragma unroll
@@ -331,6 +386,44 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemm_tc_kernel(const GemmTcPara
         }
       }
       if (p.colsum && n_ok) atomicAdd(&p.colsum[n], csum);
+      if (p.ln_out && p.ksplit > 1) {
+        // K split: every slice of this token tile has added its part to y with atomics; the slice that arrives LAST (all N <= 128 features
+        // are one feature tile) reads the sums back from L2 and finishes residual + LayerNorm for the tile's tokens
+        volatile unsigned& ln_last = *reinterpret_cast<volatile unsigned*>(tmem_slot + 2);       // inside the 256-byte barrier block (no static shared memory: the kernel opts in to all 227 KB as dynamic)
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (quad == 0 && lane == 0) ln_last = atomicAdd(&p.ln_counters[g.m0 / kGmTileM], 1u) == (unsigned)p.ksplit - 1;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (ln_last) {
+          __threadfence();
+          for (int tok = quad; tok < m_hi; tok += 4) {                    // one warp per token, 4 features per lane
+            const int m = g.m0 + tok;
+            float x4[4], sum = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int e = lane + 32 * k;
+              x4[k] = e < p.N ? __ldcg(&p.y[(size_t)m * p.N + e]) + p.ln_res[(size_t)m * p.N + e] : 0.f;
+              sum += x4[k];
+            }
+            const float mean = warp_sum(sum) / p.N;
+            float q = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (lane + 32 * k < p.N) {
+                const float d = x4[k] - mean;
+                q += d * d;
+              }
+            const float rstd = rsqrtf(warp_sum(q) / p.N + p.ln_eps);
+            const int bb = m / p.ln_S, ss = m - bb * p.ln_S;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int e = lane + 32 * k;
+              if (e < p.N) p.ln_out[((size_t)bb * p.N + e) * p.ln_S + ss] = (x4[k] - mean) * rstd * p.ln_w[e] + p.ln_b[e];
+            }
+          }
+          if (quad == 0 && lane == 0) p.ln_counters[g.m0 / kGmTileM] = 0u;
+        }
+      }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       gm_arrive(&acc_empty[buf]);
     }
@@ -428,7 +521,9 @@ int mpa_gemm_tc_run(const mpa_gemm_tc_desc* d, void* stream) {
   void *y_tok = d->y_tok, *y_feat = d->y_feat;
   const int M = d->M, N = d->N, K = d->K, relu = d->relu, fmt = d->fmt, x_rows = d->x_rows, w_rows = d->w_rows, y_tok_rows = d->y_tok_rows,
             y_tok_chunks = d->y_tok_chunks, y_feat_rows = d->y_feat_rows;
-  const bool extra = y_tok || y_feat || mask_tok || colsum;
+  const bool extra = y_tok || y_feat || mask_tok || colsum || d->ln_out;
+  MPA_REQUIRE(!d->ln_out || (d->ln_res && d->ln_w && d->ln_b && d->ln_S > 0 && N <= kGmTileN && !y_tok && !y_feat && !mask_tok && !colsum && !relu),
+              "gemm_tc: the LayerNorm epilogue needs N <= 128, its residual / weight / bias and no other epilogue output");
   MPA_REQUIRE(x_chunks && w_chunks && (y || extra) && M > 0 && N > 0 && K > 0, "gemm_tc: bad argument");
   MPA_REQUIRE(fmt == MPA_FMT_F16 || fmt == MPA_FMT_BF16, "gemm_tc: fmt must be MPA_FMT_F16 or MPA_FMT_BF16");
   MPA_REQUIRE((((uintptr_t)x_chunks | (uintptr_t)w_chunks | (uintptr_t)y_tok | (uintptr_t)y_feat | (uintptr_t)mask_tok) & 15) == 0,
@@ -456,6 +551,7 @@ int mpa_gemm_tc_run(const mpa_gemm_tc_desc* d, void* stream) {
   p.y_feat = (uint16_t*)y_feat; p.y_feat_rows = y_feat_rows;
   p.mask_tok = (const uint16_t*)mask_tok; p.colsum = colsum;
   p.bf16 = fmt == MPA_FMT_BF16;
+  p.ln_res = d->ln_res; p.ln_w = d->ln_w; p.ln_b = d->ln_b; p.ln_out = d->ln_out; p.ln_eps = d->ln_eps; p.ln_S = d->ln_S;
   p.y_mn2 = d->y_mn2; p.y_ms1 = d->y_ms1; p.y_ms2 = d->y_mn2 > 0 || d->y_ms2 != 0 ? d->y_ms2 : (long long)N;
   p.y_nn2 = d->y_nn2; p.y_ns1 = d->y_ns1; p.y_ns2 = d->y_nn2 > 0 || d->y_ns2 != 0 ? d->y_ns2 : 1;
   int dev = 0, sms = 148;
@@ -463,7 +559,8 @@ int mpa_gemm_tc_run(const mpa_gemm_tc_desc* d, void* stream) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int tiles = p.n_tiles_n * p.n_tiles_m, stages = p.KC / kGmChunksPerStage;
   int ks = 1;
-  if (!relu && !extra && tiles < sms && stages >= 8) {
+  const bool ln_only = d->ln_out && !y_tok && !y_feat && !mask_tok && !colsum;
+  if (!relu && (!extra || (ln_only && y)) && tiles < sms && stages >= 8) {
     ks = sms / tiles;
     if (ks > stages / 4) ks = stages / 4;
     if (ks < 1) ks = 1;
@@ -472,13 +569,25 @@ int mpa_gemm_tc_run(const mpa_gemm_tc_desc* d, void* stream) {
   }
   p.ksplit = ks;
   p.n_units = tiles * ks;
+  if (d->ln_out && ks > 1) {
+    static unsigned* counters[64] = {nullptr};
+    int cd = dev < 0 || dev >= 64 ? 0 : dev;
+    if (!counters[cd]) {
+      if (cudaMalloc(&counters[cd], sizeof(unsigned) * 65536) != cudaSuccess || cudaMemset(counters[cd], 0, sizeof(unsigned) * 65536) != cudaSuccess) {
+        set_error("gemm_tc: counter allocation failed");
+        return MPA_ERR_CUDA;
+      }
+    }
+    MPA_REQUIRE(p.n_tiles_m <= 65536, "gemm_tc: too many token tiles for the LayerNorm epilogue");
+    p.ln_counters = counters[cd];
+  }
   const uint32_t f = (fmt == MPA_FMT_BF16) ? 1u : 0u;
   p.idesc = (1u << 4) | (f << 7) | (f << 10) | ((uint32_t)(kGmTileM >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   // the K slices meet in atomics: a dense result is zeroed here, a strided one (y_mn2 / y_nn2 / explicit strides) by the caller
   const bool dense_y = d->y_mn2 == 0 && d->y_nn2 == 0 && d->y_ms2 == 0 && d->y_ns2 == 0;
   if (ks > 1 && dense_y) cudaMemsetAsync(y, 0, sizeof(float) * (size_t)M * N, (cudaStream_t)stream);
   if (ks > 1 && !dense_y && !d->y_zeroed) ks = 1, p.ksplit = 1, p.n_units = tiles;
-  const size_t smem = (size_t)kGmStages * (kGmWBytes + kGmXBytes) + 256 + 4 * kGmTrBytes;
+  const size_t smem = (size_t)kGmStages * (kGmWBytes + kGmXBytes) + 256 + (4 * kGmTrBytes > kGmLnBytes ? 4 * kGmTrBytes : kGmLnBytes);
   {
     static unsigned char flags[64];
     cudaError_t e = opt_in_max_smem(gemm_tc_kernel, flags);

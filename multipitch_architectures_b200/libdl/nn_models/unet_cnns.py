@@ -128,8 +128,15 @@ def _enc_run_tc(self, x, fmt, pe, w_qkv, b_qkv, w_proj, b_proj):
         h1c = ops.gemm_tc_chunks(h1, 256, fmt)
     hid_feat = torch.empty(Np8 * Mp * 16, dtype=torch.uint8, device=dev)
     ops.gemm_tc_ex(h1c, w1c, self.mlp[0].bias, M, Dm, E, True, fmt, y_feat=hid_feat, y_feat_rows=Mp)
-    mo = ops.gemm_tc_ex(hid_feat, w2c, self.mlp[2].bias, M, E, Dm, False, fmt, y=f32(M, E))
     out = torch.empty_like(x)
+    if E <= 128:
+        # residual + LayerNorm2 in the second product's epilogue, written straight to NCHW: the layer is 3 launches (attention half, MLP
+        # product 1, MLP product 2).  Few token tiles (the reference batch of 50: 11 tiles): the product is split over K, the slices meet
+        # in atomics on `mo`, and the slice that arrives last finishes the tile's LayerNorm from L2.
+        ops.gemm_tc_ex(hid_feat, w2c, self.mlp[2].bias, M, E, Dm, False, fmt, y=f32(M, E),
+                       ln=(h1, self.layernorm2.weight, self.layernorm2.bias, self.layernorm2.eps, out, S))
+        return out
+    mo = ops.gemm_tc_ex(hid_feat, w2c, self.mlp[2].bias, M, E, Dm, False, fmt, y=f32(M, E))
     _lib.call('add_layernorm_tok_f32', h1, mo, self.layernorm2.weight, self.layernorm2.bias, None, out, _lib.i64(M), E, S,
               float(self.layernorm2.eps), sp())
     return out

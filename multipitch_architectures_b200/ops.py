@@ -562,7 +562,9 @@ class GemmTcDesc(_ct.Structure):
                 ('M', _ct.c_int), ('N', _ct.c_int), ('K', _ct.c_int), ('relu', _ct.c_int), ('fmt', _ct.c_int), ('x_rows', _ct.c_int),
                 ('w_rows', _ct.c_int), ('y_tok', _ct.c_void_p), ('y_tok_rows', _ct.c_int), ('y_tok_chunks', _ct.c_int), ('y_feat', _ct.c_void_p),
                 ('y_feat_rows', _ct.c_int), ('mask_tok', _ct.c_void_p), ('colsum', _ct.c_void_p), ('y_mn2', _ct.c_int), ('y_nn2', _ct.c_int),
-                ('y_zeroed', _ct.c_int), ('y_ms1', _ct.c_longlong), ('y_ms2', _ct.c_longlong), ('y_ns1', _ct.c_longlong), ('y_ns2', _ct.c_longlong)]
+                ('y_zeroed', _ct.c_int), ('y_ms1', _ct.c_longlong), ('y_ms2', _ct.c_longlong), ('y_ns1', _ct.c_longlong), ('y_ns2', _ct.c_longlong),
+                ('ln_res', _ct.c_void_p), ('ln_w', _ct.c_void_p), ('ln_b', _ct.c_void_p), ('ln_out', _ct.c_void_p), ('ln_eps', _ct.c_float),
+                ('ln_S', _ct.c_int)]
 
 
 def _dptr(t):
@@ -574,7 +576,7 @@ def _dptr(t):
 
 
 def gemm_tc_ex(x_chunks, w_chunks, bias, M, N, K, relu, fmt, y=None, x_rows=0, w_rows=0, y_tok=None, y_tok_rows=0, y_tok_chunks=0, y_feat=None,
-               y_feat_rows=0, mask_tok=None, colsum=None, y_m=None, y_n=None, y_zeroed=False):
+               y_feat_rows=0, mask_tok=None, colsum=None, y_m=None, y_n=None, y_zeroed=False, ln=None):
     """mpa_gemm_tc_run: the tcgen05 product on pre-chunked operands; optional 16-bit operand-layout copies of the result (y_tok / y_feat),
     ReLU-backward mask and bias-gradient sums in the epilogue, and a strided fp32 result (y_m / y_n = (n2, s1, s2) two-level indices)."""
     d = GemmTcDesc()
@@ -586,6 +588,9 @@ def gemm_tc_ex(x_chunks, w_chunks, bias, M, N, K, relu, fmt, y=None, x_rows=0, w
         d.y_mn2, d.y_ms1, d.y_ms2 = y_m
     if y_n is not None:
         d.y_nn2, d.y_ns1, d.y_ns2 = y_n
+    if ln is not None:          # (residual [M,N], weight, bias, eps, out NCHW [B,N,S...], S): residual + LayerNorm in the epilogue
+        res, w, b, eps, out, S = ln
+        d.ln_res, d.ln_w, d.ln_b, d.ln_out, d.ln_eps, d.ln_S = _dptr(res), _dptr(w), _dptr(b), _dptr(out), float(eps), int(S)
     rc = _lib.lib().mpa_gemm_tc_run(_ct.byref(d), stream_ptr())
     if rc != 0:
         raise _lib.MpaError(f'mpa_gemm_tc_run failed ({rc}): {_lib.last_error()}')

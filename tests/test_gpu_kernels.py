@@ -221,6 +221,31 @@ def test_encoder_layer(ops):
     assert (got - ref).abs().max() < 5e-5
 
 
+@pytest.mark.parametrize('B,E,mlp', [(330, 128, 512), (400, 64, 256), (12, 128, 512), (50, 128, 8192), (50, 64, 256)])
+def test_encoder_layer_tensor_core_path_with_layernorm_epilogue(ops, B, E, mlp):
+    """transformer_enc_layer (unet_cnns.py:131-159) on the tensor-core inference path: from 64 token tiles on (B * 52 >= 16384 tokens) the second
+    add & LayerNorm runs in the epilogue of the MLP's second product (3 launches per layer); smaller batches keep the split-K product + add&LN
+    kernel.  Both against the fp32 sequence of the same layer."""
+    from multipitch_architectures_b200 import _lib
+    from multipitch_architectures_b200.libdl.nn_models.unet_cnns import transformer_enc_layer
+    torch.manual_seed(5)
+    layer = transformer_enc_layer(embed_dim=E, num_heads=8, mlp_dim=mlp, p_dropout=0.2, pos_encoding='sinusoidal').cuda().eval()
+    x = rnd(B, E, 4, 13, seed=31).cuda()
+    with torch.no_grad():
+        ref = layer.run(x)
+        n0 = _lib.launch_count()
+        got = layer.run(x, ops.FMT_F16)
+        n1 = _lib.launch_count()
+        got2 = layer.run(x, ops.FMT_F16)
+        launches = _lib.launch_count() - n1
+    assert (got - got2).abs().max().item() < 1e-4          # (split-K slices meet in fp32 atomics: the order varies from run to run)
+    err = (got - ref).abs().max().item()
+    print(f'B={B} E={E}: fp16 tensor-core layer vs fp32 max|d| {err:.2e}; launches per forward {launches} (first call incl. operand preparation {n1 - n0})')
+    assert err < 4e-3 * max(1.0, ref.abs().max().item())
+    if B <= 64 and E >= 64:                      # the fused attention half (<= 64 items per position) + two MLP products
+        assert launches <= 3
+
+
 @pytest.mark.parametrize('B,Cin,H,W,Cout', [(25, 80, 75, 72, 50), (256, 20, 75, 72, 10), (3, 7, 75, 72, 5), (2, 100, 9, 13, 80),
                                             # thin layers (Cout <= 4, W % 4 == 0): the HBM-bound matrix-vector kernels
                                             (256, 10, 75, 72, 1), (5, 10, 75, 72, 1), (7, 6, 20, 216, 3), (40, 3, 11, 8, 4), (4, 1, 1, 72, 1),
