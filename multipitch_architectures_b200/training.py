@@ -93,6 +93,7 @@ def _wgrad(conv, x, g, gw, gb):
          conv.padding[1], stream_ptr())
 
 
+WGRAD_SIDE = True          # test knob: False = weight gradients on the main stream, in front of the data gradient of their layer
 PACK_MULTI = True          # test knob: False = one weight-packing launch per convolution and direction
 ROWS_TC = True             # test knob: False = conv3 of the bf16 models on the fp32 strided-GEMM kernels (conv_rows.cu)
 
@@ -227,6 +228,7 @@ class TcConv:
                 plan.fresh = plan.table is not None and PACK_MULTI      # second half of a step: the operands were refreshed by the first
             try:
                 yield
+                cls.join()
                 if PACK_MULTI:
                     plan.build()
             finally:
@@ -255,6 +257,33 @@ class TcConv:
             b = ops.CP8(B, C, T, F, pitch, cls.PF, cls.PT, dev, fmt=fmt)
             cls._pool[key] = b
         return b
+
+    # Weight gradients on a side stream: inside a fused train step (scope set) the weight gradient of a convolution is independent of
+    # everything that follows it in the backward (it reads the saved input planes and the dy planes of its own layer — pooled per layer,
+    # not reused within the step — and writes its own slice of the flat gradient buffer), so it is issued on a second stream and joined
+    # at the end of the backward: the small, latency-bound layers of the deep U-Net levels then run side by side with the data-gradient
+    # chain instead of in front of it.  Under CUDA-graph capture the fork / join become parallel branches of the graph.
+    _side_streams, _side_dirty = {}, False
+
+    @classmethod
+    def wgrad_async(cls, dev, fn):
+        if not WGRAD_SIDE or cls._scope is None:
+            return fn()
+        side = cls._side_streams.get(str(dev))
+        if side is None:
+            side = cls._side_streams[str(dev)] = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fn()
+        cls._side_dirty = True
+
+    @classmethod
+    def join(cls):
+        """The current stream waits for the weight gradients issued so far."""
+        if cls._side_dirty:
+            for side in cls._side_streams.values():
+                torch.cuda.current_stream().wait_stream(side)
+            cls._side_dirty = False
 
     @classmethod
     def _raw(cls, tag, nbytes, zero, dev):
@@ -325,7 +354,7 @@ class TcConv:
         B, Cout, T, F = gc.B, gc.C, gc.T, gc.F
         _, Cin, KH, KW = conv.weight.shape
         dev = gc.buf.device
-        ops.conv_wgrad_tc(xc, gc, gw, (KH, KW))
+        cls.wgrad_async(dev, lambda: ops.conv_wgrad_tc(xc, gc, gw, (KH, KW)))
         if gb is not None:
             ops.channel_sum_cp8(gc, out=gb)
         if not need_dx:
@@ -372,7 +401,7 @@ def _tc_s3_backward(tag, conv, xc, g, gw, gb, keep_cp8=False):
     Cin, F = conv.weight.shape[1], xc.F
     gc = TcConv._buf(tag + ':g3', B, Cout, T, F, g.device, fmt)
     call('nchw_to_cp8_strided', g, gc.ptr(), B, Cout, T, Fo, F, 3, 1, gc.pitch, gc.pf, gc.pt, fmt, gc.ncs, stream_ptr())
-    ops.conv_wgrad_tc(xc, gc, gw, (3, 3))
+    TcConv.wgrad_async(g.device, lambda: ops.conv_wgrad_tc(xc, gc, gw, (3, 3)))
     ops.channel_sum(g, out=gb)
     gxc = TcConv._buf(tag + ':gx', B, Cin, T, F, g.device, fmt)
     zb = TcConv._zero_bias(g.device)
