@@ -126,9 +126,11 @@ def _rows_tc_backward(conv, x, g, gw, gb, need_dx):
     fm = ops.FMT_BF16
     B, Cin, H, W = x.shape
     Cout, K, Mt = conv.weight.shape[0], Cin * H, B * W
-    gt = ops.strided_chunks(g, Cout, Mt, 256, fm, (Cout, 0, W), (W, Cout * W, 1))
-    xt = ops.strided_chunks(x, K, Mt, 128, fm, (K, 0, W), (W, K * W, 1))
-    ops.gemm_tc_ex(gt, xt, None, Cout, K, Mt, False, fm, y=gw.view(Cout, K))
+    def wgrad():
+        gt = ops.strided_chunks(g, Cout, Mt, 256, fm, (Cout, 0, W), (W, Cout * W, 1))
+        xt = ops.strided_chunks(x, K, Mt, 128, fm, (K, 0, W), (W, K * W, 1))
+        ops.gemm_tc_ex(gt, xt, None, Cout, K, Mt, False, fm, y=gw.view(Cout, K))
+    TcConv.wgrad_async(g.device, wgrad, keep=(g, x))
     ops.channel_sum(g, out=gb)
     if not need_dx:
         return None
@@ -265,10 +267,15 @@ class TcConv:
     # chain instead of in front of it.  Under CUDA-graph capture the fork / join become parallel branches of the graph.
     _side_streams, _side_dirty = {}, False
 
+    _keep = []
+
     @classmethod
-    def wgrad_async(cls, dev, fn):
+    def wgrad_async(cls, dev, fn, keep=()):
+        """keep: tensors allocated on the main stream that `fn` reads — held until the join, so that the allocator cannot hand their memory
+        to later main-stream work while the side stream still reads it."""
         if not WGRAD_SIDE or cls._scope is None:
             return fn()
+        cls._keep.extend(keep)
         side = cls._side_streams.get(str(dev))
         if side is None:
             side = cls._side_streams[str(dev)] = torch.cuda.Stream(device=dev)
@@ -284,6 +291,7 @@ class TcConv:
             for side in cls._side_streams.values():
                 torch.cuda.current_stream().wait_stream(side)
             cls._side_dirty = False
+        cls._keep.clear()
 
     @classmethod
     def _raw(cls, tag, nbytes, zero, dev):

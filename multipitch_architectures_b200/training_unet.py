@@ -314,13 +314,16 @@ class Tape:
                  G[name + '.layernorm1.weight'], G[name + '.layernorm1.bias'], B, E, S, H, int(pe is not None), float(p_drop),
                  ctypes_u64(self.seed), ctypes_u64(site_tok), ctypes_u64(site_att), sd_b, sm_b, stream_ptr())
             x.acc(g_x)
-            dWp = gemm(g_p, att, E, E, M, 1)                        # [E,E] = g_p^T att
-            dbp = colsum(g_p, M, E)
-            dWf = gemm(g_qkv, t, 3 * E, E, M, 1)                    # [3E,E] = g_qkv^T t
-            colsum(g_qkv, M, 3 * E, out=G[name + '.attn.in_proj_bias'])
-            call('enc_fold_bwd_f32', dWf, dWp, dbp, *params, G[name + '.attn.in_proj_weight'], G[name + '.q_linear.weight'],
-                 G[name + '.k_linear.weight'], G[name + '.v_linear.weight'], G[name + '.o_linear.weight'], G[name + '.attn.out_proj.weight'],
-                 G[name + '.attn.out_proj.bias'], E, stream_ptr())
+
+            def weight_grads():                                     # reductions over all tokens: off the data-gradient chain
+                dWp = gemm(g_p, att, E, E, M, 1)                    # [E,E] = g_p^T att
+                dbp = colsum(g_p, M, E)
+                dWf = gemm(g_qkv, t, 3 * E, E, M, 1)                # [3E,E] = g_qkv^T t
+                colsum(g_qkv, M, 3 * E, out=G[name + '.attn.in_proj_bias'])
+                call('enc_fold_bwd_f32', dWf, dWp, dbp, *params, G[name + '.attn.in_proj_weight'], G[name + '.q_linear.weight'],
+                     G[name + '.k_linear.weight'], G[name + '.v_linear.weight'], G[name + '.o_linear.weight'], G[name + '.attn.out_proj.weight'],
+                     G[name + '.attn.out_proj.bias'], E, stream_ptr())
+            TcConv.wgrad_async(dev, weight_grads, keep=(g_p, g_qkv, att, t))
         self.push(bwd)
         return h1
 
@@ -435,9 +438,12 @@ class Tape:
 
         def bwd_mlp_tc():
             g_m2 = m2.g
-            # dW2 [E, Dm] = g_m2^T hid
-            ops.gemm_tc_ex(ops.gemm_tc_chunks(g_m2, 256, fm, True), hid_tok, None, E, Dm, M, False, fm, y=G[name + '.mlp.2.weight'], w_rows=rows_t)
-            colsum(g_m2, M, E, out=G[name + '.mlp.2.bias'])
+
+            def dw2():                                              # dW2 [E, Dm] = g_m2^T hid, d b2: off the data-gradient chain
+                ops.gemm_tc_ex(ops.gemm_tc_chunks(g_m2, 256, fm, True), hid_tok, None, E, Dm, M, False, fm, y=G[name + '.mlp.2.weight'],
+                               w_rows=rows_t)
+                colsum(g_m2, M, E, out=G[name + '.mlp.2.bias'])
+            TcConv.wgrad_async(dev, dw2, keep=(g_m2,))
             # g_hid = (g_m2 W2) * [hid > 0] -> both operand layouts, bias gradient = its column sums
             ghid_tok = TcConv._raw(name + ':ghid_tok', KCt * rows_t * 16, True, dev)
             ghid_feat = TcConv._raw(name + ':ghid_feat', Np8 * Mp * 16, False, dev)
@@ -446,7 +452,8 @@ class Tape:
             ops.gemm_tc_ex(ops.gemm_tc_chunks(g_m2, 256, fm), ops.gemm_tc_chunks(W2, 128, fm, True), None, M, Dm, E, False, fm, y_tok=ghid_tok,
                            y_tok_rows=rows_t, y_tok_chunks=KCt, y_feat=ghid_feat, y_feat_rows=Mp, mask_tok=hid_tok, colsum=gb1)
             # dW1 [Dm, E] = g_hid^T h1;  g_h1 [M, E] = g_hid W1
-            ops.gemm_tc_ex(ghid_tok, ops.gemm_tc_chunks(h1.d, 128, fm, True), None, Dm, E, M, False, fm, y=G[name + '.mlp.0.weight'], x_rows=rows_t)
+            TcConv.wgrad_async(dev, lambda: ops.gemm_tc_ex(ghid_tok, ops.gemm_tc_chunks(h1.d, 128, fm, True), None, Dm, E, M, False, fm,
+                                                           y=G[name + '.mlp.0.weight'], x_rows=rows_t), keep=(h1.d,))
             h1.acc(ops.gemm_tc_ex(ghid_feat, ops.gemm_tc_chunks(W1, 128, fm, True), None, M, E, Dm, False, fm, y=f32(M, E)))
 
         def bwd_mlp():
