@@ -418,8 +418,8 @@ int mpa_pool3_bwd_dropout_split_cp8(const void* a_cp8, const void* g_out_cp8, vo
 /* U-Net family, bf16 training mode, CP8-resident (train_unet_cp8.cu): the element-wise stages between two tensor-core convolutions of a
  * training step on the 16-bit planes themselves.  Geometry arguments as mpa_nchw_to_cp8; every `ncs_*` is the chunk-plane stride per item
  * of that buffer (0 = C/8; larger for a channel view of a concat buffer); C % 8 == 0; fmt = MPA_FMT_BF16 | MPA_FMT_F16.
- *   mpa_bn_stats_cp8       stats[0..C) = batch mean, stats[C..2C) = biased batch variance of y (two-pass per slice + Chan merge in a fixed
- *                          order); running_mean / running_var (optional) <- (1-m)*running + m*(mean | var*n/(n-1)), num_batches_tracked += 1:
+ *   mpa_bn_stats_cp8       stats[0..C) = batch mean, stats[C..2C) = biased batch variance of y (one pass: per slice the sums of the deviations
+ *                          from `pivot[c]` (optional; the producing convolution's bias) and of their squares, then Chan's merge in a fixed order); running_mean / running_var (optional) <- (1-m)*running + m*(mean | var*n/(n-1)), num_batches_tracked += 1:
  *                          nn.BatchNorm2d in training mode (libdl/nn_models/unet_cnns.py:39,44 — double_conv's BatchNorm2d layers)
  *   mpa_bn_relu_apply_cp8  out = max(0, (y - mean) * rsqrt(var + eps) * weight + bias)        (unet_cnns.py:39-41: BatchNorm2d -> ReLU)
  *   mpa_bn_relu_bwd_cp8    the backward of that pair: g' = g * [out > 0] (out recomputed from y), g_bias = sum g', g_weight = sum g' * xhat,
@@ -433,8 +433,8 @@ int mpa_pool3_bwd_dropout_split_cp8(const void* a_cp8, const void* g_out_cp8, vo
  *                          in row-major order (ATen); `a` is the un-pooled activation, pooled level = (T/2, F/2)   (unet_cnns.py:60-61 `down`)
  *   mpa_upsample2x_bwd_cp8 g_low = adjoint of mpa_upsample2x_cp8 (bilinear x2, align_corners=True, zero pad to (Ts, Fs)) applied to g_up
  *                          (unet_cnns.py:83-101 `unet_up_concat_padding`) */
-int mpa_bn_stats_cp8(const void* y_cp8, float* stats, int B, int C, int T, int F, int pitch, int pf, int pt, int ncs, int fmt,
-                     float* running_mean, float* running_var, float momentum, long long* num_batches_tracked, void* stream);
+int mpa_bn_stats_cp8(const void* y_cp8, float* stats, const float* pivot, int B, int C, int T, int F, int pitch, int pf, int pt, int ncs,
+                     int fmt, float* running_mean, float* running_var, float momentum, long long* num_batches_tracked, void* stream);
 int mpa_bn_relu_apply_cp8(const void* y_cp8, void* out_cp8, const float* stats, const float* weight, const float* bias, float eps, int B,
                           int C, int T, int F, int pitch, int pf, int pt, int ncs_y, int ncs_out, int out_split, int out_pitch, int fmt,
                           void* stream);

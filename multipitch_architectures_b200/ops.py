@@ -291,7 +291,7 @@ def upsample2x_cp8(low, out):
 
 
 # ---- U-Net training stages on the planes (train_unet_cp8.cu) -----------------------------------------
-def bn_stats_cp8(y, bn=None, update_running=True):
+def bn_stats_cp8(y, bn=None, update_running=True, pivot=None):
     """[2C] fp32 = (batch mean | biased batch variance) of the CP8 tensor y; with `bn` (nn.BatchNorm2d, train mode) its running
     statistics and num_batches_tracked are updated in the same launch pair."""
     stats = torch.empty(2 * y.C, dtype=torch.float32, device=y.buf.device)
@@ -300,7 +300,7 @@ def bn_stats_cp8(y, bn=None, update_running=True):
     if bn is not None and update_running and bn.track_running_stats:
         rm, rv, nbt = bn.running_mean, bn.running_var, bn.num_batches_tracked
         mom = bn.momentum if bn.momentum is not None else 0.1
-    call('bn_stats_cp8', y.ptr(), stats, y.B, y.C, y.T, y.F, y.pitch, y.pf, y.pt, y.ncs, y.fmt, rm, rv, float(mom), nbt, stream_ptr())
+    call('bn_stats_cp8', y.ptr(), stats, pivot, y.B, y.C, y.T, y.F, y.pitch, y.pf, y.pt, y.ncs, y.fmt, rm, rv, float(mom), nbt, stream_ptr())
     return stats
 
 

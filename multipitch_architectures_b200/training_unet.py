@@ -195,10 +195,10 @@ class Tape:
         self.push(bwd)
         return out
 
-    def bn_relu_cp8(self, name, bn, y, dst, conv_bias_name, split=0):
+    def bn_relu_cp8(self, name, bn, y, dst, conv_bias_name, split=0, conv_bias=None):
         """BatchNorm2d (train mode, running statistics updated) + ReLU on the planes, written into `dst` (a buffer or a channel view of a
         concat buffer; split = s: phase-split planes, the hand-over to the head's stride-(1, s) convolution and back)."""
-        stats = ops.bn_stats_cp8(y.d, bn)
+        stats = ops.bn_stats_cp8(y.d, bn, pivot=conv_bias)
         out = Node(ops.bn_relu_apply_cp8(y.d, stats, bn, dst, split))
 
         def bwd():
@@ -214,10 +214,10 @@ class Tape:
         n0, n1, n4, n5 = (f'{name}.double_conv.{i}' for i in (0, 1, 4, 5))
         xc = x.d
         mid = TcConv._buf(n1 + ':a', xc.B, seq[0].weight.shape[0], xc.T, xc.F, xc.buf.device, xc.fmt)
-        a1 = self.bn_relu_cp8(n1, seq[1], self.conv_cp8(n0, seq[0], x, need_dx), mid, n0 + '.bias')
+        a1 = self.bn_relu_cp8(n1, seq[1], self.conv_cp8(n0, seq[0], x, need_dx), mid, n0 + '.bias', conv_bias=seq[0].bias)
         if dst is None:
             dst = TcConv._buf(n5 + ':a', xc.B, seq[4].weight.shape[0], xc.T, xc.F, xc.buf.device, xc.fmt)
-        return self.bn_relu_cp8(n5, seq[5], self.conv_cp8(n4, seq[4], a1), dst, n4 + '.bias', split)
+        return self.bn_relu_cp8(n5, seq[5], self.conv_cp8(n4, seq[4], a1), dst, n4 + '.bias', split, conv_bias=seq[4].bias)
 
     def maxpool_cp8(self, tag, x):
         xc = x.d
