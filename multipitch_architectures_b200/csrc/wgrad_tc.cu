@@ -13,6 +13,8 @@
 // Work items = (filter-row set, input-chunk group of <= 4 chunks, slice of the B*T x-rows); an item keeps its <= 4 accumulators
 // (128 lanes x KW*8 columns each) in TMEM over its whole slice and flushes them with fp32 atomicAdd into gw.
 // The g rows live in a shared-memory ring whose slots ascend with t (one new row per x row; the RS-1 wrapping slots are mirrored).
+// KH x 1 filters (`wide`): with one tap an MMA per input chunk would have N = 16 columns; instead up to 16 input chunks of a group are the
+// N groups of ONE MMA (their slabs sit at a uniform stride in the x stage: SBO = slab bytes), N = 8 * chunks <= 128, one accumulator.
 #include "common.cuh"
 #include <cuda.h>
 #include <string.h>
@@ -34,6 +36,7 @@ struct WgradParams {
   int RS, n_sets, CG, n_cgroups, n_splits, n_items;
   int slots, slot_bytes, gslab_bytes, xslab_bytes, xstage_bytes, x_off, bar_off;
   uint32_t idesc;
+  int wide;                    // KW == 1: the CG input chunks of a group are the N groups of ONE accumulator (B descriptor SBO = slab stride)
 };
 
 __device__ __forceinline__ uint32_t wg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -231,12 +234,19 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgradPara
         const uint32_t b_lo0 = (xs16 + (uint32_t)xst * xst16) | lo_fixed;
         const bool last_of_patch = (s == p.T - 1) || (q == it.q1 - 1);
         if (wg_elect_one()) {
-          for (int c = 0; c < it.nchunks; ++c) {
-            const uint32_t tmem_d = tmem_u + (uint32_t)c * 128u;
-            const uint32_t b_lo = b_lo0 + (uint32_t)c * xsl16;
+          if (p.wide) {
+            const uint32_t bw_hi = xsl16 | (1u << 14);                       // B: next N group = next input chunk's slab
             for (int ks = 0; ks < ksteps; ++ks)
-              wg_mma(tmem_d, ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)ks * 16u), ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + (uint32_t)ks * 16u),
+              wg_mma(tmem_u, ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)ks * 16u), ((uint64_t)bw_hi << 32) | (uint64_t)(b_lo0 + (uint32_t)ks * 16u),
                      p.idesc, (first && ks == 0) ? 0u : 1u);
+          } else {
+            for (int c = 0; c < it.nchunks; ++c) {
+              const uint32_t tmem_d = tmem_u + (uint32_t)c * 128u;
+              const uint32_t b_lo = b_lo0 + (uint32_t)c * xsl16;
+              for (int ks = 0; ks < ksteps; ++ks)
+                wg_mma(tmem_d, ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)ks * 16u), ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + (uint32_t)ks * 16u),
+                       p.idesc, (first && ks == 0) ? 0u : 1u);
+            }
           }
           wg_commit(&x_empty[xst]);
           // the oldest g row is done; at the end of a patch (or of the slice) so are the others
@@ -264,7 +274,24 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgradPara
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const bool row_ok = (r < it.nset) && (co < p.Cout);
       const int kh = it.kh_hi - r;
-      for (int c = 0; c < it.nchunks; ++c) {
+      if (p.wide) {
+        // one accumulator: column n = (input chunk n / 8 of the group, channel n % 8), the single tap kw = 0
+        for (int c0 = 0; c0 < it.nchunks * 8; c0 += 32) {
+          uint32_t v[32];
+          wg_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (row_ok) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int n = c0 + i;
+              const int ci = (it.c0 + (n >> 3)) * 8 + (n & 7);
+              if (n < it.nchunks * 8 && ci < p.Cin)
+                atomicAdd(p.gw + ((size_t)(p.co0 + co) * p.Cin_total + p.ci0 + ci) * p.KH + kh, __uint_as_float(v[i]));
+            }
+          }
+        }
+      }
+      for (int c = 0; c < (p.wide ? 0 : it.nchunks); ++c) {
         for (int c0 = 0; c0 < ncols; c0 += 32) {
           uint32_t v[32];
           wg_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 128 + c0), v);
@@ -327,11 +354,15 @@ int mpa_conv_wgrad_tc(const void* x_cp8, const void* g_cp8, const void* zero_row
   p.RS = 16 / p.NCo;
   if (p.RS > KH) p.RS = KH;
   p.n_sets = (KH + p.RS - 1) / p.RS;
-  p.CG = p.NC < 4 ? p.NC : 4;
+  p.wide = KW == 1 && p.NC >= 2;
+  p.CG = p.wide ? (p.NC < 16 ? (p.NC + 1) / 2 * 2 : 16) : (p.NC < 4 ? p.NC : 4);
   p.n_cgroups = (p.NC + p.CG - 1) / p.CG;
   p.gslab_bytes = pitch * 16;
   p.slot_bytes = p.NCo * p.gslab_bytes;
   p.xslab_bytes = ((pitch + 2 * (KW / 2) + 1 + 7) / 8 * 8) * 16;
+  // wide mode: as many chunks per group as leave room for a minimal row ring
+  while (p.wide && p.CG > 2 && (size_t)kWgXStages * p.CG * p.xslab_bytes + 1024 + (size_t)(2 * p.RS) * p.NCo * p.gslab_bytes > 227 * 1024) p.CG -= 2;
+  p.n_cgroups = (p.NC + p.CG - 1) / p.CG;
   p.xstage_bytes = p.CG * p.xslab_bytes;
   const size_t fixed = (size_t)kWgXStages * p.xstage_bytes + 1024;
   int slots = p.RS + 3;
@@ -357,7 +388,7 @@ int mpa_conv_wgrad_tc(const void* x_cp8, const void* g_cp8, const void* zero_row
   p.n_splits = splits;
   p.n_items = n_types * splits;
   const uint32_t f = (fmt == MPA_FMT_BF16) ? 1u : 0u;
-  const int N = (KW * 8 + 15) / 16 * 16;                   // M = 128 needs N % 16 == 0: the extra taps land in ignored columns
+  const int N = p.wide ? p.CG * 8 : (KW * 8 + 15) / 16 * 16;   // M = 128 needs N % 16 == 0: the extra taps / chunks land in ignored columns
   p.idesc = (1u << 4) | (f << 7) | (f << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   {
     static unsigned char flags[64];

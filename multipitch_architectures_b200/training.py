@@ -421,11 +421,10 @@ def _tc_s3_backward(tag, conv, xc, g, gw, gb, keep_cp8=False):
     return gxc if keep_cp8 else ops.cp8_to_nchw(gxc)
 
 
-# Phase-split form of the head's stride-(1,3) conv2 in TRAINING (the inference path uses it).  Correct (tests/test_gpu_unet_cp8.py) but measured
-# slower than the stride-1 3x3 convolution on full-width / zero-inserted planes and therefore off: the forward gains (SAUnet:L 118 -> 65 us) are
-# lost in the weight gradient, whose KW = 1 form leaves wgrad_tc_kernel with N = 32 MMA columns per input-chunk group (298 -> 534 us; CNN:XS
-# 211 -> 406 us), and the phase-split reads / writes of the neighbouring element-wise kernels cost another ~100 us.
-S3_SPLIT = False
+# Phase-split form of the head's stride-(1,3) conv2 in TRAINING (the inference path uses it): test knob, False = the stride-1 3x3 convolution on
+# full-width / zero-inserted planes.  It pays only together with wgrad_tc_kernel's wide-N mode (KH x 1 filters: the input chunks of a group are
+# the N groups of one MMA); with one N = 16 MMA per chunk the weight gradient alone lost more than the forward gained (SAUnet:L 298 -> 534 us).
+S3_SPLIT = True
 
 
 def _s3_split_eligible(model, conv, F):
