@@ -69,6 +69,12 @@ int mpa_layernorm_cf_cp8(const float* x, const float* ln_w, const float* ln_b, v
                          int pt, float eps, float gamma_log, int fmt, void* stream);
 int mpa_layernorm_cf_param_grad_cp8(const float* x, const void* g_cp8, float* g_w, float* g_b, int B, int C, int T, int F, int pitch, int pf,
                                     int pt, int fmt, float eps, float gamma_log, void* stream);
+/* Pixel-per-thread forms of the two calls above (F <= 256): the forward also leaves (mean, rstd) of every (b,t) row in stats [B*T][2]
+ * (may be NULL), and the parameter gradient reads them instead of re-reducing every row (same reference lines). */
+int mpa_layernorm_cf_cp8_stats(const float* x, const float* ln_w, const float* ln_b, void* out_cp8, float* stats, int B, int C, int T, int F,
+                               int pitch, int pf, int pt, float eps, float gamma_log, int fmt, void* stream);
+int mpa_layernorm_cf_param_grad_cp8_stats(const float* x, const void* g_cp8, const float* stats, float* g_w, float* g_b, int B, int C, int T,
+                                          int F, int pitch, int pf, int pt, int fmt, float gamma_log, void* stream);
 
 /* Frame-major variant used by the streaming inference engine: frames [C][N][F] (the HCQT layout) ->
  * normalised frames; rows s with s < lead or s >= lead+N are the patch zero padding and come out as ln_b

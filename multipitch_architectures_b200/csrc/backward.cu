@@ -138,6 +138,137 @@ __global__ void __launch_bounds__(128) maxpool_time_bwd_col_kernel(const float* 
   }
 }
 
+// k = 13 (the head's MaxPool((13,1)), basic_cnns.py:180 / unet_cnns.py:379) for the training patch length T: same result as
+// maxpool_time_bwd_col_kernel<13> bit for bit (the windows of a column are routed in the same order), with a fraction of its instructions.
+// That kernel spent ~200 instructions per element: a 13-way compare / select scan per window, 13 predicated adds to route the gradient, 26
+// register moves to slide the window and a whole Philox draw per element of which it used one lane of four.  Here
+//  * the first arg-max of every window comes from a doubling table built on the fly (pairs -> fours -> eights -> two overlapping eights;
+//    `>` keeps the left operand on ties, so the first maximum wins): 4 compare + select steps per row, the rows fully unrolled so that the
+//    delay lines between the levels are register renaming,
+//  * the gradient is routed with one read-modify-write of the thread's own shared-memory column,
+//  * a Philox draw serves its 4 lanes = the 4 neighbouring bins of a thread quad: each thread draws for every fourth row and the quad
+//    exchanges 16 keep bits with two shuffles,
+//  * act'(a) needs one sign bit per row (3 registers).
+constexpr int kPool13Threads = 128;
+
+__device__ __forceinline__ void first_max(float& v, int& i, float bv, int bi) {
+  const bool r = bv > v;
+  v = r ? bv : v;
+  i = r ? bi : i;
+}
+
+template <int T>
+__global__ void __launch_bounds__(kPool13Threads) maxpool13_bwd_table_kernel(const float* __restrict__ a, const float* __restrict__ g_p,
+                                                                            float* __restrict__ g_a, long long n_cols, int F, int act,
+                                                                            float act_param, DropoutArgs d) {
+  extern __shared__ float acc[];                        // [T][128]: column of thread x at acc[t * 128 + x]
+  constexpr int H = 6, NW = (T + 31) / 32;
+  const long long col_raw = blockIdx.x * (long long)kPool13Threads + threadIdx.x;
+  const bool on = col_raw < n_cols;                     // n_cols % 4 == 0: a quad is on or off as a whole
+  const long long col = on ? col_raw : n_cols - 1;
+  const long long plane = col / F;
+  const int f = (int)(col - plane * F);
+  const size_t base = (size_t)plane * T * F + f;
+  const float* ap = a + base;
+  const float* gp = g_p + base;
+  const int q = threadIdx.x & 3;                        // == f & 3 == lane of this bin in its Philox draw (F % 4 == 0)
+  const bool drop = d.p > 0.f;
+  const unsigned long long d_off = drop ? dropout_offset(d) : 0ull;
+  const float d_scale = drop ? 1.f / (1.f - d.p) : 1.f;
+  const uint32_t thr = drop ? (uint32_t)ceilf(d.p * 16777216.f) << 8 : 0u;
+#pragma unroll
+  for (int t = 0; t < T; ++t) acc[t * kPool13Threads + threadIdx.x] = 0.f;
+  float a2v[3], a4v[5], a8v[6], gq[7], xs[8], gs[8];
+  int a2i[3], a4i[5], a8i[6];
+  uint32_t pos[NW], keep16 = 0u;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { a2v[i] = -INFINITY; a2i[i] = 0; }
+#pragma unroll
+  for (int i = 0; i < 5; ++i) { a4v[i] = -INFINITY; a4i[i] = 0; }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { a8v[i] = -INFINITY; a8i[i] = 0; }
+#pragma unroll
+  for (int i = 0; i < NW; ++i) pos[i] = 0u;
+  float xprev = -INFINITY;
+  // position p: sample a[p] arrives (p >= T: -inf); pairs [p-1,p], fours [p-3,p], eights [p-7,p] complete; window t = p - 6 = [p-12, p]
+#pragma unroll
+  for (int p = 0; p < T + H; ++p) {
+    if ((p & 7) == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        xs[j] = p + j < T ? ap[(size_t)(p + j) * F] : -INFINITY;
+        gs[j] = p + j < T ? gp[(size_t)(p + j) * F] : 0.f;
+      }
+    }
+    if (drop && (p & 3) == 0 && p < T) {
+      // this thread draws for row p + q; afterwards bit 4 j + c of keep16 = keep flag of lane c of row p + j
+      const uint4 r = dropout_bits((long long)((base - q + (size_t)(p + q) * F) >> 2), d.seed, d_off);
+      uint32_t k4 = (r.x >= thr ? 1u : 0u) | (r.y >= thr ? 2u : 0u) | (r.z >= thr ? 4u : 0u) | (r.w >= thr ? 8u : 0u);
+      k4 <<= 4 * q;
+      k4 |= __shfl_xor_sync(0xffffffffu, k4, 1);
+      k4 |= __shfl_xor_sync(0xffffffffu, k4, 2);
+      keep16 = k4 >> q;
+    }
+    const float xp = xs[p & 7];
+    float g = gs[p & 7];
+    if (p < T) {
+      if (drop) g = __fmul_rn(g, (keep16 >> (4 * (p & 3))) & 1u ? d_scale : 0.f);
+      const bool ps = act == MPA_ACT_RELU ? xp > 0.f : xp >= 0.f;
+      pos[p >> 5] |= ps ? 1u << (p & 31) : 0u;
+    }
+    gq[p % 7] = g;
+    // pairs: A2[p-1] = first max of (a[p-1], a[p])
+    {
+      float v = xprev;
+      int i = p - 1;
+      first_max(v, i, xp, p);
+      a2v[(p + 2) % 3] = v;      // slot of s = p - 1: (s + 3) % 3
+      a2i[(p + 2) % 3] = i;
+    }
+    // fours: A4[p-3] = (A2[p-3], A2[p-1])
+    {
+      float v = a2v[p % 3];      // s = p - 3: (s + 3) % 3
+      int i = a2i[p % 3];
+      first_max(v, i, a2v[(p + 2) % 3], a2i[(p + 2) % 3]);
+      a4v[(p + 2) % 5] = v;      // s = p - 3: (s + 5) % 5
+      a4i[(p + 2) % 5] = i;
+    }
+    // eights: A8[p-7] = (A4[p-7], A4[p-3])
+    {
+      float v = a4v[(p + 3) % 5];   // s = p - 7: (s + 10) % 5
+      int i = a4i[(p + 3) % 5];
+      first_max(v, i, a4v[(p + 2) % 5], a4i[(p + 2) % 5]);
+      a8v[(p + 5) % 6] = v;      // s = p - 7: (s + 12) % 6
+      a8i[(p + 5) % 6] = i;
+    }
+    if (p >= H) {
+      // window t = p - 6: (A8[p-12], A8[p-7])
+      float v = a8v[p % 6];      // s = p - 12: (s + 12) % 6
+      int i = a8i[p % 6];
+      first_max(v, i, a8v[(p + 5) % 6], a8i[(p + 5) % 6]);
+      acc[i * kPool13Threads + threadIdx.x] += gq[(p - H) % 7];
+    }
+    xprev = xp;
+  }
+  if (!on) return;
+  const float dneg = act == MPA_ACT_LRELU ? act_param : (act == MPA_ACT_RELU ? 0.f : 1.f);
+  float* op = g_a + base;
+#pragma unroll
+  for (int t = 0; t < T; ++t) op[(size_t)t * F] = acc[t * kPool13Threads + threadIdx.x] * ((pos[t >> 5] >> (t & 31)) & 1u ? 1.f : dneg);
+}
+
+constexpr int kPool13T = 75;       // the training patch length of every model (hcqt_datasets.py context 75)
+static inline bool pool13_table_eligible(int k, int T, int F) { return k == 13 && T == kPool13T && F % 4 == 0; }
+static int pool13_table_launch(const float* a, const float* g, float* g_a, int B, int C, int F, int act, float act_param, DropoutArgs d,
+                               cudaStream_t st) {
+  static unsigned char flags[64];
+  constexpr size_t smem = (size_t)kPool13T * kPool13Threads * sizeof(float);
+  if (opt_in_max_smem(maxpool13_bwd_table_kernel<kPool13T>, flags) != cudaSuccess) return MPA_ERR_CUDA;
+  const long long n_cols = (long long)B * C * F;
+  maxpool13_bwd_table_kernel<kPool13T><<<ceil_div(n_cols, kPool13Threads), kPool13Threads, smem, st>>>(a, g, g_a, n_cols, F, act, act_param, d);
+  return MPA_OK;
+}
+
 // narrow tensors (the head's 72 bins): whole warps only, so that one wave of CTAs covers all (item, channel) planes
 static inline int pool_col_threads(int F) { return F >= 128 ? 128 : (F + 31) / 32 * 32; }
 
@@ -394,6 +525,11 @@ int mpa_maxpool_time_bwd_f32(const float* a, const float* g_pool, float* g_a, in
     const int threads = pool_col_threads(F);
     const dim3 grid(B * C, ceil_div(F, threads));
     const DropoutArgs nod{0.f, 0ull, 0ull, nullptr, 0ull};
+    if (pool13_table_eligible(k, T, F)) {
+      MPA_REQUIRE(pool13_table_launch(a, g_pool, g_a, B, C, F, act, act_param, nod, (cudaStream_t)stream) == MPA_OK, "maxpool_time_bwd: shared memory opt-in failed");
+      MPA_CHECK_LAUNCH("maxpool_time_bwd_col");
+      return MPA_OK;
+    }
     if (k == 3) maxpool_time_bwd_col_kernel<3><<<grid, threads, 0, (cudaStream_t)stream>>>(a, g_pool, g_a, T, F, act, act_param, nod);
     else maxpool_time_bwd_col_kernel<13><<<grid, threads, 0, (cudaStream_t)stream>>>(a, g_pool, g_a, T, F, act, act_param, nod);
     MPA_CHECK_LAUNCH("maxpool_time_bwd_col");
@@ -482,6 +618,11 @@ int mpa_maxpool_time_bwd_dropout_f32(const float* a, const float* g_out, float* 
   const int threads = pool_col_threads(F);
   const dim3 grid(B * C, ceil_div(F, threads));
   const DropoutArgs d{p, seed, offset, step_dev, step_mul};
+  if (pool13_table_eligible(k, T, F)) {
+    MPA_REQUIRE(pool13_table_launch(a, g_out, g_a, B, C, F, act, act_param, d, (cudaStream_t)stream) == MPA_OK, "maxpool_time_bwd_dropout: shared memory opt-in failed");
+    MPA_CHECK_LAUNCH("maxpool_time_bwd_dropout");
+    return MPA_OK;
+  }
   if (k == 3) maxpool_time_bwd_col_kernel<3><<<grid, threads, 0, (cudaStream_t)stream>>>(a, g_out, g_a, T, F, act, act_param, d);
   else maxpool_time_bwd_col_kernel<13><<<grid, threads, 0, (cudaStream_t)stream>>>(a, g_out, g_a, T, F, act, act_param, d);
   MPA_CHECK_LAUNCH("maxpool_time_bwd_dropout");

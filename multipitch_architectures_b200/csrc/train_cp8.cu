@@ -272,6 +272,147 @@ __global__ void __launch_bounds__(kCp8Threads) pool3_bwd_dropout_cp8_kernel(cons
   }
 }
 
+
+// ---- LayerNorm([C,F]) on the network input, one thread per pixel (basic_cnns.py:371,411; unet_cnns.py:364) ------------------------------
+// The row kernels of elementwise.cu / backward.cu give one CTA to one (item, frame) row and reach ~1 TB/s (11 strided scalars per thread,
+// 2-byte gathers of the 16-bit gradient, the row statistics recomputed in the backward).  Here a thread owns one bin f of a row with all
+// C <= 8 channels: C coalesced fp32 loads in, ONE 16-byte CP8 pixel out (forward) / in (gradient); a CTA walks over a range of rows two at
+// a time (both rows' loads in flight before the first reduction) and the forward leaves (mean, rstd) per row for the parameter gradient.
+constexpr int kLnPixThreads = 256;
+
+// sums of two values over the 8 warps of the CTA; `sh` = 16 floats not touched since the last barrier
+__device__ __forceinline__ void block_sum2_8w(float& a, float& b, float* sh) {
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if ((threadIdx.x & 31) == 0) {
+    sh[threadIdx.x >> 5] = a;
+    sh[8 + (threadIdx.x >> 5)] = b;
+  }
+  __syncthreads();
+  a = ((sh[0] + sh[1]) + (sh[2] + sh[3])) + ((sh[4] + sh[5]) + (sh[6] + sh[7]));
+  b = ((sh[8] + sh[9]) + (sh[10] + sh[11])) + ((sh[12] + sh[13]) + (sh[14] + sh[15]));
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(kLnPixThreads, 4) layernorm_pix_cp8_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                          const float* __restrict__ bsh, uint4* __restrict__ out,
+                                                                          float2* __restrict__ stats, int rows, int rpb, int C, int T, int F, int TP,
+                                                                          int P, int pf, int pt, float eps, float gamma_log) {
+  __shared__ float sh[32];       // two regions: the barrier of the second reduction of a row pair frees the first region again
+  const int f = threadIdx.x;
+  const bool on = f < F;
+  float wc[8], bc[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    wc[c] = (on && c < C) ? w[c * F + f] : 0.f;
+    bc[c] = (on && c < C) ? bsh[c * F + f] : 0.f;
+  }
+  const float inv_n = 1.f / (float)(C * F);
+  const size_t cs = (size_t)T * F;
+  const int r0 = blockIdx.x * rpb, r1 = min(rows, r0 + rpb);
+  for (int r = r0; r < r1; r += 2) {
+    const bool two = r + 1 < r1;
+    const int ba = r / T, ta = r - ba * T, rb = two ? r + 1 : r, bb = rb / T, tb = rb - bb * T;
+    const float* xa = x + ((size_t)ba * C * T + ta) * F + f;
+    const float* xb = x + ((size_t)bb * C * T + tb) * F + f;
+    float va[8], vb[8], sa = 0.f, sb = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      va[c] = (on && c < C) ? xa[c * cs] : 0.f;
+      vb[c] = (on && c < C) ? xb[c * cs] : 0.f;
+    }
+    if (gamma_log > 0.f) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        if (on && c < C) {
+          va[c] = logf(__fadd_rn(1.f, __fmul_rn(gamma_log, va[c])));
+          vb[c] = logf(__fadd_rn(1.f, __fmul_rn(gamma_log, vb[c])));
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      sa += va[c];
+      sb += vb[c];
+    }
+    block_sum2_8w(sa, sb, sh);
+    const float ma = sa * inv_n, mb = sb * inv_n;
+    float qa = 0.f, qb = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      if (on && c < C) {
+        const float da = va[c] - ma, db = vb[c] - mb;
+        qa = fmaf(da, da, qa);
+        qb = fmaf(db, db, qb);
+      }
+    }
+    block_sum2_8w(qa, qb, sh + 16);
+    const float ra = rsqrtf(qa * inv_n + eps), rbs = rsqrtf(qb * inv_n + eps);
+    if (on) {
+      float oa[8], ob[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        oa[c] = c < C ? fmaf((va[c] - ma) * ra, wc[c], bc[c]) : 0.f;
+        ob[c] = c < C ? fmaf((vb[c] - mb) * rbs, wc[c], bc[c]) : 0.f;
+      }
+      out[((size_t)ba * TP + pt + ta) * P + pf + f] = pack8<FMT>(oa);
+      if (two) out[((size_t)bb * TP + pt + tb) * P + pf + f] = pack8<FMT>(ob);
+    }
+    if (stats && threadIdx.x == 0) {
+      stats[r] = make_float2(ma, ra);
+      if (two) stats[r + 1] = make_float2(mb, rbs);
+    }
+  }
+}
+
+// gw[c,f] += sum_rows g * (x - mean) * rstd, gb[c,f] += sum_rows g over the CTA's rows; g = the CP8 planes the first convolution's data
+// gradient wrote, (mean, rstd) from the forward.  12 atomics per thread and CTA (gw / gb zeroed by the launcher).
+template <int FMT>
+__global__ void __launch_bounds__(kLnPixThreads, 4) layernorm_pix_param_grad_cp8_kernel(const float* __restrict__ x, const uint4* __restrict__ g,
+                                                                                     const float2* __restrict__ stats, float* __restrict__ gw,
+                                                                                     float* __restrict__ gb, int rows, int rpb, int C, int T, int F,
+                                                                                     int TP, int P, int pf, int pt, float gamma_log) {
+  const int f = threadIdx.x;
+  if (f >= F) return;
+  float aw[8], ab[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) aw[c] = ab[c] = 0.f;
+  const size_t cs = (size_t)T * F;
+  const int r0 = blockIdx.x * rpb, r1 = min(rows, r0 + rpb);
+#pragma unroll 2
+  for (int r = r0; r < r1; ++r) {
+    const int b = r / T, t = r - b * T;
+    const float2 st = stats[r];
+    const float* xr = x + ((size_t)b * C * T + t) * F + f;
+    float gv[8], xv[8];
+    unpack8<FMT>(g[((size_t)b * TP + pt + t) * P + pf + f], gv);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) xv[c] = c < C ? xr[c * cs] : 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      if (c < C) {
+        float v = xv[c];
+        if (gamma_log > 0.f) v = logf(__fadd_rn(1.f, __fmul_rn(gamma_log, v)));
+        aw[c] = fmaf(gv[c], (v - st.x) * st.y, aw[c]);
+        ab[c] += gv[c];
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    if (c < C) {
+      atomicAdd(&gw[c * F + f], aw[c]);
+      atomicAdd(&gb[c * F + f], ab[c]);
+    }
+  }
+}
+
+static inline int ln_rows_per_block(int rows, int ctas_per_sm) {
+  int rpb = ceil_div(rows, 148 * ctas_per_sm);
+  rpb = (rpb + 1) & ~1;
+  return rpb < 2 ? 2 : rpb;
+}
+
 }  // namespace mpa
 
 using namespace mpa;
@@ -361,6 +502,44 @@ int mpa_channel_sum_cp8(const void* g_cp8, float* out, int B, int C, int T, int 
   int rc = channel_sum_cp8_launch((const uint4*)g_cp8, out, B, C, T, F, T + 2 * pt, pitch, pf, pt, ncs, fmt, (cudaStream_t)stream);
   if (rc != MPA_OK) return rc;
   MPA_CHECK_LAUNCH("channel_sum_cp8");
+  return MPA_OK;
+}
+
+// LayerNorm([C,F]) -> CP8 planes with one thread per pixel; stats (optional) [B*T] (mean, rstd) for mpa_layernorm_cf_param_grad_cp8_stats
+int mpa_layernorm_cf_cp8_stats(const float* x, const float* ln_w, const float* ln_b, void* out_cp8, float* stats, int B, int C, int T, int F,
+                               int pitch, int pf, int pt, float eps, float gamma_log, int fmt, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(x && ln_w && ln_b && out_cp8 && B > 0 && C > 0 && C <= 8 && T > 0 && F > 0 && F <= kLnPixThreads && pitch >= pf + F && pt >= 0 &&
+                  (fmt == MPA_FMT_BF16 || fmt == MPA_FMT_F16) && (long long)B * T < (1ll << 31),
+              "layernorm_cf_cp8_stats: bad argument (C <= 8, F <= 256, 16-bit formats)");
+  const int rows = B * T, rpb = ln_rows_per_block(rows, 4), grid = ceil_div(rows, rpb);
+  if (fmt == MPA_FMT_BF16)
+    layernorm_pix_cp8_kernel<MPA_FMT_BF16><<<grid, kLnPixThreads, 0, (cudaStream_t)stream>>>(x, ln_w, ln_b, (uint4*)out_cp8, (float2*)stats, rows, rpb,
+                                                                                            C, T, F, T + 2 * pt, pitch, pf, pt, eps, gamma_log);
+  else
+    layernorm_pix_cp8_kernel<MPA_FMT_F16><<<grid, kLnPixThreads, 0, (cudaStream_t)stream>>>(x, ln_w, ln_b, (uint4*)out_cp8, (float2*)stats, rows, rpb,
+                                                                                           C, T, F, T + 2 * pt, pitch, pf, pt, eps, gamma_log);
+  MPA_CHECK_LAUNCH("layernorm_cf_cp8_stats");
+  return MPA_OK;
+}
+
+int mpa_layernorm_cf_param_grad_cp8_stats(const float* x, const void* g_cp8, const float* stats, float* g_w, float* g_b, int B, int C, int T, int F,
+                                          int pitch, int pf, int pt, int fmt, float gamma_log, void* stream) {
+  MPA_CHECK_ARCH();
+  MPA_REQUIRE(x && g_cp8 && stats && g_w && g_b && B > 0 && C > 0 && C <= 8 && T > 0 && F > 0 && F <= kLnPixThreads && pitch >= pf + F &&
+                  pt >= 0 && (fmt == MPA_FMT_BF16 || fmt == MPA_FMT_F16) && (long long)B * T < (1ll << 31),
+              "layernorm_cf_param_grad_cp8_stats: bad argument (C <= 8, F <= 256, 16-bit formats)");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(g_w, 0, sizeof(float) * (size_t)C * F, st);
+  cudaMemsetAsync(g_b, 0, sizeof(float) * (size_t)C * F, st);
+  const int rows = B * T, rpb = ln_rows_per_block(rows, 4), grid = ceil_div(rows, rpb);
+  if (fmt == MPA_FMT_BF16)
+    layernorm_pix_param_grad_cp8_kernel<MPA_FMT_BF16><<<grid, kLnPixThreads, 0, st>>>(x, (const uint4*)g_cp8, (const float2*)stats, g_w, g_b, rows, rpb,
+                                                                                     C, T, F, T + 2 * pt, pitch, pf, pt, gamma_log);
+  else
+    layernorm_pix_param_grad_cp8_kernel<MPA_FMT_F16><<<grid, kLnPixThreads, 0, st>>>(x, (const uint4*)g_cp8, (const float2*)stats, g_w, g_b, rows, rpb,
+                                                                                    C, T, F, T + 2 * pt, pitch, pf, pt, gamma_log);
+  MPA_CHECK_LAUNCH("layernorm_cf_param_grad_cp8_stats");
   return MPA_OK;
 }
 

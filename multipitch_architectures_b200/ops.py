@@ -31,20 +31,33 @@ def layernorm_cf(x, w, b, eps=1e-5, gamma_log=0.0):
     return out
 
 
-def layernorm_cf_cp8(x, w, b, eps, out, gamma_log=0.0):
-    """LayerNorm([C,F]) of x [B,C,T,F] fp32 written straight into the CP8 planes `out` (one chunk: C <= 8)."""
+def layernorm_cf_cp8(x, w, b, eps, out, gamma_log=0.0, stats=None):
+    """LayerNorm([C,F]) of x [B,C,T,F] fp32 written straight into the CP8 planes `out` (one chunk: C <= 8).
+    stats: optional fp32 [B*T, 2] that receives (mean, rstd) of every row for layernorm_cf_param_grad_cp8 (pixel-per-thread kernels, F <= 256)."""
     B, C, T, F = x.shape
     assert (out.B, out.T, out.F) == (B, T, F) and out.NC == 1 and out.ncs == 1
-    call('layernorm_cf_cp8', _f32(x), _f32(w), _f32(b), out.ptr(), B, C, T, F, out.pitch, out.pf, out.pt, float(eps), float(gamma_log), out.fmt,
-         stream_ptr())
+    if F <= 256:
+        assert stats is None or (stats.dtype == torch.float32 and stats.numel() == 2 * B * T and stats.is_contiguous())
+        call('layernorm_cf_cp8_stats', _f32(x), _f32(w), _f32(b), out.ptr(), stats, B, C, T, F, out.pitch, out.pf, out.pt, float(eps),
+             float(gamma_log), out.fmt, stream_ptr())
+    else:
+        assert stats is None
+        call('layernorm_cf_cp8', _f32(x), _f32(w), _f32(b), out.ptr(), B, C, T, F, out.pitch, out.pf, out.pt, float(eps), float(gamma_log), out.fmt,
+             stream_ptr())
     return out
 
 
-def layernorm_cf_param_grad_cp8(x, g, gw, gb, eps, gamma_log=0.0):
-    """gw / gb [C,F] (overwritten) = gradients of the LayerNorm([C,F]) affine parameters; g: CP8 gradient wrt the LayerNorm output."""
+def layernorm_cf_param_grad_cp8(x, g, gw, gb, eps, gamma_log=0.0, stats=None):
+    """gw / gb [C,F] (overwritten) = gradients of the LayerNorm([C,F]) affine parameters; g: CP8 gradient wrt the LayerNorm output;
+    stats: the forward's (mean, rstd) rows (None: the row kernel re-reduces every row)."""
     B, C, T, F = x.shape
     assert (g.B, g.T, g.F) == (B, T, F) and g.ncs == 1
-    call('layernorm_cf_param_grad_cp8', _f32(x), g.ptr(), gw, gb, B, C, T, F, g.pitch, g.pf, g.pt, g.fmt, float(eps), float(gamma_log), stream_ptr())
+    if stats is not None:
+        call('layernorm_cf_param_grad_cp8_stats', _f32(x), g.ptr(), stats, gw, gb, B, C, T, F, g.pitch, g.pf, g.pt, g.fmt, float(gamma_log),
+             stream_ptr())
+    else:
+        call('layernorm_cf_param_grad_cp8', _f32(x), g.ptr(), gw, gb, B, C, T, F, g.pitch, g.pf, g.pt, g.fmt, float(eps), float(gamma_log),
+             stream_ptr())
 
 
 def conv2d(x, wp, bias, Cout, ksize, stride=(1, 1), padding=(0, 0), act=ACT_NONE, act_param=0.0,

@@ -496,7 +496,8 @@ def _cnn_train_forward_cp8(model, blocks, x, sv, site, drop):
     z = x           # (device of the buffers below)
     ln = model.layernorm
     # LayerNorm writes the first convolution's input planes directly (no fp32 copy of the normalised patch, no converter pass)
-    xc = ops.layernorm_cf_cp8(x, ln.weight, ln.bias, ln.eps, TcConv._buf(blocks[0][0] + ':x', B, C0, T, F, x.device, fmt))
+    sv['ln_stats'] = torch.empty(B * T, 2, dtype=torch.float32, device=x.device) if F <= 256 else None   # (mean, rstd) rows for the parameter gradient
+    xc = ops.layernorm_cf_cp8(x, ln.weight, ln.bias, ln.eps, TcConv._buf(blocks[0][0] + ':x', B, C0, T, F, x.device, fmt), stats=sv['ln_stats'])
     sd, sm = _step_args()
     split = 3 if _s3_split_eligible(model, model.conv2[0], F) else 0
     for bi, (name, conv) in enumerate(blocks):
@@ -606,7 +607,8 @@ def cnn_train_backward(model, sv, g_y, grads):
             call('pool3_bwd_dropout_split_cp8', yc.ptr(), gzc.ptr(), gc.ptr(), yc.B, yc.C, yc.T, yc.F, yc.pitch, yc.pf, yc.pt, fmt, ops.ACT_LRELU,
                  float(a), float(p), ctypes_u64(seed), ctypes_u64(site[0]), sd, sm, sp, gzc.pitch if sp else 0, stream_ptr())
             gzc = TcConv.backward_cp8(name, conv, xc, gc, grads[f'{name}.0.weight'], grads[f'{name}.0.bias'], need_dx=True)
-        ops.layernorm_cf_param_grad_cp8(sv['x'], gzc, grads['layernorm.weight'], grads['layernorm.bias'], model.layernorm.eps)
+        ops.layernorm_cf_param_grad_cp8(sv['x'], gzc, grads['layernorm.weight'], grads['layernorm.bias'], model.layernorm.eps,
+                                        stats=sv.get('ln_stats'))
         return grads
     elif sv.get('x2c') is not None:
         g_z = _tc_s3_backward('conv2', c2, sv['x2c'], g, grads['conv2.0.weight'], grads['conv2.0.bias'])

@@ -177,8 +177,10 @@ class Tape:
     def layernorm_cf_cp8(self, ln, x, dst):
         """LayerNorm([C,F]) on the network input, written straight into the first convolution's planes; the parameter gradients read the
         planes the first convolution's data gradient wrote."""
-        out = Node(ops.layernorm_cf_cp8(x, ln.weight, ln.bias, ln.eps, dst))
-        self.push(lambda: ops.layernorm_cf_param_grad_cp8(x, out.g, self.grads['layernorm.weight'], self.grads['layernorm.bias'], ln.eps))
+        B, _, T, F = x.shape
+        stats = torch.empty(B * T, 2, dtype=torch.float32, device=x.device) if F <= 256 else None     # (mean, rstd) rows for the parameter gradient
+        out = Node(ops.layernorm_cf_cp8(x, ln.weight, ln.bias, ln.eps, dst, stats=stats))
+        self.push(lambda: ops.layernorm_cf_param_grad_cp8(x, out.g, self.grads['layernorm.weight'], self.grads['layernorm.bias'], ln.eps, stats=stats))
         return out
 
     # ---------------------------------------------------------------------------------------------- CP8-resident stages (bf16)

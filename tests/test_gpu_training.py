@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
+import torch.nn.functional as F_
 
 from tests.refshapes import build_model
 from tests.weights import fill_state_dict, synth_patches, synth_targets
@@ -141,6 +142,39 @@ def test_cnn_graph_replayed_step_equals_eager_step():
     assert len(set(round(v, 4) for v in res[True])) == 6
 
 
+@pytest.mark.parametrize('B,C,F,p,act', [(3, 20, 72, 0.2, 'lrelu'), (2, 5, 216, 0.0, 'lrelu'), (1, 3, 8, 0.5, 'relu'), (2, 7, 36, 0.2, 'none')])
+def test_pool13_backward_table_kernel(B, C, F, p, act):
+    """backward.cu maxpool13_bwd_table_kernel (T = 75, k = 13: doubling-table first arg-max, shared-memory routing, quad-shared Philox
+    draws) against torch autograd of MaxPool2d((13,1), 1, (6,0)) on plateau inputs (ties: the first maximum wins) and against
+    dropout -> backward in two kernels (same masks)."""
+    from multipitch_architectures_b200 import _lib, ops
+    from multipitch_architectures_b200.training import ctypes_u64
+    T, seed, off = 75, 0x5EED, 41
+    code = {'lrelu': ops.ACT_LRELU, 'relu': ops.ACT_RELU, 'none': ops.ACT_NONE}[act]
+    z = (rnd(B, C, T, F, seed=11) * 2).round() / 2 + 0.25     # plateaus: many ties inside a window; no exact zeros (the kernel's lrelu'(0) = 1)
+    z.requires_grad_(True)
+    a = {'lrelu': lambda v: F_.leaky_relu(v, 0.3), 'relu': F_.relu, 'none': lambda v: v}[act](z)
+    g = rnd(B, C, T, F, seed=12)
+    gm = torch.empty_like(g).cuda()
+    if p > 0:
+        _lib.call('dropout_f32', g.cuda(), gm, _lib.i64(g.numel()), float(p), ctypes_u64(seed), ctypes_u64(off), _lib.stream_ptr())
+    else:
+        gm.copy_(g)
+    F_.max_pool2d(a, (13, 1), stride=1, padding=(6, 0)).backward(gm.cpu())
+    got = torch.empty_like(gm)
+    _lib.call('maxpool_time_bwd_dropout_f32', a.detach().cuda(), g.cuda(), got, B, C, T, F, 13, code, 0.3, float(p), ctypes_u64(seed), ctypes_u64(off),
+              None, ctypes_u64(0), _lib.stream_ptr())
+    assert (got.cpu() - z.grad).abs().max() <= 1e-6 * max(1.0, z.grad.abs().max().item())
+    two = torch.empty_like(gm)
+    _lib.call('maxpool_time_bwd_f32', a.detach().cuda(), gm, two, B, C, T, F, 13, code, 0.3, _lib.stream_ptr())
+    assert torch.equal(two, got)
+    # the generic column kernel (any T) on the same columns, cut to T - 1 rows where the last window differs: compare rows far from the cut
+    a74, g74 = a.detach()[:, :, :74].contiguous().cuda(), gm[:, :, :74].contiguous()
+    old = torch.empty_like(g74)
+    _lib.call('maxpool_time_bwd_f32', a74, g74, old, B, C, 74, F, 13, code, 0.3, _lib.stream_ptr())
+    assert torch.equal(old[:, :, :60], two[:, :, :60])
+
+
 def test_fused_pool_dropout_kernels_equal_the_separate_kernels():
     """MaxPool -> Dropout (-> + residual) in one kernel and its backward with the mask re-drawn on the fly: bit-identical to
     maxpool_time -> dropout -> add and dropout -> maxpool_time_bwd (same Philox convention), through a whole training step."""
@@ -216,6 +250,48 @@ def test_cp8_pool_dropout_kernels_equal_the_nchw_kernels(B, C, T, F, p):
     s = ops.channel_sum_cp8(gac)
     ref = got.double().sum(dim=(0, 2, 3))
     assert s.shape == (C,) and (s.double() - ref).abs().max().item() <= 1e-5 * max(1.0, got.double().abs().sum(dim=(0, 2, 3)).max().item())
+
+
+@pytest.mark.parametrize('B,C,T,F,gamma', [(3, 6, 75, 216, 0.0), (2, 6, 7, 216, 10.0), (5, 3, 1, 40, 0.0), (1, 8, 9, 256, 0.0)])
+def test_layernorm_pixel_kernels_cp8(B, C, T, F, gamma):
+    """train_cp8.cu pixel-per-thread LayerNorm([C,F]) -> CP8 planes (+ per-row mean / rstd) and the parameter gradient that reads them:
+    against nn.LayerNorm + autograd on the transposed view (basic_cnns.py:371,411) and against the row kernels they replace."""
+    from multipitch_architectures_b200 import ops
+    fmt = ops.FMT_BF16
+    x = rnd(B, C, T, F, seed=3).abs().contiguous()
+    w, b = 1 + 0.1 * rnd(C, F, seed=4), 0.1 * rnd(C, F, seed=5)
+    xin = torch.log(1 + gamma * x) if gamma > 0 else x
+    wt, bt = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = F_ln(xin, wt, bt)
+    xc, wc, bc = x.cuda(), w.cuda(), b.cuda()
+    stats = torch.empty(B * T, 2, device='cuda')
+    out = ops.layernorm_cf_cp8(xc, wc, bc, 1e-5, ops.CP8(B, C, T, F, fmt=fmt), gamma_log=gamma, stats=stats)
+    got = ops.cp8_to_nchw(out).cpu()
+    assert (got - ref.detach().bfloat16().float()).abs().max() <= 2 ** -7 * ref.detach().abs().max()          # one bf16 rounding of the same value
+    assert (got - ref.detach()).abs().max() <= 2 ** -8 * ref.detach().abs().max() + 1e-6
+    assert torch.equal(out.buf[..., :out.pf, :], torch.zeros_like(out.buf[..., :out.pf, :])) and (out.buf[:, :, 0] == 0).all()
+    if C < 8:
+        assert (out.buf[..., C:] == 0).all()
+    mu = xin.transpose(1, 2).reshape(B * T, -1).mean(1)
+    var = xin.transpose(1, 2).reshape(B * T, -1).var(1, unbiased=False)
+    assert (stats[:, 0].cpu() - mu).abs().max() < 1e-5 and (stats[:, 1].cpu() * torch.sqrt(var + 1e-5) - 1).abs().max() < 1e-5
+    # parameter gradients from a 16-bit gradient on the planes
+    g = rnd(B, C, T, F, seed=6).bfloat16().float()
+    ref.backward(g)
+    gcp = ops.nchw_to_cp8(g.cuda(), fmt=fmt)
+    gw, gb = torch.empty(C, F, device='cuda'), torch.empty(C, F, device='cuda')
+    ops.layernorm_cf_param_grad_cp8(xc, gcp, gw, gb, 1e-5, gamma_log=gamma, stats=stats)
+    tol = 2e-5 * max(1.0, wt.grad.abs().max().item())
+    assert (gw.cpu() - wt.grad).abs().max() < tol and (gb.cpu() - bt.grad).abs().max() < tol
+    if C * F <= 1408:                                                                                          # the row kernel's limit
+        gw0, gb0 = torch.empty_like(gw), torch.empty_like(gb)
+        ops.layernorm_cf_param_grad_cp8(xc, gcp, gw0, gb0, 1e-5, gamma_log=gamma)                              # row kernel (no saved statistics)
+        assert (gw0 - gw).abs().max() < tol and (gb0 - gb).abs().max() < tol
+
+
+def F_ln(x, w, b):
+    C, Fb = w.shape
+    return F.layer_norm(x.transpose(1, 2), [C, Fb], w, b, 1e-5).transpose(1, 2)
 
 
 @pytest.mark.parametrize('name,p', [('cnn_xs', None), ('dcnn_tiny', None), ('dcnn_tiny', 0.0)])

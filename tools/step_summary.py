@@ -10,7 +10,7 @@ from launch_summary import load
 
 if __name__ == '__main__':
     seq = load(sys.argv[1])
-    idx = [i for i, (k, v) in enumerate(seq) if 'layernorm_cf_kernel' in k or 'layernorm_cf_cp8_kernel' in k]
+    idx = [i for i, (k, v) in enumerate(seq) if 'layernorm_cf_kernel' in k or 'layernorm_cf_cp8_kernel' in k or 'layernorm_pix_cp8_kernel' in k]
     st = seq[idx[-2]:idx[-1]]
     print(f'{len(st)} launches per step, {sum(v for k, v in st):.0f} us')
     tot, cnt = collections.Counter(), collections.Counter()
