@@ -31,12 +31,12 @@ def layernorm_cf(x, w, b, eps=1e-5, gamma_log=0.0):
     return out
 
 
-def layernorm_cf_cp8(x, w, b, eps, out, gamma_log=0.0, stats=None):
+def layernorm_cf_cp8(x, w, b, eps, out, gamma_log=0.0, stats=None, pixel=True):
     """LayerNorm([C,F]) of x [B,C,T,F] fp32 written straight into the CP8 planes `out` (one chunk: C <= 8).
     stats: optional fp32 [B*T, 2] that receives (mean, rstd) of every row for layernorm_cf_param_grad_cp8 (pixel-per-thread kernels, F <= 256)."""
     B, C, T, F = x.shape
     assert (out.B, out.T, out.F) == (B, T, F) and out.NC == 1 and out.ncs == 1
-    if F <= 256:
+    if F <= 256 and pixel:
         assert stats is None or (stats.dtype == torch.float32 and stats.numel() == 2 * B * T and stats.is_contiguous())
         call('layernorm_cf_cp8_stats', _f32(x), _f32(w), _f32(b), out.ptr(), stats, B, C, T, F, out.pitch, out.pf, out.pt, float(eps),
              float(gamma_log), out.fmt, stream_ptr())

@@ -480,6 +480,7 @@ def _tc_s3_backward_split(tag, conv, xs, g, gw, gb):
 
 
 CP8_RESIDENT = True          # test knob: False = every block crosses nchw<->CP8 converters and pools in fp32 NCHW (identical results)
+LN_PIXEL = True          # LayerNorm -> CP8 and its parameter gradient on the pixel-per-thread kernels (False: row kernels)
 
 
 def _cp8_resident(model, blocks, F):
@@ -496,8 +497,11 @@ def _cnn_train_forward_cp8(model, blocks, x, sv, site, drop):
     z = x           # (device of the buffers below)
     ln = model.layernorm
     # LayerNorm writes the first convolution's input planes directly (no fp32 copy of the normalised patch, no converter pass)
-    sv['ln_stats'] = torch.empty(B * T, 2, dtype=torch.float32, device=x.device) if F <= 256 else None   # (mean, rstd) rows for the parameter gradient
-    xc = ops.layernorm_cf_cp8(x, ln.weight, ln.bias, ln.eps, TcConv._buf(blocks[0][0] + ':x', B, C0, T, F, x.device, fmt), stats=sv['ln_stats'])
+    # pixel-per-thread LayerNorm kernels (train_cp8.cu): (mean, rstd) of every row saved for the parameter gradient.  LN_PIXEL = False keeps
+    # the row kernels, whose fp32 sums run in the order of the fp32 NCHW path (bit-for-bit tape comparisons in the tests)
+    sv['ln_stats'] = torch.empty(B * T, 2, dtype=torch.float32, device=x.device) if (F <= 256 and LN_PIXEL) else None
+    xc = ops.layernorm_cf_cp8(x, ln.weight, ln.bias, ln.eps, TcConv._buf(blocks[0][0] + ':x', B, C0, T, F, x.device, fmt), stats=sv['ln_stats'],
+                              pixel=LN_PIXEL)
     sd, sm = _step_args()
     split = 3 if _s3_split_eligible(model, model.conv2[0], F) else 0
     for bi, (name, conv) in enumerate(blocks):

@@ -301,8 +301,9 @@ def test_cp8_resident_training_step_equals_the_converter_path(name, p):
     the order of the fp32 atomics, block bias gradients up to the 16-bit rounding of the summed gradient."""
     from multipitch_architectures_b200 import training as TR
     res = {}
-    for resident in (True, False):
-        TR.CP8_RESIDENT = resident
+    for resident in (True, False, 'pixel_ln'):
+        TR.CP8_RESIDENT = bool(resident)
+        TR.LN_PIXEL = resident == 'pixel_ln'      # the row LayerNorm kernels sum in the order of the fp32 NCHW path: bit-for-bit comparison
         try:
             m = build_model(name, precision='bf16')
             m.load_state_dict(fill_state_dict(m.state_dict(), 9, scheme='torch_default'))
@@ -317,9 +318,16 @@ def test_cp8_resident_training_step_equals_the_converter_path(name, p):
             loss.backward()
             res[resident] = (y.detach().clone(), {k: q.grad.clone() for k, q in m.named_parameters()}, TR._lib.launch_count() - n0)
         finally:
-            TR.CP8_RESIDENT = True
+            TR.CP8_RESIDENT = TR.LN_PIXEL = True
     assert torch.equal(res[True][0], res[False][0])
     assert res[True][2] < res[False][2]                        # fewer launches: the converters are gone
+    # default path (pixel-per-thread LayerNorm, another fp32 summation order: single 16-bit roundings of the normalised input flip)
+    assert (res['pixel_ln'][0] - res[True][0]).abs().max().item() < 2e-3
+    gn = sum(float((g.double() ** 2).sum()) for g in res[True][1].values()) ** 0.5
+    for k in res[True][1]:
+        # flipped roundings move single arg-max routings of the pools: compare the tensors as a whole
+        a, b = res['pixel_ln'][1][k].double(), res[True][1][k].double()
+        assert float((a - b).norm()) <= 0.1 * float(b.norm()) + 1e-3 * gn, (k, float((a - b).norm()), float(b.norm()), gn)
     n_blocks = 1 if name == 'cnn_xs' else 3
     block_bias = {'conv1.0.bias'} | {f'prefilt_list.{i}.0.bias' for i in range(n_blocks - 1)}
     for k in res[True][1]:
