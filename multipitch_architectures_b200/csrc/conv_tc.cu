@@ -36,7 +36,8 @@ constexpr int kStageMMAs = 8;                 // MMAs (K=16 steps) per weight st
 constexpr int kATileBytes = 2 * 128 * 16;     // one MMA's A tile: [2 k-slices][128 rows][16 B]
 constexpr int kAStageBytes = kStageMMAs * kATileBytes;
 constexpr int kMaxAStages = 5;             // weight stages: as many as fit next to the activation slabs (>= 2)
-constexpr int kNumBStages = 2;
+constexpr int kNumBStages = 2;              // minimum number of activation stages (what the stage sizing guarantees)
+constexpr int kMaxBStages = 8;              // thin inputs: as many as fit next to the weight stages (b_stages)
 constexpr int kThreads = 320;                 // producer warp, MMA warp, 8 epilogue warps
 constexpr int kMaxRingS = 24;                // ring positions (<= J + 4, J <= 16) and activation stages of the ring main loop
 constexpr int kMaxRingB = 8;
@@ -71,7 +72,7 @@ struct ConvTcParams {
   // ---- geometry
   int n_patches, NC, Cout, J, T, F, KH, KW, P, N, pf, pt_out, TP_out, T_out, row0, NCo;
   int n_seg, y_lo[2], y_hi[2], z_lo[2], z_hi[2], seg_groups[2], groups_per_patch;
-  int mmas_per_row, n_units, slab_px, epi_off, a_stages, btab_off;
+  int mmas_per_row, n_units, slab_px, epi_off, a_stages, b_stages, btab_off;
   int resident;             // tile main loop: the whole weight set fits in the A stages -> loaded once per CTA, never re-streamed
   long long out_patch_stride;  // elements (16-bit) between patches in `out`
   int act;
@@ -532,12 +533,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
   const int kNumAStages = p.a_stages;
   uint8_t* a_smem = smem;                                // [a_stages][kAStageBytes]
   uint8_t* b_smem = smem + kNumAStages * kAStageBytes;   // [kNumBStages][NC][slab_px][16B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + kNumBStages * bstage_bytes);
+  const int nbs = p.b_stages;                            // 2 .. kMaxBStages activation stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + nbs * bstage_bytes);
   uint64_t* a_full = bars;
   uint64_t* a_empty = bars + kMaxAStages;
   uint64_t* b_full = bars + 2 * kMaxAStages;
-  uint64_t* b_empty = b_full + kNumBStages;
-  uint64_t* acc_full = b_empty + kNumBStages;            // [2]
+  uint64_t* b_empty = b_full + kMaxBStages;
+  uint64_t* acc_full = b_empty + kMaxBStages;            // [2]
   uint64_t* acc_empty = acc_full + 2;                    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   uint32_t* btab = reinterpret_cast<uint32_t*>(smem + p.btab_off);         // [mmas_per_row padded to 8] B-descriptor low words
@@ -550,7 +552,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
     }
-    for (int i = 0; i < kNumBStages; ++i) {
+    for (int i = 0; i < nbs; ++i) {
       mbar_init(&b_full[i], 1);
       mbar_init(&b_empty[i], 1);
     }
@@ -563,7 +565,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
   if (p.Rs > 1) {
     // skipped rows and the over-read tail of a stage are never written by a copy: they must hold finite values (their columns feed
     // outputs that are discarded, or meet zero weights)
-    for (int i = threadIdx.x; i < kNumBStages * bstage_bytes / 16; i += kThreads) reinterpret_cast<uint4*>(b_smem)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < nbs * bstage_bytes / 16; i += kThreads) reinterpret_cast<uint4*>(b_smem)[i] = make_uint4(0, 0, 0, 0);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
@@ -644,7 +646,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
                 bulk_g2s(dst + c * slab_plane_bytes, src + (long long)c * cs, (uint32_t)slab_plane_bytes, &b_full[b_stage]);
             }
             __syncwarp();
-            if (++b_stage == kNumBStages) { b_stage = 0; b_phase ^= 1; }
+            if (++b_stage == nbs) { b_stage = 0; b_phase ^= 1; }
             // weight stages of this K row (split precision: W_hi and W_lo tiles against the hi planes, W_hi tiles against the lo planes)
             if (p.resident) continue;
             const int q0 = gi * (p.G / 2) * p.KW;
@@ -724,7 +726,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
           }
           if (elect_one_sync()) tc_commit(&b_empty[b_stage]);         // frees the activation slab of this row
           __syncwarp();
-          if (++b_stage == kNumBStages) { b_stage = 0; b_phase ^= 1; }
+          if (++b_stage == nbs) { b_stage = 0; b_phase ^= 1; }
           }
           }
         }
@@ -1661,6 +1663,13 @@ static int launch_conv_tc(ConvTcParams& p, int Cin, cudaStream_t stream, int* gr
     int a_stages = kMaxAStages;
     while (a_stages > 2 && (size_t)a_stages * kAStageBytes + b_bytes + tail > 227 * 1024) --a_stages;
     p.a_stages = a_stages;
+    // thin inputs (one or two chunks: the first layer of every model, the 6 -> 20 / 8 -> 8 / 16 -> 16 convolutions): a stage feeds only
+    // ~8 MMAs (~450 tensor clocks), so two stages cover less than the latency of a bulk copy that misses L2 (ncu: CNN:XS conv1 forward
+    // 67 % tensor-active against 90 % for its 3-chunk data gradient); take as many stages as fit
+    int b_stages = kNumBStages;
+    const size_t bstage1 = (size_t)p.G * p.slab_px * 16;
+    while (b_stages < kMaxBStages && (size_t)a_stages * kAStageBytes + (size_t)(b_stages + 1) * bstage1 + tail <= 227 * 1024) ++b_stages;
+    p.b_stages = b_stages;
     p.resident = (!p.x3 && p.n_groups == 1 && (p.KH + p.J - 1) * ((p.mmas_per_row + kStageMMAs - 1) / kStageMMAs) <= a_stages) ? 1 : 0;
     MPA_REQUIRE(p.mmas_per_row <= 128, "conv_tc: too many K steps per row (%d)", p.mmas_per_row);
     p.tiles_per_row = p.x3 ? 3 * p.mmas_per_row : p.mmas_per_row;
@@ -1681,7 +1690,7 @@ static int launch_conv_tc(ConvTcParams& p, int Cin, cudaStream_t stream, int* gr
         if (p.x3) p.btab[p.mmas_per_row + q] = p.btab[q];      // the W_lo pass walks the same (hi) slab again
       }
     }
-    size_t off = (size_t)a_stages * kAStageBytes + b_bytes;
+    size_t off = (size_t)a_stages * kAStageBytes + (size_t)b_stages * bstage1;
     p.btab_off = (int)(off + 256);
     off += 256 + (size_t)(p.mmas_per_row + 8) * 4;      // barriers + tmem slot (256 B), descriptor table
     off = (off + 127) / 128 * 128;
