@@ -316,6 +316,14 @@ int mpa_head_tail_cp8(const void* x_cp8, const float* w3, const float* b3, const
                       const float* w43, const float* b43, float* out, int B, int C1, int T, int Fo, int C2, int C3,
                       float a_lrelu, int fmt, void* stream);
 
+/* The head behind conv2 for the CNN family in one launch (basic_cnns.py:180-195 / :396-408): y compact 16-bit planes
+ * [B][ceil(C1/8)][75][Fo][8] = LeakyReLU(conv2) -> out [B,Fo] fp32 = sigmoid(conv4.3(lrelu(conv4.0(lrelu(conv3(maxpool13(y))))))).
+ * w3_packed [ceil(C1/8)][75][8][C2P] fp32 (C2P = 12 for C2 <= 12, else 16; zero padded), w40 [C3][C2], w43 [C3].
+ * T == 75, C1 <= 64, C2 <= 16, C3 <= 64, fp16 / bf16 planes. */
+int mpa_head_pool_conv3_tail_cp8(const void* y_cp8, const float* w3_packed, const float* b3, const float* w40, const float* b40,
+                                 const float* w43, const float* b43, float* out, int B, int C1, int T, int Fo, int C2, int C3,
+                                 float a_lrelu, int fmt, void* stream);
+
 /* conv4.0 (1x1) + LeakyReLU + conv4.3 (1x1) + sigmoid on the activated conv3 output h [B][ceil(C2/8)][R][Fo][8] (compact 16-bit
  * planes, any widths) -> out [B][R][Fo] fp32 (basic_cnns.py:403-408). */
 int mpa_head_tail2_cp8(const void* h_cp8, const float* w40, const float* b40, const float* w43, const float* b43,

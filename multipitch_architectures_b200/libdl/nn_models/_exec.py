@@ -182,9 +182,15 @@ def head_tc(cache, model, zc, a, split=None, out=None, pool=None):
         cin_pad = zc.C if zc.C != conv2.weight.shape[1] else None          # the producer padded its channels to whole chunks
         for wp, b, c0, c in _folded_tc(cache, 'conv2', conv2, None, fmt, dev, cin_pad=cin_pad):
             ops.conv_tc(zc, wp, b, c, (3, 3), ops.ACT_LRELU, a, subsample=(3, 1), out=yc.channels(c0, c))
+    n_rows = zc.T - KH3 + 1
+    if (FUSED_THIN_TAIL and fmt in (ops.FMT_F16, ops.FMT_BF16) and KH3 == 75 and n_rows == 1 and conv3.weight.shape[0] <= 16 and C1p <= 64
+            and c40.weight.shape[0] <= 64):
+        # CNN family (conv3 far too thin for the tensor cores): pool13 + conv3 + conv4.* in one pass over the conv2 output
+        w3p = cache.get(f'conv3:rows{C1p}', [conv3.weight], lambda: ops.pack_conv3_rows(conv3.weight, C1p))
+        o = ops.head_pool_conv3_tail(yc, w3p, conv3.bias, c40.weight, c40.bias, c43.weight, c43.bias, a, out=out)
+        return o.reshape(zc.B, 1, 1, yc.F)
     yc = ops.pool_time_res_cp8(yc, 13, out=ops.compact_cp8(zc.B, C1p, zc.T, Fin // 3, dev, fmt, pool, 'head:p') if pool is not None else None)
     C2p = (conv3.weight.shape[0] + 7) // 8 * 8
-    n_rows = zc.T - KH3 + 1
     hc = ops.compact_cp8(zc.B, C2p, n_rows, yc.F, dev, fmt, pool, 'head:h')
     for wp, b, c0, c in _folded_tc(cache, 'conv3', conv3, None, fmt, dev, cin_pad=C1p, J=1):
         ops.conv_tc(yc, wp, b, c, (KH3, 1), ops.ACT_LRELU, a, out=hc.channels(c0, c), J=1, rows=(KH3 // 2, n_rows))
@@ -286,6 +292,7 @@ def unet_up_f32(model, x5, skips, train):
 # ------------------------------------------------------------------------------------------------------------------
 # U-Net family on the tcgen05 path (eval mode: BatchNorm folded into the packed weights / bias)
 LEVEL_PF = 8
+FUSED_THIN_TAIL = True        # CNN-family head: pool13 + conv3 + conv4.* in one launch (False: pool kernel, tcgen05 conv3, tail kernel)
 
 
 def level_geometry(T0, F0, n_levels=5):

@@ -365,6 +365,29 @@ def head_tail(x, w3, b3, w40, b40, w43, b43, a_lrelu):
     return out
 
 
+def pack_conv3_rows(w3, C1p):
+    """conv3.weight [C2, C1, 75, 1] -> [C1p/8][75][8][C2P] fp32 (C2P = 12 or 16; zero padded): the operand of head_pool_conv3_tail."""
+    C2, C1, T = w3.shape[0], w3.shape[1], w3.shape[2]
+    C2P = 12 if C2 <= 12 else 16
+    wp = torch.zeros(C1p, T, C2P, dtype=torch.float32, device=w3.device)
+    wp[:C1, :, :C2] = w3.detach().float().reshape(C2, C1, T).permute(1, 2, 0)
+    return wp.reshape(C1p // 8, 8, T, C2P).permute(0, 2, 1, 3).contiguous()
+
+
+def head_pool_conv3_tail(y, w3p, b3, w40, b40, w43, b43, a_lrelu, out=None):
+    """y: compact CP8 [B][NC1][75][Fo][8] (activated conv2 output) -> [B,Fo] fp32 =
+    sigmoid(conv4.3(lrelu(conv4.0(lrelu(conv3(maxpool13(y))))))) in one launch (C2 <= 16; w3p from pack_conv3_rows)."""
+    C3 = w40.shape[0]
+    C2 = w40.reshape(C3, -1).shape[1]
+    if out is None:
+        out = torch.empty(y.B, y.F, dtype=torch.float32, device=y.buf.device)
+    assert out.is_contiguous() and out.numel() == y.B * y.F and y.compact and y.chunk0 == 0 and y.ncs == y.NC
+    assert w3p.shape[0] == y.NC and w3p.is_contiguous()
+    call('head_pool_conv3_tail_cp8', y.ptr(), w3p, b3, w40.reshape(C3, -1).contiguous(), b40, w43.reshape(-1).contiguous(), b43, out, y.B, y.NC * 8,
+         y.T, y.F, C2, C3, float(a_lrelu), y.fmt, stream_ptr())
+    return out
+
+
 def head_tail2(h, w40, b40, w43, b43, a_lrelu, out=None):
     """h: compact CP8 [B][NC2][R][Fo][8] (activated conv3 output) -> [B,R,Fo] fp32 = sigmoid(conv4.3(lrelu(conv4.0(h))))."""
     C3 = w40.shape[0]

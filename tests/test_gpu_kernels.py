@@ -175,6 +175,39 @@ def test_conv_tc_subsampled_output_pool13_and_head_tail(ops, prec, dt):
     assert (got.cpu() - ref.reshape(B, 72)).abs().max() < 1e-5
 
 
+@pytest.mark.parametrize('prec,dt', FMTS)
+@pytest.mark.parametrize('B,C1,C2,C3,Fo', [(3, 30, 10, 1, 72), (2, 20, 10, 1, 72), (5, 40, 16, 12, 24), (1, 64, 3, 2, 9)])
+def test_fused_pool13_conv3_tail(ops, prec, dt, B, C1, C2, C3, Fo):
+    """head.cu head_pool_conv3_tail_kernel: MaxPool((13,1)) + conv3 (75x1) + LReLU + conv4.0 + LReLU + conv4.3 + sigmoid in one launch on
+    compact 16-bit planes, against torch on the same 16-bit values (basic_cnns.py:180-195) and against the three-launch sequence."""
+    from multipitch_architectures_b200.libdl.nn_models import _exec
+    import torch.nn as nn
+    fmt, T = ops.fmt_of(prec), 75
+    y = (rnd(B, C1, T, Fo, seed=1) * 2).round() / 2 + 0.1 * rnd(B, C1, T, Fo, seed=2)
+    y = y.to(dt).float()
+    torch.manual_seed(3)
+    conv3, c40, c43 = nn.Conv2d(C1, C2, (75, 1)), nn.Conv2d(C2, C3, (1, 1)), nn.Conv2d(C3, 1, (1, 1))
+    with torch.no_grad():
+        ref = torch.sigmoid(c43(F.leaky_relu(c40(F.leaky_relu(conv3(F.max_pool2d(y, (13, 1), (1, 1), (6, 0))), 0.3)), 0.3))).reshape(B, Fo)
+    C1p = (C1 + 7) // 8 * 8
+    yc = ops.compact_cp8(B, C1p, T, Fo, 'cuda', fmt)
+    yc.buf.zero_()
+    ops.nchw_to_cp8(y.cuda(), out=yc.channels(0, C1))
+    conv3, c40, c43 = conv3.cuda(), c40.cuda(), c43.cuda()
+    w3p = ops.pack_conv3_rows(conv3.weight, C1p)
+    got = ops.head_pool_conv3_tail(yc, w3p, conv3.bias, c40.weight, c40.bias, c43.weight, c43.bias, 0.3).cpu()
+    assert (got - ref).abs().max() < 2e-5
+    # the sequence it replaces: pool kernel, tcgen05 conv3 (16-bit weights and hidden activations), tail kernel
+    cache = _exec.ParamCache()
+    pc = ops.pool_time_res_cp8(yc, 13)
+    C2p = (C2 + 7) // 8 * 8
+    hc = ops.compact_cp8(B, C2p, 1, Fo, 'cuda', fmt)
+    for wp, b, c0, c in _exec._folded_tc(cache, 'conv3', conv3, None, fmt, 'cuda', cin_pad=C1p, J=1):
+        ops.conv_tc(pc, wp, b, c, (75, 1), ops.ACT_LRELU, 0.3, out=hc.channels(c0, c), J=1, rows=(37, 1))
+    seq = ops.head_tail2(hc, _exec._pad_cols(c40.weight.reshape(C3, -1), C2p), c40.bias, c43.weight, c43.bias, 0.3).cpu().reshape(B, Fo)
+    assert (got - seq).abs().max() < (2e-2 if prec == 'bf16' else 3e-3)
+
+
 @pytest.mark.parametrize('C1,C2,C3,T', [(40, 30, 10, 75), (100, 80, 50, 75), (180, 150, 100, 75), (20, 10, 1, 90)])
 def test_conv3_on_tensor_cores_and_general_tail(ops, C1, C2, C3, T):
     """conv3 (75x1 VALID) as the row-windowed 'same' convolution on compact planes (KW == 1, pitch 72 -> MMA N 80), with
