@@ -1348,12 +1348,16 @@ __global__ void upsample2x_x3_kernel(const uint4* __restrict__ low, uint4* __res
 __device__ __forceinline__ void pack_weights_range(const float* __restrict__ w, uint16_t* __restrict__ out, long long total, int Cin, int Cout,
                                                    int KH, int KW, int J, int NC, int mpr, int fmt, int transpose_flip, int Cout_total, int co0,
                                                    long long first, long long step, int split = 0, int C0 = 0) {
+  // one thread per 16-byte group = the 8 input channels of one (tile row, K slice): the position is decoded once per group and the group
+  // leaves as one 16-byte store; the all-zero groups of the shifted row blocks (j >= J, filter row outside [0, KH)) touch no weight.
+  // (One thread per 16-bit element: 134 us per SAUnet:L training step for ~25 M elements, bound by the index arithmetic.)
+  // first / step / total are in elements; groups never straddle a caller's range (all are multiples of 8).
   const int n_paired = (NC / 2) * KW;
-  for (long long idx = first; idx < total; idx += step) {
-    const int e = (int)(idx & 7);
-    const int mrow = (int)((idx >> 3) & 127);
-    const int kc = (int)((idx >> 10) & 1);
-    const long long tile = idx >> 11;
+  const long long total8 = total >> 3, step8 = step;       // thread i of the caller's step handles groups first/8 + i, + step, ...
+  for (long long g = first; g < total8; g += step8) {
+    const int mrow = (int)(g & 127);
+    const int kc = (int)((g >> 7) & 1);
+    const long long tile = g >> 8;
     const int q = (int)(tile % mpr), r = (int)(tile / mpr);
     int df, c;
     if (q < n_paired) {
@@ -1365,26 +1369,48 @@ __device__ __forceinline__ void pack_weights_range(const float* __restrict__ w, 
       c = NC - 1;
     }
     const int j = mrow / Cout, co = mrow - j * Cout;
-    const int kh = r - j, ci = c * 8 + e;
-    float v = 0.f;
+    const int kh = r - j;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
     if (split) {
       // phase-split form of a KH x split / stride (1, split) convolution with real weights w[Cout][C0][KH][split]: logical input channel
       // ph * C0p + c = (tap ph, real channel c), one tap column.  Forward: Cin = split * C0p;  data gradient (transpose_flip): the logical
       // OUTPUT channels are the split ones (Cout_total = split * C0p), rows flipped, the column tap is the phase itself
       if (df < 1 && j < J && kh >= 0 && kh < KH) {
         if (!transpose_flip) {
-          const int C0p = Cin / split, ph = ci / C0p, c0r = ci - ph * C0p;
-          if (ci < Cin && c0r < C0 && co0 + co < Cout_total) v = w[(((size_t)(co0 + co) * C0 + c0r) * KH + kh) * split + ph];
+          const int C0p = Cin / split;
+          if (co0 + co < Cout_total) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int ci = c * 8 + e, ph = ci / C0p, c0r = ci - ph * C0p;
+              if (ci < Cin && c0r < C0) v[e] = w[(((size_t)(co0 + co) * C0 + c0r) * KH + kh) * split + ph];
+            }
+          }
         } else {
           const int C0p = Cout_total / split, o = co0 + co, ph = o / C0p, c0r = o - ph * C0p;
-          if (o < Cout_total && c0r < C0 && ci < Cin) v = w[(((size_t)ci * C0 + c0r) * KH + (KH - 1 - kh)) * split + ph];
+          if (o < Cout_total && c0r < C0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int ci = c * 8 + e;
+              if (ci < Cin) v[e] = w[(((size_t)ci * C0 + c0r) * KH + (KH - 1 - kh)) * split + ph];
+            }
+          }
         }
       }
-    } else if (df < KW && j < J && kh >= 0 && kh < KH && ci < Cin && co0 + co < Cout_total) {
-      v = transpose_flip ? w[(((size_t)ci * Cout_total + co0 + co) * KH + (KH - 1 - kh)) * KW + (KW - 1 - df)]
-                         : w[(((size_t)(co0 + co) * Cin + ci) * KH + kh) * KW + df];
+    } else if (df < KW && j < J && kh >= 0 && kh < KH && co0 + co < Cout_total) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int ci = c * 8 + e;
+        if (ci < Cin)
+          v[e] = transpose_flip ? w[(((size_t)ci * Cout_total + co0 + co) * KH + (KH - 1 - kh)) * KW + (KW - 1 - df)]
+                                : w[(((size_t)(co0 + co) * Cin + ci) * KH + kh) * KW + df];
+      }
     }
-    out[idx] = cvt16(v, fmt);
+    uint32_t h[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h[e] = (uint32_t)cvt16(v[2 * e], fmt) | ((uint32_t)cvt16(v[2 * e + 1], fmt) << 16);
+    *reinterpret_cast<uint4*>(out + g * 8) = make_uint4(h[0], h[1], h[2], h[3]);
   }
 }
 __global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, long long total, int Cin, int Cout, int KH, int KW,
@@ -1415,7 +1441,7 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackJobDe
   const long long first = (long long)((int)blockIdx.x - j.block0) * kPackPerBlock;
   const long long last = first + kPackPerBlock < j.total ? first + kPackPerBlock : j.total;
   pack_weights_range(j.w, j.out, last, j.Cin, j.Cout, j.KH, j.KW, j.J, j.NC, j.mpr, j.fmt, j.transpose_flip, j.Cout_total, j.co0,
-                     first + threadIdx.x, 256, j.split, j.C0);
+                     (first >> 3) + threadIdx.x, 256, j.split, j.C0);       // 2048 elements per block = one 16-byte group per thread
 }
 
 static inline int grid_for(long long total, int block) {
