@@ -1432,9 +1432,15 @@ constexpr int kPackPerBlock = 2048;
 __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackJobDev* __restrict__ jobs, int n_jobs) {
   __shared__ int job;
   if (threadIdx.x == 0) {
-    int j = 0;
-    while (j + 1 < n_jobs && (int)blockIdx.x >= jobs[j + 1].block0) ++j;
-    job = j;
+    // last job whose first block is <= blockIdx.x (block0 ascending): bisection — the linear scan was a chain of up to n_jobs dependent loads
+    // in front of every block's work
+    int lo = 0, hi = n_jobs - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if ((int)blockIdx.x >= jobs[mid].block0) lo = mid;
+      else hi = mid - 1;
+    }
+    job = lo;
   }
   __syncthreads();
   const PackJobDev j = jobs[job];
