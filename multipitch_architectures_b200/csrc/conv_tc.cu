@@ -1174,6 +1174,57 @@ __global__ void pool_time_col_cp8_kernel(const uint4* __restrict__ y, const uint
   }
 }
 
+// k = 13, T = 75 (the head's MaxPool((13,1)) on a whole patch): the 13-frame maximum from a doubling table built on the fly — pairs -> fours ->
+// eights -> two overlapping eights, 4 packed max operations per frame and chunk instead of 12 plus a 13-register window shift; the 81
+// positions are fully unrolled so that the delay lines between the levels are register renaming.  (The column kernel above ran at
+// 3.6 TB/s on the Unet:M head, bound by its ~110 instructions per 16-byte pixel.)
+template <int FMT>
+__global__ void __launch_bounds__(128) pool13_table_cp8_kernel(const uint4* __restrict__ y, const uint4* __restrict__ res, uint4* __restrict__ out,
+                                                               long long total, int NCk, int ncs_y, int ncs_res, int ncs_out, int F, int TP, int P,
+                                                               int pf, int pt) {
+  constexpr int T = 75, H = 6;
+  const uint32_t ninf = FMT == MPA_FMT_BF16 ? 0xFF80FF80u : 0xFC00FC00u;
+  const uint4 NINF = make_uint4(ninf, ninf, ninf, ninf);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i % F);
+    long long r = i / F;
+    const int ck = (int)(r % NCk);
+    const long long b = r / NCk;
+    const uint4* yp = y + (((size_t)b * ncs_y + ck) * TP + pt) * P + pf + f;
+    uint4* op = out + (((size_t)b * ncs_out + ck) * TP + pt) * P + pf + f;
+    const uint4* rp = res ? res + (((size_t)b * ncs_res + ck) * TP + pt) * P + pf + f : nullptr;
+    uint4 xprev = NINF, a2[3], a4[5], a8[6], xs[6];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) a2[j] = NINF;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) a4[j] = NINF;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) a8[j] = NINF;
+#pragma unroll
+    for (int p = 0; p < T + H; ++p) {
+      if (p % 6 == 0) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) xs[j] = p + j < T ? yp[(size_t)(p + j) * P] : NINF;
+      }
+      const uint4 xp = xs[p % 6];
+      // pairs [p-1,p] -> slot (p+2)%3; fours [p-3,p] -> slot (p+2)%5; eights [p-7,p] -> slot (p+5)%6
+      a2[(p + 2) % 3] = xprev;
+      max8<FMT>(a2[(p + 2) % 3], xp);
+      a4[(p + 2) % 5] = a2[p % 3];
+      max8<FMT>(a4[(p + 2) % 5], a2[(p + 2) % 3]);
+      a8[(p + 5) % 6] = a4[(p + 3) % 5];
+      max8<FMT>(a8[(p + 5) % 6], a4[(p + 2) % 5]);
+      xprev = xp;
+      if (p >= H) {
+        uint4 c = a8[p % 6];                       // frames [p-12, p-5] and [p-7, p]: the window of frame p - 6
+        max8<FMT>(c, a8[(p + 5) % 6]);
+        if (rp) add8<FMT>(c, rp[(size_t)(p - H) * P]);
+        op[(size_t)(p - H) * P] = c;
+      }
+    }
+  }
+}
+
 // MaxPool2d((2,2)) floor mode between two CP8 geometries
 template <int FMT>
 __global__ void maxpool2x2_cp8_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, long long total, int NCk, int ncs_in, int ncs_out,
@@ -1963,6 +2014,14 @@ int mpa_pool_time_res_cp8(const void* y_cp8, const void* res_cp8, void* out_cp8,
     MPA_REQUIRE(!((ncs_y | ncs_res | ncs_out) & 1), "pool_time_res_cp8(fp16x3): chunk strides must be even");
     pool_time_res_x3_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)y_cp8, (const uint4*)res_cp8, (uint4*)out_cp8, total, NCk,
                                                                                      ncs_y, ncs_res, ncs_out, T, F, T + 2 * pt, pitch, pf, pt, k / 2);
+  } else if (k == 13 && T == 75) {
+    const long long cols = (long long)n_patches * NCk * F;
+    if (fmt == MPA_FMT_BF16)
+      pool13_table_cp8_kernel<MPA_FMT_BF16><<<grid_for(cols, 128), 128, 0, (cudaStream_t)stream>>>(
+          (const uint4*)y_cp8, (const uint4*)res_cp8, (uint4*)out_cp8, cols, NCk, ncs_y, ncs_res, ncs_out, F, T + 2 * pt, pitch, pf, pt);
+    else
+      pool13_table_cp8_kernel<MPA_FMT_F16><<<grid_for(cols, 128), 128, 0, (cudaStream_t)stream>>>(
+          (const uint4*)y_cp8, (const uint4*)res_cp8, (uint4*)out_cp8, cols, NCk, ncs_y, ncs_res, ncs_out, F, T + 2 * pt, pitch, pf, pt);
   } else if (k == 13 && T >= 13) {
     const long long cols = (long long)n_patches * NCk * F;
     if (fmt == MPA_FMT_BF16)
