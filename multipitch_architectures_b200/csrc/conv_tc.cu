@@ -992,17 +992,37 @@ static inline uint16_t f32_to_bf16_rne(float f) {
   return (uint16_t)(u >> 16);
 }
 
+// (f, t, ck, b) of a flat element index over [b][ck][t][f]: 32-bit divisions when the tensor has < 2^31 elements (always, in practice) —
+// the three 64-bit divisions cost ~300 instructions per 16-byte pixel and bound the element-wise U-Net kernels
+__device__ __forceinline__ void decode_ftcb(long long i, bool small, int Fd, int Td, int NCk, int& f, int& t, int& ck, long long& b) {
+  if (small) {
+    unsigned u = (unsigned)i;
+    const unsigned q1 = u / (unsigned)Fd;
+    f = (int)(u - q1 * (unsigned)Fd);
+    const unsigned q2 = q1 / (unsigned)Td;
+    t = (int)(q1 - q2 * (unsigned)Td);
+    const unsigned q3 = q2 / (unsigned)NCk;
+    ck = (int)(q2 - q3 * (unsigned)NCk);
+    b = (long long)q3;
+  } else {
+    f = (int)(i % Fd);
+    long long r = i / Fd;
+    t = (int)(r % Td);
+    r /= Td;
+    ck = (int)(r % NCk);
+    b = r / NCk;
+  }
+}
+
 // CP8 <-> NCHW converters ------------------------------------------------------------------------------
 __global__ void nchw_to_cp8_kernel(const float* __restrict__ x, uint16_t* __restrict__ out, long long total, int C, int T,
                                    int F, int NCk, int NCs, int TP, int P, int pf, int pt, int fmt) {
   // one thread per (b, chunk, t, f): gathers 8 channels -> one 16-byte store
+  const bool small = total < (1ll << 31);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int f = (int)(i % F);
-    long long r = i / F;
-    int t = (int)(r % T);
-    r /= T;
-    int ck = (int)(r % NCk);
-    int b = (int)(r / NCk);
+    int f, t, ck;
+    long long b;
+    decode_ftcb(i, small, F, T, NCk, f, t, ck, b);
     __align__(16) uint16_t v[8];
     if (fmt == MPA_FMT_F16X3) {
       __align__(16) uint16_t lo[8];
@@ -1030,13 +1050,11 @@ __global__ void nchw_to_cp8_kernel(const float* __restrict__ x, uint16_t* __rest
 // zero it was initialised with): the zero-inserted gradient of a stride-(1,s) convolution evaluated as a sub-sampled stride-1 one
 __global__ void nchw_to_cp8_strided_kernel(const float* __restrict__ x, uint16_t* __restrict__ out, long long total, int C, int T, int Fs, int NCk,
                                            int NCs, int TP, int P, int pf, int pt, int fmt, int stride, int offset) {
+  const bool small = total < (1ll << 31);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int f = (int)(i % Fs);
-    long long r = i / Fs;
-    int t = (int)(r % T);
-    r /= T;
-    int ck = (int)(r % NCk);
-    int b = (int)(r / NCk);
+    int f, t, ck;
+    long long b;
+    decode_ftcb(i, small, Fs, T, NCk, f, t, ck, b);
     __align__(16) uint16_t v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -1050,13 +1068,11 @@ __global__ void nchw_to_cp8_strided_kernel(const float* __restrict__ x, uint16_t
 // one thread per (b, chunk, t, f): one 16-byte load -> 8 channel planes (each store coalesced across the threads of a row)
 __global__ void cp8_to_nchw_kernel(const uint16_t* __restrict__ in, float* __restrict__ out, long long total, int C, int T,
                                    int F, int NCk, int NCs, int TP, int P, int pf, int pt, int fmt) {
+  const bool small = total < (1ll << 31);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int f = (int)(i % F);
-    long long r = i / F;
-    int t = (int)(r % T);
-    r /= T;
-    int ck = (int)(r % NCk);
-    int b = (int)(r / NCk);
+    int f, t, ck;
+    long long b;
+    decode_ftcb(i, small, F, T, NCk, f, t, ck, b);
     __align__(16) uint16_t v[8];
     *reinterpret_cast<uint4*>(v) = *reinterpret_cast<const uint4*>(in + ((((size_t)b * NCs + ck) * TP + pt + t) * P + pf + f) * 8);
     if (fmt == MPA_FMT_F16X3) {
@@ -1116,13 +1132,11 @@ template <int FMT>
 __global__ void pool_time_res_cp8_kernel(const uint4* __restrict__ y, const uint4* __restrict__ res, uint4* __restrict__ out,
                                          long long total, int NCk, int ncs_y, int ncs_res, int ncs_out, int T, int F, int TP, int P, int pf,
                                          int pt, int half) {
+  const bool small = total < (1ll << 31);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int f = (int)(i % F);
-    long long r = i / F;
-    int t = (int)(r % T);
-    r /= T;
-    const int ck = (int)(r % NCk);
-    const long long b = r / NCk;
+    int f, t, ck;
+    long long b;
+    decode_ftcb(i, small, F, T, NCk, f, t, ck, b);
     const size_t in_plane = ((size_t)b * ncs_y + ck);
     const size_t base = (in_plane * TP + pt + t) * P + pf + f;
     uint4 c = y[base];
@@ -1229,13 +1243,11 @@ __global__ void __launch_bounds__(128) pool13_table_cp8_kernel(const uint4* __re
 template <int FMT>
 __global__ void maxpool2x2_cp8_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, long long total, int NCk, int ncs_in, int ncs_out,
                                       int To, int Fo, int TPi, int Pi, int pfi, int pti, int TPo, int Po, int pfo, int pto) {
+  const bool small = total < (1ll << 31);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int f = (int)(i % Fo);
-    long long r = i / Fo;
-    int t = (int)(r % To);
-    r /= To;
-    const int ck = (int)(r % NCk);
-    const long long b = r / NCk;
+    int f, t, ck;
+    long long b;
+    decode_ftcb(i, small, Fo, To, NCk, f, t, ck, b);
     const size_t ib = ((((size_t)b * ncs_in + ck) * TPi + pti + 2 * t) * Pi) + pfi + 2 * f;
     uint4 c = in[ib];
     max8<FMT>(c, in[ib + 1]);
@@ -1255,13 +1267,11 @@ __global__ void upsample2x_cp8_kernel(const uint16_t* __restrict__ low, uint16_t
   const int top = (Ts - Tu) / 2, left = (Fs - Fu) / 2;
   const float ry = Tu > 1 ? (float)(Tl - 1) / (float)(Tu - 1) : 0.f;
   const float rx = Fu > 1 ? (float)(Fl - 1) / (float)(Fu - 1) : 0.f;
+  const bool small = total < (1ll << 31);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int f = (int)(i % Fs);
-    long long r = i / Fs;
-    int t = (int)(r % Ts);
-    r /= Ts;
-    const int ck = (int)(r % NCk);
-    const long long b = r / NCk;
+    int f, t, ck;
+    long long b;
+    decode_ftcb(i, small, Fs, Ts, NCk, f, t, ck, b);
     __align__(16) uint16_t o[8];
     const int tu = t - top, fu = f - left;
     if (tu < 0 || tu >= Tu || fu < 0 || fu >= Fu) {
@@ -1309,13 +1319,11 @@ __global__ void pool_time_res_x3_kernel(const uint4* __restrict__ y, const uint4
                                         int ncs_y, int ncs_res, int ncs_out, int T, int F, int TP, int P, int pf, int pt, int half) {
   const size_t plane = (size_t)TP * P;
   const X3Plane Y{y, (size_t)(ncs_y / 2) * plane}, R{res, (size_t)(ncs_res / 2) * plane};
+  const bool small = total < (1ll << 31);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int f = (int)(i % F);
-    long long r = i / F;
-    int t = (int)(r % T);
-    r /= T;
-    const int ck = (int)(r % NCk);
-    const long long b = r / NCk;
+    int f, t, ck;
+    long long b;
+    decode_ftcb(i, small, F, T, NCk, f, t, ck, b);
     const size_t base = (((size_t)b * ncs_y + ck) * TP + pt + t) * P + pf + f;
     float c[8], o[8];
     Y.load(base, c);
@@ -1337,13 +1345,11 @@ __global__ void pool_time_res_x3_kernel(const uint4* __restrict__ y, const uint4
 __global__ void maxpool2x2_x3_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, long long total, int NCk, int ncs_in, int ncs_out, int To,
                                      int Fo, int TPi, int Pi, int pfi, int pti, int TPo, int Po, int pfo, int pto) {
   const X3Plane I{in, (size_t)(ncs_in / 2) * TPi * Pi};
+  const bool small = total < (1ll << 31);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int f = (int)(i % Fo);
-    long long r = i / Fo;
-    int t = (int)(r % To);
-    r /= To;
-    const int ck = (int)(r % NCk);
-    const long long b = r / NCk;
+    int f, t, ck;
+    long long b;
+    decode_ftcb(i, small, Fo, To, NCk, f, t, ck, b);
     const size_t ib = ((((size_t)b * ncs_in + ck) * TPi + pti + 2 * t) * Pi) + pfi + 2 * f;
     float c[8], o[8];
     I.load(ib, c);
@@ -1364,13 +1370,11 @@ __global__ void upsample2x_x3_kernel(const uint4* __restrict__ low, uint4* __res
   const float ry = Tu > 1 ? (float)(Tl - 1) / (float)(Tu - 1) : 0.f;
   const float rx = Fu > 1 ? (float)(Fl - 1) / (float)(Fu - 1) : 0.f;
   const X3Plane L{low, (size_t)(ncs_in / 2) * TPl * Pl};
+  const bool small = total < (1ll << 31);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int f = (int)(i % Fs);
-    long long r = i / Fs;
-    int t = (int)(r % Ts);
-    r /= Ts;
-    const int ck = (int)(r % NCk);
-    const long long b = r / NCk;
+    int f, t, ck;
+    long long b;
+    decode_ftcb(i, small, Fs, Ts, NCk, f, t, ck, b);
     float o[8];
     const int tu = t - top, fu = f - left;
     if (tu < 0 || tu >= Tu || fu < 0 || fu >= Fu) {
