@@ -96,6 +96,12 @@ struct ConvTcParams {
   // work units were so small that fixed per-unit costs, not the tensor pipe, set the pace).  The R rows arrive as R separate copies;
   // rows outside the plane (+ guard rows) are skipped, their columns only feed outputs that are never stored.
   int Rs, pt_in;
+  // Rs > 1: the R spaced rows of ALL planes of a stage arrive as ONE tensor-map copy (cp.async.bulk.tensor, box = pitch x R rows at row
+  // stride Rs x G planes; rows outside [0, T) are zero-filled by the copy unit) instead of R * G bulk copies of one 1.3 KB row each — the
+  // copy unit retires ~1 bulk copy per 150 clocks whatever its size, which made these layers copy-issue bound (ncu, CNN:XS conv2: 127 copies
+  // = 19 k clocks per work unit, the MMA warp waiting 57 % of its time for a stage).  tma = 0: the descriptor could not be built.
+  int tma;
+  alignas(64) CUtensorMap tmap;
   uint32_t btab[256];       // tile main loop: B-descriptor low words of one K row, (offset >> 4) | (LBO >> 4) << 16 (x3: the row twice)
   // ---- ring main loop (conv_tc_ring_kernel): un-duplicated weight pieces, see below
   int ring_on, ring_S, ring_npos, ring_ps, ring_sbo, ring_nb, ring_b_off, ring_bar_off;
@@ -526,10 +532,10 @@ __device__ __forceinline__ void epilogue_role(const ConvTcParams& p, uint32_t tm
 
 // ------------------------------------------------------------------------------------------ kernel
 template <bool X3>
-__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams p) {
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int slab_plane_bytes = p.slab_px * 16;
-  const int bstage_bytes = min(p.G, p.NC) * slab_plane_bytes;   // one patch, one input row, one chunk group
+  const int bstage_bytes = min(p.G, p.NC) * slab_plane_bytes + (p.tma ? 128 : 0);   // one patch, one input row, one chunk group (+ zero pad: the odd chunk's dummy K slice over-reads one pixel)
   const int kNumAStages = p.a_stages;
   uint8_t* a_smem = smem;                                // [a_stages][kAStageBytes]
   uint8_t* b_smem = smem + kNumAStages * kAStageBytes;   // [kNumBStages][NC][slab_px][16B]
@@ -612,7 +618,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
             // activation slab of this input row: chunk group gi (split precision: the hi planes, then the lo planes)
             const int planes = min(p.G, p.NC - gi * p.G);
             uint8_t* dst = b_smem + b_stage * bstage_bytes;
-            if (p.Rs > 1) {
+            if (p.tma) {
+              // spaced merged rows of all planes of the stage in one tensor-map copy
+              if (lane == 0) {
+                mbar_wait(&b_empty[b_stage], b_phase ^ 1);
+                mbar_expect_tx(&b_full[b_stage], (uint32_t)(min(p.G, p.NC) * slab_plane_bytes));
+                asm volatile(
+                    "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+                        smem_u32(dst)),
+                    "l"(reinterpret_cast<uint64_t>(&p.tmap)), "r"(0), "r"(row), "r"(gi * p.G), "r"(ui.b), "r"(smem_u32(&b_full[b_stage]))
+                    : "memory");
+              }
+            } else if (p.Rs > 1) {
               // spaced merged rows: one copy of `pitch` pixels per (plane, merged row); rows beyond the guard rows are left out
               int n_ok = 0;
               for (int rr = 0; rr < p.R; ++rr) {
@@ -1703,12 +1720,31 @@ int mpa_conv_tc_ring_pack_weights(const float* w, void* packed, int Cin, int Cou
   return MPA_OK;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on the symbol); nullptr when unavailable
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                      const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeFn tensor_map_encoder() {
+  static TensorMapEncodeFn fn = nullptr;
+  static int tried = 0;
+  if (!__atomic_load_n(&tried, __ATOMIC_ACQUIRE)) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (TensorMapEncodeFn)sym;
+    __atomic_store_n(&tried, 1, __ATOMIC_RELEASE);
+  }
+  return fn;
+}
+
 // smem layout, grid and launch shared by both entry points (p: everything but the smem offsets filled in)
 static int launch_conv_tc(ConvTcParams& p, int Cin, cudaStream_t stream, int* grid_out) {
   p.mmas_per_row = mmas_per_row(p.NC, p.KW);
   p.slab_px = (p.N + 2 * (p.KW / 2) + 1 + 7) / 8 * 8;
   if (p.R < 1) p.R = 1;
   if (p.Rs < 1) p.Rs = 1;
+  p.tma = 0;
+  if (p.Rs > 1 && !p.x3 && !p.ring_on && p.in_e == p.T && p.KW == 1 && tensor_map_encoder()) p.tma = 1;      // decided before the stage sizing
+  if (p.tma) p.slab_px = p.N;                 // dense box: [plane][R rows][pitch] (the pad behind a stage takes the one-pixel over-read)
   size_t smem = 0;
   if (p.x3) {
     MPA_REQUIRE(!p.ring_on, "conv_tc: the ring main loop has no split-precision variant");
@@ -1738,7 +1774,7 @@ static int launch_conv_tc(ConvTcParams& p, int Cin, cudaStream_t stream, int* gr
     p.epi_off = (int)off;
     smem = off + 8 * 32 * kEpiPitch * 2;
   } else {
-    const size_t tail = 256 + (size_t)(p.mmas_per_row + 8) * 4 + 128 + 8 * 32 * kEpiPitch * 2;   // barriers, table, staging
+    const size_t tail = 256 + (size_t)(p.mmas_per_row + 8) * 4 + 128 + 8 * 32 * kEpiPitch * 2 + (p.tma ? kMaxBStages * 128 : 0);   // barriers, table, staging, stage pads
     // chunks per activation stage: all of them when two stages fit next to >= 2 weight stages, else the largest even group that does
     // (wide-K layers; one group = G/2 * KW consecutive MMAs of the row)
     p.G = p.NC;
@@ -1754,9 +1790,21 @@ static int launch_conv_tc(ConvTcParams& p, int Cin, cudaStream_t stream, int* gr
     // ~8 MMAs (~450 tensor clocks), so two stages cover less than the latency of a bulk copy that misses L2 (ncu: CNN:XS conv1 forward
     // 67 % tensor-active against 90 % for its 3-chunk data gradient); take as many stages as fit
     int b_stages = kNumBStages;
-    const size_t bstage1 = (size_t)p.G * p.slab_px * 16;
+    const size_t bstage1 = (size_t)p.G * p.slab_px * 16 + (p.tma ? 128 : 0);
     while (b_stages < kMaxBStages && (size_t)a_stages * kAStageBytes + (size_t)(b_stages + 1) * bstage1 + tail <= 227 * 1024) ++b_stages;
     p.b_stages = b_stages;
+    if (p.tma) {
+      // global tensor [patch][plane][row 0 .. T-1][pitch * 2 x 8 bytes]; box = one stage
+      const cuuint64_t gdim[4] = {(cuuint64_t)p.P * 2, (cuuint64_t)p.T, (cuuint64_t)p.NC, (cuuint64_t)p.n_patches};
+      const cuuint64_t gstr[3] = {(cuuint64_t)p.P * 16, (cuuint64_t)p.in_edge_chunk_stride, (cuuint64_t)p.in_edge_patch_stride};
+      const cuuint32_t box[4] = {(cuuint32_t)p.P * 2, (cuuint32_t)((p.R - 1) * p.Rs + 1), (cuuint32_t)p.G, 1u};
+      const cuuint32_t estr[4] = {1u, (cuuint32_t)p.Rs, 1u, 1u};
+      const CUresult r = tensor_map_encoder()(&p.tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<uint8_t*>(p.in_edge), gdim, gstr, box, estr,
+                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      MPA_REQUIRE(r == CUDA_SUCCESS && p.P * 2 <= 256 && box[1] <= 256 && p.G <= 256,
+                  "conv_tc: cuTensorMapEncodeTiled failed (%d) for pitch %d, R %d, Rs %d, G %d", (int)r, p.P, p.R, p.Rs, p.G);
+    }
     p.resident = (!p.x3 && p.n_groups == 1 && (p.KH + p.J - 1) * ((p.mmas_per_row + kStageMMAs - 1) / kStageMMAs) <= a_stages) ? 1 : 0;
     MPA_REQUIRE(p.mmas_per_row <= 128, "conv_tc: too many K steps per row (%d)", p.mmas_per_row);
     p.tiles_per_row = p.x3 ? 3 * p.mmas_per_row : p.mmas_per_row;
