@@ -96,7 +96,7 @@ struct ConvTcParams {
   // work units were so small that fixed per-unit costs, not the tensor pipe, set the pace).  The R rows arrive as R separate copies;
   // rows outside the plane (+ guard rows) are skipped, their columns only feed outputs that are never stored.
   int Rs, pt_in;
-  // Rs > 1: the R spaced rows of ALL planes of a stage arrive as ONE tensor-map copy (cp.async.bulk.tensor, box = pitch x R rows at row
+  // Row-merged modes (R > 1, consecutive or spaced rows): the R rows of ALL planes of a stage arrive as ONE tensor-map copy (cp.async.bulk.tensor, box = pitch x R rows at row
   // stride Rs x G planes; rows outside [0, T) are zero-filled by the copy unit) instead of R * G bulk copies of one 1.3 KB row each — the
   // copy unit retires ~1 bulk copy per 150 clocks whatever its size, which made these layers copy-issue bound (ncu, CNN:XS conv2: 127 copies
   // = 19 k clocks per work unit, the MMA warp waiting 57 % of its time for a stage).  tma = 0: the descriptor could not be built.
@@ -568,7 +568,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (p.Rs > 1) {
+  if (p.Rs > 1 || p.tma) {
     // skipped rows and the over-read tail of a stage are never written by a copy: they must hold finite values (their columns feed
     // outputs that are discarded, or meet zero weights)
     for (int i = threadIdx.x; i < nbs * bstage_bytes / 16; i += kThreads) reinterpret_cast<uint4*>(b_smem)[i] = make_uint4(0, 0, 0, 0);
@@ -1743,7 +1743,7 @@ static int launch_conv_tc(ConvTcParams& p, int Cin, cudaStream_t stream, int* gr
   if (p.R < 1) p.R = 1;
   if (p.Rs < 1) p.Rs = 1;
   p.tma = 0;
-  if (p.Rs > 1 && !p.x3 && !p.ring_on && p.in_e == p.T && p.KW == 1 && tensor_map_encoder()) p.tma = 1;      // decided before the stage sizing
+  if ((p.Rs > 1 || p.R > 1) && !p.x3 && !p.ring_on && p.in_e == p.T && p.KW == 1 && tensor_map_encoder()) p.tma = 1;      // decided before the stage sizing
   if (p.tma) p.slab_px = p.N;                 // dense box: [plane][R rows][pitch] (the pad behind a stage takes the one-pixel over-read)
   size_t smem = 0;
   if (p.x3) {
