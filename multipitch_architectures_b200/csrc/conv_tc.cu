@@ -100,7 +100,7 @@ struct ConvTcParams {
   // stride Rs x G planes; rows outside [0, T) are zero-filled by the copy unit) instead of R * G bulk copies of one 1.3 KB row each — the
   // copy unit retires ~1 bulk copy per 150 clocks whatever its size, which made these layers copy-issue bound (ncu, CNN:XS conv2: 127 copies
   // = 19 k clocks per work unit, the MMA warp waiting 57 % of its time for a stage).  tma = 0: the descriptor could not be built.
-  int tma;
+  int tma, tma_c0;   // 1: merged rows, 2: one row of all planes (narrow levels); tma_c0: inner start coordinate
   alignas(64) CUtensorMap tmap;
   uint32_t btab[256];       // tile main loop: B-descriptor low words of one K row, (offset >> 4) | (LBO >> 4) << 16 (x3: the row twice)
   // ---- ring main loop (conv_tc_ring_kernel): un-duplicated weight pieces, see below
@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 asm volatile(
                     "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
                         smem_u32(dst)),
-                    "l"(reinterpret_cast<uint64_t>(&p.tmap)), "r"(0), "r"(row), "r"(gi * p.G), "r"(ui.b), "r"(smem_u32(&b_full[b_stage]))
+                    "l"(reinterpret_cast<uint64_t>(&p.tmap)), "r"(p.tma_c0), "r"(row), "r"(gi * p.G), "r"(ui.b), "r"(smem_u32(&b_full[b_stage]))
                     : "memory");
               }
             } else if (p.Rs > 1) {
@@ -1743,8 +1743,17 @@ static int launch_conv_tc(ConvTcParams& p, int Cin, cudaStream_t stream, int* gr
   if (p.R < 1) p.R = 1;
   if (p.Rs < 1) p.Rs = 1;
   p.tma = 0;
-  if ((p.Rs > 1 || p.R > 1) && !p.x3 && !p.ring_on && p.in_e == p.T && p.KW == 1 && tensor_map_encoder()) p.tma = 1;      // decided before the stage sizing
-  if (p.tma) p.slab_px = p.N;                 // dense box: [plane][R rows][pitch] (the pad behind a stage takes the one-pixel over-read)
+  p.tma_c0 = 0;
+  const bool tma_ok = !p.x3 && !p.ring_on && p.in_e == p.T && tensor_map_encoder();      // decided before the stage sizing
+  if (tma_ok && (p.Rs > 1 || p.R > 1) && p.KW == 1) {
+    p.tma = 1;
+    p.slab_px = p.N;                          // dense box: [plane][R rows][pitch] (the pad behind a stage takes the one-pixel over-read)
+  } else if (tma_ok && p.R == 1 && p.Rs == 1 && p.NC >= 2 && p.slab_px <= 128) {
+    // narrow planes (the deeper U-Net levels): one input row of ALL chunk planes of a stage in one copy.  A stage of a 3x3 / 5x5 / 9x9
+    // filter on a <= 64-bin level feeds the tensor pipe for 100-300 clocks — less than two of the NC bulk copies it used to take.
+    p.tma = 2;
+    p.tma_c0 = -2 * (p.KW / 2);               // the slab starts KW/2 pixels left of column 0 (8-byte elements)
+  }
   size_t smem = 0;
   if (p.x3) {
     MPA_REQUIRE(!p.ring_on, "conv_tc: the ring main loop has no split-precision variant");
@@ -1797,12 +1806,12 @@ static int launch_conv_tc(ConvTcParams& p, int Cin, cudaStream_t stream, int* gr
       // global tensor [patch][plane][row 0 .. T-1][pitch * 2 x 8 bytes]; box = one stage
       const cuuint64_t gdim[4] = {(cuuint64_t)p.P * 2, (cuuint64_t)p.T, (cuuint64_t)p.NC, (cuuint64_t)p.n_patches};
       const cuuint64_t gstr[3] = {(cuuint64_t)p.P * 16, (cuuint64_t)p.in_edge_chunk_stride, (cuuint64_t)p.in_edge_patch_stride};
-      const cuuint32_t box[4] = {(cuuint32_t)p.P * 2, (cuuint32_t)((p.R - 1) * p.Rs + 1), (cuuint32_t)p.G, 1u};
+      const cuuint32_t box[4] = {(cuuint32_t)(p.tma == 2 ? p.slab_px * 2 : p.P * 2), (cuuint32_t)((p.R - 1) * p.Rs + 1), (cuuint32_t)p.G, 1u};
       const cuuint32_t estr[4] = {1u, (cuuint32_t)p.Rs, 1u, 1u};
       const CUresult r = tensor_map_encoder()(&p.tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<uint8_t*>(p.in_edge), gdim, gstr, box, estr,
                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      MPA_REQUIRE(r == CUDA_SUCCESS && p.P * 2 <= 256 && box[1] <= 256 && p.G <= 256,
+      MPA_REQUIRE(r == CUDA_SUCCESS && box[0] <= 256 && box[1] <= 256 && p.G <= 256,
                   "conv_tc: cuTensorMapEncodeTiled failed (%d) for pitch %d, R %d, Rs %d, G %d", (int)r, p.P, p.R, p.Rs, p.G);
     }
     p.resident = (!p.x3 && p.n_groups == 1 && (p.KH + p.J - 1) * ((p.mmas_per_row + kStageMMAs - 1) / kStageMMAs) <= a_stages) ? 1 : 0;
