@@ -1,6 +1,7 @@
 // Shared helpers for libmpa (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -101,6 +102,22 @@ __device__ __forceinline__ float dropout_factor_at(long long i, float p, float s
 }
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on the symbol); nullptr when unavailable
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                      const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static inline TensorMapEncodeFn tensor_map_encoder() {
+  static TensorMapEncodeFn fn = nullptr;
+  static int tried = 0;
+  if (!__atomic_load_n(&tried, __ATOMIC_ACQUIRE)) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (TensorMapEncodeFn)sym;
+    __atomic_store_n(&tried, 1, __ATOMIC_RELEASE);
+  }
+  return fn;
+}
 
 // Opt a kernel into the maximum dynamic shared memory once per (kernel, device) for the whole PROCESS.  (The attribute is a
 // property of the function on the device, not of the calling thread: per-thread bookkeeping lets an autograd worker thread

@@ -1720,22 +1720,6 @@ int mpa_conv_tc_ring_pack_weights(const float* w, void* packed, int Cin, int Cou
   return MPA_OK;
 }
 
-// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on the symbol); nullptr when unavailable
-typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                      const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static TensorMapEncodeFn tensor_map_encoder() {
-  static TensorMapEncodeFn fn = nullptr;
-  static int tried = 0;
-  if (!__atomic_load_n(&tried, __ATOMIC_ACQUIRE)) {
-    void* sym = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = (TensorMapEncodeFn)sym;
-    __atomic_store_n(&tried, 1, __ATOMIC_RELEASE);
-  }
-  return fn;
-}
-
 // smem layout, grid and launch shared by both entry points (p: everything but the smem offsets filled in)
 static int launch_conv_tc(ConvTcParams& p, int Cin, cudaStream_t stream, int* grid_out) {
   p.mmas_per_row = mmas_per_row(p.NC, p.KW);

@@ -49,6 +49,11 @@ struct GemmTcParams {
   float ln_eps;
   int ln_S;
   unsigned* ln_counters;     // K split: arrival counter per token tile (zero on entry, reset by the last arriver)
+  // a stage's 8 K chunks of each operand tile as ONE tensor-map copy (the copy unit retires ~1 bulk copy per 150 clocks whatever its size:
+  // 16 copies of 2-4 KB per stage of 4 MMAs = 256 tensor clocks left the encoder products copy-issue bound at 3-17 % tensor-active)
+  int tma;
+  alignas(64) CUtensorMap tm_x;   // [KC][Mpad / 128][128 rows x 16 B]: box 8 x 2 x 2 KB
+  alignas(64) CUtensorMap tm_w;   // [KC][Npad / 128][128 rows x 16 B]: box 8 x 1 x 2 KB
 };
 __device__ __forceinline__ long long gm_off(int i, int n2, long long s1, long long s2) {
   return n2 > 0 ? (long long)(i / n2) * s1 + (long long)(i % n2) * s2 : (long long)i * s2;
@@ -96,6 +101,12 @@ __device__ __forceinline__ void gm_bulk(void* dst_smem, const void* src_gmem, ui
                "l"(src_gmem), "r"(bytes), "r"(gm_smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ void gm_tensor3(void* dst_smem, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                   gm_smem_u32(dst_smem)),
+               "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(gm_smem_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ bool gm_elect() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -140,7 +151,7 @@ __device__ __forceinline__ GmUnit gm_decode(const GemmTcParams& p, int u) {
   return g;
 }
 
-__global__ void __launch_bounds__(kGmThreads, 1) gemm_tc_kernel(const GemmTcParams p) {
+__global__ void __launch_bounds__(kGmThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* w_smem = smem;                                        // [stages][8 chunks][128 rows][16 B]
   uint8_t* x_smem = smem + kGmStages * kGmWBytes;                 // [stages][8 chunks][256 rows][16 B]
@@ -181,7 +192,12 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemm_tc_kernel(const GemmTcPara
           gm_expect_tx(&full[st], (uint32_t)(kGmWBytes + kGmXBytes));
         }
         __syncwarp();
-        if (lane < 2 * kGmChunksPerStage) {
+        if (p.tma) {
+          if (lane == 0) {
+            gm_tensor3(w_smem + st * kGmWBytes, &p.tm_w, 0, g.n0 / 128, kc, &full[st]);
+            gm_tensor3(x_smem + st * kGmXBytes, &p.tm_x, 0, g.m0 / 128, kc, &full[st]);
+          }
+        } else if (lane < 2 * kGmChunksPerStage) {
           const int c = lane >> 1;
           if (lane & 1)
             gm_bulk(x_smem + st * kGmXBytes + c * (kGmTileM * 16), p.x + ((size_t)(kc + c) * p.Mpad + g.m0) * 16, kGmTileM * 16, &full[st]);
@@ -606,6 +622,20 @@ int mpa_gemm_tc_run(const mpa_gemm_tc_desc* d, void* stream) {
   const bool dense_y = d->y_mn2 == 0 && d->y_nn2 == 0 && d->y_ms2 == 0 && d->y_ns2 == 0;
   if (ks > 1 && dense_y) cudaMemsetAsync(y, 0, sizeof(float) * (size_t)M * N, (cudaStream_t)stream);
   if (ks > 1 && !dense_y && !d->y_zeroed) ks = 1, p.ksplit = 1, p.n_units = tiles;
+  p.tma = 0;
+  if (TensorMapEncodeFn enc = tensor_map_encoder()) {
+    if (p.Mpad % 128 == 0 && p.Npad % 128 == 0) {
+      const cuuint64_t xd[3] = {256, (cuuint64_t)(p.Mpad / 128), (cuuint64_t)p.KC}, xs[2] = {2048, (cuuint64_t)p.Mpad * 16};
+      const cuuint64_t wd[3] = {256, (cuuint64_t)(p.Npad / 128), (cuuint64_t)p.KC}, ws[2] = {2048, (cuuint64_t)p.Npad * 16};
+      const cuuint32_t xb[3] = {256, kGmTileM / 128, kGmChunksPerStage}, wb[3] = {256, kGmTileN / 128, kGmChunksPerStage}, es[3] = {1, 1, 1};
+      const CUresult r1 = enc(&p.tm_x, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<uint8_t*>(p.x), xd, xs, xb, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      const CUresult r2 = enc(&p.tm_w, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<uint8_t*>(p.w), wd, ws, wb, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      MPA_REQUIRE(r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS, "gemm_tc: cuTensorMapEncodeTiled failed (%d, %d)", (int)r1, (int)r2);
+      p.tma = 1;
+    }
+  }
   const size_t smem = (size_t)kGmStages * (kGmWBytes + kGmXBytes) + 256 + (4 * kGmTrBytes > kGmLnBytes ? 4 * kGmTrBytes : kGmLnBytes);
   {
     static unsigned char flags[64];
