@@ -37,6 +37,11 @@ struct WgradParams {
   int slots, slot_bytes, gslab_bytes, xslab_bytes, xstage_bytes, x_off, bar_off;
   uint32_t idesc;
   int wide;                    // KW == 1: the CG input chunks of a group are the N groups of ONE accumulator (B descriptor SBO = slab stride)
+  // one g row of ALL NCo output chunks as ONE tensor-map copy (rank 5: a 3.5 KB row is two halves of <= 256 8-byte elements; rows outside
+  // [0, T) are zero-filled by the copy unit, which replaces the zero row).  The copy unit retires ~1 bulk copy per 150 clocks whatever
+  // its size: NCo = 16 copies per x row against ~900 tensor clocks made the 16 -> 128 layer copy-issue bound.
+  int tma;
+  alignas(64) CUtensorMap tm_g;
 };
 
 __device__ __forceinline__ uint32_t wg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -125,7 +130,7 @@ __device__ __forceinline__ WgItem wg_decode(const WgradParams& p, int item) {
   return it;
 }
 
-__global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgradParams p) {
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_constant__ WgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* ring = smem;                                   // [slots + RS - 1][NCo][P px][16 B]
   uint8_t* xs = smem + p.x_off;                           // [kWgXStages][CG][slab px][16 B]
@@ -182,7 +187,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgradPara
             __syncwarp();
             uint8_t* dst = ring + (size_t)pos * p.slot_bytes;
             const bool inside = (t >= 0 && t < p.T);
-            const int n_copies = p.NCo * (mirror ? 2 : 1);
+            const int n_copies = p.tma ? 0 : p.NCo * (mirror ? 2 : 1);
+            if (p.tma && lane == 0) {
+              for (int mir = 0; mir < (mirror ? 2 : 1); ++mir)
+                asm volatile(
+                    "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(
+                        wg_smem_u32(dst + (mir ? (size_t)S * p.slot_bytes : 0))),
+                    "l"(reinterpret_cast<uint64_t>(&p.tm_g)), "r"(0), "r"(0), "r"(t), "r"(0), "r"(b), "r"(wg_smem_u32(&g_full[pos]))
+                    : "memory");
+            }
             for (int i = lane; i < n_copies; i += 32) {
               const int ck = i % p.NCo, mir = i / p.NCo;
               const uint8_t* src = inside ? p.g + (long long)b * p.g_item_stride + (long long)ck * p.g_chunk_stride + (long long)t * p.P * 16
@@ -396,6 +409,18 @@ int mpa_conv_wgrad_tc(const void* x_cp8, const void* g_cp8, const void* zero_row
     if (e != cudaSuccess) {
       set_error("conv_wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return MPA_ERR_CUDA;
+    }
+  }
+  p.tma = 0;
+  if (TensorMapEncodeFn enc = tensor_map_encoder()) {
+    if (p.NCo >= 2) {
+      const cuuint64_t gd[5] = {(cuuint64_t)pitch, 2, (cuuint64_t)T, (cuuint64_t)p.NCo, (cuuint64_t)n_items};
+      const cuuint64_t gs[4] = {(cuuint64_t)pitch * 8, (cuuint64_t)pitch * 16, (cuuint64_t)p.g_chunk_stride, (cuuint64_t)p.g_item_stride};
+      const cuuint32_t bx[5] = {(cuuint32_t)pitch, 2, 1, (cuuint32_t)p.NCo, 1}, es[5] = {1, 1, 1, 1, 1};
+      const CUresult r = enc(&p.tm_g, CU_TENSOR_MAP_DATA_TYPE_UINT64, 5, const_cast<uint8_t*>(p.g), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      MPA_REQUIRE(r == CUDA_SUCCESS, "conv_wgrad_tc: cuTensorMapEncodeTiled failed (%d) for pitch %d, T %d, NCo %d", (int)r, pitch, T, p.NCo);
+      p.tma = 1;
     }
   }
   const int grid = p.n_items < sms ? p.n_items : sms;
