@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <stdarg.h>
 #include "../../include/mpa.h"
 
@@ -112,7 +113,8 @@ static inline TensorMapEncodeFn tensor_map_encoder() {
   if (!__atomic_load_n(&tried, __ATOMIC_ACQUIRE)) {
     void* sym = nullptr;
     cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+    const char* off = getenv("MPA_NO_TENSOR_MAP");          // A/B switch and test hook: "1" keeps every kernel on its bulk-copy loops
+    if (!(off && off[0] == '1') && cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
       fn = (TensorMapEncodeFn)sym;
     __atomic_store_n(&tried, 1, __ATOMIC_RELEASE);
   }

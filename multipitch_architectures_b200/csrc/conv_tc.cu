@@ -101,6 +101,7 @@ struct ConvTcParams {
   // copy unit retires ~1 bulk copy per 150 clocks whatever its size, which made these layers copy-issue bound (ncu, CNN:XS conv2: 127 copies
   // = 19 k clocks per work unit, the MMA warp waiting 57 % of its time for a stage).  tma = 0: the descriptor could not be built.
   int tma, tma_c0;   // 1: merged rows, 2: one row of all planes (narrow levels); tma_c0: inner start coordinate
+  int bpad;          // zero bytes behind every activation stage (set with the tensor-map layouts; kept when the descriptor cannot be built)
   alignas(64) CUtensorMap tmap;
   uint32_t btab[256];       // tile main loop: B-descriptor low words of one K row, (offset >> 4) | (LBO >> 4) << 16 (x3: the row twice)
   // ---- ring main loop (conv_tc_ring_kernel): un-duplicated weight pieces, see below
@@ -535,7 +536,7 @@ template <bool X3>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int slab_plane_bytes = p.slab_px * 16;
-  const int bstage_bytes = min(p.G, p.NC) * slab_plane_bytes + (p.tma ? 128 : 0);   // one patch, one input row, one chunk group (+ zero pad: the odd chunk's dummy K slice over-reads one pixel)
+  const int bstage_bytes = min(p.G, p.NC) * slab_plane_bytes + p.bpad;   // one patch, one input row, one chunk group (+ zero pad: the odd chunk's dummy K slice over-reads one pixel)
   const int kNumAStages = p.a_stages;
   uint8_t* a_smem = smem;                                // [a_stages][kAStageBytes]
   uint8_t* b_smem = smem + kNumAStages * kAStageBytes;   // [kNumBStages][NC][slab_px][16B]
@@ -568,7 +569,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (p.Rs > 1 || p.tma) {
+  if (p.Rs > 1 || p.bpad) {
     // skipped rows and the over-read tail of a stage are never written by a copy: they must hold finite values (their columns feed
     // outputs that are discarded, or meet zero weights)
     for (int i = threadIdx.x; i < nbs * bstage_bytes / 16; i += kThreads) reinterpret_cast<uint4*>(b_smem)[i] = make_uint4(0, 0, 0, 0);
@@ -1738,6 +1739,7 @@ static int launch_conv_tc(ConvTcParams& p, int Cin, cudaStream_t stream, int* gr
     p.tma = 2;
     p.tma_c0 = -2 * (p.KW / 2);               // the slab starts KW/2 pixels left of column 0 (8-byte elements)
   }
+  p.bpad = p.tma ? 128 : 0;
   size_t smem = 0;
   if (p.x3) {
     MPA_REQUIRE(!p.ring_on, "conv_tc: the ring main loop has no split-precision variant");
@@ -1767,7 +1769,7 @@ static int launch_conv_tc(ConvTcParams& p, int Cin, cudaStream_t stream, int* gr
     p.epi_off = (int)off;
     smem = off + 8 * 32 * kEpiPitch * 2;
   } else {
-    const size_t tail = 256 + (size_t)(p.mmas_per_row + 8) * 4 + 128 + 8 * 32 * kEpiPitch * 2 + (p.tma ? kMaxBStages * 128 : 0);   // barriers, table, staging, stage pads
+    const size_t tail = 256 + (size_t)(p.mmas_per_row + 8) * 4 + 128 + 8 * 32 * kEpiPitch * 2 + (size_t)kMaxBStages * p.bpad;   // barriers, table, staging, stage pads
     // chunks per activation stage: all of them when two stages fit next to >= 2 weight stages, else the largest even group that does
     // (wide-K layers; one group = G/2 * KW consecutive MMAs of the row)
     p.G = p.NC;
@@ -1783,7 +1785,7 @@ static int launch_conv_tc(ConvTcParams& p, int Cin, cudaStream_t stream, int* gr
     // ~8 MMAs (~450 tensor clocks), so two stages cover less than the latency of a bulk copy that misses L2 (ncu: CNN:XS conv1 forward
     // 67 % tensor-active against 90 % for its 3-chunk data gradient); take as many stages as fit
     int b_stages = kNumBStages;
-    const size_t bstage1 = (size_t)p.G * p.slab_px * 16 + (p.tma ? 128 : 0);
+    const size_t bstage1 = (size_t)p.G * p.slab_px * 16 + p.bpad;
     while (b_stages < kMaxBStages && (size_t)a_stages * kAStageBytes + (size_t)(b_stages + 1) * bstage1 + tail <= 227 * 1024) ++b_stages;
     p.b_stages = b_stages;
     if (p.tma) {
@@ -1795,8 +1797,8 @@ static int launch_conv_tc(ConvTcParams& p, int Cin, cudaStream_t stream, int* gr
       const CUresult r = tensor_map_encoder()(&p.tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<uint8_t*>(p.in_edge), gdim, gstr, box, estr,
                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      MPA_REQUIRE(r == CUDA_SUCCESS && box[0] <= 256 && box[1] <= 256 && p.G <= 256,
-                  "conv_tc: cuTensorMapEncodeTiled failed (%d) for pitch %d, R %d, Rs %d, G %d", (int)r, p.P, p.R, p.Rs, p.G);
+      // not encodable (an unusual geometry): the bulk-copy loops below handle the same stage layout
+      if (!(r == CUDA_SUCCESS && box[0] <= 256 && box[1] <= 256 && p.G <= 256)) p.tma = 0;
     }
     p.resident = (!p.x3 && p.n_groups == 1 && (p.KH + p.J - 1) * ((p.mmas_per_row + kStageMMAs - 1) / kStageMMAs) <= a_stages) ? 1 : 0;
     MPA_REQUIRE(p.mmas_per_row <= 128, "conv_tc: too many K steps per row (%d)", p.mmas_per_row);

@@ -632,8 +632,7 @@ int mpa_gemm_tc_run(const mpa_gemm_tc_desc* d, void* stream) {
                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       const CUresult r2 = enc(&p.tm_w, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<uint8_t*>(p.w), wd, ws, wb, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      MPA_REQUIRE(r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS, "gemm_tc: cuTensorMapEncodeTiled failed (%d, %d)", (int)r1, (int)r2);
-      p.tma = 1;
+      p.tma = (r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS) ? 1 : 0;          // else: the bulk-copy loop
     }
   }
   const size_t smem = (size_t)kGmStages * (kGmWBytes + kGmXBytes) + 256 + (4 * kGmTrBytes > kGmLnBytes ? 4 * kGmTrBytes : kGmLnBytes);
