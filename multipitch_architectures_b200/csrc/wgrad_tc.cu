@@ -42,6 +42,10 @@ struct WgradParams {
   // its size: NCo = 16 copies per x row against ~900 tensor clocks made the 16 -> 128 layer copy-issue bound.
   int tma;
   alignas(64) CUtensorMap tm_g;
+  // narrow planes (slab <= 128 pixels): the x row of ALL chunks of the item's group in one copy (the wide-N mode of KH x 1 filters issued up
+  // to 16 copies of 1.4 KB per x row for ~100 tensor clocks of MMAs)
+  int tma_x;
+  alignas(64) CUtensorMap tm_x;
 };
 
 __device__ __forceinline__ uint32_t wg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -206,11 +210,17 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
           }
           if (lane == 0) {
             wg_mbar_wait(&x_empty[xst], xph ^ 1);
-            wg_mbar_expect_tx(&x_full[xst], (uint32_t)(it.nchunks * p.xslab_bytes));
+            wg_mbar_expect_tx(&x_full[xst], (uint32_t)((p.tma_x ? p.CG : it.nchunks) * p.xslab_bytes));
+            if (p.tma_x)
+              asm volatile(
+                  "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+                      wg_smem_u32(xs + (size_t)xst * p.xstage_bytes)),
+                  "l"(reinterpret_cast<uint64_t>(&p.tm_x)), "r"(-2 * p.pw), "r"(s), "r"(it.c0), "r"(b), "r"(wg_smem_u32(&x_full[xst]))
+                  : "memory");
           }
           __syncwarp();
           const uint8_t* xsrc = p.x + (long long)b * p.x_item_stride + ((long long)s * p.P - p.pw) * 16;
-          for (int c = lane; c < it.nchunks; c += 32)
+          for (int c = lane; c < (p.tma_x ? 0 : it.nchunks); c += 32)
             wg_bulk_g2s(xs + (size_t)xst * p.xstage_bytes + (size_t)c * p.xslab_bytes, xsrc + (long long)(it.c0 + c) * p.x_chunk_stride,
                         (uint32_t)p.xslab_bytes, &x_full[xst]);
           __syncwarp();
@@ -420,6 +430,18 @@ int mpa_conv_wgrad_tc(const void* x_cp8, const void* g_cp8, const void* zero_row
       const CUresult r = enc(&p.tm_g, CU_TENSOR_MAP_DATA_TYPE_UINT64, 5, const_cast<uint8_t*>(p.g), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       p.tma = r == CUDA_SUCCESS ? 1 : 0;                                 // else: one bulk copy per output chunk
+    }
+  }
+  p.tma_x = 0;
+  if (TensorMapEncodeFn enc = tensor_map_encoder()) {
+    const int xslab_px = p.xslab_bytes / 16;
+    if (p.NC >= 2 && xslab_px <= 128 && (p.xstage_bytes % 128) == 0) {
+      const cuuint64_t xd[4] = {(cuuint64_t)pitch * 2, (cuuint64_t)T, (cuuint64_t)p.NC, (cuuint64_t)n_items};
+      const cuuint64_t xs_[3] = {(cuuint64_t)pitch * 16, (cuuint64_t)p.x_chunk_stride, (cuuint64_t)p.x_item_stride};
+      const cuuint32_t bx[4] = {(cuuint32_t)xslab_px * 2, 1, (cuuint32_t)p.CG, 1}, es[4] = {1, 1, 1, 1};
+      const CUresult r = enc(&p.tm_x, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<uint8_t*>(p.x), xd, xs_, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      p.tma_x = r == CUDA_SUCCESS ? 1 : 0;
     }
   }
   const int grid = p.n_items < sms ? p.n_items : sms;
