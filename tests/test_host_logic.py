@@ -336,3 +336,45 @@ def test_cp8_resident_training_path_eligibility():
         assert TR._cp8_resident(m, _exec.cnn_blocks(m), 216) is False
     finally:
         TR.CP8_RESIDENT = True
+
+
+def test_conv3_row_packing_layout_and_pool13_doubling_table():
+    """Host side of the fused CNN head (head.cu head_pool_conv3_tail_kernel): the conv3 operand layout [chunk][frame][channel][C2P] written by
+    ops.pack_conv3_rows, and the doubling-table recurrence the pool13 kernels unroll (pairs -> fours -> eights -> two overlapping eights with
+    delay lines of length 3 / 5 / 6) against max_pool1d((13), 1, 6) — the index arithmetic of maxpool13_bwd_table_kernel / pool13_table_cp8_kernel."""
+    from multipitch_architectures_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    for C2, C1, C1p in [(10, 20, 24), (16, 40, 40), (3, 5, 8)]:
+        w = torch.randn(C2, C1, 75, 1, generator=g)
+        wp = ops.pack_conv3_rows(w, C1p)
+        C2P = 12 if C2 <= 12 else 16
+        assert tuple(wp.shape) == (C1p // 8, 75, 8, C2P) and wp.is_contiguous()
+        for ck, t, c8, co in [(0, 0, 0, 0), (C1p // 8 - 1, 74, 7, C2P - 1), (1 % (C1p // 8), 37, 3, C2 - 1), (0, 5, 4, 1)]:
+            ci = ck * 8 + c8
+            want = float(w[co, ci, t, 0]) if (co < C2 and ci < C1) else 0.0
+            assert float(wp[ck, t, c8, co]) == want
+    # the recurrence with the kernels' ring slots
+    T, H = 75, 6
+    x = torch.randn(T, generator=g).round()        # plateaus
+    ninf = float('-inf')
+    a2, a4, a8 = [ninf] * 3, [ninf] * 5, [ninf] * 6
+    i2, i4, i8 = [0] * 3, [0] * 5, [0] * 6
+    xprev, out, arg = ninf, [], []
+
+    def first_max(v, i, bv, bi):
+        return (bv, bi) if bv > v else (v, i)
+    for p in range(T + H):
+        xp = float(x[p]) if p < T else ninf
+        a2[(p + 2) % 3], i2[(p + 2) % 3] = first_max(xprev, p - 1, xp, p)
+        a4[(p + 2) % 5], i4[(p + 2) % 5] = first_max(a2[p % 3], i2[p % 3], a2[(p + 2) % 3], i2[(p + 2) % 3])
+        a8[(p + 5) % 6], i8[(p + 5) % 6] = first_max(a4[(p + 3) % 5], i4[(p + 3) % 5], a4[(p + 2) % 5], i4[(p + 2) % 5])
+        xprev = xp
+        if p >= H:
+            v, i = first_max(a8[p % 6], i8[p % 6], a8[(p + 5) % 6], i8[(p + 5) % 6])
+            out.append(v)
+            arg.append(i)
+    want, idx = torch.nn.functional.max_pool1d(x.view(1, 1, T), 13, 1, 6, return_indices=True)
+    assert torch.equal(torch.tensor(out), want.view(-1))
+    # first maximum of every window (what the backward routes the gradient to)
+    first = [min(j for j in range(max(0, t - 6), min(T, t + 7)) if x[j] == want.view(-1)[t]) for t in range(T)]
+    assert arg == first
